@@ -1,0 +1,1238 @@
+/*
+ * idocp_oracle.c -- CPU ORACLE (TEST INFRASTRUCTURE, NOT THE PRODUCT).  See idocp_oracle.h.
+ *
+ * Restates, in plain C and in the reference's own operation order, the per-iteration Newton
+ * step of idocp's UnOCPSolver for the iiwa14.  File:line citations point
+ * into the reference tree.  PARITY UNPINNED at the pinocchio boundary (see header).
+ *
+ * Canonical reduction order: every sum / dot product runs over ascending index,
+ * left to right; Eigen's vectorised reductions are not reproducible elsewhere, so this file
+ * DEFINES the order and the CUDA kernels follow it.
+ */
+#include "idocp_oracle.h"
+#include "model_iiwa14.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define NV ORACLE_NV
+#define NC ORACLE_NC
+#define NN (NV * NV)
+
+/* ------------------------------------------------------------------------------------------ */
+/* small helpers                                                                               */
+/* ------------------------------------------------------------------------------------------ */
+static inline void cross3(const double* a, const double* b, double* c) {
+  c[0] = a[1] * b[2] - a[2] * b[1];
+  c[1] = a[2] * b[0] - a[0] * b[2];
+  c[2] = a[0] * b[1] - a[1] * b[0];
+}
+static inline double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+/* y = A x for a symmetric 3x3 stored (xx,xy,xz,yy,yz,zz) */
+static inline void sym3_mul(const double* A, const double* x, double* y) {
+  y[0] = A[0] * x[0] + A[1] * x[1] + A[2] * x[2];
+  y[1] = A[1] * x[0] + A[3] * x[1] + A[4] * x[2];
+  y[2] = A[2] * x[0] + A[4] * x[1] + A[5] * x[2];
+}
+
+double oracle_splitmix_uniform(unsigned long long seed, unsigned long long index) {
+  unsigned long long z = seed + (index + 1ULL) * 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  z = z ^ (z >> 31);
+  return (double)(z >> 11) * (1.0 / 9007199254740992.0); /* [0,1) */
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* robot/: RNEA and its analytical derivatives                                                 */
+/* ------------------------------------------------------------------------------------------ */
+
+/* Robot::RNEA -> pinocchio::rnea (include/idocp/robot/robot.hxx:444-460).
+ * Featherstone's recursive Newton-Euler in body frames, [linear; angular] spatial vectors,
+ * gravity folded into the base acceleration a_0 = (0,0,+9.81). */
+void oracle_rnea(const double* q, const double* v, const double* a, double* tau) {
+  double vl[NV][3], vw[NV][3], fl[NV][3], fw[NV][3], R[NV][9];
+  double al_p[3] = {0.0, 0.0, IIWA14_GRAVITY}, aw_p[3] = {0, 0, 0}, vl_p[3] = {0, 0, 0}, vw_p[3] = {0, 0, 0};
+  for (int i = 0; i < NV; ++i) {
+    const double c = cos(q[i]), s = sin(q[i]);
+    const double* P = IIWA14_PLACEMENT_R[i];
+    const double* pp = IIWA14_PLACEMENT_P[i];
+    /* liMi rotation = placement * Rz(q) (row-major, child -> parent) */
+    double* Ri = R[i];
+    for (int r = 0; r < 3; ++r) {
+      Ri[3 * r + 0] = c * P[3 * r + 0] + s * P[3 * r + 1];
+      Ri[3 * r + 1] = -s * P[3 * r + 0] + c * P[3 * r + 1];
+      Ri[3 * r + 2] = P[3 * r + 2];
+    }
+    /* actInv of the parent's motion: lin = R^T (v - p x w), ang = R^T w */
+    double t[3], u[3], vli[3], vwi[3], ali[3], awi[3];
+    cross3(pp, vw_p, t);
+    for (int k = 0; k < 3; ++k) u[k] = vl_p[k] - t[k];
+    for (int k = 0; k < 3; ++k) {
+      vli[k] = Ri[k] * u[0] + Ri[3 + k] * u[1] + Ri[6 + k] * u[2];
+      vwi[k] = Ri[k] * vw_p[0] + Ri[3 + k] * vw_p[1] + Ri[6 + k] * vw_p[2];
+    }
+    cross3(pp, aw_p, t);
+    for (int k = 0; k < 3; ++k) u[k] = al_p[k] - t[k];
+    for (int k = 0; k < 3; ++k) {
+      ali[k] = Ri[k] * u[0] + Ri[3 + k] * u[1] + Ri[6 + k] * u[2];
+      awi[k] = Ri[k] * aw_p[0] + Ri[3 + k] * aw_p[1] + Ri[6 + k] * aw_p[2];
+    }
+    /* v_i = S qd + ..., a_i = S qdd + v_i x (S qd) + ...   with S = (0,0,0, 0,0,1) */
+    vwi[2] += v[i];
+    /* v x (S qd): lin = v_l x (z qd), ang = w x (z qd) */
+    ali[0] += vli[1] * v[i];
+    ali[1] += -vli[0] * v[i];
+    awi[0] += vwi[1] * v[i];
+    awi[1] += -vwi[0] * v[i];
+    awi[2] += a[i];
+    /* f = Y a + v x* (Y v), Y = (m, c, Ic):  Y x = ( m (xl + xw x c) ; Ic xw + c x lin ) */
+    const double m = IIWA14_MASS[i];
+    const double* cm = IIWA14_COM[i];
+    const double* Ic = IIWA14_INERTIA[i];
+    double hl[3], hw[3], gl[3], gw[3], tmp[3];
+    cross3(vwi, cm, tmp);
+    for (int k = 0; k < 3; ++k) hl[k] = m * (vli[k] + tmp[k]);
+    sym3_mul(Ic, vwi, hw);
+    cross3(cm, hl, tmp);
+    for (int k = 0; k < 3; ++k) hw[k] += tmp[k];
+    cross3(awi, cm, tmp);
+    for (int k = 0; k < 3; ++k) gl[k] = m * (ali[k] + tmp[k]);
+    sym3_mul(Ic, awi, gw);
+    cross3(cm, gl, tmp);
+    for (int k = 0; k < 3; ++k) gw[k] += tmp[k];
+    /* v x* h = (w x hl ; w x hw + vl x hl) */
+    double c1[3], c2[3], c3[3];
+    cross3(vwi, hl, c1);
+    cross3(vwi, hw, c2);
+    cross3(vli, hl, c3);
+    for (int k = 0; k < 3; ++k) {
+      fl[i][k] = gl[k] + c1[k];
+      fw[i][k] = gw[k] + c2[k] + c3[k];
+      vl[i][k] = vli[k]; vw[i][k] = vwi[k];
+      vl_p[k] = vli[k]; vw_p[k] = vwi[k]; al_p[k] = ali[k]; aw_p[k] = awi[k];
+    }
+  }
+  for (int i = NV - 1; i >= 0; --i) {
+    tau[i] = fw[i][2];
+    if (i > 0) {
+      /* f_parent += liMi.act(f): lin = R f, ang = R n + p x (R f) */
+      const double* Ri = R[i];
+      const double* pp = IIWA14_PLACEMENT_P[i];
+      double l[3], n[3], t[3];
+      for (int r = 0; r < 3; ++r) {
+        l[r] = Ri[3 * r] * fl[i][0] + Ri[3 * r + 1] * fl[i][1] + Ri[3 * r + 2] * fl[i][2];
+        n[r] = Ri[3 * r] * fw[i][0] + Ri[3 * r + 1] * fw[i][1] + Ri[3 * r + 2] * fw[i][2];
+      }
+      cross3(pp, l, t);
+      for (int k = 0; k < 3; ++k) { fl[i - 1][k] += l[k]; fw[i - 1][k] += n[k] + t[k]; }
+    }
+  }
+  (void)vl; (void)vw;
+}
+
+/* per-joint world-frame quantities of the derivative algorithm */
+typedef struct {
+  double Sl[3], Sw[3], dSl[3], dSw[3], Bl[3], Bw[3];
+  double m, mc[3], Ib[6], hl[3], ha[3], Sym[6], fl[3], fa[3];
+  double Ul[3], Uw[3], Ww[3], Gl[3], Gw[3], Hl[3], Hw[3];
+} joint_world_t;
+
+/* Robot::RNEADerivatives -> pinocchio::computeRNEADerivatives + lower-triangle mirror of dtau/da
+ * (include/idocp/robot/robot.hxx:466-500).  Analytical derivatives of Carpentier & Mansard
+ * (RSS 2018) in the WORLD frame; the composite matrices are kept in their structured form
+ *   I^C = (m, mc, Ibar)   [10 numbers],   D^C m = (-2 hl x m_w ; Sym m_w - ha x m_w)   [12 numbers]
+ * (derivation: DESIGN.md "RNEA derivatives"; mirrored in oracle/np_mirror.py).
+ * Also returns tau = rnea(q,v,a) when tau != NULL. */
+static void rnea_derivatives_impl(const double* q, const double* v, const double* a, double* tau,
+                                  double* dq, double* dv, double* da) {
+  joint_world_t J[NV];
+  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
+  double vl[3] = {0, 0, 0}, vw[3] = {0, 0, 0}, al[3] = {0, 0, IIWA14_GRAVITY}, aw[3] = {0, 0, 0};
+  for (int i = 0; i < NV; ++i) {
+    joint_world_t* j = &J[i];
+    const double c = cos(q[i]), s = sin(q[i]);
+    const double* P = IIWA14_PLACEMENT_R[i];
+    const double* pp = IIWA14_PLACEMENT_P[i];
+    double L[9], Rn[9];
+    for (int r = 0; r < 3; ++r) {
+      L[3 * r + 0] = c * P[3 * r + 0] + s * P[3 * r + 1];
+      L[3 * r + 1] = -s * P[3 * r + 0] + c * P[3 * r + 1];
+      L[3 * r + 2] = P[3 * r + 2];
+    }
+    for (int r = 0; r < 3; ++r) p[r] += R[3 * r] * pp[0] + R[3 * r + 1] * pp[1] + R[3 * r + 2] * pp[2];
+    for (int r = 0; r < 3; ++r)
+      for (int k = 0; k < 3; ++k)
+        Rn[3 * r + k] = R[3 * r] * L[k] + R[3 * r + 1] * L[3 + k] + R[3 * r + 2] * L[6 + k];
+    memcpy(R, Rn, sizeof(R));
+    const double z[3] = {R[2], R[5], R[8]};
+    cross3(p, z, j->Sl);
+    for (int k = 0; k < 3; ++k) j->Sw[k] = z[k];
+    for (int k = 0; k < 3; ++k) { vw[k] += j->Sw[k] * v[i]; vl[k] += j->Sl[k] * v[i]; }
+    double t1[3], t2[3], t3[3], t4[3];
+    cross3(vw, j->Sl, t1); cross3(vl, j->Sw, t2);
+    for (int k = 0; k < 3; ++k) j->dSl[k] = t1[k] + t2[k];
+    cross3(vw, j->Sw, j->dSw);
+    for (int k = 0; k < 3; ++k) {
+      aw[k] += j->Sw[k] * a[i] + j->dSw[k] * v[i];
+      al[k] += j->Sl[k] * a[i] + j->dSl[k] * v[i];
+    }
+    cross3(aw, j->Sl, t1); cross3(al, j->Sw, t2); cross3(vw, j->dSl, t3); cross3(vl, j->dSw, t4);
+    for (int k = 0; k < 3; ++k) j->Bl[k] = t1[k] + t2[k] + t3[k] + t4[k];
+    cross3(aw, j->Sw, t1); cross3(vw, j->dSw, t2);
+    for (int k = 0; k < 3; ++k) j->Bw[k] = t1[k] + t2[k];
+    /* world inertia about the world origin */
+    const double m = IIWA14_MASS[i];
+    const double* cm = IIWA14_COM[i];
+    const double* Ic = IIWA14_INERTIA[i];
+    double cw[3];
+    for (int r = 0; r < 3; ++r) cw[r] = R[3 * r] * cm[0] + R[3 * r + 1] * cm[1] + R[3 * r + 2] * cm[2] + p[r];
+    j->m = m;
+    for (int k = 0; k < 3; ++k) j->mc[k] = m * cw[k];
+    /* R Ic R^T */
+    double RI[9];
+    for (int r = 0; r < 3; ++r) {
+      const double r0 = R[3 * r], r1 = R[3 * r + 1], r2 = R[3 * r + 2];
+      RI[3 * r + 0] = r0 * Ic[0] + r1 * Ic[1] + r2 * Ic[2];
+      RI[3 * r + 1] = r0 * Ic[1] + r1 * Ic[3] + r2 * Ic[4];
+      RI[3 * r + 2] = r0 * Ic[2] + r1 * Ic[4] + r2 * Ic[5];
+    }
+    const double cc = dot3(cw, cw);
+    int idx = 0;
+    for (int r = 0; r < 3; ++r)
+      for (int k = r; k < 3; ++k) {
+        double e = RI[3 * r] * R[3 * k] + RI[3 * r + 1] * R[3 * k + 1] + RI[3 * r + 2] * R[3 * k + 2];
+        e += m * ((r == k ? cc : 0.0) - cw[r] * cw[k]);
+        j->Ib[idx++] = e;
+      }
+    /* momentum and force */
+    double Iw[3], Ia[3];
+    cross3(vw, j->mc, t1);
+    for (int k = 0; k < 3; ++k) j->hl[k] = m * vl[k] + t1[k];
+    cross3(j->mc, vl, t1); sym3_mul(j->Ib, vw, Iw);
+    for (int k = 0; k < 3; ++k) j->ha[k] = t1[k] + Iw[k];
+    cross3(aw, j->mc, t1); cross3(vw, j->hl, t2);
+    for (int k = 0; k < 3; ++k) j->fl[k] = m * al[k] + t1[k] + t2[k];
+    cross3(j->mc, al, t1); sym3_mul(j->Ib, aw, Ia); cross3(vw, j->ha, t2); cross3(vl, j->hl, t3);
+    for (int k = 0; k < 3; ++k) j->fa[k] = t1[k] + Ia[k] + t2[k] + t3[k];
+    /* Sym = -(vl mc^T + mc vl^T) + 2 (mc.vl) 1 + [w] Ibar + ([w] Ibar)^T */
+    const double* I6 = j->Ib;
+    const double Ifull[9] = {I6[0], I6[1], I6[2], I6[1], I6[3], I6[4], I6[2], I6[4], I6[5]};
+    double wI[9];
+    for (int k = 0; k < 3; ++k) { /* column k of [w] Ibar = w x Ibar[:,k] */
+      const double col[3] = {Ifull[k], Ifull[3 + k], Ifull[6 + k]};
+      double o[3];
+      cross3(vw, col, o);
+      wI[k] = o[0]; wI[3 + k] = o[1]; wI[6 + k] = o[2];
+    }
+    const double mcv = dot3(j->mc, vl);
+    idx = 0;
+    for (int r = 0; r < 3; ++r)
+      for (int k = r; k < 3; ++k) {
+        double e = -(vl[r] * j->mc[k] + j->mc[r] * vl[k]) + wI[3 * r + k] + wI[3 * k + r];
+        if (r == k) e += 2.0 * mcv;
+        j->Sym[idx++] = e;
+      }
+  }
+  /* backward sweep: composite (suffix) sums and the per-joint force-like vectors */
+  double mC = 0, mcC[3] = {0, 0, 0}, IC[6] = {0, 0, 0, 0, 0, 0}, hlC[3] = {0, 0, 0}, haC[3] = {0, 0, 0};
+  double SymC[6] = {0, 0, 0, 0, 0, 0}, Fl[3] = {0, 0, 0}, Fa[3] = {0, 0, 0};
+  for (int i = NV - 1; i >= 0; --i) {
+    joint_world_t* j = &J[i];
+    mC += j->m;
+    for (int k = 0; k < 3; ++k) { mcC[k] += j->mc[k]; hlC[k] += j->hl[k]; haC[k] += j->ha[k]; Fl[k] += j->fl[k]; Fa[k] += j->fa[k]; }
+    for (int k = 0; k < 6; ++k) { IC[k] += j->Ib[k]; SymC[k] += j->Sym[k]; }
+    double t1[3], t2[3], t3[3], t4[3], t5[3];
+    if (tau) tau[i] = dot3(j->Sl, Fl) + dot3(j->Sw, Fa);
+    /* U = I^C S */
+    cross3(j->Sw, mcC, t1);
+    for (int k = 0; k < 3; ++k) j->Ul[k] = mC * j->Sl[k] + t1[k];
+    cross3(mcC, j->Sl, t1); sym3_mul(IC, j->Sw, t2);
+    for (int k = 0; k < 3; ++k) j->Uw[k] = t1[k] + t2[k];
+    /* W = D^C^T S (angular part only; the linear part is identically zero) */
+    cross3(hlC, j->Sl, t1); sym3_mul(SymC, j->Sw, t2); cross3(haC, j->Sw, t3);
+    for (int k = 0; k < 3; ++k) j->Ww[k] = 2.0 * t1[k] + t2[k] + t3[k];
+    /* G = S x* F + I^C B + D^C dS */
+    cross3(j->Sw, Fl, t1); cross3(j->Bw, mcC, t2); cross3(hlC, j->dSw, t3);
+    for (int k = 0; k < 3; ++k) j->Gl[k] = t1[k] + mC * j->Bl[k] + t2[k] - 2.0 * t3[k];
+    cross3(j->Sw, Fa, t1); cross3(j->Sl, Fl, t2); cross3(mcC, j->Bl, t3); sym3_mul(IC, j->Bw, t4);
+    sym3_mul(SymC, j->dSw, t5);
+    double t6[3];
+    cross3(haC, j->dSw, t6);
+    for (int k = 0; k < 3; ++k) j->Gw[k] = t1[k] + t2[k] + t3[k] + t4[k] + t5[k] - t6[k];
+    /* H = D^C S + 2 I^C dS */
+    cross3(hlC, j->Sw, t1); cross3(j->dSw, mcC, t2);
+    for (int k = 0; k < 3; ++k) j->Hl[k] = -2.0 * t1[k] + 2.0 * (mC * j->dSl[k] + t2[k]);
+    sym3_mul(SymC, j->Sw, t1); cross3(haC, j->Sw, t2); cross3(mcC, j->dSl, t3); sym3_mul(IC, j->dSw, t4);
+    for (int k = 0; k < 3; ++k) j->Hw[k] = t1[k] - t2[k] + 2.0 * (t3[k] + t4[k]);
+  }
+  if (!dq) return;
+  for (int c = 0; c < NV; ++c) {
+    const joint_world_t* b = &J[c];
+    for (int r = 0; r < NV; ++r) {
+      const joint_world_t* x = &J[r];
+      if (r <= c) {
+        dq[c * NV + r] = dot3(x->Sl, b->Gl) + dot3(x->Sw, b->Gw);
+        dv[c * NV + r] = dot3(x->Sl, b->Hl) + dot3(x->Sw, b->Hw);
+        const double mm = dot3(x->Sl, b->Ul) + dot3(x->Sw, b->Uw);
+        da[c * NV + r] = mm;
+        da[r * NV + c] = mm; /* robot.hxx:496-499: strictly-lower triangle mirrored from the upper */
+      } else {
+        dq[c * NV + r] = dot3(x->Ul, b->Bl) + dot3(x->Uw, b->Bw) + dot3(x->Ww, b->dSw);
+        dv[c * NV + r] = dot3(x->Ww, b->Sw) + 2.0 * (dot3(x->Ul, b->dSl) + dot3(x->Uw, b->dSw));
+      }
+    }
+  }
+}
+
+void oracle_rnea_derivatives(const double* q, const double* v, const double* a,
+                             double* dq, double* dv, double* da) {
+  rnea_derivatives_impl(q, v, a, NULL, dq, dv, da);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* problem                                                                                     */
+/* ------------------------------------------------------------------------------------------ */
+void oracle_problem_default(oracle_problem_t* p) {
+  memset(p, 0, sizeof(*p));
+  p->N = 20;
+  p->T = 1.0;
+  for (int i = 0; i < NV; ++i) {
+    p->q_min[i] = IIWA14_Q_MIN[i];
+    p->q_max[i] = IIWA14_Q_MAX[i];
+    p->v_max[i] = IIWA14_V_MAX[i];
+    p->u_max[i] = IIWA14_EFFORT_MAX[i];
+  }
+  p->barrier = 1.0e-04;
+  p->fraction_rate = 0.995;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* data types                                                                                  */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct { double lmd[NV], gmm[NV], q[NV], v[NV], a[NV], u[NV], beta[NV]; } split_solution_t;
+typedef struct { double dlmd[NV], dgmm[NV], dq[NV], dv[NV], da[NV], du[NV], dbeta[NV]; } split_direction_t;
+/* ConstraintComponentData (constraints/constraint_component_data.hxx:12-21) */
+typedef struct { double slack[NV], dual[NV], residual[NV], duality[NV], dslack[NV], ddual[NV]; } cdata_t;
+
+/* component order = JointConstraintsFactory push_back order regrouped by kinematics level
+ * (src/utils/joint_constraints_factory.cpp:30-35, constraints/constraints.hxx:23-34):
+ * 0 pos-lower 1 pos-upper | 2 vel-lower 3 vel-upper | 4 torque-lower 5 torque-upper */
+enum { C_POS_LO = 0, C_POS_UP, C_VEL_LO, C_VEL_UP, C_TRQ_LO, C_TRQ_UP };
+
+typedef struct {
+  /* SplitKKTResidual / SplitKKTMatrix pieces the unconstrained path touches */
+  double lq[NV], lv[NV], la[NV], lu[NV], Fq[NV], Fv[NV];
+  double Qqq[NN];                 /* full (task-space cost fills it densely) */
+  double Qvv[NV], Qaa[NV], Quu[NV]; /* diagonals */
+  /* UnconstrainedDynamics members (unocp/unconstrained_dynamics.hxx) */
+  double ID[NV], dIDdq[NN], dIDdv[NN], dIDda[NN], lu_condensed[NV];
+  /* SplitUnKKTMatrix blocks (order a,q,v; split_unkkt_matrix.hxx:31-118) and SplitUnKKTResidual */
+  double uQaa[NN], uQaq[NN], uQav[NN], uQqq[NN], uQqv[NN], uQvq[NN], uQvv[NN];
+  double ula[NV], ulq[NV], ulv[NV], uFq[NV], uFv[NV];
+  /* LQR policy + Riccati factorisation */
+  double K[NV * 2 * NV], k[NV];
+  cdata_t c[NC];
+  int active[NC];
+} stage_t;
+
+typedef struct { double Pqq[NN], Pqv[NN], Pvq[NN], Pvv[NN], sq[NV], sv[NV]; } riccati_t;
+
+#define FILTER_MAX 256
+typedef struct { int n; double cost[FILTER_MAX], viol[FILTER_MAX]; } filter_t;
+
+struct oracle_unocp {
+  oracle_problem_t p;
+  int N;
+  double dt;
+  split_solution_t* s;      /* N+1 */
+  split_direction_t* d;     /* N+1 */
+  stage_t* st;              /* N */
+  riccati_t* ric;           /* N+1 */
+  /* terminal stage */
+  double t_lq[NV], t_lv[NV], t_Qqq[NN], t_Qvv[NN];
+  double primal_step, dual_step, max_primal_step;
+  filter_t filter;
+  split_solution_t* s_try;  /* N+1 */
+  int stage_threads;
+};
+
+/* ------------------------------------------------------------------------------------------ */
+/* constraints/ : pdipm + the six joint-limit components                                       */
+/* ------------------------------------------------------------------------------------------ */
+/* constraints_data.hpp:18-43: which kinematics levels are live at a time stage */
+static void set_active(int time_stage, int* active) {
+  const int pos = time_stage >= 2, vel = time_stage >= 1, acc = time_stage >= 0;
+  active[C_POS_LO] = active[C_POS_UP] = pos;
+  active[C_VEL_LO] = active[C_VEL_UP] = vel;
+  active[C_TRQ_LO] = active[C_TRQ_UP] = acc;
+}
+
+/* g such that slack = g at initialisation and residual = -g + slack  (e.g.
+ * joint_position_lower_limit.cpp:50-55,84-89; siblings differ by sign/variable only) */
+static inline double con_margin(const oracle_problem_t* p, int comp, const split_solution_t* s, int j) {
+  switch (comp) {
+    case C_POS_LO: return s->q[j] - p->q_min[j];
+    case C_POS_UP: return p->q_max[j] - s->q[j];
+    case C_VEL_LO: return s->v[j] - (-p->v_max[j]);
+    case C_VEL_UP: return p->v_max[j] - s->v[j];
+    case C_TRQ_LO: return s->u[j] - (-p->u_max[j]);
+    default:       return p->u_max[j] - s->u[j];
+  }
+}
+
+/* pdipm::SetSlackAndDualPositive (constraints/pdipm.hxx:13-23) */
+static void set_slack_and_dual(const oracle_problem_t* p, stage_t* st, const split_solution_t* s) {
+  for (int c = 0; c < NC; ++c) {
+    cdata_t* d = &st->c[c];
+    memset(d, 0, sizeof(*d));
+    if (!st->active[c]) continue;
+    for (int j = 0; j < NV; ++j) {
+      double sl = con_margin(p, c, s, j);
+      while (sl < p->barrier) sl += p->barrier;
+      d->slack[j] = sl;
+      d->dual[j] = p->barrier / sl;
+    }
+  }
+}
+
+/* computePrimalAndDualResidual of every live component (e.g. joint_position_lower_limit.cpp:84-89)
+ * + pdipm::ComputeDuality (pdipm.hxx:26-31).  Written exactly as the reference: residual =
+ * (limit - x + slack) for lower limits, (x - limit + slack) for upper limits. */
+static void compute_primal_dual_residual(const oracle_problem_t* p, stage_t* st, const split_solution_t* s) {
+  for (int c = 0; c < NC; ++c) {
+    if (!st->active[c]) continue;
+    cdata_t* d = &st->c[c];
+    for (int j = 0; j < NV; ++j) {
+      double r;
+      switch (c) {
+        case C_POS_LO: r = p->q_min[j] - s->q[j] + d->slack[j]; break;
+        case C_POS_UP: r = s->q[j] - p->q_max[j] + d->slack[j]; break;
+        case C_VEL_LO: r = (-p->v_max[j]) - s->v[j] + d->slack[j]; break;
+        case C_VEL_UP: r = s->v[j] - p->v_max[j] + d->slack[j]; break;
+        case C_TRQ_LO: r = (-p->u_max[j]) - s->u[j] + d->slack[j]; break;
+        default:       r = s->u[j] - p->u_max[j] + d->slack[j]; break;
+      }
+      d->residual[j] = r;
+      d->duality[j] = d->slack[j] * d->dual[j] - p->barrier;
+    }
+  }
+}
+
+static inline double* con_grad(stage_t* st, int comp) {
+  return comp <= C_POS_UP ? st->lq : (comp <= C_VEL_UP ? st->lv : st->lu);
+}
+static inline double con_sign(int comp) { return (comp & 1) ? 1.0 : -1.0; } /* lower: -, upper: + */
+
+/* Constraints::augmentDualResidual (constraints.hxx:153-172; joint_*_limit.cpp augmentDualResidual) */
+static void augment_dual_residual(stage_t* st, double dt) {
+  for (int c = 0; c < NC; ++c) {
+    if (!st->active[c]) continue;
+    double* l = con_grad(st, c);
+    const double sg = con_sign(c);
+    for (int j = 0; j < NV; ++j) l[j] += sg * (dt * st->c[c].dual[j]);
+  }
+}
+
+/* Constraints::condenseSlackAndDual (e.g. joint_position_lower_limit.cpp:64-74) */
+static void condense_slack_and_dual(const oracle_problem_t* p, stage_t* st, const split_solution_t* s, double dt) {
+  compute_primal_dual_residual(p, st, s);
+  for (int c = 0; c < NC; ++c) {
+    if (!st->active[c]) continue;
+    cdata_t* d = &st->c[c];
+    double* l = con_grad(st, c);
+    const double sg = con_sign(c);
+    for (int j = 0; j < NV; ++j) {
+      const double h = dt * d->dual[j] / d->slack[j];
+      if (c <= C_POS_UP) st->Qqq[j * NV + j] += h;
+      else if (c <= C_VEL_UP) st->Qvv[j] += h;
+      else st->Quu[j] += h;
+      l[j] += sg * (dt * (d->dual[j] * d->residual[j] - d->duality[j]) / d->slack[j]);
+    }
+  }
+}
+
+/* computeSlackAndDualDirection (e.g. joint_torques_upper_limit.cpp:75-80) + pdipm::ComputeDualDirection
+ * (pdipm.hxx:76-81) */
+static void compute_slack_dual_direction(stage_t* st, const split_direction_t* d) {
+  for (int c = 0; c < NC; ++c) {
+    if (!st->active[c]) continue;
+    cdata_t* cd = &st->c[c];
+    const double* dx = c <= C_POS_UP ? d->dq : (c <= C_VEL_UP ? d->dv : d->du);
+    for (int j = 0; j < NV; ++j) {
+      cd->dslack[j] = ((c & 1) ? -dx[j] : dx[j]) - cd->residual[j];
+      cd->ddual[j] = -(cd->dual[j] * cd->dslack[j] + cd->duality[j]) / cd->slack[j];
+    }
+  }
+}
+
+/* pdipm::FractionToBoundary (pdipm.hxx:52-73), literal: only fractions strictly inside (0,1) count */
+static double fraction_to_boundary(double rate, const double* vec, const double* dvec) {
+  double mn = 1.0;
+  for (int i = 0; i < NV; ++i) {
+    const double f = -rate * (vec[i] / dvec[i]);
+    if (f > 0 && f < 1) {
+      if (f < mn) mn = f;
+    }
+  }
+  return mn;
+}
+
+static double max_slack_step(const oracle_problem_t* p, const stage_t* st) {
+  double mn = 1.0;
+  for (int c = 0; c < NC; ++c) {
+    if (!st->active[c]) continue;
+    const double f = fraction_to_boundary(p->fraction_rate, st->c[c].slack, st->c[c].dslack);
+    if (f < mn) mn = f;
+  }
+  return mn;
+}
+static double max_dual_step(const oracle_problem_t* p, const stage_t* st) {
+  double mn = 1.0;
+  for (int c = 0; c < NC; ++c) {
+    if (!st->active[c]) continue;
+    const double f = fraction_to_boundary(p->fraction_rate, st->c[c].dual, st->c[c].ddual);
+    if (f < mn) mn = f;
+  }
+  return mn;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* cost/ : ConfigurationSpaceCost (src/cost/configuration_space_cost.cpp:241-396)              */
+/* ------------------------------------------------------------------------------------------ */
+static void stage_cost_derivatives(const oracle_problem_t* p, double dt, const split_solution_t* s, stage_t* st) {
+  for (int j = 0; j < NV; ++j) {
+    st->lq[j] += dt * p->q_weight[j] * (s->q[j] - p->q_ref[j]);
+    st->lv[j] += dt * p->v_weight[j] * (s->v[j] - p->v_ref[j]);
+    st->la[j] += dt * p->a_weight[j] * s->a[j];
+    st->lu[j] += dt * p->u_weight[j] * (s->u[j] - p->u_ref[j]);
+  }
+}
+static void stage_cost_hessian(const oracle_problem_t* p, double dt, stage_t* st) {
+  for (int j = 0; j < NV; ++j) {
+    st->Qqq[j * NV + j] += dt * p->q_weight[j];
+    st->Qvv[j] += dt * p->v_weight[j];
+    st->Qaa[j] += dt * p->a_weight[j];
+    st->Quu[j] += dt * p->u_weight[j];
+  }
+}
+static double stage_cost(const oracle_problem_t* p, double dt, const split_solution_t* s) {
+  double l = 0, part;
+  part = 0; for (int j = 0; j < NV; ++j) part += p->q_weight[j] * (s->q[j] - p->q_ref[j]) * (s->q[j] - p->q_ref[j]);
+  l += part;
+  part = 0; for (int j = 0; j < NV; ++j) part += p->v_weight[j] * (s->v[j] - p->v_ref[j]) * (s->v[j] - p->v_ref[j]);
+  l += part;
+  part = 0; for (int j = 0; j < NV; ++j) part += p->a_weight[j] * s->a[j] * s->a[j];
+  l += part;
+  part = 0; for (int j = 0; j < NV; ++j) part += p->u_weight[j] * (s->u[j] - p->u_ref[j]) * (s->u[j] - p->u_ref[j]);
+  l += part;
+  return 0.5 * dt * l;
+}
+static double terminal_cost(const oracle_problem_t* p, const split_solution_t* s) {
+  double l = 0, part;
+  part = 0; for (int j = 0; j < NV; ++j) part += p->qf_weight[j] * (s->q[j] - p->q_ref[j]) * (s->q[j] - p->q_ref[j]);
+  l += part;
+  part = 0; for (int j = 0; j < NV; ++j) part += p->vf_weight[j] * (s->v[j] - p->v_ref[j]) * (s->v[j] - p->v_ref[j]);
+  l += part;
+  return 0.5 * l;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* SplitUnOCP (unocp/split_unocp.hxx)                                                          */
+/* ------------------------------------------------------------------------------------------ */
+/* steps 1-4 of SURVEY A.2, shared by linearizeOCP (:69-99) and computeKKTResidual (:141-161) */
+static void stage_residual_common(const oracle_problem_t* p, double dt, const split_solution_t* s,
+                                  const split_solution_t* sn, stage_t* st, int with_derivatives) {
+  memset(st->lq, 0, sizeof(double) * NV); memset(st->lv, 0, sizeof(double) * NV);
+  memset(st->la, 0, sizeof(double) * NV); memset(st->lu, 0, sizeof(double) * NV);
+  stage_cost_derivatives(p, dt, s, st);
+  augment_dual_residual(st, dt);
+  /* stateequation::linearizeForwardEuler (ocp/state_equation.hxx:11-37,210-221) */
+  for (int j = 0; j < NV; ++j) {
+    st->Fq[j] = s->q[j] - sn->q[j];
+    st->Fq[j] += dt * s->v[j];
+    st->Fv[j] = s->v[j] + dt * s->a[j] - sn->v[j];
+  }
+  for (int j = 0; j < NV; ++j) {
+    st->lq[j] += sn->lmd[j] - s->lmd[j];
+    st->lv[j] += dt * sn->lmd[j] + sn->gmm[j] - s->gmm[j];
+    st->la[j] += dt * sn->gmm[j];
+  }
+  /* UnconstrainedDynamics::linearizeUnconstrainedDynamics (unocp/unconstrained_dynamics.hxx:55-65,166-177) */
+  (void)with_derivatives;
+  rnea_derivatives_impl(s->q, s->v, s->a, st->ID, st->dIDdq, st->dIDdv, st->dIDda);
+  for (int j = 0; j < NV; ++j) st->ID[j] -= s->u[j];
+  for (int j = 0; j < NV; ++j) {
+    double tq = 0, tv = 0, ta = 0;
+    for (int k = 0; k < NV; ++k) {
+      tq += st->dIDdq[j * NV + k] * s->beta[k];
+      tv += st->dIDdv[j * NV + k] * s->beta[k];
+      ta += st->dIDda[j * NV + k] * s->beta[k];
+    }
+    st->lq[j] += dt * tq;
+    st->lv[j] += dt * tv;
+    st->la[j] += dt * ta;
+    st->lu[j] -= dt * s->beta[j];
+  }
+}
+
+/* SplitUnOCP::linearizeOCP (unocp/split_unocp.hxx:69-99) */
+static void split_unocp_linearize(const oracle_problem_t* p, double dt, const split_solution_t* s,
+                                  const split_solution_t* sn, stage_t* st) {
+  memset(st->Qqq, 0, sizeof(st->Qqq));
+  memset(st->Qvv, 0, sizeof(st->Qvv)); memset(st->Qaa, 0, sizeof(st->Qaa)); memset(st->Quu, 0, sizeof(st->Quu));
+  stage_residual_common(p, dt, s, sn, st, 1);
+  stage_cost_hessian(p, dt, st);
+  condense_slack_and_dual(p, st, s, dt);
+  /* UnconstrainedDynamics::condenseUnconstrainedDynamics (unconstrained_dynamics.hxx:68-94) */
+  for (int j = 0; j < NV; ++j) st->lu_condensed[j] = st->lu[j] + st->Quu[j] * st->ID[j];
+  for (int j = 0; j < NV; ++j) {
+    double tq = 0, tv = 0, ta = 0;
+    for (int k = 0; k < NV; ++k) {
+      tq += st->dIDdq[j * NV + k] * st->lu_condensed[k];
+      tv += st->dIDdv[j * NV + k] * st->lu_condensed[k];
+      ta += st->dIDda[j * NV + k] * st->lu_condensed[k];
+    }
+    st->ulq[j] = st->lq[j] + tq;
+    st->ulv[j] = st->lv[j] + tv;
+    st->ula[j] = st->la[j] + ta;
+    st->uFq[j] = st->Fq[j];
+    st->uFv[j] = st->Fv[j];
+  }
+  /* Q_xy = (dID_dx)^T diag(Quu) (dID_dy) */
+  for (int c = 0; c < NV; ++c)
+    for (int r = 0; r < NV; ++r) {
+      double qq = 0, qv = 0, vv = 0, aq = 0, av = 0, aa = 0;
+      for (int k = 0; k < NV; ++k) {
+        const double Dq = st->Quu[k] * st->dIDdq[c * NV + k];
+        const double Dv = st->Quu[k] * st->dIDdv[c * NV + k];
+        const double Da = st->Quu[k] * st->dIDda[c * NV + k];
+        qq += st->dIDdq[r * NV + k] * Dq;
+        qv += st->dIDdq[r * NV + k] * Dv;
+        vv += st->dIDdv[r * NV + k] * Dv;
+        aq += st->dIDda[r * NV + k] * Dq;
+        av += st->dIDda[r * NV + k] * Dv;
+        aa += st->dIDda[r * NV + k] * Da;
+      }
+      st->uQqq[c * NV + r] = qq + st->Qqq[c * NV + r];
+      st->uQqv[c * NV + r] = qv;
+      st->uQvv[c * NV + r] = vv + (r == c ? st->Qvv[r] : 0.0);
+      st->uQaq[c * NV + r] = aq;
+      st->uQav[c * NV + r] = av;
+      st->uQaa[c * NV + r] = aa + (r == c ? st->Qaa[r] : 0.0);
+    }
+}
+
+/* SplitUnOCP::computeKKTResidual (split_unocp.hxx:141-161) */
+static void split_unocp_kkt_residual(const oracle_problem_t* p, double dt, const split_solution_t* s,
+                                     const split_solution_t* sn, stage_t* st) {
+  compute_primal_dual_residual(p, st, s);
+  stage_residual_common(p, dt, s, sn, st, 0);
+}
+
+static double sqnorm(const double* x) {
+  double r = 0;
+  for (int j = 0; j < NV; ++j) r += x[j] * x[j];
+  return r;
+}
+static double l1norm(const double* x) {
+  double r = 0;
+  for (int j = 0; j < NV; ++j) r += fabs(x[j]);
+  return r;
+}
+
+/* SplitUnOCP::squaredNormKKTResidual (split_unocp.hxx:164-174) */
+static double split_unocp_sqnorm(const stage_t* st, double dt) {
+  double e = 0;
+  e += sqnorm(st->lq) + sqnorm(st->lv);   /* lx */
+  e += sqnorm(st->la);
+  e += sqnorm(st->lu);
+  e += sqnorm(st->Fq) + sqnorm(st->Fv);   /* Fx */
+  e += dt * dt * sqnorm(st->ID);
+  double c2 = 0;
+  for (int c = 0; c < NC; ++c)
+    if (st->active[c]) c2 += sqnorm(st->c[c].residual) + sqnorm(st->c[c].duality);
+  e += dt * dt * c2;
+  return e;
+}
+
+/* UnconstrainedDynamics::computeCondensedDirection (unconstrained_dynamics.hxx:97-106) +
+ * Constraints::computeSlackAndDualDirection */
+static void split_unocp_condensed_direction(stage_t* st, double dt, split_direction_t* d) {
+  for (int r = 0; r < NV; ++r) {
+    double acc = st->ID[r];
+    double t = 0;
+    for (int c = 0; c < NV; ++c) t += st->dIDdq[c * NV + r] * d->dq[c];
+    acc += t;
+    t = 0;
+    for (int c = 0; c < NV; ++c) t += st->dIDdv[c * NV + r] * d->dv[c];
+    acc += t;
+    t = 0;
+    for (int c = 0; c < NV; ++c) t += st->dIDda[c * NV + r] * d->da[c];
+    acc += t;
+    d->du[r] = acc;
+  }
+  for (int r = 0; r < NV; ++r) d->dbeta[r] = (st->lu[r] + st->Quu[r] * d->du[r]) / dt;
+  compute_slack_dual_direction(st, d);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Riccati recursion (unocp/backward_unriccati_recursion_factorizer.hxx,                        */
+/* unocp/split_unriccati_factorizer.hxx, src/unocp/unriccati_recursion.cpp)                    */
+/* ------------------------------------------------------------------------------------------ */
+/* Eigen::LLT<MatrixXd, Lower>: unblocked left-looking Cholesky reading the lower triangle only
+ * (SURVEY A.7); returns 0 on success, k+1 when pivot k is not positive. */
+static int llt_lower(const double* A, int n, double* L) {
+  for (int i = 0; i < n * n; ++i) L[i] = 0.0;
+  for (int k = 0; k < n; ++k) {
+    double x = A[k * n + k];
+    for (int j = 0; j < k; ++j) x -= L[j * n + k] * L[j * n + k];
+    if (!(x > 0.0)) return k + 1;
+    x = sqrt(x);
+    L[k * n + k] = x;
+    for (int i = k + 1; i < n; ++i) {
+      double y = A[k * n + i];
+      for (int j = 0; j < k; ++j) y -= L[j * n + i] * L[j * n + k];
+      L[k * n + i] = y / x;
+    }
+  }
+  return 0;
+}
+/* x = (L L^T)^-1 b : forward then backward substitution, one right-hand side */
+static void llt_solve(const double* L, int n, const double* b, double* x) {
+  for (int i = 0; i < n; ++i) {
+    double y = b[i];
+    for (int j = 0; j < i; ++j) y -= L[j * n + i] * x[j];
+    x[i] = y / L[i * n + i];
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double y = x[i];
+    for (int j = i + 1; j < n; ++j) y -= L[i * n + j] * x[j];
+    x[i] = y / L[i * n + i];
+  }
+}
+
+/* SplitUnRiccatiFactorizer::backwardRiccatiRecursion (split_unriccati_factorizer.hxx:30-46) */
+static int riccati_backward_stage(const riccati_t* rn, double dt, stage_t* st, riccati_t* r) {
+  /* BackwardUnRiccatiRecursionFactorizer::factorizeKKTMatrix (:29-54) */
+  for (int c = 0; c < NV; ++c)
+    for (int rr = 0; rr < NV; ++rr) {
+      const int i = c * NV + rr, it = rr * NV + c;
+      st->uQqq[i] += rn->Pqq[i];
+      st->uQqv[i] += dt * rn->Pqq[i];
+      st->uQqv[i] += rn->Pqv[i];
+      st->uQvv[i] += dt * dt * rn->Pqq[i];
+      st->uQvv[i] += dt * rn->Pqv[i];
+      st->uQvv[i] += dt * rn->Pqv[it];
+      st->uQvv[i] += rn->Pvv[i];
+      st->uQaq[i] += dt * rn->Pqv[it];            /* Qaq^T += dt Pqv */
+      st->uQav[i] += dt * dt * rn->Pqv[it];       /* Qav^T += dt^2 Pqv + dt Pvv */
+      st->uQav[i] += dt * rn->Pvv[it];
+      st->uQaa[i] += dt * dt * rn->Pvv[i];
+    }
+  for (int c = 0; c < NV; ++c)
+    for (int rr = 0; rr < NV; ++rr) st->uQvq[c * NV + rr] = st->uQqv[rr * NV + c];
+  for (int j = 0; j < NV; ++j) {
+    double t1 = 0, t2 = 0;
+    for (int k = 0; k < NV; ++k) {
+      t1 += rn->Pqv[j * NV + k] * st->uFq[k];     /* (Pqv^T Fq)_j */
+      t2 += rn->Pvv[k * NV + j] * st->uFv[k];     /* (Pvv Fv)_j   */
+    }
+    st->ula[j] += dt * t1;
+    st->ula[j] += dt * t2;
+    st->ula[j] -= dt * rn->sv[j];
+  }
+  /* llt_.compute(Qaa); K = -llt_.solve(Qax); k = -llt_.solve(la) (:37-40) */
+  double L[NN], x[NV];
+  const int info = llt_lower(st->uQaa, NV, L);
+  for (int c = 0; c < NV; ++c) {
+    llt_solve(L, NV, &st->uQaq[c * NV], x);
+    for (int j = 0; j < NV; ++j) st->K[c * NV + j] = -x[j];
+    llt_solve(L, NV, &st->uQav[c * NV], x);
+    for (int j = 0; j < NV; ++j) st->K[(NV + c) * NV + j] = -x[j];
+  }
+  llt_solve(L, NV, st->ula, x);
+  for (int j = 0; j < NV; ++j) st->k[j] = -x[j];
+  /* factorizeRiccatiFactorization (:57-89) */
+  double GK[NV * 2 * NV];
+  for (int c = 0; c < 2 * NV; ++c)
+    for (int rr = 0; rr < NV; ++rr) {
+      double t = 0;
+      for (int k = 0; k < NV; ++k) t += st->uQaa[k * NV + rr] * st->K[c * NV + k];
+      GK[c * NV + rr] = t;
+    }
+  const double* Kq = st->K;
+  const double* Kv = st->K + NN;
+  const double* GKq = GK;
+  const double* GKv = GK + NN;
+  for (int c = 0; c < NV; ++c)
+    for (int rr = 0; rr < NV; ++rr) {
+      double tqq = 0, tqv = 0, tvv = 0;
+      for (int k = 0; k < NV; ++k) {
+        tqq += Kq[rr * NV + k] * GKq[c * NV + k];
+        tqv += Kq[rr * NV + k] * GKv[c * NV + k];
+        tvv += Kv[rr * NV + k] * GKv[c * NV + k];
+      }
+      r->Pqq[c * NV + rr] = st->uQqq[c * NV + rr] - tqq;
+      r->Pqv[c * NV + rr] = st->uQqv[c * NV + rr] - tqv;
+      r->Pvv[c * NV + rr] = st->uQvv[c * NV + rr] - tvv;
+    }
+  for (int c = 0; c < NV; ++c)
+    for (int rr = 0; rr < NV; ++rr) r->Pvq[c * NV + rr] = r->Pqv[rr * NV + c];
+  /* preserve the symmetry */
+  for (int c = 0; c < NV; ++c)
+    for (int rr = c; rr < NV; ++rr) {
+      const double a = 0.5 * (r->Pqq[c * NV + rr] + r->Pqq[rr * NV + c]);
+      r->Pqq[c * NV + rr] = a; r->Pqq[rr * NV + c] = a;
+      const double b = 0.5 * (r->Pvv[c * NV + rr] + r->Pvv[rr * NV + c]);
+      r->Pvv[c * NV + rr] = b; r->Pvv[rr * NV + c] = b;
+    }
+  for (int j = 0; j < NV; ++j) {
+    double t1 = 0, t2 = 0;
+    for (int k = 0; k < NV; ++k) {
+      t1 += rn->Pqq[k * NV + j] * st->uFq[k];
+      t2 += rn->Pqv[k * NV + j] * st->uFv[k];
+    }
+    r->sq[j] = rn->sq[j];
+    r->sq[j] -= t1;
+    r->sq[j] -= t2;
+  }
+  for (int j = 0; j < NV; ++j) {
+    double t1 = 0, t2 = 0;
+    for (int k = 0; k < NV; ++k) {
+      t1 += rn->Pqv[j * NV + k] * st->uFq[k];     /* Pqv^T Fq */
+      t2 += rn->Pvv[k * NV + j] * st->uFv[k];
+    }
+    r->sv[j] = rn->sv[j];
+    r->sv[j] += dt * r->sq[j];
+    r->sv[j] -= t1;
+    r->sv[j] -= t2;
+  }
+  for (int j = 0; j < NV; ++j) {
+    r->sq[j] -= st->ulq[j];
+    r->sv[j] -= st->ulv[j];
+  }
+  for (int j = 0; j < NV; ++j) {
+    double t1 = 0, t2 = 0;
+    for (int k = 0; k < NV; ++k) {
+      t1 += st->uQaq[j * NV + k] * st->k[k];      /* Qaq^T k */
+      t2 += st->uQav[j * NV + k] * st->k[k];
+    }
+    r->sq[j] -= t1;
+    r->sv[j] -= t2;
+  }
+  return info;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* UnLineSearch + LineSearchFilter (line_search/unline_search.hpp:62-133,                      */
+/* src/line_search/unline_search.cpp:56-135, src/line_search/line_search_filter.cpp:34-80)     */
+/* ------------------------------------------------------------------------------------------ */
+static int filter_is_accepted(const filter_t* f, double cost, double viol) {
+  for (int i = 0; i < f->n; ++i)
+    if (cost >= f->cost[i] && viol >= f->viol[i]) return 0;
+  return 1;
+}
+static void filter_augment(filter_t* f, double cost, double viol) {
+  int w = 0;
+  for (int i = 0; i < f->n; ++i) {
+    if (cost <= f->cost[i] && viol <= f->viol[i]) continue; /* erased */
+    f->cost[w] = f->cost[i]; f->viol[w] = f->viol[i]; ++w;
+  }
+  f->n = w;
+  if (f->n < FILTER_MAX) {
+    f->cost[f->n] = cost - 0.005 * viol;       /* line_search_filter.hpp:16-17 */
+    f->viol[f->n] = (1 - 0.005) * viol;
+    ++f->n;
+  }
+}
+
+/* SplitUnOCP::stageCost (split_unocp.hxx:177-196): cost + dt * barrier(slack + alpha dslack) */
+static double split_unocp_stage_cost(const oracle_problem_t* p, double dt, const stage_t* st,
+                                     const split_solution_t* s, double alpha) {
+  double cost = stage_cost(p, dt, s);
+  double bar = 0;
+  for (int c = 0; c < NC; ++c) {
+    if (!st->active[c]) continue;
+    double lg = 0;
+    for (int j = 0; j < NV; ++j) {
+      const double sl = alpha > 0 ? st->c[c].slack[j] + alpha * st->c[c].dslack[j] : st->c[c].slack[j];
+      lg += log(sl);
+    }
+    bar += -p->barrier * lg;
+  }
+  cost += dt * bar;
+  return cost;
+}
+
+/* SplitUnOCP::constraintViolation (split_unocp.hxx:199-217); note it overwrites residual/duality,
+ * Fx and ID of the stage exactly as the reference does (the solver re-linearises afterwards). */
+static double split_unocp_violation(const oracle_problem_t* p, double dt, stage_t* st,
+                                    const split_solution_t* s, const double* qn, const double* vn) {
+  compute_primal_dual_residual(p, st, s);
+  for (int j = 0; j < NV; ++j) {
+    st->Fq[j] = s->q[j] - qn[j];
+    st->Fq[j] += dt * s->v[j];
+    st->Fv[j] = s->v[j] + dt * s->a[j] - vn[j];
+  }
+  oracle_rnea(s->q, s->v, s->a, st->ID);
+  for (int j = 0; j < NV; ++j) st->ID[j] -= s->u[j];
+  double viol = 0;
+  viol += l1norm(st->Fq) + l1norm(st->Fv);
+  viol += dt * l1norm(st->ID);
+  double c1 = 0;
+  for (int c = 0; c < NC; ++c)
+    if (st->active[c]) c1 += l1norm(st->c[c].residual);
+  viol += dt * c1;
+  return viol;
+}
+
+static void cost_and_violation(oracle_unocp_t* o, const split_solution_t* s, double alpha,
+                               double* cost, double* viol) {
+  double cs = 0, vs = 0;
+  for (int i = 0; i <= o->N; ++i) {
+    if (i < o->N) {
+      cs += split_unocp_stage_cost(&o->p, o->dt, &o->st[i], &s[i], alpha);
+      vs += split_unocp_violation(&o->p, o->dt, &o->st[i], &s[i], s[i + 1].q, s[i + 1].v);
+    } else {
+      cs += terminal_cost(&o->p, &s[i]);
+    }
+  }
+  *cost = cs; *viol = vs;
+}
+
+static double line_search_step(oracle_unocp_t* o, double max_primal) {
+  double cost, viol;
+  if (o->filter.n == 0) {
+    cost_and_violation(o, o->s, 0.0, &cost, &viol);
+    filter_augment(&o->filter, cost, viol);
+  }
+  const double min_step = 0.05, rate = 0.75;       /* unline_search.hpp:25-26 */
+  double alpha = max_primal;
+  while (alpha > min_step) {
+    for (int i = 0; i <= o->N; ++i) {
+      split_solution_t* t = &o->s_try[i];
+      for (int j = 0; j < NV; ++j) {
+        t->q[j] = o->s[i].q[j] + alpha * o->d[i].dq[j];
+        t->v[j] = o->s[i].v[j] + alpha * o->d[i].dv[j];
+        t->a[j] = o->s[i].a[j] + alpha * o->d[i].da[j];
+        t->u[j] = o->s[i].u[j] + alpha * o->d[i].du[j];
+      }
+    }
+    cost_and_violation(o, o->s_try, alpha, &cost, &viol);
+    if (filter_is_accepted(&o->filter, cost, viol)) {
+      filter_augment(&o->filter, cost, viol);
+      break;
+    }
+    alpha *= rate;
+  }
+  return alpha > min_step ? alpha : min_step;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* UnOCPSolver (src/unocp/unocp_solver.cpp)                                                    */
+/* ------------------------------------------------------------------------------------------ */
+oracle_unocp_t* oracle_unocp_create(const oracle_problem_t* p) {
+  if (p->N <= 0 || !(p->T > 0)) return NULL;
+  oracle_unocp_t* o = (oracle_unocp_t*)calloc(1, sizeof(*o));
+  o->p = *p;
+  o->N = p->N;
+  o->dt = p->T / p->N;
+  o->s = (split_solution_t*)calloc(o->N + 1, sizeof(split_solution_t));
+  o->s_try = (split_solution_t*)calloc(o->N + 1, sizeof(split_solution_t));
+  o->d = (split_direction_t*)calloc(o->N + 1, sizeof(split_direction_t));
+  o->st = (stage_t*)calloc(o->N, sizeof(stage_t));
+  o->ric = (riccati_t*)calloc(o->N + 1, sizeof(riccati_t));
+  o->stage_threads = 1;
+  oracle_unocp_init_constraints(o);  /* the reference ctor ends with initConstraints() (:48) */
+  return o;
+}
+
+void oracle_unocp_destroy(oracle_unocp_t* o) {
+  if (!o) return;
+  free(o->s); free(o->s_try); free(o->d); free(o->st); free(o->ric); free(o);
+}
+
+void oracle_unocp_set_stage_threads(oracle_unocp_t* o, int nthreads) { o->stage_threads = nthreads > 0 ? nthreads : 1; }
+
+/* UnOCPSolver::initConstraints (:59-70) */
+void oracle_unocp_init_constraints(oracle_unocp_t* o) {
+  for (int i = 0; i < o->N; ++i) {
+    set_active(i, o->st[i].active);
+    set_slack_and_dual(&o->p, &o->st[i], &o->s[i]);
+  }
+}
+
+/* UnOCPSolver::setSolution (:157-181) */
+int oracle_unocp_set_solution(oracle_unocp_t* o, const char* name, const double* value) {
+  for (int i = 0; i <= o->N; ++i) {
+    double* dst;
+    if (!strcmp(name, "q")) dst = o->s[i].q;
+    else if (!strcmp(name, "v")) dst = o->s[i].v;
+    else if (!strcmp(name, "a")) dst = o->s[i].a;
+    else if (!strcmp(name, "u")) dst = o->s[i].u;
+    else return -1;
+    memcpy(dst, value, sizeof(double) * NV);
+  }
+  oracle_unocp_init_constraints(o);
+  return 0;
+}
+
+/* TerminalOCP::linearizeOCP / computeKKTResidual (ocp/terminal_ocp.hxx:50-66,120-136) */
+static void terminal_linearize(oracle_unocp_t* o, int with_hessian) {
+  const oracle_problem_t* p = &o->p;
+  const split_solution_t* s = &o->s[o->N];
+  for (int j = 0; j < NV; ++j) {
+    o->t_lq[j] = 0; o->t_lv[j] = 0;
+    o->t_lq[j] += p->qf_weight[j] * (s->q[j] - p->q_ref[j]);
+    o->t_lv[j] += p->vf_weight[j] * (s->v[j] - p->v_ref[j]);
+    o->t_lq[j] -= s->lmd[j];
+    o->t_lv[j] -= s->gmm[j];
+  }
+  if (with_hessian) {
+    memset(o->t_Qqq, 0, sizeof(o->t_Qqq));
+    memset(o->t_Qvv, 0, sizeof(o->t_Qvv));
+    for (int j = 0; j < NV; ++j) {
+      o->t_Qqq[j * NV + j] += p->qf_weight[j];
+      o->t_Qvv[j * NV + j] += p->vf_weight[j];
+    }
+  }
+}
+
+/* UnOCPSolver::updateSolution (:73-134) */
+void oracle_unocp_update_solution(oracle_unocp_t* o, double t, const double* q, const double* v,
+                                  int line_search) {
+  (void)t; /* ConfigurationSpaceCost is time-invariant */
+  const int N = o->N;
+  const double dt = o->dt;
+#pragma omp parallel for num_threads(o->stage_threads) if (o->stage_threads > 1)
+  for (int i = 0; i <= N; ++i) {
+    if (i < N) split_unocp_linearize(&o->p, dt, &o->s[i], &o->s[i + 1], &o->st[i]);
+    else terminal_linearize(o, 1);
+  }
+  /* UnRiccatiRecursion::backwardRiccatiRecursionTerminal (src/unocp/unriccati_recursion.cpp:39-47):
+   * Pqv of the terminal stage stays zero as allocated */
+  riccati_t* rN = &o->ric[N];
+  memcpy(rN->Pqq, o->t_Qqq, sizeof(rN->Pqq));
+  memcpy(rN->Pvv, o->t_Qvv, sizeof(rN->Pvv));
+  memset(rN->Pqv, 0, sizeof(rN->Pqv)); memset(rN->Pvq, 0, sizeof(rN->Pvq));
+  for (int j = 0; j < NV; ++j) { rN->sq[j] = -o->t_lq[j]; rN->sv[j] = -o->t_lv[j]; }
+  for (int i = N - 1; i >= 0; --i) riccati_backward_stage(&o->ric[i + 1], dt, &o->st[i], &o->ric[i]);
+  for (int j = 0; j < NV; ++j) {
+    o->d[0].dq[j] = q[j] - o->s[0].q[j];
+    o->d[0].dv[j] = v[j] - o->s[0].v[j];
+  }
+  /* forwardRiccatiRecursion (split_unriccati_factorizer.hxx:49-57) */
+  for (int i = 0; i < N; ++i) {
+    split_direction_t* d = &o->d[i];
+    split_direction_t* dn = &o->d[i + 1];
+    const stage_t* st = &o->st[i];
+    for (int r = 0; r < NV; ++r) {
+      double acc = 0;
+      for (int c = 0; c < NV; ++c) acc += st->K[c * NV + r] * d->dq[c];
+      for (int c = 0; c < NV; ++c) acc += st->K[(NV + c) * NV + r] * d->dv[c];
+      d->da[r] = acc + st->k[r];
+    }
+    for (int j = 0; j < NV; ++j) {
+      dn->dq[j] = st->uFq[j] + d->dq[j];
+      dn->dv[j] = st->uFv[j] + d->dv[j];
+      dn->dq[j] += dt * d->dv[j];
+      dn->dv[j] += dt * d->da[j];
+    }
+  }
+  double primal = 1.0, dual = 1.0;
+#pragma omp parallel for num_threads(o->stage_threads) if (o->stage_threads > 1)
+  for (int i = 0; i <= N; ++i) {
+    /* computeCostateDirection (:60-68) */
+    const riccati_t* r = &o->ric[i];
+    split_direction_t* d = &o->d[i];
+    for (int j = 0; j < NV; ++j) {
+      double t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+      for (int k = 0; k < NV; ++k) {
+        t1 += r->Pqq[k * NV + j] * d->dq[k];
+        t2 += r->Pqv[k * NV + j] * d->dv[k];
+        t3 += r->Pqv[j * NV + k] * d->dq[k];   /* Pqv^T dq */
+        t4 += r->Pvv[k * NV + j] * d->dv[k];
+      }
+      d->dlmd[j] = t1; d->dlmd[j] += t2; d->dlmd[j] -= r->sq[j];
+      d->dgmm[j] = t3; d->dgmm[j] += t4; d->dgmm[j] -= r->sv[j];
+    }
+    if (i < N) split_unocp_condensed_direction(&o->st[i], dt, d);
+  }
+  for (int i = 0; i < N; ++i) {
+    const double ps = max_slack_step(&o->p, &o->st[i]);
+    const double ds = max_dual_step(&o->p, &o->st[i]);
+    if (ps < primal) primal = ps;
+    if (ds < dual) dual = ds;
+  }
+  o->max_primal_step = primal;
+  if (line_search) primal = line_search_step(o, primal);
+  o->primal_step = primal;
+  o->dual_step = dual;
+#pragma omp parallel for num_threads(o->stage_threads) if (o->stage_threads > 1)
+  for (int i = 0; i <= N; ++i) {
+    split_solution_t* s = &o->s[i];
+    const split_direction_t* d = &o->d[i];
+    for (int j = 0; j < NV; ++j) {
+      s->lmd[j] += primal * d->dlmd[j];
+      s->gmm[j] += primal * d->dgmm[j];
+      s->q[j] += primal * d->dq[j];
+      s->v[j] += primal * d->dv[j];
+    }
+    if (i < N) {
+      for (int j = 0; j < NV; ++j) {
+        s->a[j] += primal * d->da[j];
+        s->u[j] += primal * d->du[j];
+        s->beta[j] += primal * d->dbeta[j];
+      }
+      stage_t* st = &o->st[i];
+      for (int c = 0; c < NC; ++c) {
+        if (!st->active[c]) continue;
+        for (int j = 0; j < NV; ++j) {
+          st->c[c].slack[j] += primal * st->c[c].dslack[j];
+          st->c[c].dual[j] += dual * st->c[c].ddual[j];
+        }
+      }
+    }
+  }
+}
+
+/* UnOCPSolver::computeKKTResidual (:205-225) */
+void oracle_unocp_compute_kkt_residual(oracle_unocp_t* o, double t, const double* q, const double* v) {
+  (void)t; (void)q; (void)v; /* q_prev only matters for a floating base; x0 does not enter the residual */
+#pragma omp parallel for num_threads(o->stage_threads) if (o->stage_threads > 1)
+  for (int i = 0; i <= o->N; ++i) {
+    if (i < o->N) split_unocp_kkt_residual(&o->p, o->dt, &o->s[i], &o->s[i + 1], &o->st[i]);
+    else terminal_linearize(o, 0);
+  }
+}
+
+/* UnOCPSolver::KKTError (:190-202) */
+double oracle_unocp_kkt_error(oracle_unocp_t* o) {
+  double e = 0;
+  for (int i = 0; i < o->N; ++i) e += split_unocp_sqnorm(&o->st[i], o->dt);
+  e += sqnorm(o->t_lq) + sqnorm(o->t_lv);  /* TerminalOCP::squaredNormKKTResidual (terminal_ocp.hxx:139-144) */
+  return sqrt(e);
+}
+
+void oracle_unocp_clear_line_search_filter(oracle_unocp_t* o) { o->filter.n = 0; }
+
+/* UnOCPSolver::isCurrentSolutionFeasible (:228-237) */
+int oracle_unocp_is_feasible(oracle_unocp_t* o) {
+  for (int i = 0; i < o->N; ++i)
+    for (int c = 0; c < NC; ++c) {
+      if (!o->st[i].active[c]) continue;
+      for (int j = 0; j < NV; ++j)
+        if (con_margin(&o->p, c, &o->s[i], j) < 0) return 0;
+    }
+  return 1;
+}
+
+int oracle_unocp_get_solution(const oracle_unocp_t* o, const char* name, double* out) {
+  const int full = !strcmp(name, "lmd") || !strcmp(name, "gmm") || !strcmp(name, "q") || !strcmp(name, "v");
+  const int n = full ? o->N + 1 : o->N;
+  for (int i = 0; i < n; ++i) {
+    const double* src;
+    if (!strcmp(name, "lmd")) src = o->s[i].lmd;
+    else if (!strcmp(name, "gmm")) src = o->s[i].gmm;
+    else if (!strcmp(name, "q")) src = o->s[i].q;
+    else if (!strcmp(name, "v")) src = o->s[i].v;
+    else if (!strcmp(name, "a")) src = o->s[i].a;
+    else if (!strcmp(name, "u")) src = o->s[i].u;
+    else if (!strcmp(name, "beta")) src = o->s[i].beta;
+    else return -1;
+    memcpy(out + i * NV, src, sizeof(double) * NV);
+  }
+  return n;
+}
+
+int oracle_unocp_get_direction(const oracle_unocp_t* o, const char* name, double* out) {
+  const int full = !strcmp(name, "dlmd") || !strcmp(name, "dgmm") || !strcmp(name, "dq") || !strcmp(name, "dv");
+  const int n = full ? o->N + 1 : o->N;
+  for (int i = 0; i < n; ++i) {
+    const double* src;
+    if (!strcmp(name, "dlmd")) src = o->d[i].dlmd;
+    else if (!strcmp(name, "dgmm")) src = o->d[i].dgmm;
+    else if (!strcmp(name, "dq")) src = o->d[i].dq;
+    else if (!strcmp(name, "dv")) src = o->d[i].dv;
+    else if (!strcmp(name, "da")) src = o->d[i].da;
+    else if (!strcmp(name, "du")) src = o->d[i].du;
+    else if (!strcmp(name, "dbeta")) src = o->d[i].dbeta;
+    else return -1;
+    memcpy(out + i * NV, src, sizeof(double) * NV);
+  }
+  return n;
+}
+
+int oracle_unocp_get_constraint_data(const oracle_unocp_t* o, const char* name, double* out) {
+  for (int i = 0; i < o->N; ++i)
+    for (int c = 0; c < NC; ++c) {
+      const cdata_t* d = &o->st[i].c[c];
+      const double* src;
+      if (!strcmp(name, "slack")) src = d->slack;
+      else if (!strcmp(name, "dual")) src = d->dual;
+      else if (!strcmp(name, "residual")) src = d->residual;
+      else if (!strcmp(name, "duality")) src = d->duality;
+      else if (!strcmp(name, "dslack")) src = d->dslack;
+      else if (!strcmp(name, "ddual")) src = d->ddual;
+      else return -1;
+      double* dst = out + (i * NC + c) * NV;
+      if (o->st[i].active[c]) memcpy(dst, src, sizeof(double) * NV);
+      else memset(dst, 0, sizeof(double) * NV);
+    }
+  return o->N;
+}
+
+void oracle_unocp_get_step_sizes(const oracle_unocp_t* o, double* out) {
+  out[0] = o->primal_step; out[1] = o->dual_step; out[2] = o->max_primal_step;
+}
+
+void oracle_unocp_get_unkkt(const oracle_unocp_t* o, int stage, double* Q, double* res) {
+  const stage_t* st = &o->st[stage];
+  const int D = 3 * NV;
+  memset(Q, 0, sizeof(double) * D * D);
+  const double* blk[3][3] = {{st->uQaa, st->uQaq, st->uQav}, {NULL, st->uQqq, st->uQqv}, {NULL, st->uQvq, st->uQvv}};
+  for (int br = 0; br < 3; ++br)
+    for (int bc = 0; bc < 3; ++bc) {
+      if (!blk[br][bc]) continue;
+      for (int c = 0; c < NV; ++c)
+        for (int r = 0; r < NV; ++r) Q[(bc * NV + c) * D + br * NV + r] = blk[br][bc][c * NV + r];
+    }
+  memcpy(res, st->uFq, sizeof(double) * NV);
+  memcpy(res + NV, st->uFv, sizeof(double) * NV);
+  memcpy(res + 2 * NV, st->ula, sizeof(double) * NV);
+  memcpy(res + 3 * NV, st->ulq, sizeof(double) * NV);
+  memcpy(res + 4 * NV, st->ulv, sizeof(double) * NV);
+}
+
+void oracle_unocp_get_riccati(const oracle_unocp_t* o, int stage, double* Pqq, double* Pqv, double* Pvv,
+                              double* sq, double* sv, double* K, double* k) {
+  const riccati_t* r = &o->ric[stage];
+  memcpy(Pqq, r->Pqq, sizeof(r->Pqq)); memcpy(Pqv, r->Pqv, sizeof(r->Pqv)); memcpy(Pvv, r->Pvv, sizeof(r->Pvv));
+  memcpy(sq, r->sq, sizeof(r->sq)); memcpy(sv, r->sv, sizeof(r->sv));
+  if (stage < o->N && K && k) {
+    memcpy(K, o->st[stage].K, sizeof(o->st[stage].K));
+    memcpy(k, o->st[stage].k, sizeof(o->st[stage].k));
+  }
+}
+
+/* batch drivers: OpenMP over instances, each instance single-threaded (BASELINE.md mode B) */
+void oracle_unocp_batch_update_solution(oracle_unocp_t** os, int batch, double t, const double* q0,
+                                        const double* v0, int line_search, int nthreads) {
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+  for (int b = 0; b < batch; ++b)
+    oracle_unocp_update_solution(os[b], t, q0 + (size_t)b * NV, v0 + (size_t)b * NV, line_search);
+}
+
+void oracle_unocp_batch_kkt(oracle_unocp_t** os, int batch, double t, const double* q0,
+                            const double* v0, double* kkt_out, int nthreads) {
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+  for (int b = 0; b < batch; ++b) {
+    oracle_unocp_compute_kkt_residual(os[b], t, q0 + (size_t)b * NV, v0 + (size_t)b * NV);
+    kkt_out[b] = oracle_unocp_kkt_error(os[b]);
+  }
+}
