@@ -1,0 +1,327 @@
+#!/usr/bin/env python3
+"""bench.py -- batched SQP iterations/sec of the iiwa14 UnOCPSolver hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched through torch.distributed.run)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+One "step" = one updateSolution (one SQP / Newton iteration) of EVERY instance of the batch.
+Workload = BASELINE.json configs[2]: examples/iiwa14/unocp_benchmark.cpp problem (N=20, T=1),
+16384 random initial states per GPU (counter-based splitmix64, seed 20240001).
+Weak scaling: every rank owns its own 16384 instances, no data-path collective.
+
+  value  : instance-iterations/s over all ranks with q0/v0 already resident in HBM
+  e2e    : same through the public host API (updateSolution(host q, host v) + getStageSolution("u", 0)):
+           H2D of x0 and D2H of the first control input inside the timed region
+  roofline / cpu_baseline : see DESIGN.md "Measurement"
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 20240001
+BATCH_PER_GPU = 16384
+HORIZON_N = 20
+NV = 7
+# algorithmic FP64 work / mandatory HBM bytes per instance-iteration
+FLOP_PER_UNIT = 0.46e6
+BYTES_PER_UNIT = 44e3
+# algorithmic bytes per (instance, stage) of each kernel = its mandatory inputs + outputs, unpadded
+# doubles (DESIGN.md "Kernels"):  linearize: s_i 49 + s_{i+1} 28 + slack/dual 84 in; Q 231 + res 35 + exp 147 out
+KERNEL_ALGO_DOUBLES_PER_STAGE = {
+    "linearize": 49 + 28 + 84 + 231 + 35 + 147,
+    "riccati": 231 + 35 + 2 * (105 + 105 + 14) + 147 + 21 + 84 + 49,
+    "update": 2 * (49 + 84) + 49,
+}
+
+
+def splitmix_uniform(seed, index):
+    """Counter-based splitmix64 -> double in [0,1); vectorised twin of oracle_splitmix_uniform."""
+    idx = np.asarray(index, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + (idx + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def initial_states(first_instance, count, q_min, q_max):
+    """q0_j = c_j + 0.8 h_j U(-1,1), v0_j = 0.5 U(-1,1); element index = instance*14 + j."""
+    inst = np.arange(first_instance, first_instance + count, dtype=np.uint64)[:, None]
+    j = np.arange(NV, dtype=np.uint64)[None, :]
+    uq = 2.0 * splitmix_uniform(SEED, inst * np.uint64(14) + j) - 1.0
+    uv = 2.0 * splitmix_uniform(SEED, inst * np.uint64(14) + np.uint64(7) + j) - 1.0
+    c = 0.5 * (np.asarray(q_max) + np.asarray(q_min))
+    h = 0.5 * (np.asarray(q_max) - np.asarray(q_min))
+    return np.ascontiguousarray(c + 0.8 * h * uq), np.ascontiguousarray(0.5 * uv)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(s[3 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get("hbm_gbs"), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def oracle_throughput(seconds_target, q_min, q_max, threads=None, per_step_instances=None, steps=None, warmup=0):
+    """Times the CPU oracle (restatement of idocp's UnOCPSolver) on the host cores, OpenMP over
+    instances, every instance single-threaded (BASELINE.md mode B).  Returns (units/s, cores, sample)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as O
+    cores = threads or os.cpu_count() or 1
+    prob = O.benchmark_problem(N=HORIZON_N, T=1.0)
+    nb = per_step_instances or max(cores * 16, 256)
+    q0, v0 = initial_states(0, nb, q_min, q_max)
+    batch = O.Batch(prob, nb)
+    for b, s in enumerate(batch.solvers):
+        s.set_solution("q", q0[b])
+        s.set_solution("v", v0[b])
+    for _ in range(max(warmup, 1)):
+        batch.update_solution(0.0, q0, v0, False, cores)
+    if steps is None:
+        t0 = time.perf_counter()
+        batch.update_solution(0.0, q0, v0, False, cores)
+        one = time.perf_counter() - t0
+        steps = int(max(3, min(2000, seconds_target / max(one, 1e-6))))
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        batch.update_solution(0.0, q0, v0, False, cores)
+        times.append(time.perf_counter() - t0)
+    total = float(np.sum(times))
+    sample = "%d instances x %d updateSolution sweeps, OpenMP over instances, %d threads" % (nb, steps, cores)
+    return nb * steps / total, cores, sample, total / steps * 1e3
+
+
+def run_reference(args, rank, world):
+    """--impl reference: idocp's own CPU algorithm.  The upstream library cannot be built in this
+    image (Eigen/Boost/pinocchio/urdfdom absent), so this times the oracle restatement."""
+    if rank != 0:
+        return
+    import ctypes  # noqa: F401
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as O
+    p = O.default_problem()
+    q_min, q_max = list(p.q_min), list(p.q_max)
+    cores = os.cpu_count() or 1
+    per_step = max(cores * 32, 512)
+    value, cores, sample, ms = oracle_throughput(None, q_min, q_max, cores, per_step, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "batched SQP iterations/sec (iiwa14 N=20, FP64)", "value": value,
+        "unit": "instance-iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "iiwa14 UnOCPSolver unocp_benchmark problem, N=20, T=1, random initial states "
+                               "(splitmix64 seed %d); bounded sample of %d instances per step" % (SEED, per_step)},
+        "cpu_baseline": {"value": value, "unit": "instance-iterations/s", "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "instance-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "oracle restatement of idocp (oracle/idocp_oracle.c), not the upstream binary: pinocchio/Eigen absent",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="instances per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.warmup < 3:
+        args.warmup = 3
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import idocp_b200 as I
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    lib = I.default_library()
+    prob = I.benchmark_problem(lib, N=HORIZON_N, T=1.0)
+    B = args.batch
+    q0, v0 = initial_states(rank * B, B, list(prob.q_min), list(prob.q_max))
+    solver = I.UnOCPSolver(prob, B, device=local_rank)
+    solver.setSolution("q", q0)
+    solver.setSolution("v", v0)
+    stream = torch.cuda.ExternalStream(solver.stream(), device=local_rank)
+    q_dev = torch.from_numpy(q0).cuda(local_rank)
+    v_dev = torch.from_numpy(v0).cuda(local_rank)
+    q_pin = torch.from_numpy(q0).pin_memory()
+    v_pin = torch.from_numpy(v0).pin_memory()
+    u_pin = torch.empty((B, NV), dtype=torch.float64).pin_memory()
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident arm -----------------------------------------------------------------
+    for _ in range(args.warmup):
+        solver.updateSolutionDevice(0.0, q_dev.data_ptr(), v_dev.data_ptr())
+    solver.sync()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    solver.setProfiling(True)
+    launches0 = solver.launchCount()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        solver.updateSolutionDevice(0.0, q_dev.data_ptr(), v_dev.data_ptr())
+    e1.record(stream)
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = solver.launchCount() - launches0
+    profile = solver.getProfile()
+    solver.setProfiling(False)
+
+    # ---- end-to-end arm: host buffers through the public API ----------------------------------
+    q_host = q_pin.numpy()
+    v_host = v_pin.numpy()
+    u_host = u_pin.numpy()
+    for _ in range(3):
+        solver.updateSolution(0.0, q_host, v_host)
+        solver.getStageSolution("u", 0, out=u_host)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        solver.updateSolution(0.0, q_host, v_host)
+        solver.getStageSolution("u", 0, out=u_host)
+    e1.record(stream)
+    barrier()
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), e2e_wall_ms))
+    if rank == 0:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+
+    # sanity: the batch must have stayed numerically healthy
+    solver.computeKKTResidualDevice(0.0, q_dev.data_ptr(), v_dev.data_ptr())
+    kkt = solver.KKTError()
+    status = solver.getStatus()
+
+    units = float(B) * world * args.steps
+    value = units / (ms_total * 1e-3)
+    e2e_value = units / (e2e_ms * 1e-3)
+    hbm_peak, peak_src = measured_peaks()
+    # dominant kernel by measured device time
+    stages = B * HORIZON_N
+    kern = {}
+    for name, (ms, calls) in profile.items():
+        if calls and name in KERNEL_ALGO_DOUBLES_PER_STAGE:
+            per_launch_ms = ms / calls
+            gbs = KERNEL_ALGO_DOUBLES_PER_STAGE[name] * 8.0 * stages / (per_launch_ms * 1e-3) / 1e9
+            kern[name] = {"ms_per_launch": per_launch_ms, "algo_gbs": gbs, "share": ms}
+    tot = sum(k["share"] for k in kern.values()) or 1.0
+    for k in kern.values():
+        k["share"] = k["share"] / tot
+    dom = max(kern, key=lambda n: kern[n]["ms_per_launch"]) if kern else None
+    roofline = None
+    if dom:
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["algo_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                    "frac": kern[dom]["algo_gbs"] / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "kernels": kern,
+                    "step_hbm_frac": BYTES_PER_UNIT * value / world / 1e9 / hbm_peak,
+                    "step_fp64_tflops": FLOP_PER_UNIT * value / world / 1e12}
+
+    line = {
+        "metric": "batched SQP iterations/sec (iiwa14 N=20, FP64)", "value": value, "unit": "instance-iterations/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+        "us_per_iteration": ms_total / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "iiwa14 config-space UnOCPSolver (examples/iiwa14/unocp_benchmark.cpp problem), N=20, "
+                               "T=1, %d random initial states per GPU (splitmix64 seed %d), line_search=false" % (B, SEED),
+                   "batch_per_gpu": B, "horizon": HORIZON_N, "parallelism": "batch-sharded x%d, no collective" % world,
+                   "l2_policy": "working set %.1f GB per GPU >> 126 MB L2 (inputs larger than L2)" % (B * 450e3 / 1e9)},
+        "e2e": {"value": e2e_value, "unit": "instance-iterations/s", "h2d_bytes_per_step": 2 * B * NV * 8,
+                "d2h_bytes_per_step": B * NV * 8, "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "clocks": sampler.summary() if rank == 0 else None,
+        "health": {"kkt_max": float(np.nanmax(kkt)), "kkt_nan": int(np.isnan(kkt).sum()),
+                   "status_nonzero": int((status != 0).sum())},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cval, cores, sample, _ = oracle_throughput(args.cpu_seconds, list(prob.q_min), list(prob.q_max))
+        line["cpu_baseline"] = {"value": cval, "unit": "instance-iterations/s", "cores": cores, "kind": "port",
+                                "sample": sample}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

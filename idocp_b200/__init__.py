@@ -1,0 +1,9 @@
+"""idocp_b200 -- B200-native batched optimal-control engine for idocp's Newton-step hot path.
+
+Everything numerical runs in the CUDA library ``libidocp_b200.so`` (sm_100a) behind the C-ABI of
+``include/idocp_b200.h``; this package only marshals arguments.  No CPU fallback exists.
+"""
+from .capi import Idocp_b200Error, Library, Problem, default_library  # noqa: F401
+from .solvers import UnOCPSolver, UnParNMPCSolver, benchmark_problem, config_space_problem  # noqa: F401
+
+__version__ = "0.1"

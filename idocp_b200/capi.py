@@ -1,0 +1,128 @@
+"""ctypes binding of the C-ABI (include/idocp_b200.h).
+
+The product library is the nvcc-built ``idocp_b200/libidocp_b200.so`` (sm_100a).  There is no CPU
+fallback: if the library is missing, or no CUDA device is usable, loading / creation raises.
+``Library(path)`` with an explicit path exists so that the CPU-only test-suite can load the SIMT
+emulator build of the same sources (tests/emu) -- it is never chosen automatically.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIBRARY = os.path.join(_HERE, "libidocp_b200.so")
+
+DIMV = 7
+NUM_CONSTRAINTS = 6
+ROBOT_IIWA14 = 0
+SOLVER_UNOCP = 0
+SOLVER_UNPARNMPC = 1
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+class Problem(C.Structure):
+    """idocp_b200_problem (include/idocp_b200.h)."""
+    _fields_ = [
+        ("robot", C.c_int), ("N", C.c_int), ("T", C.c_double),
+        ("q_ref", C.c_double * DIMV), ("v_ref", C.c_double * DIMV), ("u_ref", C.c_double * DIMV),
+        ("q_weight", C.c_double * DIMV), ("v_weight", C.c_double * DIMV), ("a_weight", C.c_double * DIMV),
+        ("u_weight", C.c_double * DIMV), ("qf_weight", C.c_double * DIMV), ("vf_weight", C.c_double * DIMV),
+        ("q_min", C.c_double * DIMV), ("q_max", C.c_double * DIMV),
+        ("v_max", C.c_double * DIMV), ("u_max", C.c_double * DIMV),
+        ("barrier", C.c_double), ("fraction_rate", C.c_double),
+        ("task_enabled", C.c_int),
+        ("task_q_weight", C.c_double * 6), ("task_qf_weight", C.c_double * 6),
+        ("task_center", C.c_double * 3), ("task_radius", C.c_double),
+        ("task_t0", C.c_double), ("task_tf", C.c_double),
+        ("task_rot_ref", C.c_double * 9),
+    ]
+
+
+class Idocp_b200Error(RuntimeError):
+    pass
+
+
+EXPORTS = [
+    "idocp_b200_problem_default", "idocp_b200_create", "idocp_b200_destroy", "idocp_b200_set_solution",
+    "idocp_b200_init_constraints", "idocp_b200_init_backward_correction", "idocp_b200_update_solution",
+    "idocp_b200_update_solution_device", "idocp_b200_compute_kkt_residual",
+    "idocp_b200_compute_kkt_residual_device", "idocp_b200_kkt_error", "idocp_b200_get_solution", "idocp_b200_get_stage_solution",
+    "idocp_b200_get_direction", "idocp_b200_get_constraint_data", "idocp_b200_get_step_sizes",
+    "idocp_b200_get_unkkt", "idocp_b200_get_status", "idocp_b200_is_feasible",
+    "idocp_b200_clear_line_search_filter", "idocp_b200_sync", "idocp_b200_launch_count", "idocp_b200_stream",
+    "idocp_b200_set_profiling", "idocp_b200_get_profile", "idocp_b200_last_error", "idocp_b200_version",
+]
+
+
+class Library:
+    def __init__(self, path=None):
+        path = path or DEFAULT_LIBRARY
+        if not os.path.exists(path):
+            raise Idocp_b200Error(
+                "CUDA extension %s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)" % path)
+        self.path = path
+        L = C.CDLL(path)
+        for name in EXPORTS:
+            if not hasattr(L, name):
+                raise Idocp_b200Error("library %s does not export %s" % (path, name))
+        L.idocp_b200_last_error.restype = C.c_char_p
+        L.idocp_b200_version.restype = C.c_char_p
+        L.idocp_b200_update_solution.argtypes = [C.c_void_p, C.c_double, _dp, _dp, C.c_int]
+        L.idocp_b200_update_solution_device.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int]
+        L.idocp_b200_compute_kkt_residual.argtypes = [C.c_void_p, C.c_double, _dp, _dp]
+        L.idocp_b200_compute_kkt_residual_device.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+        L.idocp_b200_init_backward_correction.argtypes = [C.c_void_p, C.c_double]
+        L.idocp_b200_create.argtypes = [C.POINTER(Problem), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.idocp_b200_destroy.argtypes = [C.c_void_p]
+        L.idocp_b200_set_solution.argtypes = [C.c_void_p, C.c_char_p, _dp, C.c_int]
+        L.idocp_b200_init_constraints.argtypes = [C.c_void_p]
+        L.idocp_b200_kkt_error.argtypes = [C.c_void_p, _dp]
+        L.idocp_b200_get_solution.argtypes = [C.c_void_p, C.c_char_p, _dp]
+        L.idocp_b200_get_stage_solution.argtypes = [C.c_void_p, C.c_char_p, C.c_int, _dp]
+        L.idocp_b200_get_direction.argtypes = [C.c_void_p, C.c_char_p, _dp]
+        L.idocp_b200_get_constraint_data.argtypes = [C.c_void_p, C.c_char_p, _dp]
+        L.idocp_b200_get_step_sizes.argtypes = [C.c_void_p, _dp, _dp]
+        L.idocp_b200_get_unkkt.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+        L.idocp_b200_get_status.argtypes = [C.c_void_p, _ip]
+        L.idocp_b200_is_feasible.argtypes = [C.c_void_p, _ip]
+        L.idocp_b200_clear_line_search_filter.argtypes = [C.c_void_p]
+        L.idocp_b200_sync.argtypes = [C.c_void_p]
+        L.idocp_b200_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
+        L.idocp_b200_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.idocp_b200_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.idocp_b200_get_profile.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), _dp,
+                                             C.POINTER(C.c_longlong)]
+        self.L = L
+
+    def check(self, rc):
+        if rc < 0:
+            raise Idocp_b200Error("idocp_b200 error %d: %s" % (rc, self.L.idocp_b200_last_error().decode()))
+        return rc
+
+    def version(self):
+        return self.L.idocp_b200_version().decode()
+
+    def default_problem(self, robot=ROBOT_IIWA14):
+        p = Problem()
+        self.check(self.L.idocp_b200_problem_default(robot, C.byref(p)))
+        return p
+
+
+_default = None
+
+
+def default_library():
+    """The CUDA library; raises when it has not been built."""
+    global _default
+    if _default is None:
+        _default = Library()
+    return _default
+
+
+def dptr(a):
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_dp)

@@ -1,0 +1,657 @@
+// capi.cu -- C-ABI of the engine (include/idocp_b200.h): handle management, host<->device
+// staging and kernel launches.  Compiled by nvcc for sm_100a into libidocp_b200.so.
+// (tests/emu builds the same file with g++ against a SIMT emulator -- test infrastructure.)
+#ifdef IDOCP_B200_EMU
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#endif
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/idocp_b200.h"
+#include "model_iiwa14.h"
+#include "unocp_kernels.cuh"
+#include "unparnmpc_kernels.cuh"
+
+using namespace idocp_b200;
+
+#ifdef IDOCP_B200_EMU
+#define IDOCP_LAUNCH(h, cls, kern, grid, block, smem, ...)                                   \
+  do {                                                                                       \
+    (h)->begin_kernel(cls);                                                                  \
+    emu::launch(dim3(grid), dim3(block), (smem), [&]() { kern(__VA_ARGS__); });              \
+    (h)->end_kernel(cls);                                                                    \
+  } while (0)
+#else
+#define IDOCP_LAUNCH(h, cls, kern, grid, block, smem, ...)                                   \
+  do {                                                                                       \
+    (h)->begin_kernel(cls);                                                                  \
+    auto kfn_ = kern;                                                                        \
+    kfn_<<<(grid), (block), (smem), (h)->stream>>>(__VA_ARGS__);                             \
+    (h)->end_kernel(cls);                                                                    \
+  } while (0)
+#endif
+
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+#define CUDA_OK(expr)                                                                        \
+  do {                                                                                       \
+    cudaError_t e_ = (expr);                                                                 \
+    if (e_ != cudaSuccess)                                                                   \
+      return fail(IDOCP_B200_CUDA_ERROR, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+enum KernelClass { KC_LINEARIZE = 0, KC_RICCATI, KC_UPDATE, KC_KKT, KC_MISC, KC_PARNMPC_COARSE, KC_PARNMPC_CORR,
+                   KC_LINESEARCH, KC_NUM };
+static const char* kKernelClassNames[KC_NUM] = {"linearize", "riccati", "update", "kkt", "misc",
+                                                "parnmpc_coarse", "parnmpc_correction", "line_search"};
+
+struct idocp_b200_solver {
+  idocp_b200_problem prob;
+  int kind = 0, device = 0;
+  int B = 0, Bp = 0, N = 0;
+  cudaStream_t stream = nullptr;
+  DevProblem* d_prob = nullptr;
+  DevProblem h_prob;
+  Layout L;
+  std::vector<void*> allocs;
+  double* d_q0 = nullptr;
+  double* d_v0 = nullptr;
+  double* d_stage = nullptr;   // staging buffer for getters / setters
+  size_t stage_doubles = 0;
+  long long launches = 0;
+  // profiling: 0 off, 1 = CUDA events recorded around every launch on the launching stream and
+  // resolved lazily in get_profile (no host synchronisation inside the timed region)
+  int profiling = 0;
+  struct ProfRec { int cls; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> event_pool;
+  double prof_ms[KC_NUM] = {0};
+  long long prof_calls[KC_NUM] = {0};
+  cudaEvent_t cur_e0 = nullptr;
+  cudaEvent_t take_event() {
+    if (!event_pool.empty()) { cudaEvent_t e = event_pool.back(); event_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+  void resolve_profile() {
+    if (prof_recs.empty()) return;
+    cudaStreamSynchronize(stream);
+    for (auto& r : prof_recs) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, r.e0, r.e1);
+      prof_ms[r.cls] += ms;
+      prof_calls[r.cls] += 1;
+      event_pool.push_back(r.e0);
+      event_pool.push_back(r.e1);
+    }
+    prof_recs.clear();
+  }
+  // UnParNMPC extras
+  ParNMPCLayout PL;
+
+  void begin_kernel(int) {
+    ++launches;
+    if (profiling) {
+      cur_e0 = take_event();
+      cudaEventRecord(cur_e0, stream);
+    }
+  }
+  void end_kernel(int cls) {
+    if (profiling) {
+      cudaEvent_t e1 = take_event();
+      cudaEventRecord(e1, stream);
+      prof_recs.push_back(ProfRec{cls, cur_e0, e1});
+    }
+  }
+  template <typename T>
+  int alloc(T** p, size_t count) {
+    void* q = nullptr;
+    if (cudaMalloc(&q, count * sizeof(T)) != cudaSuccess) return -1;
+    cudaMemsetAsync(q, 0, count * sizeof(T), stream);
+    allocs.push_back(q);
+    *p = static_cast<T*>(q);
+    return 0;
+  }
+};
+
+extern "C" const char* idocp_b200_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char* idocp_b200_version(void) {
+#ifdef IDOCP_B200_EMU
+  return "idocp_b200 0.1 (SIMT emulator build -- tests only)";
+#else
+  return "idocp_b200 0.1 (sm_100a)";
+#endif
+}
+
+extern "C" int idocp_b200_problem_default(int robot, idocp_b200_problem* p) {
+  if (!p) return fail(IDOCP_B200_INVALID_ARGUMENT, "problem_default: null pointer");
+  if (robot != IDOCP_B200_ROBOT_IIWA14) return fail(IDOCP_B200_UNSUPPORTED, "only the iiwa14 is supported");
+  std::memset(p, 0, sizeof(*p));
+  p->robot = robot;
+  p->N = 20;
+  p->T = 1.0;
+  for (int i = 0; i < NV; ++i) {
+    p->q_min[i] = IIWA14_Q_MIN[i];
+    p->q_max[i] = IIWA14_Q_MAX[i];
+    p->v_max[i] = IIWA14_V_MAX[i];
+    p->u_max[i] = IIWA14_EFFORT_MAX[i];
+  }
+  p->barrier = 1.0e-04;
+  p->fraction_rate = 0.995;
+  return IDOCP_B200_OK;
+}
+
+static void fill_dev_problem(const idocp_b200_problem& p, DevProblem& d) {
+  std::memset(&d, 0, sizeof(d));
+  d.N = p.N;
+  d.T = p.T;
+  d.dt = p.T / p.N;
+  for (int i = 0; i < NV; ++i) {
+    d.q_ref[i] = p.q_ref[i]; d.v_ref[i] = p.v_ref[i]; d.u_ref[i] = p.u_ref[i];
+    d.q_weight[i] = p.q_weight[i]; d.v_weight[i] = p.v_weight[i]; d.a_weight[i] = p.a_weight[i];
+    d.u_weight[i] = p.u_weight[i]; d.qf_weight[i] = p.qf_weight[i]; d.vf_weight[i] = p.vf_weight[i];
+    d.q_min[i] = p.q_min[i]; d.q_max[i] = p.q_max[i]; d.v_max[i] = p.v_max[i]; d.u_max[i] = p.u_max[i];
+  }
+  d.barrier = p.barrier;
+  d.fraction_rate = p.fraction_rate;
+  d.gravity = IIWA14_GRAVITY;
+  for (int j = 0; j < 8; ++j) {
+    double* m = d.model + j * MODEL_STRIDE;
+    if (j < NV) {
+      for (int k = 0; k < 9; ++k) m[k] = IIWA14_PLACEMENT_R[j][k];
+      for (int k = 0; k < 3; ++k) m[9 + k] = IIWA14_PLACEMENT_P[j][k];
+      m[12] = IIWA14_MASS[j];
+      for (int k = 0; k < 3; ++k) m[13 + k] = IIWA14_COM[j][k];
+      for (int k = 0; k < 6; ++k) m[16 + k] = IIWA14_INERTIA[j][k];
+    } else {
+      m[0] = m[4] = m[8] = 1.0;  // padding joint: identity placement, zero mass
+    }
+  }
+}
+
+static int parnmpc_update(idocp_b200_solver*, double, const double*, const double*, int) {
+  return fail(IDOCP_B200_UNSUPPORTED, "UnParNMPCSolver is not implemented yet");
+}
+static int parnmpc_kkt_residual(idocp_b200_solver*, double, const double*, const double*) {
+  return fail(IDOCP_B200_UNSUPPORTED, "UnParNMPCSolver is not implemented yet");
+}
+static int parnmpc_init_backward_correction(idocp_b200_solver*, double) {
+  return fail(IDOCP_B200_UNSUPPORTED, "UnParNMPCSolver is not implemented yet");
+}
+
+static int grid_for(long tasks) { return static_cast<int>((tasks + OCTETS_PER_CTA - 1) / OCTETS_PER_CTA); }
+
+static int do_init_constraints(idocp_b200_solver* h) {
+  const int off = h->kind == IDOCP_B200_SOLVER_UNPARNMPC ? 1 : 0;
+  IDOCP_LAUNCH(h, KC_MISC, k_init_constraints, grid_for(static_cast<long>(h->N) * h->Bp), CTA_THREADS, 0, h->d_prob,
+               h->L, off);
+  CUDA_OK(cudaGetLastError());
+  return IDOCP_B200_OK;
+}
+
+extern "C" int idocp_b200_create(const idocp_b200_problem* p, int solver_kind, int batch, int device,
+                                 idocp_b200_solver** out) {
+  if (!p || !out) return fail(IDOCP_B200_INVALID_ARGUMENT, "create: null pointer");
+  *out = nullptr;
+  if (p->robot != IDOCP_B200_ROBOT_IIWA14) return fail(IDOCP_B200_UNSUPPORTED, "only the iiwa14 is supported");
+  if (!(p->T > 0)) return fail(IDOCP_B200_INVALID_ARGUMENT, "invalid value: T must be positive!");
+  if (p->N <= 0) return fail(IDOCP_B200_INVALID_ARGUMENT, "invalid value: N must be positive!");
+  if (batch <= 0) return fail(IDOCP_B200_INVALID_ARGUMENT, "invalid value: batch must be positive!");
+  if (!(p->barrier > 0) || !(p->fraction_rate > 0) || p->fraction_rate > 1)
+    return fail(IDOCP_B200_INVALID_ARGUMENT, "invalid value: barrier / fraction_rate");
+  if (solver_kind != IDOCP_B200_SOLVER_UNOCP && solver_kind != IDOCP_B200_SOLVER_UNPARNMPC)
+    return fail(IDOCP_B200_INVALID_ARGUMENT, "unknown solver kind");
+  if (p->task_enabled) return fail(IDOCP_B200_UNSUPPORTED, "task-space cost is not implemented yet");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return fail(IDOCP_B200_NO_DEVICE, "no CUDA device available (there is no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(IDOCP_B200_INVALID_ARGUMENT, "invalid device index");
+  CUDA_OK(cudaSetDevice(device));
+  idocp_b200_solver* h = new idocp_b200_solver();
+  h->prob = *p;
+  h->kind = solver_kind;
+  h->device = device;
+  h->B = batch;
+  h->Bp = (batch + 3) / 4 * 4;
+  h->N = p->N;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return fail(IDOCP_B200_CUDA_ERROR, "cudaStreamCreate failed");
+  }
+  fill_dev_problem(*p, h->h_prob);
+  const size_t N = h->N, Bp = h->Bp, slot = Bp * OCT;
+  const bool par = solver_kind == IDOCP_B200_SOLVER_UNPARNMPC;
+  Layout& L = h->L;
+  std::memset(&L, 0, sizeof(L));
+  L.B = h->B; L.Bp = h->Bp; L.N = h->N;
+  int rc = 0;
+  rc |= h->alloc(&h->d_prob, 1);
+  rc |= h->alloc(&L.sol, S_NUM * (N + 1) * slot);
+  rc |= h->alloc(&L.slack, NC * N * slot);
+  rc |= h->alloc(&L.dual, NC * N * slot);
+  rc |= h->alloc(&L.kktQ, static_cast<size_t>(K_NUMBLK) * NV * N * slot);
+  rc |= h->alloc(&L.kktR, R_NUM * N * slot);
+  rc |= h->alloc(&L.expd, E_NUM * N * slot);
+  if (!par) rc |= h->alloc(&L.ric, RC_NUM * N * slot);
+  rc |= h->alloc(&L.dir, D_NUM * (N + 1) * slot);
+  rc |= h->alloc(&L.steps, 2 * Bp);
+  rc |= h->alloc(&L.kkt_stage, (N + 1) * Bp);
+  rc |= h->alloc(&L.kkt_err, Bp);
+  rc |= h->alloc(&L.status, Bp);
+  rc |= h->alloc(&h->d_q0, Bp * NV);
+  rc |= h->alloc(&h->d_v0, Bp * NV);
+  {
+    const size_t Bz = static_cast<size_t>(h->B);
+    size_t need = Bz * N * NC * NV;                      // get_constraint_data
+    if (need < Bz * (N + 1) * NV) need = Bz * (N + 1) * NV;  // get_solution / get_direction / set_solution
+    if (need < Bz * 2) need = Bz * 2;
+    h->stage_doubles = need;
+  }
+  rc |= h->alloc(&h->d_stage, h->stage_doubles);
+  if (par) rc |= parnmpc_alloc(h->PL, h->N, h->Bp, [&](double** pp, size_t n) { return h->alloc(pp, n); });
+  if (rc != 0) {
+    idocp_b200_destroy(h);
+    return fail(IDOCP_B200_CUDA_ERROR, "device memory allocation failed");
+  }
+  if (cudaMemcpyAsync(h->d_prob, &h->h_prob, sizeof(DevProblem), cudaMemcpyHostToDevice, h->stream) != cudaSuccess) {
+    idocp_b200_destroy(h);
+    return fail(IDOCP_B200_CUDA_ERROR, "problem upload failed");
+  }
+#ifndef IDOCP_B200_EMU
+  cudaFuncSetAttribute(k_linearize<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       OCTETS_PER_CTA * OCT * PAIR_TILE * (int)sizeof(double));
+  cudaFuncSetAttribute(k_linearize<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       OCTETS_PER_CTA * OCT * PAIR_TILE * (int)sizeof(double));
+#endif
+  const int irc = do_init_constraints(h);  // the reference ctor ends with initConstraints() (unocp_solver.cpp:48)
+  if (irc != IDOCP_B200_OK) {
+    idocp_b200_destroy(h);
+    return irc;
+  }
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  *out = h;
+  return IDOCP_B200_OK;
+}
+
+extern "C" int idocp_b200_destroy(idocp_b200_solver* h) {
+  if (!h) return IDOCP_B200_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void* p : h->allocs) cudaFree(p);
+  h->resolve_profile();
+  for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return IDOCP_B200_OK;
+}
+
+static int field_index(const char* name) {
+  if (!name) return -1;
+  if (!std::strcmp(name, "lmd")) return S_LMD;
+  if (!std::strcmp(name, "gmm")) return S_GMM;
+  if (!std::strcmp(name, "q")) return S_Q;
+  if (!std::strcmp(name, "v")) return S_V;
+  if (!std::strcmp(name, "a")) return S_A;
+  if (!std::strcmp(name, "u")) return S_U;
+  if (!std::strcmp(name, "beta")) return S_BETA;
+  return -1;
+}
+static int dir_index(const char* name) {
+  if (!name) return -1;
+  if (!std::strcmp(name, "dlmd")) return D_LMD;
+  if (!std::strcmp(name, "dgmm")) return D_GMM;
+  if (!std::strcmp(name, "dq")) return D_Q;
+  if (!std::strcmp(name, "dv")) return D_V;
+  if (!std::strcmp(name, "da")) return D_A;
+  if (!std::strcmp(name, "du")) return D_U;
+  if (!std::strcmp(name, "dbeta")) return D_BETA;
+  return -1;
+}
+
+extern "C" int idocp_b200_set_solution(idocp_b200_solver* h, const char* name, const double* value, int broadcast) {
+  if (!h || !value) return fail(IDOCP_B200_INVALID_ARGUMENT, "set_solution: null pointer");
+  const int f = field_index(name);
+  if (f != S_Q && f != S_V && f != S_A && f != S_U)
+    return fail(IDOCP_B200_INVALID_ARGUMENT, "invalid arugment: name must be q, v, a, or u!");
+  CUDA_OK(cudaSetDevice(h->device));
+  const size_t n = broadcast ? NV : static_cast<size_t>(h->B) * NV;
+  CUDA_OK(cudaMemcpyAsync(h->d_stage, value, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  // UnOCPSolver: all N+1 stages (a, u: harmless on the terminal slot, never read);
+  // UnParNMPCSolver stores stages 1..N at index 0..N-1
+  const int nst = h->kind == IDOCP_B200_SOLVER_UNPARNMPC ? h->N : h->N + 1;
+  const long total = static_cast<long>(nst) * h->Bp * OCT;
+  IDOCP_LAUNCH(h, KC_MISC, k_set_solution, static_cast<int>((total + 255) / 256), 256, 0, h->L, f, h->d_stage,
+               broadcast ? 1 : 0, nst);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(h->stream));  // `value` may be pageable host memory reused by the caller
+  return do_init_constraints(h);
+}
+
+extern "C" int idocp_b200_init_constraints(idocp_b200_solver* h) {
+  if (!h) return fail(IDOCP_B200_INVALID_ARGUMENT, "null handle");
+  CUDA_OK(cudaSetDevice(h->device));
+  return do_init_constraints(h);
+}
+
+static int upload_x0(idocp_b200_solver* h, const double* q, const double* v) {
+  if (!q || !v) return fail(IDOCP_B200_INVALID_ARGUMENT, "q / v: null pointer");
+  const size_t n = static_cast<size_t>(h->B) * NV * sizeof(double);
+  CUDA_OK(cudaMemcpyAsync(h->d_q0, q, n, cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(cudaMemcpyAsync(h->d_v0, v, n, cudaMemcpyHostToDevice, h->stream));
+  return IDOCP_B200_OK;
+}
+
+static int unocp_update(idocp_b200_solver* h, const double* d_q, const double* d_v, int line_search) {
+  if (line_search) return fail(IDOCP_B200_UNSUPPORTED, "line search is not implemented yet");
+  const int lin_smem = OCTETS_PER_CTA * OCT * PAIR_TILE * static_cast<int>(sizeof(double));
+  const int ric_smem = OCTETS_PER_CTA * RIC_SMEM_PER_OCT * static_cast<int>(sizeof(double));
+  IDOCP_LAUNCH(h, KC_LINEARIZE, k_linearize<false>, grid_for(static_cast<long>(h->N) * h->Bp), CTA_THREADS, lin_smem,
+               h->d_prob, h->L);
+  IDOCP_LAUNCH(h, KC_RICCATI, k_riccati, grid_for(h->Bp), CTA_THREADS, ric_smem, h->d_prob, h->L, d_q, d_v);
+  IDOCP_LAUNCH(h, KC_UPDATE, k_update, grid_for(static_cast<long>(h->N + 1) * h->Bp), CTA_THREADS, 0, h->d_prob, h->L,
+               static_cast<const double*>(nullptr));
+  CUDA_OK(cudaGetLastError());
+  return IDOCP_B200_OK;
+}
+
+extern "C" int idocp_b200_update_solution_device(idocp_b200_solver* h, double t, const double* d_q, const double* d_v,
+                                                 int line_search) {
+  if (!h || !d_q || !d_v) return fail(IDOCP_B200_INVALID_ARGUMENT, "update_solution: null pointer");
+  (void)t;  // ConfigurationSpaceCost is time invariant
+  CUDA_OK(cudaSetDevice(h->device));
+  if (h->kind == IDOCP_B200_SOLVER_UNOCP) return unocp_update(h, d_q, d_v, line_search);
+  return parnmpc_update(h, t, d_q, d_v, line_search);
+}
+
+extern "C" int idocp_b200_update_solution(idocp_b200_solver* h, double t, const double* q, const double* v,
+                                          int line_search) {
+  if (!h) return fail(IDOCP_B200_INVALID_ARGUMENT, "null handle");
+  CUDA_OK(cudaSetDevice(h->device));
+  const int rc = upload_x0(h, q, v);
+  if (rc != IDOCP_B200_OK) return rc;
+  return idocp_b200_update_solution_device(h, t, h->d_q0, h->d_v0, line_search);
+}
+
+extern "C" int idocp_b200_compute_kkt_residual_device(idocp_b200_solver* h, double t, const double* d_q,
+                                                      const double* d_v) {
+  if (!h || !d_q || !d_v) return fail(IDOCP_B200_INVALID_ARGUMENT, "compute_kkt_residual: null pointer");
+  (void)t;
+  CUDA_OK(cudaSetDevice(h->device));
+  if (h->kind == IDOCP_B200_SOLVER_UNPARNMPC) return parnmpc_kkt_residual(h, t, d_q, d_v);
+  const int lin_smem = OCTETS_PER_CTA * OCT * PAIR_TILE * static_cast<int>(sizeof(double));
+  IDOCP_LAUNCH(h, KC_KKT, k_linearize<true>, grid_for(static_cast<long>(h->N + 1) * h->Bp), CTA_THREADS, lin_smem,
+               h->d_prob, h->L);
+  IDOCP_LAUNCH(h, KC_KKT, k_kkt_sum, (h->Bp + 127) / 128, 128, 0, h->L, h->N + 1);
+  CUDA_OK(cudaGetLastError());
+  return IDOCP_B200_OK;
+}
+
+extern "C" int idocp_b200_compute_kkt_residual(idocp_b200_solver* h, double t, const double* q, const double* v) {
+  if (!h) return fail(IDOCP_B200_INVALID_ARGUMENT, "null handle");
+  CUDA_OK(cudaSetDevice(h->device));
+  const int rc = upload_x0(h, q, v);
+  if (rc != IDOCP_B200_OK) return rc;
+  return idocp_b200_compute_kkt_residual_device(h, t, h->d_q0, h->d_v0);
+}
+
+extern "C" int idocp_b200_kkt_error(idocp_b200_solver* h, double* out) {
+  if (!h || !out) return fail(IDOCP_B200_INVALID_ARGUMENT, "kkt_error: null pointer");
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaMemcpyAsync(out, h->L.kkt_err, static_cast<size_t>(h->B) * sizeof(double), cudaMemcpyDeviceToHost,
+                          h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return IDOCP_B200_OK;
+}
+
+// gather [slot][stage][Bp][8] -> out[b][stage][7]
+__global__ void k_gather(const double* __restrict__ src, int slot, int nstage_alloc, int nstage, int B, int Bp,
+                         double* __restrict__ out) {
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long total = static_cast<long>(B) * nstage * NV;
+  if (idx >= total) return;
+  const int j = static_cast<int>(idx % NV);
+  const long t = idx / NV;
+  const int i = static_cast<int>(t % nstage);
+  const int b = static_cast<int>(t / nstage);
+  out[idx] = src[slot_index(slot, nstage_alloc, i, Bp, b, j)];
+}
+
+static int gather_to_host(idocp_b200_solver* h, const double* src, int slot, int nstage_alloc, int nstage,
+                          double* out) {
+  const long total = static_cast<long>(h->B) * nstage * NV;
+  if (static_cast<size_t>(total) > h->stage_doubles) return fail(IDOCP_B200_INVALID_ARGUMENT, "staging buffer too small");
+  IDOCP_LAUNCH(h, KC_MISC, k_gather, static_cast<int>((total + 255) / 256), 256, 0, src, slot, nstage_alloc, nstage,
+               h->B, h->Bp, h->d_stage);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(out, h->d_stage, total * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return IDOCP_B200_OK;
+}
+
+extern "C" int idocp_b200_get_solution(idocp_b200_solver* h, const char* name, double* out) {
+  if (!h || !out) return fail(IDOCP_B200_INVALID_ARGUMENT, "get_solution: null pointer");
+  const int f = field_index(name);
+  if (f < 0) return fail(IDOCP_B200_INVALID_ARGUMENT, "get_solution: unknown field");
+  CUDA_OK(cudaSetDevice(h->device));
+  const bool full = (f == S_LMD || f == S_GMM || f == S_Q || f == S_V) && h->kind == IDOCP_B200_SOLVER_UNOCP;
+  return gather_to_host(h, h->L.sol, f, h->N + 1, full ? h->N + 1 : h->N, out);
+}
+
+// one stage of one field: out[b][7]
+__global__ void k_gather_stage(const double* __restrict__ src, int slot, int nstage_alloc, int stage, int B, int Bp,
+                               double* __restrict__ out) {
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long>(B) * OCT) return;
+  const int j = static_cast<int>(idx & 7);
+  const int b = static_cast<int>(idx >> 3);
+  if (j < NV) out[static_cast<size_t>(b) * NV + j] = src[slot_index(slot, nstage_alloc, stage, Bp, b, j)];
+}
+
+extern "C" int idocp_b200_get_stage_solution(idocp_b200_solver* h, const char* name, int stage, double* out) {
+  if (!h || !out) return fail(IDOCP_B200_INVALID_ARGUMENT, "get_stage_solution: null pointer");
+  const int f = field_index(name);
+  if (f < 0) return fail(IDOCP_B200_INVALID_ARGUMENT, "get_stage_solution: unknown field");
+  const bool full = (f == S_LMD || f == S_GMM || f == S_Q || f == S_V) && h->kind == IDOCP_B200_SOLVER_UNOCP;
+  if (stage < 0 || stage >= (full ? h->N + 1 : h->N))
+    return fail(IDOCP_B200_INVALID_ARGUMENT, "get_stage_solution: stage out of range");
+  CUDA_OK(cudaSetDevice(h->device));
+  const long total = static_cast<long>(h->B) * OCT;
+  IDOCP_LAUNCH(h, KC_MISC, k_gather_stage, static_cast<int>((total + 255) / 256), 256, 0, h->L.sol, f, h->N + 1, stage,
+               h->B, h->Bp, h->d_stage);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(out, h->d_stage, static_cast<size_t>(h->B) * NV * sizeof(double), cudaMemcpyDeviceToHost,
+                          h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return IDOCP_B200_OK;
+}
+
+extern "C" int idocp_b200_get_direction(idocp_b200_solver* h, const char* name, double* out) {
+  if (!h || !out) return fail(IDOCP_B200_INVALID_ARGUMENT, "get_direction: null pointer");
+  const int f = dir_index(name);
+  if (f < 0) return fail(IDOCP_B200_INVALID_ARGUMENT, "get_direction: unknown field");
+  CUDA_OK(cudaSetDevice(h->device));
+  const bool full = (f == D_LMD || f == D_GMM || f == D_Q || f == D_V) && h->kind == IDOCP_B200_SOLVER_UNOCP;
+  return gather_to_host(h, h->L.dir, f, h->N + 1, full ? h->N + 1 : h->N, out);
+}
+
+// out[b][N][6][7]
+__global__ void k_gather_constraints(const double* __restrict__ src, int N, int B, int Bp, double* __restrict__ out) {
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long total = static_cast<long>(B) * N * NC * NV;
+  if (idx >= total) return;
+  const int j = static_cast<int>(idx % NV);
+  long t = idx / NV;
+  const int c = static_cast<int>(t % NC);
+  t /= NC;
+  const int i = static_cast<int>(t % N);
+  const int b = static_cast<int>(t / N);
+  out[idx] = src[slot_index(c, N, i, Bp, b, j)];
+}
+
+extern "C" int idocp_b200_get_constraint_data(idocp_b200_solver* h, const char* name, double* out) {
+  if (!h || !out || !name) return fail(IDOCP_B200_INVALID_ARGUMENT, "get_constraint_data: null pointer");
+  const double* src = nullptr;
+  if (!std::strcmp(name, "slack")) src = h->L.slack;
+  else if (!std::strcmp(name, "dual")) src = h->L.dual;
+  else return fail(IDOCP_B200_INVALID_ARGUMENT, "get_constraint_data: name must be slack or dual");
+  CUDA_OK(cudaSetDevice(h->device));
+  const long total = static_cast<long>(h->B) * h->N * NC * NV;
+  IDOCP_LAUNCH(h, KC_MISC, k_gather_constraints, static_cast<int>((total + 255) / 256), 256, 0, src, h->N, h->B, h->Bp,
+               h->d_stage);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(out, h->d_stage, total * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return IDOCP_B200_OK;
+}
+
+extern "C" int idocp_b200_get_step_sizes(idocp_b200_solver* h, double* primal, double* dual) {
+  if (!h) return fail(IDOCP_B200_INVALID_ARGUMENT, "null handle");
+  CUDA_OK(cudaSetDevice(h->device));
+  const size_t n = static_cast<size_t>(h->B) * sizeof(double);
+  if (primal) CUDA_OK(cudaMemcpyAsync(primal, h->L.steps, n, cudaMemcpyDeviceToHost, h->stream));
+  if (dual) CUDA_OK(cudaMemcpyAsync(dual, h->L.steps + h->Bp, n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return IDOCP_B200_OK;
+}
+
+// Q[b][21*21] column-major (block order a,q,v), res[b][35]
+__global__ void k_gather_unkkt(Layout L, int stage, double* __restrict__ Q, double* __restrict__ res) {
+  const int b = blockIdx.x;
+  if (b >= L.B) return;
+  const int D = 3 * NV;
+  for (int e = threadIdx.x; e < D * D; e += blockDim.x) Q[static_cast<size_t>(b) * D * D + e] = 0.0;
+  __syncthreads();
+  // blocks: (row-block, col-block) of the [a,q,v] ordering
+  const int blk[K_NUMBLK][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
+  for (int e = threadIdx.x; e < K_NUMBLK * NV * NV; e += blockDim.x) {
+    const int k = e / (NV * NV);
+    const int r = (e / NV) % NV;
+    const int c = e % NV;
+    const double val = L.kktQ[slot_index(k * NV + r, L.N, stage, L.Bp, b, c)];
+    Q[static_cast<size_t>(b) * D * D + static_cast<size_t>(blk[k][1] * NV + c) * D + blk[k][0] * NV + r] = val;
+  }
+  for (int e = threadIdx.x; e < R_NUM * NV; e += blockDim.x)
+    res[static_cast<size_t>(b) * R_NUM * NV + e] = L.kktR[slot_index(e / NV, L.N, stage, L.Bp, b, e % NV)];
+}
+
+extern "C" int idocp_b200_get_unkkt(idocp_b200_solver* h, int stage, double* Q, double* res) {
+  if (!h || !Q || !res) return fail(IDOCP_B200_INVALID_ARGUMENT, "get_unkkt: null pointer");
+  if (stage < 0 || stage >= h->N) return fail(IDOCP_B200_INVALID_ARGUMENT, "get_unkkt: stage out of range");
+  CUDA_OK(cudaSetDevice(h->device));
+  double* dQ = nullptr;
+  double* dres = nullptr;
+  CUDA_OK(cudaMalloc(&dQ, static_cast<size_t>(h->B) * 441 * sizeof(double)));
+  CUDA_OK(cudaMalloc(&dres, static_cast<size_t>(h->B) * 35 * sizeof(double)));
+  IDOCP_LAUNCH(h, KC_MISC, k_gather_unkkt, h->B, 128, 0, h->L, stage, dQ, dres);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(Q, dQ, static_cast<size_t>(h->B) * 441 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(res, dres, static_cast<size_t>(h->B) * 35 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(dQ);
+  cudaFree(dres);
+  if (e != cudaSuccess) return fail(IDOCP_B200_CUDA_ERROR, cudaGetErrorString(e));
+  return IDOCP_B200_OK;
+}
+
+extern "C" int idocp_b200_get_status(idocp_b200_solver* h, int* out) {
+  if (!h || !out) return fail(IDOCP_B200_INVALID_ARGUMENT, "get_status: null pointer");
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaMemcpyAsync(out, h->L.status, static_cast<size_t>(h->B) * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return IDOCP_B200_OK;
+}
+
+__global__ void k_is_feasible(const DevProblem* __restrict__ Pp, Layout L, int stage_offset, int* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= L.B) return;
+  const DevProblem& P = *Pp;
+  int ok = 1;
+  for (int i = 0; i < L.N; ++i)
+    for (int j = 0; j < NV; ++j) {
+      const LaneLimits lim = load_limits(P, j);
+      const double q = L.sol[slot_index(S_Q, L.N + 1, i, L.Bp, b, j)];
+      const double v = L.sol[slot_index(S_V, L.N + 1, i, L.Bp, b, j)];
+      const double u = L.sol[slot_index(S_U, L.N + 1, i, L.Bp, b, j)];
+      for (int c = 0; c < NC; ++c)
+        if (comp_active(c, i + stage_offset) && con_margin(c, lim, q, v, u) < 0) ok = 0;
+    }
+  out[b] = ok;
+}
+
+extern "C" int idocp_b200_is_feasible(idocp_b200_solver* h, int* out) {
+  if (!h || !out) return fail(IDOCP_B200_INVALID_ARGUMENT, "is_feasible: null pointer");
+  CUDA_OK(cudaSetDevice(h->device));
+  int* d = reinterpret_cast<int*>(h->d_stage);
+  const int off = h->kind == IDOCP_B200_SOLVER_UNPARNMPC ? 1 : 0;
+  IDOCP_LAUNCH(h, KC_MISC, k_is_feasible, (h->B + 127) / 128, 128, 0, h->d_prob, h->L, off, d);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(out, d, static_cast<size_t>(h->B) * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return IDOCP_B200_OK;
+}
+
+extern "C" int idocp_b200_clear_line_search_filter(idocp_b200_solver* h) {
+  if (!h) return fail(IDOCP_B200_INVALID_ARGUMENT, "null handle");
+  return IDOCP_B200_OK;
+}
+
+extern "C" int idocp_b200_init_backward_correction(idocp_b200_solver* h, double t) {
+  if (!h) return fail(IDOCP_B200_INVALID_ARGUMENT, "null handle");
+  if (h->kind != IDOCP_B200_SOLVER_UNPARNMPC)
+    return fail(IDOCP_B200_INVALID_ARGUMENT, "init_backward_correction: not an UnParNMPC solver");
+  CUDA_OK(cudaSetDevice(h->device));
+  return parnmpc_init_backward_correction(h, t);
+}
+
+extern "C" int idocp_b200_sync(idocp_b200_solver* h) {
+  if (!h) return fail(IDOCP_B200_INVALID_ARGUMENT, "null handle");
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return IDOCP_B200_OK;
+}
+
+extern "C" int idocp_b200_launch_count(idocp_b200_solver* h, long long* out) {
+  if (!h || !out) return fail(IDOCP_B200_INVALID_ARGUMENT, "launch_count: null pointer");
+  *out = h->launches;
+  return IDOCP_B200_OK;
+}
+
+extern "C" int idocp_b200_stream(idocp_b200_solver* h, void** out) {
+  if (!h || !out) return fail(IDOCP_B200_INVALID_ARGUMENT, "stream: null pointer");
+  *out = reinterpret_cast<void*>(h->stream);
+  return IDOCP_B200_OK;
+}
+
+extern "C" int idocp_b200_set_profiling(idocp_b200_solver* h, int enabled) {
+  if (!h) return fail(IDOCP_B200_INVALID_ARGUMENT, "null handle");
+  h->resolve_profile();
+  h->profiling = enabled != 0;
+  for (int k = 0; k < KC_NUM; ++k) { h->prof_ms[k] = 0; h->prof_calls[k] = 0; }
+  return IDOCP_B200_OK;
+}
+
+extern "C" int idocp_b200_get_profile(idocp_b200_solver* h, int cap, const char** names, double* ms, long long* calls) {
+  if (!h || !names || !ms || !calls) return fail(IDOCP_B200_INVALID_ARGUMENT, "get_profile: null pointer");
+  h->resolve_profile();
+  int n = 0;
+  for (int k = 0; k < KC_NUM && n < cap; ++k) {
+    if (h->prof_calls[k] == 0) continue;
+    names[n] = kKernelClassNames[k];
+    ms[n] = h->prof_ms[k];
+    calls[n] = h->prof_calls[k];
+    ++n;
+  }
+  return n;
+}

@@ -1,0 +1,187 @@
+// chain_dynamics.cuh -- lane-parallel inverse dynamics (RNEA) and its analytical derivatives
+// for a serial chain of revolute-Z joints (iiwa14), one joint per lane of an octet.
+//
+// Replaces Robot::RNEA / Robot::RNEADerivatives, i.e. pinocchio::rnea and
+// pinocchio::computeRNEADerivatives (reference include/idocp/robot/robot.hxx:444-500).
+//
+// Formulation (DESIGN.md "RNEA derivatives"): all spatial quantities are expressed in the WORLD
+// frame, [linear; angular].  Then the recursions over the chain become prefix / suffix sums over
+// the lanes of the octet, and everything else is lane-local 3-vector algebra:
+//   world transforms  : inclusive prefix PRODUCT of the local joint transforms (3 shuffle rounds)
+//   v_i, a_i          : prefix sums of S_i qd_i and S_i qdd_i + dS_i qd_i
+//   composites        : suffix sums of  I_i=(m,mc,Ibar) [10],  D_i=(hl,ha,Sym) [12],  f_i [6]
+// The 6x6 composite "doYcrb" matrix of Carpentier & Mansard has only 12 independent entries:
+//   D m = (-2 hl x m_w ; Sym m_w - ha x m_w).
+// Pairwise phase (lane c owns column c):
+//   r <= c: dq[r][c] = S_r.G_c    dv[r][c] = S_r.H_c    M[r][c] = S_r.U_c
+//   r >  c: dq[r][c] = U_r.B_c + Ww_r.dSw_c   dv[r][c] = Ww_r.Sw_c + 2 U_r.dS_c   M[r][c] = S_c.U_r
+#pragma once
+#include "common.cuh"
+
+namespace idocp_b200 {
+
+struct JointDyn {
+  V3 Sl, Sw, dSl, dSw, Bl, Bw;
+  V3 Ul, Uw, Ww, Gl, Gw, Hl, Hw;
+  double tau;
+};
+
+// Forward + backward world-frame sweeps.  `mdl` points at this lane's row of the model table.
+// Lane 7 (padding) must be called with q = qd = qdd = 0; its model row has zero mass.
+__device__ __forceinline__ void chain_world_sweep(int lane, double q, double qd, double qdd,
+                                                  const double* __restrict__ mdl, double gravity,
+                                                  JointDyn& J) {
+  double sn, cs;
+  IDOCP_SINCOS(q, &sn, &cs);
+  // local transform: placement * Rz(q)
+  double R[9];
+  V3 p = v3(mdl[9], mdl[10], mdl[11]);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const double a0 = mdl[3 * r], a1 = mdl[3 * r + 1];
+    R[3 * r + 0] = cs * a0 + sn * a1;
+    R[3 * r + 1] = -sn * a0 + cs * a1;
+    R[3 * r + 2] = mdl[3 * r + 2];
+  }
+  // inclusive prefix product over the chain: X_l <- X_0 X_1 ... X_l
+#pragma unroll
+  for (int d = 1; d < OCT; d <<= 1) {
+    double Rs[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Rs[k] = oct_up(R[k], d);
+    const V3 ps = oct_up(p, d);
+    if (lane >= d) {
+      p = v3(ps.x + (Rs[0] * p.x + Rs[1] * p.y + Rs[2] * p.z),
+             ps.y + (Rs[3] * p.x + Rs[4] * p.y + Rs[5] * p.z),
+             ps.z + (Rs[6] * p.x + Rs[7] * p.y + Rs[8] * p.z));
+      double Rn[9];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          Rn[3 * r + k] = Rs[3 * r] * R[k] + Rs[3 * r + 1] * R[3 + k] + Rs[3 * r + 2] * R[6 + k];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) R[k] = Rn[k];
+    }
+  }
+  const V3 z = v3(R[2], R[5], R[8]);
+  J.Sl = cross(p, z);
+  J.Sw = z;
+  // velocities
+  const V3 vw = oct_prefix_sum(qd * J.Sw, lane);
+  const V3 vl = oct_prefix_sum(qd * J.Sl, lane);
+  J.dSl = cross(vw, J.Sl) + cross(vl, J.Sw);
+  J.dSw = cross(vw, J.Sw);
+  // accelerations (gravity enters as the base acceleration (0,0,+g))
+  const V3 aw = oct_prefix_sum(qdd * J.Sw + qd * J.dSw, lane);
+  V3 al = oct_prefix_sum(qdd * J.Sl + qd * J.dSl, lane);
+  al.z += gravity;
+  J.Bl = cross(aw, J.Sl) + cross(al, J.Sw) + cross(vw, J.dSl) + cross(vl, J.dSw);
+  J.Bw = cross(aw, J.Sw) + cross(vw, J.dSw);
+  // world inertia about the world origin
+  const double m = mdl[12];
+  const V3 cm = v3(mdl[13], mdl[14], mdl[15]);
+  const V3 cw = v3(R[0] * cm.x + R[1] * cm.y + R[2] * cm.z + p.x, R[3] * cm.x + R[4] * cm.y + R[5] * cm.z + p.y,
+                   R[6] * cm.x + R[7] * cm.y + R[8] * cm.z + p.z);
+  V3 mc = m * cw;
+  S3 Ib;
+  {
+    const double i0 = mdl[16], i1 = mdl[17], i2 = mdl[18], i3 = mdl[19], i4 = mdl[20], i5 = mdl[21];
+    double RI[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const double r0 = R[3 * r], r1 = R[3 * r + 1], r2 = R[3 * r + 2];
+      RI[3 * r + 0] = r0 * i0 + r1 * i1 + r2 * i2;
+      RI[3 * r + 1] = r0 * i1 + r1 * i3 + r2 * i4;
+      RI[3 * r + 2] = r0 * i2 + r1 * i4 + r2 * i5;
+    }
+    const double cc = dot(cw, cw);
+    Ib.xx = RI[0] * R[0] + RI[1] * R[1] + RI[2] * R[2] + m * (cc - cw.x * cw.x);
+    Ib.xy = RI[0] * R[3] + RI[1] * R[4] + RI[2] * R[5] + m * (0.0 - cw.x * cw.y);
+    Ib.xz = RI[0] * R[6] + RI[1] * R[7] + RI[2] * R[8] + m * (0.0 - cw.x * cw.z);
+    Ib.yy = RI[3] * R[3] + RI[4] * R[4] + RI[5] * R[5] + m * (cc - cw.y * cw.y);
+    Ib.yz = RI[3] * R[6] + RI[4] * R[7] + RI[5] * R[8] + m * (0.0 - cw.y * cw.z);
+    Ib.zz = RI[6] * R[6] + RI[7] * R[7] + RI[8] * R[8] + m * (cc - cw.z * cw.z);
+  }
+  V3 hl = m * vl + cross(vw, mc);
+  V3 ha = cross(mc, vl) + mul(Ib, vw);
+  V3 fl = m * al + cross(aw, mc) + cross(vw, hl);
+  V3 fa = cross(mc, al) + mul(Ib, aw) + cross(vw, ha) + cross(vl, hl);
+  S3 Sym;
+  {
+    // wI[r][k] = (vw x Ib[:,k])_r
+    const V3 c0 = cross(vw, v3(Ib.xx, Ib.xy, Ib.xz));
+    const V3 c1 = cross(vw, v3(Ib.xy, Ib.yy, Ib.yz));
+    const V3 c2 = cross(vw, v3(Ib.xz, Ib.yz, Ib.zz));
+    const double mcv = dot(mc, vl);
+    Sym.xx = -(vl.x * mc.x + mc.x * vl.x) + c0.x + c0.x + 2.0 * mcv;
+    Sym.xy = -(vl.x * mc.y + mc.x * vl.y) + c1.x + c0.y;
+    Sym.xz = -(vl.x * mc.z + mc.x * vl.z) + c2.x + c0.z;
+    Sym.yy = -(vl.y * mc.y + mc.y * vl.y) + c1.y + c1.y + 2.0 * mcv;
+    Sym.yz = -(vl.y * mc.z + mc.y * vl.z) + c2.y + c1.z;
+    Sym.zz = -(vl.z * mc.z + mc.z * vl.z) + c2.z + c2.z + 2.0 * mcv;
+  }
+  // composite (suffix) sums
+  const double mC = oct_suffix_sum(m, lane);
+  mc = oct_suffix_sum(mc, lane);
+  Ib.xx = oct_suffix_sum(Ib.xx, lane); Ib.xy = oct_suffix_sum(Ib.xy, lane); Ib.xz = oct_suffix_sum(Ib.xz, lane);
+  Ib.yy = oct_suffix_sum(Ib.yy, lane); Ib.yz = oct_suffix_sum(Ib.yz, lane); Ib.zz = oct_suffix_sum(Ib.zz, lane);
+  hl = oct_suffix_sum(hl, lane);
+  ha = oct_suffix_sum(ha, lane);
+  Sym.xx = oct_suffix_sum(Sym.xx, lane); Sym.xy = oct_suffix_sum(Sym.xy, lane); Sym.xz = oct_suffix_sum(Sym.xz, lane);
+  Sym.yy = oct_suffix_sum(Sym.yy, lane); Sym.yz = oct_suffix_sum(Sym.yz, lane); Sym.zz = oct_suffix_sum(Sym.zz, lane);
+  fl = oct_suffix_sum(fl, lane);
+  fa = oct_suffix_sum(fa, lane);
+  // per-joint vectors
+  J.tau = dot(J.Sl, fl) + dot(J.Sw, fa);
+  J.Ul = mC * J.Sl + cross(J.Sw, mc);
+  J.Uw = cross(mc, J.Sl) + mul(Ib, J.Sw);
+  J.Ww = 2.0 * cross(hl, J.Sl) + mul(Sym, J.Sw) + cross(ha, J.Sw);
+  J.Gl = cross(J.Sw, fl) + mC * J.Bl + cross(J.Bw, mc) - 2.0 * cross(hl, J.dSw);
+  J.Gw = cross(J.Sw, fa) + cross(J.Sl, fl) + cross(mc, J.Bl) + mul(Ib, J.Bw) + mul(Sym, J.dSw) - cross(ha, J.dSw);
+  J.Hl = (-2.0) * cross(hl, J.Sw) + 2.0 * (mC * J.dSl + cross(J.dSw, mc));
+  J.Hw = mul(Sym, J.Sw) - cross(ha, J.Sw) + 2.0 * (cross(mc, J.dSl) + mul(Ib, J.dSw));
+}
+
+// tau only (used by the line search): same world sweep without the derivative vectors
+__device__ __forceinline__ double chain_rnea(int lane, double q, double qd, double qdd,
+                                             const double* __restrict__ mdl, double gravity) {
+  JointDyn J;
+  chain_world_sweep(lane, q, qd, qdd, mdl, gravity, J);
+  return J.tau;
+}
+
+constexpr int PAIR_TILE = 25;  // doubles per lane in the exchange tile (odd: conflict-free transposes)
+
+// Pairwise phase: produces column `lane` of dtau/dq, dtau/dv and M = dtau/da (rows r = 0..6).
+// `tile` = this octet's shared-memory tile [8][PAIR_TILE].
+__device__ __forceinline__ void chain_pair_phase(int lane, const JointDyn& J, double* __restrict__ tile,
+                                                 double (&dqc)[NV], double (&dvc)[NV], double (&Mc)[NV]) {
+  double* mine = tile + lane * PAIR_TILE;
+  mine[0] = J.Sl.x; mine[1] = J.Sl.y; mine[2] = J.Sl.z;
+  mine[3] = J.Sw.x; mine[4] = J.Sw.y; mine[5] = J.Sw.z;
+  mine[6] = J.Ul.x; mine[7] = J.Ul.y; mine[8] = J.Ul.z;
+  mine[9] = J.Uw.x; mine[10] = J.Uw.y; mine[11] = J.Uw.z;
+  mine[12] = J.Ww.x; mine[13] = J.Ww.y; mine[14] = J.Ww.z;
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < NV; ++r) {
+    const double* o = tile + r * PAIR_TILE;
+    const V3 Sl = v3(o[0], o[1], o[2]), Sw = v3(o[3], o[4], o[5]);
+    const V3 Ul = v3(o[6], o[7], o[8]), Uw = v3(o[9], o[10], o[11]);
+    const V3 Ww = v3(o[12], o[13], o[14]);
+    const double up_q = dot(Sl, J.Gl) + dot(Sw, J.Gw);
+    const double up_v = dot(Sl, J.Hl) + dot(Sw, J.Hw);
+    const double up_m = dot(Sl, J.Ul) + dot(Sw, J.Uw);
+    const double lo_q = dot(Ul, J.Bl) + dot(Uw, J.Bw) + dot(Ww, J.dSw);
+    const double lo_v = dot(Ww, J.Sw) + 2.0 * (dot(Ul, J.dSl) + dot(Uw, J.dSw));
+    const double lo_m = dot(J.Sl, Ul) + dot(J.Sw, Uw);
+    const bool upper = (r <= lane);
+    dqc[r] = upper ? up_q : lo_q;
+    dvc[r] = upper ? up_v : lo_v;
+    Mc[r] = upper ? up_m : lo_m;
+  }
+  __syncwarp();
+}
+
+}  // namespace idocp_b200

@@ -1,0 +1,211 @@
+"""Host-side mirror of idocp's solver interface for a BATCH of instances.
+
+Same method names, argument meaning and call order as the reference classes
+(include/idocp/unocp/unocp_solver.hpp:37-170, unparnmpc_solver.hpp:37-171); every vector argument
+gains a leading batch dimension.  The C++ twin of these classes is include/idocp_b200/*.hpp.
+All arithmetic happens in the CUDA library behind the C-ABI; nothing here computes.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import DIMV, NUM_CONSTRAINTS, SOLVER_UNOCP, SOLVER_UNPARNMPC, Idocp_b200Error, Problem, dptr
+
+__all__ = ["UnOCPSolver", "UnParNMPCSolver", "benchmark_problem", "config_space_problem", "Problem"]
+
+
+def _fill(arr, value):
+    value = np.broadcast_to(np.asarray(value, dtype=np.float64), (len(arr),))
+    for i in range(len(arr)):
+        arr[i] = float(value[i])
+
+
+def benchmark_problem(lib=None, N=20, T=1.0):
+    """examples/iiwa14/unocp_benchmark.cpp:22-46 (BASELINE.json configs[2], the metric config)."""
+    lib = lib or capi.default_library()
+    p = lib.default_problem()
+    p.N, p.T = N, T
+    _fill(p.u_max, 200.0)
+    _fill(p.q_ref, -5.0)
+    _fill(p.v_ref, -9.0)
+    _fill(p.q_weight, 10.0)
+    _fill(p.qf_weight, 10.0)
+    _fill(p.v_weight, 0.1)
+    _fill(p.vf_weight, 0.1)
+    _fill(p.a_weight, 0.01)
+    _fill(p.u_weight, 0.0)
+    return p
+
+
+def config_space_problem(lib=None):
+    """examples/iiwa14/config_space_ocp.cpp:26-61 (BASELINE.json configs[0])."""
+    lib = lib or capi.default_library()
+    p = lib.default_problem()
+    p.N, p.T = 60, 3.0
+    _fill(p.u_max, 50.0)
+    _fill(p.v_max, np.pi / 2)
+    _fill(p.q_ref, [0, np.pi / 2, 0, np.pi / 2, 0, np.pi / 2, 0])
+    _fill(p.q_weight, 10.0)
+    _fill(p.qf_weight, 10.0)
+    _fill(p.v_weight, 0.01)
+    _fill(p.vf_weight, 0.01)
+    _fill(p.a_weight, 0.01)
+    return p
+
+
+class _BatchSolver:
+    kind = None
+
+    def __init__(self, problem, batch, device=0, lib=None):
+        self.lib = lib or capi.default_library()
+        self.batch = int(batch)
+        self.N = int(problem.N)
+        self.problem = problem
+        self._h = C.c_void_p()
+        self.lib.check(self.lib.L.idocp_b200_create(C.byref(problem), self.kind, self.batch, device,
+                                                    C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.L.idocp_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- reference API -----------------------------------------------------------------------
+    def _x(self, a):
+        a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+        if a.shape == (DIMV,):
+            a = np.ascontiguousarray(np.broadcast_to(a, (self.batch, DIMV)))
+        if a.shape != (self.batch, DIMV):
+            raise ValueError("expected an array of shape (%d, %d) or (%d,)" % (self.batch, DIMV, DIMV))
+        return a
+
+    def setSolution(self, name, value):
+        """UnOCPSolver::setSolution: value (dimv,) is written to all stages of all instances;
+        value (batch, dimv) gives every instance its own vector."""
+        value = np.ascontiguousarray(np.asarray(value, dtype=np.float64))
+        if value.shape == (DIMV,):
+            bc = 1
+        elif value.shape == (self.batch, DIMV):
+            bc = 0
+        else:
+            raise ValueError("setSolution: bad shape %s" % (value.shape,))
+        self.lib.check(self.lib.L.idocp_b200_set_solution(self._h, name.encode(), dptr(value), bc))
+
+    def initConstraints(self):
+        self.lib.check(self.lib.L.idocp_b200_init_constraints(self._h))
+
+    def updateSolution(self, t, q, v, line_search=False):
+        q, v = self._x(q), self._x(v)
+        self.lib.check(self.lib.L.idocp_b200_update_solution(self._h, float(t), dptr(q), dptr(v), int(line_search)))
+
+    def updateSolutionDevice(self, t, q_ptr, v_ptr, line_search=False):
+        """q_ptr / v_ptr: device addresses (e.g. torch.Tensor.data_ptr()) of (batch, dimv) float64."""
+        self.lib.check(self.lib.L.idocp_b200_update_solution_device(self._h, float(t), C.c_void_p(q_ptr),
+                                                                    C.c_void_p(v_ptr), int(line_search)))
+
+    def computeKKTResidual(self, t, q, v):
+        q, v = self._x(q), self._x(v)
+        self.lib.check(self.lib.L.idocp_b200_compute_kkt_residual(self._h, float(t), dptr(q), dptr(v)))
+
+    def computeKKTResidualDevice(self, t, q_ptr, v_ptr):
+        self.lib.check(self.lib.L.idocp_b200_compute_kkt_residual_device(self._h, float(t), C.c_void_p(q_ptr),
+                                                                         C.c_void_p(v_ptr)))
+
+    def KKTError(self):
+        out = np.zeros(self.batch)
+        self.lib.check(self.lib.L.idocp_b200_kkt_error(self._h, dptr(out)))
+        return out
+
+    def _nstages(self, name, full_names):
+        return self.N + 1 if (name in full_names and self.kind == SOLVER_UNOCP) else self.N
+
+    def getSolution(self, name):
+        out = np.zeros((self.batch, self._nstages(name, ("q", "v", "lmd", "gmm")), DIMV))
+        self.lib.check(self.lib.L.idocp_b200_get_solution(self._h, name.encode(), dptr(out)))
+        return out
+
+    def getStageSolution(self, name, stage, out=None):
+        """UnOCPSolver::getSolution(int stage), one field: (batch, dimv)."""
+        if out is None:
+            out = np.zeros((self.batch, DIMV))
+        self.lib.check(self.lib.L.idocp_b200_get_stage_solution(self._h, name.encode(), int(stage), dptr(out)))
+        return out
+
+    def clearLineSearchFilter(self):
+        self.lib.check(self.lib.L.idocp_b200_clear_line_search_filter(self._h))
+
+    def isCurrentSolutionFeasible(self):
+        out = np.zeros(self.batch, dtype=np.int32)
+        self.lib.check(self.lib.L.idocp_b200_is_feasible(self._h, out.ctypes.data_as(C.POINTER(C.c_int))))
+        return out.astype(bool)
+
+    # -- additions for parity tests / measurement ----------------------------------------------
+    def getDirection(self, name):
+        out = np.zeros((self.batch, self._nstages(name, ("dq", "dv", "dlmd", "dgmm")), DIMV))
+        self.lib.check(self.lib.L.idocp_b200_get_direction(self._h, name.encode(), dptr(out)))
+        return out
+
+    def getConstraintData(self, name):
+        out = np.zeros((self.batch, self.N, NUM_CONSTRAINTS, DIMV))
+        self.lib.check(self.lib.L.idocp_b200_get_constraint_data(self._h, name.encode(), dptr(out)))
+        return out
+
+    def getStepSizes(self):
+        p, d = np.zeros(self.batch), np.zeros(self.batch)
+        self.lib.check(self.lib.L.idocp_b200_get_step_sizes(self._h, dptr(p), dptr(d)))
+        return p, d
+
+    def getUnKKT(self, stage):
+        Q = np.zeros((self.batch, 21, 21))
+        res = np.zeros((self.batch, 35))
+        self.lib.check(self.lib.L.idocp_b200_get_unkkt(self._h, int(stage), dptr(Q), dptr(res)))
+        return np.ascontiguousarray(Q.transpose(0, 2, 1)), res   # column-major -> [row, col]
+
+    def getStatus(self):
+        out = np.zeros(self.batch, dtype=np.int32)
+        self.lib.check(self.lib.L.idocp_b200_get_status(self._h, out.ctypes.data_as(C.POINTER(C.c_int))))
+        return out
+
+    def sync(self):
+        self.lib.check(self.lib.L.idocp_b200_sync(self._h))
+
+    def launchCount(self):
+        n = C.c_longlong(0)
+        self.lib.check(self.lib.L.idocp_b200_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def stream(self):
+        s = C.c_void_p()
+        self.lib.check(self.lib.L.idocp_b200_stream(self._h, C.byref(s)))
+        return s.value or 0
+
+    def setProfiling(self, enabled):
+        self.lib.check(self.lib.L.idocp_b200_set_profiling(self._h, int(enabled)))
+
+    def getProfile(self):
+        cap = 16
+        names = (C.c_char_p * cap)()
+        ms = np.zeros(cap)
+        calls = (C.c_longlong * cap)()
+        n = self.lib.check(self.lib.L.idocp_b200_get_profile(self._h, cap, names, dptr(ms), calls))
+        return {names[i].decode(): (ms[i], calls[i]) for i in range(n)}
+
+
+class UnOCPSolver(_BatchSolver):
+    """Batched idocp::UnOCPSolver (Riccati recursion)."""
+    kind = SOLVER_UNOCP
+
+
+class UnParNMPCSolver(_BatchSolver):
+    """Batched idocp::UnParNMPCSolver (ParNMPC backward correction)."""
+    kind = SOLVER_UNPARNMPC
+
+    def initBackwardCorrection(self, t):
+        self.lib.check(self.lib.L.idocp_b200_init_backward_correction(self._h, float(t)))

@@ -1,0 +1,156 @@
+/*
+ * idocp_b200.h -- C-ABI of the B200-native batched optimal-control engine.
+ *
+ * Drop-in boundary for idocp's data-parallel Newton-step hot path.  The reference
+ * (mayataka/idocp) has no FFI; its "operator API" for this path is the public C++ interface
+ * of its solver classes.  Each entry point below replaces one of those methods for a BATCH
+ * of independent OCP instances (the reference solves one instance per solver object), and the
+ * C++ host classes in include/idocp_b200/ (*.hpp) re-create the reference's class API on top.
+ *
+ * Conventions
+ *  - plain pointers and sizes, no torch / Eigen types;
+ *  - every function returns 0 on success, a negative idocp_b200_status on error, and never
+ *    exits the process (the reference prints + std::exit, unocp_solver.cpp:33-47); the text of
+ *    the last error of the calling thread is returned by idocp_b200_last_error();
+ *  - host arrays are row-major [batch][...]; `dimv` = 7 for the iiwa14;
+ *  - one handle = one CUDA device + one stream; calls on a handle are serialised, asynchronous
+ *    with respect to the host until a getter / idocp_b200_sync();
+ *  - there is NO CPU fallback: creation fails when no CUDA device is usable.
+ */
+#ifndef IDOCP_B200_H_
+#define IDOCP_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IDOCP_B200_DIMV 7          /* iiwa14: nq = nv = nu */
+#define IDOCP_B200_NUM_CONSTRAINTS 6 /* JointConstraintsFactory: pos/vel/torque x lower/upper */
+
+typedef enum {
+  IDOCP_B200_OK = 0,
+  IDOCP_B200_INVALID_ARGUMENT = -1,
+  IDOCP_B200_CUDA_ERROR = -2,
+  IDOCP_B200_NO_DEVICE = -3,
+  IDOCP_B200_UNSUPPORTED = -4
+} idocp_b200_status;
+
+/* per-instance numerical status bits (idocp_b200_get_status) -- the reference only asserts in
+ * Debug builds (split_unriccati_factorizer.hxx:38,41-42) */
+#define IDOCP_B200_STATUS_CHOL_FAIL 1  /* a Cholesky pivot was <= 0 or NaN */
+#define IDOCP_B200_STATUS_NAN       2  /* a step size / KKT error was NaN */
+
+typedef enum {
+  IDOCP_B200_ROBOT_IIWA14 = 0
+} idocp_b200_robot;
+
+typedef enum {
+  IDOCP_B200_SOLVER_UNOCP = 0,     /* idocp::UnOCPSolver      (include/idocp/unocp/unocp_solver.hpp:25-188)   */
+  IDOCP_B200_SOLVER_UNPARNMPC = 1  /* idocp::UnParNMPCSolver  (include/idocp/unocp/unparnmpc_solver.hpp:37-171) */
+} idocp_b200_solver_kind;
+
+/*
+ * Problem descriptor = the closed, POD form of what the reference builds from plug-ins:
+ *   Robot limits             robot/robot.hxx:699-709, Robot::setJointEffortLimit/VelocityLimit
+ *   ConfigurationSpaceCost   src/cost/configuration_space_cost.cpp:241-396
+ *   JointConstraintsFactory  src/utils/joint_constraints_factory.cpp:22-37 (six joint-limit
+ *                            components, barrier / fraction-to-boundary of
+ *                            constraints/joint_position_lower_limit.hpp:19-20)
+ *   TimeVaryingTaskSpace6DCost (optional) src/cost/time_varying_task_space_6d_cost.cpp:68-195
+ */
+typedef struct {
+  int robot;                /* idocp_b200_robot */
+  int N;                    /* number of horizon stages  (UnOCPSolver ctor argument N) */
+  double T;                 /* horizon length            (ctor argument T)             */
+  double q_ref[IDOCP_B200_DIMV], v_ref[IDOCP_B200_DIMV], u_ref[IDOCP_B200_DIMV];
+  double q_weight[IDOCP_B200_DIMV], v_weight[IDOCP_B200_DIMV], a_weight[IDOCP_B200_DIMV];
+  double u_weight[IDOCP_B200_DIMV], qf_weight[IDOCP_B200_DIMV], vf_weight[IDOCP_B200_DIMV];
+  double q_min[IDOCP_B200_DIMV], q_max[IDOCP_B200_DIMV];
+  double v_max[IDOCP_B200_DIMV], u_max[IDOCP_B200_DIMV];
+  double barrier;           /* 1e-4  */
+  double fraction_rate;     /* 0.995 */
+  int task_enabled;         /* TimeVaryingTaskSpace6DCost on the end-effector frame */
+  double task_q_weight[6], task_qf_weight[6];
+  double task_center[3], task_radius, task_t0, task_tf;
+  double task_rot_ref[9];
+} idocp_b200_problem;
+
+typedef struct idocp_b200_solver idocp_b200_solver; /* opaque */
+
+/* fills robot limits (URDF), barrier 1e-4, fraction 0.995, N = 20, T = 1, zero weights */
+int idocp_b200_problem_default(int robot, idocp_b200_problem* p);
+
+/* UnOCPSolver::UnOCPSolver(robot, cost, constraints, T, N, nthreads) / UnParNMPCSolver ctor
+ * (src/unocp/unocp_solver.cpp:11-49).  `nthreads` has no meaning on the GPU and is not taken.
+ * Like the reference ctor it ends with initConstraints() on the zero solution. */
+int idocp_b200_create(const idocp_b200_problem* p, int solver_kind, int batch, int device,
+                      idocp_b200_solver** out);
+int idocp_b200_destroy(idocp_b200_solver* h);
+
+/* UnOCPSolver::setSolution(name, value) (unocp_solver.cpp:157-181): name in {"q","v","a","u"};
+ * broadcast != 0: value[dimv] is written to every stage of every instance (the reference call);
+ * broadcast == 0: value[batch][dimv] gives each instance its own vector (all stages).
+ * Ends with initConstraints() like the reference. */
+int idocp_b200_set_solution(idocp_b200_solver* h, const char* name, const double* value, int broadcast);
+/* UnOCPSolver::initConstraints() (unocp_solver.cpp:59-70) */
+int idocp_b200_init_constraints(idocp_b200_solver* h);
+/* UnParNMPCSolver::initBackwardCorrection(t) (src/unocp/unparnmpc_solver.cpp:69-71) */
+int idocp_b200_init_backward_correction(idocp_b200_solver* h, double t);
+
+/* UnOCPSolver::updateSolution(t, q, v, line_search) (unocp_solver.cpp:73-134), one SQP
+ * iteration of every instance.  q, v: HOST arrays [batch][dimv] (initial state per instance). */
+int idocp_b200_update_solution(idocp_b200_solver* h, double t, const double* q, const double* v,
+                               int line_search);
+/* same, q and v already resident in device memory ([batch][dimv] doubles on the handle's device) */
+int idocp_b200_update_solution_device(idocp_b200_solver* h, double t, const double* d_q,
+                                      const double* d_v, int line_search);
+/* UnOCPSolver::computeKKTResidual(t, q, v) (unocp_solver.cpp:205-225) */
+int idocp_b200_compute_kkt_residual(idocp_b200_solver* h, double t, const double* q, const double* v);
+int idocp_b200_compute_kkt_residual_device(idocp_b200_solver* h, double t, const double* d_q,
+                                           const double* d_v);
+/* UnOCPSolver::KKTError() (unocp_solver.cpp:190-202): out[batch]; reads the residual buffers of
+ * the last computeKKTResidual, exactly like the reference. */
+int idocp_b200_kkt_error(idocp_b200_solver* h, double* out);
+
+/* UnOCPSolver::getSolution(name) (unocp_solver.cpp:240-264): name in
+ * {"q","v","lmd","gmm"} -> out[batch][N+1][dimv]; {"a","u","beta"} -> out[batch][N][dimv]
+ * (UnParNMPC: N stages for every field). */
+int idocp_b200_get_solution(idocp_b200_solver* h, const char* name, double* out);
+/* UnOCPSolver::getSolution(int stage) (unocp_solver.cpp:137-141), one field of one stage:
+ * out[batch][dimv] */
+int idocp_b200_get_stage_solution(idocp_b200_solver* h, const char* name, int stage, double* out);
+/* Newton direction of the last updateSolution ({"dq","dv","dlmd","dgmm"}: N+1 stages;
+ * {"da","du","dbeta"}: N stages) -- for parity tests; the reference keeps it in d_ */
+int idocp_b200_get_direction(idocp_b200_solver* h, const char* name, double* out);
+/* ConstraintComponentData fields {"slack","dual"}: out[batch][N][6][dimv] (inactive rows 0) */
+int idocp_b200_get_constraint_data(idocp_b200_solver* h, const char* name, double* out);
+/* primal / dual step sizes of the last updateSolution, out arrays [batch] (either may be NULL) */
+int idocp_b200_get_step_sizes(idocp_b200_solver* h, double* primal, double* dual);
+/* condensed KKT data of the last linearisation for one stage (parity tests):
+ * Q[batch][21*21] column-major in block order (a,q,v) as SplitUnKKTMatrix, lower blocks
+ * (qa, va) left zero; res[batch][35] = [Fq,Fv,la,lq,lv] as SplitUnKKTResidual */
+int idocp_b200_get_unkkt(idocp_b200_solver* h, int stage, double* Q, double* res);
+int idocp_b200_get_status(idocp_b200_solver* h, int* out);
+/* UnOCPSolver::isCurrentSolutionFeasible() (unocp_solver.cpp:228-237): out[batch] 0/1 */
+int idocp_b200_is_feasible(idocp_b200_solver* h, int* out);
+/* UnOCPSolver::clearLineSearchFilter() (unocp_solver.cpp:185-187) */
+int idocp_b200_clear_line_search_filter(idocp_b200_solver* h);
+
+int idocp_b200_sync(idocp_b200_solver* h);
+/* number of kernels this handle has launched since creation (bench.py "gpu_launches") */
+int idocp_b200_launch_count(idocp_b200_solver* h, long long* out);
+/* CUDA stream of the handle as an opaque pointer (for event timing on the launching stream) */
+int idocp_b200_stream(idocp_b200_solver* h, void** out);
+/* per-kernel-class device time: while profiling is enabled every launch is bracketed by CUDA
+ * events on the launching stream (no host sync inside the timed region); get_profile resolves them:
+ * names[i], total ms[i], calls[i]; returns the number of entries (<= cap) */
+int idocp_b200_set_profiling(idocp_b200_solver* h, int enabled);
+int idocp_b200_get_profile(idocp_b200_solver* h, int cap, const char** names, double* ms, long long* calls);
+
+const char* idocp_b200_last_error(void);
+const char* idocp_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IDOCP_B200_H_ */

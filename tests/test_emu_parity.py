@@ -1,0 +1,94 @@
+"""CUDA sources under the SIMT emulator vs the oracle (CPU-only container).
+
+This exercises the exact kernel code (idocp_b200/csrc/*.cuh: octet shuffles, shared-memory tiles,
+launch geometry, C-ABI staging) with a g++ build in which every CUDA thread is a fiber.  It is a
+check of the lane-parallel algorithms, not the product path: the GPU parity proper is
+tests/test_gpu_parity.py (-m gpu)."""
+import numpy as np
+import pytest
+
+import idocp_b200 as I
+from conftest import make_states
+from helpers import check_iteration, check_solution, make_pair, rel_close
+
+
+def test_emulator_library_is_not_the_default():
+    assert "emu" not in I.capi.DEFAULT_LIBRARY
+
+
+@pytest.mark.parametrize("batch", [1, 5])
+def test_unocp_iterations_match_oracle(emu_lib, oracle, batch):
+    prob = I.benchmark_problem(emu_lib)
+    q0, v0 = make_states(batch, 100 + batch)
+    solver, oracles = make_pair(I, oracle, emu_lib, prob, q0, v0)
+    for it in range(4):
+        check_iteration(solver, oracles, q0, v0)
+    check_solution(solver, oracles)
+    for name in ("slack", "dual"):
+        x = solver.getConstraintData(name)
+        ref = np.array([o.get_constraint_data(name) for o in oracles])
+        for c in range(6):   # scale-relative per component (slack = limit - x cancels digits near a bound)
+            assert rel_close(x[:, :, c], ref[:, :, c]), (name, c)
+    assert np.all(solver.getStatus() == 0)
+    assert np.array_equal(solver.isCurrentSolutionFeasible(), [o.is_feasible() for o in oracles])
+
+
+def test_unocp_condensed_kkt_matches_oracle(emu_lib, oracle):
+    """k_linearize output (21x21 Q, 35 residual) vs SplitUnOCP::linearizeOCP of the oracle.
+    The oracle's Riccati sweep updates Q in place, so compare the last stage, whose update adds only
+    the diagonal terminal P (dt^2-scaled), by undoing it, and Fx / lq / lv everywhere."""
+    prob = I.benchmark_problem(emu_lib)
+    q0, v0 = make_states(3, 7)
+    solver, oracles = make_pair(I, oracle, emu_lib, prob, q0, v0)
+    check_iteration(solver, oracles, q0, v0)       # move off the initial guess
+    solver.updateSolution(0.0, q0, v0)
+    for b, o in enumerate(oracles):
+        o.update_solution(0.0, q0[b], v0[b])
+    dt = prob.T / prob.N
+    for stage in (0, 1, 2, prob.N - 1):
+        Q, res = solver.getUnKKT(stage)
+        for b, o in enumerate(oracles):
+            Qo, ro = o.get_unkkt(stage)
+            assert np.allclose(res[b][:14], ro[:14], rtol=1e-11, atol=1e-12)
+            assert np.allclose(res[b][21:], ro[21:], rtol=1e-9, atol=1e-9)
+            if stage == prob.N - 1:
+                Pqq, Pvv = np.diag([10.0] * 7), np.diag([0.1] * 7)
+                Qo = Qo.copy()
+                Qo[7:14, 7:14] -= Pqq
+                Qo[7:14, 14:21] -= dt * Pqq
+                Qo[14:21, 14:21] -= dt * dt * Pqq + Pvv
+                Qo[0:7, 14:21] -= dt * Pvv
+                Qo[0:7, 0:7] -= dt * dt * Pvv
+                Qo[14:21, 7:14] = 0.0     # Qvq is only formed by the Riccati step
+                scale = np.max(np.abs(Qo))
+                assert np.max(np.abs(Q[b] - Qo)) <= 1e-9 * scale
+
+
+def test_config_space_problem_long_horizon(emu_lib, oracle):
+    """BASELINE configs[0] shape (N=60, T=3) for a couple of iterations."""
+    prob = I.config_space_problem(emu_lib)
+    q0 = np.array([[np.pi / 2, 0, np.pi / 2, 0, np.pi / 2, 0, np.pi / 2]])
+    v0 = np.zeros((1, 7))
+    solver, oracles = make_pair(I, oracle, emu_lib, prob, q0, v0)
+    for _ in range(2):
+        check_iteration(solver, oracles, q0, v0)
+    check_solution(solver, oracles)
+
+
+def test_error_paths(emu_lib):
+    prob = I.benchmark_problem(emu_lib)
+    bad = I.benchmark_problem(emu_lib)
+    bad.N = 0
+    with pytest.raises(I.Idocp_b200Error, match="N must be positive"):
+        I.UnOCPSolver(bad, 2, lib=emu_lib)
+    bad = I.benchmark_problem(emu_lib)
+    bad.T = -1.0
+    with pytest.raises(I.Idocp_b200Error, match="T must be positive"):
+        I.UnOCPSolver(bad, 2, lib=emu_lib)
+    s = I.UnOCPSolver(prob, 2, lib=emu_lib)
+    with pytest.raises(I.Idocp_b200Error, match="name must be q, v, a, or u"):
+        s.setSolution("lmd", np.zeros(7))
+    with pytest.raises(I.Idocp_b200Error):
+        s.getSolution("nope")
+    with pytest.raises(ValueError):
+        s.updateSolution(0.0, np.zeros((3, 7)), np.zeros((3, 7)))
