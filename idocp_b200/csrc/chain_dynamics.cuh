@@ -15,6 +15,9 @@
 // Pairwise phase (lane c owns column c):
 //   r <= c: dq[r][c] = S_r.G_c    dv[r][c] = S_r.H_c    M[r][c] = S_r.U_c
 //   r >  c: dq[r][c] = U_r.B_c + Ww_r.dSw_c   dv[r][c] = Ww_r.Sw_c + 2 U_r.dS_c   M[r][c] = S_c.U_r
+//
+// Every expression below is part of the canonical arithmetic (octet.cuh): the oracle's
+// rnea_derivatives_impl repeats it operation by operation.
 #pragma once
 #include "common.cuh"
 
@@ -32,18 +35,18 @@ __device__ __forceinline__ void chain_world_sweep(int lane, double q, double qd,
                                                   const double* __restrict__ mdl, double gravity,
                                                   JointDyn& J) {
   double sn, cs;
-  IDOCP_SINCOS(q, &sn, &cs);
+  canon_sincos(q, &sn, &cs);
   // local transform: placement * Rz(q)
   double R[9];
   V3 p = v3(mdl[9], mdl[10], mdl[11]);
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
     const double a0 = mdl[3 * r], a1 = mdl[3 * r + 1];
-    R[3 * r + 0] = cs * a0 + sn * a1;
-    R[3 * r + 1] = -sn * a0 + cs * a1;
+    R[3 * r + 0] = fma(sn, a1, cs * a0);
+    R[3 * r + 1] = fma(cs, a1, -(sn * a0));
     R[3 * r + 2] = mdl[3 * r + 2];
   }
-  // inclusive prefix product over the chain: X_l <- X_0 X_1 ... X_l
+  // inclusive prefix product over the chain: X_l <- X_0 X_1 ... X_l  (Hillis-Steele tree order)
 #pragma unroll
   for (int d = 1; d < OCT; d <<= 1) {
     double Rs[9];
@@ -51,15 +54,15 @@ __device__ __forceinline__ void chain_world_sweep(int lane, double q, double qd,
     for (int k = 0; k < 9; ++k) Rs[k] = oct_up(R[k], d);
     const V3 ps = oct_up(p, d);
     if (lane >= d) {
-      p = v3(ps.x + (Rs[0] * p.x + Rs[1] * p.y + Rs[2] * p.z),
-             ps.y + (Rs[3] * p.x + Rs[4] * p.y + Rs[5] * p.z),
-             ps.z + (Rs[6] * p.x + Rs[7] * p.y + Rs[8] * p.z));
+      p = v3(fma(Rs[2], p.z, fma(Rs[1], p.y, fma(Rs[0], p.x, ps.x))),
+             fma(Rs[5], p.z, fma(Rs[4], p.y, fma(Rs[3], p.x, ps.y))),
+             fma(Rs[8], p.z, fma(Rs[7], p.y, fma(Rs[6], p.x, ps.z))));
       double Rn[9];
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int k = 0; k < 3; ++k)
-          Rn[3 * r + k] = Rs[3 * r] * R[k] + Rs[3 * r + 1] * R[3 + k] + Rs[3 * r + 2] * R[6 + k];
+          Rn[3 * r + k] = fma(Rs[3 * r + 2], R[6 + k], fma(Rs[3 * r + 1], R[3 + k], Rs[3 * r] * R[k]));
 #pragma unroll
       for (int k = 0; k < 9; ++k) R[k] = Rn[k];
     }
@@ -73,16 +76,17 @@ __device__ __forceinline__ void chain_world_sweep(int lane, double q, double qd,
   J.dSl = cross(vw, J.Sl) + cross(vl, J.Sw);
   J.dSw = cross(vw, J.Sw);
   // accelerations (gravity enters as the base acceleration (0,0,+g))
-  const V3 aw = oct_prefix_sum(qdd * J.Sw + qd * J.dSw, lane);
-  V3 al = oct_prefix_sum(qdd * J.Sl + qd * J.dSl, lane);
+  const V3 aw = oct_prefix_sum(fmav(qd, J.dSw, qdd * J.Sw), lane);
+  V3 al = oct_prefix_sum(fmav(qd, J.dSl, qdd * J.Sl), lane);
   al.z += gravity;
-  J.Bl = cross(aw, J.Sl) + cross(al, J.Sw) + cross(vw, J.dSl) + cross(vl, J.dSw);
+  J.Bl = ((cross(aw, J.Sl) + cross(al, J.Sw)) + cross(vw, J.dSl)) + cross(vl, J.dSw);
   J.Bw = cross(aw, J.Sw) + cross(vw, J.dSw);
   // world inertia about the world origin
   const double m = mdl[12];
   const V3 cm = v3(mdl[13], mdl[14], mdl[15]);
-  const V3 cw = v3(R[0] * cm.x + R[1] * cm.y + R[2] * cm.z + p.x, R[3] * cm.x + R[4] * cm.y + R[5] * cm.z + p.y,
-                   R[6] * cm.x + R[7] * cm.y + R[8] * cm.z + p.z);
+  const V3 cw = v3(fma(R[2], cm.z, fma(R[1], cm.y, fma(R[0], cm.x, p.x))),
+                   fma(R[5], cm.z, fma(R[4], cm.y, fma(R[3], cm.x, p.y))),
+                   fma(R[8], cm.z, fma(R[7], cm.y, fma(R[6], cm.x, p.z))));
   V3 mc = m * cw;
   S3 Ib;
   {
@@ -91,35 +95,35 @@ __device__ __forceinline__ void chain_world_sweep(int lane, double q, double qd,
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const double r0 = R[3 * r], r1 = R[3 * r + 1], r2 = R[3 * r + 2];
-      RI[3 * r + 0] = r0 * i0 + r1 * i1 + r2 * i2;
-      RI[3 * r + 1] = r0 * i1 + r1 * i3 + r2 * i4;
-      RI[3 * r + 2] = r0 * i2 + r1 * i4 + r2 * i5;
+      RI[3 * r + 0] = fma(r2, i2, fma(r1, i1, r0 * i0));
+      RI[3 * r + 1] = fma(r2, i4, fma(r1, i3, r0 * i1));
+      RI[3 * r + 2] = fma(r2, i5, fma(r1, i4, r0 * i2));
     }
     const double cc = dot(cw, cw);
-    Ib.xx = RI[0] * R[0] + RI[1] * R[1] + RI[2] * R[2] + m * (cc - cw.x * cw.x);
-    Ib.xy = RI[0] * R[3] + RI[1] * R[4] + RI[2] * R[5] + m * (0.0 - cw.x * cw.y);
-    Ib.xz = RI[0] * R[6] + RI[1] * R[7] + RI[2] * R[8] + m * (0.0 - cw.x * cw.z);
-    Ib.yy = RI[3] * R[3] + RI[4] * R[4] + RI[5] * R[5] + m * (cc - cw.y * cw.y);
-    Ib.yz = RI[3] * R[6] + RI[4] * R[7] + RI[5] * R[8] + m * (0.0 - cw.y * cw.z);
-    Ib.zz = RI[6] * R[6] + RI[7] * R[7] + RI[8] * R[8] + m * (cc - cw.z * cw.z);
+    Ib.xx = fma(m, cc - cw.x * cw.x, fma(RI[2], R[2], fma(RI[1], R[1], RI[0] * R[0])));
+    Ib.xy = fma(m, -(cw.x * cw.y), fma(RI[2], R[5], fma(RI[1], R[4], RI[0] * R[3])));
+    Ib.xz = fma(m, -(cw.x * cw.z), fma(RI[2], R[8], fma(RI[1], R[7], RI[0] * R[6])));
+    Ib.yy = fma(m, cc - cw.y * cw.y, fma(RI[5], R[5], fma(RI[4], R[4], RI[3] * R[3])));
+    Ib.yz = fma(m, -(cw.y * cw.z), fma(RI[5], R[8], fma(RI[4], R[7], RI[3] * R[6])));
+    Ib.zz = fma(m, cc - cw.z * cw.z, fma(RI[8], R[8], fma(RI[7], R[7], RI[6] * R[6])));
   }
-  V3 hl = m * vl + cross(vw, mc);
+  V3 hl = fmav(m, vl, cross(vw, mc));
   V3 ha = cross(mc, vl) + mul(Ib, vw);
-  V3 fl = m * al + cross(aw, mc) + cross(vw, hl);
-  V3 fa = cross(mc, al) + mul(Ib, aw) + cross(vw, ha) + cross(vl, hl);
+  V3 fl = fmav(m, al, cross(aw, mc)) + cross(vw, hl);
+  V3 fa = ((cross(mc, al) + mul(Ib, aw)) + cross(vw, ha)) + cross(vl, hl);
   S3 Sym;
   {
-    // wI[r][k] = (vw x Ib[:,k])_r
+    // wI[r][k] = (vw x Ib[:,k])_r ;  Sym = -(vl mc^T + mc vl^T) + 2 (mc.vl) 1 + wI + wI^T
     const V3 c0 = cross(vw, v3(Ib.xx, Ib.xy, Ib.xz));
     const V3 c1 = cross(vw, v3(Ib.xy, Ib.yy, Ib.yz));
     const V3 c2 = cross(vw, v3(Ib.xz, Ib.yz, Ib.zz));
     const double mcv = dot(mc, vl);
-    Sym.xx = -(vl.x * mc.x + mc.x * vl.x) + c0.x + c0.x + 2.0 * mcv;
-    Sym.xy = -(vl.x * mc.y + mc.x * vl.y) + c1.x + c0.y;
-    Sym.xz = -(vl.x * mc.z + mc.x * vl.z) + c2.x + c0.z;
-    Sym.yy = -(vl.y * mc.y + mc.y * vl.y) + c1.y + c1.y + 2.0 * mcv;
-    Sym.yz = -(vl.y * mc.z + mc.y * vl.z) + c2.y + c1.z;
-    Sym.zz = -(vl.z * mc.z + mc.z * vl.z) + c2.z + c2.z + 2.0 * mcv;
+    Sym.xx = 2.0 * (c0.x + (mcv - vl.x * mc.x));
+    Sym.xy = (c1.x + c0.y) - fma(vl.x, mc.y, mc.x * vl.y);
+    Sym.xz = (c2.x + c0.z) - fma(vl.x, mc.z, mc.x * vl.z);
+    Sym.yy = 2.0 * (c1.y + (mcv - vl.y * mc.y));
+    Sym.yz = (c2.y + c1.z) - fma(vl.y, mc.z, mc.y * vl.z);
+    Sym.zz = 2.0 * (c2.z + (mcv - vl.z * mc.z));
   }
   // composite (suffix) sums
   const double mC = oct_suffix_sum(m, lane);
@@ -134,13 +138,13 @@ __device__ __forceinline__ void chain_world_sweep(int lane, double q, double qd,
   fa = oct_suffix_sum(fa, lane);
   // per-joint vectors
   J.tau = dot(J.Sl, fl) + dot(J.Sw, fa);
-  J.Ul = mC * J.Sl + cross(J.Sw, mc);
+  J.Ul = fmav(mC, J.Sl, cross(J.Sw, mc));
   J.Uw = cross(mc, J.Sl) + mul(Ib, J.Sw);
-  J.Ww = 2.0 * cross(hl, J.Sl) + mul(Sym, J.Sw) + cross(ha, J.Sw);
-  J.Gl = cross(J.Sw, fl) + mC * J.Bl + cross(J.Bw, mc) - 2.0 * cross(hl, J.dSw);
-  J.Gw = cross(J.Sw, fa) + cross(J.Sl, fl) + cross(mc, J.Bl) + mul(Ib, J.Bw) + mul(Sym, J.dSw) - cross(ha, J.dSw);
-  J.Hl = (-2.0) * cross(hl, J.Sw) + 2.0 * (mC * J.dSl + cross(J.dSw, mc));
-  J.Hw = mul(Sym, J.Sw) - cross(ha, J.Sw) + 2.0 * (cross(mc, J.dSl) + mul(Ib, J.dSw));
+  J.Ww = fmav(2.0, cross(hl, J.Sl), mul(Sym, J.Sw)) + cross(ha, J.Sw);
+  J.Gl = fmav(-2.0, cross(hl, J.dSw), fmav(mC, J.Bl, cross(J.Sw, fl)) + cross(J.Bw, mc));
+  J.Gw = ((((cross(J.Sw, fa) + cross(J.Sl, fl)) + cross(mc, J.Bl)) + mul(Ib, J.Bw)) + mul(Sym, J.dSw)) - cross(ha, J.dSw);
+  J.Hl = 2.0 * (fmav(mC, J.dSl, cross(J.dSw, mc)) - cross(hl, J.Sw));
+  J.Hw = fmav(2.0, cross(mc, J.dSl) + mul(Ib, J.dSw), mul(Sym, J.Sw) - cross(ha, J.Sw));
 }
 
 // tau only (used by the line search): same world sweep without the derivative vectors
@@ -173,8 +177,8 @@ __device__ __forceinline__ void chain_pair_phase(int lane, const JointDyn& J, do
     const double up_q = dot(Sl, J.Gl) + dot(Sw, J.Gw);
     const double up_v = dot(Sl, J.Hl) + dot(Sw, J.Hw);
     const double up_m = dot(Sl, J.Ul) + dot(Sw, J.Uw);
-    const double lo_q = dot(Ul, J.Bl) + dot(Uw, J.Bw) + dot(Ww, J.dSw);
-    const double lo_v = dot(Ww, J.Sw) + 2.0 * (dot(Ul, J.dSl) + dot(Uw, J.dSw));
+    const double lo_q = (dot(Ul, J.Bl) + dot(Uw, J.Bw)) + dot(Ww, J.dSw);
+    const double lo_v = fma(2.0, dot(Ul, J.dSl) + dot(Uw, J.dSw), dot(Ww, J.Sw));
     const double lo_m = dot(J.Sl, Ul) + dot(J.Sw, Uw);
     const bool upper = (r <= lane);
     dqc[r] = upper ? up_q : lo_q;

@@ -1,4 +1,4 @@
-// octet.cuh -- "octet" execution model helpers (sm_100a).
+// octet.cuh -- "octet" execution model helpers (sm_100a) and the CANONICAL ARITHMETIC.
 //
 // One OCTET = 8 consecutive lanes of a warp works on one (instance, stage) pair or one
 // instance; lane l < 7 owns joint l / matrix column l of the 7-dof iiwa14, lane 7 is padding.
@@ -8,6 +8,12 @@
 // HBM layout ("slots"): every per-joint vector is one 64-byte slot [8 doubles]; arrays are
 // [slot][instance][8] so the 4 octets of a warp (4 consecutive instances) touch 256 contiguous
 // bytes per load/store.
+//
+// Canonical arithmetic: the library is compiled with -fmad=false, so the compiler never
+// contracts a*b+c on its own; every fused multiply-add is written explicitly with fma().
+// The CPU oracle (oracle/idocp_oracle.c, gcc -ffp-contract=off) performs the SAME sequence of
+// IEEE-754 operations (same fma placement, same tree order in the prefix/suffix scans, same
+// polynomial sin/cos), which makes the GPU results bit-identical to the oracle's.
 #pragma once
 #ifndef IDOCP_B200_EMU
 #include <cuda_runtime.h>
@@ -27,18 +33,44 @@ __device__ __forceinline__ V3 v3(double x, double y, double z) { return V3{x, y,
 __device__ __forceinline__ V3 operator+(V3 a, V3 b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; }
 __device__ __forceinline__ V3 operator-(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
 __device__ __forceinline__ V3 operator*(double s, V3 a) { return V3{s * a.x, s * a.y, s * a.z}; }
+// s * a + b, fused
+__device__ __forceinline__ V3 fmav(double s, V3 a, V3 b) { return V3{fma(s, a.x, b.x), fma(s, a.y, b.y), fma(s, a.z, b.z)}; }
 __device__ __forceinline__ V3 cross(V3 a, V3 b) {
-  return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+  return V3{fma(a.y, b.z, -(a.z * b.y)), fma(a.z, b.x, -(a.x * b.z)), fma(a.x, b.y, -(a.y * b.x))};
 }
-__device__ __forceinline__ double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ double dot(V3 a, V3 b) { return fma(a.z, b.z, fma(a.y, b.y, a.x * b.x)); }
 
 // symmetric 3x3 (xx,xy,xz,yy,yz,zz)
 struct S3 {
   double xx, xy, xz, yy, yz, zz;
 };
 __device__ __forceinline__ V3 mul(const S3& A, V3 b) {
-  return V3{A.xx * b.x + A.xy * b.y + A.xz * b.z, A.xy * b.x + A.yy * b.y + A.yz * b.z,
-            A.xz * b.x + A.yz * b.y + A.zz * b.z};
+  return V3{fma(A.xz, b.z, fma(A.xy, b.y, A.xx * b.x)), fma(A.yz, b.z, fma(A.yy, b.y, A.xy * b.x)),
+            fma(A.zz, b.z, fma(A.yz, b.y, A.xz * b.x))};
+}
+
+// sin / cos for |x| up to a few pi: Cody-Waite reduction by pi/2 + the classic degree-13/14
+// minimax kernels, written with explicit fma so that the oracle can repeat it bit for bit.
+__device__ __forceinline__ void canon_sincos(double x, double* sn, double* cs) {
+  const double k = rint(x * 6.36619772367581382433e-01);            // x * 2/pi
+  double r = fma(-k, 1.57079632673412561417e+00, x);                // pi/2, first 33 bits
+  r = fma(-k, 6.07710050650619224932e-11, r);                       // pi/2 tail
+  const double z = r * r;
+  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  ps = fma(z, ps, 2.75573137070700676789e-06);
+  ps = fma(z, ps, -1.98412698298579493134e-04);
+  ps = fma(z, ps, 8.33333333332248946124e-03);
+  ps = fma(z, ps, -1.66666666666666324348e-01);
+  const double s = fma(r * z, ps, r);
+  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  pc = fma(z, pc, -2.75573143513906633035e-07);
+  pc = fma(z, pc, 2.48015872894767294178e-05);
+  pc = fma(z, pc, -1.38888888888741095749e-03);
+  pc = fma(z, pc, 4.16666666666666019037e-02);
+  const double c = fma(z * z, pc, fma(-0.5, z, 1.0));
+  const int q = static_cast<int>(k) & 3;
+  *sn = (q == 0) ? s : (q == 1) ? c : (q == 2) ? -s : -c;
+  *cs = (q == 0) ? c : (q == 1) ? -s : (q == 2) ? -c : s;
 }
 
 __device__ __forceinline__ int lane_in_octet() { return threadIdx.x & 7; }
@@ -52,7 +84,7 @@ __device__ __forceinline__ V3 oct_down(V3 a, int d) {
   return V3{oct_down(a.x, d), oct_down(a.y, d), oct_down(a.z, d)};
 }
 
-// inclusive prefix sum over the octet (lane order 0..7)
+// inclusive prefix sum over the octet (lane order 0..7), Hillis-Steele tree order
 __device__ __forceinline__ double oct_prefix_sum(double x, int lane) {
 #pragma unroll
   for (int d = 1; d < OCT; d <<= 1) {

@@ -187,43 +187,42 @@ __global__ void __launch_bounds__(CTA_THREADS) k_linearize(const DevProblem* __r
     const double sg = (c & 1) ? g : -g;
     if (c < 2) lq += sg; else if (c < 4) lv += sg; else lu += sg;
   }
-  double Fq = q - qn;
-  Fq += dt * v;
-  const double Fv = v + dt * a - vn;
+  const double Fq = fma(dt, v, q - qn);
+  const double Fv = fma(dt, a, v) - vn;
   lq += lmdn - lmd;
-  lv += dt * lmdn + gmmn - gmm;
-  la += dt * gmmn;
+  lv += fma(dt, lmdn, gmmn) - gmm;
+  la = fma(dt, gmmn, la);
   {
     double tq = 0.0, tv = 0.0, ta = 0.0;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const double bk = oct_bcast(beta, k);
-      tq += dqc[k] * bk;
-      tv += dvc[k] * bk;
-      ta += Mc[k] * bk;
+      tq = fma(dqc[k], bk, tq);
+      tv = fma(dvc[k], bk, tv);
+      ta = fma(Mc[k], bk, ta);
     }
-    lq += dt * tq;
-    lv += dt * tv;
-    la += dt * ta;
-    lu -= dt * beta;
+    lq = fma(dt, tq, lq);
+    lv = fma(dt, tv, lv);
+    la = fma(dt, ta, la);
+    lu = fma(-dt, beta, lu);
   }
 
   if (RESIDUAL_ONLY) {
     // SplitUnOCP::squaredNormKKTResidual (split_unocp.hxx:164-174), canonical order
     double e = 0.0;
     const double z = act ? 1.0 : 0.0;
-    e += oct_sum_ordered(z * lq * lq) + oct_sum_ordered(z * lv * lv);
-    e += oct_sum_ordered(z * la * la);
-    e += oct_sum_ordered(z * lu * lu);
-    e += oct_sum_ordered(z * Fq * Fq) + oct_sum_ordered(z * Fv * Fv);
-    e += dt * dt * oct_sum_ordered(z * ID * ID);
+    e += oct_sum_ordered(z * (lq * lq)) + oct_sum_ordered(z * (lv * lv));
+    e += oct_sum_ordered(z * (la * la));
+    e += oct_sum_ordered(z * (lu * lu));
+    e += oct_sum_ordered(z * (Fq * Fq)) + oct_sum_ordered(z * (Fv * Fv));
+    e += dt * dt * oct_sum_ordered(z * (ID * ID));
     double c2 = 0.0;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       if (!comp_active(c, i)) continue;
       const double r = con_residual(c, lim, q, v, u, slack[c]);
       const double dl = slack[c] * dual[c] - P.barrier;
-      c2 += oct_sum_ordered(z * r * r) + oct_sum_ordered(z * dl * dl);
+      c2 += oct_sum_ordered(z * (r * r)) + oct_sum_ordered(z * (dl * dl));
     }
     e += dt * dt * c2;
     if (lane == 0) L.kkt_stage[static_cast<size_t>(i) * Bp + b] = e;
@@ -252,16 +251,16 @@ __global__ void __launch_bounds__(CTA_THREADS) k_linearize(const DevProblem* __r
     Quu_d = 0.0;
   }
   // ---- eliminate u (step 7, unconstrained_dynamics.hxx:68-94) ----
-  const double lu_c = act ? lu + Quu_d * ID : 0.0;
+  const double lu_c = act ? fma(Quu_d, ID, lu) : 0.0;
   double ulq = lq, ulv = lv, ula = la;
   {
     double tq = 0.0, tv = 0.0, ta = 0.0;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const double lk = oct_bcast(lu_c, k);
-      tq += dqc[k] * lk;
-      tv += dvc[k] * lk;
-      ta += Mc[k] * lk;
+      tq = fma(dqc[k], lk, tq);
+      tv = fma(dvc[k], lk, tv);
+      ta = fma(Mc[k], lk, ta);
     }
     ulq += tq; ulv += tv; ula += ta;
   }
@@ -309,12 +308,12 @@ __global__ void __launch_bounds__(CTA_THREADS) k_linearize(const DevProblem* __r
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const double xq = o[k], xv = o[NV + k], xa = o[2 * NV + k];
-      qq += xq * Dq[k];
-      qv += xq * Dv[k];
-      vv += xv * Dv[k];
-      aq += xa * Dq[k];
-      av += xa * Dv[k];
-      aa += xa * Da[k];
+      qq = fma(xq, Dq[k], qq);
+      qv = fma(xq, Dv[k], qv);
+      vv = fma(xv, Dv[k], vv);
+      aq = fma(xa, Dq[k], aq);
+      av = fma(xa, Dv[k], av);
+      aa = fma(xa, Da[k], aa);
     }
     const bool diag = (r == lane);
     L.kktQ[slot_index(K_QQ * NV + r, Ns, i, Bp, b, lane)] = qq + (diag ? Qqq_d : 0.0);
@@ -347,6 +346,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_riccati(const DevProblem* __res
   if (b >= L.Bp) b = L.Bp - 1;
   const int N = L.N, Bp = L.Bp, ns = L.N + 1;
   const double dt = P.dt;
+  const double dt2 = dt * dt;
   const bool act = lane < NV;
   const int ln = act ? lane : 0;
   int chol_fail = 0;
@@ -393,24 +393,24 @@ __global__ void __launch_bounds__(CTA_THREADS) k_riccati(const DevProblem* __res
     // x-blocks are folded into the P update below (same operation order per entry)
 #pragma unroll
     for (int r = 0; r < NV; ++r) {
-      Qaq[r] += dt * Pvq[r];
-      Qav[r] += dt * dt * Pvq[r];
-      Qav[r] += dt * Pvv[r];
-      Qaa[r] += dt * dt * Pvv[r];
+      Qaq[r] = fma(dt, Pvq[r], Qaq[r]);
+      Qav[r] = fma(dt2, Pvq[r], Qav[r]);
+      Qav[r] = fma(dt, Pvv[r], Qav[r]);
+      Qaa[r] = fma(dt2, Pvv[r], Qaa[r]);
     }
     // products of the OLD P with Fx (used by la and by the s recursion)
     double pqqF = 0.0, pvqF = 0.0, pqvF = 0.0, pvvF = 0.0;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const double fq = oct_bcast(Fq, k), fv = oct_bcast(Fv, k);
-      pqqF += Pqq[k] * fq;   // (Pqq Fq)_c   (row c = column c, symmetric)
-      pvqF += Pvq[k] * fv;   // (Pqv Fv)_c
-      pqvF += Pqv[k] * fq;   // (Pqv^T Fq)_c
-      pvvF += Pvv[k] * fv;   // (Pvv Fv)_c
+      pqqF = fma(Pqq[k], fq, pqqF);   // (Pqq Fq)_c   (row c = column c, symmetric)
+      pvqF = fma(Pvq[k], fv, pvqF);   // (Pqv Fv)_c
+      pqvF = fma(Pqv[k], fq, pqvF);   // (Pqv^T Fq)_c
+      pvvF = fma(Pvv[k], fv, pvvF);   // (Pvv Fv)_c
     }
-    la += dt * pqvF;
-    la += dt * pvvF;
-    la -= dt * sv;
+    la = fma(dt, pqvF, la);
+    la = fma(dt, pvvF, la);
+    la = fma(-dt, sv, la);
     // share Qaa (tile A: tA[col][row]) and la
 #pragma unroll
     for (int r = 0; r < NV; ++r) tA[lane * RIC_TILE + r] = Qaa[r];
@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_riccati(const DevProblem* __res
     for (int k = 0; k < NV; ++k) {
       double x = tA[k * RIC_TILE + k];
 #pragma unroll
-      for (int j = 0; j < k; ++j) x -= Lm[j][k] * Lm[j][k];
+      for (int j = 0; j < k; ++j) x = fma(-Lm[j][k], Lm[j][k], x);
       if (!(x > 0.0)) chol_fail = 1;
       x = sqrt(x);
       Lm[k][k] = x;
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_riccati(const DevProblem* __res
       for (int r = k + 1; r < NV; ++r) {
         double y = tA[k * RIC_TILE + r];
 #pragma unroll
-        for (int j = 0; j < k; ++j) y -= Lm[j][r] * Lm[j][k];
+        for (int j = 0; j < k; ++j) y = fma(-Lm[j][r], Lm[j][k], y);
         Lm[k][r] = y * rdiag[k];
       }
     }
@@ -442,14 +442,18 @@ __global__ void __launch_bounds__(CTA_THREADS) k_riccati(const DevProblem* __res
     for (int r = 0; r < NV; ++r) {
       double y1 = Qaq[r], y2 = Qav[r], y3 = tA[r * RIC_TILE + NV];
 #pragma unroll
-      for (int j = 0; j < r; ++j) { y1 -= Lm[j][r] * Kq[j]; y2 -= Lm[j][r] * Kv[j]; y3 -= Lm[j][r] * kk[j]; }
+      for (int j = 0; j < r; ++j) {
+        y1 = fma(-Lm[j][r], Kq[j], y1); y2 = fma(-Lm[j][r], Kv[j], y2); y3 = fma(-Lm[j][r], kk[j], y3);
+      }
       Kq[r] = y1 * rdiag[r]; Kv[r] = y2 * rdiag[r]; kk[r] = y3 * rdiag[r];
     }
 #pragma unroll
     for (int r = NV - 1; r >= 0; --r) {
       double y1 = Kq[r], y2 = Kv[r], y3 = kk[r];
 #pragma unroll
-      for (int j = r + 1; j < NV; ++j) { y1 -= Lm[r][j] * Kq[j]; y2 -= Lm[r][j] * Kv[j]; y3 -= Lm[r][j] * kk[j]; }
+      for (int j = r + 1; j < NV; ++j) {
+        y1 = fma(-Lm[r][j], Kq[j], y1); y2 = fma(-Lm[r][j], Kv[j], y2); y3 = fma(-Lm[r][j], kk[j], y3);
+      }
       Kq[r] = y1 * rdiag[r]; Kv[r] = y2 * rdiag[r]; kk[r] = y3 * rdiag[r];
     }
 #pragma unroll
@@ -462,8 +466,8 @@ __global__ void __launch_bounds__(CTA_THREADS) k_riccati(const DevProblem* __res
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         const double g = tA[k * RIC_TILE + r];
-        t1 += g * Kq[k];
-        t2 += g * Kv[k];
+        t1 = fma(g, Kq[k], t1);
+        t2 = fma(g, Kv[k], t2);
       }
       GKq[r] = t1; GKv[r] = t2;
     }
@@ -475,11 +479,11 @@ __global__ void __launch_bounds__(CTA_THREADS) k_riccati(const DevProblem* __res
     double nsq, nsv;
     {
       nsq = sq; nsq -= pqqF; nsq -= pvqF;
-      nsv = sv; nsv += dt * nsq; nsv -= pqvF; nsv -= pvvF;
+      nsv = fma(dt, nsq, sv); nsv -= pqvF; nsv -= pvvF;
       nsq -= lq; nsv -= lv;
       double t5 = 0.0, t6 = 0.0;
 #pragma unroll
-      for (int k = 0; k < NV; ++k) { t5 += Qaq[k] * kk[k]; t6 += Qav[k] * kk[k]; }
+      for (int k = 0; k < NV; ++k) { t5 = fma(Qaq[k], kk[k], t5); t6 = fma(Qav[k], kk[k], t6); }
       nsq -= t5; nsv -= t6;
     }
     // F-blocks of factorizeKKTMatrix (:34-43) + P = Qxx - K^T (Qaa K) (:64-75), row by row
@@ -489,19 +493,19 @@ __global__ void __launch_bounds__(CTA_THREADS) k_riccati(const DevProblem* __res
       double Qqv = L.kktQ[slot_index(K_QV * NV + r, N, i, Bp, b, lane)];
       double Qvv = L.kktQ[slot_index(K_VV * NV + r, N, i, Bp, b, lane)];
       Qqq += Pqq[r];
-      Qqv += dt * Pqq[r];
+      Qqv = fma(dt, Pqq[r], Qqv);
       Qqv += Pqv[r];
-      Qvv += dt * dt * Pqq[r];
-      Qvv += dt * Pqv[r];
-      Qvv += dt * Pvq[r];
+      Qvv = fma(dt2, Pqq[r], Qvv);
+      Qvv = fma(dt, Pqv[r], Qvv);
+      Qvv = fma(dt, Pvq[r], Qvv);
       Qvv += Pvv[r];
       double tqq = 0.0, tqv = 0.0, tvv = 0.0;
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         const double kq = tB[r * RIC_TILE + k], kv = tB[r * RIC_TILE + NV + k];
-        tqq += kq * GKq[k];
-        tqv += kq * GKv[k];
-        tvv += kv * GKv[k];
+        tqq = fma(kq, GKq[k], tqq);
+        tqv = fma(kq, GKv[k], tqv);
+        tvv = fma(kv, GKv[k], tvv);
       }
       Pqq[r] = Qqq - tqq;
       Pqv[r] = Qqv - tqv;
@@ -562,9 +566,9 @@ __global__ void __launch_bounds__(CTA_THREADS) k_riccati(const DevProblem* __res
     {
       double acc = 0.0;
 #pragma unroll
-      for (int c = 0; c < NV; ++c) acc += L.ric[slot_index(RC_KQ + c, N, i, Bp, b, lane)] * dqk[c];
+      for (int c = 0; c < NV; ++c) acc = fma(L.ric[slot_index(RC_KQ + c, N, i, Bp, b, lane)], dqk[c], acc);
 #pragma unroll
-      for (int c = 0; c < NV; ++c) acc += L.ric[slot_index(RC_KV + c, N, i, Bp, b, lane)] * dvk[c];
+      for (int c = 0; c < NV; ++c) acc = fma(L.ric[slot_index(RC_KV + c, N, i, Bp, b, lane)], dvk[c], acc);
       da = acc + L.ric[slot_index(RC_K, N, i, Bp, b, lane)];
     }
     // costate direction (split_unriccati_factorizer.hxx:60-68)
@@ -573,10 +577,10 @@ __global__ void __launch_bounds__(CTA_THREADS) k_riccati(const DevProblem* __res
       double t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0;
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
-        t1 += L.ric[slot_index(RC_PQQ + k, N, i, Bp, b, lane)] * dqk[k];
-        t2 += L.ric[slot_index(RC_PVQ + k, N, i, Bp, b, lane)] * dvk[k];
-        t3 += L.ric[slot_index(RC_PQV + k, N, i, Bp, b, lane)] * dqk[k];
-        t4 += L.ric[slot_index(RC_PVV + k, N, i, Bp, b, lane)] * dvk[k];
+        t1 = fma(L.ric[slot_index(RC_PQQ + k, N, i, Bp, b, lane)], dqk[k], t1);
+        t2 = fma(L.ric[slot_index(RC_PVQ + k, N, i, Bp, b, lane)], dvk[k], t2);
+        t3 = fma(L.ric[slot_index(RC_PQV + k, N, i, Bp, b, lane)], dqk[k], t3);
+        t4 = fma(L.ric[slot_index(RC_PVV + k, N, i, Bp, b, lane)], dvk[k], t4);
       }
       dlmd = t1; dlmd += t2; dlmd -= L.ric[slot_index(RC_SQ, N, i, Bp, b, lane)];
       dgmm = t3; dgmm += t4; dgmm -= L.ric[slot_index(RC_SV, N, i, Bp, b, lane)];
@@ -587,18 +591,18 @@ __global__ void __launch_bounds__(CTA_THREADS) k_riccati(const DevProblem* __res
       double acc = L.expd[slot_index(E_ID, N, i, Bp, b, lane)];
       double t = 0.0;
 #pragma unroll
-      for (int c = 0; c < NV; ++c) t += L.expd[slot_index(E_DQ + c, N, i, Bp, b, lane)] * dqk[c];
+      for (int c = 0; c < NV; ++c) t = fma(L.expd[slot_index(E_DQ + c, N, i, Bp, b, lane)], dqk[c], t);
       acc += t;
       t = 0.0;
 #pragma unroll
-      for (int c = 0; c < NV; ++c) t += L.expd[slot_index(E_DV + c, N, i, Bp, b, lane)] * dvk[c];
+      for (int c = 0; c < NV; ++c) t = fma(L.expd[slot_index(E_DV + c, N, i, Bp, b, lane)], dvk[c], t);
       acc += t;
       t = 0.0;
 #pragma unroll
-      for (int c = 0; c < NV; ++c) t += L.expd[slot_index(E_M + c, N, i, Bp, b, lane)] * oct_bcast(da, c);
+      for (int c = 0; c < NV; ++c) t = fma(L.expd[slot_index(E_M + c, N, i, Bp, b, lane)], oct_bcast(da, c), t);
       acc += t;
       du = acc;
-      dbeta = (L.expd[slot_index(E_LU, N, i, Bp, b, lane)] + L.expd[slot_index(E_QUU, N, i, Bp, b, lane)] * du) / dt;
+      dbeta = fma(L.expd[slot_index(E_QUU, N, i, Bp, b, lane)], du, L.expd[slot_index(E_LU, N, i, Bp, b, lane)]) / dt;
     }
     // slack / dual directions and fraction-to-boundary
     if (act) {
@@ -614,7 +618,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_riccati(const DevProblem* __res
         const double dty = sl * dl - P.barrier;
         const double dx = c < 2 ? dq : (c < 4 ? dv : du);
         const double dslack = ((c & 1) ? -dx : dx) - r;
-        const double ddual = -(dl * dslack + dty) / sl;
+        const double ddual = -fma(dl, dslack, dty) / sl;
         min_p = fraction_row(P.fraction_rate, sl, dslack, min_p);
         min_d = fraction_row(P.fraction_rate, dl, ddual, min_d);
       }
@@ -629,8 +633,8 @@ __global__ void __launch_bounds__(CTA_THREADS) k_riccati(const DevProblem* __res
     // forwardRiccatiRecursion (split_unriccati_factorizer.hxx:49-57)
     double ndq = L.kktR[slot_index(R_FQ, N, i, Bp, b, lane)] + dq;
     double ndv = L.kktR[slot_index(R_FV, N, i, Bp, b, lane)] + dv;
-    ndq += dt * dv;
-    ndv += dt * da;
+    ndq = fma(dt, dv, ndq);
+    ndv = fma(dt, da, ndv);
     dq = act ? ndq : 0.0;
     dv = act ? ndv : 0.0;
   }
@@ -687,18 +691,18 @@ __global__ void __launch_bounds__(CTA_THREADS) k_update(const DevProblem* __rest
   const double q = L.sol[iq], v = L.sol[iv];
   const double dq = L.dir[slot_index(D_Q, ns, i, Bp, b, lane)];
   const double dv = L.dir[slot_index(D_V, ns, i, Bp, b, lane)];
-  L.sol[il] += ap * L.dir[slot_index(D_LMD, ns, i, Bp, b, lane)];
-  L.sol[ig] += ap * L.dir[slot_index(D_GMM, ns, i, Bp, b, lane)];
-  L.sol[iq] = q + ap * dq;
-  L.sol[iv] = v + ap * dv;
+  L.sol[il] = fma(ap, L.dir[slot_index(D_LMD, ns, i, Bp, b, lane)], L.sol[il]);
+  L.sol[ig] = fma(ap, L.dir[slot_index(D_GMM, ns, i, Bp, b, lane)], L.sol[ig]);
+  L.sol[iq] = fma(ap, dq, q);
+  L.sol[iv] = fma(ap, dv, v);
   if (i == N) return;
   const size_t ia = slot_index(S_A, ns, i, Bp, b, lane), iu = slot_index(S_U, ns, i, Bp, b, lane);
   const size_t ib = slot_index(S_BETA, ns, i, Bp, b, lane);
   const double u = L.sol[iu];
   const double du = L.dir[slot_index(D_U, ns, i, Bp, b, lane)];
-  L.sol[ia] += ap * L.dir[slot_index(D_A, ns, i, Bp, b, lane)];
-  L.sol[iu] = u + ap * du;
-  L.sol[ib] += ap * L.dir[slot_index(D_BETA, ns, i, Bp, b, lane)];
+  L.sol[ia] = fma(ap, L.dir[slot_index(D_A, ns, i, Bp, b, lane)], L.sol[ia]);
+  L.sol[iu] = fma(ap, du, u);
+  L.sol[ib] = fma(ap, L.dir[slot_index(D_BETA, ns, i, Bp, b, lane)], L.sol[ib]);
   const LaneLimits lim = load_limits(P, lane);
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
@@ -709,9 +713,9 @@ __global__ void __launch_bounds__(CTA_THREADS) k_update(const DevProblem* __rest
     const double dty = sl * dl - P.barrier;
     const double dx = c < 2 ? dq : (c < 4 ? dv : du);
     const double dslack = ((c & 1) ? -dx : dx) - r;
-    const double ddual = -(dl * dslack + dty) / sl;
-    L.slack[is] = sl + ap * dslack;
-    L.dual[is] = dl + ad * ddual;
+    const double ddual = -fma(dl, dslack, dty) / sl;
+    L.slack[is] = fma(ap, dslack, sl);
+    L.dual[is] = fma(ad, ddual, dl);
   }
 }
 

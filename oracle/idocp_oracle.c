@@ -26,12 +26,54 @@
 /* ------------------------------------------------------------------------------------------ */
 /* small helpers                                                                               */
 /* ------------------------------------------------------------------------------------------ */
+/* CANONICAL ARITHMETIC (shared convention with idocp_b200/csrc/octet.cuh): this file is compiled
+ * with -ffp-contract=off, every fused multiply-add is an explicit fma(), and the helpers below use
+ * the same operation trees as their CUDA twins, so that the GPU results can be compared bit for bit. */
+typedef struct { double x, y, z; } v3_t;
+typedef struct { double xx, xy, xz, yy, yz, zz; } s3_t;
+static inline v3_t V3(double x, double y, double z) { v3_t r = {x, y, z}; return r; }
+static inline v3_t vadd(v3_t a, v3_t b) { return V3(a.x + b.x, a.y + b.y, a.z + b.z); }
+static inline v3_t vsub(v3_t a, v3_t b) { return V3(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline v3_t vscale(double s, v3_t a) { return V3(s * a.x, s * a.y, s * a.z); }
+static inline v3_t vfma(double s, v3_t a, v3_t b) { return V3(fma(s, a.x, b.x), fma(s, a.y, b.y), fma(s, a.z, b.z)); }
+static inline v3_t vcross(v3_t a, v3_t b) {
+  return V3(fma(a.y, b.z, -(a.z * b.y)), fma(a.z, b.x, -(a.x * b.z)), fma(a.x, b.y, -(a.y * b.x)));
+}
+static inline double vdot(v3_t a, v3_t b) { return fma(a.z, b.z, fma(a.y, b.y, a.x * b.x)); }
+static inline v3_t smul(s3_t A, v3_t b) {
+  return V3(fma(A.xz, b.z, fma(A.xy, b.y, A.xx * b.x)), fma(A.yz, b.z, fma(A.yy, b.y, A.xy * b.x)),
+            fma(A.zz, b.z, fma(A.yz, b.y, A.xz * b.x)));
+}
+/* sin / cos: Cody-Waite reduction by pi/2 + degree-13/14 minimax kernels (twin of canon_sincos) */
+static inline void canon_sincos(double x, double* sn, double* cs) {
+  const double k = rint(x * 6.36619772367581382433e-01);
+  double r = fma(-k, 1.57079632673412561417e+00, x);
+  r = fma(-k, 6.07710050650619224932e-11, r);
+  const double z = r * r;
+  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  ps = fma(z, ps, 2.75573137070700676789e-06);
+  ps = fma(z, ps, -1.98412698298579493134e-04);
+  ps = fma(z, ps, 8.33333333332248946124e-03);
+  ps = fma(z, ps, -1.66666666666666324348e-01);
+  const double s = fma(r * z, ps, r);
+  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  pc = fma(z, pc, -2.75573143513906633035e-07);
+  pc = fma(z, pc, 2.48015872894767294178e-05);
+  pc = fma(z, pc, -1.38888888888741095749e-03);
+  pc = fma(z, pc, 4.16666666666666019037e-02);
+  const double c = fma(z * z, pc, fma(-0.5, z, 1.0));
+  const int q = ((int)k) & 3;
+  *sn = (q == 0) ? s : (q == 1) ? c : (q == 2) ? -s : -c;
+  *cs = (q == 0) ? c : (q == 1) ? -s : (q == 2) ? -c : s;
+}
+void oracle_canon_sincos(double x, double* sn, double* cs) { canon_sincos(x, sn, cs); }
+
+/* plain (non-canonical) helpers of the independent body-frame RNEA below */
 static inline void cross3(const double* a, const double* b, double* c) {
   c[0] = a[1] * b[2] - a[2] * b[1];
   c[1] = a[2] * b[0] - a[0] * b[2];
   c[2] = a[0] * b[1] - a[1] * b[0];
 }
-static inline double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 /* y = A x for a symmetric 3x3 stored (xx,xy,xz,yy,yz,zz) */
 static inline void sym3_mul(const double* A, const double* x, double* y) {
   y[0] = A[0] * x[0] + A[1] * x[1] + A[2] * x[2];
@@ -137,138 +179,193 @@ void oracle_rnea(const double* q, const double* v, const double* a, double* tau)
 
 /* per-joint world-frame quantities of the derivative algorithm */
 typedef struct {
-  double Sl[3], Sw[3], dSl[3], dSw[3], Bl[3], Bw[3];
-  double m, mc[3], Ib[6], hl[3], ha[3], Sym[6], fl[3], fa[3];
-  double Ul[3], Uw[3], Ww[3], Gl[3], Gw[3], Hl[3], Hw[3];
+  v3_t Sl, Sw, dSl, dSw, Bl, Bw;
+  v3_t Ul, Uw, Ww, Gl, Gw, Hl, Hw;
+  double tau;
 } joint_world_t;
+
+#define LANES 8 /* the GPU works on octets: 7 joints + one zero-mass padding lane */
+
+/* Hillis-Steele inclusive scans over the 8 lanes, in the exact tree order of the GPU shuffles
+ * (octet.cuh: oct_prefix_sum / oct_suffix_sum) */
+static void prefix_sum8(double* x) {
+  for (int d = 1; d < LANES; d <<= 1) {
+    double y[LANES];
+    for (int l = 0; l < LANES; ++l) y[l] = x[l >= d ? l - d : l];
+    for (int l = 0; l < LANES; ++l) if (l >= d) x[l] += y[l];
+  }
+}
+static void suffix_sum8(double* x) {
+  for (int d = 1; d < LANES; d <<= 1) {
+    double y[LANES];
+    for (int l = 0; l < LANES; ++l) y[l] = x[l + d < LANES ? l + d : l];
+    for (int l = 0; l < LANES; ++l) if (l + d < LANES) x[l] += y[l];
+  }
+}
+static void prefix_sum8_v(v3_t* v) {
+  double a[LANES], b[LANES], c[LANES];
+  for (int l = 0; l < LANES; ++l) { a[l] = v[l].x; b[l] = v[l].y; c[l] = v[l].z; }
+  prefix_sum8(a); prefix_sum8(b); prefix_sum8(c);
+  for (int l = 0; l < LANES; ++l) v[l] = V3(a[l], b[l], c[l]);
+}
+static void suffix_sum8_v(v3_t* v) {
+  double a[LANES], b[LANES], c[LANES];
+  for (int l = 0; l < LANES; ++l) { a[l] = v[l].x; b[l] = v[l].y; c[l] = v[l].z; }
+  suffix_sum8(a); suffix_sum8(b); suffix_sum8(c);
+  for (int l = 0; l < LANES; ++l) v[l] = V3(a[l], b[l], c[l]);
+}
 
 /* Robot::RNEADerivatives -> pinocchio::computeRNEADerivatives + lower-triangle mirror of dtau/da
  * (include/idocp/robot/robot.hxx:466-500).  Analytical derivatives of Carpentier & Mansard
  * (RSS 2018) in the WORLD frame; the composite matrices are kept in their structured form
  *   I^C = (m, mc, Ibar)   [10 numbers],   D^C m = (-2 hl x m_w ; Sym m_w - ha x m_w)   [12 numbers]
  * (derivation: DESIGN.md "RNEA derivatives"; mirrored in oracle/np_mirror.py).
+ * The chain recursions are evaluated as tree-ordered scans over 8 "lanes" (7 joints + a zero-mass
+ * pad) so that the operation order equals the GPU kernel's (chain_dynamics.cuh).
  * Also returns tau = rnea(q,v,a) when tau != NULL. */
 static void rnea_derivatives_impl(const double* q, const double* v, const double* a, double* tau,
                                   double* dq, double* dv, double* da) {
-  joint_world_t J[NV];
-  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
-  double vl[3] = {0, 0, 0}, vw[3] = {0, 0, 0}, al[3] = {0, 0, IIWA14_GRAVITY}, aw[3] = {0, 0, 0};
-  for (int i = 0; i < NV; ++i) {
-    joint_world_t* j = &J[i];
-    const double c = cos(q[i]), s = sin(q[i]);
-    const double* P = IIWA14_PLACEMENT_R[i];
-    const double* pp = IIWA14_PLACEMENT_P[i];
-    double L[9], Rn[9];
-    for (int r = 0; r < 3; ++r) {
-      L[3 * r + 0] = c * P[3 * r + 0] + s * P[3 * r + 1];
-      L[3 * r + 1] = -s * P[3 * r + 0] + c * P[3 * r + 1];
-      L[3 * r + 2] = P[3 * r + 2];
+  joint_world_t J[LANES];
+  double R[LANES][9];
+  v3_t p[LANES];
+  /* local transforms: placement * Rz(q) */
+  for (int l = 0; l < LANES; ++l) {
+    if (l < NV) {
+      double sn, cs;
+      canon_sincos(q[l], &sn, &cs);
+      const double* P = IIWA14_PLACEMENT_R[l];
+      for (int r = 0; r < 3; ++r) {
+        const double a0 = P[3 * r], a1 = P[3 * r + 1];
+        R[l][3 * r + 0] = fma(sn, a1, cs * a0);
+        R[l][3 * r + 1] = fma(cs, a1, -(sn * a0));
+        R[l][3 * r + 2] = P[3 * r + 2];
+      }
+      p[l] = V3(IIWA14_PLACEMENT_P[l][0], IIWA14_PLACEMENT_P[l][1], IIWA14_PLACEMENT_P[l][2]);
+    } else {
+      for (int k = 0; k < 9; ++k) R[l][k] = (k % 4 == 0) ? 1.0 : 0.0;
+      p[l] = V3(0, 0, 0);
     }
-    for (int r = 0; r < 3; ++r) p[r] += R[3 * r] * pp[0] + R[3 * r + 1] * pp[1] + R[3 * r + 2] * pp[2];
-    for (int r = 0; r < 3; ++r)
-      for (int k = 0; k < 3; ++k)
-        Rn[3 * r + k] = R[3 * r] * L[k] + R[3 * r + 1] * L[3 + k] + R[3 * r + 2] * L[6 + k];
-    memcpy(R, Rn, sizeof(R));
-    const double z[3] = {R[2], R[5], R[8]};
-    cross3(p, z, j->Sl);
-    for (int k = 0; k < 3; ++k) j->Sw[k] = z[k];
-    for (int k = 0; k < 3; ++k) { vw[k] += j->Sw[k] * v[i]; vl[k] += j->Sl[k] * v[i]; }
-    double t1[3], t2[3], t3[3], t4[3];
-    cross3(vw, j->Sl, t1); cross3(vl, j->Sw, t2);
-    for (int k = 0; k < 3; ++k) j->dSl[k] = t1[k] + t2[k];
-    cross3(vw, j->Sw, j->dSw);
-    for (int k = 0; k < 3; ++k) {
-      aw[k] += j->Sw[k] * a[i] + j->dSw[k] * v[i];
-      al[k] += j->Sl[k] * a[i] + j->dSl[k] * v[i];
+  }
+  /* inclusive prefix product X_l <- X_0 ... X_l */
+  for (int d = 1; d < LANES; d <<= 1) {
+    double Rs[LANES][9];
+    v3_t ps[LANES];
+    for (int l = 0; l < LANES; ++l) {
+      const int src = l >= d ? l - d : l;
+      memcpy(Rs[l], R[src], sizeof(Rs[l]));
+      ps[l] = p[src];
     }
-    cross3(aw, j->Sl, t1); cross3(al, j->Sw, t2); cross3(vw, j->dSl, t3); cross3(vl, j->dSw, t4);
-    for (int k = 0; k < 3; ++k) j->Bl[k] = t1[k] + t2[k] + t3[k] + t4[k];
-    cross3(aw, j->Sw, t1); cross3(vw, j->dSw, t2);
-    for (int k = 0; k < 3; ++k) j->Bw[k] = t1[k] + t2[k];
-    /* world inertia about the world origin */
-    const double m = IIWA14_MASS[i];
-    const double* cm = IIWA14_COM[i];
-    const double* Ic = IIWA14_INERTIA[i];
-    double cw[3];
-    for (int r = 0; r < 3; ++r) cw[r] = R[3 * r] * cm[0] + R[3 * r + 1] * cm[1] + R[3 * r + 2] * cm[2] + p[r];
-    j->m = m;
-    for (int k = 0; k < 3; ++k) j->mc[k] = m * cw[k];
-    /* R Ic R^T */
+    for (int l = d; l < LANES; ++l) {
+      const double* S = Rs[l];
+      const v3_t pl = p[l];
+      p[l] = V3(fma(S[2], pl.z, fma(S[1], pl.y, fma(S[0], pl.x, ps[l].x))),
+                fma(S[5], pl.z, fma(S[4], pl.y, fma(S[3], pl.x, ps[l].y))),
+                fma(S[8], pl.z, fma(S[7], pl.y, fma(S[6], pl.x, ps[l].z))));
+      double Rn[9];
+      for (int r = 0; r < 3; ++r)
+        for (int k = 0; k < 3; ++k)
+          Rn[3 * r + k] = fma(S[3 * r + 2], R[l][6 + k], fma(S[3 * r + 1], R[l][3 + k], S[3 * r] * R[l][k]));
+      memcpy(R[l], Rn, sizeof(Rn));
+    }
+  }
+  v3_t vw[LANES], vl[LANES], aw[LANES], al[LANES];
+  double qd[LANES], qdd[LANES];
+  for (int l = 0; l < LANES; ++l) {
+    qd[l] = l < NV ? v[l] : 0.0;
+    qdd[l] = l < NV ? a[l] : 0.0;
+    J[l].Sw = V3(R[l][2], R[l][5], R[l][8]);
+    J[l].Sl = vcross(p[l], J[l].Sw);
+    vw[l] = vscale(qd[l], J[l].Sw);
+    vl[l] = vscale(qd[l], J[l].Sl);
+  }
+  prefix_sum8_v(vw); prefix_sum8_v(vl);
+  for (int l = 0; l < LANES; ++l) {
+    J[l].dSl = vadd(vcross(vw[l], J[l].Sl), vcross(vl[l], J[l].Sw));
+    J[l].dSw = vcross(vw[l], J[l].Sw);
+    aw[l] = vfma(qd[l], J[l].dSw, vscale(qdd[l], J[l].Sw));
+    al[l] = vfma(qd[l], J[l].dSl, vscale(qdd[l], J[l].Sl));
+  }
+  prefix_sum8_v(aw); prefix_sum8_v(al);
+  double mS[LANES];
+  v3_t mc[LANES], hl[LANES], ha[LANES], fl[LANES], fa[LANES];
+  s3_t Ib[LANES], Sym[LANES];
+  for (int l = 0; l < LANES; ++l) {
+    joint_world_t* j = &J[l];
+    al[l].z += IIWA14_GRAVITY;
+    j->Bl = vadd(vadd(vadd(vcross(aw[l], j->Sl), vcross(al[l], j->Sw)), vcross(vw[l], j->dSl)), vcross(vl[l], j->dSw));
+    j->Bw = vadd(vcross(aw[l], j->Sw), vcross(vw[l], j->dSw));
+    const double m = l < NV ? IIWA14_MASS[l] : 0.0;
+    const v3_t cm = l < NV ? V3(IIWA14_COM[l][0], IIWA14_COM[l][1], IIWA14_COM[l][2]) : V3(0, 0, 0);
+    const double* Rl = R[l];
+    const v3_t cw = V3(fma(Rl[2], cm.z, fma(Rl[1], cm.y, fma(Rl[0], cm.x, p[l].x))),
+                       fma(Rl[5], cm.z, fma(Rl[4], cm.y, fma(Rl[3], cm.x, p[l].y))),
+                       fma(Rl[8], cm.z, fma(Rl[7], cm.y, fma(Rl[6], cm.x, p[l].z))));
+    mS[l] = m;
+    mc[l] = vscale(m, cw);
+    double i0 = 0, i1 = 0, i2 = 0, i3 = 0, i4 = 0, i5 = 0;
+    if (l < NV) {
+      i0 = IIWA14_INERTIA[l][0]; i1 = IIWA14_INERTIA[l][1]; i2 = IIWA14_INERTIA[l][2];
+      i3 = IIWA14_INERTIA[l][3]; i4 = IIWA14_INERTIA[l][4]; i5 = IIWA14_INERTIA[l][5];
+    }
     double RI[9];
     for (int r = 0; r < 3; ++r) {
-      const double r0 = R[3 * r], r1 = R[3 * r + 1], r2 = R[3 * r + 2];
-      RI[3 * r + 0] = r0 * Ic[0] + r1 * Ic[1] + r2 * Ic[2];
-      RI[3 * r + 1] = r0 * Ic[1] + r1 * Ic[3] + r2 * Ic[4];
-      RI[3 * r + 2] = r0 * Ic[2] + r1 * Ic[4] + r2 * Ic[5];
+      const double r0 = Rl[3 * r], r1 = Rl[3 * r + 1], r2 = Rl[3 * r + 2];
+      RI[3 * r + 0] = fma(r2, i2, fma(r1, i1, r0 * i0));
+      RI[3 * r + 1] = fma(r2, i4, fma(r1, i3, r0 * i1));
+      RI[3 * r + 2] = fma(r2, i5, fma(r1, i4, r0 * i2));
     }
-    const double cc = dot3(cw, cw);
-    int idx = 0;
-    for (int r = 0; r < 3; ++r)
-      for (int k = r; k < 3; ++k) {
-        double e = RI[3 * r] * R[3 * k] + RI[3 * r + 1] * R[3 * k + 1] + RI[3 * r + 2] * R[3 * k + 2];
-        e += m * ((r == k ? cc : 0.0) - cw[r] * cw[k]);
-        j->Ib[idx++] = e;
-      }
-    /* momentum and force */
-    double Iw[3], Ia[3];
-    cross3(vw, j->mc, t1);
-    for (int k = 0; k < 3; ++k) j->hl[k] = m * vl[k] + t1[k];
-    cross3(j->mc, vl, t1); sym3_mul(j->Ib, vw, Iw);
-    for (int k = 0; k < 3; ++k) j->ha[k] = t1[k] + Iw[k];
-    cross3(aw, j->mc, t1); cross3(vw, j->hl, t2);
-    for (int k = 0; k < 3; ++k) j->fl[k] = m * al[k] + t1[k] + t2[k];
-    cross3(j->mc, al, t1); sym3_mul(j->Ib, aw, Ia); cross3(vw, j->ha, t2); cross3(vl, j->hl, t3);
-    for (int k = 0; k < 3; ++k) j->fa[k] = t1[k] + Ia[k] + t2[k] + t3[k];
-    /* Sym = -(vl mc^T + mc vl^T) + 2 (mc.vl) 1 + [w] Ibar + ([w] Ibar)^T */
-    const double* I6 = j->Ib;
-    const double Ifull[9] = {I6[0], I6[1], I6[2], I6[1], I6[3], I6[4], I6[2], I6[4], I6[5]};
-    double wI[9];
-    for (int k = 0; k < 3; ++k) { /* column k of [w] Ibar = w x Ibar[:,k] */
-      const double col[3] = {Ifull[k], Ifull[3 + k], Ifull[6 + k]};
-      double o[3];
-      cross3(vw, col, o);
-      wI[k] = o[0]; wI[3 + k] = o[1]; wI[6 + k] = o[2];
-    }
-    const double mcv = dot3(j->mc, vl);
-    idx = 0;
-    for (int r = 0; r < 3; ++r)
-      for (int k = r; k < 3; ++k) {
-        double e = -(vl[r] * j->mc[k] + j->mc[r] * vl[k]) + wI[3 * r + k] + wI[3 * k + r];
-        if (r == k) e += 2.0 * mcv;
-        j->Sym[idx++] = e;
-      }
+    const double cc = vdot(cw, cw);
+    Ib[l].xx = fma(m, cc - cw.x * cw.x, fma(RI[2], Rl[2], fma(RI[1], Rl[1], RI[0] * Rl[0])));
+    Ib[l].xy = fma(m, -(cw.x * cw.y), fma(RI[2], Rl[5], fma(RI[1], Rl[4], RI[0] * Rl[3])));
+    Ib[l].xz = fma(m, -(cw.x * cw.z), fma(RI[2], Rl[8], fma(RI[1], Rl[7], RI[0] * Rl[6])));
+    Ib[l].yy = fma(m, cc - cw.y * cw.y, fma(RI[5], Rl[5], fma(RI[4], Rl[4], RI[3] * Rl[3])));
+    Ib[l].yz = fma(m, -(cw.y * cw.z), fma(RI[5], Rl[8], fma(RI[4], Rl[7], RI[3] * Rl[6])));
+    Ib[l].zz = fma(m, cc - cw.z * cw.z, fma(RI[8], Rl[8], fma(RI[7], Rl[7], RI[6] * Rl[6])));
+    hl[l] = vfma(m, vl[l], vcross(vw[l], mc[l]));
+    ha[l] = vadd(vcross(mc[l], vl[l]), smul(Ib[l], vw[l]));
+    fl[l] = vadd(vfma(m, al[l], vcross(aw[l], mc[l])), vcross(vw[l], hl[l]));
+    fa[l] = vadd(vadd(vadd(vcross(mc[l], al[l]), smul(Ib[l], aw[l])), vcross(vw[l], ha[l])), vcross(vl[l], hl[l]));
+    const v3_t c0 = vcross(vw[l], V3(Ib[l].xx, Ib[l].xy, Ib[l].xz));
+    const v3_t c1 = vcross(vw[l], V3(Ib[l].xy, Ib[l].yy, Ib[l].yz));
+    const v3_t c2 = vcross(vw[l], V3(Ib[l].xz, Ib[l].yz, Ib[l].zz));
+    const double mcv = vdot(mc[l], vl[l]);
+    const v3_t vL = vl[l], mC_ = mc[l];
+    Sym[l].xx = 2.0 * (c0.x + (mcv - vL.x * mC_.x));
+    Sym[l].xy = (c1.x + c0.y) - fma(vL.x, mC_.y, mC_.x * vL.y);
+    Sym[l].xz = (c2.x + c0.z) - fma(vL.x, mC_.z, mC_.x * vL.z);
+    Sym[l].yy = 2.0 * (c1.y + (mcv - vL.y * mC_.y));
+    Sym[l].yz = (c2.y + c1.z) - fma(vL.y, mC_.z, mC_.y * vL.z);
+    Sym[l].zz = 2.0 * (c2.z + (mcv - vL.z * mC_.z));
   }
-  /* backward sweep: composite (suffix) sums and the per-joint force-like vectors */
-  double mC = 0, mcC[3] = {0, 0, 0}, IC[6] = {0, 0, 0, 0, 0, 0}, hlC[3] = {0, 0, 0}, haC[3] = {0, 0, 0};
-  double SymC[6] = {0, 0, 0, 0, 0, 0}, Fl[3] = {0, 0, 0}, Fa[3] = {0, 0, 0};
-  for (int i = NV - 1; i >= 0; --i) {
-    joint_world_t* j = &J[i];
-    mC += j->m;
-    for (int k = 0; k < 3; ++k) { mcC[k] += j->mc[k]; hlC[k] += j->hl[k]; haC[k] += j->ha[k]; Fl[k] += j->fl[k]; Fa[k] += j->fa[k]; }
-    for (int k = 0; k < 6; ++k) { IC[k] += j->Ib[k]; SymC[k] += j->Sym[k]; }
-    double t1[3], t2[3], t3[3], t4[3], t5[3];
-    if (tau) tau[i] = dot3(j->Sl, Fl) + dot3(j->Sw, Fa);
-    /* U = I^C S */
-    cross3(j->Sw, mcC, t1);
-    for (int k = 0; k < 3; ++k) j->Ul[k] = mC * j->Sl[k] + t1[k];
-    cross3(mcC, j->Sl, t1); sym3_mul(IC, j->Sw, t2);
-    for (int k = 0; k < 3; ++k) j->Uw[k] = t1[k] + t2[k];
-    /* W = D^C^T S (angular part only; the linear part is identically zero) */
-    cross3(hlC, j->Sl, t1); sym3_mul(SymC, j->Sw, t2); cross3(haC, j->Sw, t3);
-    for (int k = 0; k < 3; ++k) j->Ww[k] = 2.0 * t1[k] + t2[k] + t3[k];
-    /* G = S x* F + I^C B + D^C dS */
-    cross3(j->Sw, Fl, t1); cross3(j->Bw, mcC, t2); cross3(hlC, j->dSw, t3);
-    for (int k = 0; k < 3; ++k) j->Gl[k] = t1[k] + mC * j->Bl[k] + t2[k] - 2.0 * t3[k];
-    cross3(j->Sw, Fa, t1); cross3(j->Sl, Fl, t2); cross3(mcC, j->Bl, t3); sym3_mul(IC, j->Bw, t4);
-    sym3_mul(SymC, j->dSw, t5);
-    double t6[3];
-    cross3(haC, j->dSw, t6);
-    for (int k = 0; k < 3; ++k) j->Gw[k] = t1[k] + t2[k] + t3[k] + t4[k] + t5[k] - t6[k];
-    /* H = D^C S + 2 I^C dS */
-    cross3(hlC, j->Sw, t1); cross3(j->dSw, mcC, t2);
-    for (int k = 0; k < 3; ++k) j->Hl[k] = -2.0 * t1[k] + 2.0 * (mC * j->dSl[k] + t2[k]);
-    sym3_mul(SymC, j->Sw, t1); cross3(haC, j->Sw, t2); cross3(mcC, j->dSl, t3); sym3_mul(IC, j->dSw, t4);
-    for (int k = 0; k < 3; ++k) j->Hw[k] = t1[k] - t2[k] + 2.0 * (t3[k] + t4[k]);
+  /* composite (suffix) sums */
+  suffix_sum8(mS);
+  suffix_sum8_v(mc); suffix_sum8_v(hl); suffix_sum8_v(ha); suffix_sum8_v(fl); suffix_sum8_v(fa);
+  {
+    double t[6][LANES], u[6][LANES];
+    for (int l = 0; l < LANES; ++l) {
+      t[0][l] = Ib[l].xx; t[1][l] = Ib[l].xy; t[2][l] = Ib[l].xz; t[3][l] = Ib[l].yy; t[4][l] = Ib[l].yz; t[5][l] = Ib[l].zz;
+      u[0][l] = Sym[l].xx; u[1][l] = Sym[l].xy; u[2][l] = Sym[l].xz; u[3][l] = Sym[l].yy; u[4][l] = Sym[l].yz; u[5][l] = Sym[l].zz;
+    }
+    for (int k = 0; k < 6; ++k) { suffix_sum8(t[k]); suffix_sum8(u[k]); }
+    for (int l = 0; l < LANES; ++l) {
+      Ib[l].xx = t[0][l]; Ib[l].xy = t[1][l]; Ib[l].xz = t[2][l]; Ib[l].yy = t[3][l]; Ib[l].yz = t[4][l]; Ib[l].zz = t[5][l];
+      Sym[l].xx = u[0][l]; Sym[l].xy = u[1][l]; Sym[l].xz = u[2][l]; Sym[l].yy = u[3][l]; Sym[l].yz = u[4][l]; Sym[l].zz = u[5][l];
+    }
+  }
+  for (int l = 0; l < NV; ++l) {
+    joint_world_t* j = &J[l];
+    const double mC = mS[l];
+    j->tau = vdot(j->Sl, fl[l]) + vdot(j->Sw, fa[l]);
+    if (tau) tau[l] = j->tau;
+    j->Ul = vfma(mC, j->Sl, vcross(j->Sw, mc[l]));
+    j->Uw = vadd(vcross(mc[l], j->Sl), smul(Ib[l], j->Sw));
+    j->Ww = vadd(vfma(2.0, vcross(hl[l], j->Sl), smul(Sym[l], j->Sw)), vcross(ha[l], j->Sw));
+    j->Gl = vfma(-2.0, vcross(hl[l], j->dSw), vadd(vfma(mC, j->Bl, vcross(j->Sw, fl[l])), vcross(j->Bw, mc[l])));
+    j->Gw = vsub(vadd(vadd(vadd(vadd(vcross(j->Sw, fa[l]), vcross(j->Sl, fl[l])), vcross(mc[l], j->Bl)), smul(Ib[l], j->Bw)),
+                      smul(Sym[l], j->dSw)),
+                 vcross(ha[l], j->dSw));
+    j->Hl = vscale(2.0, vsub(vfma(mC, j->dSl, vcross(j->dSw, mc[l])), vcross(hl[l], j->Sw)));
+    j->Hw = vfma(2.0, vadd(vcross(mc[l], j->dSl), smul(Ib[l], j->dSw)), vsub(smul(Sym[l], j->Sw), vcross(ha[l], j->Sw)));
   }
   if (!dq) return;
   for (int c = 0; c < NV; ++c) {
@@ -276,14 +373,15 @@ static void rnea_derivatives_impl(const double* q, const double* v, const double
     for (int r = 0; r < NV; ++r) {
       const joint_world_t* x = &J[r];
       if (r <= c) {
-        dq[c * NV + r] = dot3(x->Sl, b->Gl) + dot3(x->Sw, b->Gw);
-        dv[c * NV + r] = dot3(x->Sl, b->Hl) + dot3(x->Sw, b->Hw);
-        const double mm = dot3(x->Sl, b->Ul) + dot3(x->Sw, b->Uw);
-        da[c * NV + r] = mm;
-        da[r * NV + c] = mm; /* robot.hxx:496-499: strictly-lower triangle mirrored from the upper */
+        dq[c * NV + r] = vdot(x->Sl, b->Gl) + vdot(x->Sw, b->Gw);
+        dv[c * NV + r] = vdot(x->Sl, b->Hl) + vdot(x->Sw, b->Hw);
+        da[c * NV + r] = vdot(x->Sl, b->Ul) + vdot(x->Sw, b->Uw);
       } else {
-        dq[c * NV + r] = dot3(x->Ul, b->Bl) + dot3(x->Uw, b->Bw) + dot3(x->Ww, b->dSw);
-        dv[c * NV + r] = dot3(x->Ww, b->Sw) + 2.0 * (dot3(x->Ul, b->dSl) + dot3(x->Uw, b->dSw));
+        dq[c * NV + r] = (vdot(x->Ul, b->Bl) + vdot(x->Uw, b->Bw)) + vdot(x->Ww, b->dSw);
+        dv[c * NV + r] = fma(2.0, vdot(x->Ul, b->dSl) + vdot(x->Uw, b->dSw), vdot(x->Ww, b->Sw));
+        /* robot.hxx:496-499: strictly-lower triangle of dtau/da mirrored from the upper one:
+         * M[r][c] = M[c][r] = S_c . U_r */
+        da[c * NV + r] = vdot(b->Sl, x->Ul) + vdot(b->Sw, x->Uw);
       }
     }
   }
@@ -465,7 +563,7 @@ static void compute_slack_dual_direction(stage_t* st, const split_direction_t* d
     const double* dx = c <= C_POS_UP ? d->dq : (c <= C_VEL_UP ? d->dv : d->du);
     for (int j = 0; j < NV; ++j) {
       cd->dslack[j] = ((c & 1) ? -dx[j] : dx[j]) - cd->residual[j];
-      cd->ddual[j] = -(cd->dual[j] * cd->dslack[j] + cd->duality[j]) / cd->slack[j];
+      cd->ddual[j] = -fma(cd->dual[j], cd->dslack[j], cd->duality[j]) / cd->slack[j];
     }
   }
 }
@@ -553,14 +651,13 @@ static void stage_residual_common(const oracle_problem_t* p, double dt, const sp
   augment_dual_residual(st, dt);
   /* stateequation::linearizeForwardEuler (ocp/state_equation.hxx:11-37,210-221) */
   for (int j = 0; j < NV; ++j) {
-    st->Fq[j] = s->q[j] - sn->q[j];
-    st->Fq[j] += dt * s->v[j];
-    st->Fv[j] = s->v[j] + dt * s->a[j] - sn->v[j];
+    st->Fq[j] = fma(dt, s->v[j], s->q[j] - sn->q[j]);
+    st->Fv[j] = fma(dt, s->a[j], s->v[j]) - sn->v[j];
   }
   for (int j = 0; j < NV; ++j) {
     st->lq[j] += sn->lmd[j] - s->lmd[j];
-    st->lv[j] += dt * sn->lmd[j] + sn->gmm[j] - s->gmm[j];
-    st->la[j] += dt * sn->gmm[j];
+    st->lv[j] += fma(dt, sn->lmd[j], sn->gmm[j]) - s->gmm[j];
+    st->la[j] = fma(dt, sn->gmm[j], st->la[j]);
   }
   /* UnconstrainedDynamics::linearizeUnconstrainedDynamics (unocp/unconstrained_dynamics.hxx:55-65,166-177) */
   (void)with_derivatives;
@@ -569,14 +666,14 @@ static void stage_residual_common(const oracle_problem_t* p, double dt, const sp
   for (int j = 0; j < NV; ++j) {
     double tq = 0, tv = 0, ta = 0;
     for (int k = 0; k < NV; ++k) {
-      tq += st->dIDdq[j * NV + k] * s->beta[k];
-      tv += st->dIDdv[j * NV + k] * s->beta[k];
-      ta += st->dIDda[j * NV + k] * s->beta[k];
+      tq = fma(st->dIDdq[j * NV + k], s->beta[k], tq);
+      tv = fma(st->dIDdv[j * NV + k], s->beta[k], tv);
+      ta = fma(st->dIDda[j * NV + k], s->beta[k], ta);
     }
-    st->lq[j] += dt * tq;
-    st->lv[j] += dt * tv;
-    st->la[j] += dt * ta;
-    st->lu[j] -= dt * s->beta[j];
+    st->lq[j] = fma(dt, tq, st->lq[j]);
+    st->lv[j] = fma(dt, tv, st->lv[j]);
+    st->la[j] = fma(dt, ta, st->la[j]);
+    st->lu[j] = fma(-dt, s->beta[j], st->lu[j]);
   }
 }
 
@@ -589,13 +686,13 @@ static void split_unocp_linearize(const oracle_problem_t* p, double dt, const sp
   stage_cost_hessian(p, dt, st);
   condense_slack_and_dual(p, st, s, dt);
   /* UnconstrainedDynamics::condenseUnconstrainedDynamics (unconstrained_dynamics.hxx:68-94) */
-  for (int j = 0; j < NV; ++j) st->lu_condensed[j] = st->lu[j] + st->Quu[j] * st->ID[j];
+  for (int j = 0; j < NV; ++j) st->lu_condensed[j] = fma(st->Quu[j], st->ID[j], st->lu[j]);
   for (int j = 0; j < NV; ++j) {
     double tq = 0, tv = 0, ta = 0;
     for (int k = 0; k < NV; ++k) {
-      tq += st->dIDdq[j * NV + k] * st->lu_condensed[k];
-      tv += st->dIDdv[j * NV + k] * st->lu_condensed[k];
-      ta += st->dIDda[j * NV + k] * st->lu_condensed[k];
+      tq = fma(st->dIDdq[j * NV + k], st->lu_condensed[k], tq);
+      tv = fma(st->dIDdv[j * NV + k], st->lu_condensed[k], tv);
+      ta = fma(st->dIDda[j * NV + k], st->lu_condensed[k], ta);
     }
     st->ulq[j] = st->lq[j] + tq;
     st->ulv[j] = st->lv[j] + tv;
@@ -611,12 +708,12 @@ static void split_unocp_linearize(const oracle_problem_t* p, double dt, const sp
         const double Dq = st->Quu[k] * st->dIDdq[c * NV + k];
         const double Dv = st->Quu[k] * st->dIDdv[c * NV + k];
         const double Da = st->Quu[k] * st->dIDda[c * NV + k];
-        qq += st->dIDdq[r * NV + k] * Dq;
-        qv += st->dIDdq[r * NV + k] * Dv;
-        vv += st->dIDdv[r * NV + k] * Dv;
-        aq += st->dIDda[r * NV + k] * Dq;
-        av += st->dIDda[r * NV + k] * Dv;
-        aa += st->dIDda[r * NV + k] * Da;
+        qq = fma(st->dIDdq[r * NV + k], Dq, qq);
+        qv = fma(st->dIDdq[r * NV + k], Dv, qv);
+        vv = fma(st->dIDdv[r * NV + k], Dv, vv);
+        aq = fma(st->dIDda[r * NV + k], Dq, aq);
+        av = fma(st->dIDda[r * NV + k], Dv, av);
+        aa = fma(st->dIDda[r * NV + k], Da, aa);
       }
       st->uQqq[c * NV + r] = qq + st->Qqq[c * NV + r];
       st->uQqv[c * NV + r] = qv;
@@ -666,17 +763,17 @@ static void split_unocp_condensed_direction(stage_t* st, double dt, split_direct
   for (int r = 0; r < NV; ++r) {
     double acc = st->ID[r];
     double t = 0;
-    for (int c = 0; c < NV; ++c) t += st->dIDdq[c * NV + r] * d->dq[c];
+    for (int c = 0; c < NV; ++c) t = fma(st->dIDdq[c * NV + r], d->dq[c], t);
     acc += t;
     t = 0;
-    for (int c = 0; c < NV; ++c) t += st->dIDdv[c * NV + r] * d->dv[c];
+    for (int c = 0; c < NV; ++c) t = fma(st->dIDdv[c * NV + r], d->dv[c], t);
     acc += t;
     t = 0;
-    for (int c = 0; c < NV; ++c) t += st->dIDda[c * NV + r] * d->da[c];
+    for (int c = 0; c < NV; ++c) t = fma(st->dIDda[c * NV + r], d->da[c], t);
     acc += t;
     d->du[r] = acc;
   }
-  for (int r = 0; r < NV; ++r) d->dbeta[r] = (st->lu[r] + st->Quu[r] * d->du[r]) / dt;
+  for (int r = 0; r < NV; ++r) d->dbeta[r] = fma(st->Quu[r], d->du[r], st->lu[r]) / dt;
   compute_slack_dual_direction(st, d);
 }
 
@@ -685,84 +782,89 @@ static void split_unocp_condensed_direction(stage_t* st, double dt, split_direct
 /* unocp/split_unriccati_factorizer.hxx, src/unocp/unriccati_recursion.cpp)                    */
 /* ------------------------------------------------------------------------------------------ */
 /* Eigen::LLT<MatrixXd, Lower>: unblocked left-looking Cholesky reading the lower triangle only
- * (SURVEY A.7); returns 0 on success, k+1 when pivot k is not positive. */
-static int llt_lower(const double* A, int n, double* L) {
+ * (SURVEY A.7); returns 0 on success, k+1 when pivot k is not positive.  Canonical arithmetic:
+ * the divisions by the diagonal are multiplications by its reciprocal rd[k] = 1 / L_kk (one
+ * rounding more than Eigen's division, far inside the unpinned Eigen boundary). */
+static int llt_lower(const double* A, int n, double* L, double* rd) {
+  int info = 0;
   for (int i = 0; i < n * n; ++i) L[i] = 0.0;
   for (int k = 0; k < n; ++k) {
     double x = A[k * n + k];
-    for (int j = 0; j < k; ++j) x -= L[j * n + k] * L[j * n + k];
-    if (!(x > 0.0)) return k + 1;
+    for (int j = 0; j < k; ++j) x = fma(-L[j * n + k], L[j * n + k], x);
+    if (!(x > 0.0) && !info) info = k + 1;
     x = sqrt(x);
     L[k * n + k] = x;
+    rd[k] = 1.0 / x;
     for (int i = k + 1; i < n; ++i) {
       double y = A[k * n + i];
-      for (int j = 0; j < k; ++j) y -= L[j * n + i] * L[j * n + k];
-      L[k * n + i] = y / x;
+      for (int j = 0; j < k; ++j) y = fma(-L[j * n + i], L[j * n + k], y);
+      L[k * n + i] = y * rd[k];
     }
   }
-  return 0;
+  return info;
 }
 /* x = (L L^T)^-1 b : forward then backward substitution, one right-hand side */
-static void llt_solve(const double* L, int n, const double* b, double* x) {
+static void llt_solve(const double* L, const double* rd, int n, const double* b, double* x) {
   for (int i = 0; i < n; ++i) {
     double y = b[i];
-    for (int j = 0; j < i; ++j) y -= L[j * n + i] * x[j];
-    x[i] = y / L[i * n + i];
+    for (int j = 0; j < i; ++j) y = fma(-L[j * n + i], x[j], y);
+    x[i] = y * rd[i];
   }
   for (int i = n - 1; i >= 0; --i) {
     double y = x[i];
-    for (int j = i + 1; j < n; ++j) y -= L[i * n + j] * x[j];
-    x[i] = y / L[i * n + i];
+    for (int j = i + 1; j < n; ++j) y = fma(-L[i * n + j], x[j], y);
+    x[i] = y * rd[i];
   }
 }
 
 /* SplitUnRiccatiFactorizer::backwardRiccatiRecursion (split_unriccati_factorizer.hxx:30-46) */
 static int riccati_backward_stage(const riccati_t* rn, double dt, stage_t* st, riccati_t* r) {
   /* BackwardUnRiccatiRecursionFactorizer::factorizeKKTMatrix (:29-54) */
+  const double dt2 = dt * dt;
   for (int c = 0; c < NV; ++c)
     for (int rr = 0; rr < NV; ++rr) {
       const int i = c * NV + rr, it = rr * NV + c;
       st->uQqq[i] += rn->Pqq[i];
-      st->uQqv[i] += dt * rn->Pqq[i];
+      st->uQqv[i] = fma(dt, rn->Pqq[i], st->uQqv[i]);
       st->uQqv[i] += rn->Pqv[i];
-      st->uQvv[i] += dt * dt * rn->Pqq[i];
-      st->uQvv[i] += dt * rn->Pqv[i];
-      st->uQvv[i] += dt * rn->Pqv[it];
+      st->uQvv[i] = fma(dt2, rn->Pqq[i], st->uQvv[i]);
+      st->uQvv[i] = fma(dt, rn->Pqv[i], st->uQvv[i]);
+      st->uQvv[i] = fma(dt, rn->Pqv[it], st->uQvv[i]);
       st->uQvv[i] += rn->Pvv[i];
-      st->uQaq[i] += dt * rn->Pqv[it];            /* Qaq^T += dt Pqv */
-      st->uQav[i] += dt * dt * rn->Pqv[it];       /* Qav^T += dt^2 Pqv + dt Pvv */
-      st->uQav[i] += dt * rn->Pvv[it];
-      st->uQaa[i] += dt * dt * rn->Pvv[i];
+      st->uQaq[i] = fma(dt, rn->Pqv[it], st->uQaq[i]);            /* Qaq^T += dt Pqv */
+      st->uQav[i] = fma(dt2, rn->Pqv[it], st->uQav[i]);           /* Qav^T += dt^2 Pqv + dt Pvv */
+      st->uQav[i] = fma(dt, rn->Pvv[it], st->uQav[i]);
+      st->uQaa[i] = fma(dt2, rn->Pvv[i], st->uQaa[i]);
     }
   for (int c = 0; c < NV; ++c)
     for (int rr = 0; rr < NV; ++rr) st->uQvq[c * NV + rr] = st->uQqv[rr * NV + c];
   for (int j = 0; j < NV; ++j) {
     double t1 = 0, t2 = 0;
     for (int k = 0; k < NV; ++k) {
-      t1 += rn->Pqv[j * NV + k] * st->uFq[k];     /* (Pqv^T Fq)_j */
-      t2 += rn->Pvv[k * NV + j] * st->uFv[k];     /* (Pvv Fv)_j   */
+      t1 = fma(rn->Pqv[j * NV + k], st->uFq[k], t1);     /* (Pqv^T Fq)_j */
+      t2 = fma(rn->Pvv[k * NV + j], st->uFv[k], t2);     /* (Pvv Fv)_j   */
     }
-    st->ula[j] += dt * t1;
-    st->ula[j] += dt * t2;
-    st->ula[j] -= dt * rn->sv[j];
+    st->ula[j] = fma(dt, t1, st->ula[j]);
+    st->ula[j] = fma(dt, t2, st->ula[j]);
+    st->ula[j] = fma(-dt, rn->sv[j], st->ula[j]);
   }
   /* llt_.compute(Qaa); K = -llt_.solve(Qax); k = -llt_.solve(la) (:37-40) */
-  double L[NN], x[NV];
-  const int info = llt_lower(st->uQaa, NV, L);
+  double L[NN], rd[NV], x[NV];
+  const int info = llt_lower(st->uQaa, NV, L, rd);
   for (int c = 0; c < NV; ++c) {
-    llt_solve(L, NV, &st->uQaq[c * NV], x);
+    llt_solve(L, rd, NV, &st->uQaq[c * NV], x);
     for (int j = 0; j < NV; ++j) st->K[c * NV + j] = -x[j];
-    llt_solve(L, NV, &st->uQav[c * NV], x);
+    llt_solve(L, rd, NV, &st->uQav[c * NV], x);
     for (int j = 0; j < NV; ++j) st->K[(NV + c) * NV + j] = -x[j];
   }
-  llt_solve(L, NV, st->ula, x);
+  llt_solve(L, rd, NV, st->ula, x);
   for (int j = 0; j < NV; ++j) st->k[j] = -x[j];
   /* factorizeRiccatiFactorization (:57-89) */
   double GK[NV * 2 * NV];
   for (int c = 0; c < 2 * NV; ++c)
     for (int rr = 0; rr < NV; ++rr) {
       double t = 0;
-      for (int k = 0; k < NV; ++k) t += st->uQaa[k * NV + rr] * st->K[c * NV + k];
+      for (int k = 0; k < NV; ++k) t = fma(st->uQaa[k * NV + rr], st->K[c * NV + k], t);
       GK[c * NV + rr] = t;
     }
   const double* Kq = st->K;
@@ -773,9 +875,9 @@ static int riccati_backward_stage(const riccati_t* rn, double dt, stage_t* st, r
     for (int rr = 0; rr < NV; ++rr) {
       double tqq = 0, tqv = 0, tvv = 0;
       for (int k = 0; k < NV; ++k) {
-        tqq += Kq[rr * NV + k] * GKq[c * NV + k];
-        tqv += Kq[rr * NV + k] * GKv[c * NV + k];
-        tvv += Kv[rr * NV + k] * GKv[c * NV + k];
+        tqq = fma(Kq[rr * NV + k], GKq[c * NV + k], tqq);
+        tqv = fma(Kq[rr * NV + k], GKv[c * NV + k], tqv);
+        tvv = fma(Kv[rr * NV + k], GKv[c * NV + k], tvv);
       }
       r->Pqq[c * NV + rr] = st->uQqq[c * NV + rr] - tqq;
       r->Pqv[c * NV + rr] = st->uQqv[c * NV + rr] - tqv;
@@ -794,8 +896,8 @@ static int riccati_backward_stage(const riccati_t* rn, double dt, stage_t* st, r
   for (int j = 0; j < NV; ++j) {
     double t1 = 0, t2 = 0;
     for (int k = 0; k < NV; ++k) {
-      t1 += rn->Pqq[k * NV + j] * st->uFq[k];
-      t2 += rn->Pqv[k * NV + j] * st->uFv[k];
+      t1 = fma(rn->Pqq[k * NV + j], st->uFq[k], t1);
+      t2 = fma(rn->Pqv[k * NV + j], st->uFv[k], t2);
     }
     r->sq[j] = rn->sq[j];
     r->sq[j] -= t1;
@@ -804,11 +906,10 @@ static int riccati_backward_stage(const riccati_t* rn, double dt, stage_t* st, r
   for (int j = 0; j < NV; ++j) {
     double t1 = 0, t2 = 0;
     for (int k = 0; k < NV; ++k) {
-      t1 += rn->Pqv[j * NV + k] * st->uFq[k];     /* Pqv^T Fq */
-      t2 += rn->Pvv[k * NV + j] * st->uFv[k];
+      t1 = fma(rn->Pqv[j * NV + k], st->uFq[k], t1);     /* Pqv^T Fq */
+      t2 = fma(rn->Pvv[k * NV + j], st->uFv[k], t2);
     }
-    r->sv[j] = rn->sv[j];
-    r->sv[j] += dt * r->sq[j];
+    r->sv[j] = fma(dt, r->sq[j], rn->sv[j]);
     r->sv[j] -= t1;
     r->sv[j] -= t2;
   }
@@ -819,8 +920,8 @@ static int riccati_backward_stage(const riccati_t* rn, double dt, stage_t* st, r
   for (int j = 0; j < NV; ++j) {
     double t1 = 0, t2 = 0;
     for (int k = 0; k < NV; ++k) {
-      t1 += st->uQaq[j * NV + k] * st->k[k];      /* Qaq^T k */
-      t2 += st->uQav[j * NV + k] * st->k[k];
+      t1 = fma(st->uQaq[j * NV + k], st->k[k], t1);      /* Qaq^T k */
+      t2 = fma(st->uQav[j * NV + k], st->k[k], t2);
     }
     r->sq[j] -= t1;
     r->sv[j] -= t2;
@@ -879,7 +980,7 @@ static double split_unocp_violation(const oracle_problem_t* p, double dt, stage_
     st->Fq[j] += dt * s->v[j];
     st->Fv[j] = s->v[j] + dt * s->a[j] - vn[j];
   }
-  oracle_rnea(s->q, s->v, s->a, st->ID);
+  rnea_derivatives_impl(s->q, s->v, s->a, st->ID, NULL, NULL, NULL);
   for (int j = 0; j < NV; ++j) st->ID[j] -= s->u[j];
   double viol = 0;
   viol += l1norm(st->Fq) + l1norm(st->Fv);
@@ -917,10 +1018,10 @@ static double line_search_step(oracle_unocp_t* o, double max_primal) {
     for (int i = 0; i <= o->N; ++i) {
       split_solution_t* t = &o->s_try[i];
       for (int j = 0; j < NV; ++j) {
-        t->q[j] = o->s[i].q[j] + alpha * o->d[i].dq[j];
-        t->v[j] = o->s[i].v[j] + alpha * o->d[i].dv[j];
-        t->a[j] = o->s[i].a[j] + alpha * o->d[i].da[j];
-        t->u[j] = o->s[i].u[j] + alpha * o->d[i].du[j];
+        t->q[j] = fma(alpha, o->d[i].dq[j], o->s[i].q[j]);
+        t->v[j] = fma(alpha, o->d[i].dv[j], o->s[i].v[j]);
+        t->a[j] = fma(alpha, o->d[i].da[j], o->s[i].a[j]);
+        t->u[j] = fma(alpha, o->d[i].du[j], o->s[i].u[j]);
       }
     }
     cost_and_violation(o, o->s_try, alpha, &cost, &viol);
@@ -1033,15 +1134,15 @@ void oracle_unocp_update_solution(oracle_unocp_t* o, double t, const double* q, 
     const stage_t* st = &o->st[i];
     for (int r = 0; r < NV; ++r) {
       double acc = 0;
-      for (int c = 0; c < NV; ++c) acc += st->K[c * NV + r] * d->dq[c];
-      for (int c = 0; c < NV; ++c) acc += st->K[(NV + c) * NV + r] * d->dv[c];
+      for (int c = 0; c < NV; ++c) acc = fma(st->K[c * NV + r], d->dq[c], acc);
+      for (int c = 0; c < NV; ++c) acc = fma(st->K[(NV + c) * NV + r], d->dv[c], acc);
       d->da[r] = acc + st->k[r];
     }
     for (int j = 0; j < NV; ++j) {
       dn->dq[j] = st->uFq[j] + d->dq[j];
       dn->dv[j] = st->uFv[j] + d->dv[j];
-      dn->dq[j] += dt * d->dv[j];
-      dn->dv[j] += dt * d->da[j];
+      dn->dq[j] = fma(dt, d->dv[j], dn->dq[j]);
+      dn->dv[j] = fma(dt, d->da[j], dn->dv[j]);
     }
   }
   double primal = 1.0, dual = 1.0;
@@ -1053,10 +1154,10 @@ void oracle_unocp_update_solution(oracle_unocp_t* o, double t, const double* q, 
     for (int j = 0; j < NV; ++j) {
       double t1 = 0, t2 = 0, t3 = 0, t4 = 0;
       for (int k = 0; k < NV; ++k) {
-        t1 += r->Pqq[k * NV + j] * d->dq[k];
-        t2 += r->Pqv[k * NV + j] * d->dv[k];
-        t3 += r->Pqv[j * NV + k] * d->dq[k];   /* Pqv^T dq */
-        t4 += r->Pvv[k * NV + j] * d->dv[k];
+        t1 = fma(r->Pqq[k * NV + j], d->dq[k], t1);
+        t2 = fma(r->Pqv[k * NV + j], d->dv[k], t2);
+        t3 = fma(r->Pqv[j * NV + k], d->dq[k], t3);   /* Pqv^T dq */
+        t4 = fma(r->Pvv[k * NV + j], d->dv[k], t4);
       }
       d->dlmd[j] = t1; d->dlmd[j] += t2; d->dlmd[j] -= r->sq[j];
       d->dgmm[j] = t3; d->dgmm[j] += t4; d->dgmm[j] -= r->sv[j];
@@ -1078,23 +1179,23 @@ void oracle_unocp_update_solution(oracle_unocp_t* o, double t, const double* q, 
     split_solution_t* s = &o->s[i];
     const split_direction_t* d = &o->d[i];
     for (int j = 0; j < NV; ++j) {
-      s->lmd[j] += primal * d->dlmd[j];
-      s->gmm[j] += primal * d->dgmm[j];
-      s->q[j] += primal * d->dq[j];
-      s->v[j] += primal * d->dv[j];
+      s->lmd[j] = fma(primal, d->dlmd[j], s->lmd[j]);
+      s->gmm[j] = fma(primal, d->dgmm[j], s->gmm[j]);
+      s->q[j] = fma(primal, d->dq[j], s->q[j]);
+      s->v[j] = fma(primal, d->dv[j], s->v[j]);
     }
     if (i < N) {
       for (int j = 0; j < NV; ++j) {
-        s->a[j] += primal * d->da[j];
-        s->u[j] += primal * d->du[j];
-        s->beta[j] += primal * d->dbeta[j];
+        s->a[j] = fma(primal, d->da[j], s->a[j]);
+        s->u[j] = fma(primal, d->du[j], s->u[j]);
+        s->beta[j] = fma(primal, d->dbeta[j], s->beta[j]);
       }
       stage_t* st = &o->st[i];
       for (int c = 0; c < NC; ++c) {
         if (!st->active[c]) continue;
         for (int j = 0; j < NV; ++j) {
-          st->c[c].slack[j] += primal * st->c[c].dslack[j];
-          st->c[c].dual[j] += dual * st->c[c].ddual[j];
+          st->c[c].slack[j] = fma(primal, st->c[c].dslack[j], st->c[c].slack[j]);
+          st->c[c].dual[j] = fma(dual, st->c[c].ddual[j], st->c[c].dual[j]);
         }
       }
     }

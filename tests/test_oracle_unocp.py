@@ -195,21 +195,20 @@ def test_golden_vectors(oracle):
             s.update_solution(0.0, q0, v0)
             if str(it) in rec["directions"]:
                 for n, ref in rec["directions"][str(it)].items():
-                    assert np.allclose(s.get_direction(n), np.array(ref), rtol=1e-9, atol=1e-12), n
+                    assert np.array_equal(s.get_direction(n), np.array(ref)), n
             st = s.step_sizes()
-            assert np.isclose(st[0], rec["primal"][it], rtol=1e-9) and np.isclose(st[1], rec["dual"][it], rtol=1e-9)
+            assert st[0] == rec["primal"][it] and st[1] == rec["dual"][it]
             s.compute_kkt_residual(0.0, q0, v0)
             kkt.append(s.kkt_error())
-        assert np.allclose(kkt, rec["kkt"], rtol=1e-7, atol=1e-8)
+        assert np.array_equal(kkt, rec["kkt"])
         for n, ref in rec["final"].items():
-            assert np.allclose(s.get_solution(n), np.array(ref), rtol=1e-9, atol=1e-10), n
+            assert np.array_equal(s.get_solution(n), np.array(ref)), n
     for rec in G["rnea"]:
         q, v, a = np.array(rec["q"]), np.array(rec["v"]), np.array(rec["a"])
-        assert np.allclose(O.rnea(q, v, a), rec["tau"], rtol=1e-12, atol=1e-12)
+        assert np.allclose(O.rnea(q, v, a), rec["tau"], rtol=1e-12, atol=1e-12)   # libm sin/cos: not canonical
         dq, dv, da = O.rnea_derivatives(q, v, a)
-        assert np.allclose(dq, rec["dtau_dq"], rtol=1e-12, atol=1e-12)
-        assert np.allclose(dv, rec["dtau_dv"], rtol=1e-12, atol=1e-12)
-        assert np.allclose(da, rec["dtau_da"], rtol=1e-12, atol=1e-12)
+        assert np.array_equal(dq, rec["dtau_dq"]) and np.array_equal(dv, rec["dtau_dv"])
+        assert np.array_equal(da, rec["dtau_da"])
 
 
 def test_filter_line_search_bounds(oracle):
