@@ -37,8 +37,13 @@ BYTES_PER_UNIT = 44e3
 # algorithmic bytes per (instance, stage) of each kernel = its mandatory inputs + outputs, unpadded
 # doubles (DESIGN.md "Kernels"):  linearize: s_i 49 + s_{i+1} 28 + slack/dual 84 in; Q 231 + res 35 + exp 147 out
 KERNEL_ALGO_DOUBLES_PER_STAGE = {
+    # s_i 49 + (q,v,lmd,gmm)_{i+1} 28 + slack/dual 84 in; Q (3 sym 28 + 3 full 49) 231 + res 35 + expansion 147 out
     "linearize": 49 + 28 + 84 + 231 + 35 + 147,
-    "riccati": 231 + 35 + 2 * (105 + 105 + 14) + 147 + 21 + 84 + 49,
+    # Q 231 + res 35 in; K 98 + k 7 + P (28+49+28) + s 14 out; forward: K,k 105 + Fx 14 in, (dq,dv,da) 21 out
+    "riccati": 231 + 35 + 105 + 105 + 14 + 105 + 14 + 21,
+    # P,s 119 + expansion 147 + (dq,dv,da) 21 + (q,v,u) 21 + slack/dual 84 in; (dlmd,dgmm,du,dbeta) 28 out
+    "expand": 119 + 147 + 21 + 21 + 84 + 28,
+    # s 49 + slack/dual 84 + d 49 in; s 49 + slack/dual 84 out
     "update": 2 * (49 + 84) + 49,
 }
 

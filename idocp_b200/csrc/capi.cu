@@ -49,9 +49,9 @@ static int fail(int code, const std::string& msg) {
       return fail(IDOCP_B200_CUDA_ERROR, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
-enum KernelClass { KC_LINEARIZE = 0, KC_RICCATI, KC_UPDATE, KC_KKT, KC_MISC, KC_PARNMPC_COARSE, KC_PARNMPC_CORR,
-                   KC_LINESEARCH, KC_NUM };
-static const char* kKernelClassNames[KC_NUM] = {"linearize", "riccati", "update", "kkt", "misc",
+enum KernelClass { KC_LINEARIZE = 0, KC_RICCATI, KC_EXPAND, KC_UPDATE, KC_KKT, KC_MISC, KC_PARNMPC_COARSE,
+                   KC_PARNMPC_CORR, KC_LINESEARCH, KC_NUM };
+static const char* kKernelClassNames[KC_NUM] = {"linearize", "riccati", "expand", "update", "kkt", "misc",
                                                 "parnmpc_coarse", "parnmpc_correction", "line_search"};
 
 struct idocp_b200_solver {
@@ -77,6 +77,9 @@ struct idocp_b200_solver {
   double prof_ms[KC_NUM] = {0};
   long long prof_calls[KC_NUM] = {0};
   cudaEvent_t cur_e0 = nullptr;
+  // UnParNMPC extras
+  ParNMPCLayout PL;
+
   cudaEvent_t take_event() {
     if (!event_pool.empty()) { cudaEvent_t e = event_pool.back(); event_pool.pop_back(); return e; }
     cudaEvent_t e = nullptr;
@@ -96,9 +99,6 @@ struct idocp_b200_solver {
     }
     prof_recs.clear();
   }
-  // UnParNMPC extras
-  ParNMPCLayout PL;
-
   void begin_kernel(int) {
     ++launches;
     if (profiling) {
@@ -122,6 +122,7 @@ struct idocp_b200_solver {
     *p = static_cast<T*>(q);
     return 0;
   }
+  int stage_offset() const { return kind == IDOCP_B200_SOLVER_UNPARNMPC ? 1 : 0; }
 };
 
 extern "C" const char* idocp_b200_last_error(void) { return g_last_error.c_str(); }
@@ -189,12 +190,19 @@ static int parnmpc_init_backward_correction(idocp_b200_solver*, double) {
   return fail(IDOCP_B200_UNSUPPORTED, "UnParNMPCSolver is not implemented yet");
 }
 
-static int grid_for(long tasks) { return static_cast<int>((tasks + OCTETS_PER_CTA - 1) / OCTETS_PER_CTA); }
+// grid of a per-stage kernel: one warp per (stage, group)
+static int stage_grid(const idocp_b200_solver* h, int nstages) {
+  const long tasks = static_cast<long>(nstages) * h->L.G;
+  return static_cast<int>((tasks + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+}
+// grid of a per-instance kernel: one warp per group
+static int group_grid(const idocp_b200_solver* h) { return (h->L.G + WARPS_PER_CTA - 1) / WARPS_PER_CTA; }
+static const int kLinSmem = OCTETS_PER_CTA * OCT * PAIR_TILE * static_cast<int>(sizeof(double));
+static const int kRicSmem = OCTETS_PER_CTA * RIC_SMEM_PER_OCT * static_cast<int>(sizeof(double));
 
 static int do_init_constraints(idocp_b200_solver* h) {
-  const int off = h->kind == IDOCP_B200_SOLVER_UNPARNMPC ? 1 : 0;
-  IDOCP_LAUNCH(h, KC_MISC, k_init_constraints, grid_for(static_cast<long>(h->N) * h->Bp), CTA_THREADS, 0, h->d_prob,
-               h->L, off);
+  IDOCP_LAUNCH(h, KC_MISC, k_init_constraints, stage_grid(h, h->N), CTA_THREADS, 0, h->d_prob, h->L,
+               h->stage_offset());
   CUDA_OK(cudaGetLastError());
   return IDOCP_B200_OK;
 }
@@ -229,21 +237,18 @@ extern "C" int idocp_b200_create(const idocp_b200_problem* p, int solver_kind, i
     return fail(IDOCP_B200_CUDA_ERROR, "cudaStreamCreate failed");
   }
   fill_dev_problem(*p, h->h_prob);
-  const size_t N = h->N, Bp = h->Bp, slot = Bp * OCT;
+  const size_t N = h->N, Bp = h->Bp, G = Bp / 4;
   const bool par = solver_kind == IDOCP_B200_SOLVER_UNPARNMPC;
   Layout& L = h->L;
   std::memset(&L, 0, sizeof(L));
-  L.B = h->B; L.Bp = h->Bp; L.N = h->N;
+  L.B = h->B; L.Bp = h->Bp; L.G = static_cast<int>(G); L.N = h->N;
   int rc = 0;
   rc |= h->alloc(&h->d_prob, 1);
-  rc |= h->alloc(&L.sol, S_NUM * (N + 1) * slot);
-  rc |= h->alloc(&L.slack, NC * N * slot);
-  rc |= h->alloc(&L.dual, NC * N * slot);
-  rc |= h->alloc(&L.kktQ, static_cast<size_t>(K_NUMBLK) * NV * N * slot);
-  rc |= h->alloc(&L.kktR, R_NUM * N * slot);
-  rc |= h->alloc(&L.expd, E_NUM * N * slot);
-  if (!par) rc |= h->alloc(&L.ric, RC_NUM * N * slot);
-  rc |= h->alloc(&L.dir, D_NUM * (N + 1) * slot);
+  rc |= h->alloc(&L.X, (N + 1) * G * X_NUM * SLOT);
+  rc |= h->alloc(&L.KQ, N * G * KQ_NUM * SLOT);
+  rc |= h->alloc(&L.W, N * G * W_NUM * SLOT);
+  rc |= h->alloc(&L.D, (N + 1) * G * D_NUM * SLOT);
+  rc |= h->alloc(&L.smin, 2 * N * Bp);
   rc |= h->alloc(&L.steps, 2 * Bp);
   rc |= h->alloc(&L.kkt_stage, (N + 1) * Bp);
   rc |= h->alloc(&L.kkt_err, Bp);
@@ -252,9 +257,9 @@ extern "C" int idocp_b200_create(const idocp_b200_problem* p, int solver_kind, i
   rc |= h->alloc(&h->d_v0, Bp * NV);
   {
     const size_t Bz = static_cast<size_t>(h->B);
-    size_t need = Bz * N * NC * NV;                      // get_constraint_data
-    if (need < Bz * (N + 1) * NV) need = Bz * (N + 1) * NV;  // get_solution / get_direction / set_solution
-    if (need < Bz * 2) need = Bz * 2;
+    size_t need = Bz * N * NC * NV;                              // get_constraint_data
+    if (need < Bz * (N + 1) * NV) need = Bz * (N + 1) * NV;      // get_solution / get_direction / set_solution
+    if (need < Bz * (441 + 35)) need = Bz * (441 + 35);          // get_unkkt
     h->stage_doubles = need;
   }
   rc |= h->alloc(&h->d_stage, h->stage_doubles);
@@ -267,12 +272,6 @@ extern "C" int idocp_b200_create(const idocp_b200_problem* p, int solver_kind, i
     idocp_b200_destroy(h);
     return fail(IDOCP_B200_CUDA_ERROR, "problem upload failed");
   }
-#ifndef IDOCP_B200_EMU
-  cudaFuncSetAttribute(k_linearize<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       OCTETS_PER_CTA * OCT * PAIR_TILE * (int)sizeof(double));
-  cudaFuncSetAttribute(k_linearize<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       OCTETS_PER_CTA * OCT * PAIR_TILE * (int)sizeof(double));
-#endif
   const int irc = do_init_constraints(h);  // the reference ctor ends with initConstraints() (unocp_solver.cpp:48)
   if (irc != IDOCP_B200_OK) {
     idocp_b200_destroy(h);
@@ -287,9 +286,9 @@ extern "C" int idocp_b200_destroy(idocp_b200_solver* h) {
   if (!h) return IDOCP_B200_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  for (void* p : h->allocs) cudaFree(p);
   h->resolve_profile();
   for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
+  for (void* p : h->allocs) cudaFree(p);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return IDOCP_B200_OK;
@@ -297,13 +296,13 @@ extern "C" int idocp_b200_destroy(idocp_b200_solver* h) {
 
 static int field_index(const char* name) {
   if (!name) return -1;
-  if (!std::strcmp(name, "lmd")) return S_LMD;
-  if (!std::strcmp(name, "gmm")) return S_GMM;
-  if (!std::strcmp(name, "q")) return S_Q;
-  if (!std::strcmp(name, "v")) return S_V;
-  if (!std::strcmp(name, "a")) return S_A;
-  if (!std::strcmp(name, "u")) return S_U;
-  if (!std::strcmp(name, "beta")) return S_BETA;
+  if (!std::strcmp(name, "lmd")) return X_LMD;
+  if (!std::strcmp(name, "gmm")) return X_GMM;
+  if (!std::strcmp(name, "q")) return X_Q;
+  if (!std::strcmp(name, "v")) return X_V;
+  if (!std::strcmp(name, "a")) return X_A;
+  if (!std::strcmp(name, "u")) return X_U;
+  if (!std::strcmp(name, "beta")) return X_BETA;
   return -1;
 }
 static int dir_index(const char* name) {
@@ -321,7 +320,7 @@ static int dir_index(const char* name) {
 extern "C" int idocp_b200_set_solution(idocp_b200_solver* h, const char* name, const double* value, int broadcast) {
   if (!h || !value) return fail(IDOCP_B200_INVALID_ARGUMENT, "set_solution: null pointer");
   const int f = field_index(name);
-  if (f != S_Q && f != S_V && f != S_A && f != S_U)
+  if (f != X_Q && f != X_V && f != X_A && f != X_U)
     return fail(IDOCP_B200_INVALID_ARGUMENT, "invalid arugment: name must be q, v, a, or u!");
   CUDA_OK(cudaSetDevice(h->device));
   const size_t n = broadcast ? NV : static_cast<size_t>(h->B) * NV;
@@ -353,12 +352,10 @@ static int upload_x0(idocp_b200_solver* h, const double* q, const double* v) {
 
 static int unocp_update(idocp_b200_solver* h, const double* d_q, const double* d_v, int line_search) {
   if (line_search) return fail(IDOCP_B200_UNSUPPORTED, "line search is not implemented yet");
-  const int lin_smem = OCTETS_PER_CTA * OCT * PAIR_TILE * static_cast<int>(sizeof(double));
-  const int ric_smem = OCTETS_PER_CTA * RIC_SMEM_PER_OCT * static_cast<int>(sizeof(double));
-  IDOCP_LAUNCH(h, KC_LINEARIZE, k_linearize<false>, grid_for(static_cast<long>(h->N) * h->Bp), CTA_THREADS, lin_smem,
-               h->d_prob, h->L);
-  IDOCP_LAUNCH(h, KC_RICCATI, k_riccati, grid_for(h->Bp), CTA_THREADS, ric_smem, h->d_prob, h->L, d_q, d_v);
-  IDOCP_LAUNCH(h, KC_UPDATE, k_update, grid_for(static_cast<long>(h->N + 1) * h->Bp), CTA_THREADS, 0, h->d_prob, h->L,
+  IDOCP_LAUNCH(h, KC_LINEARIZE, k_linearize<false>, stage_grid(h, h->N), CTA_THREADS, kLinSmem, h->d_prob, h->L);
+  IDOCP_LAUNCH(h, KC_RICCATI, k_riccati, group_grid(h), CTA_THREADS, kRicSmem, h->d_prob, h->L, d_q, d_v);
+  IDOCP_LAUNCH(h, KC_EXPAND, k_expand, stage_grid(h, h->N + 1), CTA_THREADS, 0, h->d_prob, h->L, 0);
+  IDOCP_LAUNCH(h, KC_UPDATE, k_update, stage_grid(h, h->N + 1), CTA_THREADS, 0, h->d_prob, h->L, 0,
                static_cast<const double*>(nullptr));
   CUDA_OK(cudaGetLastError());
   return IDOCP_B200_OK;
@@ -388,9 +385,7 @@ extern "C" int idocp_b200_compute_kkt_residual_device(idocp_b200_solver* h, doub
   (void)t;
   CUDA_OK(cudaSetDevice(h->device));
   if (h->kind == IDOCP_B200_SOLVER_UNPARNMPC) return parnmpc_kkt_residual(h, t, d_q, d_v);
-  const int lin_smem = OCTETS_PER_CTA * OCT * PAIR_TILE * static_cast<int>(sizeof(double));
-  IDOCP_LAUNCH(h, KC_KKT, k_linearize<true>, grid_for(static_cast<long>(h->N + 1) * h->Bp), CTA_THREADS, lin_smem,
-               h->d_prob, h->L);
+  IDOCP_LAUNCH(h, KC_KKT, k_linearize<true>, stage_grid(h, h->N + 1), CTA_THREADS, kLinSmem, h->d_prob, h->L);
   IDOCP_LAUNCH(h, KC_KKT, k_kkt_sum, (h->Bp + 127) / 128, 128, 0, h->L, h->N + 1);
   CUDA_OK(cudaGetLastError());
   return IDOCP_B200_OK;
@@ -413,8 +408,8 @@ extern "C" int idocp_b200_kkt_error(idocp_b200_solver* h, double* out) {
   return IDOCP_B200_OK;
 }
 
-// gather [slot][stage][Bp][8] -> out[b][stage][7]
-__global__ void k_gather(const double* __restrict__ src, int slot, int nstage_alloc, int nstage, int B, int Bp,
+// gather one slot of `nstage` stages: out[b][stage][7]
+__global__ void k_gather(const double* __restrict__ src, int ns, int slot, int nstage, int B, int G,
                          double* __restrict__ out) {
   const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long total = static_cast<long>(B) * nstage * NV;
@@ -423,19 +418,22 @@ __global__ void k_gather(const double* __restrict__ src, int slot, int nstage_al
   const long t = idx / NV;
   const int i = static_cast<int>(t % nstage);
   const int b = static_cast<int>(t / nstage);
-  out[idx] = src[slot_index(slot, nstage_alloc, i, Bp, b, j)];
+  out[idx] = src[elem_index(ns, G, i, b, slot, j)];
 }
 
-static int gather_to_host(idocp_b200_solver* h, const double* src, int slot, int nstage_alloc, int nstage,
-                          double* out) {
+static int gather_to_host(idocp_b200_solver* h, const double* src, int ns, int slot, int nstage, double* out) {
   const long total = static_cast<long>(h->B) * nstage * NV;
   if (static_cast<size_t>(total) > h->stage_doubles) return fail(IDOCP_B200_INVALID_ARGUMENT, "staging buffer too small");
-  IDOCP_LAUNCH(h, KC_MISC, k_gather, static_cast<int>((total + 255) / 256), 256, 0, src, slot, nstage_alloc, nstage,
-               h->B, h->Bp, h->d_stage);
+  IDOCP_LAUNCH(h, KC_MISC, k_gather, static_cast<int>((total + 255) / 256), 256, 0, src, ns, slot, nstage, h->B,
+               h->L.G, h->d_stage);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaMemcpyAsync(out, h->d_stage, total * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));
   return IDOCP_B200_OK;
+}
+
+static bool full_horizon(const idocp_b200_solver* h, int f) {
+  return (f == X_LMD || f == X_GMM || f == X_Q || f == X_V) && h->kind == IDOCP_B200_SOLVER_UNOCP;
 }
 
 extern "C" int idocp_b200_get_solution(idocp_b200_solver* h, const char* name, double* out) {
@@ -443,31 +441,29 @@ extern "C" int idocp_b200_get_solution(idocp_b200_solver* h, const char* name, d
   const int f = field_index(name);
   if (f < 0) return fail(IDOCP_B200_INVALID_ARGUMENT, "get_solution: unknown field");
   CUDA_OK(cudaSetDevice(h->device));
-  const bool full = (f == S_LMD || f == S_GMM || f == S_Q || f == S_V) && h->kind == IDOCP_B200_SOLVER_UNOCP;
-  return gather_to_host(h, h->L.sol, f, h->N + 1, full ? h->N + 1 : h->N, out);
+  return gather_to_host(h, h->L.X, X_NUM, f, full_horizon(h, f) ? h->N + 1 : h->N, out);
 }
 
 // one stage of one field: out[b][7]
-__global__ void k_gather_stage(const double* __restrict__ src, int slot, int nstage_alloc, int stage, int B, int Bp,
+__global__ void k_gather_stage(const double* __restrict__ src, int ns, int slot, int stage, int B, int G,
                                double* __restrict__ out) {
   const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long>(B) * OCT) return;
   const int j = static_cast<int>(idx & 7);
   const int b = static_cast<int>(idx >> 3);
-  if (j < NV) out[static_cast<size_t>(b) * NV + j] = src[slot_index(slot, nstage_alloc, stage, Bp, b, j)];
+  if (j < NV) out[static_cast<size_t>(b) * NV + j] = src[elem_index(ns, G, stage, b, slot, j)];
 }
 
 extern "C" int idocp_b200_get_stage_solution(idocp_b200_solver* h, const char* name, int stage, double* out) {
   if (!h || !out) return fail(IDOCP_B200_INVALID_ARGUMENT, "get_stage_solution: null pointer");
   const int f = field_index(name);
   if (f < 0) return fail(IDOCP_B200_INVALID_ARGUMENT, "get_stage_solution: unknown field");
-  const bool full = (f == S_LMD || f == S_GMM || f == S_Q || f == S_V) && h->kind == IDOCP_B200_SOLVER_UNOCP;
-  if (stage < 0 || stage >= (full ? h->N + 1 : h->N))
+  if (stage < 0 || stage >= (full_horizon(h, f) ? h->N + 1 : h->N))
     return fail(IDOCP_B200_INVALID_ARGUMENT, "get_stage_solution: stage out of range");
   CUDA_OK(cudaSetDevice(h->device));
   const long total = static_cast<long>(h->B) * OCT;
-  IDOCP_LAUNCH(h, KC_MISC, k_gather_stage, static_cast<int>((total + 255) / 256), 256, 0, h->L.sol, f, h->N + 1, stage,
-               h->B, h->Bp, h->d_stage);
+  IDOCP_LAUNCH(h, KC_MISC, k_gather_stage, static_cast<int>((total + 255) / 256), 256, 0, h->L.X, X_NUM, f, stage,
+               h->B, h->L.G, h->d_stage);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaMemcpyAsync(out, h->d_stage, static_cast<size_t>(h->B) * NV * sizeof(double), cudaMemcpyDeviceToHost,
                           h->stream));
@@ -481,11 +477,12 @@ extern "C" int idocp_b200_get_direction(idocp_b200_solver* h, const char* name, 
   if (f < 0) return fail(IDOCP_B200_INVALID_ARGUMENT, "get_direction: unknown field");
   CUDA_OK(cudaSetDevice(h->device));
   const bool full = (f == D_LMD || f == D_GMM || f == D_Q || f == D_V) && h->kind == IDOCP_B200_SOLVER_UNOCP;
-  return gather_to_host(h, h->L.dir, f, h->N + 1, full ? h->N + 1 : h->N, out);
+  return gather_to_host(h, h->L.D, D_NUM, f, full ? h->N + 1 : h->N, out);
 }
 
 // out[b][N][6][7]
-__global__ void k_gather_constraints(const double* __restrict__ src, int N, int B, int Bp, double* __restrict__ out) {
+__global__ void k_gather_constraints(const double* __restrict__ X, int first_slot, int N, int B, int G,
+                                     double* __restrict__ out) {
   const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long total = static_cast<long>(B) * N * NC * NV;
   if (idx >= total) return;
@@ -495,19 +492,19 @@ __global__ void k_gather_constraints(const double* __restrict__ src, int N, int 
   t /= NC;
   const int i = static_cast<int>(t % N);
   const int b = static_cast<int>(t / N);
-  out[idx] = src[slot_index(c, N, i, Bp, b, j)];
+  out[idx] = X[elem_index(X_NUM, G, i, b, first_slot + c, j)];
 }
 
 extern "C" int idocp_b200_get_constraint_data(idocp_b200_solver* h, const char* name, double* out) {
   if (!h || !out || !name) return fail(IDOCP_B200_INVALID_ARGUMENT, "get_constraint_data: null pointer");
-  const double* src = nullptr;
-  if (!std::strcmp(name, "slack")) src = h->L.slack;
-  else if (!std::strcmp(name, "dual")) src = h->L.dual;
+  int first = -1;
+  if (!std::strcmp(name, "slack")) first = X_SLACK;
+  else if (!std::strcmp(name, "dual")) first = X_DUAL;
   else return fail(IDOCP_B200_INVALID_ARGUMENT, "get_constraint_data: name must be slack or dual");
   CUDA_OK(cudaSetDevice(h->device));
   const long total = static_cast<long>(h->B) * h->N * NC * NV;
-  IDOCP_LAUNCH(h, KC_MISC, k_gather_constraints, static_cast<int>((total + 255) / 256), 256, 0, src, h->N, h->B, h->Bp,
-               h->d_stage);
+  IDOCP_LAUNCH(h, KC_MISC, k_gather_constraints, static_cast<int>((total + 255) / 256), 256, 0, h->L.X, first, h->N,
+               h->B, h->L.G, h->d_stage);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaMemcpyAsync(out, h->d_stage, total * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));
@@ -531,37 +528,31 @@ __global__ void k_gather_unkkt(Layout L, int stage, double* __restrict__ Q, doub
   const int D = 3 * NV;
   for (int e = threadIdx.x; e < D * D; e += blockDim.x) Q[static_cast<size_t>(b) * D * D + e] = 0.0;
   __syncthreads();
-  // blocks: (row-block, col-block) of the [a,q,v] ordering
-  const int blk[K_NUMBLK][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
-  for (int e = threadIdx.x; e < K_NUMBLK * NV * NV; e += blockDim.x) {
+  // (row-block, col-block) of the [a,q,v] ordering for the blocks AA, AQ, AV, QQ, QV, VV
+  const int blk[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
+  for (int e = threadIdx.x; e < 6 * NV * NV; e += blockDim.x) {
     const int k = e / (NV * NV);
     const int r = (e / NV) % NV;
     const int c = e % NV;
-    const double val = L.kktQ[slot_index(k * NV + r, L.N, stage, L.Bp, b, c)];
+    const double val = L.KQ[elem_index(KQ_NUM, L.G, stage, b, k * NV + r, c)];
     Q[static_cast<size_t>(b) * D * D + static_cast<size_t>(blk[k][1] * NV + c) * D + blk[k][0] * NV + r] = val;
   }
-  for (int e = threadIdx.x; e < R_NUM * NV; e += blockDim.x)
-    res[static_cast<size_t>(b) * R_NUM * NV + e] = L.kktR[slot_index(e / NV, L.N, stage, L.Bp, b, e % NV)];
+  for (int e = threadIdx.x; e < 5 * NV; e += blockDim.x)
+    res[static_cast<size_t>(b) * 5 * NV + e] = L.KQ[elem_index(KQ_NUM, L.G, stage, b, KQ_FQ + e / NV, e % NV)];
 }
 
 extern "C" int idocp_b200_get_unkkt(idocp_b200_solver* h, int stage, double* Q, double* res) {
   if (!h || !Q || !res) return fail(IDOCP_B200_INVALID_ARGUMENT, "get_unkkt: null pointer");
   if (stage < 0 || stage >= h->N) return fail(IDOCP_B200_INVALID_ARGUMENT, "get_unkkt: stage out of range");
   CUDA_OK(cudaSetDevice(h->device));
-  double* dQ = nullptr;
-  double* dres = nullptr;
-  CUDA_OK(cudaMalloc(&dQ, static_cast<size_t>(h->B) * 441 * sizeof(double)));
-  CUDA_OK(cudaMalloc(&dres, static_cast<size_t>(h->B) * 35 * sizeof(double)));
+  double* dQ = h->d_stage;
+  double* dres = h->d_stage + static_cast<size_t>(h->B) * 441;
   IDOCP_LAUNCH(h, KC_MISC, k_gather_unkkt, h->B, 128, 0, h->L, stage, dQ, dres);
-  cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess)
-    e = cudaMemcpyAsync(Q, dQ, static_cast<size_t>(h->B) * 441 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
-  if (e == cudaSuccess)
-    e = cudaMemcpyAsync(res, dres, static_cast<size_t>(h->B) * 35 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  cudaFree(dQ);
-  cudaFree(dres);
-  if (e != cudaSuccess) return fail(IDOCP_B200_CUDA_ERROR, cudaGetErrorString(e));
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(Q, dQ, static_cast<size_t>(h->B) * 441 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaMemcpyAsync(res, dres, static_cast<size_t>(h->B) * 35 * sizeof(double), cudaMemcpyDeviceToHost,
+                          h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
   return IDOCP_B200_OK;
 }
 
@@ -581,9 +572,9 @@ __global__ void k_is_feasible(const DevProblem* __restrict__ Pp, Layout L, int s
   for (int i = 0; i < L.N; ++i)
     for (int j = 0; j < NV; ++j) {
       const LaneLimits lim = load_limits(P, j);
-      const double q = L.sol[slot_index(S_Q, L.N + 1, i, L.Bp, b, j)];
-      const double v = L.sol[slot_index(S_V, L.N + 1, i, L.Bp, b, j)];
-      const double u = L.sol[slot_index(S_U, L.N + 1, i, L.Bp, b, j)];
+      const double q = L.X[elem_index(X_NUM, L.G, i, b, X_Q, j)];
+      const double v = L.X[elem_index(X_NUM, L.G, i, b, X_V, j)];
+      const double u = L.X[elem_index(X_NUM, L.G, i, b, X_U, j)];
       for (int c = 0; c < NC; ++c)
         if (comp_active(c, i + stage_offset) && con_margin(c, lim, q, v, u) < 0) ok = 0;
     }
@@ -594,8 +585,7 @@ extern "C" int idocp_b200_is_feasible(idocp_b200_solver* h, int* out) {
   if (!h || !out) return fail(IDOCP_B200_INVALID_ARGUMENT, "is_feasible: null pointer");
   CUDA_OK(cudaSetDevice(h->device));
   int* d = reinterpret_cast<int*>(h->d_stage);
-  const int off = h->kind == IDOCP_B200_SOLVER_UNPARNMPC ? 1 : 0;
-  IDOCP_LAUNCH(h, KC_MISC, k_is_feasible, (h->B + 127) / 128, 128, 0, h->d_prob, h->L, off, d);
+  IDOCP_LAUNCH(h, KC_MISC, k_is_feasible, (h->B + 127) / 128, 128, 0, h->d_prob, h->L, h->stage_offset(), d);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaMemcpyAsync(out, d, static_cast<size_t>(h->B) * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));

@@ -34,6 +34,7 @@ struct JointDyn {
 __device__ __forceinline__ void chain_world_sweep(int lane, double q, double qd, double qdd,
                                                   const double* __restrict__ mdl, double gravity,
                                                   JointDyn& J) {
+  const ScanFlags sf = scan_flags(lane);
   double sn, cs;
   canon_sincos(q, &sn, &cs);
   // local transform: placement * Rz(q)
@@ -71,13 +72,13 @@ __device__ __forceinline__ void chain_world_sweep(int lane, double q, double qd,
   J.Sl = cross(p, z);
   J.Sw = z;
   // velocities
-  const V3 vw = oct_prefix_sum(qd * J.Sw, lane);
-  const V3 vl = oct_prefix_sum(qd * J.Sl, lane);
+  const V3 vw = oct_prefix_sum(qd * J.Sw, sf);
+  const V3 vl = oct_prefix_sum(qd * J.Sl, sf);
   J.dSl = cross(vw, J.Sl) + cross(vl, J.Sw);
   J.dSw = cross(vw, J.Sw);
   // accelerations (gravity enters as the base acceleration (0,0,+g))
-  const V3 aw = oct_prefix_sum(fmav(qd, J.dSw, qdd * J.Sw), lane);
-  V3 al = oct_prefix_sum(fmav(qd, J.dSl, qdd * J.Sl), lane);
+  const V3 aw = oct_prefix_sum(fmav(qd, J.dSw, qdd * J.Sw), sf);
+  V3 al = oct_prefix_sum(fmav(qd, J.dSl, qdd * J.Sl), sf);
   al.z += gravity;
   J.Bl = ((cross(aw, J.Sl) + cross(al, J.Sw)) + cross(vw, J.dSl)) + cross(vl, J.dSw);
   J.Bw = cross(aw, J.Sw) + cross(vw, J.dSw);
@@ -126,16 +127,16 @@ __device__ __forceinline__ void chain_world_sweep(int lane, double q, double qd,
     Sym.zz = 2.0 * (c2.z + (mcv - vl.z * mc.z));
   }
   // composite (suffix) sums
-  const double mC = oct_suffix_sum(m, lane);
-  mc = oct_suffix_sum(mc, lane);
-  Ib.xx = oct_suffix_sum(Ib.xx, lane); Ib.xy = oct_suffix_sum(Ib.xy, lane); Ib.xz = oct_suffix_sum(Ib.xz, lane);
-  Ib.yy = oct_suffix_sum(Ib.yy, lane); Ib.yz = oct_suffix_sum(Ib.yz, lane); Ib.zz = oct_suffix_sum(Ib.zz, lane);
-  hl = oct_suffix_sum(hl, lane);
-  ha = oct_suffix_sum(ha, lane);
-  Sym.xx = oct_suffix_sum(Sym.xx, lane); Sym.xy = oct_suffix_sum(Sym.xy, lane); Sym.xz = oct_suffix_sum(Sym.xz, lane);
-  Sym.yy = oct_suffix_sum(Sym.yy, lane); Sym.yz = oct_suffix_sum(Sym.yz, lane); Sym.zz = oct_suffix_sum(Sym.zz, lane);
-  fl = oct_suffix_sum(fl, lane);
-  fa = oct_suffix_sum(fa, lane);
+  const double mC = oct_suffix_sum(m, sf);
+  mc = oct_suffix_sum(mc, sf);
+  Ib.xx = oct_suffix_sum(Ib.xx, sf); Ib.xy = oct_suffix_sum(Ib.xy, sf); Ib.xz = oct_suffix_sum(Ib.xz, sf);
+  Ib.yy = oct_suffix_sum(Ib.yy, sf); Ib.yz = oct_suffix_sum(Ib.yz, sf); Ib.zz = oct_suffix_sum(Ib.zz, sf);
+  hl = oct_suffix_sum(hl, sf);
+  ha = oct_suffix_sum(ha, sf);
+  Sym.xx = oct_suffix_sum(Sym.xx, sf); Sym.xy = oct_suffix_sum(Sym.xy, sf); Sym.xz = oct_suffix_sum(Sym.xz, sf);
+  Sym.yy = oct_suffix_sum(Sym.yy, sf); Sym.yz = oct_suffix_sum(Sym.yz, sf); Sym.zz = oct_suffix_sum(Sym.zz, sf);
+  fl = oct_suffix_sum(fl, sf);
+  fa = oct_suffix_sum(fa, sf);
   // per-joint vectors
   J.tau = dot(J.Sl, fl) + dot(J.Sw, fa);
   J.Ul = fmav(mC, J.Sl, cross(J.Sw, mc));

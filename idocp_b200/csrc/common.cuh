@@ -4,11 +4,9 @@
 
 #ifdef IDOCP_B200_EMU
 #define IDOCP_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::g_block->smem.data())
-#define IDOCP_SINCOS(x, s, c) sincos_emu((x), (s), (c))
 #else
 #define IDOCP_DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char name##_raw[]; \
   type* name = reinterpret_cast<type*>(name##_raw)
-#define IDOCP_SINCOS(x, s, c) sincos((x), (s), (c))
 #endif
 
 namespace idocp_b200 {
@@ -29,41 +27,53 @@ struct DevProblem {
   double model[8 * MODEL_STRIDE];
 };
 
-// solution fields (one slot each, per stage)
-enum SolField { S_LMD = 0, S_GMM, S_Q, S_V, S_A, S_U, S_BETA, S_NUM };
-// condensed KKT blocks written by linearize: 7 slots (rows) each, lane = column
-enum KktBlock { K_AA = 0, K_AQ, K_AV, K_QQ, K_QV, K_VV, K_NUMBLK };
-// condensed residual slots
-enum KktRes { R_FQ = 0, R_FV, R_LA, R_LQ, R_LV, R_NUM };
-// expansion data slots written by linearize for the direction expansion:
-//  ID, lu (after constraint condensing), Quu diag, rows of dID/dq (7), rows of dID/dv (7), col of M (7)
-enum ExpSlot { E_ID = 0, E_LU, E_QUU, E_DQ = 3, E_DV = 10, E_M = 17, E_NUM = 24 };
-// Riccati data kept for the forward pass: rows of Kq (7), rows of Kv (7), k, cols of Pqq, Pqv, Pvq, Pvv, sq, sv
-enum RicSlot { RC_KQ = 0, RC_KV = 7, RC_K = 14, RC_PQQ = 15, RC_PQV = 22, RC_PVQ = 29, RC_PVV = 36, RC_SQ = 43, RC_SV = 44, RC_NUM = 45 };
-// direction slots
-enum DirField { D_LMD = 0, D_GMM, D_Q, D_V, D_A, D_U, D_BETA, D_NUM };
+// ---------------------------------------------------------------------------------------------
+// HBM layout.  A SLOT is one 64-byte vector (8 doubles: 7 joints + pad) of one instance.  Four
+// consecutive instances form a GROUP (= the 4 octets of one warp); every array is
+//     [stage][group][slot][4 instances][8 lanes]
+// so that (i) one warp-wide load/store of a slot is 256 contiguous, aligned bytes, (ii) all slots
+// of one (stage, group) record are contiguous (a few KB: DRAM-page friendly), and (iii) inside a
+// kernel a slot is addressed as  record_base + slot * 32  with a compile-time constant offset.
+// ---------------------------------------------------------------------------------------------
+constexpr int SLOT = 32;  // doubles per (slot, group)
 
-// All arrays are [slot][stage][instance(padded to 4)][8] doubles.
+// stage state X: solution + interior-point state                      [N+1 stages]
+enum XSlot { X_LMD = 0, X_GMM, X_Q, X_V, X_A, X_U, X_BETA, X_SLACK = 7, X_DUAL = 13, X_NUM = 19 };
+// condensed KKT system KQ written by k_linearize: six 7x7 blocks (slot = row, lane = column)
+// and the residual [Fq,Fv,la,lq,lv]                                   [N stages]
+enum KQSlot { KQ_AA = 0, KQ_AQ = 7, KQ_AV = 14, KQ_QQ = 21, KQ_QV = 28, KQ_VV = 35,
+              KQ_FQ = 42, KQ_FV, KQ_LA, KQ_LQ, KQ_LV, KQ_NUM = 47 };
+// factor data W: Riccati gains (rows of Kq, Kv; k), Riccati matrices (columns of Pqq,Pqv,Pvq,Pvv;
+// sq,sv) and the expansion data of the condensed inverse dynamics (ID, lu, Quu diag, rows of
+// dID/dq and dID/dv, column of M)                                    [N stages]
+enum WSlot { W_KQ = 0, W_KV = 7, W_K = 14, W_PQQ = 15, W_PQV = 22, W_PVQ = 29, W_PVV = 36, W_SQ = 43, W_SV = 44,
+             W_ID = 45, W_LU = 46, W_QUU = 47, W_DQ = 48, W_DV = 55, W_M = 62, W_NUM = 69 };
+// Newton direction D                                                  [N+1 stages]
+enum DSlot { D_LMD = 0, D_GMM, D_Q, D_V, D_A, D_U, D_BETA, D_NUM = 7 };
+
 struct Layout {
   int B;     // instances
-  int Bp;    // padded to a multiple of 4 (one warp = 4 octets)
-  int N;     // stages with controls; solution has N+1 stages
-  double* sol;    // [S_NUM][N+1]
-  double* slack;  // [NC][N]
-  double* dual;   // [NC][N]
-  double* kktQ;   // [K_NUMBLK*7][N]
-  double* kktR;   // [R_NUM][N]
-  double* expd;   // [E_NUM][N]
-  double* ric;    // [RC_NUM][N]
-  double* dir;    // [D_NUM][N+1]
-  double* steps;  // [2][Bp] primal, dual
+  int Bp;    // padded to a multiple of 4
+  int G;     // groups = Bp / 4
+  int N;     // stages with controls; X and D have N+1 stages
+  double* X;
+  double* KQ;
+  double* W;
+  double* D;
+  double* smin;       // [2][N][Bp] per-stage fraction-to-boundary minima (primal, dual)
+  double* steps;      // [2][Bp] primal, dual step sizes of the last iteration
   double* kkt_stage;  // [N+1][Bp] squared KKT norms per stage
   double* kkt_err;    // [Bp]
   int* status;        // [Bp]
 };
 
-__device__ __forceinline__ size_t slot_index(int slot, int nstage, int stage, int Bp, int b, int lane) {
-  return ((static_cast<size_t>(slot) * nstage + stage) * Bp + b) * OCT + lane;
+// element index of (stage, instance b, slot, joint j) in an array with `ns` slots per record
+__host__ __device__ __forceinline__ size_t elem_index(int ns, int G, int stage, int b, int slot, int j) {
+  return ((static_cast<size_t>(stage) * G + (b >> 2)) * ns + slot) * SLOT + (b & 3) * OCT + j;
+}
+// this thread's pointer into the record of (stage, group g): add slot * SLOT to address a slot
+__device__ __forceinline__ double* rec_ptr(double* base, int ns, int G, int stage, int g) {
+  return base + (static_cast<size_t>(stage) * G + g) * (static_cast<size_t>(ns) * SLOT) + (threadIdx.x & 31);
 }
 
 // constraint activity by time stage (reference constraints/constraints_data.hpp:18-43)

@@ -84,29 +84,38 @@ __device__ __forceinline__ V3 oct_down(V3 a, int d) {
   return V3{oct_down(a.x, d), oct_down(a.y, d), oct_down(a.z, d)};
 }
 
-// inclusive prefix sum over the octet (lane order 0..7), Hillis-Steele tree order
-__device__ __forceinline__ double oct_prefix_sum(double x, int lane) {
-#pragma unroll
-  for (int d = 1; d < OCT; d <<= 1) {
-    const double y = oct_up(x, d);
-    if (lane >= d) x += y;
-  }
+// Hillis-Steele inclusive scans over the octet.  The "add only where the source lane exists"
+// predicate is applied as x = fma(y, flag, x) with flag in {0.0, 1.0}: fma(y, 1, x) == x + y and
+// fma(y, 0, x) == x exactly, i.e. bit-identical to a predicated add, in one FP64 instruction.
+struct ScanFlags {
+  double p1, p2, p4;  // prefix: lane >= d
+  double s1, s2, s4;  // suffix: lane + d < 8
+};
+__device__ __forceinline__ ScanFlags scan_flags(int lane) {
+  ScanFlags f;
+  f.p1 = lane >= 1 ? 1.0 : 0.0; f.p2 = lane >= 2 ? 1.0 : 0.0; f.p4 = lane >= 4 ? 1.0 : 0.0;
+  f.s1 = lane + 1 < OCT ? 1.0 : 0.0; f.s2 = lane + 2 < OCT ? 1.0 : 0.0; f.s4 = lane + 4 < OCT ? 1.0 : 0.0;
+  return f;
+}
+// inclusive prefix sum (lane order 0..7)
+__device__ __forceinline__ double oct_prefix_sum(double x, const ScanFlags& f) {
+  x = fma(oct_up(x, 1), f.p1, x);
+  x = fma(oct_up(x, 2), f.p2, x);
+  x = fma(oct_up(x, 4), f.p4, x);
   return x;
 }
-__device__ __forceinline__ V3 oct_prefix_sum(V3 a, int lane) {
-  return V3{oct_prefix_sum(a.x, lane), oct_prefix_sum(a.y, lane), oct_prefix_sum(a.z, lane)};
+__device__ __forceinline__ V3 oct_prefix_sum(V3 a, const ScanFlags& f) {
+  return V3{oct_prefix_sum(a.x, f), oct_prefix_sum(a.y, f), oct_prefix_sum(a.z, f)};
 }
 // inclusive suffix sum: x_l <- sum_{k >= l} x_k   (lane 7 must hold 0)
-__device__ __forceinline__ double oct_suffix_sum(double x, int lane) {
-#pragma unroll
-  for (int d = 1; d < OCT; d <<= 1) {
-    const double y = oct_down(x, d);
-    if (lane + d < OCT) x += y;
-  }
+__device__ __forceinline__ double oct_suffix_sum(double x, const ScanFlags& f) {
+  x = fma(oct_down(x, 1), f.s1, x);
+  x = fma(oct_down(x, 2), f.s2, x);
+  x = fma(oct_down(x, 4), f.s4, x);
   return x;
 }
-__device__ __forceinline__ V3 oct_suffix_sum(V3 a, int lane) {
-  return V3{oct_suffix_sum(a.x, lane), oct_suffix_sum(a.y, lane), oct_suffix_sum(a.z, lane)};
+__device__ __forceinline__ V3 oct_suffix_sum(V3 a, const ScanFlags& f) {
+  return V3{oct_suffix_sum(a.x, f), oct_suffix_sum(a.y, f), oct_suffix_sum(a.z, f)};
 }
 __device__ __forceinline__ double oct_min(double x) {
 #pragma unroll

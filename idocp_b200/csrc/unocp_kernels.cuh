@@ -1,25 +1,29 @@
 // unocp_kernels.cuh -- the batched Newton step of idocp's UnOCPSolver (fixed base, no contacts).
 //
 //   k_linearize   <-> SplitUnOCP::linearizeOCP / computeKKTResidual + squaredNormKKTResidual
-//                     (reference include/idocp/unocp/split_unocp.hxx:69-99,141-174), one octet per
-//                     (instance, stage)
-//   k_riccati     <-> UnRiccatiRecursion backward/forward (src/unocp/unriccati_recursion.cpp:39-65,
-//                     unocp/split_unriccati_factorizer.hxx:30-68, backward_unriccati_recursion_
-//                     factorizer.hxx:29-89) + computeCondensedDirection + fraction-to-boundary
-//                     (unocp_solver.cpp:96-115), one octet per instance, serial over the horizon
-//   k_update      <-> updatePrimal / updateDual (unocp_solver.cpp:121-133)
+//                     (reference include/idocp/unocp/split_unocp.hxx:69-99,141-174); one octet per
+//                     (instance, stage), fully parallel
+//   k_riccati     <-> UnRiccatiRecursion backward + forward recursion (src/unocp/unriccati_
+//                     recursion.cpp:39-65, unocp/split_unriccati_factorizer.hxx:30-57,
+//                     backward_unriccati_recursion_factorizer.hxx:29-89); one octet per instance,
+//                     serial over the horizon
+//   k_expand      <-> computeCostateDirection + SplitUnOCP::computeCondensedDirection +
+//                     max{Primal,Dual}StepSize (unocp_solver.cpp:103-113); one octet per
+//                     (instance, stage), fully parallel
+//   k_update      <-> min over stages + updatePrimal / updateDual (unocp_solver.cpp:114-133)
 //   k_kkt_sum     <-> UnOCPSolver::KKTError (unocp_solver.cpp:190-202)
 //   k_init_constraints <-> UnOCPSolver::initConstraints (unocp_solver.cpp:59-70)
 //
 // Lane l < 7 of an octet owns joint l (all cost / constraint / state-equation algebra is lane
-// local) and column l of every 7x7 block.
+// local) and column l of every 7x7 block.  One warp = one GROUP of 4 instances (common.cuh).
 #pragma once
 #include "chain_dynamics.cuh"
 
 namespace idocp_b200 {
 
-constexpr int OCTETS_PER_CTA = 16;  // 128 threads
-constexpr int CTA_THREADS = OCTETS_PER_CTA * OCT;
+constexpr int WARPS_PER_CTA = 4;
+constexpr int OCTETS_PER_CTA = 4 * WARPS_PER_CTA;  // 16 octets, 128 threads
+constexpr int CTA_THREADS = 32 * WARPS_PER_CTA;
 
 // ---------------------------------------------------------------------------------------------
 // constraints: primal-dual interior point rows of the six joint-limit components.
@@ -65,6 +69,17 @@ __device__ __forceinline__ LaneLimits load_limits(const DevProblem& P, int lane)
   return LaneLimits{P.q_min[lane], P.q_max[lane], P.v_max[lane], P.u_max[lane]};
 }
 
+// warp-task decomposition of the per-stage kernels: task = (stage, group)
+struct StageTask {
+  int stage, g;
+};
+__device__ __forceinline__ StageTask stage_task(const Layout& L, int nstages) {
+  long wt = static_cast<long>(blockIdx.x) * WARPS_PER_CTA + (threadIdx.x >> 5);
+  const long ntask = static_cast<long>(nstages) * L.G;
+  if (wt >= ntask) wt = ntask - 1;  // tail warps redo the last task: identical, idempotent stores
+  return StageTask{static_cast<int>(wt / L.G), static_cast<int>(wt % L.G)};
+}
+
 // ---------------------------------------------------------------------------------------------
 // k_init_constraints: slack = margin (pushed above the barrier), dual = barrier / slack
 // (pdipm::SetSlackAndDualPositive, pdipm.hxx:13-23)
@@ -73,31 +88,25 @@ __global__ void __launch_bounds__(CTA_THREADS) k_init_constraints(const DevProbl
                                                                   int stage_offset) {
   const DevProblem& P = *Pp;
   const int lane = lane_in_octet();
-  const long task = static_cast<long>(blockIdx.x) * OCTETS_PER_CTA + (threadIdx.x >> 3);
-  const long ntask = static_cast<long>(L.N) * L.Bp;
-  if (task >= ntask) return;
-  const int i = static_cast<int>(task / L.Bp);
-  const int b = static_cast<int>(task % L.Bp);
-  const int ns = L.N + 1;
+  const StageTask t = stage_task(L, L.N);
+  double* X = rec_ptr(L.X, X_NUM, L.G, t.stage, t.g);
   const LaneLimits lim = load_limits(P, lane);
-  const double q = L.sol[slot_index(S_Q, ns, i, L.Bp, b, lane)];
-  const double v = L.sol[slot_index(S_V, ns, i, L.Bp, b, lane)];
-  const double u = L.sol[slot_index(S_U, ns, i, L.Bp, b, lane)];
+  const double q = X[X_Q * SLOT], v = X[X_V * SLOT], u = X[X_U * SLOT];
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     double sl = 0.0, du = 0.0;
-    if (comp_active(c, i + stage_offset) && lane < NV) {
+    if (comp_active(c, t.stage + stage_offset) && lane < NV) {
       sl = con_margin(c, lim, q, v, u);
       int guard = 0;
       while (sl < P.barrier && guard < (1 << 20)) { sl += P.barrier; ++guard; }
       du = P.barrier / sl;
     }
-    L.slack[slot_index(c, L.N, i, L.Bp, b, lane)] = sl;
-    L.dual[slot_index(c, L.N, i, L.Bp, b, lane)] = du;
+    X[(X_SLACK + c) * SLOT] = sl;
+    X[(X_DUAL + c) * SLOT] = du;
   }
 }
 
-// set one solution field of every stage from value[b][7] (broadcast: value[7])
+// set one solution field of `nstages` stages from value[b][7] (broadcast: value[7])
 __global__ void k_set_solution(Layout L, int field, const double* __restrict__ value, int broadcast, int nstages) {
   const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long total = static_cast<long>(nstages) * L.Bp * OCT;
@@ -108,7 +117,7 @@ __global__ void k_set_solution(Layout L, int field, const double* __restrict__ v
   const int i = static_cast<int>(t / L.Bp);
   double val = 0.0;
   if (lane < NV && b < L.B) val = broadcast ? value[lane] : value[static_cast<size_t>(b) * NV + lane];
-  L.sol[slot_index(field, L.N + 1, i, L.Bp, b, lane)] = val;
+  L.X[elem_index(X_NUM, L.G, i, b, field, lane)] = val;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -123,21 +132,14 @@ __global__ void __launch_bounds__(CTA_THREADS) k_linearize(const DevProblem* __r
   const int lane = lane_in_octet();
   const int oct = threadIdx.x >> 3;
   double* tile = smem + oct * (OCT * PAIR_TILE);
-  const int nstage_tasks = RESIDUAL_ONLY ? L.N + 1 : L.N;
-  const long ntask = static_cast<long>(nstage_tasks) * L.Bp;
-  long task = static_cast<long>(blockIdx.x) * OCTETS_PER_CTA + oct;
-  if (task >= ntask) task = ntask - 1;  // tail octets redo the last task (keeps the warp convergent); stores are idempotent
-  const int i = static_cast<int>(task / L.Bp);
-  const int b = static_cast<int>(task % L.Bp);
-  const int ns = L.N + 1;
-  const int Bp = L.Bp;
+  const StageTask t = stage_task(L, RESIDUAL_ONLY ? L.N + 1 : L.N);
+  const int i = t.stage;
+  const int b = t.g * 4 + ((threadIdx.x >> 3) & 3);
   const double dt = P.dt;
   const bool act = lane < NV;
+  const double* X = rec_ptr(L.X, X_NUM, L.G, i, t.g);
 
-  const double q = L.sol[slot_index(S_Q, ns, i, Bp, b, lane)];
-  const double v = L.sol[slot_index(S_V, ns, i, Bp, b, lane)];
-  const double lmd = L.sol[slot_index(S_LMD, ns, i, Bp, b, lane)];
-  const double gmm = L.sol[slot_index(S_GMM, ns, i, Bp, b, lane)];
+  const double q = X[X_Q * SLOT], v = X[X_V * SLOT], lmd = X[X_LMD * SLOT], gmm = X[X_GMM * SLOT];
 
   if (RESIDUAL_ONLY && i == L.N) {
     // TerminalOCP::computeKKTResidual + squaredNormKKTResidual (ocp/terminal_ocp.hxx:120-144)
@@ -148,22 +150,18 @@ __global__ void __launch_bounds__(CTA_THREADS) k_linearize(const DevProblem* __r
     lv -= gmm;
     if (!act) { lq = 0.0; lv = 0.0; }
     const double e = oct_sum_ordered(lq * lq) + oct_sum_ordered(lv * lv);
-    if (lane == 0) L.kkt_stage[static_cast<size_t>(i) * Bp + b] = e;
+    if (lane == 0) L.kkt_stage[static_cast<size_t>(i) * L.Bp + b] = e;
     return;
   }
 
-  const double a = L.sol[slot_index(S_A, ns, i, Bp, b, lane)];
-  const double u = L.sol[slot_index(S_U, ns, i, Bp, b, lane)];
-  const double beta = L.sol[slot_index(S_BETA, ns, i, Bp, b, lane)];
-  const double qn = L.sol[slot_index(S_Q, ns, i + 1, Bp, b, lane)];
-  const double vn = L.sol[slot_index(S_V, ns, i + 1, Bp, b, lane)];
-  const double lmdn = L.sol[slot_index(S_LMD, ns, i + 1, Bp, b, lane)];
-  const double gmmn = L.sol[slot_index(S_GMM, ns, i + 1, Bp, b, lane)];
+  const double a = X[X_A * SLOT], u = X[X_U * SLOT], beta = X[X_BETA * SLOT];
+  const double* Xn = X + static_cast<size_t>(L.G) * (X_NUM * SLOT);  // next stage, same group
+  const double qn = Xn[X_Q * SLOT], vn = Xn[X_V * SLOT], lmdn = Xn[X_LMD * SLOT], gmmn = Xn[X_GMM * SLOT];
   double slack[NC], dual[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
-    slack[c] = L.slack[slot_index(c, L.N, i, Bp, b, lane)];
-    dual[c] = L.dual[slot_index(c, L.N, i, Bp, b, lane)];
+    slack[c] = X[(X_SLACK + c) * SLOT];
+    dual[c] = X[(X_DUAL + c) * SLOT];
   }
   const LaneLimits lim = load_limits(P, lane);
 
@@ -225,7 +223,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_linearize(const DevProblem* __r
       c2 += oct_sum_ordered(z * (r * r)) + oct_sum_ordered(z * (dl * dl));
     }
     e += dt * dt * c2;
-    if (lane == 0) L.kkt_stage[static_cast<size_t>(i) * Bp + b] = e;
+    if (lane == 0) L.kkt_stage[static_cast<size_t>(i) * L.Bp + b] = e;
     return;
   }
 
@@ -240,8 +238,9 @@ __global__ void __launch_bounds__(CTA_THREADS) k_linearize(const DevProblem* __r
       if (!comp_active(c, i)) continue;
       const double r = con_residual(c, lim, q, v, u, slack[c]);
       const double dl = slack[c] * dual[c] - P.barrier;
-      const double h = dt * dual[c] / slack[c];
-      const double g = dt * (dual[c] * r - dl) / slack[c];
+      const double rs = 1.0 / slack[c];
+      const double h = (dt * dual[c]) * rs;
+      const double g = (dt * fma(dual[c], r, -dl)) * rs;
       const double sg = (c & 1) ? g : -g;
       if (c < 2) { Qqq_d += h; lq += sg; }
       else if (c < 4) { Qvv_d += h; lv += sg; }
@@ -264,15 +263,16 @@ __global__ void __launch_bounds__(CTA_THREADS) k_linearize(const DevProblem* __r
     }
     ulq += tq; ulv += tv; ula += ta;
   }
-  const size_t Ns = L.N;
-  L.kktR[slot_index(R_FQ, Ns, i, Bp, b, lane)] = Fq;
-  L.kktR[slot_index(R_FV, Ns, i, Bp, b, lane)] = Fv;
-  L.kktR[slot_index(R_LA, Ns, i, Bp, b, lane)] = ula;
-  L.kktR[slot_index(R_LQ, Ns, i, Bp, b, lane)] = ulq;
-  L.kktR[slot_index(R_LV, Ns, i, Bp, b, lane)] = ulv;
-  L.expd[slot_index(E_ID, Ns, i, Bp, b, lane)] = ID;
-  L.expd[slot_index(E_LU, Ns, i, Bp, b, lane)] = lu;
-  L.expd[slot_index(E_QUU, Ns, i, Bp, b, lane)] = Quu_d;
+  double* KQ = rec_ptr(L.KQ, KQ_NUM, L.G, i, t.g);
+  double* W = rec_ptr(L.W, W_NUM, L.G, i, t.g);
+  KQ[KQ_FQ * SLOT] = Fq;
+  KQ[KQ_FV * SLOT] = Fv;
+  KQ[KQ_LA * SLOT] = ula;
+  KQ[KQ_LQ * SLOT] = ulq;
+  KQ[KQ_LV * SLOT] = ulv;
+  W[W_ID * SLOT] = ID;
+  W[W_LU * SLOT] = lu;
+  W[W_QUU * SLOT] = Quu_d;
 
   // exchange the columns of dID/dq, dID/dv, M through the tile: tile[lane][0..20]
   double* mine = tile + lane * PAIR_TILE;
@@ -284,12 +284,13 @@ __global__ void __launch_bounds__(CTA_THREADS) k_linearize(const DevProblem* __r
   }
   __syncwarp();
   // expansion data in ROW layout (lane r holds row r): row r, col c = tile[c][r]
+  const int ln = act ? lane : 0;
 #pragma unroll
   for (int c = 0; c < NV; ++c) {
     const double* o = tile + c * PAIR_TILE;
-    L.expd[slot_index(E_DQ + c, Ns, i, Bp, b, lane)] = o[lane < NV ? lane : 0];
-    L.expd[slot_index(E_DV + c, Ns, i, Bp, b, lane)] = o[NV + (lane < NV ? lane : 0)];
-    L.expd[slot_index(E_M + c, Ns, i, Bp, b, lane)] = Mc[c];
+    W[(W_DQ + c) * SLOT] = o[ln];
+    W[(W_DV + c) * SLOT] = o[NV + ln];
+    W[(W_M + c) * SLOT] = Mc[c];
   }
   // own columns scaled by diag(Quu):  D*[k] = Quu_k * d*[k][c]
   double Dq[NV], Dv[NV], Da[NV];
@@ -316,18 +317,19 @@ __global__ void __launch_bounds__(CTA_THREADS) k_linearize(const DevProblem* __r
       aa = fma(xa, Da[k], aa);
     }
     const bool diag = (r == lane);
-    L.kktQ[slot_index(K_QQ * NV + r, Ns, i, Bp, b, lane)] = qq + (diag ? Qqq_d : 0.0);
-    L.kktQ[slot_index(K_QV * NV + r, Ns, i, Bp, b, lane)] = qv;
-    L.kktQ[slot_index(K_VV * NV + r, Ns, i, Bp, b, lane)] = vv + (diag ? Qvv_d : 0.0);
-    L.kktQ[slot_index(K_AQ * NV + r, Ns, i, Bp, b, lane)] = aq;
-    L.kktQ[slot_index(K_AV * NV + r, Ns, i, Bp, b, lane)] = av;
-    L.kktQ[slot_index(K_AA * NV + r, Ns, i, Bp, b, lane)] = aa + (diag ? Qaa_d : 0.0);
+    KQ[(KQ_QQ + r) * SLOT] = qq + (diag ? Qqq_d : 0.0);
+    KQ[(KQ_QV + r) * SLOT] = qv;
+    KQ[(KQ_VV + r) * SLOT] = vv + (diag ? Qvv_d : 0.0);
+    KQ[(KQ_AQ + r) * SLOT] = aq;
+    KQ[(KQ_AV + r) * SLOT] = av;
+    KQ[(KQ_AA + r) * SLOT] = aa + (diag ? Qaa_d : 0.0);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_riccati: backward Riccati recursion, forward recursion, costate / condensed directions and
-// fraction-to-boundary step sizes.  One octet per instance; lane c owns column c.
+// k_riccati: backward Riccati recursion + forward recursion.  One octet per instance (one warp =
+// one group of 4 instances); lane c owns column c.  Writes the gains / Riccati matrices to W and
+// (dq, dv, da) to D; everything else of the direction is expanded in parallel by k_expand.
 // ---------------------------------------------------------------------------------------------
 constexpr int RIC_TILE = 17;               // odd stride (doubles) -> conflict-free transposed reads
 constexpr int RIC_SMEM_PER_OCT = 2 * OCT * RIC_TILE;
@@ -341,23 +343,26 @@ __global__ void __launch_bounds__(CTA_THREADS) k_riccati(const DevProblem* __res
   const int oct = threadIdx.x >> 3;
   double* tA = smem + oct * RIC_SMEM_PER_OCT;         // [8][RIC_TILE]
   double* tB = tA + OCT * RIC_TILE;                   // [8][RIC_TILE]
-  int b = blockIdx.x * OCTETS_PER_CTA + oct;
-  const bool valid = b < L.B;
-  if (b >= L.Bp) b = L.Bp - 1;
-  const int N = L.N, Bp = L.Bp, ns = L.N + 1;
+  int g = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+  if (g >= L.G) g = L.G - 1;     // tail warps redo the last group (identical, idempotent stores)
+  const int b = g * 4 + (oct & 3);
+  const bool valid = b < L.B;    // padded instances (B <= b < Bp) are computed but never reported
+  const int N = L.N;
   const double dt = P.dt;
   const double dt2 = dt * dt;
   const bool act = lane < NV;
   const int ln = act ? lane : 0;
   int chol_fail = 0;
+  const size_t xstride = static_cast<size_t>(L.G) * (X_NUM * SLOT);
+  const size_t kstride = static_cast<size_t>(L.G) * (KQ_NUM * SLOT);
+  const size_t wstride = static_cast<size_t>(L.G) * (W_NUM * SLOT);
+  const size_t dstride = static_cast<size_t>(L.G) * (D_NUM * SLOT);
 
   // ---- terminal stage: P_N = diag(qf, vf), s_N = -l_N (unriccati_recursion.cpp:39-47) ----
   double Pqq[NV], Pqv[NV], Pvq[NV], Pvv[NV], sq, sv;
   {
-    const double q = L.sol[slot_index(S_Q, ns, N, Bp, b, lane)];
-    const double v = L.sol[slot_index(S_V, ns, N, Bp, b, lane)];
-    const double lmd = L.sol[slot_index(S_LMD, ns, N, Bp, b, lane)];
-    const double gmm = L.sol[slot_index(S_GMM, ns, N, Bp, b, lane)];
+    const double* X = rec_ptr(L.X, X_NUM, L.G, N, g);
+    const double q = X[X_Q * SLOT], v = X[X_V * SLOT], lmd = X[X_LMD * SLOT], gmm = X[X_GMM * SLOT];
     double lq = 0.0, lv = 0.0;
     lq += P.qf_weight[lane] * (q - P.q_ref[lane]);
     lv += P.vf_weight[lane] * (v - P.v_ref[lane]);
@@ -375,19 +380,19 @@ __global__ void __launch_bounds__(CTA_THREADS) k_riccati(const DevProblem* __res
   }
 
   // ---- backward recursion ----
-  for (int i = N - 1; i >= 0; --i) {
+  const double* KQ = rec_ptr(L.KQ, KQ_NUM, L.G, N - 1, g);
+  double* W = rec_ptr(L.W, W_NUM, L.G, N - 1, g);
+  for (int i = N - 1; i >= 0; --i, KQ -= kstride, W -= wstride) {
     double Qaa[NV], Qaq[NV], Qav[NV];
 #pragma unroll
     for (int r = 0; r < NV; ++r) {
-      Qaa[r] = L.kktQ[slot_index(K_AA * NV + r, N, i, Bp, b, lane)];
-      Qaq[r] = L.kktQ[slot_index(K_AQ * NV + r, N, i, Bp, b, lane)];
-      Qav[r] = L.kktQ[slot_index(K_AV * NV + r, N, i, Bp, b, lane)];
+      Qaa[r] = KQ[(KQ_AA + r) * SLOT];
+      Qaq[r] = KQ[(KQ_AQ + r) * SLOT];
+      Qav[r] = KQ[(KQ_AV + r) * SLOT];
     }
-    const double Fq = L.kktR[slot_index(R_FQ, N, i, Bp, b, lane)];
-    const double Fv = L.kktR[slot_index(R_FV, N, i, Bp, b, lane)];
-    double la = L.kktR[slot_index(R_LA, N, i, Bp, b, lane)];
-    const double lq = L.kktR[slot_index(R_LQ, N, i, Bp, b, lane)];
-    const double lv = L.kktR[slot_index(R_LV, N, i, Bp, b, lane)];
+    const double Fq = KQ[KQ_FQ * SLOT], Fv = KQ[KQ_FV * SLOT];
+    double la = KQ[KQ_LA * SLOT];
+    const double lq = KQ[KQ_LQ * SLOT], lv = KQ[KQ_LV * SLOT];
 
     // factorizeKKTMatrix, a-blocks (backward_unriccati_recursion_factorizer.hxx:44-53); the
     // x-blocks are folded into the P update below (same operation order per entry)
@@ -416,8 +421,8 @@ __global__ void __launch_bounds__(CTA_THREADS) k_riccati(const DevProblem* __res
     for (int r = 0; r < NV; ++r) tA[lane * RIC_TILE + r] = Qaa[r];
     tA[lane * RIC_TILE + NV] = la;
     __syncwarp();
-    // Cholesky of Qaa (lower triangle), redundantly in every lane: Lc[k][i], i >= k
-    double Lm[NV][NV];  // Lm[col][row]; only row >= col used
+    // Cholesky of Qaa (lower triangle), redundantly in every lane: Lm[col][row], row >= col
+    double Lm[NV][NV];
     double rdiag[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
@@ -465,9 +470,9 @@ __global__ void __launch_bounds__(CTA_THREADS) k_riccati(const DevProblem* __res
       double t1 = 0.0, t2 = 0.0;
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
-        const double g = tA[k * RIC_TILE + r];
-        t1 = fma(g, Kq[k], t1);
-        t2 = fma(g, Kv[k], t2);
+        const double gq = tA[k * RIC_TILE + r];
+        t1 = fma(gq, Kq[k], t1);
+        t2 = fma(gq, Kv[k], t2);
       }
       GKq[r] = t1; GKv[r] = t2;
     }
@@ -489,9 +494,9 @@ __global__ void __launch_bounds__(CTA_THREADS) k_riccati(const DevProblem* __res
     // F-blocks of factorizeKKTMatrix (:34-43) + P = Qxx - K^T (Qaa K) (:64-75), row by row
 #pragma unroll
     for (int r = 0; r < NV; ++r) {
-      double Qqq = L.kktQ[slot_index(K_QQ * NV + r, N, i, Bp, b, lane)];
-      double Qqv = L.kktQ[slot_index(K_QV * NV + r, N, i, Bp, b, lane)];
-      double Qvv = L.kktQ[slot_index(K_VV * NV + r, N, i, Bp, b, lane)];
+      double Qqq = KQ[(KQ_QQ + r) * SLOT];
+      double Qqv = KQ[(KQ_QV + r) * SLOT];
+      double Qvv = KQ[(KQ_VV + r) * SLOT];
       Qqq += Pqq[r];
       Qqv = fma(dt, Pqq[r], Qqv);
       Qqv += Pqv[r];
@@ -514,10 +519,10 @@ __global__ void __launch_bounds__(CTA_THREADS) k_riccati(const DevProblem* __res
     // K in row layout for the forward pass: lane r gets Kq[r][c] = tB[c][r]
 #pragma unroll
     for (int c = 0; c < NV; ++c) {
-      L.ric[slot_index(RC_KQ + c, N, i, Bp, b, lane)] = tB[c * RIC_TILE + ln];
-      L.ric[slot_index(RC_KV + c, N, i, Bp, b, lane)] = tB[c * RIC_TILE + NV + ln];
+      W[(W_KQ + c) * SLOT] = tB[c * RIC_TILE + ln];
+      W[(W_KV + c) * SLOT] = tB[c * RIC_TILE + NV + ln];
     }
-    L.ric[slot_index(RC_K, N, i, Bp, b, lane)] = kk[ln];
+    W[W_K * SLOT] = kk[ln];
     __syncwarp();
     // transposes through the tiles: Pvq = Pqv^T, symmetrise Pqq and Pvv
 #pragma unroll
@@ -538,112 +543,93 @@ __global__ void __launch_bounds__(CTA_THREADS) k_riccati(const DevProblem* __res
     sq = nsq; sv = nsv;
 #pragma unroll
     for (int r = 0; r < NV; ++r) {
-      L.ric[slot_index(RC_PQQ + r, N, i, Bp, b, lane)] = Pqq[r];
-      L.ric[slot_index(RC_PQV + r, N, i, Bp, b, lane)] = Pqv[r];
-      L.ric[slot_index(RC_PVQ + r, N, i, Bp, b, lane)] = Pvq[r];
-      L.ric[slot_index(RC_PVV + r, N, i, Bp, b, lane)] = Pvv[r];
+      W[(W_PQQ + r) * SLOT] = Pqq[r];
+      W[(W_PQV + r) * SLOT] = Pqv[r];
+      W[(W_PVQ + r) * SLOT] = Pvq[r];
+      W[(W_PVV + r) * SLOT] = Pvv[r];
     }
-    L.ric[slot_index(RC_SQ, N, i, Bp, b, lane)] = sq;
-    L.ric[slot_index(RC_SV, N, i, Bp, b, lane)] = sv;
+    W[W_SQ * SLOT] = sq;
+    W[W_SV * SLOT] = sv;
   }
 
-  // ---- forward recursion + directions + step sizes ----
-  const LaneLimits lim = load_limits(P, lane);
+  // ---- forward recursion: da = K dx + k, dx+ = Fx + A dx + B da (split_unriccati_factorizer.hxx:49-57) ----
   double dq, dv;
   {
+    const double* X0 = rec_ptr(L.X, X_NUM, L.G, 0, g);
     const size_t bi = static_cast<size_t>(valid ? b : 0) * NV + ln;
-    dq = q0[bi] - L.sol[slot_index(S_Q, ns, 0, Bp, b, lane)];
-    dv = v0[bi] - L.sol[slot_index(S_V, ns, 0, Bp, b, lane)];
+    dq = q0[bi] - X0[X_Q * SLOT];
+    dv = v0[bi] - X0[X_V * SLOT];
     if (!act) { dq = 0.0; dv = 0.0; }
   }
-  double min_p = 1.0, min_d = 1.0;
+  KQ = rec_ptr(L.KQ, KQ_NUM, L.G, 0, g);
+  W = rec_ptr(L.W, W_NUM, L.G, 0, g);
+  double* D = rec_ptr(L.D, D_NUM, L.G, 0, g);
+  // software pipeline: the gains of stage i+1 are loaded while stage i is being applied
+  double Kr[2 * NV], kr, Fq, Fv;
+#pragma unroll
+  for (int c = 0; c < 2 * NV; ++c) Kr[c] = W[(W_KQ + c) * SLOT];
+  kr = W[W_K * SLOT];
+  Fq = KQ[KQ_FQ * SLOT];
+  Fv = KQ[KQ_FV * SLOT];
   for (int i = 0; i < N; ++i) {
-    double dqk[NV], dvk[NV];
+    double Kn[2 * NV], kn = 0.0, Fqn = 0.0, Fvn = 0.0;
+    if (i + 1 < N) {
+      const double* Wn = W + wstride;
+      const double* KQn = KQ + kstride;
 #pragma unroll
-    for (int k = 0; k < NV; ++k) { dqk[k] = oct_bcast(dq, k); dvk[k] = oct_bcast(dv, k); }
-    // da = K dx + k  (row layout)
-    double da;
-    {
-      double acc = 0.0;
+      for (int c = 0; c < 2 * NV; ++c) Kn[c] = Wn[(W_KQ + c) * SLOT];
+      kn = Wn[W_K * SLOT];
+      Fqn = KQn[KQ_FQ * SLOT];
+      Fvn = KQn[KQ_FV * SLOT];
+    } else {
 #pragma unroll
-      for (int c = 0; c < NV; ++c) acc = fma(L.ric[slot_index(RC_KQ + c, N, i, Bp, b, lane)], dqk[c], acc);
-#pragma unroll
-      for (int c = 0; c < NV; ++c) acc = fma(L.ric[slot_index(RC_KV + c, N, i, Bp, b, lane)], dvk[c], acc);
-      da = acc + L.ric[slot_index(RC_K, N, i, Bp, b, lane)];
+      for (int c = 0; c < 2 * NV; ++c) Kn[c] = 0.0;
     }
-    // costate direction (split_unriccati_factorizer.hxx:60-68)
-    double dlmd, dgmm;
-    {
-      double t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0;
+    double acc = 0.0;
 #pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        t1 = fma(L.ric[slot_index(RC_PQQ + k, N, i, Bp, b, lane)], dqk[k], t1);
-        t2 = fma(L.ric[slot_index(RC_PVQ + k, N, i, Bp, b, lane)], dvk[k], t2);
-        t3 = fma(L.ric[slot_index(RC_PQV + k, N, i, Bp, b, lane)], dqk[k], t3);
-        t4 = fma(L.ric[slot_index(RC_PVV + k, N, i, Bp, b, lane)], dvk[k], t4);
-      }
-      dlmd = t1; dlmd += t2; dlmd -= L.ric[slot_index(RC_SQ, N, i, Bp, b, lane)];
-      dgmm = t3; dgmm += t4; dgmm -= L.ric[slot_index(RC_SV, N, i, Bp, b, lane)];
-    }
-    // du = ID + dID/dq dq + dID/dv dv + M da ; dbeta = (lu + Quu du) / dt
-    double du, dbeta;
-    {
-      double acc = L.expd[slot_index(E_ID, N, i, Bp, b, lane)];
-      double t = 0.0;
+    for (int c = 0; c < NV; ++c) acc = fma(Kr[c], oct_bcast(dq, c), acc);
 #pragma unroll
-      for (int c = 0; c < NV; ++c) t = fma(L.expd[slot_index(E_DQ + c, N, i, Bp, b, lane)], dqk[c], t);
-      acc += t;
-      t = 0.0;
-#pragma unroll
-      for (int c = 0; c < NV; ++c) t = fma(L.expd[slot_index(E_DV + c, N, i, Bp, b, lane)], dvk[c], t);
-      acc += t;
-      t = 0.0;
-#pragma unroll
-      for (int c = 0; c < NV; ++c) t = fma(L.expd[slot_index(E_M + c, N, i, Bp, b, lane)], oct_bcast(da, c), t);
-      acc += t;
-      du = acc;
-      dbeta = fma(L.expd[slot_index(E_QUU, N, i, Bp, b, lane)], du, L.expd[slot_index(E_LU, N, i, Bp, b, lane)]) / dt;
-    }
-    // slack / dual directions and fraction-to-boundary
-    if (act) {
-      const double q = L.sol[slot_index(S_Q, ns, i, Bp, b, lane)];
-      const double v = L.sol[slot_index(S_V, ns, i, Bp, b, lane)];
-      const double u = L.sol[slot_index(S_U, ns, i, Bp, b, lane)];
-#pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        if (!comp_active(c, i)) continue;
-        const double sl = L.slack[slot_index(c, N, i, Bp, b, lane)];
-        const double dl = L.dual[slot_index(c, N, i, Bp, b, lane)];
-        const double r = con_residual(c, lim, q, v, u, sl);
-        const double dty = sl * dl - P.barrier;
-        const double dx = c < 2 ? dq : (c < 4 ? dv : du);
-        const double dslack = ((c & 1) ? -dx : dx) - r;
-        const double ddual = -fma(dl, dslack, dty) / sl;
-        min_p = fraction_row(P.fraction_rate, sl, dslack, min_p);
-        min_d = fraction_row(P.fraction_rate, dl, ddual, min_d);
-      }
-    }
-    L.dir[slot_index(D_LMD, ns, i, Bp, b, lane)] = dlmd;
-    L.dir[slot_index(D_GMM, ns, i, Bp, b, lane)] = dgmm;
-    L.dir[slot_index(D_Q, ns, i, Bp, b, lane)] = dq;
-    L.dir[slot_index(D_V, ns, i, Bp, b, lane)] = dv;
-    L.dir[slot_index(D_A, ns, i, Bp, b, lane)] = da;
-    L.dir[slot_index(D_U, ns, i, Bp, b, lane)] = du;
-    L.dir[slot_index(D_BETA, ns, i, Bp, b, lane)] = dbeta;
-    // forwardRiccatiRecursion (split_unriccati_factorizer.hxx:49-57)
-    double ndq = L.kktR[slot_index(R_FQ, N, i, Bp, b, lane)] + dq;
-    double ndv = L.kktR[slot_index(R_FV, N, i, Bp, b, lane)] + dv;
+    for (int c = 0; c < NV; ++c) acc = fma(Kr[NV + c], oct_bcast(dv, c), acc);
+    const double da = acc + kr;
+    D[D_Q * SLOT] = dq;
+    D[D_V * SLOT] = dv;
+    D[D_A * SLOT] = da;
+    double ndq = Fq + dq;
+    double ndv = Fv + dv;
     ndq = fma(dt, dv, ndq);
     ndv = fma(dt, da, ndv);
     dq = act ? ndq : 0.0;
     dv = act ? ndv : 0.0;
+#pragma unroll
+    for (int c = 0; c < 2 * NV; ++c) Kr[c] = Kn[c];
+    kr = kn; Fq = Fqn; Fv = Fvn;
+    KQ += kstride; W += wstride; D += dstride;
   }
-  // terminal costate direction: P_N = diag, s_N recomputed
-  {
-    const double q = L.sol[slot_index(S_Q, ns, N, Bp, b, lane)];
-    const double v = L.sol[slot_index(S_V, ns, N, Bp, b, lane)];
-    const double lmd = L.sol[slot_index(S_LMD, ns, N, Bp, b, lane)];
-    const double gmm = L.sol[slot_index(S_GMM, ns, N, Bp, b, lane)];
+  D[D_Q * SLOT] = dq;   // terminal stage
+  D[D_V * SLOT] = dv;
+  const int any_fail = __shfl_xor_sync(FULL, chol_fail, 1, OCT) | chol_fail;
+  if (lane == 0 && valid && any_fail) L.status[b] |= 1;
+  (void)xstride;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_expand: per (instance, stage): costate direction dlmd, dgmm = P dx - s; condensed direction
+// du = ID + dID [dq,dv,da], dbeta = (lu + Quu du)/dt; slack/dual directions; per-stage
+// fraction-to-boundary minima.  Terminal stage: costate only (P_N = diag, s_N recomputed).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CTA_THREADS) k_expand(const DevProblem* __restrict__ Pp, Layout L, int stage_offset) {
+  const DevProblem& P = *Pp;
+  const int lane = lane_in_octet();
+  const StageTask t = stage_task(L, L.N + 1);
+  const int i = t.stage;
+  const int b = t.g * 4 + ((threadIdx.x >> 3) & 3);
+  const int N = L.N;
+  const bool act = lane < NV;
+  const double* X = rec_ptr(L.X, X_NUM, L.G, i, t.g);
+  double* D = rec_ptr(L.D, D_NUM, L.G, i, t.g);
+  const double dq = D[D_Q * SLOT], dv = D[D_V * SLOT];
+  if (i == N) {
+    const double q = X[X_Q * SLOT], v = X[X_V * SLOT], lmd = X[X_LMD * SLOT], gmm = X[X_GMM * SLOT];
     double lq = 0.0, lv = 0.0;
     lq += P.qf_weight[lane] * (q - P.q_ref[lane]);
     lv += P.vf_weight[lane] * (v - P.v_ref[lane]);
@@ -651,71 +637,136 @@ __global__ void __launch_bounds__(CTA_THREADS) k_riccati(const DevProblem* __res
     lv -= gmm;
     double dlmd = P.qf_weight[lane] * dq; dlmd -= -lq;
     double dgmm = P.vf_weight[lane] * dv; dgmm -= -lv;
-    L.dir[slot_index(D_LMD, ns, N, Bp, b, lane)] = dlmd;
-    L.dir[slot_index(D_GMM, ns, N, Bp, b, lane)] = dgmm;
-    L.dir[slot_index(D_Q, ns, N, Bp, b, lane)] = dq;
-    L.dir[slot_index(D_V, ns, N, Bp, b, lane)] = dv;
+    D[D_LMD * SLOT] = dlmd;
+    D[D_GMM * SLOT] = dgmm;
+    return;
+  }
+  const double* W = rec_ptr(L.W, W_NUM, L.G, i, t.g);
+  const double da = D[D_A * SLOT];
+  double dqk[NV], dvk[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) { dqk[k] = oct_bcast(dq, k); dvk[k] = oct_bcast(dv, k); }
+  // costate direction (split_unriccati_factorizer.hxx:60-68)
+  double dlmd, dgmm;
+  {
+    double t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      t1 = fma(W[(W_PQQ + k) * SLOT], dqk[k], t1);
+      t2 = fma(W[(W_PVQ + k) * SLOT], dvk[k], t2);
+      t3 = fma(W[(W_PQV + k) * SLOT], dqk[k], t3);
+      t4 = fma(W[(W_PVV + k) * SLOT], dvk[k], t4);
+    }
+    dlmd = t1; dlmd += t2; dlmd -= W[W_SQ * SLOT];
+    dgmm = t3; dgmm += t4; dgmm -= W[W_SV * SLOT];
+  }
+  // du = ID + dID/dq dq + dID/dv dv + M da ; dbeta = (lu + Quu du) / dt
+  double du, dbeta;
+  {
+    double acc = W[W_ID * SLOT];
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) s = fma(W[(W_DQ + c) * SLOT], dqk[c], s);
+    acc += s;
+    s = 0.0;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) s = fma(W[(W_DV + c) * SLOT], dvk[c], s);
+    acc += s;
+    s = 0.0;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) s = fma(W[(W_M + c) * SLOT], oct_bcast(da, c), s);
+    acc += s;
+    du = acc;
+    dbeta = fma(W[W_QUU * SLOT], du, W[W_LU * SLOT]) / P.dt;
+  }
+  D[D_LMD * SLOT] = dlmd;
+  D[D_GMM * SLOT] = dgmm;
+  D[D_U * SLOT] = du;
+  D[D_BETA * SLOT] = dbeta;
+  // slack / dual directions and fraction-to-boundary
+  double min_p = 1.0, min_d = 1.0;
+  if (act) {
+    const LaneLimits lim = load_limits(P, lane);
+    const double q = X[X_Q * SLOT], v = X[X_V * SLOT], u = X[X_U * SLOT];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      if (!comp_active(c, i + stage_offset)) continue;
+      const double sl = X[(X_SLACK + c) * SLOT];
+      const double dl = X[(X_DUAL + c) * SLOT];
+      const double r = con_residual(c, lim, q, v, u, sl);
+      const double dty = sl * dl - P.barrier;
+      const double dx = c < 2 ? dq : (c < 4 ? dv : du);
+      const double dslack = ((c & 1) ? -dx : dx) - r;
+      const double ddual = -fma(dl, dslack, dty) / sl;
+      min_p = fraction_row(P.fraction_rate, sl, dslack, min_p);
+      min_d = fraction_row(P.fraction_rate, dl, ddual, min_d);
+    }
   }
   min_p = oct_min(min_p);
   min_d = oct_min(min_d);
-  const int any_fail = __shfl_xor_sync(FULL, chol_fail, 1, OCT) | chol_fail;
-  if (lane == 0 && valid) {
-    L.steps[b] = min_p;
-    L.steps[Bp + b] = min_d;
-    int st = any_fail ? 1 : 0;
-    if (!(min_p == min_p) || !(min_d == min_d)) st |= 2;
-    L.status[b] |= st;
+  if (lane == 0) {
+    L.smin[static_cast<size_t>(i) * L.Bp + b] = min_p;
+    L.smin[(static_cast<size_t>(N) + i) * L.Bp + b] = min_d;
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_update: s += alpha_p d, slack += alpha_p dslack, dual += alpha_d ddual
-// (unocp_solver.cpp:121-133; split_solution.hxx:215-239; constraints_impl.hxx:181-196).
-// dslack / ddual are recomputed from (s, slack, dual, d) instead of being stored.
+// k_update: alpha = min over stages (unocp_solver.cpp:114-115), then s += alpha_p d,
+// slack += alpha_p dslack, dual += alpha_d ddual (unocp_solver.cpp:121-133; split_solution.hxx:
+// 215-239; constraints_impl.hxx:181-196).  dslack / ddual are recomputed from (s, slack, dual, d)
+// instead of being stored.  `primal_override` (line search) replaces the primal step when given.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CTA_THREADS) k_update(const DevProblem* __restrict__ Pp, Layout L,
+__global__ void __launch_bounds__(CTA_THREADS) k_update(const DevProblem* __restrict__ Pp, Layout L, int stage_offset,
                                                         const double* __restrict__ primal_override) {
   const DevProblem& P = *Pp;
   const int lane = lane_in_octet();
-  const long task = static_cast<long>(blockIdx.x) * OCTETS_PER_CTA + (threadIdx.x >> 3);
-  const long ntask = static_cast<long>(L.N + 1) * L.Bp;
-  if (task >= ntask) return;
-  const int i = static_cast<int>(task / L.Bp);
-  const int b = static_cast<int>(task % L.Bp);
-  const int N = L.N, ns = L.N + 1, Bp = L.Bp;
+  // read-modify-write kernel: tail warps must NOT redo a task (whole warps exit together)
+  if (static_cast<long>(blockIdx.x) * WARPS_PER_CTA + (threadIdx.x >> 5) >= static_cast<long>(L.N + 1) * L.G) return;
+  const StageTask t = stage_task(L, L.N + 1);
+  const int i = t.stage;
+  const int b = t.g * 4 + ((threadIdx.x >> 3) & 3);
+  const int N = L.N;
+  // min over the N per-stage minima, lanes striding over the stages
+  double ap = 1.0, ad = 1.0;
+  for (int s = lane; s < N; s += OCT) {
+    ap = fmin(ap, L.smin[static_cast<size_t>(s) * L.Bp + b]);
+    ad = fmin(ad, L.smin[(static_cast<size_t>(N) + s) * L.Bp + b]);
+  }
+  ap = oct_min(ap);
+  ad = oct_min(ad);
+  if (i == 0 && lane == 0) {
+    L.steps[b] = ap;
+    L.steps[L.Bp + b] = ad;
+    if (!(ap == ap) || !(ad == ad)) L.status[b] |= 2;
+  }
+  if (primal_override) ap = primal_override[b];
   if (lane >= NV) return;
-  const double ap = primal_override ? primal_override[b] : L.steps[b];
-  const double ad = L.steps[Bp + b];
-  const size_t iq = slot_index(S_Q, ns, i, Bp, b, lane), iv = slot_index(S_V, ns, i, Bp, b, lane);
-  const size_t il = slot_index(S_LMD, ns, i, Bp, b, lane), ig = slot_index(S_GMM, ns, i, Bp, b, lane);
-  const double q = L.sol[iq], v = L.sol[iv];
-  const double dq = L.dir[slot_index(D_Q, ns, i, Bp, b, lane)];
-  const double dv = L.dir[slot_index(D_V, ns, i, Bp, b, lane)];
-  L.sol[il] = fma(ap, L.dir[slot_index(D_LMD, ns, i, Bp, b, lane)], L.sol[il]);
-  L.sol[ig] = fma(ap, L.dir[slot_index(D_GMM, ns, i, Bp, b, lane)], L.sol[ig]);
-  L.sol[iq] = fma(ap, dq, q);
-  L.sol[iv] = fma(ap, dv, v);
+  double* X = rec_ptr(L.X, X_NUM, L.G, i, t.g);
+  const double* D = rec_ptr(L.D, D_NUM, L.G, i, t.g);
+  const double q = X[X_Q * SLOT], v = X[X_V * SLOT];
+  const double dq = D[D_Q * SLOT], dv = D[D_V * SLOT];
+  X[X_LMD * SLOT] = fma(ap, D[D_LMD * SLOT], X[X_LMD * SLOT]);
+  X[X_GMM * SLOT] = fma(ap, D[D_GMM * SLOT], X[X_GMM * SLOT]);
+  X[X_Q * SLOT] = fma(ap, dq, q);
+  X[X_V * SLOT] = fma(ap, dv, v);
   if (i == N) return;
-  const size_t ia = slot_index(S_A, ns, i, Bp, b, lane), iu = slot_index(S_U, ns, i, Bp, b, lane);
-  const size_t ib = slot_index(S_BETA, ns, i, Bp, b, lane);
-  const double u = L.sol[iu];
-  const double du = L.dir[slot_index(D_U, ns, i, Bp, b, lane)];
-  L.sol[ia] = fma(ap, L.dir[slot_index(D_A, ns, i, Bp, b, lane)], L.sol[ia]);
-  L.sol[iu] = fma(ap, du, u);
-  L.sol[ib] = fma(ap, L.dir[slot_index(D_BETA, ns, i, Bp, b, lane)], L.sol[ib]);
+  const double u = X[X_U * SLOT];
+  const double du = D[D_U * SLOT];
+  X[X_A * SLOT] = fma(ap, D[D_A * SLOT], X[X_A * SLOT]);
+  X[X_U * SLOT] = fma(ap, du, u);
+  X[X_BETA * SLOT] = fma(ap, D[D_BETA * SLOT], X[X_BETA * SLOT]);
   const LaneLimits lim = load_limits(P, lane);
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
-    if (!comp_active(c, i)) continue;
-    const size_t is = slot_index(c, N, i, Bp, b, lane);
-    const double sl = L.slack[is], dl = L.dual[is];
+    if (!comp_active(c, i + stage_offset)) continue;
+    const double sl = X[(X_SLACK + c) * SLOT], dl = X[(X_DUAL + c) * SLOT];
     const double r = con_residual(c, lim, q, v, u, sl);
     const double dty = sl * dl - P.barrier;
     const double dx = c < 2 ? dq : (c < 4 ? dv : du);
     const double dslack = ((c & 1) ? -dx : dx) - r;
     const double ddual = -fma(dl, dslack, dty) / sl;
-    L.slack[is] = fma(ap, dslack, sl);
-    L.dual[is] = fma(ad, ddual, dl);
+    X[(X_SLACK + c) * SLOT] = fma(ap, dslack, sl);
+    X[(X_DUAL + c) * SLOT] = fma(ad, ddual, dl);
   }
 }
 

@@ -545,11 +545,13 @@ static void condense_slack_and_dual(const oracle_problem_t* p, stage_t* st, cons
     double* l = con_grad(st, c);
     const double sg = con_sign(c);
     for (int j = 0; j < NV; ++j) {
-      const double h = dt * d->dual[j] / d->slack[j];
+      /* canonical arithmetic: the two divisions by the slack share one reciprocal */
+      const double rs = 1.0 / d->slack[j];
+      const double h = (dt * d->dual[j]) * rs;
       if (c <= C_POS_UP) st->Qqq[j * NV + j] += h;
       else if (c <= C_VEL_UP) st->Qvv[j] += h;
       else st->Quu[j] += h;
-      l[j] += sg * (dt * (d->dual[j] * d->residual[j] - d->duality[j]) / d->slack[j]);
+      l[j] += sg * ((dt * fma(d->dual[j], d->residual[j], -d->duality[j])) * rs);
     }
   }
 }

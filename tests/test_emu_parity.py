@@ -16,7 +16,7 @@ def test_emulator_library_is_not_the_default():
     assert "emu" not in I.capi.DEFAULT_LIBRARY
 
 
-@pytest.mark.parametrize("batch", [1, 5])
+@pytest.mark.parametrize("batch", [1, 5, 8])
 def test_unocp_iterations_match_oracle(emu_lib, oracle, batch):
     prob = I.benchmark_problem(emu_lib)
     q0, v0 = make_states(batch, 100 + batch)
