@@ -21,6 +21,12 @@
 
 namespace idocp_b200 {
 
+#ifndef IDOCP_LIN_MINB
+#define IDOCP_LIN_MINB 2   // min resident CTAs/SM of k_linearize (register cap = 65536 / (128 * MINB))
+#endif
+#ifndef IDOCP_RIC_MINB
+#define IDOCP_RIC_MINB 2
+#endif
 constexpr int WARPS_PER_CTA = 4;
 constexpr int OCTETS_PER_CTA = 4 * WARPS_PER_CTA;  // 16 octets, 128 threads
 constexpr int CTA_THREADS = 32 * WARPS_PER_CTA;
@@ -126,7 +132,7 @@ __global__ void k_set_solution(Layout L, int field, const double* __restrict__ v
 // RESIDUAL_ONLY = true : computeKKTResidual + squaredNormKKTResidual (writes kkt_stage only)
 // RESIDUAL_ONLY = false: linearizeOCP (writes condensed KKT blocks, residual, expansion data)
 template <bool RESIDUAL_ONLY>
-__global__ void __launch_bounds__(CTA_THREADS) k_linearize(const DevProblem* __restrict__ Pp, Layout L) {
+__global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_linearize(const DevProblem* __restrict__ Pp, Layout L) {
   IDOCP_DYN_SMEM(double, smem);
   const DevProblem& P = *Pp;
   const int lane = lane_in_octet();
@@ -334,7 +340,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_linearize(const DevProblem* __r
 constexpr int RIC_TILE = 17;               // odd stride (doubles) -> conflict-free transposed reads
 constexpr int RIC_SMEM_PER_OCT = 2 * OCT * RIC_TILE;
 
-__global__ void __launch_bounds__(CTA_THREADS) k_riccati(const DevProblem* __restrict__ Pp, Layout L,
+__global__ void __launch_bounds__(CTA_THREADS, IDOCP_RIC_MINB) k_riccati(const DevProblem* __restrict__ Pp, Layout L,
                                                          const double* __restrict__ q0,
                                                          const double* __restrict__ v0) {
   IDOCP_DYN_SMEM(double, smem);

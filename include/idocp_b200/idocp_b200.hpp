@@ -1,0 +1,311 @@
+// idocp_b200.hpp -- C++ host layer: idocp's solver-facing class API re-created on top of the
+// C-ABI (include/idocp_b200.h).  Header-only; link against libidocp_b200.so.
+//
+// A user of the reference switches by replacing `#include "idocp/..."` with this header and the
+// namespace `idocp` with `idocp_b200`; the class and method names, argument meaning and call
+// order are those of the reference:
+//   idocp::Robot                      include/idocp/robot/robot.hpp           (limits only: the rigid-body
+//                                                                             arithmetic lives in the kernels)
+//   idocp::ConfigurationSpaceCost     include/idocp/cost/configuration_space_cost.hpp
+//   idocp::CostFunction               include/idocp/cost/cost_function.hpp
+//   idocp::Constraints, JointConstraintsFactory   include/idocp/constraints/constraints.hpp,
+//                                     include/idocp/utils/joint_constraints_factory.hpp
+//   idocp::UnOCPSolver                include/idocp/unocp/unocp_solver.hpp:25-188
+//   idocp::UnParNMPCSolver            include/idocp/unocp/unparnmpc_solver.hpp:37-171
+//   idocp::ocpbenchmarker             include/idocp/utils/ocp_benchmarker.hxx:13-51
+// Differences, all additive: Eigen is not required (a minimal VectorXd is provided), and every
+// solver takes an optional `batch` (default 1 = exactly the reference object) with batched
+// overloads taking row-major [batch][dimv] arrays.  Like the reference, argument errors print to
+// std::cerr and std::exit(EXIT_FAILURE) (unocp_solver.cpp:33-47); `nthreads` is accepted and ignored.
+#ifndef IDOCP_B200_HPP_
+#define IDOCP_B200_HPP_
+
+#include <chrono>
+#include <cstdlib>
+#include <iostream>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../idocp_b200.h"
+
+namespace idocp_b200 {
+
+// minimal dense vector standing in for Eigen::VectorXd
+class VectorXd {
+ public:
+  VectorXd() {}
+  explicit VectorXd(int n) : d_(n, 0.0) {}
+  VectorXd(std::initializer_list<double> v) : d_(v) {}
+  static VectorXd Zero(int n) { return VectorXd(n); }
+  static VectorXd Constant(int n, double v) { VectorXd x(n); for (auto& e : x.d_) e = v; return x; }
+  int size() const { return static_cast<int>(d_.size()); }
+  double& operator[](int i) { return d_[i]; }
+  double operator[](int i) const { return d_[i]; }
+  double& coeffRef(int i) { return d_[i]; }
+  double coeff(int i) const { return d_[i]; }
+  const double* data() const { return d_.data(); }
+  double* data() { return d_.data(); }
+ private:
+  std::vector<double> d_;
+};
+
+namespace detail {
+[[noreturn]] inline void die(const std::string& what) {
+  std::cerr << what << '\n';
+  std::exit(EXIT_FAILURE);
+}
+inline void check(int rc) {
+  if (rc < 0) die(std::string("idocp_b200: ") + idocp_b200_last_error());
+}
+inline void copy7(const VectorXd& v, double* dst, const char* what) {
+  if (v.size() != IDOCP_B200_DIMV) die(std::string("invalid size: ") + what + ".size() must be 7!");
+  for (int i = 0; i < IDOCP_B200_DIMV; ++i) dst[i] = v[i];
+}
+}  // namespace detail
+
+// Robot: the fixed-base iiwa14.  The URDF itself is turned into constant tables off-line
+// (tools/gen_robot_model.py); the path is accepted for source compatibility.
+class Robot {
+ public:
+  explicit Robot(const std::string& path_to_urdf = "") : urdf_(path_to_urdf) {
+    detail::check(idocp_b200_problem_default(IDOCP_B200_ROBOT_IIWA14, &p_));
+  }
+  int dimq() const { return IDOCP_B200_DIMV; }
+  int dimv() const { return IDOCP_B200_DIMV; }
+  int dimu() const { return IDOCP_B200_DIMV; }
+  bool hasFloatingBase() const { return false; }
+  int maxPointContacts() const { return 0; }
+  void setJointEffortLimit(const VectorXd& v) { detail::copy7(v, p_.u_max, "joint_effort_limit"); }
+  void setJointVelocityLimit(const VectorXd& v) { detail::copy7(v, p_.v_max, "joint_velocity_limit"); }
+  void setLowerJointPositionLimit(const VectorXd& v) { detail::copy7(v, p_.q_min, "lower_joint_position_limit"); }
+  void setUpperJointPositionLimit(const VectorXd& v) { detail::copy7(v, p_.q_max, "upper_joint_position_limit"); }
+  const idocp_b200_problem& limits() const { return p_; }
+ private:
+  std::string urdf_;
+  idocp_b200_problem p_;
+};
+
+class ConfigurationSpaceCost {
+ public:
+  explicit ConfigurationSpaceCost(const Robot&) { detail::check(idocp_b200_problem_default(0, &p_)); }
+  void set_q_ref(const VectorXd& v) { detail::copy7(v, p_.q_ref, "q_ref"); }
+  void set_v_ref(const VectorXd& v) { detail::copy7(v, p_.v_ref, "v_ref"); }
+  void set_u_ref(const VectorXd& v) { detail::copy7(v, p_.u_ref, "u_ref"); }
+  void set_q_weight(const VectorXd& v) { detail::copy7(v, p_.q_weight, "q_weight"); }
+  void set_v_weight(const VectorXd& v) { detail::copy7(v, p_.v_weight, "v_weight"); }
+  void set_a_weight(const VectorXd& v) { detail::copy7(v, p_.a_weight, "a_weight"); }
+  void set_u_weight(const VectorXd& v) { detail::copy7(v, p_.u_weight, "u_weight"); }
+  void set_qf_weight(const VectorXd& v) { detail::copy7(v, p_.qf_weight, "qf_weight"); }
+  void set_vf_weight(const VectorXd& v) { detail::copy7(v, p_.vf_weight, "vf_weight"); }
+  const idocp_b200_problem& params() const { return p_; }
+ private:
+  idocp_b200_problem p_;
+};
+
+// closed registry of cost components: ConfigurationSpaceCost is the supported component
+class CostFunction {
+ public:
+  void push_back(const std::shared_ptr<ConfigurationSpaceCost>& c) {
+    if (config_) detail::die("idocp_b200: only one ConfigurationSpaceCost component is supported");
+    config_ = c;
+  }
+  const std::shared_ptr<ConfigurationSpaceCost>& config() const { return config_; }
+ private:
+  std::shared_ptr<ConfigurationSpaceCost> config_;
+};
+
+class Constraints {
+ public:
+  void setBarrier(double b) { if (!(b > 0)) detail::die("invalid argment: barrier must be positive"); barrier_ = b; }
+  void setFractionToBoundaryRate(double r) {
+    if (!(r > 0) || r > 1) detail::die("invalid argment: fraction_to_boundary_rate must be in (0, 1]");
+    rate_ = r;
+  }
+  double barrier() const { return barrier_; }
+  double fractionToBoundaryRate() const { return rate_; }
+ private:
+  double barrier_ = 1.0e-04, rate_ = 0.995;
+};
+
+// src/utils/joint_constraints_factory.cpp:22-37: position, velocity, torque lower+upper limits
+class JointConstraintsFactory {
+ public:
+  explicit JointConstraintsFactory(const Robot&) {}
+  std::shared_ptr<Constraints> create() const { return std::make_shared<Constraints>(); }
+};
+
+namespace detail {
+inline idocp_b200_problem make_problem(const Robot& robot, const std::shared_ptr<CostFunction>& cost,
+                                       const std::shared_ptr<Constraints>& constraints, double T, int N) {
+  if (!cost || !cost->config()) die("idocp_b200: the cost function needs a ConfigurationSpaceCost component");
+  if (!constraints) die("idocp_b200: constraints must not be null");
+  idocp_b200_problem p = cost->config()->params();
+  const idocp_b200_problem& l = robot.limits();
+  for (int i = 0; i < IDOCP_B200_DIMV; ++i) {
+    p.q_min[i] = l.q_min[i]; p.q_max[i] = l.q_max[i]; p.v_max[i] = l.v_max[i]; p.u_max[i] = l.u_max[i];
+  }
+  p.barrier = constraints->barrier();
+  p.fraction_rate = constraints->fractionToBoundaryRate();
+  p.T = T;
+  p.N = N;
+  return p;
+}
+
+class SolverBase {
+ public:
+  SolverBase(int kind, const Robot& robot, const std::shared_ptr<CostFunction>& cost,
+             const std::shared_ptr<Constraints>& constraints, double T, int N, int nthreads, int batch, int device)
+      : N_(N), batch_(batch), kind_(kind) {
+    try {
+      if (T <= 0) throw std::out_of_range("invalid value: T must be positive!");
+      if (N <= 0) throw std::out_of_range("invalid value: N must be positive!");
+      if (nthreads <= 0) throw std::out_of_range("invalid value: nthreads must be positive!");
+      if (batch <= 0) throw std::out_of_range("invalid value: batch must be positive!");
+    } catch (const std::exception& e) {
+      die(e.what());
+    }
+    const idocp_b200_problem p = make_problem(robot, cost, constraints, T, N);
+    idocp_b200_solver* h = nullptr;
+    check(idocp_b200_create(&p, kind, batch, device, &h));
+    h_ = std::shared_ptr<idocp_b200_solver>(h, [](idocp_b200_solver* x) { idocp_b200_destroy(x); });
+  }
+  int batch() const { return batch_; }
+  void initConstraints() { check(idocp_b200_init_constraints(h_.get())); }
+  // reference signature (one x0, broadcast to the whole batch)
+  void updateSolution(double t, const VectorXd& q, const VectorXd& v, bool line_search = false) {
+    rep(q, v);
+    check(idocp_b200_update_solution(h_.get(), t, qb_.data(), vb_.data(), line_search ? 1 : 0));
+  }
+  // batched: q, v row-major [batch][dimv]
+  void updateSolution(double t, const double* q, const double* v, bool line_search = false) {
+    check(idocp_b200_update_solution(h_.get(), t, q, v, line_search ? 1 : 0));
+  }
+  void computeKKTResidual(double t, const VectorXd& q, const VectorXd& v) {
+    rep(q, v);
+    check(idocp_b200_compute_kkt_residual(h_.get(), t, qb_.data(), vb_.data()));
+  }
+  void computeKKTResidual(double t, const double* q, const double* v) {
+    check(idocp_b200_compute_kkt_residual(h_.get(), t, q, v));
+  }
+  // KKT error of instance 0 (the reference return value); KKTErrors() gives all of them
+  double KKTError() { return KKTErrors()[0]; }
+  std::vector<double> KKTErrors() {
+    std::vector<double> k(batch_);
+    check(idocp_b200_kkt_error(h_.get(), k.data()));
+    return k;
+  }
+  void setSolution(const std::string& name, const VectorXd& value) {
+    try {
+      if (name != "q" && name != "v" && name != "a" && name != "u")
+        throw std::invalid_argument("invalid arugment: name must be q, v, a, or u!");
+    } catch (const std::exception& e) {
+      die(e.what());
+    }
+    double x[IDOCP_B200_DIMV];
+    copy7(value, x, name.c_str());
+    check(idocp_b200_set_solution(h_.get(), name.c_str(), x, 1));
+  }
+  void setSolution(const std::string& name, const double* value_per_instance) {
+    check(idocp_b200_set_solution(h_.get(), name.c_str(), value_per_instance, 0));
+  }
+  // getSolution(name) of instance `instance`: one VectorXd per stage
+  std::vector<VectorXd> getSolution(const std::string& name, int instance = 0) const {
+    const bool full = (name == "q" || name == "v" || name == "lmd" || name == "gmm") && kind_ == IDOCP_B200_SOLVER_UNOCP;
+    const int ns = full ? N_ + 1 : N_;
+    std::vector<double> buf(static_cast<size_t>(batch_) * ns * IDOCP_B200_DIMV);
+    check(idocp_b200_get_solution(h_.get(), name.c_str(), buf.data()));
+    std::vector<VectorXd> out;
+    for (int i = 0; i < ns; ++i) {
+      VectorXd x(IDOCP_B200_DIMV);
+      for (int j = 0; j < IDOCP_B200_DIMV; ++j) x[j] = buf[(static_cast<size_t>(instance) * ns + i) * IDOCP_B200_DIMV + j];
+      out.push_back(x);
+    }
+    return out;
+  }
+  void getSolutionBatch(const std::string& name, double* out) const {
+    check(idocp_b200_get_solution(h_.get(), name.c_str(), out));
+  }
+  void clearLineSearchFilter() { check(idocp_b200_clear_line_search_filter(h_.get())); }
+  bool isCurrentSolutionFeasible() {
+    std::vector<int> f(batch_);
+    check(idocp_b200_is_feasible(h_.get(), f.data()));
+    for (int b = 0; b < batch_; ++b)
+      if (!f[b]) { std::cout << "INFEASIBLE instance " << b << std::endl; return false; }
+    return true;
+  }
+  void sync() { check(idocp_b200_sync(h_.get())); }
+  idocp_b200_solver* handle() { return h_.get(); }
+
+ protected:
+  void rep(const VectorXd& q, const VectorXd& v) {
+    qb_.resize(static_cast<size_t>(batch_) * IDOCP_B200_DIMV);
+    vb_.resize(qb_.size());
+    double x[IDOCP_B200_DIMV], y[IDOCP_B200_DIMV];
+    copy7(q, x, "q");
+    copy7(v, y, "v");
+    for (int b = 0; b < batch_; ++b)
+      for (int j = 0; j < IDOCP_B200_DIMV; ++j) {
+        qb_[static_cast<size_t>(b) * IDOCP_B200_DIMV + j] = x[j];
+        vb_[static_cast<size_t>(b) * IDOCP_B200_DIMV + j] = y[j];
+      }
+  }
+  std::shared_ptr<idocp_b200_solver> h_;
+  int N_, batch_, kind_;
+  std::vector<double> qb_, vb_;
+};
+}  // namespace detail
+
+class UnOCPSolver : public detail::SolverBase {
+ public:
+  UnOCPSolver(const Robot& robot, const std::shared_ptr<CostFunction>& cost,
+              const std::shared_ptr<Constraints>& constraints, const double T, const int N, const int nthreads = 1,
+              const int batch = 1, const int device = 0)
+      : SolverBase(IDOCP_B200_SOLVER_UNOCP, robot, cost, constraints, T, N, nthreads, batch, device) {}
+};
+
+class UnParNMPCSolver : public detail::SolverBase {
+ public:
+  UnParNMPCSolver(const Robot& robot, const std::shared_ptr<CostFunction>& cost,
+                  const std::shared_ptr<Constraints>& constraints, const double T, const int N,
+                  const int nthreads = 1, const int batch = 1, const int device = 0)
+      : SolverBase(IDOCP_B200_SOLVER_UNPARNMPC, robot, cost, constraints, T, N, nthreads, batch, device) {}
+  void initBackwardCorrection(const double t) { detail::check(idocp_b200_init_backward_correction(h_.get(), t)); }
+};
+
+// include/idocp/utils/ocp_benchmarker.hxx:13-51
+namespace ocpbenchmarker {
+template <typename OCPSolverType>
+inline void CPUTime(OCPSolverType& ocp_solver, const double t, const VectorXd& q, const VectorXd& v,
+                    const int num_iteration, const bool line_search) {
+  ocp_solver.sync();
+  const auto start_clock = std::chrono::system_clock::now();
+  for (int i = 0; i < num_iteration; ++i) ocp_solver.updateSolution(t, q, v, line_search);
+  ocp_solver.sync();
+  const auto end_clock = std::chrono::system_clock::now();
+  const double ms = 1e-03 * std::chrono::duration_cast<std::chrono::microseconds>(end_clock - start_clock).count();
+  std::cout << "---------- OCP benchmark : CPU time ----------" << std::endl;
+  std::cout << "total CPU time: " << ms << "[ms]" << std::endl;
+  std::cout << "CPU time per update: " << ms / num_iteration << "[ms]" << std::endl;
+  std::cout << "-----------------------------------" << std::endl << std::endl;
+}
+
+template <typename OCPSolverType>
+inline void Convergence(OCPSolverType& ocp_solver, const double t, const VectorXd& q, const VectorXd& v,
+                        const int num_iteration, const bool line_search) {
+  std::cout << "---------- OCP benchmark : Convergence ----------" << std::endl;
+  ocp_solver.computeKKTResidual(t, q, v);
+  std::cout << "Initial KKT error = " << ocp_solver.KKTError() << std::endl;
+  for (int i = 0; i < num_iteration; ++i) {
+    ocp_solver.updateSolution(t, q, v, line_search);
+    ocp_solver.computeKKTResidual(t, q, v);
+    std::cout << "KKT error after iteration " << i + 1 << " = " << ocp_solver.KKTError() << std::endl;
+  }
+  std::cout << "-----------------------------------" << std::endl << std::endl;
+}
+}  // namespace ocpbenchmarker
+
+}  // namespace idocp_b200
+
+#endif  // IDOCP_B200_HPP_
