@@ -16,6 +16,7 @@
 #include "../../include/idocp_b200.h"
 #include "model_iiwa14.h"
 #include "unocp_kernels.cuh"
+#include "line_search_kernels.cuh"
 #include "unparnmpc_kernels.cuh"
 
 using namespace idocp_b200;
@@ -79,6 +80,9 @@ struct idocp_b200_solver {
   cudaEvent_t cur_e0 = nullptr;
   // UnParNMPC extras
   ParNMPCLayout PL;
+  // line search (allocated on first use)
+  LineSearchLayout LS;
+  bool ls_ready = false;
 
   cudaEvent_t take_event() {
     if (!event_pool.empty()) { cudaEvent_t e = event_pool.back(); event_pool.pop_back(); return e; }
@@ -249,7 +253,7 @@ extern "C" int idocp_b200_create(const idocp_b200_problem* p, int solver_kind, i
   rc |= h->alloc(&L.W, N * G * W_NUM * SLOT);
   rc |= h->alloc(&L.D, (N + 1) * G * D_NUM * SLOT);
   rc |= h->alloc(&L.smin, 2 * N * Bp);
-  rc |= h->alloc(&L.steps, 2 * Bp);
+  rc |= h->alloc(&L.steps, 3 * Bp);
   rc |= h->alloc(&L.kkt_stage, (N + 1) * Bp);
   rc |= h->alloc(&L.kkt_err, Bp);
   rc |= h->alloc(&L.status, Bp);
@@ -350,13 +354,50 @@ static int upload_x0(idocp_b200_solver* h, const double* q, const double* v) {
   return IDOCP_B200_OK;
 }
 
+static int ensure_line_search(idocp_b200_solver* h) {
+  if (h->ls_ready) return IDOCP_B200_OK;
+  const size_t N = h->N, Bp = h->Bp;
+  int rc = 0;
+  rc |= h->alloc(&h->LS.cost, (N + 1) * Bp);
+  rc |= h->alloc(&h->LS.viol, N * Bp);
+  rc |= h->alloc(&h->LS.alpha, Bp);
+  rc |= h->alloc(&h->LS.state, Bp);
+  rc |= h->alloc(&h->LS.flt_n, Bp);
+  rc |= h->alloc(&h->LS.flt_cost, Bp * LS_FILTER_CAP);
+  rc |= h->alloc(&h->LS.flt_viol, Bp * LS_FILTER_CAP);
+  if (rc != 0) return fail(IDOCP_B200_CUDA_ERROR, "line-search buffers: device memory allocation failed");
+  h->ls_ready = true;
+  return IDOCP_B200_OK;
+}
+
+// UnLineSearch::computeStepSize for the whole batch: lock-step rounds, no host synchronisation
+static int run_line_search(idocp_b200_solver* h) {
+  const int rc = ensure_line_search(h);
+  if (rc != IDOCP_B200_OK) return rc;
+  const int off = h->stage_offset();
+  const int fgrid = (h->B + 127) / 128;
+  IDOCP_LAUNCH(h, KC_LINESEARCH, k_ls_begin, group_grid(h), CTA_THREADS, 0, h->L);
+  IDOCP_LAUNCH(h, KC_LINESEARCH, k_ls_eval, stage_grid(h, h->N + 1), CTA_THREADS, 0, h->d_prob, h->L, h->LS, 0, off);
+  IDOCP_LAUNCH(h, KC_LINESEARCH, k_ls_filter, fgrid, 128, 0, h->L, h->LS, 0);
+  for (int trial = 0; trial < LS_MAX_TRIALS; ++trial) {
+    IDOCP_LAUNCH(h, KC_LINESEARCH, k_ls_eval, stage_grid(h, h->N + 1), CTA_THREADS, 0, h->d_prob, h->L, h->LS, 1, off);
+    IDOCP_LAUNCH(h, KC_LINESEARCH, k_ls_filter, fgrid, 128, 0, h->L, h->LS, 1);
+  }
+  CUDA_OK(cudaGetLastError());
+  return IDOCP_B200_OK;
+}
+
 static int unocp_update(idocp_b200_solver* h, const double* d_q, const double* d_v, int line_search) {
-  if (line_search) return fail(IDOCP_B200_UNSUPPORTED, "line search is not implemented yet");
   IDOCP_LAUNCH(h, KC_LINEARIZE, k_linearize<false>, stage_grid(h, h->N), CTA_THREADS, kLinSmem, h->d_prob, h->L);
   IDOCP_LAUNCH(h, KC_RICCATI, k_riccati, group_grid(h), CTA_THREADS, kRicSmem, h->d_prob, h->L, d_q, d_v);
   IDOCP_LAUNCH(h, KC_EXPAND, k_expand, stage_grid(h, h->N + 1), CTA_THREADS, 0, h->d_prob, h->L, 0);
-  IDOCP_LAUNCH(h, KC_UPDATE, k_update, stage_grid(h, h->N + 1), CTA_THREADS, 0, h->d_prob, h->L, 0,
-               static_cast<const double*>(nullptr));
+  const double* override_alpha = nullptr;
+  if (line_search) {
+    const int rc = run_line_search(h);
+    if (rc != IDOCP_B200_OK) return rc;
+    override_alpha = h->LS.alpha;
+  }
+  IDOCP_LAUNCH(h, KC_UPDATE, k_update, stage_grid(h, h->N + 1), CTA_THREADS, 0, h->d_prob, h->L, 0, override_alpha);
   CUDA_OK(cudaGetLastError());
   return IDOCP_B200_OK;
 }
@@ -594,6 +635,10 @@ extern "C" int idocp_b200_is_feasible(idocp_b200_solver* h, int* out) {
 
 extern "C" int idocp_b200_clear_line_search_filter(idocp_b200_solver* h) {
   if (!h) return fail(IDOCP_B200_INVALID_ARGUMENT, "null handle");
+  if (!h->ls_ready) return IDOCP_B200_OK;  // never used: already empty
+  CUDA_OK(cudaSetDevice(h->device));
+  IDOCP_LAUNCH(h, KC_LINESEARCH, k_ls_clear, (h->B + 127) / 128, 128, 0, h->LS, h->B);
+  CUDA_OK(cudaGetLastError());
   return IDOCP_B200_OK;
 }
 

@@ -61,7 +61,7 @@ struct Layout {
   double* W;
   double* D;
   double* smin;       // [2][N][Bp] per-stage fraction-to-boundary minima (primal, dual)
-  double* steps;      // [2][Bp] primal, dual step sizes of the last iteration
+  double* steps;      // [3][Bp] primal step applied, dual step, fraction-to-boundary primal step
   double* kkt_stage;  // [N+1][Bp] squared KKT norms per stage
   double* kkt_err;    // [Bp]
   int* status;        // [Bp]

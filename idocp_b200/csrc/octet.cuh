@@ -73,6 +73,41 @@ __device__ __forceinline__ void canon_sincos(double x, double* sn, double* cs) {
   *cs = (q == 0) ? c : (q == 1) ? -s : (q == 2) ? -c : s;
 }
 
+// natural logarithm of a positive normal double (barrier cost of the line search): the classic
+// k*ln2 + log(1+f) reduction with the degree-14 minimax polynomial in s = f/(2+f), one code path,
+// written with plain IEEE operations so that the oracle repeats it bit for bit (<= 2 ulp).
+__device__ __forceinline__ double canon_log(double x) {
+  long long bits;
+#ifdef IDOCP_B200_EMU
+  memcpy(&bits, &x, sizeof(bits));
+#else
+  bits = __double_as_longlong(x);
+#endif
+  int hx = static_cast<int>(bits >> 32);
+  int k = (hx >> 20) - 1023;
+  hx &= 0x000fffff;
+  const int i = (hx + 0x95f64) & 0x100000;       // mantissa >= sqrt(2): use x/2, k+1
+  k += (i >> 20);
+  const long long nb = (static_cast<long long>(hx | (i ^ 0x3ff00000)) << 32) | (bits & 0xffffffffLL);
+  double m;
+#ifdef IDOCP_B200_EMU
+  memcpy(&m, &nb, sizeof(m));
+#else
+  m = __longlong_as_double(nb);
+#endif
+  const double f = m - 1.0;
+  const double s = f / (2.0 + f);
+  const double dk = static_cast<double>(k);
+  const double z = s * s;
+  const double w = z * z;
+  const double t1 = w * (3.999999999940941908e-01 + w * (2.222219843214978396e-01 + w * 1.531383769920937332e-01));
+  const double t2 = z * (6.666666666666735130e-01 +
+                         w * (2.857142874366239149e-01 + w * (1.818357216161805012e-01 + w * 1.479819860511658591e-01)));
+  const double R = t2 + t1;
+  const double hfsq = 0.5 * f * f;
+  return dk * 6.93147180369123816490e-01 - ((hfsq - (s * (hfsq + R) + dk * 1.90821492927058770002e-10)) - f);
+}
+
 __device__ __forceinline__ int lane_in_octet() { return threadIdx.x & 7; }
 
 // width-8 shuffles on doubles / V3

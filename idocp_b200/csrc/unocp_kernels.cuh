@@ -740,12 +740,14 @@ __global__ void __launch_bounds__(CTA_THREADS) k_update(const DevProblem* __rest
   }
   ap = oct_min(ap);
   ad = oct_min(ad);
+  const double amax = ap;
+  if (primal_override) ap = primal_override[b];
   if (i == 0 && lane == 0) {
-    L.steps[b] = ap;
-    L.steps[L.Bp + b] = ad;
+    L.steps[b] = ap;                 // primal step applied (after the line search, if any)
+    L.steps[L.Bp + b] = ad;          // dual step
+    L.steps[2 * L.Bp + b] = amax;    // fraction-to-boundary primal step
     if (!(ap == ap) || !(ad == ad)) L.status[b] |= 2;
   }
-  if (primal_override) ap = primal_override[b];
   if (lane >= NV) return;
   double* X = rec_ptr(L.X, X_NUM, L.G, i, t.g);
   const double* D = rec_ptr(L.D, D_NUM, L.G, i, t.g);

@@ -67,6 +67,31 @@ static inline void canon_sincos(double x, double* sn, double* cs) {
   *cs = (q == 0) ? c : (q == 1) ? -s : (q == 2) ? -c : s;
 }
 void oracle_canon_sincos(double x, double* sn, double* cs) { canon_sincos(x, sn, cs); }
+/* natural logarithm of a positive normal double (twin of canon_log in octet.cuh) */
+static inline double canon_log(double x) {
+  long long bits;
+  memcpy(&bits, &x, sizeof(bits));
+  int hx = (int)(bits >> 32);
+  int k = (hx >> 20) - 1023;
+  hx &= 0x000fffff;
+  const int i = (hx + 0x95f64) & 0x100000;
+  k += (i >> 20);
+  const long long nb = ((long long)(hx | (i ^ 0x3ff00000)) << 32) | (bits & 0xffffffffLL);
+  double m;
+  memcpy(&m, &nb, sizeof(m));
+  const double f = m - 1.0;
+  const double s = f / (2.0 + f);
+  const double dk = (double)k;
+  const double z = s * s;
+  const double w = z * z;
+  const double t1 = w * (3.999999999940941908e-01 + w * (2.222219843214978396e-01 + w * 1.531383769920937332e-01));
+  const double t2 = z * (6.666666666666735130e-01 +
+                         w * (2.857142874366239149e-01 + w * (1.818357216161805012e-01 + w * 1.479819860511658591e-01)));
+  const double R = t2 + t1;
+  const double hfsq = 0.5 * f * f;
+  return dk * 6.93147180369123816490e-01 - ((hfsq - (s * (hfsq + R) + dk * 1.90821492927058770002e-10)) - f);
+}
+double oracle_canon_log(double x) { return canon_log(x); }
 
 /* plain (non-canonical) helpers of the independent body-frame RNEA below */
 static inline void cross3(const double* a, const double* b, double* c) {
@@ -963,8 +988,8 @@ static double split_unocp_stage_cost(const oracle_problem_t* p, double dt, const
     if (!st->active[c]) continue;
     double lg = 0;
     for (int j = 0; j < NV; ++j) {
-      const double sl = alpha > 0 ? st->c[c].slack[j] + alpha * st->c[c].dslack[j] : st->c[c].slack[j];
-      lg += log(sl);
+      const double sl = alpha > 0 ? fma(alpha, st->c[c].dslack[j], st->c[c].slack[j]) : st->c[c].slack[j];
+      lg += canon_log(sl);
     }
     bar += -p->barrier * lg;
   }
@@ -978,9 +1003,8 @@ static double split_unocp_violation(const oracle_problem_t* p, double dt, stage_
                                     const split_solution_t* s, const double* qn, const double* vn) {
   compute_primal_dual_residual(p, st, s);
   for (int j = 0; j < NV; ++j) {
-    st->Fq[j] = s->q[j] - qn[j];
-    st->Fq[j] += dt * s->v[j];
-    st->Fv[j] = s->v[j] + dt * s->a[j] - vn[j];
+    st->Fq[j] = fma(dt, s->v[j], s->q[j] - qn[j]);
+    st->Fv[j] = fma(dt, s->a[j], s->v[j]) - vn[j];
   }
   rnea_derivatives_impl(s->q, s->v, s->a, st->ID, NULL, NULL, NULL);
   for (int j = 0; j < NV; ++j) st->ID[j] -= s->u[j];

@@ -118,6 +118,16 @@ inline T __shfl_xor_sync(unsigned, T x, int m, int width = 32) {
   const int src = lane ^ m;
   return emu_exchange(x, (src >= base + width || src < base) ? lane : src);
 }
+inline int __any_sync(unsigned, int pred) {
+  const int tid = threadIdx.x;
+  emu::g_block->xbuf[tid] = pred ? 1.0 : 0.0;
+  emu::warp_barrier();
+  const int w = tid / 32;
+  int any = 0;
+  for (int l = 0; l < emu::warp_nthreads(w); ++l) any |= (emu::g_block->xbuf[w * 32 + l] != 0.0);
+  emu::warp_barrier();
+  return any;
+}
 template <typename T>
 inline T __ldg(const T* p) { return *p; }
 inline double __drcp_rn(double x) { return 1.0 / x; }

@@ -63,6 +63,28 @@ def test_unocp_condensed_kkt_matches_oracle(emu_lib, oracle):
                 assert np.max(np.abs(Q[b] - Qo)) <= 1e-9 * scale
 
 
+def test_filter_line_search_matches_oracle(emu_lib, oracle):
+    """updateSolution(..., line_search=True): UnLineSearch + LineSearchFilter (unline_search.hpp:62-91)
+    as lock-step batched rounds; step sizes (accepted / backtracked / floored) bit-identical."""
+    import bench
+    prob = I.benchmark_problem(emu_lib)
+    q0, v0 = bench.initial_states(100, 5, list(prob.q_min), list(prob.q_max))
+    solver, oracles = make_pair(I, oracle, emu_lib, prob, q0, v0)
+    seen = set()
+    for it in range(6):
+        check_iteration(solver, oracles, q0, v0, line_search=True)
+        p, _ = solver.getStepSizes()
+        assert np.all(p >= 0.05) and np.all(p <= 1.0)
+        seen.update(np.round(p, 6).tolist())
+    assert 0.05 in seen and len(seen) > 2        # floor reached and non-trivial steps taken
+    check_solution(solver, oracles)
+    # clearLineSearchFilter on both sides keeps them in lock-step
+    solver.clearLineSearchFilter()
+    for o in oracles:
+        o.clear_line_search_filter()
+    check_iteration(solver, oracles, q0, v0, line_search=True)
+
+
 def test_config_space_problem_long_horizon(emu_lib, oracle):
     """BASELINE configs[0] shape (N=60, T=3) for a couple of iterations."""
     prob = I.config_space_problem(emu_lib)
