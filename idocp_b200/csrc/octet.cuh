@@ -77,6 +77,7 @@ __device__ __forceinline__ void canon_sincos(double x, double* sn, double* cs) {
 // k*ln2 + log(1+f) reduction with the degree-14 minimax polynomial in s = f/(2+f), one code path,
 // written with plain IEEE operations so that the oracle repeats it bit for bit (<= 2 ulp).
 __device__ __forceinline__ double canon_log(double x) {
+  if (!(x > 0.0)) return (x == 0.0) ? -1.0 / 0.0 : 0.0 / 0.0;  // log(0) = -inf, log(<0) = NaN as std::log
   long long bits;
 #ifdef IDOCP_B200_EMU
   memcpy(&bits, &x, sizeof(bits));

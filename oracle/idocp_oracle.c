@@ -69,6 +69,7 @@ static inline void canon_sincos(double x, double* sn, double* cs) {
 void oracle_canon_sincos(double x, double* sn, double* cs) { canon_sincos(x, sn, cs); }
 /* natural logarithm of a positive normal double (twin of canon_log in octet.cuh) */
 static inline double canon_log(double x) {
+  if (!(x > 0.0)) return (x == 0.0) ? -INFINITY : NAN;  /* as std::log */
   long long bits;
   memcpy(&bits, &x, sizeof(bits));
   int hx = (int)(bits >> 32);
