@@ -1364,3 +1364,494 @@ void oracle_unocp_batch_kkt(oracle_unocp_t** os, int batch, double t, const doub
     kkt_out[b] = oracle_unocp_kkt_error(os[b]);
   }
 }
+
+/* ========================================================================================== */
+/* UnParNMPCSolver (src/unocp/unparnmpc_solver.cpp, src/unocp/unbackward_correction.cpp,       */
+/* unocp/split_unparnmpc.hxx, terminal_unparnmpc.hxx, split_unbackward_correction.hxx,         */
+/* split_unkkt_matrix_inverter.hxx).  Stages 1..N are stored at index 0..N-1.     */
+/* ========================================================================================== */
+#define NX (2 * NV)        /* 14 */
+#define NQ3 (3 * NV)       /* 21 */
+#define NK (5 * NV)        /* 35 */
+
+struct oracle_unparnmpc {
+  oracle_problem_t p;
+  int N;
+  double dt;
+  split_solution_t* s;       /* N */
+  split_solution_t* s_new;   /* N */
+  split_direction_t* d;      /* N: du doubles as "da" during the corrections, like the reference */
+  stage_t* st;               /* N */
+  double* KKTinv;            /* N x 35 x 35, column-major; order [lmd,gmm | a,q,v] */
+  double* aux;               /* N x 14 x 14, column-major */
+  double* xres;              /* N x 14 */
+  double primal_step, dual_step, max_primal_step;
+  filter_t filter;
+  split_solution_t* s_try;
+  int chol_info;             /* first non-zero LLT info of the last updateSolution (0 = all factorizations succeeded) */
+};
+
+oracle_unparnmpc_t* oracle_unparnmpc_create(const oracle_problem_t* p) {
+  if (p->N <= 0 || !(p->T > 0)) return NULL;
+  oracle_unparnmpc_t* o = (oracle_unparnmpc_t*)calloc(1, sizeof(*o));
+  o->p = *p;
+  o->N = p->N;
+  o->dt = p->T / p->N;
+  o->s = (split_solution_t*)calloc(o->N, sizeof(split_solution_t));
+  o->s_new = (split_solution_t*)calloc(o->N, sizeof(split_solution_t));
+  o->s_try = (split_solution_t*)calloc(o->N, sizeof(split_solution_t));
+  o->d = (split_direction_t*)calloc(o->N, sizeof(split_direction_t));
+  o->st = (stage_t*)calloc(o->N, sizeof(stage_t));
+  o->KKTinv = (double*)calloc((size_t)o->N * NK * NK, sizeof(double));
+  o->aux = (double*)calloc((size_t)o->N * NX * NX, sizeof(double));
+  o->xres = (double*)calloc((size_t)o->N * NX, sizeof(double));
+  oracle_unparnmpc_init_constraints(o);
+  return o;
+}
+
+void oracle_unparnmpc_destroy(oracle_unparnmpc_t* o) {
+  if (!o) return;
+  free(o->s); free(o->s_new); free(o->s_try); free(o->d); free(o->st); free(o->KKTinv); free(o->aux); free(o->xres);
+  free(o);
+}
+
+/* UnParNMPCSolver::initConstraints (:54-66): stage index i uses time step i+1 */
+void oracle_unparnmpc_init_constraints(oracle_unparnmpc_t* o) {
+  for (int i = 0; i < o->N; ++i) {
+    set_active(i + 1, o->st[i].active);
+    set_slack_and_dual(&o->p, &o->st[i], &o->s[i]);
+  }
+}
+
+int oracle_unparnmpc_set_solution(oracle_unparnmpc_t* o, const char* name, const double* value) {
+  for (int i = 0; i < o->N; ++i) {
+    double* dst;
+    if (!strcmp(name, "q")) dst = o->s[i].q;
+    else if (!strcmp(name, "v")) dst = o->s[i].v;
+    else if (!strcmp(name, "a")) dst = o->s[i].a;
+    else if (!strcmp(name, "u")) dst = o->s[i].u;
+    else return -1;
+    memcpy(dst, value, sizeof(double) * NV);
+  }
+  oracle_unparnmpc_init_constraints(o);
+  return 0;
+}
+
+/* UnBackwardCorrection::initAuxMat (:55-64): every aux_mat = terminal cost Hessian (Qxx) */
+void oracle_unparnmpc_init_backward_correction(oracle_unparnmpc_t* o, double t) {
+  (void)t;
+  for (int i = 0; i < o->N; ++i) {
+    double* A = o->aux + (size_t)i * NX * NX;
+    memset(A, 0, sizeof(double) * NX * NX);
+    for (int j = 0; j < NV; ++j) {
+      A[j * NX + j] = o->p.qf_weight[j];
+      A[(NV + j) * NX + NV + j] = o->p.vf_weight[j];
+    }
+  }
+}
+
+/* gradient part shared by SplitUnParNMPC::linearizeOCP (split_unparnmpc.hxx:69-101) /
+ * computeKKTResidual (:141-163) and the TerminalUnParNMPC twins (terminal_unparnmpc.hxx:70-102);
+ * backward Euler: stateequation::linearizeBackwardEuler[Terminal] (state_equation.hxx:111-167,224-236) */
+static void parnmpc_residual_common(const oracle_problem_t* p, double dt, const double* q_prev, const double* v_prev,
+                                    const split_solution_t* s, const split_solution_t* sn, stage_t* st) {
+  const int terminal = (sn == NULL);
+  memset(st->lq, 0, sizeof(double) * NV); memset(st->lv, 0, sizeof(double) * NV);
+  memset(st->la, 0, sizeof(double) * NV); memset(st->lu, 0, sizeof(double) * NV);
+  stage_cost_derivatives(p, dt, s, st);
+  if (terminal)
+    for (int j = 0; j < NV; ++j) {
+      st->lq[j] += p->qf_weight[j] * (s->q[j] - p->q_ref[j]);
+      st->lv[j] += p->vf_weight[j] * (s->v[j] - p->v_ref[j]);
+    }
+  augment_dual_residual(st, dt);
+  for (int j = 0; j < NV; ++j) {
+    st->Fq[j] = fma(dt, s->v[j], q_prev[j] - s->q[j]);
+    st->Fv[j] = fma(dt, s->a[j], v_prev[j] - s->v[j]);
+  }
+  for (int j = 0; j < NV; ++j) {
+    if (terminal) {
+      st->lq[j] -= s->lmd[j];
+      st->lv[j] += fma(dt, s->lmd[j], -s->gmm[j]);
+    } else {
+      st->lq[j] += sn->lmd[j] - s->lmd[j];
+      st->lv[j] += fma(dt, s->lmd[j], -s->gmm[j]) + sn->gmm[j];
+    }
+    st->la[j] = fma(dt, s->gmm[j], st->la[j]);
+  }
+  rnea_derivatives_impl(s->q, s->v, s->a, st->ID, st->dIDdq, st->dIDdv, st->dIDda);
+  for (int j = 0; j < NV; ++j) st->ID[j] -= s->u[j];
+  for (int j = 0; j < NV; ++j) {
+    double tq = 0, tv = 0, ta = 0;
+    for (int k = 0; k < NV; ++k) {
+      tq = fma(st->dIDdq[j * NV + k], s->beta[k], tq);
+      tv = fma(st->dIDdv[j * NV + k], s->beta[k], tv);
+      ta = fma(st->dIDda[j * NV + k], s->beta[k], ta);
+    }
+    st->lq[j] = fma(dt, tq, st->lq[j]);
+    st->lv[j] = fma(dt, tv, st->lv[j]);
+    st->la[j] = fma(dt, ta, st->la[j]);
+    st->lu[j] = fma(-dt, s->beta[j], st->lu[j]);
+  }
+}
+
+/* condensing shared with the UnOCP path (unconstrained_dynamics.hxx:68-94) */
+static void condense_unconstrained_dynamics(stage_t* st) {
+  for (int j = 0; j < NV; ++j) st->lu_condensed[j] = fma(st->Quu[j], st->ID[j], st->lu[j]);
+  for (int j = 0; j < NV; ++j) {
+    double tq = 0, tv = 0, ta = 0;
+    for (int k = 0; k < NV; ++k) {
+      tq = fma(st->dIDdq[j * NV + k], st->lu_condensed[k], tq);
+      tv = fma(st->dIDdv[j * NV + k], st->lu_condensed[k], tv);
+      ta = fma(st->dIDda[j * NV + k], st->lu_condensed[k], ta);
+    }
+    st->ulq[j] = st->lq[j] + tq;
+    st->ulv[j] = st->lv[j] + tv;
+    st->ula[j] = st->la[j] + ta;
+    st->uFq[j] = st->Fq[j];
+    st->uFv[j] = st->Fv[j];
+  }
+  for (int c = 0; c < NV; ++c)
+    for (int r = 0; r < NV; ++r) {
+      double qq = 0, qv = 0, vv = 0, aq = 0, av = 0, aa = 0;
+      for (int k = 0; k < NV; ++k) {
+        const double Dq = st->Quu[k] * st->dIDdq[c * NV + k];
+        const double Dv = st->Quu[k] * st->dIDdv[c * NV + k];
+        const double Da = st->Quu[k] * st->dIDda[c * NV + k];
+        qq = fma(st->dIDdq[r * NV + k], Dq, qq);
+        qv = fma(st->dIDdq[r * NV + k], Dv, qv);
+        vv = fma(st->dIDdv[r * NV + k], Dv, vv);
+        aq = fma(st->dIDda[r * NV + k], Dq, aq);
+        av = fma(st->dIDda[r * NV + k], Dv, av);
+        aa = fma(st->dIDda[r * NV + k], Da, aa);
+      }
+      st->uQqq[c * NV + r] = qq + st->Qqq[c * NV + r];
+      st->uQqv[c * NV + r] = qv;
+      st->uQvv[c * NV + r] = vv + (r == c ? st->Qvv[r] : 0.0);
+      st->uQaq[c * NV + r] = aq;
+      st->uQav[c * NV + r] = av;
+      st->uQaa[c * NV + r] = aa + (r == c ? st->Qaa[r] : 0.0);
+    }
+}
+
+static void parnmpc_linearize(const oracle_problem_t* p, double dt, const double* q_prev, const double* v_prev,
+                              const split_solution_t* s, const split_solution_t* sn, stage_t* st) {
+  const int terminal = (sn == NULL);
+  memset(st->Qqq, 0, sizeof(st->Qqq));
+  memset(st->Qvv, 0, sizeof(st->Qvv)); memset(st->Qaa, 0, sizeof(st->Qaa)); memset(st->Quu, 0, sizeof(st->Quu));
+  parnmpc_residual_common(p, dt, q_prev, v_prev, s, sn, st);
+  stage_cost_hessian(p, dt, st);
+  if (terminal)
+    for (int j = 0; j < NV; ++j) {
+      st->Qqq[j * NV + j] += p->qf_weight[j];
+      st->Qvv[j] += p->vf_weight[j];
+    }
+  condense_slack_and_dual(p, st, s, dt);
+  condense_unconstrained_dynamics(st);
+}
+
+/* SplitUnKKTMatrixInverter::invert (split_unkkt_matrix_inverter.hxx:40-79) on the 21x21 Q (block
+ * order a,q,v) -> 35x35 inverse of [[0 F],[F^T Q]], order [lmd,gmm | a,q,v]; all column-major */
+static int invert_unkkt(double dt, const double* Q, double* Kinv) {
+  double L[NQ3 * NQ3], rd[NQ3], Qinv[NQ3 * NQ3], e[NQ3], x[NQ3];
+  int info = llt_lower(Q, NQ3, L, rd);
+  for (int c = 0; c < NQ3; ++c) {
+    for (int k = 0; k < NQ3; ++k) e[k] = (k == c) ? 1.0 : 0.0;
+    llt_solve(L, rd, NQ3, e, x);
+    for (int r = 0; r < NQ3; ++r) Qinv[c * NQ3 + r] = x[r];
+  }
+  /* FQinv (14 x 21): rows Fq: -Qinv[q rows] + dt Qinv[v rows]; rows Fv: dt Qinv[a rows] - Qinv[v rows] */
+  double FQ[NX * NQ3];
+  for (int c = 0; c < NQ3; ++c)
+    for (int r = 0; r < NV; ++r) {
+      FQ[c * NX + r] = fma(dt, Qinv[c * NQ3 + 2 * NV + r], -Qinv[c * NQ3 + NV + r]);
+      FQ[c * NX + NV + r] = fma(dt, Qinv[c * NQ3 + r], -Qinv[c * NQ3 + 2 * NV + r]);
+    }
+  /* S = FQinv F^T (14 x 14): S[:, q-part] = -FQ[:, q cols] + dt FQ[:, v cols]; S[:, v-part] = dt FQ[:, a cols] - FQ[:, v cols] */
+  double S[NX * NX];
+  for (int c = 0; c < NV; ++c)
+    for (int r = 0; r < NX; ++r) {
+      S[c * NX + r] = fma(dt, FQ[(2 * NV + c) * NX + r], -FQ[(NV + c) * NX + r]);
+      S[(NV + c) * NX + r] = fma(dt, FQ[c * NX + r], -FQ[(2 * NV + c) * NX + r]);
+    }
+  double LS[NX * NX], rdS[NX], Sinv[NX * NX];
+  const int info2 = llt_lower(S, NX, LS, rdS);
+  if (!info && info2) info = 100 + info2;
+  for (int c = 0; c < NX; ++c) {
+    for (int k = 0; k < NX; ++k) e[k] = (k == c) ? 1.0 : 0.0;
+    llt_solve(LS, rdS, NX, e, x);
+    for (int r = 0; r < NX; ++r) Sinv[c * NX + r] = x[r];
+  }
+  /* top-left = -Sinv */
+  for (int c = 0; c < NX; ++c)
+    for (int r = 0; r < NX; ++r) Kinv[c * NK + r] = -Sinv[c * NX + r];
+  /* top-right = -(top-left * FQinv)  (14 x 21) */
+  double TR[NX * NQ3];
+  for (int c = 0; c < NQ3; ++c)
+    for (int r = 0; r < NX; ++r) {
+      double t = 0;
+      for (int k = 0; k < NX; ++k) t = fma(Kinv[k * NK + r], FQ[c * NX + k], t);
+      TR[c * NX + r] = -t;
+      Kinv[(NX + c) * NK + r] = -t;
+      Kinv[r * NK + NX + c] = -t;        /* bottom-left = top-right^T */
+    }
+  /* bottom-right = Qinv - TR^T S TR */
+  double STR[NX * NQ3];
+  for (int c = 0; c < NQ3; ++c)
+    for (int r = 0; r < NX; ++r) {
+      double t = 0;
+      for (int k = 0; k < NX; ++k) t = fma(S[k * NX + r], TR[c * NX + k], t);
+      STR[c * NX + r] = t;
+    }
+  for (int c = 0; c < NQ3; ++c)
+    for (int r = 0; r < NQ3; ++r) {
+      double t = 0;
+      for (int k = 0; k < NX; ++k) t = fma(TR[r * NX + k], STR[c * NX + k], t);
+      Kinv[(NX + c) * NK + NX + r] = Qinv[c * NQ3 + r] - t;
+    }
+  return info;
+}
+
+/* assemble the 21x21 Q (order a,q,v) of a stage as SplitUnBackwardCorrection::coarseUpdate sees it
+ * (split_unbackward_correction.hxx:37-53): Qxx += aux_next, then Qvq = Qqv^T, Qxa = Qax^T */
+static void assemble_parnmpc_Q(const stage_t* st, const double* aux_next, double* Q) {
+  for (int c = 0; c < NV; ++c)
+    for (int r = 0; r < NV; ++r) {
+      double qq = st->uQqq[c * NV + r], qv = st->uQqv[c * NV + r], vv = st->uQvv[c * NV + r];
+      if (aux_next) {
+        qq += aux_next[c * NX + r];
+        qv += aux_next[(NV + c) * NX + r];
+        vv += aux_next[(NV + c) * NX + NV + r];
+      }
+      Q[c * NQ3 + r] = st->uQaa[c * NV + r];                       /* aa */
+      Q[(NV + c) * NQ3 + r] = st->uQaq[c * NV + r];                /* aq */
+      Q[(2 * NV + c) * NQ3 + r] = st->uQav[c * NV + r];            /* av */
+      Q[r * NQ3 + NV + c] = st->uQaq[c * NV + r];                  /* qa = aq^T */
+      Q[r * NQ3 + 2 * NV + c] = st->uQav[c * NV + r];              /* va = av^T */
+      Q[(NV + c) * NQ3 + NV + r] = qq;                             /* qq */
+      Q[(2 * NV + c) * NQ3 + NV + r] = qv;                         /* qv */
+      Q[(NV + r) * NQ3 + 2 * NV + c] = qv;                         /* vq = qv^T */
+      Q[(2 * NV + c) * NQ3 + 2 * NV + r] = vv;                     /* vv */
+    }
+}
+
+/* UnParNMPCSolver::updateSolution (:74-102) */
+void oracle_unparnmpc_update_solution(oracle_unparnmpc_t* o, double t, const double* q, const double* v,
+                                      int line_search) {
+  (void)t;
+  const int N = o->N;
+  const double dt = o->dt;
+  const oracle_problem_t* p = &o->p;
+  o->chol_info = 0;
+  /* UnBackwardCorrection::coarseUpdate (:67-97) */
+  for (int i = 0; i < N; ++i) {
+    const double* qp = i == 0 ? q : o->s[i - 1].q;
+    const double* vp = i == 0 ? v : o->s[i - 1].v;
+    stage_t* st = &o->st[i];
+    parnmpc_linearize(p, dt, qp, vp, &o->s[i], i < N - 1 ? &o->s[i + 1] : NULL, st);
+    double Q[NQ3 * NQ3];
+    assemble_parnmpc_Q(st, i < N - 1 ? o->aux + (size_t)(i + 1) * NX * NX : NULL, Q);
+    double* Kinv = o->KKTinv + (size_t)i * NK * NK;
+    const int info = invert_unkkt(dt, Q, Kinv);
+    if (info && !o->chol_info) o->chol_info = 1000 * (i + 1) + info;
+    /* d = KKT^-1 residual, residual order [Fq,Fv,la,lq,lv]; d order [dlmd,dgmm,du(=da),dq,dv] */
+    double res[NK], dd[NK];
+    memcpy(res, st->uFq, sizeof(double) * NV); memcpy(res + NV, st->uFv, sizeof(double) * NV);
+    memcpy(res + 2 * NV, st->ula, sizeof(double) * NV); memcpy(res + 3 * NV, st->ulq, sizeof(double) * NV);
+    memcpy(res + 4 * NV, st->ulv, sizeof(double) * NV);
+    for (int r = 0; r < NK; ++r) {
+      double acc = 0;
+      for (int c = 0; c < NK; ++c) acc = fma(Kinv[c * NK + r], res[c], acc);
+      dd[r] = acc;
+    }
+    split_direction_t* d = &o->d[i];
+    split_solution_t* sn = &o->s_new[i];
+    const split_solution_t* s = &o->s[i];
+    for (int j = 0; j < NV; ++j) {
+      d->dlmd[j] = dd[j]; d->dgmm[j] = dd[NV + j]; d->du[j] = dd[2 * NV + j];
+      d->dq[j] = dd[3 * NV + j]; d->dv[j] = dd[4 * NV + j];
+      sn->lmd[j] = s->lmd[j] - d->dlmd[j];
+      sn->gmm[j] = s->gmm[j] - d->dgmm[j];
+      sn->a[j] = s->a[j] - d->du[j];
+      sn->q[j] = s->q[j] - d->dq[j];
+      sn->v[j] = s->v[j] - d->dv[j];
+    }
+  }
+  /* UnBackwardCorrection::backwardCorrection (:100-134) */
+  for (int i = N - 2; i >= 0; --i) {          /* backwardCorrectionSerial */
+    const double* Kinv = o->KKTinv + (size_t)i * NK * NK;
+    double* xr = o->xres + (size_t)i * NX;
+    for (int j = 0; j < NV; ++j) {
+      xr[j] = o->s_new[i + 1].lmd[j] - o->s[i + 1].lmd[j];
+      xr[NV + j] = o->s_new[i + 1].gmm[j] - o->s[i + 1].gmm[j];
+    }
+    for (int r = 0; r < NX; ++r) {
+      double acc = 0;
+      for (int c = 0; c < NX; ++c) acc = fma(Kinv[(NK - NX + c) * NK + r], xr[c], acc);
+      if (r < NV) o->s_new[i].lmd[r] -= acc; else o->s_new[i].gmm[r - NV] -= acc;
+    }
+  }
+  for (int i = N - 2; i >= 0; --i) {          /* backwardCorrectionParallel */
+    const double* Kinv = o->KKTinv + (size_t)i * NK * NK;
+    const double* xr = o->xres + (size_t)i * NX;
+    for (int r = 0; r < NQ3; ++r) {
+      double acc = 0;
+      for (int c = 0; c < NX; ++c) acc = fma(Kinv[(NK - NX + c) * NK + NX + r], xr[c], acc);
+      if (r < NV) { o->d[i].du[r] = acc; o->s_new[i].a[r] -= acc; }
+      else if (r < 2 * NV) { o->d[i].dq[r - NV] = acc; o->s_new[i].q[r - NV] -= acc; }
+      else { o->d[i].dv[r - 2 * NV] = acc; o->s_new[i].v[r - 2 * NV] -= acc; }
+    }
+  }
+  for (int i = 1; i < N; ++i) {               /* forwardCorrectionSerial */
+    const double* Kinv = o->KKTinv + (size_t)i * NK * NK;
+    double* xr = o->xres + (size_t)i * NX;
+    for (int j = 0; j < NV; ++j) {
+      xr[j] = o->s_new[i - 1].q[j] - o->s[i - 1].q[j];
+      xr[NV + j] = o->s_new[i - 1].v[j] - o->s[i - 1].v[j];
+    }
+    for (int r = 0; r < NX; ++r) {
+      double acc = 0;
+      for (int c = 0; c < NX; ++c) acc = fma(Kinv[c * NK + NK - NX + r], xr[c], acc);
+      if (r < NV) o->s_new[i].q[r] -= acc; else o->s_new[i].v[r - NV] -= acc;
+    }
+  }
+  double primal = 1.0, dual = 1.0;
+  for (int i = 0; i < N; ++i) {               /* forwardCorrectionParallel + directions */
+    const double* Kinv = o->KKTinv + (size_t)i * NK * NK;
+    split_direction_t* d = &o->d[i];
+    split_solution_t* sn = &o->s_new[i];
+    const split_solution_t* s = &o->s[i];
+    if (i > 0) {
+      const double* xr = o->xres + (size_t)i * NX;
+      for (int r = 0; r < NQ3; ++r) {
+        double acc = 0;
+        for (int c = 0; c < NX; ++c) acc = fma(Kinv[c * NK + r], xr[c], acc);
+        if (r < NV) { d->dlmd[r] = acc; sn->lmd[r] -= acc; }
+        else if (r < 2 * NV) { d->dgmm[r - NV] = acc; sn->gmm[r - NV] -= acc; }
+        else { d->du[r - 2 * NV] = acc; sn->a[r - 2 * NV] -= acc; }
+      }
+      double* A = o->aux + (size_t)i * NX * NX;   /* aux_mat = -KKT^-1[0:14, 0:14] */
+      for (int c = 0; c < NX; ++c)
+        for (int r = 0; r < NX; ++r) A[c * NX + r] = -Kinv[c * NK + r];
+    }
+    /* SplitUnBackwardCorrection::computeDirection (:113-121) */
+    for (int j = 0; j < NV; ++j) {
+      d->dlmd[j] = sn->lmd[j] - s->lmd[j];
+      d->dgmm[j] = sn->gmm[j] - s->gmm[j];
+      d->da[j] = sn->a[j] - s->a[j];
+      d->dq[j] = sn->q[j] - s->q[j];
+      d->dv[j] = sn->v[j] - s->v[j];
+    }
+    split_unocp_condensed_direction(&o->st[i], dt, d);
+    const double ps = max_slack_step(p, &o->st[i]);
+    const double ds = max_dual_step(p, &o->st[i]);
+    if (ps < primal) primal = ps;
+    if (ds < dual) dual = ds;
+  }
+  o->max_primal_step = primal;
+  (void)line_search;  /* the ParNMPC line search is not restated yet (SURVEY 8a row a11 covers UnOCP) */
+  o->primal_step = primal;
+  o->dual_step = dual;
+  for (int i = 0; i < N; ++i) {
+    split_solution_t* s = &o->s[i];
+    const split_direction_t* d = &o->d[i];
+    for (int j = 0; j < NV; ++j) {
+      s->lmd[j] = fma(primal, d->dlmd[j], s->lmd[j]);
+      s->gmm[j] = fma(primal, d->dgmm[j], s->gmm[j]);
+      s->q[j] = fma(primal, d->dq[j], s->q[j]);
+      s->v[j] = fma(primal, d->dv[j], s->v[j]);
+      s->a[j] = fma(primal, d->da[j], s->a[j]);
+      s->u[j] = fma(primal, d->du[j], s->u[j]);
+      s->beta[j] = fma(primal, d->dbeta[j], s->beta[j]);
+    }
+    stage_t* st = &o->st[i];
+    for (int c = 0; c < NC; ++c) {
+      if (!st->active[c]) continue;
+      for (int j = 0; j < NV; ++j) {
+        st->c[c].slack[j] = fma(primal, st->c[c].dslack[j], st->c[c].slack[j]);
+        st->c[c].dual[j] = fma(dual, st->c[c].ddual[j], st->c[c].dual[j]);
+      }
+    }
+  }
+}
+
+/* UnParNMPCSolver::computeKKTResidual (:171-192) and KKTError (:157-168) */
+void oracle_unparnmpc_compute_kkt_residual(oracle_unparnmpc_t* o, double t, const double* q, const double* v) {
+  (void)t;
+  for (int i = 0; i < o->N; ++i) {
+    const double* qp = i == 0 ? q : o->s[i - 1].q;
+    const double* vp = i == 0 ? v : o->s[i - 1].v;
+    compute_primal_dual_residual(&o->p, &o->st[i], &o->s[i]);
+    parnmpc_residual_common(&o->p, o->dt, qp, vp, &o->s[i], i < o->N - 1 ? &o->s[i + 1] : NULL, &o->st[i]);
+  }
+}
+
+double oracle_unparnmpc_kkt_error(oracle_unparnmpc_t* o) {
+  double e = 0;
+  for (int i = 0; i < o->N; ++i) e += split_unocp_sqnorm(&o->st[i], o->dt);
+  return sqrt(e);
+}
+
+int oracle_unparnmpc_get_solution(const oracle_unparnmpc_t* o, const char* name, double* out) {
+  for (int i = 0; i < o->N; ++i) {
+    const double* src;
+    if (!strcmp(name, "lmd")) src = o->s[i].lmd;
+    else if (!strcmp(name, "gmm")) src = o->s[i].gmm;
+    else if (!strcmp(name, "q")) src = o->s[i].q;
+    else if (!strcmp(name, "v")) src = o->s[i].v;
+    else if (!strcmp(name, "a")) src = o->s[i].a;
+    else if (!strcmp(name, "u")) src = o->s[i].u;
+    else if (!strcmp(name, "beta")) src = o->s[i].beta;
+    else return -1;
+    memcpy(out + i * NV, src, sizeof(double) * NV);
+  }
+  return o->N;
+}
+
+int oracle_unparnmpc_get_direction(const oracle_unparnmpc_t* o, const char* name, double* out) {
+  for (int i = 0; i < o->N; ++i) {
+    const double* src;
+    if (!strcmp(name, "dlmd")) src = o->d[i].dlmd;
+    else if (!strcmp(name, "dgmm")) src = o->d[i].dgmm;
+    else if (!strcmp(name, "dq")) src = o->d[i].dq;
+    else if (!strcmp(name, "dv")) src = o->d[i].dv;
+    else if (!strcmp(name, "da")) src = o->d[i].da;
+    else if (!strcmp(name, "du")) src = o->d[i].du;
+    else if (!strcmp(name, "dbeta")) src = o->d[i].dbeta;
+    else return -1;
+    memcpy(out + i * NV, src, sizeof(double) * NV);
+  }
+  return o->N;
+}
+
+void oracle_unparnmpc_get_step_sizes(const oracle_unparnmpc_t* o, double* out) {
+  out[0] = o->primal_step; out[1] = o->dual_step; out[2] = o->max_primal_step;
+}
+
+/* parity getter: 35x35 KKT inverse of a stage (column-major) */
+void oracle_unparnmpc_get_kkt_inverse(const oracle_unparnmpc_t* o, int stage, double* out) {
+  memcpy(out, o->KKTinv + (size_t)stage * NK * NK, sizeof(double) * NK * NK);
+}
+
+void oracle_unparnmpc_batch_update_solution(oracle_unparnmpc_t** os, int batch, double t, const double* q0,
+                                            const double* v0, int line_search, int nthreads) {
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+  for (int b = 0; b < batch; ++b)
+    oracle_unparnmpc_update_solution(os[b], t, q0 + (size_t)b * NV, v0 + (size_t)b * NV, line_search);
+}
+
+void oracle_unparnmpc_batch_kkt(oracle_unparnmpc_t** os, int batch, double t, const double* q0,
+                                const double* v0, double* kkt_out, int nthreads) {
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+  for (int b = 0; b < batch; ++b) {
+    oracle_unparnmpc_compute_kkt_residual(os[b], t, q0 + (size_t)b * NV, v0 + (size_t)b * NV);
+    kkt_out[b] = oracle_unparnmpc_kkt_error(os[b]);
+  }
+}
+
+/* parity getter: the 21x21 Q a stage's coarse update inverted is not stored; re-assemble it from
+ * the stage data of the last linearisation (aux of the NEXT iteration is already in place, so this
+ * is only exact before the first update) -- used by tests through oracle_invert_unkkt instead */
+int oracle_invert_unkkt(double dt, const double* Q, double* Kinv) { return invert_unkkt(dt, Q, Kinv); }
+
+int oracle_unparnmpc_chol_info(const oracle_unparnmpc_t* o) { return o->chol_info; }

@@ -100,6 +100,11 @@ double oracle_unparnmpc_kkt_error(oracle_unparnmpc_t* o);
 int  oracle_unparnmpc_get_solution(const oracle_unparnmpc_t* o, const char* name, double* out);
 int  oracle_unparnmpc_get_direction(const oracle_unparnmpc_t* o, const char* name, double* out);
 void oracle_unparnmpc_get_step_sizes(const oracle_unparnmpc_t* o, double* out);
+/* 35x35 inverse of [[0 F],[F^T Q]] of a stage (column-major, order [lmd,gmm | a,q,v]) */
+void oracle_unparnmpc_get_kkt_inverse(const oracle_unparnmpc_t* o, int stage, double* out);
+int  oracle_unparnmpc_chol_info(const oracle_unparnmpc_t* o);
+/* SplitUnKKTMatrixInverter::invert (unocp/split_unkkt_matrix_inverter.hxx:40-79) on a 21x21 Q */
+int  oracle_invert_unkkt(double dt, const double* Q, double* Kinv);
 void oracle_unparnmpc_batch_update_solution(oracle_unparnmpc_t** os, int batch, double t, const double* q0,
                                             const double* v0, int line_search, int nthreads);
 void oracle_unparnmpc_batch_kkt(oracle_unparnmpc_t** os, int batch, double t, const double* q0,

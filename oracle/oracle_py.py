@@ -224,6 +224,23 @@ class UnParNMPCSolver(_SolverBase):
     def init_backward_correction(self, t):
         self.L.oracle_unparnmpc_init_backward_correction(self.h, C.c_double(t))
 
+    def get_kkt_inverse(self, stage):
+        """35x35 KKT inverse of the last coarse update, order [lmd,gmm | a,q,v], numpy [row, col]."""
+        out = np.zeros((35, 35))
+        self.L.oracle_unparnmpc_get_kkt_inverse(self.h, stage, _p(out))
+        return out.T.copy()
+
+    def chol_info(self):
+        return int(self.L.oracle_unparnmpc_chol_info(self.h))
+
+
+def invert_unkkt(dt, Q):
+    """SplitUnKKTMatrixInverter::invert on a 21x21 Q (numpy [row, col]); returns (info, 35x35 inverse)."""
+    Qc = np.asfortranarray(np.asarray(Q, dtype=np.float64))
+    out = np.zeros((35, 35))
+    info = lib().oracle_invert_unkkt(C.c_double(dt), Qc.ctypes.data_as(_dp), _p(out))
+    return info, out.T.copy()
+
 
 class Batch:
     """A batch of independent oracle solvers driven with OpenMP over instances (BASELINE.md mode B)."""
