@@ -184,16 +184,6 @@ static void fill_dev_problem(const idocp_b200_problem& p, DevProblem& d) {
   }
 }
 
-static int parnmpc_update(idocp_b200_solver*, double, const double*, const double*, int) {
-  return fail(IDOCP_B200_UNSUPPORTED, "UnParNMPCSolver is not implemented yet");
-}
-static int parnmpc_kkt_residual(idocp_b200_solver*, double, const double*, const double*) {
-  return fail(IDOCP_B200_UNSUPPORTED, "UnParNMPCSolver is not implemented yet");
-}
-static int parnmpc_init_backward_correction(idocp_b200_solver*, double) {
-  return fail(IDOCP_B200_UNSUPPORTED, "UnParNMPCSolver is not implemented yet");
-}
-
 // grid of a per-stage kernel: one warp per (stage, group)
 static int stage_grid(const idocp_b200_solver* h, int nstages) {
   const long tasks = static_cast<long>(nstages) * h->L.G;
@@ -267,7 +257,12 @@ extern "C" int idocp_b200_create(const idocp_b200_problem* p, int solver_kind, i
     h->stage_doubles = need;
   }
   rc |= h->alloc(&h->d_stage, h->stage_doubles);
-  if (par) rc |= parnmpc_alloc(h->PL, h->N, h->Bp, [&](double** pp, size_t n) { return h->alloc(pp, n); });
+  if (par) {
+    rc |= parnmpc_alloc(h->PL, h->N, h->Bp, [&](double** pp, size_t n) { return h->alloc(pp, n); });
+    if (cudaFuncSetAttribute(k_parnmpc_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, INV_SMEM_BYTES) !=
+        cudaSuccess)
+      rc |= -1;
+  }
   if (rc != 0) {
     idocp_b200_destroy(h);
     return fail(IDOCP_B200_CUDA_ERROR, "device memory allocation failed");
@@ -388,16 +383,56 @@ static int run_line_search(idocp_b200_solver* h) {
 }
 
 static int unocp_update(idocp_b200_solver* h, const double* d_q, const double* d_v, int line_search) {
-  IDOCP_LAUNCH(h, KC_LINEARIZE, k_linearize<false>, stage_grid(h, h->N), CTA_THREADS, kLinSmem, h->d_prob, h->L);
+  IDOCP_LAUNCH(h, KC_LINEARIZE, (k_linearize<false, false>), stage_grid(h, h->N), CTA_THREADS, kLinSmem, h->d_prob,
+               h->L, d_q, d_v);
   IDOCP_LAUNCH(h, KC_RICCATI, k_riccati, group_grid(h), CTA_THREADS, kRicSmem, h->d_prob, h->L, d_q, d_v);
-  IDOCP_LAUNCH(h, KC_EXPAND, k_expand, stage_grid(h, h->N + 1), CTA_THREADS, 0, h->d_prob, h->L, 0);
+  IDOCP_LAUNCH(h, KC_EXPAND, k_expand<false>, stage_grid(h, h->N + 1), CTA_THREADS, 0, h->d_prob, h->L, 0);
   const double* override_alpha = nullptr;
   if (line_search) {
     const int rc = run_line_search(h);
     if (rc != IDOCP_B200_OK) return rc;
     override_alpha = h->LS.alpha;
   }
-  IDOCP_LAUNCH(h, KC_UPDATE, k_update, stage_grid(h, h->N + 1), CTA_THREADS, 0, h->d_prob, h->L, 0, override_alpha);
+  IDOCP_LAUNCH(h, KC_UPDATE, k_update, stage_grid(h, h->N + 1), CTA_THREADS, 0, h->d_prob, h->L, 0, override_alpha,
+               h->N + 1);
+  CUDA_OK(cudaGetLastError());
+  return IDOCP_B200_OK;
+}
+
+// UnParNMPCSolver::updateSolution (src/unocp/unparnmpc_solver.cpp:74-102)
+static int parnmpc_update(idocp_b200_solver* h, double, const double* d_q, const double* d_v, int line_search) {
+  if (line_search) return fail(IDOCP_B200_UNSUPPORTED, "UnParNMPCSolver: line_search=true is not implemented yet");
+  const int N = h->N;
+  // UnBackwardCorrection::coarseUpdate (src/unocp/unbackward_correction.cpp:67-97)
+  IDOCP_LAUNCH(h, KC_LINEARIZE, (k_linearize<false, true>), stage_grid(h, N), CTA_THREADS, kLinSmem, h->d_prob, h->L,
+               d_q, d_v);
+  IDOCP_LAUNCH(h, KC_PARNMPC_COARSE, k_parnmpc_invert, N * h->L.G, CTA_THREADS, INV_SMEM_BYTES, h->d_prob, h->L, h->PL);
+  // UnBackwardCorrection::backwardCorrection (:100-134)
+  if (N > 1) {
+    IDOCP_LAUNCH(h, KC_PARNMPC_CORR, k_parnmpc_backward_serial, group_grid(h), CTA_THREADS, 0, h->L, h->PL);
+    IDOCP_LAUNCH(h, KC_PARNMPC_CORR, k_parnmpc_backward_parallel, stage_grid(h, N - 1), CTA_THREADS, 0, h->L, h->PL);
+    IDOCP_LAUNCH(h, KC_PARNMPC_CORR, k_parnmpc_forward_serial, group_grid(h), CTA_THREADS, 0, h->L, h->PL);
+  }
+  IDOCP_LAUNCH(h, KC_PARNMPC_CORR, k_parnmpc_forward_parallel, stage_grid(h, N), CTA_THREADS, 0, h->L, h->PL);
+  IDOCP_LAUNCH(h, KC_EXPAND, k_expand<true>, stage_grid(h, N), CTA_THREADS, 0, h->d_prob, h->L, 1);
+  IDOCP_LAUNCH(h, KC_UPDATE, k_update, stage_grid(h, N), CTA_THREADS, 0, h->d_prob, h->L, 1,
+               static_cast<const double*>(nullptr), N);
+  CUDA_OK(cudaGetLastError());
+  return IDOCP_B200_OK;
+}
+
+// UnParNMPCSolver::computeKKTResidual (src/unocp/unparnmpc_solver.cpp:171-192)
+static int parnmpc_kkt_residual(idocp_b200_solver* h, double, const double* d_q, const double* d_v) {
+  IDOCP_LAUNCH(h, KC_KKT, (k_linearize<true, true>), stage_grid(h, h->N), CTA_THREADS, kLinSmem, h->d_prob, h->L, d_q,
+               d_v);
+  IDOCP_LAUNCH(h, KC_KKT, k_kkt_sum, (h->Bp + 127) / 128, 128, 0, h->L, h->N);
+  CUDA_OK(cudaGetLastError());
+  return IDOCP_B200_OK;
+}
+
+// UnParNMPCSolver::initBackwardCorrection (src/unocp/unparnmpc_solver.cpp:69-71)
+static int parnmpc_init_backward_correction(idocp_b200_solver* h, double) {
+  IDOCP_LAUNCH(h, KC_MISC, k_parnmpc_init_aux, stage_grid(h, h->N), CTA_THREADS, 0, h->d_prob, h->L, h->PL);
   CUDA_OK(cudaGetLastError());
   return IDOCP_B200_OK;
 }
@@ -426,7 +461,8 @@ extern "C" int idocp_b200_compute_kkt_residual_device(idocp_b200_solver* h, doub
   (void)t;
   CUDA_OK(cudaSetDevice(h->device));
   if (h->kind == IDOCP_B200_SOLVER_UNPARNMPC) return parnmpc_kkt_residual(h, t, d_q, d_v);
-  IDOCP_LAUNCH(h, KC_KKT, k_linearize<true>, stage_grid(h, h->N + 1), CTA_THREADS, kLinSmem, h->d_prob, h->L);
+  IDOCP_LAUNCH(h, KC_KKT, (k_linearize<true, false>), stage_grid(h, h->N + 1), CTA_THREADS, kLinSmem, h->d_prob, h->L,
+               d_q, d_v);
   IDOCP_LAUNCH(h, KC_KKT, k_kkt_sum, (h->Bp + 127) / 128, 128, 0, h->L, h->N + 1);
   CUDA_OK(cudaGetLastError());
   return IDOCP_B200_OK;

@@ -131,15 +131,23 @@ __global__ void k_set_solution(Layout L, int field, const double* __restrict__ v
 // ---------------------------------------------------------------------------------------------
 // RESIDUAL_ONLY = true : computeKKTResidual + squaredNormKKTResidual (writes kkt_stage only)
 // RESIDUAL_ONLY = false: linearizeOCP (writes condensed KKT blocks, residual, expansion data)
-template <bool RESIDUAL_ONLY>
-__global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_linearize(const DevProblem* __restrict__ Pp, Layout L) {
+// BACKWARD_EULER = false: SplitUnOCP (forward Euler, stages 0..N-1 + terminal stage N)
+// BACKWARD_EULER = true : SplitUnParNMPC / TerminalUnParNMPC (unocp/split_unparnmpc.hxx:69-101,141-174;
+//                         terminal_unparnmpc.hxx:70-102,155-193): stages 1..N stored at index 0..N-1, the
+//                         previous state of index 0 is the measured x0 = (q0, v0), index N-1 also carries
+//                         the terminal cost; constraint masks use time stage index + 1
+template <bool RESIDUAL_ONLY, bool BACKWARD_EULER>
+__global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_linearize(const DevProblem* __restrict__ Pp, Layout L,
+                                                                           const double* __restrict__ q0,
+                                                                           const double* __restrict__ v0) {
   IDOCP_DYN_SMEM(double, smem);
   const DevProblem& P = *Pp;
   const int lane = lane_in_octet();
   const int oct = threadIdx.x >> 3;
   double* tile = smem + oct * (OCT * PAIR_TILE);
-  const StageTask t = stage_task(L, RESIDUAL_ONLY ? L.N + 1 : L.N);
+  const StageTask t = stage_task(L, (RESIDUAL_ONLY && !BACKWARD_EULER) ? L.N + 1 : L.N);
   const int i = t.stage;
+  const int ts = BACKWARD_EULER ? i + 1 : i;   // time stage of the constraint masks
   const int b = t.g * 4 + ((threadIdx.x >> 3) & 3);
   const double dt = P.dt;
   const bool act = lane < NV;
@@ -147,7 +155,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_linearize(const
 
   const double q = X[X_Q * SLOT], v = X[X_V * SLOT], lmd = X[X_LMD * SLOT], gmm = X[X_GMM * SLOT];
 
-  if (RESIDUAL_ONLY && i == L.N) {
+  if (RESIDUAL_ONLY && !BACKWARD_EULER && i == L.N) {
     // TerminalOCP::computeKKTResidual + squaredNormKKTResidual (ocp/terminal_ocp.hxx:120-144)
     double lq = 0.0, lv = 0.0;
     lq += P.qf_weight[lane] * (q - P.q_ref[lane]);
@@ -161,8 +169,24 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_linearize(const
   }
 
   const double a = X[X_A * SLOT], u = X[X_U * SLOT], beta = X[X_BETA * SLOT];
+  const bool last = BACKWARD_EULER && (i == L.N - 1);                // TerminalUnParNMPC
   const double* Xn = X + static_cast<size_t>(L.G) * (X_NUM * SLOT);  // next stage, same group
-  const double qn = Xn[X_Q * SLOT], vn = Xn[X_V * SLOT], lmdn = Xn[X_LMD * SLOT], gmmn = Xn[X_GMM * SLOT];
+  // forward Euler: (q, v, lmd, gmm) of the next stage; backward Euler: (q, v) of the previous stage
+  // (x0 for index 0) and (lmd, gmm) of the next stage (none for the last one)
+  double qn, vn, lmdn = 0.0, gmmn = 0.0;
+  if (!BACKWARD_EULER) {
+    qn = Xn[X_Q * SLOT]; vn = Xn[X_V * SLOT]; lmdn = Xn[X_LMD * SLOT]; gmmn = Xn[X_GMM * SLOT];
+  } else {
+    if (i == 0) {
+      const size_t bi = static_cast<size_t>(b < L.B ? b : 0) * NV + (act ? lane : 0);
+      qn = act ? q0[bi] : 0.0;
+      vn = act ? v0[bi] : 0.0;
+    } else {
+      const double* Xp = X - static_cast<size_t>(L.G) * (X_NUM * SLOT);
+      qn = Xp[X_Q * SLOT]; vn = Xp[X_V * SLOT];
+    }
+    if (!last) { lmdn = Xn[X_LMD * SLOT]; gmmn = Xn[X_GMM * SLOT]; }
+  }
   double slack[NC], dual[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
@@ -184,18 +208,38 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_linearize(const
   lv += dt * P.v_weight[lane] * (v - P.v_ref[lane]);
   la += dt * P.a_weight[lane] * a;
   lu += dt * P.u_weight[lane] * (u - P.u_ref[lane]);
+  if (last) {   // + computeTerminalCostDerivatives (terminal_unparnmpc.hxx:84)
+    lq += P.qf_weight[lane] * (q - P.q_ref[lane]);
+    lv += P.vf_weight[lane] * (v - P.v_ref[lane]);
+  }
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
-    if (!comp_active(c, i)) continue;
+    if (!comp_active(c, ts)) continue;
     const double g = dt * dual[c];
     const double sg = (c & 1) ? g : -g;
     if (c < 2) lq += sg; else if (c < 4) lv += sg; else lu += sg;
   }
-  const double Fq = fma(dt, v, q - qn);
-  const double Fv = fma(dt, a, v) - vn;
-  lq += lmdn - lmd;
-  lv += fma(dt, lmdn, gmmn) - gmm;
-  la = fma(dt, gmmn, la);
+  double Fq, Fv;
+  if (!BACKWARD_EULER) {
+    // stateequation::linearizeForwardEuler (ocp/state_equation.hxx:11-37,210-221)
+    Fq = fma(dt, v, q - qn);
+    Fv = fma(dt, a, v) - vn;
+    lq += lmdn - lmd;
+    lv += fma(dt, lmdn, gmmn) - gmm;
+    la = fma(dt, gmmn, la);
+  } else {
+    // stateequation::linearizeBackwardEuler[Terminal] (ocp/state_equation.hxx:111-167,224-236)
+    Fq = fma(dt, v, qn - q);
+    Fv = fma(dt, a, vn - v);
+    if (last) {
+      lq -= lmd;
+      lv += fma(dt, lmd, -gmm);
+    } else {
+      lq += lmdn - lmd;
+      lv += fma(dt, lmd, -gmm) + gmmn;
+    }
+    la = fma(dt, gmm, la);
+  }
   {
     double tq = 0.0, tv = 0.0, ta = 0.0;
 #pragma unroll
@@ -223,7 +267,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_linearize(const
     double c2 = 0.0;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      if (!comp_active(c, i)) continue;
+      if (!comp_active(c, ts)) continue;
       const double r = con_residual(c, lim, q, v, u, slack[c]);
       const double dl = slack[c] * dual[c] - P.barrier;
       c2 += oct_sum_ordered(z * (r * r)) + oct_sum_ordered(z * (dl * dl));
@@ -238,10 +282,14 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_linearize(const
   double Qvv_d = dt * P.v_weight[lane];
   const double Qaa_d = dt * P.a_weight[lane];
   double Quu_d = dt * P.u_weight[lane];
+  if (last) {   // + computeTerminalCostHessian (terminal_unparnmpc.hxx:93)
+    Qqq_d += P.qf_weight[lane];
+    Qvv_d += P.vf_weight[lane];
+  }
   if (act) {
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      if (!comp_active(c, i)) continue;
+      if (!comp_active(c, ts)) continue;
       const double r = con_residual(c, lim, q, v, u, slack[c]);
       const double dl = slack[c] * dual[c] - P.barrier;
       const double rs = 1.0 / slack[c];
@@ -623,10 +671,13 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_RIC_MINB) k_riccati(const D
 // du = ID + dID [dq,dv,da], dbeta = (lu + Quu du)/dt; slack/dual directions; per-stage
 // fraction-to-boundary minima.  Terminal stage: costate only (P_N = diag, s_N recomputed).
 // ---------------------------------------------------------------------------------------------
+// PARNMPC = true (UnParNMPCSolver): N stages, none terminal, the costate direction is already in D
+// (k_parnmpc_forward_parallel); only the condensed direction and the step sizes are computed.
+template <bool PARNMPC>
 __global__ void __launch_bounds__(CTA_THREADS) k_expand(const DevProblem* __restrict__ Pp, Layout L, int stage_offset) {
   const DevProblem& P = *Pp;
   const int lane = lane_in_octet();
-  const StageTask t = stage_task(L, L.N + 1);
+  const StageTask t = stage_task(L, PARNMPC ? L.N : L.N + 1);
   const int i = t.stage;
   const int b = t.g * 4 + ((threadIdx.x >> 3) & 3);
   const int N = L.N;
@@ -634,7 +685,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_expand(const DevProblem* __rest
   const double* X = rec_ptr(L.X, X_NUM, L.G, i, t.g);
   double* D = rec_ptr(L.D, D_NUM, L.G, i, t.g);
   const double dq = D[D_Q * SLOT], dv = D[D_V * SLOT];
-  if (i == N) {
+  if (!PARNMPC && i == N) {
     const double q = X[X_Q * SLOT], v = X[X_V * SLOT], lmd = X[X_LMD * SLOT], gmm = X[X_GMM * SLOT];
     double lq = 0.0, lv = 0.0;
     lq += P.qf_weight[lane] * (q - P.q_ref[lane]);
@@ -653,8 +704,8 @@ __global__ void __launch_bounds__(CTA_THREADS) k_expand(const DevProblem* __rest
 #pragma unroll
   for (int k = 0; k < NV; ++k) { dqk[k] = oct_bcast(dq, k); dvk[k] = oct_bcast(dv, k); }
   // costate direction (split_unriccati_factorizer.hxx:60-68)
-  double dlmd, dgmm;
-  {
+  double dlmd = 0.0, dgmm = 0.0;
+  if (!PARNMPC) {
     double t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
@@ -685,8 +736,10 @@ __global__ void __launch_bounds__(CTA_THREADS) k_expand(const DevProblem* __rest
     du = acc;
     dbeta = fma(W[W_QUU * SLOT], du, W[W_LU * SLOT]) / P.dt;
   }
-  D[D_LMD * SLOT] = dlmd;
-  D[D_GMM * SLOT] = dgmm;
+  if (!PARNMPC) {
+    D[D_LMD * SLOT] = dlmd;
+    D[D_GMM * SLOT] = dgmm;
+  }
   D[D_U * SLOT] = du;
   D[D_BETA * SLOT] = dbeta;
   // slack / dual directions and fraction-to-boundary
@@ -722,13 +775,15 @@ __global__ void __launch_bounds__(CTA_THREADS) k_expand(const DevProblem* __rest
 // 215-239; constraints_impl.hxx:181-196).  dslack / ddual are recomputed from (s, slack, dual, d)
 // instead of being stored.  `primal_override` (line search) replaces the primal step when given.
 // ---------------------------------------------------------------------------------------------
+// `nstages` = N + 1 with the terminal stage at index N (UnOCPSolver) or N without one (UnParNMPCSolver,
+// src/unocp/unparnmpc_solver.cpp:88-101).
 __global__ void __launch_bounds__(CTA_THREADS) k_update(const DevProblem* __restrict__ Pp, Layout L, int stage_offset,
-                                                        const double* __restrict__ primal_override) {
+                                                        const double* __restrict__ primal_override, int nstages) {
   const DevProblem& P = *Pp;
   const int lane = lane_in_octet();
   // read-modify-write kernel: tail warps must NOT redo a task (whole warps exit together)
-  if (static_cast<long>(blockIdx.x) * WARPS_PER_CTA + (threadIdx.x >> 5) >= static_cast<long>(L.N + 1) * L.G) return;
-  const StageTask t = stage_task(L, L.N + 1);
+  if (static_cast<long>(blockIdx.x) * WARPS_PER_CTA + (threadIdx.x >> 5) >= static_cast<long>(nstages) * L.G) return;
+  const StageTask t = stage_task(L, nstages);
   const int i = t.stage;
   const int b = t.g * 4 + ((threadIdx.x >> 3) & 3);
   const int N = L.N;

@@ -1,19 +1,438 @@
-// unparnmpc_kernels.cuh -- batched UnParNMPCSolver (backward-Euler stages, per-stage KKT
-// inversion, backward/forward correction).  (reference src/unocp/unparnmpc_solver.cpp,
-// src/unocp/unbackward_correction.cpp)
+// unparnmpc_kernels.cuh -- batched UnParNMPCSolver: per-stage KKT inversion (coarse update) and the
+// backward / forward correction sweeps.
+//
+//   k_parnmpc_invert            <-> SplitUnBackwardCorrection::coarseUpdate + SplitUnKKTMatrixInverter::invert
+//                                   (unocp/split_unbackward_correction.hxx:37-62, split_unkkt_matrix_inverter.hxx:40-79)
+//   k_parnmpc_backward_serial   <-> backwardCorrectionSerial   (split_unbackward_correction.hxx:71-79)
+//   k_parnmpc_backward_parallel <-> backwardCorrectionParallel (:82-90)
+//   k_parnmpc_forward_serial    <-> forwardCorrectionSerial    (:93-101)
+//   k_parnmpc_forward_parallel  <-> forwardCorrectionParallel + auxMat + computeDirection (:104-121;
+//                                   src/unocp/unbackward_correction.cpp:114-133)
+//   k_parnmpc_init_aux          <-> UnBackwardCorrection::initAuxMat (src/unocp/unbackward_correction.cpp:55-64)
+//
+// The stage linearisation is k_linearize<.., BACKWARD_EULER = true> (unocp_kernels.cuh); the condensed
+// direction, step sizes and the update are k_expand<true> / k_update.
+//
+// Stages 1..N of the reference are stored at index 0..N-1.  KKT system of a stage, unknown order
+// [dlmd, dgmm | da, dq, dv], matrix [[0, F],[F^T, Q]], F = [[0,-I,dt I],[dt I,0,-I]], Q in block order (a,q,v).
+// Notation for the blocks of the 35x35 inverse: TL = inv[0:14,0:14] = -S^-1, TR = inv[0:14,14:35],
+// BL = TR^T, BR = inv[14:35,14:35].
 #pragma once
 #include "unocp_kernels.cuh"
 
 namespace idocp_b200 {
 
+constexpr int NX2 = 2 * NV;   // 14
+constexpr int NQ3 = 3 * NV;   // 21
+constexpr int NKKT = 5 * NV;  // 35
+
+// s_new of the backward correction: [N stages]
+enum SNSlot { SN_LMD = 0, SN_GMM, SN_A, SN_Q, SN_V, SN_NUM = 5 };
+// x_res of the correction sweeps (head, tail): [N stages]
+enum XRSlot { XR_H = 0, XR_T, XR_NUM = 2 };
+// Blocks of the KKT inverse that the corrections use, stored for mat-vecs "lane = row, slot = column":
+// slot (c, rb) = first + c * nrb + rb holds rows 7 rb .. 7 rb + 6 of column c of the block.
+//   BS: inv[0:14, 21:35]   (14 x 14)  backwardCorrectionSerial      BP: inv[14:35, 21:35] (21 x 14)  ...Parallel
+//   FS: inv[21:35, 0:14]   (14 x 14)  forwardCorrectionSerial       FP: inv[0:21, 0:14]   (21 x 14)  ...Parallel
+enum KISlot { KI_BS = 0, KI_BP = 28, KI_FS = 70, KI_FP = 98, KI_NUM = 140 };
+// aux_mat (14 x 14), slot (c, rb) = c * 2 + rb: [N stages] (index 0 is never used)
+constexpr int AUX_NUM = 28;
+
 struct ParNMPCLayout {
-  double* aux = nullptr;   // aux_mat per stage
+  double* SN = nullptr;
+  double* XR = nullptr;
+  double* KI = nullptr;
+  double* AUX = nullptr;
 };
 
 template <typename Alloc>
 inline int parnmpc_alloc(ParNMPCLayout& PL, int N, int Bp, Alloc alloc) {
-  (void)PL; (void)N; (void)Bp; (void)alloc;
-  return 0;
+  const size_t G = static_cast<size_t>(Bp) / 4, n = static_cast<size_t>(N);
+  int rc = 0;
+  rc |= alloc(&PL.SN, n * G * SN_NUM * SLOT);
+  rc |= alloc(&PL.XR, n * G * XR_NUM * SLOT);
+  rc |= alloc(&PL.KI, n * G * KI_NUM * SLOT);
+  rc |= alloc(&PL.AUX, n * G * AUX_NUM * SLOT);
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_parnmpc_init_aux: every aux_mat = Hessian of the terminal cost = diag(qf_weight, vf_weight)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CTA_THREADS) k_parnmpc_init_aux(const DevProblem* __restrict__ Pp, Layout L,
+                                                                  ParNMPCLayout PL) {
+  const DevProblem& P = *Pp;
+  const int lane = lane_in_octet();
+  const StageTask t = stage_task(L, L.N);
+  double* A = rec_ptr(PL.AUX, AUX_NUM, L.G, t.stage, t.g);
+#pragma unroll
+  for (int c = 0; c < NX2; ++c) {
+    A[(c * 2 + 0) * SLOT] = (c < NV && lane == c) ? P.qf_weight[lane] : 0.0;
+    A[(c * 2 + 1) * SLOT] = (c >= NV && lane == c - NV) ? P.vf_weight[lane] : 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_parnmpc_invert: one WARP per (instance, stage); one CTA = the 4 instances of a group.
+// All matrices live in shared memory (column-major, odd column strides: conflict-free for
+// "lane = row" accesses) or, column per lane, in registers.  Every element is produced by the
+// same ascending-index fma chain as in the oracle (invert_unkkt), so the result is bit-identical.
+// ---------------------------------------------------------------------------------------------
+constexpr int INV_LDQ = NQ3;       // 21 (odd)
+constexpr int INV_LDX = NX2 + 1;   // 15 (odd)
+// per-warp shared memory (doubles)
+constexpr int INV_OFF_A = 0;                          // Q -> L (21 x 21), later BR
+constexpr int INV_OFF_RD = INV_OFF_A + NQ3 * INV_LDQ;  // reciprocal pivots (21)
+constexpr int INV_OFF_FQ = INV_OFF_RD + 24;           // FQinv (14 x 21), column stride 15
+constexpr int INV_OFF_S = INV_OFF_FQ + NQ3 * INV_LDX;  // S (14 x 14); first used as staging of aux_next
+constexpr int INV_OFF_LS = INV_OFF_S + NX2 * INV_LDX;  // LLT(S)
+constexpr int INV_OFF_TL = INV_OFF_LS + NX2 * INV_LDX; // TL (14 x 14)
+constexpr int INV_OFF_TR = INV_OFF_TL + NX2 * INV_LDX; // TR (14 x 21)
+constexpr int INV_OFF_RES = INV_OFF_TR + NQ3 * INV_LDX; // residual (35)
+constexpr int INV_SMEM_PER_WARP = INV_OFF_RES + 36;
+constexpr int INV_SMEM_BYTES = WARPS_PER_CTA * INV_SMEM_PER_WARP * static_cast<int>(sizeof(double));
+
+// left-looking Cholesky of the lower triangle of the n x n matrix at A (column stride ld), in place;
+// lane = row.  Eigen::LLT<Lower> semantics; divisions by the pivot are multiplications by
+// its reciprocal rd[k] (canonical arithmetic, oracle llt_lower).  Returns non-zero on a bad pivot.
+template <int n>
+__device__ __forceinline__ int warp_llt(double* __restrict__ A, int ld, double* __restrict__ rd, int wl) {
+  int fail = 0;
+  for (int k = 0; k < n; ++k) {
+    double x = 0.0;
+    if (wl >= k && wl < n) {
+      x = A[k * ld + wl];
+      for (int j = 0; j < k; ++j) x = fma(-A[j * ld + wl], A[j * ld + k], x);
+    }
+    const double piv = __shfl_sync(FULL, x, k);
+    if (!(piv > 0.0)) fail = 1;
+    const double s = sqrt(piv);
+    const double r = 1.0 / s;
+    if (wl == k) { A[k * ld + k] = s; rd[k] = r; }
+    else if (wl > k && wl < n) A[k * ld + wl] = x * r;
+    __syncwarp();
+  }
+  return fail;
+}
+
+// column `c` of (L L^T)^-1: forward + backward substitution of the unit vector e_c (oracle llt_solve)
+template <int n>
+__device__ __forceinline__ void warp_llt_solve_unit(const double* __restrict__ Lm, int ld, const double* __restrict__ rd,
+                                                    int c, double (&y)[n]) {
+#pragma unroll
+  for (int i = 0; i < n; ++i) {
+    double acc = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+    for (int j = 0; j < i; ++j) acc = fma(-Lm[j * ld + i], y[j], acc);
+    y[i] = acc * rd[i];
+  }
+#pragma unroll
+  for (int i = n - 1; i >= 0; --i) {
+    double acc = y[i];
+#pragma unroll
+    for (int j = i + 1; j < n; ++j) acc = fma(-Lm[i * ld + j], y[j], acc);
+    y[i] = acc * rd[i];
+  }
+}
+
+__global__ void __launch_bounds__(CTA_THREADS) k_parnmpc_invert(const DevProblem* __restrict__ Pp, Layout L,
+                                                                ParNMPCLayout PL) {
+  IDOCP_DYN_SMEM(double, smem);
+  const DevProblem& P = *Pp;
+  const int wl = threadIdx.x & 31;           // lane in the warp
+  const int inst = threadIdx.x >> 5;         // instance of the group = warp of the CTA
+  const int i = blockIdx.x / L.G;            // stage index
+  const int g = blockIdx.x % L.G;
+  const int N = L.N;
+  const double dt = P.dt;
+  double* sm = smem + inst * INV_SMEM_PER_WARP;
+  double* A = sm + INV_OFF_A;
+  double* rd = sm + INV_OFF_RD;
+  double* FQ = sm + INV_OFF_FQ;
+  double* S = sm + INV_OFF_S;
+  double* LS = sm + INV_OFF_LS;
+  double* TL = sm + INV_OFF_TL;
+  double* TR = sm + INV_OFF_TR;
+  double* res = sm + INV_OFF_RES;
+  // this warp's view of a (stage, group) record: element (slot, j) of its instance
+  const size_t go = static_cast<size_t>(inst) * OCT;
+  const int sub = wl >> 3, j8 = wl & 7;      // 4 slots are moved per warp instruction
+  const double* KQ = L.KQ + (static_cast<size_t>(i) * L.G + g) * (KQ_NUM * SLOT) + go;
+
+  // ---- aux_mat of the next stage (none for the last stage) -> staging in S: aux(R, C) = S[C * 15 + R] ----
+  const bool has_aux = (i < N - 1);
+  if (has_aux) {
+    const double* AX = PL.AUX + (static_cast<size_t>(i + 1) * L.G + g) * (AUX_NUM * SLOT) + go;
+    for (int s0 = 0; s0 < AUX_NUM; s0 += 4) {
+      const int slot = s0 + sub;
+      const double val = AX[slot * SLOT + j8];
+      if (j8 < NV) S[(slot >> 1) * INV_LDX + (slot & 1) * NV + j8] = val;
+    }
+  }
+  __syncwarp();
+  // ---- Q (lower triangle, as SplitUnBackwardCorrection::coarseUpdate leaves it: Qxx += aux_next, then
+  //      Qvq = Qqv^T and Qxa = Qax^T) and the residual [Fq, Fv, la, lq, lv] ----
+  for (int s0 = 0; s0 < KQ_NUM + 1; s0 += 4) {
+    const int slot = s0 + sub;
+    if (slot >= KQ_NUM) continue;
+    const double val = KQ[slot * SLOT + j8];
+    if (j8 >= NV) continue;
+    if (slot >= KQ_FQ) { res[(slot - KQ_FQ) * NV + j8] = val; continue; }
+    const int blk = slot / NV, r = slot - blk * NV, c = j8;
+    switch (blk) {
+      case 0: if (r >= c) A[c * INV_LDQ + r] = val; break;                                  // aa
+      case 1: A[r * INV_LDQ + NV + c] = val; break;                                         // qa = aq^T
+      case 2: A[r * INV_LDQ + 2 * NV + c] = val; break;                                     // va = av^T
+      case 3: if (r >= c) A[(NV + c) * INV_LDQ + NV + r] = has_aux ? val + S[c * INV_LDX + r] : val; break;
+      case 4: A[(NV + r) * INV_LDQ + 2 * NV + c] = has_aux ? val + S[(NV + c) * INV_LDX + r] : val; break;  // vq = qv^T
+      default: if (r >= c) A[(2 * NV + c) * INV_LDQ + 2 * NV + r] = has_aux ? val + S[(NV + c) * INV_LDX + NV + r] : val; break;
+    }
+  }
+  __syncwarp();
+
+  // ---- llt_Q_.compute(Q); Qinv = llt_Q_.solve(I): lane c holds column c ----
+  int fail = warp_llt<NQ3>(A, INV_LDQ, rd, wl);
+  double y[NQ3];
+  const int cq = wl < NQ3 ? wl : 0;
+  warp_llt_solve_unit<NQ3>(A, INV_LDQ, rd, cq, y);
+  // ---- FQinv (14 x 21): rows Fq = -Qinv[q rows] + dt Qinv[v rows]; rows Fv = dt Qinv[a rows] - Qinv[v rows] ----
+  double fq[NX2];
+#pragma unroll
+  for (int r = 0; r < NV; ++r) {
+    fq[r] = fma(dt, y[2 * NV + r], -y[NV + r]);
+    fq[NV + r] = fma(dt, y[r], -y[2 * NV + r]);
+  }
+  if (wl < NQ3) {
+#pragma unroll
+    for (int r = 0; r < NX2; ++r) FQ[wl * INV_LDX + r] = fq[r];
+  }
+  __syncwarp();
+  // ---- S = FQinv F^T (14 x 14) ----
+  for (int e = wl; e < NX2 * NX2; e += 32) {
+    const int cc = e / NX2, r = e - cc * NX2;
+    double sv;
+    if (cc < NV) sv = fma(dt, FQ[(2 * NV + cc) * INV_LDX + r], -FQ[(NV + cc) * INV_LDX + r]);
+    else sv = fma(dt, FQ[(cc - NV) * INV_LDX + r], -FQ[(NV + cc) * INV_LDX + r]);
+    S[cc * INV_LDX + r] = sv;
+    LS[cc * INV_LDX + r] = sv;
+  }
+  __syncwarp();
+  // ---- llt_S_.compute(S); TL = -llt_S_.solve(I) ----
+  fail |= warp_llt<NX2>(LS, INV_LDX, rd, wl);
+  {
+    double z[NX2];
+    const int cs = wl < NX2 ? wl : 0;
+    warp_llt_solve_unit<NX2>(LS, INV_LDX, rd, cs, z);
+    if (wl < NX2) {
+#pragma unroll
+      for (int r = 0; r < NX2; ++r) TL[wl * INV_LDX + r] = -z[r];
+    }
+  }
+  __syncwarp();
+  // ---- TR = -(TL FQinv) (14 x 21), lane c = column c ----
+  double tr[NX2];
+#pragma unroll
+  for (int r = 0; r < NX2; ++r) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < NX2; ++k) t = fma(TL[k * INV_LDX + r], fq[k], t);
+    tr[r] = -t;
+  }
+  if (wl < NQ3) {
+#pragma unroll
+    for (int r = 0; r < NX2; ++r) TR[wl * INV_LDX + r] = tr[r];
+  }
+  __syncwarp();
+  // ---- BR = Qinv - TR^T (S TR) (21 x 21), stored over A (column stride 21) ----
+  {
+    double st[NX2];
+#pragma unroll
+    for (int r = 0; r < NX2; ++r) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < NX2; ++k) t = fma(S[k * INV_LDX + r], tr[k], t);
+      st[r] = t;
+    }
+#pragma unroll
+    for (int r = 0; r < NQ3; ++r) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < NX2; ++k) t = fma(TR[r * INV_LDX + k], st[k], t);
+      y[r] -= t;
+    }
+  }
+  if (wl < NQ3) {
+#pragma unroll
+    for (int r = 0; r < NQ3; ++r) A[wl * INV_LDQ + r] = y[r];
+  }
+  __syncwarp();
+
+  // ---- d = KKT^-1 residual; s_new = s - d (lmd, gmm, a, q, v): lane = row, two passes (35 rows) ----
+  const double* X = L.X + (static_cast<size_t>(i) * L.G + g) * (X_NUM * SLOT) + go;
+  double* SN = PL.SN + (static_cast<size_t>(i) * L.G + g) * (SN_NUM * SLOT) + go;
+  for (int R = wl; R < NKKT; R += 32) {
+    double acc = 0.0;
+    if (R < NX2) {
+      for (int c = 0; c < NX2; ++c) acc = fma(TL[c * INV_LDX + R], res[c], acc);
+      for (int c = 0; c < NQ3; ++c) acc = fma(TR[c * INV_LDX + R], res[NX2 + c], acc);
+    } else {
+      const int rr = R - NX2;
+      for (int c = 0; c < NX2; ++c) acc = fma(TR[rr * INV_LDX + c], res[c], acc);
+      for (int c = 0; c < NQ3; ++c) acc = fma(A[c * INV_LDQ + rr], res[NX2 + c], acc);
+    }
+    const int f = R / NV, jj = R - f * NV;   // f: 0 lmd 1 gmm 2 a 3 q 4 v
+    const int xs = f == 0 ? X_LMD : (f == 1 ? X_GMM : (f == 2 ? X_A : (f == 3 ? X_Q : X_V)));
+    SN[f * SLOT + jj] = X[xs * SLOT + jj] - acc;
+  }
+
+  // ---- blocks of the inverse for the correction sweeps ----
+  double* KI = PL.KI + (static_cast<size_t>(i) * L.G + g) * (KI_NUM * SLOT) + go;
+  for (int s0 = 0; s0 < KI_NUM; s0 += 4) {
+    const int slot = s0 + sub;
+    double val = 0.0;
+    if (j8 < NV) {
+      if (slot < KI_BP) {                         // BS: inv[7 rb + j][21 + c] = TR(7 rb + j, 7 + c)
+        const int c = slot >> 1, rb = slot & 1;
+        val = TR[(NV + c) * INV_LDX + rb * NV + j8];
+      } else if (slot < KI_FS) {                  // BP: inv[14 + 7 rb + j][21 + c] = BR(7 rb + j, 7 + c)
+        const int s = slot - KI_BP, c = s / 3, rb = s - c * 3;
+        val = A[(NV + c) * INV_LDQ + rb * NV + j8];
+      } else if (slot < KI_FP) {                  // FS: inv[21 + 7 rb + j][c] = TR(c, 7 + 7 rb + j)
+        const int s = slot - KI_FS, c = s >> 1, rb = s & 1;
+        val = TR[(NV + rb * NV + j8) * INV_LDX + c];
+      } else {                                    // FP: inv[7 rb + j][c] = TL(7 rb + j, c) | TR(c, j)
+        const int s = slot - KI_FP, c = s / 3, rb = s - c * 3;
+        val = rb < 2 ? TL[c * INV_LDX + rb * NV + j8] : TR[j8 * INV_LDX + c];
+      }
+    }
+    KI[slot * SLOT + j8] = val;
+  }
+  if (fail && wl == 0) {
+    const int b = g * 4 + inst;
+    if (b < L.B) L.status[b] |= 1;
+  }
+}
+
+// y[rb] = sum_c M[c][rb][lane] * xr[c], c ascending (xr[c] = head for c < 7, tail otherwise): the
+// "lane = row, slot = column" mat-vec of the correction sweeps
+template <int NRB>
+__device__ __forceinline__ void oct_matvec14(const double* __restrict__ M, double xh, double xt, double (&y)[NRB]) {
+#pragma unroll
+  for (int rb = 0; rb < NRB; ++rb) y[rb] = 0.0;
+#pragma unroll
+  for (int c = 0; c < NX2; ++c) {
+    const double xc = oct_bcast(c < NV ? xh : xt, c < NV ? c : c - NV);
+#pragma unroll
+    for (int rb = 0; rb < NRB; ++rb) y[rb] = fma(M[(c * NRB + rb) * SLOT], xc, y[rb]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_parnmpc_backward_serial: i = N-2 .. 0:  x_res = s_new[i+1].(lmd,gmm) - s[i+1].(lmd,gmm);
+// s_new[i].(lmd,gmm) -= inv_i[0:14, 21:35] x_res.  One octet per instance.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CTA_THREADS) k_parnmpc_backward_serial(Layout L, ParNMPCLayout PL) {
+  const int g = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+  if (g >= L.G) return;   // read-modify-write kernel: tail warps must not redo a group (whole warps exit)
+  const int N = L.N;
+  const size_t xs = static_cast<size_t>(L.G) * (X_NUM * SLOT), ss = static_cast<size_t>(L.G) * (SN_NUM * SLOT);
+  const size_t ks = static_cast<size_t>(L.G) * (KI_NUM * SLOT), rs = static_cast<size_t>(L.G) * (XR_NUM * SLOT);
+  const double* X = rec_ptr(L.X, X_NUM, L.G, N - 1, g);
+  double* SN = rec_ptr(PL.SN, SN_NUM, L.G, N - 1, g);
+  const double* KI = rec_ptr(PL.KI, KI_NUM, L.G, N - 1, g);
+  double* XR = rec_ptr(PL.XR, XR_NUM, L.G, N - 1, g);
+  double nl = SN[SN_LMD * SLOT], ng = SN[SN_GMM * SLOT];   // corrected s_new of stage i + 1
+  for (int i = N - 2; i >= 0; --i) {
+    const double xh = nl - X[X_LMD * SLOT];
+    const double xt = ng - X[X_GMM * SLOT];
+    X -= xs; SN -= ss; KI -= ks; XR -= rs;
+    XR[XR_H * SLOT] = xh;
+    XR[XR_T * SLOT] = xt;
+    double y[2];
+    oct_matvec14<2>(KI + KI_BS * SLOT, xh, xt, y);
+    nl = SN[SN_LMD * SLOT] - y[0];
+    ng = SN[SN_GMM * SLOT] - y[1];
+    SN[SN_LMD * SLOT] = nl;
+    SN[SN_GMM * SLOT] = ng;
+  }
+}
+
+// k_parnmpc_backward_parallel: stages 0..N-2: s_new.(a,q,v) -= inv_i[14:35, 21:35] x_res
+__global__ void __launch_bounds__(CTA_THREADS) k_parnmpc_backward_parallel(Layout L, ParNMPCLayout PL) {
+  if (static_cast<long>(blockIdx.x) * WARPS_PER_CTA + (threadIdx.x >> 5) >= static_cast<long>(L.N - 1) * L.G) return;
+  const StageTask t = stage_task(L, L.N - 1);
+  double* SN = rec_ptr(PL.SN, SN_NUM, L.G, t.stage, t.g);
+  const double* KI = rec_ptr(PL.KI, KI_NUM, L.G, t.stage, t.g);
+  const double* XR = rec_ptr(PL.XR, XR_NUM, L.G, t.stage, t.g);
+  double y[3];
+  oct_matvec14<3>(KI + KI_BP * SLOT, XR[XR_H * SLOT], XR[XR_T * SLOT], y);
+  SN[SN_A * SLOT] -= y[0];
+  SN[SN_Q * SLOT] -= y[1];
+  SN[SN_V * SLOT] -= y[2];
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_parnmpc_forward_serial: i = 1 .. N-1:  x_res = s_new[i-1].(q,v) - s[i-1].(q,v);
+// s_new[i].(q,v) -= inv_i[21:35, 0:14] x_res.  One octet per instance.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CTA_THREADS) k_parnmpc_forward_serial(Layout L, ParNMPCLayout PL) {
+  const int g = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+  if (g >= L.G) return;   // read-modify-write kernel: tail warps must not redo a group (whole warps exit)
+  const int N = L.N;
+  const size_t xs = static_cast<size_t>(L.G) * (X_NUM * SLOT), ss = static_cast<size_t>(L.G) * (SN_NUM * SLOT);
+  const size_t ks = static_cast<size_t>(L.G) * (KI_NUM * SLOT), rs = static_cast<size_t>(L.G) * (XR_NUM * SLOT);
+  const double* X = rec_ptr(L.X, X_NUM, L.G, 0, g);
+  double* SN = rec_ptr(PL.SN, SN_NUM, L.G, 0, g);
+  const double* KI = rec_ptr(PL.KI, KI_NUM, L.G, 0, g);
+  double* XR = rec_ptr(PL.XR, XR_NUM, L.G, 0, g);
+  double nq = SN[SN_Q * SLOT], nv = SN[SN_V * SLOT];       // corrected s_new of stage i - 1
+  for (int i = 1; i < N; ++i) {
+    const double xh = nq - X[X_Q * SLOT];
+    const double xt = nv - X[X_V * SLOT];
+    X += xs; SN += ss; KI += ks; XR += rs;
+    XR[XR_H * SLOT] = xh;
+    XR[XR_T * SLOT] = xt;
+    double y[2];
+    oct_matvec14<2>(KI + KI_FS * SLOT, xh, xt, y);
+    nq = SN[SN_Q * SLOT] - y[0];
+    nv = SN[SN_V * SLOT] - y[1];
+    SN[SN_Q * SLOT] = nq;
+    SN[SN_V * SLOT] = nv;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_parnmpc_forward_parallel: stages 1..N-1: s_new.(lmd,gmm,a) -= inv_i[0:21, 0:14] x_res and
+// aux_mat[i] = -inv_i[0:14, 0:14]; every stage: d = s_new - s (computeDirection).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CTA_THREADS) k_parnmpc_forward_parallel(Layout L, ParNMPCLayout PL) {
+  if (static_cast<long>(blockIdx.x) * WARPS_PER_CTA + (threadIdx.x >> 5) >= static_cast<long>(L.N) * L.G) return;
+  const StageTask t = stage_task(L, L.N);
+  const int i = t.stage;
+  const double* X = rec_ptr(L.X, X_NUM, L.G, i, t.g);
+  double* SN = rec_ptr(PL.SN, SN_NUM, L.G, i, t.g);
+  double* D = rec_ptr(L.D, D_NUM, L.G, i, t.g);
+  double nl = SN[SN_LMD * SLOT], ng = SN[SN_GMM * SLOT], na = SN[SN_A * SLOT];
+  if (i > 0) {
+    const double* KI = rec_ptr(PL.KI, KI_NUM, L.G, i, t.g);
+    const double* XR = rec_ptr(PL.XR, XR_NUM, L.G, i, t.g);
+    double* AX = rec_ptr(PL.AUX, AUX_NUM, L.G, i, t.g);
+    double y[3];
+    oct_matvec14<3>(KI + KI_FP * SLOT, XR[XR_H * SLOT], XR[XR_T * SLOT], y);
+    nl -= y[0];
+    ng -= y[1];
+    na -= y[2];
+#pragma unroll
+    for (int c = 0; c < NX2; ++c) {
+      AX[(c * 2 + 0) * SLOT] = -KI[(KI_FP + c * 3 + 0) * SLOT];
+      AX[(c * 2 + 1) * SLOT] = -KI[(KI_FP + c * 3 + 1) * SLOT];
+    }
+  }
+  D[D_LMD * SLOT] = nl - X[X_LMD * SLOT];
+  D[D_GMM * SLOT] = ng - X[X_GMM * SLOT];
+  D[D_A * SLOT] = na - X[X_A * SLOT];
+  D[D_Q * SLOT] = SN[SN_Q * SLOT] - X[X_Q * SLOT];
+  D[D_V * SLOT] = SN[SN_V * SLOT] - X[X_V * SLOT];
 }
 
 }  // namespace idocp_b200

@@ -37,6 +37,10 @@ def make_pair(I, O, lib, problem, q0, v0, kind="unocp"):
     for b, o in enumerate(oracles):
         o.set_solution("q", q0[b])
         o.set_solution("v", v0[b])
+    if kind != "unocp":   # examples/iiwa14/unparnmpc_benchmark.cpp:49-51
+        solver.initBackwardCorrection(0.0)
+        for o in oracles:
+            o.init_backward_correction(0.0)
     return solver, oracles
 
 

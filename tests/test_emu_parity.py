@@ -96,6 +96,19 @@ def test_config_space_problem_long_horizon(emu_lib, oracle):
     check_solution(solver, oracles)
 
 
+@pytest.mark.parametrize("batch,N", [(1, 1), (2, 2), (5, 6)])
+def test_unparnmpc_iterations_match_oracle(emu_lib, oracle, batch, N):
+    """UnParNMPCSolver (backward-Euler stages, explicit 35x35 KKT inverse per stage, backward/forward
+    correction sweeps): directions, step sizes, KKT error and iterate bit-identical to the oracle."""
+    prob = I.benchmark_problem(emu_lib, N=N, T=0.05 * N)
+    q0, v0 = make_states(batch, 300 + batch)
+    solver, oracles = make_pair(I, oracle, emu_lib, prob, q0, v0, kind="unparnmpc")
+    for it in range(3):
+        check_iteration(solver, oracles, q0, v0)
+    check_solution(solver, oracles)
+    assert np.all(solver.getStatus() == 0)
+
+
 def test_error_paths(emu_lib):
     prob = I.benchmark_problem(emu_lib)
     bad = I.benchmark_problem(emu_lib)
