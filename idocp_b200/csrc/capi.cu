@@ -192,7 +192,7 @@ static int stage_grid(const idocp_b200_solver* h, int nstages) {
 // grid of a per-instance kernel: one warp per group
 static int group_grid(const idocp_b200_solver* h) { return (h->L.G + WARPS_PER_CTA - 1) / WARPS_PER_CTA; }
 static const int kLinSmem = OCTETS_PER_CTA * OCT * PAIR_TILE * static_cast<int>(sizeof(double));
-static const int kRicSmem = OCTETS_PER_CTA * RIC_SMEM_PER_OCT * static_cast<int>(sizeof(double));
+static const int kRicSmem = RIC_SMEM_DOUBLES * static_cast<int>(sizeof(double));
 
 static int do_init_constraints(idocp_b200_solver* h) {
   IDOCP_LAUNCH(h, KC_MISC, k_init_constraints, stage_grid(h, h->N), CTA_THREADS, 0, h->d_prob, h->L,
@@ -257,6 +257,7 @@ extern "C" int idocp_b200_create(const idocp_b200_problem* p, int solver_kind, i
     h->stage_doubles = need;
   }
   rc |= h->alloc(&h->d_stage, h->stage_doubles);
+  if (cudaFuncSetAttribute(k_riccati, cudaFuncAttributeMaxDynamicSharedMemorySize, kRicSmem) != cudaSuccess) rc |= -1;
   if (par) {
     rc |= parnmpc_alloc(h->PL, h->N, h->Bp, [&](double** pp, size_t n) { return h->alloc(pp, n); });
     if (cudaFuncSetAttribute(k_parnmpc_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, INV_SMEM_BYTES) !=

@@ -18,6 +18,7 @@
 // local) and column l of every 7x7 block.  One warp = one GROUP of 4 instances (common.cuh).
 #pragma once
 #include "chain_dynamics.cuh"
+#include "tma.cuh"
 
 namespace idocp_b200 {
 
@@ -387,6 +388,24 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_linearize(const
 // ---------------------------------------------------------------------------------------------
 constexpr int RIC_TILE = 17;               // odd stride (doubles) -> conflict-free transposed reads
 constexpr int RIC_SMEM_PER_OCT = 2 * OCT * RIC_TILE;
+// The condensed KKT record of (stage, group) is streamed into shared memory by the TMA engine one
+// stage ahead of its use, in two halves with separate barriers so that each half-buffer can be
+// re-armed as soon as its values sit in registers:
+//   half A = a-blocks + residual (slots AA, AQ, AV | FQ..LV: 21 + 5 slots), half X = x-blocks (QQ, QV, VV)
+// The forward recursion streams (rows of K, k | Fq, Fv) of the stages through a 3-deep ring in the
+// same per-warp region: its body is ~100 instructions per stage, i.e. pure memory latency otherwise.
+constexpr int RIC_BUFA_SLOTS = 3 * NV + 5;
+constexpr int RIC_BUFX_SLOTS = 3 * NV;
+constexpr int RIC_RING = 3;
+constexpr int RIC_RING_SLOTS = 2 * NV + 1 + 2;                                        // Kq, Kv, k | Fq, Fv
+constexpr int RIC_WARP_SLOTS = (RIC_RING * RIC_RING_SLOTS > RIC_BUFA_SLOTS + RIC_BUFX_SLOTS)
+                                   ? RIC_RING * RIC_RING_SLOTS : RIC_BUFA_SLOTS + RIC_BUFX_SLOTS;
+constexpr int RIC_OFF_STREAM = OCTETS_PER_CTA * RIC_SMEM_PER_OCT;                     // doubles
+constexpr int RIC_OFF_BARS = RIC_OFF_STREAM + WARPS_PER_CTA * RIC_WARP_SLOTS * SLOT;
+constexpr int RIC_NBARS = 2 + RIC_RING;
+constexpr int RIC_SMEM_DOUBLES = RIC_OFF_BARS + RIC_NBARS * WARPS_PER_CTA;
+static_assert(KQ_AA == 0 && KQ_QQ == 3 * NV && KQ_FQ == 6 * NV && KQ_NUM == 6 * NV + 5, "record layout");
+static_assert(W_KQ == 0 && W_KV == NV && W_K == 2 * NV && KQ_FV == KQ_FQ + 1, "record layout");
 
 __global__ void __launch_bounds__(CTA_THREADS, IDOCP_RIC_MINB) k_riccati(const DevProblem* __restrict__ Pp, Layout L,
                                                          const double* __restrict__ q0,
@@ -402,13 +421,50 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_RIC_MINB) k_riccati(const D
   const int b = g * 4 + (oct & 3);
   const bool valid = b < L.B;    // padded instances (B <= b < Bp) are computed but never reported
   const int N = L.N;
+  // TMA stream of the condensed KKT records (see RIC_BUFA_SLOTS)
+  const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
+  double* stream = smem + RIC_OFF_STREAM + warp * (RIC_WARP_SLOTS * SLOT);
+  const double* bufA = stream + wl;
+  const double* bufX = stream + RIC_BUFA_SLOTS * SLOT + wl;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RIC_OFF_BARS) + RIC_NBARS * warp;
+  const double* kq_rec = L.KQ + static_cast<size_t>(g) * (KQ_NUM * SLOT);   // + stage * kstride
+  const double* w_rec = L.W + static_cast<size_t>(g) * (W_NUM * SLOT);
+  if (wl == 0) {
+#pragma unroll
+    for (int k = 0; k < RIC_NBARS; ++k) tma_bar_init(&bars[k], 1);
+  }
+  __syncwarp();
+  auto issue_half_a = [&](int stage) {
+    const double* src = kq_rec + static_cast<size_t>(stage) * L.G * (KQ_NUM * SLOT);
+    tma_bar_expect(&bars[0], RIC_BUFA_SLOTS * SLOT * 8);
+    tma_load_1d(stream, src + KQ_AA * SLOT, 3 * NV * SLOT * 8, &bars[0]);
+    tma_load_1d(stream + 3 * NV * SLOT, src + KQ_FQ * SLOT, 5 * SLOT * 8, &bars[0]);
+  };
+  auto issue_half_x = [&](int stage) {
+    const double* src = kq_rec + static_cast<size_t>(stage) * L.G * (KQ_NUM * SLOT);
+    tma_bar_expect(&bars[1], RIC_BUFX_SLOTS * SLOT * 8);
+    tma_load_1d(stream + RIC_BUFA_SLOTS * SLOT, src + KQ_QQ * SLOT, RIC_BUFX_SLOTS * SLOT * 8, &bars[1]);
+  };
+  auto issue_forward = [&](int stage) {   // ring entry stage % RIC_RING
+    const int e = stage % RIC_RING;
+    double* dst = stream + e * (RIC_RING_SLOTS * SLOT);
+    tma_bar_expect(&bars[2 + e], RIC_RING_SLOTS * SLOT * 8);
+    tma_load_1d(dst, w_rec + static_cast<size_t>(stage) * L.G * (W_NUM * SLOT) + W_KQ * SLOT, (2 * NV + 1) * SLOT * 8,
+                &bars[2 + e]);
+    tma_load_1d(dst + (2 * NV + 1) * SLOT, kq_rec + static_cast<size_t>(stage) * L.G * (KQ_NUM * SLOT) + KQ_FQ * SLOT,
+                2 * SLOT * 8, &bars[2 + e]);
+  };
+  if (wl == 0) {
+    issue_half_a(N - 1);
+    issue_half_x(N - 1);
+  }
+  uint32_t phase = 0;
   const double dt = P.dt;
   const double dt2 = dt * dt;
   const bool act = lane < NV;
   const int ln = act ? lane : 0;
   int chol_fail = 0;
   const size_t xstride = static_cast<size_t>(L.G) * (X_NUM * SLOT);
-  const size_t kstride = static_cast<size_t>(L.G) * (KQ_NUM * SLOT);
   const size_t wstride = static_cast<size_t>(L.G) * (W_NUM * SLOT);
   const size_t dstride = static_cast<size_t>(L.G) * (D_NUM * SLOT);
 
@@ -434,19 +490,21 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_RIC_MINB) k_riccati(const D
   }
 
   // ---- backward recursion ----
-  const double* KQ = rec_ptr(L.KQ, KQ_NUM, L.G, N - 1, g);
   double* W = rec_ptr(L.W, W_NUM, L.G, N - 1, g);
-  for (int i = N - 1; i >= 0; --i, KQ -= kstride, W -= wstride) {
+  for (int i = N - 1; i >= 0; --i, W -= wstride, phase ^= 1) {
     double Qaa[NV], Qaq[NV], Qav[NV];
+    tma_bar_wait(&bars[0], phase);
 #pragma unroll
     for (int r = 0; r < NV; ++r) {
-      Qaa[r] = KQ[(KQ_AA + r) * SLOT];
-      Qaq[r] = KQ[(KQ_AQ + r) * SLOT];
-      Qav[r] = KQ[(KQ_AV + r) * SLOT];
+      Qaa[r] = bufA[(KQ_AA + r) * SLOT];
+      Qaq[r] = bufA[(KQ_AQ + r) * SLOT];
+      Qav[r] = bufA[(KQ_AV + r) * SLOT];
     }
-    const double Fq = KQ[KQ_FQ * SLOT], Fv = KQ[KQ_FV * SLOT];
-    double la = KQ[KQ_LA * SLOT];
-    const double lq = KQ[KQ_LQ * SLOT], lv = KQ[KQ_LV * SLOT];
+    const double Fq = bufA[(3 * NV + 0) * SLOT], Fv = bufA[(3 * NV + 1) * SLOT];
+    double la = bufA[(3 * NV + 2) * SLOT];
+    const double lq = bufA[(3 * NV + 3) * SLOT], lv = bufA[(3 * NV + 4) * SLOT];
+    __syncwarp();                              // half A is in registers: stream the next stage into it
+    if (wl == 0 && i > 0) issue_half_a(i - 1);
 
     // factorizeKKTMatrix, a-blocks (backward_unriccati_recursion_factorizer.hxx:44-53); the
     // x-blocks are folded into the P update below (same operation order per entry)
@@ -546,11 +604,12 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_RIC_MINB) k_riccati(const D
       nsq -= t5; nsv -= t6;
     }
     // F-blocks of factorizeKKTMatrix (:34-43) + P = Qxx - K^T (Qaa K) (:64-75), row by row
+    tma_bar_wait(&bars[1], phase);
 #pragma unroll
     for (int r = 0; r < NV; ++r) {
-      double Qqq = KQ[(KQ_QQ + r) * SLOT];
-      double Qqv = KQ[(KQ_QV + r) * SLOT];
-      double Qvv = KQ[(KQ_VV + r) * SLOT];
+      double Qqq = bufX[(0 * NV + r) * SLOT];
+      double Qqv = bufX[(1 * NV + r) * SLOT];
+      double Qvv = bufX[(2 * NV + r) * SLOT];
       Qqq += Pqq[r];
       Qqv = fma(dt, Pqq[r], Qqv);
       Qqv += Pqv[r];
@@ -577,7 +636,8 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_RIC_MINB) k_riccati(const D
       W[(W_KV + c) * SLOT] = tB[c * RIC_TILE + NV + ln];
     }
     W[W_K * SLOT] = kk[ln];
-    __syncwarp();
+    __syncwarp();                              // half X consumed by every lane (and tile B read)
+    if (wl == 0 && i > 0) issue_half_x(i - 1);
     // transposes through the tiles: Pvq = Pqv^T, symmetrise Pqq and Pvv
 #pragma unroll
     for (int r = 0; r < NV; ++r) { tA[lane * RIC_TILE + r] = Pqv[r]; tB[lane * RIC_TILE + r] = Pqq[r]; }
@@ -615,30 +675,25 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_RIC_MINB) k_riccati(const D
     dv = v0[bi] - X0[X_V * SLOT];
     if (!act) { dq = 0.0; dv = 0.0; }
   }
-  KQ = rec_ptr(L.KQ, KQ_NUM, L.G, 0, g);
-  W = rec_ptr(L.W, W_NUM, L.G, 0, g);
   double* D = rec_ptr(L.D, D_NUM, L.G, 0, g);
-  // software pipeline: the gains of stage i+1 are loaded while stage i is being applied
-  double Kr[2 * NV], kr, Fq, Fv;
-#pragma unroll
-  for (int c = 0; c < 2 * NV; ++c) Kr[c] = W[(W_KQ + c) * SLOT];
-  kr = W[W_K * SLOT];
-  Fq = KQ[KQ_FQ * SLOT];
-  Fv = KQ[KQ_FV * SLOT];
+  // the gains were written by this warp through the generic proxy: order those writes before the
+  // TMA engine reads them back, then fill the ring
+  tma_fence_global_writes();
+  __syncwarp();
+  if (wl == 0) {
+    for (int i = 0; i < RIC_RING && i < N; ++i) issue_forward(i);
+  }
   for (int i = 0; i < N; ++i) {
-    double Kn[2 * NV], kn = 0.0, Fqn = 0.0, Fvn = 0.0;
-    if (i + 1 < N) {
-      const double* Wn = W + wstride;
-      const double* KQn = KQ + kstride;
+    const int e = i % RIC_RING;
+    tma_bar_wait(&bars[2 + e], (i / RIC_RING) & 1);
+    const double* ring = stream + e * (RIC_RING_SLOTS * SLOT) + wl;
+    double Kr[2 * NV];
 #pragma unroll
-      for (int c = 0; c < 2 * NV; ++c) Kn[c] = Wn[(W_KQ + c) * SLOT];
-      kn = Wn[W_K * SLOT];
-      Fqn = KQn[KQ_FQ * SLOT];
-      Fvn = KQn[KQ_FV * SLOT];
-    } else {
-#pragma unroll
-      for (int c = 0; c < 2 * NV; ++c) Kn[c] = 0.0;
-    }
+    for (int c = 0; c < 2 * NV; ++c) Kr[c] = ring[c * SLOT];
+    const double kr = ring[2 * NV * SLOT];
+    const double Fq = ring[(2 * NV + 1) * SLOT], Fv = ring[(2 * NV + 2) * SLOT];
+    __syncwarp();                              // ring entry is in registers: refill it
+    if (wl == 0 && i + RIC_RING < N) issue_forward(i + RIC_RING);
     double acc = 0.0;
 #pragma unroll
     for (int c = 0; c < NV; ++c) acc = fma(Kr[c], oct_bcast(dq, c), acc);
@@ -654,10 +709,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_RIC_MINB) k_riccati(const D
     ndv = fma(dt, da, ndv);
     dq = act ? ndq : 0.0;
     dv = act ? ndv : 0.0;
-#pragma unroll
-    for (int c = 0; c < 2 * NV; ++c) Kr[c] = Kn[c];
-    kr = kn; Fq = Fqn; Fv = Fvn;
-    KQ += kstride; W += wstride; D += dstride;
+    D += dstride;
   }
   D[D_Q * SLOT] = dq;   // terminal stage
   D[D_V * SLOT] = dv;

@@ -93,23 +93,27 @@ constexpr int INV_SMEM_PER_WARP = INV_OFF_RES + 36;
 constexpr int INV_SMEM_BYTES = WARPS_PER_CTA * INV_SMEM_PER_WARP * static_cast<int>(sizeof(double));
 
 // left-looking Cholesky of the lower triangle of the n x n matrix at A (column stride ld), in place;
-// lane = row.  Eigen::LLT<Lower> semantics; divisions by the pivot are multiplications by
-// its reciprocal rd[k] (canonical arithmetic, oracle llt_lower).  Returns non-zero on a bad pivot.
+// lane = row; the lane keeps its own row of L in registers, the pivot row comes from shared memory
+// as a broadcast.  Eigen::LLT<Lower> semantics; divisions by the pivot are
+// multiplications by its reciprocal rd[k] (canonical arithmetic, oracle llt_lower).  Fully unrolled:
+// every element is the same ascending-j fma chain as in the oracle.  Returns non-zero on a bad pivot.
 template <int n>
 __device__ __forceinline__ int warp_llt(double* __restrict__ A, int ld, double* __restrict__ rd, int wl) {
   int fail = 0;
+  double Lrow[n];
+  const int row = wl < n ? wl : n - 1;   // idle lanes shadow the last row (never stored)
+#pragma unroll
   for (int k = 0; k < n; ++k) {
-    double x = 0.0;
-    if (wl >= k && wl < n) {
-      x = A[k * ld + wl];
-      for (int j = 0; j < k; ++j) x = fma(-A[j * ld + wl], A[j * ld + k], x);
-    }
+    double x = A[k * ld + row];
+#pragma unroll
+    for (int j = 0; j < k; ++j) x = fma(-Lrow[j], A[j * ld + k], x);
     const double piv = __shfl_sync(FULL, x, k);
     if (!(piv > 0.0)) fail = 1;
     const double s = sqrt(piv);
     const double r = 1.0 / s;
-    if (wl == k) { A[k * ld + k] = s; rd[k] = r; }
-    else if (wl > k && wl < n) A[k * ld + wl] = x * r;
+    Lrow[k] = (wl == k) ? s : x * r;
+    if (wl >= k && wl < n) A[k * ld + wl] = Lrow[k];
+    if (wl == k) rd[k] = r;
     __syncwarp();
   }
   return fail;
@@ -135,8 +139,31 @@ __device__ __forceinline__ void warp_llt_solve_unit(const double* __restrict__ L
   }
 }
 
-__global__ void __launch_bounds__(CTA_THREADS) k_parnmpc_invert(const DevProblem* __restrict__ Pp, Layout L,
-                                                                ParNMPCLayout PL) {
+// moves `nslots` slots of this warp's instance between a (stage, group) record and a per-lane
+// functor, 4 slots per warp instruction (lane = 8 * sub + j): all global accesses of the loop are
+// issued back to back (full unroll), i.e. one memory latency per record
+template <int nslots, typename F>
+__device__ __forceinline__ void warp_load_slots(const double* __restrict__ rec, int wl, F&& f) {
+  const int sub = wl >> 3, j8 = wl & 7;
+  double val[(nslots + 3) / 4];
+#pragma unroll
+  for (int k = 0; k < (nslots + 3) / 4; ++k) {
+    const int slot = 4 * k + sub;
+    val[k] = slot < nslots ? rec[slot * SLOT + j8] : 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < (nslots + 3) / 4; ++k) {
+    const int slot = 4 * k + sub;
+    if (slot < nslots && j8 < NV) f(slot, j8, val[k]);
+  }
+}
+
+#ifndef IDOCP_INV_MINB
+#define IDOCP_INV_MINB 2   // tools/sweep_inv.sh: 254 regs 6.2 ms, 168 regs 7.9 ms, 128 regs 9.0 ms (spills)
+#endif
+
+__global__ void __launch_bounds__(CTA_THREADS, IDOCP_INV_MINB) k_parnmpc_invert(const DevProblem* __restrict__ Pp,
+                                                                                Layout L, ParNMPCLayout PL) {
   IDOCP_DYN_SMEM(double, smem);
   const DevProblem& P = *Pp;
   const int wl = threadIdx.x & 31;           // lane in the warp
@@ -157,28 +184,20 @@ __global__ void __launch_bounds__(CTA_THREADS) k_parnmpc_invert(const DevProblem
   // this warp's view of a (stage, group) record: element (slot, j) of its instance
   const size_t go = static_cast<size_t>(inst) * OCT;
   const int sub = wl >> 3, j8 = wl & 7;      // 4 slots are moved per warp instruction
-  const double* KQ = L.KQ + (static_cast<size_t>(i) * L.G + g) * (KQ_NUM * SLOT) + go;
 
   // ---- aux_mat of the next stage (none for the last stage) -> staging in S: aux(R, C) = S[C * 15 + R] ----
   const bool has_aux = (i < N - 1);
   if (has_aux) {
-    const double* AX = PL.AUX + (static_cast<size_t>(i + 1) * L.G + g) * (AUX_NUM * SLOT) + go;
-    for (int s0 = 0; s0 < AUX_NUM; s0 += 4) {
-      const int slot = s0 + sub;
-      const double val = AX[slot * SLOT + j8];
-      if (j8 < NV) S[(slot >> 1) * INV_LDX + (slot & 1) * NV + j8] = val;
-    }
+    warp_load_slots<AUX_NUM>(PL.AUX + (static_cast<size_t>(i + 1) * L.G + g) * (AUX_NUM * SLOT) + go, wl,
+                             [&](int slot, int j, double val) { S[(slot >> 1) * INV_LDX + (slot & 1) * NV + j] = val; });
   }
   __syncwarp();
   // ---- Q (lower triangle, as SplitUnBackwardCorrection::coarseUpdate leaves it: Qxx += aux_next, then
   //      Qvq = Qqv^T and Qxa = Qax^T) and the residual [Fq, Fv, la, lq, lv] ----
-  for (int s0 = 0; s0 < KQ_NUM + 1; s0 += 4) {
-    const int slot = s0 + sub;
-    if (slot >= KQ_NUM) continue;
-    const double val = KQ[slot * SLOT + j8];
-    if (j8 >= NV) continue;
-    if (slot >= KQ_FQ) { res[(slot - KQ_FQ) * NV + j8] = val; continue; }
-    const int blk = slot / NV, r = slot - blk * NV, c = j8;
+  warp_load_slots<KQ_NUM>(L.KQ + (static_cast<size_t>(i) * L.G + g) * (KQ_NUM * SLOT) + go, wl,
+                          [&](int slot, int c, double val) {
+    if (slot >= KQ_FQ) { res[(slot - KQ_FQ) * NV + c] = val; return; }
+    const int blk = slot / NV, r = slot - blk * NV;
     switch (blk) {
       case 0: if (r >= c) A[c * INV_LDQ + r] = val; break;                                  // aa
       case 1: A[r * INV_LDQ + NV + c] = val; break;                                         // qa = aq^T
@@ -187,7 +206,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_parnmpc_invert(const DevProblem
       case 4: A[(NV + r) * INV_LDQ + 2 * NV + c] = has_aux ? val + S[(NV + c) * INV_LDX + r] : val; break;  // vq = qv^T
       default: if (r >= c) A[(2 * NV + c) * INV_LDQ + 2 * NV + r] = has_aux ? val + S[(NV + c) * INV_LDX + NV + r] : val; break;
     }
-  }
+  });
   __syncwarp();
 
   // ---- llt_Q_.compute(Q); Qinv = llt_Q_.solve(I): lane c holds column c ----
@@ -196,25 +215,26 @@ __global__ void __launch_bounds__(CTA_THREADS) k_parnmpc_invert(const DevProblem
   const int cq = wl < NQ3 ? wl : 0;
   warp_llt_solve_unit<NQ3>(A, INV_LDQ, rd, cq, y);
   // ---- FQinv (14 x 21): rows Fq = -Qinv[q rows] + dt Qinv[v rows]; rows Fv = dt Qinv[a rows] - Qinv[v rows] ----
-  double fq[NX2];
-#pragma unroll
-  for (int r = 0; r < NV; ++r) {
-    fq[r] = fma(dt, y[2 * NV + r], -y[NV + r]);
-    fq[NV + r] = fma(dt, y[r], -y[2 * NV + r]);
-  }
   if (wl < NQ3) {
 #pragma unroll
-    for (int r = 0; r < NX2; ++r) FQ[wl * INV_LDX + r] = fq[r];
+    for (int r = 0; r < NV; ++r) {
+      FQ[wl * INV_LDX + r] = fma(dt, y[2 * NV + r], -y[NV + r]);
+      FQ[wl * INV_LDX + NV + r] = fma(dt, y[r], -y[2 * NV + r]);
+    }
   }
   __syncwarp();
   // ---- S = FQinv F^T (14 x 14) ----
-  for (int e = wl; e < NX2 * NX2; e += 32) {
-    const int cc = e / NX2, r = e - cc * NX2;
-    double sv;
-    if (cc < NV) sv = fma(dt, FQ[(2 * NV + cc) * INV_LDX + r], -FQ[(NV + cc) * INV_LDX + r]);
-    else sv = fma(dt, FQ[(cc - NV) * INV_LDX + r], -FQ[(NV + cc) * INV_LDX + r]);
-    S[cc * INV_LDX + r] = sv;
-    LS[cc * INV_LDX + r] = sv;
+#pragma unroll
+  for (int e0 = 0; e0 < NX2 * NX2; e0 += 32) {
+    const int e = e0 + wl;
+    if (e < NX2 * NX2) {
+      const int cc = e / NX2, r = e - cc * NX2;
+      double sv;
+      if (cc < NV) sv = fma(dt, FQ[(2 * NV + cc) * INV_LDX + r], -FQ[(NV + cc) * INV_LDX + r]);
+      else sv = fma(dt, FQ[(cc - NV) * INV_LDX + r], -FQ[(NV + cc) * INV_LDX + r]);
+      S[cc * INV_LDX + r] = sv;
+      LS[cc * INV_LDX + r] = sv;
+    }
   }
   __syncwarp();
   // ---- llt_S_.compute(S); TL = -llt_S_.solve(I) ----
@@ -229,14 +249,19 @@ __global__ void __launch_bounds__(CTA_THREADS) k_parnmpc_invert(const DevProblem
     }
   }
   __syncwarp();
-  // ---- TR = -(TL FQinv) (14 x 21), lane c = column c ----
+  // ---- TR = -(TL FQinv) (14 x 21), lane c = column c (own column of FQinv re-read from shared memory) ----
   double tr[NX2];
+  {
+    double fq[NX2];
 #pragma unroll
-  for (int r = 0; r < NX2; ++r) {
-    double t = 0.0;
+    for (int k = 0; k < NX2; ++k) fq[k] = FQ[cq * INV_LDX + k];
 #pragma unroll
-    for (int k = 0; k < NX2; ++k) t = fma(TL[k * INV_LDX + r], fq[k], t);
-    tr[r] = -t;
+    for (int r = 0; r < NX2; ++r) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < NX2; ++k) t = fma(TL[k * INV_LDX + r], fq[k], t);
+      tr[r] = -t;
+    }
   }
   if (wl < NQ3) {
 #pragma unroll
@@ -270,42 +295,53 @@ __global__ void __launch_bounds__(CTA_THREADS) k_parnmpc_invert(const DevProblem
   // ---- d = KKT^-1 residual; s_new = s - d (lmd, gmm, a, q, v): lane = row, two passes (35 rows) ----
   const double* X = L.X + (static_cast<size_t>(i) * L.G + g) * (X_NUM * SLOT) + go;
   double* SN = PL.SN + (static_cast<size_t>(i) * L.G + g) * (SN_NUM * SLOT) + go;
-  for (int R = wl; R < NKKT; R += 32) {
-    double acc = 0.0;
-    if (R < NX2) {
-      for (int c = 0; c < NX2; ++c) acc = fma(TL[c * INV_LDX + R], res[c], acc);
-      for (int c = 0; c < NQ3; ++c) acc = fma(TR[c * INV_LDX + R], res[NX2 + c], acc);
-    } else {
-      const int rr = R - NX2;
-      for (int c = 0; c < NX2; ++c) acc = fma(TR[rr * INV_LDX + c], res[c], acc);
-      for (int c = 0; c < NQ3; ++c) acc = fma(A[c * INV_LDQ + rr], res[NX2 + c], acc);
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int R = pass * 32 + wl;
+    if (R < NKKT) {
+      const int f = R / NV, jj = R - f * NV;   // f: 0 lmd 1 gmm 2 a 3 q 4 v
+      const int xs = f == 0 ? X_LMD : (f == 1 ? X_GMM : (f == 2 ? X_A : (f == 3 ? X_Q : X_V)));
+      const double sx = X[xs * SLOT + jj];
+      double acc = 0.0;
+      if (R < NX2) {
+#pragma unroll
+        for (int c = 0; c < NX2; ++c) acc = fma(TL[c * INV_LDX + R], res[c], acc);
+#pragma unroll
+        for (int c = 0; c < NQ3; ++c) acc = fma(TR[c * INV_LDX + R], res[NX2 + c], acc);
+      } else {
+        const int rr = R - NX2;
+#pragma unroll
+        for (int c = 0; c < NX2; ++c) acc = fma(TR[rr * INV_LDX + c], res[c], acc);
+#pragma unroll
+        for (int c = 0; c < NQ3; ++c) acc = fma(A[c * INV_LDQ + rr], res[NX2 + c], acc);
+      }
+      SN[f * SLOT + jj] = sx - acc;
     }
-    const int f = R / NV, jj = R - f * NV;   // f: 0 lmd 1 gmm 2 a 3 q 4 v
-    const int xs = f == 0 ? X_LMD : (f == 1 ? X_GMM : (f == 2 ? X_A : (f == 3 ? X_Q : X_V)));
-    SN[f * SLOT + jj] = X[xs * SLOT + jj] - acc;
   }
 
-  // ---- blocks of the inverse for the correction sweeps ----
+  // ---- blocks of the inverse for the correction sweeps (pad lanes are written as zeros) ----
   double* KI = PL.KI + (static_cast<size_t>(i) * L.G + g) * (KI_NUM * SLOT) + go;
-  for (int s0 = 0; s0 < KI_NUM; s0 += 4) {
-    const int slot = s0 + sub;
-    double val = 0.0;
-    if (j8 < NV) {
-      if (slot < KI_BP) {                         // BS: inv[7 rb + j][21 + c] = TR(7 rb + j, 7 + c)
-        const int c = slot >> 1, rb = slot & 1;
-        val = TR[(NV + c) * INV_LDX + rb * NV + j8];
-      } else if (slot < KI_FS) {                  // BP: inv[14 + 7 rb + j][21 + c] = BR(7 rb + j, 7 + c)
-        const int s = slot - KI_BP, c = s / 3, rb = s - c * 3;
-        val = A[(NV + c) * INV_LDQ + rb * NV + j8];
-      } else if (slot < KI_FP) {                  // FS: inv[21 + 7 rb + j][c] = TR(c, 7 + 7 rb + j)
-        const int s = slot - KI_FS, c = s >> 1, rb = s & 1;
-        val = TR[(NV + rb * NV + j8) * INV_LDX + c];
-      } else {                                    // FP: inv[7 rb + j][c] = TL(7 rb + j, c) | TR(c, j)
-        const int s = slot - KI_FP, c = s / 3, rb = s - c * 3;
-        val = rb < 2 ? TL[c * INV_LDX + rb * NV + j8] : TR[j8 * INV_LDX + c];
-      }
-    }
-    KI[slot * SLOT + j8] = val;
+  const bool real = j8 < NV;
+#pragma unroll
+  for (int k = 0; k < KI_BP / 4; ++k) {           // BS: inv[7 rb + j][21 + c] = TR(7 rb + j, 7 + c)
+    const int slot = 4 * k + sub, c = slot >> 1, rb = slot & 1;
+    KI[(KI_BS + slot) * SLOT + j8] = real ? TR[(NV + c) * INV_LDX + rb * NV + j8] : 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < (KI_FS - KI_BP + 3) / 4; ++k) {   // BP: inv[14 + 7 rb + j][21 + c] = BR(7 rb + j, 7 + c)
+    const int slot = 4 * k + sub, c = slot / 3, rb = slot - c * 3;
+    if (slot < KI_FS - KI_BP) KI[(KI_BP + slot) * SLOT + j8] = real ? A[(NV + c) * INV_LDQ + rb * NV + j8] : 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < (KI_FP - KI_FS) / 4; ++k) {  // FS: inv[21 + 7 rb + j][c] = TR(c, 7 + 7 rb + j)
+    const int slot = 4 * k + sub, c = slot >> 1, rb = slot & 1;
+    KI[(KI_FS + slot) * SLOT + j8] = real ? TR[(NV + rb * NV + j8) * INV_LDX + c] : 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < (KI_NUM - KI_FP + 3) / 4; ++k) {  // FP: inv[7 rb + j][c] = TL(7 rb + j, c) | TR(c, j)
+    const int slot = 4 * k + sub, c = slot / 3, rb = slot - c * 3;
+    if (slot < KI_NUM - KI_FP)
+      KI[(KI_FP + slot) * SLOT + j8] = real ? (rb < 2 ? TL[c * INV_LDX + rb * NV + j8] : TR[j8 * INV_LDX + c]) : 0.0;
   }
   if (fail && wl == 0) {
     const int b = g * 4 + inst;
