@@ -53,7 +53,7 @@ EXPORTS = [
     "idocp_b200_get_direction", "idocp_b200_get_constraint_data", "idocp_b200_get_step_sizes",
     "idocp_b200_get_unkkt", "idocp_b200_get_status", "idocp_b200_is_feasible",
     "idocp_b200_clear_line_search_filter", "idocp_b200_sync", "idocp_b200_launch_count", "idocp_b200_stream",
-    "idocp_b200_set_profiling", "idocp_b200_get_profile", "idocp_b200_last_error", "idocp_b200_version",
+    "idocp_b200_set_task_reference", "idocp_b200_set_profiling", "idocp_b200_get_profile", "idocp_b200_last_error", "idocp_b200_version",
 ]
 
 
@@ -91,6 +91,7 @@ class Library:
         L.idocp_b200_is_feasible.argtypes = [C.c_void_p, _ip]
         L.idocp_b200_clear_line_search_filter.argtypes = [C.c_void_p]
         L.idocp_b200_sync.argtypes = [C.c_void_p]
+        L.idocp_b200_set_task_reference.argtypes = [C.c_void_p, _dp]
         L.idocp_b200_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
         L.idocp_b200_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.idocp_b200_set_profiling.argtypes = [C.c_void_p, C.c_int]

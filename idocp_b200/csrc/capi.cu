@@ -170,6 +170,15 @@ static void fill_dev_problem(const idocp_b200_problem& p, DevProblem& d) {
   d.barrier = p.barrier;
   d.fraction_rate = p.fraction_rate;
   d.gravity = IIWA14_GRAVITY;
+  // TimeVaryingTaskSpace6DCost::set_q_6d_weight(position_weight, rotation_weight) stores head<3> = rotation,
+  // tail<3> = position (time_varying_task_space_6d_cost.cpp:43-58) and applies them to diff_6d = [linear; angular]
+  d.task_enabled = p.task_enabled ? 1 : 0;
+  for (int k = 0; k < 3; ++k) {
+    d.task_w6[k] = p.task_q_weight[3 + k];  d.task_w6[3 + k] = p.task_q_weight[k];
+    d.task_wf6[k] = p.task_qf_weight[3 + k]; d.task_wf6[3 + k] = p.task_qf_weight[k];
+  }
+  for (int k = 0; k < 9; ++k) d.ee[k] = IIWA14_EE_PLACEMENT_R[k];
+  for (int k = 0; k < 3; ++k) d.ee[9 + k] = IIWA14_EE_PLACEMENT_P[k];
   for (int j = 0; j < 8; ++j) {
     double* m = d.model + j * MODEL_STRIDE;
     if (j < NV) {
@@ -213,7 +222,6 @@ extern "C" int idocp_b200_create(const idocp_b200_problem* p, int solver_kind, i
     return fail(IDOCP_B200_INVALID_ARGUMENT, "invalid value: barrier / fraction_rate");
   if (solver_kind != IDOCP_B200_SOLVER_UNOCP && solver_kind != IDOCP_B200_SOLVER_UNPARNMPC)
     return fail(IDOCP_B200_INVALID_ARGUMENT, "unknown solver kind");
-  if (p->task_enabled) return fail(IDOCP_B200_UNSUPPORTED, "task-space cost is not implemented yet");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
     return fail(IDOCP_B200_NO_DEVICE, "no CUDA device available (there is no CPU fallback)");
@@ -239,7 +247,8 @@ extern "C" int idocp_b200_create(const idocp_b200_problem* p, int solver_kind, i
   int rc = 0;
   rc |= h->alloc(&h->d_prob, 1);
   rc |= h->alloc(&L.X, (N + 1) * G * X_NUM * SLOT);
-  rc |= h->alloc(&L.KQ, N * G * KQ_NUM * SLOT);
+  rc |= h->alloc(&L.KQ, (N + 1) * G * KQ_NUM * SLOT);   // record N: dense terminal Hessian of the task-space cost
+  rc |= h->alloc(&L.task_ref, (N + 1) * 12);
   rc |= h->alloc(&L.W, N * G * W_NUM * SLOT);
   rc |= h->alloc(&L.D, (N + 1) * G * D_NUM * SLOT);
   rc |= h->alloc(&L.smin, 2 * N * Bp);
@@ -257,7 +266,8 @@ extern "C" int idocp_b200_create(const idocp_b200_problem* p, int solver_kind, i
     h->stage_doubles = need;
   }
   rc |= h->alloc(&h->d_stage, h->stage_doubles);
-  if (cudaFuncSetAttribute(k_riccati, cudaFuncAttributeMaxDynamicSharedMemorySize, kRicSmem) != cudaSuccess) rc |= -1;
+  if (cudaFuncSetAttribute(k_riccati<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRicSmem) != cudaSuccess) rc |= -1;
+  if (cudaFuncSetAttribute(k_riccati<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRicSmem) != cudaSuccess) rc |= -1;
   if (par) {
     rc |= parnmpc_alloc(h->PL, h->N, h->Bp, [&](double** pp, size_t n) { return h->alloc(pp, n); });
     if (cudaFuncSetAttribute(k_parnmpc_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, INV_SMEM_BYTES) !=
@@ -271,6 +281,17 @@ extern "C" int idocp_b200_create(const idocp_b200_problem* p, int solver_kind, i
   if (cudaMemcpyAsync(h->d_prob, &h->h_prob, sizeof(DevProblem), cudaMemcpyHostToDevice, h->stream) != cudaSuccess) {
     idocp_b200_destroy(h);
     return fail(IDOCP_B200_CUDA_ERROR, "problem upload failed");
+  }
+  {
+    // until set_task_reference is called: identity placements (only read when the task-space cost is enabled)
+    std::vector<double> ident((N + 1) * 12, 0.0);
+    for (size_t i = 0; i <= N; ++i) ident[i * 12] = ident[i * 12 + 4] = ident[i * 12 + 8] = 1.0;
+    if (cudaMemcpyAsync(L.task_ref, ident.data(), ident.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream) !=
+            cudaSuccess ||
+        cudaStreamSynchronize(h->stream) != cudaSuccess) {
+      idocp_b200_destroy(h);
+      return fail(IDOCP_B200_CUDA_ERROR, "task reference upload failed");
+    }
   }
   const int irc = do_init_constraints(h);  // the reference ctor ends with initConstraints() (unocp_solver.cpp:48)
   if (irc != IDOCP_B200_OK) {
@@ -373,10 +394,17 @@ static int run_line_search(idocp_b200_solver* h) {
   const int off = h->stage_offset();
   const int fgrid = (h->B + 127) / 128;
   IDOCP_LAUNCH(h, KC_LINESEARCH, k_ls_begin, group_grid(h), CTA_THREADS, 0, h->L);
-  IDOCP_LAUNCH(h, KC_LINESEARCH, k_ls_eval, stage_grid(h, h->N + 1), CTA_THREADS, 0, h->d_prob, h->L, h->LS, 0, off);
+  const bool task = h->prob.task_enabled != 0;
+  auto eval = [&](int mode) {
+    if (task)
+      IDOCP_LAUNCH(h, KC_LINESEARCH, k_ls_eval<true>, stage_grid(h, h->N + 1), CTA_THREADS, 0, h->d_prob, h->L, h->LS, mode, off);
+    else
+      IDOCP_LAUNCH(h, KC_LINESEARCH, k_ls_eval<false>, stage_grid(h, h->N + 1), CTA_THREADS, 0, h->d_prob, h->L, h->LS, mode, off);
+  };
+  eval(0);
   IDOCP_LAUNCH(h, KC_LINESEARCH, k_ls_filter, fgrid, 128, 0, h->L, h->LS, 0);
   for (int trial = 0; trial < LS_MAX_TRIALS; ++trial) {
-    IDOCP_LAUNCH(h, KC_LINESEARCH, k_ls_eval, stage_grid(h, h->N + 1), CTA_THREADS, 0, h->d_prob, h->L, h->LS, 1, off);
+    eval(1);
     IDOCP_LAUNCH(h, KC_LINESEARCH, k_ls_filter, fgrid, 128, 0, h->L, h->LS, 1);
   }
   CUDA_OK(cudaGetLastError());
@@ -384,10 +412,17 @@ static int run_line_search(idocp_b200_solver* h) {
 }
 
 static int unocp_update(idocp_b200_solver* h, const double* d_q, const double* d_v, int line_search) {
-  IDOCP_LAUNCH(h, KC_LINEARIZE, (k_linearize<false, false>), stage_grid(h, h->N), CTA_THREADS, kLinSmem, h->d_prob,
-               h->L, d_q, d_v);
-  IDOCP_LAUNCH(h, KC_RICCATI, k_riccati, group_grid(h), CTA_THREADS, kRicSmem, h->d_prob, h->L, d_q, d_v);
-  IDOCP_LAUNCH(h, KC_EXPAND, k_expand<false>, stage_grid(h, h->N + 1), CTA_THREADS, 0, h->d_prob, h->L, 0);
+  if (h->prob.task_enabled) {
+    IDOCP_LAUNCH(h, KC_LINEARIZE, (k_linearize<false, false, true>), stage_grid(h, h->N + 1), CTA_THREADS, kLinSmem,
+                 h->d_prob, h->L, d_q, d_v);
+    IDOCP_LAUNCH(h, KC_RICCATI, k_riccati<true>, group_grid(h), CTA_THREADS, kRicSmem, h->d_prob, h->L, d_q, d_v);
+    IDOCP_LAUNCH(h, KC_EXPAND, (k_expand<false, true>), stage_grid(h, h->N + 1), CTA_THREADS, 0, h->d_prob, h->L, 0);
+  } else {
+    IDOCP_LAUNCH(h, KC_LINEARIZE, (k_linearize<false, false, false>), stage_grid(h, h->N), CTA_THREADS, kLinSmem,
+                 h->d_prob, h->L, d_q, d_v);
+    IDOCP_LAUNCH(h, KC_RICCATI, k_riccati<false>, group_grid(h), CTA_THREADS, kRicSmem, h->d_prob, h->L, d_q, d_v);
+    IDOCP_LAUNCH(h, KC_EXPAND, (k_expand<false, false>), stage_grid(h, h->N + 1), CTA_THREADS, 0, h->d_prob, h->L, 0);
+  }
   const double* override_alpha = nullptr;
   if (line_search) {
     const int rc = run_line_search(h);
@@ -405,8 +440,12 @@ static int parnmpc_update(idocp_b200_solver* h, double, const double* d_q, const
   if (line_search) return fail(IDOCP_B200_UNSUPPORTED, "UnParNMPCSolver: line_search=true is not implemented yet");
   const int N = h->N;
   // UnBackwardCorrection::coarseUpdate (src/unocp/unbackward_correction.cpp:67-97)
-  IDOCP_LAUNCH(h, KC_LINEARIZE, (k_linearize<false, true>), stage_grid(h, N), CTA_THREADS, kLinSmem, h->d_prob, h->L,
-               d_q, d_v);
+  if (h->prob.task_enabled)
+    IDOCP_LAUNCH(h, KC_LINEARIZE, (k_linearize<false, true, true>), stage_grid(h, N), CTA_THREADS, kLinSmem, h->d_prob,
+                 h->L, d_q, d_v);
+  else
+    IDOCP_LAUNCH(h, KC_LINEARIZE, (k_linearize<false, true, false>), stage_grid(h, N), CTA_THREADS, kLinSmem, h->d_prob,
+                 h->L, d_q, d_v);
   IDOCP_LAUNCH(h, KC_PARNMPC_COARSE, k_parnmpc_invert, N * h->L.G, CTA_THREADS, INV_SMEM_BYTES, h->d_prob, h->L, h->PL);
   // UnBackwardCorrection::backwardCorrection (:100-134)
   if (N > 1) {
@@ -415,7 +454,7 @@ static int parnmpc_update(idocp_b200_solver* h, double, const double* d_q, const
     IDOCP_LAUNCH(h, KC_PARNMPC_CORR, k_parnmpc_forward_serial, group_grid(h), CTA_THREADS, 0, h->L, h->PL);
   }
   IDOCP_LAUNCH(h, KC_PARNMPC_CORR, k_parnmpc_forward_parallel, stage_grid(h, N), CTA_THREADS, 0, h->L, h->PL);
-  IDOCP_LAUNCH(h, KC_EXPAND, k_expand<true>, stage_grid(h, N), CTA_THREADS, 0, h->d_prob, h->L, 1);
+  IDOCP_LAUNCH(h, KC_EXPAND, (k_expand<true, false>), stage_grid(h, N), CTA_THREADS, 0, h->d_prob, h->L, 1);
   IDOCP_LAUNCH(h, KC_UPDATE, k_update, stage_grid(h, N), CTA_THREADS, 0, h->d_prob, h->L, 1,
                static_cast<const double*>(nullptr), N);
   CUDA_OK(cudaGetLastError());
@@ -424,8 +463,12 @@ static int parnmpc_update(idocp_b200_solver* h, double, const double* d_q, const
 
 // UnParNMPCSolver::computeKKTResidual (src/unocp/unparnmpc_solver.cpp:171-192)
 static int parnmpc_kkt_residual(idocp_b200_solver* h, double, const double* d_q, const double* d_v) {
-  IDOCP_LAUNCH(h, KC_KKT, (k_linearize<true, true>), stage_grid(h, h->N), CTA_THREADS, kLinSmem, h->d_prob, h->L, d_q,
-               d_v);
+  if (h->prob.task_enabled)
+    IDOCP_LAUNCH(h, KC_KKT, (k_linearize<true, true, true>), stage_grid(h, h->N), CTA_THREADS, kLinSmem, h->d_prob, h->L,
+                 d_q, d_v);
+  else
+    IDOCP_LAUNCH(h, KC_KKT, (k_linearize<true, true, false>), stage_grid(h, h->N), CTA_THREADS, kLinSmem, h->d_prob, h->L,
+                 d_q, d_v);
   IDOCP_LAUNCH(h, KC_KKT, k_kkt_sum, (h->Bp + 127) / 128, 128, 0, h->L, h->N);
   CUDA_OK(cudaGetLastError());
   return IDOCP_B200_OK;
@@ -433,7 +476,11 @@ static int parnmpc_kkt_residual(idocp_b200_solver* h, double, const double* d_q,
 
 // UnParNMPCSolver::initBackwardCorrection (src/unocp/unparnmpc_solver.cpp:69-71)
 static int parnmpc_init_backward_correction(idocp_b200_solver* h, double) {
-  IDOCP_LAUNCH(h, KC_MISC, k_parnmpc_init_aux, stage_grid(h, h->N), CTA_THREADS, 0, h->d_prob, h->L, h->PL);
+  if (h->prob.task_enabled)
+    IDOCP_LAUNCH(h, KC_MISC, k_parnmpc_init_aux<true>, stage_grid(h, h->N), CTA_THREADS, kLinSmem, h->d_prob, h->L, h->PL);
+  else
+    IDOCP_LAUNCH(h, KC_MISC, k_parnmpc_init_aux<false>, stage_grid(h, h->N), CTA_THREADS, kLinSmem, h->d_prob, h->L,
+                 h->PL);
   CUDA_OK(cudaGetLastError());
   return IDOCP_B200_OK;
 }
@@ -462,8 +509,12 @@ extern "C" int idocp_b200_compute_kkt_residual_device(idocp_b200_solver* h, doub
   (void)t;
   CUDA_OK(cudaSetDevice(h->device));
   if (h->kind == IDOCP_B200_SOLVER_UNPARNMPC) return parnmpc_kkt_residual(h, t, d_q, d_v);
-  IDOCP_LAUNCH(h, KC_KKT, (k_linearize<true, false>), stage_grid(h, h->N + 1), CTA_THREADS, kLinSmem, h->d_prob, h->L,
-               d_q, d_v);
+  if (h->prob.task_enabled)
+    IDOCP_LAUNCH(h, KC_KKT, (k_linearize<true, false, true>), stage_grid(h, h->N + 1), CTA_THREADS, kLinSmem, h->d_prob,
+                 h->L, d_q, d_v);
+  else
+    IDOCP_LAUNCH(h, KC_KKT, (k_linearize<true, false, false>), stage_grid(h, h->N + 1), CTA_THREADS, kLinSmem, h->d_prob,
+                 h->L, d_q, d_v);
   IDOCP_LAUNCH(h, KC_KKT, k_kkt_sum, (h->Bp + 127) / 128, 128, 0, h->L, h->N + 1);
   CUDA_OK(cudaGetLastError());
   return IDOCP_B200_OK;
@@ -685,6 +736,15 @@ extern "C" int idocp_b200_init_backward_correction(idocp_b200_solver* h, double 
     return fail(IDOCP_B200_INVALID_ARGUMENT, "init_backward_correction: not an UnParNMPC solver");
   CUDA_OK(cudaSetDevice(h->device));
   return parnmpc_init_backward_correction(h, t);
+}
+
+extern "C" int idocp_b200_set_task_reference(idocp_b200_solver* h, const double* table) {
+  if (!h || !table) return fail(IDOCP_B200_INVALID_ARGUMENT, "set_task_reference: null pointer");
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaMemcpyAsync(h->L.task_ref, table, static_cast<size_t>(h->N + 1) * 12 * sizeof(double),
+                          cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));  // `table` may be pageable host memory reused by the caller
+  return IDOCP_B200_OK;
 }
 
 extern "C" int idocp_b200_sync(idocp_b200_solver* h) {

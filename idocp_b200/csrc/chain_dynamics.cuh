@@ -29,17 +29,13 @@ struct JointDyn {
   double tau;
 };
 
-// Forward + backward world-frame sweeps.  `mdl` points at this lane's row of the model table.
-// Lane 7 (padding) must be called with q = qd = qdd = 0; its model row has zero mass.
-__device__ __forceinline__ void chain_world_sweep(int lane, double q, double qd, double qdd,
-                                                  const double* __restrict__ mdl, double gravity,
-                                                  JointDyn& J) {
-  const ScanFlags sf = scan_flags(lane);
+// World placement of this lane's joint frame: local transform placement * Rz(q), then the inclusive
+// prefix product X_l <- X_0 X_1 ... X_l over the chain (Hillis-Steele tree order).  R row-major
+// (joint -> world), p = origin of the joint frame.  `mdl` points at this lane's row of the model table.
+__device__ __forceinline__ void chain_fk(int lane, double q, const double* __restrict__ mdl, double (&R)[9], V3& p) {
   double sn, cs;
   canon_sincos(q, &sn, &cs);
-  // local transform: placement * Rz(q)
-  double R[9];
-  V3 p = v3(mdl[9], mdl[10], mdl[11]);
+  p = v3(mdl[9], mdl[10], mdl[11]);
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
     const double a0 = mdl[3 * r], a1 = mdl[3 * r + 1];
@@ -47,7 +43,6 @@ __device__ __forceinline__ void chain_world_sweep(int lane, double q, double qd,
     R[3 * r + 1] = fma(cs, a1, -(sn * a0));
     R[3 * r + 2] = mdl[3 * r + 2];
   }
-  // inclusive prefix product over the chain: X_l <- X_0 X_1 ... X_l  (Hillis-Steele tree order)
 #pragma unroll
   for (int d = 1; d < OCT; d <<= 1) {
     double Rs[9];
@@ -68,6 +63,14 @@ __device__ __forceinline__ void chain_world_sweep(int lane, double q, double qd,
       for (int k = 0; k < 9; ++k) R[k] = Rn[k];
     }
   }
+}
+
+// Forward + backward world-frame sweeps on top of the placements of chain_fk.
+// Lane 7 (padding) must be called with q = qd = qdd = 0; its model row has zero mass.
+__device__ __forceinline__ void chain_world_sweep_from_fk(int lane, const double (&R)[9], V3 p, double qd, double qdd,
+                                                          const double* __restrict__ mdl, double gravity,
+                                                          JointDyn& J) {
+  const ScanFlags sf = scan_flags(lane);
   const V3 z = v3(R[2], R[5], R[8]);
   J.Sl = cross(p, z);
   J.Sw = z;
@@ -146,6 +149,14 @@ __device__ __forceinline__ void chain_world_sweep(int lane, double q, double qd,
   J.Gw = ((((cross(J.Sw, fa) + cross(J.Sl, fl)) + cross(mc, J.Bl)) + mul(Ib, J.Bw)) + mul(Sym, J.dSw)) - cross(ha, J.dSw);
   J.Hl = 2.0 * (fmav(mC, J.dSl, cross(J.dSw, mc)) - cross(hl, J.Sw));
   J.Hw = fmav(2.0, cross(mc, J.dSl) + mul(Ib, J.dSw), mul(Sym, J.Sw) - cross(ha, J.Sw));
+}
+
+__device__ __forceinline__ void chain_world_sweep(int lane, double q, double qd, double qdd,
+                                                  const double* __restrict__ mdl, double gravity, JointDyn& J) {
+  double R[9];
+  V3 p;
+  chain_fk(lane, q, mdl, R, p);
+  chain_world_sweep_from_fk(lane, R, p, qd, qdd, mdl, gravity, J);
 }
 
 // tau only (used by the line search): same world sweep without the derivative vectors

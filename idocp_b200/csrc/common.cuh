@@ -25,6 +25,13 @@ struct DevProblem {
   double barrier, fraction_rate;
   double gravity;
   double model[8 * MODEL_STRIDE];
+  // TimeVaryingTaskSpace6DCost on the end-effector frame (task_space_cost.cuh): frame placement in the last
+  // joint's frame [R row-major (9), p (3)] and the weights in the reference's internal order, i.e. applied
+  // to diff_6d = [linear; angular]: w6 = [rotation_weight, position_weight]
+  // (src/cost/time_varying_task_space_6d_cost.cpp:43-58)
+  int task_enabled;
+  double ee[12];
+  double task_w6[6], task_wf6[6];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -65,6 +72,7 @@ struct Layout {
   double* kkt_stage;  // [N+1][Bp] squared KKT norms per stage
   double* kkt_err;    // [Bp]
   int* status;        // [Bp]
+  double* task_ref;   // [N+1][12] host-sampled SE3 reference per stage index (R row-major, p); see capi.cu
 };
 
 // element index of (stage, instance b, slot, joint j) in an array with `ns` slots per record

@@ -82,6 +82,9 @@ __device__ __forceinline__ bool ls_participates(const LineSearchLayout& LS, int 
 // ---------------------------------------------------------------------------------------------
 // k_ls_eval: cost and constraint violation of s + alpha d for every (instance, stage).
 // ---------------------------------------------------------------------------------------------
+// TASK = true: + TimeVaryingTaskSpace6DCost::computeStageCost / computeTerminalCost
+// (src/cost/time_varying_task_space_6d_cost.cpp:68-90)
+template <bool TASK>
 __global__ void __launch_bounds__(CTA_THREADS) k_ls_eval(const DevProblem* __restrict__ Pp, Layout L,
                                                          LineSearchLayout LS, int mode, int stage_offset) {
   const DevProblem& P = *Pp;
@@ -107,7 +110,16 @@ __global__ void __launch_bounds__(CTA_THREADS) k_ls_eval(const DevProblem* __res
     double l = 0.0;
     l += oct_sum_ordered(z * (P.qf_weight[lane] * (qt - P.q_ref[lane]) * (qt - P.q_ref[lane])));
     l += oct_sum_ordered(z * (P.vf_weight[lane] * (vt - P.v_ref[lane]) * (vt - P.v_ref[lane])));
-    if (lane == 0 && part) LS.cost[static_cast<size_t>(N) * L.Bp + b] = 0.5 * l;
+    double tc = 0.5 * l;
+    if (TASK) {
+      double R[9];
+      V3 p;
+      chain_fk(lane, act ? qt : 0.0, P.model + lane * MODEL_STRIDE, R, p);
+      TaskEval te;
+      task_evaluate<false>(R, p, P.ee, L.task_ref + static_cast<size_t>(N) * 12, te);
+      tc += 0.5 * task_weighted_sqnorm(te, P.task_wf6);
+    }
+    if (lane == 0 && part) LS.cost[static_cast<size_t>(N) * L.Bp + b] = tc;
     return;
   }
   const double a = X[X_A * SLOT], u = X[X_U * SLOT];
@@ -123,6 +135,14 @@ __global__ void __launch_bounds__(CTA_THREADS) k_ls_eval(const DevProblem* __res
   l += oct_sum_ordered(z * (P.a_weight[lane] * at * at));
   l += oct_sum_ordered(z * (P.u_weight[lane] * (ut - P.u_ref[lane]) * (ut - P.u_ref[lane])));
   double cost = 0.5 * dt * l;
+  double R[9];
+  V3 p;
+  chain_fk(lane, act ? qt : 0.0, P.model + lane * MODEL_STRIDE, R, p);
+  if (TASK) {
+    TaskEval te;
+    task_evaluate<false>(R, p, P.ee, L.task_ref + static_cast<size_t>(i) * 12, te);
+    cost += 0.5 * dt * task_weighted_sqnorm(te, P.task_w6);
+  }
   const LaneLimits lim = load_limits(P, lane);
   double bar = 0.0, c1 = 0.0;
 #pragma unroll
@@ -145,9 +165,9 @@ __global__ void __launch_bounds__(CTA_THREADS) k_ls_eval(const DevProblem* __res
   // ---- SplitUnOCP::constraintViolation (split_unocp.hxx:199-217) ----
   const double Fq = fma(dt, vt, qt - qnt);
   const double Fv = fma(dt, at, vt) - vnt;
-  const double tau = chain_rnea(lane, act ? qt : 0.0, act ? vt : 0.0, act ? at : 0.0, P.model + lane * MODEL_STRIDE,
-                                P.gravity);
-  const double ID = tau - ut;
+  JointDyn J;
+  chain_world_sweep_from_fk(lane, R, p, act ? vt : 0.0, act ? at : 0.0, P.model + lane * MODEL_STRIDE, P.gravity, J);
+  const double ID = J.tau - ut;
   double viol = 0.0;
   viol += oct_sum_ordered(z * fabs(Fq)) + oct_sum_ordered(z * fabs(Fv));
   viol += dt * oct_sum_ordered(z * fabs(ID));

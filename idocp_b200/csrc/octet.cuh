@@ -109,6 +109,54 @@ __device__ __forceinline__ double canon_log(double x) {
   return dk * 6.93147180369123816490e-01 - ((hfsq - (s * (hfsq + R) + dk * 1.90821492927058770002e-10)) - f);
 }
 
+// acos on [-1, 1]: the fdlibm e_acos.c algorithm with plain IEEE operations (task-space cost: log3 of
+// the end-effector rotation error); the oracle repeats it bit for bit.
+__device__ __forceinline__ double canon_acos_poly(double z) {
+  const double pS0 = 1.66666666666666657415e-01, pS1 = -3.25565818622400915405e-01, pS2 = 2.01212532134862925881e-01,
+               pS3 = -4.00555345006794114027e-02, pS4 = 7.91534994289814532176e-04, pS5 = 3.47933107596021167570e-05;
+  const double qS1 = -2.40339491173441421878e+00, qS2 = 2.02094576023350569471e+00, qS3 = -6.88283971605453293030e-01,
+               qS4 = 7.70381505559019352791e-02;
+  const double pp = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+  const double qq = 1.0 + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+  return pp / qq;
+}
+__device__ __forceinline__ double canon_acos(double x) {
+  const double pio2_hi = 1.57079632679489655800e+00, pio2_lo = 6.12323399573676603587e-17;
+  const double pi = 3.14159265358979311600e+00;
+  if (!(x > -1.0)) return pi;
+  if (!(x < 1.0)) return 0.0;
+  if (fabs(x) < 0.5) {
+    const double r = canon_acos_poly(x * x);
+    return pio2_hi - (x - (pio2_lo - x * r));
+  }
+  if (x < 0.0) {
+    const double z = (1.0 + x) * 0.5;
+    const double sq = sqrt(z);
+    const double r = canon_acos_poly(z);
+    const double w = r * sq - pio2_lo;
+    return pi - 2.0 * (sq + w);
+  }
+  const double z = (1.0 - x) * 0.5;
+  const double sq = sqrt(z);
+  long long bits;
+#ifdef IDOCP_B200_EMU
+  memcpy(&bits, &sq, sizeof(bits));
+#else
+  bits = __double_as_longlong(sq);
+#endif
+  bits &= static_cast<long long>(0xffffffff00000000ULL);   // df = sq with the low word cleared
+  double df;
+#ifdef IDOCP_B200_EMU
+  memcpy(&df, &bits, sizeof(df));
+#else
+  df = __longlong_as_double(bits);
+#endif
+  const double c = (z - df * df) / (sq + df);
+  const double r = canon_acos_poly(z);
+  const double w = r * sq + c;
+  return 2.0 * (df + w);
+}
+
 __device__ __forceinline__ int lane_in_octet() { return threadIdx.x & 7; }
 
 // width-8 shuffles on doubles / V3

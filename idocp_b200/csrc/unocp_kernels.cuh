@@ -18,6 +18,7 @@
 // local) and column l of every 7x7 block.  One warp = one GROUP of 4 instances (common.cuh).
 #pragma once
 #include "chain_dynamics.cuh"
+#include "task_space_cost.cuh"
 #include "tma.cuh"
 
 namespace idocp_b200 {
@@ -137,7 +138,10 @@ __global__ void k_set_solution(Layout L, int field, const double* __restrict__ v
 //                         terminal_unparnmpc.hxx:70-102,155-193): stages 1..N stored at index 0..N-1, the
 //                         previous state of index 0 is the measured x0 = (q0, v0), index N-1 also carries
 //                         the terminal cost; constraint masks use time stage index + 1
-template <bool RESIDUAL_ONLY, bool BACKWARD_EULER>
+// TASK = true: + TimeVaryingTaskSpace6DCost (task_space_cost.cuh).  With the forward-Euler solver the kernel
+//               then also covers the terminal stage N (TerminalOCP::linearizeOCP, ocp/terminal_ocp.hxx:50-66)
+//               and leaves its dense Hessian / gradient in record N of KQ for k_riccati and k_expand.
+template <bool RESIDUAL_ONLY, bool BACKWARD_EULER, bool TASK>
 __global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_linearize(const DevProblem* __restrict__ Pp, Layout L,
                                                                            const double* __restrict__ q0,
                                                                            const double* __restrict__ v0) {
@@ -146,7 +150,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_linearize(const
   const int lane = lane_in_octet();
   const int oct = threadIdx.x >> 3;
   double* tile = smem + oct * (OCT * PAIR_TILE);
-  const StageTask t = stage_task(L, (RESIDUAL_ONLY && !BACKWARD_EULER) ? L.N + 1 : L.N);
+  const StageTask t = stage_task(L, ((RESIDUAL_ONLY || TASK) && !BACKWARD_EULER) ? L.N + 1 : L.N);
   const int i = t.stage;
   const int ts = BACKWARD_EULER ? i + 1 : i;   // time stage of the constraint masks
   const int b = t.g * 4 + ((threadIdx.x >> 3) & 3);
@@ -156,16 +160,37 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_linearize(const
 
   const double q = X[X_Q * SLOT], v = X[X_V * SLOT], lmd = X[X_LMD * SLOT], gmm = X[X_GMM * SLOT];
 
-  if (RESIDUAL_ONLY && !BACKWARD_EULER && i == L.N) {
-    // TerminalOCP::computeKKTResidual + squaredNormKKTResidual (ocp/terminal_ocp.hxx:120-144)
+  if ((RESIDUAL_ONLY || TASK) && !BACKWARD_EULER && i == L.N) {
+    // TerminalOCP::linearizeOCP / computeKKTResidual + squaredNormKKTResidual (ocp/terminal_ocp.hxx:50-66,120-144)
     double lq = 0.0, lv = 0.0;
     lq += P.qf_weight[lane] * (q - P.q_ref[lane]);
     lv += P.vf_weight[lane] * (v - P.v_ref[lane]);
+    double hf[NV];
+    if (TASK) {
+      double R[9];
+      V3 p;
+      chain_fk(lane, act ? q : 0.0, P.model + lane * MODEL_STRIDE, R, p);
+      TaskEval te;
+      task_evaluate<true>(R, p, P.ee, L.task_ref + static_cast<size_t>(i) * 12, te);
+      task_share_columns(lane, te, tile);
+      double gf;
+      task_gradient_hessian(te, P.task_wf6, tile, gf, hf);
+      lq += gf;
+    }
     lq -= lmd;
     lv -= gmm;
     if (!act) { lq = 0.0; lv = 0.0; }
-    const double e = oct_sum_ordered(lq * lq) + oct_sum_ordered(lv * lv);
-    if (lane == 0) L.kkt_stage[static_cast<size_t>(i) * L.Bp + b] = e;
+    if (RESIDUAL_ONLY) {
+      const double e = oct_sum_ordered(lq * lq) + oct_sum_ordered(lv * lv);
+      if (lane == 0) L.kkt_stage[static_cast<size_t>(i) * L.Bp + b] = e;
+    } else {
+      // terminal record: rows of Qqq_N (slot = row, lane = column), lq_N, lv_N
+      double* KQ = rec_ptr(L.KQ, KQ_NUM, L.G, i, t.g);
+#pragma unroll
+      for (int r = 0; r < NV; ++r) KQ[(KQ_QQ + r) * SLOT] = (r == lane ? P.qf_weight[lane] : 0.0) + (act ? hf[r] : 0.0);
+      KQ[KQ_LQ * SLOT] = lq;
+      KQ[KQ_LV * SLOT] = lv;
+    }
     return;
   }
 
@@ -198,7 +223,22 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_linearize(const
 
   // ---- inverse dynamics and its derivatives (UnconstrainedDynamics::linearizeInverseDynamics) ----
   JointDyn J;
-  chain_world_sweep(lane, q, v, a, P.model + lane * MODEL_STRIDE, P.gravity, J);
+  double task_g = 0.0, task_gf = 0.0;   // JJ^T W diff of the stage / terminal task-space cost (this lane's entry)
+  double task_h[NV], task_hf[NV];       // rows of JJ^T W JJ (this lane's column)
+  {
+    double R[9];
+    V3 p;
+    chain_fk(lane, q, P.model + lane * MODEL_STRIDE, R, p);
+    if (TASK) {
+      TaskEval te;
+      task_evaluate<true>(R, p, P.ee, L.task_ref + static_cast<size_t>(i) * 12, te);
+      task_share_columns(lane, te, tile);
+      task_gradient_hessian(te, P.task_w6, tile, task_g, task_h);
+      if (last) task_gradient_hessian(te, P.task_wf6, tile, task_gf, task_hf);
+      __syncwarp();   // the tile is reused by chain_pair_phase
+    }
+    chain_world_sweep_from_fk(lane, R, p, v, a, P.model + lane * MODEL_STRIDE, P.gravity, J);
+  }
   double dqc[NV], dvc[NV], Mc[NV];
   chain_pair_phase(lane, J, tile, dqc, dvc, Mc);
   const double ID = J.tau - u;
@@ -209,9 +249,11 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_linearize(const
   lv += dt * P.v_weight[lane] * (v - P.v_ref[lane]);
   la += dt * P.a_weight[lane] * a;
   lu += dt * P.u_weight[lane] * (u - P.u_ref[lane]);
+  if (TASK) lq += dt * task_g;
   if (last) {   // + computeTerminalCostDerivatives (terminal_unparnmpc.hxx:84)
     lq += P.qf_weight[lane] * (q - P.q_ref[lane]);
     lv += P.vf_weight[lane] * (v - P.v_ref[lane]);
+    if (TASK) lq += task_gf;
   }
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
@@ -283,9 +325,28 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_linearize(const
   double Qvv_d = dt * P.v_weight[lane];
   const double Qaa_d = dt * P.a_weight[lane];
   double Quu_d = dt * P.u_weight[lane];
+  // off-diagonal entries of the un-condensed Qqq (task-space Gauss-Newton term only), row r of this lane's column
+  double Qqq_off[NV];
+#pragma unroll
+  for (int r = 0; r < NV; ++r) Qqq_off[r] = 0.0;
+  if (TASK) {
+#pragma unroll
+    for (int r = 0; r < NV; ++r) {
+      const double hr = dt * task_h[r];
+      if (r == lane) Qqq_d += hr;
+      Qqq_off[r] = hr;
+    }
+  }
   if (last) {   // + computeTerminalCostHessian (terminal_unparnmpc.hxx:93)
     Qqq_d += P.qf_weight[lane];
     Qvv_d += P.vf_weight[lane];
+    if (TASK) {
+#pragma unroll
+      for (int r = 0; r < NV; ++r) {
+        if (r == lane) Qqq_d += task_hf[r];
+        Qqq_off[r] += task_hf[r];
+      }
+    }
   }
   if (act) {
 #pragma unroll
@@ -372,7 +433,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_linearize(const
       aa = fma(xa, Da[k], aa);
     }
     const bool diag = (r == lane);
-    KQ[(KQ_QQ + r) * SLOT] = qq + (diag ? Qqq_d : 0.0);
+    KQ[(KQ_QQ + r) * SLOT] = qq + (diag ? Qqq_d : (TASK && act ? Qqq_off[r] : 0.0));
     KQ[(KQ_QV + r) * SLOT] = qv;
     KQ[(KQ_VV + r) * SLOT] = vv + (diag ? Qvv_d : 0.0);
     KQ[(KQ_AQ + r) * SLOT] = aq;
@@ -407,6 +468,8 @@ constexpr int RIC_SMEM_DOUBLES = RIC_OFF_BARS + RIC_NBARS * WARPS_PER_CTA;
 static_assert(KQ_AA == 0 && KQ_QQ == 3 * NV && KQ_FQ == 6 * NV && KQ_NUM == 6 * NV + 5, "record layout");
 static_assert(W_KQ == 0 && W_KV == NV && W_K == 2 * NV && KQ_FV == KQ_FQ + 1, "record layout");
 
+// TASK = true: the terminal Hessian / gradient are dense and come from record N of KQ (k_linearize<.., true>)
+template <bool TASK>
 __global__ void __launch_bounds__(CTA_THREADS, IDOCP_RIC_MINB) k_riccati(const DevProblem* __restrict__ Pp, Layout L,
                                                          const double* __restrict__ q0,
                                                          const double* __restrict__ v0) {
@@ -487,6 +550,12 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_RIC_MINB) k_riccati(const D
       Pqv[r] = 0.0;
       Pvq[r] = 0.0;
     }
+    if (TASK) {
+      const double* KQN = rec_ptr(L.KQ, KQ_NUM, L.G, N, g);
+#pragma unroll
+      for (int r = 0; r < NV; ++r) Pqq[r] = KQN[(KQ_QQ + r) * SLOT];
+      sq = -KQN[KQ_LQ * SLOT];
+    }
   }
 
   // ---- backward recursion ----
@@ -524,6 +593,14 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_RIC_MINB) k_riccati(const D
       pvqF = fma(Pvq[k], fv, pvqF);   // (Pqv Fv)_c
       pqvF = fma(Pqv[k], fq, pqvF);   // (Pqv^T Fq)_c
       pvvF = fma(Pvv[k], fv, pvvF);   // (Pvv Fv)_c
+    }
+    if (TASK && i == N - 1) {
+      // the dense terminal Pqq_N = Qqq_N (Gauss-Newton term of the task-space cost) is not bitwise symmetric:
+      // (Pqq Fq)_c needs ROW c, which each lane reads from the terminal record itself
+      const double* rec = L.KQ + (static_cast<size_t>(N) * L.G + g) * (KQ_NUM * SLOT) + (oct & 3) * OCT;
+      pqqF = 0.0;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) pqqF = fma(rec[(KQ_QQ + ln) * SLOT + k], oct_bcast(Fq, k), pqqF);
     }
     la = fma(dt, pqvF, la);
     la = fma(dt, pvvF, la);
@@ -725,7 +802,8 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_RIC_MINB) k_riccati(const D
 // ---------------------------------------------------------------------------------------------
 // PARNMPC = true (UnParNMPCSolver): N stages, none terminal, the costate direction is already in D
 // (k_parnmpc_forward_parallel); only the condensed direction and the step sizes are computed.
-template <bool PARNMPC>
+// TASK = true: the terminal P_N = Qqq_N is dense (record N of KQ)
+template <bool PARNMPC, bool TASK>
 __global__ void __launch_bounds__(CTA_THREADS) k_expand(const DevProblem* __restrict__ Pp, Layout L, int stage_offset) {
   const DevProblem& P = *Pp;
   const int lane = lane_in_octet();
@@ -746,6 +824,17 @@ __global__ void __launch_bounds__(CTA_THREADS) k_expand(const DevProblem* __rest
     lv -= gmm;
     double dlmd = P.qf_weight[lane] * dq; dlmd -= -lq;
     double dgmm = P.vf_weight[lane] * dv; dgmm -= -lv;
+    if (TASK) {
+      // dlmd = Pqq_N dq - sq with row `lane` of the dense Pqq_N (each lane reads its own row) and sq = -lq_N
+      const double* rec = L.KQ + (static_cast<size_t>(N) * L.G + t.g) * (KQ_NUM * SLOT) + ((threadIdx.x >> 3) & 3) * OCT;
+      const int row = act ? lane : 0;
+      double t1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) t1 = fma(rec[(KQ_QQ + row) * SLOT + k], oct_bcast(dq, k), t1);
+      dlmd = t1;
+      dlmd -= -rec[KQ_LQ * SLOT + row];
+      if (!act) dlmd = 0.0;
+    }
     D[D_LMD * SLOT] = dlmd;
     D[D_GMM * SLOT] = dgmm;
     return;

@@ -59,15 +59,48 @@ inline int parnmpc_alloc(ParNMPCLayout& PL, int N, int Bp, Alloc alloc) {
 // ---------------------------------------------------------------------------------------------
 // k_parnmpc_init_aux: every aux_mat = Hessian of the terminal cost = diag(qf_weight, vf_weight)
 // ---------------------------------------------------------------------------------------------
+// TASK = true: + the (dense) Gauss-Newton Hessian of the terminal task-space cost at s[N-1]
+// (TerminalUnParNMPC::computeTerminalCostHessian, terminal_unparnmpc.hxx:230-241)
+template <bool TASK>
 __global__ void __launch_bounds__(CTA_THREADS) k_parnmpc_init_aux(const DevProblem* __restrict__ Pp, Layout L,
                                                                   ParNMPCLayout PL) {
+  IDOCP_DYN_SMEM(double, smem);
   const DevProblem& P = *Pp;
   const int lane = lane_in_octet();
   const StageTask t = stage_task(L, L.N);
   double* A = rec_ptr(PL.AUX, AUX_NUM, L.G, t.stage, t.g);
+  double col[NV];   // aux(lane, c), c = 0..6: row `lane` of the q-q block
+#pragma unroll
+  for (int c = 0; c < NV; ++c) col[c] = (lane == c) ? P.qf_weight[lane] : 0.0;
+  if (TASK) {
+    double* tile = smem + (threadIdx.x >> 3) * (OCT * PAIR_TILE);
+    const bool act = lane < NV;
+    const double* X = rec_ptr(L.X, X_NUM, L.G, L.N - 1, t.g);
+    double R[9];
+    V3 p;
+    chain_fk(lane, act ? X[X_Q * SLOT] : 0.0, P.model + lane * MODEL_STRIDE, R, p);
+    TaskEval te;
+    task_evaluate<true>(R, p, P.ee, L.task_ref + static_cast<size_t>(L.N - 1) * 12, te);
+    task_share_columns(lane, te, tile);
+    double gf, hf[NV];
+    task_gradient_hessian(te, P.task_wf6, tile, gf, hf);
+    __syncwarp();
+    // transpose through the tile: lane j needs H(j, c), owned by lane c as hf[j]
+    double* mine = tile + lane * PAIR_TILE;
+#pragma unroll
+    for (int r = 0; r < NV; ++r) mine[r] = hf[r];
+    __syncwarp();
+    const int ln = act ? lane : 0;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) col[c] += tile[c * PAIR_TILE + ln];
+    if (!act) {
+#pragma unroll
+      for (int c = 0; c < NV; ++c) col[c] = 0.0;
+    }
+  }
 #pragma unroll
   for (int c = 0; c < NX2; ++c) {
-    A[(c * 2 + 0) * SLOT] = (c < NV && lane == c) ? P.qf_weight[lane] : 0.0;
+    A[(c * 2 + 0) * SLOT] = c < NV ? col[c] : 0.0;
     A[(c * 2 + 1) * SLOT] = (c >= NV && lane == c - NV) ? P.vf_weight[lane] : 0.0;
   }
 }

@@ -12,7 +12,8 @@ import numpy as np
 from . import capi
 from .capi import DIMV, NUM_CONSTRAINTS, SOLVER_UNOCP, SOLVER_UNPARNMPC, Idocp_b200Error, Problem, dptr
 
-__all__ = ["UnOCPSolver", "UnParNMPCSolver", "benchmark_problem", "config_space_problem", "Problem"]
+__all__ = ["UnOCPSolver", "UnParNMPCSolver", "benchmark_problem", "config_space_problem", "task_space_problem",
+           "task_space_circle_ref", "Problem"]
 
 
 def _fill(arr, value):
@@ -52,6 +53,30 @@ def config_space_problem(lib=None):
     _fill(p.vf_weight, 0.01)
     _fill(p.a_weight, 0.01)
     return p
+
+
+def task_space_problem(lib=None, N=120, T=6.0):
+    """examples/iiwa14/task_space_ocp.cpp:55-84 (BASELINE.json configs[1] problem): joint limits 50 / pi/2,
+    ConfigurationSpaceCost (v, a weights 0.01) + TimeVaryingTaskSpace6DCost with weights 1000."""
+    lib = lib or capi.default_library()
+    p = lib.default_problem()
+    p.N, p.T = N, T
+    _fill(p.u_max, 50.0)
+    _fill(p.v_max, np.pi / 2)
+    _fill(p.v_weight, 0.01)
+    _fill(p.vf_weight, 0.01)
+    _fill(p.a_weight, 0.01)
+    p.task_enabled = 1
+    _fill(p.task_q_weight, 1000.0)
+    _fill(p.task_qf_weight, 1000.0)
+    return p
+
+
+def task_space_circle_ref(t):
+    """TimeVaryingTaskSpace6DRef::compute_q_6d_ref of examples/iiwa14/task_space_ocp.cpp:21-46
+    -> [R_ref row-major (9), p_ref (3)]."""
+    return np.array([0.0, 0.0, 1.0, 0.0, 1.0, 0.0, -1.0, 0.0, 0.0,
+                     0.546, 0.1 * np.sin(np.pi * t), 0.76 + 0.1 * np.cos(np.pi * t)])
 
 
 class _BatchSolver:
@@ -100,6 +125,22 @@ class _BatchSolver:
 
     def initConstraints(self):
         self.lib.check(self.lib.L.idocp_b200_init_constraints(self._h))
+
+    def stageTimes(self, t):
+        """Time at which every stage index is linearised (unocp_solver.cpp:80-93 / unbackward_correction.cpp:73-95)."""
+        dt = self.problem.T / self.N
+        if self.kind == SOLVER_UNOCP:
+            return [t + i * dt for i in range(self.N)] + [t + self.problem.T]
+        return [t + (i + 1) * dt for i in range(self.N - 1)] + [t + self.problem.T, t + self.N * dt]
+
+    def setTaskReference(self, ref, t=0.0):
+        """TimeVaryingTaskSpace6DCost reference: `ref` is the user's compute_q_6d_ref(t) -> 12 doubles
+        (R row-major, p), sampled here on the host at every stage time, or an (N+1, 12) table."""
+        table = np.array([ref(x) for x in self.stageTimes(t)]) if callable(ref) else np.asarray(ref, dtype=np.float64)
+        table = np.ascontiguousarray(table, dtype=np.float64)
+        if table.shape != (self.N + 1, 12):
+            raise ValueError("task reference table must have shape (%d, 12)" % (self.N + 1))
+        self.lib.check(self.lib.L.idocp_b200_set_task_reference(self._h, dptr(table)))
 
     def updateSolution(self, t, q, v, line_search=False):
         q, v = self._x(q), self._x(v)

@@ -69,9 +69,11 @@ typedef struct {
   double v_max[IDOCP_B200_DIMV], u_max[IDOCP_B200_DIMV];
   double barrier;           /* 1e-4  */
   double fraction_rate;     /* 0.995 */
-  int task_enabled;         /* TimeVaryingTaskSpace6DCost on the end-effector frame */
-  double task_q_weight[6], task_qf_weight[6];
-  double task_center[3], task_radius, task_t0, task_tf;
+  int task_enabled;         /* TimeVaryingTaskSpace6DCost on the end-effector frame (frame id 22 of
+                               examples/iiwa14/task_space_ocp.cpp:67) */
+  double task_q_weight[6], task_qf_weight[6]; /* [position xyz, rotation xyz] = the arguments of
+                               set_q_6d_weight / set_qf_6d_weight (time_varying_task_space_6d_cost.cpp:43-58) */
+  double task_center[3], task_radius, task_t0, task_tf; /* reserved (the reference is a host-sampled table) */
   double task_rot_ref[9];
 } idocp_b200_problem;
 
@@ -135,6 +137,14 @@ int idocp_b200_get_status(idocp_b200_solver* h, int* out);
 int idocp_b200_is_feasible(idocp_b200_solver* h, int* out);
 /* UnOCPSolver::clearLineSearchFilter() (unocp_solver.cpp:185-187) */
 int idocp_b200_clear_line_search_filter(idocp_b200_solver* h);
+
+/* TimeVaryingTaskSpace6DRefBase::compute_q_6d_ref(t, SE3&) (cost/time_varying_task_space_6d_cost.hpp:39-40)
+ * is a user-derived host virtual: the host layer samples it at the time of every stage index and hands the
+ * samples over as table[N+1][12] = [R_ref row-major (9), p_ref (3)]:
+ *   UnOCPSolver     row i = t + i dt (i < N), row N = t + T        (unocp_solver.cpp:80-93)
+ *   UnParNMPCSolver row i = t + (i+1) dt (i < N-1), row N-1 = t + T (unbackward_correction.cpp:73-95), row N unused
+ * Call it before updateSolution / computeKKTResidual / initBackwardCorrection whenever t changes. */
+int idocp_b200_set_task_reference(idocp_b200_solver* h, const double* table);
 
 int idocp_b200_sync(idocp_b200_solver* h);
 /* number of kernels this handle has launched since creation (bench.py "gpu_launches") */

@@ -104,16 +104,79 @@ class ConfigurationSpaceCost {
   idocp_b200_problem p_;
 };
 
-// closed registry of cost components: ConfigurationSpaceCost is the supported component
+// minimal stand-ins for Eigen::Vector3d / Eigen::Matrix3d / pinocchio::SE3 in the task-space reference plug-in
+struct Vector3d {
+  double d[3] = {0, 0, 0};
+  Vector3d() {}
+  Vector3d(double x, double y, double z) { d[0] = x; d[1] = y; d[2] = z; }
+  static Vector3d Constant(double v) { return Vector3d(v, v, v); }
+  double& coeffRef(int i) { return d[i]; }
+  double operator[](int i) const { return d[i]; }
+};
+struct Matrix3d {
+  double d[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};   // row-major
+  double& operator()(int r, int c) { return d[3 * r + c]; }
+  double operator()(int r, int c) const { return d[3 * r + c]; }
+};
+struct SE3 {
+  Matrix3d rotation;
+  Vector3d translation;
+  SE3() {}
+  SE3(const Matrix3d& R, const Vector3d& p) : rotation(R), translation(p) {}
+};
+
+// cost/time_varying_task_space_6d_cost.hpp:22-41: user-derived reference; a HOST virtual, sampled by the solver
+// at the time of every stage and uploaded as a table (idocp_b200_set_task_reference)
+class TimeVaryingTaskSpace6DRefBase {
+ public:
+  TimeVaryingTaskSpace6DRefBase() {}
+  virtual ~TimeVaryingTaskSpace6DRefBase() {}
+  virtual void compute_q_6d_ref(const double t, SE3& se3_ref) const = 0;
+};
+
+// cost/time_varying_task_space_6d_cost.hpp:44-150.  Supported frame: the end-effector frame of the iiwa14
+// (frame id 22 = iiwa_link_ee_kuka, examples/iiwa14/task_space_ocp.cpp:67).
+class TimeVaryingTaskSpace6DCost {
+ public:
+  TimeVaryingTaskSpace6DCost(const Robot&, const int frame_id, const std::shared_ptr<TimeVaryingTaskSpace6DRefBase>& ref)
+      : ref_(ref) {
+    if (frame_id != 22) detail::die("idocp_b200: TimeVaryingTaskSpace6DCost supports frame_id 22 (iiwa_link_ee_kuka) only");
+    for (int k = 0; k < 6; ++k) q_[k] = qf_[k] = 0.0;
+  }
+  void set_ref(const std::shared_ptr<TimeVaryingTaskSpace6DRefBase>& ref) { ref_ = ref; }
+  // arguments exactly as in the reference: (position_weight, rotation_weight)
+  void set_q_6d_weight(const Vector3d& position_weight, const Vector3d& rotation_weight) {
+    for (int k = 0; k < 3; ++k) { q_[k] = position_weight[k]; q_[3 + k] = rotation_weight[k]; }
+  }
+  void set_qf_6d_weight(const Vector3d& position_weight, const Vector3d& rotation_weight) {
+    for (int k = 0; k < 3; ++k) { qf_[k] = position_weight[k]; qf_[3 + k] = rotation_weight[k]; }
+  }
+  const double* q_6d_weight() const { return q_; }
+  const double* qf_6d_weight() const { return qf_; }
+  const std::shared_ptr<TimeVaryingTaskSpace6DRefBase>& ref() const { return ref_; }
+ private:
+  std::shared_ptr<TimeVaryingTaskSpace6DRefBase> ref_;
+  double q_[6], qf_[6];
+};
+
+// closed registry of cost components: one ConfigurationSpaceCost and, optionally, one
+// TimeVaryingTaskSpace6DCost (push_back order of the reference examples: configuration cost first)
 class CostFunction {
  public:
   void push_back(const std::shared_ptr<ConfigurationSpaceCost>& c) {
     if (config_) detail::die("idocp_b200: only one ConfigurationSpaceCost component is supported");
+    if (task_) detail::die("idocp_b200: push the ConfigurationSpaceCost before the task-space cost");
     config_ = c;
   }
+  void push_back(const std::shared_ptr<TimeVaryingTaskSpace6DCost>& c) {
+    if (task_) detail::die("idocp_b200: only one TimeVaryingTaskSpace6DCost component is supported");
+    task_ = c;
+  }
   const std::shared_ptr<ConfigurationSpaceCost>& config() const { return config_; }
+  const std::shared_ptr<TimeVaryingTaskSpace6DCost>& task() const { return task_; }
  private:
   std::shared_ptr<ConfigurationSpaceCost> config_;
+  std::shared_ptr<TimeVaryingTaskSpace6DCost> task_;
 };
 
 class Constraints {
@@ -150,6 +213,13 @@ inline idocp_b200_problem make_problem(const Robot& robot, const std::shared_ptr
   p.fraction_rate = constraints->fractionToBoundaryRate();
   p.T = T;
   p.N = N;
+  if (cost->task()) {
+    p.task_enabled = 1;
+    for (int k = 0; k < 6; ++k) {
+      p.task_q_weight[k] = cost->task()->q_6d_weight()[k];
+      p.task_qf_weight[k] = cost->task()->qf_6d_weight()[k];
+    }
+  }
   return p;
 }
 
@@ -157,7 +227,7 @@ class SolverBase {
  public:
   SolverBase(int kind, const Robot& robot, const std::shared_ptr<CostFunction>& cost,
              const std::shared_ptr<Constraints>& constraints, double T, int N, int nthreads, int batch, int device)
-      : N_(N), batch_(batch), kind_(kind) {
+      : N_(N), batch_(batch), kind_(kind), T_(T), task_(cost ? cost->task() : nullptr) {
     try {
       if (T <= 0) throw std::out_of_range("invalid value: T must be positive!");
       if (N <= 0) throw std::out_of_range("invalid value: N must be positive!");
@@ -176,17 +246,21 @@ class SolverBase {
   // reference signature (one x0, broadcast to the whole batch)
   void updateSolution(double t, const VectorXd& q, const VectorXd& v, bool line_search = false) {
     rep(q, v);
+    sampleTaskReference(t);
     check(idocp_b200_update_solution(h_.get(), t, qb_.data(), vb_.data(), line_search ? 1 : 0));
   }
   // batched: q, v row-major [batch][dimv]
   void updateSolution(double t, const double* q, const double* v, bool line_search = false) {
+    sampleTaskReference(t);
     check(idocp_b200_update_solution(h_.get(), t, q, v, line_search ? 1 : 0));
   }
   void computeKKTResidual(double t, const VectorXd& q, const VectorXd& v) {
     rep(q, v);
+    sampleTaskReference(t);
     check(idocp_b200_compute_kkt_residual(h_.get(), t, qb_.data(), vb_.data()));
   }
   void computeKKTResidual(double t, const double* q, const double* v) {
+    sampleTaskReference(t);
     check(idocp_b200_compute_kkt_residual(h_.get(), t, q, v));
   }
   // KKT error of instance 0 (the reference return value); KKTErrors() gives all of them
@@ -239,6 +313,26 @@ class SolverBase {
   idocp_b200_solver* handle() { return h_.get(); }
 
  protected:
+  // the user's compute_q_6d_ref at the time of every stage index (unocp_solver.cpp:80-93: t + i dt, terminal
+  // t + T; unbackward_correction.cpp:73-95: t + (i+1) dt, last stage t + T), re-sampled only when t changes
+  void sampleTaskReference(double t) {
+    if (!task_ || !task_->ref()) return;
+    if (task_sampled_ && t == task_t_) return;
+    const double dt = T_ / N_;
+    std::vector<double> table(static_cast<size_t>(N_ + 1) * 12);
+    for (int i = 0; i <= N_; ++i) {
+      double ti;
+      if (kind_ == IDOCP_B200_SOLVER_UNOCP) ti = i < N_ ? t + i * dt : t + T_;
+      else ti = i < N_ - 1 ? t + (i + 1) * dt : (i == N_ - 1 ? t + T_ : t + N_ * dt);
+      SE3 ref;
+      task_->ref()->compute_q_6d_ref(ti, ref);
+      for (int k = 0; k < 9; ++k) table[static_cast<size_t>(i) * 12 + k] = ref.rotation.d[k];
+      for (int k = 0; k < 3; ++k) table[static_cast<size_t>(i) * 12 + 9 + k] = ref.translation.d[k];
+    }
+    check(idocp_b200_set_task_reference(h_.get(), table.data()));
+    task_sampled_ = true;
+    task_t_ = t;
+  }
   void rep(const VectorXd& q, const VectorXd& v) {
     qb_.resize(static_cast<size_t>(batch_) * IDOCP_B200_DIMV);
     vb_.resize(qb_.size());
@@ -253,6 +347,10 @@ class SolverBase {
   }
   std::shared_ptr<idocp_b200_solver> h_;
   int N_, batch_, kind_;
+  double T_;
+  std::shared_ptr<TimeVaryingTaskSpace6DCost> task_;
+  bool task_sampled_ = false;
+  double task_t_ = 0.0;
   std::vector<double> qb_, vb_;
 };
 }  // namespace detail
@@ -271,7 +369,10 @@ class UnParNMPCSolver : public detail::SolverBase {
                   const std::shared_ptr<Constraints>& constraints, const double T, const int N,
                   const int nthreads = 1, const int batch = 1, const int device = 0)
       : SolverBase(IDOCP_B200_SOLVER_UNPARNMPC, robot, cost, constraints, T, N, nthreads, batch, device) {}
-  void initBackwardCorrection(const double t) { detail::check(idocp_b200_init_backward_correction(h_.get(), t)); }
+  void initBackwardCorrection(const double t) {
+    sampleTaskReference(t);
+    detail::check(idocp_b200_init_backward_correction(h_.get(), t));
+  }
 };
 
 // include/idocp/utils/ocp_benchmarker.hxx:13-51

@@ -241,19 +241,10 @@ static void suffix_sum8_v(v3_t* v) {
   for (int l = 0; l < LANES; ++l) v[l] = V3(a[l], b[l], c[l]);
 }
 
-/* Robot::RNEADerivatives -> pinocchio::computeRNEADerivatives + lower-triangle mirror of dtau/da
- * (include/idocp/robot/robot.hxx:466-500).  Analytical derivatives of Carpentier & Mansard
- * (RSS 2018) in the WORLD frame; the composite matrices are kept in their structured form
- *   I^C = (m, mc, Ibar)   [10 numbers],   D^C m = (-2 hl x m_w ; Sym m_w - ha x m_w)   [12 numbers]
- * (derivation: DESIGN.md "RNEA derivatives"; mirrored in oracle/np_mirror.py).
- * The chain recursions are evaluated as tree-ordered scans over 8 "lanes" (7 joints + a zero-mass
- * pad) so that the operation order equals the GPU kernel's (chain_dynamics.cuh).
- * Also returns tau = rnea(q,v,a) when tau != NULL. */
-static void rnea_derivatives_impl(const double* q, const double* v, const double* a, double* tau,
-                                  double* dq, double* dv, double* da) {
-  joint_world_t J[LANES];
-  double R[LANES][9];
-  v3_t p[LANES];
+/* world placements of the 7 joint frames (+ the zero-mass pad lane): local transform placement * Rz(q),
+ * then the inclusive prefix product X_l <- X_0 ... X_l in the GPU's Hillis-Steele tree order
+ * (chain_dynamics.cuh: chain_fk).  R row-major (joint -> world), p = origin of the joint frame. */
+static void chain_fk(const double* q, double R[LANES][9], v3_t* p) {
   /* local transforms: placement * Rz(q) */
   for (int l = 0; l < LANES; ++l) {
     if (l < NV) {
@@ -294,6 +285,22 @@ static void rnea_derivatives_impl(const double* q, const double* v, const double
       memcpy(R[l], Rn, sizeof(Rn));
     }
   }
+}
+
+/* Robot::RNEADerivatives -> pinocchio::computeRNEADerivatives + lower-triangle mirror of dtau/da
+ * (include/idocp/robot/robot.hxx:466-500).  Analytical derivatives of Carpentier & Mansard
+ * (RSS 2018) in the WORLD frame; the composite matrices are kept in their structured form
+ *   I^C = (m, mc, Ibar)   [10 numbers],   D^C m = (-2 hl x m_w ; Sym m_w - ha x m_w)   [12 numbers]
+ * (derivation: DESIGN.md "RNEA derivatives"; mirrored in oracle/np_mirror.py).
+ * The chain recursions are evaluated as tree-ordered scans over 8 "lanes" (7 joints + a zero-mass
+ * pad) so that the operation order equals the GPU kernel's (chain_dynamics.cuh).
+ * Also returns tau = rnea(q,v,a) when tau != NULL. */
+static void rnea_derivatives_impl(const double* q, const double* v, const double* a, double* tau,
+                                  double* dq, double* dv, double* da) {
+  joint_world_t J[LANES];
+  double R[LANES][9];
+  v3_t p[LANES];
+  chain_fk(q, R, p);
   v3_t vw[LANES], vl[LANES], aw[LANES], al[LANES];
   double qd[LANES], qdd[LANES];
   for (int l = 0; l < LANES; ++l) {
@@ -418,6 +425,275 @@ void oracle_rnea_derivatives(const double* q, const double* v, const double* a,
   rnea_derivatives_impl(q, v, a, NULL, dq, dv, da);
 }
 
+
+/* ------------------------------------------------------------------------------------------ */
+/* cost/ : TimeVaryingTaskSpace6DCost (src/cost/time_varying_task_space_6d_cost.cpp:68-195)    */
+/* on the end-effector frame.  pinocchio pieces restated from their published algorithms       */
+/* (pinocchio is absent): framePlacement / getFrameJacobian(LOCAL) (robot.hxx:186,193-203),    */
+/* log6 / Jlog6 / log3 / Jlog3 (pinocchio/spatial/log.hxx).  PARITY UNPINNED like the rest.    */
+/* ------------------------------------------------------------------------------------------ */
+/* acos on [-1, 1]: the fdlibm e_acos.c algorithm with plain IEEE operations (twin of canon_acos in
+ * octet.cuh) */
+static inline double canon_acos(double x) {
+  const double pio2_hi = 1.57079632679489655800e+00, pio2_lo = 6.12323399573676603587e-17;
+  const double pi = 3.14159265358979311600e+00;
+  const double pS0 = 1.66666666666666657415e-01, pS1 = -3.25565818622400915405e-01, pS2 = 2.01212532134862925881e-01,
+               pS3 = -4.00555345006794114027e-02, pS4 = 7.91534994289814532176e-04, pS5 = 3.47933107596021167570e-05;
+  const double qS1 = -2.40339491173441421878e+00, qS2 = 2.02094576023350569471e+00, qS3 = -6.88283971605453293030e-01,
+               qS4 = 7.70381505559019352791e-02;
+  if (!(x > -1.0)) return pi;      /* x <= -1 (and NaN -> pi, never reached with a clamped argument) */
+  if (!(x < 1.0)) return 0.0;
+  const double ax = fabs(x);
+  if (ax < 0.5) {
+    const double z = x * x;
+    const double pp = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+    const double qq = 1.0 + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+    const double r = pp / qq;
+    return pio2_hi - (x - (pio2_lo - x * r));
+  }
+  if (x < 0.0) {
+    const double z = (1.0 + x) * 0.5;
+    const double pp = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+    const double qq = 1.0 + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+    const double sq = sqrt(z);
+    const double r = pp / qq;
+    const double w = r * sq - pio2_lo;
+    return pi - 2.0 * (sq + w);
+  }
+  {
+    const double z = (1.0 - x) * 0.5;
+    const double sq = sqrt(z);
+    long long bits;
+    memcpy(&bits, &sq, sizeof(bits));
+    bits &= (long long)0xffffffff00000000ULL;   /* df = sq with the low word cleared */
+    double df;
+    memcpy(&df, &bits, sizeof(df));
+    const double c = (z - df * df) / (sq + df);
+    const double pp = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+    const double qq = 1.0 + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+    const double r = pp / qq;
+    const double w = r * sq + c;
+    return 2.0 * (df + w);
+  }
+}
+double oracle_canon_acos(double x) { return canon_acos(x); }
+
+#define TASK_TAYLOR 1.220703125e-04   /* TaylorSeriesExpansion<double>::precision<3>() = eps^(1/4) = 2^-13 */
+#define TASK_PI 3.14159265358979311600e+00
+
+static inline double dot3r(const double* row, v3_t x) { return fma(row[2], x.z, fma(row[1], x.y, row[0] * x.x)); }
+/* y = M^T x for a row-major 3x3 */
+static inline v3_t mulT3(const double* M, v3_t x) {
+  return V3(fma(M[6], x.z, fma(M[3], x.y, M[0] * x.x)), fma(M[7], x.z, fma(M[4], x.y, M[1] * x.x)),
+            fma(M[8], x.z, fma(M[5], x.y, M[2] * x.x)));
+}
+/* M += skew(v) */
+static inline void add_skew(v3_t v, double* M) {
+  M[1] -= v.z; M[2] += v.y; M[3] += v.z; M[5] -= v.x; M[6] -= v.y; M[7] += v.x;
+}
+
+/* pinocchio::log3(R, theta) */
+static v3_t log3_canon(const double* R, double* theta_out) {
+  const double tr = (R[0] + R[4]) + R[8];
+  double theta;
+  if (tr > 3.0) theta = 0.0;
+  else if (tr < -1.0) theta = TASK_PI;
+  else theta = canon_acos((tr - 1.0) * 0.5);
+  *theta_out = theta;
+  if (theta >= TASK_PI - 1e-2) {
+    double sn, cphi;
+    canon_sincos(theta - TASK_PI, &sn, &cphi);
+    const double beta = (theta * theta) / (1.0 + cphi);
+    const double t0 = (R[0] + cphi) * beta, t1 = (R[4] + cphi) * beta, t2 = (R[8] + cphi) * beta;
+    return V3((R[7] > R[5] ? 1.0 : -1.0) * (t0 > 0.0 ? sqrt(t0) : 0.0),
+              (R[2] > R[6] ? 1.0 : -1.0) * (t1 > 0.0 ? sqrt(t1) : 0.0),
+              (R[3] > R[1] ? 1.0 : -1.0) * (t2 > 0.0 ? sqrt(t2) : 0.0));
+  }
+  double t = 1.0;
+  if (theta > TASK_TAYLOR) {
+    double sn, cs;
+    canon_sincos(theta, &sn, &cs);
+    t = theta / sn;
+  }
+  t *= 0.5;
+  return V3(t * (R[7] - R[5]), t * (R[2] - R[6]), t * (R[3] - R[1]));
+}
+
+/* pinocchio::Jlog3(theta, log, Jlog) */
+static void jlog3_canon(double theta, v3_t w, double* A) {
+  double alpha, diag;
+  if (theta < TASK_TAYLOR) {
+    alpha = 1.0 / 12.0 + (theta * theta) / 720.0;
+    diag = 0.5 * (2.0 - (theta * theta) / 6.0);
+  } else {
+    double st, ct;
+    canon_sincos(theta, &st, &ct);
+    const double st_1mct = st / (1.0 - ct);
+    alpha = 1.0 / (theta * theta) - st_1mct / (2.0 * theta);
+    diag = 0.5 * (theta * st_1mct);
+  }
+  const v3_t aw = vscale(alpha, w);
+  const double wv[3] = {w.x, w.y, w.z}, av[3] = {aw.x, aw.y, aw.z};
+  for (int r = 0; r < 3; ++r)
+    for (int k = 0; k < 3; ++k) A[3 * r + k] = av[r] * wv[k];
+  A[0] += diag; A[4] += diag; A[8] += diag;
+  add_skew(vscale(0.5, w), A);
+}
+
+typedef struct {
+  double diff[6];        /* log6(SE3_ref^-1 * oMf) = [linear; angular] */
+  double JJ[6 * NV];     /* Jlog6 * frame Jacobian (LOCAL), JJ[c * 6 + k] = row k of column c */
+} task_eval_t;
+
+/* diff_6d and JJ_6d of computeStageCostDerivatives (:105-119).  ref12 = [R_ref row-major (9), p_ref (3)]
+ * as produced by the user's TimeVaryingTaskSpace6DRefBase::compute_q_6d_ref(t) (sampled on the host). */
+static void task_evaluate(const double* q, const double* ref12, task_eval_t* te, int with_jacobian) {
+  double R[LANES][9];
+  v3_t p[LANES];
+  chain_fk(q, R, p);
+  /* robot.framePlacement(frame_id): oMf = oMi[parent joint] * frame placement */
+  const double* R6 = R[IIWA14_EE_PARENT_JOINT];
+  const double* E = IIWA14_EE_PLACEMENT_R;
+  double Rf[9];
+  for (int r = 0; r < 3; ++r)
+    for (int k = 0; k < 3; ++k)
+      Rf[3 * r + k] = fma(R6[3 * r + 2], E[6 + k], fma(R6[3 * r + 1], E[3 + k], R6[3 * r] * E[k]));
+  const v3_t ep = V3(IIWA14_EE_PLACEMENT_P[0], IIWA14_EE_PLACEMENT_P[1], IIWA14_EE_PLACEMENT_P[2]);
+  const v3_t p6 = p[IIWA14_EE_PARENT_JOINT];
+  const v3_t pf = V3(fma(R6[2], ep.z, fma(R6[1], ep.y, fma(R6[0], ep.x, p6.x))),
+                     fma(R6[5], ep.z, fma(R6[4], ep.y, fma(R6[3], ep.x, p6.y))),
+                     fma(R6[8], ep.z, fma(R6[7], ep.y, fma(R6[6], ep.x, p6.z))));
+  /* diff_SE3 = SE3_ref^-1 * oMf */
+  double Rd[9];
+  for (int r = 0; r < 3; ++r)
+    for (int k = 0; k < 3; ++k)
+      Rd[3 * r + k] = fma(ref12[6 + r], Rf[6 + k], fma(ref12[3 + r], Rf[3 + k], ref12[r] * Rf[k]));
+  const v3_t pd = mulT3(ref12, vsub(pf, V3(ref12[9], ref12[10], ref12[11])));
+  /* pinocchio::log6 */
+  double theta;
+  const v3_t w = log3_canon(Rd, &theta);
+  const double t2 = theta * theta;
+  double st = 0.0, ct = 1.0;
+  if (!(theta < TASK_TAYLOR)) canon_sincos(theta, &st, &ct);
+  {
+    double alpha, beta;
+    if (theta < TASK_TAYLOR) {
+      alpha = (1.0 - t2 / 12.0) - (t2 * t2) / 720.0;
+      beta = 1.0 / 12.0 + t2 / 720.0;
+    } else {
+      alpha = (theta * st) / (2.0 * (1.0 - ct));
+      beta = 1.0 / t2 - st / ((2.0 * theta) * (1.0 - ct));
+    }
+    const v3_t v = vfma(beta * vdot(w, pd), w, vfma(-0.5, vcross(w, pd), vscale(alpha, pd)));
+    te->diff[0] = v.x; te->diff[1] = v.y; te->diff[2] = v.z;
+    te->diff[3] = w.x; te->diff[4] = w.y; te->diff[5] = w.z;
+  }
+  if (!with_jacobian) return;
+  /* pinocchio::Jlog6: [[A, B], [0, A]] */
+  double A[9], B[9], C[9];
+  jlog3_canon(theta, w, A);
+  {
+    double beta, bdot;
+    if (theta < TASK_TAYLOR) {
+      beta = 1.0 / 12.0 + t2 / 720.0;
+      bdot = 1.0 / 360.0;
+    } else {
+      const double tinv = 1.0 / theta, t2inv = tinv * tinv;
+      const double inv_2_2ct = 1.0 / (2.0 * (1.0 - ct));
+      beta = t2inv - (st * tinv) * inv_2_2ct;
+      bdot = -2.0 * (t2inv * t2inv) + ((1.0 + st * tinv) * t2inv) * inv_2_2ct;
+    }
+    const double wTp = vdot(w, pd);
+    const v3_t v3 = vsub(vscale(bdot * wTp, w), vscale(fma(t2, bdot, 2.0 * beta), pd));
+    const v3_t bw = vscale(beta, w);
+    const double v3v[3] = {v3.x, v3.y, v3.z}, bwv[3] = {bw.x, bw.y, bw.z}, wv[3] = {w.x, w.y, w.z},
+                 pv[3] = {pd.x, pd.y, pd.z};
+    for (int r = 0; r < 3; ++r)
+      for (int k = 0; k < 3; ++k) C[3 * r + k] = fma(bwv[r], pv[k], v3v[r] * wv[k]);
+    const double dg = wTp * beta;
+    C[0] += dg; C[4] += dg; C[8] += dg;
+    add_skew(vscale(0.5, pd), C);
+    for (int r = 0; r < 3; ++r)
+      for (int k = 0; k < 3; ++k) B[3 * r + k] = fma(C[3 * r + 2], A[6 + k], fma(C[3 * r + 1], A[3 + k], C[3 * r] * A[k]));
+  }
+  /* getFrameJacobian(frame, LOCAL) column c = [Rf^T (S_l + S_w x pf); Rf^T S_w] with the world-frame joint
+   * axes S_w = z_c, S_l = p_c x z_c; JJ = Jlog6 * J */
+  for (int c = 0; c < NV; ++c) {
+    const v3_t Sw = V3(R[c][2], R[c][5], R[c][8]);
+    const v3_t Sl = vcross(p[c], Sw);
+    const v3_t Jl = mulT3(Rf, vadd(Sl, vcross(Sw, pf)));
+    const v3_t Ja = mulT3(Rf, Sw);
+    for (int r = 0; r < 3; ++r) {
+      te->JJ[c * 6 + r] = dot3r(A + 3 * r, Jl) + dot3r(B + 3 * r, Ja);
+      te->JJ[c * 6 + 3 + r] = dot3r(A + 3 * r, Ja);
+    }
+  }
+}
+
+/* set_q_6d_weight(position_weight, rotation_weight) stores head<3> = rotation_weight, tail<3> =
+ * position_weight (time_varying_task_space_6d_cost.cpp:45-50) while diff_6d = [linear; angular]: the
+ * rotation weight multiplies the linear part.  Restated as is.  wpr = [position(3), rotation(3)]. */
+static inline double task_w6(const double* wpr, int k) { return k < 3 ? wpr[3 + k] : wpr[k - 3]; }
+
+/* lq += scale * JJ^T diag(w6) diff (:116-118, :132-133) */
+static void task_add_gradient(const task_eval_t* te, const double* wpr, double scale, int use_scale, double* lq) {
+  for (int c = 0; c < NV; ++c) {
+    double acc = 0;
+    for (int k = 0; k < 6; ++k) acc = fma(te->JJ[c * 6 + k], task_w6(wpr, k) * te->diff[k], acc);
+    lq[c] += use_scale ? scale * acc : acc;
+  }
+}
+/* Qqq += scale * JJ^T diag(w6) JJ (:161-162, :175-176) */
+static void task_add_hessian(const task_eval_t* te, const double* wpr, double scale, int use_scale, double* Qqq) {
+  for (int c = 0; c < NV; ++c)
+    for (int r = 0; r < NV; ++r) {
+      double acc = 0;
+      for (int k = 0; k < 6; ++k) acc = fma(te->JJ[r * 6 + k], task_w6(wpr, k) * te->JJ[c * 6 + k], acc);
+      Qqq[c * NV + r] += use_scale ? scale * acc : acc;
+    }
+}
+/* sum(w6 * diff^2) (:74, :87) */
+static double task_weighted_sqnorm(const task_eval_t* te, const double* wpr) {
+  double l = 0;
+  for (int k = 0; k < 6; ++k) l += (task_w6(wpr, k) * te->diff[k]) * te->diff[k];
+  return l;
+}
+
+/* parity / test getter: diff_6d (6) and JJ_6d (6 x 7, column-major) for a configuration and a reference */
+void oracle_task_evaluate(const double* q, const double* ref12, double* diff6, double* JJ) {
+  task_eval_t te;
+  task_evaluate(q, ref12, &te, 1);
+  memcpy(diff6, te.diff, sizeof(te.diff));
+  memcpy(JJ, te.JJ, sizeof(te.JJ));
+}
+/* end-effector placement oMf (R row-major 9, p 3) and LOCAL frame Jacobian (6 x 7 column-major, [lin; ang]) */
+void oracle_frame_kinematics(const double* q, double* oMf12, double* J) {
+  double R[LANES][9];
+  v3_t p[LANES];
+  chain_fk(q, R, p);
+  const double* R6 = R[IIWA14_EE_PARENT_JOINT];
+  const double* E = IIWA14_EE_PLACEMENT_R;
+  double Rf[9];
+  for (int r = 0; r < 3; ++r)
+    for (int k = 0; k < 3; ++k)
+      Rf[3 * r + k] = fma(R6[3 * r + 2], E[6 + k], fma(R6[3 * r + 1], E[3 + k], R6[3 * r] * E[k]));
+  const v3_t ep = V3(IIWA14_EE_PLACEMENT_P[0], IIWA14_EE_PLACEMENT_P[1], IIWA14_EE_PLACEMENT_P[2]);
+  const v3_t p6 = p[IIWA14_EE_PARENT_JOINT];
+  const v3_t pf = V3(fma(R6[2], ep.z, fma(R6[1], ep.y, fma(R6[0], ep.x, p6.x))),
+                     fma(R6[5], ep.z, fma(R6[4], ep.y, fma(R6[3], ep.x, p6.y))),
+                     fma(R6[8], ep.z, fma(R6[7], ep.y, fma(R6[6], ep.x, p6.z))));
+  memcpy(oMf12, Rf, sizeof(Rf));
+  oMf12[9] = pf.x; oMf12[10] = pf.y; oMf12[11] = pf.z;
+  for (int c = 0; c < NV; ++c) {
+    const v3_t Sw = V3(R[c][2], R[c][5], R[c][8]);
+    const v3_t Sl = vcross(p[c], Sw);
+    const v3_t Jl = mulT3(Rf, vadd(Sl, vcross(Sw, pf)));
+    const v3_t Ja = mulT3(Rf, Sw);
+    J[c * 6 + 0] = Jl.x; J[c * 6 + 1] = Jl.y; J[c * 6 + 2] = Jl.z;
+    J[c * 6 + 3] = Ja.x; J[c * 6 + 4] = Ja.y; J[c * 6 + 5] = Ja.z;
+  }
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* problem                                                                                     */
 /* ------------------------------------------------------------------------------------------ */
@@ -462,6 +738,7 @@ typedef struct {
   double K[NV * 2 * NV], k[NV];
   cdata_t c[NC];
   int active[NC];
+  task_eval_t te;                 /* CostFunctionData of the task-space cost (diff_6d, JJ_6d) */
 } stage_t;
 
 typedef struct { double Pqq[NN], Pqv[NN], Pvq[NN], Pvv[NN], sq[NV], sv[NV]; } riccati_t;
@@ -483,6 +760,7 @@ struct oracle_unocp {
   filter_t filter;
   split_solution_t* s_try;  /* N+1 */
   int stage_threads;
+  double* task_ref;         /* (N+1) x 12: SE3 reference of every stage's time (R row-major, p) */
 };
 
 /* ------------------------------------------------------------------------------------------ */
@@ -630,14 +908,23 @@ static double max_dual_step(const oracle_problem_t* p, const stage_t* st) {
 /* ------------------------------------------------------------------------------------------ */
 /* cost/ : ConfigurationSpaceCost (src/cost/configuration_space_cost.cpp:241-396)              */
 /* ------------------------------------------------------------------------------------------ */
-static void stage_cost_derivatives(const oracle_problem_t* p, double dt, const split_solution_t* s, stage_t* st) {
+/* CostFunction::computeStageCostDerivatives (cost/cost_function.hxx:78-85): components in push_back
+ * order, ConfigurationSpaceCost then (when enabled) TimeVaryingTaskSpace6DCost with the reference
+ * SE3 `ref` of this stage's time */
+static void stage_cost_derivatives(const oracle_problem_t* p, double dt, const split_solution_t* s, stage_t* st,
+                                   const double* ref) {
   for (int j = 0; j < NV; ++j) {
     st->lq[j] += dt * p->q_weight[j] * (s->q[j] - p->q_ref[j]);
     st->lv[j] += dt * p->v_weight[j] * (s->v[j] - p->v_ref[j]);
     st->la[j] += dt * p->a_weight[j] * s->a[j];
     st->lu[j] += dt * p->u_weight[j] * (s->u[j] - p->u_ref[j]);
   }
+  if (p->task_enabled) {
+    task_evaluate(s->q, ref, &st->te, 1);
+    task_add_gradient(&st->te, p->task_q_weight, dt, 1, st->lq);
+  }
 }
+/* CostFunction::computeStageCostHessian (:107-114) */
 static void stage_cost_hessian(const oracle_problem_t* p, double dt, stage_t* st) {
   for (int j = 0; j < NV; ++j) {
     st->Qqq[j * NV + j] += dt * p->q_weight[j];
@@ -645,6 +932,18 @@ static void stage_cost_hessian(const oracle_problem_t* p, double dt, stage_t* st
     st->Qaa[j] += dt * p->a_weight[j];
     st->Quu[j] += dt * p->u_weight[j];
   }
+  if (p->task_enabled) task_add_hessian(&st->te, p->task_q_weight, dt, 1, st->Qqq);
+}
+/* CostFunction::computeStageCost / computeTerminalCost: sum of the components' values */
+static double task_stage_cost(const oracle_problem_t* p, double dt, const double* q, const double* ref) {
+  task_eval_t te;
+  task_evaluate(q, ref, &te, 0);
+  return 0.5 * dt * task_weighted_sqnorm(&te, p->task_q_weight);
+}
+static double task_terminal_cost(const oracle_problem_t* p, const double* q, const double* ref) {
+  task_eval_t te;
+  task_evaluate(q, ref, &te, 0);
+  return 0.5 * task_weighted_sqnorm(&te, p->task_qf_weight);
 }
 static double stage_cost(const oracle_problem_t* p, double dt, const split_solution_t* s) {
   double l = 0, part;
@@ -672,10 +971,10 @@ static double terminal_cost(const oracle_problem_t* p, const split_solution_t* s
 /* ------------------------------------------------------------------------------------------ */
 /* steps 1-4 of SURVEY A.2, shared by linearizeOCP (:69-99) and computeKKTResidual (:141-161) */
 static void stage_residual_common(const oracle_problem_t* p, double dt, const split_solution_t* s,
-                                  const split_solution_t* sn, stage_t* st, int with_derivatives) {
+                                  const split_solution_t* sn, stage_t* st, int with_derivatives, const double* ref) {
   memset(st->lq, 0, sizeof(double) * NV); memset(st->lv, 0, sizeof(double) * NV);
   memset(st->la, 0, sizeof(double) * NV); memset(st->lu, 0, sizeof(double) * NV);
-  stage_cost_derivatives(p, dt, s, st);
+  stage_cost_derivatives(p, dt, s, st, ref);
   augment_dual_residual(st, dt);
   /* stateequation::linearizeForwardEuler (ocp/state_equation.hxx:11-37,210-221) */
   for (int j = 0; j < NV; ++j) {
@@ -707,10 +1006,10 @@ static void stage_residual_common(const oracle_problem_t* p, double dt, const sp
 
 /* SplitUnOCP::linearizeOCP (unocp/split_unocp.hxx:69-99) */
 static void split_unocp_linearize(const oracle_problem_t* p, double dt, const split_solution_t* s,
-                                  const split_solution_t* sn, stage_t* st) {
+                                  const split_solution_t* sn, stage_t* st, const double* ref) {
   memset(st->Qqq, 0, sizeof(st->Qqq));
   memset(st->Qvv, 0, sizeof(st->Qvv)); memset(st->Qaa, 0, sizeof(st->Qaa)); memset(st->Quu, 0, sizeof(st->Quu));
-  stage_residual_common(p, dt, s, sn, st, 1);
+  stage_residual_common(p, dt, s, sn, st, 1, ref);
   stage_cost_hessian(p, dt, st);
   condense_slack_and_dual(p, st, s, dt);
   /* UnconstrainedDynamics::condenseUnconstrainedDynamics (unconstrained_dynamics.hxx:68-94) */
@@ -754,9 +1053,9 @@ static void split_unocp_linearize(const oracle_problem_t* p, double dt, const sp
 
 /* SplitUnOCP::computeKKTResidual (split_unocp.hxx:141-161) */
 static void split_unocp_kkt_residual(const oracle_problem_t* p, double dt, const split_solution_t* s,
-                                     const split_solution_t* sn, stage_t* st) {
+                                     const split_solution_t* sn, stage_t* st, const double* ref) {
   compute_primal_dual_residual(p, st, s);
-  stage_residual_common(p, dt, s, sn, st, 0);
+  stage_residual_common(p, dt, s, sn, st, 0, ref);
 }
 
 static double sqnorm(const double* x) {
@@ -982,8 +1281,9 @@ static void filter_augment(filter_t* f, double cost, double viol) {
 
 /* SplitUnOCP::stageCost (split_unocp.hxx:177-196): cost + dt * barrier(slack + alpha dslack) */
 static double split_unocp_stage_cost(const oracle_problem_t* p, double dt, const stage_t* st,
-                                     const split_solution_t* s, double alpha) {
+                                     const split_solution_t* s, double alpha, const double* ref) {
   double cost = stage_cost(p, dt, s);
+  if (p->task_enabled) cost += task_stage_cost(p, dt, s->q, ref);
   double bar = 0;
   for (int c = 0; c < NC; ++c) {
     if (!st->active[c]) continue;
@@ -1024,10 +1324,12 @@ static void cost_and_violation(oracle_unocp_t* o, const split_solution_t* s, dou
   double cs = 0, vs = 0;
   for (int i = 0; i <= o->N; ++i) {
     if (i < o->N) {
-      cs += split_unocp_stage_cost(&o->p, o->dt, &o->st[i], &s[i], alpha);
+      cs += split_unocp_stage_cost(&o->p, o->dt, &o->st[i], &s[i], alpha, o->task_ref + (size_t)i * 12);
       vs += split_unocp_violation(&o->p, o->dt, &o->st[i], &s[i], s[i + 1].q, s[i + 1].v);
     } else {
-      cs += terminal_cost(&o->p, &s[i]);
+      double tc = terminal_cost(&o->p, &s[i]);
+      if (o->p.task_enabled) tc += task_terminal_cost(&o->p, s[i].q, o->task_ref + (size_t)i * 12);
+      cs += tc;
     }
   }
   *cost = cs; *viol = vs;
@@ -1075,6 +1377,8 @@ oracle_unocp_t* oracle_unocp_create(const oracle_problem_t* p) {
   o->d = (split_direction_t*)calloc(o->N + 1, sizeof(split_direction_t));
   o->st = (stage_t*)calloc(o->N, sizeof(stage_t));
   o->ric = (riccati_t*)calloc(o->N + 1, sizeof(riccati_t));
+  o->task_ref = (double*)calloc((size_t)(o->N + 1) * 12, sizeof(double));
+  for (int i = 0; i <= o->N; ++i) o->task_ref[i * 12] = o->task_ref[i * 12 + 4] = o->task_ref[i * 12 + 8] = 1.0;
   o->stage_threads = 1;
   oracle_unocp_init_constraints(o);  /* the reference ctor ends with initConstraints() (:48) */
   return o;
@@ -1082,7 +1386,7 @@ oracle_unocp_t* oracle_unocp_create(const oracle_problem_t* p) {
 
 void oracle_unocp_destroy(oracle_unocp_t* o) {
   if (!o) return;
-  free(o->s); free(o->s_try); free(o->d); free(o->st); free(o->ric); free(o);
+  free(o->s); free(o->s_try); free(o->d); free(o->st); free(o->ric); free(o->task_ref); free(o);
 }
 
 void oracle_unocp_set_stage_threads(oracle_unocp_t* o, int nthreads) { o->stage_threads = nthreads > 0 ? nthreads : 1; }
@@ -1118,6 +1422,13 @@ static void terminal_linearize(oracle_unocp_t* o, int with_hessian) {
     o->t_lq[j] = 0; o->t_lv[j] = 0;
     o->t_lq[j] += p->qf_weight[j] * (s->q[j] - p->q_ref[j]);
     o->t_lv[j] += p->vf_weight[j] * (s->v[j] - p->v_ref[j]);
+  }
+  task_eval_t te;
+  if (p->task_enabled) {   /* TimeVaryingTaskSpace6DCost::computeTerminalCostDerivatives at t + T */
+    task_evaluate(s->q, o->task_ref + (size_t)o->N * 12, &te, 1);
+    task_add_gradient(&te, p->task_qf_weight, 1.0, 0, o->t_lq);
+  }
+  for (int j = 0; j < NV; ++j) {
     o->t_lq[j] -= s->lmd[j];
     o->t_lv[j] -= s->gmm[j];
   }
@@ -1128,6 +1439,7 @@ static void terminal_linearize(oracle_unocp_t* o, int with_hessian) {
       o->t_Qqq[j * NV + j] += p->qf_weight[j];
       o->t_Qvv[j * NV + j] += p->vf_weight[j];
     }
+    if (p->task_enabled) task_add_hessian(&te, p->task_qf_weight, 1.0, 0, o->t_Qqq);
   }
 }
 
@@ -1139,7 +1451,7 @@ void oracle_unocp_update_solution(oracle_unocp_t* o, double t, const double* q, 
   const double dt = o->dt;
 #pragma omp parallel for num_threads(o->stage_threads) if (o->stage_threads > 1)
   for (int i = 0; i <= N; ++i) {
-    if (i < N) split_unocp_linearize(&o->p, dt, &o->s[i], &o->s[i + 1], &o->st[i]);
+    if (i < N) split_unocp_linearize(&o->p, dt, &o->s[i], &o->s[i + 1], &o->st[i], o->task_ref + (size_t)i * 12);
     else terminal_linearize(o, 1);
   }
   /* UnRiccatiRecursion::backwardRiccatiRecursionTerminal (src/unocp/unriccati_recursion.cpp:39-47):
@@ -1234,7 +1546,7 @@ void oracle_unocp_compute_kkt_residual(oracle_unocp_t* o, double t, const double
   (void)t; (void)q; (void)v; /* q_prev only matters for a floating base; x0 does not enter the residual */
 #pragma omp parallel for num_threads(o->stage_threads) if (o->stage_threads > 1)
   for (int i = 0; i <= o->N; ++i) {
-    if (i < o->N) split_unocp_kkt_residual(&o->p, o->dt, &o->s[i], &o->s[i + 1], &o->st[i]);
+    if (i < o->N) split_unocp_kkt_residual(&o->p, o->dt, &o->s[i], &o->s[i + 1], &o->st[i], o->task_ref + (size_t)i * 12);
     else terminal_linearize(o, 0);
   }
 }
@@ -1388,6 +1700,7 @@ struct oracle_unparnmpc {
   double primal_step, dual_step, max_primal_step;
   filter_t filter;
   split_solution_t* s_try;
+  double* task_ref;          /* (N+1) x 12: rows 0..N-1 = stage times, row N = line-search time of the last stage */
   int chol_info;             /* first non-zero LLT info of the last updateSolution (0 = all factorizations succeeded) */
 };
 
@@ -1405,6 +1718,8 @@ oracle_unparnmpc_t* oracle_unparnmpc_create(const oracle_problem_t* p) {
   o->KKTinv = (double*)calloc((size_t)o->N * NK * NK, sizeof(double));
   o->aux = (double*)calloc((size_t)o->N * NX * NX, sizeof(double));
   o->xres = (double*)calloc((size_t)o->N * NX, sizeof(double));
+  o->task_ref = (double*)calloc((size_t)(o->N + 1) * 12, sizeof(double));
+  for (int i = 0; i <= o->N; ++i) o->task_ref[i * 12] = o->task_ref[i * 12 + 4] = o->task_ref[i * 12 + 8] = 1.0;
   oracle_unparnmpc_init_constraints(o);
   return o;
 }
@@ -1412,6 +1727,7 @@ oracle_unparnmpc_t* oracle_unparnmpc_create(const oracle_problem_t* p) {
 void oracle_unparnmpc_destroy(oracle_unparnmpc_t* o) {
   if (!o) return;
   free(o->s); free(o->s_new); free(o->s_try); free(o->d); free(o->st); free(o->KKTinv); free(o->aux); free(o->xres);
+  free(o->task_ref);
   free(o);
 }
 
@@ -1440,13 +1756,21 @@ int oracle_unparnmpc_set_solution(oracle_unparnmpc_t* o, const char* name, const
 /* UnBackwardCorrection::initAuxMat (:55-64): every aux_mat = terminal cost Hessian (Qxx) */
 void oracle_unparnmpc_init_backward_correction(oracle_unparnmpc_t* o, double t) {
   (void)t;
+  /* TerminalUnParNMPC::computeTerminalCostHessian (terminal_unparnmpc.hxx:230-241) at s[N-1], time t + T */
+  double Qqq[NN];
+  memset(Qqq, 0, sizeof(Qqq));
+  for (int j = 0; j < NV; ++j) Qqq[j * NV + j] += o->p.qf_weight[j];
+  if (o->p.task_enabled) {
+    task_eval_t te;
+    task_evaluate(o->s[o->N - 1].q, o->task_ref + (size_t)(o->N - 1) * 12, &te, 1);
+    task_add_hessian(&te, o->p.task_qf_weight, 1.0, 0, Qqq);
+  }
   for (int i = 0; i < o->N; ++i) {
     double* A = o->aux + (size_t)i * NX * NX;
     memset(A, 0, sizeof(double) * NX * NX);
-    for (int j = 0; j < NV; ++j) {
-      A[j * NX + j] = o->p.qf_weight[j];
-      A[(NV + j) * NX + NV + j] = o->p.vf_weight[j];
-    }
+    for (int c = 0; c < NV; ++c)
+      for (int r = 0; r < NV; ++r) A[c * NX + r] = Qqq[c * NV + r];
+    for (int j = 0; j < NV; ++j) A[(NV + j) * NX + NV + j] = o->p.vf_weight[j];
   }
 }
 
@@ -1454,16 +1778,19 @@ void oracle_unparnmpc_init_backward_correction(oracle_unparnmpc_t* o, double t) 
  * computeKKTResidual (:141-163) and the TerminalUnParNMPC twins (terminal_unparnmpc.hxx:70-102);
  * backward Euler: stateequation::linearizeBackwardEuler[Terminal] (state_equation.hxx:111-167,224-236) */
 static void parnmpc_residual_common(const oracle_problem_t* p, double dt, const double* q_prev, const double* v_prev,
-                                    const split_solution_t* s, const split_solution_t* sn, stage_t* st) {
+                                    const split_solution_t* s, const split_solution_t* sn, stage_t* st,
+                                    const double* ref) {
   const int terminal = (sn == NULL);
   memset(st->lq, 0, sizeof(double) * NV); memset(st->lv, 0, sizeof(double) * NV);
   memset(st->la, 0, sizeof(double) * NV); memset(st->lu, 0, sizeof(double) * NV);
-  stage_cost_derivatives(p, dt, s, st);
-  if (terminal)
+  stage_cost_derivatives(p, dt, s, st, ref);
+  if (terminal) {   /* + computeTerminalCostDerivatives at the same time t + T */
     for (int j = 0; j < NV; ++j) {
       st->lq[j] += p->qf_weight[j] * (s->q[j] - p->q_ref[j]);
       st->lv[j] += p->vf_weight[j] * (s->v[j] - p->v_ref[j]);
     }
+    if (p->task_enabled) task_add_gradient(&st->te, p->task_qf_weight, 1.0, 0, st->lq);
+  }
   augment_dual_residual(st, dt);
   for (int j = 0; j < NV; ++j) {
     st->Fq[j] = fma(dt, s->v[j], q_prev[j] - s->q[j]);
@@ -1535,17 +1862,19 @@ static void condense_unconstrained_dynamics(stage_t* st) {
 }
 
 static void parnmpc_linearize(const oracle_problem_t* p, double dt, const double* q_prev, const double* v_prev,
-                              const split_solution_t* s, const split_solution_t* sn, stage_t* st) {
+                              const split_solution_t* s, const split_solution_t* sn, stage_t* st, const double* ref) {
   const int terminal = (sn == NULL);
   memset(st->Qqq, 0, sizeof(st->Qqq));
   memset(st->Qvv, 0, sizeof(st->Qvv)); memset(st->Qaa, 0, sizeof(st->Qaa)); memset(st->Quu, 0, sizeof(st->Quu));
-  parnmpc_residual_common(p, dt, q_prev, v_prev, s, sn, st);
+  parnmpc_residual_common(p, dt, q_prev, v_prev, s, sn, st, ref);
   stage_cost_hessian(p, dt, st);
-  if (terminal)
+  if (terminal) {
     for (int j = 0; j < NV; ++j) {
       st->Qqq[j * NV + j] += p->qf_weight[j];
       st->Qvv[j] += p->vf_weight[j];
     }
+    if (p->task_enabled) task_add_hessian(&st->te, p->task_qf_weight, 1.0, 0, st->Qqq);
+  }
   condense_slack_and_dual(p, st, s, dt);
   condense_unconstrained_dynamics(st);
 }
@@ -1648,7 +1977,7 @@ void oracle_unparnmpc_update_solution(oracle_unparnmpc_t* o, double t, const dou
     const double* qp = i == 0 ? q : o->s[i - 1].q;
     const double* vp = i == 0 ? v : o->s[i - 1].v;
     stage_t* st = &o->st[i];
-    parnmpc_linearize(p, dt, qp, vp, &o->s[i], i < N - 1 ? &o->s[i + 1] : NULL, st);
+    parnmpc_linearize(p, dt, qp, vp, &o->s[i], i < N - 1 ? &o->s[i + 1] : NULL, st, o->task_ref + (size_t)i * 12);
     double Q[NQ3 * NQ3];
     assemble_parnmpc_Q(st, i < N - 1 ? o->aux + (size_t)(i + 1) * NX * NX : NULL, Q);
     double* Kinv = o->KKTinv + (size_t)i * NK * NK;
@@ -1782,7 +2111,8 @@ void oracle_unparnmpc_compute_kkt_residual(oracle_unparnmpc_t* o, double t, cons
     const double* qp = i == 0 ? q : o->s[i - 1].q;
     const double* vp = i == 0 ? v : o->s[i - 1].v;
     compute_primal_dual_residual(&o->p, &o->st[i], &o->s[i]);
-    parnmpc_residual_common(&o->p, o->dt, qp, vp, &o->s[i], i < o->N - 1 ? &o->s[i + 1] : NULL, &o->st[i]);
+    parnmpc_residual_common(&o->p, o->dt, qp, vp, &o->s[i], i < o->N - 1 ? &o->s[i + 1] : NULL, &o->st[i],
+                            o->task_ref + (size_t)i * 12);
   }
 }
 
@@ -1855,3 +2185,13 @@ void oracle_unparnmpc_batch_kkt(oracle_unparnmpc_t** os, int batch, double t, co
 int oracle_invert_unkkt(double dt, const double* Q, double* Kinv) { return invert_unkkt(dt, Q, Kinv); }
 
 int oracle_unparnmpc_chol_info(const oracle_unparnmpc_t* o) { return o->chol_info; }
+
+/* host-sampled reference of the task-space cost: table[(N+1)][12], row i = compute_q_6d_ref at the time of
+ * stage index i (UnOCPSolver: t + i dt, row N = t + T; UnParNMPCSolver: t + (i+1) dt, row N-1 = t + T,
+ * row N = t + N dt used only by the line search) */
+void oracle_unocp_set_task_ref(oracle_unocp_t* o, const double* table) {
+  memcpy(o->task_ref, table, sizeof(double) * (size_t)(o->N + 1) * 12);
+}
+void oracle_unparnmpc_set_task_ref(oracle_unparnmpc_t* o, const double* table) {
+  memcpy(o->task_ref, table, sizeof(double) * (size_t)(o->N + 1) * 12);
+}

@@ -40,9 +40,10 @@ typedef struct {
    * effector frame, reference = circle of examples/iiwa14/task_space_ocp.cpp:21-46.
    * Disabled when task_enabled == 0. */
   int task_enabled;
-  double task_q_weight[6], task_qf_weight[6];  /* [trans xyz, rot xyz] as set_q_6d_weight(trans, rot) */
-  double task_center[3], task_radius, task_t0, task_tf; /* pos_ref(t) = center + r*(0, sin, cos)(2*pi*(t-t0)/ ... ) */
-  double task_rot_ref[9];     /* row-major rotation reference */
+  double task_q_weight[6], task_qf_weight[6];  /* [position xyz, rotation xyz] = the arguments of set_q_6d_weight /
+                                                  set_qf_6d_weight (time_varying_task_space_6d_cost.cpp:43-58) */
+  double task_center[3], task_radius, task_t0, task_tf; /* unused by the engine: the reference is a host-sampled table */
+  double task_rot_ref[9];
 } oracle_problem_t;
 
 void oracle_problem_default(oracle_problem_t* p);
@@ -109,6 +110,13 @@ void oracle_unparnmpc_batch_update_solution(oracle_unparnmpc_t** os, int batch, 
                                             const double* v0, int line_search, int nthreads);
 void oracle_unparnmpc_batch_kkt(oracle_unparnmpc_t** os, int batch, double t, const double* q0,
                                 const double* v0, double* kkt_out, int nthreads);
+
+/* TimeVaryingTaskSpace6DCost: host-sampled reference table [(N+1)][12] (R row-major, p), see idocp_oracle.c */
+void oracle_unocp_set_task_ref(oracle_unocp_t* o, const double* table);
+void oracle_unparnmpc_set_task_ref(oracle_unparnmpc_t* o, const double* table);
+void oracle_task_evaluate(const double* q, const double* ref12, double* diff6, double* JJ);
+void oracle_frame_kinematics(const double* q, double* oMf12, double* J);
+double oracle_canon_acos(double x);
 
 /* splitmix64 counter-based generator shared by oracle, bench and tests */
 double oracle_splitmix_uniform(unsigned long long seed, unsigned long long index);

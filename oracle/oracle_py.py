@@ -106,6 +106,42 @@ def config_space_problem():
     return p
 
 
+def task_space_problem(N=120, T=6.0):
+    """examples/iiwa14/task_space_ocp.cpp:55-84 (cost / limits; the 6D reference is sampled by task_space_ref)."""
+    p = default_problem()
+    p.N, p.T = N, T
+    for i in range(NV):
+        p.u_max[i] = 50.0
+        p.v_max[i] = np.pi / 2
+        p.q_weight[i] = 0.0
+        p.qf_weight[i] = 0.0
+        p.v_weight[i] = 0.01
+        p.vf_weight[i] = 0.01
+        p.a_weight[i] = 0.01
+    p.task_enabled = 1
+    for k in range(6):
+        p.task_q_weight[k] = 1000.0
+        p.task_qf_weight[k] = 1000.0
+    return p
+
+
+def task_space_ref(t):
+    """TimeVaryingTaskSpace6DRef::compute_q_6d_ref of examples/iiwa14/task_space_ocp.cpp:21-46 -> [R row-major, p]."""
+    rotm = [0.0, 0.0, 1.0, 0.0, 1.0, 0.0, -1.0, 0.0, 0.0]
+    pos = [0.546, 0.0 + 0.1 * np.sin(np.pi * t), 0.76 + 0.1 * np.cos(np.pi * t)]
+    return np.array(rotm + pos)
+
+
+def task_ref_table(ref_fn, t, T, N, kind="unocp"):
+    """Rows = the SE3 reference at the time each stage index is linearised at (see oracle_unocp_set_task_ref)."""
+    dt = T / N
+    if kind == "unocp":
+        times = [t + i * dt for i in range(N)] + [t + T]
+    else:
+        times = [t + (i + 1) * dt for i in range(N - 1)] + [t + T, t + N * dt]
+    return np.ascontiguousarray(np.array([ref_fn(x) for x in times]))
+
+
 def rnea(q, v, a):
     q, v, a = _vec(q), _vec(v), _vec(a)
     tau = np.zeros(NV)
@@ -150,6 +186,11 @@ class _SolverBase:
 
     def init_constraints(self):
         self._f("init_constraints")(self.h)
+
+    def set_task_ref(self, table):
+        table = _vec(table)
+        assert table.shape == (self.N + 1, 12)
+        self._f("set_task_ref")(self.h, _p(table))
 
     def update_solution(self, t, q, v, line_search=False):
         q, v = _vec(q), _vec(v)
@@ -264,3 +305,26 @@ class Batch:
         f = getattr(self.L, "oracle_%s_batch_kkt" % self.kind)
         f(self.arr, self.batch, C.c_double(t), _p(q0), _p(v0), _p(out), int(nthreads))
         return out
+
+
+def task_evaluate(q, ref12):
+    """diff_6d = log6(SE3_ref^-1 oMf) [lin; ang] and JJ = Jlog6 * J_frame(LOCAL) as numpy (6, 7)."""
+    q, ref12 = _vec(q), _vec(ref12)
+    diff, JJ = np.zeros(6), np.zeros((7, 6))
+    lib().oracle_task_evaluate(_p(q), _p(ref12), _p(diff), _p(JJ))
+    return diff, JJ.T.copy()
+
+
+def frame_kinematics(q):
+    """End-effector (frame 22) placement (R (3,3), p (3,)) and LOCAL frame Jacobian (6, 7)."""
+    q = _vec(q)
+    M, J = np.zeros(12), np.zeros((7, 6))
+    lib().oracle_frame_kinematics(_p(q), _p(M), _p(J))
+    return M[:9].reshape(3, 3).copy(), M[9:].copy(), J.T.copy()
+
+
+def canon_acos(x):
+    f = lib().oracle_canon_acos
+    f.restype = C.c_double
+    f.argtypes = [C.c_double]
+    return f(float(x))

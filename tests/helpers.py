@@ -15,8 +15,12 @@ def rel_close(x, ref, rtol=RTOL, floor=1e-12):
 
 def copy_problem(src, dst):
     """Copy the fields shared by idocp_b200.Problem and oracle_py.Problem."""
-    for name in ("N", "T", "barrier", "fraction_rate"):
+    for name in ("N", "T", "barrier", "fraction_rate", "task_enabled"):
         setattr(dst, name, getattr(src, name))
+    for name in ("task_q_weight", "task_qf_weight"):
+        a, b = getattr(src, name), getattr(dst, name)
+        for i in range(6):
+            b[i] = a[i]
     for name in ("q_ref", "v_ref", "u_ref", "q_weight", "v_weight", "a_weight", "u_weight", "qf_weight",
                  "vf_weight", "q_min", "q_max", "v_max", "u_max"):
         a, b = getattr(src, name), getattr(dst, name)
@@ -25,7 +29,8 @@ def copy_problem(src, dst):
     return dst
 
 
-def make_pair(I, O, lib, problem, q0, v0, kind="unocp"):
+def make_pair(I, O, lib, problem, q0, v0, kind="unocp", task_ref=None, t=0.0):
+    """task_ref: the user's compute_q_6d_ref(t) -> 12 doubles, sampled by both sides at the stage times."""
     batch = q0.shape[0]
     cls = I.UnOCPSolver if kind == "unocp" else I.UnParNMPCSolver
     solver = cls(problem, batch, lib=lib)
@@ -37,6 +42,11 @@ def make_pair(I, O, lib, problem, q0, v0, kind="unocp"):
     for b, o in enumerate(oracles):
         o.set_solution("q", q0[b])
         o.set_solution("v", v0[b])
+    if task_ref is not None:
+        solver.setTaskReference(task_ref, t)
+        table = O.task_ref_table(task_ref, t, problem.T, problem.N, kind)
+        for o in oracles:
+            o.set_task_ref(table)
     if kind != "unocp":   # examples/iiwa14/unparnmpc_benchmark.cpp:49-51
         solver.initBackwardCorrection(0.0)
         for o in oracles:

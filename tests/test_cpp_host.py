@@ -8,7 +8,7 @@ import pytest
 
 from conftest import GOLDEN, ROOT
 
-EXE = os.path.join(ROOT, "build", "unocp_benchmark")
+EXE = os.path.join(ROOT, "build", "iiwa14_batch")
 
 
 def _build():
@@ -17,7 +17,7 @@ def _build():
     os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)
     lib = os.path.join(ROOT, "idocp_b200")
     subprocess.check_call(["g++", "-std=c++17", "-Wall", "-I" + os.path.join(ROOT, "include"),
-                           os.path.join(ROOT, "examples", "unocp_benchmark.cpp"), "-L" + lib, "-lidocp_b200",
+                           os.path.join(ROOT, "examples", "iiwa14_batch.cpp"), "-L" + lib, "-lidocp_b200",
                            "-Wl,-rpath," + lib, "-o", EXE])
 
 
@@ -26,20 +26,29 @@ def test_example_compiles_and_fails_loudly_without_gpu():
     _build()
     if torch.cuda.is_available():
         pytest.skip("GPU present")
-    res = subprocess.run([EXE], capture_output=True, text=True)
+    res = subprocess.run([EXE, "benchmark", "unocp"], capture_output=True, text=True)
     assert res.returncode != 0
     assert "no CUDA device" in res.stderr
 
 
 @pytest.mark.gpu
-def test_example_reproduces_golden_convergence():
-    """examples/unocp_benchmark.cpp (twin of the reference example) prints the KKT history of the
-    q = 2, v = 0 instance: must equal the committed golden vector digit for digit."""
+@pytest.mark.parametrize("problem,kind,iters,golden_file,key", [
+    ("benchmark", "unocp", 50, "unocp_golden.json", "unocp_benchmark_reference_instance"),
+    ("config", "unocp", 30, "unocp_golden.json", "config_space_ocp"),
+    ("benchmark", "unparnmpc", 20, "solvers_golden.json", "unparnmpc_benchmark_reference_instance"),
+    ("task", "unocp", 30, "solvers_golden.json", "task_space_ocp_unocp"),
+    ("task", "unparnmpc", 30, "solvers_golden.json", "task_space_ocp_unparnmpc"),
+])
+def test_example_reproduces_golden_convergence(problem, kind, iters, golden_file, key):
+    """examples/iiwa14_batch.cpp drives the C++ host classes (Robot, ConfigurationSpaceCost,
+    TimeVaryingTaskSpace6DCost with a user-derived reference, JointConstraintsFactory, UnOCPSolver /
+    UnParNMPCSolver, ocpbenchmarker) on the reference's three iiwa14 set-ups; the printed KKT history of
+    instance 0 of a batch of 3 must equal the committed golden vectors digit for digit."""
     _build()
-    out = subprocess.run([EXE, "3", "20"], capture_output=True, text=True, check=True).stdout
+    out = subprocess.run([EXE, problem, kind, "3", str(iters), "5"], capture_output=True, text=True, check=True).stdout
     kkt = [float(x) for x in re.findall(r"KKT error(?: after iteration \d+)? = (\S+)", out)]
-    with open(os.path.join(GOLDEN, "unocp_golden.json")) as f:
-        ref = json.load(f)["unocp_benchmark_reference_instance"]["kkt"]
-    assert len(kkt) == 51
+    with open(os.path.join(GOLDEN, golden_file)) as f:
+        ref = json.load(f)[key]["kkt"]
+    assert len(kkt) == iters + 1
     assert kkt == ref
     assert "CPU time per update" in out

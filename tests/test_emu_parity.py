@@ -109,6 +109,21 @@ def test_unparnmpc_iterations_match_oracle(emu_lib, oracle, batch, N):
     assert np.all(solver.getStatus() == 0)
 
 
+@pytest.mark.parametrize("kind,N,line_search", [("unocp", 4, False), ("unparnmpc", 4, False), ("unocp", 3, True)])
+def test_task_space_cost_matches_oracle(emu_lib, oracle, kind, N, line_search):
+    """TimeVaryingTaskSpace6DCost (examples/iiwa14/task_space_ocp.cpp problem, short horizon): frame
+    kinematics, log6 / Jlog6, dense Gauss-Newton Hessian (also at the terminal stage and in the ParNMPC
+    aux matrix), line-search cost -- bit-identical to the oracle."""
+    prob = I.task_space_problem(emu_lib, N=N, T=0.05 * N)
+    rng = np.random.default_rng(3)
+    q0 = np.array([0, np.pi / 2, 0, np.pi / 2, 0, np.pi / 2, 0]) + rng.uniform(-0.3, 0.3, (3, 7))
+    v0 = rng.uniform(-0.2, 0.2, (3, 7))
+    solver, oracles = make_pair(I, oracle, emu_lib, prob, q0, v0, kind=kind, task_ref=I.task_space_circle_ref)
+    for it in range(3):
+        check_iteration(solver, oracles, q0, v0, line_search=line_search)
+    check_solution(solver, oracles)
+
+
 def test_error_paths(emu_lib):
     prob = I.benchmark_problem(emu_lib)
     bad = I.benchmark_problem(emu_lib)

@@ -117,3 +117,31 @@ def test_coarse_update_and_corrections_match_numpy(oracle):
     Fv = v - before["v"][0] + dt * before["a"][0]
     assert np.allclose(r0[:7], Fq, atol=1e-7 * max(1.0, np.abs(Fq).max()))
     assert np.allclose(r0[7:14], Fv, atol=1e-7 * max(1.0, np.abs(Fv).max()))
+
+
+@pytest.mark.parametrize("key,iters", [("unparnmpc_benchmark_reference_instance", 20), ("config_space_unparnmpc", 60)])
+def test_golden_histories(oracle, key, iters):
+    """examples/iiwa14/unparnmpc_benchmark.cpp instance (q = 2, v = 0) and the config-space problem through the
+    ParNMPC driver: KKT error / step sizes of every iteration equal the committed golden vectors."""
+    import json
+    import os
+    from conftest import GOLDEN
+    O = oracle
+    with open(os.path.join(GOLDEN, "solvers_golden.json")) as f:
+        rec = json.load(f)[key]
+    if key.startswith("unparnmpc_benchmark"):
+        p = O.benchmark_problem()
+    else:
+        p = O.config_space_problem()
+        p.N, p.T = 20, 1.0
+    q0, v0 = np.array(rec["q0"]), np.array(rec["v0"])
+    s = _solver(O, p, q0, v0)
+    s.compute_kkt_residual(0.0, q0, v0)
+    kkt = [s.kkt_error()]
+    for it in range(iters):
+        s.update_solution(0.0, q0, v0)
+        st = s.step_sizes()
+        assert st[0] == rec["primal"][it] and st[1] == rec["dual"][it]
+        s.compute_kkt_residual(0.0, q0, v0)
+        kkt.append(s.kkt_error())
+    assert kkt == rec["kkt"]
