@@ -388,24 +388,34 @@ static int ensure_line_search(idocp_b200_solver* h) {
 }
 
 // UnLineSearch::computeStepSize for the whole batch: lock-step rounds, no host synchronisation
-static int run_line_search(idocp_b200_solver* h) {
+static int run_line_search(idocp_b200_solver* h, const double* d_q, const double* d_v) {
   const int rc = ensure_line_search(h);
   if (rc != IDOCP_B200_OK) return rc;
   const int off = h->stage_offset();
+  const bool par = h->kind == IDOCP_B200_SOLVER_UNPARNMPC;
+  const int ncost = par ? h->N : h->N + 1;
   const int fgrid = (h->B + 127) / 128;
-  IDOCP_LAUNCH(h, KC_LINESEARCH, k_ls_begin, group_grid(h), CTA_THREADS, 0, h->L);
   const bool task = h->prob.task_enabled != 0;
+  IDOCP_LAUNCH(h, KC_LINESEARCH, k_ls_begin, group_grid(h), CTA_THREADS, 0, h->L);
   auto eval = [&](int mode) {
-    if (task)
-      IDOCP_LAUNCH(h, KC_LINESEARCH, k_ls_eval<true>, stage_grid(h, h->N + 1), CTA_THREADS, 0, h->d_prob, h->L, h->LS, mode, off);
-    else
-      IDOCP_LAUNCH(h, KC_LINESEARCH, k_ls_eval<false>, stage_grid(h, h->N + 1), CTA_THREADS, 0, h->d_prob, h->L, h->LS, mode, off);
+    const int grid = stage_grid(h, ncost);
+    if (par) {
+      if (task)
+        IDOCP_LAUNCH(h, KC_LINESEARCH, (k_ls_eval<true, true>), grid, CTA_THREADS, 0, h->d_prob, h->L, h->LS, mode, off, d_q, d_v);
+      else
+        IDOCP_LAUNCH(h, KC_LINESEARCH, (k_ls_eval<false, true>), grid, CTA_THREADS, 0, h->d_prob, h->L, h->LS, mode, off, d_q, d_v);
+    } else {
+      if (task)
+        IDOCP_LAUNCH(h, KC_LINESEARCH, (k_ls_eval<true, false>), grid, CTA_THREADS, 0, h->d_prob, h->L, h->LS, mode, off, d_q, d_v);
+      else
+        IDOCP_LAUNCH(h, KC_LINESEARCH, (k_ls_eval<false, false>), grid, CTA_THREADS, 0, h->d_prob, h->L, h->LS, mode, off, d_q, d_v);
+    }
   };
   eval(0);
-  IDOCP_LAUNCH(h, KC_LINESEARCH, k_ls_filter, fgrid, 128, 0, h->L, h->LS, 0);
+  IDOCP_LAUNCH(h, KC_LINESEARCH, k_ls_filter, fgrid, 128, 0, h->L, h->LS, 0, ncost);
   for (int trial = 0; trial < LS_MAX_TRIALS; ++trial) {
     eval(1);
-    IDOCP_LAUNCH(h, KC_LINESEARCH, k_ls_filter, fgrid, 128, 0, h->L, h->LS, 1);
+    IDOCP_LAUNCH(h, KC_LINESEARCH, k_ls_filter, fgrid, 128, 0, h->L, h->LS, 1, ncost);
   }
   CUDA_OK(cudaGetLastError());
   return IDOCP_B200_OK;
@@ -425,7 +435,7 @@ static int unocp_update(idocp_b200_solver* h, const double* d_q, const double* d
   }
   const double* override_alpha = nullptr;
   if (line_search) {
-    const int rc = run_line_search(h);
+    const int rc = run_line_search(h, d_q, d_v);
     if (rc != IDOCP_B200_OK) return rc;
     override_alpha = h->LS.alpha;
   }
@@ -437,7 +447,6 @@ static int unocp_update(idocp_b200_solver* h, const double* d_q, const double* d
 
 // UnParNMPCSolver::updateSolution (src/unocp/unparnmpc_solver.cpp:74-102)
 static int parnmpc_update(idocp_b200_solver* h, double, const double* d_q, const double* d_v, int line_search) {
-  if (line_search) return fail(IDOCP_B200_UNSUPPORTED, "UnParNMPCSolver: line_search=true is not implemented yet");
   const int N = h->N;
   // UnBackwardCorrection::coarseUpdate (src/unocp/unbackward_correction.cpp:67-97)
   if (h->prob.task_enabled)
@@ -455,8 +464,13 @@ static int parnmpc_update(idocp_b200_solver* h, double, const double* d_q, const
   }
   IDOCP_LAUNCH(h, KC_PARNMPC_CORR, k_parnmpc_forward_parallel, stage_grid(h, N), CTA_THREADS, 0, h->L, h->PL);
   IDOCP_LAUNCH(h, KC_EXPAND, (k_expand<true, false>), stage_grid(h, N), CTA_THREADS, 0, h->d_prob, h->L, 1);
-  IDOCP_LAUNCH(h, KC_UPDATE, k_update, stage_grid(h, N), CTA_THREADS, 0, h->d_prob, h->L, 1,
-               static_cast<const double*>(nullptr), N);
+  const double* override_alpha = nullptr;
+  if (line_search) {
+    const int rc = run_line_search(h, d_q, d_v);
+    if (rc != IDOCP_B200_OK) return rc;
+    override_alpha = h->LS.alpha;
+  }
+  IDOCP_LAUNCH(h, KC_UPDATE, k_update, stage_grid(h, N), CTA_THREADS, 0, h->d_prob, h->L, 1, override_alpha, N);
   CUDA_OK(cudaGetLastError());
   return IDOCP_B200_OK;
 }

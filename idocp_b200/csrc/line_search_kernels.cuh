@@ -84,12 +84,16 @@ __device__ __forceinline__ bool ls_participates(const LineSearchLayout& LS, int 
 // ---------------------------------------------------------------------------------------------
 // TASK = true: + TimeVaryingTaskSpace6DCost::computeStageCost / computeTerminalCost
 // (src/cost/time_varying_task_space_6d_cost.cpp:68-90)
-template <bool TASK>
+// BACKWARD_EULER = true: UnParNMPCSolver (src/line_search/unline_search.cpp:87-122; split_unparnmpc.hxx:177-224,
+// terminal_unparnmpc.hxx:196-227): N stages, the last one adds the terminal cost, the state-equation defect
+// uses the TRIAL previous stage (x0 for index 0), the last stage's reference time is t + N dt (table row N)
+template <bool TASK, bool BACKWARD_EULER>
 __global__ void __launch_bounds__(CTA_THREADS) k_ls_eval(const DevProblem* __restrict__ Pp, Layout L,
-                                                         LineSearchLayout LS, int mode, int stage_offset) {
+                                                         LineSearchLayout LS, int mode, int stage_offset,
+                                                         const double* __restrict__ q0, const double* __restrict__ v0) {
   const DevProblem& P = *Pp;
   const int lane = lane_in_octet();
-  const StageTask t = stage_task(L, L.N + 1);
+  const StageTask t = stage_task(L, BACKWARD_EULER ? L.N : L.N + 1);
   const int i = t.stage;
   const int b = t.g * 4 + ((threadIdx.x >> 3) & 3);
   const bool part = ls_participates(LS, b, L.B, mode);
@@ -105,7 +109,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_ls_eval(const DevProblem* __res
   const double dq = D[D_Q * SLOT], dv = D[D_V * SLOT];
   // UnLineSearch::computeTrySolution (unline_search.hpp:125-133): q, v, a, u only
   const double qt = fma(alpha, dq, q), vt = fma(alpha, dv, v);
-  if (i == N) {
+  if (!BACKWARD_EULER && i == N) {
     // TerminalOCP::terminalCost -> ConfigurationSpaceCost::computeTerminalCost (configuration_space_cost.cpp:259-273)
     double l = 0.0;
     l += oct_sum_ordered(z * (P.qf_weight[lane] * (qt - P.q_ref[lane]) * (qt - P.q_ref[lane])));
@@ -126,8 +130,21 @@ __global__ void __launch_bounds__(CTA_THREADS) k_ls_eval(const DevProblem* __res
   const double da = D[D_A * SLOT], du = D[D_U * SLOT];
   const double at = fma(alpha, da, a), ut = fma(alpha, du, u);
   const size_t xs = static_cast<size_t>(L.G) * (X_NUM * SLOT), ds = static_cast<size_t>(L.G) * (D_NUM * SLOT);
-  const double qnt = fma(alpha, D[ds + D_Q * SLOT], X[xs + X_Q * SLOT]);
-  const double vnt = fma(alpha, D[ds + D_V * SLOT], X[xs + X_V * SLOT]);
+  const bool last = BACKWARD_EULER && (i == N - 1);
+  // neighbour state of the state equation at the trial point: next stage (forward Euler) / previous stage or
+  // the measured x0 (backward Euler)
+  double qnt, vnt;
+  if (!BACKWARD_EULER) {
+    qnt = fma(alpha, D[ds + D_Q * SLOT], X[xs + X_Q * SLOT]);
+    vnt = fma(alpha, D[ds + D_V * SLOT], X[xs + X_V * SLOT]);
+  } else if (i == 0) {
+    const size_t bi = static_cast<size_t>(b < L.B ? b : 0) * NV + (act ? lane : 0);
+    qnt = act ? q0[bi] : 0.0;
+    vnt = act ? v0[bi] : 0.0;
+  } else {
+    qnt = fma(alpha, *(D - ds + D_Q * SLOT), *(X - xs + X_Q * SLOT));
+    vnt = fma(alpha, *(D - ds + D_V * SLOT), *(X - xs + X_V * SLOT));
+  }
   // ---- SplitUnOCP::stageCost (split_unocp.hxx:177-196) ----
   double l = 0.0;
   l += oct_sum_ordered(z * (P.q_weight[lane] * (qt - P.q_ref[lane]) * (qt - P.q_ref[lane])));
@@ -138,10 +155,18 @@ __global__ void __launch_bounds__(CTA_THREADS) k_ls_eval(const DevProblem* __res
   double R[9];
   V3 p;
   chain_fk(lane, act ? qt : 0.0, P.model + lane * MODEL_STRIDE, R, p);
+  TaskEval te;
   if (TASK) {
-    TaskEval te;
-    task_evaluate<false>(R, p, P.ee, L.task_ref + static_cast<size_t>(i) * 12, te);
+    task_evaluate<false>(R, p, P.ee, L.task_ref + static_cast<size_t>(last ? N : i) * 12, te);
     cost += 0.5 * dt * task_weighted_sqnorm(te, P.task_w6);
+  }
+  if (last) {   // TerminalUnParNMPC::stageCost: + computeTerminalCost
+    double lf = 0.0;
+    lf += oct_sum_ordered(z * (P.qf_weight[lane] * (qt - P.q_ref[lane]) * (qt - P.q_ref[lane])));
+    lf += oct_sum_ordered(z * (P.vf_weight[lane] * (vt - P.v_ref[lane]) * (vt - P.v_ref[lane])));
+    double tc = 0.5 * lf;
+    if (TASK) tc += 0.5 * task_weighted_sqnorm(te, P.task_wf6);
+    cost += tc;
   }
   const LaneLimits lim = load_limits(P, lane);
   double bar = 0.0, c1 = 0.0;
@@ -163,8 +188,8 @@ __global__ void __launch_bounds__(CTA_THREADS) k_ls_eval(const DevProblem* __res
   }
   cost += dt * bar;
   // ---- SplitUnOCP::constraintViolation (split_unocp.hxx:199-217) ----
-  const double Fq = fma(dt, vt, qt - qnt);
-  const double Fv = fma(dt, at, vt) - vnt;
+  const double Fq = BACKWARD_EULER ? fma(dt, vt, qnt - qt) : fma(dt, vt, qt - qnt);
+  const double Fv = BACKWARD_EULER ? fma(dt, at, vnt - vt) : fma(dt, at, vt) - vnt;
   JointDyn J;
   chain_world_sweep_from_fk(lane, R, p, act ? vt : 0.0, act ? at : 0.0, P.model + lane * MODEL_STRIDE, P.gravity, J);
   const double ID = J.tau - ut;
@@ -179,9 +204,11 @@ __global__ void __launch_bounds__(CTA_THREADS) k_ls_eval(const DevProblem* __res
 }
 
 // sum of the per-stage values in ascending stage order (UnLineSearch::totalCosts / totalViolations)
-__device__ __forceinline__ void ls_totals(const Layout& L, const LineSearchLayout& LS, int b, double& cost, double& viol) {
+// ncost = N + 1 (UnOCPSolver: N stages + terminal) or N (UnParNMPCSolver)
+__device__ __forceinline__ void ls_totals(const Layout& L, const LineSearchLayout& LS, int b, int ncost, double& cost,
+                                          double& viol) {
   double cs = 0.0, vs = 0.0;
-  for (int i = 0; i <= L.N; ++i) {
+  for (int i = 0; i < ncost; ++i) {
     cs += LS.cost[static_cast<size_t>(i) * L.Bp + b];
     if (i < L.N) vs += LS.viol[static_cast<size_t>(i) * L.Bp + b];
   }
@@ -193,13 +220,13 @@ __device__ __forceinline__ void ls_totals(const Layout& L, const LineSearchLayou
 //  mode 0: augment empty filters with the current point, then start the search at alpha_max
 //  mode 1: one backtracking decision
 // ---------------------------------------------------------------------------------------------
-__global__ void k_ls_filter(Layout L, LineSearchLayout LS, int mode) {
+__global__ void k_ls_filter(Layout L, LineSearchLayout LS, int mode, int ncost) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= L.B) return;
   if (mode == 0) {
     if (LS.flt_n[b] == 0) {
       double cost, viol;
-      ls_totals(L, LS, b, cost, viol);
+      ls_totals(L, LS, b, ncost, cost, viol);
       filter_augment(LS, b, cost, viol, L.status);
     }
     const double amax = L.steps[2 * L.Bp + b];
@@ -210,7 +237,7 @@ __global__ void k_ls_filter(Layout L, LineSearchLayout LS, int mode) {
   }
   if (LS.state[b] != 0) return;
   double cost, viol;
-  ls_totals(L, LS, b, cost, viol);
+  ls_totals(L, LS, b, ncost, cost, viol);
   if (filter_accepts(LS, b, cost, viol)) {
     filter_augment(LS, b, cost, viol, L.status);
     LS.state[b] = 1;

@@ -1964,6 +1964,92 @@ static void assemble_parnmpc_Q(const stage_t* st, const double* aux_next, double
     }
 }
 
+
+/* UnLineSearch::computeCostAndViolation(UnParNMPC&, ...) (src/line_search/unline_search.cpp:87-122):
+ * SplitUnParNMPC::stageCost / constraintViolation (unocp/split_unparnmpc.hxx:177-224), TerminalUnParNMPC twins
+ * (terminal_unparnmpc.hxx:196-227).  `s` is the current or the trial solution; the previous state of stage i
+ * is s[i-1] of THAT solution (x0 for i = 0).  The last stage is evaluated at t + N dt (:113-119), row N of the
+ * task reference table. */
+static void parnmpc_cost_and_violation(oracle_unparnmpc_t* o, const double* q, const double* v,
+                                       const split_solution_t* s, double alpha, double* cost, double* viol) {
+  const oracle_problem_t* p = &o->p;
+  const int N = o->N;
+  const double dt = o->dt;
+  double cs = 0, vs = 0;
+  for (int i = 0; i < N; ++i) {
+    stage_t* st = &o->st[i];
+    const int last = (i == N - 1);
+    const double* ref = o->task_ref + (size_t)(last ? N : i) * 12;
+    double c = stage_cost(p, dt, &s[i]);
+    if (p->task_enabled) c += task_stage_cost(p, dt, s[i].q, ref);
+    if (last) {
+      double tc = terminal_cost(p, &s[i]);
+      if (p->task_enabled) tc += task_terminal_cost(p, s[i].q, ref);
+      c += tc;
+    }
+    double bar = 0;
+    for (int k = 0; k < NC; ++k) {
+      if (!st->active[k]) continue;
+      double lg = 0;
+      for (int j = 0; j < NV; ++j) {
+        const double sl = alpha > 0 ? fma(alpha, st->c[k].dslack[j], st->c[k].slack[j]) : st->c[k].slack[j];
+        lg += canon_log(sl);
+      }
+      bar += -p->barrier * lg;
+    }
+    c += dt * bar;
+    cs += c;
+    /* constraintViolation: overwrites residual, Fx and ID of the stage, as the reference does */
+    const double* qp = i == 0 ? q : s[i - 1].q;
+    const double* vp = i == 0 ? v : s[i - 1].v;
+    compute_primal_dual_residual(p, st, &s[i]);
+    for (int j = 0; j < NV; ++j) {
+      st->Fq[j] = fma(dt, s[i].v[j], qp[j] - s[i].q[j]);
+      st->Fv[j] = fma(dt, s[i].a[j], vp[j] - s[i].v[j]);
+    }
+    rnea_derivatives_impl(s[i].q, s[i].v, s[i].a, st->ID, NULL, NULL, NULL);
+    for (int j = 0; j < NV; ++j) st->ID[j] -= s[i].u[j];
+    double vi = 0;
+    vi += l1norm(st->Fq) + l1norm(st->Fv);
+    vi += dt * l1norm(st->ID);
+    double c1 = 0;
+    for (int k = 0; k < NC; ++k)
+      if (st->active[k]) c1 += l1norm(st->c[k].residual);
+    vi += dt * c1;
+    vs += vi;
+  }
+  *cost = cs; *viol = vs;
+}
+
+/* UnLineSearch::computeStepSize<UnParNMPC> (line_search/unline_search.hpp:62-91) */
+static double parnmpc_line_search_step(oracle_unparnmpc_t* o, const double* q, const double* v, double max_primal) {
+  double cost, viol;
+  if (o->filter.n == 0) {
+    parnmpc_cost_and_violation(o, q, v, o->s, 0.0, &cost, &viol);
+    filter_augment(&o->filter, cost, viol);
+  }
+  const double min_step = 0.05, rate = 0.75;
+  double alpha = max_primal;
+  while (alpha > min_step) {
+    for (int i = 0; i < o->N; ++i) {
+      split_solution_t* t = &o->s_try[i];
+      for (int j = 0; j < NV; ++j) {
+        t->q[j] = fma(alpha, o->d[i].dq[j], o->s[i].q[j]);
+        t->v[j] = fma(alpha, o->d[i].dv[j], o->s[i].v[j]);
+        t->a[j] = fma(alpha, o->d[i].da[j], o->s[i].a[j]);
+        t->u[j] = fma(alpha, o->d[i].du[j], o->s[i].u[j]);
+      }
+    }
+    parnmpc_cost_and_violation(o, q, v, o->s_try, alpha, &cost, &viol);
+    if (filter_is_accepted(&o->filter, cost, viol)) {
+      filter_augment(&o->filter, cost, viol);
+      break;
+    }
+    alpha *= rate;
+  }
+  return alpha > min_step ? alpha : min_step;
+}
+
 /* UnParNMPCSolver::updateSolution (:74-102) */
 void oracle_unparnmpc_update_solution(oracle_unparnmpc_t* o, double t, const double* q, const double* v,
                                       int line_search) {
@@ -2078,7 +2164,7 @@ void oracle_unparnmpc_update_solution(oracle_unparnmpc_t* o, double t, const dou
     if (ds < dual) dual = ds;
   }
   o->max_primal_step = primal;
-  (void)line_search;  /* the ParNMPC line search is not restated yet (SURVEY 8a row a11 covers UnOCP) */
+  if (line_search) primal = parnmpc_line_search_step(o, q, v, primal);
   o->primal_step = primal;
   o->dual_step = dual;
   for (int i = 0; i < N; ++i) {
@@ -2195,3 +2281,5 @@ void oracle_unocp_set_task_ref(oracle_unocp_t* o, const double* table) {
 void oracle_unparnmpc_set_task_ref(oracle_unparnmpc_t* o, const double* table) {
   memcpy(o->task_ref, table, sizeof(double) * (size_t)(o->N + 1) * 12);
 }
+
+void oracle_unparnmpc_clear_line_search_filter(oracle_unparnmpc_t* o) { o->filter.n = 0; }

@@ -98,6 +98,7 @@ void oracle_unparnmpc_update_solution(oracle_unparnmpc_t* o, double t, const dou
                                       int line_search);
 void oracle_unparnmpc_compute_kkt_residual(oracle_unparnmpc_t* o, double t, const double* q, const double* v);
 double oracle_unparnmpc_kkt_error(oracle_unparnmpc_t* o);
+void oracle_unparnmpc_clear_line_search_filter(oracle_unparnmpc_t* o);
 int  oracle_unparnmpc_get_solution(const oracle_unparnmpc_t* o, const char* name, double* out);
 int  oracle_unparnmpc_get_direction(const oracle_unparnmpc_t* o, const char* name, double* out);
 void oracle_unparnmpc_get_step_sizes(const oracle_unparnmpc_t* o, double* out);

@@ -265,6 +265,9 @@ class UnParNMPCSolver(_SolverBase):
     def init_backward_correction(self, t):
         self.L.oracle_unparnmpc_init_backward_correction(self.h, C.c_double(t))
 
+    def clear_line_search_filter(self):
+        self.L.oracle_unparnmpc_clear_line_search_filter(self.h)
+
     def get_kkt_inverse(self, stage):
         """35x35 KKT inverse of the last coarse update, order [lmd,gmm | a,q,v], numpy [row, col]."""
         out = np.zeros((35, 35))

@@ -124,6 +124,35 @@ def test_task_space_cost_matches_oracle(emu_lib, oracle, kind, N, line_search):
     check_solution(solver, oracles)
 
 
+@pytest.mark.parametrize("task", [False, True])
+def test_unparnmpc_filter_line_search_matches_oracle(emu_lib, oracle, task):
+    """UnLineSearch::computeStepSize<UnParNMPC> (unline_search.hpp:62-91, unline_search.cpp:87-122): backward-Euler
+    defects against the TRIAL previous stage, terminal cost on the last stage, last-stage reference time t + N dt."""
+    if task:
+        prob = I.task_space_problem(emu_lib, N=4, T=0.2)
+        rng = np.random.default_rng(3)
+        q0 = np.array([0, np.pi / 2, 0, np.pi / 2, 0, np.pi / 2, 0]) + rng.uniform(-0.3, 0.3, (3, 7))
+        v0 = rng.uniform(-0.2, 0.2, (3, 7))
+        solver, oracles = make_pair(I, oracle, emu_lib, prob, q0, v0, kind="unparnmpc", task_ref=I.task_space_circle_ref)
+    else:
+        prob = I.config_space_problem(emu_lib)
+        prob.N, prob.T = 5, 0.25
+        rng = np.random.default_rng(4)
+        q0, v0 = rng.uniform(-1, 1, (3, 7)), rng.uniform(-0.2, 0.2, (3, 7))
+        solver, oracles = make_pair(I, oracle, emu_lib, prob, q0, v0, kind="unparnmpc")
+    steps = []
+    for it in range(4):
+        check_iteration(solver, oracles, q0, v0, line_search=True)
+        steps.append(solver.getStepSizes()[0])
+    steps = np.array(steps)
+    assert steps.min() == 0.05 and len(np.unique(steps)) > 3
+    check_solution(solver, oracles)
+    solver.clearLineSearchFilter()
+    for o in oracles:
+        o.clear_line_search_filter()
+    check_iteration(solver, oracles, q0, v0, line_search=True)
+
+
 def test_error_paths(emu_lib):
     prob = I.benchmark_problem(emu_lib)
     bad = I.benchmark_problem(emu_lib)
