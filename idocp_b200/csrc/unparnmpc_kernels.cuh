@@ -118,8 +118,8 @@ constexpr int INV_OFF_A = 0;                          // Q -> L (21 x 21), later
 constexpr int INV_OFF_RD = INV_OFF_A + NQ3 * INV_LDQ;  // reciprocal pivots (21)
 constexpr int INV_OFF_FQ = INV_OFF_RD + 24;           // FQinv (14 x 21), column stride 15
 constexpr int INV_OFF_S = INV_OFF_FQ + NQ3 * INV_LDX;  // S (14 x 14); first used as staging of aux_next
-constexpr int INV_OFF_LS = INV_OFF_S + NX2 * INV_LDX;  // LLT(S)
-constexpr int INV_OFF_TL = INV_OFF_LS + NX2 * INV_LDX; // TL (14 x 14)
+constexpr int INV_OFF_LS = INV_OFF_S + NX2 * INV_LDX;  // LLT(S), then TL = -S^-1 in place (14 x 14)
+constexpr int INV_OFF_TL = INV_OFF_LS;
 constexpr int INV_OFF_TR = INV_OFF_TL + NX2 * INV_LDX; // TR (14 x 21)
 constexpr int INV_OFF_RES = INV_OFF_TR + NQ3 * INV_LDX; // residual (35)
 constexpr int INV_SMEM_PER_WARP = INV_OFF_RES + 36;
@@ -153,6 +153,13 @@ __device__ __forceinline__ int warp_llt(double* __restrict__ A, int ld, double* 
 }
 
 // column `c` of (L L^T)^-1: forward + backward substitution of the unit vector e_c (oracle llt_solve)
+// The compiler barrier after every row keeps the (address-independent) shared-memory loads of L from being
+// hoisted above the whole unrolled substitution, which would cost hundreds of registers (spills).
+#ifdef IDOCP_B200_EMU
+#define IDOCP_SCHED_FENCE() __syncwarp()
+#else
+#define IDOCP_SCHED_FENCE() __syncwarp()
+#endif
 template <int n>
 __device__ __forceinline__ void warp_llt_solve_unit(const double* __restrict__ Lm, int ld, const double* __restrict__ rd,
                                                     int c, double (&y)[n]) {
@@ -162,6 +169,7 @@ __device__ __forceinline__ void warp_llt_solve_unit(const double* __restrict__ L
 #pragma unroll
     for (int j = 0; j < i; ++j) acc = fma(-Lm[j * ld + i], y[j], acc);
     y[i] = acc * rd[i];
+    IDOCP_SCHED_FENCE();
   }
 #pragma unroll
   for (int i = n - 1; i >= 0; --i) {
@@ -169,6 +177,7 @@ __device__ __forceinline__ void warp_llt_solve_unit(const double* __restrict__ L
 #pragma unroll
     for (int j = i + 1; j < n; ++j) acc = fma(-Lm[i * ld + j], y[j], acc);
     y[i] = acc * rd[i];
+    IDOCP_SCHED_FENCE();
   }
 }
 
@@ -242,17 +251,22 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_INV_MINB) k_parnmpc_invert(
   });
   __syncwarp();
 
-  // ---- llt_Q_.compute(Q); Qinv = llt_Q_.solve(I): lane c holds column c ----
+  // ---- llt_Q_.compute(Q); Qinv = llt_Q_.solve(I): lane c computes column c, then parks it over L (dead) ----
   int fail = warp_llt<NQ3>(A, INV_LDQ, rd, wl);
-  double y[NQ3];
   const int cq = wl < NQ3 ? wl : 0;
-  warp_llt_solve_unit<NQ3>(A, INV_LDQ, rd, cq, y);
-  // ---- FQinv (14 x 21): rows Fq = -Qinv[q rows] + dt Qinv[v rows]; rows Fv = dt Qinv[a rows] - Qinv[v rows] ----
-  if (wl < NQ3) {
+  {
+    double y[NQ3];
+    warp_llt_solve_unit<NQ3>(A, INV_LDQ, rd, cq, y);
+    __syncwarp();   // every lane is done reading L
+    if (wl < NQ3) {
 #pragma unroll
-    for (int r = 0; r < NV; ++r) {
-      FQ[wl * INV_LDX + r] = fma(dt, y[2 * NV + r], -y[NV + r]);
-      FQ[wl * INV_LDX + NV + r] = fma(dt, y[r], -y[2 * NV + r]);
+      for (int r = 0; r < NQ3; ++r) A[wl * INV_LDQ + r] = y[r];
+      // FQinv (14 x 21): rows Fq = -Qinv[q rows] + dt Qinv[v rows]; rows Fv = dt Qinv[a rows] - Qinv[v rows]
+#pragma unroll
+      for (int r = 0; r < NV; ++r) {
+        FQ[wl * INV_LDX + r] = fma(dt, y[2 * NV + r], -y[NV + r]);
+        FQ[wl * INV_LDX + NV + r] = fma(dt, y[r], -y[2 * NV + r]);
+      }
     }
   }
   __syncwarp();
@@ -270,12 +284,13 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_INV_MINB) k_parnmpc_invert(
     }
   }
   __syncwarp();
-  // ---- llt_S_.compute(S); TL = -llt_S_.solve(I) ----
+  // ---- llt_S_.compute(S); TL = -llt_S_.solve(I), written over the factor once every lane has solved ----
   fail |= warp_llt<NX2>(LS, INV_LDX, rd, wl);
   {
     double z[NX2];
     const int cs = wl < NX2 ? wl : 0;
     warp_llt_solve_unit<NX2>(LS, INV_LDX, rd, cs, z);
+    __syncwarp();
     if (wl < NX2) {
 #pragma unroll
       for (int r = 0; r < NX2; ++r) TL[wl * INV_LDX + r] = -z[r];
@@ -283,26 +298,26 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_INV_MINB) k_parnmpc_invert(
   }
   __syncwarp();
   // ---- TR = -(TL FQinv) (14 x 21), lane c = column c (own column of FQinv re-read from shared memory) ----
-  double tr[NX2];
   {
-    double fq[NX2];
+    double tr[NX2];
+    {
+      double fq[NX2];
 #pragma unroll
-    for (int k = 0; k < NX2; ++k) fq[k] = FQ[cq * INV_LDX + k];
+      for (int k = 0; k < NX2; ++k) fq[k] = FQ[cq * INV_LDX + k];
 #pragma unroll
-    for (int r = 0; r < NX2; ++r) {
-      double t = 0.0;
+      for (int r = 0; r < NX2; ++r) {
+        double t = 0.0;
 #pragma unroll
-      for (int k = 0; k < NX2; ++k) t = fma(TL[k * INV_LDX + r], fq[k], t);
-      tr[r] = -t;
+        for (int k = 0; k < NX2; ++k) t = fma(TL[k * INV_LDX + r], fq[k], t);
+        tr[r] = -t;
+      }
     }
-  }
-  if (wl < NQ3) {
+    if (wl < NQ3) {
 #pragma unroll
-    for (int r = 0; r < NX2; ++r) TR[wl * INV_LDX + r] = tr[r];
-  }
-  __syncwarp();
-  // ---- BR = Qinv - TR^T (S TR) (21 x 21), stored over A (column stride 21) ----
-  {
+      for (int r = 0; r < NX2; ++r) TR[wl * INV_LDX + r] = tr[r];
+    }
+    __syncwarp();
+    // ---- BR = Qinv - TR^T (S TR) (21 x 21), in place over the parked Qinv ----
     double st[NX2];
 #pragma unroll
     for (int r = 0; r < NX2; ++r) {
@@ -311,17 +326,15 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_INV_MINB) k_parnmpc_invert(
       for (int k = 0; k < NX2; ++k) t = fma(S[k * INV_LDX + r], tr[k], t);
       st[r] = t;
     }
+    if (wl < NQ3) {
 #pragma unroll
-    for (int r = 0; r < NQ3; ++r) {
-      double t = 0.0;
+      for (int r = 0; r < NQ3; ++r) {
+        double t = 0.0;
 #pragma unroll
-      for (int k = 0; k < NX2; ++k) t = fma(TR[r * INV_LDX + k], st[k], t);
-      y[r] -= t;
+        for (int k = 0; k < NX2; ++k) t = fma(TR[r * INV_LDX + k], st[k], t);
+        A[wl * INV_LDQ + r] -= t;
+      }
     }
-  }
-  if (wl < NQ3) {
-#pragma unroll
-    for (int r = 0; r < NQ3; ++r) A[wl * INV_LDQ + r] = y[r];
   }
   __syncwarp();
 
