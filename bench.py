@@ -48,6 +48,15 @@ KERNEL_ALGO_DOUBLES_PER_STAGE = {
 }
 
 
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of each kernel from the committed ncu
+# --set full capture profiles/r1f_ncu_full_unocp.txt (same workload: 16384 instances, N = 20); reported as
+# roofline.traffic only when the bench runs that workload.  FP64-pipe utilisation from the same capture.
+NCU_DRAM_BYTES_PER_LAUNCH = {"linearize": 0.463256e9 + 1.430249e9, "riccati": 1.279708e9 + 0.990071e9,
+                             "expand": 1.503709e9 + 0.087223e9, "update": 0.550980e9 + 0.334739e9}
+NCU_FP64_PIPE_PCT = {"linearize": 46.2, "riccati": 28.7, "expand": 15.2, "update": 9.3}
+NCU_SOURCE = "profiles/r1f_ncu_full_unocp.txt"
+
+
 def splitmix_uniform(seed, index):
     """Counter-based splitmix64 -> double in [0,1); vectorised twin of oracle_splitmix_uniform."""
     idx = np.asarray(index, dtype=np.uint64)
@@ -289,6 +298,10 @@ def main():
             per_launch_ms = ms / calls
             gbs = KERNEL_ALGO_DOUBLES_PER_STAGE[name] * 8.0 * stages / (per_launch_ms * 1e-3) / 1e9
             kern[name] = {"ms_per_launch": per_launch_ms, "algo_gbs": gbs, "share": ms}
+            if B == BATCH_PER_GPU:
+                kern[name]["ncu_dram_bytes"] = NCU_DRAM_BYTES_PER_LAUNCH[name]
+                kern[name]["ncu_dram_gbs_at_measured_time"] = NCU_DRAM_BYTES_PER_LAUNCH[name] / (per_launch_ms * 1e-3) / 1e9
+                kern[name]["ncu_fp64_pipe_pct"] = NCU_FP64_PIPE_PCT[name]
     tot = sum(k["share"] for k in kern.values()) or 1.0
     for k in kern.values():
         k["share"] = k["share"] / tot
@@ -296,7 +309,13 @@ def main():
     roofline = None
     if dom:
         roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["algo_gbs"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": kern[dom]["algo_gbs"] / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "frac": kern[dom]["algo_gbs"] / hbm_peak,
+                    "traffic": NCU_DRAM_BYTES_PER_LAUNCH[dom] if B == BATCH_PER_GPU else None,
+                    "traffic_source": NCU_SOURCE if B == BATCH_PER_GPU else None,
+                    "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": KERNEL_ALGO_DOUBLES_PER_STAGE[dom] * 8.0 * stages,
+                    "note": "k_linearize is FP64/issue-limited (ncu: FP64 pipe 46 %, DRAM 46 %), the other three "
+                            "kernels are HBM-streaming; FP64 has no tensor-core path at 7x7 (DESIGN.md section 4)",
                     "kernels": kern,
                     "step_hbm_frac": BYTES_PER_UNIT * value / world / 1e9 / hbm_peak,
                     "step_fp64_tflops": FLOP_PER_UNIT * value / world / 1e12}
