@@ -8,3 +8,4 @@ from .solvers import (UnOCPSolver, UnParNMPCSolver, benchmark_problem, config_sp
                       task_space_circle_ref, task_space_problem)
 
 __version__ = "0.1"
+from .hybrid import ContactSequence, OCPDiscretizer  # noqa: F401,E402

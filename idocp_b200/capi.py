@@ -41,6 +41,33 @@ class Problem(C.Structure):
     ]
 
 
+MAX_GRID = 1024
+MAX_EVENTS = 64
+
+
+class ScheduledStage(C.Structure):
+    """idocp_b200_scheduled_stage."""
+    _fields_ = [("kind", C.c_int), ("index", C.c_int), ("t", C.c_double), ("dt", C.c_double),
+                ("contact_phase", C.c_int), ("constraint_stage", C.c_int), ("before_impulse", C.c_int),
+                ("switching_impulse", C.c_int)]
+
+
+class OCPDiscretization(C.Structure):
+    """idocp_b200_ocp_discretization."""
+    _fields_ = [
+        ("well_defined", C.c_int), ("N", C.c_int), ("N_impulse", C.c_int), ("N_lift", C.c_int),
+        ("t", C.c_double * (MAX_GRID + 1)), ("dt", C.c_double * (MAX_GRID + 1)),
+        ("contact_phase", C.c_int * (MAX_GRID + 1)),
+        ("impulse_index_after_time_stage", C.c_int * (MAX_GRID + 1)),
+        ("lift_index_after_time_stage", C.c_int * (MAX_GRID + 1)),
+        ("time_stage_before_impulse", C.c_int * MAX_EVENTS), ("time_stage_before_lift", C.c_int * MAX_EVENTS),
+        ("t_impulse", C.c_double * MAX_EVENTS), ("t_lift", C.c_double * MAX_EVENTS),
+        ("dt_aux", C.c_double * MAX_EVENTS), ("dt_lift", C.c_double * MAX_EVENTS),
+        ("num_stages", C.c_int),
+        ("stages", ScheduledStage * (MAX_GRID + 1 + 3 * MAX_EVENTS)),
+    ]
+
+
 class Idocp_b200Error(RuntimeError):
     pass
 
@@ -53,7 +80,14 @@ EXPORTS = [
     "idocp_b200_get_direction", "idocp_b200_get_constraint_data", "idocp_b200_get_step_sizes",
     "idocp_b200_get_unkkt", "idocp_b200_get_status", "idocp_b200_is_feasible",
     "idocp_b200_clear_line_search_filter", "idocp_b200_sync", "idocp_b200_launch_count", "idocp_b200_stream",
-    "idocp_b200_set_task_reference", "idocp_b200_set_profiling", "idocp_b200_get_profile", "idocp_b200_last_error", "idocp_b200_version",
+    "idocp_b200_set_task_reference", "idocp_b200_set_profiling", "idocp_b200_get_profile",
+    "idocp_b200_contact_sequence_create", "idocp_b200_contact_sequence_destroy",
+    "idocp_b200_contact_sequence_set_uniform", "idocp_b200_contact_sequence_push_back",
+    "idocp_b200_contact_sequence_pop_back", "idocp_b200_contact_sequence_pop_front",
+    "idocp_b200_contact_sequence_update_event_time", "idocp_b200_contact_sequence_set_contact_points",
+    "idocp_b200_contact_sequence_counts", "idocp_b200_contact_sequence_get_phase",
+    "idocp_b200_contact_sequence_get_impulse", "idocp_b200_contact_sequence_get_lift_time",
+    "idocp_b200_discretize_ocp", "idocp_b200_last_error", "idocp_b200_version",
 ]
 
 
@@ -92,6 +126,20 @@ class Library:
         L.idocp_b200_clear_line_search_filter.argtypes = [C.c_void_p]
         L.idocp_b200_sync.argtypes = [C.c_void_p]
         L.idocp_b200_set_task_reference.argtypes = [C.c_void_p, _dp]
+        L.idocp_b200_contact_sequence_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.idocp_b200_contact_sequence_destroy.argtypes = [C.c_void_p]
+        L.idocp_b200_contact_sequence_set_uniform.argtypes = [C.c_void_p, _ip, _dp]
+        L.idocp_b200_contact_sequence_push_back.argtypes = [C.c_void_p, _ip, _dp, C.c_double]
+        L.idocp_b200_contact_sequence_pop_back.argtypes = [C.c_void_p]
+        L.idocp_b200_contact_sequence_pop_front.argtypes = [C.c_void_p]
+        L.idocp_b200_contact_sequence_update_event_time.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
+        L.idocp_b200_contact_sequence_set_contact_points.argtypes = [C.c_void_p, C.c_int, _dp]
+        L.idocp_b200_contact_sequence_counts.argtypes = [C.c_void_p, _ip, _ip, _ip]
+        L.idocp_b200_contact_sequence_get_phase.argtypes = [C.c_void_p, C.c_int, _ip, _dp]
+        L.idocp_b200_contact_sequence_get_impulse.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _dp]
+        L.idocp_b200_contact_sequence_get_lift_time.argtypes = [C.c_void_p, C.c_int, _dp]
+        L.idocp_b200_discretize_ocp.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_double,
+                                                C.POINTER(OCPDiscretization)]
         L.idocp_b200_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
         L.idocp_b200_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.idocp_b200_set_profiling.argtypes = [C.c_void_p, C.c_int]

@@ -801,3 +801,5 @@ extern "C" int idocp_b200_get_profile(idocp_b200_solver* h, int cap, const char*
   }
   return n;
 }
+
+#include "hybrid_capi.inc"

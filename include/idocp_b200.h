@@ -157,6 +157,68 @@ int idocp_b200_stream(idocp_b200_solver* h, void** out);
 int idocp_b200_set_profiling(idocp_b200_solver* h, int enabled);
 int idocp_b200_get_profile(idocp_b200_solver* h, int cap, const char** names, double* ms, long long* calls);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Host-side contact schedule of the hybrid OCP (implementation
+ * include/idocp_b200/hybrid.hpp; no device work).  Contact activity arrays are int[max_point_contacts] (0/1),
+ * contact points double[max_point_contacts][3] (may be NULL = zeros).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct idocp_b200_contact_sequence idocp_b200_contact_sequence; /* opaque */
+/* ContactSequence::ContactSequence(robot, max_num_events) (hybrid/contact_sequence.hxx:10-29): starts with one
+ * phase without active contacts */
+int idocp_b200_contact_sequence_create(int max_point_contacts, int max_num_events, idocp_b200_contact_sequence** out);
+int idocp_b200_contact_sequence_destroy(idocp_b200_contact_sequence* cs);
+/* setContactStatusUniformly (:50-54) */
+int idocp_b200_contact_sequence_set_uniform(idocp_b200_contact_sequence* cs, const int* is_active,
+                                            const double* contact_points);
+/* push_back(contact_status, event_time) (:56-110): the event (impulse if a contact becomes active, else lift;
+ * hybrid/discrete_event.hxx:78-104) between the last phase and the new status; errors carry the reference's text */
+int idocp_b200_contact_sequence_push_back(idocp_b200_contact_sequence* cs, const int* is_active,
+                                          const double* contact_points, double event_time);
+int idocp_b200_contact_sequence_pop_back(idocp_b200_contact_sequence* cs);   /* :113-132 */
+int idocp_b200_contact_sequence_pop_front(idocp_b200_contact_sequence* cs);  /* :135-154 */
+/* updateImpulseTime / updateLiftTime (:157-240) */
+int idocp_b200_contact_sequence_update_event_time(idocp_b200_contact_sequence* cs, int is_impulse, int index, double time);
+/* setContactPoints(contact_phase, contact_points) (:243-262) */
+int idocp_b200_contact_sequence_set_contact_points(idocp_b200_contact_sequence* cs, int contact_phase,
+                                                   const double* contact_points);
+/* numContactPhases / numImpulseEvents / numLiftEvents (:265-282); any pointer may be NULL */
+int idocp_b200_contact_sequence_counts(const idocp_b200_contact_sequence* cs, int* num_contact_phases,
+                                       int* num_impulse_events, int* num_lift_events);
+/* contactStatus(contact_phase) / impulseStatus(impulse_index) + impulseTime / liftTime (:285-316) */
+int idocp_b200_contact_sequence_get_phase(const idocp_b200_contact_sequence* cs, int contact_phase, int* is_active,
+                                          double* contact_points);
+int idocp_b200_contact_sequence_get_impulse(const idocp_b200_contact_sequence* cs, int impulse_index, int* is_active,
+                                            double* contact_points, double* time);
+int idocp_b200_contact_sequence_get_lift_time(const idocp_b200_contact_sequence* cs, int lift_index, double* time);
+
+#define IDOCP_B200_MAX_GRID 1024   /* capacity of the tables below: N <= 1024 grid stages, <= 64 events */
+#define IDOCP_B200_MAX_EVENTS 64
+/* one row of the flattened schedule, in the order the Riccati recursion visits the stages
+ * (src/ocp/riccati_recursion_solver.cpp:48-107): kind 0 grid, 1 impulse, 2 aux, 3 lift, 4 terminal */
+typedef struct {
+  int kind, index;
+  double t, dt;
+  int contact_phase;      /* ContactSequence::contactStatus(contact_phase) is active on the stage */
+  int constraint_stage;   /* constraints mask index: grid index; 0 for aux / lift; -1 impulse (ocp_linearizer.cpp:40-68) */
+  int before_impulse;     /* the switching constraint of impulse `switching_impulse` is imposed on this grid stage */
+  int switching_impulse;
+} idocp_b200_scheduled_stage;
+/* OCPDiscretizer after discretizeOCP(contact_sequence, t) (hybrid/ocp_discretizer.hxx:61-72, getters :75-202) */
+typedef struct {
+  int well_defined;       /* isWellDefined() and every event inside the horizon found its stage */
+  int N, N_impulse, N_lift;
+  double t[IDOCP_B200_MAX_GRID + 1], dt[IDOCP_B200_MAX_GRID + 1];
+  int contact_phase[IDOCP_B200_MAX_GRID + 1];
+  int impulse_index_after_time_stage[IDOCP_B200_MAX_GRID + 1], lift_index_after_time_stage[IDOCP_B200_MAX_GRID + 1];
+  int time_stage_before_impulse[IDOCP_B200_MAX_EVENTS], time_stage_before_lift[IDOCP_B200_MAX_EVENTS];
+  double t_impulse[IDOCP_B200_MAX_EVENTS], t_lift[IDOCP_B200_MAX_EVENTS];
+  double dt_aux[IDOCP_B200_MAX_EVENTS], dt_lift[IDOCP_B200_MAX_EVENTS];
+  int num_stages;         /* = N + 1 + 2 N_impulse + N_lift when well defined */
+  idocp_b200_scheduled_stage stages[IDOCP_B200_MAX_GRID + 1 + 3 * IDOCP_B200_MAX_EVENTS];
+} idocp_b200_ocp_discretization;
+int idocp_b200_discretize_ocp(const idocp_b200_contact_sequence* cs, double T, int N, double t,
+                              idocp_b200_ocp_discretization* out);
+
 const char* idocp_b200_last_error(void);
 const char* idocp_b200_version(void);
 

@@ -29,6 +29,7 @@
 #include <vector>
 
 #include "../idocp_b200.h"
+#include "hybrid.hpp"
 
 namespace idocp_b200 {
 
@@ -77,6 +78,8 @@ class Robot {
   int dimu() const { return IDOCP_B200_DIMV; }
   bool hasFloatingBase() const { return false; }
   int maxPointContacts() const { return 0; }
+  // robot.hxx:721: the fixed-base iiwa14 has no point contacts
+  ContactStatus createContactStatus() const { return ContactStatus(maxPointContacts()); }
   void setJointEffortLimit(const VectorXd& v) { detail::copy7(v, p_.u_max, "joint_effort_limit"); }
   void setJointVelocityLimit(const VectorXd& v) { detail::copy7(v, p_.v_max, "joint_velocity_limit"); }
   void setLowerJointPositionLimit(const VectorXd& v) { detail::copy7(v, p_.q_min, "lower_joint_position_limit"); }

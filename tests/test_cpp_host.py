@@ -52,3 +52,20 @@ def test_example_reproduces_golden_convergence(problem, kind, iters, golden_file
     assert len(kkt) == iters + 1
     assert kkt == ref
     assert "CPU time per update" in out
+
+
+def test_contact_schedule_example_runs_on_the_host():
+    """examples/contact_schedule.cpp: the C++ schedule classes (include/idocp_b200/hybrid.hpp) are pure host code;
+    the trotting schedule of SURVEY Appendix C has 36 stages, impulses at 1.0 and 1.5, one lift at 0.5."""
+    os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)
+    exe = os.path.join(ROOT, "build", "contact_schedule")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "contact_schedule.cpp"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.splitlines()
+    assert out[0] == "well defined: 1  N = 30  impulses = 2  lifts = 1  stages = 36"
+    kinds = [line.split()[0] for line in out[1:]]
+    assert len(kinds) == 36 and kinds.count("impulse") == 2 and kinds.count("aux") == 2 and kinds.count("lift") == 1
+    assert kinds[-1] == "terminal"
+    assert sum("switching constraint" in line for line in out) == 2
+    lift = [line for line in out if line.startswith("lift")][0]
+    assert "t = 0.5000" in lift and "feet = 0110" in lift
