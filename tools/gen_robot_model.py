@@ -139,12 +139,52 @@ def load_chain(urdf_path):
             model["frames"].append((j.get("name"), parent_joint, R_new.copy(), p_new.copy()))
             if typ == "fixed":
                 visit(child, parent_joint, R_new, p_new)
+            elif typ == "floating":
+                # pinocchio: URDF `floating` -> JointModelFreeFlyer (nq 7, nv 6); placement = joint origin
+                assert parent_joint == -1 and "base" not in model
+                model["base"] = {"name": j.get("name"), "R": R_new, "p": p_new, "inertia": Inertia()}
+                model["base_frames_from"] = len(model["frames"])
+                visit_base(child)
             elif typ in ("revolute", "continuous"):
                 axis = _vec(j.find("axis").get("xyz"))
                 lim = j.find("limit")
                 idx = len(model["names"])
                 model["names"].append(j.get("name"))
                 model["parent"].append(parent_joint)
+                model["R"].append(R_new)
+                model["p"].append(p_new)
+                model["axis"].append(axis)
+                model["inertia"].append(Inertia())
+                model["q_min"].append(float(lim.get("lower")))
+                model["q_max"].append(float(lim.get("upper")))
+                model["v_max"].append(float(lim.get("velocity")))
+                model["effort"].append(float(lim.get("effort")))
+                visit(child, idx, np.eye(3), np.zeros(3))
+            else:
+                raise NotImplementedError(typ)
+
+    def visit_base(link_name):
+        # bodies behind the free-flyer: the movable-joint index space restarts at -1 == "the base body"
+        state = {"in_base": True}
+        visit_in_base(link_name, np.eye(3), np.zeros(3))
+
+    def visit_in_base(link_name, R_acc, p_acc):
+        model["frames"].append((link_name, -1, R_acc.copy(), p_acc.copy()))
+        model["base"]["inertia"] = model["base"]["inertia"] + link_inertia(link_name).transformed(R_acc, p_acc)
+        for j in children.get(link_name, []):
+            Rj, pj = parse_origin(j)
+            R_new, p_new = R_acc @ Rj, p_acc + R_acc @ pj
+            typ = j.get("type")
+            child = j.find("child").get("link")
+            model["frames"].append((j.get("name"), -1, R_new.copy(), p_new.copy()))
+            if typ == "fixed":
+                visit_in_base(child, R_new, p_new)
+            elif typ in ("revolute", "continuous"):
+                axis = _vec(j.find("axis").get("xyz"))
+                lim = j.find("limit")
+                idx = len(model["names"])
+                model["names"].append(j.get("name"))
+                model["parent"].append(-1)
                 model["R"].append(R_new)
                 model["p"].append(p_new)
                 model["axis"].append(axis)
@@ -224,7 +264,80 @@ def emit_iiwa14():
         print("  frame", i, nm)
 
 
+ANYMAL_URDF = "/root/reference/examples/anymal/anymal_b_simple_description/urdf/anymal.urdf"
+ANYMAL_CONTACT_FRAMES = [14, 24, 34, 44]  # LF, LH, RF, RH feet (examples/anymal/anymal_trotting.cpp:30)
+
+
+def emit_anymal():
+    m = load_chain(ANYMAL_URDF)
+    n = len(m["names"])
+    assert n == 12 and "base" in m
+    assert m["names"] == ["LF_HAA", "LF_HFE", "LF_KFE", "LH_HAA", "LH_HFE", "LH_KFE",
+                          "RF_HAA", "RF_HFE", "RF_KFE", "RH_HAA", "RH_HFE", "RH_KFE"]
+    assert m["parent"] == [-1, 0, 1, -1, 3, 4, -1, 6, 7, -1, 9, 10]
+    assert np.allclose(m["base"]["R"], np.eye(3)) and np.allclose(m["base"]["p"], 0)
+    axis_id = []
+    for ax in m["axis"]:
+        k = int(np.argmax(np.abs(ax)))
+        assert np.allclose(ax, np.eye(3)[k])
+        axis_id.append(k)
+    for R in m["R"]:
+        assert np.allclose(R, np.eye(3))       # every ANYmal joint origin is a pure translation
+    frame_names = [f[0] for f in m["frames"]]
+    feet = ANYMAL_CONTACT_FRAMES
+    assert [frame_names[f] for f in feet] == ["LF_FOOT", "LH_FOOT", "RF_FOOT", "RH_FOOT"]
+    bodies = [m["base"]["inertia"]] + m["inertia"]
+    total_mass = sum(b.m for b in bodies)
+    hdr = []
+    hdr.append("/* GENERATED by tools/gen_robot_model.py from the ANYmal-B URDF -- do not edit.\n"
+               " * Free-flyer base (q: xyz + quaternion xyzw, v: body-frame linear+angular) + 4 legs x 3 revolute joints.\n"
+               " * Reference: src/robot/robot.cpp:8-85 (pinocchio::urdf::buildModel + contact frames), robot.hxx:699-709.\n"
+               " * Body 0 = base, body 1+j = child of joint j.  JOINT_PARENT: -1 = base.  JOINT_AXIS: 0/1/2 = X/Y/Z.\n"
+               " * Every joint origin is a pure translation (JOINT_P, in the parent joint frame).\n"
+               " * INERTIA is (xx,xy,xz,yy,yz,zz) about the body's centre of mass in the joint frame. */\n")
+    hdr.append("#ifndef IDOCP_B200_MODEL_ANYMAL_H_\n#define IDOCP_B200_MODEL_ANYMAL_H_\n")
+    hdr.append("#define ANYMAL_NJ 12\n#define ANYMAL_NV 18\n#define ANYMAL_NQ 19\n#define ANYMAL_NB 13\n"
+               "#define ANYMAL_NCONTACT 4\n#define ANYMAL_GRAVITY 9.81\n#define ANYMAL_TOTAL_MASS %.17g\n" % total_mass)
+    hdr.append("static const int ANYMAL_JOINT_PARENT[12] = {%s};\n" % ", ".join(str(p) for p in m["parent"]))
+    hdr.append("static const int ANYMAL_JOINT_AXIS[12] = {%s};\n" % ", ".join(str(a) for a in axis_id))
+    hdr.append(c_array("ANYMAL_JOINT_P", m["p"]))
+    hdr.append(c_array("ANYMAL_MASS", [b.m for b in bodies]))
+    hdr.append(c_array("ANYMAL_COM", [b.c for b in bodies]))
+    hdr.append(c_array("ANYMAL_INERTIA", [[b.I[0, 0], b.I[0, 1], b.I[0, 2], b.I[1, 1], b.I[1, 2], b.I[2, 2]]
+                                          for b in bodies]))
+    hdr.append(c_array("ANYMAL_Q_MIN", m["q_min"]))
+    hdr.append(c_array("ANYMAL_Q_MAX", m["q_max"]))
+    hdr.append(c_array("ANYMAL_V_MAX", m["v_max"]))
+    hdr.append(c_array("ANYMAL_EFFORT_MAX", m["effort"]))
+    hdr.append("/* contact frames %s (examples/anymal/anymal_trotting.cpp:30), parent joint = the leg's KFE */\n" % feet)
+    hdr.append("static const int ANYMAL_CONTACT_FRAME_ID[4] = {%s};\n" % ", ".join(str(f) for f in feet))
+    hdr.append("static const int ANYMAL_CONTACT_PARENT_JOINT[4] = {%s};\n"
+               % ", ".join(str(m["frames"][f][1]) for f in feet))
+    for f in feet:
+        assert np.allclose(m["frames"][f][2], np.eye(3))
+    hdr.append(c_array("ANYMAL_CONTACT_P", [m["frames"][f][3] for f in feet]))
+    hdr.append("#endif\n")
+    text = "\n".join(hdr)
+    for rel in ("idocp_b200/csrc/model_anymal.h", "oracle/model_anymal.h"):
+        with open(os.path.join(REPO, rel), "w") as f:
+            f.write(text)
+    fixture = {
+        "names": m["names"], "parent": m["parent"], "axis": axis_id,
+        "p": [p.tolist() for p in m["p"]],
+        "mass": [b.m for b in bodies], "com": [b.c.tolist() for b in bodies],
+        "inertia": [b.I.tolist() for b in bodies], "total_mass": total_mass,
+        "q_min": m["q_min"], "q_max": m["q_max"], "v_max": m["v_max"], "effort": m["effort"],
+        "frames": frame_names, "contact_frames": feet,
+        "contact_parent": [m["frames"][f][1] for f in feet],
+        "contact_p": [m["frames"][f][3].tolist() for f in feet],
+    }
+    with open(os.path.join(REPO, "tests/golden/model_anymal.json"), "w") as f:
+        json.dump(fixture, f, indent=1)
+    print("anymal: %d joints, %d frames, total mass %.6f" % (n, len(frame_names), total_mass))
+
+
 if __name__ == "__main__":
     if not os.path.exists(IIWA_URDF):
         sys.exit("reference URDF not found (run in the build container)")
     emit_iiwa14()
+    emit_anymal()
