@@ -101,3 +101,117 @@ def mjtjinv(M, J):
     out = np.zeros((NV + dimf, NV + dimf))
     info = lib().oracle_fb_mjtjinv(_p(_a(M, NV * NV)), _p(J), dimf, _p(out))
     return out, info
+
+
+# ------------------------------------------------------------------------------------------------
+# OCPSolver oracle (oracle/fb_ocp.c)
+# ------------------------------------------------------------------------------------------------
+K_GRID, K_IMPULSE, K_AUX, K_LIFT, K_TERMINAL = range(5)
+NCOMP = 8
+
+
+class FbProblem(C.Structure):
+    _fields_ = [
+        ("T", C.c_double), ("N", C.c_int), ("max_num_impulse", C.c_int),
+        ("q_weight", C.c_double * NV), ("v_weight", C.c_double * NV), ("a_weight", C.c_double * NV),
+        ("qf_weight", C.c_double * NV), ("vf_weight", C.c_double * NV), ("qi_weight", C.c_double * NV),
+        ("vi_weight", C.c_double * NV), ("dvi_weight", C.c_double * NV),
+        ("f_weight", C.c_double * 12), ("f_ref", C.c_double * 12), ("fi_weight", C.c_double * 12), ("fi_ref", C.c_double * 12),
+        ("q_min", C.c_double * NU), ("q_max", C.c_double * NU), ("v_max", C.c_double * NU), ("u_max", C.c_double * NU),
+        ("mu", C.c_double), ("barrier", C.c_double), ("fraction_rate", C.c_double),
+        ("enable", C.c_int * NCOMP),
+    ]
+
+    def set(self, name, values):
+        arr = getattr(self, name)
+        vals = np.asarray(values, dtype=float).ravel()
+        assert len(arr) == vals.size, (name, len(arr), vals.size)
+        for i, x in enumerate(vals):
+            arr[i] = x
+
+
+_SIZES = dict(q=19, f=12, mu=12, nu_passive=6, xi=12, u=12, du=12, daf=30, dbetamu=30, dnu_passive=6, dxi=12, lf=12, lu=12,
+              lu_passive=6, P=12, IDC=30, Qxx=36 * 36, Qxu=36 * 18, Quu=18 * 18, Qff=144, Fvq=324, Fvv=324, Fvu=216, Fqq6=36, Fqv6=36,
+              MJtJinv=900, MJ_dIDC=30 * 36, MJ_IDC=30, dIDCdqv=30 * 36, dCda=12 * 18, Mm=324, K=12 * 36, k=12, Pqq=324, Pqv=324,
+              Pvv=324, Phix=12 * 36, Phia=12 * 18, Phiu=144, cM=12 * 36, cm=12, Fqq_prev_inv=36, Fqq_inv=36, laf=30,
+              Qafqv=30 * 36, Qafu=30 * 18, kkt=1, slack=6 * 12 + 40, dual=6 * 12 + 40)
+
+
+class FbOCP:
+    def __init__(self, problem, contact_sequence):
+        self.L = lib()
+        L = self.L
+        L.oracle_fb_ocp_create.restype = C.c_void_p
+        L.oracle_fb_ocp_create.argtypes = [C.POINTER(FbProblem), C.c_void_p]
+        L.oracle_fb_ocp_destroy.argtypes = [C.c_void_p]
+        L.oracle_fb_ocp_set_solution.argtypes = [C.c_void_p, C.c_char_p, _dp]
+        L.oracle_fb_ocp_set_reference.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp]
+        L.oracle_fb_ocp_discretize.argtypes = [C.c_void_p, C.c_double]
+        L.oracle_fb_ocp_chain.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 2 + [_dp] * 2 + [C.POINTER(C.c_int)] * 2
+        L.oracle_fb_ocp_init_constraints.argtypes = [C.c_void_p, C.c_double]
+        L.oracle_fb_ocp_update_solution.argtypes = [C.c_void_p, C.c_double, _dp, _dp]
+        L.oracle_fb_ocp_compute_kkt_residual.argtypes = [C.c_void_p, C.c_double, _dp, _dp]
+        L.oracle_fb_ocp_kkt_error.restype = C.c_double
+        L.oracle_fb_ocp_kkt_error.argtypes = [C.c_void_p]
+        L.oracle_fb_ocp_get_step_sizes.argtypes = [C.c_void_p, _dp]
+        L.oracle_fb_ocp_get.argtypes = [C.c_void_p, C.c_int, C.c_char_p, _dp]
+        L.oracle_fb_ocp_set.argtypes = [C.c_void_p, C.c_int, C.c_char_p, _dp]
+        L.oracle_fb_ocp_set_threads.argtypes = [C.c_void_p, C.c_int]
+        assert L.oracle_fb_problem_size() == C.sizeof(FbProblem)
+        self.problem = problem
+        self.cs = contact_sequence
+        self.h = C.c_void_p(L.oracle_fb_ocp_create(C.byref(problem), contact_sequence.h))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.oracle_fb_ocp_destroy(self.h)
+            self.h = None
+
+    def set_threads(self, n):
+        self.L.oracle_fb_ocp_set_threads(self.h, int(n))
+
+    def set_solution(self, name, value):
+        assert self.L.oracle_fb_ocp_set_solution(self.h, name.encode(), _p(_a(value))) == 0
+
+    def set_reference(self, kind, index, q_ref, v_ref):
+        self.L.oracle_fb_ocp_set_reference(self.h, int(kind), int(index), _p(_a(q_ref, NQ)), _p(_a(v_ref, NV)))
+
+    def discretize(self, t):
+        return self.L.oracle_fb_ocp_discretize(self.h, float(t))
+
+    def chain(self):
+        n = 2048
+        kind, index = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        t, dt = np.zeros(n), np.zeros(n)
+        dimf, dimi = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        ip = C.POINTER(C.c_int)
+        m = self.L.oracle_fb_ocp_chain(self.h, kind.ctypes.data_as(ip), index.ctypes.data_as(ip), _p(t), _p(dt),
+                                       dimf.ctypes.data_as(ip), dimi.ctypes.data_as(ip))
+        return [dict(kind=int(kind[e]), index=int(index[e]), t=float(t[e]), dt=float(dt[e]), dimf=int(dimf[e]), dimi=int(dimi[e]))
+                for e in range(m)]
+
+    def init_constraints(self, t):
+        return self.L.oracle_fb_ocp_init_constraints(self.h, float(t))
+
+    def update_solution(self, t, q, v):
+        return self.L.oracle_fb_ocp_update_solution(self.h, float(t), _p(_a(q, NQ)), _p(_a(v, NV)))
+
+    def compute_kkt_residual(self, t, q, v):
+        return self.L.oracle_fb_ocp_compute_kkt_residual(self.h, float(t), _p(_a(q, NQ)), _p(_a(v, NV)))
+
+    def kkt_error(self):
+        return self.L.oracle_fb_ocp_kkt_error(self.h)
+
+    def step_sizes(self):
+        out = np.zeros(2)
+        self.L.oracle_fb_ocp_get_step_sizes(self.h, _p(out))
+        return out
+
+    def get(self, e, name):
+        out = np.zeros(_SIZES.get(name, NV))
+        n = self.L.oracle_fb_ocp_get(self.h, int(e), name.encode(), _p(out))
+        assert n == out.size, (name, n, out.size)
+        return out
+
+    def set(self, e, name, value):
+        assert self.L.oracle_fb_ocp_set(self.h, int(e), name.encode(), _p(_a(value))) == 0

@@ -19,9 +19,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#define HY_MAX_CONTACTS 8
-#define HY_MAX_EVENTS 64
-#define HY_MAX_N 1024
+#include "hybrid_oracle.h"
 
 typedef struct {
   int max_point_contacts;
@@ -72,7 +70,7 @@ static int hy_status_equal(const hy_status_t* a, const hy_status_t* b) {
 }
 
 /* ContactSequence: the reference's deques as arrays with explicit sizes */
-typedef struct oracle_contact_sequence {
+struct oracle_contact_sequence {
   int max_point_contacts, max_num_events;
   hy_status_t default_status;
   int n_status;
@@ -87,7 +85,7 @@ typedef struct oracle_contact_sequence {
   int n_event;
   double event_time[HY_MAX_EVENTS];
   int is_impulse_event[HY_MAX_EVENTS];
-} oracle_contact_sequence_t;
+};
 
 static void hy_status_init(hy_status_t* s, int n) {
   memset(s, 0, sizeof(*s));
@@ -246,14 +244,7 @@ double oracle_cs_lift_time(const oracle_contact_sequence_t* cs, int lift_index) 
 /* countTimeStages, countContactPhase.  A fresh discretiser per call (the reference object keeps arrays of   */
 /* earlier calls; with a shrinking event count it would read those stale entries at index N_impulse).       */
 /* ------------------------------------------------------------------------------------------------------ */
-typedef struct {
-  int N, N_impulse, N_lift, well_defined;
-  double t[HY_MAX_N + 1], dt[HY_MAX_N + 1];
-  int contact_phase[HY_MAX_N + 1], impulse_after[HY_MAX_N + 1], lift_after[HY_MAX_N + 1];
-  int before_impulse_flag[HY_MAX_N + 1], before_lift_flag[HY_MAX_N + 1];
-  int stage_before_impulse[HY_MAX_EVENTS + 1], stage_before_lift[HY_MAX_EVENTS + 1];
-  double t_impulse[HY_MAX_EVENTS + 1], t_lift[HY_MAX_EVENTS + 1], dt_aux[HY_MAX_EVENTS + 1], dt_lift[HY_MAX_EVENTS + 1];
-} oracle_discretization_t;
+/* oracle_discretization_t: hybrid_oracle.h */
 
 static int hy_well_defined(const oracle_discretization_t* d) {
   for (int i = 0; i < d->N; ++i)

@@ -1,0 +1,154 @@
+"""The reference's ANYmal example problems as plain data (used by the oracle tests and the GPU parity tests).
+
+anymal_trotting: examples/anymal/anymal_trotting.cpp:30-196 (cost weights, constraints, contact schedule, initial
+guess); the time-varying configuration reference is TrottingConfigurationSpaceCost::update_q_ref
+(include/idocp/cost/trotting_configuration_space_cost.hpp:126-164), sampled at the time of every stage."""
+import math
+
+import numpy as np
+
+import fb_py
+import hybrid_py
+
+Q_STANDING = np.array([0, 0, 0.4792, 0, 0, 0, 1, -0.1, 0.7, -1.0, -0.1, -0.7, 1.0, 0.1, 0.7, -1.0, 0.1, -0.7, 1.0])
+TOTAL_WEIGHT = 30.475397462000004 * 9.81
+
+
+def trotting_q_ref(t, t_start, t_period, q_standing, step_length, swing):
+    """swing: dict front_swing_knee, hip_swing_knee, front_stance_knee, hip_stance_knee (others unused upstream)."""
+    q = np.array(q_standing, dtype=float)
+    if t > t_start:
+        tau = t - t_start
+        steps = math.floor(tau / t_period)
+        tau_step = tau - steps * t_period
+        rate = tau_step / t_period
+        sin2 = math.sin(0.5 * math.pi * rate)
+        q[0] += (steps + rate) * step_length
+        if steps % 2 == 0:
+            q[9] -= sin2 * swing.get("front_swing_knee", 0.0)
+            q[12] -= sin2 * swing.get("hip_stance_knee", 0.0)
+            q[15] += sin2 * swing.get("front_stance_knee", 0.0)
+            q[18] += sin2 * swing.get("hip_swing_knee", 0.0)
+        else:
+            q[9] += sin2 * swing.get("front_stance_knee", 0.0)
+            q[12] += sin2 * swing.get("hip_swing_knee", 0.0)
+            q[15] -= sin2 * swing.get("front_swing_knee", 0.0)
+            q[18] -= sin2 * swing.get("hip_stance_knee", 0.0)
+    return q
+
+
+def standing_contact_points(fb):
+    z = np.zeros(18)
+    return np.stack([fb.contact(Q_STANDING, z, z, i, 0.05, np.zeros(3))["P"] for i in range(4)])
+
+
+class TrottingProblem:
+    """anymal_trotting.cpp with `steps` impulse phases (the shipped example: 2 steps, T = 1.55, N = 30)."""
+
+    def __init__(self, steps=2):
+        self.step_length, self.t_start, self.t_period = 0.15, 0.5, 0.5
+        self.swing = dict(front_swing_knee=1.7, hip_swing_knee=1.7)
+        self.T = self.t_start + steps * self.t_period + 0.05
+        self.N = 10 + 10 * steps          # the example's table: (T, N) = (1.55, 30), (2.55, 50), (3.55, 70), ...
+        self.steps = steps
+        self.max_num_impulse = steps + 1
+        p = fb_py.FbProblem()
+        p.T, p.N, p.max_num_impulse = self.T, self.N, self.max_num_impulse
+        qw = np.full(18, 10.0)
+        vw = np.array([1.0] * 6 + [0.1] * 12)
+        aw = np.array([0.1] * 6 + [0.01] * 12)
+        for nm in ("q_weight", "qf_weight", "qi_weight"):
+            p.set(nm, qw)
+        for nm in ("v_weight", "vf_weight", "vi_weight"):
+            p.set(nm, vw)
+        p.set("a_weight", aw)
+        p.set("dvi_weight", aw)
+        p.set("f_weight", np.full(12, 0.001))
+        p.set("fi_weight", np.full(12, 0.001))
+        fref = np.tile([0, 0, TOTAL_WEIGHT / 4], 4)
+        p.set("f_ref", fref)
+        p.set("fi_ref", np.zeros(12))          # ContactForceCost::fi_ref_ stays zero (set_f_ref only touches f_ref_)
+        p.set("q_min", np.full(12, -9.42))
+        p.set("q_max", np.full(12, 9.42))
+        p.set("v_max", np.full(12, 15.0))
+        p.set("u_max", np.full(12, 80.0))
+        p.mu, p.barrier, p.fraction_rate = 0.7, 1.0e-4, 0.995
+        for c in range(8):
+            p.enable[c] = 1
+        self.problem = p
+        self.v_ref = np.zeros(18)
+        self.v_ref[0] = self.step_length / self.t_period
+        self.q0 = Q_STANDING.copy()
+        self.v0 = np.zeros(18)
+        self.f_init = np.array([0, 0, 0.25 * TOTAL_WEIGHT])
+
+    def contact_sequence(self, fb):
+        cs = hybrid_py.ContactSequence(4, self.max_num_impulse + 2)
+        pts = standing_contact_points(fb)
+        cs.set_uniform([1, 1, 1, 1], pts)
+        cs.push_back([0, 1, 1, 0], self.t_start, pts)
+        pts = pts.copy()
+        pts[0, 0] += 0.5 * self.step_length
+        pts[3, 0] += 0.5 * self.step_length
+        cs.push_back([1, 0, 0, 1], self.t_start + self.t_period, pts)
+        for i in range(2, self.steps + 1):
+            pts = pts.copy()
+            if i % 2 == 0:
+                pts[1, 0] += self.step_length
+                pts[2, 0] += self.step_length
+                cs.push_back([0, 1, 1, 0], self.t_start + i * self.t_period, pts)
+            else:
+                pts[0, 0] += self.step_length
+                pts[3, 0] += self.step_length
+                cs.push_back([1, 0, 0, 1], self.t_start + i * self.t_period, pts)
+        return cs
+
+    def q_ref(self, t):
+        return trotting_q_ref(t, self.t_start, self.t_period, Q_STANDING, self.step_length, self.swing)
+
+    def make_oracle(self, fb, t=0.0, q0=None, v0=None):
+        """OCPSolver construction + initial guess + initConstraints exactly as the example's main()."""
+        cs = self.contact_sequence(fb)
+        ocp = fb.FbOCP(self.problem, cs)
+        ocp.set_solution("q", self.q0 if q0 is None else q0)
+        ocp.set_solution("v", self.v0 if v0 is None else v0)
+        ocp.set_solution("f", self.f_init)
+        self.set_references(ocp, t)
+        ocp.init_constraints(t)
+        return ocp
+
+    def set_references(self, ocp, t):
+        ocp.discretize(t)
+        for el in ocp.chain():
+            kind = fb_py.K_GRID if el["kind"] == fb_py.K_TERMINAL else el["kind"]
+            ocp.set_reference(kind, el["index"], self.q_ref(el["t"]), self.v_ref)
+
+
+class JumpingProblem(TrottingProblem):
+    """A flight phase: all feet leave at t_lift (a lift stage, dimf = 0 afterwards) and touch down at t_land
+    (an impulse with four contacts), in the style of examples/anymal/anymal_jumping.cpp."""
+
+    def __init__(self, jump_length=0.2, t_lift=0.42, t_land=0.73, T=1.1, N=22):
+        super().__init__(steps=2)
+        self.T, self.N, self.max_num_impulse = T, N, 2
+        self.problem.T, self.problem.N, self.problem.max_num_impulse = T, N, 2
+        self.jump_length, self.t_lift, self.t_land = jump_length, t_lift, t_land
+        self.v_ref = np.zeros(18)
+
+    def contact_sequence(self, fb):
+        cs = hybrid_py.ContactSequence(4, 4)
+        pts = standing_contact_points(fb)
+        cs.set_uniform([1, 1, 1, 1], pts)
+        cs.push_back([0, 0, 0, 0], self.t_lift, pts)
+        pts = pts.copy()
+        pts[:, 0] += self.jump_length
+        cs.push_back([1, 1, 1, 1], self.t_land, pts)
+        return cs
+
+    def q_ref(self, t):
+        q = Q_STANDING.copy()
+        if t > self.t_land:
+            q[0] += self.jump_length
+        elif t > self.t_lift:
+            q[0] += self.jump_length * (t - self.t_lift) / (self.t_land - self.t_lift)
+        return q

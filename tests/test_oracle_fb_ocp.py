@@ -1,0 +1,176 @@
+"""Oracle of the ANYmal OCPSolver path (oracle/fb_ocp.c): identities of the reference's unit tests and convergence of
+its shipped example.  The reference pins no numbers here -- "parity unpinned"."""
+import numpy as np
+import pytest
+
+import anymal_problems as ap
+
+
+@pytest.fixture(scope="module")
+def fb(oracle):
+    import fb_py
+    fb_py.lib()
+    return fb_py
+
+
+def run(ocp, pr, iters, t=0.0, q=None, v=None):
+    q = pr.q0 if q is None else q
+    v = pr.v0 if v is None else v
+    hist = []
+    for _ in range(iters):
+        ocp.compute_kkt_residual(t, q, v)
+        hist.append(ocp.kkt_error())
+        assert ocp.update_solution(t, q, v) == 0
+    ocp.compute_kkt_residual(t, q, v)
+    hist.append(ocp.kkt_error())
+    return np.array(hist)
+
+
+def test_chain_of_the_trotting_example(fb):
+    pr = ap.TrottingProblem()
+    ocp = pr.make_oracle(fb)
+    ch = ocp.chain()
+    kinds = [c["kind"] for c in ch]
+    # N = 30 grid stages + terminal, one lift (t = 0.5), two impulses (t = 1.0, 1.5) with their aux stages
+    assert len(ch) == 30 + 1 + 1 + 2 * 2
+    assert kinds.count(fb.K_LIFT) == 1 and kinds.count(fb.K_IMPULSE) == 2 and kinds.count(fb.K_AUX) == 2
+    # the switching constraint sits two chain elements ahead of every impulse (ocp_linearizer.hxx:139-150)
+    for e, c in enumerate(ch):
+        expect = 6 if (e + 2 < len(ch) and ch[e + 2]["kind"] == fb.K_IMPULSE) else 0
+        assert c["dimi"] == expect
+    assert abs(sum(c["dt"] for c in ch) - pr.T) < 1e-12
+
+
+def test_trotting_example_converges(fb):
+    # examples/anymal/anymal_trotting.cpp: ocpbenchmarker::Convergence(ocp_solver, t, q, v, 25, false)
+    pr = ap.TrottingProblem()
+    ocp = pr.make_oracle(fb)
+    hist = run(ocp, pr, 25)
+    assert hist[0] > 50 and hist[-1] < 1e-9
+    assert np.all(np.isfinite(hist))
+    ch = ocp.chain()
+    qT = ocp.get(len(ch) - 1, "q")
+    assert 0.05 < qT[0] < 0.40 and abs(qT[2] - 0.4792) < 0.05     # walked forward, still upright
+    for e, c in enumerate(ch[:-1]):
+        assert np.abs(ocp.get(e, "Fq")).max() < 1e-9 and np.abs(ocp.get(e, "Fv")).max() < 1e-9
+        assert np.abs(ocp.get(e, "IDC")[:18 + c["dimf"]]).max() < 1e-8
+        assert np.abs(ocp.get(e, "P")[:c["dimi"]]).max(initial=0.0) < 1e-9
+        f = ocp.get(e, "f").reshape(4, 3)
+        if c["kind"] != fb.K_IMPULSE:
+            assert np.abs(ocp.get(e, "u")).max() <= 80.0
+    # friction cone on the active feet of a mid-stance stage
+    f = ocp.get(3, "f").reshape(4, 3)
+    assert np.all(f[:, 2] > 0) and np.all(np.abs(f[:, :2]) <= 0.7 / np.sqrt(2) * f[:, 2:3] + 1e-9)
+    assert abs(f[:, 2].sum() - ap.TOTAL_WEIGHT) < 0.2 * ap.TOTAL_WEIGHT
+
+
+def test_expanded_direction_solves_the_linearised_contact_dynamics(fb):
+    # test/ocp/contact_dynamics_test.cpp: the condensed/expanded (da, df) satisfy the linearised ID and Baumgarte rows
+    pr = ap.TrottingProblem()
+    ocp = pr.make_oracle(fb)
+    run(ocp, pr, 2)
+    # one more update: every stage keeps the linearisation data of the point the direction was computed at
+    ocp.update_solution(0.0, pr.q0, pr.v0)
+    for e, c in enumerate(ocp.chain()[:-1]):
+        dimf = c["dimf"]
+        n = 18 + dimf
+        dIDC = ocp.get(e, "dIDCdqv").reshape(30, 36)[:n]
+        M = ocp.get(e, "Mm").reshape(18, 18)
+        J = ocp.get(e, "dCda").reshape(12, 18)[:dimf]
+        IDC = ocp.get(e, "IDC")[:n]
+        dx = np.concatenate([ocp.get(e, "dq"), ocp.get(e, "dv")])
+        daf = ocp.get(e, "daf")[:n]
+        da, df = daf[:18], daf[18:]
+        du_full = np.zeros(18)
+        if c["kind"] != fb.K_IMPULSE:
+            du_full[6:] = ocp.get(e, "du")
+        lhs_id = dIDC[:18] @ dx + M @ da - J.T @ df - du_full + IDC[:18]
+        lhs_c = dIDC[18:] @ dx + J @ da + IDC[18:]
+        scale = max(1.0, np.abs(IDC).max())
+        assert np.abs(lhs_id).max() < 1e-8 * scale, (e, c, np.abs(lhs_id).max())
+        assert np.abs(lhs_c).max() < 1e-8 * scale, (e, c)
+        K = np.zeros((n, n))
+        K[:18, :18] = M
+        K[:18, 18:] = J.T
+        K[18:, :18] = J
+        assert np.allclose(ocp.get(e, "MJtJinv").reshape(30, 30)[:n, :n] @ K, np.eye(n), atol=1e-8)
+
+
+def test_riccati_factorisation_identities(fb):
+    # test/ocp/split_riccati_factorizer_test.cpp: P symmetric, K = -G^-1 H^T on unconstrained stages,
+    # forward recursion reproduces the linearised state equation
+    pr = ap.TrottingProblem()
+    ocp = pr.make_oracle(fb)
+    run(ocp, pr, 1)
+    ocp.update_solution(0.0, pr.q0, pr.v0)
+    ch = ocp.chain()
+    for e, c in enumerate(ch[:-1]):
+        Pqq, Pvv = ocp.get(e, "Pqq").reshape(18, 18), ocp.get(e, "Pvv").reshape(18, 18)
+        if c["dimi"] == 0:
+            assert np.array_equal(Pqq, Pqq.T) and np.array_equal(Pvv, Pvv.T)
+        else:   # the two Schur corrections are subtracted after the symmetrisation (split_riccati_factorizer.hxx:88-96)
+            assert np.allclose(Pqq, Pqq.T, rtol=1e-12, atol=1e-9) and np.allclose(Pvv, Pvv.T, rtol=1e-12, atol=1e-9)
+        if c["kind"] == fb.K_IMPULSE:
+            continue
+        G = ocp.get(e, "Quu").reshape(18, 18)[6:, 6:]
+        H = ocp.get(e, "Qxu").reshape(36, 18)[:, 6:]
+        K = ocp.get(e, "K").reshape(12, 36)
+        assert np.all(np.linalg.eigvalsh(0.5 * (G + G.T)) > 0)
+        if c["dimi"] == 0:
+            assert np.allclose(G @ K, -H.T, rtol=1e-9, atol=1e-9 * np.abs(H).max())
+        else:
+            # constrained stage (split_riccati_factorizer.hxx:55-100): [G D^T; D 0] [K; M] = -[H^T; Phix]
+            D = ocp.get(e, "Phiu").reshape(12, 12)[:c["dimi"]]
+            Mx = ocp.get(e, "cM").reshape(12, 36)[:c["dimi"]]
+            Phix = ocp.get(e, "Phix").reshape(12, 36)[:c["dimi"]]
+            assert np.allclose(G @ K + D.T @ Mx, -H.T, rtol=1e-8, atol=1e-8 * np.abs(H).max())
+            assert np.allclose(D @ K, -Phix, rtol=1e-8, atol=1e-8 * max(1, np.abs(Phix).max()))
+            # the direction keeps the linearised switching constraint: Phix dx + Phiu du + P = 0
+            dx = np.concatenate([ocp.get(e, "dq"), ocp.get(e, "dv")])
+            r = Phix @ dx + D @ ocp.get(e, "du") + ocp.get(e, "P")[:c["dimi"]]
+            assert np.abs(r).max() < 1e-9
+
+
+def test_threads_do_not_change_bits(fb):
+    pr = ap.TrottingProblem()
+    a, b = pr.make_oracle(fb), pr.make_oracle(fb)
+    b.set_threads(4)
+    ha, hb = run(a, pr, 4), run(b, pr, 4)
+    assert np.array_equal(ha, hb)
+    for e in range(len(a.chain())):
+        assert np.array_equal(a.get(e, "q"), b.get(e, "q")) and np.array_equal(a.get(e, "lmd"), b.get(e, "lmd"))
+
+
+def test_four_step_trot_and_perturbed_initial_state(fb):
+    pr = ap.TrottingProblem(steps=4)
+    rng = np.random.default_rng(0)
+    dq = np.concatenate([rng.uniform(-0.01, 0.01, 3), rng.uniform(-0.02, 0.02, 3), rng.uniform(-0.02, 0.02, 12)])
+    q0 = fb.integrate(pr.q0, dq)
+    v0 = rng.uniform(-0.1, 0.1, 18)
+    ocp = pr.make_oracle(fb, q0=q0, v0=v0)
+    hist = run(ocp, pr, 40, q=q0, v=v0)
+    assert hist[-1] < 1e-8, hist[-5:]
+
+
+def test_flight_phase_lift_stage_and_four_foot_touch_down(fb):
+    # a flight phase (dimf = 0), a lift stage carrying the switching constraint of a 12-dimensional touch-down.
+    # Gauss-Newton without line search converges slowly here, as upstream does (anymal_jumping.cpp: 155 iterations).
+    pr = ap.JumpingProblem(0.1, 0.6, 0.75, 1.3, 26)
+    for nm, w in (("q_weight", [1, 1, 1] + [10] * 15), ("v_weight", [0.01] * 3 + [0.1] * 15), ("a_weight", [0.01] * 18)):
+        pr.problem.set(nm, w)
+        pr.problem.set({"q_weight": "qf_weight", "v_weight": "vf_weight", "a_weight": "dvi_weight"}[nm], w)
+        if nm != "a_weight":
+            pr.problem.set({"q_weight": "qi_weight", "v_weight": "vi_weight"}[nm], w)
+    ocp = pr.make_oracle(fb)
+    ch = ocp.chain()
+    kinds = [c["kind"] for c in ch]
+    assert kinds.count(fb.K_LIFT) == 1 and kinds.count(fb.K_IMPULSE) == 1
+    assert any(c["dimf"] == 0 for c in ch)
+    lift = kinds.index(fb.K_LIFT)
+    assert sum(c["dimi"] == 12 for c in ch) == 1
+    hist = run(ocp, pr, 80)
+    assert np.all(np.isfinite(hist)) and hist[-1] < 2e-2 and hist[-1] < hist[-10] < hist[-20]
+    # the feet are off the ground during the flight and land on the shifted contact points
+    imp = kinds.index(fb.K_IMPULSE)
+    P = np.stack([fb.contact(ocp.get(imp, "q"), np.zeros(18), np.zeros(18), i, 0.05, np.zeros(3))["P"] for i in range(4)])
+    assert np.allclose(P[:, 0], ap.standing_contact_points(fb)[:, 0] + 0.1, atol=5e-3)
