@@ -9,3 +9,5 @@ from .solvers import (UnOCPSolver, UnParNMPCSolver, benchmark_problem, config_sp
 
 __version__ = "0.1"
 from .hybrid import ContactSequence, OCPDiscretizer  # noqa: F401,E402
+from .ocp_solver import OCPSolver  # noqa: F401,E402
+from .capi import FbProblem  # noqa: F401,E402

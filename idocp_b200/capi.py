@@ -68,6 +68,23 @@ class OCPDiscretization(C.Structure):
     ]
 
 
+FB_NUM_CONSTRAINTS = 8
+
+
+class FbProblem(C.Structure):
+    """idocp_b200_fb_problem (include/idocp_b200.h): OCPSolver problem data of the floating-base robot."""
+    _fields_ = [
+        ("T", C.c_double), ("N", C.c_int), ("max_num_impulse", C.c_int),
+        ("q_weight", C.c_double * 18), ("v_weight", C.c_double * 18), ("a_weight", C.c_double * 18),
+        ("qf_weight", C.c_double * 18), ("vf_weight", C.c_double * 18), ("qi_weight", C.c_double * 18),
+        ("vi_weight", C.c_double * 18), ("dvi_weight", C.c_double * 18),
+        ("f_weight", C.c_double * 12), ("f_ref", C.c_double * 12), ("fi_weight", C.c_double * 12), ("fi_ref", C.c_double * 12),
+        ("q_min", C.c_double * 12), ("q_max", C.c_double * 12), ("v_max", C.c_double * 12), ("u_max", C.c_double * 12),
+        ("mu", C.c_double), ("barrier", C.c_double), ("fraction_rate", C.c_double),
+        ("enable", C.c_int * FB_NUM_CONSTRAINTS),
+    ]
+
+
 class Idocp_b200Error(RuntimeError):
     pass
 
@@ -88,6 +105,11 @@ EXPORTS = [
     "idocp_b200_contact_sequence_counts", "idocp_b200_contact_sequence_get_phase",
     "idocp_b200_contact_sequence_get_impulse", "idocp_b200_contact_sequence_get_lift_time",
     "idocp_b200_discretize_ocp", "idocp_b200_last_error", "idocp_b200_version",
+    "idocp_b200_fb_create", "idocp_b200_fb_destroy", "idocp_b200_fb_set_solution", "idocp_b200_fb_set_cost_reference",
+    "idocp_b200_fb_discretize", "idocp_b200_fb_init_constraints", "idocp_b200_fb_update_solution",
+    "idocp_b200_fb_compute_kkt_residual", "idocp_b200_fb_kkt_error", "idocp_b200_fb_get_step_sizes", "idocp_b200_fb_get",
+    "idocp_b200_fb_sync", "idocp_b200_fb_launch_count", "idocp_b200_fb_stream", "idocp_b200_fb_set_profiling",
+    "idocp_b200_fb_get_profile", "idocp_b200_fb_record_bytes",
 ]
 
 
@@ -145,6 +167,22 @@ class Library:
         L.idocp_b200_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.idocp_b200_get_profile.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), _dp,
                                              C.POINTER(C.c_longlong)]
+        L.idocp_b200_fb_create.argtypes = [C.POINTER(FbProblem), C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.idocp_b200_fb_destroy.argtypes = [C.c_void_p]
+        L.idocp_b200_fb_set_solution.argtypes = [C.c_void_p, C.c_char_p, _dp, C.c_int]
+        L.idocp_b200_fb_set_cost_reference.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp]
+        L.idocp_b200_fb_discretize.argtypes = [C.c_void_p, C.c_double, C.c_int, _ip, _ip, _dp, _dp, _ip, _ip]
+        L.idocp_b200_fb_init_constraints.argtypes = [C.c_void_p, C.c_double]
+        L.idocp_b200_fb_update_solution.argtypes = [C.c_void_p, C.c_double, _dp, _dp, C.c_int]
+        L.idocp_b200_fb_compute_kkt_residual.argtypes = [C.c_void_p, C.c_double, _dp, _dp]
+        L.idocp_b200_fb_kkt_error.argtypes = [C.c_void_p, _dp]
+        L.idocp_b200_fb_get_step_sizes.argtypes = [C.c_void_p, _dp]
+        L.idocp_b200_fb_get.argtypes = [C.c_void_p, C.c_int, C.c_char_p, _dp]
+        L.idocp_b200_fb_sync.argtypes = [C.c_void_p]
+        L.idocp_b200_fb_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
+        L.idocp_b200_fb_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.idocp_b200_fb_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.idocp_b200_fb_get_profile.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), _dp, C.POINTER(C.c_longlong)]
         self.L = L
 
     def check(self, rc):

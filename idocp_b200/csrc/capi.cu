@@ -7,7 +7,9 @@
 #include <cuda_runtime.h>
 #endif
 
+#include <array>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -18,6 +20,7 @@
 #include "unocp_kernels.cuh"
 #include "line_search_kernels.cuh"
 #include "unparnmpc_kernels.cuh"
+#include "fb_kernels.cuh"
 
 using namespace idocp_b200;
 
@@ -51,23 +54,15 @@ static int fail(int code, const std::string& msg) {
   } while (0)
 
 enum KernelClass { KC_LINEARIZE = 0, KC_RICCATI, KC_EXPAND, KC_UPDATE, KC_KKT, KC_MISC, KC_PARNMPC_COARSE,
-                   KC_PARNMPC_CORR, KC_LINESEARCH, KC_NUM };
+                   KC_PARNMPC_CORR, KC_LINESEARCH, KC_FB_LINEARIZE, KC_FB_RICCATI, KC_FB_FORWARD, KC_FB_EXPAND, KC_FB_UPDATE,
+                   KC_FB_KKT, KC_NUM };
 static const char* kKernelClassNames[KC_NUM] = {"linearize", "riccati", "expand", "update", "kkt", "misc",
-                                                "parnmpc_coarse", "parnmpc_correction", "line_search"};
+                                                "parnmpc_coarse", "parnmpc_correction", "line_search", "fb_linearize",
+                                                "fb_riccati_backward", "fb_riccati_forward", "fb_expand", "fb_update", "fb_kkt"};
 
-struct idocp_b200_solver {
-  idocp_b200_problem prob;
-  int kind = 0, device = 0;
-  int B = 0, Bp = 0, N = 0;
+// launch bookkeeping shared by every solver handle: stream, launch counter, per-kernel-class event timing
+struct LaunchProfiler {
   cudaStream_t stream = nullptr;
-  DevProblem* d_prob = nullptr;
-  DevProblem h_prob;
-  Layout L;
-  std::vector<void*> allocs;
-  double* d_q0 = nullptr;
-  double* d_v0 = nullptr;
-  double* d_stage = nullptr;   // staging buffer for getters / setters
-  size_t stage_doubles = 0;
   long long launches = 0;
   // profiling: 0 off, 1 = CUDA events recorded around every launch on the launching stream and
   // resolved lazily in get_profile (no host synchronisation inside the timed region)
@@ -78,11 +73,7 @@ struct idocp_b200_solver {
   double prof_ms[KC_NUM] = {0};
   long long prof_calls[KC_NUM] = {0};
   cudaEvent_t cur_e0 = nullptr;
-  // UnParNMPC extras
-  ParNMPCLayout PL;
-  // line search (allocated on first use)
-  LineSearchLayout LS;
-  bool ls_ready = false;
+  std::vector<void*> allocs;
 
   cudaEvent_t take_event() {
     if (!event_pool.empty()) { cudaEvent_t e = event_pool.back(); event_pool.pop_back(); return e; }
@@ -126,6 +117,25 @@ struct idocp_b200_solver {
     *p = static_cast<T*>(q);
     return 0;
   }
+};
+
+struct idocp_b200_solver : LaunchProfiler {
+  idocp_b200_problem prob;
+  int kind = 0, device = 0;
+  int B = 0, Bp = 0, N = 0;
+  DevProblem* d_prob = nullptr;
+  DevProblem h_prob;
+  Layout L;
+  double* d_q0 = nullptr;
+  double* d_v0 = nullptr;
+  double* d_stage = nullptr;   // staging buffer for getters / setters
+  size_t stage_doubles = 0;
+  // UnParNMPC extras
+  ParNMPCLayout PL;
+  // line search (allocated on first use)
+  LineSearchLayout LS;
+  bool ls_ready = false;
+
   int stage_offset() const { return kind == IDOCP_B200_SOLVER_UNPARNMPC ? 1 : 0; }
 };
 
@@ -803,3 +813,4 @@ extern "C" int idocp_b200_get_profile(idocp_b200_solver* h, int cap, const char*
 }
 
 #include "hybrid_capi.inc"
+#include "fb_capi.inc"

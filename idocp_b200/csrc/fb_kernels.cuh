@@ -1,0 +1,1705 @@
+// fb_kernels.cuh -- batched OCPSolver Newton step for the floating-base robot (ANYmal), SURVEY.md §8 row a12.
+//
+// Reference path (file:line):
+//   OCPSolver::updateSolution / computeKKTResidual / KKTError       src/ocp/ocp_solver.cpp:67-92,202-213
+//   OCPLinearizer::runParallel, integrateSolution                   include/idocp/ocp/ocp_linearizer.hxx:113-228, src/ocp/ocp_linearizer.cpp:140-221
+//   SplitOCP / ImpulseSplitOCP / TerminalOCP ::linearizeOCP         ocp/split_ocp.hxx:58-134, impulse/impulse_split_ocp.hxx:47-72, ocp/terminal_ocp.hxx:50-66
+//   ContactDynamics, ImpulseDynamicsForwardEuler                    ocp/contact_dynamics.hxx:48-200, impulse/impulse_dynamics_forward_euler.hxx:25-150
+//   stateequation::linearize/condenseForwardEuler (SE(3) blocks)    ocp/state_equation.hxx:11-110
+//   ForwardSwitchingConstraint                                      ocp/forward_switching_constraint.hxx:27-68
+//   RiccatiRecursionSolver, SplitRiccatiFactorizer (+ constrained)  src/ocp/riccati_recursion_solver.cpp:48-251, ocp/split_riccati_factorizer.hxx:36-148
+//   Robot::RNEA/RNEADerivatives/computeMJtJinv/Baumgarte*           robot/robot.hxx:246-350,444-615, robot/point_contact.hxx:67-205
+//
+// Mapping: one CTA per (instance, stage of the hybrid chain) for the stage-parallel kernels, one CTA per instance
+// for the serial Riccati sweeps.  Every working matrix of a stage lives in shared memory; every output element of a
+// dense product is one ascending-index fma chain owned by one thread (fb_mm), so the result does not depend on the
+// thread mapping and is bit-identical to the serial oracle.  Records in HBM are arrays of structs indexed
+// [slot][instance]: a CTA reads and writes contiguous, aligned runs.
+#pragma once
+#include "fb_math.cuh"
+
+namespace idocp_b200 {
+
+enum { FB_GRID = 0, FB_IMPULSE = 1, FB_AUX = 2, FB_LIFT = 3, FB_TERMINAL = 4 };
+enum { FBC_POS_LO = 0, FBC_POS_UP, FBC_VEL_LO, FBC_VEL_UP, FBC_TRQ_LO, FBC_TRQ_UP, FBC_FRICTION, FBC_IMPULSE_FRICTION, FBC_NCOMP };
+#define FB_NCON 112   /* 6 x 12 joint limits, 20 friction-cone rows, 20 impulse friction-cone rows */
+__host__ __device__ inline int fbc_offset(int c) { return c < FBC_FRICTION ? 12 * c : (c == FBC_FRICTION ? 72 : 92); }
+__host__ __device__ inline int fbc_dim(int c) { return c < FBC_FRICTION ? 12 : 20; }
+
+struct FbDevProblem {
+  double T;
+  int N, max_num_impulse;
+  double q_weight[FB_NV], v_weight[FB_NV], a_weight[FB_NV], qf_weight[FB_NV], vf_weight[FB_NV], qi_weight[FB_NV], vi_weight[FB_NV],
+      dvi_weight[FB_NV];
+  double f_weight[FB_MAXF], f_ref[FB_MAXF], fi_weight[FB_MAXF], fi_ref[FB_MAXF];
+  double q_min[FB_NU], q_max[FB_NU], v_max[FB_NU], u_max[FB_NU];
+  double mu, barrier, fraction_rate;
+  int enable[FBC_NCOMP];
+};
+
+// one element of the hybrid chain (shared by the whole batch)
+struct FbElem {
+  int kind, slot, next_slot, prev_slot, sw, dimf, dimi, pad;
+  int active[FB_NC], imp_active[FB_NC], cactive[FBC_NCOMP];
+  double t, dt, dt_next;
+  double cpoints[FB_MAXF], ipoints[FB_MAXF], ref_q[FB_NQ], ref_v[FB_NV];
+};
+
+// ---- HBM records, [slot][instance] ----
+struct FbSol {   // SplitSolution / ImpulseSplitSolution (a = dv at an impulse) + slack / dual of ConstraintsData
+  double lmd[FB_NV], gmm[FB_NV], q[FB_NQ], v[FB_NV], a[FB_NV], u[FB_NU], beta[FB_NV], nu_passive[FB_NPASS], f[FB_MAXF], mu[FB_MAXF],
+      xi[FB_MAXF];
+  double slack[FB_NCON], dual[FB_NCON];
+};
+struct FbDir {   // SplitDirection + the direction part of ConstraintsData
+  double dlmd[FB_NV], dgmm[FB_NV], dq[FB_NV], dv[FB_NV], du[FB_NU], daf[FB_NVF], dbetamu[FB_NVF], dnu_passive[FB_NPASS], dxi[FB_MAXF];
+  double residual[FB_NCON], duality[FB_NCON], dslack[FB_NCON], ddual[FB_NCON];
+  double max_primal, max_dual, kkt_sq, info;
+};
+struct FbKKT {   // condensed SplitKKTMatrix / SplitKKTResidual + SplitStateConstraintJacobian
+  double Qxx[FB_NX * FB_NX], Qxu[FB_NX * FB_NV], Quu[FB_NV * FB_NV];
+  double Fqq6[36], Fqv6[36], Fqq_prev_inv[36], Fvq[FB_NV * FB_NV], Fvv[FB_NV * FB_NV], Fvu[FB_NV * FB_NU];
+  double lq[FB_NV], lv[FB_NV], lu[FB_NU], lu_passive[FB_NPASS], Fq[FB_NV], Fv[FB_NV];
+  double Phix[FB_MAXF * FB_NX], Phiu[FB_MAXF * FB_NU], P[FB_MAXF];
+};
+struct FbExp {   // ContactDynamicsData needed by the expansion
+  double MJtJinv[FB_NVF * FB_NVF], MJ_dIDC[FB_NVF * FB_NX], MJ_IDC[FB_NVF], Qafqv[FB_NVF * FB_NX], Qafu[FB_NVF * FB_NV], laf[FB_NVF];
+};
+struct FbRic {   // LQRStateFeedbackPolicy, SplitRiccatiFactorization, SplitConstrainedRiccatiFactorization
+  double K[FB_NU * FB_NX], k[FB_NU], Pqq[FB_NV * FB_NV], Pqv[FB_NV * FB_NV], Pvv[FB_NV * FB_NV], sq[FB_NV], sv[FB_NV], cM[FB_MAXF * FB_NX],
+      cm[FB_MAXF];
+};
+
+struct FbArrays {
+  int B, n_slots, n_elems;
+  const FbDevProblem* prob;
+  const FbElem* elems;
+  FbSol* sol;
+  FbDir* dir;
+  FbKKT* kkt;
+  FbExp* exp;
+  FbRic* ric;
+  const double* q0;   // [B][19]
+  const double* v0;   // [B][18]
+  double* steps;      // [B][2]
+  double* kkt_err;    // [B]
+};
+
+#define FB_FOR(i, n) for (int i = threadIdx.x; i < (n); i += blockDim.x)
+enum { FBM_SET = 0, FBM_ADD = 1, FBM_SUB = 2 };
+
+// C (m x n, ldc) {=, +=, -=} A (m x k) B (k x n): one ascending-k fma chain per element, elements dealt to threads.
+// The caller separates dependent calls with __syncthreads().
+template <int MODE>
+__device__ __forceinline__ void fb_mm(int m, int n, int k, const double* __restrict__ A, int ars, int acs, const double* __restrict__ B,
+                                      int brs, int bcs, double* C, int ldc) {
+  const int total = m * n;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int i = e / n, j = e - i * n;
+    const double* a = A + i * ars;
+    const double* b = B + j * bcs;
+    double acc;
+    int l0 = 0;
+    if (MODE == FBM_SET) {
+      if (k == 0) { C[i * ldc + j] = 0.0; continue; }
+      acc = a[0] * b[0];
+      l0 = 1;
+    } else {
+      acc = C[i * ldc + j];
+    }
+    if (MODE == FBM_SUB)
+      for (int l = l0; l < k; ++l) acc = fma(-a[l * acs], b[l * brs], acc);
+    else
+      for (int l = l0; l < k; ++l) acc = fma(a[l * acs], b[l * brs], acc);
+    C[i * ldc + j] = acc;
+  }
+}
+template <int MODE>
+__device__ __forceinline__ void fb_mv(int m, int k, const double* A, int ars, int acs, const double* x, double* y) {
+  fb_mm<MODE>(m, 1, k, A, ars, acs, x, 1, 1, y, 1);
+}
+__device__ inline double fb_sqnorm(const double* x, int n) {
+  double acc = 0.0;
+  for (int i = 0; i < n; ++i) acc = fma(x[i], x[i], acc);
+  return acc;
+}
+__device__ inline void fb_copy(double* dst, const double* src, int n) { FB_FOR(i, n) dst[i] = src[i]; }
+__device__ inline void fb_zero(double* dst, int n) { FB_FOR(i, n) dst[i] = 0.0; }
+
+// Cholesky of an n x n matrix (n <= 32) by ONE warp: lane i owns row i.  L[j*ldl + i] = L_ij (i >= j), rd[k] = 1/L_kk.
+// Same per-element chains as the serial left-looking form.  Call with all lanes of warp 0; others skip.
+__device__ inline int fb_llt_warp(const double* A, int lda, int n, double* L, int ldl, double* rd) {
+  const int lane = threadIdx.x & 31;
+  int info = 0;
+  for (int k = 0; k < n; ++k) {
+    if (lane == k) {
+      double x = A[k * lda + k];
+      for (int j = 0; j < k; ++j) x = fma(-L[j * ldl + k], L[j * ldl + k], x);
+      if (!(x > 0.0)) info = k + 1;
+      x = sqrt(x);
+      L[k * ldl + k] = x;
+      rd[k] = 1.0 / x;
+    }
+    __syncwarp();
+    if (lane > k && lane < n) {
+      double y = A[lane * lda + k];
+      for (int j = 0; j < k; ++j) y = fma(-L[j * ldl + lane], L[j * ldl + k], y);
+      L[k * ldl + lane] = y * rd[k];
+    }
+    __syncwarp();
+  }
+  // first failing pivot over the lanes
+  for (int k = 0; k < n; ++k) {
+    const int v = __shfl_sync(0xffffffffu, info, k);
+    if (v) return v;
+  }
+  return 0;
+}
+// x := (L L^T)^-1 x, one right-hand side with stride incx, executed by the calling thread
+__device__ inline void fb_llt_solve(const double* L, int ldl, const double* rd, int n, double* x, int incx) {
+  for (int i = 0; i < n; ++i) {
+    double y = x[i * incx];
+    for (int j = 0; j < i; ++j) y = fma(-L[j * ldl + i], x[j * incx], y);
+    x[i * incx] = y * rd[i];
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double y = x[i * incx];
+    for (int j = i + 1; j < n; ++j) y = fma(-L[i * ldl + j], x[j * incx], y);
+    x[i * incx] = y * rd[i];
+  }
+}
+
+// ---- friction cone (constraints/linearized_friction_cone.hpp:72-85, .cpp:25-29) ----
+__device__ inline void fb_friction_residual(double mu, const double* f, double* r) {
+  const double s = mu * f[2] / 1.41421356237309514547e+00;
+  r[0] = -f[2];
+  r[1] = f[0] - s;
+  r[2] = -f[0] - s;
+  r[3] = f[1] - s;
+  r[4] = -f[1] - s;
+}
+__device__ inline double fb_friction_jac(double mu, int e, int x) {
+  const double m = -(mu / 1.41421356237309514547e+00);
+  if (x == 2) return e == 0 ? -1.0 : m;
+  if (x == 0) return e == 1 ? 1.0 : (e == 2 ? -1.0 : 0.0);
+  return e == 3 ? 1.0 : (e == 4 ? -1.0 : 0.0);
+}
+
+// =====================================================================================================
+// shared-memory workspace of the linearisation kernel
+// =====================================================================================================
+struct FbLinWork {
+  // inputs
+  double lmd[FB_NV], gmm[FB_NV], q[FB_NQ], v[FB_NV], a[FB_NV], u[FB_NU], beta[FB_NV], nu_passive[FB_NPASS], f[FB_MAXF], mu[FB_MAXF],
+      xi[FB_MAXF], slack[FB_NCON], dual[FB_NCON];
+  double nlmd[FB_NV], ngmm[FB_NV], nq[FB_NQ], nv[FB_NV], qprev[FB_NQ];
+  double fm[FB_MAXF], mu_stack[FB_MAXF];
+  // kinematics (world frame)
+  double R[FB_NB][9], p[FB_NB][3], S[FB_NV][6], ov[FB_NB][6], oa[FB_NB][6], dV[FB_NV][6];
+  // dynamics
+  fb_inertia_t Y[FB_NB];
+  fb_dinertia_t D[FB_NB];
+  double F[FB_NB][6], agf[FB_NB][6];
+  double U[FB_NV][6], W[FB_NV][6], dFv[FB_NV][6], dFq[FB_NV][6], dFqa[FB_NV][6], dAq[FB_NV][6], dAv[FB_NV][6];
+  // frames (one set per contact, processed by its own warp)
+  double frP[FB_NC][3], frV[FB_NC][6], frA[FB_NC][6];
+  // SE(3) blocks
+  double qdiff[FB_NV], J6c[36], Fqq_prev6[36], Fqq_inv[36], tmp6[36], fq6[6], dqv[FB_NV], q2[FB_NQ], Jq6[36], Jv6[36];
+  // SplitKKTResidual
+  double lq[FB_NV], lv[FB_NV], la[FB_NV], lf[FB_MAXF], lu_passive[FB_NPASS], lu[FB_NU], Fq[FB_NV], Fv[FB_NV], P[FB_MAXF];
+  // ContactDynamicsData
+  double IDC[FB_NVF], dIDCdqv[FB_NVF * FB_NX], Mm[FB_NV * FB_NV], dCda[FB_MAXF * FB_NV];
+  double L[FB_NV * FB_NV], rd[FB_NV], Minv[FB_NV * FB_NV], JMi[FB_MAXF * FB_NV], Sm[FB_MAXF * FB_MAXF], Ls[FB_MAXF * FB_MAXF], rds[FB_MAXF],
+      Si[FB_MAXF * FB_MAXF];
+  double MJtJinv[FB_NVF * FB_NVF], MJ_dIDC[FB_NVF * FB_NX], MJ_IDC[FB_NVF], Qafqv[FB_NVF * FB_NX], Qafu[FB_NVF * FB_NV], laf[FB_NVF];
+  // SplitKKTMatrix
+  double Qxx[FB_NX * FB_NX], Qxu[FB_NX * FB_NV], Quu[FB_NV * FB_NV], Qaa[FB_NV], Qff[FB_MAXF * FB_MAXF];
+  double Fqq6[36], Fqv6[36], Fqq_prev_inv[36], Fvq[FB_NV * FB_NV], Fvv[FB_NV * FB_NV], Fvu[FB_NV * FB_NU];
+  // switching constraint
+  double Pq[FB_MAXF * FB_NV], Phix[FB_MAXF * FB_NX], Phia[FB_MAXF * FB_NV], Phiu[FB_MAXF * FB_NU], PJv[FB_MAXF * FB_NV];
+  // constraints
+  double residual[FB_NCON], duality[FB_NCON];
+  double t18[FB_NV], tf[FB_MAXF], part[8];
+  int info;
+};
+
+// ---- cooperative forward kinematics: base by thread 0, then one thread per leg (robot.hxx:193-230) ----
+// v, a may be nullptr (zero).  Ends with a __syncthreads().
+__device__ inline void fb_forward_kinematics(FbLinWork& w, const double* q, const double* v, const double* a) {
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    fb_quat_to_R(q + 3, w.R[0]);
+    for (int i = 0; i < 3; ++i) w.p[0][i] = q[i];
+    for (int c = 0; c < 3; ++c) {
+      const double e[3] = {w.R[0][c], w.R[0][3 + c], w.R[0][6 + c]};
+      for (int i = 0; i < 3; ++i) { w.S[c][i] = e[i]; w.S[c][3 + i] = 0.0; }
+      fb_cross(w.p[0], e, w.S[3 + c]);
+      for (int i = 0; i < 3; ++i) w.S[3 + c][3 + i] = e[i];
+    }
+    for (int i = 0; i < 6; ++i) {
+      double accv = 0.0, acca = 0.0;
+      if (v) { accv = w.S[0][i] * v[0]; for (int c = 1; c < 6; ++c) accv = fma(w.S[c][i], v[c], accv); }
+      if (a) { acca = w.S[0][i] * a[0]; for (int c = 1; c < 6; ++c) acca = fma(w.S[c][i], a[c], acca); }
+      w.ov[0][i] = accv;
+      w.oa[0][i] = acca;
+    }
+    for (int c = 0; c < 6; ++c)
+      for (int i = 0; i < 6; ++i) w.dV[c][i] = 0.0;
+  }
+  __syncthreads();
+  if (tid < 4) {
+    for (int jj = 0; jj < 3; ++jj) {
+      const int j = 3 * tid + jj;
+      const int b = 1 + j, pb = fb_parent_body(b), c = 6 + j;
+      const double* Rp = w.R[pb];
+      double* Rb = w.R[b];
+      double sn, cs;
+      canon_sincos(q[7 + j], &sn, &cs);
+      if (ANYMAL_JOINT_AXIS[j] == 0) {
+        for (int i = 0; i < 3; ++i) {
+          Rb[3 * i] = Rp[3 * i];
+          Rb[3 * i + 1] = fma(cs, Rp[3 * i + 1], sn * Rp[3 * i + 2]);
+          Rb[3 * i + 2] = fma(cs, Rp[3 * i + 2], -(sn * Rp[3 * i + 1]));
+        }
+      } else {
+        for (int i = 0; i < 3; ++i) {
+          Rb[3 * i] = fma(cs, Rp[3 * i], -(sn * Rp[3 * i + 2]));
+          Rb[3 * i + 1] = Rp[3 * i + 1];
+          Rb[3 * i + 2] = fma(cs, Rp[3 * i + 2], sn * Rp[3 * i]);
+        }
+      }
+      const double* P = ANYMAL_JOINT_P[j];
+      for (int i = 0; i < 3; ++i) w.p[b][i] = fma(Rp[3 * i + 2], P[2], fma(Rp[3 * i + 1], P[1], fma(Rp[3 * i], P[0], w.p[pb][i])));
+      const int ax = ANYMAL_JOINT_AXIS[j];
+      const double e[3] = {Rb[ax], Rb[3 + ax], Rb[6 + ax]};
+      fb_cross(w.p[b], e, w.S[c]);
+      for (int i = 0; i < 3; ++i) w.S[c][3 + i] = e[i];
+      fb_mxm(w.ov[pb], w.S[c], w.dV[c]);
+      const double qd = v ? v[c] : 0.0, qdd = a ? a[c] : 0.0;
+      for (int i = 0; i < 6; ++i) {
+        w.ov[b][i] = fma(w.S[c][i], qd, w.ov[pb][i]);
+        w.oa[b][i] = fma(w.dV[c][i], qd, fma(w.S[c][i], qdd, w.oa[pb][i]));
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__device__ inline void fb_contact_point(const FbLinWork& w, int i, double* P) {
+  const int b = 1 + ANYMAL_CONTACT_PARENT_JOINT[i];
+  const double* R = w.R[b];
+  const double* pc = ANYMAL_CONTACT_P[i];
+  for (int r = 0; r < 3; ++r) P[r] = fma(R[3 * r + 2], pc[2], fma(R[3 * r + 1], pc[1], fma(R[3 * r], pc[0], w.p[b][r])));
+}
+__device__ inline void fb_body_inertia(const FbLinWork& w, int b, fb_inertia_t* Y) {
+  const double m = ANYMAL_MASS[b];
+  double c[3], T[9];
+  const double* R = w.R[b];
+  for (int i = 0; i < 3; ++i)
+    c[i] = fma(R[3 * i + 2], ANYMAL_COM[b][2], fma(R[3 * i + 1], ANYMAL_COM[b][1], fma(R[3 * i], ANYMAL_COM[b][0], w.p[b][i])));
+  const double* Ic = ANYMAL_INERTIA[b];
+  const double If[9] = {Ic[0], Ic[1], Ic[2], Ic[1], Ic[3], Ic[4], Ic[2], Ic[4], Ic[5]};
+  fb_mul33(R, If, T);
+  const double cc = fb_dot3(c, c);
+  const int ii[6] = {0, 0, 0, 1, 1, 2}, jj[6] = {0, 1, 2, 1, 2, 2};
+  for (int e = 0; e < 6; ++e) {
+    const int i = ii[e], j = jj[e];
+    const double iw = fma(T[3 * i + 2], R[3 * j + 2], fma(T[3 * i + 1], R[3 * j + 1], T[3 * i] * R[3 * j]));
+    const double par = (i == j) ? (cc - c[i] * c[j]) : -(c[i] * c[j]);
+    Y->I[e] = fma(m, par, iw);
+  }
+  Y->m = m;
+  for (int i = 0; i < 3; ++i) Y->h[i] = m * c[i];
+}
+__device__ inline void fb_pullback(const double* Rf, const double* Pf, const double* x, double* y) {
+  double t[3], u[3];
+  fb_cross(x + 3, Pf, t);
+  for (int i = 0; i < 3; ++i) u[i] = x[i] + t[i];
+  fb_rotT(Rf, u, y);
+  fb_rotT(Rf, x + 3, y + 3);
+}
+__device__ inline int fb_in_support(int contact, int c) { return c < 6 || (c - 6) / 3 == contact; }
+
+// ---- RNEA + computeRNEADerivatives with the contact wrenches (robot.hxx:444-500): tau -> w.IDC[0:18],
+// d tau/dq, /dv -> w.dIDCdqv rows 0..17, d tau/da -> w.Mm.  with_dv = false: RNEAImpulseDerivatives (the velocity
+// block stays zero).  fm = LOCAL contact forces, zero for inactive contacts. ----
+__device__ inline void fb_rnea_derivatives(FbLinWork& w, double gravity, bool with_dv) {
+  const int tid = threadIdx.x;
+  if (tid < FB_NB) {
+    const int b = tid;
+    fb_body_inertia(w, b, &w.Y[b]);
+    for (int i = 0; i < 6; ++i) w.agf[b][i] = w.oa[b][i];
+    w.agf[b][2] = w.oa[b][2] + gravity;
+    double Ya[6], h[6], vh[6];
+    fb_Ymul(&w.Y[b], w.agf[b], Ya);
+    fb_Ymul(&w.Y[b], w.ov[b], h);
+    fb_mxf(w.ov[b], h, vh);
+    for (int i = 0; i < 6; ++i) w.F[b][i] = Ya[i] + vh[i];
+    fb_dinertia(&w.Y[b], w.ov[b], &w.D[b]);
+  }
+  __syncthreads();
+  if (tid < FB_NC) {   // every contact sits on its own body (the shank of its leg)
+    const int b = 1 + ANYMAL_CONTACT_PARENT_JOINT[tid];
+    double P[3], W6[6];
+    fb_contact_point(w, tid, P);
+    fb_rot(w.R[b], w.fm + 3 * tid, W6);
+    fb_cross(P, W6, W6 + 3);
+    for (int e = 0; e < 6; ++e) w.F[b][e] -= W6[e];
+  }
+  __syncthreads();
+  // composites, leaves to root: inside every leg by its own thread, then the base collects the hips in the
+  // serial order b = 10, 7, 4, 1 (the reverse body order of pinocchio's backward pass)
+  if (tid < 4) {
+    for (int b = 3 * tid + 3; b > 3 * tid + 1; --b) {
+      const int pb = b - 1;
+      w.Y[pb].m += w.Y[b].m;
+      for (int i = 0; i < 3; ++i) { w.Y[pb].h[i] += w.Y[b].h[i]; w.D[pb].pl[i] += w.D[b].pl[i]; w.D[pb].pa[i] += w.D[b].pa[i]; }
+      for (int i = 0; i < 6; ++i) { w.Y[pb].I[i] += w.Y[b].I[i]; w.D[pb].S[i] += w.D[b].S[i]; w.F[pb][i] += w.F[b][i]; }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int b = 10; b >= 1; b -= 3) {
+      w.Y[0].m += w.Y[b].m;
+      for (int i = 0; i < 3; ++i) { w.Y[0].h[i] += w.Y[b].h[i]; w.D[0].pl[i] += w.D[b].pl[i]; w.D[0].pa[i] += w.D[b].pa[i]; }
+      for (int i = 0; i < 6; ++i) { w.Y[0].I[i] += w.Y[b].I[i]; w.D[0].S[i] += w.D[b].S[i]; w.F[0][i] += w.F[b][i]; }
+    }
+  }
+  __syncthreads();
+  if (tid < FB_NV) {
+    const int c = tid, b = fb_body_of_dof(c);
+    w.IDC[c] = fb_dot6(w.S[c], w.F[b]);
+    double dJ[6], t1[6], t2[6];
+    fb_mxm(w.ov[b], w.S[c], dJ);
+    if (b == 0) {
+      const double a0[6] = {0.0, 0.0, gravity, 0.0, 0.0, 0.0};
+      fb_mxm(a0, w.S[c], w.dAq[c]);
+    } else {
+      const int pb = fb_parent_body(b);
+      fb_mxm(w.agf[pb], w.S[c], t1);
+      fb_mxm(w.ov[pb], w.dV[c], t2);
+      for (int i = 0; i < 6; ++i) w.dAq[c][i] = t1[i] + t2[i];
+    }
+    for (int i = 0; i < 6; ++i) w.dAv[c][i] = dJ[i] + w.dV[c][i];
+    fb_Ymul(&w.Y[b], w.S[c], w.U[c]);
+    fb_DTmul(&w.D[b], w.S[c], w.W[c]);
+    fb_Dmul(&w.D[b], w.S[c], t1);
+    fb_Ymul(&w.Y[b], w.dAv[c], t2);
+    for (int i = 0; i < 6; ++i) w.dFv[c][i] = t1[i] + t2[i];
+    fb_Dmul(&w.D[b], w.dV[c], t1);
+    fb_Ymul(&w.Y[b], w.dAq[c], t2);
+    for (int i = 0; i < 6; ++i) w.dFq[c][i] = t1[i] + t2[i];
+    fb_mxf(w.S[c], w.F[b], t1);
+    for (int i = 0; i < 6; ++i) w.dFqa[c][i] = w.dFq[c][i] + t1[i];
+  }
+  __syncthreads();
+  FB_FOR(e, FB_NV * FB_NV) {
+    const int r = e / FB_NV, c = e - r * FB_NV;
+    double eq = 0.0, ev = 0.0, em = 0.0;
+    if (fb_same_joint(r, c)) {
+      eq = fb_dot6(w.S[r], w.dFq[c]);
+      ev = fb_dot6(w.S[r], w.dFv[c]);
+      em = fb_dot6(w.S[r], w.U[c]);
+    } else if (fb_is_ancestor(r, c)) {
+      eq = fb_dot6(w.S[r], w.dFqa[c]);
+      ev = fb_dot6(w.S[r], w.dFv[c]);
+      em = fb_dot6(w.S[r], w.U[c]);
+    } else if (fb_is_ancestor(c, r)) {
+      eq = fb_dot6(w.dAq[c], w.U[r]) + fb_dot6(w.dV[c], w.W[r]);
+      ev = fb_dot6(w.dAv[c], w.U[r]) + fb_dot6(w.S[c], w.W[r]);
+    }
+    w.dIDCdqv[r * FB_NX + c] = eq;
+    w.dIDCdqv[r * FB_NX + FB_NV + c] = with_dv ? ev : 0.0;
+    if (c >= r) w.Mm[r * FB_NV + c] = em;
+  }
+  __syncthreads();
+  FB_FOR(e, FB_NV * FB_NV) {   // robot.hxx:496-499: lower triangle := transpose of the upper one
+    const int r = e / FB_NV, c = e - r * FB_NV;
+    if (c < r) w.Mm[e] = w.Mm[c * FB_NV + r];
+  }
+  __syncthreads();
+}
+
+// ---- Baumgarte residual / derivatives of every active contact (point_contact.hxx:67-144) or, at an impulse, the
+// contact velocity residual / derivatives (:147-176).  Contact i is handled by warp i; row block k = its rank among
+// the active contacts.  Writes IDC[18+3k..], dIDCdqv rows 18+3k.., dCda rows 3k... ----
+__device__ inline void fb_contact_rows(FbLinWork& w, const FbElem& el, bool impulse, double baumgarte) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < FB_NC && el.active[warp]) {
+    const int i = warp;
+    int k = 0;
+    for (int j = 0; j < i; ++j) k += el.active[j];
+    const int bi = 1 + ANYMAL_CONTACT_PARENT_JOINT[i];
+    const double* Rf = w.R[bi];
+    if (lane == 0) {
+      fb_contact_point(w, i, w.frP[i]);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      fb_pullback(Rf, w.frP[i], w.ov[bi], w.frV[i]);
+      fb_pullback(Rf, w.frP[i], w.oa[bi], w.frA[i]);
+    }
+    __syncwarp();
+    const double* P = w.frP[i];
+    const double* vF = w.frV[i];
+    if (lane == 0) {
+      double* C = w.IDC + FB_NV + 3 * k;
+      if (!impulse) {
+        const double wv = 2.0 / baumgarte, wp = 1.0 / (baumgarte * baumgarte);
+        double wxv[3];
+        fb_cross(vF + 3, vF, wxv);
+        for (int x = 0; x < 3; ++x) {
+          const double acl = w.frA[i][x] + wxv[x];
+          C[x] = fma(wp, P[x] - el.cpoints[3 * i + x], fma(wv, vF[x], acl));
+        }
+      } else {
+        for (int x = 0; x < 3; ++x) C[x] = vF[x];
+      }
+    }
+    if (lane < FB_NV) {
+      const int c = lane;
+      double J[6] = {0, 0, 0, 0, 0, 0}, vq[6] = {0, 0, 0, 0, 0, 0}, aq[6] = {0, 0, 0, 0, 0, 0}, av[6] = {0, 0, 0, 0, 0, 0};
+      if (fb_in_support(i, c)) {
+        fb_pullback(Rf, P, w.S[c], J);
+        const int b = fb_body_of_dof(c);
+        double u[6], x6[6], t1[6], t2[6];
+        if (b == 0) {
+          for (int e = 0; e < 6; ++e) u[e] = w.ov[bi][e];
+        } else {
+          const int pb = fb_parent_body(b);
+          for (int e = 0; e < 6; ++e) u[e] = w.ov[bi][e] - w.ov[pb][e];
+          fb_pullback(Rf, P, w.dV[c], vq);
+        }
+        if (!impulse) {
+          fb_mxm(w.ov[b], w.S[c], t1);
+          fb_mxm(w.S[c], u, t2);
+          for (int e = 0; e < 6; ++e) x6[e] = t1[e] + t2[e];
+          fb_pullback(Rf, P, x6, av);
+          if (b != 0) {
+            const int pb = fb_parent_body(b);
+            fb_mxm(w.oa[pb], w.S[c], t1);
+            fb_mxm(w.dV[c], u, t2);
+            for (int e = 0; e < 6; ++e) x6[e] = t1[e] + t2[e];
+            fb_pullback(Rf, P, x6, aq);
+          }
+        }
+      }
+      double* rq = w.dIDCdqv + (FB_NV + 3 * k) * FB_NX + c;
+      double* rv = rq + FB_NV;
+      double* ra = w.dCda + (3 * k) * FB_NV + c;
+      if (!impulse) {
+        const double wv = 2.0 / baumgarte, wp = 1.0 / (baumgarte * baumgarte);
+        const double* vl = vF;
+        const double* va = vF + 3;
+        double t1[3], t2[3], RJ[3];
+        fb_cross(va, vq, t1);
+        fb_cross(vl, vq + 3, t2);
+        fb_rot(Rf, J, RJ);
+        for (int x = 0; x < 3; ++x) rq[x * FB_NX] = fma(wp, RJ[x], fma(wv, vq[x], (aq[x] + t1[x]) + t2[x]));
+        fb_cross(va, J, t1);
+        fb_cross(vl, J + 3, t2);
+        for (int x = 0; x < 3; ++x) rv[x * FB_NX] = fma(wv, J[x], (av[x] + t1[x]) + t2[x]);
+        for (int x = 0; x < 3; ++x) ra[x * FB_NV] = J[x];
+      } else {
+        for (int x = 0; x < 3; ++x) { rq[x * FB_NX] = vq[x]; rv[x * FB_NX] = J[x]; ra[x * FB_NV] = J[x]; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// ---- Robot::computeMJtJinv (robot.hxx:576-615) as dense Cholesky: MJtJinv = [[M, J^T], [J, 0]]^-1 ----
+__device__ inline void fb_MJtJinv(FbLinWork& w, int dimf) {
+  const int n = FB_NV, ld = FB_NVF, tid = threadIdx.x;
+  if (tid < 32) {
+    const int info = fb_llt_warp(w.Mm, n, n, w.L, n, w.rd);
+    if (tid == 0 && info && !w.info) w.info = info;
+  }
+  __syncthreads();
+  if (tid < n) {
+    for (int r = 0; r < n; ++r) w.Minv[r * n + tid] = (r == tid) ? 1.0 : 0.0;
+    fb_llt_solve(w.L, n, w.rd, n, w.Minv + tid, n);
+  }
+  __syncthreads();
+  fb_mm<FBM_SET>(dimf, n, n, w.dCda, n, 1, w.Minv, n, 1, w.JMi, n);
+  __syncthreads();
+  fb_mm<FBM_SET>(dimf, dimf, n, w.JMi, n, 1, w.dCda, 1, n, w.Sm, dimf);
+  __syncthreads();
+  if (dimf > 0) {
+    if (tid < 32) {
+      const int info = fb_llt_warp(w.Sm, dimf, dimf, w.Ls, dimf, w.rds);
+      if (tid == 0 && info && !w.info) w.info = 100 + info;
+    }
+    __syncthreads();
+    if (tid < dimf) {
+      for (int r = 0; r < dimf; ++r) w.Si[r * dimf + tid] = (r == tid) ? 1.0 : 0.0;
+      fb_llt_solve(w.Ls, dimf, w.rds, dimf, w.Si + tid, dimf);
+    }
+    __syncthreads();
+  }
+  FB_FOR(e, dimf * dimf) { const int r = e / dimf, c = e - r * dimf; w.MJtJinv[(n + r) * ld + n + c] = -w.Si[e]; }
+  fb_mm<FBM_SET>(n, dimf, dimf, w.JMi, 1, n, w.Si, dimf, 1, w.MJtJinv + n, ld);     // TR = (J Minv)^T S^-1
+  __syncthreads();
+  FB_FOR(e, n * n) {                                                                   // TL = Minv - TR (J Minv)
+    const int r = e / n, c = e - r * n;
+    double acc = w.Minv[e];
+    for (int j = 0; j < dimf; ++j) acc = fma(-w.MJtJinv[r * ld + n + j], w.JMi[j * n + c], acc);
+    w.MJtJinv[r * ld + c] = acc;
+  }
+  FB_FOR(e, dimf * n) { const int r = e / n, c = e - r * n; w.MJtJinv[(n + r) * ld + c] = w.MJtJinv[c * ld + n + r]; }   // BL = TR^T
+  __syncthreads();
+}
+
+// =====================================================================================================
+// K1: linearisation of one stage.  grid = B * n_elems CTAs (instance-major), 128 threads.
+// =====================================================================================================
+template <bool RESIDUAL_ONLY>
+__global__ void __launch_bounds__(128) k_fb_linearize(FbArrays A) {
+  IDOCP_DYN_SMEM(FbLinWork, wp);
+  FbLinWork& w = *wp;
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x / A.n_elems, e = blockIdx.x - b * A.n_elems;
+  const FbElem& el = A.elems[e];
+  const FbDevProblem& pr = *A.prob;
+  const int kind = el.kind;
+  const bool impulse = kind == FB_IMPULSE, terminal = kind == FB_TERMINAL;
+  const double dt = (impulse || terminal) ? 1.0 : el.dt;
+  const int dimf = terminal ? 0 : el.dimf, nvf = FB_NV + dimf, dimi = el.sw ? el.dimi : 0;
+  const FbSol& S = A.sol[(size_t)el.slot * A.B + b];
+  FbDir& Dr = A.dir[(size_t)el.slot * A.B + b];
+  FbKKT& Kt = A.kkt[(size_t)el.slot * A.B + b];
+  FbExp& Ex = A.exp[(size_t)el.slot * A.B + b];
+
+  // ---- load ----
+  fb_copy(w.lmd, S.lmd, sizeof(FbSol) / sizeof(double));   // lmd .. dual are laid out identically in FbSol and FbLinWork
+  if (!terminal) {
+    const FbSol& Nx = A.sol[(size_t)el.next_slot * A.B + b];
+    fb_copy(w.nlmd, Nx.lmd, FB_NV);
+    fb_copy(w.ngmm, Nx.gmm, FB_NV);
+    fb_copy(w.nq, Nx.q, FB_NQ);
+    fb_copy(w.nv, Nx.v, FB_NV);
+  }
+  if (el.prev_slot >= 0) fb_copy(w.qprev, A.sol[(size_t)el.prev_slot * A.B + b].q, FB_NQ);
+  else fb_copy(w.qprev, A.q0 + (size_t)b * FB_NQ, FB_NQ);
+  fb_zero(w.lq, 3 * FB_NV + FB_MAXF + FB_NPASS + FB_NU + 2 * FB_NV + FB_MAXF);   // lq .. P
+  if (!RESIDUAL_ONLY) {
+    fb_zero(w.Qxx, FB_NX * FB_NX + FB_NX * FB_NV + FB_NV * FB_NV + FB_NV + FB_MAXF * FB_MAXF);   // Qxx, Qxu, Quu, Qaa, Qff
+    fb_zero(w.Fqq6, 3 * 36 + 2 * FB_NV * FB_NV + FB_NV * FB_NU);                                   // Fqq6 .. Fvu
+    fb_zero(w.Pq, FB_MAXF * FB_NV);
+  }
+  fb_zero(w.IDC, FB_NVF + FB_NVF * FB_NX);
+  fb_zero(w.dCda, FB_MAXF * FB_NV);
+  if (tid == 0) w.info = 0;
+  __syncthreads();
+  if (tid < FB_MAXF) {   // forces of inactive contacts are zero for the dynamics; stacks of the active ones
+    const int i = tid / 3;
+    w.fm[tid] = (!terminal && el.active[i]) ? w.f[tid] : 0.0;
+    if (!terminal && el.active[i]) {
+      int k = 0;
+      for (int j = 0; j < i; ++j) k += el.active[j];
+      w.mu_stack[3 * k + tid % 3] = w.mu[tid];
+    }
+  }
+  // ---- SE(3) pieces, one thread each (different warps) ----
+  if (tid == 0) {   // cost: qdiff, J_qdiff (trotting_configuration_space_cost.cpp:295-300)
+    fb_subtract(w.q, el.ref_q, w.qdiff);
+    fb_dsubtract_dplus(w.q, el.ref_q, w.J6c);
+  }
+  if (tid == 32 && !terminal) {   // state equation residual and d/dq (state_equation.hxx:11-40,220-228)
+    fb_subtract(w.q, w.nq, w.Fq);
+    fb_dsubtract_dplus(w.q, w.nq, w.Fqq6);
+  }
+  if (tid == 64) {
+    fb_dsubtract_dminus(w.qprev, w.q, w.Fqq_prev6);
+    if (!RESIDUAL_ONLY) fb_dsubtract_inverse(w.Fqq_prev6, w.Fqq_prev_inv);
+  }
+  if (tid == 96 && !terminal && !RESIDUAL_ONLY) {
+    fb_dsubtract_dminus(w.q, w.nq, w.tmp6);
+    fb_dsubtract_inverse(w.tmp6, w.Fqq_inv);
+  }
+  __syncthreads();
+
+  // ---- cost gradient; constraints: residual/duality, augmentDualResidual; state equation ----
+  const double* wq = terminal ? pr.qf_weight : (impulse ? pr.qi_weight : pr.q_weight);
+  const double* wv = terminal ? pr.vf_weight : (impulse ? pr.vi_weight : pr.v_weight);
+  const double* wa = impulse ? pr.dvi_weight : pr.a_weight;
+  const double sc = (terminal || impulse) ? 1.0 : dt;
+  if (tid < FB_NV) {
+    const int j = tid;
+    if (j < 6) {
+      double acc = w.J6c[j] * (wq[0] * w.qdiff[0]);
+      for (int k = 1; k < 6; ++k) acc = fma(w.J6c[6 * k + j], wq[k] * w.qdiff[k], acc);
+      w.lq[j] += sc * acc;
+    } else {
+      w.lq[j] += sc * (wq[j] * w.qdiff[j]);
+    }
+    w.lv[j] += sc * (wv[j] * (w.v[j] - el.ref_v[j]));
+    if (!terminal) w.la[j] += sc * (wa[j] * w.a[j]);
+  }
+  if (tid >= 32 && tid < 32 + FB_MAXF && !terminal) {   // ContactForceCost gradient (contact_force_cost.cpp:161-187)
+    const int x = tid - 32, i = x / 3;
+    if (el.active[i]) {
+      int k = 0;
+      for (int j = 0; j < i; ++j) k += el.active[j];
+      const double* fw = impulse ? pr.fi_weight : pr.f_weight;
+      const double* fr = impulse ? pr.fi_ref : pr.f_ref;
+      w.lf[3 * k + x % 3] += sc * (fw[x] * (w.f[x] - fr[x]));
+    }
+  }
+  // computePrimalAndDualResidual (needed by the KKT error and by condenseSlackAndDual alike)
+  if (!terminal) {
+    FB_FOR(idx, FB_NCON) {
+      int c = idx < 72 ? idx / 12 : (idx < 92 ? FBC_FRICTION : FBC_IMPULSE_FRICTION);
+      const int j = idx - fbc_offset(c);
+      double res = 0.0, dua = 0.0;
+      if (el.cactive[c]) {
+        const double sl = w.slack[idx];
+        if (c >= FBC_FRICTION) {
+          const int i = j / 5;
+          if (el.active[i]) {
+            double r5[5];
+            fb_friction_residual(pr.mu, w.f + 3 * i, r5);
+            res = r5[j % 5] + sl;
+            dua = sl * w.dual[idx] - pr.barrier;
+          }
+        } else {
+          switch (c) {
+            case FBC_POS_LO: res = pr.q_min[j] - w.q[7 + j] + sl; break;
+            case FBC_POS_UP: res = w.q[7 + j] - pr.q_max[j] + sl; break;
+            case FBC_VEL_LO: res = (-pr.v_max[j]) - w.v[6 + j] + sl; break;
+            case FBC_VEL_UP: res = w.v[6 + j] - pr.v_max[j] + sl; break;
+            case FBC_TRQ_LO: res = (-pr.u_max[j]) - w.u[j] + sl; break;
+            default:         res = w.u[j] - pr.u_max[j] + sl; break;
+          }
+          dua = sl * w.dual[idx] - pr.barrier;
+        }
+      }
+      w.residual[idx] = res;
+      w.duality[idx] = dua;
+    }
+  }
+  __syncthreads();
+  if (terminal) {
+    // TerminalOCP::linearizeOCP (terminal_ocp.hxx:50-66), linearizeForwardEulerTerminal (state_equation.hxx:66-82)
+    if (tid < FB_NV) {
+      const int j = tid;
+      if (j < 6) {
+        double acc = w.lq[j];
+        for (int k = 0; k < 6; ++k) acc = fma(w.Fqq_prev6[6 * k + j], w.lmd[k], acc);
+        w.lq[j] = acc;
+      } else {
+        w.lq[j] -= w.lmd[j];
+      }
+      w.lv[j] -= w.gmm[j];
+    }
+    __syncthreads();
+    if (!RESIDUAL_ONLY) {
+      FB_FOR(x, 36) {
+        const int r = x / 6, c = x - 6 * r;
+        double acc = w.J6c[r] * (wq[0] * w.J6c[c]);
+        for (int k = 1; k < 6; ++k) acc = fma(w.J6c[6 * k + r], wq[k] * w.J6c[6 * k + c], acc);
+        w.Qxx[r * FB_NX + c] += acc;
+      }
+      if (tid >= 64 && tid < 64 + FB_NV) {
+        const int j = tid - 64;
+        if (j >= 6) w.Qxx[j * FB_NX + j] += wq[j];
+        w.Qxx[(FB_NV + j) * FB_NX + FB_NV + j] += wv[j];
+      }
+      __syncthreads();
+      fb_copy(Kt.Qxx, w.Qxx, FB_NX * FB_NX);
+      fb_copy(Kt.Fqq_prev_inv, w.Fqq_prev_inv, 36);
+    }
+    fb_copy(Kt.lq, w.lq, FB_NV);
+    fb_copy(Kt.lv, w.lv, FB_NV);
+    if (tid == 0) {
+      Dr.kkt_sq = fb_sqnorm(w.lq, FB_NV) + fb_sqnorm(w.lv, FB_NV);
+      Dr.info = 0.0;
+    }
+    return;
+  }
+  // augmentDualResidual: joint limits on lq / lv / lu tails, friction cones on lf
+  if (tid < FB_NU) {
+    const int j = tid;
+    for (int c = 0; c < 6; ++c) {
+      if (!el.cactive[c]) continue;
+      double* l = c <= FBC_POS_UP ? w.lq + 6 : (c <= FBC_VEL_UP ? w.lv + 6 : w.lu);
+      const double sg = (c & 1) ? 1.0 : -1.0;
+      l[j] += sg * (dt * w.dual[12 * c + j]);
+    }
+  }
+  if (tid >= 32 && tid < 32 + FB_MAXF) {
+    const int x = tid - 32, i = x / 3, xx = x % 3;
+    const int c = impulse ? FBC_IMPULSE_FRICTION : FBC_FRICTION;
+    if (el.cactive[c] && el.active[i]) {
+      int k = 0;
+      for (int j = 0; j < i; ++j) k += el.active[j];
+      const double* du5 = w.dual + fbc_offset(c) + 5 * i;
+      double acc = fb_friction_jac(pr.mu, 0, xx) * du5[0];
+      for (int ee = 1; ee < 5; ++ee) acc = fma(fb_friction_jac(pr.mu, ee, xx), du5[ee], acc);
+      w.lf[3 * k + xx] += dt * acc;
+    }
+  }
+  __syncthreads();
+  // linearizeForwardEuler / linearizeImpulseForwardEuler
+  if (tid < FB_NV) {
+    const int j = tid;
+    if (!impulse) {
+      w.Fq[j] = fma(dt, w.v[j], w.Fq[j]);
+      w.Fv[j] = fma(dt, w.a[j], w.v[j]) - w.nv[j];
+    } else {
+      w.Fv[j] = (w.v[j] + w.a[j]) - w.nv[j];
+    }
+    if (j < 6) {
+      double acc = w.lq[j];
+      for (int k = 0; k < 6; ++k) acc = fma(w.Fqq6[6 * k + j], w.nlmd[k], acc);
+      for (int k = 0; k < 6; ++k) acc = fma(w.Fqq_prev6[6 * k + j], w.lmd[k], acc);
+      w.lq[j] = acc;
+    } else {
+      w.lq[j] += w.nlmd[j] - w.lmd[j];
+    }
+    if (!impulse) {
+      w.lv[j] += (fma(dt, w.nlmd[j], w.ngmm[j]) - w.gmm[j]);
+      w.la[j] = fma(dt, w.ngmm[j], w.la[j]);
+    } else {
+      w.lv[j] += (w.ngmm[j] - w.gmm[j]);
+      w.la[j] += w.ngmm[j];
+    }
+  }
+  __syncthreads();
+  if (!RESIDUAL_ONLY) {
+    // condenseForwardEuler: Fqq := -Fqq_inv Fqq, Fqv := -dt Fqq_inv, Fq[0:6] := -Fqq_inv Fq[0:6]
+    FB_FOR(x, 36) {
+      const int r = x / 6, c = x - 6 * r;
+      double acc = w.Fqq_inv[6 * r] * w.Fqq6[c];
+      for (int k = 1; k < 6; ++k) acc = fma(w.Fqq_inv[6 * r + k], w.Fqq6[6 * k + c], acc);
+      w.tmp6[x] = -acc;
+      if (!impulse) w.Fqv6[x] = -dt * w.Fqq_inv[x];
+    }
+    if (tid >= 64 && tid < 70) {
+      const int r = tid - 64;
+      double acc = w.Fqq_inv[6 * r] * w.Fq[0];
+      for (int k = 1; k < 6; ++k) acc = fma(w.Fqq_inv[6 * r + k], w.Fq[k], acc);
+      w.fq6[r] = -acc;
+    }
+    __syncthreads();
+    FB_FOR(x, 36) w.Fqq6[x] = w.tmp6[x];
+    if (tid >= 64 && tid < 70) w.Fq[tid - 64] = w.fq6[tid - 64];
+    __syncthreads();
+  }
+
+  // ---- contact dynamics: kinematics, RNEA + derivatives, contact rows ----
+  const double baumgarte = pr.T / pr.N;
+  if (!impulse) {
+    fb_forward_kinematics(w, w.q, w.v, w.a);
+    fb_rnea_derivatives(w, ANYMAL_GRAVITY, true);
+    if (tid < FB_NU) w.IDC[6 + tid] -= w.u[tid];
+  } else {
+    fb_forward_kinematics(w, w.q, nullptr, w.a);
+    fb_rnea_derivatives(w, 0.0, false);
+    if (tid < FB_NV) w.t18[tid] = w.v[tid] + w.a[tid];
+    __syncthreads();
+    fb_forward_kinematics(w, w.q, w.t18, nullptr);
+  }
+  fb_contact_rows(w, el, impulse, baumgarte);
+  // augment: lq += dt dIDdq^T beta, lv += dt dIDdv^T beta, la += dt M^T beta, lf -= dt dCda beta, lu ...
+  {
+    const double* dIDdq = w.dIDCdqv;
+    const double* dIDdv = w.dIDCdqv + FB_NV;
+    const double* dCdq = w.dIDCdqv + FB_NV * FB_NX;
+    const double* dCdv = dCdq + FB_NV;
+    if (tid < FB_NV) {
+      const int j = tid;
+      double acc = dIDdq[j] * w.beta[0];
+      for (int k = 1; k < FB_NV; ++k) acc = fma(dIDdq[k * FB_NX + j], w.beta[k], acc);
+      w.lq[j] = fma(dt, acc, w.lq[j]);
+      if (!impulse) {
+        acc = dIDdv[j] * w.beta[0];
+        for (int k = 1; k < FB_NV; ++k) acc = fma(dIDdv[k * FB_NX + j], w.beta[k], acc);
+        w.lv[j] = fma(dt, acc, w.lv[j]);
+      }
+      acc = w.Mm[j] * w.beta[0];
+      for (int k = 1; k < FB_NV; ++k) acc = fma(w.Mm[k * FB_NV + j], w.beta[k], acc);
+      w.la[j] = fma(dt, acc, w.la[j]);
+      if (dimf > 0) {
+        acc = dCdq[j] * w.mu_stack[0];
+        for (int k = 1; k < dimf; ++k) acc = fma(dCdq[k * FB_NX + j], w.mu_stack[k], acc);
+        w.lq[j] = fma(dt, acc, w.lq[j]);
+        acc = dCdv[j] * w.mu_stack[0];
+        for (int k = 1; k < dimf; ++k) acc = fma(dCdv[k * FB_NX + j], w.mu_stack[k], acc);
+        w.lv[j] = fma(dt, acc, w.lv[j]);
+        acc = w.dCda[j] * w.mu_stack[0];
+        for (int k = 1; k < dimf; ++k) acc = fma(w.dCda[k * FB_NV + j], w.mu_stack[k], acc);
+        w.la[j] = fma(dt, acc, w.la[j]);
+      }
+    }
+    if (tid >= 32 && tid < 32 + dimf) {
+      const int j = tid - 32;
+      double acc = w.dCda[j * FB_NV] * w.beta[0];
+      for (int k = 1; k < FB_NV; ++k) acc = fma(w.dCda[j * FB_NV + k], w.beta[k], acc);
+      w.lf[j] = fma(-dt, acc, w.lf[j]);
+    }
+    if (!impulse && tid >= 64 && tid < 64 + FB_NV) {
+      const int j = tid - 64;
+      if (j < FB_NPASS) w.lu_passive[j] = fma(-dt, w.beta[j], dt * w.nu_passive[j]);
+      else w.lu[j - 6] = fma(-dt, w.beta[j], w.lu[j - 6]);
+    }
+  }
+  __syncthreads();
+
+  if (RESIDUAL_ONLY) {
+    // (the switching-constraint residual and its multiplier terms are added below, shared with the full path)
+  } else {
+    // ---- cost Hessian ----
+    FB_FOR(x, 36) {
+      const int r = x / 6, c = x - 6 * r;
+      double acc = w.J6c[r] * (wq[0] * w.J6c[c]);
+      for (int k = 1; k < 6; ++k) acc = fma(w.J6c[6 * k + r], wq[k] * w.J6c[6 * k + c], acc);
+      w.Qxx[r * FB_NX + c] += sc * acc;
+    }
+    if (tid >= 64 && tid < 64 + FB_NV) {
+      const int j = tid - 64;
+      if (j >= 6) w.Qxx[j * FB_NX + j] += sc * wq[j];
+      w.Qxx[(FB_NV + j) * FB_NX + FB_NV + j] += sc * wv[j];
+      w.Qaa[j] += sc * wa[j];
+    }
+    if (tid >= 96 && tid < 96 + FB_MAXF) {
+      const int x = tid - 96, i = x / 3;
+      if (el.active[i]) {
+        int k = 0;
+        for (int j = 0; j < i; ++j) k += el.active[j];
+        const double* fw = impulse ? pr.fi_weight : pr.f_weight;
+        w.Qff[(3 * k + x % 3) * FB_MAXF + 3 * k + x % 3] += sc * fw[x];
+      }
+    }
+    __syncthreads();
+    // ---- condenseSlackAndDual ----
+    if (tid < FB_NU) {
+      const int j = tid;
+      for (int c = 0; c < 6; ++c) {
+        if (!el.cactive[c]) continue;
+        const int idx = 12 * c + j;
+        const double rs = 1.0 / w.slack[idx];
+        const double h = (dt * w.dual[idx]) * rs;
+        if (c <= FBC_POS_UP) w.Qxx[(6 + j) * FB_NX + 6 + j] += h;
+        else if (c <= FBC_VEL_UP) w.Qxx[(FB_NV + 6 + j) * FB_NX + FB_NV + 6 + j] += h;
+        else w.Quu[(6 + j) * FB_NV + 6 + j] += h;
+        double* l = c <= FBC_POS_UP ? w.lq + 6 : (c <= FBC_VEL_UP ? w.lv + 6 : w.lu);
+        const double sg = (c & 1) ? 1.0 : -1.0;
+        l[j] += sg * ((dt * fma(w.dual[idx], w.residual[idx], -w.duality[idx])) * rs);
+      }
+    }
+    {
+      const int c = impulse ? FBC_IMPULSE_FRICTION : FBC_FRICTION;
+      if (el.cactive[c] && tid >= 32 && tid < 32 + FB_MAXF) {
+        const int x = tid - 32, i = x / 3, xx = x % 3;
+        if (el.active[i]) {
+          int k = 0;
+          for (int j = 0; j < i; ++j) k += el.active[j];
+          const int o = fbc_offset(c) + 5 * i;
+          double r5[5], w5[5];
+          for (int ee = 0; ee < 5; ++ee) {
+            const double rs = 1.0 / w.slack[o + ee];
+            r5[ee] = fma(w.dual[o + ee], w.residual[o + ee], -w.duality[o + ee]) * rs;
+            w5[ee] = w.dual[o + ee] * rs;
+          }
+          double acc = fb_friction_jac(pr.mu, 0, xx) * r5[0];
+          for (int ee = 1; ee < 5; ++ee) acc = fma(fb_friction_jac(pr.mu, ee, xx), r5[ee], acc);
+          w.lf[3 * k + xx] += dt * acc;
+          for (int y = 0; y < 3; ++y) {
+            double h = fb_friction_jac(pr.mu, 0, xx) * (w5[0] * fb_friction_jac(pr.mu, 0, y));
+            for (int ee = 1; ee < 5; ++ee) h = fma(fb_friction_jac(pr.mu, ee, xx), w5[ee] * fb_friction_jac(pr.mu, ee, y), h);
+            w.Qff[(3 * k + xx) * FB_MAXF + 3 * k + y] += dt * h;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- ForwardSwitchingConstraint::linearizeSwitchingConstraint (:27-68) ----
+  if (dimi > 0) {
+    const double c1 = el.dt + el.dt_next, c2 = el.dt * el.dt_next;
+    if (tid < FB_NV) w.dqv[tid] = fma(c2, w.a[tid], c1 * w.v[tid]);
+    __syncthreads();
+    if (tid == 0) fb_integrate(w.q, w.dqv, 1.0, w.q2);
+    if (tid == 32) fb_dintegrate_dq(w.dqv, w.Jq6);
+    if (tid == 64) fb_dintegrate_dv(w.dqv, w.Jv6);
+    __syncthreads();
+    fb_forward_kinematics(w, w.q2, nullptr, nullptr);
+    {
+      const int warp = tid >> 5, lane = tid & 31;
+      if (warp < FB_NC && el.imp_active[warp]) {
+        const int i = warp;
+        int k = 0;
+        for (int j = 0; j < i; ++j) k += el.imp_active[j];
+        const double* Rf = w.R[1 + ANYMAL_CONTACT_PARENT_JOINT[i]];
+        if (lane == 0) fb_contact_point(w, i, w.frP[i]);
+        __syncwarp();
+        if (lane == 0)
+          for (int x = 0; x < 3; ++x) w.P[3 * k + x] = w.frP[i][x] - el.ipoints[3 * i + x];
+        if (lane < FB_NV) {
+          const int c = lane;
+          double J[6] = {0, 0, 0, 0, 0, 0}, wl[3];
+          if (fb_in_support(i, c)) fb_pullback(Rf, w.frP[i], w.S[c], J);
+          fb_rot(Rf, J, wl);
+          for (int x = 0; x < 3; ++x) w.Pq[(3 * k + x) * FB_NV + c] = wl[x];
+        }
+      }
+    }
+    __syncthreads();
+    fb_mm<FBM_SET>(dimi, 6, 6, w.Pq, FB_NV, 1, w.Jq6, 6, 1, w.Phix, FB_NX);
+    fb_mm<FBM_SET>(dimi, 6, 6, w.Pq, FB_NV, 1, w.Jv6, 6, 1, w.PJv, FB_NV);
+    FB_FOR(x, dimi * (FB_NV - 6)) {
+      const int r = x / (FB_NV - 6), c = 6 + x - r * (FB_NV - 6);
+      w.Phix[r * FB_NX + c] = w.Pq[r * FB_NV + c];
+      w.PJv[r * FB_NV + c] = w.Pq[r * FB_NV + c];
+    }
+    __syncthreads();
+    FB_FOR(x, dimi * FB_NV) {
+      const int r = x / FB_NV, c = x - r * FB_NV;
+      w.Phix[r * FB_NX + FB_NV + c] = c1 * w.PJv[x];
+      w.Phia[x] = c2 * w.PJv[x];
+    }
+    __syncthreads();
+    fb_mv<FBM_ADD>(FB_NV, dimi, w.Phix, 1, FB_NX, w.xi, w.lq);
+    fb_mv<FBM_ADD>(FB_NV, dimi, w.Phix + FB_NV, 1, FB_NX, w.xi, w.lv);
+    fb_mv<FBM_ADD>(FB_NV, dimi, w.Phia, 1, FB_NV, w.xi, w.la);
+    __syncthreads();
+  }
+
+  if (RESIDUAL_ONLY) {
+    // squaredNormKKTResidual (split_ocp.hxx:263-279, impulse_split_ocp.hxx:131-142): seven partial sums by seven
+    // threads, added in the reference's order
+    if (tid == 0) w.part[0] = fb_sqnorm(w.lq, FB_NV) + fb_sqnorm(w.lv, FB_NV);
+    if (tid == 1) w.part[1] = fb_sqnorm(w.la, FB_NV);
+    if (tid == 2) w.part[2] = fb_sqnorm(w.lf, dimf);
+    if (tid == 3) { w.part[3] = fb_sqnorm(w.lu_passive, FB_NPASS); w.part[7] = fb_sqnorm(w.lu, FB_NU); }
+    if (tid == 4) w.part[4] = fb_sqnorm(w.Fq, FB_NV) + fb_sqnorm(w.Fv, FB_NV);
+    if (tid == 5) w.part[5] = fb_sqnorm(w.IDC, nvf);
+    if (tid == 6) {
+      double e2 = 0.0;
+      for (int c = 0; c < FBC_NCOMP; ++c) {
+        if (!el.cactive[c]) continue;
+        e2 += fb_sqnorm(w.residual + fbc_offset(c), fbc_dim(c)) + fb_sqnorm(w.duality + fbc_offset(c), fbc_dim(c));
+      }
+      w.part[6] = e2;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double e2 = 0.0;
+      e2 += w.part[0];
+      e2 += w.part[1];
+      e2 += w.part[2];
+      if (!impulse) { e2 += w.part[3]; e2 += w.part[7]; }
+      e2 += w.part[4];
+      if (!impulse) {
+        e2 += dt * dt * w.part[5];
+        e2 += dt * dt * w.part[6];
+        e2 += fb_sqnorm(w.P, dimi);
+      } else {
+        e2 += w.part[5];
+        e2 += w.part[6];
+      }
+      Dr.kkt_sq = e2;
+    }
+    fb_copy(Dr.residual, w.residual, 2 * FB_NCON);
+    return;
+  }
+
+  // ---- condenseContactDynamics (:105-158) / condenseImpulseDynamics ----
+  fb_MJtJinv(w, dimf);
+  fb_mm<FBM_SET>(nvf, FB_NX, nvf, w.MJtJinv, FB_NVF, 1, w.dIDCdqv, FB_NX, 1, w.MJ_dIDC, FB_NX);
+  fb_mv<FBM_SET>(nvf, nvf, w.MJtJinv, FB_NVF, 1, w.IDC, w.MJ_IDC);
+  __syncthreads();
+  FB_FOR(x, FB_NV * FB_NX) { const int r = x / FB_NX; w.Qafqv[x] = -w.Qaa[r] * w.MJ_dIDC[x]; }
+  fb_mm<FBM_SET>(dimf, FB_NX, dimf, w.Qff, FB_MAXF, 1, w.MJ_dIDC + FB_NV * FB_NX, FB_NX, 1, w.Qafqv + FB_NV * FB_NX, FB_NX);
+  if (!impulse) {
+    FB_FOR(x, FB_NV * FB_NV) { const int r = x / FB_NV, c = x - r * FB_NV; w.Qafu[x] = w.Qaa[r] * w.MJtJinv[r * FB_NVF + c]; }
+    fb_mm<FBM_SET>(dimf, FB_NV, dimf, w.Qff, FB_MAXF, 1, w.MJtJinv + FB_NV * FB_NVF, FB_NVF, 1, w.Qafu + FB_NV * FB_NV, FB_NV);
+  }
+  if (tid < FB_NV) w.laf[tid] = fma(-w.Qaa[tid], w.MJ_IDC[tid], w.la[tid]);
+  if (tid >= 32 && tid < 32 + dimf) w.laf[FB_NV + tid - 32] = -w.lf[tid - 32];
+  __syncthreads();
+  FB_FOR(x, dimf * FB_NX) w.Qafqv[FB_NV * FB_NX + x] = -w.Qafqv[FB_NV * FB_NX + x];
+  fb_mv<FBM_SUB>(dimf, dimf, w.Qff, FB_MAXF, 1, w.MJ_IDC + FB_NV, w.laf + FB_NV);
+  __syncthreads();
+  fb_mm<FBM_SUB>(FB_NX, FB_NX, nvf, w.MJ_dIDC, 1, FB_NX, w.Qafqv, FB_NX, 1, w.Qxx, FB_NX);
+  fb_mv<FBM_SUB>(FB_NV, nvf, w.MJ_dIDC, 1, FB_NX, w.laf, w.lq);
+  fb_mv<FBM_SUB>(FB_NV, nvf, w.MJ_dIDC + FB_NV, 1, FB_NX, w.laf, w.lv);
+  if (!impulse) {
+    fb_mm<FBM_SUB>(FB_NX, FB_NV, nvf, w.MJ_dIDC, 1, FB_NX, w.Qafu, FB_NV, 1, w.Qxu, FB_NV);
+    fb_mm<FBM_ADD>(FB_NV, FB_NV, nvf, w.MJtJinv, FB_NVF, 1, w.Qafu, FB_NV, 1, w.Quu, FB_NV);
+    fb_mv<FBM_ADD>(FB_NPASS, nvf, w.MJtJinv, FB_NVF, 1, w.laf, w.lu_passive);
+    fb_mv<FBM_ADD>(FB_NU, nvf, w.MJtJinv + FB_NPASS * FB_NVF, FB_NVF, 1, w.laf, w.lu);
+    FB_FOR(x, FB_NV * FB_NV) {
+      const int r = x / FB_NV, c = x - r * FB_NV;
+      w.Fvq[x] = -dt * w.MJ_dIDC[r * FB_NX + c];
+      w.Fvv[x] = -dt * w.MJ_dIDC[r * FB_NX + FB_NV + c] + (r == c ? 1.0 : 0.0);
+    }
+    FB_FOR(x, FB_NV * FB_NU) { const int r = x / FB_NU, c = x - r * FB_NU; w.Fvu[x] = dt * w.MJtJinv[r * FB_NVF + FB_NPASS + c]; }
+    if (tid < FB_NV) w.Fv[tid] = fma(-dt, w.MJ_IDC[tid], w.Fv[tid]);
+  } else {
+    FB_FOR(x, FB_NV * FB_NV) {
+      const int r = x / FB_NV, c = x - r * FB_NV;
+      w.Fvq[x] = -w.MJ_dIDC[r * FB_NX + c];
+      w.Fvv[x] = (r == c ? 1.0 : 0.0) - w.MJ_dIDC[r * FB_NX + FB_NV + c];
+    }
+    if (tid < FB_NV) w.Fv[tid] -= w.MJ_IDC[tid];
+  }
+  __syncthreads();
+  // ---- condenseSwitchingConstraint (contact_dynamics.hxx:194-200) ----
+  if (dimi > 0) {
+    fb_mm<FBM_SUB>(dimi, FB_NX, FB_NV, w.Phia, FB_NV, 1, w.MJ_dIDC, FB_NX, 1, w.Phix, FB_NX);
+    fb_mm<FBM_SET>(dimi, FB_NU, FB_NV, w.Phia, FB_NV, 1, w.MJtJinv + FB_NPASS, FB_NVF, 1, w.Phiu, FB_NU);
+    fb_mv<FBM_SUB>(dimi, FB_NV, w.Phia, FB_NV, 1, w.MJ_IDC, w.P);
+    __syncthreads();
+  }
+  // ---- store ----
+  fb_copy(Kt.Qxx, w.Qxx, FB_NX * FB_NX + FB_NX * FB_NV + FB_NV * FB_NV);   // Qxx, Qxu, Quu contiguous in both structs
+  fb_copy(Kt.Fqq6, w.Fqq6, 3 * 36 + 2 * FB_NV * FB_NV + FB_NV * FB_NU);   // Fqq6 .. Fvu
+  fb_copy(Kt.lq, w.lq, FB_NV);
+  fb_copy(Kt.lv, w.lv, FB_NV);
+  fb_copy(Kt.lu, w.lu, FB_NU);
+  fb_copy(Kt.lu_passive, w.lu_passive, FB_NPASS);
+  fb_copy(Kt.Fq, w.Fq, FB_NV);
+  fb_copy(Kt.Fv, w.Fv, FB_NV);
+  if (dimi > 0) {
+    fb_copy(Kt.Phix, w.Phix, FB_MAXF * FB_NX);
+    fb_copy(Kt.Phiu, w.Phiu, FB_MAXF * FB_NU);
+    fb_copy(Kt.P, w.P, FB_MAXF);
+  }
+  fb_copy(Ex.MJtJinv, w.MJtJinv, sizeof(FbExp) / sizeof(double));   // MJtJinv .. laf contiguous in both structs
+  fb_copy(Dr.residual, w.residual, 2 * FB_NCON);
+  if (tid == 0) Dr.info = (double)w.info;
+}
+
+// =====================================================================================================
+// K2: backward Riccati recursion, one CTA per instance, serial over the chain
+// (riccati_recursion_solver.cpp:48-107, split_riccati_factorizer.hxx:36-100, backward_riccati_recursion_factorizer.hxx:44-161,
+//  impulse twins)
+// =====================================================================================================
+struct FbRicWork {
+  // stage record (same order as FbKKT)
+  double Qxx[FB_NX * FB_NX], Qxu[FB_NX * FB_NV], Quu[FB_NV * FB_NV];
+  double Fqq6[36], Fqv6[36], Fqq_prev_inv[36], Fvq[FB_NV * FB_NV], Fvv[FB_NV * FB_NV], Fvu[FB_NV * FB_NU];
+  double lq[FB_NV], lv[FB_NV], lu[FB_NU], lu_passive[FB_NPASS], Fq[FB_NV], Fv[FB_NV];
+  double Phix[FB_MAXF * FB_NX], Phiu[FB_MAXF * FB_NU], P[FB_MAXF];
+  // next factorisation and the one being built (same order as the P.. part of FbRic)
+  double nPqq[FB_NV * FB_NV], nPqv[FB_NV * FB_NV], nPvv[FB_NV * FB_NV], nsq[FB_NV], nsv[FB_NV];
+  double K[FB_NU * FB_NX], k[FB_NU], Pqq[FB_NV * FB_NV], Pqv[FB_NV * FB_NV], Pvv[FB_NV * FB_NV], sq[FB_NV], sv[FB_NV], cM[FB_MAXF * FB_NX],
+      cm[FB_MAXF];
+  double AtPqq[FB_NV * FB_NV], AtPqv[FB_NV * FB_NV], AtPvq[FB_NV * FB_NV], AtPvv[FB_NV * FB_NV], BtPq[FB_NU * FB_NV], BtPv[FB_NU * FB_NV];
+  double GK[FB_NU * FB_NX], G[FB_NU * FB_NU], L[FB_NU * FB_NU], rd[FB_NU];
+  double Ginv[FB_NU * FB_NU], DGinv[FB_MAXF * FB_NU], Sm[FB_MAXF * FB_MAXF], Ls[FB_MAXF * FB_MAXF], rds[FB_MAXF], SinvDGinv[FB_MAXF * FB_NU];
+  double DtM[FB_NU * FB_NX], KtDtM[FB_NX * FB_NX];
+  int info;
+};
+
+__global__ void __launch_bounds__(128) k_fb_riccati_backward(FbArrays A) {
+  IDOCP_DYN_SMEM(FbRicWork, wp);
+  FbRicWork& w = *wp;
+  const int tid = threadIdx.x, b = blockIdx.x, n = A.n_elems;
+  const int NV = FB_NV, NX = FB_NX, NU = FB_NU, NPASS = FB_NPASS, MAXF = FB_MAXF;
+  // terminal stage: P = (Qqq, 0, Qvv), s = -(lq, lv)
+  {
+    const FbElem& el = A.elems[n - 1];
+    const FbKKT& Kt = A.kkt[(size_t)el.slot * A.B + b];
+    FbRic& Rc = A.ric[(size_t)el.slot * A.B + b];
+    FB_FOR(x, NV * NV) {
+      const int r = x / NV, c = x - r * NV;
+      w.nPqq[x] = Kt.Qxx[r * NX + c];
+      w.nPvv[x] = Kt.Qxx[(NV + r) * NX + NV + c];
+      w.nPqv[x] = 0.0;
+    }
+    if (tid < NV) { w.nsq[tid] = -Kt.lq[tid]; w.nsv[tid] = -Kt.lv[tid]; }
+    __syncthreads();
+    fb_copy(Rc.Pqq, w.nPqq, 3 * NV * NV + 2 * NV);
+  }
+  for (int e = n - 2; e >= 0; --e) {
+    const FbElem& el = A.elems[e];
+    const bool impulse = el.kind == FB_IMPULSE;
+    const double dt = el.dt;
+    const int dimi = el.sw ? el.dimi : 0;
+    const FbKKT& Kt = A.kkt[(size_t)el.slot * A.B + b];
+    FbRic& Rc = A.ric[(size_t)el.slot * A.B + b];
+    __syncthreads();
+    fb_copy(w.Qxx, Kt.Qxx, sizeof(FbKKT) / sizeof(double));
+    if (tid == 0) w.info = 0;
+    __syncthreads();
+    double* Qqq = w.Qxx;
+    double* Qqv = w.Qxx + NV;
+    double* Qvv = w.Qxx + NV * NX + NV;
+    // ---- factorizeKKTMatrix ----
+    fb_mm<FBM_SET>(6, NV, 6, w.Fqq6, 1, 6, w.nPqq, NV, 1, w.AtPqq, NV);
+    fb_mm<FBM_SET>(6, NV, 6, w.Fqq6, 1, 6, w.nPqv, NV, 1, w.AtPqv, NV);
+    FB_FOR(x, (NV - 6) * NV) { w.AtPqq[6 * NV + x] = w.nPqq[6 * NV + x]; w.AtPqv[6 * NV + x] = w.nPqv[6 * NV + x]; }
+    if (!impulse) {
+      fb_mm<FBM_SET>(6, NV, 6, w.Fqv6, 1, 6, w.nPqq, NV, 1, w.AtPvq, NV);
+      fb_mm<FBM_SET>(6, NV, 6, w.Fqv6, 1, 6, w.nPqv, NV, 1, w.AtPvv, NV);
+      FB_FOR(x, (NV - 6) * NV) { w.AtPvq[6 * NV + x] = dt * w.nPqq[6 * NV + x]; w.AtPvv[6 * NV + x] = dt * w.nPqv[6 * NV + x]; }
+    }
+    __syncthreads();
+    fb_mm<FBM_ADD>(NV, NV, NV, w.Fvq, 1, NV, w.nPqv, 1, NV, w.AtPqq, NV);
+    fb_mm<FBM_ADD>(NV, NV, NV, w.Fvq, 1, NV, w.nPvv, NV, 1, w.AtPqv, NV);
+    if (!impulse) {
+      fb_mm<FBM_ADD>(NV, NV, NV, w.Fvv, 1, NV, w.nPqv, 1, NV, w.AtPvq, NV);
+      fb_mm<FBM_ADD>(NV, NV, NV, w.Fvv, 1, NV, w.nPvv, NV, 1, w.AtPvv, NV);
+      fb_mm<FBM_SET>(NU, NV, NV, w.Fvu, 1, NU, w.nPqv, 1, NV, w.BtPq, NV);
+      fb_mm<FBM_SET>(NU, NV, NV, w.Fvu, 1, NU, w.nPvv, NV, 1, w.BtPv, NV);
+    } else {
+      fb_mm<FBM_SET>(NV, NV, NV, w.Fvv, 1, NV, w.nPqv, 1, NV, w.AtPvq, NV);
+      fb_mm<FBM_SET>(NV, NV, NV, w.Fvv, 1, NV, w.nPvv, NV, 1, w.AtPvv, NV);
+    }
+    __syncthreads();
+    // Factorize F: the three blocks are independent of each other, each gets its terms in the reference's order
+    fb_mm<FBM_ADD>(NV, 6, 6, w.AtPqq, NV, 1, w.Fqq6, 6, 1, Qqq, NX);
+    FB_FOR(x, NV * (NV - 6)) { const int r = x / (NV - 6), c = 6 + x - r * (NV - 6); Qqq[r * NX + c] += w.AtPqq[r * NV + c]; }
+    if (!impulse) {
+      fb_mm<FBM_ADD>(NV, 6, 6, w.AtPqq, NV, 1, w.Fqv6, 6, 1, Qqv, NX);
+      FB_FOR(x, NV * (NV - 6)) { const int r = x / (NV - 6), c = 6 + x - r * (NV - 6); Qqv[r * NX + c] = fma(dt, w.AtPqq[r * NV + c], Qqv[r * NX + c]); }
+      fb_mm<FBM_ADD>(NV, 6, 6, w.AtPvq, NV, 1, w.Fqv6, 6, 1, Qvv, NX);
+      FB_FOR(x, NV * (NV - 6)) { const int r = x / (NV - 6), c = 6 + x - r * (NV - 6); Qvv[r * NX + c] = fma(dt, w.AtPvq[r * NV + c], Qvv[r * NX + c]); }
+    }
+    __syncthreads();
+    fb_mm<FBM_ADD>(NV, NV, NV, w.AtPqv, NV, 1, w.Fvq, NV, 1, Qqq, NX);
+    fb_mm<FBM_ADD>(NV, NV, NV, w.AtPqv, NV, 1, w.Fvv, NV, 1, Qqv, NX);
+    fb_mm<FBM_ADD>(NV, NV, NV, w.AtPvv, NV, 1, w.Fvv, NV, 1, Qvv, NX);
+    if (!impulse) {
+      fb_mm<FBM_ADD>(NV, NU, NV, w.AtPqv, NV, 1, w.Fvu, NU, 1, w.Qxu + NPASS, NV);
+      fb_mm<FBM_ADD>(NV, NU, NV, w.AtPvv, NV, 1, w.Fvu, NU, 1, w.Qxu + NV * NV + NPASS, NV);
+      fb_mm<FBM_ADD>(NU, NU, NV, w.BtPv, NV, 1, w.Fvu, NU, 1, w.Quu + NPASS * NV + NPASS, NV);
+      if (tid < NU) {    // lu += BtPq Fq; lu += BtPv Fv; lu -= Fvu^T sv_next
+        double acc = w.lu[tid];
+        for (int l = 0; l < NV; ++l) acc = fma(w.BtPq[tid * NV + l], w.Fq[l], acc);
+        for (int l = 0; l < NV; ++l) acc = fma(w.BtPv[tid * NV + l], w.Fv[l], acc);
+        for (int l = 0; l < NV; ++l) acc = fma(-w.Fvu[l * NU + tid], w.nsv[l], acc);
+        w.lu[tid] = acc;
+      }
+    }
+    __syncthreads();
+    const double* Qxu = w.Qxu + NPASS;   // 36 x 12 block, leading dimension NV
+    if (!impulse) {
+      FB_FOR(x, NU * NU) { const int r = x / NU, c = x - r * NU; w.G[x] = w.Quu[(NPASS + r) * NV + NPASS + c]; }
+      __syncthreads();
+      if (tid < 32) {
+        const int info = fb_llt_warp(w.G, NU, NU, w.L, NU, w.rd);
+        if (tid == 0 && info) w.info = 200 + info;
+      }
+      __syncthreads();
+      if (dimi == 0) {
+        // K = -G^-1 Qxu^T, k = -G^-1 lu: one right-hand side per thread
+        if (tid < NX) {
+          double col[FB_NU];
+          for (int r = 0; r < NU; ++r) col[r] = Qxu[tid * NV + r];
+          fb_llt_solve(w.L, NU, w.rd, NU, col, 1);
+          for (int r = 0; r < NU; ++r) w.K[r * NX + tid] = -col[r];
+        } else if (tid == NX) {
+          double col[FB_NU];
+          for (int r = 0; r < NU; ++r) col[r] = w.lu[r];
+          fb_llt_solve(w.L, NU, w.rd, NU, col, 1);
+          for (int r = 0; r < NU; ++r) w.k[r] = -col[r];
+        }
+        __syncthreads();
+      } else {
+        // Schur complement on the switching constraint (split_riccati_factorizer.hxx:55-100)
+        if (tid < NU) {
+          for (int r = 0; r < NU; ++r) w.Ginv[r * NU + tid] = (r == tid) ? 1.0 : 0.0;
+          fb_llt_solve(w.L, NU, w.rd, NU, w.Ginv + tid, NU);
+        } else if (tid >= 32 && tid < 32 + dimi) {
+          const int r = tid - 32;
+          for (int c = 0; c < NU; ++c) w.DGinv[r * NU + c] = w.Phiu[r * NU + c];
+          fb_llt_solve(w.L, NU, w.rd, NU, w.DGinv + r * NU, 1);
+        }
+        __syncthreads();
+        fb_mm<FBM_SET>(dimi, dimi, NU, w.DGinv, NU, 1, w.Phiu, 1, NU, w.Sm, MAXF);
+        __syncthreads();
+        if (tid < 32) {
+          const int info = fb_llt_warp(w.Sm, MAXF, dimi, w.Ls, MAXF, w.rds);
+          if (tid == 0 && info && !w.info) w.info = 300 + info;
+        }
+        __syncthreads();
+        if (tid < NU) {
+          for (int r = 0; r < dimi; ++r) w.SinvDGinv[r * NU + tid] = w.DGinv[r * NU + tid];
+          fb_llt_solve(w.Ls, MAXF, w.rds, dimi, w.SinvDGinv + tid, NU);
+        }
+        __syncthreads();
+        fb_mm<FBM_SUB>(NU, NU, dimi, w.SinvDGinv, 1, NU, w.DGinv, NU, 1, w.Ginv, NU);
+        __syncthreads();
+        fb_mm<FBM_SET>(NU, NX, NU, w.Ginv, NU, 1, Qxu, 1, NV, w.K, NX);
+        fb_mv<FBM_SET>(NU, NU, w.Ginv, NU, 1, w.lu, w.k);
+        __syncthreads();
+        FB_FOR(x, NU * NX) w.K[x] = -w.K[x];
+        if (tid < NU) w.k[tid] = -w.k[tid];
+        __syncthreads();
+        fb_mm<FBM_SUB>(NU, NX, dimi, w.SinvDGinv, 1, NU, w.Phix, NX, 1, w.K, NX);
+        fb_mv<FBM_SUB>(NU, dimi, w.SinvDGinv, 1, NU, w.P, w.k);
+        if (tid >= 64 && tid < 64 + NX) {
+          const int c = tid - 64;
+          for (int r = 0; r < dimi; ++r) w.cM[r * NX + c] = w.Phix[r * NX + c];
+          fb_llt_solve(w.Ls, MAXF, w.rds, dimi, w.cM + c, NX);
+        } else if (tid == 127) {
+          for (int r = 0; r < dimi; ++r) w.cm[r] = w.P[r];
+          fb_llt_solve(w.Ls, MAXF, w.rds, dimi, w.cm, 1);
+        }
+        __syncthreads();
+        fb_mm<FBM_SUB>(dimi, NX, NU, w.SinvDGinv, NU, 1, Qxu, 1, NV, w.cM, NX);
+        fb_mv<FBM_SUB>(dimi, NU, w.SinvDGinv, NU, 1, w.lu, w.cm);
+        __syncthreads();
+      }
+    }
+    // ---- factorizeRiccatiFactorization ----
+    FB_FOR(x, NV * NV) {
+      const int r = x / NV, c = x - r * NV;
+      w.Pqq[x] = Qqq[r * NX + c];
+      w.Pqv[x] = Qqv[r * NX + c];
+      w.Pvv[x] = Qvv[r * NX + c];
+    }
+    if (!impulse) fb_mm<FBM_SET>(NU, NX, NU, w.Quu + NPASS * NV + NPASS, NV, 1, w.K, NX, 1, w.GK, NX);
+    __syncthreads();
+    if (!impulse) {
+      fb_mm<FBM_SUB>(NV, NV, NU, w.K, 1, NX, w.GK, NX, 1, w.Pqq, NV);
+      fb_mm<FBM_SUB>(NV, NV, NU, w.K, 1, NX, w.GK + NV, NX, 1, w.Pqv, NV);
+      fb_mm<FBM_SUB>(NV, NV, NU, w.K + NV, 1, NX, w.GK + NV, NX, 1, w.Pvv, NV);
+      __syncthreads();
+    }
+    FB_FOR(x, NV * NV) {   // preserve the symmetry: one thread per unordered pair
+      const int r = x / NV, c = x - r * NV;
+      if (c >= r) {
+        const double a = 0.5 * (w.Pqq[r * NV + c] + w.Pqq[c * NV + r]);
+        const double bb = 0.5 * (w.Pvv[r * NV + c] + w.Pvv[c * NV + r]);
+        w.Pqq[r * NV + c] = a; w.Pqq[c * NV + r] = a;
+        w.Pvv[r * NV + c] = bb; w.Pvv[c * NV + r] = bb;
+      }
+    }
+    if (tid >= 64 && tid < 64 + NV) {   // sq
+      const int j = tid - 64;
+      double acc;
+      if (j < 6) {
+        acc = w.Fqq6[j] * w.nsq[0];
+        for (int l = 1; l < 6; ++l) acc = fma(w.Fqq6[6 * l + j], w.nsq[l], acc);
+      } else {
+        acc = w.nsq[j];
+      }
+      for (int l = 0; l < NV; ++l) acc = fma(w.Fvq[l * NV + j], w.nsv[l], acc);
+      for (int l = 0; l < NV; ++l) acc = fma(-w.AtPqq[j * NV + l], w.Fq[l], acc);
+      for (int l = 0; l < NV; ++l) acc = fma(-w.AtPqv[j * NV + l], w.Fv[l], acc);
+      acc -= w.lq[j];
+      if (!impulse)
+        for (int l = 0; l < NU; ++l) acc = fma(-w.Qxu[j * NV + NPASS + l], w.k[l], acc);
+      w.sq[j] = acc;
+    }
+    if (tid >= 96 && tid < 96 + NV) {   // sv
+      const int j = tid - 96;
+      double acc;
+      if (!impulse) {
+        if (j < 6) {
+          acc = w.Fqv6[j] * w.nsq[0];
+          for (int l = 1; l < 6; ++l) acc = fma(w.Fqv6[6 * l + j], w.nsq[l], acc);
+        } else {
+          acc = dt * w.nsq[j];
+        }
+        for (int l = 0; l < NV; ++l) acc = fma(w.Fvv[l * NV + j], w.nsv[l], acc);
+      } else {
+        acc = w.Fvv[j] * w.nsv[0];
+        for (int l = 1; l < NV; ++l) acc = fma(w.Fvv[l * NV + j], w.nsv[l], acc);
+      }
+      for (int l = 0; l < NV; ++l) acc = fma(-w.AtPvq[j * NV + l], w.Fq[l], acc);
+      for (int l = 0; l < NV; ++l) acc = fma(-w.AtPvv[j * NV + l], w.Fv[l], acc);
+      acc -= w.lv[j];
+      if (!impulse)
+        for (int l = 0; l < NU; ++l) acc = fma(-w.Qxu[(NV + j) * NV + NPASS + l], w.k[l], acc);
+      w.sv[j] = acc;
+    }
+    __syncthreads();
+    if (dimi > 0) {
+      fb_mm<FBM_SET>(NU, NX, dimi, w.Phiu, 1, NU, w.cM, NX, 1, w.DtM, NX);
+      __syncthreads();
+      fb_mm<FBM_SET>(NX, NX, NU, w.K, 1, NX, w.DtM, NX, 1, w.KtDtM, NX);
+      __syncthreads();
+      FB_FOR(x, NV * NV) {
+        const int r = x / NV, c = x - r * NV;
+        w.Pqq[x] = (w.Pqq[x] - w.KtDtM[r * NX + c]) - w.KtDtM[c * NX + r];
+        w.Pqv[x] = (w.Pqv[x] - w.KtDtM[r * NX + NV + c]) - w.KtDtM[(NV + c) * NX + r];
+        w.Pvv[x] = (w.Pvv[x] - w.KtDtM[(NV + r) * NX + NV + c]) - w.KtDtM[(NV + c) * NX + NV + r];
+      }
+      fb_mv<FBM_SUB>(NV, dimi, w.Phix, 1, NX, w.cm, w.sq);
+      fb_mv<FBM_SUB>(NV, dimi, w.Phix + NV, 1, NX, w.cm, w.sv);
+      __syncthreads();
+    }
+    // store the factorisation, make it the "next" one
+    fb_copy(Rc.K, w.K, sizeof(FbRic) / sizeof(double));
+    fb_copy(w.nPqq, w.Pqq, 3 * NV * NV + 2 * NV);
+    if (tid == 0 && w.info) {
+      FbDir& Dr = A.dir[(size_t)el.slot * A.B + b];
+      if (Dr.info == 0.0) Dr.info = (double)w.info;
+    }
+  }
+}
+
+// =====================================================================================================
+// K3: initial state direction + forward Riccati recursion (riccati_recursion_solver.cpp:110-162), one CTA
+// (64 threads) per instance
+// =====================================================================================================
+__global__ void __launch_bounds__(64) k_fb_riccati_forward(FbArrays A) {
+  __shared__ double dq[FB_NV], dv[FB_NV], du[FB_NU], nq[FB_NV], nvv[FB_NV], t6[6];
+  const int tid = threadIdx.x, b = blockIdx.x, n = A.n_elems;
+  const int NV = FB_NV, NX = FB_NX, NU = FB_NU;
+  {
+    const FbElem& el = A.elems[0];
+    const FbSol& S = A.sol[(size_t)el.slot * A.B + b];
+    const FbKKT& Kt = A.kkt[(size_t)el.slot * A.B + b];
+    if (tid == 0) fb_subtract(A.q0 + (size_t)b * FB_NQ, S.q, dq);
+    if (tid >= 32 && tid < 32 + NV) dv[tid - 32] = A.v0[(size_t)b * NV + tid - 32] - S.v[tid - 32];
+    __syncthreads();
+    if (tid < 6) {
+      double acc = Kt.Fqq_prev_inv[6 * tid] * dq[0];
+      for (int l = 1; l < 6; ++l) acc = fma(Kt.Fqq_prev_inv[6 * tid + l], dq[l], acc);
+      t6[tid] = -acc;
+    }
+    __syncthreads();
+    if (tid < 6) dq[tid] = t6[tid];
+    __syncthreads();
+  }
+  for (int e = 0; e < n; ++e) {
+    const FbElem& el = A.elems[e];
+    const bool impulse = el.kind == FB_IMPULSE;
+    FbDir& Dr = A.dir[(size_t)el.slot * A.B + b];
+    if (tid < NV) { Dr.dq[tid] = dq[tid]; Dr.dv[tid] = dv[tid]; }
+    if (el.kind == FB_TERMINAL) break;
+    const FbKKT& Kt = A.kkt[(size_t)el.slot * A.B + b];
+    const FbRic& Rc = A.ric[(size_t)el.slot * A.B + b];
+    const double dt = el.dt;
+    if (!impulse) {
+      if (tid < NU) {
+        double acc = Rc.K[tid * NX] * dq[0];
+        for (int l = 1; l < NV; ++l) acc = fma(Rc.K[tid * NX + l], dq[l], acc);
+        for (int l = 0; l < NV; ++l) acc = fma(Rc.K[tid * NX + NV + l], dv[l], acc);
+        acc += Rc.k[tid];
+        du[tid] = acc;
+        Dr.du[tid] = acc;
+      }
+      __syncthreads();
+    }
+    if (tid < NV) {
+      const int j = tid;
+      double acc = Kt.Fq[j];
+      if (j < 6) {
+        for (int l = 0; l < 6; ++l) acc = fma(Kt.Fqq6[6 * j + l], dq[l], acc);
+        if (!impulse)
+          for (int l = 0; l < 6; ++l) acc = fma(Kt.Fqv6[6 * j + l], dv[l], acc);
+      } else {
+        acc += dq[j];
+        if (!impulse) acc = fma(dt, dv[j], acc);
+      }
+      nq[j] = acc;
+    } else if (tid >= 32 && tid < 32 + NV) {
+      const int j = tid - 32;
+      double acc = Kt.Fv[j];
+      for (int l = 0; l < NV; ++l) acc = fma(Kt.Fvq[j * NV + l], dq[l], acc);
+      for (int l = 0; l < NV; ++l) acc = fma(Kt.Fvv[j * NV + l], dv[l], acc);
+      if (!impulse)
+        for (int l = 0; l < NU; ++l) acc = fma(Kt.Fvu[j * NU + l], du[l], acc);
+      nvv[j] = acc;
+    }
+    __syncthreads();
+    if (tid < NV) { dq[tid] = nq[tid]; dv[tid] = nvv[tid]; }
+    __syncthreads();
+  }
+}
+
+// =====================================================================================================
+// K4: expansion of one stage (riccati_recursion_solver.cpp:165-241): costate direction, condensed primal
+// direction, slack / dual directions, multiplier of the switching constraint, fraction-to-boundary steps.
+// grid = B * n_elems, 64 threads.
+// =====================================================================================================
+__device__ inline double fb_fraction_to_boundary(double rate, int nn, const double* vec, const double* dvec) {
+  double mn = 1.0;
+  for (int i = 0; i < nn; ++i) {
+    const double f = -rate * (vec[i] / dvec[i]);
+    if (f > 0 && f < 1) {
+      if (f < mn) mn = f;
+    }
+  }
+  return mn;
+}
+
+__global__ void __launch_bounds__(64) k_fb_expand(FbArrays A) {
+  __shared__ double dx[FB_NX], du[FB_NU], daf[FB_NVF], dslack[FB_NCON], ddual[FB_NCON], steps[2 * FBC_NCOMP];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x / A.n_elems, e = blockIdx.x - b * A.n_elems;
+  const int NV = FB_NV, NX = FB_NX, NU = FB_NU, NVF = FB_NVF;
+  const FbElem& el = A.elems[e];
+  const FbDevProblem& pr = *A.prob;
+  const bool impulse = el.kind == FB_IMPULSE, terminal = el.kind == FB_TERMINAL;
+  const size_t rec = (size_t)el.slot * A.B + b;
+  FbDir& Dr = A.dir[rec];
+  const FbRic& Rc = A.ric[rec];
+  const FbSol& S = A.sol[rec];
+  if (tid < NV) { dx[tid] = Dr.dq[tid]; dx[NV + tid] = Dr.dv[tid]; }
+  if (tid >= 32 && tid < 32 + NU) du[tid - 32] = Dr.du[tid - 32];
+  __syncthreads();
+  // computeCostateDirection (split_riccati_factorizer.hxx:131-139)
+  if (tid < NV) {
+    const int j = tid;
+    double acc = Rc.Pqq[j * NV] * dx[0];
+    for (int l = 1; l < NV; ++l) acc = fma(Rc.Pqq[j * NV + l], dx[l], acc);
+    for (int l = 0; l < NV; ++l) acc = fma(Rc.Pqv[j * NV + l], dx[NV + l], acc);
+    Dr.dlmd[j] = acc - Rc.sq[j];
+  } else if (tid >= 32 && tid < 32 + NV) {
+    const int j = tid - 32;
+    double acc = Rc.Pqv[j] * dx[0];
+    for (int l = 1; l < NV; ++l) acc = fma(Rc.Pqv[l * NV + j], dx[l], acc);
+    for (int l = 0; l < NV; ++l) acc = fma(Rc.Pvv[j * NV + l], dx[NV + l], acc);
+    Dr.dgmm[j] = acc - Rc.sv[j];
+  }
+  if (terminal) {
+    if (tid == 0) { Dr.max_primal = 1.0; Dr.max_dual = 1.0; }
+    return;
+  }
+  const FbExp& Ex = A.exp[rec];
+  const int dimf = el.dimf, nvf = NV + dimf;
+  // computeCondensedPrimalDirection (contact_dynamics.hxx:161-168)
+  if (tid < nvf) {
+    const int j = tid;
+    double acc = Ex.MJ_dIDC[j * NX] * dx[0];
+    for (int l = 1; l < NX; ++l) acc = fma(Ex.MJ_dIDC[j * NX + l], dx[l], acc);
+    acc = -acc;
+    if (!impulse)
+      for (int l = 0; l < NU; ++l) acc = fma(Ex.MJtJinv[j * NVF + FB_NPASS + l], du[l], acc);
+    acc -= Ex.MJ_IDC[j];
+    if (j >= NV) acc = -acc;
+    daf[j] = acc;
+    Dr.daf[j] = acc;
+  }
+  if (el.sw && tid >= 32 && tid < 32 + el.dimi) {   // computeLagrangeMultiplierDirection (:142-148)
+    const int j = tid - 32;
+    double acc = Rc.cM[j * NX] * dx[0];
+    for (int l = 1; l < NX; ++l) acc = fma(Rc.cM[j * NX + l], dx[l], acc);
+    Dr.dxi[j] = acc + Rc.cm[j];
+  }
+  __syncthreads();
+  // computeSlackAndDualDirection
+  for (int idx = tid; idx < FB_NCON; idx += blockDim.x) {
+    const int c = idx < 72 ? idx / 12 : (idx < 92 ? FBC_FRICTION : FBC_IMPULSE_FRICTION);
+    const int j = idx - fbc_offset(c);
+    double ds = 0.0, dd = 0.0;
+    if (el.cactive[c]) {
+      if (c >= FBC_FRICTION) {
+        const int i = j / 5;
+        ds = 1.0; dd = 1.0;
+        if (el.active[i]) {
+          int k = 0;
+          for (int jj = 0; jj < i; ++jj) k += el.active[jj];
+          const double* df = daf + NV + 3 * k;
+          const int ee = j % 5;
+          const double Jdf = fma(fb_friction_jac(pr.mu, ee, 2), df[2], fma(fb_friction_jac(pr.mu, ee, 1), df[1], fb_friction_jac(pr.mu, ee, 0) * df[0]));
+          ds = -Jdf - Dr.residual[idx];
+          dd = -fma(S.dual[idx], ds, Dr.duality[idx]) / S.slack[idx];
+        }
+      } else {
+        const double d = c <= FBC_POS_UP ? dx[6 + j] : (c <= FBC_VEL_UP ? dx[NV + 6 + j] : du[j]);
+        ds = ((c & 1) ? -d : d) - Dr.residual[idx];
+        dd = -fma(S.dual[idx], ds, Dr.duality[idx]) / S.slack[idx];
+      }
+    }
+    dslack[idx] = ds;
+    ddual[idx] = dd;
+    Dr.dslack[idx] = ds;
+    Dr.ddual[idx] = dd;
+  }
+  __syncthreads();
+  if (tid < 2 * FBC_NCOMP) {
+    const int c = tid >> 1, o = fbc_offset(c);
+    double r = 1.0;
+    if (el.cactive[c]) r = (tid & 1) ? fb_fraction_to_boundary(pr.fraction_rate, fbc_dim(c), S.dual + o, ddual + o)
+                                     : fb_fraction_to_boundary(pr.fraction_rate, fbc_dim(c), S.slack + o, dslack + o);
+    steps[tid] = r;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double mp = 1.0, md = 1.0;
+    for (int c = 0; c < FBC_NCOMP; ++c) {
+      if (steps[2 * c] < mp) mp = steps[2 * c];
+      if (steps[2 * c + 1] < md) md = steps[2 * c + 1];
+    }
+    Dr.max_primal = mp;
+    Dr.max_dual = md;
+  }
+}
+
+// step sizes of every instance: min over the chain (exact, order-free); one thread per instance
+__global__ void k_fb_steps(FbArrays A) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= A.B) return;
+  double ap = 1.0, ad = 1.0;
+  for (int e = 0; e < A.n_elems; ++e) {
+    const FbDir& Dr = A.dir[(size_t)A.elems[e].slot * A.B + b];
+    if (Dr.max_primal < ap) ap = Dr.max_primal;
+    if (Dr.max_dual < ad) ad = Dr.max_dual;
+  }
+  A.steps[2 * b] = ap;
+  A.steps[2 * b + 1] = ad;
+}
+
+// =====================================================================================================
+// K5: condensed dual direction, costate correction, update of the solution and of slack / dual
+// (ocp_linearizer.cpp:140-221, contact_dynamics.hxx:171-190, state_equation.hxx:96-108, split_solution.hxx:215-239)
+// grid = B * n_elems, 64 threads.  Reads dgmm of the NEXT stage, which no CTA of this kernel writes.
+// =====================================================================================================
+__global__ void __launch_bounds__(64) k_fb_update(FbArrays A) {
+  __shared__ double dx[FB_NX], du[FB_NU], laf[FB_NVF], dbetamu[FB_NVF], dgn[FB_NV], dlmd[FB_NV], qn[FB_NQ], dqs[FB_NV], qs[FB_NQ];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x / A.n_elems, e = blockIdx.x - b * A.n_elems;
+  const int NV = FB_NV, NX = FB_NX, NU = FB_NU, NVF = FB_NVF, NPASS = FB_NPASS;
+  const FbElem& el = A.elems[e];
+  const bool impulse = el.kind == FB_IMPULSE, terminal = el.kind == FB_TERMINAL;
+  const size_t rec = (size_t)el.slot * A.B + b;
+  FbDir& Dr = A.dir[rec];
+  FbSol& S = A.sol[rec];
+  const FbKKT& Kt = A.kkt[rec];
+  const double ap = A.steps[2 * b], ad = A.steps[2 * b + 1];
+  const double dt = el.dt;
+  if (tid < NV) { dx[tid] = Dr.dq[tid]; dx[NV + tid] = Dr.dv[tid]; dlmd[tid] = Dr.dlmd[tid]; dqs[tid] = Dr.dq[tid]; }
+  if (tid >= 32 && tid < 32 + NU) du[tid - 32] = Dr.du[tid - 32];
+  if (tid < FB_NQ) qs[tid] = S.q[tid];
+  if (!terminal) {
+    const FbDir& Dn = A.dir[(size_t)el.next_slot * A.B + b];
+    if (tid >= 32 && tid < 32 + NV) dgn[tid - 32] = Dn.dgmm[tid - 32];
+  }
+  __syncthreads();
+  const int dimf = terminal ? 0 : el.dimf, nvf = NV + dimf;
+  if (!terminal) {
+    const FbExp& Ex = A.exp[rec];
+    if (!impulse && tid >= 32 && tid < 32 + NPASS) {
+      const int j = tid - 32;
+      const double rdt = 1.0 / dt;
+      double acc = Kt.lu_passive[j];
+      for (int l = 0; l < NU; ++l) acc = fma(Kt.Quu[j * NV + NPASS + l], du[l], acc);
+      for (int l = 0; l < NX; ++l) acc = fma(Kt.Qxu[l * NV + j], dx[l], acc);
+      double t = Ex.MJtJinv[j * NVF] * dgn[0];
+      for (int l = 1; l < NV; ++l) t = fma(Ex.MJtJinv[j * NVF + l], dgn[l], t);
+      Dr.dnu_passive[j] = -(fma(dt, t, acc)) * rdt;
+    }
+    if (tid < nvf) {
+      const int j = tid;
+      double acc = Ex.laf[j];
+      for (int l = 0; l < NX; ++l) acc = fma(Ex.Qafqv[j * NX + l], dx[l], acc);
+      if (!impulse) {
+        for (int l = 0; l < NU; ++l) acc = fma(Ex.Qafu[j * NV + NPASS + l], du[l], acc);
+        if (j < NV) acc = fma(dt, dgn[j], acc);
+      } else {
+        if (j < NV) acc += dgn[j];
+      }
+      laf[j] = acc;
+    }
+    __syncthreads();
+    if (tid < nvf) {
+      const int j = tid;
+      double acc = Ex.MJtJinv[j * NVF] * laf[0];
+      for (int l = 1; l < nvf; ++l) acc = fma(Ex.MJtJinv[j * NVF + l], laf[l], acc);
+      acc = impulse ? -acc : -acc * (1.0 / dt);
+      dbetamu[j] = acc;
+      Dr.dbetamu[j] = acc;
+    }
+  }
+  // correctCostateDirectionForwardEuler: dlmd[0:6] = -Fqq_prev_inv^T dlmd[0:6]
+  if (tid >= 48 && tid < 54) {
+    const int j = tid - 48;
+    double acc = Kt.Fqq_prev_inv[j] * dlmd[0];
+    for (int l = 1; l < 6; ++l) acc = fma(Kt.Fqq_prev_inv[6 * l + j], dlmd[l], acc);
+    Dr.dlmd[j] = -acc;
+  }
+  if (tid == 63) fb_integrate(qs, dqs, ap, qn);
+  __syncthreads();
+  // SplitSolution::integrate
+  if (tid < NV) {
+    const int j = tid;
+    const double dl = (j < 6) ? Dr.dlmd[j] : dlmd[j];
+    S.lmd[j] = fma(ap, dl, S.lmd[j]);
+    S.gmm[j] = fma(ap, Dr.dgmm[j], S.gmm[j]);
+    S.v[j] = fma(ap, dx[NV + j], S.v[j]);
+    if (!terminal) {
+      S.a[j] = fma(ap, Dr.daf[j], S.a[j]);
+      S.beta[j] = fma(ap, dbetamu[j], S.beta[j]);
+    }
+  }
+  if (tid < FB_NQ) S.q[tid] = qn[tid];
+  if (terminal) return;
+  if (!impulse) {
+    if (tid >= 32 && tid < 32 + NU) S.u[tid - 32] = fma(ap, du[tid - 32], S.u[tid - 32]);
+    if (tid >= 48 && tid < 48 + NPASS) S.nu_passive[tid - 48] = fma(ap, Dr.dnu_passive[tid - 48], S.nu_passive[tid - 48]);
+    if (el.sw && tid < el.dimi) S.xi[tid] = fma(ap, Dr.dxi[tid], S.xi[tid]);
+  }
+  if (tid >= 20 && tid < 20 + FB_MAXF) {
+    const int x = tid - 20, i = x / 3;
+    if (el.active[i]) {
+      int k = 0;
+      for (int j = 0; j < i; ++j) k += el.active[j];
+      S.f[x] = fma(ap, Dr.daf[NV + 3 * k + x % 3], S.f[x]);
+      S.mu[x] = fma(ap, dbetamu[NV + 3 * k + x % 3], S.mu[x]);
+    }
+  }
+  for (int idx = tid; idx < FB_NCON; idx += blockDim.x) {
+    const int c = idx < 72 ? idx / 12 : (idx < 92 ? FBC_FRICTION : FBC_IMPULSE_FRICTION);
+    if (el.cactive[c]) {
+      S.slack[idx] = fma(ap, Dr.dslack[idx], S.slack[idx]);
+      S.dual[idx] = fma(ad, Dr.ddual[idx], S.dual[idx]);
+    }
+  }
+}
+
+// KKT error of every instance (ocp_linearizer.cpp:97-137): sum in the reference's order (grid stages and the
+// terminal stage, impulse, aux, lift), one thread per instance
+__global__ void k_fb_kkt_sum(FbArrays A) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= A.B) return;
+  double sum = 0.0;
+  for (int pass = 0; pass < 4; ++pass)
+    for (int e = 0; e < A.n_elems; ++e) {
+      const int k = A.elems[e].kind;
+      const bool mine = (pass == 0 && (k == FB_GRID || k == FB_TERMINAL)) || (pass == 1 && k == FB_IMPULSE) ||
+                        (pass == 2 && k == FB_AUX) || (pass == 3 && k == FB_LIFT);
+      if (mine) sum += A.dir[(size_t)A.elems[e].slot * A.B + b].kkt_sq;
+    }
+  A.kkt_err[b] = sqrt(sum);
+}
+
+// initConstraints (ocp_linearizer.cpp:40-68): Constraints::setSlackAndDual on every used slot; one thread per
+// (instance, slot-table row).  rows[]: slot, kind, cactive[8]
+struct FbInitRow { int slot, kind, cactive[FBC_NCOMP]; };
+__global__ void k_fb_init_constraints(FbArrays A, const FbInitRow* rows, int n_rows) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= A.B * n_rows) return;
+  const int b = g / n_rows;
+  const FbInitRow& row = rows[g - b * n_rows];
+  const FbDevProblem& pr = *A.prob;
+  FbSol& S = A.sol[(size_t)row.slot * A.B + b];
+  for (int c = 0; c < FBC_NCOMP; ++c) {
+    const int o = fbc_offset(c);
+    for (int j = 0; j < fbc_dim(c); ++j) {
+      double sl = 0.0, du = 0.0;
+      if (row.cactive[c]) {
+        if (c >= FBC_FRICTION) {
+          double r5[5];
+          fb_friction_residual(pr.mu, S.f + 3 * (j / 5), r5);
+          sl = -r5[j % 5];
+        } else {
+          switch (c) {
+            case FBC_POS_LO: sl = S.q[7 + j] - pr.q_min[j]; break;
+            case FBC_POS_UP: sl = pr.q_max[j] - S.q[7 + j]; break;
+            case FBC_VEL_LO: sl = S.v[6 + j] - (-pr.v_max[j]); break;
+            case FBC_VEL_UP: sl = pr.v_max[j] - S.v[6 + j]; break;
+            case FBC_TRQ_LO: sl = S.u[j] - (-pr.u_max[j]); break;
+            default:         sl = pr.u_max[j] - S.u[j]; break;
+          }
+        }
+        while (sl < pr.barrier) sl += pr.barrier;
+        du = pr.barrier / sl;
+      }
+      S.slack[o + j] = sl;
+      S.dual[o + j] = du;
+    }
+  }
+}
+
+}  // namespace idocp_b200

@@ -219,6 +219,71 @@ typedef struct {
 int idocp_b200_discretize_ocp(const idocp_b200_contact_sequence* cs, double T, int N, double t,
                               idocp_b200_ocp_discretization* out);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * OCPSolver for the floating-base robot (ANYmal: free-flyer + 12 joints, 4 point contacts), SURVEY.md section 8 row a12.
+ * One handle = a batch of independent OCP instances that share the problem, the contact schedule and the cost
+ * reference and differ in the initial state and in their iterates.  Mirrors
+ *   OCPSolver(robot, cost, constraints, T, N, max_num_impulse, nthreads)   src/ocp/ocp_solver.cpp:10-48
+ *   setSolution / initConstraints / updateSolution / computeKKTResidual / KKTError / getSolution
+ *                                                                          src/ocp/ocp_solver.cpp:60-92,96-213,244-280
+ * The contact schedule (setContactStatusUniformly, pushBackContactStatus, popBack/popFront, setContactPoints:
+ * ocp_solver.cpp:173-194) is the idocp_b200_contact_sequence above; the handle borrows it and re-discretises it at
+ * the t of every call.
+ * Cost = configuration-space cost with a time-varying reference + contact-force cost:
+ *   ConfigurationSpaceCost / TrottingConfigurationSpaceCost / TimeVaryingConfigurationSpaceCost
+ *       (src/cost/trotting_configuration_space_cost.cpp:241-375): weights below, q_ref(t) / v_ref sampled by the host at
+ *       the time of every stage (idocp_b200_fb_set_cost_reference), like the 6D reference of the iiwa14 path;
+ *   ContactForceCost (src/cost/contact_force_cost.cpp:121-228): f_weight / f_ref, fi_weight / fi_ref (impulses).
+ * Constraints = JointConstraintsFactory's six joint limits on the 12 actuated joints + LinearizedFrictionCone +
+ * LinearizedImpulseFrictionCone (src/constraints/ *.cpp), enable[] in the order below.
+ * ------------------------------------------------------------------------------------------------------------ */
+#define IDOCP_B200_FB_NQ 19
+#define IDOCP_B200_FB_NV 18
+#define IDOCP_B200_FB_NU 12
+#define IDOCP_B200_FB_MAXF 12
+enum idocp_b200_fb_constraint {
+  IDOCP_B200_FB_POSITION_LOWER = 0, IDOCP_B200_FB_POSITION_UPPER, IDOCP_B200_FB_VELOCITY_LOWER, IDOCP_B200_FB_VELOCITY_UPPER,
+  IDOCP_B200_FB_TORQUES_LOWER, IDOCP_B200_FB_TORQUES_UPPER, IDOCP_B200_FB_FRICTION_CONE, IDOCP_B200_FB_IMPULSE_FRICTION_CONE,
+  IDOCP_B200_FB_NUM_CONSTRAINTS
+};
+typedef struct {
+  double T;
+  int N, max_num_impulse;
+  double q_weight[18], v_weight[18], a_weight[18], qf_weight[18], vf_weight[18], qi_weight[18], vi_weight[18], dvi_weight[18];
+  double f_weight[12], f_ref[12], fi_weight[12], fi_ref[12];   /* [contact][xyz] */
+  double q_min[12], q_max[12], v_max[12], u_max[12];           /* Robot::*JointPositionLimit etc. (robot.hxx:699-709) */
+  double mu, barrier, fraction_rate;                           /* friction coefficient; PDIPM barrier, fraction-to-boundary */
+  int enable[IDOCP_B200_FB_NUM_CONSTRAINTS];
+} idocp_b200_fb_problem;
+typedef struct idocp_b200_fb_solver idocp_b200_fb_solver; /* opaque */
+
+int idocp_b200_fb_create(const idocp_b200_fb_problem* problem, const idocp_b200_contact_sequence* contact_sequence, int batch,
+                         int device, idocp_b200_fb_solver** out);
+int idocp_b200_fb_destroy(idocp_b200_fb_solver* h);
+/* setSolution(name, value): name in q v a f u; value[dim] broadcast (per_instance = 0) or value[batch][dim]; "f" takes
+ * one 3-vector that is given to every contact */
+int idocp_b200_fb_set_solution(idocp_b200_fb_solver* h, const char* name, const double* value, int per_instance);
+/* cost reference of one slot: kind 0 grid stage (index = time stage, N = terminal), 1 impulse, 2 aux, 3 lift */
+int idocp_b200_fb_set_cost_reference(idocp_b200_fb_solver* h, int kind, int index, const double* q_ref, const double* v_ref);
+/* the chain of stages at time t in the order of the Riccati recursion; arrays of capacity cap (may be NULL);
+ * returns the number of stages.  dimi > 0: the switching constraint of the coming impulse is imposed on that stage */
+int idocp_b200_fb_discretize(idocp_b200_fb_solver* h, double t, int cap, int* kind, int* index, double* stage_t, double* dt,
+                             int* dimf, int* dimi);
+int idocp_b200_fb_init_constraints(idocp_b200_fb_solver* h, double t);
+/* q[batch][19], v[batch][18] host buffers; NULL keeps the initial states already resident on the device */
+int idocp_b200_fb_update_solution(idocp_b200_fb_solver* h, double t, const double* q, const double* v, int line_search);
+int idocp_b200_fb_compute_kkt_residual(idocp_b200_fb_solver* h, double t, const double* q, const double* v);
+int idocp_b200_fb_kkt_error(idocp_b200_fb_solver* h, double* out /* [batch] */);
+int idocp_b200_fb_get_step_sizes(idocp_b200_fb_solver* h, double* out /* [batch][2]: primal, dual */);
+/* one field of one stage of the current chain: out[batch][dim], returns dim (see fb_capi.inc for the field names) */
+int idocp_b200_fb_get(idocp_b200_fb_solver* h, int stage, const char* name, double* out);
+int idocp_b200_fb_sync(idocp_b200_fb_solver* h);
+int idocp_b200_fb_launch_count(idocp_b200_fb_solver* h, long long* out);
+int idocp_b200_fb_stream(idocp_b200_fb_solver* h, void** out);
+int idocp_b200_fb_set_profiling(idocp_b200_fb_solver* h, int enabled);
+int idocp_b200_fb_get_profile(idocp_b200_fb_solver* h, int cap, const char** names, double* ms, long long* calls);
+int idocp_b200_fb_record_bytes(void);
+
 const char* idocp_b200_last_error(void);
 const char* idocp_b200_version(void);
 

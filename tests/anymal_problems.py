@@ -152,3 +152,32 @@ class JumpingProblem(TrottingProblem):
         elif t > self.t_lift:
             q[0] += self.jump_length * (t - self.t_lift) / (self.t_land - self.t_lift)
         return q
+
+
+def make_product_solver(pr, lib, fb, batch, q0=None, v0=None, t=0.0):
+    """The product's OCPSolver (idocp_b200/ocp_solver.py over the C-ABI) set up as the example's main() does; q0 / v0
+    may be (batch, dim) arrays of per-instance initial states (also used as the initial guess, like the example)."""
+    import ctypes as C
+    import idocp_b200 as I
+    p = I.FbProblem()
+    assert C.sizeof(p) == C.sizeof(pr.problem)
+    C.memmove(C.byref(p), C.byref(pr.problem), C.sizeof(p))
+    solver = I.OCPSolver(p, batch, q_ref=lambda tt: (pr.q_ref(tt), pr.v_ref), lib=lib, max_num_events=pr.max_num_impulse + 2)
+    ocs = pr.contact_sequence(fb)
+    n_phases = ocs.counts()[0]
+    a, pts = ocs.phase(0)
+    solver.setContactStatusUniformly(a, pts)
+    # replay the oracle-side schedule through the product's own ContactSequence
+    events = []
+    ni = nl = 0
+    for k in range(1, n_phases):
+        a, pts = ocs.phase(k)
+        events.append((a, pts))
+    times = sorted([ocs.impulse(i)[2] for i in range(ocs.counts()[1])] + [ocs.lift_time(i) for i in range(ocs.counts()[2])])
+    for (a, pts), tt in zip(events, times):
+        solver.pushBackContactStatus(a, tt, pts)
+    solver.setSolution("q", pr.q0 if q0 is None else q0)
+    solver.setSolution("v", pr.v0 if v0 is None else v0)
+    solver.setSolution("f", pr.f_init)
+    solver.initConstraints(t)
+    return solver

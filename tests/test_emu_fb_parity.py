@@ -1,0 +1,86 @@
+"""The ANYmal OCPSolver kernels (idocp_b200/csrc/fb_kernels.cuh) compiled with g++ against the SIMT emulator vs the
+oracle (oracle/fb_ocp.c): bit-exact on every quantity of every stage.  CPU-side check of the cooperative code; the
+same comparison runs on the real GPU in tests/test_gpu_fb_parity.py."""
+import numpy as np
+import pytest
+
+import anymal_problems as ap
+
+SOL = ["q", "v", "a", "u", "f", "lmd", "gmm", "beta", "mu", "nu_passive", "xi"]
+DIR = ["dq", "dv", "du", "daf", "dbetamu", "dlmd", "dgmm", "dnu_passive", "dxi"]
+# condensed KKT record; Qxx / Qxu / Quu / lu are left out: the oracle's Riccati sweep updates them in place
+# (backward_riccati_recursion_factorizer.hxx:44-111) while the kernels keep the linearisation record untouched --
+# they are covered through K, k, P, s, which are functions of exactly those blocks
+KKT = ["lq", "lv", "lu_passive", "Fq", "Fv", "Fvq", "Fvv", "Fvu", "Fqq6", "Fqv6", "Fqq_prev_inv"]
+EXP = ["MJtJinv", "MJ_dIDC", "MJ_IDC", "Qafqv", "Qafu"]
+RIC = ["K", "k", "Pqq", "Pqv", "Pvv", "sq", "sv"]
+
+
+@pytest.fixture(scope="module")
+def fb(oracle):
+    import fb_py
+    fb_py.lib()
+    return fb_py
+
+
+def masked(name, arr, c, fb):
+    """Entries the path defines (stacked blocks are only meaningful up to dimf / dimi)."""
+    arr = np.array(arr, dtype=float)
+    nvf, dimf, dimi = 18 + c["dimf"], c["dimf"], c["dimi"]
+    if name in ("daf", "dbetamu", "MJ_IDC"):
+        arr[nvf:] = 0
+    elif name == "MJtJinv":
+        m = arr.reshape(30, 30); m[nvf:] = 0; m[:, nvf:] = 0
+    elif name in ("MJ_dIDC", "Qafqv", "Qafu"):
+        arr.reshape(30, -1)[nvf:] = 0
+    elif name in ("dxi", "xi"):
+        arr[dimi:] = 0
+    return arr
+
+
+def compare(ocp, solver, fb, names, b=0, only_kinds=None):
+    bad = []
+    for e, c in enumerate(ocp.chain()):
+        if only_kinds is not None and c["kind"] not in only_kinds:
+            continue
+        for nm in names:
+            if c["kind"] == fb.K_TERMINAL and nm not in ("q", "v", "lmd", "gmm", "dq", "dv", "dlmd", "dgmm", "lq", "lv", "Pqq", "Pvv",
+                                                         "sq", "sv", "Fqq_prev_inv"):
+                continue
+            if c["kind"] == fb.K_IMPULSE and nm in ("u", "du", "nu_passive", "dnu_passive", "lu", "lu_passive", "Qxu", "Quu", "Fvu",
+                                                    "Fqv6", "Qafu", "K", "k", "xi", "dxi"):
+                continue
+            if nm in ("xi", "dxi") and c["dimi"] == 0:
+                continue
+            x = masked(nm, ocp.get(e, nm), c, fb)
+            y = masked(nm, solver.get(e, nm)[b], c, fb)
+            if nm == "Qxx":    # the Qvq block is dead storage on both sides (the recursion rebuilds it from Qqv)
+                x.reshape(36, 36)[18:, :18] = 0
+                y.reshape(36, 36)[18:, :18] = 0
+            if not np.array_equal(x, y):
+                bad.append((e, c["kind"], nm, float(np.nanmax(np.abs(x - y)))))
+    return bad
+
+
+def test_trotting_iterations_bit_exact(fb, emu_lib):
+    pr = ap.TrottingProblem()
+    ocp = pr.make_oracle(fb)
+    solver = ap.make_product_solver(pr, emu_lib, fb, batch=1)
+    ch = solver.chain()
+    assert [(c["kind"], c["index"], c["dimf"], c["dimi"]) for c in ch] == [(c["kind"], c["index"], c["dimf"], c["dimi"]) for c in ocp.chain()]
+    assert np.array_equal([c["dt"] for c in ch], [c["dt"] for c in ocp.chain()])
+    assert compare(ocp, solver, fb, SOL) == []
+    for e in range(len(ch)):
+        assert np.array_equal(ocp.get(e, "slack"), solver.get(e, "slack")[0]), e
+        assert np.array_equal(ocp.get(e, "dual"), solver.get(e, "dual")[0]), e
+    for it in range(3):
+        ocp.compute_kkt_residual(0.0, pr.q0, pr.v0)
+        solver.computeKKTResidual(0.0, pr.q0, pr.v0)
+        assert solver.KKTError()[0] == ocp.kkt_error(), (it, solver.KKTError()[0], ocp.kkt_error())
+        assert ocp.update_solution(0.0, pr.q0, pr.v0) == 0
+        solver.updateSolution(0.0, pr.q0, pr.v0)
+        assert compare(ocp, solver, fb, KKT + EXP) == [], it
+        assert compare(ocp, solver, fb, RIC) == [], it
+        assert compare(ocp, solver, fb, DIR) == [], it
+        assert np.array_equal(solver.stepSizes()[0], ocp.step_sizes())
+        assert compare(ocp, solver, fb, SOL) == [], it

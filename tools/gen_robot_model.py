@@ -201,14 +201,14 @@ def load_chain(urdf_path):
     return model
 
 
-def c_array(name, arr, fmt="%.17g"):
+def c_array(name, arr, fmt="%.17g", qual="static const"):
     a = np.asarray(arr, dtype=float)
     dims = "".join("[%d]" % d for d in a.shape)
     def rec(x):
         if x.ndim == 1:
             return "{" + ", ".join(fmt % v for v in x) + "}"
         return "{\n  " + ",\n  ".join(rec(y) for y in x) + "}"
-    return "static const double %s%s = %s;\n" % (name, dims, rec(a))
+    return "%s double %s%s = %s;\n" % (qual, name, dims, rec(a))
 
 
 def emit_iiwa14():
@@ -298,24 +298,26 @@ def emit_anymal():
     hdr.append("#ifndef IDOCP_B200_MODEL_ANYMAL_H_\n#define IDOCP_B200_MODEL_ANYMAL_H_\n")
     hdr.append("#define ANYMAL_NJ 12\n#define ANYMAL_NV 18\n#define ANYMAL_NQ 19\n#define ANYMAL_NB 13\n"
                "#define ANYMAL_NCONTACT 4\n#define ANYMAL_GRAVITY 9.81\n#define ANYMAL_TOTAL_MASS %.17g\n" % total_mass)
-    hdr.append("static const int ANYMAL_JOINT_PARENT[12] = {%s};\n" % ", ".join(str(p) for p in m["parent"]))
-    hdr.append("static const int ANYMAL_JOINT_AXIS[12] = {%s};\n" % ", ".join(str(a) for a in axis_id))
-    hdr.append(c_array("ANYMAL_JOINT_P", m["p"]))
-    hdr.append(c_array("ANYMAL_MASS", [b.m for b in bodies]))
-    hdr.append(c_array("ANYMAL_COM", [b.c for b in bodies]))
+    hdr.append("/* storage class of the tables: plain C by default, __device__ in the CUDA build (fb_math.cuh) */\n"
+               "#ifndef ANYMAL_TABLE\n#define ANYMAL_TABLE static const\n#endif\n")
+    hdr.append("ANYMAL_TABLE int ANYMAL_JOINT_PARENT[12] = {%s};\n" % ", ".join(str(p) for p in m["parent"]))
+    hdr.append("ANYMAL_TABLE int ANYMAL_JOINT_AXIS[12] = {%s};\n" % ", ".join(str(a) for a in axis_id))
+    hdr.append(c_array("ANYMAL_JOINT_P", m["p"], qual="ANYMAL_TABLE"))
+    hdr.append(c_array("ANYMAL_MASS", [b.m for b in bodies], qual="ANYMAL_TABLE"))
+    hdr.append(c_array("ANYMAL_COM", [b.c for b in bodies], qual="ANYMAL_TABLE"))
     hdr.append(c_array("ANYMAL_INERTIA", [[b.I[0, 0], b.I[0, 1], b.I[0, 2], b.I[1, 1], b.I[1, 2], b.I[2, 2]]
-                                          for b in bodies]))
-    hdr.append(c_array("ANYMAL_Q_MIN", m["q_min"]))
-    hdr.append(c_array("ANYMAL_Q_MAX", m["q_max"]))
-    hdr.append(c_array("ANYMAL_V_MAX", m["v_max"]))
-    hdr.append(c_array("ANYMAL_EFFORT_MAX", m["effort"]))
+                                          for b in bodies], qual="ANYMAL_TABLE"))
+    hdr.append(c_array("ANYMAL_Q_MIN", m["q_min"], qual="ANYMAL_TABLE"))
+    hdr.append(c_array("ANYMAL_Q_MAX", m["q_max"], qual="ANYMAL_TABLE"))
+    hdr.append(c_array("ANYMAL_V_MAX", m["v_max"], qual="ANYMAL_TABLE"))
+    hdr.append(c_array("ANYMAL_EFFORT_MAX", m["effort"], qual="ANYMAL_TABLE"))
     hdr.append("/* contact frames %s (examples/anymal/anymal_trotting.cpp:30), parent joint = the leg's KFE */\n" % feet)
-    hdr.append("static const int ANYMAL_CONTACT_FRAME_ID[4] = {%s};\n" % ", ".join(str(f) for f in feet))
-    hdr.append("static const int ANYMAL_CONTACT_PARENT_JOINT[4] = {%s};\n"
+    hdr.append("ANYMAL_TABLE int ANYMAL_CONTACT_FRAME_ID[4] = {%s};\n" % ", ".join(str(f) for f in feet))
+    hdr.append("ANYMAL_TABLE int ANYMAL_CONTACT_PARENT_JOINT[4] = {%s};\n"
                % ", ".join(str(m["frames"][f][1]) for f in feet))
     for f in feet:
         assert np.allclose(m["frames"][f][2], np.eye(3))
-    hdr.append(c_array("ANYMAL_CONTACT_P", [m["frames"][f][3] for f in feet]))
+    hdr.append(c_array("ANYMAL_CONTACT_P", [m["frames"][f][3] for f in feet], qual="ANYMAL_TABLE"))
     hdr.append("#endif\n")
     text = "\n".join(hdr)
     for rel in ("idocp_b200/csrc/model_anymal.h", "oracle/model_anymal.h"):
