@@ -1,0 +1,105 @@
+"""ANYmal OCPSolver on the GPU (through the C-ABI) vs the oracle: bit-exact per iteration on a batch of perturbed
+initial states, identical KKT-error histories to convergence, and size-independent properties at a larger batch."""
+import numpy as np
+import pytest
+
+import anymal_problems as ap
+from test_emu_fb_parity import DIR, EXP, KKT, RIC, SOL, compare
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fb(oracle):
+    import fb_py
+    fb_py.lib()
+    return fb_py
+
+
+def perturbed_states(fb, pr, batch, seed):
+    rng = np.random.default_rng(seed)
+    q0 = np.zeros((batch, 19))
+    v0 = np.zeros((batch, 18))
+    for b in range(batch):
+        dq = np.concatenate([rng.uniform(-0.01, 0.01, 3), rng.uniform(-0.02, 0.02, 3), rng.uniform(-0.02, 0.02, 12)])
+        q0[b] = fb.integrate(pr.q0, dq)
+        v0[b] = rng.uniform(-0.1, 0.1, 18)
+    q0[0], v0[0] = pr.q0, pr.v0
+    return q0, v0
+
+
+def test_batch_iterations_bit_exact(fb, gpu_lib):
+    pr = ap.TrottingProblem()
+    B = 6
+    q0, v0 = perturbed_states(fb, pr, B, 1)
+    solver = ap.make_product_solver(pr, gpu_lib, fb, batch=B, q0=q0, v0=v0)
+    oracles = [pr.make_oracle(fb, q0=q0[b], v0=v0[b]) for b in range(B)]
+    for it in range(4):
+        solver.computeKKTResidual(0.0, q0, v0)
+        kkt = solver.KKTError()
+        for b, o in enumerate(oracles):
+            o.compute_kkt_residual(0.0, q0[b], v0[b])
+            assert kkt[b] == o.kkt_error(), (it, b, kkt[b], o.kkt_error())
+        solver.updateSolution(0.0, q0, v0)
+        steps = solver.stepSizes()
+        for b, o in enumerate(oracles):
+            assert o.update_solution(0.0, q0[b], v0[b]) == 0
+            assert np.array_equal(steps[b], o.step_sizes())
+            for names in (KKT + EXP, RIC, DIR, SOL):
+                assert compare(o, solver, fb, names, b=b) == [], (it, b)
+
+
+def test_convergence_history_identical(fb, gpu_lib):
+    # examples/anymal/anymal_trotting.cpp: 25 iterations; iteration-by-iteration KKT errors equal the oracle's bits
+    pr = ap.TrottingProblem()
+    B = 4
+    q0, v0 = perturbed_states(fb, pr, B, 2)
+    solver = ap.make_product_solver(pr, gpu_lib, fb, batch=B, q0=q0, v0=v0)
+    oracles = [pr.make_oracle(fb, q0=q0[b], v0=v0[b]) for b in range(B)]
+    for it in range(25):
+        solver.computeKKTResidual(0.0, q0, v0)
+        kkt = solver.KKTError()
+        for b, o in enumerate(oracles):
+            o.compute_kkt_residual(0.0, q0[b], v0[b])
+            assert kkt[b] == o.kkt_error(), (it, b)
+            o.update_solution(0.0, q0[b], v0[b])
+        solver.updateSolution(0.0, q0, v0)
+    solver.computeKKTResidual(0.0, q0, v0)
+    assert np.all(solver.KKTError() < 1e-8)
+    e_last = len(solver.chain()) - 1
+    for b, o in enumerate(oracles):
+        assert np.array_equal(solver.get(e_last, "q")[b], o.get(e_last, "q"))
+
+
+def test_flight_phase_bit_exact(fb, gpu_lib):
+    pr = ap.JumpingProblem(0.1, 0.6, 0.75, 1.3, 26)
+    solver = ap.make_product_solver(pr, gpu_lib, fb, batch=2)
+    o = pr.make_oracle(fb)
+    for it in range(5):
+        o.update_solution(0.0, pr.q0, pr.v0)
+        solver.updateSolution(0.0, pr.q0, pr.v0)
+        for names in (KKT + EXP, RIC, DIR, SOL):
+            assert compare(o, solver, fb, names, b=1) == [], it
+
+
+def test_large_batch_properties(fb, gpu_lib):
+    # size-independent properties at a batch the oracle would need minutes for: identical instances give identical
+    # bits wherever they sit in the batch; the KKT error decreases to convergence for every instance
+    pr = ap.TrottingProblem()
+    B = 256
+    q0, v0 = perturbed_states(fb, pr, 8, 3)
+    q0 = np.tile(q0, (B // 8, 1))
+    v0 = np.tile(v0, (B // 8, 1))
+    solver = ap.make_product_solver(pr, gpu_lib, fb, batch=B, q0=q0, v0=v0)
+    hist = []
+    for it in range(25):
+        solver.computeKKTResidual(0.0, q0, v0)
+        hist.append(solver.KKTError())
+        solver.updateSolution(0.0, q0, v0)
+    hist = np.array(hist)
+    assert np.all(np.isfinite(hist)) and np.all(hist[-1] < 1e-7)
+    assert np.array_equal(hist[:, :8], hist[:, 8:16]) and np.array_equal(hist[:, :8], hist[:, -8:])
+    e_mid = len(solver.chain()) // 2
+    u = solver.get(e_mid, "u")
+    assert np.array_equal(u[:8], u[-8:])
+    assert solver.launchCount() > 0
