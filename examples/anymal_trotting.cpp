@@ -1,0 +1,121 @@
+// anymal_trotting.cpp -- the reference's examples/anymal/anymal_trotting.cpp on the batched GPU engine.  The body of
+// main() is the reference's, with the namespace changed, QuadrupedRobot for Robot(path, contact_frames), the Hybrid*
+// containers for CostFunction / Constraints, and a `batch` argument (all instances start from the same state here).
+//   g++ -std=c++17 -Iinclude examples/anymal_trotting.cpp -Lidocp_b200 -lidocp_b200 -Wl,-rpath,$PWD/idocp_b200 -o build/anymal_trotting
+#include <cstdlib>
+#include <iomanip>
+#include <iostream>
+#include <memory>
+#include <string>
+
+#include "idocp_b200/ocp_solver.hpp"
+
+namespace idocp = idocp_b200;
+
+int main(int argc, char* argv[]) {
+  const int batch = argc > 1 ? std::atoi(argv[1]) : 1;
+  std::vector<int> contact_frames = {14, 24, 34, 44};  // LF, LH, RF, RH
+  const std::string path_to_urdf = "../anymal_b_simple_description/urdf/anymal.urdf";
+  idocp::QuadrupedRobot robot(path_to_urdf, contact_frames);
+
+  const double step_length = 0.15;
+  const double t_start = 0.5;
+  const double t_period = 0.5;
+
+  auto cost = std::make_shared<idocp::HybridCostFunction>();
+  idocp::VectorXd q_standing = {0, 0, 0.4792, 0, 0, 0, 1, -0.1, 0.7, -1.0, -0.1, -0.7, 1.0, 0.1, 0.7, -1.0, 0.1, -0.7, 1.0};
+  idocp::VectorXd q_weight = idocp::VectorXd::Constant(robot.dimv(), 10);
+  idocp::VectorXd v_weight = {1, 1, 1, 1, 1, 1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1};
+  idocp::VectorXd a_weight = {0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.01, 0.01, 0.01, 0.01, 0.01, 0.01, 0.01, 0.01, 0.01, 0.01, 0.01, 0.01};
+  idocp::TrottingSwingAngles swing_angles;
+  swing_angles.front_swing_knee = 1.7;
+  swing_angles.hip_swing_knee = 1.7;
+  auto config_cost = std::make_shared<idocp::TrottingConfigurationSpaceCost>(robot);
+  config_cost->set_ref(t_start, t_period, q_standing, step_length, swing_angles);
+  config_cost->set_q_weight(q_weight);
+  config_cost->set_qf_weight(q_weight);
+  config_cost->set_qi_weight(q_weight);
+  config_cost->set_v_weight(v_weight);
+  config_cost->set_vf_weight(v_weight);
+  config_cost->set_vi_weight(v_weight);
+  config_cost->set_a_weight(a_weight);
+  config_cost->set_dvi_weight(a_weight);
+  cost->push_back(config_cost);
+
+  auto contact_cost = std::make_shared<idocp::ContactForceCost>(robot);
+  std::vector<idocp::Vector3d> f_weight(contact_frames.size(), idocp::Vector3d(0.001, 0.001, 0.001));
+  contact_cost->set_f_weight(f_weight);
+  contact_cost->set_fi_weight(f_weight);
+  contact_cost->set_f_ref(robot);
+  cost->push_back(contact_cost);
+
+  auto constraints = std::make_shared<idocp::HybridConstraints>();
+  const double mu = 0.7;
+  constraints->push_back(std::make_shared<idocp::JointPositionLowerLimit>(robot));
+  constraints->push_back(std::make_shared<idocp::JointPositionUpperLimit>(robot));
+  constraints->push_back(std::make_shared<idocp::JointVelocityLowerLimit>(robot));
+  constraints->push_back(std::make_shared<idocp::JointVelocityUpperLimit>(robot));
+  constraints->push_back(std::make_shared<idocp::JointTorquesLowerLimit>(robot));
+  constraints->push_back(std::make_shared<idocp::JointTorquesUpperLimit>(robot));
+  constraints->push_back(std::make_shared<idocp::LinearizedFrictionCone>(robot, mu));
+  constraints->push_back(std::make_shared<idocp::LinearizedImpulseFrictionCone>(robot, mu));
+
+  // 2 steps
+  const double T = 1.55;  // t_start + max_num_impulse_phase * t_period + 0.05
+  const int N = 30;
+  const int max_num_impulse_phase = 2;
+  const int nthreads = 4;
+  const double t = 0;
+  idocp::OCPSolver ocp_solver(robot, cost, constraints, T, N, max_num_impulse_phase + 1, nthreads, batch);
+
+  robot.updateFrameKinematics(q_standing);
+  std::vector<idocp::Vector3d> contact_points(robot.maxPointContacts());
+  robot.getContactPoints(contact_points);
+  auto contact_status_initial = robot.createContactStatus();
+  contact_status_initial.activateContacts({0, 1, 2, 3});
+  contact_status_initial.setContactPoints(idocp::toPoints(contact_points));
+  ocp_solver.setContactStatusUniformly(contact_status_initial);
+
+  auto contact_status_even = robot.createContactStatus();
+  contact_status_even.activateContacts({1, 2});
+  contact_status_even.setContactPoints(idocp::toPoints(contact_points));
+  ocp_solver.pushBackContactStatus(contact_status_even, t_start);
+
+  auto contact_status_odd = robot.createContactStatus();
+  contact_points[0].coeffRef(0) += 0.5 * step_length;
+  contact_points[3].coeffRef(0) += 0.5 * step_length;
+  contact_status_odd.activateContacts({0, 3});
+  contact_status_odd.setContactPoints(idocp::toPoints(contact_points));
+  ocp_solver.pushBackContactStatus(contact_status_odd, t_start + t_period);
+
+  for (int i = 2; i <= max_num_impulse_phase; ++i) {
+    if (i % 2 == 0) {
+      contact_points[1].coeffRef(0) += step_length;
+      contact_points[2].coeffRef(0) += step_length;
+      contact_status_even.setContactPoints(idocp::toPoints(contact_points));
+      ocp_solver.pushBackContactStatus(contact_status_even, t_start + i * t_period);
+    } else {
+      contact_points[0].coeffRef(0) += step_length;
+      contact_points[3].coeffRef(0) += step_length;
+      contact_status_odd.setContactPoints(idocp::toPoints(contact_points));
+      ocp_solver.pushBackContactStatus(contact_status_odd, t_start + i * t_period);
+    }
+  }
+
+  idocp::VectorXd q = q_standing;
+  idocp::VectorXd v = idocp::VectorXd::Zero(robot.dimv());
+  ocp_solver.setSolution("q", q);
+  ocp_solver.setSolution("v", v);
+  idocp::Vector3d f_init(0, 0, 0.25 * robot.totalWeight());
+  ocp_solver.setSolution("f", f_init);
+
+  ocp_solver.initConstraints(t);
+
+  const bool line_search = false;
+  std::cout << std::setprecision(17);
+  idocp::ocpbenchmarker::Convergence(ocp_solver, t, q, v, 25, line_search);
+  idocp::ocpbenchmarker::CPUTime(ocp_solver, t, q, v, 20, line_search);
+  const auto qs = ocp_solver.getSolution("q");
+  std::cout << "base x at the end of the horizon: " << qs.back()[0] << std::endl;
+  return 0;
+}

@@ -109,7 +109,8 @@ EXPORTS = [
     "idocp_b200_fb_discretize", "idocp_b200_fb_init_constraints", "idocp_b200_fb_update_solution",
     "idocp_b200_fb_compute_kkt_residual", "idocp_b200_fb_kkt_error", "idocp_b200_fb_get_step_sizes", "idocp_b200_fb_get",
     "idocp_b200_fb_sync", "idocp_b200_fb_launch_count", "idocp_b200_fb_stream", "idocp_b200_fb_set_profiling",
-    "idocp_b200_fb_get_profile", "idocp_b200_fb_record_bytes",
+    "idocp_b200_fb_get_profile", "idocp_b200_fb_record_bytes", "idocp_b200_fb_problem_default",
+    "idocp_b200_fb_total_weight", "idocp_b200_fb_contact_frame_positions",
 ]
 
 
@@ -171,7 +172,7 @@ class Library:
         L.idocp_b200_fb_destroy.argtypes = [C.c_void_p]
         L.idocp_b200_fb_set_solution.argtypes = [C.c_void_p, C.c_char_p, _dp, C.c_int]
         L.idocp_b200_fb_set_cost_reference.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp]
-        L.idocp_b200_fb_discretize.argtypes = [C.c_void_p, C.c_double, C.c_int, _ip, _ip, _dp, _dp, _ip, _ip]
+        L.idocp_b200_fb_discretize.argtypes = [C.c_void_p, C.c_double, C.c_int, _ip, _ip, _dp, _dp, _ip, _ip, _ip]
         L.idocp_b200_fb_init_constraints.argtypes = [C.c_void_p, C.c_double]
         L.idocp_b200_fb_update_solution.argtypes = [C.c_void_p, C.c_double, _dp, _dp, C.c_int]
         L.idocp_b200_fb_compute_kkt_residual.argtypes = [C.c_void_p, C.c_double, _dp, _dp]
@@ -183,6 +184,9 @@ class Library:
         L.idocp_b200_fb_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.idocp_b200_fb_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.idocp_b200_fb_get_profile.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), _dp, C.POINTER(C.c_longlong)]
+        L.idocp_b200_fb_problem_default.argtypes = [C.POINTER(FbProblem)]
+        L.idocp_b200_fb_total_weight.restype = C.c_double
+        L.idocp_b200_fb_contact_frame_positions.argtypes = [_dp, _dp]
         self.L = L
 
     def check(self, rc):

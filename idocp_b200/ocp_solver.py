@@ -74,7 +74,7 @@ class OCPSolver:
         ip = C.POINTER(C.c_int)
         n = self.lib.check(self.lib.L.idocp_b200_fb_discretize(self._h, float(t), cap, kind.ctypes.data_as(ip),
                                                                index.ctypes.data_as(ip), capi.dptr(tt), capi.dptr(dt),
-                                                               dimf.ctypes.data_as(ip), dimi.ctypes.data_as(ip)))
+                                                               dimf.ctypes.data_as(ip), dimi.ctypes.data_as(ip), None))
         self._chain = [dict(kind=int(kind[e]), index=int(index[e]), t=float(tt[e]), dt=float(dt[e]), dimf=int(dimf[e]),
                             dimi=int(dimi[e])) for e in range(n)]
         return self._chain

@@ -265,10 +265,11 @@ int idocp_b200_fb_destroy(idocp_b200_fb_solver* h);
 int idocp_b200_fb_set_solution(idocp_b200_fb_solver* h, const char* name, const double* value, int per_instance);
 /* cost reference of one slot: kind 0 grid stage (index = time stage, N = terminal), 1 impulse, 2 aux, 3 lift */
 int idocp_b200_fb_set_cost_reference(idocp_b200_fb_solver* h, int kind, int index, const double* q_ref, const double* v_ref);
-/* the chain of stages at time t in the order of the Riccati recursion; arrays of capacity cap (may be NULL);
- * returns the number of stages.  dimi > 0: the switching constraint of the coming impulse is imposed on that stage */
+/* the chain of stages at time t in the order of the Riccati recursion; arrays of capacity cap (may be NULL;
+ * active is [cap][4], the contact / impulse status of the stage); returns the number of stages.
+ * dimi > 0: the switching constraint of the coming impulse is imposed on that stage */
 int idocp_b200_fb_discretize(idocp_b200_fb_solver* h, double t, int cap, int* kind, int* index, double* stage_t, double* dt,
-                             int* dimf, int* dimi);
+                             int* dimf, int* dimi, int* active);
 int idocp_b200_fb_init_constraints(idocp_b200_fb_solver* h, double t);
 /* q[batch][19], v[batch][18] host buffers; NULL keeps the initial states already resident on the device */
 int idocp_b200_fb_update_solution(idocp_b200_fb_solver* h, double t, const double* q, const double* v, int line_search);
@@ -283,6 +284,11 @@ int idocp_b200_fb_stream(idocp_b200_fb_solver* h, void** out);
 int idocp_b200_fb_set_profiling(idocp_b200_fb_solver* h, int enabled);
 int idocp_b200_fb_get_profile(idocp_b200_fb_solver* h, int cap, const char** names, double* ms, long long* calls);
 int idocp_b200_fb_record_bytes(void);
+/* host-side model facts of ANYmal (the reference's Robot is a host object) */
+int idocp_b200_fb_problem_default(idocp_b200_fb_problem* problem);   /* URDF joint limits, barrier 1e-4, rate 0.995 */
+double idocp_b200_fb_total_weight(void);                               /* Robot::totalWeight (robot.hxx:746-748) */
+/* Robot::updateFrameKinematics(q) + getContactPoints (robot.hxx:233-238,737-743): out[4][3] */
+int idocp_b200_fb_contact_frame_positions(const double* q, double* out);
 
 const char* idocp_b200_last_error(void);
 const char* idocp_b200_version(void);

@@ -1,0 +1,379 @@
+// ocp_solver.hpp -- C++ host layer of the hybrid OCPSolver (floating-base ANYmal with point contacts) on top of the
+// C-ABI (include/idocp_b200.h, idocp_b200_fb_*).  Header-only; link against libidocp_b200.so.
+//
+// Same idea as idocp_b200.hpp: the reference's class and method names, argument meaning and call order
+// (examples/anymal/anymal_trotting.cpp compiles against this header after replacing the namespace):
+//   idocp::Robot(path_to_urdf, contact_frames)   include/idocp/robot/robot.hpp   -> QuadrupedRobot
+//   idocp::TrottingConfigurationSpaceCost        include/idocp/cost/trotting_configuration_space_cost.hpp
+//   idocp::ContactForceCost                      include/idocp/cost/contact_force_cost.hpp
+//   idocp::Joint{Position,Velocity,Torques}{Lower,Upper}Limit, LinearizedFrictionCone, LinearizedImpulseFrictionCone
+//                                                include/idocp/constraints/ *.hpp
+//   idocp::OCPSolver                             include/idocp/ocp/ocp_solver.hpp:28-230
+// The reference's cost / constraint plug-ins are host virtuals; here they are a closed registry of POD-parameterised
+// components, and the one user-defined piece (a time-varying configuration reference, update_q_ref) stays a host
+// virtual that is sampled at the time of every stage before each call.
+#ifndef IDOCP_B200_OCP_SOLVER_HPP_
+#define IDOCP_B200_OCP_SOLVER_HPP_
+
+#include <array>
+#include <cmath>
+#include <cstring>
+
+#include "idocp_b200.hpp"
+
+namespace idocp_b200 {
+
+// Robot(path_to_urdf, contact_frames): ANYmal-B with the four foot frames {14, 24, 34, 44} (LF, LH, RF, RH)
+class QuadrupedRobot {
+ public:
+  explicit QuadrupedRobot(const std::string& path_to_urdf = "", const std::vector<int>& contact_frames = {14, 24, 34, 44})
+      : urdf_(path_to_urdf), frames_(contact_frames) {
+    if (contact_frames != std::vector<int>{14, 24, 34, 44})
+      detail::die("invalid argument: the contact frames of ANYmal must be {14, 24, 34, 44}");
+    detail::check(idocp_b200_fb_problem_default(&p_));
+  }
+  int dimq() const { return IDOCP_B200_FB_NQ; }
+  int dimv() const { return IDOCP_B200_FB_NV; }
+  int dimu() const { return IDOCP_B200_FB_NU; }
+  int max_dimf() const { return IDOCP_B200_FB_MAXF; }
+  int dim_passive() const { return 6; }
+  bool hasFloatingBase() const { return true; }
+  int maxPointContacts() const { return 4; }
+  ContactStatus createContactStatus() const { return ContactStatus(maxPointContacts()); }
+  double totalWeight() const { return idocp_b200_fb_total_weight(); }
+  void updateFrameKinematics(const VectorXd& q) {
+    if (q.size() != dimq()) detail::die("invalid size: q.size() must be 19");
+    detail::check(idocp_b200_fb_contact_frame_positions(q.data(), points_));
+  }
+  void getContactPoints(std::vector<Vector3d>& contact_points) const {
+    contact_points.resize(4);
+    for (int i = 0; i < 4; ++i) contact_points[i] = Vector3d(points_[3 * i], points_[3 * i + 1], points_[3 * i + 2]);
+  }
+  const idocp_b200_fb_problem& limits() const { return p_; }
+ private:
+  std::string urdf_;
+  std::vector<int> frames_;
+  idocp_b200_fb_problem p_;
+  double points_[12] = {0};
+};
+
+inline std::vector<Point3> toPoints(const std::vector<Vector3d>& v) {
+  std::vector<Point3> out;
+  for (const auto& e : v) out.push_back(Point3{e[0], e[1], e[2]});
+  return out;
+}
+
+namespace detail {
+inline void copyN(const VectorXd& v, double* dst, int n, const char* what) {
+  if (v.size() != n) die(std::string("invalid size: ") + what + ".size() must be " + std::to_string(n) + "!");
+  for (int i = 0; i < n; ++i) dst[i] = v[i];
+}
+}  // namespace detail
+
+// a configuration-space cost whose reference is a function of time: q_ref(t) is sampled on the host per stage
+class ConfigurationReferenceBase {
+ public:
+  virtual ~ConfigurationReferenceBase() {}
+  virtual void update_q_ref(const double t, VectorXd& q_ref) const = 0;
+};
+
+struct TrottingSwingAngles {
+  double front_swing_thigh = 0, front_swing_knee = 0, front_stance_thigh = 0, front_stance_knee = 0, hip_swing_thigh = 0,
+         hip_swing_knee = 0, hip_stance_thigh = 0, hip_stance_knee = 0;
+};
+
+// trotting_configuration_space_cost.hpp:52-164
+class TrottingConfigurationSpaceCost : public ConfigurationReferenceBase {
+ public:
+  explicit TrottingConfigurationSpaceCost(const QuadrupedRobot&) { std::memset(&w_, 0, sizeof(w_)); }
+  void set_ref(const double t_start, const double t_period, const VectorXd& q_standing, const double step_length,
+               const TrottingSwingAngles& swing_angles) {
+    if (q_standing.size() != 19) detail::die("invalid size: q_standing.size() must be 19!");
+    if (t_period <= 0) detail::die("invalid argment: t_period must be positive!");
+    if (step_length <= 0) detail::die("invalid argment: step_length must be positive!");
+    t_start_ = t_start; t_period_ = t_period; q_standing_ = q_standing; step_length_ = step_length;
+    v_ref_ = VectorXd::Zero(18);
+    v_ref_[0] = step_length / t_period;
+    swing_ = swing_angles;
+  }
+  void set_q_weight(const VectorXd& v) { detail::copyN(v, w_.q_weight, 18, "q_weight"); }
+  void set_v_weight(const VectorXd& v) { detail::copyN(v, w_.v_weight, 18, "v_weight"); }
+  void set_a_weight(const VectorXd& v) { detail::copyN(v, w_.a_weight, 18, "a_weight"); }
+  void set_qf_weight(const VectorXd& v) { detail::copyN(v, w_.qf_weight, 18, "qf_weight"); }
+  void set_vf_weight(const VectorXd& v) { detail::copyN(v, w_.vf_weight, 18, "vf_weight"); }
+  void set_qi_weight(const VectorXd& v) { detail::copyN(v, w_.qi_weight, 18, "qi_weight"); }
+  void set_vi_weight(const VectorXd& v) { detail::copyN(v, w_.vi_weight, 18, "vi_weight"); }
+  void set_dvi_weight(const VectorXd& v) { detail::copyN(v, w_.dvi_weight, 18, "dvi_weight"); }
+  void update_q_ref(const double t, VectorXd& q_ref) const override {
+    q_ref = q_standing_;
+    if (t > t_start_) {
+      const double tau = t - t_start_;
+      const int steps = static_cast<int>(std::floor(tau / t_period_));
+      const double rate = (tau - steps * t_period_) / t_period_;
+      const double sin2 = std::sin(M_PI_2 * rate);
+      q_ref[0] += (steps + rate) * step_length_;
+      if (steps % 2 == 0) {
+        q_ref[9] -= sin2 * swing_.front_swing_knee;
+        q_ref[12] -= sin2 * swing_.hip_stance_knee;
+        q_ref[15] += sin2 * swing_.front_stance_knee;
+        q_ref[18] += sin2 * swing_.hip_swing_knee;
+      } else {
+        q_ref[9] += sin2 * swing_.front_stance_knee;
+        q_ref[12] += sin2 * swing_.hip_swing_knee;
+        q_ref[15] -= sin2 * swing_.front_swing_knee;
+        q_ref[18] -= sin2 * swing_.hip_stance_knee;
+      }
+    }
+  }
+  const VectorXd& v_ref() const { return v_ref_; }
+  const idocp_b200_fb_problem& weights() const { return w_; }
+ private:
+  idocp_b200_fb_problem w_;
+  double t_start_ = 0, t_period_ = 1, step_length_ = 0;
+  VectorXd q_standing_, v_ref_;
+  TrottingSwingAngles swing_;
+};
+
+// contact_force_cost.hpp
+class ContactForceCost {
+ public:
+  explicit ContactForceCost(const QuadrupedRobot&) { std::memset(&w_, 0, sizeof(w_)); }
+  void set_f_ref(const QuadrupedRobot& robot) {
+    for (int i = 0; i < 4; ++i) { w_.f_ref[3 * i] = 0; w_.f_ref[3 * i + 1] = 0; w_.f_ref[3 * i + 2] = robot.totalWeight() / 4; }
+  }
+  void set_f_ref(const std::vector<Vector3d>& f) { set3(f, w_.f_ref, "f_ref"); }
+  void set_f_weight(const std::vector<Vector3d>& f) { set3(f, w_.f_weight, "f_weight"); }
+  void set_fi_ref(const std::vector<Vector3d>& f) { set3(f, w_.fi_ref, "f_ref"); }
+  void set_fi_weight(const std::vector<Vector3d>& f) { set3(f, w_.fi_weight, "f_weight"); }
+  const idocp_b200_fb_problem& weights() const { return w_; }
+ private:
+  static void set3(const std::vector<Vector3d>& f, double* dst, const char* what) {
+    if (f.size() != 4) detail::die(std::string("invalid size: ") + what + ".size() must be 4!");
+    for (int i = 0; i < 4; ++i)
+      for (int x = 0; x < 3; ++x) dst[3 * i + x] = f[i][x];
+  }
+  idocp_b200_fb_problem w_;
+};
+
+class HybridCostFunction {
+ public:
+  void push_back(const std::shared_ptr<TrottingConfigurationSpaceCost>& c) { config_ = c; }
+  void push_back(const std::shared_ptr<ContactForceCost>& c) { force_ = c; }
+  const std::shared_ptr<TrottingConfigurationSpaceCost>& config() const { return config_; }
+  const std::shared_ptr<ContactForceCost>& force() const { return force_; }
+ private:
+  std::shared_ptr<TrottingConfigurationSpaceCost> config_;
+  std::shared_ptr<ContactForceCost> force_;
+};
+
+// constraints: closed registry, one tag class per reference component
+struct HybridConstraintComponent {
+  int id;
+  double mu;
+};
+#define IDOCP_B200_JOINT_LIMIT(Name, Id)                                   \
+  struct Name : HybridConstraintComponent {                                 \
+    explicit Name(const QuadrupedRobot&) : HybridConstraintComponent{Id, 0.0} {} \
+  }
+IDOCP_B200_JOINT_LIMIT(JointPositionLowerLimit, IDOCP_B200_FB_POSITION_LOWER);
+IDOCP_B200_JOINT_LIMIT(JointPositionUpperLimit, IDOCP_B200_FB_POSITION_UPPER);
+IDOCP_B200_JOINT_LIMIT(JointVelocityLowerLimit, IDOCP_B200_FB_VELOCITY_LOWER);
+IDOCP_B200_JOINT_LIMIT(JointVelocityUpperLimit, IDOCP_B200_FB_VELOCITY_UPPER);
+IDOCP_B200_JOINT_LIMIT(JointTorquesLowerLimit, IDOCP_B200_FB_TORQUES_LOWER);
+IDOCP_B200_JOINT_LIMIT(JointTorquesUpperLimit, IDOCP_B200_FB_TORQUES_UPPER);
+#undef IDOCP_B200_JOINT_LIMIT
+struct LinearizedFrictionCone : HybridConstraintComponent {
+  LinearizedFrictionCone(const QuadrupedRobot&, const double mu) : HybridConstraintComponent{IDOCP_B200_FB_FRICTION_CONE, mu} {
+    if (mu <= 0) detail::die("invalid value: mu must be positive!");
+  }
+};
+struct LinearizedImpulseFrictionCone : HybridConstraintComponent {
+  LinearizedImpulseFrictionCone(const QuadrupedRobot&, const double mu)
+      : HybridConstraintComponent{IDOCP_B200_FB_IMPULSE_FRICTION_CONE, mu} {
+    if (mu <= 0) detail::die("invalid value: mu must be positive!");
+  }
+};
+class HybridConstraints {
+ public:
+  template <typename Component>
+  void push_back(const std::shared_ptr<Component>& c) {
+    enable_[c->id] = 1;
+    if (c->mu > 0) mu_ = c->mu;
+  }
+  void setBarrier(double b) { if (!(b > 0)) detail::die("invalid argment: barrier must be positive"); barrier_ = b; }
+  void setFractionToBoundaryRate(double r) { if (!(r > 0) || r > 1) detail::die("invalid argment: rate"); rate_ = r; }
+  const int* enable() const { return enable_; }
+  double mu() const { return mu_; }
+  double barrier() const { return barrier_; }
+  double fractionToBoundaryRate() const { return rate_; }
+ private:
+  int enable_[IDOCP_B200_FB_NUM_CONSTRAINTS] = {0};
+  double mu_ = 0.7, barrier_ = 1.0e-04, rate_ = 0.995;
+};
+
+// OCPSolver(robot, cost, constraints, T, N, max_num_impulse, nthreads) for `batch` instances
+class OCPSolver {
+ public:
+  OCPSolver(const QuadrupedRobot& robot, const std::shared_ptr<HybridCostFunction>& cost,
+            const std::shared_ptr<HybridConstraints>& constraints, const double T, const int N, const int max_num_impulse = 0,
+            const int nthreads = 1, const int batch = 1, const int device = 0)
+      : cost_(cost), batch_(batch) {
+    if (T <= 0) detail::die("invalid value: T must be positive!");
+    if (N <= 0) detail::die("invalid value: N must be positive!");
+    if (max_num_impulse < 0) detail::die("invalid value: max_num_impulse must be non-negative!");
+    if (nthreads <= 0) detail::die("invalid value: nthreads must be positive!");
+    idocp_b200_fb_problem p = robot.limits();
+    p.T = T; p.N = N; p.max_num_impulse = max_num_impulse;
+    if (cost->config()) {
+      const idocp_b200_fb_problem& w = cost->config()->weights();
+      std::memcpy(p.q_weight, w.q_weight, sizeof(double) * 18 * 8);   // q_weight .. dvi_weight are contiguous
+    }
+    if (cost->force()) {
+      const idocp_b200_fb_problem& w = cost->force()->weights();
+      std::memcpy(p.f_weight, w.f_weight, sizeof(double) * 12 * 4);   // f_weight, f_ref, fi_weight, fi_ref
+    }
+    for (int c = 0; c < IDOCP_B200_FB_NUM_CONSTRAINTS; ++c) p.enable[c] = constraints->enable()[c];
+    p.mu = constraints->mu(); p.barrier = constraints->barrier(); p.fraction_rate = constraints->fractionToBoundaryRate();
+    idocp_b200_contact_sequence* cs = nullptr;
+    detail::check(idocp_b200_contact_sequence_create(4, 2 * max_num_impulse + 2, &cs));
+    cs_.reset(cs, [](idocp_b200_contact_sequence* x) { idocp_b200_contact_sequence_destroy(x); });
+    idocp_b200_fb_solver* h = nullptr;
+    detail::check(idocp_b200_fb_create(&p, cs, batch, device, &h));
+    h_.reset(h, [](idocp_b200_fb_solver* x) { idocp_b200_fb_destroy(x); });
+    prob_ = p;
+  }
+  int batch() const { return batch_; }
+  // contact schedule (ocp_solver.cpp:173-194)
+  void setContactStatusUniformly(const ContactStatus& s) {
+    std::vector<int> a; std::vector<double> pts;
+    pack(s, a, pts);
+    detail::check(idocp_b200_contact_sequence_set_uniform(cs_.get(), a.data(), pts.data()));
+  }
+  void pushBackContactStatus(const ContactStatus& s, const double switching_time) {
+    std::vector<int> a; std::vector<double> pts;
+    pack(s, a, pts);
+    detail::check(idocp_b200_contact_sequence_push_back(cs_.get(), a.data(), pts.data(), switching_time));
+  }
+  void popBackContactStatus() { detail::check(idocp_b200_contact_sequence_pop_back(cs_.get())); }
+  void popFrontContactStatus() { detail::check(idocp_b200_contact_sequence_pop_front(cs_.get())); }
+  void setContactPoints(const int contact_phase, const std::vector<Vector3d>& contact_points) {
+    std::vector<double> pts;
+    for (const auto& e : contact_points) { pts.push_back(e[0]); pts.push_back(e[1]); pts.push_back(e[2]); }
+    detail::check(idocp_b200_contact_sequence_set_contact_points(cs_.get(), contact_phase, pts.data()));
+  }
+  // setSolution(name, value): broadcast to every instance and stage ("f": one 3-vector for every contact)
+  void setSolution(const std::string& name, const VectorXd& value) {
+    detail::check(idocp_b200_fb_set_solution(h_.get(), name.c_str(), value.data(), 0));
+  }
+  void setSolution(const std::string& name, const Vector3d& value) {
+    detail::check(idocp_b200_fb_set_solution(h_.get(), name.c_str(), value.d, 0));
+  }
+  void setSolution(const std::string& name, const double* value_per_instance) {
+    detail::check(idocp_b200_fb_set_solution(h_.get(), name.c_str(), value_per_instance, 1));
+  }
+  void initConstraints(const double t) {
+    sampleReference(t);
+    detail::check(idocp_b200_fb_init_constraints(h_.get(), t));
+  }
+  void updateSolution(const double t, const VectorXd& q, const VectorXd& v, const bool line_search = false) {
+    replicate(q, v);
+    updateSolution(t, q_.data(), v_.data(), line_search);
+  }
+  void updateSolution(const double t, const double* q, const double* v, const bool line_search = false) {
+    sampleReference(t);
+    detail::check(idocp_b200_fb_update_solution(h_.get(), t, q, v, line_search ? 1 : 0));
+  }
+  void computeKKTResidual(const double t, const VectorXd& q, const VectorXd& v) {
+    replicate(q, v);
+    computeKKTResidual(t, q_.data(), v_.data());
+  }
+  void computeKKTResidual(const double t, const double* q, const double* v) {
+    sampleReference(t);
+    detail::check(idocp_b200_fb_compute_kkt_residual(h_.get(), t, q, v));
+  }
+  double KKTError() { return KKTErrors()[0]; }
+  std::vector<double> KKTErrors() {
+    std::vector<double> out(batch_);
+    detail::check(idocp_b200_fb_kkt_error(h_.get(), out.data()));
+    return out;
+  }
+  // getSolution(name): the grid stages 0..N (q, v) or 0..N-1 (a, f, u) of one instance (ocp_solver.cpp:244-280)
+  std::vector<VectorXd> getSolution(const std::string& name, const int instance = 0) {
+    const int n = discretize();
+    std::vector<VectorXd> out;
+    std::vector<double> buf(static_cast<size_t>(batch_) * 36 * 36);
+    for (int e = 0; e < n; ++e) {
+      const bool grid = kind_[e] == 0, terminal = kind_[e] == 4;
+      if (!(grid || (terminal && (name == "q" || name == "v")))) continue;
+      const int dim = idocp_b200_fb_get(h_.get(), e, name.c_str(), buf.data());
+      detail::check(dim);
+      VectorXd x(name == "f" ? dimf_[e] : dim);
+      if (name == "f") {   // f_stack(): the active contacts only
+        int k = 0;
+        for (int i = 0; i < 4; ++i)
+          if (active_[e][i]) { for (int c = 0; c < 3; ++c) x[k++] = buf[static_cast<size_t>(instance) * dim + 3 * i + c]; }
+      } else {
+        for (int j = 0; j < dim; ++j) x[j] = buf[static_cast<size_t>(instance) * dim + j];
+      }
+      out.push_back(x);
+    }
+    return out;
+  }
+  void sync() { detail::check(idocp_b200_fb_sync(h_.get())); }
+  idocp_b200_fb_solver* handle() { return h_.get(); }
+
+ private:
+  static void pack(const ContactStatus& s, std::vector<int>& a, std::vector<double>& pts) {
+    if (s.maxPointContacts() != 4) detail::die("invalid argument: contact status must have 4 contacts");
+    for (int i = 0; i < 4; ++i) {
+      a.push_back(s.isContactActive(i) ? 1 : 0);
+      for (int c = 0; c < 3; ++c) pts.push_back(s.contactPoint(i)[c]);
+    }
+  }
+  int discretize() {
+    const int cap = IDOCP_B200_MAX_GRID + 1 + 3 * IDOCP_B200_MAX_EVENTS;
+    kind_.assign(cap, 0); index_.assign(cap, 0); t_.assign(cap, 0.0); dimf_.assign(cap, 0);
+    std::vector<int> act(static_cast<size_t>(cap) * 4, 0);
+    const int n = idocp_b200_fb_discretize(h_.get(), t_last_, cap, kind_.data(), index_.data(), t_.data(), nullptr, dimf_.data(), nullptr,
+                                           act.data());
+    detail::check(n);
+    active_.assign(n, {0, 0, 0, 0});
+    for (int e = 0; e < n; ++e)
+      for (int i = 0; i < 4; ++i) active_[e][i] = act[4 * e + i];
+    return n;
+  }
+  // the reference evaluates update_q_ref(t) inside every cost call; here once per stage and call
+  void sampleReference(const double t) {
+    t_last_ = t;
+    const int n = discretize();
+    if (!cost_->config()) return;
+    VectorXd q_ref(19);
+    for (int e = 0; e < n; ++e) {
+      cost_->config()->update_q_ref(t_[e], q_ref);
+      const int kind = kind_[e] == 4 ? 0 : kind_[e];
+      detail::check(idocp_b200_fb_set_cost_reference(h_.get(), kind, index_[e], q_ref.data(), cost_->config()->v_ref().data()));
+    }
+  }
+  void replicate(const VectorXd& q, const VectorXd& v) {
+    if (q.size() != 19) detail::die("invalid size: q.size() must be 19!");
+    if (v.size() != 18) detail::die("invalid size: v.size() must be 18!");
+    q_.resize(static_cast<size_t>(batch_) * 19);
+    v_.resize(static_cast<size_t>(batch_) * 18);
+    for (int b = 0; b < batch_; ++b) {
+      for (int j = 0; j < 19; ++j) q_[static_cast<size_t>(b) * 19 + j] = q[j];
+      for (int j = 0; j < 18; ++j) v_[static_cast<size_t>(b) * 18 + j] = v[j];
+    }
+  }
+  std::shared_ptr<HybridCostFunction> cost_;
+  std::shared_ptr<idocp_b200_contact_sequence> cs_;
+  std::shared_ptr<idocp_b200_fb_solver> h_;
+  idocp_b200_fb_problem prob_;
+  int batch_ = 1;
+  double t_last_ = 0.0;
+  std::vector<int> kind_, index_, dimf_;
+  std::vector<double> t_, q_, v_;
+  std::vector<std::array<int, 4>> active_;
+};
+
+}  // namespace idocp_b200
+#endif  // IDOCP_B200_OCP_SOLVER_HPP_

@@ -81,10 +81,11 @@ class TrottingProblem:
         self.q0 = Q_STANDING.copy()
         self.v0 = np.zeros(18)
         self.f_init = np.array([0, 0, 0.25 * TOTAL_WEIGHT])
+        self.standing_points = None     # override of the contact points of the standing pose (default: the oracle's FK)
 
     def contact_sequence(self, fb):
         cs = hybrid_py.ContactSequence(4, self.max_num_impulse + 2)
-        pts = standing_contact_points(fb)
+        pts = standing_contact_points(fb) if self.standing_points is None else np.array(self.standing_points, dtype=float)
         cs.set_uniform([1, 1, 1, 1], pts)
         cs.push_back([0, 1, 1, 0], self.t_start, pts)
         pts = pts.copy()

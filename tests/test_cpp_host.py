@@ -69,3 +69,42 @@ def test_contact_schedule_example_runs_on_the_host():
     assert sum("switching constraint" in line for line in out) == 2
     lift = [line for line in out if line.startswith("lift")][0]
     assert "t = 0.5000" in lift and "feet = 0110" in lift
+
+
+ANYMAL_EXE = os.path.join(ROOT, "build", "anymal_trotting")
+
+
+def _build_anymal():
+    import __graft_entry__ as g
+    g.build_cuda()
+    os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)
+    lib = os.path.join(ROOT, "idocp_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "anymal_trotting.cpp"), "-L" + lib, "-lidocp_b200",
+                           "-Wl,-rpath," + lib, "-o", ANYMAL_EXE])
+
+
+def test_anymal_example_compiles_and_fails_loudly_without_gpu():
+    import torch
+    _build_anymal()
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    res = subprocess.run([ANYMAL_EXE, "2"], capture_output=True, text=True)
+    assert res.returncode != 0
+    assert "no CUDA device" in res.stderr
+
+
+@pytest.mark.gpu
+def test_anymal_trotting_example_reproduces_golden_convergence():
+    """examples/anymal_trotting.cpp = the reference's examples/anymal/anymal_trotting.cpp on the C++ host classes
+    (QuadrupedRobot, TrottingConfigurationSpaceCost, ContactForceCost, joint limits, friction cones, OCPSolver with the
+    contact schedule); the printed KKT history of instance 0 of a batch of 3 equals the golden vectors digit for digit
+    (the host class computes the contact points and the cost reference itself)."""
+    _build_anymal()
+    out = subprocess.run([ANYMAL_EXE, "3"], capture_output=True, text=True, check=True).stdout
+    kkt = [float(x) for x in re.findall(r"KKT error(?: after iteration \d+)? = (\S+)", out)]
+    with open(os.path.join(GOLDEN, "anymal_trotting_golden.json")) as f:
+        ref = json.load(f)["kkt"]
+    assert len(kkt) == 26
+    assert kkt == ref
+    assert "CPU time per update" in out
