@@ -54,10 +54,10 @@ static int fail(int code, const std::string& msg) {
   } while (0)
 
 enum KernelClass { KC_LINEARIZE = 0, KC_RICCATI, KC_EXPAND, KC_UPDATE, KC_KKT, KC_MISC, KC_PARNMPC_COARSE,
-                   KC_PARNMPC_CORR, KC_LINESEARCH, KC_FB_LINEARIZE, KC_FB_RICCATI, KC_FB_FORWARD, KC_FB_EXPAND, KC_FB_UPDATE,
+                   KC_PARNMPC_CORR, KC_LINESEARCH, KC_FB_LINEARIZE, KC_FB_CONDENSE, KC_FB_RICCATI, KC_FB_FORWARD, KC_FB_EXPAND, KC_FB_UPDATE,
                    KC_FB_KKT, KC_NUM };
 static const char* kKernelClassNames[KC_NUM] = {"linearize", "riccati", "expand", "update", "kkt", "misc",
-                                                "parnmpc_coarse", "parnmpc_correction", "line_search", "fb_linearize",
+                                                "parnmpc_coarse", "parnmpc_correction", "line_search", "fb_robot", "fb_condense",
                                                 "fb_riccati_backward", "fb_riccati_forward", "fb_expand", "fb_update", "fb_kkt"};
 
 // launch bookkeeping shared by every solver handle: stream, launch counter, per-kernel-class event timing

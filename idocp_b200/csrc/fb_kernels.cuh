@@ -79,6 +79,7 @@ struct FbArrays {
   FbKKT* kkt;
   FbExp* exp;
   FbRic* ric;
+  struct FbLin* lin;   // K1a -> K1b hand-over records
   const double* q0;   // [B][19]
   const double* v0;   // [B][18]
   double* steps;      // [B][2]
@@ -88,30 +89,49 @@ struct FbArrays {
 #define FB_FOR(i, n) for (int i = threadIdx.x; i < (n); i += blockDim.x)
 enum { FBM_SET = 0, FBM_ADD = 1, FBM_SUB = 2 };
 
-// C (m x n, ldc) {=, +=, -=} A (m x k) B (k x n): one ascending-k fma chain per element, elements dealt to threads.
+// C (m x n, ldc) {=, +=, -=} A (m x k) B (k x n): one ascending-k fma chain per element.  A thread owns a 2 x 2 tile
+// of C: four independent chains in flight (the chains are latency-bound otherwise) and half the shared-memory
+// loads per fma; the chain of every element is unchanged, so the bits do not depend on the tiling.
 // The caller separates dependent calls with __syncthreads().
 template <int MODE>
 __device__ __forceinline__ void fb_mm(int m, int n, int k, const double* __restrict__ A, int ars, int acs, const double* __restrict__ B,
                                       int brs, int bcs, double* C, int ldc) {
-  const int total = m * n;
-  for (int e = threadIdx.x; e < total; e += blockDim.x) {
-    const int i = e / n, j = e - i * n;
-    const double* a = A + i * ars;
-    const double* b = B + j * bcs;
-    double acc;
+  const int tm = (m + 1) >> 1, tn = (n + 1) >> 1, total = tm * tn;
+  for (int t = threadIdx.x; t < total; t += blockDim.x) {
+    const int ti = t / tn, tj = t - ti * tn;
+    const int i0 = 2 * ti, j0 = 2 * tj;
+    const bool hi = i0 + 1 < m, hj = j0 + 1 < n;
+    const double* a0 = A + i0 * ars;
+    const double* a1 = A + (hi ? i0 + 1 : i0) * ars;
+    const double* b0 = B + j0 * bcs;
+    const double* b1 = B + (hj ? j0 + 1 : j0) * bcs;
+    double c00, c01, c10, c11;
     int l0 = 0;
     if (MODE == FBM_SET) {
-      if (k == 0) { C[i * ldc + j] = 0.0; continue; }
-      acc = a[0] * b[0];
+      if (k == 0) {
+        C[i0 * ldc + j0] = 0.0;
+        if (hj) C[i0 * ldc + j0 + 1] = 0.0;
+        if (hi) { C[(i0 + 1) * ldc + j0] = 0.0; if (hj) C[(i0 + 1) * ldc + j0 + 1] = 0.0; }
+        continue;
+      }
+      const double x0 = a0[0], x1 = a1[0], y0 = b0[0], y1 = b1[0];
+      c00 = x0 * y0; c01 = x0 * y1; c10 = x1 * y0; c11 = x1 * y1;
       l0 = 1;
     } else {
-      acc = C[i * ldc + j];
+      c00 = C[i0 * ldc + j0];
+      c01 = hj ? C[i0 * ldc + j0 + 1] : 0.0;
+      c10 = hi ? C[(i0 + 1) * ldc + j0] : 0.0;
+      c11 = (hi && hj) ? C[(i0 + 1) * ldc + j0 + 1] : 0.0;
     }
-    if (MODE == FBM_SUB)
-      for (int l = l0; l < k; ++l) acc = fma(-a[l * acs], b[l * brs], acc);
-    else
-      for (int l = l0; l < k; ++l) acc = fma(a[l * acs], b[l * brs], acc);
-    C[i * ldc + j] = acc;
+    for (int l = l0; l < k; ++l) {
+      double x0 = a0[l * acs], x1 = a1[l * acs];
+      const double y0 = b0[l * brs], y1 = b1[l * brs];
+      if (MODE == FBM_SUB) { x0 = -x0; x1 = -x1; }
+      c00 = fma(x0, y0, c00); c01 = fma(x0, y1, c01); c10 = fma(x1, y0, c10); c11 = fma(x1, y1, c11);
+    }
+    C[i0 * ldc + j0] = c00;
+    if (hj) C[i0 * ldc + j0 + 1] = c01;
+    if (hi) { C[(i0 + 1) * ldc + j0] = c10; if (hj) C[(i0 + 1) * ldc + j0 + 1] = c11; }
   }
 }
 template <int MODE>
@@ -186,10 +206,25 @@ __device__ inline double fb_friction_jac(double mu, int e, int x) {
 }
 
 // =====================================================================================================
-// shared-memory workspace of the linearisation kernel
+// K1a: rigid-body + stage-local linearisation, ONE WARP per (instance, stage)
+//   forward kinematics, RNEA and its derivatives with contact wrenches, Baumgarte / impulse-velocity rows, cost
+//   gradient + sparse Hessian, PDIPM residuals and condensing, SE(3) state-equation blocks, switching constraint.
+//   Everything here is O(n) .. O(n^2) with at most 18-way parallelism: a warp per stage keeps 8+ stages in flight
+//   per SM without block barriers.  The dense O(n^3) condensing is K1b.
 // =====================================================================================================
-struct FbLinWork {
-  // inputs
+#define FBW_FOR(i, n) for (int i = lane; i < (n); i += 32)
+
+// per-stage record handed from K1a to K1b (HBM, [slot][instance])
+struct FbLin {
+  double IDC[FB_NVF], dIDCdqv[FB_NVF * FB_NX], Mm[FB_NV * FB_NV], dCda[FB_MAXF * FB_NV];
+  double lq[FB_NV], lv[FB_NV], la[FB_NV], lf[FB_MAXF], lu_passive[FB_NPASS], lu[FB_NU], Fq[FB_NV], Fv[FB_NV], P[FB_MAXF];
+  double Qqq6[36], Qqq_d[FB_NV], Qvv_d[FB_NV], Quu_d[FB_NU], Qaa[FB_NV], Qff[FB_MAXF * FB_MAXF];
+  double Fqq6[36], Fqv6[36], Fqq_prev_inv[36];
+  double Phix[FB_MAXF * FB_NX], Phia[FB_MAXF * FB_NV];
+};
+
+struct FbRobotWork {
+  // inputs (same order as FbSol)
   double lmd[FB_NV], gmm[FB_NV], q[FB_NQ], v[FB_NV], a[FB_NV], u[FB_NU], beta[FB_NV], nu_passive[FB_NPASS], f[FB_MAXF], mu[FB_MAXF],
       xi[FB_MAXF], slack[FB_NCON], dual[FB_NCON];
   double nlmd[FB_NV], ngmm[FB_NV], nq[FB_NQ], nv[FB_NV], qprev[FB_NQ];
@@ -201,33 +236,42 @@ struct FbLinWork {
   fb_dinertia_t D[FB_NB];
   double F[FB_NB][6], agf[FB_NB][6];
   double U[FB_NV][6], W[FB_NV][6], dFv[FB_NV][6], dFq[FB_NV][6], dFqa[FB_NV][6], dAq[FB_NV][6], dAv[FB_NV][6];
-  // frames (one set per contact, processed by its own warp)
-  double frP[FB_NC][3], frV[FB_NC][6], frA[FB_NC][6];
-  // SE(3) blocks
-  double qdiff[FB_NV], J6c[36], Fqq_prev6[36], Fqq_inv[36], tmp6[36], fq6[6], dqv[FB_NV], q2[FB_NQ], Jq6[36], Jv6[36];
-  // SplitKKTResidual
-  double lq[FB_NV], lv[FB_NV], la[FB_NV], lf[FB_MAXF], lu_passive[FB_NPASS], lu[FB_NU], Fq[FB_NV], Fv[FB_NV], P[FB_MAXF];
-  // ContactDynamicsData
-  double IDC[FB_NVF], dIDCdqv[FB_NVF * FB_NX], Mm[FB_NV * FB_NV], dCda[FB_MAXF * FB_NV];
-  double L[FB_NV * FB_NV], rd[FB_NV], Minv[FB_NV * FB_NV], JMi[FB_MAXF * FB_NV], Sm[FB_MAXF * FB_MAXF], Ls[FB_MAXF * FB_MAXF], rds[FB_MAXF],
-      Si[FB_MAXF * FB_MAXF];
-  double MJtJinv[FB_NVF * FB_NVF], MJ_dIDC[FB_NVF * FB_NX], MJ_IDC[FB_NVF], Qafqv[FB_NVF * FB_NX], Qafu[FB_NVF * FB_NV], laf[FB_NVF];
-  // SplitKKTMatrix
-  double Qxx[FB_NX * FB_NX], Qxu[FB_NX * FB_NV], Quu[FB_NV * FB_NV], Qaa[FB_NV], Qff[FB_MAXF * FB_MAXF];
-  double Fqq6[36], Fqv6[36], Fqq_prev_inv[36], Fvq[FB_NV * FB_NV], Fvv[FB_NV * FB_NV], Fvu[FB_NV * FB_NU];
-  // switching constraint
-  double Pq[FB_MAXF * FB_NV], Phix[FB_MAXF * FB_NX], Phia[FB_MAXF * FB_NV], Phiu[FB_MAXF * FB_NU], PJv[FB_MAXF * FB_NV];
-  // constraints
+  double frP[3], frV[6], frA[6];
+  // SE(3) blocks: three relative placements (cost reference, next stage, previous stage)
+  double relR[3][9], relp[3][3], relJ[3][36], rellog[3][6], relX[2][36], Fqq_prev6[36], Fqq_inv[36], tmp6[36], fq6[6];
+  double dqv[FB_NV], q2[FB_NQ], Jq6[36], Jv6[36], Pq[FB_MAXF * FB_NV], PJv[FB_MAXF * FB_NV];
   double residual[FB_NCON], duality[FB_NCON];
-  double t18[FB_NV], tf[FB_MAXF], part[8];
-  int info;
+  double t18[FB_NV], part[8];
 };
 
-// ---- cooperative forward kinematics: base by thread 0, then one thread per leg (robot.hxx:193-230) ----
-// v, a may be nullptr (zero).  Ends with a __syncthreads().
-__device__ inline void fb_forward_kinematics(FbLinWork& w, const double* q, const double* v, const double* a) {
-  const int tid = threadIdx.x;
-  if (tid == 0) {
+template <int MODE>
+__device__ __forceinline__ void fbw_mm(int lane, int m, int n, int k, const double* A, int ars, int acs, const double* B, int brs, int bcs,
+                                       double* C, int ldc) {
+  const int total = m * n;
+  for (int e = lane; e < total; e += 32) {
+    const int i = e / n, j = e - i * n;
+    const double* a = A + i * ars;
+    const double* b = B + j * bcs;
+    double acc;
+    int l0 = 0;
+    if (MODE == FBM_SET) {
+      if (k == 0) { C[i * ldc + j] = 0.0; continue; }
+      acc = a[0] * b[0];
+      l0 = 1;
+    } else {
+      acc = C[i * ldc + j];
+    }
+    if (MODE == FBM_SUB)
+      for (int l = l0; l < k; ++l) acc = fma(-a[l * acs], b[l * brs], acc);
+    else
+      for (int l = l0; l < k; ++l) acc = fma(a[l * acs], b[l * brs], acc);
+    C[i * ldc + j] = acc;
+  }
+}
+
+// forwardKinematics in the world frame: base by lane 0, then one lane per leg (robot.hxx:193-230); v, a may be null
+__device__ __noinline__ void fbw_forward_kinematics(FbRobotWork& w, int lane, const double* q, const double* v, const double* a) {
+  if (lane == 0) {
     fb_quat_to_R(q + 3, w.R[0]);
     for (int i = 0; i < 3; ++i) w.p[0][i] = q[i];
     for (int c = 0; c < 3; ++c) {
@@ -246,10 +290,10 @@ __device__ inline void fb_forward_kinematics(FbLinWork& w, const double* q, cons
     for (int c = 0; c < 6; ++c)
       for (int i = 0; i < 6; ++i) w.dV[c][i] = 0.0;
   }
-  __syncthreads();
-  if (tid < 4) {
+  __syncwarp();
+  if (lane < 4) {
     for (int jj = 0; jj < 3; ++jj) {
-      const int j = 3 * tid + jj;
+      const int j = 3 * lane + jj;
       const int b = 1 + j, pb = fb_parent_body(b), c = 6 + j;
       const double* Rp = w.R[pb];
       double* Rb = w.R[b];
@@ -282,16 +326,16 @@ __device__ inline void fb_forward_kinematics(FbLinWork& w, const double* q, cons
       }
     }
   }
-  __syncthreads();
+  __syncwarp();
 }
 
-__device__ inline void fb_contact_point(const FbLinWork& w, int i, double* P) {
+__device__ inline void fbw_contact_point(const FbRobotWork& w, int i, double* P) {
   const int b = 1 + ANYMAL_CONTACT_PARENT_JOINT[i];
   const double* R = w.R[b];
   const double* pc = ANYMAL_CONTACT_P[i];
   for (int r = 0; r < 3; ++r) P[r] = fma(R[3 * r + 2], pc[2], fma(R[3 * r + 1], pc[1], fma(R[3 * r], pc[0], w.p[b][r])));
 }
-__device__ inline void fb_body_inertia(const FbLinWork& w, int b, fb_inertia_t* Y) {
+__device__ inline void fbw_body_inertia(const FbRobotWork& w, int b, fb_inertia_t* Y) {
   const double m = ANYMAL_MASS[b];
   double c[3], T[9];
   const double* R = w.R[b];
@@ -320,14 +364,12 @@ __device__ inline void fb_pullback(const double* Rf, const double* Pf, const dou
 }
 __device__ inline int fb_in_support(int contact, int c) { return c < 6 || (c - 6) / 3 == contact; }
 
-// ---- RNEA + computeRNEADerivatives with the contact wrenches (robot.hxx:444-500): tau -> w.IDC[0:18],
-// d tau/dq, /dv -> w.dIDCdqv rows 0..17, d tau/da -> w.Mm.  with_dv = false: RNEAImpulseDerivatives (the velocity
-// block stays zero).  fm = LOCAL contact forces, zero for inactive contacts. ----
-__device__ inline void fb_rnea_derivatives(FbLinWork& w, double gravity, bool with_dv) {
-  const int tid = threadIdx.x;
-  if (tid < FB_NB) {
-    const int b = tid;
-    fb_body_inertia(w, b, &w.Y[b]);
+// RNEA + computeRNEADerivatives with the contact wrenches (robot.hxx:444-500): tau -> L.IDC[0:18], d tau/dq, /dv ->
+// L.dIDCdqv rows 0..17, d tau/da -> L.Mm (all in HBM; written once).  with_dv = false: RNEAImpulseDerivatives.
+__device__ __noinline__ void fbw_rnea_derivatives(FbRobotWork& w, int lane, double gravity, bool with_dv, FbLin& L, bool derivatives) {
+  if (lane < FB_NB) {
+    const int b = lane;
+    fbw_body_inertia(w, b, &w.Y[b]);
     for (int i = 0; i < 6; ++i) w.agf[b][i] = w.oa[b][i];
     w.agf[b][2] = w.oa[b][2] + gravity;
     double Ya[6], h[6], vh[6];
@@ -337,69 +379,73 @@ __device__ inline void fb_rnea_derivatives(FbLinWork& w, double gravity, bool wi
     for (int i = 0; i < 6; ++i) w.F[b][i] = Ya[i] + vh[i];
     fb_dinertia(&w.Y[b], w.ov[b], &w.D[b]);
   }
-  __syncthreads();
-  if (tid < FB_NC) {   // every contact sits on its own body (the shank of its leg)
-    const int b = 1 + ANYMAL_CONTACT_PARENT_JOINT[tid];
+  __syncwarp();
+  if (lane < FB_NC) {   // every contact sits on its own body (the shank of its leg)
+    const int b = 1 + ANYMAL_CONTACT_PARENT_JOINT[lane];
     double P[3], W6[6];
-    fb_contact_point(w, tid, P);
-    fb_rot(w.R[b], w.fm + 3 * tid, W6);
+    fbw_contact_point(w, lane, P);
+    fb_rot(w.R[b], w.fm + 3 * lane, W6);
     fb_cross(P, W6, W6 + 3);
     for (int e = 0; e < 6; ++e) w.F[b][e] -= W6[e];
   }
-  __syncthreads();
-  // composites, leaves to root: inside every leg by its own thread, then the base collects the hips in the
-  // serial order b = 10, 7, 4, 1 (the reverse body order of pinocchio's backward pass)
-  if (tid < 4) {
-    for (int b = 3 * tid + 3; b > 3 * tid + 1; --b) {
+  __syncwarp();
+  // composites, leaves to root: inside every leg by its own lane, then the base collects the hips in the serial
+  // order b = 10, 7, 4, 1 (the reverse body order of pinocchio's backward pass)
+  if (lane < 4) {
+    for (int b = 3 * lane + 3; b > 3 * lane + 1; --b) {
       const int pb = b - 1;
       w.Y[pb].m += w.Y[b].m;
       for (int i = 0; i < 3; ++i) { w.Y[pb].h[i] += w.Y[b].h[i]; w.D[pb].pl[i] += w.D[b].pl[i]; w.D[pb].pa[i] += w.D[b].pa[i]; }
       for (int i = 0; i < 6; ++i) { w.Y[pb].I[i] += w.Y[b].I[i]; w.D[pb].S[i] += w.D[b].S[i]; w.F[pb][i] += w.F[b][i]; }
     }
   }
-  __syncthreads();
-  if (tid == 0) {
+  __syncwarp();
+  if (lane == 0) {
     for (int b = 10; b >= 1; b -= 3) {
       w.Y[0].m += w.Y[b].m;
       for (int i = 0; i < 3; ++i) { w.Y[0].h[i] += w.Y[b].h[i]; w.D[0].pl[i] += w.D[b].pl[i]; w.D[0].pa[i] += w.D[b].pa[i]; }
       for (int i = 0; i < 6; ++i) { w.Y[0].I[i] += w.Y[b].I[i]; w.D[0].S[i] += w.D[b].S[i]; w.F[0][i] += w.F[b][i]; }
     }
   }
-  __syncthreads();
-  if (tid < FB_NV) {
-    const int c = tid, b = fb_body_of_dof(c);
-    w.IDC[c] = fb_dot6(w.S[c], w.F[b]);
-    double dJ[6], t1[6], t2[6];
-    fb_mxm(w.ov[b], w.S[c], dJ);
-    if (b == 0) {
-      const double a0[6] = {0.0, 0.0, gravity, 0.0, 0.0, 0.0};
-      fb_mxm(a0, w.S[c], w.dAq[c]);
-    } else {
-      const int pb = fb_parent_body(b);
-      fb_mxm(w.agf[pb], w.S[c], t1);
-      fb_mxm(w.ov[pb], w.dV[c], t2);
-      for (int i = 0; i < 6; ++i) w.dAq[c][i] = t1[i] + t2[i];
+  __syncwarp();
+  if (lane < FB_NV) {
+    const int c = lane, b = fb_body_of_dof(c);
+    L.IDC[c] = fb_dot6(w.S[c], w.F[b]);
+    if (derivatives) {
+      double dJ[6], t1[6], t2[6];
+      fb_mxm(w.ov[b], w.S[c], dJ);
+      if (b == 0) {
+        const double a0[6] = {0.0, 0.0, gravity, 0.0, 0.0, 0.0};
+        fb_mxm(a0, w.S[c], w.dAq[c]);
+      } else {
+        const int pb = fb_parent_body(b);
+        fb_mxm(w.agf[pb], w.S[c], t1);
+        fb_mxm(w.ov[pb], w.dV[c], t2);
+        for (int i = 0; i < 6; ++i) w.dAq[c][i] = t1[i] + t2[i];
+      }
+      for (int i = 0; i < 6; ++i) w.dAv[c][i] = dJ[i] + w.dV[c][i];
+      fb_Ymul(&w.Y[b], w.S[c], w.U[c]);
+      fb_DTmul(&w.D[b], w.S[c], w.W[c]);
+      fb_Dmul(&w.D[b], w.S[c], t1);
+      fb_Ymul(&w.Y[b], w.dAv[c], t2);
+      for (int i = 0; i < 6; ++i) w.dFv[c][i] = t1[i] + t2[i];
+      fb_Dmul(&w.D[b], w.dV[c], t1);
+      fb_Ymul(&w.Y[b], w.dAq[c], t2);
+      for (int i = 0; i < 6; ++i) w.dFq[c][i] = t1[i] + t2[i];
+      fb_mxf(w.S[c], w.F[b], t1);
+      for (int i = 0; i < 6; ++i) w.dFqa[c][i] = w.dFq[c][i] + t1[i];
     }
-    for (int i = 0; i < 6; ++i) w.dAv[c][i] = dJ[i] + w.dV[c][i];
-    fb_Ymul(&w.Y[b], w.S[c], w.U[c]);
-    fb_DTmul(&w.D[b], w.S[c], w.W[c]);
-    fb_Dmul(&w.D[b], w.S[c], t1);
-    fb_Ymul(&w.Y[b], w.dAv[c], t2);
-    for (int i = 0; i < 6; ++i) w.dFv[c][i] = t1[i] + t2[i];
-    fb_Dmul(&w.D[b], w.dV[c], t1);
-    fb_Ymul(&w.Y[b], w.dAq[c], t2);
-    for (int i = 0; i < 6; ++i) w.dFq[c][i] = t1[i] + t2[i];
-    fb_mxf(w.S[c], w.F[b], t1);
-    for (int i = 0; i < 6; ++i) w.dFqa[c][i] = w.dFq[c][i] + t1[i];
   }
-  __syncthreads();
-  FB_FOR(e, FB_NV * FB_NV) {
+  __syncwarp();
+  if (!derivatives) return;
+  FBW_FOR(e, FB_NV * FB_NV) {
     const int r = e / FB_NV, c = e - r * FB_NV;
     double eq = 0.0, ev = 0.0, em = 0.0;
+    // d tau/da: robot.hxx:496-499 overwrites the strictly lower triangle with the mirror of the upper one
     if (fb_same_joint(r, c)) {
       eq = fb_dot6(w.S[r], w.dFq[c]);
       ev = fb_dot6(w.S[r], w.dFv[c]);
-      em = fb_dot6(w.S[r], w.U[c]);
+      em = c >= r ? fb_dot6(w.S[r], w.U[c]) : fb_dot6(w.S[c], w.U[r]);
     } else if (fb_is_ancestor(r, c)) {
       eq = fb_dot6(w.S[r], w.dFqa[c]);
       ev = fb_dot6(w.S[r], w.dFv[c]);
@@ -407,249 +453,145 @@ __device__ inline void fb_rnea_derivatives(FbLinWork& w, double gravity, bool wi
     } else if (fb_is_ancestor(c, r)) {
       eq = fb_dot6(w.dAq[c], w.U[r]) + fb_dot6(w.dV[c], w.W[r]);
       ev = fb_dot6(w.dAv[c], w.U[r]) + fb_dot6(w.S[c], w.W[r]);
+      em = fb_dot6(w.S[c], w.U[r]);
     }
-    w.dIDCdqv[r * FB_NX + c] = eq;
-    w.dIDCdqv[r * FB_NX + FB_NV + c] = with_dv ? ev : 0.0;
-    if (c >= r) w.Mm[r * FB_NV + c] = em;
+    L.dIDCdqv[r * FB_NX + c] = eq;
+    L.dIDCdqv[r * FB_NX + FB_NV + c] = with_dv ? ev : 0.0;
+    L.Mm[e] = em;
   }
-  __syncthreads();
-  FB_FOR(e, FB_NV * FB_NV) {   // robot.hxx:496-499: lower triangle := transpose of the upper one
-    const int r = e / FB_NV, c = e - r * FB_NV;
-    if (c < r) w.Mm[e] = w.Mm[c * FB_NV + r];
-  }
-  __syncthreads();
+  __syncwarp();
 }
 
-// ---- Baumgarte residual / derivatives of every active contact (point_contact.hxx:67-144) or, at an impulse, the
-// contact velocity residual / derivatives (:147-176).  Contact i is handled by warp i; row block k = its rank among
-// the active contacts.  Writes IDC[18+3k..], dIDCdqv rows 18+3k.., dCda rows 3k... ----
-__device__ inline void fb_contact_rows(FbLinWork& w, const FbElem& el, bool impulse, double baumgarte) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp < FB_NC && el.active[warp]) {
-    const int i = warp;
-    int k = 0;
-    for (int j = 0; j < i; ++j) k += el.active[j];
-    const int bi = 1 + ANYMAL_CONTACT_PARENT_JOINT[i];
-    const double* Rf = w.R[bi];
-    if (lane == 0) {
-      fb_contact_point(w, i, w.frP[i]);
+// one relative placement M = M(q_minus)^-1 M(q_plus), its log6 and Jlog6 (robot.hxx subtractConfiguration /
+// dSubtractdConfigurationPlus); lanes 0..2 run it in lock-step on three pairs
+__device__ __noinline__ void fbw_se3_pair(const double* q_plus, const double* q_minus, double* R, double* p, double* log18, double* J) {
+  fb_relative(q_minus, q_plus, R, p);
+  fb_log6(R, p, log18);   // the base block; the joint part of the difference is a plain subtraction (done by the callers)
+  fb_Jlog6(R, p, J);
+}
+// dSubtractdConfigurationMinus from the pieces above: J1 (-Ad(M^-1)) (robot.hxx:138-153)
+__device__ __noinline__ void fbw_dminus(const double* R, const double* p, const double* J1, double* J6) {
+  double X[36];
+  double Sk[9] = {0, -p[2], p[1], p[2], 0, -p[0], -p[1], p[0], 0}, RtS[9];
+  fb_mulT33(R, Sk, RtS);
+  for (int r = 0; r < 3; ++r)
+    for (int k = 0; k < 3; ++k) {
+      X[6 * r + k] = -R[3 * k + r];
+      X[6 * r + 3 + k] = RtS[3 * r + k];
+      X[6 * (3 + r) + k] = 0.0;
+      X[6 * (3 + r) + 3 + k] = -R[3 * k + r];
     }
-    __syncwarp();
-    if (lane == 0) {
-      fb_pullback(Rf, w.frP[i], w.ov[bi], w.frV[i]);
-      fb_pullback(Rf, w.frP[i], w.oa[bi], w.frA[i]);
+  for (int r = 0; r < 6; ++r)
+    for (int k = 0; k < 6; ++k) {
+      double acc = J1[6 * r] * X[k];
+      for (int j = 1; j < 6; ++j) acc = fma(J1[6 * r + j], X[6 * j + k], acc);
+      J6[6 * r + k] = acc;
     }
-    __syncwarp();
-    const double* P = w.frP[i];
-    const double* vF = w.frV[i];
-    if (lane == 0) {
-      double* C = w.IDC + FB_NV + 3 * k;
-      if (!impulse) {
-        const double wv = 2.0 / baumgarte, wp = 1.0 / (baumgarte * baumgarte);
-        double wxv[3];
-        fb_cross(vF + 3, vF, wxv);
-        for (int x = 0; x < 3; ++x) {
-          const double acl = w.frA[i][x] + wxv[x];
-          C[x] = fma(wp, P[x] - el.cpoints[3 * i + x], fma(wv, vF[x], acl));
-        }
-      } else {
-        for (int x = 0; x < 3; ++x) C[x] = vF[x];
-      }
-    }
-    if (lane < FB_NV) {
-      const int c = lane;
-      double J[6] = {0, 0, 0, 0, 0, 0}, vq[6] = {0, 0, 0, 0, 0, 0}, aq[6] = {0, 0, 0, 0, 0, 0}, av[6] = {0, 0, 0, 0, 0, 0};
-      if (fb_in_support(i, c)) {
-        fb_pullback(Rf, P, w.S[c], J);
-        const int b = fb_body_of_dof(c);
-        double u[6], x6[6], t1[6], t2[6];
-        if (b == 0) {
-          for (int e = 0; e < 6; ++e) u[e] = w.ov[bi][e];
-        } else {
-          const int pb = fb_parent_body(b);
-          for (int e = 0; e < 6; ++e) u[e] = w.ov[bi][e] - w.ov[pb][e];
-          fb_pullback(Rf, P, w.dV[c], vq);
-        }
-        if (!impulse) {
-          fb_mxm(w.ov[b], w.S[c], t1);
-          fb_mxm(w.S[c], u, t2);
-          for (int e = 0; e < 6; ++e) x6[e] = t1[e] + t2[e];
-          fb_pullback(Rf, P, x6, av);
-          if (b != 0) {
-            const int pb = fb_parent_body(b);
-            fb_mxm(w.oa[pb], w.S[c], t1);
-            fb_mxm(w.dV[c], u, t2);
-            for (int e = 0; e < 6; ++e) x6[e] = t1[e] + t2[e];
-            fb_pullback(Rf, P, x6, aq);
-          }
-        }
-      }
-      double* rq = w.dIDCdqv + (FB_NV + 3 * k) * FB_NX + c;
-      double* rv = rq + FB_NV;
-      double* ra = w.dCda + (3 * k) * FB_NV + c;
-      if (!impulse) {
-        const double wv = 2.0 / baumgarte, wp = 1.0 / (baumgarte * baumgarte);
-        const double* vl = vF;
-        const double* va = vF + 3;
-        double t1[3], t2[3], RJ[3];
-        fb_cross(va, vq, t1);
-        fb_cross(vl, vq + 3, t2);
-        fb_rot(Rf, J, RJ);
-        for (int x = 0; x < 3; ++x) rq[x * FB_NX] = fma(wp, RJ[x], fma(wv, vq[x], (aq[x] + t1[x]) + t2[x]));
-        fb_cross(va, J, t1);
-        fb_cross(vl, J + 3, t2);
-        for (int x = 0; x < 3; ++x) rv[x * FB_NX] = fma(wv, J[x], (av[x] + t1[x]) + t2[x]);
-        for (int x = 0; x < 3; ++x) ra[x * FB_NV] = J[x];
-      } else {
-        for (int x = 0; x < 3; ++x) { rq[x * FB_NX] = vq[x]; rv[x * FB_NX] = J[x]; ra[x * FB_NV] = J[x]; }
-      }
-    }
-  }
-  __syncthreads();
 }
 
-// ---- Robot::computeMJtJinv (robot.hxx:576-615) as dense Cholesky: MJtJinv = [[M, J^T], [J, 0]]^-1 ----
-__device__ inline void fb_MJtJinv(FbLinWork& w, int dimf) {
-  const int n = FB_NV, ld = FB_NVF, tid = threadIdx.x;
-  if (tid < 32) {
-    const int info = fb_llt_warp(w.Mm, n, n, w.L, n, w.rd);
-    if (tid == 0 && info && !w.info) w.info = info;
-  }
-  __syncthreads();
-  if (tid < n) {
-    for (int r = 0; r < n; ++r) w.Minv[r * n + tid] = (r == tid) ? 1.0 : 0.0;
-    fb_llt_solve(w.L, n, w.rd, n, w.Minv + tid, n);
-  }
-  __syncthreads();
-  fb_mm<FBM_SET>(dimf, n, n, w.dCda, n, 1, w.Minv, n, 1, w.JMi, n);
-  __syncthreads();
-  fb_mm<FBM_SET>(dimf, dimf, n, w.JMi, n, 1, w.dCda, 1, n, w.Sm, dimf);
-  __syncthreads();
-  if (dimf > 0) {
-    if (tid < 32) {
-      const int info = fb_llt_warp(w.Sm, dimf, dimf, w.Ls, dimf, w.rds);
-      if (tid == 0 && info && !w.info) w.info = 100 + info;
-    }
-    __syncthreads();
-    if (tid < dimf) {
-      for (int r = 0; r < dimf; ++r) w.Si[r * dimf + tid] = (r == tid) ? 1.0 : 0.0;
-      fb_llt_solve(w.Ls, dimf, w.rds, dimf, w.Si + tid, dimf);
-    }
-    __syncthreads();
-  }
-  FB_FOR(e, dimf * dimf) { const int r = e / dimf, c = e - r * dimf; w.MJtJinv[(n + r) * ld + n + c] = -w.Si[e]; }
-  fb_mm<FBM_SET>(n, dimf, dimf, w.JMi, 1, n, w.Si, dimf, 1, w.MJtJinv + n, ld);     // TR = (J Minv)^T S^-1
-  __syncthreads();
-  FB_FOR(e, n * n) {                                                                   // TL = Minv - TR (J Minv)
-    const int r = e / n, c = e - r * n;
-    double acc = w.Minv[e];
-    for (int j = 0; j < dimf; ++j) acc = fma(-w.MJtJinv[r * ld + n + j], w.JMi[j * n + c], acc);
-    w.MJtJinv[r * ld + c] = acc;
-  }
-  FB_FOR(e, dimf * n) { const int r = e / n, c = e - r * n; w.MJtJinv[(n + r) * ld + c] = w.MJtJinv[c * ld + n + r]; }   // BL = TR^T
-  __syncthreads();
-}
+#define FB_ROBOT_WARPS 4
 
-// =====================================================================================================
-// K1: linearisation of one stage.  grid = B * n_elems CTAs (instance-major), 128 threads.
-// =====================================================================================================
 template <bool RESIDUAL_ONLY>
-__global__ void __launch_bounds__(128) k_fb_linearize(FbArrays A) {
-  IDOCP_DYN_SMEM(FbLinWork, wp);
-  FbLinWork& w = *wp;
-  const int tid = threadIdx.x;
-  const int b = blockIdx.x / A.n_elems, e = blockIdx.x - b * A.n_elems;
+__global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, FbLin* lin) {
+  IDOCP_DYN_SMEM(FbRobotWork, wbase);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int stage = blockIdx.x * FB_ROBOT_WARPS + warp;
+  if (stage >= A.B * A.n_elems) return;
+  FbRobotWork& w = wbase[warp];
+  const int b = stage / A.n_elems, e = stage - b * A.n_elems;
   const FbElem& el = A.elems[e];
   const FbDevProblem& pr = *A.prob;
   const int kind = el.kind;
   const bool impulse = kind == FB_IMPULSE, terminal = kind == FB_TERMINAL;
   const double dt = (impulse || terminal) ? 1.0 : el.dt;
   const int dimf = terminal ? 0 : el.dimf, nvf = FB_NV + dimf, dimi = el.sw ? el.dimi : 0;
-  const FbSol& S = A.sol[(size_t)el.slot * A.B + b];
-  FbDir& Dr = A.dir[(size_t)el.slot * A.B + b];
-  FbKKT& Kt = A.kkt[(size_t)el.slot * A.B + b];
-  FbExp& Ex = A.exp[(size_t)el.slot * A.B + b];
+  const size_t rec = (size_t)el.slot * A.B + b;
+  const FbSol& S = A.sol[rec];
+  FbDir& Dr = A.dir[rec];
+  FbLin& L = lin[rec];
 
   // ---- load ----
-  fb_copy(w.lmd, S.lmd, sizeof(FbSol) / sizeof(double));   // lmd .. dual are laid out identically in FbSol and FbLinWork
+  {
+    const double* src = S.lmd;
+    double* dst = w.lmd;
+    FBW_FOR(i, (int)(sizeof(FbSol) / sizeof(double))) dst[i] = src[i];
+  }
   if (!terminal) {
     const FbSol& Nx = A.sol[(size_t)el.next_slot * A.B + b];
-    fb_copy(w.nlmd, Nx.lmd, FB_NV);
-    fb_copy(w.ngmm, Nx.gmm, FB_NV);
-    fb_copy(w.nq, Nx.q, FB_NQ);
-    fb_copy(w.nv, Nx.v, FB_NV);
+    FBW_FOR(i, FB_NV) { w.nlmd[i] = Nx.lmd[i]; w.ngmm[i] = Nx.gmm[i]; w.nv[i] = Nx.v[i]; }
+    FBW_FOR(i, FB_NQ) w.nq[i] = Nx.q[i];
   }
-  if (el.prev_slot >= 0) fb_copy(w.qprev, A.sol[(size_t)el.prev_slot * A.B + b].q, FB_NQ);
-  else fb_copy(w.qprev, A.q0 + (size_t)b * FB_NQ, FB_NQ);
-  fb_zero(w.lq, 3 * FB_NV + FB_MAXF + FB_NPASS + FB_NU + 2 * FB_NV + FB_MAXF);   // lq .. P
-  if (!RESIDUAL_ONLY) {
-    fb_zero(w.Qxx, FB_NX * FB_NX + FB_NX * FB_NV + FB_NV * FB_NV + FB_NV + FB_MAXF * FB_MAXF);   // Qxx, Qxu, Quu, Qaa, Qff
-    fb_zero(w.Fqq6, 3 * 36 + 2 * FB_NV * FB_NV + FB_NV * FB_NU);                                   // Fqq6 .. Fvu
-    fb_zero(w.Pq, FB_MAXF * FB_NV);
+  {
+    const double* qp = el.prev_slot >= 0 ? A.sol[(size_t)el.prev_slot * A.B + b].q : A.q0 + (size_t)b * FB_NQ;
+    FBW_FOR(i, FB_NQ) w.qprev[i] = qp[i];
   }
-  fb_zero(w.IDC, FB_NVF + FB_NVF * FB_NX);
-  fb_zero(w.dCda, FB_MAXF * FB_NV);
-  if (tid == 0) w.info = 0;
-  __syncthreads();
-  if (tid < FB_MAXF) {   // forces of inactive contacts are zero for the dynamics; stacks of the active ones
-    const int i = tid / 3;
-    w.fm[tid] = (!terminal && el.active[i]) ? w.f[tid] : 0.0;
+  __syncwarp();
+  if (lane < FB_MAXF) {   // forces of inactive contacts are zero for the dynamics; stacks of the active ones
+    const int i = lane / 3;
+    w.fm[lane] = (!terminal && el.active[i]) ? w.f[lane] : 0.0;
     if (!terminal && el.active[i]) {
       int k = 0;
       for (int j = 0; j < i; ++j) k += el.active[j];
-      w.mu_stack[3 * k + tid % 3] = w.mu[tid];
+      w.mu_stack[3 * k + lane % 3] = w.mu[lane];
     }
   }
-  // ---- SE(3) pieces, one thread each (different warps) ----
-  if (tid == 0) {   // cost: qdiff, J_qdiff (trotting_configuration_space_cost.cpp:295-300)
-    fb_subtract(w.q, el.ref_q, w.qdiff);
-    fb_dsubtract_dplus(w.q, el.ref_q, w.J6c);
+  // ---- SE(3): lanes 0..2 in lock-step on (q, q_ref), (q, q_next), (q_prev, q) ----
+  if (lane < 3 && !(terminal && lane == 1)) {
+    const double* qp = lane == 2 ? w.qprev : w.q;
+    const double* qm = lane == 0 ? el.ref_q : (lane == 1 ? w.nq : w.q);
+    fbw_se3_pair(qp, qm, w.relR[lane], w.relp[lane], w.rellog[lane], w.relJ[lane]);
   }
-  if (tid == 32 && !terminal) {   // state equation residual and d/dq (state_equation.hxx:11-40,220-228)
-    fb_subtract(w.q, w.nq, w.Fq);
-    fb_dsubtract_dplus(w.q, w.nq, w.Fqq6);
+  __syncwarp();
+  // (rellog holds 6 base entries; the joint differences are recomputed where needed)
+  if (!RESIDUAL_ONLY) {
+    if ((lane == 1 && !terminal) || lane == 2) fbw_dminus(w.relR[lane], w.relp[lane], w.relJ[lane], lane == 1 ? w.tmp6 : w.Fqq_prev6);
+    __syncwarp();
+    if ((lane == 1 && !terminal) || lane == 2) fb_dsubtract_inverse(lane == 1 ? w.tmp6 : w.Fqq_prev6, lane == 1 ? w.Fqq_inv : L.Fqq_prev_inv);
+  } else {
+    if (lane == 2) fbw_dminus(w.relR[2], w.relp[2], w.relJ[2], w.Fqq_prev6);
   }
-  if (tid == 64) {
-    fb_dsubtract_dminus(w.qprev, w.q, w.Fqq_prev6);
-    if (!RESIDUAL_ONLY) fb_dsubtract_inverse(w.Fqq_prev6, w.Fqq_prev_inv);
-  }
-  if (tid == 96 && !terminal && !RESIDUAL_ONLY) {
-    fb_dsubtract_dminus(w.q, w.nq, w.tmp6);
-    fb_dsubtract_inverse(w.tmp6, w.Fqq_inv);
-  }
-  __syncthreads();
+  __syncwarp();
+  const double* J6c = w.relJ[0];
+  const double* Fqq6 = w.relJ[1];
 
-  // ---- cost gradient; constraints: residual/duality, augmentDualResidual; state equation ----
+  // ---- cost gradient (trotting_configuration_space_cost.cpp:283-311) ----
   const double* wq = terminal ? pr.qf_weight : (impulse ? pr.qi_weight : pr.q_weight);
   const double* wv = terminal ? pr.vf_weight : (impulse ? pr.vi_weight : pr.v_weight);
   const double* wa = impulse ? pr.dvi_weight : pr.a_weight;
   const double sc = (terminal || impulse) ? 1.0 : dt;
-  if (tid < FB_NV) {
-    const int j = tid;
+  double lq = 0.0, lv = 0.0, la = 0.0, Fq = 0.0, Fv = 0.0;   // lane j < 18 owns element j of the stage vectors
+  double lf = 0.0;                                             // lane j < 12 owns lf[j] (stacked)
+  double lu = 0.0, lup = 0.0;                                  // lane j < 12 owns lu[j]; lane j < 6 owns lu_passive[j]
+  // contact owning stacked row `lane` (for lf): ci = contact index, cx = axis
+  int ci = -1, cx = 0;
+  if (!terminal && lane < dimf) {
+    int k = lane / 3, cnt = 0;
+    for (int i = 0; i < FB_NC; ++i)
+      if (el.active[i]) { if (cnt == k) ci = i; ++cnt; }
+    cx = lane % 3;
+  }
+  if (lane < FB_NV) {
+    const int j = lane;
+    const double qd = j < 6 ? w.rellog[0][j] : (w.q[1 + j] - el.ref_q[1 + j]);
     if (j < 6) {
-      double acc = w.J6c[j] * (wq[0] * w.qdiff[0]);
-      for (int k = 1; k < 6; ++k) acc = fma(w.J6c[6 * k + j], wq[k] * w.qdiff[k], acc);
-      w.lq[j] += sc * acc;
+      double acc = J6c[j] * (wq[0] * w.rellog[0][0]);
+      for (int k = 1; k < 6; ++k) acc = fma(J6c[6 * k + j], wq[k] * w.rellog[0][k], acc);
+      lq += sc * acc;
     } else {
-      w.lq[j] += sc * (wq[j] * w.qdiff[j]);
+      lq += sc * (wq[j] * qd);
     }
-    w.lv[j] += sc * (wv[j] * (w.v[j] - el.ref_v[j]));
-    if (!terminal) w.la[j] += sc * (wa[j] * w.a[j]);
+    lv += sc * (wv[j] * (w.v[j] - el.ref_v[j]));
+    if (!terminal) la += sc * (wa[j] * w.a[j]);
   }
-  if (tid >= 32 && tid < 32 + FB_MAXF && !terminal) {   // ContactForceCost gradient (contact_force_cost.cpp:161-187)
-    const int x = tid - 32, i = x / 3;
-    if (el.active[i]) {
-      int k = 0;
-      for (int j = 0; j < i; ++j) k += el.active[j];
-      const double* fw = impulse ? pr.fi_weight : pr.f_weight;
-      const double* fr = impulse ? pr.fi_ref : pr.f_ref;
-      w.lf[3 * k + x % 3] += sc * (fw[x] * (w.f[x] - fr[x]));
-    }
+  if (ci >= 0) {   // ContactForceCost gradient (contact_force_cost.cpp:161-187)
+    const double* fw = impulse ? pr.fi_weight : pr.f_weight;
+    const double* fr = impulse ? pr.fi_ref : pr.f_ref;
+    lf += sc * (fw[3 * ci + cx] * (w.f[3 * ci + cx] - fr[3 * ci + cx]));
   }
-  // computePrimalAndDualResidual (needed by the KKT error and by condenseSlackAndDual alike)
+  // computePrimalAndDualResidual
   if (!terminal) {
-    FB_FOR(idx, FB_NCON) {
-      int c = idx < 72 ? idx / 12 : (idx < 92 ? FBC_FRICTION : FBC_IMPULSE_FRICTION);
+    FBW_FOR(idx, FB_NCON) {
+      const int c = idx < 72 ? idx / 12 : (idx < 92 ? FBC_FRICTION : FBC_IMPULSE_FRICTION);
       const int j = idx - fbc_offset(c);
       double res = 0.0, dua = 0.0;
       if (el.cactive[c]) {
@@ -676,307 +618,384 @@ __global__ void __launch_bounds__(128) k_fb_linearize(FbArrays A) {
       }
       w.residual[idx] = res;
       w.duality[idx] = dua;
+      Dr.residual[idx] = res;
+      Dr.duality[idx] = dua;
     }
   }
-  __syncthreads();
+  __syncwarp();
   if (terminal) {
     // TerminalOCP::linearizeOCP (terminal_ocp.hxx:50-66), linearizeForwardEulerTerminal (state_equation.hxx:66-82)
-    if (tid < FB_NV) {
-      const int j = tid;
+    if (lane < FB_NV) {
+      const int j = lane;
       if (j < 6) {
-        double acc = w.lq[j];
-        for (int k = 0; k < 6; ++k) acc = fma(w.Fqq_prev6[6 * k + j], w.lmd[k], acc);
-        w.lq[j] = acc;
+        for (int k = 0; k < 6; ++k) lq = fma(w.Fqq_prev6[6 * k + j], w.lmd[k], lq);
       } else {
-        w.lq[j] -= w.lmd[j];
+        lq -= w.lmd[j];
       }
-      w.lv[j] -= w.gmm[j];
+      lv -= w.gmm[j];
+      L.lq[j] = lq;
+      L.lv[j] = lv;
     }
-    __syncthreads();
     if (!RESIDUAL_ONLY) {
-      FB_FOR(x, 36) {
+      FBW_FOR(x, 36) {
         const int r = x / 6, c = x - 6 * r;
-        double acc = w.J6c[r] * (wq[0] * w.J6c[c]);
-        for (int k = 1; k < 6; ++k) acc = fma(w.J6c[6 * k + r], wq[k] * w.J6c[6 * k + c], acc);
-        w.Qxx[r * FB_NX + c] += acc;
+        double acc = J6c[r] * (wq[0] * J6c[c]);
+        for (int k = 1; k < 6; ++k) acc = fma(J6c[6 * k + r], wq[k] * J6c[6 * k + c], acc);
+        L.Qqq6[x] = 0.0 + acc;
       }
-      if (tid >= 64 && tid < 64 + FB_NV) {
-        const int j = tid - 64;
-        if (j >= 6) w.Qxx[j * FB_NX + j] += wq[j];
-        w.Qxx[(FB_NV + j) * FB_NX + FB_NV + j] += wv[j];
+      if (lane < FB_NV) {
+        L.Qqq_d[lane] = lane >= 6 ? 0.0 + wq[lane] : 0.0;
+        L.Qvv_d[lane] = 0.0 + wv[lane];
       }
-      __syncthreads();
-      fb_copy(Kt.Qxx, w.Qxx, FB_NX * FB_NX);
-      fb_copy(Kt.Fqq_prev_inv, w.Fqq_prev_inv, 36);
     }
-    fb_copy(Kt.lq, w.lq, FB_NV);
-    fb_copy(Kt.lv, w.lv, FB_NV);
-    if (tid == 0) {
-      Dr.kkt_sq = fb_sqnorm(w.lq, FB_NV) + fb_sqnorm(w.lv, FB_NV);
+    __syncwarp();
+    if (lane == 0) {
+      Dr.kkt_sq = fb_sqnorm(L.lq, FB_NV) + fb_sqnorm(L.lv, FB_NV);
       Dr.info = 0.0;
     }
     return;
   }
-  // augmentDualResidual: joint limits on lq / lv / lu tails, friction cones on lf
-  if (tid < FB_NU) {
-    const int j = tid;
-    for (int c = 0; c < 6; ++c) {
+  // augmentDualResidual: joint limits on the lq / lv / lu tails, friction cones on lf
+  if (lane >= 6 && lane < FB_NV) {
+    const int j = lane - 6;
+    for (int c = 0; c < 4; ++c) {
       if (!el.cactive[c]) continue;
-      double* l = c <= FBC_POS_UP ? w.lq + 6 : (c <= FBC_VEL_UP ? w.lv + 6 : w.lu);
       const double sg = (c & 1) ? 1.0 : -1.0;
-      l[j] += sg * (dt * w.dual[12 * c + j]);
+      if (c <= FBC_POS_UP) lq += sg * (dt * w.dual[12 * c + j]);
+      else lv += sg * (dt * w.dual[12 * c + j]);
     }
   }
-  if (tid >= 32 && tid < 32 + FB_MAXF) {
-    const int x = tid - 32, i = x / 3, xx = x % 3;
-    const int c = impulse ? FBC_IMPULSE_FRICTION : FBC_FRICTION;
-    if (el.cactive[c] && el.active[i]) {
-      int k = 0;
-      for (int j = 0; j < i; ++j) k += el.active[j];
-      const double* du5 = w.dual + fbc_offset(c) + 5 * i;
-      double acc = fb_friction_jac(pr.mu, 0, xx) * du5[0];
-      for (int ee = 1; ee < 5; ++ee) acc = fma(fb_friction_jac(pr.mu, ee, xx), du5[ee], acc);
-      w.lf[3 * k + xx] += dt * acc;
+  if (lane < FB_NU) {
+    for (int c = 4; c < 6; ++c) {
+      if (!el.cactive[c]) continue;
+      const double sg = (c & 1) ? 1.0 : -1.0;
+      lu += sg * (dt * w.dual[12 * c + lane]);
     }
   }
-  __syncthreads();
-  // linearizeForwardEuler / linearizeImpulseForwardEuler
-  if (tid < FB_NV) {
-    const int j = tid;
+  const int cfr = impulse ? FBC_IMPULSE_FRICTION : FBC_FRICTION;
+  if (ci >= 0 && el.cactive[cfr]) {
+    const double* du5 = w.dual + fbc_offset(cfr) + 5 * ci;
+    double acc = fb_friction_jac(pr.mu, 0, cx) * du5[0];
+    for (int ee = 1; ee < 5; ++ee) acc = fma(fb_friction_jac(pr.mu, ee, cx), du5[ee], acc);
+    lf += dt * acc;
+  }
+  // linearizeForwardEuler / linearizeImpulseForwardEuler (state_equation.hxx:11-40)
+  if (lane < FB_NV) {
+    const int j = lane;
+    Fq = j < 6 ? w.rellog[1][j] : (w.q[1 + j] - w.nq[1 + j]);
     if (!impulse) {
-      w.Fq[j] = fma(dt, w.v[j], w.Fq[j]);
-      w.Fv[j] = fma(dt, w.a[j], w.v[j]) - w.nv[j];
+      Fq = fma(dt, w.v[j], Fq);
+      Fv = fma(dt, w.a[j], w.v[j]) - w.nv[j];
     } else {
-      w.Fv[j] = (w.v[j] + w.a[j]) - w.nv[j];
+      Fv = (w.v[j] + w.a[j]) - w.nv[j];
     }
     if (j < 6) {
-      double acc = w.lq[j];
-      for (int k = 0; k < 6; ++k) acc = fma(w.Fqq6[6 * k + j], w.nlmd[k], acc);
-      for (int k = 0; k < 6; ++k) acc = fma(w.Fqq_prev6[6 * k + j], w.lmd[k], acc);
-      w.lq[j] = acc;
+      for (int k = 0; k < 6; ++k) lq = fma(Fqq6[6 * k + j], w.nlmd[k], lq);
+      for (int k = 0; k < 6; ++k) lq = fma(w.Fqq_prev6[6 * k + j], w.lmd[k], lq);
     } else {
-      w.lq[j] += w.nlmd[j] - w.lmd[j];
+      lq += w.nlmd[j] - w.lmd[j];
     }
     if (!impulse) {
-      w.lv[j] += (fma(dt, w.nlmd[j], w.ngmm[j]) - w.gmm[j]);
-      w.la[j] = fma(dt, w.ngmm[j], w.la[j]);
+      lv += (fma(dt, w.nlmd[j], w.ngmm[j]) - w.gmm[j]);
+      la = fma(dt, w.ngmm[j], la);
     } else {
-      w.lv[j] += (w.ngmm[j] - w.gmm[j]);
-      w.la[j] += w.ngmm[j];
+      lv += (w.ngmm[j] - w.gmm[j]);
+      la += w.ngmm[j];
     }
+    w.t18[j] = Fq;
   }
-  __syncthreads();
+  __syncwarp();
   if (!RESIDUAL_ONLY) {
     // condenseForwardEuler: Fqq := -Fqq_inv Fqq, Fqv := -dt Fqq_inv, Fq[0:6] := -Fqq_inv Fq[0:6]
-    FB_FOR(x, 36) {
+    FBW_FOR(x, 36) {
       const int r = x / 6, c = x - 6 * r;
-      double acc = w.Fqq_inv[6 * r] * w.Fqq6[c];
-      for (int k = 1; k < 6; ++k) acc = fma(w.Fqq_inv[6 * r + k], w.Fqq6[6 * k + c], acc);
-      w.tmp6[x] = -acc;
-      if (!impulse) w.Fqv6[x] = -dt * w.Fqq_inv[x];
+      double acc = w.Fqq_inv[6 * r] * Fqq6[c];
+      for (int k = 1; k < 6; ++k) acc = fma(w.Fqq_inv[6 * r + k], Fqq6[6 * k + c], acc);
+      L.Fqq6[x] = -acc;
+      L.Fqv6[x] = impulse ? 0.0 : -dt * w.Fqq_inv[x];
     }
-    if (tid >= 64 && tid < 70) {
-      const int r = tid - 64;
-      double acc = w.Fqq_inv[6 * r] * w.Fq[0];
-      for (int k = 1; k < 6; ++k) acc = fma(w.Fqq_inv[6 * r + k], w.Fq[k], acc);
-      w.fq6[r] = -acc;
+    if (lane < 6) {
+      double acc = w.Fqq_inv[6 * lane] * w.t18[0];
+      for (int k = 1; k < 6; ++k) acc = fma(w.Fqq_inv[6 * lane + k], w.t18[k], acc);
+      Fq = -acc;
     }
-    __syncthreads();
-    FB_FOR(x, 36) w.Fqq6[x] = w.tmp6[x];
-    if (tid >= 64 && tid < 70) w.Fq[tid - 64] = w.fq6[tid - 64];
-    __syncthreads();
   }
+  __syncwarp();
 
   // ---- contact dynamics: kinematics, RNEA + derivatives, contact rows ----
   const double baumgarte = pr.T / pr.N;
   if (!impulse) {
-    fb_forward_kinematics(w, w.q, w.v, w.a);
-    fb_rnea_derivatives(w, ANYMAL_GRAVITY, true);
-    if (tid < FB_NU) w.IDC[6 + tid] -= w.u[tid];
+    fbw_forward_kinematics(w, lane, w.q, w.v, w.a);
+    fbw_rnea_derivatives(w, lane, ANYMAL_GRAVITY, true, L, true);
+    if (lane < FB_NU) L.IDC[6 + lane] -= w.u[lane];
   } else {
-    fb_forward_kinematics(w, w.q, nullptr, w.a);
-    fb_rnea_derivatives(w, 0.0, false);
-    if (tid < FB_NV) w.t18[tid] = w.v[tid] + w.a[tid];
-    __syncthreads();
-    fb_forward_kinematics(w, w.q, w.t18, nullptr);
+    fbw_forward_kinematics(w, lane, w.q, nullptr, w.a);
+    fbw_rnea_derivatives(w, lane, 0.0, false, L, true);
+    if (lane < FB_NV) w.t18[lane] = w.v[lane] + w.a[lane];
+    __syncwarp();
+    fbw_forward_kinematics(w, lane, w.q, w.t18, nullptr);
   }
-  fb_contact_rows(w, el, impulse, baumgarte);
+  // rows of every active contact, one after the other; lane = dof
+  {
+    int k = 0;
+    for (int i = 0; i < FB_NC; ++i) {
+      if (!el.active[i]) continue;
+      const int bi = 1 + ANYMAL_CONTACT_PARENT_JOINT[i];
+      const double* Rf = w.R[bi];
+      if (lane == 0) fbw_contact_point(w, i, w.frP);
+      __syncwarp();
+      if (lane == 0) fb_pullback(Rf, w.frP, w.ov[bi], w.frV);
+      if (lane == 1) fb_pullback(Rf, w.frP, w.oa[bi], w.frA);
+      __syncwarp();
+      const double* P = w.frP;
+      const double* vF = w.frV;
+      if (lane == 31) {
+        double* C = L.IDC + FB_NV + 3 * k;
+        if (!impulse) {
+          const double wvv = 2.0 / baumgarte, wpp = 1.0 / (baumgarte * baumgarte);
+          double wxv[3];
+          fb_cross(vF + 3, vF, wxv);
+          for (int x = 0; x < 3; ++x) {
+            const double acl = w.frA[x] + wxv[x];
+            C[x] = fma(wpp, P[x] - el.cpoints[3 * i + x], fma(wvv, vF[x], acl));
+          }
+        } else {
+          for (int x = 0; x < 3; ++x) C[x] = vF[x];
+        }
+      }
+      if (lane < FB_NV) {
+        const int c = lane;
+        double J[6] = {0, 0, 0, 0, 0, 0}, vq[6] = {0, 0, 0, 0, 0, 0}, aq[6] = {0, 0, 0, 0, 0, 0}, av[6] = {0, 0, 0, 0, 0, 0};
+        if (fb_in_support(i, c)) {
+          fb_pullback(Rf, P, w.S[c], J);
+          const int bb = fb_body_of_dof(c);
+          double u[6], x6[6], t1[6], t2[6];
+          if (bb == 0) {
+            for (int ee = 0; ee < 6; ++ee) u[ee] = w.ov[bi][ee];
+          } else {
+            const int pb = fb_parent_body(bb);
+            for (int ee = 0; ee < 6; ++ee) u[ee] = w.ov[bi][ee] - w.ov[pb][ee];
+            fb_pullback(Rf, P, w.dV[c], vq);
+          }
+          if (!impulse) {
+            fb_mxm(w.ov[bb], w.S[c], t1);
+            fb_mxm(w.S[c], u, t2);
+            for (int ee = 0; ee < 6; ++ee) x6[ee] = t1[ee] + t2[ee];
+            fb_pullback(Rf, P, x6, av);
+            if (bb != 0) {
+              const int pb = fb_parent_body(bb);
+              fb_mxm(w.oa[pb], w.S[c], t1);
+              fb_mxm(w.dV[c], u, t2);
+              for (int ee = 0; ee < 6; ++ee) x6[ee] = t1[ee] + t2[ee];
+              fb_pullback(Rf, P, x6, aq);
+            }
+          }
+        }
+        double* rq = L.dIDCdqv + (FB_NV + 3 * k) * FB_NX + c;
+        double* rv = rq + FB_NV;
+        double* ra = L.dCda + (3 * k) * FB_NV + c;
+        if (!impulse) {
+          const double wvv = 2.0 / baumgarte, wpp = 1.0 / (baumgarte * baumgarte);
+          const double* vl = vF;
+          const double* va = vF + 3;
+          double t1[3], t2[3], RJ[3];
+          fb_cross(va, vq, t1);
+          fb_cross(vl, vq + 3, t2);
+          fb_rot(Rf, J, RJ);
+          for (int x = 0; x < 3; ++x) rq[x * FB_NX] = fma(wpp, RJ[x], fma(wvv, vq[x], (aq[x] + t1[x]) + t2[x]));
+          fb_cross(va, J, t1);
+          fb_cross(vl, J + 3, t2);
+          for (int x = 0; x < 3; ++x) rv[x * FB_NX] = fma(wvv, J[x], (av[x] + t1[x]) + t2[x]);
+          for (int x = 0; x < 3; ++x) ra[x * FB_NV] = J[x];
+        } else {
+          for (int x = 0; x < 3; ++x) { rq[x * FB_NX] = vq[x]; rv[x * FB_NX] = J[x]; ra[x * FB_NV] = J[x]; }
+        }
+      }
+      __syncwarp();
+      ++k;
+    }
+  }
+  __syncwarp();
   // augment: lq += dt dIDdq^T beta, lv += dt dIDdv^T beta, la += dt M^T beta, lf -= dt dCda beta, lu ...
   {
-    const double* dIDdq = w.dIDCdqv;
-    const double* dIDdv = w.dIDCdqv + FB_NV;
-    const double* dCdq = w.dIDCdqv + FB_NV * FB_NX;
+    const double* dIDdq = L.dIDCdqv;
+    const double* dIDdv = L.dIDCdqv + FB_NV;
+    const double* dCdq = L.dIDCdqv + FB_NV * FB_NX;
     const double* dCdv = dCdq + FB_NV;
-    if (tid < FB_NV) {
-      const int j = tid;
+    if (lane < FB_NV) {
+      const int j = lane;
       double acc = dIDdq[j] * w.beta[0];
       for (int k = 1; k < FB_NV; ++k) acc = fma(dIDdq[k * FB_NX + j], w.beta[k], acc);
-      w.lq[j] = fma(dt, acc, w.lq[j]);
+      lq = fma(dt, acc, lq);
       if (!impulse) {
         acc = dIDdv[j] * w.beta[0];
         for (int k = 1; k < FB_NV; ++k) acc = fma(dIDdv[k * FB_NX + j], w.beta[k], acc);
-        w.lv[j] = fma(dt, acc, w.lv[j]);
+        lv = fma(dt, acc, lv);
       }
-      acc = w.Mm[j] * w.beta[0];
-      for (int k = 1; k < FB_NV; ++k) acc = fma(w.Mm[k * FB_NV + j], w.beta[k], acc);
-      w.la[j] = fma(dt, acc, w.la[j]);
+      acc = L.Mm[j] * w.beta[0];
+      for (int k = 1; k < FB_NV; ++k) acc = fma(L.Mm[k * FB_NV + j], w.beta[k], acc);
+      la = fma(dt, acc, la);
       if (dimf > 0) {
         acc = dCdq[j] * w.mu_stack[0];
         for (int k = 1; k < dimf; ++k) acc = fma(dCdq[k * FB_NX + j], w.mu_stack[k], acc);
-        w.lq[j] = fma(dt, acc, w.lq[j]);
+        lq = fma(dt, acc, lq);
         acc = dCdv[j] * w.mu_stack[0];
         for (int k = 1; k < dimf; ++k) acc = fma(dCdv[k * FB_NX + j], w.mu_stack[k], acc);
-        w.lv[j] = fma(dt, acc, w.lv[j]);
-        acc = w.dCda[j] * w.mu_stack[0];
-        for (int k = 1; k < dimf; ++k) acc = fma(w.dCda[k * FB_NV + j], w.mu_stack[k], acc);
-        w.la[j] = fma(dt, acc, w.la[j]);
+        lv = fma(dt, acc, lv);
+        acc = L.dCda[j] * w.mu_stack[0];
+        for (int k = 1; k < dimf; ++k) acc = fma(L.dCda[k * FB_NV + j], w.mu_stack[k], acc);
+        la = fma(dt, acc, la);
       }
     }
-    if (tid >= 32 && tid < 32 + dimf) {
-      const int j = tid - 32;
-      double acc = w.dCda[j * FB_NV] * w.beta[0];
-      for (int k = 1; k < FB_NV; ++k) acc = fma(w.dCda[j * FB_NV + k], w.beta[k], acc);
-      w.lf[j] = fma(-dt, acc, w.lf[j]);
+    if (lane < dimf) {
+      const int j = lane;
+      double acc = L.dCda[j * FB_NV] * w.beta[0];
+      for (int k = 1; k < FB_NV; ++k) acc = fma(L.dCda[j * FB_NV + k], w.beta[k], acc);
+      lf = fma(-dt, acc, lf);
     }
-    if (!impulse && tid >= 64 && tid < 64 + FB_NV) {
-      const int j = tid - 64;
-      if (j < FB_NPASS) w.lu_passive[j] = fma(-dt, w.beta[j], dt * w.nu_passive[j]);
-      else w.lu[j - 6] = fma(-dt, w.beta[j], w.lu[j - 6]);
+    if (!impulse) {
+      if (lane < FB_NPASS) lup = fma(-dt, w.beta[lane], dt * w.nu_passive[lane]);
+      if (lane < FB_NU) lu = fma(-dt, w.beta[6 + lane], lu);
     }
   }
-  __syncthreads();
 
-  if (RESIDUAL_ONLY) {
-    // (the switching-constraint residual and its multiplier terms are added below, shared with the full path)
-  } else {
-    // ---- cost Hessian ----
-    FB_FOR(x, 36) {
+  if (!RESIDUAL_ONLY) {
+    // ---- cost Hessian (sparse part of Qxx, Qaa, Qff) and condenseSlackAndDual ----
+    FBW_FOR(x, 36) {
       const int r = x / 6, c = x - 6 * r;
-      double acc = w.J6c[r] * (wq[0] * w.J6c[c]);
-      for (int k = 1; k < 6; ++k) acc = fma(w.J6c[6 * k + r], wq[k] * w.J6c[6 * k + c], acc);
-      w.Qxx[r * FB_NX + c] += sc * acc;
+      double acc = J6c[r] * (wq[0] * J6c[c]);
+      for (int k = 1; k < 6; ++k) acc = fma(J6c[6 * k + r], wq[k] * J6c[6 * k + c], acc);
+      L.Qqq6[x] = 0.0 + sc * acc;
     }
-    if (tid >= 64 && tid < 64 + FB_NV) {
-      const int j = tid - 64;
-      if (j >= 6) w.Qxx[j * FB_NX + j] += sc * wq[j];
-      w.Qxx[(FB_NV + j) * FB_NX + FB_NV + j] += sc * wv[j];
-      w.Qaa[j] += sc * wa[j];
+    FBW_FOR(x, FB_MAXF * FB_MAXF) L.Qff[x] = 0.0;
+    __syncwarp();
+    double qqd = 0.0, qvd = 0.0, qud = 0.0;
+    if (lane < FB_NV) {
+      const int j = lane;
+      if (j >= 6) qqd += sc * wq[j];
+      qvd += sc * wv[j];
+      L.Qaa[j] = 0.0 + sc * wa[j];
     }
-    if (tid >= 96 && tid < 96 + FB_MAXF) {
-      const int x = tid - 96, i = x / 3;
-      if (el.active[i]) {
-        int k = 0;
-        for (int j = 0; j < i; ++j) k += el.active[j];
-        const double* fw = impulse ? pr.fi_weight : pr.f_weight;
-        w.Qff[(3 * k + x % 3) * FB_MAXF + 3 * k + x % 3] += sc * fw[x];
-      }
+    if (ci >= 0) {
+      const double* fw = impulse ? pr.fi_weight : pr.f_weight;
+      L.Qff[lane * FB_MAXF + lane] += sc * fw[3 * ci + cx];
     }
-    __syncthreads();
-    // ---- condenseSlackAndDual ----
-    if (tid < FB_NU) {
-      const int j = tid;
-      for (int c = 0; c < 6; ++c) {
+    if (lane >= 6 && lane < FB_NV) {
+      const int j = lane - 6;
+      for (int c = 0; c < 4; ++c) {
         if (!el.cactive[c]) continue;
         const int idx = 12 * c + j;
         const double rs = 1.0 / w.slack[idx];
         const double h = (dt * w.dual[idx]) * rs;
-        if (c <= FBC_POS_UP) w.Qxx[(6 + j) * FB_NX + 6 + j] += h;
-        else if (c <= FBC_VEL_UP) w.Qxx[(FB_NV + 6 + j) * FB_NX + FB_NV + 6 + j] += h;
-        else w.Quu[(6 + j) * FB_NV + 6 + j] += h;
-        double* l = c <= FBC_POS_UP ? w.lq + 6 : (c <= FBC_VEL_UP ? w.lv + 6 : w.lu);
         const double sg = (c & 1) ? 1.0 : -1.0;
-        l[j] += sg * ((dt * fma(w.dual[idx], w.residual[idx], -w.duality[idx])) * rs);
+        const double g = sg * ((dt * fma(w.dual[idx], w.residual[idx], -w.duality[idx])) * rs);
+        if (c <= FBC_POS_UP) { qqd += h; lq += g; }
+        else { qvd += h; lv += g; }
       }
     }
-    {
-      const int c = impulse ? FBC_IMPULSE_FRICTION : FBC_FRICTION;
-      if (el.cactive[c] && tid >= 32 && tid < 32 + FB_MAXF) {
-        const int x = tid - 32, i = x / 3, xx = x % 3;
-        if (el.active[i]) {
-          int k = 0;
-          for (int j = 0; j < i; ++j) k += el.active[j];
-          const int o = fbc_offset(c) + 5 * i;
-          double r5[5], w5[5];
-          for (int ee = 0; ee < 5; ++ee) {
-            const double rs = 1.0 / w.slack[o + ee];
-            r5[ee] = fma(w.dual[o + ee], w.residual[o + ee], -w.duality[o + ee]) * rs;
-            w5[ee] = w.dual[o + ee] * rs;
-          }
-          double acc = fb_friction_jac(pr.mu, 0, xx) * r5[0];
-          for (int ee = 1; ee < 5; ++ee) acc = fma(fb_friction_jac(pr.mu, ee, xx), r5[ee], acc);
-          w.lf[3 * k + xx] += dt * acc;
-          for (int y = 0; y < 3; ++y) {
-            double h = fb_friction_jac(pr.mu, 0, xx) * (w5[0] * fb_friction_jac(pr.mu, 0, y));
-            for (int ee = 1; ee < 5; ++ee) h = fma(fb_friction_jac(pr.mu, ee, xx), w5[ee] * fb_friction_jac(pr.mu, ee, y), h);
-            w.Qff[(3 * k + xx) * FB_MAXF + 3 * k + y] += dt * h;
-          }
-        }
+    if (lane < FB_NU) {
+      for (int c = 4; c < 6; ++c) {
+        if (!el.cactive[c]) continue;
+        const int idx = 12 * c + lane;
+        const double rs = 1.0 / w.slack[idx];
+        qud += (dt * w.dual[idx]) * rs;
+        const double sg = (c & 1) ? 1.0 : -1.0;
+        lu += sg * ((dt * fma(w.dual[idx], w.residual[idx], -w.duality[idx])) * rs);
+      }
+      L.Quu_d[lane] = qud;
+    }
+    if (lane < FB_NV) { L.Qqq_d[lane] = qqd; L.Qvv_d[lane] = qvd; }
+    if (ci >= 0 && el.cactive[cfr]) {
+      int k = lane / 3;
+      const int o = fbc_offset(cfr) + 5 * ci;
+      double r5[5], w5[5];
+      for (int ee = 0; ee < 5; ++ee) {
+        const double rs = 1.0 / w.slack[o + ee];
+        r5[ee] = fma(w.dual[o + ee], w.residual[o + ee], -w.duality[o + ee]) * rs;
+        w5[ee] = w.dual[o + ee] * rs;
+      }
+      double acc = fb_friction_jac(pr.mu, 0, cx) * r5[0];
+      for (int ee = 1; ee < 5; ++ee) acc = fma(fb_friction_jac(pr.mu, ee, cx), r5[ee], acc);
+      lf += dt * acc;
+      for (int y = 0; y < 3; ++y) {
+        double h = fb_friction_jac(pr.mu, 0, cx) * (w5[0] * fb_friction_jac(pr.mu, 0, y));
+        for (int ee = 1; ee < 5; ++ee) h = fma(fb_friction_jac(pr.mu, ee, cx), w5[ee] * fb_friction_jac(pr.mu, ee, y), h);
+        L.Qff[(3 * k + cx) * FB_MAXF + 3 * k + y] += dt * h;
       }
     }
-    __syncthreads();
   }
 
   // ---- ForwardSwitchingConstraint::linearizeSwitchingConstraint (:27-68) ----
   if (dimi > 0) {
     const double c1 = el.dt + el.dt_next, c2 = el.dt * el.dt_next;
-    if (tid < FB_NV) w.dqv[tid] = fma(c2, w.a[tid], c1 * w.v[tid]);
-    __syncthreads();
-    if (tid == 0) fb_integrate(w.q, w.dqv, 1.0, w.q2);
-    if (tid == 32) fb_dintegrate_dq(w.dqv, w.Jq6);
-    if (tid == 64) fb_dintegrate_dv(w.dqv, w.Jv6);
-    __syncthreads();
-    fb_forward_kinematics(w, w.q2, nullptr, nullptr);
+    __syncwarp();
+    if (lane < FB_NV) w.dqv[lane] = fma(c2, w.a[lane], c1 * w.v[lane]);
+    __syncwarp();
+    if (lane == 0) fb_integrate(w.q, w.dqv, 1.0, w.q2);
+    __syncwarp();
+    if (lane == 0) fb_dintegrate_dq(w.dqv, w.Jq6);
+    __syncwarp();
+    if (lane == 0) fb_dintegrate_dv(w.dqv, w.Jv6);
+    __syncwarp();
+    fbw_forward_kinematics(w, lane, w.q2, nullptr, nullptr);
     {
-      const int warp = tid >> 5, lane = tid & 31;
-      if (warp < FB_NC && el.imp_active[warp]) {
-        const int i = warp;
-        int k = 0;
-        for (int j = 0; j < i; ++j) k += el.imp_active[j];
+      int k = 0;
+      for (int i = 0; i < FB_NC; ++i) {
+        if (!el.imp_active[i]) continue;
         const double* Rf = w.R[1 + ANYMAL_CONTACT_PARENT_JOINT[i]];
-        if (lane == 0) fb_contact_point(w, i, w.frP[i]);
+        if (lane == 0) fbw_contact_point(w, i, w.frP);
         __syncwarp();
-        if (lane == 0)
-          for (int x = 0; x < 3; ++x) w.P[3 * k + x] = w.frP[i][x] - el.ipoints[3 * i + x];
+        if (lane < 3) L.P[3 * k + lane] = w.frP[lane] - el.ipoints[3 * i + lane];
         if (lane < FB_NV) {
           const int c = lane;
           double J[6] = {0, 0, 0, 0, 0, 0}, wl[3];
-          if (fb_in_support(i, c)) fb_pullback(Rf, w.frP[i], w.S[c], J);
+          if (fb_in_support(i, c)) fb_pullback(Rf, w.frP, w.S[c], J);
           fb_rot(Rf, J, wl);
           for (int x = 0; x < 3; ++x) w.Pq[(3 * k + x) * FB_NV + c] = wl[x];
         }
+        __syncwarp();
+        ++k;
       }
     }
-    __syncthreads();
-    fb_mm<FBM_SET>(dimi, 6, 6, w.Pq, FB_NV, 1, w.Jq6, 6, 1, w.Phix, FB_NX);
-    fb_mm<FBM_SET>(dimi, 6, 6, w.Pq, FB_NV, 1, w.Jv6, 6, 1, w.PJv, FB_NV);
-    FB_FOR(x, dimi * (FB_NV - 6)) {
+    __syncwarp();
+    fbw_mm<FBM_SET>(lane, dimi, 6, 6, w.Pq, FB_NV, 1, w.Jq6, 6, 1, L.Phix, FB_NX);
+    fbw_mm<FBM_SET>(lane, dimi, 6, 6, w.Pq, FB_NV, 1, w.Jv6, 6, 1, w.PJv, FB_NV);
+    FBW_FOR(x, dimi * (FB_NV - 6)) {
       const int r = x / (FB_NV - 6), c = 6 + x - r * (FB_NV - 6);
-      w.Phix[r * FB_NX + c] = w.Pq[r * FB_NV + c];
+      L.Phix[r * FB_NX + c] = w.Pq[r * FB_NV + c];
       w.PJv[r * FB_NV + c] = w.Pq[r * FB_NV + c];
     }
-    __syncthreads();
-    FB_FOR(x, dimi * FB_NV) {
+    __syncwarp();
+    FBW_FOR(x, dimi * FB_NV) {
       const int r = x / FB_NV, c = x - r * FB_NV;
-      w.Phix[r * FB_NX + FB_NV + c] = c1 * w.PJv[x];
-      w.Phia[x] = c2 * w.PJv[x];
+      L.Phix[r * FB_NX + FB_NV + c] = c1 * w.PJv[x];
+      L.Phia[x] = c2 * w.PJv[x];
     }
-    __syncthreads();
-    fb_mv<FBM_ADD>(FB_NV, dimi, w.Phix, 1, FB_NX, w.xi, w.lq);
-    fb_mv<FBM_ADD>(FB_NV, dimi, w.Phix + FB_NV, 1, FB_NX, w.xi, w.lv);
-    fb_mv<FBM_ADD>(FB_NV, dimi, w.Phia, 1, FB_NV, w.xi, w.la);
-    __syncthreads();
+    __syncwarp();
+    if (lane < FB_NV) {
+      const int j = lane;
+      for (int l = 0; l < dimi; ++l) lq = fma(L.Phix[l * FB_NX + j], w.xi[l], lq);
+      for (int l = 0; l < dimi; ++l) lv = fma(L.Phix[l * FB_NX + FB_NV + j], w.xi[l], lv);
+      for (int l = 0; l < dimi; ++l) la = fma(L.Phia[l * FB_NV + j], w.xi[l], la);
+    }
   }
+  // ---- store the stage vectors ----
+  if (lane < FB_NV) { L.lq[lane] = lq; L.lv[lane] = lv; L.la[lane] = la; L.Fq[lane] = Fq; L.Fv[lane] = Fv; }
+  if (lane < FB_MAXF) L.lf[lane] = lane < dimf ? lf : 0.0;
+  if (lane < FB_NU) L.lu[lane] = lu;
+  if (lane < FB_NPASS) L.lu_passive[lane] = lup;
+  __syncwarp();
 
   if (RESIDUAL_ONLY) {
-    // squaredNormKKTResidual (split_ocp.hxx:263-279, impulse_split_ocp.hxx:131-142): seven partial sums by seven
-    // threads, added in the reference's order
-    if (tid == 0) w.part[0] = fb_sqnorm(w.lq, FB_NV) + fb_sqnorm(w.lv, FB_NV);
-    if (tid == 1) w.part[1] = fb_sqnorm(w.la, FB_NV);
-    if (tid == 2) w.part[2] = fb_sqnorm(w.lf, dimf);
-    if (tid == 3) { w.part[3] = fb_sqnorm(w.lu_passive, FB_NPASS); w.part[7] = fb_sqnorm(w.lu, FB_NU); }
-    if (tid == 4) w.part[4] = fb_sqnorm(w.Fq, FB_NV) + fb_sqnorm(w.Fv, FB_NV);
-    if (tid == 5) w.part[5] = fb_sqnorm(w.IDC, nvf);
-    if (tid == 6) {
+    // squaredNormKKTResidual (split_ocp.hxx:263-279, impulse_split_ocp.hxx:131-142): partial sums by seven lanes,
+    // added in the reference's order
+    if (lane == 0) w.part[0] = fb_sqnorm(L.lq, FB_NV) + fb_sqnorm(L.lv, FB_NV);
+    if (lane == 1) w.part[1] = fb_sqnorm(L.la, FB_NV);
+    if (lane == 2) w.part[2] = fb_sqnorm(L.lf, dimf);
+    if (lane == 3) { w.part[3] = fb_sqnorm(L.lu_passive, FB_NPASS); w.part[7] = fb_sqnorm(L.lu, FB_NU); }
+    if (lane == 4) w.part[4] = fb_sqnorm(L.Fq, FB_NV) + fb_sqnorm(L.Fv, FB_NV);
+    if (lane == 5) w.part[5] = fb_sqnorm(L.IDC, nvf);
+    if (lane == 6) {
       double e2 = 0.0;
       for (int c = 0; c < FBC_NCOMP; ++c) {
         if (!el.cactive[c]) continue;
@@ -984,8 +1003,8 @@ __global__ void __launch_bounds__(128) k_fb_linearize(FbArrays A) {
       }
       w.part[6] = e2;
     }
-    __syncthreads();
-    if (tid == 0) {
+    __syncwarp();
+    if (lane == 0) {
       double e2 = 0.0;
       e2 += w.part[0];
       e2 += w.part[1];
@@ -995,83 +1014,214 @@ __global__ void __launch_bounds__(128) k_fb_linearize(FbArrays A) {
       if (!impulse) {
         e2 += dt * dt * w.part[5];
         e2 += dt * dt * w.part[6];
-        e2 += fb_sqnorm(w.P, dimi);
+        e2 += fb_sqnorm(L.P, dimi);
       } else {
         e2 += w.part[5];
         e2 += w.part[6];
       }
       Dr.kkt_sq = e2;
     }
-    fb_copy(Dr.residual, w.residual, 2 * FB_NCON);
+  }
+}
+
+// =====================================================================================================
+// K1b: dense condensing of one stage, one CTA (128 threads) per (instance, stage)
+//   computeMJtJinv (robot.hxx:576-615), condenseContactDynamics (contact_dynamics.hxx:105-158) /
+//   condenseImpulseDynamics (impulse_dynamics_forward_euler.hxx:64-105), condenseSwitchingConstraint (:194-200).
+//   Results go straight to the HBM records of the Riccati sweep (FbKKT) and of the expansion (FbExp).
+// =====================================================================================================
+struct FbDenseWork {
+  double IDC[FB_NVF], dIDCdqv[FB_NVF * FB_NX], Mm[FB_NV * FB_NV], dCda[FB_MAXF * FB_NV];
+  double lq[FB_NV], lv[FB_NV], la[FB_NV], lf[FB_MAXF], lu_passive[FB_NPASS], lu[FB_NU], Fq[FB_NV], Fv[FB_NV], P[FB_MAXF];
+  double Qqq6[36], Qqq_d[FB_NV], Qvv_d[FB_NV], Quu_d[FB_NU], Qaa[FB_NV], Qff[FB_MAXF * FB_MAXF];
+  double Fqq6[36], Fqv6[36], Fqq_prev_inv[36];
+  double Phix[FB_MAXF * FB_NX], Phia[FB_MAXF * FB_NV];
+  // ^ same order as FbLin
+  double MJtJinv[FB_NVF * FB_NVF], MJ_dIDC[FB_NVF * FB_NX], MJ_IDC[FB_NVF], laf[FB_NVF];
+  union {
+    struct { double L[FB_NV * FB_NV], rd[FB_NV], Minv[FB_NV * FB_NV], JMi[FB_MAXF * FB_NV], Sm[FB_MAXF * FB_MAXF], Ls[FB_MAXF * FB_MAXF],
+                 rds[FB_MAXF], Si[FB_MAXF * FB_MAXF]; } f;          // factorisation scratch (dead once MJtJinv is formed)
+    struct { double Qafqv[FB_NVF * FB_NX], Qafu[FB_NVF * FB_NV]; } c;   // condensing products
+  } s;
+  int info;
+};
+
+__global__ void __launch_bounds__(128) k_fb_condense(FbArrays A, const FbLin* lin) {
+  IDOCP_DYN_SMEM(FbDenseWork, wp);
+  FbDenseWork& w = *wp;
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x / A.n_elems, e = blockIdx.x - b * A.n_elems;
+  const FbElem& el = A.elems[e];
+  const size_t rec = (size_t)el.slot * A.B + b;
+  FbKKT& Kt = A.kkt[rec];
+  const FbLin& L = lin[rec];
+  const int NV = FB_NV, NX = FB_NX, NU = FB_NU, NVF = FB_NVF, NPASS = FB_NPASS, MAXF = FB_MAXF;
+  if (el.kind == FB_TERMINAL) {
+    // the terminal stage has no dynamics: Qxx = cost Hessian, lx
+    FB_FOR(x, NX * NX) {
+      const int r = x / NX, c = x - r * NX;
+      double v = 0.0;
+      if (r < 6 && c < 6) v = L.Qqq6[6 * r + c];
+      else if (r == c) v = r < NV ? L.Qqq_d[r] : L.Qvv_d[r - NV];
+      Kt.Qxx[x] = v;
+    }
+    fb_copy(Kt.Fqq_prev_inv, L.Fqq_prev_inv, 36);
+    fb_copy(Kt.lq, L.lq, NV);
+    fb_copy(Kt.lv, L.lv, NV);
     return;
   }
-
-  // ---- condenseContactDynamics (:105-158) / condenseImpulseDynamics ----
-  fb_MJtJinv(w, dimf);
-  fb_mm<FBM_SET>(nvf, FB_NX, nvf, w.MJtJinv, FB_NVF, 1, w.dIDCdqv, FB_NX, 1, w.MJ_dIDC, FB_NX);
-  fb_mv<FBM_SET>(nvf, nvf, w.MJtJinv, FB_NVF, 1, w.IDC, w.MJ_IDC);
+  const bool impulse = el.kind == FB_IMPULSE;
+  const double dt = impulse ? 1.0 : el.dt;
+  const int dimf = el.dimf, nvf = NV + dimf, dimi = el.sw ? el.dimi : 0;
+  FbExp& Ex = A.exp[rec];
+  FbDir& Dr = A.dir[rec];
+  fb_copy(w.IDC, L.IDC, sizeof(FbLin) / sizeof(double));
+  if (tid == 0) w.info = 0;
   __syncthreads();
-  FB_FOR(x, FB_NV * FB_NX) { const int r = x / FB_NX; w.Qafqv[x] = -w.Qaa[r] * w.MJ_dIDC[x]; }
-  fb_mm<FBM_SET>(dimf, FB_NX, dimf, w.Qff, FB_MAXF, 1, w.MJ_dIDC + FB_NV * FB_NX, FB_NX, 1, w.Qafqv + FB_NV * FB_NX, FB_NX);
-  if (!impulse) {
-    FB_FOR(x, FB_NV * FB_NV) { const int r = x / FB_NV, c = x - r * FB_NV; w.Qafu[x] = w.Qaa[r] * w.MJtJinv[r * FB_NVF + c]; }
-    fb_mm<FBM_SET>(dimf, FB_NV, dimf, w.Qff, FB_MAXF, 1, w.MJtJinv + FB_NV * FB_NVF, FB_NVF, 1, w.Qafu + FB_NV * FB_NV, FB_NV);
-  }
-  if (tid < FB_NV) w.laf[tid] = fma(-w.Qaa[tid], w.MJ_IDC[tid], w.la[tid]);
-  if (tid >= 32 && tid < 32 + dimf) w.laf[FB_NV + tid - 32] = -w.lf[tid - 32];
-  __syncthreads();
-  FB_FOR(x, dimf * FB_NX) w.Qafqv[FB_NV * FB_NX + x] = -w.Qafqv[FB_NV * FB_NX + x];
-  fb_mv<FBM_SUB>(dimf, dimf, w.Qff, FB_MAXF, 1, w.MJ_IDC + FB_NV, w.laf + FB_NV);
-  __syncthreads();
-  fb_mm<FBM_SUB>(FB_NX, FB_NX, nvf, w.MJ_dIDC, 1, FB_NX, w.Qafqv, FB_NX, 1, w.Qxx, FB_NX);
-  fb_mv<FBM_SUB>(FB_NV, nvf, w.MJ_dIDC, 1, FB_NX, w.laf, w.lq);
-  fb_mv<FBM_SUB>(FB_NV, nvf, w.MJ_dIDC + FB_NV, 1, FB_NX, w.laf, w.lv);
-  if (!impulse) {
-    fb_mm<FBM_SUB>(FB_NX, FB_NV, nvf, w.MJ_dIDC, 1, FB_NX, w.Qafu, FB_NV, 1, w.Qxu, FB_NV);
-    fb_mm<FBM_ADD>(FB_NV, FB_NV, nvf, w.MJtJinv, FB_NVF, 1, w.Qafu, FB_NV, 1, w.Quu, FB_NV);
-    fb_mv<FBM_ADD>(FB_NPASS, nvf, w.MJtJinv, FB_NVF, 1, w.laf, w.lu_passive);
-    fb_mv<FBM_ADD>(FB_NU, nvf, w.MJtJinv + FB_NPASS * FB_NVF, FB_NVF, 1, w.laf, w.lu);
-    FB_FOR(x, FB_NV * FB_NV) {
-      const int r = x / FB_NV, c = x - r * FB_NV;
-      w.Fvq[x] = -dt * w.MJ_dIDC[r * FB_NX + c];
-      w.Fvv[x] = -dt * w.MJ_dIDC[r * FB_NX + FB_NV + c] + (r == c ? 1.0 : 0.0);
+  // ---- MJtJinv = [[M, J^T], [J, 0]]^-1 by dense Cholesky ----
+  {
+    const int n = NV, ld = NVF;
+    if (tid < 32) {
+      const int info = fb_llt_warp(w.Mm, n, n, w.s.f.L, n, w.s.f.rd);
+      if (tid == 0 && info && !w.info) w.info = info;
     }
-    FB_FOR(x, FB_NV * FB_NU) { const int r = x / FB_NU, c = x - r * FB_NU; w.Fvu[x] = dt * w.MJtJinv[r * FB_NVF + FB_NPASS + c]; }
-    if (tid < FB_NV) w.Fv[tid] = fma(-dt, w.MJ_IDC[tid], w.Fv[tid]);
-  } else {
-    FB_FOR(x, FB_NV * FB_NV) {
-      const int r = x / FB_NV, c = x - r * FB_NV;
-      w.Fvq[x] = -w.MJ_dIDC[r * FB_NX + c];
-      w.Fvv[x] = (r == c ? 1.0 : 0.0) - w.MJ_dIDC[r * FB_NX + FB_NV + c];
+    __syncthreads();
+    if (tid < n) {
+      for (int r = 0; r < n; ++r) w.s.f.Minv[r * n + tid] = (r == tid) ? 1.0 : 0.0;
+      fb_llt_solve(w.s.f.L, n, w.s.f.rd, n, w.s.f.Minv + tid, n);
     }
-    if (tid < FB_NV) w.Fv[tid] -= w.MJ_IDC[tid];
-  }
-  __syncthreads();
-  // ---- condenseSwitchingConstraint (contact_dynamics.hxx:194-200) ----
-  if (dimi > 0) {
-    fb_mm<FBM_SUB>(dimi, FB_NX, FB_NV, w.Phia, FB_NV, 1, w.MJ_dIDC, FB_NX, 1, w.Phix, FB_NX);
-    fb_mm<FBM_SET>(dimi, FB_NU, FB_NV, w.Phia, FB_NV, 1, w.MJtJinv + FB_NPASS, FB_NVF, 1, w.Phiu, FB_NU);
-    fb_mv<FBM_SUB>(dimi, FB_NV, w.Phia, FB_NV, 1, w.MJ_IDC, w.P);
+    __syncthreads();
+    fb_mm<FBM_SET>(dimf, n, n, w.dCda, n, 1, w.s.f.Minv, n, 1, w.s.f.JMi, n);
+    __syncthreads();
+    fb_mm<FBM_SET>(dimf, dimf, n, w.s.f.JMi, n, 1, w.dCda, 1, n, w.s.f.Sm, dimf);
+    __syncthreads();
+    if (dimf > 0) {
+      if (tid < 32) {
+        const int info = fb_llt_warp(w.s.f.Sm, dimf, dimf, w.s.f.Ls, dimf, w.s.f.rds);
+        if (tid == 0 && info && !w.info) w.info = 100 + info;
+      }
+      __syncthreads();
+      if (tid < dimf) {
+        for (int r = 0; r < dimf; ++r) w.s.f.Si[r * dimf + tid] = (r == tid) ? 1.0 : 0.0;
+        fb_llt_solve(w.s.f.Ls, dimf, w.s.f.rds, dimf, w.s.f.Si + tid, dimf);
+      }
+      __syncthreads();
+    }
+    FB_FOR(x, dimf * dimf) { const int r = x / dimf, c = x - r * dimf; w.MJtJinv[(n + r) * ld + n + c] = -w.s.f.Si[x]; }
+    fb_mm<FBM_SET>(n, dimf, dimf, w.s.f.JMi, 1, n, w.s.f.Si, dimf, 1, w.MJtJinv + n, ld);     // TR = (J Minv)^T S^-1
+    __syncthreads();
+    FB_FOR(x, n * n) {                                                                          // TL = Minv - TR (J Minv)
+      const int r = x / n, c = x - r * n;
+      double acc = w.s.f.Minv[x];
+      for (int j = 0; j < dimf; ++j) acc = fma(-w.MJtJinv[r * ld + n + j], w.s.f.JMi[j * n + c], acc);
+      w.MJtJinv[r * ld + c] = acc;
+    }
+    FB_FOR(x, dimf * n) { const int r = x / n, c = x - r * n; w.MJtJinv[(n + r) * ld + c] = w.MJtJinv[c * ld + n + r]; }   // BL = TR^T
     __syncthreads();
   }
-  // ---- store ----
-  fb_copy(Kt.Qxx, w.Qxx, FB_NX * FB_NX + FB_NX * FB_NV + FB_NV * FB_NV);   // Qxx, Qxu, Quu contiguous in both structs
-  fb_copy(Kt.Fqq6, w.Fqq6, 3 * 36 + 2 * FB_NV * FB_NV + FB_NV * FB_NU);   // Fqq6 .. Fvu
-  fb_copy(Kt.lq, w.lq, FB_NV);
-  fb_copy(Kt.lv, w.lv, FB_NV);
-  fb_copy(Kt.lu, w.lu, FB_NU);
-  fb_copy(Kt.lu_passive, w.lu_passive, FB_NPASS);
-  fb_copy(Kt.Fq, w.Fq, FB_NV);
-  fb_copy(Kt.Fv, w.Fv, FB_NV);
-  if (dimi > 0) {
-    fb_copy(Kt.Phix, w.Phix, FB_MAXF * FB_NX);
-    fb_copy(Kt.Phiu, w.Phiu, FB_MAXF * FB_NU);
-    fb_copy(Kt.P, w.P, FB_MAXF);
+  // ---- condensing ----
+  fb_mm<FBM_SET>(nvf, NX, nvf, w.MJtJinv, NVF, 1, w.dIDCdqv, NX, 1, w.MJ_dIDC, NX);
+  fb_mv<FBM_SET>(nvf, nvf, w.MJtJinv, NVF, 1, w.IDC, w.MJ_IDC);
+  __syncthreads();
+  double* Qafqv = w.s.c.Qafqv;
+  double* Qafu = w.s.c.Qafu;
+  FB_FOR(x, NV * NX) { const int r = x / NX; Qafqv[x] = -w.Qaa[r] * w.MJ_dIDC[x]; }
+  fb_mm<FBM_SET>(dimf, NX, dimf, w.Qff, MAXF, 1, w.MJ_dIDC + NV * NX, NX, 1, Qafqv + NV * NX, NX);
+  if (!impulse) {
+    FB_FOR(x, NV * NV) { const int r = x / NV, c = x - r * NV; Qafu[x] = w.Qaa[r] * w.MJtJinv[r * NVF + c]; }
+    fb_mm<FBM_SET>(dimf, NV, dimf, w.Qff, MAXF, 1, w.MJtJinv + NV * NVF, NVF, 1, Qafu + NV * NV, NV);
   }
-  fb_copy(Ex.MJtJinv, w.MJtJinv, sizeof(FbExp) / sizeof(double));   // MJtJinv .. laf contiguous in both structs
-  fb_copy(Dr.residual, w.residual, 2 * FB_NCON);
+  if (tid < NV) w.laf[tid] = fma(-w.Qaa[tid], w.MJ_IDC[tid], w.la[tid]);
+  if (tid >= 32 && tid < 32 + dimf) w.laf[NV + tid - 32] = -w.lf[tid - 32];
+  __syncthreads();
+  FB_FOR(x, dimf * NX) Qafqv[NV * NX + x] = -Qafqv[NV * NX + x];
+  fb_mv<FBM_SUB>(dimf, dimf, w.Qff, MAXF, 1, w.MJ_IDC + NV, w.laf + NV);
+  __syncthreads();
+  // Qxx -= MJ_dIDC^T Qafqv, starting from the sparse cost / constraint Hessian; the Qvq block is never read
+  // (the Riccati sweep rebuilds it from Qqv, backward_riccati_recursion_factorizer.hxx:93) and is left untouched
+  FB_FOR(x, NX * NX) {
+    const int r = x / NX, c = x - r * NX;
+    if (r >= NV && c < NV) continue;
+    double acc = 0.0;
+    if (r < 6 && c < 6) acc = w.Qqq6[6 * r + c];
+    else if (r == c) acc = r < NV ? w.Qqq_d[r] : w.Qvv_d[r - NV];
+    for (int l = 0; l < nvf; ++l) acc = fma(-w.MJ_dIDC[l * NX + r], Qafqv[l * NX + c], acc);
+    Kt.Qxx[x] = acc;
+  }
+  if (tid < NV) {
+    double acc = w.lq[tid];
+    for (int l = 0; l < nvf; ++l) acc = fma(-w.MJ_dIDC[l * NX + tid], w.laf[l], acc);
+    Kt.lq[tid] = acc;
+  } else if (tid >= 32 && tid < 32 + NV) {
+    const int j = tid - 32;
+    double acc = w.lv[j];
+    for (int l = 0; l < nvf; ++l) acc = fma(-w.MJ_dIDC[l * NX + NV + j], w.laf[l], acc);
+    Kt.lv[j] = acc;
+  }
+  if (!impulse) {
+    FB_FOR(x, NX * NV) {
+      const int r = x / NV, c = x - r * NV;
+      double acc = 0.0;
+      for (int l = 0; l < nvf; ++l) acc = fma(-w.MJ_dIDC[l * NX + r], Qafu[l * NV + c], acc);
+      Kt.Qxu[x] = acc;
+    }
+    FB_FOR(x, NV * NV) {
+      const int r = x / NV, c = x - r * NV;
+      double acc = (r == c && r >= NPASS) ? w.Quu_d[r - NPASS] : 0.0;
+      for (int l = 0; l < nvf; ++l) acc = fma(w.MJtJinv[r * NVF + l], Qafu[l * NV + c], acc);
+      Kt.Quu[x] = acc;
+    }
+    if (tid >= 64 && tid < 64 + NV) {
+      const int j = tid - 64;
+      double acc = j < NPASS ? w.lu_passive[j] : w.lu[j - NPASS];
+      for (int l = 0; l < nvf; ++l) acc = fma(w.MJtJinv[j * NVF + l], w.laf[l], acc);
+      if (j < NPASS) Kt.lu_passive[j] = acc; else Kt.lu[j - NPASS] = acc;
+    }
+    FB_FOR(x, NV * NV) {
+      const int r = x / NV, c = x - r * NV;
+      Kt.Fvq[x] = -dt * w.MJ_dIDC[r * NX + c];
+      Kt.Fvv[x] = -dt * w.MJ_dIDC[r * NX + NV + c] + (r == c ? 1.0 : 0.0);
+    }
+    FB_FOR(x, NV * NU) { const int r = x / NU, c = x - r * NU; Kt.Fvu[x] = dt * w.MJtJinv[r * NVF + NPASS + c]; }
+    if (tid >= 96 && tid < 96 + NV) Kt.Fv[tid - 96] = fma(-dt, w.MJ_IDC[tid - 96], w.Fv[tid - 96]);
+  } else {
+    FB_FOR(x, NV * NV) {
+      const int r = x / NV, c = x - r * NV;
+      Kt.Fvq[x] = -w.MJ_dIDC[r * NX + c];
+      Kt.Fvv[x] = (r == c ? 1.0 : 0.0) - w.MJ_dIDC[r * NX + NV + c];
+    }
+    if (tid >= 96 && tid < 96 + NV) Kt.Fv[tid - 96] = w.Fv[tid - 96] - w.MJ_IDC[tid - 96];
+  }
+  fb_copy(Kt.Fq, w.Fq, NV);
+  fb_copy(Kt.Fqq6, w.Fqq6, 3 * 36);   // Fqq6, Fqv6, Fqq_prev_inv
+  // ---- condenseSwitchingConstraint ----
+  if (dimi > 0) {
+    FB_FOR(x, dimi * NX) {
+      const int r = x / NX, c = x - r * NX;
+      double acc = w.Phix[x];
+      for (int l = 0; l < NV; ++l) acc = fma(-w.Phia[r * NV + l], w.MJ_dIDC[l * NX + c], acc);
+      Kt.Phix[x] = acc;
+    }
+    FB_FOR(x, dimi * NU) {
+      const int r = x / NU, c = x - r * NU;
+      double acc = w.Phia[r * NV] * w.MJtJinv[NPASS + c];
+      for (int l = 1; l < NV; ++l) acc = fma(w.Phia[r * NV + l], w.MJtJinv[l * NVF + NPASS + c], acc);
+      Kt.Phiu[x] = acc;
+    }
+    if (tid < dimi) {
+      double acc = w.P[tid];
+      for (int l = 0; l < NV; ++l) acc = fma(-w.Phia[tid * NV + l], w.MJ_IDC[l], acc);
+      Kt.P[tid] = acc;
+    }
+  }
+  // ---- expansion record ----
+  fb_copy(Ex.MJtJinv, w.MJtJinv, NVF * NVF + NVF * NX + NVF);   // MJtJinv, MJ_dIDC, MJ_IDC
+  fb_copy(Ex.Qafqv, Qafqv, NVF * NX);
+  fb_copy(Ex.Qafu, Qafu, NVF * NV);
+  fb_copy(Ex.laf, w.laf, NVF);
   if (tid == 0) Dr.info = (double)w.info;
 }
+
 
 // =====================================================================================================
 // K2: backward Riccati recursion, one CTA per instance, serial over the chain

@@ -24,6 +24,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline __attribute__((always_inline))
+#define __noinline__ inline
 #define __restrict__ __restrict
 #define __launch_bounds__(...)
 #define __constant__ static
