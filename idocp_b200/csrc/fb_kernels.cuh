@@ -41,7 +41,8 @@ struct FbDevProblem {
 struct FbElem {
   int kind, slot, next_slot, prev_slot, sw, dimf, dimi, pad;
   int active[FB_NC], imp_active[FB_NC], cactive[FBC_NCOMP];
-  double t, dt, dt_next;
+  int ls_next_slot, ls_sw, ls_imp_active[FB_NC], pad2[2];   // LineSearch::computeCostAndViolation (line_search.cpp:64-197)
+  double t, dt, dt_next, ls_dt_next, ls_ipoints[FB_MAXF];
   double cpoints[FB_MAXF], ipoints[FB_MAXF], ref_q[FB_NQ], ref_v[FB_NV];
 };
 
@@ -55,6 +56,7 @@ struct FbDir {   // SplitDirection + the direction part of ConstraintsData
   double dlmd[FB_NV], dgmm[FB_NV], dq[FB_NV], dv[FB_NV], du[FB_NU], daf[FB_NVF], dbetamu[FB_NVF], dnu_passive[FB_NPASS], dxi[FB_MAXF];
   double residual[FB_NCON], duality[FB_NCON], dslack[FB_NCON], ddual[FB_NCON];
   double max_primal, max_dual, kkt_sq, info;
+  double ls_cost, ls_viol;   // LineSearch: stage cost / constraint violation of the trial point
 };
 struct FbKKT {   // condensed SplitKKTMatrix / SplitKKTResidual + SplitStateConstraintJacobian
   double Qxx[FB_NX * FB_NX], Qxu[FB_NX * FB_NV], Quu[FB_NV * FB_NV];
@@ -84,7 +86,15 @@ struct FbArrays {
   const double* v0;   // [B][18]
   double* steps;      // [B][2]
   double* kkt_err;    // [B]
+  // filter line search (line_search_kernels.cuh has the fixed-base twin)
+  double* ls_alpha;   // [B] current / final primal step size
+  int* ls_state;      // [B] 0 searching, 1 finished
+  int* ls_n;          // [B] filter sizes
+  double* ls_fcost;   // [B][FB_LS_FILTER_CAP]
+  double* ls_fviol;   // [B][FB_LS_FILTER_CAP]
+  int* ls_status;     // [B] bit 2: filter capacity exceeded
 };
+#define FB_LS_FILTER_CAP 256
 
 #define FB_FOR(i, n) for (int i = threadIdx.x; i < (n); i += blockDim.x)
 enum { FBM_SET = 0, FBM_ADD = 1, FBM_SUB = 2 };
@@ -1850,6 +1860,317 @@ __global__ void k_fb_init_constraints(FbArrays A, const FbInitRow* rows, int n_r
       S.dual[o + j] = du;
     }
   }
+}
+
+// =====================================================================================================
+// LineSearch for OCPSolver (line_search/line_search.hpp:62-158, src/line_search/line_search.cpp:64-197,
+// line_search_filter.cpp:34-65): every instance carries its own (alpha, state, filter); the host launches lock-step
+// rounds  k_fb_ls_eval (warp per (instance, stage): stage cost and constraint violation of the trial point
+// s + alpha d)  ->  k_fb_ls_filter (thread per instance); finished instances drop out.
+// =====================================================================================================
+template <bool INITIAL>
+__global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_ls_eval(FbArrays A, FbLin* lin) {
+  IDOCP_DYN_SMEM(FbRobotWork, wbase);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int stage = blockIdx.x * FB_ROBOT_WARPS + warp;
+  if (stage >= A.B * A.n_elems) return;
+  FbRobotWork& w = wbase[warp];
+  const int b = stage / A.n_elems, e = stage - b * A.n_elems;
+  if (INITIAL) { if (A.ls_n[b] != 0) return; } else { if (A.ls_state[b] != 0) return; }
+  const double alpha = INITIAL ? 0.0 : A.ls_alpha[b];
+  const FbElem& el = A.elems[e];
+  const FbDevProblem& pr = *A.prob;
+  const int kind = el.kind;
+  const bool impulse = kind == FB_IMPULSE, terminal = kind == FB_TERMINAL;
+  const double dt = el.dt;
+  const size_t rec = (size_t)el.slot * A.B + b;
+  const FbSol& S = A.sol[rec];
+  FbDir& Dr = A.dir[rec];
+  FbLin& L = lin[rec];
+  const int dimf = terminal ? 0 : el.dimf, nvf = FB_NV + dimf;
+  // ---- trial point (computeSolution, line_search.hpp:130-158); alpha = 0: the current point itself ----
+  FBW_FOR(i, FB_NCON) { w.slack[i] = S.slack[i]; w.dual[i] = Dr.dslack[i]; }   // w.dual holds dslack here
+  if (lane < FB_NV) {
+    const int j = lane;
+    w.v[j] = INITIAL ? S.v[j] : fma(alpha, Dr.dv[j], S.v[j]);
+    if (!terminal) w.a[j] = INITIAL ? S.a[j] : fma(alpha, Dr.daf[j], S.a[j]);
+    w.dqv[j] = Dr.dq[j];
+  }
+  if (lane < FB_NU && !terminal) {
+    if (!impulse) w.u[lane] = INITIAL ? S.u[lane] : fma(alpha, Dr.du[lane], S.u[lane]);
+    const int i = lane / 3;
+    int k = 0;
+    for (int j = 0; j < i; ++j) k += el.active[j];
+    const double fcur = S.f[lane];
+    w.f[lane] = (INITIAL || !el.active[i]) ? fcur : fma(alpha, Dr.daf[FB_NV + 3 * k + lane % 3], fcur);
+    w.fm[lane] = el.active[i] ? w.f[lane] : 0.0;
+  }
+  FBW_FOR(i, FB_NQ) w.q2[i] = S.q[i];
+  if (!terminal) {
+    const size_t nrec = (size_t)el.ls_next_slot * A.B + b;
+    const FbSol& Nx = A.sol[nrec];
+    const FbDir& Dn = A.dir[nrec];
+    FBW_FOR(i, FB_NQ) w.qprev[i] = Nx.q[i];
+    if (lane < FB_NV) { w.t18[lane] = Dn.dq[lane]; w.nv[lane] = INITIAL ? Nx.v[lane] : fma(alpha, Dn.dv[lane], Nx.v[lane]); }
+  }
+  __syncwarp();
+  if (INITIAL) {
+    FBW_FOR(i, FB_NQ) { w.q[i] = w.q2[i]; w.nq[i] = w.qprev[i]; }
+  } else if (lane < 2 && !(terminal && lane == 1)) {
+    fb_integrate(lane == 0 ? w.q2 : w.qprev, lane == 0 ? w.dqv : w.t18, alpha, lane == 0 ? w.q : w.nq);
+  }
+  __syncwarp();
+  // q - q_ref and (not terminal) q - q_next, base blocks by lanes 0 and 1 in lock-step
+  if (lane < 2 && !(terminal && lane == 1)) {
+    double R[9], p3[3];
+    fb_relative(lane == 0 ? el.ref_q : w.nq, w.q, R, p3);
+    fb_log6(R, p3, w.rellog[lane]);
+  }
+  __syncwarp();
+  // ---- stage cost (split_ocp.hxx:282-298 / impulse_split_ocp.hxx:145-158 / terminal_ocp.hxx:89-95) ----
+  const double* wq = terminal ? pr.qf_weight : (impulse ? pr.qi_weight : pr.q_weight);
+  const double* wv = terminal ? pr.vf_weight : (impulse ? pr.vi_weight : pr.v_weight);
+  const double* wa = impulse ? pr.dvi_weight : pr.a_weight;
+  // logs of the trial slacks by all lanes, summed in ascending order below
+  if (!terminal) {
+    FBW_FOR(idx, FB_NCON) {
+      const int c = idx < 72 ? idx / 12 : (idx < 92 ? FBC_FRICTION : FBC_IMPULSE_FRICTION);
+      double lg = 0.0, ar = 0.0;
+      if (el.cactive[c]) {
+        lg = canon_log(INITIAL ? w.slack[idx] : fma(alpha, w.dual[idx], w.slack[idx]));
+        const int j = idx - fbc_offset(c);
+        if (c >= FBC_FRICTION) {
+          const int i = j / 5;
+          if (el.active[i]) {
+            double r5[5];
+            fb_friction_residual(pr.mu, w.f + 3 * i, r5);
+            ar = fabs(r5[j % 5] + w.slack[idx]);
+          }
+        } else {
+          const double sl = w.slack[idx];
+          double res;
+          switch (c) {
+            case FBC_POS_LO: res = pr.q_min[j] - w.q[7 + j] + sl; break;
+            case FBC_POS_UP: res = w.q[7 + j] - pr.q_max[j] + sl; break;
+            case FBC_VEL_LO: res = (-pr.v_max[j]) - w.v[6 + j] + sl; break;
+            case FBC_VEL_UP: res = w.v[6 + j] - pr.v_max[j] + sl; break;
+            case FBC_TRQ_LO: res = (-pr.u_max[j]) - w.u[j] + sl; break;
+            default:         res = w.u[j] - pr.u_max[j] + sl; break;
+          }
+          ar = fabs(res);
+        }
+      }
+      w.duality[idx] = lg;
+      w.residual[idx] = ar;
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    const double half = (terminal || impulse) ? 0.5 : 0.5 * dt;
+    double l = 0.0;
+    for (int j = 0; j < FB_NV; ++j) { const double d = j < 6 ? w.rellog[0][j] : (w.q[1 + j] - el.ref_q[1 + j]); l = fma(wq[j] * d, d, l); }
+    for (int j = 0; j < FB_NV; ++j) { const double d = w.v[j] - el.ref_v[j]; l = fma(wv[j] * d, d, l); }
+    if (!terminal)
+      for (int j = 0; j < FB_NV; ++j) l = fma(wa[j] * w.a[j], w.a[j], l);
+    double cost = half * l;
+    if (!terminal) {
+      const double* fw = impulse ? pr.fi_weight : pr.f_weight;
+      const double* fr = impulse ? pr.fi_ref : pr.f_ref;
+      double lf = 0.0;
+      for (int i = 0; i < FB_NC; ++i)
+        if (el.active[i])
+          for (int x = 0; x < 3; ++x) { const double d = w.f[3 * i + x] - fr[3 * i + x]; lf = fma(fw[3 * i + x] * d, d, lf); }
+      cost += half * lf;
+      double bc = 0.0;
+      for (int c = 0; c < FBC_NCOMP; ++c) {
+        if (!el.cactive[c]) continue;
+        double sl = 0.0;
+        for (int j = 0; j < fbc_dim(c); ++j) sl += w.duality[fbc_offset(c) + j];
+        bc += -pr.barrier * sl;
+      }
+      cost += (impulse ? 1.0 : dt) * bc;
+    }
+    Dr.ls_cost = cost;
+    if (terminal) Dr.ls_viol = 0.0;
+  }
+  if (terminal) return;
+  // ---- constraint violation (split_ocp.hxx:301-346 / impulse_split_ocp.hxx:178-194) ----
+  if (lane == 1) {
+    double cl1 = 0.0;
+    for (int c = 0; c < FBC_NCOMP; ++c) {
+      if (!el.cactive[c]) continue;
+      double s1 = 0.0;
+      for (int j = 0; j < fbc_dim(c); ++j) s1 += w.residual[fbc_offset(c) + j];
+      cl1 += s1;
+    }
+    w.part[0] = cl1;
+  }
+  if (lane == 2) {
+    double fx = 0.0;
+    for (int j = 0; j < FB_NV; ++j) {
+      const double d = j < 6 ? w.rellog[1][j] : (w.q[1 + j] - w.nq[1 + j]);
+      fx += fabs(impulse ? d : fma(dt, w.v[j], d));
+    }
+    for (int j = 0; j < FB_NV; ++j) fx += fabs(impulse ? (w.v[j] + w.a[j]) - w.nv[j] : fma(dt, w.a[j], w.v[j]) - w.nv[j]);
+    w.part[1] = fx;
+  }
+  __syncwarp();
+  const double baumgarte = pr.T / pr.N;
+  if (!impulse) {
+    fbw_forward_kinematics(w, lane, w.q, w.v, w.a);
+    fbw_rnea_derivatives(w, lane, ANYMAL_GRAVITY, true, L, false);
+    if (lane < FB_NU) L.IDC[6 + lane] -= w.u[lane];
+  } else {
+    fbw_forward_kinematics(w, lane, w.q, nullptr, w.a);
+    fbw_rnea_derivatives(w, lane, 0.0, false, L, false);
+    if (lane < FB_NV) w.t18[lane] = w.v[lane] + w.a[lane];
+    __syncwarp();
+    fbw_forward_kinematics(w, lane, w.q, w.t18, nullptr);
+  }
+  {
+    int k = 0;
+    for (int i = 0; i < FB_NC; ++i) {
+      if (!el.active[i]) continue;
+      if (lane == 0) {
+        const int bi = 1 + ANYMAL_CONTACT_PARENT_JOINT[i];
+        const double* Rf = w.R[bi];
+        double P[3], vF[6], aF[6];
+        fbw_contact_point(w, i, P);
+        fb_pullback(Rf, P, w.ov[bi], vF);
+        double* C = L.IDC + FB_NV + 3 * k;
+        if (!impulse) {
+          fb_pullback(Rf, P, w.oa[bi], aF);
+          const double wvv = 2.0 / baumgarte, wpp = 1.0 / (baumgarte * baumgarte);
+          double wxv[3];
+          fb_cross(vF + 3, vF, wxv);
+          for (int x = 0; x < 3; ++x) {
+            const double acl = aF[x] + wxv[x];
+            C[x] = fma(wpp, P[x] - el.cpoints[3 * i + x], fma(wvv, vF[x], acl));
+          }
+        } else {
+          for (int x = 0; x < 3; ++x) C[x] = vF[x];
+        }
+      }
+      ++k;
+    }
+  }
+  __syncwarp();
+  double pl1 = 0.0;
+  if (!impulse && el.ls_sw) {
+    // computeSwitchingConstraintResidual (forward_switching_constraint.hxx:57-68) at the trial point
+    const double c1 = el.dt + el.ls_dt_next, c2 = el.dt * el.ls_dt_next;
+    if (lane < FB_NV) w.dqv[lane] = fma(c2, w.a[lane], c1 * w.v[lane]);
+    __syncwarp();
+    if (lane == 0) fb_integrate(w.q, w.dqv, 1.0, w.q2);
+    __syncwarp();
+    fbw_forward_kinematics(w, lane, w.q2, nullptr, nullptr);
+    if (lane == 0) {
+      for (int i = 0; i < FB_NC; ++i) {
+        if (!el.ls_imp_active[i]) continue;
+        double P[3];
+        fbw_contact_point(w, i, P);
+        for (int x = 0; x < 3; ++x) pl1 += fabs(P[x] - el.ls_ipoints[3 * i + x]);
+      }
+    }
+  }
+  if (lane == 0) {
+    double idl1 = 0.0;
+    for (int j = 0; j < nvf; ++j) idl1 += fabs(L.IDC[j]);
+    const double cl1 = w.part[0], fx = w.part[1];
+    double viol;
+    if (impulse) viol = (cl1 + fx) + idl1;
+    else {
+      viol = (fx + dt * idl1) + dt * cl1;
+      if (el.ls_sw) viol += pl1;
+    }
+    Dr.ls_viol = viol;
+  }
+}
+
+// totals in the reference's order: grid stages (with the terminal stage), impulse, aux, lift (line_search.hpp:174-182)
+__device__ inline void fb_ls_totals(const FbArrays& A, int b, double& cost, double& viol) {
+  double c = 0.0, v = 0.0;
+  for (int pass = 0; pass < 4; ++pass) {
+    double cs = 0.0, vs = 0.0;
+    for (int e = 0; e < A.n_elems; ++e) {
+      const int k = A.elems[e].kind;
+      const bool mine = (pass == 0 && (k == FB_GRID || k == FB_TERMINAL)) || (pass == 1 && k == FB_IMPULSE) ||
+                        (pass == 2 && k == FB_AUX) || (pass == 3 && k == FB_LIFT);
+      if (!mine) continue;
+      const FbDir& Dr = A.dir[(size_t)A.elems[e].slot * A.B + b];
+      cs += Dr.ls_cost;
+      vs += Dr.ls_viol;
+    }
+    c = pass == 0 ? cs : c + cs;
+    v = pass == 0 ? vs : v + vs;
+  }
+  cost = c;
+  viol = v;
+}
+__device__ inline void fb_filter_augment(const FbArrays& A, int b, double cost, double viol) {
+  double* fc = A.ls_fcost + (size_t)b * FB_LS_FILTER_CAP;
+  double* fv = A.ls_fviol + (size_t)b * FB_LS_FILTER_CAP;
+  int n = A.ls_n[b], w = 0;
+  for (int i = 0; i < n; ++i) {
+    if (cost <= fc[i] && viol <= fv[i]) continue;   // dominated entry erased
+    fc[w] = fc[i]; fv[w] = fv[i]; ++w;
+  }
+  if (w < FB_LS_FILTER_CAP) {
+    fc[w] = cost - 0.005 * viol;       // line_search_filter.hpp:16-17
+    fv[w] = (1 - 0.005) * viol;
+    ++w;
+  } else {
+    A.ls_status[b] |= 4;
+  }
+  A.ls_n[b] = w;
+}
+// mode 0: augment empty filters with the current point, start the search at the fraction-to-boundary step;
+// mode 1: one backtracking decision (alpha *= 0.75 while alpha > 0.05); mode 2: publish alpha as the primal step
+__global__ void k_fb_ls_filter(FbArrays A, int mode) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= A.B) return;
+  if (mode == 0) {
+    if (A.ls_n[b] == 0) {
+      double cost, viol;
+      fb_ls_totals(A, b, cost, viol);
+      fb_filter_augment(A, b, cost, viol);
+    }
+    const double amax = A.steps[2 * b];
+    const bool go = amax > 0.05;
+    A.ls_alpha[b] = go ? amax : 0.05;
+    A.ls_state[b] = go ? 0 : 1;
+    return;
+  }
+  if (mode == 2) {
+    A.steps[2 * b] = A.ls_alpha[b];
+    return;
+  }
+  if (A.ls_state[b] != 0) return;
+  double cost, viol;
+  fb_ls_totals(A, b, cost, viol);
+  bool accepted = true;
+  {
+    const double* fc = A.ls_fcost + (size_t)b * FB_LS_FILTER_CAP;
+    const double* fv = A.ls_fviol + (size_t)b * FB_LS_FILTER_CAP;
+    for (int i = 0; i < A.ls_n[b]; ++i)
+      if (cost >= fc[i] && viol >= fv[i]) { accepted = false; break; }
+  }
+  if (accepted) {
+    fb_filter_augment(A, b, cost, viol);
+    A.ls_state[b] = 1;
+    return;
+  }
+  const double an = A.ls_alpha[b] * 0.75;
+  if (an > 0.05) {
+    A.ls_alpha[b] = an;
+  } else {
+    A.ls_alpha[b] = 0.05;
+    A.ls_state[b] = 1;
+  }
+}
+__global__ void k_fb_ls_clear(FbArrays A) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < A.B) A.ls_n[b] = 0;
 }
 
 }  // namespace idocp_b200

@@ -13,7 +13,7 @@ from .hybrid import ContactSequence
 KIND_GRID, KIND_IMPULSE, KIND_AUX, KIND_LIFT, KIND_TERMINAL = range(5)
 NQ, NV, NU = 19, 18, 12
 
-_FIELD_DIMS = dict(q=19, f=12, mu=12, nu_passive=6, xi=12, u=12, du=12, daf=30, dbetamu=30, dnu_passive=6, dxi=12, lu=12,
+_FIELD_DIMS = dict(ls_cost=1, ls_viol=1, q=19, f=12, mu=12, nu_passive=6, xi=12, u=12, du=12, daf=30, dbetamu=30, dnu_passive=6, dxi=12, lu=12,
                    lu_passive=6, P=12, Qxx=36 * 36, Qxu=36 * 18, Quu=18 * 18, Fvq=324, Fvv=324, Fvu=216, Fqq6=36, Fqv6=36,
                    Fqq_prev_inv=36, MJtJinv=900, MJ_dIDC=30 * 36, MJ_IDC=30, Qafqv=30 * 36, Qafu=30 * 18, laf=30, K=12 * 36, k=12,
                    Pqq=324, Pqv=324, Pvv=324, Phix=12 * 36, Phiu=144, cM=12 * 36, cm=12, kkt=1, info=1, max_primal=1, max_dual=1,
@@ -111,6 +111,9 @@ class OCPSolver:
         self._sample_reference(t)
         q, v = self._state(q, v)
         self.lib.check(self.lib.L.idocp_b200_fb_compute_kkt_residual(self._h, float(t), capi.dptr(q), capi.dptr(v)))
+
+    def clearLineSearchFilter(self):
+        self.lib.check(self.lib.L.idocp_b200_fb_clear_line_search_filter(self._h))
 
     def KKTError(self):
         out = np.zeros(self.B)

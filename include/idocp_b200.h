@@ -275,6 +275,7 @@ int idocp_b200_fb_init_constraints(idocp_b200_fb_solver* h, double t);
 int idocp_b200_fb_update_solution(idocp_b200_fb_solver* h, double t, const double* q, const double* v, int line_search);
 int idocp_b200_fb_compute_kkt_residual(idocp_b200_fb_solver* h, double t, const double* q, const double* v);
 int idocp_b200_fb_kkt_error(idocp_b200_fb_solver* h, double* out /* [batch] */);
+int idocp_b200_fb_clear_line_search_filter(idocp_b200_fb_solver* h);   /* clearLineSearchFilter() ocp_solver.cpp:197-199 */
 int idocp_b200_fb_get_step_sizes(idocp_b200_fb_solver* h, double* out /* [batch][2]: primal, dual */);
 /* one field of one stage of the current chain: out[batch][dim], returns dim (see fb_capi.inc for the field names) */
 int idocp_b200_fb_get(idocp_b200_fb_solver* h, int stage, const char* name, double* out);

@@ -291,6 +291,7 @@ class OCPSolver {
     sampleReference(t);
     detail::check(idocp_b200_fb_compute_kkt_residual(h_.get(), t, q, v));
   }
+  void clearLineSearchFilter() { detail::check(idocp_b200_fb_clear_line_search_filter(h_.get())); }
   double KKTError() { return KKTErrors()[0]; }
   std::vector<double> KKTErrors() {
     std::vector<double> out(batch_);

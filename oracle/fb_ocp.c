@@ -77,6 +77,8 @@ typedef struct {
   double K[NU * NX], k[NU], Pqq[NV * NV], Pqv[NV * NV], Pvv[NV * NV], sq[NV], sv[NV], cM[MAXF * NX], cm[MAXF];
   double max_primal, max_dual, kkt_sq;
   int chol_info;
+  /* --- LineSearch: trial point s + alpha d (line_search.hpp:130-158) and its stage cost / violation --- */
+  double tq[NQ], tv[NV], ta[NV], tu[NU], tf[FB_NC][3], ls_cost, ls_viol;
 } stage_t;
 
 typedef struct {
@@ -86,6 +88,9 @@ typedef struct {
   int cstage;     /* createConstraintsData argument */
   int sw_impulse; /* >= 0: the switching constraint of this impulse is imposed here */
   double dt_next;
+  int ls_next;    /* chain position whose (q, v) closes the state equation in LineSearch::computeCostAndViolation */
+  int ls_impulse; /* >= 0: impulse whose switching residual the line search adds on this stage */
+  double ls_dt_next;
 } elem_t;
 
 #define MAX_ELEMS (HY_MAX_N + 1 + 3 * HY_MAX_EVENTS)
@@ -100,6 +105,8 @@ typedef struct oracle_fb_ocp {
   double primal_step, dual_step;
   double q0_prev[NQ];
   int nthreads;
+  int filter_n;
+  double filter_cost[256], filter_viol[256];
 } oracle_fb_ocp_t;
 
 /* ---------------------------------------------------------------------------------------------- */
@@ -182,15 +189,19 @@ static inline double limit_margin(const oracle_fb_problem_t* p, int c, const sta
     default:       return p->u_max[j] - s->u[j];
   }
 }
-static inline double limit_residual(const oracle_fb_problem_t* p, int c, const stage_t* s, int j, double slack) {
+static inline double limit_residual_at(const oracle_fb_problem_t* p, int c, const double* q, const double* v, const double* u, int j,
+                                       double slack) {
   switch (c) {
-    case C_POS_LO: return p->q_min[j] - s->q[7 + j] + slack;
-    case C_POS_UP: return s->q[7 + j] - p->q_max[j] + slack;
-    case C_VEL_LO: return (-p->v_max[j]) - s->v[6 + j] + slack;
-    case C_VEL_UP: return s->v[6 + j] - p->v_max[j] + slack;
-    case C_TRQ_LO: return (-p->u_max[j]) - s->u[j] + slack;
-    default:       return s->u[j] - p->u_max[j] + slack;
+    case C_POS_LO: return p->q_min[j] - q[7 + j] + slack;
+    case C_POS_UP: return q[7 + j] - p->q_max[j] + slack;
+    case C_VEL_LO: return (-p->v_max[j]) - v[6 + j] + slack;
+    case C_VEL_UP: return v[6 + j] - p->v_max[j] + slack;
+    case C_TRQ_LO: return (-p->u_max[j]) - u[j] + slack;
+    default:       return u[j] - p->u_max[j] + slack;
   }
+}
+static inline double limit_residual(const oracle_fb_problem_t* p, int c, const stage_t* s, int j, double slack) {
+  return limit_residual_at(p, c, s->q, s->v, s->u, j, slack);
 }
 static inline double limit_sign(int c) { return (c & 1) ? 1.0 : -1.0; } /* lower: -, upper: + */
 
@@ -1078,17 +1089,17 @@ static int discretize(oracle_fb_ocp_t* o, double t) {
   int n = 0;
   for (int i = 0; i < d->N; ++i) {
     elem_t* e = &o->elems[n++];
-    *e = (elem_t){K_GRID, i, slot_of(o, K_GRID, i), d->t[i], d->dt[i], d->contact_phase[i], i, -1, 0.0};
+    *e = (elem_t){K_GRID, i, slot_of(o, K_GRID, i), d->t[i], d->dt[i], d->contact_phase[i], i, -1, 0.0, -1, -1, 0.0};
     if (d->before_impulse_flag[i]) {
       const int k = d->impulse_after[i];
-      o->elems[n++] = (elem_t){K_IMPULSE, k, slot_of(o, K_IMPULSE, k), d->t_impulse[k], 0.0, k, -1, -1, 0.0};
-      o->elems[n++] = (elem_t){K_AUX, k, slot_of(o, K_AUX, k), d->t_impulse[k], d->dt_aux[k], d->contact_phase[i + 1], 0, -1, 0.0};
+      o->elems[n++] = (elem_t){K_IMPULSE, k, slot_of(o, K_IMPULSE, k), d->t_impulse[k], 0.0, k, -1, -1, 0.0, -1, -1, 0.0};
+      o->elems[n++] = (elem_t){K_AUX, k, slot_of(o, K_AUX, k), d->t_impulse[k], d->dt_aux[k], d->contact_phase[i + 1], 0, -1, 0.0, -1, -1, 0.0};
     } else if (d->before_lift_flag[i]) {
       const int k = d->lift_after[i];
-      o->elems[n++] = (elem_t){K_LIFT, k, slot_of(o, K_LIFT, k), d->t_lift[k], d->dt_lift[k], d->contact_phase[i + 1], 0, -1, 0.0};
+      o->elems[n++] = (elem_t){K_LIFT, k, slot_of(o, K_LIFT, k), d->t_lift[k], d->dt_lift[k], d->contact_phase[i + 1], 0, -1, 0.0, -1, -1, 0.0};
     }
   }
-  o->elems[n++] = (elem_t){K_TERMINAL, d->N, slot_of(o, K_GRID, d->N), d->t[d->N], 0.0, d->contact_phase[d->N], -1, -1, 0.0};
+  o->elems[n++] = (elem_t){K_TERMINAL, d->N, slot_of(o, K_GRID, d->N), d->t[d->N], 0.0, d->contact_phase[d->N], -1, -1, 0.0, -1, -1, 0.0};
   o->n_elems = n;
   /* switching constraint: imposed two chain elements ahead of an impulse (ocp_linearizer.hxx:139-150,196-214) */
   for (int e = 0; e + 2 < n; ++e)
@@ -1096,6 +1107,23 @@ static int discretize(oracle_fb_ocp_t* o, double t) {
       o->elems[e].sw_impulse = o->elems[e + 2].index;
       o->elems[e].dt_next = o->elems[e + 1].dt;
     }
+  /* LineSearch::computeCostAndViolation (line_search.cpp:64-197): a grid stage is always closed with the NEXT GRID
+   * stage (the impulse / lift branches of :84-103 are overwritten by the if / else of :104-121) and carries the
+   * switching residual whenever that next grid stage precedes an impulse; aux, lift and impulse stages use their
+   * chain successor. */
+  for (int e = 0; e < n; ++e) {
+    elem_t* el = &o->elems[e];
+    el->ls_next = e + 1 < n ? e + 1 : -1;
+    el->ls_impulse = el->sw_impulse;
+    el->ls_dt_next = el->dt_next;
+    if (el->kind == K_GRID) {
+      int g = e + 1;
+      while (g < n && o->elems[g].kind != K_GRID && o->elems[g].kind != K_TERMINAL) ++g;
+      el->ls_next = g;
+      el->ls_impulse = (g + 1 < n && o->elems[g].kind == K_GRID && o->elems[g + 1].kind == K_IMPULSE) ? o->elems[g + 1].index : -1;
+      el->ls_dt_next = o->elems[g].dt;
+    }
+  }
   /* statuses */
   for (int e = 0; e < n; ++e) {
     const elem_t* el = &o->elems[e];
@@ -1220,8 +1248,217 @@ int oracle_fb_ocp_init_constraints(oracle_fb_ocp_t* o, double t) {
   return rc;
 }
 
-/* OCPSolver::updateSolution (ocp_solver.cpp:67-92), line_search = false */
-int oracle_fb_ocp_update_solution(oracle_fb_ocp_t* o, double t, const double* q, const double* v) {
+
+/* ---------------------------------------------------------------------------------------------- */
+/* LineSearch (line_search/line_search.hpp:62-158, src/line_search/line_search.cpp:64-197),          */
+/* LineSearchFilter (src/line_search/line_search_filter.cpp:34-65)                                   */
+/* ---------------------------------------------------------------------------------------------- */
+static int filter_is_accepted(const oracle_fb_ocp_t* o, double cost, double viol) {
+  for (int i = 0; i < o->filter_n; ++i)
+    if (cost >= o->filter_cost[i] && viol >= o->filter_viol[i]) return 0;
+  return 1;
+}
+static void filter_augment(oracle_fb_ocp_t* o, double cost, double viol) {
+  int w = 0;
+  for (int i = 0; i < o->filter_n; ++i) {
+    if (cost <= o->filter_cost[i] && viol <= o->filter_viol[i]) continue;
+    o->filter_cost[w] = o->filter_cost[i]; o->filter_viol[w] = o->filter_viol[i]; ++w;
+  }
+  o->filter_n = w;
+  if (w < 256) {
+    o->filter_cost[w] = cost - 0.005 * viol;      /* line_search_filter.hpp:16-17 */
+    o->filter_viol[w] = (1 - 0.005) * viol;
+    o->filter_n = w + 1;
+  }
+}
+/* computeSolution (line_search.hpp:130-158); alpha = 0: the current point itself */
+static void make_trial(stage_t* st, int kind, double alpha) {
+  if (alpha == 0.0) {
+    memcpy(st->tq, st->q, sizeof(st->tq)); memcpy(st->tv, st->v, sizeof(st->tv)); memcpy(st->ta, st->a, sizeof(st->ta));
+    memcpy(st->tu, st->u, sizeof(st->tu)); memcpy(st->tf, st->f, sizeof(st->tf));
+    return;
+  }
+  fb_integrate(st->q, st->dq, alpha, st->tq);
+  for (int j = 0; j < NV; ++j) st->tv[j] = fma(alpha, st->dv[j], st->v[j]);
+  if (kind == K_TERMINAL) return;
+  for (int j = 0; j < NV; ++j) st->ta[j] = fma(alpha, st->daf[j], st->a[j]);
+  if (kind != K_IMPULSE)
+    for (int j = 0; j < NU; ++j) st->tu[j] = fma(alpha, st->du[j], st->u[j]);
+  int k = 0;
+  for (int i = 0; i < FB_NC; ++i) {
+    for (int x = 0; x < 3; ++x) st->tf[i][x] = st->active[i] ? fma(alpha, st->daf[NV + 3 * k + x], st->f[i][x]) : st->f[i][x];
+    if (st->active[i]) ++k;
+  }
+}
+/* SplitOCP::stageCost (split_ocp.hxx:282-298), ImpulseSplitOCP::stageCost, TerminalOCP::terminalCost */
+static double trial_stage_cost(const oracle_fb_problem_t* p, const stage_t* st, int kind, double dt, double alpha) {
+  const double* wq = kind == K_TERMINAL ? p->qf_weight : (kind == K_IMPULSE ? p->qi_weight : p->q_weight);
+  const double* wv = kind == K_TERMINAL ? p->vf_weight : (kind == K_IMPULSE ? p->vi_weight : p->v_weight);
+  const double* wa = kind == K_IMPULSE ? p->dvi_weight : p->a_weight;
+  const double half = (kind == K_TERMINAL || kind == K_IMPULSE) ? 0.5 : 0.5 * dt;
+  double qdiff[NV], l = 0.0;
+  fb_subtract(st->tq, st->ref_q, qdiff);
+  for (int j = 0; j < NV; ++j) l = fma(wq[j] * qdiff[j], qdiff[j], l);
+  for (int j = 0; j < NV; ++j) { const double d = st->tv[j] - st->ref_v[j]; l = fma(wv[j] * d, d, l); }
+  if (kind != K_TERMINAL)
+    for (int j = 0; j < NV; ++j) l = fma(wa[j] * st->ta[j], st->ta[j], l);
+  double cost = half * l;
+  if (kind == K_TERMINAL) return cost;
+  const double* fw = kind == K_IMPULSE ? p->fi_weight : p->f_weight;
+  const double* fr = kind == K_IMPULSE ? p->fi_ref : p->f_ref;
+  double lf = 0.0;
+  for (int i = 0; i < FB_NC; ++i)
+    if (st->active[i])
+      for (int x = 0; x < 3; ++x) { const double d = st->tf[i][x] - fr[3 * i + x]; lf = fma(fw[3 * i + x] * d, d, lf); }
+  cost += half * lf;
+  double bc = 0.0;
+  for (int c = 0; c < NCOMP; ++c) {
+    if (!st->cactive[c]) continue;
+    double sl = 0.0;
+    for (int j = 0; j < comp_dim(c); ++j)
+      sl += oracle_canon_log(alpha > 0.0 ? fma(alpha, st->c[c].dslack[j], st->c[c].slack[j]) : st->c[c].slack[j]);
+    bc += -p->barrier * sl;
+  }
+  cost += (kind == K_IMPULSE ? 1.0 : dt) * bc;
+  return cost;
+}
+/* SplitOCP::constraintViolation (split_ocp.hxx:301-346), ImpulseSplitOCP::constraintViolation (:178-194) at the
+ * trial point; (q_next, v_next) of the trial point of the closing stage */
+static double trial_violation(const oracle_fb_problem_t* p, stage_t* st, const elem_t* e, const double* q_next,
+                              const double* v_next, const int* imp_active, const double (*ipoints)[3]) {
+  const int impulse = e->kind == K_IMPULSE;
+  const double dt = e->dt;
+  /* constraints: residual with the trial solution and the current slack */
+  double cl1 = 0.0;
+  for (int c = 0; c < NCOMP; ++c) {
+    if (!st->cactive[c]) continue;
+    double s1 = 0.0;
+    if (c >= C_FRICTION) {
+      for (int i = 0; i < FB_NC; ++i) {
+        double r[5];
+        if (st->active[i]) friction_residual(p->mu, st->tf[i], r);
+        for (int x = 0; x < 5; ++x) s1 += st->active[i] ? fabs(r[x] + st->c[c].slack[5 * i + x]) : 0.0;
+      }
+    } else {
+      for (int j = 0; j < NU; ++j) s1 += fabs(limit_residual_at(p, c, st->tq, st->tv, st->tu, j, st->c[c].slack[j]));
+    }
+    cl1 += s1;
+  }
+  /* state equation */
+  double Fq[NV], fx = 0.0;
+  fb_subtract(st->tq, q_next, Fq);
+  for (int j = 0; j < NV; ++j) { const double r = impulse ? Fq[j] : fma(dt, st->tv[j], Fq[j]); fx += fabs(r); }
+  for (int j = 0; j < NV; ++j) {
+    const double r = impulse ? (st->tv[j] + st->ta[j]) - v_next[j] : fma(dt, st->ta[j], st->tv[j]) - v_next[j];
+    fx += fabs(r);
+  }
+  /* (impulse) inverse dynamics and contact rows */
+  double f[FB_NC][3], IDC[NVF], idl1 = 0.0;
+  fb_kin_t kin;
+  for (int i = 0; i < FB_NC; ++i)
+    for (int x = 0; x < 3; ++x) f[i][x] = st->active[i] ? st->tf[i][x] : 0.0;
+  if (!impulse) {
+    fb_forward_kinematics(st->tq, st->tv, st->ta, &kin);
+    fb_rnea_derivatives(&kin, f, ANYMAL_GRAVITY, IDC, NULL, NULL, NULL);
+    for (int j = 0; j < NU; ++j) IDC[6 + j] -= st->tu[j];
+  } else {
+    double vpdv[NV];
+    fb_forward_kinematics(st->tq, NULL, st->ta, &kin);
+    fb_rnea_derivatives(&kin, f, 0.0, IDC, NULL, NULL, NULL);
+    for (int j = 0; j < NV; ++j) vpdv[j] = st->tv[j] + st->ta[j];
+    fb_forward_kinematics(st->tq, vpdv, NULL, &kin);
+  }
+  int k = 0;
+  for (int i = 0; i < FB_NC; ++i) {
+    if (!st->active[i]) continue;
+    fb_frame_t fr;
+    fb_frame_kinematics(&kin, i, 0, &fr);
+    if (!impulse) fb_baumgarte_residual(&fr, p->T / p->N, st->cpoints[i], IDC + NV + 3 * k);
+    else for (int x = 0; x < 3; ++x) IDC[NV + 3 * k + x] = fr.vF[x];
+    ++k;
+  }
+  for (int j = 0; j < NV + st->dimf; ++j) idl1 += fabs(IDC[j]);
+  if (impulse) return (cl1 + fx) + idl1;
+  double viol = (fx + dt * idl1) + dt * cl1;
+  if (e->ls_impulse >= 0) {
+    /* computeSwitchingConstraintResidual (forward_switching_constraint.hxx:57-68) at the trial point */
+    double dqv[NV], q2[NQ], pl1 = 0.0;
+    const double c1 = e->dt + e->ls_dt_next, c2 = e->dt * e->ls_dt_next;
+    for (int j = 0; j < NV; ++j) dqv[j] = fma(c2, st->ta[j], c1 * st->tv[j]);
+    fb_integrate(st->tq, dqv, 1.0, q2);
+    fb_forward_kinematics(q2, NULL, NULL, &kin);
+    for (int i = 0; i < FB_NC; ++i) {
+      if (!imp_active[i]) continue;
+      double P[3];
+      fb_contact_point(&kin, i, P);
+      for (int x = 0; x < 3; ++x) pl1 += fabs(P[x] - ipoints[i][x]);
+    }
+    viol += pl1;
+  }
+  return viol;
+}
+/* computeCostAndViolation + totalCosts / totalViolations: sums in the reference's order (grid stages with the
+ * terminal stage, impulse, aux, lift) */
+static void ls_cost_and_violation(oracle_fb_ocp_t* o, double alpha, double* cost, double* viol) {
+  const int n = o->n_elems;
+  for (int e = 0; e < n; ++e) make_trial(&o->slots[o->elems[e].slot], o->elems[e].kind, alpha);
+#pragma omp parallel for schedule(dynamic) num_threads(o->nthreads)
+  for (int e = 0; e < n; ++e) {
+    const elem_t* el = &o->elems[e];
+    stage_t* st = &o->slots[el->slot];
+    st->ls_cost = trial_stage_cost(&o->p, st, el->kind, el->dt, alpha);
+    st->ls_viol = 0.0;
+    if (el->kind == K_TERMINAL) continue;
+    const stage_t* nx = &o->slots[o->elems[el->ls_next].slot];
+    int act[HY_MAX_CONTACTS] = {0};
+    double pts[HY_MAX_CONTACTS * 3] = {0}, time;
+    double ip[FB_NC][3];
+    if (el->ls_impulse >= 0) oracle_cs_get_impulse(o->cs, el->ls_impulse, act, pts, &time);
+    for (int i = 0; i < FB_NC; ++i)
+      for (int x = 0; x < 3; ++x) ip[i][x] = pts[3 * i + x];
+    st->ls_viol = trial_violation(&o->p, st, el, nx->tq, nx->tv, act, (const double (*)[3])ip);
+  }
+  double c = 0.0, v = 0.0;
+  for (int pass = 0; pass < 4; ++pass) {
+    double cs = 0.0, vs = 0.0;
+    for (int e = 0; e < n; ++e) {
+      const int k = o->elems[e].kind;
+      const int mine = (pass == 0 && (k == K_GRID || k == K_TERMINAL)) || (pass == 1 && k == K_IMPULSE) ||
+                       (pass == 2 && k == K_AUX) || (pass == 3 && k == K_LIFT);
+      if (!mine) continue;
+      cs += o->slots[o->elems[e].slot].ls_cost;
+      vs += o->slots[o->elems[e].slot].ls_viol;
+    }
+    c = pass == 0 ? cs : c + cs;
+    v = pass == 0 ? vs : v + vs;
+  }
+  *cost = c;
+  *viol = v;
+}
+static double line_search_step(oracle_fb_ocp_t* o, double max_primal) {
+  double cost, viol;
+  if (o->filter_n == 0) {
+    ls_cost_and_violation(o, 0.0, &cost, &viol);
+    filter_augment(o, cost, viol);
+  }
+  double alpha = max_primal;
+  while (alpha > 0.05) {
+    ls_cost_and_violation(o, alpha, &cost, &viol);
+    if (filter_is_accepted(o, cost, viol)) {
+      filter_augment(o, cost, viol);
+      break;
+    }
+    alpha *= 0.75;
+  }
+  return alpha > 0.05 ? alpha : 0.05;
+}
+void oracle_fb_ocp_clear_line_search_filter(oracle_fb_ocp_t* o) { o->filter_n = 0; }
+int oracle_fb_ocp_filter_size(const oracle_fb_ocp_t* o) { return o->filter_n; }
+/* cost / violation totals of the point s + alpha d of the last direction (tests) */
+void oracle_fb_ocp_cost_and_violation(oracle_fb_ocp_t* o, double alpha, double* out) { ls_cost_and_violation(o, alpha, &out[0], &out[1]); }
+
+/* OCPSolver::updateSolution (ocp_solver.cpp:67-92) */
+int oracle_fb_ocp_update_solution_ls(oracle_fb_ocp_t* o, double t, const double* q, const double* v, int line_search) {
   const int rc = discretize(o, t);
   if (rc == -1 || rc == -2) return rc;
   const int n = o->n_elems;
@@ -1285,6 +1522,7 @@ int oracle_fb_ocp_update_solution(oracle_fb_ocp_t* o, double t, const double* q,
     if (st->max_primal < ap) ap = st->max_primal;
     if (st->max_dual < ad) ad = st->max_dual;
   }
+  if (line_search) ap = line_search_step(o, ap);
   o->primal_step = ap;
   o->dual_step = ad;
   /* OCPLinearizer::integrateSolution (ocp_linearizer.cpp:140-221) */
@@ -1300,6 +1538,10 @@ int oracle_fb_ocp_update_solution(oracle_fb_ocp_t* o, double t, const double* q,
   for (int e = 0; e < n; ++e)
     if (o->slots[o->elems[e].slot].chol_info && !info) info = o->slots[o->elems[e].slot].chol_info;
   return info ? 1000 + info : rc;
+}
+
+int oracle_fb_ocp_update_solution(oracle_fb_ocp_t* o, double t, const double* q, const double* v) {
+  return oracle_fb_ocp_update_solution_ls(o, t, q, v, 0);
 }
 
 /* OCPSolver::computeKKTResidual / KKTError (ocp_solver.cpp:202-213, ocp_linearizer.cpp:97-137) */
@@ -1341,6 +1583,8 @@ int oracle_fb_ocp_get(const oracle_fb_ocp_t* o, int e, const char* name, double*
   GET("Fqq_prev_inv", Fqq_prev_inv) GET("Fqq_inv", Fqq_inv) GET("laf", laf) GET("Qafqv", Qafqv) GET("Qafu", Qafu)
 #undef GET
   if (!strcmp(name, "kkt")) { out[0] = st->kkt_sq; return 1; }
+  if (!strcmp(name, "ls_cost")) { out[0] = st->ls_cost; return 1; }
+  if (!strcmp(name, "ls_viol")) { out[0] = st->ls_viol; return 1; }
   if (!strncmp(name, "slack", 5) || !strncmp(name, "dual", 4)) {
     int n = 0;
     for (int c = 0; c < NCOMP; ++c) {

@@ -130,7 +130,7 @@ class FbProblem(C.Structure):
             arr[i] = x
 
 
-_SIZES = dict(q=19, f=12, mu=12, nu_passive=6, xi=12, u=12, du=12, daf=30, dbetamu=30, dnu_passive=6, dxi=12, lf=12, lu=12,
+_SIZES = dict(ls_cost=1, ls_viol=1, q=19, f=12, mu=12, nu_passive=6, xi=12, u=12, du=12, daf=30, dbetamu=30, dnu_passive=6, dxi=12, lf=12, lu=12,
               lu_passive=6, P=12, IDC=30, Qxx=36 * 36, Qxu=36 * 18, Quu=18 * 18, Qff=144, Fvq=324, Fvv=324, Fvu=216, Fqq6=36, Fqv6=36,
               MJtJinv=900, MJ_dIDC=30 * 36, MJ_IDC=30, dIDCdqv=30 * 36, dCda=12 * 18, Mm=324, K=12 * 36, k=12, Pqq=324, Pqv=324,
               Pvv=324, Phix=12 * 36, Phia=12 * 18, Phiu=144, cM=12 * 36, cm=12, Fqq_prev_inv=36, Fqq_inv=36, laf=30,
@@ -150,6 +150,10 @@ class FbOCP:
         L.oracle_fb_ocp_chain.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 2 + [_dp] * 2 + [C.POINTER(C.c_int)] * 2
         L.oracle_fb_ocp_init_constraints.argtypes = [C.c_void_p, C.c_double]
         L.oracle_fb_ocp_update_solution.argtypes = [C.c_void_p, C.c_double, _dp, _dp]
+        L.oracle_fb_ocp_update_solution_ls.argtypes = [C.c_void_p, C.c_double, _dp, _dp, C.c_int]
+        L.oracle_fb_ocp_clear_line_search_filter.argtypes = [C.c_void_p]
+        L.oracle_fb_ocp_filter_size.argtypes = [C.c_void_p]
+        L.oracle_fb_ocp_cost_and_violation.argtypes = [C.c_void_p, C.c_double, _dp]
         L.oracle_fb_ocp_compute_kkt_residual.argtypes = [C.c_void_p, C.c_double, _dp, _dp]
         L.oracle_fb_ocp_kkt_error.restype = C.c_double
         L.oracle_fb_ocp_kkt_error.argtypes = [C.c_void_p]
@@ -193,8 +197,19 @@ class FbOCP:
     def init_constraints(self, t):
         return self.L.oracle_fb_ocp_init_constraints(self.h, float(t))
 
-    def update_solution(self, t, q, v):
-        return self.L.oracle_fb_ocp_update_solution(self.h, float(t), _p(_a(q, NQ)), _p(_a(v, NV)))
+    def update_solution(self, t, q, v, line_search=False):
+        return self.L.oracle_fb_ocp_update_solution_ls(self.h, float(t), _p(_a(q, NQ)), _p(_a(v, NV)), int(line_search))
+
+    def clear_line_search_filter(self):
+        self.L.oracle_fb_ocp_clear_line_search_filter(self.h)
+
+    def filter_size(self):
+        return self.L.oracle_fb_ocp_filter_size(self.h)
+
+    def cost_and_violation(self, alpha):
+        out = np.zeros(2)
+        self.L.oracle_fb_ocp_cost_and_violation(self.h, float(alpha), _p(out))
+        return out
 
     def compute_kkt_residual(self, t, q, v):
         return self.L.oracle_fb_ocp_compute_kkt_residual(self.h, float(t), _p(_a(q, NQ)), _p(_a(v, NV)))

@@ -182,3 +182,106 @@ def make_product_solver(pr, lib, fb, batch, q0=None, v0=None, t=0.0):
     solver.setSolution("f", pr.f_init)
     solver.initConstraints(t)
     return solver
+
+
+class RunningProblem(TrottingProblem):
+    """examples/anymal/anymal_running.cpp:28-229: T = 7, N = 240, a running gait with flight phases (26 impulses,
+    14 lifts), TimeVaryingConfigurationSpaceCost (cost/time_varying_configuration_space_cost.hpp:98-118: the reference
+    moves with v_ref between t_begin and t_end) and a contact-force cost; `steps` shortens the gait for the tests
+    (the example uses 10; T and N shrink with it so that the schedule still ends in a four-foot stance)."""
+
+    def __init__(self, steps=10, fb=None):
+        import fb_py as _fb
+        self.fb = fb or _fb
+        self.stride, self.additive_stride_hip, self.t_start = 0.4, 0.2, 1.0
+        self.t_front_swing, self.t_front_hip_swing, self.t_hip_swing = 0.135, 0.05, 0.165
+        self.t_period = self.t_front_swing + self.t_front_hip_swing + self.t_hip_swing
+        self.steps = steps
+        self.max_num_impulse = (steps + 3) * 2
+        if steps == 10:
+            self.T, self.N = 7.0, 240
+        else:   # same grid spacing, horizon ending 0.6 s after the last touch-down
+            t_last = self.t_start + 0.30 + 0.34 + steps * self.t_period + 0.35
+            self.N = int(math.ceil((t_last + 0.6) / (7.0 / 240)))
+            self.T = self.N * (7.0 / 240)
+        p = fb_py.FbProblem()
+        p.T, p.N, p.max_num_impulse = self.T, self.N, self.max_num_impulse
+        qw = np.array([1.0] * 3 + [10.0] * 15)
+        vw = np.array([0.01] * 3 + [0.1] * 15)
+        aw = np.full(18, 0.01)
+        for nm in ("q_weight", "qf_weight", "qi_weight"):
+            p.set(nm, qw)
+        for nm in ("v_weight", "vf_weight", "vi_weight"):
+            p.set(nm, vw)
+        p.set("a_weight", aw)
+        p.set("dvi_weight", aw)
+        p.set("f_weight", np.tile([0.1, 0.1, 1.0e-07], 4))
+        p.set("fi_weight", np.tile([0.1, 0.1, 1.0e-07], 4))
+        p.set("f_ref", np.tile([0, 0, 70.0], 4))
+        p.set("fi_ref", np.zeros(12))
+        p.set("q_min", np.full(12, -9.42))
+        p.set("q_max", np.full(12, 9.42))
+        p.set("v_max", np.full(12, 15.0))
+        p.set("u_max", np.full(12, 80.0))
+        p.mu, p.barrier, p.fraction_rate = 0.8, 1.0e-4, 0.995
+        for c in range(8):
+            p.enable[c] = 1
+        self.problem = p
+        self.q_begin = Q_STANDING.copy()
+        self.q_begin[0] = -3.0
+        self.v_ref_moving = np.zeros(18)
+        self.v_ref_moving[0] = self.stride / self.t_period
+        self.t_begin, self.t_end = self.t_start, self.t_start + (0.5 + steps) * self.t_period
+        self.q_end = self.fb.integrate(self.q_begin, self.v_ref_moving, self.t_end - self.t_begin)
+        self.q0 = self.q_begin.copy()
+        self.v0 = np.zeros(18)
+        self.f_init = np.array([0, 0, 0.25 * TOTAL_WEIGHT])
+        self.standing_points = None
+        self._v_ref_t = None
+
+    def q_ref(self, t):
+        if self.t_begin < t < self.t_end:
+            self.v_ref = self.v_ref_moving
+            return self.fb.integrate(self.q_begin, self.v_ref_moving, t - self.t_begin)
+        self.v_ref = np.zeros(18)
+        return self.q_begin.copy() if t <= self.t_begin else self.q_end.copy()
+
+    def set_references(self, ocp, t):
+        ocp.discretize(t)
+        for el in ocp.chain():
+            kind = fb_py.K_GRID if el["kind"] == fb_py.K_TERMINAL else el["kind"]
+            q_ref = self.q_ref(el["t"])
+            ocp.set_reference(kind, el["index"], q_ref, self.v_ref)
+
+    def contact_sequence(self, fb):
+        z = np.zeros(18)
+        pts = np.stack([fb.contact(self.q_begin, z, z, i, 0.05, np.zeros(3))["P"] for i in range(4)])
+        if self.standing_points is not None:
+            pts = np.array(self.standing_points, dtype=float)
+        cs = hybrid_py.ContactSequence(4, 64)
+        ALL, FRONT_SWING, FLY, HIP_SWING = [1, 1, 1, 1], [0, 1, 0, 1], [0, 0, 0, 0], [1, 0, 1, 0]
+        st, ah = self.stride, self.additive_stride_hip
+        t0 = self.t_start
+        cs.set_uniform(ALL, pts)
+        cs.push_back(FRONT_SWING, t0, pts)
+        cs.push_back(FLY, t0 + 0.125, pts)
+        pts = pts + np.array([[0.25 * st], [0.25 * st + 0.5 * ah], [0.25 * st], [0.25 * st + 0.5 * ah]]) * np.array([1.0, 0, 0])
+        cs.push_back(HIP_SWING, t0 + 0.125 + 0.05, pts)
+        t_initial, t_initial2 = 0.125 + 0.05 + 0.125, 0.135 + 0.055 + 0.15
+        cs.push_back(FRONT_SWING, t0 + t_initial, pts)
+        cs.push_back(FLY, t0 + t_initial + 0.135, pts)
+        pts = pts + np.array([[0.5 * st], [0.5 * st + 0.5 * ah], [0.5 * st], [0.5 * st + 0.5 * ah]]) * np.array([1.0, 0, 0])
+        cs.push_back(HIP_SWING, t0 + t_initial + 0.135 + 0.055, pts)
+        t_end_init = t0 + t_initial + t_initial2
+        for i in range(self.steps):
+            cs.push_back(FRONT_SWING, t_end_init + i * self.t_period, pts)
+            cs.push_back(FLY, t_end_init + i * self.t_period + self.t_front_swing, pts)
+            pts = pts + np.array([st, 0, 0])
+            cs.push_back(HIP_SWING, t_end_init + i * self.t_period + self.t_front_swing + self.t_front_hip_swing, pts)
+        tl = t_end_init + self.steps * self.t_period
+        cs.push_back(FRONT_SWING, tl, pts)
+        cs.push_back(FLY, tl + 0.15, pts)
+        pts = pts + np.array([[0.5 * st], [0.5 * st - ah], [0.5 * st], [0.5 * st - ah]]) * np.array([1.0, 0, 0])
+        cs.push_back(HIP_SWING, tl + 0.15 + 0.05, pts)
+        cs.push_back(ALL, tl + 0.35, pts)
+        return cs

@@ -84,3 +84,26 @@ def test_trotting_iterations_bit_exact(fb, emu_lib):
         assert compare(ocp, solver, fb, DIR) == [], it
         assert np.array_equal(solver.stepSizes()[0], ocp.step_sizes())
         assert compare(ocp, solver, fb, SOL) == [], it
+
+
+def test_filter_line_search_bit_exact(fb, emu_lib):
+    # LineSearch::computeStepSize for OCPSolver (line_search.hpp:62-93) on a problem where the search backtracks
+    pr = ap.JumpingProblem(0.1, 0.6, 0.75, 1.3, 26)
+    ocp = pr.make_oracle(fb)
+    solver = ap.make_product_solver(pr, emu_lib, fb, batch=1)
+    steps = []
+    for it in range(4):
+        assert ocp.update_solution(0.0, pr.q0, pr.v0, True) == 0
+        solver.updateSolution(0.0, pr.q0, pr.v0, True)
+        assert np.array_equal(solver.stepSizes()[0], ocp.step_sizes()), (it, solver.stepSizes()[0], ocp.step_sizes())
+        steps.append(ocp.step_sizes()[0])
+        assert compare(ocp, solver, fb, SOL) == [], it
+    assert min(steps) < 0.9          # the filter rejected at least one full fraction-to-boundary step
+    assert ocp.filter_size() >= 2
+    # clearLineSearchFilter: the next call re-evaluates the current point first
+    ocp.clear_line_search_filter()
+    solver.clearLineSearchFilter()
+    assert ocp.update_solution(0.0, pr.q0, pr.v0, True) == 0
+    solver.updateSolution(0.0, pr.q0, pr.v0, True)
+    assert np.array_equal(solver.stepSizes()[0], ocp.step_sizes())
+    assert compare(ocp, solver, fb, SOL) == []

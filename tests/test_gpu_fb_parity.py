@@ -103,3 +103,56 @@ def test_large_batch_properties(fb, gpu_lib):
     u = solver.get(e_mid, "u")
     assert np.array_equal(u[:8], u[-8:])
     assert solver.launchCount() > 0
+
+
+def test_filter_line_search_bit_exact(fb, gpu_lib):
+    # LineSearch for OCPSolver (line_search.hpp:62-93): per-instance step sizes, filters and iterates equal the oracle's
+    pr = ap.JumpingProblem(0.1, 0.6, 0.75, 1.3, 26)
+    B = 4
+    q0, v0 = perturbed_states(fb, pr, B, 5)
+    q0 = np.array([fb.integrate(pr.q0, 0.25 * fb.subtract(q0[b], pr.q0)) for b in range(B)])
+    v0 = 0.25 * v0
+    solver = ap.make_product_solver(pr, gpu_lib, fb, batch=B, q0=q0, v0=v0)
+    oracles = [pr.make_oracle(fb, q0=q0[b], v0=v0[b]) for b in range(B)]
+    seen = set()
+    compared = 0
+    for it in range(6):
+        solver.updateSolution(0.0, q0, v0, True)
+        steps = solver.stepSizes()
+        rcs = [o.update_solution(0.0, q0[b], v0[b], True) for b, o in enumerate(oracles)]
+        for b, o in enumerate(oracles):
+            assert np.array_equal(steps[b], o.step_sizes()), (it, b, steps[b], o.step_sizes())
+            seen.add(float(steps[b][0]))
+        if any(rcs):    # the 0.05 floor of the search can leave the interior (upstream behaviour): stop comparing
+            break
+        for b, o in enumerate(oracles):
+            assert compare(o, solver, fb, SOL, b=b) == [], (it, b)
+        compared += 1
+    assert compared >= 3 and len(seen) > 2       # instances backtracked differently
+    solver.clearLineSearchFilter()
+    for o in oracles:
+        o.clear_line_search_filter()
+    solver.updateSolution(0.0, q0, v0, True)
+    for b, o in enumerate(oracles):
+        o.update_solution(0.0, q0[b], v0[b], True)
+        assert np.array_equal(solver.stepSizes()[b], o.step_sizes())
+
+
+def test_running_gait_with_flight_phases_bit_exact(fb, gpu_lib):
+    # examples/anymal/anymal_running.cpp shortened to one stride: 8 impulses, 5 lifts, flight phases (dimf = 0), the
+    # switching constraint on lift stages, a time-varying configuration reference
+    pr = ap.RunningProblem(steps=1)
+    solver = ap.make_product_solver(pr, gpu_lib, fb, batch=2)
+    o = pr.make_oracle(fb)
+    o.set_threads(8)
+    kinds = [c["kind"] for c in solver.chain()]
+    assert kinds.count(fb.K_IMPULSE) == 8 and kinds.count(fb.K_LIFT) == 5
+    assert [(c["kind"], c["index"], c["dimf"], c["dimi"]) for c in solver.chain()] == [(c["kind"], c["index"], c["dimf"], c["dimi"]) for c in o.chain()]
+    for it in range(3):
+        o.compute_kkt_residual(0.0, pr.q0, pr.v0)
+        solver.computeKKTResidual(0.0, pr.q0, pr.v0)
+        assert solver.KKTError()[1] == o.kkt_error()
+        assert o.update_solution(0.0, pr.q0, pr.v0) == 0
+        solver.updateSolution(0.0, pr.q0, pr.v0)
+        for names in (KKT + EXP, RIC, DIR, SOL):
+            assert compare(o, solver, fb, names, b=1) == [], it

@@ -174,3 +174,62 @@ def test_flight_phase_lift_stage_and_four_foot_touch_down(fb):
     imp = kinds.index(fb.K_IMPULSE)
     P = np.stack([fb.contact(ocp.get(imp, "q"), np.zeros(18), np.zeros(18), i, 0.05, np.zeros(3))["P"] for i in range(4)])
     assert np.allclose(P[:, 0], ap.standing_contact_points(fb)[:, 0] + 0.1, atol=5e-3)
+
+
+def test_filter_line_search(fb):
+    # LineSearch::computeStepSize (line_search.hpp:62-93) + LineSearchFilter (line_search_filter.cpp:34-65)
+    pr = ap.JumpingProblem(0.1, 0.6, 0.75, 1.3, 26)
+    a, b = pr.make_oracle(fb), pr.make_oracle(fb)
+    for it in range(6):
+        # the direction and the fraction-to-boundary step do not depend on the flag
+        assert b.update_solution(0.0, pr.q0, pr.v0, False) == 0
+        amax = b.step_sizes()[0]
+        n0 = a.filter_size()
+        assert a.update_solution(0.0, pr.q0, pr.v0, True) == 0
+        alpha = a.step_sizes()[0]
+        # alpha is alpha_max * 0.75^k for some k >= 0, or the floor 0.05
+        ks = [amax * 0.75 ** k for k in range(12)]
+        assert alpha == 0.05 or any(alpha == x for x in ks), (alpha, amax)
+        assert a.filter_size() >= 1 and a.filter_size() <= n0 + 2
+        # keep the two solvers on the same iterate: copy a's iterate into b
+        for e in range(len(a.chain())):
+            for nm in ("q", "v", "a", "u", "f", "lmd", "gmm", "beta", "mu", "nu_passive", "xi"):
+                b.set(e, nm, a.get(e, nm))
+        # (slack / dual are not settable: stop comparing directions after the first divergence)
+        break
+    # cost / violation of the current point at a converged solution: every stage is feasible EXCEPT the grid stages
+    # right before an event -- upstream closes their state equation with the next GRID stage instead of the lift /
+    # impulse stage (line_search.cpp:84-121: the first if / else-if is overwritten by the second if / else); kept
+    pr = ap.TrottingProblem()
+    c = pr.make_oracle(fb)
+    for _ in range(25):
+        c.update_solution(0.0, pr.q0, pr.v0, False)
+    tot = c.cost_and_violation(0.0)
+    ch = c.chain()
+    per_stage = np.array([c.get(e, "ls_viol")[0] for e in range(len(ch))])
+    before_event = [e for e in range(len(ch) - 1) if ch[e]["kind"] == fb.K_GRID and ch[e + 1]["kind"] in (fb.K_IMPULSE, fb.K_LIFT)]
+    assert len(before_event) == 3
+    mask = np.ones(len(ch), bool)
+    mask[before_event] = False
+    assert np.all(per_stage[mask] < 1e-8) and np.all(per_stage[before_event] > 0.5)
+    assert abs(tot[1] - per_stage.sum()) < 1e-9 and np.isfinite(tot[0])
+    c.update_solution(0.0, pr.q0, pr.v0, True)
+    assert c.filter_size() >= 1
+    c.clear_line_search_filter()
+    assert c.filter_size() == 0
+
+
+def test_running_gait_one_stride(fb):
+    # examples/anymal/anymal_running.cpp shortened to one stride of the loop (flight phases between the swings)
+    pr = ap.RunningProblem(steps=1)
+    ocp = pr.make_oracle(fb)
+    ocp.set_threads(8)
+    ch = ocp.chain()
+    kinds = [c["kind"] for c in ch]
+    assert kinds.count(fb.K_IMPULSE) == 8 and kinds.count(fb.K_LIFT) == 5 and any(c["dimf"] == 0 for c in ch)
+    hist = run(ocp, pr, 40)
+    assert np.all(np.isfinite(hist)) and hist[-1] < 1e-5 * hist[0]
+    full = ap.RunningProblem(steps=10)
+    o2 = full.make_oracle(fb)
+    k2 = [c["kind"] for c in o2.chain()]
+    assert (full.T, full.N) == (7.0, 240) and k2.count(fb.K_IMPULSE) == 26 and k2.count(fb.K_LIFT) == 14   # the example's schedule
