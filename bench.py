@@ -180,6 +180,197 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------
+# ANYmal workloads (BASELINE.json configs[3], configs[4]): batched OCPSolver with contacts and impulses
+# ---------------------------------------------------------------------------------------------------
+ANYMAL_BATCH = {"anymal_trotting": 4096, "anymal_running": 1024}
+ANYMAL_LINE_SEARCH = {"anymal_trotting": False, "anymal_running": True}
+# algorithmic doubles per (instance, stage) of the heavy kernels at dimf = 12: mandatory inputs + outputs
+FB_ALGO_DOUBLES_PER_STAGE = {
+    "fb_robot": (181 + 224 + 73 + 19) + (30 + 1080 + 324 + 216 + 132 + 240 + 108),
+    "fb_condense": (30 + 1080 + 324 + 216 + 132 + 240 + 108) + (972 + 648 + 324 + 972 + 90) + 3660,
+    "fb_riccati_backward": (972 + 648 + 324 + 972 + 90) + (432 + 12 + 972 + 36),
+}
+# about 0.45 MFLOP per stage of the ANYmal path
+FB_FLOP_PER_STAGE = 0.45e6
+
+
+def anymal_problem(name, lib=None):
+    from idocp_b200 import problems as P
+    return P.AnymalTrotting(lib=lib) if name == "anymal_trotting" else P.AnymalRunning(lib=lib)
+
+
+def anymal_oracle_throughput(name, seconds_target, steps=None, warmup=1):
+    """CPU oracle of the ANYmal OCPSolver (oracle/fb_ocp.c) on the host cores: one oracle object per instance, a
+    thread pool over instances (ctypes releases the GIL), every instance single-threaded = BASELINE.md mode B."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import anymal_problems as tp
+    import fb_py
+    import oracle_py
+    from idocp_b200 import problems as P
+    oracle_py.build()
+    fb_py.lib()
+    cores = os.cpu_count() or 1
+    pr = tp.TrottingProblem() if name == "anymal_trotting" else tp.RunningProblem(10)
+    ls = ANYMAL_LINE_SEARCH[name]
+    nb = 2 * cores
+    q0, v0 = P.anymal_initial_states(0, nb, q_nominal=pr.q0)
+    solvers = [pr.make_oracle(fb_py, q0=q0[b], v0=v0[b]) for b in range(nb)]
+    for _ in range(max(warmup, 1)):
+        fb_py.batch_update_solution(solvers, 0.0, q0, v0, ls, cores)
+    t0 = time.perf_counter()
+    fb_py.batch_update_solution(solvers, 0.0, q0, v0, ls, cores)
+    first = time.perf_counter() - t0
+    if steps is None:
+        steps = int(max(2, min(200, seconds_target / max(first, 1e-6))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fb_py.batch_update_solution(solvers, 0.0, q0, v0, ls, cores)
+    total = time.perf_counter() - t0
+    cores_used = cores
+    sample = "%d instances x %d updateSolution sweeps, OpenMP over instances, %d threads" % (nb, steps, cores_used)
+    return nb * steps / total, cores_used, sample, total / steps * 1e3
+
+
+def anymal_metric(name):
+    return ("batched SQP iterations/sec (ANYmal trotting OCPSolver N=30, FP64)" if name == "anymal_trotting"
+            else "batched SQP iterations/sec (ANYmal running OCPSolver N=240, filter line search, FP64)")
+
+
+def run_reference_anymal(args, rank):
+    if rank != 0:
+        return
+    value, cores, sample, ms = anymal_oracle_throughput(args.workload, None, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": anymal_metric(args.workload), "value": value, "unit": "instance-iterations/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s (examples/anymal/%s.cpp problem), perturbed initial states (splitmix64 seed 20240004); "
+                               "bounded sample of %d instances per step" % (args.workload, args.workload, 2 * cores)},
+        "cpu_baseline": {"value": value, "unit": "instance-iterations/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "instance-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "oracle restatement of idocp's OCPSolver (oracle/fb_ocp.c), not the upstream binary: pinocchio/Eigen absent",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_anymal(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    import idocp_b200 as I
+    from idocp_b200 import problems as P
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = I.default_library()
+    pr = anymal_problem(args.workload, lib)
+    ls = ANYMAL_LINE_SEARCH[args.workload]
+    B = args.batch if args.batch != BATCH_PER_GPU else ANYMAL_BATCH[args.workload]
+    q0, v0 = P.anymal_initial_states(rank * B, B, q_nominal=pr.q_nominal)
+    solver = P.make_solver(pr, B, q0, v0, device=local_rank, lib=lib)
+    n_stages = len(solver.chain())
+    stream = torch.cuda.ExternalStream(solver.stream(), device=local_rank)
+    u_host = np.zeros((B, 12))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    solver.updateSolution(0.0, q0, v0, ls)          # uploads x0 and the cost reference once
+    for _ in range(args.warmup):
+        solver.updateSolutionResident(0.0, ls)
+    solver.sync()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    solver.setProfiling(True)
+    launches0 = solver.launchCount()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        solver.updateSolutionResident(0.0, ls)
+    e1.record(stream)
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = solver.launchCount() - launches0
+    profile = solver.getProfile()
+    solver.setProfiling(False)
+    # end-to-end: host states in, first control input out, through the public API
+    for _ in range(3):
+        solver.updateSolution(0.0, q0, v0, ls)
+        u_host[:] = solver.get(0, "u")
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        solver.updateSolution(0.0, q0, v0, ls)
+        u_host[:] = solver.get(0, "u")
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    if rank == 0:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    solver.computeKKTResidual(0.0, q0, v0)
+    kkt = solver.KKTError()
+    units = float(B) * world * args.steps
+    value = units / (ms_total * 1e-3)
+    hbm_peak, peak_src = measured_peaks()
+    stages = B * n_stages
+    kern = {}
+    for name, rec in profile.items():
+        if rec["calls"]:
+            per = rec["ms"] / args.steps
+            kern[name] = {"ms_per_step": per, "launches_per_step": rec["calls"] / args.steps}
+            if name in FB_ALGO_DOUBLES_PER_STAGE:
+                kern[name]["algo_gbs"] = FB_ALGO_DOUBLES_PER_STAGE[name] * 8.0 * stages / (per * 1e-3) / 1e9
+    dom = max((n for n in kern if "algo_gbs" in kern[n]), key=lambda n: kern[n]["ms_per_step"], default=None)
+    roofline = None
+    if dom:
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["algo_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                    "frac": kern[dom]["algo_gbs"] / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": FB_ALGO_DOUBLES_PER_STAGE[dom] * 8.0 * stages,
+                    "note": "the ANYmal kernels are latency-bound (dependent FP64 chains of the factorisations, 8-16 resident "
+                            "warps / SM; ncu: profiles/r1i_ncu_full_k_fb_*.txt), neither HBM- nor FP64-throughput-bound",
+                    "kernels": kern,
+                    "step_fp64_tflops": FB_FLOP_PER_STAGE * n_stages * value / world / 1e12}
+    line = {
+        "metric": anymal_metric(args.workload), "value": value, "unit": "instance-iterations/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s: OCPSolver on examples/anymal/%s.cpp (T=%g, N=%d, %d stages incl. impulse / aux / lift), %d "
+                               "perturbed initial states per GPU (splitmix64 seed 20240004), line_search=%s"
+                               % (args.workload, args.workload, pr.T, pr.N, n_stages, B, str(ls).lower()),
+                   "batch_per_gpu": B, "stages": n_stages, "parallelism": "batch-sharded x%d, no collective" % world,
+                   "l2_policy": "working set %.1f GB per GPU >> 126 MB L2" % (B * n_stages * 127e3 / 1e9)},
+        "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "instance-iterations/s", "h2d_bytes_per_step": B * 37 * 8,
+                "d2h_bytes_per_step": B * 12 * 8, "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches), "roofline": roofline, "clocks": sampler.summary() if rank == 0 else None,
+        "health": {"kkt_median": float(np.nanmedian(kkt)), "kkt_nan": int(np.isnan(kkt).sum())},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cval, cores, sample, _ = anymal_oracle_throughput(args.workload, args.cpu_seconds)
+        line["cpu_baseline"] = {"value": cval, "unit": "instance-iterations/s", "cores": cores, "kind": "port", "sample": sample}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -189,6 +380,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="instances per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--workload", default="iiwa14_unocp", choices=["iiwa14_unocp", "anymal_trotting", "anymal_running"],
+                    help="iiwa14_unocp = BASELINE configs[2] (the headline); anymal_* = configs[3] / configs[4]")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -196,6 +389,12 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
 
+    if args.workload != "iiwa14_unocp":
+        if args.impl == "reference":
+            run_reference_anymal(args, rank)
+        else:
+            run_anymal(args, rank, local_rank, world)
+        return
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

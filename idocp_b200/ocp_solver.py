@@ -107,6 +107,15 @@ class OCPSolver:
         q, v = self._state(q, v)
         self.lib.check(self.lib.L.idocp_b200_fb_update_solution(self._h, float(t), capi.dptr(q), capi.dptr(v), int(line_search)))
 
+    def updateSolutionResident(self, t, line_search=False):
+        """updateSolution with the initial states and the cost reference already resident on the device."""
+        self.lib.check(self.lib.L.idocp_b200_fb_update_solution(self._h, float(t), None, None, int(line_search)))
+
+    def stream(self):
+        p = C.c_void_p()
+        self.lib.check(self.lib.L.idocp_b200_fb_stream(self._h, C.byref(p)))
+        return p.value or 0
+
     def computeKKTResidual(self, t, q, v):
         self._sample_reference(t)
         q, v = self._state(q, v)

@@ -1544,6 +1544,14 @@ int oracle_fb_ocp_update_solution(oracle_fb_ocp_t* o, double t, const double* q,
   return oracle_fb_ocp_update_solution_ls(o, t, q, v, 0);
 }
 
+/* full-host-core mode of the CPU baseline (BASELINE.md mode B): OpenMP over independent instances, every instance
+ * single-threaded (nested parallelism is off, so the stage loops inside run serially) */
+void oracle_fb_ocp_batch_update_solution(oracle_fb_ocp_t** os, int batch, double t, const double* q, const double* v,
+                                         int line_search, int nthreads) {
+#pragma omp parallel for schedule(dynamic) num_threads(nthreads)
+  for (int b = 0; b < batch; ++b) oracle_fb_ocp_update_solution_ls(os[b], t, q + (size_t)b * NQ, v + (size_t)b * NV, line_search);
+}
+
 /* OCPSolver::computeKKTResidual / KKTError (ocp_solver.cpp:202-213, ocp_linearizer.cpp:97-137) */
 int oracle_fb_ocp_compute_kkt_residual(oracle_fb_ocp_t* o, double t, const double* q, const double* v) {
   (void)v;

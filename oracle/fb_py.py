@@ -230,3 +230,12 @@ class FbOCP:
 
     def set(self, e, name, value):
         assert self.L.oracle_fb_ocp_set(self.h, int(e), name.encode(), _p(_a(value))) == 0
+
+
+def batch_update_solution(solvers, t, q, v, line_search=False, nthreads=1):
+    """OpenMP over instances (one FbOCP per instance), every instance single-threaded."""
+    L = lib()
+    L.oracle_fb_ocp_batch_update_solution.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_double, _dp, _dp, C.c_int, C.c_int]
+    arr = (C.c_void_p * len(solvers))(*[s.h for s in solvers])
+    L.oracle_fb_ocp_batch_update_solution(arr, len(solvers), float(t), _p(_a(q, len(solvers) * NQ)), _p(_a(v, len(solvers) * NV)),
+                                          int(line_search), int(nthreads))

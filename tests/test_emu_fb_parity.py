@@ -107,3 +107,44 @@ def test_filter_line_search_bit_exact(fb, emu_lib):
     solver.updateSolution(0.0, pr.q0, pr.v0, True)
     assert np.array_equal(solver.stepSizes()[0], ocp.step_sizes())
     assert compare(ocp, solver, fb, SOL) == []
+
+
+def test_receding_horizon_calls_bit_exact(fb, emu_lib):
+    # the MPC caller one step outside the path: updateSolution at advancing t re-discretises the
+    # schedule (stage times, the shortened stage before an event, slot <-> stage mapping), events leave the horizon
+    # through popFrontContactStatus and enter through pushBackContactStatus (ocp_solver.cpp:174-194)
+    pr = ap.TrottingProblem()
+    ocp = pr.make_oracle(fb)
+    solver = ap.make_product_solver(pr, emu_lib, fb, batch=1)
+    cs = ocp.cs
+    q, v = pr.q0.copy(), pr.v0.copy()
+    for t in (0.0, 0.013, 0.04, 0.31, 0.47):
+        pr.set_references(ocp, t)
+        assert ocp.update_solution(t, q, v) == 0
+        solver.updateSolution(t, q, v)
+        assert [(c["kind"], c["index"], c["dimf"], c["dimi"]) for c in solver.chain()] == \
+               [(c["kind"], c["index"], c["dimf"], c["dimi"]) for c in ocp.chain()]
+        assert np.array_equal([c["dt"] for c in solver.chain()], [c["dt"] for c in ocp.chain()])
+        assert np.array_equal(solver.stepSizes()[0], ocp.step_sizes()), t
+        assert compare(ocp, solver, fb, SOL) == [], t
+        # the plant moves: the next initial state is the second stage of the current solution
+        q, v = ocp.get(1, "q"), ocp.get(1, "v")
+    # the first event (lift at 0.5) has passed: drop it, append a new touch-down at the end of the horizon
+    cs.pop_front()
+    solver.popFrontContactStatus()
+    a, pts = cs.phase(cs.counts()[0] - 1)
+    pts = pts.copy()
+    pts[0, 0] += pr.step_length
+    pts[3, 0] += pr.step_length
+    t = 0.52
+    assert cs.push_back([1, 0, 0, 1], t + pr.T - 0.02, pts) == 0
+    solver.pushBackContactStatus([1, 0, 0, 1], t + pr.T - 0.02, pts)
+    for t in (0.52, 0.55):
+        pr.set_references(ocp, t)
+        rc = ocp.update_solution(t, q, v)
+        solver.updateSolution(t, q, v)
+        assert [(c["kind"], c["index"], c["dimf"], c["dimi"]) for c in solver.chain()] == \
+               [(c["kind"], c["index"], c["dimf"], c["dimi"]) for c in ocp.chain()]
+        assert np.array_equal(solver.stepSizes()[0], ocp.step_sizes()), t
+        if rc == 0:
+            assert compare(ocp, solver, fb, SOL) == [], t
