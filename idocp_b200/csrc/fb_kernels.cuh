@@ -156,37 +156,61 @@ __device__ inline double fb_sqnorm(const double* x, int n) {
 __device__ inline void fb_copy(double* dst, const double* src, int n) { FB_FOR(i, n) dst[i] = src[i]; }
 __device__ inline void fb_zero(double* dst, int n) { FB_FOR(i, n) dst[i] = 0.0; }
 
-// Cholesky of an n x n matrix (n <= 32) by ONE warp: lane i owns row i.  L[j*ldl + i] = L_ij (i >= j), rd[k] = 1/L_kk.
-// Same per-element chains as the serial left-looking form.  Call with all lanes of warp 0; others skip.
-__device__ inline int fb_llt_warp(const double* A, int lda, int n, double* L, int ldl, double* rd) {
+// Cholesky of an n x n matrix (n <= 32) by ONE warp, right-looking and IN PLACE on the lower triangle of A: lane i
+// owns row i; after column k the lanes below update their own trailing entries with independent fmas (no dependent
+// chain longer than one fma per step).  Every element still receives its updates in ascending k, so the bits equal
+// the serial left-looking form of the oracle.  L[j*ldl + i] = L_ij (i >= j), rd[k] = 1/L_kk.
+__device__ inline int fb_llt_warp(double* A, int lda, int n, double* L, int ldl, double* rd) {
   const int lane = threadIdx.x & 31;
   int info = 0;
   for (int k = 0; k < n; ++k) {
     if (lane == k) {
       double x = A[k * lda + k];
-      for (int j = 0; j < k; ++j) x = fma(-L[j * ldl + k], L[j * ldl + k], x);
       if (!(x > 0.0)) info = k + 1;
       x = sqrt(x);
       L[k * ldl + k] = x;
       rd[k] = 1.0 / x;
     }
     __syncwarp();
-    if (lane > k && lane < n) {
-      double y = A[lane * lda + k];
-      for (int j = 0; j < k; ++j) y = fma(-L[j * ldl + lane], L[j * ldl + k], y);
-      L[k * ldl + lane] = y * rd[k];
-    }
+    if (lane > k && lane < n) L[k * ldl + lane] = A[lane * lda + k] * rd[k];
     __syncwarp();
+    if (lane > k && lane < n) {
+      const double lik = L[k * ldl + lane];
+      for (int j = k + 1; j <= lane; ++j) A[lane * lda + j] = fma(-lik, L[k * ldl + j], A[lane * lda + j]);
+    }
   }
-  // first failing pivot over the lanes
-  for (int k = 0; k < n; ++k) {
+  __syncwarp();
+  for (int k = 0; k < n; ++k) {   // first failing pivot over the lanes
     const int v = __shfl_sync(0xffffffffu, info, k);
     if (v) return v;
   }
   return 0;
 }
-// x := (L L^T)^-1 x, one right-hand side with stride incx, executed by the calling thread
-__device__ inline void fb_llt_solve(const double* L, int ldl, const double* rd, int n, double* x, int incx) {
+// x := (L L^T)^-1 x for one right-hand side (stride incx) by the calling thread, in place and column-oriented: as soon
+// as x_j is known every remaining entry is updated by an independent fma (no dependent chain across i).
+// Forward: entry i receives its terms in ascending j; backward: in descending j (the oracle's order).
+template <int N>
+__device__ __forceinline__ void fb_llt_solve_n(const double* __restrict__ L, int ldl, const double* __restrict__ rd, double* x, int incx) {
+  double y[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) y[i] = x[i * incx];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    y[j] *= rd[j];
+#pragma unroll
+    for (int i = j + 1; i < N; ++i) y[i] = fma(-L[j * ldl + i], y[j], y[i]);
+  }
+#pragma unroll
+  for (int j = N - 1; j >= 0; --j) {
+    y[j] *= rd[j];
+#pragma unroll
+    for (int i = 0; i < j; ++i) y[i] = fma(-L[i * ldl + j], y[j], y[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) x[i * incx] = y[i];
+}
+// same arithmetic for a run-time n (row-oriented, in place)
+__device__ __noinline__ void fb_llt_solve(const double* L, int ldl, const double* rd, int n, double* x, int incx) {
   for (int i = 0; i < n; ++i) {
     double y = x[i * incx];
     for (int j = 0; j < i; ++j) y = fma(-L[j * ldl + i], x[j * incx], y);
@@ -194,7 +218,7 @@ __device__ inline void fb_llt_solve(const double* L, int ldl, const double* rd, 
   }
   for (int i = n - 1; i >= 0; --i) {
     double y = x[i * incx];
-    for (int j = i + 1; j < n; ++j) y = fma(-L[i * ldl + j], x[j * incx], y);
+    for (int j = n - 1; j > i; --j) y = fma(-L[i * ldl + j], x[j * incx], y);
     x[i * incx] = y * rd[i];
   }
 }
@@ -1056,7 +1080,7 @@ struct FbDenseWork {
   int info;
 };
 
-__global__ void __launch_bounds__(128) k_fb_condense(FbArrays A, const FbLin* lin) {
+__global__ void __launch_bounds__(128, 4) k_fb_condense(FbArrays A, const FbLin* lin) {
   IDOCP_DYN_SMEM(FbDenseWork, wp);
   FbDenseWork& w = *wp;
   const int tid = threadIdx.x;
@@ -1098,7 +1122,11 @@ __global__ void __launch_bounds__(128) k_fb_condense(FbArrays A, const FbLin* li
     __syncthreads();
     if (tid < n) {
       for (int r = 0; r < n; ++r) w.s.f.Minv[r * n + tid] = (r == tid) ? 1.0 : 0.0;
+#ifdef FB_MINV_REG
+      fb_llt_solve_n<FB_NV>(w.s.f.L, n, w.s.f.rd, w.s.f.Minv + tid, n);
+#else
       fb_llt_solve(w.s.f.L, n, w.s.f.rd, n, w.s.f.Minv + tid, n);
+#endif
     }
     __syncthreads();
     fb_mm<FBM_SET>(dimf, n, n, w.dCda, n, 1, w.s.f.Minv, n, 1, w.s.f.JMi, n);
@@ -1255,7 +1283,7 @@ struct FbRicWork {
   int info;
 };
 
-__global__ void __launch_bounds__(128) k_fb_riccati_backward(FbArrays A) {
+__global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
   IDOCP_DYN_SMEM(FbRicWork, wp);
   FbRicWork& w = *wp;
   const int tid = threadIdx.x, b = blockIdx.x, n = A.n_elems;
@@ -1351,12 +1379,12 @@ __global__ void __launch_bounds__(128) k_fb_riccati_backward(FbArrays A) {
         if (tid < NX) {
           double col[FB_NU];
           for (int r = 0; r < NU; ++r) col[r] = Qxu[tid * NV + r];
-          fb_llt_solve(w.L, NU, w.rd, NU, col, 1);
+          fb_llt_solve_n<FB_NU>(w.L, NU, w.rd, col, 1);
           for (int r = 0; r < NU; ++r) w.K[r * NX + tid] = -col[r];
         } else if (tid == NX) {
           double col[FB_NU];
           for (int r = 0; r < NU; ++r) col[r] = w.lu[r];
-          fb_llt_solve(w.L, NU, w.rd, NU, col, 1);
+          fb_llt_solve_n<FB_NU>(w.L, NU, w.rd, col, 1);
           for (int r = 0; r < NU; ++r) w.k[r] = -col[r];
         }
         __syncthreads();
@@ -1364,11 +1392,11 @@ __global__ void __launch_bounds__(128) k_fb_riccati_backward(FbArrays A) {
         // Schur complement on the switching constraint (split_riccati_factorizer.hxx:55-100)
         if (tid < NU) {
           for (int r = 0; r < NU; ++r) w.Ginv[r * NU + tid] = (r == tid) ? 1.0 : 0.0;
-          fb_llt_solve(w.L, NU, w.rd, NU, w.Ginv + tid, NU);
+          fb_llt_solve_n<FB_NU>(w.L, NU, w.rd, w.Ginv + tid, NU);
         } else if (tid >= 32 && tid < 32 + dimi) {
           const int r = tid - 32;
           for (int c = 0; c < NU; ++c) w.DGinv[r * NU + c] = w.Phiu[r * NU + c];
-          fb_llt_solve(w.L, NU, w.rd, NU, w.DGinv + r * NU, 1);
+          fb_llt_solve_n<FB_NU>(w.L, NU, w.rd, w.DGinv + r * NU, 1);
         }
         __syncthreads();
         fb_mm<FBM_SET>(dimi, dimi, NU, w.DGinv, NU, 1, w.Phiu, 1, NU, w.Sm, MAXF);

@@ -838,9 +838,9 @@ static inline void fb_llt_solve(const double* L, int ldl, const double* rd, int 
     for (int j = 0; j < i; ++j) y = fma(-L[j * ldl + i], x[j * incx], y);
     x[i * incx] = y * rd[i];
   }
-  for (int i = n - 1; i >= 0; --i) {
+  for (int i = n - 1; i >= 0; --i) {   /* L^T x = z: the terms of row i are subtracted from the last column backwards */
     double y = x[i * incx];
-    for (int j = i + 1; j < n; ++j) y = fma(-L[i * ldl + j], x[j * incx], y);
+    for (int j = n - 1; j > i; --j) y = fma(-L[i * ldl + j], x[j * incx], y);
     x[i * incx] = y * rd[i];
   }
 }

@@ -163,7 +163,7 @@ def make_product_solver(pr, lib, fb, batch, q0=None, v0=None, t=0.0):
     p = I.FbProblem()
     assert C.sizeof(p) == C.sizeof(pr.problem)
     C.memmove(C.byref(p), C.byref(pr.problem), C.sizeof(p))
-    solver = I.OCPSolver(p, batch, q_ref=lambda tt: (pr.q_ref(tt), pr.v_ref), lib=lib, max_num_events=pr.max_num_impulse + 2)
+    solver = I.OCPSolver(p, batch, q_ref=lambda tt: (pr.q_ref(tt), pr.v_ref), lib=lib, max_num_events=60)
     ocs = pr.contact_sequence(fb)
     n_phases = ocs.counts()[0]
     a, pts = ocs.phase(0)
