@@ -80,3 +80,67 @@ def test_initial_states_are_inside_the_joint_limits():
     # counter-based: shard k of size n == rows [k n, (k+1) n) of the big batch
     q1, _ = bench.initial_states(1024, 16, list(p.q_min), list(p.q_max))
     assert np.array_equal(q1, q0[1024:1040])
+
+
+def _anymal_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import anymal_problems as tp
+    import fb_py
+    import oracle_py
+    from idocp_b200 import problems as P
+    oracle_py.build()
+    fb_py.lib()
+    B = 2
+    pr = tp.TrottingProblem()
+    q0, v0 = P.anymal_initial_states(rank * B, B, q_nominal=pr.q0)
+    kkt = np.zeros(B)
+    for b in range(B):
+        o = pr.make_oracle(fb_py, q0=q0[b], v0=v0[b])
+        o.update_solution(0.0, q0[b], v0[b])
+        o.compute_kkt_residual(0.0, q0[b], v0[b])
+        kkt[b] = o.kkt_error()
+    gathered = [torch.zeros(B, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(gathered, torch.from_numpy(kkt))
+    if rank == 0:
+        out.put([g.numpy() for g in gathered])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_of_the_anymal_batch():
+    """bench.py --workload anymal_*: rank r owns instances [r B, (r+1) B) of the counter-based splitmix64 stream; the
+    union of two shards is the single-process batch (ANYmal OCPSolver, no data-path collective)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import anymal_problems as tp
+    import fb_py
+    import oracle_py
+    from idocp_b200 import problems as P
+    oracle_py.build()
+    fb_py.lib()
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 30100 + (os.getpid() % 500)
+    procs = [ctx.Process(target=_anymal_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    gathered = out.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    pr = tp.TrottingProblem()
+    q0, v0 = P.anymal_initial_states(0, 4, q_nominal=pr.q0)
+    assert np.allclose(np.linalg.norm(q0[:, 3:7], axis=1), 1.0, atol=1e-15)
+    assert np.all(np.abs(q0[:, :3] - pr.q0[:3]) <= 0.01) and np.all(np.abs(q0[:, 7:] - pr.q0[7:]) <= 0.02) and np.all(np.abs(v0) <= 0.1)
+    ref = []
+    for b in range(4):
+        o = pr.make_oracle(fb_py, q0=q0[b], v0=v0[b])
+        o.update_solution(0.0, q0[b], v0[b])
+        o.compute_kkt_residual(0.0, q0[b], v0[b])
+        ref.append(o.kkt_error())
+    assert np.array_equal(np.concatenate(gathered), np.array(ref))
