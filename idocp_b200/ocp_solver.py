@@ -150,6 +150,14 @@ class OCPSolver:
                 out.append(self.get(e, name))
         return out
 
+    def getStateFeedbackGain(self, time_stage):
+        """(Kq, Kv), each (B, 12, 18): du = Kq dq + Kv dv at grid stage `time_stage` (ocp_solver.cpp:103-113)."""
+        for e, el in enumerate(self._chain):
+            if el["kind"] == KIND_GRID and el["index"] == time_stage:
+                K = self.get(e, "K").reshape(self.B, 12, 36)
+                return K[:, :, :18].copy(), K[:, :, 18:].copy()
+        raise ValueError("time_stage outside the horizon")
+
     def chain(self):
         return self._chain
 

@@ -320,6 +320,25 @@ class OCPSolver {
     }
     return out;
   }
+  // getStateFeedbackGain(time_stage, Kq, Kv) (ocp_solver.cpp:103-113, riccati_recursion_solver.cpp:254-260): the LQR
+  // gain du = Kq dq + Kv dv of the last Riccati sweep at a grid stage, row-major 12 x 18 each
+  void getStateFeedbackGain(const int time_stage, std::vector<double>& Kq, std::vector<double>& Kv, const int instance = 0) {
+    const int n = discretize();
+    for (int e = 0; e < n; ++e) {
+      if (kind_[e] != 0 || index_[e] != time_stage) continue;
+      std::vector<double> buf(static_cast<size_t>(batch_) * 12 * 36);
+      detail::check(idocp_b200_fb_get(h_.get(), e, "K", buf.data()));
+      Kq.assign(12 * 18, 0.0);
+      Kv.assign(12 * 18, 0.0);
+      for (int r = 0; r < 12; ++r)
+        for (int c = 0; c < 18; ++c) {
+          Kq[r * 18 + c] = buf[static_cast<size_t>(instance) * 432 + r * 36 + c];
+          Kv[r * 18 + c] = buf[static_cast<size_t>(instance) * 432 + r * 36 + 18 + c];
+        }
+      return;
+    }
+    detail::die("invalid argument: time_stage outside the horizon");
+  }
   void sync() { detail::check(idocp_b200_fb_sync(h_.get())); }
   idocp_b200_fb_solver* handle() { return h_.get(); }
 

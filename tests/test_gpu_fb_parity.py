@@ -99,6 +99,8 @@ def test_large_batch_properties(fb, gpu_lib):
     hist = np.array(hist)
     assert np.all(np.isfinite(hist)) and np.all(hist[-1] < 1e-7)
     assert np.array_equal(hist[:, :8], hist[:, 8:16]) and np.array_equal(hist[:, :8], hist[:, -8:])
+    Kq, Kv = solver.getStateFeedbackGain(3)
+    assert Kq.shape == (B, 12, 18) and np.array_equal(Kq[:8], Kq[-8:]) and np.all(np.isfinite(Kv))
     e_mid = len(solver.chain()) // 2
     u = solver.get(e_mid, "u")
     assert np.array_equal(u[:8], u[-8:])
