@@ -70,11 +70,75 @@ inline void copyN(const VectorXd& v, double* dst, int n, const char* what) {
 }
 }  // namespace detail
 
-// a configuration-space cost whose reference is a function of time: q_ref(t) is sampled on the host per stage
-class ConfigurationReferenceBase {
+// Configuration-space costs of the floating-base robot.  The reference q_ref(t) (and v_ref(t)) is a host-side function
+// of the stage time in every one of the reference's classes; it is sampled per stage and call.
+class ConfigurationSpaceCostBase {
  public:
-  virtual ~ConfigurationReferenceBase() {}
+  ConfigurationSpaceCostBase() { std::memset(&w_, 0, sizeof(w_)); }
+  virtual ~ConfigurationSpaceCostBase() {}
   virtual void update_q_ref(const double t, VectorXd& q_ref) const = 0;
+  virtual VectorXd v_ref(const double t) const = 0;
+  void set_q_weight(const VectorXd& v) { detail::copyN(v, w_.q_weight, 18, "q_weight"); }
+  void set_v_weight(const VectorXd& v) { detail::copyN(v, w_.v_weight, 18, "v_weight"); }
+  void set_a_weight(const VectorXd& v) { detail::copyN(v, w_.a_weight, 18, "a_weight"); }
+  void set_qf_weight(const VectorXd& v) { detail::copyN(v, w_.qf_weight, 18, "qf_weight"); }
+  void set_vf_weight(const VectorXd& v) { detail::copyN(v, w_.vf_weight, 18, "vf_weight"); }
+  void set_qi_weight(const VectorXd& v) { detail::copyN(v, w_.qi_weight, 18, "qi_weight"); }
+  void set_vi_weight(const VectorXd& v) { detail::copyN(v, w_.vi_weight, 18, "vi_weight"); }
+  void set_dvi_weight(const VectorXd& v) { detail::copyN(v, w_.dvi_weight, 18, "dvi_weight"); }
+  const idocp_b200_fb_problem& weights() const { return w_; }
+ protected:
+  idocp_b200_fb_problem w_;
+};
+// user-defined references derive from this name, as from the reference's cost classes
+typedef ConfigurationSpaceCostBase ConfigurationReferenceBase;
+
+// cost/configuration_space_cost.hpp for the floating base: constant q_ref, v_ref
+class FloatingBaseConfigurationSpaceCost : public ConfigurationSpaceCostBase {
+ public:
+  explicit FloatingBaseConfigurationSpaceCost(const QuadrupedRobot&) : q_ref_(19), v_ref_(18) { q_ref_[6] = 1.0; }
+  void set_q_ref(const VectorXd& q) { if (q.size() != 19) detail::die("invalid size: q_ref.size() must be 19!"); q_ref_ = q; }
+  void set_v_ref(const VectorXd& v) { if (v.size() != 18) detail::die("invalid size: v_ref.size() must be 18!"); v_ref_ = v; }
+  void update_q_ref(const double, VectorXd& q_ref) const override { q_ref = q_ref_; }
+  VectorXd v_ref(const double) const override { return v_ref_; }
+ private:
+  VectorXd q_ref_, v_ref_;
+};
+
+// cost/time_varying_configuration_space_cost.hpp:98-118: the reference moves with v_ref between t_begin and t_end.
+// (integrateConfiguration(q_begin, v_ref, dt) on the free-flyer is evaluated for a base twist that is a pure
+// translation, which is what the reference's examples use; a general twist is rejected.)
+class TimeVaryingConfigurationSpaceCost : public ConfigurationSpaceCostBase {
+ public:
+  explicit TimeVaryingConfigurationSpaceCost(const QuadrupedRobot&) {}
+  void set_ref(const QuadrupedRobot&, const double t_begin, const double t_end, const VectorXd& q_begin, const VectorXd& v) {
+    if (t_begin >= t_end) detail::die("invalid argment: t_begin < t_end must be hold!");
+    if (q_begin.size() != 19) detail::die("invalid size: q_begin.size() must be 19!");
+    if (v.size() != 18) detail::die("invalid size: v.size() must be 18!");
+    if (v[3] != 0.0 || v[4] != 0.0 || v[5] != 0.0) detail::die("unsupported: the reference twist must not rotate the base");
+    t_begin_ = t_begin; t_end_ = t_end; q_begin_ = q_begin; v_ref_ = v;
+    q_end_ = moved(t_end - t_begin);
+  }
+  void update_q_ref(const double t, VectorXd& q_ref) const override {
+    if (t > t_begin_ && t < t_end_) q_ref = moved(t - t_begin_);
+    else if (t <= t_begin_) q_ref = q_begin_;
+    else q_ref = q_end_;
+  }
+  VectorXd v_ref(const double t) const override { return (t > t_begin_ && t < t_end_) ? v_ref_ : VectorXd::Zero(18); }
+ private:
+  VectorXd moved(const double dt) const {
+    VectorXd q = q_begin_;
+    // p += R(quat) * (v_lin dt); joints += v dt
+    const double x = q[3], y = q[4], z = q[5], w = q[6];
+    const double R[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                         2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                         2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)};
+    for (int i = 0; i < 3; ++i) q[i] += dt * (R[3 * i] * v_ref_[0] + R[3 * i + 1] * v_ref_[1] + R[3 * i + 2] * v_ref_[2]);
+    for (int j = 0; j < 12; ++j) q[7 + j] += dt * v_ref_[6 + j];
+    return q;
+  }
+  double t_begin_ = 0, t_end_ = 1;
+  VectorXd q_begin_, q_end_, v_ref_;
 };
 
 struct TrottingSwingAngles {
@@ -83,9 +147,9 @@ struct TrottingSwingAngles {
 };
 
 // trotting_configuration_space_cost.hpp:52-164
-class TrottingConfigurationSpaceCost : public ConfigurationReferenceBase {
+class TrottingConfigurationSpaceCost : public ConfigurationSpaceCostBase {
  public:
-  explicit TrottingConfigurationSpaceCost(const QuadrupedRobot&) { std::memset(&w_, 0, sizeof(w_)); }
+  explicit TrottingConfigurationSpaceCost(const QuadrupedRobot&) {}
   void set_ref(const double t_start, const double t_period, const VectorXd& q_standing, const double step_length,
                const TrottingSwingAngles& swing_angles) {
     if (q_standing.size() != 19) detail::die("invalid size: q_standing.size() must be 19!");
@@ -96,14 +160,6 @@ class TrottingConfigurationSpaceCost : public ConfigurationReferenceBase {
     v_ref_[0] = step_length / t_period;
     swing_ = swing_angles;
   }
-  void set_q_weight(const VectorXd& v) { detail::copyN(v, w_.q_weight, 18, "q_weight"); }
-  void set_v_weight(const VectorXd& v) { detail::copyN(v, w_.v_weight, 18, "v_weight"); }
-  void set_a_weight(const VectorXd& v) { detail::copyN(v, w_.a_weight, 18, "a_weight"); }
-  void set_qf_weight(const VectorXd& v) { detail::copyN(v, w_.qf_weight, 18, "qf_weight"); }
-  void set_vf_weight(const VectorXd& v) { detail::copyN(v, w_.vf_weight, 18, "vf_weight"); }
-  void set_qi_weight(const VectorXd& v) { detail::copyN(v, w_.qi_weight, 18, "qi_weight"); }
-  void set_vi_weight(const VectorXd& v) { detail::copyN(v, w_.vi_weight, 18, "vi_weight"); }
-  void set_dvi_weight(const VectorXd& v) { detail::copyN(v, w_.dvi_weight, 18, "dvi_weight"); }
   void update_q_ref(const double t, VectorXd& q_ref) const override {
     q_ref = q_standing_;
     if (t > t_start_) {
@@ -125,10 +181,8 @@ class TrottingConfigurationSpaceCost : public ConfigurationReferenceBase {
       }
     }
   }
-  const VectorXd& v_ref() const { return v_ref_; }
-  const idocp_b200_fb_problem& weights() const { return w_; }
+  VectorXd v_ref(const double) const override { return v_ref_; }
  private:
-  idocp_b200_fb_problem w_;
   double t_start_ = 0, t_period_ = 1, step_length_ = 0;
   VectorXd q_standing_, v_ref_;
   TrottingSwingAngles swing_;
@@ -157,12 +211,15 @@ class ContactForceCost {
 
 class HybridCostFunction {
  public:
+  void push_back(const std::shared_ptr<ConfigurationSpaceCostBase>& c) { config_ = c; }
   void push_back(const std::shared_ptr<TrottingConfigurationSpaceCost>& c) { config_ = c; }
+  void push_back(const std::shared_ptr<TimeVaryingConfigurationSpaceCost>& c) { config_ = c; }
+  void push_back(const std::shared_ptr<FloatingBaseConfigurationSpaceCost>& c) { config_ = c; }
   void push_back(const std::shared_ptr<ContactForceCost>& c) { force_ = c; }
-  const std::shared_ptr<TrottingConfigurationSpaceCost>& config() const { return config_; }
+  const std::shared_ptr<ConfigurationSpaceCostBase>& config() const { return config_; }
   const std::shared_ptr<ContactForceCost>& force() const { return force_; }
  private:
-  std::shared_ptr<TrottingConfigurationSpaceCost> config_;
+  std::shared_ptr<ConfigurationSpaceCostBase> config_;
   std::shared_ptr<ContactForceCost> force_;
 };
 
@@ -371,7 +428,8 @@ class OCPSolver {
     for (int e = 0; e < n; ++e) {
       cost_->config()->update_q_ref(t_[e], q_ref);
       const int kind = kind_[e] == 4 ? 0 : kind_[e];
-      detail::check(idocp_b200_fb_set_cost_reference(h_.get(), kind, index_[e], q_ref.data(), cost_->config()->v_ref().data()));
+      const VectorXd v_ref = cost_->config()->v_ref(t_[e]);
+      detail::check(idocp_b200_fb_set_cost_reference(h_.get(), kind, index_[e], q_ref.data(), v_ref.data()));
     }
   }
   void replicate(const VectorXd& q, const VectorXd& v) {

@@ -108,3 +108,32 @@ def test_anymal_trotting_example_reproduces_golden_convergence():
     assert len(kkt) == 26
     assert kkt == ref
     assert "CPU time per update" in out
+
+
+RUNNING_EXE = os.path.join(ROOT, "build", "anymal_running")
+
+
+def _build_running():
+    import __graft_entry__ as g
+    g.build_cuda()
+    os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)
+    lib = os.path.join(ROOT, "idocp_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "anymal_running.cpp"), "-L" + lib, "-lidocp_b200",
+                           "-Wl,-rpath," + lib, "-o", RUNNING_EXE])
+
+
+def test_anymal_running_example_compiles():
+    _build_running()
+
+
+@pytest.mark.gpu
+def test_anymal_running_example_reproduces_golden_convergence():
+    """examples/anymal_running.cpp = the reference's examples/anymal/anymal_running.cpp (T = 7, N = 240, 26 impulses, 14
+    lifts, flight phases, TimeVaryingConfigurationSpaceCost): first 8 iterations of instance 0 of a batch of 2."""
+    _build_running()
+    out = subprocess.run([RUNNING_EXE, "2", "8", "0"], capture_output=True, text=True, check=True).stdout
+    kkt = [float(x) for x in re.findall(r"KKT error(?: after iteration \d+)? = (\S+)", out)]
+    with open(os.path.join(GOLDEN, "anymal_running_golden.json")) as f:
+        ref = json.load(f)["kkt"]
+    assert kkt == ref

@@ -50,6 +50,26 @@ def main():
     with open(os.path.join(ROOT, "tests", "golden", "anymal_trotting_golden.json"), "w") as f:
         json.dump(rec, f, indent=1)
     print("anymal_trotting: KKT %.3e -> %.3e" % (rec["kkt"][0], rec["kkt"][-1]))
+    # examples/anymal/anymal_running.cpp, first 8 iterations (the example runs 350)
+    rp = ap.RunningProblem(10)
+    pts = np.zeros((4, 3))
+    lib.check(lib.L.idocp_b200_fb_contact_frame_positions(capi.dptr(np.ascontiguousarray(rp.q_begin)), capi.dptr(pts)))
+    rp.standing_points = pts
+    ocp = rp.make_oracle(fb_py)
+    ocp.set_threads(8)
+    rec = {"chain": [[c["kind"], c["index"], c["t"], c["dt"], c["dimf"], c["dimi"]] for c in ocp.chain()], "kkt": [], "primal": [], "dual": []}
+    ocp.compute_kkt_residual(0.0, rp.q0, rp.v0)
+    rec["kkt"].append(ocp.kkt_error())
+    for it in range(8):
+        assert ocp.update_solution(0.0, rp.q0, rp.v0) == 0
+        st = ocp.step_sizes()
+        rec["primal"].append(float(st[0]))
+        rec["dual"].append(float(st[1]))
+        ocp.compute_kkt_residual(0.0, rp.q0, rp.v0)
+        rec["kkt"].append(ocp.kkt_error())
+    with open(os.path.join(ROOT, "tests", "golden", "anymal_running_golden.json"), "w") as f:
+        json.dump(rec, f, indent=1)
+    print("anymal_running: KKT %.3e -> %.3e, %d stages" % (rec["kkt"][0], rec["kkt"][-1], len(rec["chain"])))
 
 
 if __name__ == "__main__":
