@@ -1267,19 +1267,31 @@ __global__ void __launch_bounds__(128, 4) k_fb_condense(FbArrays A, const FbLin*
 //  impulse twins)
 // =====================================================================================================
 struct FbRicWork {
-  // stage record (same order as FbKKT)
-  double Qxx[FB_NX * FB_NX], Qxu[FB_NX * FB_NV], Quu[FB_NV * FB_NV];
-  double Fqq6[36], Fqv6[36], Fqq_prev_inv[36], Fvq[FB_NV * FB_NV], Fvv[FB_NV * FB_NV], Fvu[FB_NV * FB_NU];
-  double lq[FB_NV], lv[FB_NV], lu[FB_NU], lu_passive[FB_NPASS], Fq[FB_NV], Fv[FB_NV];
+  // stage record: the blocks of FbKKT the recursion reads, Qxu / Quu reduced to their actuated columns (leading dimension NU)
+  double Qxx[FB_NX * FB_NX], Qxu[FB_NX * FB_NU], Quu[FB_NU * FB_NU];
+  double Fqq6[36], Fqv6[36], Fvq[FB_NV * FB_NV], Fvv[FB_NV * FB_NV], Fvu[FB_NV * FB_NU];
+  double lq[FB_NV], lv[FB_NV], lu[FB_NU], Fq[FB_NV], Fv[FB_NV];
   double Phix[FB_MAXF * FB_NX], Phiu[FB_MAXF * FB_NU], P[FB_MAXF];
-  // next factorisation and the one being built (same order as the P.. part of FbRic)
-  double nPqq[FB_NV * FB_NV], nPqv[FB_NV * FB_NV], nPvv[FB_NV * FB_NV], nsq[FB_NV], nsv[FB_NV];
+  // the factorisation (same order as FbRic): on entry to a stage Pqq / Pqv / Pvv still hold the NEXT stage's P, which is dead once
+  // the A^T P / B^T P products are formed, so the stage's own P is built in the same place
   double K[FB_NU * FB_NX], k[FB_NU], Pqq[FB_NV * FB_NV], Pqv[FB_NV * FB_NV], Pvv[FB_NV * FB_NV], sq[FB_NV], sv[FB_NV], cM[FB_MAXF * FB_NX],
       cm[FB_MAXF];
-  double AtPqq[FB_NV * FB_NV], AtPqv[FB_NV * FB_NV], AtPvq[FB_NV * FB_NV], AtPvv[FB_NV * FB_NV], BtPq[FB_NU * FB_NV], BtPv[FB_NU * FB_NV];
-  double GK[FB_NU * FB_NX], G[FB_NU * FB_NU], L[FB_NU * FB_NU], rd[FB_NU];
-  double Ginv[FB_NU * FB_NU], DGinv[FB_MAXF * FB_NU], Sm[FB_MAXF * FB_MAXF], Ls[FB_MAXF * FB_MAXF], rds[FB_MAXF], SinvDGinv[FB_MAXF * FB_NU];
-  double DtM[FB_NU * FB_NX], KtDtM[FB_NX * FB_NX];
+  double nsq[FB_NV], nsv[FB_NV];
+  // scratch whose lifetimes do not overlap shares storage
+  union {
+    struct { double AtPqq[FB_NV * FB_NV], AtPqv[FB_NV * FB_NV], AtPvq[FB_NV * FB_NV], AtPvv[FB_NV * FB_NV]; };   // until sq / sv
+    double KtDtM[FB_NX * FB_NX];                                                                                   // after sq / sv
+  };
+  union {
+    struct { double BtPq[FB_NU * FB_NV], BtPv[FB_NU * FB_NV]; };   // until lu is complete
+    double GK[FB_NU * FB_NX];                                      // factorizeRiccatiFactorization
+  };
+  double G[FB_NU * FB_NU], L[FB_NU * FB_NU], rd[FB_NU];
+  union {
+    struct { double Ginv[FB_NU * FB_NU], DGinv[FB_MAXF * FB_NU], Sm[FB_MAXF * FB_MAXF]; };   // gain computation
+    double DtM[FB_NU * FB_NX];                                                               // constrained tail
+  };
+  double Ls[FB_MAXF * FB_MAXF], rds[FB_MAXF], SinvDGinv[FB_MAXF * FB_NU];
   int info;
 };
 
@@ -1295,13 +1307,16 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
     FbRic& Rc = A.ric[(size_t)el.slot * A.B + b];
     FB_FOR(x, NV * NV) {
       const int r = x / NV, c = x - r * NV;
-      w.nPqq[x] = Kt.Qxx[r * NX + c];
-      w.nPvv[x] = Kt.Qxx[(NV + r) * NX + NV + c];
-      w.nPqv[x] = 0.0;
+      w.Pqq[x] = Kt.Qxx[r * NX + c];
+      w.Pvv[x] = Kt.Qxx[(NV + r) * NX + NV + c];
+      w.Pqv[x] = 0.0;
     }
-    if (tid < NV) { w.nsq[tid] = -Kt.lq[tid]; w.nsv[tid] = -Kt.lv[tid]; }
+    if (tid < NV) {
+      const double a = -Kt.lq[tid], c = -Kt.lv[tid];
+      w.nsq[tid] = a; w.sq[tid] = a; w.nsv[tid] = c; w.sv[tid] = c;
+    }
     __syncthreads();
-    fb_copy(Rc.Pqq, w.nPqq, 3 * NV * NV + 2 * NV);
+    fb_copy(Rc.Pqq, w.Pqq, 3 * NV * NV + 2 * NV);
   }
   for (int e = n - 2; e >= 0; --e) {
     const FbElem& el = A.elems[e];
@@ -1311,32 +1326,39 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
     const FbKKT& Kt = A.kkt[(size_t)el.slot * A.B + b];
     FbRic& Rc = A.ric[(size_t)el.slot * A.B + b];
     __syncthreads();
-    fb_copy(w.Qxx, Kt.Qxx, sizeof(FbKKT) / sizeof(double));
+    fb_copy(w.Qxx, Kt.Qxx, NX * NX);
+    FB_FOR(x, NX * NU) { const int r = x / NU, c = x - r * NU; w.Qxu[x] = Kt.Qxu[r * NV + NPASS + c]; }
+    FB_FOR(x, NU * NU) { const int r = x / NU, c = x - r * NU; w.Quu[x] = Kt.Quu[(NPASS + r) * NV + NPASS + c]; }
+    fb_copy(w.Fqq6, Kt.Fqq6, 72);
+    fb_copy(w.Fvq, Kt.Fvq, 2 * NV * NV + NV * NU);
+    fb_copy(w.lq, Kt.lq, 2 * NV + NU);
+    fb_copy(w.Fq, Kt.Fq, 2 * NV);
+    if (dimi > 0) fb_copy(w.Phix, Kt.Phix, MAXF * NX + MAXF * NU + MAXF);
     if (tid == 0) w.info = 0;
     __syncthreads();
     double* Qqq = w.Qxx;
     double* Qqv = w.Qxx + NV;
     double* Qvv = w.Qxx + NV * NX + NV;
     // ---- factorizeKKTMatrix ----
-    fb_mm<FBM_SET>(6, NV, 6, w.Fqq6, 1, 6, w.nPqq, NV, 1, w.AtPqq, NV);
-    fb_mm<FBM_SET>(6, NV, 6, w.Fqq6, 1, 6, w.nPqv, NV, 1, w.AtPqv, NV);
-    FB_FOR(x, (NV - 6) * NV) { w.AtPqq[6 * NV + x] = w.nPqq[6 * NV + x]; w.AtPqv[6 * NV + x] = w.nPqv[6 * NV + x]; }
+    fb_mm<FBM_SET>(6, NV, 6, w.Fqq6, 1, 6, w.Pqq, NV, 1, w.AtPqq, NV);
+    fb_mm<FBM_SET>(6, NV, 6, w.Fqq6, 1, 6, w.Pqv, NV, 1, w.AtPqv, NV);
+    FB_FOR(x, (NV - 6) * NV) { w.AtPqq[6 * NV + x] = w.Pqq[6 * NV + x]; w.AtPqv[6 * NV + x] = w.Pqv[6 * NV + x]; }
     if (!impulse) {
-      fb_mm<FBM_SET>(6, NV, 6, w.Fqv6, 1, 6, w.nPqq, NV, 1, w.AtPvq, NV);
-      fb_mm<FBM_SET>(6, NV, 6, w.Fqv6, 1, 6, w.nPqv, NV, 1, w.AtPvv, NV);
-      FB_FOR(x, (NV - 6) * NV) { w.AtPvq[6 * NV + x] = dt * w.nPqq[6 * NV + x]; w.AtPvv[6 * NV + x] = dt * w.nPqv[6 * NV + x]; }
+      fb_mm<FBM_SET>(6, NV, 6, w.Fqv6, 1, 6, w.Pqq, NV, 1, w.AtPvq, NV);
+      fb_mm<FBM_SET>(6, NV, 6, w.Fqv6, 1, 6, w.Pqv, NV, 1, w.AtPvv, NV);
+      FB_FOR(x, (NV - 6) * NV) { w.AtPvq[6 * NV + x] = dt * w.Pqq[6 * NV + x]; w.AtPvv[6 * NV + x] = dt * w.Pqv[6 * NV + x]; }
     }
     __syncthreads();
-    fb_mm<FBM_ADD>(NV, NV, NV, w.Fvq, 1, NV, w.nPqv, 1, NV, w.AtPqq, NV);
-    fb_mm<FBM_ADD>(NV, NV, NV, w.Fvq, 1, NV, w.nPvv, NV, 1, w.AtPqv, NV);
+    fb_mm<FBM_ADD>(NV, NV, NV, w.Fvq, 1, NV, w.Pqv, 1, NV, w.AtPqq, NV);
+    fb_mm<FBM_ADD>(NV, NV, NV, w.Fvq, 1, NV, w.Pvv, NV, 1, w.AtPqv, NV);
     if (!impulse) {
-      fb_mm<FBM_ADD>(NV, NV, NV, w.Fvv, 1, NV, w.nPqv, 1, NV, w.AtPvq, NV);
-      fb_mm<FBM_ADD>(NV, NV, NV, w.Fvv, 1, NV, w.nPvv, NV, 1, w.AtPvv, NV);
-      fb_mm<FBM_SET>(NU, NV, NV, w.Fvu, 1, NU, w.nPqv, 1, NV, w.BtPq, NV);
-      fb_mm<FBM_SET>(NU, NV, NV, w.Fvu, 1, NU, w.nPvv, NV, 1, w.BtPv, NV);
+      fb_mm<FBM_ADD>(NV, NV, NV, w.Fvv, 1, NV, w.Pqv, 1, NV, w.AtPvq, NV);
+      fb_mm<FBM_ADD>(NV, NV, NV, w.Fvv, 1, NV, w.Pvv, NV, 1, w.AtPvv, NV);
+      fb_mm<FBM_SET>(NU, NV, NV, w.Fvu, 1, NU, w.Pqv, 1, NV, w.BtPq, NV);
+      fb_mm<FBM_SET>(NU, NV, NV, w.Fvu, 1, NU, w.Pvv, NV, 1, w.BtPv, NV);
     } else {
-      fb_mm<FBM_SET>(NV, NV, NV, w.Fvv, 1, NV, w.nPqv, 1, NV, w.AtPvq, NV);
-      fb_mm<FBM_SET>(NV, NV, NV, w.Fvv, 1, NV, w.nPvv, NV, 1, w.AtPvv, NV);
+      fb_mm<FBM_SET>(NV, NV, NV, w.Fvv, 1, NV, w.Pqv, 1, NV, w.AtPvq, NV);
+      fb_mm<FBM_SET>(NV, NV, NV, w.Fvv, 1, NV, w.Pvv, NV, 1, w.AtPvv, NV);
     }
     __syncthreads();
     // Factorize F: the three blocks are independent of each other, each gets its terms in the reference's order
@@ -1353,9 +1375,9 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
     fb_mm<FBM_ADD>(NV, NV, NV, w.AtPqv, NV, 1, w.Fvv, NV, 1, Qqv, NX);
     fb_mm<FBM_ADD>(NV, NV, NV, w.AtPvv, NV, 1, w.Fvv, NV, 1, Qvv, NX);
     if (!impulse) {
-      fb_mm<FBM_ADD>(NV, NU, NV, w.AtPqv, NV, 1, w.Fvu, NU, 1, w.Qxu + NPASS, NV);
-      fb_mm<FBM_ADD>(NV, NU, NV, w.AtPvv, NV, 1, w.Fvu, NU, 1, w.Qxu + NV * NV + NPASS, NV);
-      fb_mm<FBM_ADD>(NU, NU, NV, w.BtPv, NV, 1, w.Fvu, NU, 1, w.Quu + NPASS * NV + NPASS, NV);
+      fb_mm<FBM_ADD>(NV, NU, NV, w.AtPqv, NV, 1, w.Fvu, NU, 1, w.Qxu, NU);
+      fb_mm<FBM_ADD>(NV, NU, NV, w.AtPvv, NV, 1, w.Fvu, NU, 1, w.Qxu + NV * NU, NU);
+      fb_mm<FBM_ADD>(NU, NU, NV, w.BtPv, NV, 1, w.Fvu, NU, 1, w.Quu, NU);
       if (tid < NU) {    // lu += BtPq Fq; lu += BtPv Fv; lu -= Fvu^T sv_next
         double acc = w.lu[tid];
         for (int l = 0; l < NV; ++l) acc = fma(w.BtPq[tid * NV + l], w.Fq[l], acc);
@@ -1365,9 +1387,9 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
       }
     }
     __syncthreads();
-    const double* Qxu = w.Qxu + NPASS;   // 36 x 12 block, leading dimension NV
+    const double* Qxu = w.Qxu;   // 36 x 12, leading dimension NU
     if (!impulse) {
-      FB_FOR(x, NU * NU) { const int r = x / NU, c = x - r * NU; w.G[x] = w.Quu[(NPASS + r) * NV + NPASS + c]; }
+      FB_FOR(x, NU * NU) w.G[x] = w.Quu[x];
       __syncthreads();
       if (tid < 32) {
         const int info = fb_llt_warp(w.G, NU, NU, w.L, NU, w.rd);
@@ -1378,7 +1400,7 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
         // K = -G^-1 Qxu^T, k = -G^-1 lu: one right-hand side per thread
         if (tid < NX) {
           double col[FB_NU];
-          for (int r = 0; r < NU; ++r) col[r] = Qxu[tid * NV + r];
+          for (int r = 0; r < NU; ++r) col[r] = Qxu[tid * NU + r];
           fb_llt_solve_n<FB_NU>(w.L, NU, w.rd, col, 1);
           for (int r = 0; r < NU; ++r) w.K[r * NX + tid] = -col[r];
         } else if (tid == NX) {
@@ -1413,7 +1435,7 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
         __syncthreads();
         fb_mm<FBM_SUB>(NU, NU, dimi, w.SinvDGinv, 1, NU, w.DGinv, NU, 1, w.Ginv, NU);
         __syncthreads();
-        fb_mm<FBM_SET>(NU, NX, NU, w.Ginv, NU, 1, Qxu, 1, NV, w.K, NX);
+        fb_mm<FBM_SET>(NU, NX, NU, w.Ginv, NU, 1, Qxu, 1, NU, w.K, NX);
         fb_mv<FBM_SET>(NU, NU, w.Ginv, NU, 1, w.lu, w.k);
         __syncthreads();
         FB_FOR(x, NU * NX) w.K[x] = -w.K[x];
@@ -1430,7 +1452,7 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
           fb_llt_solve(w.Ls, MAXF, w.rds, dimi, w.cm, 1);
         }
         __syncthreads();
-        fb_mm<FBM_SUB>(dimi, NX, NU, w.SinvDGinv, NU, 1, Qxu, 1, NV, w.cM, NX);
+        fb_mm<FBM_SUB>(dimi, NX, NU, w.SinvDGinv, NU, 1, Qxu, 1, NU, w.cM, NX);
         fb_mv<FBM_SUB>(dimi, NU, w.SinvDGinv, NU, 1, w.lu, w.cm);
         __syncthreads();
       }
@@ -1442,7 +1464,7 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
       w.Pqv[x] = Qqv[r * NX + c];
       w.Pvv[x] = Qvv[r * NX + c];
     }
-    if (!impulse) fb_mm<FBM_SET>(NU, NX, NU, w.Quu + NPASS * NV + NPASS, NV, 1, w.K, NX, 1, w.GK, NX);
+    if (!impulse) fb_mm<FBM_SET>(NU, NX, NU, w.Quu, NU, 1, w.K, NX, 1, w.GK, NX);
     __syncthreads();
     if (!impulse) {
       fb_mm<FBM_SUB>(NV, NV, NU, w.K, 1, NX, w.GK, NX, 1, w.Pqq, NV);
@@ -1473,7 +1495,7 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
       for (int l = 0; l < NV; ++l) acc = fma(-w.AtPqv[j * NV + l], w.Fv[l], acc);
       acc -= w.lq[j];
       if (!impulse)
-        for (int l = 0; l < NU; ++l) acc = fma(-w.Qxu[j * NV + NPASS + l], w.k[l], acc);
+        for (int l = 0; l < NU; ++l) acc = fma(-w.Qxu[j * NU + l], w.k[l], acc);
       w.sq[j] = acc;
     }
     if (tid >= 96 && tid < 96 + NV) {   // sv
@@ -1495,7 +1517,7 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
       for (int l = 0; l < NV; ++l) acc = fma(-w.AtPvv[j * NV + l], w.Fv[l], acc);
       acc -= w.lv[j];
       if (!impulse)
-        for (int l = 0; l < NU; ++l) acc = fma(-w.Qxu[(NV + j) * NV + NPASS + l], w.k[l], acc);
+        for (int l = 0; l < NU; ++l) acc = fma(-w.Qxu[(NV + j) * NU + l], w.k[l], acc);
       w.sv[j] = acc;
     }
     __syncthreads();
@@ -1514,9 +1536,9 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
       fb_mv<FBM_SUB>(NV, dimi, w.Phix + NV, 1, NX, w.cm, w.sv);
       __syncthreads();
     }
-    // store the factorisation, make it the "next" one
+    // store the factorisation; it stays in place as the "next" one
     fb_copy(Rc.K, w.K, sizeof(FbRic) / sizeof(double));
-    fb_copy(w.nPqq, w.Pqq, 3 * NV * NV + 2 * NV);
+    if (tid < NV) { w.nsq[tid] = w.sq[tid]; w.nsv[tid] = w.sv[tid]; }
     if (tid == 0 && w.info) {
       FbDir& Dr = A.dir[(size_t)el.slot * A.B + b];
       if (Dr.info == 0.0) Dr.info = (double)w.info;
