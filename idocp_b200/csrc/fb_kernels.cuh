@@ -99,39 +99,40 @@ struct FbArrays {
 #define FB_FOR(i, n) for (int i = threadIdx.x; i < (n); i += blockDim.x)
 enum { FBM_SET = 0, FBM_ADD = 1, FBM_SUB = 2 };
 
-// C (m x n, ldc) {=, +=, -=} A (m x k) B (k x n): one ascending-k fma chain per element.  A thread owns a 2 x 2 tile
-// of C: four independent chains in flight (the chains are latency-bound otherwise) and half the shared-memory
-// loads per fma; the chain of every element is unchanged, so the bits do not depend on the tiling.
+// C (m x n) {=, +=, -=} A (m x k) B (k x n): one ascending-k fma chain per element.  A thread owns a 2 x 2 tile of C
+// -- rows (i, i + ceil(m/2)), columns (j, j + ceil(n/2)), so that neighbouring lanes read neighbouring columns of B
+// (no shared-memory bank conflicts) and write neighbouring elements of C: four independent chains in flight (the
+// chains are latency-bound otherwise) and half the shared-memory loads per fma.  The chain of every element is
+// unchanged, so the bits do not depend on the tiling.  FBM_SET starts a chain with the plain product a_0 b_0;
+// FBM_ADD / FBM_SUB start it from init(i, j); store(i, j, value) receives the finished element.
 // The caller separates dependent calls with __syncthreads().
-template <int MODE>
-__device__ __forceinline__ void fb_mm(int m, int n, int k, const double* __restrict__ A, int ars, int acs, const double* __restrict__ B,
-                                      int brs, int bcs, double* C, int ldc) {
+template <int MODE, class Init, class Store>
+__device__ __forceinline__ void fb_mm_f(int m, int n, int k, const double* __restrict__ A, int ars, int acs, const double* __restrict__ B,
+                                        int brs, int bcs, Init init, Store store) {
   const int tm = (m + 1) >> 1, tn = (n + 1) >> 1, total = tm * tn;
   for (int t = threadIdx.x; t < total; t += blockDim.x) {
-    const int ti = t / tn, tj = t - ti * tn;
-    const int i0 = 2 * ti, j0 = 2 * tj;
-    const bool hi = i0 + 1 < m, hj = j0 + 1 < n;
+    const int i0 = t / tn, j0 = t - i0 * tn;
+    const int i1 = i0 + tm, j1 = j0 + tn;
+    const bool hi = i1 < m, hj = j1 < n;
     const double* a0 = A + i0 * ars;
-    const double* a1 = A + (hi ? i0 + 1 : i0) * ars;
+    const double* a1 = A + (hi ? i1 : i0) * ars;
     const double* b0 = B + j0 * bcs;
-    const double* b1 = B + (hj ? j0 + 1 : j0) * bcs;
+    const double* b1 = B + (hj ? j1 : j0) * bcs;
     double c00, c01, c10, c11;
     int l0 = 0;
     if (MODE == FBM_SET) {
       if (k == 0) {
-        C[i0 * ldc + j0] = 0.0;
-        if (hj) C[i0 * ldc + j0 + 1] = 0.0;
-        if (hi) { C[(i0 + 1) * ldc + j0] = 0.0; if (hj) C[(i0 + 1) * ldc + j0 + 1] = 0.0; }
-        continue;
+        c00 = c01 = c10 = c11 = 0.0;
+      } else {
+        const double x0 = a0[0], x1 = a1[0], y0 = b0[0], y1 = b1[0];
+        c00 = x0 * y0; c01 = x0 * y1; c10 = x1 * y0; c11 = x1 * y1;
+        l0 = 1;
       }
-      const double x0 = a0[0], x1 = a1[0], y0 = b0[0], y1 = b1[0];
-      c00 = x0 * y0; c01 = x0 * y1; c10 = x1 * y0; c11 = x1 * y1;
-      l0 = 1;
     } else {
-      c00 = C[i0 * ldc + j0];
-      c01 = hj ? C[i0 * ldc + j0 + 1] : 0.0;
-      c10 = hi ? C[(i0 + 1) * ldc + j0] : 0.0;
-      c11 = (hi && hj) ? C[(i0 + 1) * ldc + j0 + 1] : 0.0;
+      c00 = init(i0, j0);
+      c01 = hj ? init(i0, j1) : 0.0;
+      c10 = hi ? init(i1, j0) : 0.0;
+      c11 = (hi && hj) ? init(i1, j1) : 0.0;
     }
     for (int l = l0; l < k; ++l) {
       double x0 = a0[l * acs], x1 = a1[l * acs];
@@ -139,10 +140,16 @@ __device__ __forceinline__ void fb_mm(int m, int n, int k, const double* __restr
       if (MODE == FBM_SUB) { x0 = -x0; x1 = -x1; }
       c00 = fma(x0, y0, c00); c01 = fma(x0, y1, c01); c10 = fma(x1, y0, c10); c11 = fma(x1, y1, c11);
     }
-    C[i0 * ldc + j0] = c00;
-    if (hj) C[i0 * ldc + j0 + 1] = c01;
-    if (hi) { C[(i0 + 1) * ldc + j0] = c10; if (hj) C[(i0 + 1) * ldc + j0 + 1] = c11; }
+    store(i0, j0, c00);
+    if (hj) store(i0, j1, c01);
+    if (hi) { store(i1, j0, c10); if (hj) store(i1, j1, c11); }
   }
+}
+template <int MODE>
+__device__ __forceinline__ void fb_mm(int m, int n, int k, const double* __restrict__ A, int ars, int acs, const double* __restrict__ B,
+                                      int brs, int bcs, double* C, int ldc) {
+  fb_mm_f<MODE>(m, n, k, A, ars, acs, B, brs, bcs, [=](int i, int j) { return C[i * ldc + j]; },
+                [=](int i, int j, double v) { C[i * ldc + j] = v; });
 }
 template <int MODE>
 __device__ __forceinline__ void fb_mv(int m, int k, const double* A, int ars, int acs, const double* x, double* y) {
@@ -1148,11 +1155,11 @@ __global__ void __launch_bounds__(128, 4) k_fb_condense(FbArrays A, const FbLin*
     FB_FOR(x, dimf * dimf) { const int r = x / dimf, c = x - r * dimf; w.MJtJinv[(n + r) * ld + n + c] = -w.s.f.Si[x]; }
     fb_mm<FBM_SET>(n, dimf, dimf, w.s.f.JMi, 1, n, w.s.f.Si, dimf, 1, w.MJtJinv + n, ld);     // TR = (J Minv)^T S^-1
     __syncthreads();
-    FB_FOR(x, n * n) {                                                                          // TL = Minv - TR (J Minv)
-      const int r = x / n, c = x - r * n;
-      double acc = w.s.f.Minv[x];
-      for (int j = 0; j < dimf; ++j) acc = fma(-w.MJtJinv[r * ld + n + j], w.s.f.JMi[j * n + c], acc);
-      w.MJtJinv[r * ld + c] = acc;
+    {                                                                                           // TL = Minv - TR (J Minv)
+      const double* Minv = w.s.f.Minv;
+      double* TL = w.MJtJinv;
+      fb_mm_f<FBM_SUB>(n, n, dimf, w.MJtJinv + n, ld, 1, w.s.f.JMi, n, 1, [=](int r, int c) { return Minv[r * n + c]; },
+                       [=](int r, int c, double v) { TL[r * ld + c] = v; });
     }
     FB_FOR(x, dimf * n) { const int r = x / n, c = x - r * n; w.MJtJinv[(n + r) * ld + c] = w.MJtJinv[c * ld + n + r]; }   // BL = TR^T
     __syncthreads();
@@ -1177,14 +1184,16 @@ __global__ void __launch_bounds__(128, 4) k_fb_condense(FbArrays A, const FbLin*
   __syncthreads();
   // Qxx -= MJ_dIDC^T Qafqv, starting from the sparse cost / constraint Hessian; the Qvq block is never read
   // (the Riccati sweep rebuilds it from Qqv, backward_riccati_recursion_factorizer.hxx:93) and is left untouched
-  FB_FOR(x, NX * NX) {
-    const int r = x / NX, c = x - r * NX;
-    if (r >= NV && c < NV) continue;
-    double acc = 0.0;
-    if (r < 6 && c < 6) acc = w.Qqq6[6 * r + c];
-    else if (r == c) acc = r < NV ? w.Qqq_d[r] : w.Qvv_d[r - NV];
-    for (int l = 0; l < nvf; ++l) acc = fma(-w.MJ_dIDC[l * NX + r], Qafqv[l * NX + c], acc);
-    Kt.Qxx[x] = acc;
+  {
+    const double *Qqq6 = w.Qqq6, *Qqq_d = w.Qqq_d, *Qvv_d = w.Qvv_d;
+    double* Qxx = Kt.Qxx;
+    fb_mm_f<FBM_SUB>(NX, NX, nvf, w.MJ_dIDC, 1, NX, Qafqv, NX, 1,
+                     [=](int r, int c) {
+                       if (r < 6 && c < 6) return Qqq6[6 * r + c];
+                       if (r == c) return r < NV ? Qqq_d[r] : Qvv_d[r - NV];
+                       return 0.0;
+                     },
+                     [=](int r, int c, double v) { if (!(r >= NV && c < NV)) Qxx[r * NX + c] = v; });
   }
   if (tid < NV) {
     double acc = w.lq[tid];
@@ -1197,17 +1206,13 @@ __global__ void __launch_bounds__(128, 4) k_fb_condense(FbArrays A, const FbLin*
     Kt.lv[j] = acc;
   }
   if (!impulse) {
-    FB_FOR(x, NX * NV) {
-      const int r = x / NV, c = x - r * NV;
-      double acc = 0.0;
-      for (int l = 0; l < nvf; ++l) acc = fma(-w.MJ_dIDC[l * NX + r], Qafu[l * NV + c], acc);
-      Kt.Qxu[x] = acc;
-    }
-    FB_FOR(x, NV * NV) {
-      const int r = x / NV, c = x - r * NV;
-      double acc = (r == c && r >= NPASS) ? w.Quu_d[r - NPASS] : 0.0;
-      for (int l = 0; l < nvf; ++l) acc = fma(w.MJtJinv[r * NVF + l], Qafu[l * NV + c], acc);
-      Kt.Quu[x] = acc;
+    {
+      const double* Quu_d = w.Quu_d;
+      double *Qxu = Kt.Qxu, *Quu = Kt.Quu;
+      fb_mm_f<FBM_SUB>(NX, NV, nvf, w.MJ_dIDC, 1, NX, Qafu, NV, 1, [](int, int) { return 0.0; },
+                       [=](int r, int c, double v) { Qxu[r * NV + c] = v; });
+      fb_mm_f<FBM_ADD>(NV, NV, nvf, w.MJtJinv, NVF, 1, Qafu, NV, 1, [=](int r, int c) { return (r == c && r >= NPASS) ? Quu_d[r - NPASS] : 0.0; },
+                       [=](int r, int c, double v) { Quu[r * NV + c] = v; });
     }
     if (tid >= 64 && tid < 64 + NV) {
       const int j = tid - 64;
@@ -1234,17 +1239,12 @@ __global__ void __launch_bounds__(128, 4) k_fb_condense(FbArrays A, const FbLin*
   fb_copy(Kt.Fqq6, w.Fqq6, 3 * 36);   // Fqq6, Fqv6, Fqq_prev_inv
   // ---- condenseSwitchingConstraint ----
   if (dimi > 0) {
-    FB_FOR(x, dimi * NX) {
-      const int r = x / NX, c = x - r * NX;
-      double acc = w.Phix[x];
-      for (int l = 0; l < NV; ++l) acc = fma(-w.Phia[r * NV + l], w.MJ_dIDC[l * NX + c], acc);
-      Kt.Phix[x] = acc;
-    }
-    FB_FOR(x, dimi * NU) {
-      const int r = x / NU, c = x - r * NU;
-      double acc = w.Phia[r * NV] * w.MJtJinv[NPASS + c];
-      for (int l = 1; l < NV; ++l) acc = fma(w.Phia[r * NV + l], w.MJtJinv[l * NVF + NPASS + c], acc);
-      Kt.Phiu[x] = acc;
+    {
+      const double* Phix0 = w.Phix;
+      double* Phix = Kt.Phix;
+      fb_mm_f<FBM_SUB>(dimi, NX, NV, w.Phia, NV, 1, w.MJ_dIDC, NX, 1, [=](int r, int c) { return Phix0[r * NX + c]; },
+                       [=](int r, int c, double v) { Phix[r * NX + c] = v; });
+      fb_mm<FBM_SET>(dimi, NU, NV, w.Phia, NV, 1, w.MJtJinv + NPASS, NVF, 1, Kt.Phiu, NU);
     }
     if (tid < dimi) {
       double acc = w.P[tid];
