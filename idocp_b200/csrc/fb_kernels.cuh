@@ -97,6 +97,7 @@ struct FbArrays {
 #define FB_LS_FILTER_CAP 256
 
 #define FB_FOR(i, n) for (int i = threadIdx.x; i < (n); i += blockDim.x)
+#define FB_COMPILER_FENCE() asm volatile("" ::: "memory")
 enum { FBM_SET = 0, FBM_ADD = 1, FBM_SUB = 2 };
 
 // C (m x n) {=, +=, -=} A (m x k) B (k x n): one ascending-k fma chain per element.  A thread owns a 2 x 2 tile of C
@@ -161,60 +162,150 @@ __device__ inline double fb_sqnorm(const double* x, int n) {
   return acc;
 }
 __device__ inline void fb_copy(double* dst, const double* src, int n) { FB_FOR(i, n) dst[i] = src[i]; }
+// HBM record -> shared memory by a 128-thread CTA: ALL of a thread's loads are issued before its first store.  (A plain copy
+// loop through generic pointers keeps load -> store -> load order, i.e. one DRAM round trip per element and thread.)
+// index(x) maps the destination element to the source element.
+template <int N, class Index>
+__device__ __forceinline__ void fb_load_f(double* dst, const double* __restrict__ src, Index index) {
+  constexpr int R = (N + 127) / 128;
+  double r[R];
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const int x = threadIdx.x + i * 128;
+    r[i] = x < N ? __ldg(src + index(x)) : 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const int x = threadIdx.x + i * 128;
+    if (x < N) dst[x] = r[i];
+  }
+}
+template <int N>
+__device__ __forceinline__ void fb_load(double* dst, const double* __restrict__ src) {
+  fb_load_f<N>(dst, src, [](int x) { return x; });
+}
 __device__ inline void fb_zero(double* dst, int n) { FB_FOR(i, n) dst[i] = 0.0; }
 
-// Cholesky of an n x n matrix (n <= 32) by ONE warp, right-looking and IN PLACE on the lower triangle of A: lane i
-// owns row i; after column k the lanes below update their own trailing entries with independent fmas (no dependent
-// chain longer than one fma per step).  Every element still receives its updates in ascending k, so the bits equal
-// the serial left-looking form of the oracle.  L[j*ldl + i] = L_ij (i >= j), rd[k] = 1/L_kk.
-__device__ inline int fb_llt_warp(double* A, int lda, int n, double* L, int ldl, double* rd) {
-  const int lane = threadIdx.x & 31;
-  int info = 0;
+// Cholesky of an n x n matrix by the WHOLE CTA (128 threads), right-looking, n (n + 1) / 2 <= 128 E.  Every element of the
+// lower triangle is owned by one thread and lives in a register for the whole factorisation.  Column k: the owner of
+// (k, k) takes the square root and the reciprocal while the owners of (i, k) publish their finished entries; after ONE
+// barrier every owner of a trailing element reads the two entries and the reciprocal, forms the two multipliers and
+// applies its fma -- no dependent chain, no load -> store ordering, and a rolled loop (the fully unrolled register /
+// shuffle form of this ran out of instruction cache).  Every element receives its updates in ascending k and
+// L_ik = A_ik * (1 / L_kk), so the bits equal the serial left-looking form of the oracle.  A is only read.
+// L[j*ldl + i] = L_ij (i >= j), rd[k] = 1 / L_kk; *info = code + first failing pivot + 1 unless *info is set already.
+template <int E>
+__device__ __forceinline__ void fb_llt_cta(const double* A, int lda, int n, double* L, int ldl, double* rd, int* info, int code) {
+  const int total = n * (n + 1) / 2;
+  int ei[E], ej[E];
+  double a[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int x = threadIdx.x + e * 128;
+    ei[e] = -1; ej[e] = -1; a[e] = 0.0;
+    if (x < total) {
+      int i = 0;
+      while ((i + 1) * (i + 2) / 2 <= x) ++i;
+      ei[e] = i; ej[e] = x - i * (i + 1) / 2;
+      a[e] = A[i * lda + ej[e]];
+    }
+  }
   for (int k = 0; k < n; ++k) {
-    if (lane == k) {
-      double x = A[k * lda + k];
-      if (!(x > 0.0)) info = k + 1;
-      x = sqrt(x);
-      L[k * ldl + k] = x;
-      rd[k] = 1.0 / x;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      if (ej[e] == k) {
+        if (ei[e] == k) {
+          const double x = sqrt(a[e]);
+          if (!(a[e] > 0.0) && *info == 0) *info = code + k + 1;
+          L[k * ldl + k] = x;
+          rd[k] = 1.0 / x;
+        } else {
+          L[k * ldl + ei[e]] = a[e];   // still unscaled
+        }
+      }
     }
-    __syncwarp();
-    if (lane > k && lane < n) L[k * ldl + lane] = A[lane * lda + k] * rd[k];
-    __syncwarp();
-    if (lane > k && lane < n) {
-      const double lik = L[k * ldl + lane];
-      for (int j = k + 1; j <= lane; ++j) A[lane * lda + j] = fma(-lik, L[k * ldl + j], A[lane * lda + j]);
+    __syncthreads();
+    const double r = rd[k];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      if (ej[e] > k) {
+        const double lik = L[k * ldl + ei[e]] * r, ljk = L[k * ldl + ej[e]] * r;
+        a[e] = fma(-lik, ljk, a[e]);
+      }
     }
   }
-  __syncwarp();
-  for (int k = 0; k < n; ++k) {   // first failing pivot over the lanes
-    const int v = __shfl_sync(0xffffffffu, info, k);
-    if (v) return v;
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < E; ++e)
+    if (ej[e] >= 0 && ei[e] > ej[e]) L[ej[e] * ldl + ei[e]] *= rd[ej[e]];
+  __syncthreads();
+}
+// X := (L L^T)^-1 X for an n x m block of right-hand sides (X[i*ldx + c]) by the whole CTA, n m <= 128 E: every entry is owned
+// by one thread and lives in a register; step j: the owners of row j scale and publish it, after one barrier the
+// other rows apply their fma.  Forward: entry i receives its terms in ascending j; backward: in descending j -- the
+// arithmetic of fb_llt_solve_n / the oracle, element by element.
+template <int E>
+__device__ __forceinline__ void fb_llt_solve_cta(const double* L, int ldl, const double* rd, int n, double* X, int ldx, int m) {
+  const int total = n * m;
+  int ei[E], ec[E];
+  double y[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int x = threadIdx.x + e * 128;
+    ei[e] = -1; ec[e] = 0; y[e] = 0.0;
+    if (x < total) { ei[e] = x / m; ec[e] = x - ei[e] * m; y[e] = X[ei[e] * ldx + ec[e]]; }
   }
-  return 0;
+  for (int j = 0; j < n; ++j) {
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (ei[e] == j) { y[e] *= rd[j]; X[j * ldx + ec[e]] = y[e]; }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (ei[e] > j) y[e] = fma(-L[j * ldl + ei[e]], X[j * ldx + ec[e]], y[e]);
+  }
+  for (int j = n - 1; j >= 0; --j) {
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (ei[e] == j) { y[e] *= rd[j]; X[j * ldx + ec[e]] = y[e]; }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (ei[e] >= 0 && ei[e] < j) y[e] = fma(-L[ei[e] * ldl + j], X[j * ldx + ec[e]], y[e]);
+  }
+  __syncthreads();
 }
 // x := (L L^T)^-1 x for one right-hand side (stride incx) by the calling thread, in place and column-oriented: as soon
 // as x_j is known every remaining entry is updated by an independent fma (no dependent chain across i).
 // Forward: entry i receives its terms in ascending j; backward: in descending j (the oracle's order).
 template <int N>
-__device__ __forceinline__ void fb_llt_solve_n(const double* __restrict__ L, int ldl, const double* __restrict__ rd, double* x, int incx) {
+__device__ __forceinline__ void fb_llt_solve_n(const double* __restrict__ L, int ldl, const double* __restrict__ rd, double* x, int incx,
+                                               int n = N) {
+  // volatile: the loads stay in program order; hoisting all N (N - 1) / 2 of them ahead of the chain spills
+  const volatile double* Lv = L;
   double y[N];
 #pragma unroll
-  for (int i = 0; i < N; ++i) y[i] = x[i * incx];
+  for (int i = 0; i < N; ++i) y[i] = i < n ? x[i * incx] : 0.0;
 #pragma unroll
   for (int j = 0; j < N; ++j) {
-    y[j] *= rd[j];
+    if (j < n) {
+      y[j] *= rd[j];
 #pragma unroll
-    for (int i = j + 1; i < N; ++i) y[i] = fma(-L[j * ldl + i], y[j], y[i]);
+      for (int i = j + 1; i < N; ++i)
+        if (i < n) y[i] = fma(-Lv[j * ldl + i], y[j], y[i]);
+    }
   }
 #pragma unroll
   for (int j = N - 1; j >= 0; --j) {
-    y[j] *= rd[j];
+    if (j < n) {
+      y[j] *= rd[j];
 #pragma unroll
-    for (int i = 0; i < j; ++i) y[i] = fma(-L[i * ldl + j], y[j], y[i]);
+      for (int i = 0; i < j; ++i) y[i] = fma(-Lv[i * ldl + j], y[j], y[i]);
+    }
   }
 #pragma unroll
-  for (int i = 0; i < N; ++i) x[i * incx] = y[i];
+  for (int i = 0; i < N; ++i)
+    if (i < n) x[i * incx] = y[i];
 }
 // same arithmetic for a run-time n (row-oriented, in place)
 __device__ __noinline__ void fb_llt_solve(const double* L, int ldl, const double* rd, int n, double* x, int incx) {
@@ -1071,6 +1162,25 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
 //   condenseImpulseDynamics (impulse_dynamics_forward_euler.hxx:64-105), condenseSwitchingConstraint (:194-200).
 //   Results go straight to the HBM records of the Riccati sweep (FbKKT) and of the expansion (FbExp).
 // =====================================================================================================
+// Optional per-phase cycle counters of the two CTA-level kernels (tools/fb_phase_clocks.py builds a variant library with
+// -DFB_PHASE_CLOCKS; the product library carries none of this).
+#ifdef FB_PHASE_CLOCKS
+__device__ unsigned long long g_fb_phase[2][32];
+#define FB_PHASE_BEGIN() long long fb_t_prev = clock64()
+#define FB_PHASE(kernel, i)                                                               \
+  do {                                                                                    \
+    __syncthreads();                                                                      \
+    if (threadIdx.x == 0) {                                                               \
+      const long long t = clock64();                                                      \
+      atomicAdd(&g_fb_phase[kernel][i], (unsigned long long)(t - fb_t_prev));             \
+      fb_t_prev = t;                                                                      \
+    }                                                                                     \
+  } while (0)
+#else
+#define FB_PHASE_BEGIN()
+#define FB_PHASE(kernel, i)
+#endif
+
 struct FbDenseWork {
   double IDC[FB_NVF], dIDCdqv[FB_NVF * FB_NX], Mm[FB_NV * FB_NV], dCda[FB_MAXF * FB_NV];
   double lq[FB_NV], lv[FB_NV], la[FB_NV], lf[FB_MAXF], lu_passive[FB_NPASS], lu[FB_NU], Fq[FB_NV], Fv[FB_NV], P[FB_MAXF];
@@ -1116,42 +1226,30 @@ __global__ void __launch_bounds__(128, 4) k_fb_condense(FbArrays A, const FbLin*
   const int dimf = el.dimf, nvf = NV + dimf, dimi = el.sw ? el.dimi : 0;
   FbExp& Ex = A.exp[rec];
   FbDir& Dr = A.dir[rec];
-  fb_copy(w.IDC, L.IDC, sizeof(FbLin) / sizeof(double));
+  FB_PHASE_BEGIN();
+  fb_load<sizeof(FbLin) / sizeof(double)>(w.IDC, L.IDC);
   if (tid == 0) w.info = 0;
   __syncthreads();
+  FB_PHASE(0, 0);
   // ---- MJtJinv = [[M, J^T], [J, 0]]^-1 by dense Cholesky ----
   {
     const int n = NV, ld = NVF;
-    if (tid < 32) {
-      const int info = fb_llt_warp(w.Mm, n, n, w.s.f.L, n, w.s.f.rd);
-      if (tid == 0 && info && !w.info) w.info = info;
-    }
-    __syncthreads();
-    if (tid < n) {
-      for (int r = 0; r < n; ++r) w.s.f.Minv[r * n + tid] = (r == tid) ? 1.0 : 0.0;
-#ifdef FB_MINV_REG
-      fb_llt_solve_n<FB_NV>(w.s.f.L, n, w.s.f.rd, w.s.f.Minv + tid, n);
-#else
-      fb_llt_solve(w.s.f.L, n, w.s.f.rd, n, w.s.f.Minv + tid, n);
-#endif
-    }
-    __syncthreads();
+    FB_FOR(x, n * n) { const int r = x / n; w.s.f.Minv[x] = (x - r * n == r) ? 1.0 : 0.0; }
+    fb_llt_cta<2>(w.Mm, n, n, w.s.f.L, n, w.s.f.rd, &w.info, 0);
+    FB_PHASE(0, 1);
+    fb_llt_solve_cta<3>(w.s.f.L, n, w.s.f.rd, n, w.s.f.Minv, n, n);
+    FB_PHASE(0, 2);
     fb_mm<FBM_SET>(dimf, n, n, w.dCda, n, 1, w.s.f.Minv, n, 1, w.s.f.JMi, n);
     __syncthreads();
     fb_mm<FBM_SET>(dimf, dimf, n, w.s.f.JMi, n, 1, w.dCda, 1, n, w.s.f.Sm, dimf);
     __syncthreads();
+    FB_PHASE(0, 3);
     if (dimf > 0) {
-      if (tid < 32) {
-        const int info = fb_llt_warp(w.s.f.Sm, dimf, dimf, w.s.f.Ls, dimf, w.s.f.rds);
-        if (tid == 0 && info && !w.info) w.info = 100 + info;
-      }
-      __syncthreads();
-      if (tid < dimf) {
-        for (int r = 0; r < dimf; ++r) w.s.f.Si[r * dimf + tid] = (r == tid) ? 1.0 : 0.0;
-        fb_llt_solve(w.s.f.Ls, dimf, w.s.f.rds, dimf, w.s.f.Si + tid, dimf);
-      }
-      __syncthreads();
+      FB_FOR(x, dimf * dimf) { const int r = x / dimf; w.s.f.Si[x] = (x - r * dimf == r) ? 1.0 : 0.0; }
+      fb_llt_cta<1>(w.s.f.Sm, dimf, dimf, w.s.f.Ls, dimf, w.s.f.rds, &w.info, 100);
+      fb_llt_solve_cta<2>(w.s.f.Ls, dimf, w.s.f.rds, dimf, w.s.f.Si, dimf, dimf);
     }
+    FB_PHASE(0, 4);
     FB_FOR(x, dimf * dimf) { const int r = x / dimf, c = x - r * dimf; w.MJtJinv[(n + r) * ld + n + c] = -w.s.f.Si[x]; }
     fb_mm<FBM_SET>(n, dimf, dimf, w.s.f.JMi, 1, n, w.s.f.Si, dimf, 1, w.MJtJinv + n, ld);     // TR = (J Minv)^T S^-1
     __syncthreads();
@@ -1164,10 +1262,12 @@ __global__ void __launch_bounds__(128, 4) k_fb_condense(FbArrays A, const FbLin*
     FB_FOR(x, dimf * n) { const int r = x / n, c = x - r * n; w.MJtJinv[(n + r) * ld + c] = w.MJtJinv[c * ld + n + r]; }   // BL = TR^T
     __syncthreads();
   }
+  FB_PHASE(0, 5);
   // ---- condensing ----
   fb_mm<FBM_SET>(nvf, NX, nvf, w.MJtJinv, NVF, 1, w.dIDCdqv, NX, 1, w.MJ_dIDC, NX);
   fb_mv<FBM_SET>(nvf, nvf, w.MJtJinv, NVF, 1, w.IDC, w.MJ_IDC);
   __syncthreads();
+  FB_PHASE(0, 6);
   double* Qafqv = w.s.c.Qafqv;
   double* Qafu = w.s.c.Qafu;
   FB_FOR(x, NV * NX) { const int r = x / NX; Qafqv[x] = -w.Qaa[r] * w.MJ_dIDC[x]; }
@@ -1182,6 +1282,7 @@ __global__ void __launch_bounds__(128, 4) k_fb_condense(FbArrays A, const FbLin*
   FB_FOR(x, dimf * NX) Qafqv[NV * NX + x] = -Qafqv[NV * NX + x];
   fb_mv<FBM_SUB>(dimf, dimf, w.Qff, MAXF, 1, w.MJ_IDC + NV, w.laf + NV);
   __syncthreads();
+  FB_PHASE(0, 7);
   // Qxx -= MJ_dIDC^T Qafqv, starting from the sparse cost / constraint Hessian; the Qvq block is never read
   // (the Riccati sweep rebuilds it from Qqv, backward_riccati_recursion_factorizer.hxx:93) and is left untouched
   {
@@ -1252,12 +1353,14 @@ __global__ void __launch_bounds__(128, 4) k_fb_condense(FbArrays A, const FbLin*
       Kt.P[tid] = acc;
     }
   }
+  FB_PHASE(0, 8);
   // ---- expansion record ----
   fb_copy(Ex.MJtJinv, w.MJtJinv, NVF * NVF + NVF * NX + NVF);   // MJtJinv, MJ_dIDC, MJ_IDC
   fb_copy(Ex.Qafqv, Qafqv, NVF * NX);
   fb_copy(Ex.Qafu, Qafu, NVF * NV);
   fb_copy(Ex.laf, w.laf, NVF);
   if (tid == 0) Dr.info = (double)w.info;
+  FB_PHASE(0, 9);
 }
 
 
@@ -1286,7 +1389,7 @@ struct FbRicWork {
     struct { double BtPq[FB_NU * FB_NV], BtPv[FB_NU * FB_NV]; };   // until lu is complete
     double GK[FB_NU * FB_NX];                                      // factorizeRiccatiFactorization
   };
-  double G[FB_NU * FB_NU], L[FB_NU * FB_NU], rd[FB_NU];
+  double L[FB_NU * FB_NU], rd[FB_NU];
   union {
     struct { double Ginv[FB_NU * FB_NU], DGinv[FB_MAXF * FB_NU], Sm[FB_MAXF * FB_MAXF]; };   // gain computation
     double DtM[FB_NU * FB_NX];                                                               // constrained tail
@@ -1299,7 +1402,7 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
   IDOCP_DYN_SMEM(FbRicWork, wp);
   FbRicWork& w = *wp;
   const int tid = threadIdx.x, b = blockIdx.x, n = A.n_elems;
-  const int NV = FB_NV, NX = FB_NX, NU = FB_NU, NPASS = FB_NPASS, MAXF = FB_MAXF;
+  const int NV = FB_NV, NX = FB_NX, NU = FB_NU, MAXF = FB_MAXF;
   // terminal stage: P = (Qqq, 0, Qvv), s = -(lq, lv)
   {
     const FbElem& el = A.elems[n - 1];
@@ -1318,6 +1421,7 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
     __syncthreads();
     fb_copy(Rc.Pqq, w.Pqq, 3 * NV * NV + 2 * NV);
   }
+  FB_PHASE_BEGIN();
   for (int e = n - 2; e >= 0; --e) {
     const FbElem& el = A.elems[e];
     const bool impulse = el.kind == FB_IMPULSE;
@@ -1326,16 +1430,17 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
     const FbKKT& Kt = A.kkt[(size_t)el.slot * A.B + b];
     FbRic& Rc = A.ric[(size_t)el.slot * A.B + b];
     __syncthreads();
-    fb_copy(w.Qxx, Kt.Qxx, NX * NX);
-    FB_FOR(x, NX * NU) { const int r = x / NU, c = x - r * NU; w.Qxu[x] = Kt.Qxu[r * NV + NPASS + c]; }
-    FB_FOR(x, NU * NU) { const int r = x / NU, c = x - r * NU; w.Quu[x] = Kt.Quu[(NPASS + r) * NV + NPASS + c]; }
-    fb_copy(w.Fqq6, Kt.Fqq6, 72);
-    fb_copy(w.Fvq, Kt.Fvq, 2 * NV * NV + NV * NU);
-    fb_copy(w.lq, Kt.lq, 2 * NV + NU);
-    fb_copy(w.Fq, Kt.Fq, 2 * NV);
-    if (dimi > 0) fb_copy(w.Phix, Kt.Phix, MAXF * NX + MAXF * NU + MAXF);
+    fb_load<FB_NX * FB_NX>(w.Qxx, Kt.Qxx);
+    fb_load_f<FB_NX * FB_NU>(w.Qxu, Kt.Qxu, [](int x) { const int r = x / FB_NU; return r * FB_NV + FB_NPASS + (x - r * FB_NU); });
+    fb_load_f<FB_NU * FB_NU>(w.Quu, Kt.Quu, [](int x) { const int r = x / FB_NU; return (FB_NPASS + r) * FB_NV + FB_NPASS + (x - r * FB_NU); });
+    fb_load<72>(w.Fqq6, Kt.Fqq6);
+    fb_load<2 * FB_NV * FB_NV + FB_NV * FB_NU>(w.Fvq, Kt.Fvq);
+    fb_load<2 * FB_NV + FB_NU>(w.lq, Kt.lq);
+    fb_load<2 * FB_NV>(w.Fq, Kt.Fq);
+    if (dimi > 0) fb_load<FB_MAXF * FB_NX + FB_MAXF * FB_NU + FB_MAXF>(w.Phix, Kt.Phix);
     if (tid == 0) w.info = 0;
     __syncthreads();
+    FB_PHASE(1, 0);
     double* Qqq = w.Qxx;
     double* Qqv = w.Qxx + NV;
     double* Qvv = w.Qxx + NV * NX + NV;
@@ -1349,6 +1454,7 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
       FB_FOR(x, (NV - 6) * NV) { w.AtPvq[6 * NV + x] = dt * w.Pqq[6 * NV + x]; w.AtPvv[6 * NV + x] = dt * w.Pqv[6 * NV + x]; }
     }
     __syncthreads();
+    FB_PHASE(1, 1);
     fb_mm<FBM_ADD>(NV, NV, NV, w.Fvq, 1, NV, w.Pqv, 1, NV, w.AtPqq, NV);
     fb_mm<FBM_ADD>(NV, NV, NV, w.Fvq, 1, NV, w.Pvv, NV, 1, w.AtPqv, NV);
     if (!impulse) {
@@ -1361,6 +1467,7 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
       fb_mm<FBM_SET>(NV, NV, NV, w.Fvv, 1, NV, w.Pvv, NV, 1, w.AtPvv, NV);
     }
     __syncthreads();
+    FB_PHASE(1, 2);
     // Factorize F: the three blocks are independent of each other, each gets its terms in the reference's order
     fb_mm<FBM_ADD>(NV, 6, 6, w.AtPqq, NV, 1, w.Fqq6, 6, 1, Qqq, NX);
     FB_FOR(x, NV * (NV - 6)) { const int r = x / (NV - 6), c = 6 + x - r * (NV - 6); Qqq[r * NX + c] += w.AtPqq[r * NV + c]; }
@@ -1371,6 +1478,7 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
       FB_FOR(x, NV * (NV - 6)) { const int r = x / (NV - 6), c = 6 + x - r * (NV - 6); Qvv[r * NX + c] = fma(dt, w.AtPvq[r * NV + c], Qvv[r * NX + c]); }
     }
     __syncthreads();
+    FB_PHASE(1, 3);
     fb_mm<FBM_ADD>(NV, NV, NV, w.AtPqv, NV, 1, w.Fvq, NV, 1, Qqq, NX);
     fb_mm<FBM_ADD>(NV, NV, NV, w.AtPqv, NV, 1, w.Fvv, NV, 1, Qqv, NX);
     fb_mm<FBM_ADD>(NV, NV, NV, w.AtPvv, NV, 1, w.Fvv, NV, 1, Qvv, NX);
@@ -1387,15 +1495,11 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
       }
     }
     __syncthreads();
+    FB_PHASE(1, 4);
     const double* Qxu = w.Qxu;   // 36 x 12, leading dimension NU
     if (!impulse) {
-      FB_FOR(x, NU * NU) w.G[x] = w.Quu[x];
-      __syncthreads();
-      if (tid < 32) {
-        const int info = fb_llt_warp(w.G, NU, NU, w.L, NU, w.rd);
-        if (tid == 0 && info) w.info = 200 + info;
-      }
-      __syncthreads();
+      fb_llt_cta<1>(w.Quu, NU, NU, w.L, NU, w.rd, &w.info, 200);
+      FB_PHASE(1, 5);
       if (dimi == 0) {
         // K = -G^-1 Qxu^T, k = -G^-1 lu: one right-hand side per thread
         if (tid < NX) {
@@ -1423,11 +1527,7 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
         __syncthreads();
         fb_mm<FBM_SET>(dimi, dimi, NU, w.DGinv, NU, 1, w.Phiu, 1, NU, w.Sm, MAXF);
         __syncthreads();
-        if (tid < 32) {
-          const int info = fb_llt_warp(w.Sm, MAXF, dimi, w.Ls, MAXF, w.rds);
-          if (tid == 0 && info && !w.info) w.info = 300 + info;
-        }
-        __syncthreads();
+        fb_llt_cta<1>(w.Sm, MAXF, dimi, w.Ls, MAXF, w.rds, &w.info, 300);
         if (tid < NU) {
           for (int r = 0; r < dimi; ++r) w.SinvDGinv[r * NU + tid] = w.DGinv[r * NU + tid];
           fb_llt_solve(w.Ls, MAXF, w.rds, dimi, w.SinvDGinv + tid, NU);
@@ -1457,6 +1557,7 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
         __syncthreads();
       }
     }
+    FB_PHASE(1, 6);
     // ---- factorizeRiccatiFactorization ----
     FB_FOR(x, NV * NV) {
       const int r = x / NV, c = x - r * NV;
@@ -1472,6 +1573,7 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
       fb_mm<FBM_SUB>(NV, NV, NU, w.K + NV, 1, NX, w.GK + NV, NX, 1, w.Pvv, NV);
       __syncthreads();
     }
+    FB_PHASE(1, 7);
     FB_FOR(x, NV * NV) {   // preserve the symmetry: one thread per unordered pair
       const int r = x / NV, c = x - r * NV;
       if (c >= r) {
@@ -1521,6 +1623,7 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
       w.sv[j] = acc;
     }
     __syncthreads();
+    FB_PHASE(1, 8);
     if (dimi > 0) {
       fb_mm<FBM_SET>(NU, NX, dimi, w.Phiu, 1, NU, w.cM, NX, 1, w.DtM, NX);
       __syncthreads();
@@ -1536,9 +1639,11 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
       fb_mv<FBM_SUB>(NV, dimi, w.Phix + NV, 1, NX, w.cm, w.sv);
       __syncthreads();
     }
+    FB_PHASE(1, 9);
     // store the factorisation; it stays in place as the "next" one
     fb_copy(Rc.K, w.K, sizeof(FbRic) / sizeof(double));
     if (tid < NV) { w.nsq[tid] = w.sq[tid]; w.nsv[tid] = w.sv[tid]; }
+    FB_PHASE(1, 10);
     if (tid == 0 && w.info) {
       FbDir& Dr = A.dir[(size_t)el.slot * A.B + b];
       if (Dr.info == 0.0) Dr.info = (double)w.info;
