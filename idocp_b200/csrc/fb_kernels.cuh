@@ -355,6 +355,35 @@ struct FbLin {
   double Phix[FB_MAXF * FB_NX], Phia[FB_MAXF * FB_NV];
 };
 
+// Optional per-phase cycle counters of the three heavy kernels (tools/fb_phase_clocks.py builds a variant library with
+// -DFB_PHASE_CLOCKS; the product library carries none of this).
+#ifdef FB_PHASE_CLOCKS
+__device__ unsigned long long g_fb_phase[3][32];
+#define FB_PHASE_BEGIN() long long fb_t_prev = clock64()
+#define FB_PHASE(kernel, i)                                                               \
+  do {                                                                                    \
+    __syncthreads();                                                                      \
+    if (threadIdx.x == 0) {                                                               \
+      const long long t = clock64();                                                      \
+      atomicAdd(&g_fb_phase[kernel][i], (unsigned long long)(t - fb_t_prev));             \
+      fb_t_prev = t;                                                                      \
+    }                                                                                     \
+  } while (0)
+#define FBW_PHASE(kernel, i)                                                              \
+  do {                                                                                    \
+    __syncwarp();                                                                         \
+    if ((threadIdx.x & 31) == 0) {                                                        \
+      const long long t = clock64();                                                      \
+      atomicAdd(&g_fb_phase[kernel][i], (unsigned long long)(t - fb_t_prev));             \
+      fb_t_prev = t;                                                                      \
+    }                                                                                     \
+  } while (0)
+#else
+#define FB_PHASE_BEGIN()
+#define FB_PHASE(kernel, i)
+#define FBW_PHASE(kernel, i)
+#endif
+
 struct FbRobotWork {
   // inputs (same order as FbSol)
   double lmd[FB_NV], gmm[FB_NV], q[FB_NQ], v[FB_NV], a[FB_NV], u[FB_NU], beta[FB_NV], nu_passive[FB_NPASS], f[FB_MAXF], mu[FB_MAXF],
@@ -367,11 +396,13 @@ struct FbRobotWork {
   fb_inertia_t Y[FB_NB];
   fb_dinertia_t D[FB_NB];
   double F[FB_NB][6], agf[FB_NB][6];
-  double U[FB_NV][6], W[FB_NV][6], dFv[FB_NV][6], dFq[FB_NV][6], dFqa[FB_NV][6], dAq[FB_NV][6], dAv[FB_NV][6];
+  union {   // the RNEA derivative columns are dead before the switching constraint starts
+    struct { double U[FB_NV][6], W[FB_NV][6], dFv[FB_NV][6], dFq[FB_NV][6], dFqa[FB_NV][6], dAq[FB_NV][6], dAv[FB_NV][6]; };
+    struct { double dqv[FB_NV], q2[FB_NQ], Jq6[36], Jv6[36], Pq[FB_MAXF * FB_NV], PJv[FB_MAXF * FB_NV]; };
+  };
   double frP[3], frV[6], frA[6];
   // SE(3) blocks: three relative placements (cost reference, next stage, previous stage)
-  double relR[3][9], relp[3][3], relJ[3][36], rellog[3][6], relX[2][36], Fqq_prev6[36], Fqq_inv[36], tmp6[36], fq6[6];
-  double dqv[FB_NV], q2[FB_NQ], Jq6[36], Jv6[36], Pq[FB_MAXF * FB_NV], PJv[FB_MAXF * FB_NV];
+  double relR[3][9], relp[3][3], relJ[3][36], rellog[3][6], Fqq_prev6[36], Fqq_inv[36], tmp6[36], fq6[6];
   double residual[FB_NCON], duality[FB_NCON];
   double t18[FB_NV], part[8];
 };
@@ -399,6 +430,20 @@ __device__ __forceinline__ void fbw_mm(int lane, int m, int n, int k, const doub
       for (int l = l0; l < k; ++l) acc = fma(a[l * acs], b[l * brs], acc);
     C[i * ldc + j] = acc;
   }
+}
+
+// sum_k a[k * stride] x[k], k < n <= N, as one product and an ascending fma chain; a lives in HBM / L2 and its N loads are
+// issued together
+template <int N>
+__device__ __forceinline__ double fbw_colT_dot(const double* a, int stride, const double* x, int n) {
+  double r[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) r[k] = k < n ? __ldcg(a + k * stride) : 0.0;
+  double acc = r[0] * x[0];
+#pragma unroll
+  for (int k = 1; k < N; ++k)
+    if (k < n) acc = fma(r[k], x[k], acc);
+  return acc;
 }
 
 // forwardKinematics in the world frame: base by lane 0, then one lane per leg (robot.hxx:193-230); v, a may be null
@@ -621,7 +666,7 @@ __device__ __noinline__ void fbw_dminus(const double* R, const double* p, const 
     }
 }
 
-#define FB_ROBOT_WARPS 4
+#define FB_ROBOT_WARPS 5
 
 template <bool RESIDUAL_ONLY>
 __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, FbLin* lin) {
@@ -642,22 +687,34 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
   FbDir& Dr = A.dir[rec];
   FbLin& L = lin[rec];
 
+  FB_PHASE_BEGIN();
   // ---- load ----
+  // every load of the lane is issued before its first store (a copy loop through generic pointers keeps load -> store order:
+  // one DRAM round trip per element)
   {
+    constexpr int NS = (int)(sizeof(FbSol) / sizeof(double)), RS = (NS + 31) / 32;
     const double* src = S.lmd;
-    double* dst = w.lmd;
-    FBW_FOR(i, (int)(sizeof(FbSol) / sizeof(double))) dst[i] = src[i];
-  }
-  if (!terminal) {
-    const FbSol& Nx = A.sol[(size_t)el.next_slot * A.B + b];
-    FBW_FOR(i, FB_NV) { w.nlmd[i] = Nx.lmd[i]; w.ngmm[i] = Nx.gmm[i]; w.nv[i] = Nx.v[i]; }
-    FBW_FOR(i, FB_NQ) w.nq[i] = Nx.q[i];
-  }
-  {
+    const FbSol& Nx = A.sol[(size_t)(terminal ? el.slot : el.next_slot) * A.B + b];
     const double* qp = el.prev_slot >= 0 ? A.sol[(size_t)el.prev_slot * A.B + b].q : A.q0 + (size_t)b * FB_NQ;
-    FBW_FOR(i, FB_NQ) w.qprev[i] = qp[i];
+    double r[RS], n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0, p0 = 0.0;
+#pragma unroll
+    for (int i = 0; i < RS; ++i) { const int x = lane + 32 * i; r[i] = x < NS ? __ldcg(src + x) : 0.0; }
+    if (!terminal) {
+      if (lane < FB_NV) { n0 = __ldcg(Nx.lmd + lane); n1 = __ldcg(Nx.gmm + lane); n2 = __ldcg(Nx.v + lane); }
+      if (lane < FB_NQ) n3 = __ldcg(Nx.q + lane);
+    }
+    if (lane < FB_NQ) p0 = __ldcg(qp + lane);
+    double* dst = w.lmd;
+#pragma unroll
+    for (int i = 0; i < RS; ++i) { const int x = lane + 32 * i; if (x < NS) dst[x] = r[i]; }
+    if (!terminal) {
+      if (lane < FB_NV) { w.nlmd[lane] = n0; w.ngmm[lane] = n1; w.nv[lane] = n2; }
+      if (lane < FB_NQ) w.nq[lane] = n3;
+    }
+    if (lane < FB_NQ) w.qprev[lane] = p0;
   }
   __syncwarp();
+  FBW_PHASE(2, 0);
   if (lane < FB_MAXF) {   // forces of inactive contacts are zero for the dynamics; stacks of the active ones
     const int i = lane / 3;
     w.fm[lane] = (!terminal && el.active[i]) ? w.f[lane] : 0.0;
@@ -683,6 +740,7 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
     if (lane == 2) fbw_dminus(w.relR[2], w.relp[2], w.relJ[2], w.Fqq_prev6);
   }
   __syncwarp();
+  FBW_PHASE(2, 1);
   const double* J6c = w.relJ[0];
   const double* Fqq6 = w.relJ[1];
 
@@ -787,6 +845,7 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
     }
     return;
   }
+  FBW_PHASE(2, 2);
   // augmentDualResidual: joint limits on the lq / lv / lu tails, friction cones on lf
   if (lane >= 6 && lane < FB_NV) {
     const int j = lane - 6;
@@ -854,11 +913,14 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
   }
   __syncwarp();
 
+  FBW_PHASE(2, 3);
   // ---- contact dynamics: kinematics, RNEA + derivatives, contact rows ----
   const double baumgarte = pr.T / pr.N;
   if (!impulse) {
     fbw_forward_kinematics(w, lane, w.q, w.v, w.a);
+    FBW_PHASE(2, 4);
     fbw_rnea_derivatives(w, lane, ANYMAL_GRAVITY, true, L, true);
+    FBW_PHASE(2, 5);
     if (lane < FB_NU) L.IDC[6 + lane] -= w.u[lane];
   } else {
     fbw_forward_kinematics(w, lane, w.q, nullptr, w.a);
@@ -867,6 +929,7 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
     __syncwarp();
     fbw_forward_kinematics(w, lane, w.q, w.t18, nullptr);
   }
+  FBW_PHASE(2, 6);
   // rows of every active contact, one after the other; lane = dof
   {
     int k = 0;
@@ -948,49 +1011,34 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
     }
   }
   __syncwarp();
+  FBW_PHASE(2, 7);
   // augment: lq += dt dIDdq^T beta, lv += dt dIDdv^T beta, la += dt M^T beta, lf -= dt dCda beta, lu ...
   {
     const double* dIDdq = L.dIDCdqv;
     const double* dIDdv = L.dIDCdqv + FB_NV;
     const double* dCdq = L.dIDCdqv + FB_NV * FB_NX;
     const double* dCdv = dCdq + FB_NV;
+    // the matrices were written to HBM by other lanes of this warp; a column is fetched in one batch (all loads in flight),
+    // then folded in ascending k
     if (lane < FB_NV) {
       const int j = lane;
-      double acc = dIDdq[j] * w.beta[0];
-      for (int k = 1; k < FB_NV; ++k) acc = fma(dIDdq[k * FB_NX + j], w.beta[k], acc);
-      lq = fma(dt, acc, lq);
-      if (!impulse) {
-        acc = dIDdv[j] * w.beta[0];
-        for (int k = 1; k < FB_NV; ++k) acc = fma(dIDdv[k * FB_NX + j], w.beta[k], acc);
-        lv = fma(dt, acc, lv);
-      }
-      acc = L.Mm[j] * w.beta[0];
-      for (int k = 1; k < FB_NV; ++k) acc = fma(L.Mm[k * FB_NV + j], w.beta[k], acc);
-      la = fma(dt, acc, la);
+      lq = fma(dt, fbw_colT_dot<FB_NV>(dIDdq + j, FB_NX, w.beta, FB_NV), lq);
+      if (!impulse) lv = fma(dt, fbw_colT_dot<FB_NV>(dIDdv + j, FB_NX, w.beta, FB_NV), lv);
+      la = fma(dt, fbw_colT_dot<FB_NV>(L.Mm + j, FB_NV, w.beta, FB_NV), la);
       if (dimf > 0) {
-        acc = dCdq[j] * w.mu_stack[0];
-        for (int k = 1; k < dimf; ++k) acc = fma(dCdq[k * FB_NX + j], w.mu_stack[k], acc);
-        lq = fma(dt, acc, lq);
-        acc = dCdv[j] * w.mu_stack[0];
-        for (int k = 1; k < dimf; ++k) acc = fma(dCdv[k * FB_NX + j], w.mu_stack[k], acc);
-        lv = fma(dt, acc, lv);
-        acc = L.dCda[j] * w.mu_stack[0];
-        for (int k = 1; k < dimf; ++k) acc = fma(L.dCda[k * FB_NV + j], w.mu_stack[k], acc);
-        la = fma(dt, acc, la);
+        lq = fma(dt, fbw_colT_dot<FB_MAXF>(dCdq + j, FB_NX, w.mu_stack, dimf), lq);
+        lv = fma(dt, fbw_colT_dot<FB_MAXF>(dCdv + j, FB_NX, w.mu_stack, dimf), lv);
+        la = fma(dt, fbw_colT_dot<FB_MAXF>(L.dCda + j, FB_NV, w.mu_stack, dimf), la);
       }
     }
-    if (lane < dimf) {
-      const int j = lane;
-      double acc = L.dCda[j * FB_NV] * w.beta[0];
-      for (int k = 1; k < FB_NV; ++k) acc = fma(L.dCda[j * FB_NV + k], w.beta[k], acc);
-      lf = fma(-dt, acc, lf);
-    }
+    if (lane < dimf) lf = fma(-dt, fbw_colT_dot<FB_NV>(L.dCda + lane * FB_NV, 1, w.beta, FB_NV), lf);
     if (!impulse) {
       if (lane < FB_NPASS) lup = fma(-dt, w.beta[lane], dt * w.nu_passive[lane]);
       if (lane < FB_NU) lu = fma(-dt, w.beta[6 + lane], lu);
     }
   }
 
+  FBW_PHASE(2, 8);
   if (!RESIDUAL_ONLY) {
     // ---- cost Hessian (sparse part of Qxx, Qaa, Qff) and condenseSlackAndDual ----
     FBW_FOR(x, 36) {
@@ -1057,6 +1105,7 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
     }
   }
 
+  FBW_PHASE(2, 9);
   // ---- ForwardSwitchingConstraint::linearizeSwitchingConstraint (:27-68) ----
   if (dimi > 0) {
     const double c1 = el.dt + el.dt_next, c2 = el.dt * el.dt_next;
@@ -1111,6 +1160,7 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
       for (int l = 0; l < dimi; ++l) la = fma(L.Phia[l * FB_NV + j], w.xi[l], la);
     }
   }
+  FBW_PHASE(2, 10);
   // ---- store the stage vectors ----
   if (lane < FB_NV) { L.lq[lane] = lq; L.lv[lane] = lv; L.la[lane] = la; L.Fq[lane] = Fq; L.Fv[lane] = Fv; }
   if (lane < FB_MAXF) L.lf[lane] = lane < dimf ? lf : 0.0;
@@ -1162,25 +1212,6 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
 //   condenseImpulseDynamics (impulse_dynamics_forward_euler.hxx:64-105), condenseSwitchingConstraint (:194-200).
 //   Results go straight to the HBM records of the Riccati sweep (FbKKT) and of the expansion (FbExp).
 // =====================================================================================================
-// Optional per-phase cycle counters of the two CTA-level kernels (tools/fb_phase_clocks.py builds a variant library with
-// -DFB_PHASE_CLOCKS; the product library carries none of this).
-#ifdef FB_PHASE_CLOCKS
-__device__ unsigned long long g_fb_phase[2][32];
-#define FB_PHASE_BEGIN() long long fb_t_prev = clock64()
-#define FB_PHASE(kernel, i)                                                               \
-  do {                                                                                    \
-    __syncthreads();                                                                      \
-    if (threadIdx.x == 0) {                                                               \
-      const long long t = clock64();                                                      \
-      atomicAdd(&g_fb_phase[kernel][i], (unsigned long long)(t - fb_t_prev));             \
-      fb_t_prev = t;                                                                      \
-    }                                                                                     \
-  } while (0)
-#else
-#define FB_PHASE_BEGIN()
-#define FB_PHASE(kernel, i)
-#endif
-
 struct FbDenseWork {
   double IDC[FB_NVF], dIDCdqv[FB_NVF * FB_NX], Mm[FB_NV * FB_NV], dCda[FB_MAXF * FB_NV];
   double lq[FB_NV], lv[FB_NV], la[FB_NV], lf[FB_MAXF], lu_passive[FB_NPASS], lu[FB_NU], Fq[FB_NV], Fv[FB_NV], P[FB_MAXF];

@@ -131,6 +131,8 @@ inline int __any_sync(unsigned, int pred) {
 }
 template <typename T>
 inline T __ldg(const T* p) { return *p; }
+template <typename T>
+inline T __ldcg(const T* p) { return *p; }
 inline double __drcp_rn(double x) { return 1.0 / x; }
 inline double __dsqrt_rn(double x) { return std::sqrt(x); }
 inline double __ddiv_rn(double a, double b) { return a / b; }

@@ -20,6 +20,9 @@ VARIANT = os.path.join(ROOT, "build", "libidocp_b200_phase.so")
 
 CONDENSE = ["load FbLin", "LLT(M)", "M^-1 solves", "J M^-1, S", "LLT(S), S^-1", "TR / TL / BL", "MJtJinv [dIDC, IDC]",
             "Qafqv / Qafu / laf", "condensed products -> FbKKT", "FbExp store"]
+ROBOT = ["load FbSol", "SE(3) pairs, dminus, inverse", "cost gradient, constraint residuals", "state equation, Fqq condensing",
+         "forward kinematics", "RNEA + derivatives", "(impulse: second kinematics)", "contact rows", "augment (mat-vec from FbLin)",
+         "cost Hessian, slack / dual condensing", "switching constraint"]
 RICCATI = ["load FbKKT", "A^T P (6x6 part)", "A^T P, B^T P", "F^T P F (6x6 part)", "F^T P F, Qxu, Quu, lu", "LLT(G)",
            "gain K, k (+ Schur)", "P = Q - K^T G K", "symmetrise, sq, sv", "constrained tail", "store FbRic"]
 
@@ -51,19 +54,20 @@ def main():
     for _ in range(2):
         solver.updateSolution(0.0, q0, v0)
     solver.sync()
-    buf = (C.c_ulonglong * 64)()
+    buf = (C.c_ulonglong * 96)()
     fn(buf)
     iters = 5
     for _ in range(iters):
         solver.updateSolution(0.0, q0, v0)
     solver.sync()
     assert fn(buf) == 0
-    a = np.array(buf[:], dtype=np.float64).reshape(2, 32)
+    a = np.array(buf[:], dtype=np.float64).reshape(3, 32)
     n_stage = len(solver.chain())
     out = {}
-    for k, (names, units) in enumerate(((CONDENSE, B * (n_stage - 1) * iters), (RICCATI, B * (n_stage - 1) * iters))):
+    for k, (names, units) in enumerate(((CONDENSE, B * (n_stage - 1) * iters), (RICCATI, B * (n_stage - 1) * iters),
+                                        (ROBOT, B * (n_stage - 1) * iters))):
         tot = a[k].sum()
-        out["condense" if k == 0 else "riccati_backward"] = {
+        out[("condense", "riccati_backward", "robot")[k]] = {
             "cycles_per_stage": tot / units,
             "phases": {names[i]: {"cycles": a[k][i] / units, "share": a[k][i] / tot} for i in range(len(names))}}
     print(json.dumps(out, indent=1))
