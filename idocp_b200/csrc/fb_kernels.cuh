@@ -1056,9 +1056,10 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
       qvd += sc * wv[j];
       L.Qaa[j] = 0.0 + sc * wa[j];
     }
+    double qff_d = 0.0;   // diagonal entry of Qff owned by this lane (stacked row `lane`); no read-modify-write on HBM
     if (ci >= 0) {
       const double* fw = impulse ? pr.fi_weight : pr.f_weight;
-      L.Qff[lane * FB_MAXF + lane] += sc * fw[3 * ci + cx];
+      qff_d = 0.0 + sc * fw[3 * ci + cx];
     }
     if (lane >= 6 && lane < FB_NV) {
       const int j = lane - 6;
@@ -1100,8 +1101,10 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
       for (int y = 0; y < 3; ++y) {
         double h = fb_friction_jac(pr.mu, 0, cx) * (w5[0] * fb_friction_jac(pr.mu, 0, y));
         for (int ee = 1; ee < 5; ++ee) h = fma(fb_friction_jac(pr.mu, ee, cx), w5[ee] * fb_friction_jac(pr.mu, ee, y), h);
-        L.Qff[(3 * k + cx) * FB_MAXF + 3 * k + y] += dt * h;
+        L.Qff[(3 * k + cx) * FB_MAXF + 3 * k + y] = (y == cx ? qff_d : 0.0) + dt * h;
       }
+    } else if (ci >= 0) {
+      L.Qff[lane * FB_MAXF + lane] = qff_d;
     }
   }
 
@@ -1213,13 +1216,20 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
 //   Results go straight to the HBM records of the Riccati sweep (FbKKT) and of the expansion (FbExp).
 // =====================================================================================================
 struct FbDenseWork {
-  double IDC[FB_NVF], dIDCdqv[FB_NVF * FB_NX], Mm[FB_NV * FB_NV], dCda[FB_MAXF * FB_NV];
+  double IDC[FB_NVF], dIDCdqv[FB_NVF * FB_NX];
+  // FbLin from dCda to Fqq_prev_inv, same order
+  double dCda[FB_MAXF * FB_NV];
   double lq[FB_NV], lv[FB_NV], la[FB_NV], lf[FB_MAXF], lu_passive[FB_NPASS], lu[FB_NU], Fq[FB_NV], Fv[FB_NV], P[FB_MAXF];
   double Qqq6[36], Qqq_d[FB_NV], Qvv_d[FB_NV], Quu_d[FB_NU], Qaa[FB_NV], Qff[FB_MAXF * FB_MAXF];
   double Fqq6[36], Fqv6[36], Fqq_prev_inv[36];
-  double Phix[FB_MAXF * FB_NX], Phia[FB_MAXF * FB_NV];
-  // ^ same order as FbLin
-  double MJtJinv[FB_NVF * FB_NVF], MJ_dIDC[FB_NVF * FB_NX], MJ_IDC[FB_NVF], laf[FB_NVF];
+  // MJtJinv, MJ_dIDC, MJ_IDC: same order as FbExp.  The joint-space inertia matrix is dead once its Cholesky factor exists
+  // (long before MJ_dIDC is formed) and shares its storage.  Phix / Phia of the switching stages stay in HBM.
+  double MJtJinv[FB_NVF * FB_NVF];
+  union {
+    struct { double MJ_dIDC[FB_NVF * FB_NX], MJ_IDC[FB_NVF]; };
+    double Mm[FB_NV * FB_NV];
+  };
+  double laf[FB_NVF];
   union {
     struct { double L[FB_NV * FB_NV], rd[FB_NV], Minv[FB_NV * FB_NV], JMi[FB_MAXF * FB_NV], Sm[FB_MAXF * FB_MAXF], Ls[FB_MAXF * FB_MAXF],
                  rds[FB_MAXF], Si[FB_MAXF * FB_MAXF]; } f;          // factorisation scratch (dead once MJtJinv is formed)
@@ -1228,7 +1238,7 @@ struct FbDenseWork {
   int info;
 };
 
-__global__ void __launch_bounds__(128, 4) k_fb_condense(FbArrays A, const FbLin* lin) {
+__global__ void __launch_bounds__(128, 5) k_fb_condense(FbArrays A, const FbLin* lin) {
   IDOCP_DYN_SMEM(FbDenseWork, wp);
   FbDenseWork& w = *wp;
   const int tid = threadIdx.x;
@@ -1258,7 +1268,9 @@ __global__ void __launch_bounds__(128, 4) k_fb_condense(FbArrays A, const FbLin*
   FbExp& Ex = A.exp[rec];
   FbDir& Dr = A.dir[rec];
   FB_PHASE_BEGIN();
-  fb_load<sizeof(FbLin) / sizeof(double)>(w.IDC, L.IDC);
+  fb_load<FB_NVF + FB_NVF * FB_NX>(w.IDC, L.IDC);
+  fb_load<FB_NV * FB_NV>(w.Mm, L.Mm);
+  fb_load<(offsetof(FbLin, Phix) - offsetof(FbLin, dCda)) / sizeof(double)>(w.dCda, L.dCda);
   if (tid == 0) w.info = 0;
   __syncthreads();
   FB_PHASE(0, 0);
@@ -1372,15 +1384,15 @@ __global__ void __launch_bounds__(128, 4) k_fb_condense(FbArrays A, const FbLin*
   // ---- condenseSwitchingConstraint ----
   if (dimi > 0) {
     {
-      const double* Phix0 = w.Phix;
+      const double *Phix0 = L.Phix, *Phia = L.Phia;   // HBM operands: switching stages only
       double* Phix = Kt.Phix;
-      fb_mm_f<FBM_SUB>(dimi, NX, NV, w.Phia, NV, 1, w.MJ_dIDC, NX, 1, [=](int r, int c) { return Phix0[r * NX + c]; },
+      fb_mm_f<FBM_SUB>(dimi, NX, NV, Phia, NV, 1, w.MJ_dIDC, NX, 1, [=](int r, int c) { return Phix0[r * NX + c]; },
                        [=](int r, int c, double v) { Phix[r * NX + c] = v; });
-      fb_mm<FBM_SET>(dimi, NU, NV, w.Phia, NV, 1, w.MJtJinv + NPASS, NVF, 1, Kt.Phiu, NU);
+      fb_mm<FBM_SET>(dimi, NU, NV, Phia, NV, 1, w.MJtJinv + NPASS, NVF, 1, Kt.Phiu, NU);
     }
     if (tid < dimi) {
       double acc = w.P[tid];
-      for (int l = 0; l < NV; ++l) acc = fma(-w.Phia[tid * NV + l], w.MJ_IDC[l], acc);
+      for (int l = 0; l < NV; ++l) acc = fma(-L.Phia[tid * NV + l], w.MJ_IDC[l], acc);
       Kt.P[tid] = acc;
     }
   }
