@@ -344,8 +344,9 @@ def run_anymal(args, rank, local_rank, world):
         roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["algo_gbs"], "peak": hbm_peak, "unit": "GB/s",
                     "frac": kern[dom]["algo_gbs"] / hbm_peak, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": FB_ALGO_DOUBLES_PER_STAGE[dom] * 8.0 * stages,
-                    "note": "the ANYmal kernels are latency-bound (dependent FP64 chains of the factorisations, 8-16 resident "
-                            "warps / SM; ncu: profiles/r1i_ncu_full_k_fb_*.txt), neither HBM- nor FP64-throughput-bound",
+                    "note": "the ANYmal kernels are latency-bound (dependent FP64 chains of the factorisations, 10-20 resident "
+                            "warps / SM, issue slots 21-38 % busy; ncu: profiles/r1s_ncu_full_k_fb_*.txt, per-phase cycles: "
+                            "profiles/r1t_fb_phase_clocks.json), neither HBM- nor FP64-throughput-bound",
                     "kernels": kern,
                     "step_fp64_tflops": FB_FLOP_PER_STAGE * n_stages * value / world / 1e12}
     line = {
