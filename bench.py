@@ -184,6 +184,7 @@ def run_reference(args, rank, world):
 # ANYmal workloads (BASELINE.json configs[3], configs[4]): batched OCPSolver with contacts and impulses
 # ---------------------------------------------------------------------------------------------------
 ANYMAL_BATCH = {"anymal_trotting": 4096, "anymal_running": 1024}
+ANYMAL_SEED = {"anymal_trotting": 20240004, "anymal_running": 20240005}
 ANYMAL_LINE_SEARCH = {"anymal_trotting": False, "anymal_running": True}
 # algorithmic doubles per (instance, stage) of the heavy kernels at dimf = 12: mandatory inputs + outputs
 FB_ALGO_DOUBLES_PER_STAGE = {
@@ -215,7 +216,7 @@ def anymal_oracle_throughput(name, seconds_target, steps=None, warmup=1):
     pr = tp.TrottingProblem() if name == "anymal_trotting" else tp.RunningProblem(10)
     ls = ANYMAL_LINE_SEARCH[name]
     nb = 2 * cores
-    q0, v0 = P.anymal_initial_states(0, nb, q_nominal=pr.q0)
+    q0, v0 = P.anymal_initial_states(0, nb, q_nominal=pr.q0, seed=ANYMAL_SEED[name])
     solvers = [pr.make_oracle(fb_py, q0=q0[b], v0=v0[b]) for b in range(nb)]
     for _ in range(max(warmup, 1)):
         fb_py.batch_update_solution(solvers, 0.0, q0, v0, ls, cores)
@@ -246,8 +247,8 @@ def run_reference_anymal(args, rank):
         "impl": "reference", "metric": anymal_metric(args.workload), "value": value, "unit": "instance-iterations/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s (examples/anymal/%s.cpp problem), perturbed initial states (splitmix64 seed 20240004); "
-                               "bounded sample of %d instances per step" % (args.workload, args.workload, 2 * cores)},
+        "config": {"workload": "%s (examples/anymal/%s.cpp problem), perturbed initial states (splitmix64 seed %d); "
+                               "bounded sample of %d instances per step" % (args.workload, args.workload, ANYMAL_SEED[args.workload], 2 * cores)},
         "cpu_baseline": {"value": value, "unit": "instance-iterations/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "instance-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "oracle restatement of idocp's OCPSolver (oracle/fb_ocp.c), not the upstream binary: pinocchio/Eigen absent",
@@ -272,7 +273,7 @@ def run_anymal(args, rank, local_rank, world):
     pr = anymal_problem(args.workload, lib)
     ls = ANYMAL_LINE_SEARCH[args.workload]
     B = args.batch if args.batch != BATCH_PER_GPU else ANYMAL_BATCH[args.workload]
-    q0, v0 = P.anymal_initial_states(rank * B, B, q_nominal=pr.q_nominal)
+    q0, v0 = P.anymal_initial_states(rank * B, B, q_nominal=pr.q_nominal, seed=ANYMAL_SEED[args.workload])
     solver = P.make_solver(pr, B, q0, v0, device=local_rank, lib=lib)
     n_stages = len(solver.chain())
     stream = torch.cuda.ExternalStream(solver.stream(), device=local_rank)
@@ -354,8 +355,8 @@ def run_anymal(args, rank, local_rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%s: OCPSolver on examples/anymal/%s.cpp (T=%g, N=%d, %d stages incl. impulse / aux / lift), %d "
-                               "perturbed initial states per GPU (splitmix64 seed 20240004), line_search=%s"
-                               % (args.workload, args.workload, pr.T, pr.N, n_stages, B, str(ls).lower()),
+                               "perturbed initial states per GPU (splitmix64 seed %d), line_search=%s"
+                               % (args.workload, args.workload, pr.T, pr.N, n_stages, B, ANYMAL_SEED[args.workload], str(ls).lower()),
                    "batch_per_gpu": B, "stages": n_stages, "parallelism": "batch-sharded x%d, no collective" % world,
                    "l2_policy": "working set %.1f GB per GPU >> 126 MB L2" % (B * n_stages * 127e3 / 1e9)},
         "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "instance-iterations/s", "h2d_bytes_per_step": B * 37 * 8,
