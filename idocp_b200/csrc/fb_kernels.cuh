@@ -184,6 +184,13 @@ template <int N>
 __device__ __forceinline__ void fb_load(double* dst, const double* __restrict__ src) {
   fb_load_f<N>(dst, src, [](int x) { return x; });
 }
+// ask the L2 for the `bytes` starting at p (one 128-byte line per thread and round); no effect on results
+__device__ __forceinline__ void fb_prefetch_l2(const void* p, int bytes) {
+#ifndef IDOCP_B200_EMU
+  const char* c = static_cast<const char*>(p);
+  for (int o = threadIdx.x * 128; o < bytes; o += blockDim.x * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + o));
+#endif
+}
 __device__ inline void fb_zero(double* dst, int n) { FB_FOR(i, n) dst[i] = 0.0; }
 
 // Cholesky of an n x n matrix by the WHOLE CTA (128 threads), right-looking, n (n + 1) / 2 <= 128 E.  Every element of the
@@ -1555,6 +1562,8 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
     fb_load<2 * FB_NV + FB_NU>(w.lq, Kt.lq);
     fb_load<2 * FB_NV>(w.Fq, Kt.Fq);
     if (dimi > 0) fb_load<FB_MAXF * FB_NX + FB_MAXF * FB_NU + FB_MAXF>(w.Phix, Kt.Phix);
+    // the record of the stage before this one is needed ~40 k cycles from now: bring it into the L2 meanwhile
+    if (e > 0) fb_prefetch_l2(&A.kkt[(size_t)A.elems[e - 1].slot * A.B + b], (int)sizeof(FbKKT));
     if (tid == 0) w.info = 0;
     __syncthreads();
     FB_PHASE(1, 0);
