@@ -183,6 +183,13 @@ def run_reference(args, rank, world):
 # ---------------------------------------------------------------------------------------------------
 # ANYmal workloads (BASELINE.json configs[3], configs[4]): batched OCPSolver with contacts and impulses
 # ---------------------------------------------------------------------------------------------------
+# dram__bytes_read.sum + dram__bytes_write.sum, FP64-pipe and issue utilisation of ONE launch from the committed `ncu --set full`
+# captures of exactly this workload and batch (profiles/r1v_ncu_full_k_fb_*.txt); reported only when the bench runs it
+FB_NCU_SOURCE = "profiles/r1v_ncu_full_k_fb_*.txt"
+FB_NCU = {("anymal_trotting", 4096): {
+    "fb_robot": {"dram_bytes": 0.526287e9 + 2.432886e9, "fp64_pipe_pct": 19.2, "issue_active_pct": 25.6},
+    "fb_condense": {"dram_bytes": 2.580715e9 + 7.622179e9, "fp64_pipe_pct": 15.7, "issue_active_pct": 40.5},
+    "fb_riccati_backward": {"dram_bytes": 4.520526e9 + 2.181645e9, "fp64_pipe_pct": 14.5, "issue_active_pct": 23.0}}}
 ANYMAL_BATCH = {"anymal_trotting": 4096, "anymal_running": 1024}
 ANYMAL_SEED = {"anymal_trotting": 20240004, "anymal_running": 20240005}
 ANYMAL_LINE_SEARCH = {"anymal_trotting": False, "anymal_running": True}
@@ -339,14 +346,20 @@ def run_anymal(args, rank, local_rank, world):
             kern[name] = {"ms_per_step": per, "launches_per_step": rec["calls"] / args.steps}
             if name in FB_ALGO_DOUBLES_PER_STAGE:
                 kern[name]["algo_gbs"] = FB_ALGO_DOUBLES_PER_STAGE[name] * 8.0 * stages / (per * 1e-3) / 1e9
+                ncu = FB_NCU.get((args.workload, B), {}).get(name)
+                if ncu:
+                    kern[name]["ncu_dram_bytes"] = ncu["dram_bytes"]
+                    kern[name]["ncu_fp64_pipe_pct"] = ncu["fp64_pipe_pct"]
+                    kern[name]["ncu_issue_active_pct"] = ncu["issue_active_pct"]
     dom = max((n for n in kern if "algo_gbs" in kern[n]), key=lambda n: kern[n]["ms_per_step"], default=None)
     roofline = None
     if dom:
         roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["algo_gbs"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": kern[dom]["algo_gbs"] / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "frac": kern[dom]["algo_gbs"] / hbm_peak, "traffic": kern[dom].get("ncu_dram_bytes"),
+                    "traffic_source": FB_NCU_SOURCE if "ncu_dram_bytes" in kern[dom] else None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": FB_ALGO_DOUBLES_PER_STAGE[dom] * 8.0 * stages,
                     "note": "the ANYmal kernels are latency-bound (dependent FP64 chains of the factorisations, 10-20 resident "
-                            "warps / SM, issue slots 21-38 % busy; ncu: profiles/r1s_ncu_full_k_fb_*.txt, per-phase cycles: "
+                            "warps / SM, issue slots 21-38 % busy; ncu: profiles/r1v_ncu_full_k_fb_*.txt, per-phase cycles: "
                             "profiles/r1t_fb_phase_clocks.json), neither HBM- nor FP64-throughput-bound",
                     "kernels": kern,
                     "step_fp64_tflops": FB_FLOP_PER_STAGE * n_stages * value / world / 1e12}
