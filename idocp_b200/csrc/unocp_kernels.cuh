@@ -841,6 +841,17 @@ __global__ void __launch_bounds__(CTA_THREADS) k_expand(const DevProblem* __rest
   }
   const double* W = rec_ptr(L.W, W_NUM, L.G, i, t.g);
   const double da = D[D_A * SLOT];
+  // the state / slack / dual loads go out with the W loads, before the stores through D (which would fence them)
+  double xq = 0.0, xv = 0.0, xu = 0.0, slk[NC], dul[NC];
+  if (act) {
+    xq = X[X_Q * SLOT]; xv = X[X_V * SLOT]; xu = X[X_U * SLOT];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const bool on = comp_active(c, i + stage_offset);
+      slk[c] = on ? X[(X_SLACK + c) * SLOT] : 1.0;
+      dul[c] = on ? X[(X_DUAL + c) * SLOT] : 0.0;
+    }
+  }
   double dqk[NV], dvk[NV];
 #pragma unroll
   for (int k = 0; k < NV; ++k) { dqk[k] = oct_bcast(dq, k); dvk[k] = oct_bcast(dv, k); }
@@ -887,12 +898,12 @@ __global__ void __launch_bounds__(CTA_THREADS) k_expand(const DevProblem* __rest
   double min_p = 1.0, min_d = 1.0;
   if (act) {
     const LaneLimits lim = load_limits(P, lane);
-    const double q = X[X_Q * SLOT], v = X[X_V * SLOT], u = X[X_U * SLOT];
+    const double q = xq, v = xv, u = xu;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       if (!comp_active(c, i + stage_offset)) continue;
-      const double sl = X[(X_SLACK + c) * SLOT];
-      const double dl = X[(X_DUAL + c) * SLOT];
+      const double sl = slk[c];
+      const double dl = dul[c];
       const double r = con_residual(c, lim, q, v, u, sl);
       const double dty = sl * dl - P.barrier;
       const double dx = c < 2 ? dq : (c < 4 ? dv : du);
@@ -928,6 +939,23 @@ __global__ void __launch_bounds__(CTA_THREADS) k_update(const DevProblem* __rest
   const int i = t.stage;
   const int b = t.g * 4 + ((threadIdx.x >> 3) & 3);
   const int N = L.N;
+  double* X = rec_ptr(L.X, X_NUM, L.G, i, t.g);
+  const double* D = rec_ptr(L.D, D_NUM, L.G, i, t.g);
+  // every load of the record is issued before the first store and before the step-size reduction (lane 7 reads its padding slot): stores through X would otherwise fence the later loads
+  // (the compiler cannot prove that X and D do not overlap) and the kernel would pay one DRAM round trip per field
+  const double lmd = X[X_LMD * SLOT], gmm = X[X_GMM * SLOT], q = X[X_Q * SLOT], v = X[X_V * SLOT];
+  const double dlmd = D[D_LMD * SLOT], dgmm = D[D_GMM * SLOT], dq = D[D_Q * SLOT], dv = D[D_V * SLOT];
+  double a = 0.0, u = 0.0, beta = 0.0, da = 0.0, du = 0.0, dbeta = 0.0, slk[NC], dul[NC];
+  if (i != N) {
+    a = X[X_A * SLOT]; u = X[X_U * SLOT]; beta = X[X_BETA * SLOT];
+    da = D[D_A * SLOT]; du = D[D_U * SLOT]; dbeta = D[D_BETA * SLOT];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const bool on = comp_active(c, i + stage_offset);
+      slk[c] = on ? X[(X_SLACK + c) * SLOT] : 1.0;
+      dul[c] = on ? X[(X_DUAL + c) * SLOT] : 0.0;
+    }
+  }
   // min over the N per-stage minima, lanes striding over the stages
   double ap = 1.0, ad = 1.0;
   for (int s = lane; s < N; s += OCT) {
@@ -945,25 +973,19 @@ __global__ void __launch_bounds__(CTA_THREADS) k_update(const DevProblem* __rest
     if (!(ap == ap) || !(ad == ad)) L.status[b] |= 2;
   }
   if (lane >= NV) return;
-  double* X = rec_ptr(L.X, X_NUM, L.G, i, t.g);
-  const double* D = rec_ptr(L.D, D_NUM, L.G, i, t.g);
-  const double q = X[X_Q * SLOT], v = X[X_V * SLOT];
-  const double dq = D[D_Q * SLOT], dv = D[D_V * SLOT];
-  X[X_LMD * SLOT] = fma(ap, D[D_LMD * SLOT], X[X_LMD * SLOT]);
-  X[X_GMM * SLOT] = fma(ap, D[D_GMM * SLOT], X[X_GMM * SLOT]);
+  X[X_LMD * SLOT] = fma(ap, dlmd, lmd);
+  X[X_GMM * SLOT] = fma(ap, dgmm, gmm);
   X[X_Q * SLOT] = fma(ap, dq, q);
   X[X_V * SLOT] = fma(ap, dv, v);
   if (i == N) return;
-  const double u = X[X_U * SLOT];
-  const double du = D[D_U * SLOT];
-  X[X_A * SLOT] = fma(ap, D[D_A * SLOT], X[X_A * SLOT]);
+  X[X_A * SLOT] = fma(ap, da, a);
   X[X_U * SLOT] = fma(ap, du, u);
-  X[X_BETA * SLOT] = fma(ap, D[D_BETA * SLOT], X[X_BETA * SLOT]);
+  X[X_BETA * SLOT] = fma(ap, dbeta, beta);
   const LaneLimits lim = load_limits(P, lane);
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     if (!comp_active(c, i + stage_offset)) continue;
-    const double sl = X[(X_SLACK + c) * SLOT], dl = X[(X_DUAL + c) * SLOT];
+    const double sl = slk[c], dl = dul[c];
     const double r = con_residual(c, lim, q, v, u, sl);
     const double dty = sl * dl - P.barrier;
     const double dx = c < 2 ? dq : (c < 4 ? dv : du);
