@@ -49,12 +49,12 @@ KERNEL_ALGO_DOUBLES_PER_STAGE = {
 
 
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of each kernel from the committed ncu
-# --set full capture profiles/r1f_ncu_full_unocp.txt (same workload: 16384 instances, N = 20); reported as
+# --set full capture profiles/r1w_ncu_full_unocp.txt (same workload: 16384 instances, N = 20); reported as
 # roofline.traffic only when the bench runs that workload.  FP64-pipe utilisation from the same capture.
-NCU_DRAM_BYTES_PER_LAUNCH = {"linearize": 0.463256e9 + 1.430249e9, "riccati": 1.279708e9 + 0.990071e9,
-                             "expand": 1.503709e9 + 0.087223e9, "update": 0.550980e9 + 0.334739e9}
-NCU_FP64_PIPE_PCT = {"linearize": 46.2, "riccati": 28.7, "expand": 15.2, "update": 9.3}
-NCU_SOURCE = "profiles/r1f_ncu_full_unocp.txt"
+NCU_DRAM_BYTES_PER_LAUNCH = {"linearize": 0.463118e9 + 1.431644e9, "riccati": 1.279444e9 + 0.990545e9,
+                             "expand": 1.503690e9 + 0.087287e9, "update": 0.553002e9 + 0.334718e9}
+NCU_FP64_PIPE_PCT = {"linearize": 46.2, "riccati": 28.8, "expand": 15.2, "update": 11.9}
+NCU_SOURCE = "profiles/r1w_ncu_full_unocp.txt"
 
 
 def splitmix_uniform(seed, index):
