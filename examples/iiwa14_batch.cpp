@@ -1,7 +1,8 @@
 // iiwa14_batch.cpp -- drives the batched engine through the C++ host layer (the reference's class API):
 //
 //   iiwa14_batch <problem> <solver> [batch] [iterations] [timing-iterations]
-//     problem : benchmark | config | task      (cost / limits of the reference's three iiwa14 set-ups)
+//     problem : benchmark | config | task | task6d   (cost / limits of the reference's three iiwa14 set-ups;
+//               task6d = the task set-up with the constant-reference TaskSpace6DCost)
 //     solver  : unocp | unparnmpc
 //
 // Prints the KKT-error history of instance 0 (ocpbenchmarker::Convergence) and the time per batched
@@ -87,8 +88,24 @@ Setup make_setup(const std::string& problem, ob::Robot& robot) {
     s.cost->push_back(task);
     s.T = 6; s.N = 120;
     s.q0 = bent_arm(false);
+  } else if (problem == "task6d") {        // the same set-up with TaskSpace6DCost: a fixed end-effector placement
+    robot.setJointEffortLimit(ob::VectorXd::Constant(n, 50));
+    robot.setJointVelocityLimit(ob::VectorXd::Constant(n, M_PI_2));
+    joint_cost->set_v_weight(ob::VectorXd::Constant(n, 0.01));
+    joint_cost->set_vf_weight(ob::VectorXd::Constant(n, 0.01));
+    joint_cost->set_a_weight(ob::VectorXd::Constant(n, 0.01));
+    s.cost->push_back(joint_cost);
+    auto task = std::make_shared<ob::TaskSpace6DCost>(robot, 22);
+    ob::SE3 ref;
+    CircleReference().compute_q_6d_ref(0.0, ref);   // sin(0), cos(0): no libm rounding between this file and the oracle
+    task->set_q_6d_ref(ref.translation, ref.rotation);
+    task->set_q_6d_weight(ob::Vector3d::Constant(1000), ob::Vector3d::Constant(1000));
+    task->set_qf_6d_weight(ob::Vector3d::Constant(1000), ob::Vector3d::Constant(1000));
+    s.cost->push_back(task);
+    s.T = 6; s.N = 120;
+    s.q0 = bent_arm(false);
   } else {
-    std::cerr << "unknown problem '" << problem << "' (benchmark | config | task)\n";
+    std::cerr << "unknown problem '" << problem << "' (benchmark | config | task | task6d)\n";
     std::exit(EXIT_FAILURE);
   }
   return s;
@@ -109,7 +126,7 @@ void run(Solver& solver, const Setup& s, int iterations, int timing_iterations) 
 
 int main(int argc, char* argv[]) {
   if (argc < 3) {
-    std::cerr << "usage: iiwa14_batch <benchmark|config|task> <unocp|unparnmpc> [batch] [iterations] [timing-iterations]\n";
+    std::cerr << "usage: iiwa14_batch <benchmark|config|task|task6d> <unocp|unparnmpc> [batch] [iterations] [timing-iterations]\n";
     return EXIT_FAILURE;
   }
   const std::string problem = argv[1], kind = argv[2];

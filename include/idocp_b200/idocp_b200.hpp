@@ -162,8 +162,34 @@ class TimeVaryingTaskSpace6DCost {
   double q_[6], qf_[6];
 };
 
-// closed registry of cost components: one ConfigurationSpaceCost and, optionally, one
-// TimeVaryingTaskSpace6DCost (push_back order of the reference examples: configuration cost first)
+// cost/task_space_6d_cost.hpp:22-60, src/cost/task_space_6d_cost.cpp:41-176: the same stage arithmetic as the
+// time-varying component (log6 of ref^-1 * frame placement, Jlog6 * frame Jacobian) with a constant reference; it runs
+// on the same device path with the reference table filled with one placement.
+class TaskSpace6DCost {
+ public:
+  TaskSpace6DCost(const Robot& robot, const int frame_id)
+      : ref_(std::make_shared<ConstantRef>()), cost_(std::make_shared<TimeVaryingTaskSpace6DCost>(robot, frame_id, ref_)) {}
+  void set_q_6d_ref(const Vector3d& position_ref, const Matrix3d& rotation_ref) { ref_->se3 = SE3(rotation_ref, position_ref); }
+  void set_q_6d_weight(const Vector3d& position_weight, const Vector3d& rotation_weight) {
+    cost_->set_q_6d_weight(position_weight, rotation_weight);
+  }
+  void set_qf_6d_weight(const Vector3d& position_weight, const Vector3d& rotation_weight) {
+    cost_->set_qf_6d_weight(position_weight, rotation_weight);
+  }
+  // impulse stages do not exist on the fixed-base path; accepted for source compatibility
+  void set_qi_6d_weight(const Vector3d&, const Vector3d&) {}
+  const std::shared_ptr<TimeVaryingTaskSpace6DCost>& component() const { return cost_; }
+ private:
+  struct ConstantRef final : TimeVaryingTaskSpace6DRefBase {
+    SE3 se3;
+    void compute_q_6d_ref(const double, SE3& se3_ref) const override { se3_ref = se3; }
+  };
+  std::shared_ptr<ConstantRef> ref_;
+  std::shared_ptr<TimeVaryingTaskSpace6DCost> cost_;
+};
+
+// closed registry of cost components: one ConfigurationSpaceCost and, optionally, one task-space 6D cost
+// (TimeVaryingTaskSpace6DCost or TaskSpace6DCost; push_back order of the reference examples: configuration cost first)
 class CostFunction {
  public:
   void push_back(const std::shared_ptr<ConfigurationSpaceCost>& c) {
@@ -172,9 +198,10 @@ class CostFunction {
     config_ = c;
   }
   void push_back(const std::shared_ptr<TimeVaryingTaskSpace6DCost>& c) {
-    if (task_) detail::die("idocp_b200: only one TimeVaryingTaskSpace6DCost component is supported");
+    if (task_) detail::die("idocp_b200: only one task-space 6D cost component is supported");
     task_ = c;
   }
+  void push_back(const std::shared_ptr<TaskSpace6DCost>& c) { push_back(c->component()); }
   const std::shared_ptr<ConfigurationSpaceCost>& config() const { return config_; }
   const std::shared_ptr<TimeVaryingTaskSpace6DCost>& task() const { return task_; }
  private:

@@ -54,6 +54,38 @@ def test_example_reproduces_golden_convergence(problem, kind, iters, golden_file
     assert "CPU time per update" in out
 
 
+@pytest.mark.gpu
+def test_task_space_6d_cost_example_equals_the_oracle():
+    """TaskSpace6DCost (src/cost/task_space_6d_cost.cpp: constant reference placement) through the C++ host classes:
+    the KKT history of examples/iiwa14_batch.cpp `task6d` equals, digit for digit, the oracle's UnOCPSolver with the
+    reference table filled with that one placement."""
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as O
+    O.build()
+    _build()
+    iters = 10
+    out = subprocess.run([EXE, "task6d", "unocp", "3", str(iters), "0"], capture_output=True, text=True, check=True).stdout
+    kkt = [float(x) for x in re.findall(r"KKT error(?: after iteration \d+)? = (\S+)", out)]
+    problem = O.task_space_problem()
+    q0, v0 = np.array([0, np.pi / 2, 0, np.pi / 2, 0, np.pi / 2, 0]), np.zeros(7)
+    placement = O.task_space_ref(0.0)
+    s = O.UnOCPSolver(problem)
+    s.set_solution("q", q0)
+    s.set_solution("v", v0)
+    s.set_task_ref(O.task_ref_table(lambda t: placement, 0.0, problem.T, problem.N, "unocp"))
+    s.compute_kkt_residual(0.0, q0, v0)
+    ref = [s.kkt_error()]
+    for _ in range(iters):
+        s.update_solution(0.0, q0, v0, False)
+        s.compute_kkt_residual(0.0, q0, v0)
+        ref.append(s.kkt_error())
+    assert len(kkt) == iters + 1
+    assert kkt == ref
+    assert ref[-1] < 1e-2 * ref[0]
+
+
 def test_contact_schedule_example_runs_on_the_host():
     """examples/contact_schedule.cpp: the C++ schedule classes (include/idocp_b200/hybrid.hpp) are pure host code;
     the trotting schedule of SURVEY Appendix C has 36 stages, impulses at 1.0 and 1.5, one lift at 0.5."""
