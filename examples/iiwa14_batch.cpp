@@ -120,6 +120,10 @@ void run(Solver& solver, const Setup& s, int iterations, int timing_iterations) 
   std::cout << std::setprecision(17);
   ob::ocpbenchmarker::Convergence(solver, t, s.q0, v0, iterations, false);
   if (timing_iterations > 0) ob::ocpbenchmarker::CPUTime(solver, t, s.q0, v0, timing_iterations, false);
+  if (const char* dir = std::getenv("IDOCP_B200_SAVE_DIR")) {   // trajectory export in the reference's text format
+    for (const char* name : {"q", "v", "a", "u"}) solver.saveSolution(std::string(dir) + "/" + name + ".dat", name);
+    solver.printSolution("u");
+  }
 }
 
 }  // namespace

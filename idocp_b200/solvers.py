@@ -179,6 +179,14 @@ class _BatchSolver:
         self.lib.check(self.lib.L.idocp_b200_get_stage_solution(self._h, name.encode(), int(stage), dptr(out)))
         return out
 
+    def saveSolution(self, path_to_file, name, instance=0):
+        """UnOCPSolver::saveSolution (unocp_solver.cpp:312-352): one stage per line, every coefficient followed by a
+        blank, the stream's default formatting (%g); `instance` selects the member of the batch."""
+        with open(path_to_file, "w") as f:
+            if name in ("q", "v", "a", "u"):
+                for row in self.getSolution(name)[instance]:
+                    f.write("".join("%g " % x for x in row) + "\n")
+
     def clearLineSearchFilter(self):
         self.lib.check(self.lib.L.idocp_b200_clear_line_search_filter(self._h))
 

@@ -20,10 +20,13 @@
 #ifndef IDOCP_B200_HPP_
 #define IDOCP_B200_HPP_
 
+#include <algorithm>
 #include <chrono>
 #include <cstdlib>
+#include <fstream>
 #include <iostream>
 #include <memory>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -330,6 +333,48 @@ class SolverBase {
   }
   void getSolutionBatch(const std::string& name, double* out) const {
     check(idocp_b200_get_solution(h_.get(), name.c_str(), out));
+  }
+  // unocp_solver.cpp:312-352 / unparnmpc_solver.cpp: one stage per line, coefficients followed by a blank, default
+  // stream formatting.  `instance` selects the member of the batch (the reference has one).
+  void saveSolution(const std::string& path_to_file, const std::string& name, int instance = 0) const {
+    std::ofstream file(path_to_file);
+    if (name == "q" || name == "v" || name == "a" || name == "u") {
+      for (const VectorXd& x : getSolution(name, instance)) {
+        for (int j = 0; j < x.size(); ++j) file << x[j] << " ";
+        file << "\n";
+      }
+    }
+    file.close();
+  }
+  // unocp_solver.cpp:264-310: "q[i] = ..." lines in Eigen's row-vector format (columns right-aligned to the widest
+  // coefficient).  "end-effector" needs the frame kinematics on the host and is not provided.
+  void printSolution(const std::string& name = "all", const std::vector<int> frames = {}, int instance = 0) const {
+    (void)frames;
+    const bool unocp = kind_ == IDOCP_B200_SOLVER_UNOCP;
+    auto row = [](const char* n, int i, const VectorXd& x) {
+      std::vector<std::string> c;
+      size_t w = 0;
+      for (int j = 0; j < x.size(); ++j) {
+        std::ostringstream o;
+        o << x[j];
+        c.push_back(o.str());
+        w = std::max(w, c.back().size());
+      }
+      std::cout << n << "[" << i << "] = ";
+      for (size_t j = 0; j < c.size(); ++j) std::cout << (j ? " " : "") << std::string(w - c[j].size(), ' ') << c[j];
+      std::cout << std::endl;
+    };
+    if (name == "all") {
+      const auto q = getSolution("q", instance), v = getSolution("v", instance), a = getSolution("a", instance),
+                 u = getSolution("u", instance);
+      for (int i = 0; i < N_; ++i) { row("q", i, q[i]); row("v", i, v[i]); row("a", i, a[i]); row("u", i, u[i]); }
+      if (unocp) { row("q", N_, q[N_]); row("v", N_, v[N_]); }
+    } else if (name == "q" || name == "v" || name == "a" || name == "u") {
+      const auto x = getSolution(name, instance);
+      for (size_t i = 0; i < x.size(); ++i) row(name.c_str(), static_cast<int>(i), x[i]);
+    } else if (name == "end-effector") {
+      std::cout << "idocp_b200: printSolution(\"end-effector\") is not provided (frame kinematics live on the device)" << std::endl;
+    }
   }
   void clearLineSearchFilter() { check(idocp_b200_clear_line_search_filter(h_.get())); }
   bool isCurrentSolutionFeasible() {

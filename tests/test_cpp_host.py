@@ -86,6 +86,29 @@ def test_task_space_6d_cost_example_equals_the_oracle():
     assert ref[-1] < 1e-2 * ref[0]
 
 
+@pytest.mark.gpu
+def test_save_and_print_solution_formats(tmp_path):
+    """UnOCPSolver::saveSolution / printSolution (unocp_solver.cpp:264-352): N + 1 lines of q and v, N lines of a and u,
+    7 space-separated coefficients with the stream's default precision; the saved trajectory is the golden final iterate."""
+    import numpy as np
+    _build()
+    env = dict(os.environ, IDOCP_B200_SAVE_DIR=str(tmp_path))
+    out = subprocess.run([EXE, "benchmark", "unocp", "2", "50", "0"], capture_output=True, text=True, check=True, env=env).stdout
+    with open(os.path.join(GOLDEN, "unocp_golden.json")) as f:
+        final = json.load(f)["unocp_benchmark_reference_instance"]["final"]
+    for name, lines in (("q", 21), ("v", 21), ("a", 20), ("u", 20)):
+        rows = [ln for ln in open(tmp_path / (name + ".dat")).read().split("\n") if ln]
+        assert len(rows) == lines
+        assert all(ln.endswith(" ") and len(ln.split()) == 7 for ln in rows)
+        got = np.array([[float(x) for x in ln.split()] for ln in rows])
+        ref = np.array(final[name])[:lines]
+        assert np.allclose(got, ref, rtol=1e-5, atol=1e-300)
+        assert rows[0].split()[0] == "%g" % ref[0][0]
+    printed = re.findall(r"^u\[(\d+)\] = (.*)$", out, flags=re.M)
+    assert [int(i) for i, _ in printed] == list(range(20))
+    assert all(len(r.split()) == 7 for _, r in printed)
+
+
 def test_contact_schedule_example_runs_on_the_host():
     """examples/contact_schedule.cpp: the C++ schedule classes (include/idocp_b200/hybrid.hpp) are pure host code;
     the trotting schedule of SURVEY Appendix C has 36 stages, impulses at 1.0 and 1.5, one lift at 0.5."""
