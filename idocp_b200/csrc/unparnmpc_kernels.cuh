@@ -137,7 +137,8 @@ __device__ __forceinline__ int warp_llt(double* __restrict__ A, int ld, double* 
   const int row = wl < n ? wl : n - 1;   // idle lanes shadow the last row (never stored)
 #pragma unroll
   for (int k = 0; k < n; ++k) {
-    double x = A[k * ld + row];
+    // idle lanes do not touch A: their read of element (n - 1, k) would sit unordered against lane n - 1's store below
+    double x = wl < n ? A[k * ld + row] : 1.0;
 #pragma unroll
     for (int j = 0; j < k; ++j) x = fma(-Lrow[j], A[j * ld + k], x);
     const double piv = __shfl_sync(FULL, x, k);
