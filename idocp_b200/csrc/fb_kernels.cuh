@@ -107,11 +107,20 @@ enum { FBM_SET = 0, FBM_ADD = 1, FBM_SUB = 2 };
 // unchanged, so the bits do not depend on the tiling.  FBM_SET starts a chain with the plain product a_0 b_0;
 // FBM_ADD / FBM_SUB start it from init(i, j); store(i, j, value) receives the finished element.
 // The caller separates dependent calls with __syncthreads().
+// `rot` (optional): independent products issued back to back without a barrier start their tile -> thread assignment
+// where the previous one stopped (*rot is advanced by the tile count), so that e.g. four 81-tile products keep all
+// 128 threads busy (3 rounds) instead of using threads 0..80 four times.
 template <int MODE, class Init, class Store>
 __device__ __forceinline__ void fb_mm_f(int m, int n, int k, const double* __restrict__ A, int ars, int acs, const double* __restrict__ B,
-                                        int brs, int bcs, Init init, Store store) {
+                                        int brs, int bcs, Init init, Store store, int* rot = nullptr) {
   const int tm = (m + 1) >> 1, tn = (n + 1) >> 1, total = tm * tn;
-  for (int t = threadIdx.x; t < total; t += blockDim.x) {
+  int first = threadIdx.x;
+  if (rot) {
+    first = (int)threadIdx.x - *rot;
+    if (first < 0) first += blockDim.x;
+    *rot = (*rot + total) % (int)blockDim.x;
+  }
+  for (int t = first; t < total; t += blockDim.x) {
     const int i0 = t / tn, j0 = t - i0 * tn;
     const int i1 = i0 + tm, j1 = j0 + tn;
     const bool hi = i1 < m, hj = j1 < n;
@@ -148,9 +157,9 @@ __device__ __forceinline__ void fb_mm_f(int m, int n, int k, const double* __res
 }
 template <int MODE>
 __device__ __forceinline__ void fb_mm(int m, int n, int k, const double* __restrict__ A, int ars, int acs, const double* __restrict__ B,
-                                      int brs, int bcs, double* C, int ldc) {
+                                      int brs, int bcs, double* C, int ldc, int* rot = nullptr) {
   fb_mm_f<MODE>(m, n, k, A, ars, acs, B, brs, bcs, [=](int i, int j) { return C[i * ldc + j]; },
-                [=](int i, int j, double v) { C[i * ldc + j] = v; });
+                [=](int i, int j, double v) { C[i * ldc + j] = v; }, rot);
 }
 template <int MODE>
 __device__ __forceinline__ void fb_mv(int m, int k, const double* A, int ars, int acs, const double* x, double* y) {
@@ -1409,6 +1418,7 @@ __global__ void __launch_bounds__(128, 5) k_fb_condense(FbArrays A, const FbLin*
   FB_PHASE(0, 7);
   // Qxx -= MJ_dIDC^T Qafqv, starting from the sparse cost / constraint Hessian; the Qvq block is never read
   // (the Riccati sweep rebuilds it from Qqv, backward_riccati_recursion_factorizer.hxx:93) and is left untouched
+  int rot = 0;   // tile rotation across the independent products below (fb_mm_f)
   {
     const double *Qqq6 = w.Qqq6, *Qqq_d = w.Qqq_d, *Qvv_d = w.Qvv_d;
     double* Qxx = Kt.Qxx;
@@ -1418,7 +1428,7 @@ __global__ void __launch_bounds__(128, 5) k_fb_condense(FbArrays A, const FbLin*
                        if (r == c) return r < NV ? Qqq_d[r] : Qvv_d[r - NV];
                        return 0.0;
                      },
-                     [=](int r, int c, double v) { if (!(r >= NV && c < NV)) Qxx[r * NX + c] = v; });
+                     [=](int r, int c, double v) { if (!(r >= NV && c < NV)) Qxx[r * NX + c] = v; }, &rot);
   }
   if (tid < NV) {
     double acc = w.lq[tid];
@@ -1435,9 +1445,9 @@ __global__ void __launch_bounds__(128, 5) k_fb_condense(FbArrays A, const FbLin*
       const double* Quu_d = w.Quu_d;
       double *Qxu = Kt.Qxu, *Quu = Kt.Quu;
       fb_mm_f<FBM_SUB>(NX, NV, nvf, w.MJ_dIDC, 1, NX, Qafu, NV, 1, [](int, int) { return 0.0; },
-                       [=](int r, int c, double v) { Qxu[r * NV + c] = v; });
+                       [=](int r, int c, double v) { Qxu[r * NV + c] = v; }, &rot);
       fb_mm_f<FBM_ADD>(NV, NV, nvf, w.MJtJinv, NVF, 1, Qafu, NV, 1, [=](int r, int c) { return (r == c && r >= NPASS) ? Quu_d[r - NPASS] : 0.0; },
-                       [=](int r, int c, double v) { Quu[r * NV + c] = v; });
+                       [=](int r, int c, double v) { Quu[r * NV + c] = v; }, &rot);
     }
     if (tid >= 64 && tid < 64 + NV) {
       const int j = tid - 64;
@@ -1468,8 +1478,8 @@ __global__ void __launch_bounds__(128, 5) k_fb_condense(FbArrays A, const FbLin*
       const double *Phix0 = L.Phix, *Phia = L.Phia;   // HBM operands: switching stages only
       double* Phix = Kt.Phix;
       fb_mm_f<FBM_SUB>(dimi, NX, NV, Phia, NV, 1, w.MJ_dIDC, NX, 1, [=](int r, int c) { return Phix0[r * NX + c]; },
-                       [=](int r, int c, double v) { Phix[r * NX + c] = v; });
-      fb_mm<FBM_SET>(dimi, NU, NV, Phia, NV, 1, w.MJtJinv + NPASS, NVF, 1, Kt.Phiu, NU);
+                       [=](int r, int c, double v) { Phix[r * NX + c] = v; }, &rot);
+      fb_mm<FBM_SET>(dimi, NU, NV, Phia, NV, 1, w.MJtJinv + NPASS, NVF, 1, Kt.Phiu, NU, &rot);
     }
     if (tid < dimi) {
       double acc = w.P[tid];
