@@ -101,6 +101,7 @@ struct FbArrays {
 enum { FBM_SET = 0, FBM_ADD = 1, FBM_SUB = 2 };
 
 // C (m x n) {=, +=, -=} A (m x k) B (k x n): one ascending-k fma chain per element.  A thread owns a 2 x 2 tile of C
+// (3 x 3 and 4 x 4 tiles save shared-memory loads but measured 25-30 % slower: too few threads per product)
 // -- rows (i, i + ceil(m/2)), columns (j, j + ceil(n/2)), so that neighbouring lanes read neighbouring columns of B
 // (no shared-memory bank conflicts) and write neighbouring elements of C: four independent chains in flight (the
 // chains are latency-bound otherwise) and half the shared-memory loads per fma.  The chain of every element is
