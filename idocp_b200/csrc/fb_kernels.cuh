@@ -97,7 +97,6 @@ struct FbArrays {
 #define FB_LS_FILTER_CAP 256
 
 #define FB_FOR(i, n) for (int i = threadIdx.x; i < (n); i += blockDim.x)
-#define FB_COMPILER_FENCE() asm volatile("" ::: "memory")
 enum { FBM_SET = 0, FBM_ADD = 1, FBM_SUB = 2 };
 
 // C (m x n) {=, +=, -=} A (m x k) B (k x n): one ascending-k fma chain per element.  A thread owns a 2 x 2 tile of C
@@ -257,42 +256,8 @@ __device__ __forceinline__ void fb_llt_cta(const double* A, int lda, int n, doub
     if (ej[e] >= 0 && ei[e] > ej[e]) L[ej[e] * ldl + ei[e]] *= rd[ej[e]];
   __syncthreads();
 }
-// X := (L L^T)^-1 X for an n x m block of right-hand sides (X[i*ldx + c]) by the whole CTA, n m <= 128 E: every entry is owned
-// by one thread and lives in a register; step j: the owners of row j scale and publish it, after one barrier the
-// other rows apply their fma.  Forward: entry i receives its terms in ascending j; backward: in descending j -- the
-// arithmetic of fb_llt_solve_n / the oracle, element by element.
-template <int E>
-__device__ __forceinline__ void fb_llt_solve_cta(const double* L, int ldl, const double* rd, int n, double* X, int ldx, int m) {
-  const int total = n * m;
-  int ei[E], ec[E];
-  double y[E];
-#pragma unroll
-  for (int e = 0; e < E; ++e) {
-    const int x = threadIdx.x + e * 128;
-    ei[e] = -1; ec[e] = 0; y[e] = 0.0;
-    if (x < total) { ei[e] = x / m; ec[e] = x - ei[e] * m; y[e] = X[ei[e] * ldx + ec[e]]; }
-  }
-  for (int j = 0; j < n; ++j) {
-#pragma unroll
-    for (int e = 0; e < E; ++e)
-      if (ei[e] == j) { y[e] *= rd[j]; X[j * ldx + ec[e]] = y[e]; }
-    __syncthreads();
-#pragma unroll
-    for (int e = 0; e < E; ++e)
-      if (ei[e] > j) y[e] = fma(-L[j * ldl + ei[e]], X[j * ldx + ec[e]], y[e]);
-  }
-  for (int j = n - 1; j >= 0; --j) {
-#pragma unroll
-    for (int e = 0; e < E; ++e)
-      if (ei[e] == j) { y[e] *= rd[j]; X[j * ldx + ec[e]] = y[e]; }
-    __syncthreads();
-#pragma unroll
-    for (int e = 0; e < E; ++e)
-      if (ei[e] >= 0 && ei[e] < j) y[e] = fma(-L[ei[e] * ldl + j], X[j * ldx + ec[e]], y[e]);
-  }
-  __syncthreads();
-}
-// fb_llt_cta and fb_llt_solve_cta in ONE sweep: column k of the factor and step k of the forward substitution need the same
+// fb_llt_cta and X := (L L^T)^-1 X for an n x m block of right-hand sides (X[i*ldx + c], n m <= 128 EY, every entry owned
+// by one thread in a register) in ONE sweep: column k of the factor and step k of the forward substitution need the same
 // barrier (the forward step uses L_ik = A_ik r_k and the scaled y_k = y_k r_k, both formed from values published before
 // it), so the factorisation plus both substitutions cost 2 n barriers instead of 3 n.  Same arithmetic, element by element.
 template <int EA, int EY>
