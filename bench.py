@@ -57,6 +57,26 @@ NCU_FP64_PIPE_PCT = {"linearize": 46.2, "riccati": 28.8, "expand": 15.2, "update
 NCU_SOURCE = "profiles/r1w_ncu_full_unocp.txt"
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: file descriptor 1 is pointed at stderr for the rest of the process
+    (NCCL prints its version banner to fd 1 at NCCL_DEBUG=VERSION and WARN; libraries may chat), and the line is
+    written through a private duplicate of the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit_line(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def splitmix_uniform(seed, index):
     """Counter-based splitmix64 -> double in [0,1); vectorised twin of oracle_splitmix_uniform."""
     idx = np.asarray(index, dtype=np.uint64)
@@ -177,7 +197,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "instance-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "oracle restatement of idocp (oracle/idocp_oracle.c), not the upstream binary: pinocchio/Eigen absent",
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -260,7 +280,7 @@ def run_reference_anymal(args, rank):
         "e2e": {"value": value, "unit": "instance-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "oracle restatement of idocp's OCPSolver (oracle/fb_ocp.c), not the upstream binary: pinocchio/Eigen absent",
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 def run_anymal(args, rank, local_rank, world):
@@ -381,7 +401,7 @@ def run_anymal(args, rank, local_rank, world):
         cval, cores, sample, _ = anymal_oracle_throughput(args.workload, args.cpu_seconds)
         line["cpu_baseline"] = {"value": cval, "unit": "instance-iterations/s", "cores": cores, "kind": "port", "sample": sample}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -398,6 +418,7 @@ def main():
     ap.add_argument("--workload", default="iiwa14_unocp", choices=["iiwa14_unocp", "anymal_trotting", "anymal_running"],
                     help="iiwa14_unocp = BASELINE configs[2] (the headline); anymal_* = configs[3] / configs[4]")
     args = ap.parse_args()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -559,7 +580,7 @@ def main():
         line["cpu_baseline"] = {"value": cval, "unit": "instance-iterations/s", "cores": cores, "kind": "port",
                                 "sample": sample}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.destroy_process_group()
 
