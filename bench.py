@@ -519,6 +519,20 @@ def main():
         sampler.stop_flag = True
         sampler.join(timeout=2)
 
+    # ---- secondary metric: the ocpbenchmarker::Convergence pattern --------------------------
+    # (utils/ocp_benchmarker.hxx:37-51) = updateSolution + computeKKTResidual + KKTError every iteration, the KKT
+    # errors of the batch read back to the host each time; device-resident x0, reported beside `value`, not in it
+    conv_steps = max(1, min(args.steps, 50))
+    barrier()
+    e0.record(stream)
+    for _ in range(conv_steps):
+        solver.updateSolutionDevice(0.0, q_dev.data_ptr(), v_dev.data_ptr())
+        solver.computeKKTResidualDevice(0.0, q_dev.data_ptr(), v_dev.data_ptr())
+        solver.KKTError()
+    e1.record(stream)
+    barrier()
+    conv_ms = max_over_ranks(e0.elapsed_time(e1))
+
     # sanity: the batch must have stayed numerically healthy
     solver.computeKKTResidualDevice(0.0, q_dev.data_ptr(), v_dev.data_ptr())
     kkt = solver.KKTError()
@@ -570,6 +584,9 @@ def main():
         "e2e": {"value": e2e_value, "unit": "instance-iterations/s", "h2d_bytes_per_step": 2 * B * NV * 8,
                 "d2h_bytes_per_step": B * NV * 8, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
+        "convergence_pattern": {"value": float(B) * world * conv_steps / (conv_ms * 1e-3), "unit": "instance-iterations/s",
+                                "ms_per_step": conv_ms / conv_steps, "steps": conv_steps,
+                                "what": "updateSolution + computeKKTResidual + KKTError (errors read back) per iteration"},
         "roofline": roofline,
         "clocks": sampler.summary() if rank == 0 else None,
         "health": {"kkt_max": float(np.nanmax(kkt)), "kkt_nan": int(np.isnan(kkt).sum()),
