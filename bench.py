@@ -49,12 +49,12 @@ KERNEL_ALGO_DOUBLES_PER_STAGE = {
 
 
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of each kernel from the committed ncu
-# --set full capture profiles/r1w_ncu_full_unocp.txt (same workload: 16384 instances, N = 20); reported as
+# --set full capture profiles/r1zd_ncu_full_unocp.txt (same workload: 16384 instances, N = 20); reported as
 # roofline.traffic only when the bench runs that workload.  FP64-pipe utilisation from the same capture.
-NCU_DRAM_BYTES_PER_LAUNCH = {"linearize": 0.463118e9 + 1.431644e9, "riccati": 1.279444e9 + 0.990545e9,
-                             "expand": 1.503690e9 + 0.087287e9, "update": 0.553002e9 + 0.334718e9}
-NCU_FP64_PIPE_PCT = {"linearize": 46.2, "riccati": 28.8, "expand": 15.2, "update": 11.9}
-NCU_SOURCE = "profiles/r1w_ncu_full_unocp.txt"
+NCU_DRAM_BYTES_PER_LAUNCH = {"linearize": 0.463522e9 + 1.430942e9, "riccati": 1.280254e9 + 0.990146e9,
+                             "expand": 1.503689e9 + 0.088785e9, "update": 0.552751e9 + 0.335411e9}
+NCU_FP64_PIPE_PCT = {"linearize": 46.2, "riccati": 28.7, "expand": 18.1, "update": 11.9}
+NCU_SOURCE = "profiles/r1zd_ncu_full_unocp.txt"
 
 
 _JSON_OUT = None

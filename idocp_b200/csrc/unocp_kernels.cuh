@@ -29,6 +29,9 @@ namespace idocp_b200 {
 #ifndef IDOCP_RIC_MINB
 #define IDOCP_RIC_MINB 2
 #endif
+#ifndef IDOCP_EXP_MINB
+#define IDOCP_EXP_MINB 3   // k_expand holds its whole W record in registers (166): 3 warps per scheduler, 12 per SM
+#endif
 constexpr int WARPS_PER_CTA = 4;
 constexpr int OCTETS_PER_CTA = 4 * WARPS_PER_CTA;  // 16 octets, 128 threads
 constexpr int CTA_THREADS = 32 * WARPS_PER_CTA;
@@ -804,7 +807,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_RIC_MINB) k_riccati(const D
 // (k_parnmpc_forward_parallel); only the condensed direction and the step sizes are computed.
 // TASK = true: the terminal P_N = Qqq_N is dense (record N of KQ)
 template <bool PARNMPC, bool TASK>
-__global__ void __launch_bounds__(CTA_THREADS) k_expand(const DevProblem* __restrict__ Pp, Layout L, int stage_offset) {
+__global__ void __launch_bounds__(CTA_THREADS, IDOCP_EXP_MINB) k_expand(const DevProblem* __restrict__ Pp, Layout L, int stage_offset) {
   const DevProblem& P = *Pp;
   const int lane = lane_in_octet();
   const StageTask t = stage_task(L, PARNMPC ? L.N : L.N + 1);
@@ -852,6 +855,20 @@ __global__ void __launch_bounds__(CTA_THREADS) k_expand(const DevProblem* __rest
       dul[c] = on ? X[(X_DUAL + c) * SLOT] : 0.0;
     }
   }
+  // Every W slot of the record goes out before the first use: the kernel is a pure HBM stream, and 12 warps per SM
+  // with ~60 loads in flight each (166 registers) reach 6.4 TB/s where 20 warps at 95 registers, loading as the FMA
+  // chains consume, reached 5.4 TB/s (0.287 -> 0.249 ms; register CAPS of 80 / 72 for more warps: 0.36 / 0.35 ms).
+  double w_pqq[NV], w_pvq[NV], w_pqv[NV], w_pvv[NV], w_dq[NV], w_dv[NV], w_m[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    if (!PARNMPC) {
+      w_pqq[k] = W[(W_PQQ + k) * SLOT]; w_pvq[k] = W[(W_PVQ + k) * SLOT];
+      w_pqv[k] = W[(W_PQV + k) * SLOT]; w_pvv[k] = W[(W_PVV + k) * SLOT];
+    }
+    w_dq[k] = W[(W_DQ + k) * SLOT]; w_dv[k] = W[(W_DV + k) * SLOT]; w_m[k] = W[(W_M + k) * SLOT];
+  }
+  const double w_sq = PARNMPC ? 0.0 : W[W_SQ * SLOT], w_sv = PARNMPC ? 0.0 : W[W_SV * SLOT];
+  const double w_id = W[W_ID * SLOT], w_quu = W[W_QUU * SLOT], w_lu = W[W_LU * SLOT];
   double dqk[NV], dvk[NV];
 #pragma unroll
   for (int k = 0; k < NV; ++k) { dqk[k] = oct_bcast(dq, k); dvk[k] = oct_bcast(dv, k); }
@@ -861,32 +878,32 @@ __global__ void __launch_bounds__(CTA_THREADS) k_expand(const DevProblem* __rest
     double t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-      t1 = fma(W[(W_PQQ + k) * SLOT], dqk[k], t1);
-      t2 = fma(W[(W_PVQ + k) * SLOT], dvk[k], t2);
-      t3 = fma(W[(W_PQV + k) * SLOT], dqk[k], t3);
-      t4 = fma(W[(W_PVV + k) * SLOT], dvk[k], t4);
+      t1 = fma(w_pqq[k], dqk[k], t1);
+      t2 = fma(w_pvq[k], dvk[k], t2);
+      t3 = fma(w_pqv[k], dqk[k], t3);
+      t4 = fma(w_pvv[k], dvk[k], t4);
     }
-    dlmd = t1; dlmd += t2; dlmd -= W[W_SQ * SLOT];
-    dgmm = t3; dgmm += t4; dgmm -= W[W_SV * SLOT];
+    dlmd = t1; dlmd += t2; dlmd -= w_sq;
+    dgmm = t3; dgmm += t4; dgmm -= w_sv;
   }
   // du = ID + dID/dq dq + dID/dv dv + M da ; dbeta = (lu + Quu du) / dt
   double du, dbeta;
   {
-    double acc = W[W_ID * SLOT];
+    double acc = w_id;
     double s = 0.0;
 #pragma unroll
-    for (int c = 0; c < NV; ++c) s = fma(W[(W_DQ + c) * SLOT], dqk[c], s);
+    for (int c = 0; c < NV; ++c) s = fma(w_dq[c], dqk[c], s);
     acc += s;
     s = 0.0;
 #pragma unroll
-    for (int c = 0; c < NV; ++c) s = fma(W[(W_DV + c) * SLOT], dvk[c], s);
+    for (int c = 0; c < NV; ++c) s = fma(w_dv[c], dvk[c], s);
     acc += s;
     s = 0.0;
 #pragma unroll
-    for (int c = 0; c < NV; ++c) s = fma(W[(W_M + c) * SLOT], oct_bcast(da, c), s);
+    for (int c = 0; c < NV; ++c) s = fma(w_m[c], oct_bcast(da, c), s);
     acc += s;
     du = acc;
-    dbeta = fma(W[W_QUU * SLOT], du, W[W_LU * SLOT]) / P.dt;
+    dbeta = fma(w_quu, du, w_lu) / P.dt;
   }
   if (!PARNMPC) {
     D[D_LMD * SLOT] = dlmd;
