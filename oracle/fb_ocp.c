@@ -1612,3 +1612,23 @@ int oracle_fb_ocp_set(oracle_fb_ocp_t* o, int e, const char* name, const double*
 #undef SET
   return -1;
 }
+
+/* batch helpers of the test harness (OpenMP over instances): KKT errors and one field of one chain element of
+ * every instance, out[batch][size] */
+void oracle_fb_ocp_batch_kkt(oracle_fb_ocp_t** os, int batch, double t, const double* q, const double* v, double* kkt_out,
+                             int nthreads) {
+#pragma omp parallel for schedule(dynamic) num_threads(nthreads)
+  for (int b = 0; b < batch; ++b) {
+    oracle_fb_ocp_compute_kkt_residual(os[b], t, q + (size_t)b * NQ, v + (size_t)b * NV);
+    kkt_out[b] = oracle_fb_ocp_kkt_error(os[b]);
+  }
+}
+int oracle_fb_ocp_batch_get(oracle_fb_ocp_t** os, int batch, int e, const char* name, double* out, int size) {
+  int n = 0;
+  for (int b = 0; b < batch; ++b) {
+    n = oracle_fb_ocp_get(os[b], e, name, out + (size_t)b * size);
+    if (n != size) return n;
+  }
+  return n;
+}
+

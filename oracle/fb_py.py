@@ -239,3 +239,29 @@ def batch_update_solution(solvers, t, q, v, line_search=False, nthreads=1):
     arr = (C.c_void_p * len(solvers))(*[s.h for s in solvers])
     L.oracle_fb_ocp_batch_update_solution(arr, len(solvers), float(t), _p(_a(q, len(solvers) * NQ)), _p(_a(v, len(solvers) * NV)),
                                           int(line_search), int(nthreads))
+
+
+def _harr(solvers):
+    return (C.c_void_p * len(solvers))(*[s.h for s in solvers])
+
+
+def batch_kkt(solvers, t, q, v, nthreads=1):
+    """computeKKTResidual + KKTError of every instance (OpenMP over instances)."""
+    L = lib()
+    L.oracle_fb_ocp_batch_kkt.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_double, _dp, _dp, _dp, C.c_int]
+    out = np.zeros(len(solvers))
+    L.oracle_fb_ocp_batch_kkt(_harr(solvers), len(solvers), float(t), _p(_a(q, len(solvers) * NQ)), _p(_a(v, len(solvers) * NV)),
+                              _p(out), int(nthreads))
+    return out
+
+
+def batch_get(solvers, e, name):
+    """(batch, size) of one field of chain element e of every instance."""
+    L = lib()
+    L.oracle_fb_ocp_batch_get.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_char_p, _dp, C.c_int]
+    size = _SIZES.get(name, NV)
+    out = np.zeros((len(solvers), size))
+    n = L.oracle_fb_ocp_batch_get(_harr(solvers), len(solvers), int(e), name.encode(), _p(out), size)
+    assert n == size, (name, n, size)
+    return out
+

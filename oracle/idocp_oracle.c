@@ -1677,6 +1677,21 @@ void oracle_unocp_batch_kkt(oracle_unocp_t** os, int batch, double t, const doub
   }
 }
 
+/* batch getter of the test harness: which = 0 solution, 1 direction; out[batch][(N+1)*NV] (rows beyond the field's
+ * stage count are left untouched); returns the number of stages of the field */
+int oracle_unocp_batch_get(oracle_unocp_t** os, int batch, int which, const char* name, double* out) {
+  int n = 0;
+  for (int b = 0; b < batch; ++b) {
+    double* dst = out + (size_t)b * (os[b]->N + 1) * NV;
+    n = which ? oracle_unocp_get_direction(os[b], name, dst) : oracle_unocp_get_solution(os[b], name, dst);
+    if (n < 0) return n;
+  }
+  return n;
+}
+void oracle_unocp_batch_step_sizes(oracle_unocp_t** os, int batch, double* out) {
+  for (int b = 0; b < batch; ++b) oracle_unocp_get_step_sizes(os[b], out + 3 * (size_t)b);
+}
+
 /* ========================================================================================== */
 /* UnParNMPCSolver (src/unocp/unparnmpc_solver.cpp, src/unocp/unbackward_correction.cpp,       */
 /* unocp/split_unparnmpc.hxx, terminal_unparnmpc.hxx, split_unbackward_correction.hxx,         */

@@ -84,6 +84,8 @@ void oracle_unocp_batch_update_solution(oracle_unocp_t** os, int batch, double t
                                         const double* v0, int line_search, int nthreads);
 void oracle_unocp_batch_kkt(oracle_unocp_t** os, int batch, double t, const double* q0,
                             const double* v0, double* kkt_out, int nthreads);
+int  oracle_unocp_batch_get(oracle_unocp_t** os, int batch, int which, const char* name, double* out);
+void oracle_unocp_batch_step_sizes(oracle_unocp_t** os, int batch, double* out);
 /* reference threading (OpenMP over stages inside one instance = "mode A", unocp_benchmark.cpp:42) */
 void oracle_unocp_set_stage_threads(oracle_unocp_t* o, int nthreads);
 

@@ -309,6 +309,27 @@ class Batch:
         f(self.arr, self.batch, C.c_double(t), _p(q0), _p(v0), _p(out), int(nthreads))
         return out
 
+    def _get(self, which, name):
+        assert self.kind == "unocp"
+        N = self.solvers[0].N
+        out = np.zeros((self.batch, N + 1, NV))
+        n = self.L.oracle_unocp_batch_get(self.arr, self.batch, int(which), name.encode(), _p(out))
+        if n < 0:
+            raise ValueError(name)
+        return out[:, :n].copy()
+
+    def get_solution(self, name):
+        """(batch, stages, 7) of one solution field of every instance."""
+        return self._get(0, name)
+
+    def get_direction(self, name):
+        return self._get(1, name)
+
+    def step_sizes(self):
+        out = np.zeros((self.batch, 3))
+        self.L.oracle_unocp_batch_step_sizes(self.arr, self.batch, _p(out))
+        return out
+
 
 def task_evaluate(q, ref12):
     """diff_6d = log6(SE3_ref^-1 oMf) [lin; ang] and JJ = Jlog6 * J_frame(LOCAL) as numpy (6, 7)."""

@@ -1,0 +1,110 @@
+"""Scenario bodies shared by the emulator tests (CPU, tiny batches) and the GPU tests (BASELINE-sized batches): the
+library under test is a parameter, the oracle is always the checker."""
+import os
+
+import numpy as np
+
+import anymal_problems as ap
+from test_emu_fb_parity import DIR, SOL, masked
+
+THREADS = os.cpu_count() or 1
+_TERMINAL_OK = ("q", "v", "lmd", "gmm", "dq", "dv", "dlmd", "dgmm", "lq", "lv", "Pqq", "Pvv", "sq", "sv", "Fqq_prev_inv")
+_IMPULSE_SKIP = ("u", "du", "nu_passive", "dnu_passive", "lu", "lu_passive", "Qxu", "Quu", "Fvu", "Fqv6", "Qafu", "K", "k",
+                 "xi", "dxi")
+_MASKED = ("daf", "dbetamu", "MJ_IDC", "MJtJinv", "MJ_dIDC", "Qafqv", "Qafu", "dxi", "xi")
+
+
+def compare_batch(oracles, solver, fb, names, rows=None):
+    """Every field in `names` of every chain element, all instances at once (rows: boolean mask of the instances to
+    compare).  Returns [(element, kind, field, number of differing instances)]."""
+    bad = []
+    for e, c in enumerate(solver.chain()):
+        for nm in names:
+            if c["kind"] == fb.K_TERMINAL and nm not in _TERMINAL_OK:
+                continue
+            if c["kind"] == fb.K_IMPULSE and nm in _IMPULSE_SKIP:
+                continue
+            if nm in ("xi", "dxi") and c["dimi"] == 0:
+                continue
+            x = fb.batch_get(oracles, e, nm)
+            y = np.asarray(solver.get(e, nm), dtype=float).reshape(x.shape)
+            if nm in _MASKED:
+                x = np.stack([masked(nm, r, c, fb) for r in x])
+                y = np.stack([masked(nm, r, c, fb) for r in y])
+            if rows is not None:
+                x, y = x[rows], y[rows]
+            if not np.array_equal(x, y, equal_nan=True):
+                same = (x == y) | (np.isnan(x) & np.isnan(y))
+                bad.append((e, c["kind"], nm, int((~np.all(same, axis=1)).sum())))
+    return bad
+
+
+def anymal_states(pr, count, seed):
+    from idocp_b200 import problems as P
+    return P.anymal_initial_states(0, count, q_nominal=pr.q0, seed=seed)
+
+
+def chain_signature(ch):
+    return [(c["kind"], c["index"], c["dimf"], c["dimi"]) for c in ch]
+
+
+def run_state_feedback_gain(lib, fb, batch):
+    """OCPSolver::getStateFeedbackGain (riccati_recursion_solver.cpp:254-260): K of the LQR policy of a time stage."""
+    pr = ap.TrottingProblem()
+    q0, v0 = anymal_states(pr, batch, 20240004)
+    solver = ap.make_product_solver(pr, lib, fb, batch=batch, q0=q0, v0=v0)
+    oracles = [pr.make_oracle(fb, q0=q0[b], v0=v0[b]) for b in range(batch)]
+    for _ in range(2):
+        solver.updateSolution(0.0, q0, v0)
+        fb.batch_update_solution(oracles, 0.0, q0, v0, False, THREADS)
+    ch = solver.chain()
+    for stage in (0, 3, 11, pr.N - 1):
+        e = [k for k, c in enumerate(ch) if c["kind"] == fb.K_GRID and c["index"] == stage][0]
+        Kq, Kv = solver.getStateFeedbackGain(stage)
+        K = fb.batch_get(oracles, e, "K").reshape(batch, 12, 36)
+        assert np.array_equal(Kq, K[:, :, :18]) and np.array_equal(Kv, K[:, :, 18:]), stage
+
+
+def run_receding_horizon(lib, fb, batch):
+    """MPC-style use (ocp_solver.cpp:174-194): updateSolution at advancing t re-discretises the schedule, the plant moves
+    (next x0 = second stage of the current solution, per instance), the first phase is popped once its event has
+    passed and a new touch-down is pushed at the end of the horizon; 7 ticks, every instance bit for bit."""
+    pr = ap.TrottingProblem()
+    q, v = anymal_states(pr, batch, 20240004)
+    q[0], v[0] = pr.q0, pr.v0
+    solver = ap.make_product_solver(pr, lib, fb, batch=batch, q0=q, v0=v)
+    oracles = [pr.make_oracle(fb, q0=q[b], v0=v[b]) for b in range(batch)]
+
+    def tick(t, q, v):
+        for o in oracles:
+            pr.set_references(o, t)
+        rcs = [o.update_solution(t, q[b], v[b]) for b, o in enumerate(oracles)]
+        solver.updateSolution(t, q, v)
+        assert chain_signature(solver.chain()) == chain_signature(oracles[0].chain()), t
+        assert np.array_equal([c["dt"] for c in solver.chain()], [c["dt"] for c in oracles[0].chain()]), t
+        assert np.array_equal(solver.stepSizes(), np.array([o.step_sizes() for o in oracles]), equal_nan=True), t
+        ok = np.array(rcs) == 0
+        assert compare_batch(oracles, solver, fb, SOL + DIR, rows=ok) == [], t
+        return fb.batch_get(oracles, 1, "q"), fb.batch_get(oracles, 1, "v"), ok
+
+    ticks = 0
+    for t in (0.0, 0.013, 0.04, 0.31, 0.47):
+        q, v, ok = tick(t, q, v)
+        assert ok.all(), t
+        ticks += 1
+    for o in oracles:
+        o.cs.pop_front()
+    solver.popFrontContactStatus()
+    cs = oracles[0].cs
+    a, pts = cs.phase(cs.counts()[0] - 1)
+    pts = pts.copy()
+    pts[0, 0] += pr.step_length
+    pts[3, 0] += pr.step_length
+    t = 0.52
+    for o in oracles:
+        assert o.cs.push_back([1, 0, 0, 1], t + pr.T - 0.02, pts) == 0
+    solver.pushBackContactStatus([1, 0, 0, 1], t + pr.T - 0.02, pts)
+    for t in (0.52, 0.55):
+        q, v, ok = tick(t, q, v)
+        ticks += 1
+    assert ticks == 7

@@ -148,3 +148,13 @@ def test_receding_horizon_calls_bit_exact(fb, emu_lib):
         assert np.array_equal(solver.stepSizes()[0], ocp.step_sizes()), t
         if rc == 0:
             assert compare(ocp, solver, fb, SOL) == [], t
+
+
+def test_state_feedback_gain_matches_oracle_emu(fb, emu_lib):
+    import fb_scenarios
+    fb_scenarios.run_state_feedback_gain(emu_lib, fb, batch=2)
+
+
+def test_receding_horizon_batch_emu(fb, emu_lib):
+    import fb_scenarios
+    fb_scenarios.run_receding_horizon(emu_lib, fb, batch=2)
