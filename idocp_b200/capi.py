@@ -111,6 +111,7 @@ EXPORTS = [
     "idocp_b200_fb_sync", "idocp_b200_fb_launch_count", "idocp_b200_fb_stream", "idocp_b200_fb_set_profiling",
     "idocp_b200_fb_get_profile", "idocp_b200_fb_record_bytes", "idocp_b200_fb_problem_default",
     "idocp_b200_fb_total_weight", "idocp_b200_fb_contact_frame_positions", "idocp_b200_fb_clear_line_search_filter",
+    "idocp_b200_fb_set_strict_discretization",
 ]
 
 
@@ -181,6 +182,7 @@ class Library:
         L.idocp_b200_fb_get.argtypes = [C.c_void_p, C.c_int, C.c_char_p, _dp]
         L.idocp_b200_fb_sync.argtypes = [C.c_void_p]
         L.idocp_b200_fb_clear_line_search_filter.argtypes = [C.c_void_p]
+        L.idocp_b200_fb_set_strict_discretization.argtypes = [C.c_void_p, C.c_int]
         L.idocp_b200_fb_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
         L.idocp_b200_fb_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.idocp_b200_fb_set_profiling.argtypes = [C.c_void_p, C.c_int]

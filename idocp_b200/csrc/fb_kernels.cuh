@@ -2110,7 +2110,10 @@ __global__ void k_fb_init_constraints(FbArrays A, const FbInitRow* rows, int n_r
             default:         sl = pr.u_max[j] - S.u[j]; break;
           }
         }
-        while (sl < pr.barrier) sl += pr.barrier;
+        // pdipm::SetSlackAndDualPositive (pdipm.hxx:13-23); the iteration bound keeps a margin of -inf (or a huge
+        // violation in the initial guess) from hanging the stream -- same bound as k_init_constraints and the oracle
+        int guard = 0;
+        while (sl < pr.barrier && guard < (1 << 20)) { sl += pr.barrier; ++guard; }
         du = pr.barrier / sl;
       }
       S.slack[o + j] = sl;

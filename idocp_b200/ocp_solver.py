@@ -121,6 +121,11 @@ class OCPSolver:
         q, v = self._state(q, v)
         self.lib.check(self.lib.L.idocp_b200_fb_compute_kkt_residual(self._h, float(t), capi.dptr(q), capi.dptr(v)))
 
+    def setStrictDiscretization(self, strict):
+        """strict (default): a schedule that cannot be discretised at t raises; False: run on like a Release build of
+        the reference, whose assert(isWellDefined()) is compiled out (ocp_discretizer.hxx:62-72)."""
+        self.lib.check(self.lib.L.idocp_b200_fb_set_strict_discretization(self._h, int(bool(strict))))
+
     def clearLineSearchFilter(self):
         self.lib.check(self.lib.L.idocp_b200_fb_clear_line_search_filter(self._h))
 

@@ -271,6 +271,11 @@ int idocp_b200_fb_set_cost_reference(idocp_b200_fb_solver* h, int kind, int inde
 int idocp_b200_fb_discretize(idocp_b200_fb_solver* h, double t, int cap, int* kind, int* index, double* stage_t, double* dt,
                              int* dimf, int* dimi, int* active);
 int idocp_b200_fb_init_constraints(idocp_b200_fb_solver* h, double t);
+/* OCPDiscretizer::discretizeOCP asserts isWellDefined() (ocp_discretizer.hxx:62-72,231-244).  strict = 1 (default): a
+ * schedule that cannot be discretised at t (an event before t, two events in one grid interval, impulses after
+ * consecutive stages) makes initConstraints / updateSolution / computeKKTResidual / discretize return
+ * IDOCP_B200_INVALID_ARGUMENT before anything is launched.  strict = 0: run on like a Release build of the reference. */
+int idocp_b200_fb_set_strict_discretization(idocp_b200_fb_solver* h, int strict);
 /* q[batch][19], v[batch][18] host buffers; NULL keeps the initial states already resident on the device */
 int idocp_b200_fb_update_solution(idocp_b200_fb_solver* h, double t, const double* q, const double* v, int line_search);
 int idocp_b200_fb_compute_kkt_residual(idocp_b200_fb_solver* h, double t, const double* q, const double* v);

@@ -349,6 +349,8 @@ class OCPSolver {
     detail::check(idocp_b200_fb_compute_kkt_residual(h_.get(), t, q, v));
   }
   void clearLineSearchFilter() { detail::check(idocp_b200_fb_clear_line_search_filter(h_.get())); }
+  // assert(isWellDefined()) of OCPDiscretizer::discretizeOCP as a run-time error (default) or ignored like a Release build
+  void setStrictDiscretization(bool strict) { detail::check(idocp_b200_fb_set_strict_discretization(h_.get(), strict ? 1 : 0)); }
   double KKTError() { return KKTErrors()[0]; }
   std::vector<double> KKTErrors() {
     std::vector<double> out(batch_);

@@ -222,7 +222,7 @@ static void set_slack_and_dual(const oracle_fb_problem_t* p, stage_t* st) {
       } else {
         sl = limit_margin(p, c, st, j);
       }
-      while (sl < p->barrier) sl += p->barrier;
+      for (int guard = 0; sl < p->barrier && guard < (1 << 20); ++guard) sl += p->barrier;   /* bound: see k_fb_init_constraints */
       d->slack[j] = sl;
       d->dual[j] = p->barrier / sl;
     }
@@ -1239,8 +1239,15 @@ int oracle_fb_ocp_init_constraints(oracle_fb_ocp_t* o, double t) {
     else if (s == o->p.N) { for (int c = 0; c < NCOMP; ++c) st->cactive[c] = 0; continue; }
     else if (s < n1 + m) ts = -1;
     else ts = 0;
-    const int used = (s < n1) || (s < n1 + m ? s - n1 < o->disc.N_impulse
-                                  : (s < n1 + 2 * m ? s - n1 - m < o->disc.N_impulse : s - n1 - 2 * m < o->disc.N_lift));
+    /* every SCHEDULED event, also those beyond the horizon at this t: the reference's discretizer counts
+     * contact_sequence.numImpulseEvents() / numLiftEvents() (ocp_discretizer.hxx:246-262) and
+     * OCPLinearizer::initConstraints covers all of them (ocp_linearizer.cpp:40-68) */
+    int n_phases, n_imp, n_lift;
+    oracle_cs_counts(o->cs, &n_phases, &n_imp, &n_lift);
+    if (n_imp > m) n_imp = m;
+    if (n_lift > m) n_lift = m;
+    const int used = (s < n1) || (s < n1 + m ? s - n1 < n_imp
+                                  : (s < n1 + 2 * m ? s - n1 - m < n_imp : s - n1 - 2 * m < n_lift));
     set_constraint_stage(&o->p, st, ts);
     if (!used) { for (int c = 0; c < NCOMP; ++c) st->cactive[c] = 0; continue; }
     set_slack_and_dual(&o->p, st);

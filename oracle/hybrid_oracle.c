@@ -347,8 +347,14 @@ int oracle_discretize_ocp(const oracle_contact_sequence_t* cs, double T, int N_i
     if (d->before_impulse_flag[i] || d->before_lift_flag[i]) ++num_events;
   }
   d->contact_phase[d->N] = num_events;
-  /* every event of the sequence must have found its stage; isWellDefined (:205-217) */
-  d->well_defined = hy_well_defined(d) && impulse_index == d->N_impulse && lift_index == d->N_lift;
+  /* every event of the sequence must have found its stage; isWellDefined (:205-217)
+   * -- except the events beyond the end of the horizon (cell >= N_ideal), which the reference simply never visits */
+  int stray = 0;
+  for (int i = impulse_index; i < d->N_impulse; ++i)
+    if ((int)floor((d->t_impulse[i] - t) / dt_ideal) < N_ideal) stray = 1;
+  for (int i = lift_index; i < d->N_lift; ++i)
+    if ((int)floor((d->t_lift[i] - t) / dt_ideal) < N_ideal) stray = 1;
+  d->well_defined = hy_well_defined(d) && !stray;
   return 0;
 }
 

@@ -795,7 +795,7 @@ static void set_slack_and_dual(const oracle_problem_t* p, stage_t* st, const spl
     if (!st->active[c]) continue;
     for (int j = 0; j < NV; ++j) {
       double sl = con_margin(p, c, s, j);
-      while (sl < p->barrier) sl += p->barrier;
+      for (int guard = 0; sl < p->barrier && guard < (1 << 20); ++guard) sl += p->barrier;   /* bound: see k_init_constraints */
       d->slack[j] = sl;
       d->dual[j] = p->barrier / sl;
     }

@@ -108,3 +108,75 @@ def run_receding_horizon(lib, fb, batch):
         q, v, ok = tick(t, q, v)
         ticks += 1
     assert ticks == 7
+
+
+def run_event_before_t_is_an_error(lib, fb):
+    """time advanced past an event without popFrontContactStatus -> the discretisation is ill-defined
+    (the reference asserts, ocp_discretizer.hxx:62-72); the product must refuse instead of silently solving a chain
+    that dropped every later event.  The opt-out reproduces the Release-build behaviour."""
+    import idocp_b200 as I
+    pr = ap.TrottingProblem()
+    solver = ap.make_product_solver(pr, lib, fb, batch=1)
+    o = pr.make_oracle(fb)
+    t = pr.t_start + 0.07          # the first event (t_start) now lies before t
+    assert o.discretize(t) == -3
+    try:
+        solver.updateSolution(t, pr.q0, pr.v0)
+    except I.Idocp_b200Error as e:
+        assert "popFrontContactStatus" in str(e)
+    else:
+        raise AssertionError("ill-defined discretisation was accepted")
+    try:
+        solver.computeKKTResidual(t, pr.q0, pr.v0)
+    except I.Idocp_b200Error:
+        pass
+    else:
+        raise AssertionError("ill-defined discretisation was accepted by computeKKTResidual")
+    solver.setStrictDiscretization(False)
+    solver.updateSolution(t, pr.q0, pr.v0)          # runs on, like the reference built with NDEBUG
+    solver.setStrictDiscretization(True)
+    solver.popFrontContactStatus()
+    solver.updateSolution(t, pr.q0, pr.v0)          # the documented fix
+
+
+def run_event_entering_horizon_keeps_constraints(lib, fb, batch=1):
+    """an event scheduled beyond the horizon at initConstraints time enters it later (receding horizon).
+    Its impulse / aux / lift stages must carry active, initialised constraints (OCPLinearizer::initConstraints covers
+    contact_sequence.numImpulseEvents(), ocp_linearizer.cpp:40-68), not silently disabled ones."""
+    pr = ap.TrottingProblem()
+    pr.max_num_impulse = pr.problem.max_num_impulse = 4
+    cs_extra_t = pr.T + 0.3        # a fourth event, 0.3 s beyond the end of the horizon at t = 0
+    q, v = anymal_states(pr, batch, 20240004)
+
+    base_sequence = pr.contact_sequence
+
+    def sequence_with_extra(fbm):
+        cs = base_sequence(fbm)
+        a, pts = cs.phase(cs.counts()[0] - 1)
+        pts = pts.copy()
+        pts[0, 0] += pr.step_length
+        pts[3, 0] += pr.step_length
+        assert cs.push_back([1, 0, 0, 1], cs_extra_t, pts) == 0     # a touch-down: impulse + aux stages
+        return cs
+    pr.contact_sequence = sequence_with_extra
+    solver = ap.make_product_solver(pr, lib, fb, batch=batch, q0=q, v0=v)
+    oracles = [pr.make_oracle(fb, q0=q[b], v0=v[b]) for b in range(batch)]
+    n0 = len(solver.chain())
+    seen_new = False
+    for t in (0.0, 0.2, 0.41):
+        for o in oracles:
+            pr.set_references(o, t)
+        rcs = [o.update_solution(t, q[b], v[b]) for b, o in enumerate(oracles)]
+        assert not any(rcs), (t, rcs)
+        solver.updateSolution(t, q, v)
+        ch = solver.chain()
+        assert chain_signature(ch) == chain_signature(oracles[0].chain()), t
+        if len(ch) > n0:
+            seen_new = True
+            e = [k for k, c in enumerate(ch) if c["kind"] == fb.K_AUX][-1]
+            slack = np.asarray(solver.get(e, "slack"))
+            assert np.all(slack[:, 48:72] > 0), "torque-limit constraints of the entering aux stage (acceleration level) are disabled"
+            assert np.array_equal(slack, fb.batch_get(oracles, e, "slack"))
+            assert np.array_equal(np.asarray(solver.get(e - 1, "slack")), fb.batch_get(oracles, e - 1, "slack"))
+        assert compare_batch(oracles, solver, fb, SOL + DIR) == [], t
+    assert seen_new

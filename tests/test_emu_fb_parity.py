@@ -158,3 +158,13 @@ def test_state_feedback_gain_matches_oracle_emu(fb, emu_lib):
 def test_receding_horizon_batch_emu(fb, emu_lib):
     import fb_scenarios
     fb_scenarios.run_receding_horizon(emu_lib, fb, batch=2)
+
+
+def test_event_before_t_is_an_error_emu(fb, emu_lib):
+    import fb_scenarios
+    fb_scenarios.run_event_before_t_is_an_error(emu_lib, fb)
+
+
+def test_event_entering_horizon_keeps_constraints_emu(fb, emu_lib):
+    import fb_scenarios
+    fb_scenarios.run_event_entering_horizon_keeps_constraints(emu_lib, fb)

@@ -52,3 +52,13 @@ def test_state_feedback_gain_matches_oracle(fb, gpu_lib):
 def test_receding_horizon_bit_exact(fb, gpu_lib):
     import fb_scenarios
     fb_scenarios.run_receding_horizon(gpu_lib, fb, batch=16)
+
+
+def test_event_before_t_is_an_error(fb, gpu_lib):
+    import fb_scenarios
+    fb_scenarios.run_event_before_t_is_an_error(gpu_lib, fb)
+
+
+def test_event_entering_horizon_keeps_constraints(fb, gpu_lib):
+    import fb_scenarios
+    fb_scenarios.run_event_entering_horizon_keeps_constraints(gpu_lib, fb, batch=8)
