@@ -48,13 +48,74 @@ KERNEL_ALGO_DOUBLES_PER_STAGE = {
 }
 
 
-# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of each kernel from the committed ncu
-# --set full capture profiles/r1zd_ncu_full_unocp.txt (same workload: 16384 instances, N = 20); reported as
-# roofline.traffic only when the bench runs that workload.  FP64-pipe utilisation from the same capture.
-NCU_DRAM_BYTES_PER_LAUNCH = {"linearize": 0.463522e9 + 1.430942e9, "riccati": 1.280254e9 + 0.990146e9,
-                             "expand": 1.503689e9 + 0.088785e9, "update": 0.552751e9 + 0.335411e9}
-NCU_FP64_PIPE_PCT = {"linearize": 46.2, "riccati": 28.7, "expand": 18.1, "update": 11.9}
-NCU_SOURCE = "profiles/r1zd_ncu_full_unocp.txt"
+# ncu evidence is PARSED, not typed in: tools/ncu_capture.sh (run under gpurun) writes profiles/kernel_counters_<workload>.json
+# (per kernel: DRAM bytes read + written, executed FP64 thread instructions, pipe / issue utilisation of one launch at the
+# bench batch); tools/fp64_peak (DFMA microbenchmark on the B200) writes profiles/fp64_peak.json.
+KERNEL_OF_CLASS = {"linearize": "k_linearize<0,0,0>", "riccati": "k_riccati<0>", "expand": "k_expand<0,0>", "update": "k_update",
+                   "riccati_forward": "k_riccati_forward<0>", "update_linearize": "k_update_linearize<0>",
+                   "fb_robot": "k_fb_robot<0>", "fb_condense": "k_fb_condense", "fb_riccati_backward": "k_fb_riccati_backward",
+                   "parnmpc_invert": "k_parnmpc_invert"}
+# 64 DFMA / clk / SM (ncu: sm__sass_thread_inst_executed_op_dfma_pred_on.avg.peak_sustained) x 148 SMs x 1.965 GHz x 2
+FP64_PEAK_NOMINAL_TFLOPS = 64 * 148 * 1.965e9 * 2 / 1e12
+
+
+def load_kernel_counters(workload):
+    """profiles/kernel_counters_<workload>.json -> ({class name: counters}, source) or ({}, None)."""
+    path = os.path.join(ROOT, "profiles", "kernel_counters_%s.json" % workload)
+    if not os.path.exists(path):
+        return {}, None
+    with open(path) as f:
+        rec = json.load(f)
+    out = {}
+    for cls, kname in KERNEL_OF_CLASS.items():
+        if kname in rec["kernels"]:
+            out[cls] = rec["kernels"][kname]
+    return out, "profiles/kernel_counters_%s.json (%s)" % (workload, rec.get("source"))
+
+
+def fp64_peak():
+    """(burst TFLOP/s, sustained TFLOP/s, source): measured DFMA peak of this pool's B200 (tools/fp64_peak.cu)."""
+    path = os.path.join(ROOT, "profiles", "fp64_peak.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            rec = json.load(f)
+        return rec["fp64_dfma_tflops"], rec["fp64_dfma_tflops_sustained"], "measured (profiles/fp64_peak.json, tools/fp64_peak.cu)"
+    return FP64_PEAK_NOMINAL_TFLOPS, FP64_PEAK_NOMINAL_TFLOPS, "fallback: 64 DFMA/clk/SM x 148 SMs x 1965 MHz (no profiles/fp64_peak.json)"
+
+
+def kernel_roofline(name, per_launch_ms, algo_bytes, counters, batch_matches, hbm_peak, fp64_sustained):
+    """Both roofline fractions of one kernel: HBM from the ALGORITHMIC bytes, FP64 from the FP64 thread instructions
+    ncu counted for one launch at the same batch (executed work: the padding lane and redundant lanes included)."""
+    k = {"ms_per_launch": per_launch_ms, "algo_gbs": algo_bytes / (per_launch_ms * 1e-3) / 1e9}
+    k["frac_hbm"] = k["algo_gbs"] / hbm_peak
+    c = counters.get(name) if batch_matches else None
+    if c and "fp64_flop_executed" in c:
+        k["fp64_tflops"] = c["fp64_flop_executed"] / (per_launch_ms * 1e-3) / 1e12
+        k["frac_fp64"] = k["fp64_tflops"] / fp64_sustained
+        k["ncu_dram_bytes"] = c.get("dram_bytes")
+        k["ncu_dram_gbs_at_measured_time"] = c.get("dram_bytes", 0.0) / (per_launch_ms * 1e-3) / 1e9
+        k["ncu_fp64_pipe_pct"] = c.get("fp64_pipe_pct")
+        k["ncu_issue_active_pct"] = c.get("issue_active_pct")
+        k["ncu_registers"] = c.get("registers")
+    else:
+        k["frac_fp64"] = None
+    k["bound"] = "fp64" if (k["frac_fp64"] or 0.0) > k["frac_hbm"] else "hbm"
+    return k
+
+
+def roofline_object(dom, kern, algo_bytes, hbm_peak, peak_src, fp64_sustained, fp64_src, counters_src, note):
+    """The contract's roofline object for the dominant kernel: bound = the larger of its two fractions."""
+    k = kern[dom]
+    if k["bound"] == "fp64":
+        head = {"bound": "fp64", "achieved": k["fp64_tflops"], "peak": fp64_sustained, "unit": "TFLOP/s", "frac": k["frac_fp64"],
+                "peak_source": fp64_src + " (sustained figure: the kernel is timed inside a long step)"}
+    else:
+        head = {"bound": "hbm", "achieved": k["algo_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": k["frac_hbm"], "peak_source": peak_src}
+    head.update({"kernel": dom, "frac_hbm": k["frac_hbm"], "frac_fp64": k["frac_fp64"], "traffic": k.get("ncu_dram_bytes"),
+                 "traffic_source": counters_src if k.get("ncu_dram_bytes") else None,
+                 "algorithmic_bytes_per_launch": algo_bytes, "hbm_peak_gbs": hbm_peak, "fp64_peak_tflops": fp64_sustained,
+                 "fp64_peak_source": fp64_src, "note": note, "kernels": kern})
+    return head
 
 
 _JSON_OUT = None
@@ -142,56 +203,79 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def oracle_throughput(seconds_target, q_min, q_max, threads=None, per_step_instances=None, steps=None, warmup=0):
-    """Times the CPU oracle (restatement of idocp's UnOCPSolver) on the host cores, OpenMP over
-    instances, every instance single-threaded (BASELINE.md mode B).  Returns (units/s, cores, sample)."""
+CPU_WARM_SECONDS = 3.0     # both CPU legs warm up for this long first: OpenMP team start-up, page faults and the cores'
+                           # frequency ramp cost ~30 % on a cold 20-sweep run (260 k/s vs 382 k/s on one box)
+
+
+def _oracle_batch(q_min, q_max, cores):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py as O
-    cores = threads or os.cpu_count() or 1
     prob = O.benchmark_problem(N=HORIZON_N, T=1.0)
-    nb = per_step_instances or max(cores * 16, 256)
+    nb = max(cores * 16, 256)
     q0, v0 = initial_states(0, nb, q_min, q_max)
     batch = O.Batch(prob, nb)
     for b, s in enumerate(batch.solvers):
         s.set_solution("q", q0[b])
         s.set_solution("v", v0[b])
-    for _ in range(max(warmup, 1)):
+    t_end = time.perf_counter() + CPU_WARM_SECONDS
+    sweeps = 0
+    while time.perf_counter() < t_end or sweeps < 3:
         batch.update_solution(0.0, q0, v0, False, cores)
-    if steps is None:
-        t0 = time.perf_counter()
+        sweeps += 1
+    t0 = time.perf_counter()
+    batch.update_solution(0.0, q0, v0, False, cores)
+    return batch, nb, q0, v0, time.perf_counter() - t0
+
+
+def oracle_throughput(seconds_target, q_min, q_max, threads=None):
+    """cpu_baseline leg: the CPU oracle (restatement of idocp's UnOCPSolver) on the host cores, OpenMP over instances, every
+    instance single-threaded (BASELINE.md mode B), ~seconds_target of sweeps after the warm-up.
+    Returns (units/s, cores, sample, ms per sweep)."""
+    cores = threads or os.cpu_count() or 1
+    batch, nb, q0, v0, one = _oracle_batch(q_min, q_max, cores)
+    sweeps = int(max(3, min(4000, seconds_target / max(one, 1e-6))))
+    t0 = time.perf_counter()
+    for _ in range(sweeps):
         batch.update_solution(0.0, q0, v0, False, cores)
-        one = time.perf_counter() - t0
-        steps = int(max(3, min(2000, seconds_target / max(one, 1e-6))))
-    times = []
-    for _ in range(steps):
-        t0 = time.perf_counter()
-        batch.update_solution(0.0, q0, v0, False, cores)
-        times.append(time.perf_counter() - t0)
-    total = float(np.sum(times))
-    sample = "%d instances x %d updateSolution sweeps, OpenMP over instances, %d threads" % (nb, steps, cores)
-    return nb * steps / total, cores, sample, total / steps * 1e3
+    total = time.perf_counter() - t0
+    sample = "%d instances x %d updateSolution sweeps after %.0f s of warm-up sweeps, OpenMP over instances, %d threads" % (
+        nb, sweeps, CPU_WARM_SECONDS, cores)
+    return nb * sweeps / total, cores, sample, total / sweeps * 1e3
 
 
 def run_reference(args, rank, world):
-    """--impl reference: idocp's own CPU algorithm.  The upstream library cannot be built in this
-    image (Eigen/Boost/pinocchio/urdfdom absent), so this times the oracle restatement."""
+    """--impl reference: idocp's own CPU algorithm.  The upstream library cannot be built in this image (Eigen / Boost /
+    pinocchio / urdfdom absent), so this times the oracle restatement -- with the SAME protocol as the cpu_baseline leg of the
+    GPU arm (same instance sample, same warm-up): one step = R sweeps over the sample, R sized for ~0.5 s per step."""
     if rank != 0:
         return
-    import ctypes  # noqa: F401
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py as O
     p = O.default_problem()
     q_min, q_max = list(p.q_min), list(p.q_max)
     cores = os.cpu_count() or 1
-    per_step = max(cores * 32, 512)
-    value, cores, sample, ms = oracle_throughput(None, q_min, q_max, cores, per_step, args.steps, args.warmup)
+    batch, nb, q0, v0, one = _oracle_batch(q_min, q_max, cores)
+    per_step = int(max(1, min(1000, round(0.5 / max(one, 1e-6)))))
+
+    def step():
+        for _ in range(per_step):
+            batch.update_solution(0.0, q0, v0, False, cores)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    total = time.perf_counter() - t0
+    value = float(nb) * per_step * args.steps / total
+    sample = "%d instances x %d sweeps per step x %d steps after %.0f s + %d steps of warm-up, OpenMP over instances, %d threads" % (
+        nb, per_step, args.steps, CPU_WARM_SECONDS, args.warmup, cores)
     line = {
         "impl": "reference", "metric": "batched SQP iterations/sec (iiwa14 N=20, FP64)", "value": value,
         "unit": "instance-iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": "iiwa14 UnOCPSolver unocp_benchmark problem, N=20, T=1, random initial states "
-                               "(splitmix64 seed %d); bounded sample of %d instances per step" % (SEED, per_step)},
+                               "(splitmix64 seed %d); bounded sample: %d instances x %d sweeps per step" % (SEED, nb, per_step)},
         "cpu_baseline": {"value": value, "unit": "instance-iterations/s", "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "instance-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -203,13 +287,6 @@ def run_reference(args, rank, world):
 # ---------------------------------------------------------------------------------------------------
 # ANYmal workloads (BASELINE.json configs[3], configs[4]): batched OCPSolver with contacts and impulses
 # ---------------------------------------------------------------------------------------------------
-# dram__bytes_read.sum + dram__bytes_write.sum, FP64-pipe and issue utilisation of ONE launch from the committed `ncu --set full`
-# captures of exactly this workload and batch (profiles/r1v_ncu_full_k_fb_*.txt); reported only when the bench runs it
-FB_NCU_SOURCE = "profiles/r1v_ncu_full_k_fb_*.txt"
-FB_NCU = {("anymal_trotting", 4096): {
-    "fb_robot": {"dram_bytes": 0.526287e9 + 2.432886e9, "fp64_pipe_pct": 19.2, "issue_active_pct": 25.6},
-    "fb_condense": {"dram_bytes": 2.580715e9 + 7.622179e9, "fp64_pipe_pct": 15.7, "issue_active_pct": 40.5},
-    "fb_riccati_backward": {"dram_bytes": 4.520526e9 + 2.181645e9, "fp64_pipe_pct": 14.5, "issue_active_pct": 23.0}}}
 ANYMAL_BATCH = {"anymal_trotting": 4096, "anymal_running": 1024}
 ANYMAL_SEED = {"anymal_trotting": 20240004, "anymal_running": 20240005}
 ANYMAL_LINE_SEARCH = {"anymal_trotting": False, "anymal_running": True}
@@ -245,8 +322,11 @@ def anymal_oracle_throughput(name, seconds_target, steps=None, warmup=1):
     nb = 2 * cores
     q0, v0 = P.anymal_initial_states(0, nb, q_nominal=pr.q0, seed=ANYMAL_SEED[name])
     solvers = [pr.make_oracle(fb_py, q0=q0[b], v0=v0[b]) for b in range(nb)]
-    for _ in range(max(warmup, 1)):
+    t_end = time.perf_counter() + CPU_WARM_SECONDS      # same warm-up protocol in the cpu_baseline leg and the reference arm
+    n_warm = 0
+    while time.perf_counter() < t_end or n_warm < max(warmup, 1):
         fb_py.batch_update_solution(solvers, 0.0, q0, v0, ls, cores)
+        n_warm += 1
     t0 = time.perf_counter()
     fb_py.batch_update_solution(solvers, 0.0, q0, v0, ls, cores)
     first = time.perf_counter() - t0
@@ -319,6 +399,13 @@ def run_anymal(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def count_over_ranks(n):
+        if world == 1:
+            return n
+        t = torch.tensor([n], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t.item())
+
     solver.updateSolution(0.0, q0, v0, ls)          # uploads x0 and the cost reference once
     for _ in range(args.warmup):
         solver.updateSolutionResident(0.0, ls)
@@ -355,34 +442,36 @@ def run_anymal(args, rank, local_rank, world):
         sampler.join(timeout=2)
     solver.computeKKTResidual(0.0, q0, v0)
     kkt = solver.KKTError()
+    # health: an instance whose KKT error is NaN has left the interior (the 0.05 floor of the filter line search can
+    # exceed the fraction-to-boundary step, line_search.hpp:84-91 -- upstream behaviour, reproduced by the oracle at the
+    # same iteration: tests/test_gpu_baseline_configs.py::test_config4_running_full_horizon); `value` counts LIVE ones
+    live = np.isfinite(kkt)
+    n_live = count_over_ranks(int(live.sum()))
     units = float(B) * world * args.steps
-    value = units / (ms_total * 1e-3)
+    value_all = units / (ms_total * 1e-3)
+    value = float(n_live) * args.steps / (ms_total * 1e-3)
     hbm_peak, peak_src = measured_peaks()
+    _, fp64_sus, fp64_src = fp64_peak()
+    counters, counters_src = load_kernel_counters(args.workload)
     stages = B * n_stages
     kern = {}
     for name, rec in profile.items():
-        if rec["calls"]:
-            per = rec["ms"] / args.steps
-            kern[name] = {"ms_per_step": per, "launches_per_step": rec["calls"] / args.steps}
-            if name in FB_ALGO_DOUBLES_PER_STAGE:
-                kern[name]["algo_gbs"] = FB_ALGO_DOUBLES_PER_STAGE[name] * 8.0 * stages / (per * 1e-3) / 1e9
-                ncu = FB_NCU.get((args.workload, B), {}).get(name)
-                if ncu:
-                    kern[name]["ncu_dram_bytes"] = ncu["dram_bytes"]
-                    kern[name]["ncu_fp64_pipe_pct"] = ncu["fp64_pipe_pct"]
-                    kern[name]["ncu_issue_active_pct"] = ncu["issue_active_pct"]
+        if rec["calls"] and name in FB_ALGO_DOUBLES_PER_STAGE:
+            per_launch = rec["ms"] / rec["calls"]
+            kern[name] = kernel_roofline(name, per_launch, FB_ALGO_DOUBLES_PER_STAGE[name] * 8.0 * stages, counters,
+                                         B == ANYMAL_BATCH[args.workload], hbm_peak, fp64_sus)
+            kern[name]["ms_per_step"] = rec["ms"] / args.steps
+            kern[name]["launches_per_step"] = rec["calls"] / args.steps
+        elif rec["calls"]:
+            kern[name] = {"ms_per_step": rec["ms"] / args.steps, "launches_per_step": rec["calls"] / args.steps}
     dom = max((n for n in kern if "algo_gbs" in kern[n]), key=lambda n: kern[n]["ms_per_step"], default=None)
     roofline = None
     if dom:
-        roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["algo_gbs"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": kern[dom]["algo_gbs"] / hbm_peak, "traffic": kern[dom].get("ncu_dram_bytes"),
-                    "traffic_source": FB_NCU_SOURCE if "ncu_dram_bytes" in kern[dom] else None, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": FB_ALGO_DOUBLES_PER_STAGE[dom] * 8.0 * stages,
-                    "note": "the ANYmal kernels are latency-bound (dependent FP64 chains of the factorisations, 10-20 resident "
-                            "warps / SM, issue slots 21-38 % busy; ncu: profiles/r1v_ncu_full_k_fb_*.txt, per-phase cycles: "
-                            "profiles/r1t_fb_phase_clocks.json), neither HBM- nor FP64-throughput-bound",
-                    "kernels": kern,
-                    "step_fp64_tflops": FB_FLOP_PER_STAGE * n_stages * value / world / 1e12}
+        roofline = roofline_object(dom, kern, FB_ALGO_DOUBLES_PER_STAGE[dom] * 8.0 * stages, hbm_peak, peak_src, fp64_sus, fp64_src,
+                                   counters_src,
+                                   "the ANYmal kernels are latency-bound (dependent FP64 chains of the factorisations, block "
+                                   "barriers, 10-20 resident warps / SM); both fractions are reported, `bound` names the larger")
+        roofline["step_fp64_tflops_algorithmic"] = FB_FLOP_PER_STAGE * n_stages * value_all / world / 1e12
     line = {
         "metric": anymal_metric(args.workload), "value": value, "unit": "instance-iterations/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -392,10 +481,15 @@ def run_anymal(args, rank, local_rank, world):
                                % (args.workload, args.workload, pr.T, pr.N, n_stages, B, ANYMAL_SEED[args.workload], str(ls).lower()),
                    "batch_per_gpu": B, "stages": n_stages, "parallelism": "batch-sharded x%d, no collective" % world,
                    "l2_policy": "working set %.1f GB per GPU >> 126 MB L2" % (B * n_stages * 127e3 / 1e9)},
-        "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "instance-iterations/s", "h2d_bytes_per_step": B * 37 * 8,
+        "e2e": {"value": float(n_live) * args.steps / (e2e_ms * 1e-3), "unit": "instance-iterations/s", "h2d_bytes_per_step": B * 37 * 8,
                 "d2h_bytes_per_step": B * 12 * 8, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches), "roofline": roofline, "clocks": sampler.summary() if rank == 0 else None,
-        "health": {"kkt_median": float(np.nanmedian(kkt)), "kkt_nan": int(np.isnan(kkt).sum())},
+        "value_all_instances": value_all,
+        "health": {"instances": int(B) * world, "live": int(n_live), "nan": int(B) * world - int(n_live),
+                   "rank0_converged_kkt_below_1e-6": int((kkt[live] < 1e-6).sum()),
+                   "rank0_kkt_median_live": float(np.median(kkt[live])) if live.any() else None,
+                   "iterations_run": int(args.warmup + 2 * args.steps + 4),
+                   "note": "value counts live instances only (finite KKT error after the run)"},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cval, cores, sample, _ = anymal_oracle_throughput(args.workload, args.cpu_seconds)
@@ -542,35 +636,34 @@ def main():
     value = units / (ms_total * 1e-3)
     e2e_value = units / (e2e_ms * 1e-3)
     hbm_peak, peak_src = measured_peaks()
+    _, fp64_sus, fp64_src = fp64_peak()
+    counters, counters_src = load_kernel_counters("iiwa14_unocp")
     # dominant kernel by measured device time
     stages = B * HORIZON_N
     kern = {}
     for name, (ms, calls) in profile.items():
         if calls and name in KERNEL_ALGO_DOUBLES_PER_STAGE:
-            per_launch_ms = ms / calls
-            gbs = KERNEL_ALGO_DOUBLES_PER_STAGE[name] * 8.0 * stages / (per_launch_ms * 1e-3) / 1e9
-            kern[name] = {"ms_per_launch": per_launch_ms, "algo_gbs": gbs, "share": ms}
-            if B == BATCH_PER_GPU:
-                kern[name]["ncu_dram_bytes"] = NCU_DRAM_BYTES_PER_LAUNCH[name]
-                kern[name]["ncu_dram_gbs_at_measured_time"] = NCU_DRAM_BYTES_PER_LAUNCH[name] / (per_launch_ms * 1e-3) / 1e9
-                kern[name]["ncu_fp64_pipe_pct"] = NCU_FP64_PIPE_PCT[name]
+            kern[name] = kernel_roofline(name, ms / calls, KERNEL_ALGO_DOUBLES_PER_STAGE[name] * 8.0 * stages, counters,
+                                         B == BATCH_PER_GPU, hbm_peak, fp64_sus)
+            kern[name]["share"] = ms
     tot = sum(k["share"] for k in kern.values()) or 1.0
     for k in kern.values():
         k["share"] = k["share"] / tot
     dom = max(kern, key=lambda n: kern[n]["ms_per_launch"]) if kern else None
     roofline = None
     if dom:
-        roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["algo_gbs"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": kern[dom]["algo_gbs"] / hbm_peak,
-                    "traffic": NCU_DRAM_BYTES_PER_LAUNCH[dom] if B == BATCH_PER_GPU else None,
-                    "traffic_source": NCU_SOURCE if B == BATCH_PER_GPU else None,
-                    "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": KERNEL_ALGO_DOUBLES_PER_STAGE[dom] * 8.0 * stages,
-                    "note": "k_linearize is FP64/issue-limited (ncu: FP64 pipe 46 %, DRAM 46 %), the other three "
-                            "kernels are HBM-streaming; FP64 has no tensor-core path at 7x7 (DESIGN.md section 4)",
-                    "kernels": kern,
-                    "step_hbm_frac": BYTES_PER_UNIT * value / world / 1e9 / hbm_peak,
-                    "step_fp64_tflops": FLOP_PER_UNIT * value / world / 1e12}
+        roofline = roofline_object(dom, kern, KERNEL_ALGO_DOUBLES_PER_STAGE[dom] * 8.0 * stages, hbm_peak, peak_src, fp64_sus, fp64_src,
+                                   counters_src,
+                                   "per kernel: frac_hbm = algorithmic bytes / time / measured copy bandwidth, frac_fp64 = FP64 thread "
+                                   "instructions counted by ncu for one launch at this batch (DFMA = 2 flop) / time / measured DFMA "
+                                   "peak; `bound` = the larger.  FP64 has no tensor-core path at 7x7 (DESIGN.md section 4)")
+        fl = sum(counters[n]["fp64_flop_executed"] for n in kern if n in counters and "fp64_flop_executed" in counters[n])
+        roofline["step_hbm_frac_algorithmic"] = BYTES_PER_UNIT * value / world / 1e9 / hbm_peak
+        roofline["step_fp64_tflops_algorithmic"] = FLOP_PER_UNIT * value / world / 1e12
+        if fl and B == BATCH_PER_GPU:
+            roofline["step_fp64_tflops_executed"] = fl / (ms_total / args.steps * 1e-3) / 1e12
+            roofline["step_frac_fp64_executed"] = roofline["step_fp64_tflops_executed"] / fp64_sus
+            roofline["step_dram_bytes_ncu"] = sum(counters[n].get("dram_bytes", 0.0) for n in kern if n in counters)
 
     line = {
         "metric": "batched SQP iterations/sec (iiwa14 N=20, FP64)", "value": value, "unit": "instance-iterations/s",
