@@ -5,13 +5,31 @@ import os
 import numpy as np
 
 import anymal_problems as ap
-from test_emu_fb_parity import DIR, SOL, masked
+from test_emu_fb_parity import DIR, SOL
 
 THREADS = os.cpu_count() or 1
 _TERMINAL_OK = ("q", "v", "lmd", "gmm", "dq", "dv", "dlmd", "dgmm", "lq", "lv", "Pqq", "Pvv", "sq", "sv", "Fqq_prev_inv")
 _IMPULSE_SKIP = ("u", "du", "nu_passive", "dnu_passive", "lu", "lu_passive", "Qxu", "Quu", "Fvu", "Fqv6", "Qafu", "K", "k",
                  "xi", "dxi")
 _MASKED = ("daf", "dbetamu", "MJ_IDC", "MJtJinv", "MJ_dIDC", "Qafqv", "Qafu", "dxi", "xi")
+
+
+def masked_batch(name, arr, c):
+    """masked() of test_emu_fb_parity.py for (batch, size) arrays: entries the path defines (stacked blocks are only
+    meaningful up to dimf / dimi)."""
+    arr = np.array(arr, dtype=float)
+    nvf, dimi = 18 + c["dimf"], c["dimi"]
+    if name in ("daf", "dbetamu", "MJ_IDC"):
+        arr[:, nvf:] = 0
+    elif name == "MJtJinv":
+        m = arr.reshape(-1, 30, 30)
+        m[:, nvf:] = 0
+        m[:, :, nvf:] = 0
+    elif name in ("MJ_dIDC", "Qafqv", "Qafu"):
+        arr.reshape(arr.shape[0], 30, -1)[:, nvf:] = 0
+    elif name in ("dxi", "xi"):
+        arr[:, dimi:] = 0
+    return arr
 
 
 def compare_batch(oracles, solver, fb, names, rows=None):
@@ -29,8 +47,7 @@ def compare_batch(oracles, solver, fb, names, rows=None):
             x = fb.batch_get(oracles, e, nm)
             y = np.asarray(solver.get(e, nm), dtype=float).reshape(x.shape)
             if nm in _MASKED:
-                x = np.stack([masked(nm, r, c, fb) for r in x])
-                y = np.stack([masked(nm, r, c, fb) for r in y])
+                x, y = masked_batch(nm, x, c), masked_batch(nm, y, c)
             if rows is not None:
                 x, y = x[rows], y[rows]
             if not np.array_equal(x, y, equal_nan=True):

@@ -1,0 +1,38 @@
+#!/bin/bash
+# One gpurun call of the round: tests, peaks, bench lines, launch list, ncu captures.  Everything lands in gpurun_out/.
+#   gpurun --timeout 1500 -- 'bash tools/gpu_session.sh <label> [steps...]'     steps: test peak bench ref anymal running launches ncu ncufb
+L=$1; shift
+STEPS=${*:-test peak bench ref anymal launches ncu}
+mkdir -p gpurun_out/profiles
+has() { [[ " $STEPS " == *" $1 "* ]]; }
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${L}_smi.txt 2>&1
+if has peak; then
+  tools/fp64_peak > gpurun_out/${L}_fp64_peak.json 2> gpurun_out/${L}_fp64_peak.err && cp gpurun_out/${L}_fp64_peak.json profiles/fp64_peak.json
+  cat gpurun_out/${L}_fp64_peak.json
+fi
+if has test; then
+  timeout 1500 python -m pytest tests -m gpu -x -q --durations=12 > gpurun_out/${L}_pytest.log 2>&1; echo "pytest rc=$?"; tail -n 25 gpurun_out/${L}_pytest.log
+fi
+if has bench; then
+  python bench.py --steps 100 --warmup 10 > gpurun_out/${L}_bench.json 2> gpurun_out/${L}_bench.err; echo "bench rc=$?"; cut -c 1-600 gpurun_out/${L}_bench.json
+fi
+if has ref; then
+  python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/${L}_bench_reference.json 2> gpurun_out/${L}_bench_reference.err; cut -c 1-300 gpurun_out/${L}_bench_reference.json
+fi
+if has anymal; then
+  python bench.py --workload anymal_trotting --steps 20 --warmup 5 > gpurun_out/${L}_bench_anymal_trotting.json 2> gpurun_out/${L}_bench_anymal_trotting.err; cut -c 1-400 gpurun_out/${L}_bench_anymal_trotting.json
+fi
+if has running; then
+  python bench.py --workload anymal_running --steps 10 --warmup 3 > gpurun_out/${L}_bench_anymal_running.json 2> gpurun_out/${L}_bench_anymal_running.err; cut -c 1-400 gpurun_out/${L}_bench_anymal_running.json
+fi
+if has launches; then
+  ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 200 --csv --log-file gpurun_out/${L}_launches.csv \
+      python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/${L}_launches_run.log 2>&1; echo "launches rc=$?"
+fi
+if has ncu; then
+  NCU_SKIP=40 NCU_COUNT=8 tools/ncu_capture.sh $L iiwa14_unocp 'k_linearize|k_riccati|k_expand|k_update'
+fi
+if has ncufb; then
+  NCU_SKIP=30 NCU_COUNT=6 tools/ncu_capture.sh $L anymal_trotting 'k_fb_robot|k_fb_condense|k_fb_riccati_backward'
+fi
+echo "session $L done"

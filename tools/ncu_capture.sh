@@ -13,3 +13,5 @@ ncu --set full --metrics smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,sms
     -f -o "$REP" python bench.py --workload "$WORKLOAD" --steps 3 --warmup 3 --no-cpu-baseline "$@" > "gpurun_out/${LABEL}_${WORKLOAD}_ncu.log" 2>&1 || { tail -20 "gpurun_out/${LABEL}_${WORKLOAD}_ncu.log"; exit 1; }
 python tools/ncu_summary.py "$REP.ncu-rep" "profiles/${LABEL}_ncu_full_${WORKLOAD}.txt" > /dev/null
 python tools/ncu_counters.py "$REP.ncu-rep" "profiles/kernel_counters_${WORKLOAD}.json" "profiles/${LABEL}_ncu_full_${WORKLOAD}.txt"
+mkdir -p gpurun_out/profiles
+cp "profiles/${LABEL}_ncu_full_${WORKLOAD}.txt" "profiles/kernel_counters_${WORKLOAD}.json" gpurun_out/profiles/
