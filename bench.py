@@ -45,6 +45,9 @@ KERNEL_ALGO_DOUBLES_PER_STAGE = {
     "expand": 119 + 147 + 21 + 21 + 84 + 28,
     # s 49 + slack/dual 84 + d 49 in; s 49 + slack/dual 84 out
     "update": 2 * (49 + 84) + 49,
+    # the fused kernel (update of iteration k + linearisation for iteration k + 1): linearize + the direction in
+    # (d_i 49, d_{i+1} 28) + the new iterate out (s 49 + slack/dual 84)
+    "update_linearize": (49 + 28 + 84 + 231 + 35 + 147) + (49 + 28) + (49 + 84),
 }
 
 
@@ -52,7 +55,7 @@ KERNEL_ALGO_DOUBLES_PER_STAGE = {
 # (per kernel: DRAM bytes read + written, executed FP64 thread instructions, pipe / issue utilisation of one launch at the
 # bench batch); tools/fp64_peak (DFMA microbenchmark on the B200) writes profiles/fp64_peak.json.
 KERNEL_OF_CLASS = {"linearize": "k_linearize<0,0,0>", "riccati": "k_riccati<0>", "expand": "k_expand<0,0>", "update": "k_update",
-                   "riccati_forward": "k_riccati_forward<0>", "update_linearize": "k_update_linearize<0>",
+                   "update_linearize": "k_linearize<0,0,0,1>",
                    "fb_robot": "k_fb_robot<0>", "fb_condense": "k_fb_condense", "fb_riccati_backward": "k_fb_riccati_backward",
                    "parnmpc_invert": "k_parnmpc_invert"}
 # 64 DFMA / clk / SM (ncu: sm__sass_thread_inst_executed_op_dfma_pred_on.avg.peak_sustained) x 148 SMs x 1.965 GHz x 2

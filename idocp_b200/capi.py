@@ -97,7 +97,7 @@ EXPORTS = [
     "idocp_b200_get_direction", "idocp_b200_get_constraint_data", "idocp_b200_get_step_sizes",
     "idocp_b200_get_unkkt", "idocp_b200_get_status", "idocp_b200_is_feasible",
     "idocp_b200_clear_line_search_filter", "idocp_b200_sync", "idocp_b200_launch_count", "idocp_b200_stream",
-    "idocp_b200_set_task_reference", "idocp_b200_set_profiling", "idocp_b200_get_profile",
+    "idocp_b200_set_task_reference", "idocp_b200_set_profiling", "idocp_b200_get_profile", "idocp_b200_set_pipelining",
     "idocp_b200_contact_sequence_create", "idocp_b200_contact_sequence_destroy",
     "idocp_b200_contact_sequence_set_uniform", "idocp_b200_contact_sequence_push_back",
     "idocp_b200_contact_sequence_pop_back", "idocp_b200_contact_sequence_pop_front",
@@ -167,6 +167,7 @@ class Library:
         L.idocp_b200_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
         L.idocp_b200_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.idocp_b200_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.idocp_b200_set_pipelining.argtypes = [C.c_void_p, C.c_int]
         L.idocp_b200_get_profile.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), _dp,
                                              C.POINTER(C.c_longlong)]
         L.idocp_b200_fb_create.argtypes = [C.POINTER(FbProblem), C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]

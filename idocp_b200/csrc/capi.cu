@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #endif
 
+#include <algorithm>
 #include <array>
 #include <cmath>
 #include <cstddef>
@@ -55,10 +56,11 @@ static int fail(int code, const std::string& msg) {
 
 enum KernelClass { KC_LINEARIZE = 0, KC_RICCATI, KC_EXPAND, KC_UPDATE, KC_KKT, KC_MISC, KC_PARNMPC_COARSE,
                    KC_PARNMPC_CORR, KC_LINESEARCH, KC_FB_LINEARIZE, KC_FB_CONDENSE, KC_FB_RICCATI, KC_FB_FORWARD, KC_FB_EXPAND, KC_FB_UPDATE,
-                   KC_FB_KKT, KC_NUM };
+                   KC_FB_KKT, KC_UPDATE_LINEARIZE, KC_NUM };
 static const char* kKernelClassNames[KC_NUM] = {"linearize", "riccati", "expand", "update", "kkt", "misc",
                                                 "parnmpc_coarse", "parnmpc_correction", "line_search", "fb_robot", "fb_condense",
-                                                "fb_riccati_backward", "fb_riccati_forward", "fb_expand", "fb_update", "fb_kkt"};
+                                                "fb_riccati_backward", "fb_riccati_forward", "fb_expand", "fb_update", "fb_kkt",
+                                                "update_linearize"};
 
 // launch bookkeeping shared by every solver handle: stream, launch counter, per-kernel-class event timing
 struct LaunchProfiler {
@@ -135,6 +137,10 @@ struct idocp_b200_solver : LaunchProfiler {
   // line search (allocated on first use)
   LineSearchLayout LS;
   bool ls_ready = false;
+  // UnOCPSolver pipelining: updateSolution ends with k_linearize<.., FUSED> = update + linearisation of the NEW iterate,
+  // which the next updateSolution re-uses as long as nothing changed the iterate or the cost reference in between
+  bool pipelined = true;
+  bool lin_valid = false;
 
   int stage_offset() const { return kind == IDOCP_B200_SOLVER_UNPARNMPC ? 1 : 0; }
 };
@@ -214,6 +220,7 @@ static const int kLinSmem = OCTETS_PER_CTA * OCT * PAIR_TILE * static_cast<int>(
 static const int kRicSmem = RIC_SMEM_DOUBLES * static_cast<int>(sizeof(double));
 
 static int do_init_constraints(idocp_b200_solver* h) {
+  h->lin_valid = false;   // slack / dual change: the kept linearisation is stale
   IDOCP_LAUNCH(h, KC_MISC, k_init_constraints, stage_grid(h, h->N), CTA_THREADS, 0, h->d_prob, h->L,
                h->stage_offset());
   CUDA_OK(cudaGetLastError());
@@ -257,6 +264,7 @@ extern "C" int idocp_b200_create(const idocp_b200_problem* p, int solver_kind, i
   int rc = 0;
   rc |= h->alloc(&h->d_prob, 1);
   rc |= h->alloc(&L.X, (N + 1) * G * X_NUM * SLOT);
+  if (!par) rc |= h->alloc(&L.X2, (N + 1) * G * X_NUM * SLOT);
   rc |= h->alloc(&L.KQ, (N + 1) * G * KQ_NUM * SLOT);   // record N: dense terminal Hessian of the task-space cost
   rc |= h->alloc(&L.task_ref, (N + 1) * 12);
   rc |= h->alloc(&L.W, N * G * W_NUM * SLOT);
@@ -432,14 +440,19 @@ static int run_line_search(idocp_b200_solver* h, const double* d_q, const double
 }
 
 static int unocp_update(idocp_b200_solver* h, const double* d_q, const double* d_v, int line_search) {
-  if (h->prob.task_enabled) {
-    IDOCP_LAUNCH(h, KC_LINEARIZE, (k_linearize<false, false, true>), stage_grid(h, h->N + 1), CTA_THREADS, kLinSmem,
-                 h->d_prob, h->L, d_q, d_v);
+  const bool task = h->prob.task_enabled != 0;
+  if (!(h->pipelined && h->lin_valid)) {
+    if (task)
+      IDOCP_LAUNCH(h, KC_LINEARIZE, (k_linearize<false, false, true>), stage_grid(h, h->N + 1), CTA_THREADS, kLinSmem,
+                   h->d_prob, h->L, d_q, d_v, nullptr);
+    else
+      IDOCP_LAUNCH(h, KC_LINEARIZE, (k_linearize<false, false, false>), stage_grid(h, h->N), CTA_THREADS, kLinSmem,
+                   h->d_prob, h->L, d_q, d_v, nullptr);
+  }
+  if (task) {
     IDOCP_LAUNCH(h, KC_RICCATI, k_riccati<true>, group_grid(h), CTA_THREADS, kRicSmem, h->d_prob, h->L, d_q, d_v);
     IDOCP_LAUNCH(h, KC_EXPAND, (k_expand<false, true>), stage_grid(h, h->N + 1), CTA_THREADS, 0, h->d_prob, h->L, 0);
   } else {
-    IDOCP_LAUNCH(h, KC_LINEARIZE, (k_linearize<false, false, false>), stage_grid(h, h->N), CTA_THREADS, kLinSmem,
-                 h->d_prob, h->L, d_q, d_v);
     IDOCP_LAUNCH(h, KC_RICCATI, k_riccati<false>, group_grid(h), CTA_THREADS, kRicSmem, h->d_prob, h->L, d_q, d_v);
     IDOCP_LAUNCH(h, KC_EXPAND, (k_expand<false, false>), stage_grid(h, h->N + 1), CTA_THREADS, 0, h->d_prob, h->L, 0);
   }
@@ -449,8 +462,20 @@ static int unocp_update(idocp_b200_solver* h, const double* d_q, const double* d
     if (rc != IDOCP_B200_OK) return rc;
     override_alpha = h->LS.alpha;
   }
-  IDOCP_LAUNCH(h, KC_UPDATE, k_update, stage_grid(h, h->N + 1), CTA_THREADS, 0, h->d_prob, h->L, 0, override_alpha,
-               h->N + 1);
+  if (h->pipelined) {
+    // update + linearisation of the new iterate in one launch; X (old) -> X2 (new), then the two swap roles
+    if (task)
+      IDOCP_LAUNCH(h, KC_UPDATE_LINEARIZE, (k_linearize<false, false, true, true>), stage_grid(h, h->N + 1), CTA_THREADS,
+                   kLinSmem, h->d_prob, h->L, d_q, d_v, override_alpha);
+    else
+      IDOCP_LAUNCH(h, KC_UPDATE_LINEARIZE, (k_linearize<false, false, false, true>), stage_grid(h, h->N + 1), CTA_THREADS,
+                   kLinSmem, h->d_prob, h->L, d_q, d_v, override_alpha);
+    std::swap(h->L.X, h->L.X2);
+    h->lin_valid = true;
+  } else {
+    IDOCP_LAUNCH(h, KC_UPDATE, k_update, stage_grid(h, h->N + 1), CTA_THREADS, 0, h->d_prob, h->L, 0, override_alpha,
+                 h->N + 1);
+  }
   CUDA_OK(cudaGetLastError());
   return IDOCP_B200_OK;
 }
@@ -461,10 +486,10 @@ static int parnmpc_update(idocp_b200_solver* h, double, const double* d_q, const
   // UnBackwardCorrection::coarseUpdate (src/unocp/unbackward_correction.cpp:67-97)
   if (h->prob.task_enabled)
     IDOCP_LAUNCH(h, KC_LINEARIZE, (k_linearize<false, true, true>), stage_grid(h, N), CTA_THREADS, kLinSmem, h->d_prob,
-                 h->L, d_q, d_v);
+                 h->L, d_q, d_v, nullptr);
   else
     IDOCP_LAUNCH(h, KC_LINEARIZE, (k_linearize<false, true, false>), stage_grid(h, N), CTA_THREADS, kLinSmem, h->d_prob,
-                 h->L, d_q, d_v);
+                 h->L, d_q, d_v, nullptr);
   IDOCP_LAUNCH(h, KC_PARNMPC_COARSE, k_parnmpc_invert, N * h->L.G, CTA_THREADS, INV_SMEM_BYTES, h->d_prob, h->L, h->PL);
   // UnBackwardCorrection::backwardCorrection (:100-134)
   if (N > 1) {
@@ -489,10 +514,10 @@ static int parnmpc_update(idocp_b200_solver* h, double, const double* d_q, const
 static int parnmpc_kkt_residual(idocp_b200_solver* h, double, const double* d_q, const double* d_v) {
   if (h->prob.task_enabled)
     IDOCP_LAUNCH(h, KC_KKT, (k_linearize<true, true, true>), stage_grid(h, h->N), CTA_THREADS, kLinSmem, h->d_prob, h->L,
-                 d_q, d_v);
+                 d_q, d_v, nullptr);
   else
     IDOCP_LAUNCH(h, KC_KKT, (k_linearize<true, true, false>), stage_grid(h, h->N), CTA_THREADS, kLinSmem, h->d_prob, h->L,
-                 d_q, d_v);
+                 d_q, d_v, nullptr);
   IDOCP_LAUNCH(h, KC_KKT, k_kkt_sum, (h->Bp + 127) / 128, 128, 0, h->L, h->N);
   CUDA_OK(cudaGetLastError());
   return IDOCP_B200_OK;
@@ -535,10 +560,10 @@ extern "C" int idocp_b200_compute_kkt_residual_device(idocp_b200_solver* h, doub
   if (h->kind == IDOCP_B200_SOLVER_UNPARNMPC) return parnmpc_kkt_residual(h, t, d_q, d_v);
   if (h->prob.task_enabled)
     IDOCP_LAUNCH(h, KC_KKT, (k_linearize<true, false, true>), stage_grid(h, h->N + 1), CTA_THREADS, kLinSmem, h->d_prob,
-                 h->L, d_q, d_v);
+                 h->L, d_q, d_v, nullptr);
   else
     IDOCP_LAUNCH(h, KC_KKT, (k_linearize<true, false, false>), stage_grid(h, h->N + 1), CTA_THREADS, kLinSmem, h->d_prob,
-                 h->L, d_q, d_v);
+                 h->L, d_q, d_v, nullptr);
   IDOCP_LAUNCH(h, KC_KKT, k_kkt_sum, (h->Bp + 127) / 128, 128, 0, h->L, h->N + 1);
   CUDA_OK(cudaGetLastError());
   return IDOCP_B200_OK;
@@ -768,6 +793,16 @@ extern "C" int idocp_b200_set_task_reference(idocp_b200_solver* h, const double*
   CUDA_OK(cudaMemcpyAsync(h->L.task_ref, table, static_cast<size_t>(h->N + 1) * 12 * sizeof(double),
                           cudaMemcpyHostToDevice, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));  // `table` may be pageable host memory reused by the caller
+  h->lin_valid = false;                       // the kept linearisation used the old reference
+  return IDOCP_B200_OK;
+}
+
+// UnOCPSolver pipelining (default on): see k_linearize<.., FUSED>.  Off: linearise, solve, expand, update as four launches;
+// get_unkkt then shows the linearisation the last direction was computed from instead of the one kept for the next call.
+extern "C" int idocp_b200_set_pipelining(idocp_b200_solver* h, int enabled) {
+  if (!h) return fail(IDOCP_B200_INVALID_ARGUMENT, "null handle");
+  h->pipelined = enabled != 0;
+  h->lin_valid = false;
   return IDOCP_B200_OK;
 }
 

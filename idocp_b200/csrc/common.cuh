@@ -50,11 +50,12 @@ enum XSlot { X_LMD = 0, X_GMM, X_Q, X_V, X_A, X_U, X_BETA, X_SLACK = 7, X_DUAL =
 // and the residual [Fq,Fv,la,lq,lv]                                   [N stages]
 enum KQSlot { KQ_AA = 0, KQ_AQ = 7, KQ_AV = 14, KQ_QQ = 21, KQ_QV = 28, KQ_VV = 35,
               KQ_FQ = 42, KQ_FV, KQ_LA, KQ_LQ, KQ_LV, KQ_NUM = 47 };
-// factor data W: Riccati gains (rows of Kq, Kv; k), Riccati matrices (columns of Pqq,Pqv,Pvq,Pvv;
+// factor data W: Riccati gains (rows of Kq, Kv; k), Riccati matrices (columns of Pqq,Pqv,Pvv;
 // sq,sv) and the expansion data of the condensed inverse dynamics (ID, lu, Quu diag, rows of
 // dID/dq and dID/dv, column of M)                                    [N stages]
-enum WSlot { W_KQ = 0, W_KV = 7, W_K = 14, W_PQQ = 15, W_PQV = 22, W_PVQ = 29, W_PVV = 36, W_SQ = 43, W_SV = 44,
-             W_ID = 45, W_LU = 46, W_QUU = 47, W_DQ = 48, W_DV = 55, W_M = 62, W_NUM = 69 };
+// (Pvq = Pqv^T is NOT stored: k_expand transposes Pqv through shared memory -- 7 slots less to write and re-read)
+enum WSlot { W_KQ = 0, W_KV = 7, W_K = 14, W_PQQ = 15, W_PQV = 22, W_PVV = 29, W_SQ = 36, W_SV = 37,
+             W_ID = 38, W_LU = 39, W_QUU = 40, W_DQ = 41, W_DV = 48, W_M = 55, W_NUM = 62 };
 // Newton direction D                                                  [N+1 stages]
 enum DSlot { D_LMD = 0, D_GMM, D_Q, D_V, D_A, D_U, D_BETA, D_NUM = 7 };
 
@@ -64,6 +65,7 @@ struct Layout {
   int G;     // groups = Bp / 4
   int N;     // stages with controls; X and D have N+1 stages
   double* X;
+  double* X2;        // ping-pong partner of X (k_linearize<.., FUSED>: old iterate in X, new iterate in X2; the host swaps them)
   double* KQ;
   double* W;
   double* D;

@@ -144,16 +144,25 @@ __global__ void k_set_solution(Layout L, int field, const double* __restrict__ v
 // TASK = true: + TimeVaryingTaskSpace6DCost (task_space_cost.cuh).  With the forward-Euler solver the kernel
 //               then also covers the terminal stage N (TerminalOCP::linearizeOCP, ocp/terminal_ocp.hxx:50-66)
 //               and leaves its dense Hessian / gradient in record N of KQ for k_riccati and k_expand.
-template <bool RESIDUAL_ONLY, bool BACKWARD_EULER, bool TASK>
+// FUSED = true (UnOCPSolver, forward Euler only): the kernel first applies the step of the iteration that has just been
+//   expanded -- exactly k_update: alpha = min over the stages, s += alpha_p d, slack += alpha_p dslack, dual += alpha_d ddual
+//   (unocp_solver.cpp:114-133) -- reading the old iterate from L.X and writing the new one to L.X2 (ping-pong: the
+//   neighbour stage's warp still needs the OLD record of this stage), and then linearises the NEW iterate for the next
+//   updateSolution call.  The linearisation does not depend on the measured state (q0, v0 only enter the forward
+//   Riccati recursion), so the host keeps it until the iterate or the cost reference changes (capi.cu: lin_valid).
+//   The update's HBM stream hides under the FP64 work of the linearisation; one launch and one read of X less per iteration.
+template <bool RESIDUAL_ONLY, bool BACKWARD_EULER, bool TASK, bool FUSED = false>
 __global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_linearize(const DevProblem* __restrict__ Pp, Layout L,
                                                                            const double* __restrict__ q0,
-                                                                           const double* __restrict__ v0) {
+                                                                           const double* __restrict__ v0,
+                                                                           const double* __restrict__ primal_override = nullptr) {
+  static_assert(!FUSED || (!RESIDUAL_ONLY && !BACKWARD_EULER), "the fused update exists for UnOCPSolver::updateSolution only");
   IDOCP_DYN_SMEM(double, smem);
   const DevProblem& P = *Pp;
   const int lane = lane_in_octet();
   const int oct = threadIdx.x >> 3;
   double* tile = smem + oct * (OCT * PAIR_TILE);
-  const StageTask t = stage_task(L, ((RESIDUAL_ONLY || TASK) && !BACKWARD_EULER) ? L.N + 1 : L.N);
+  const StageTask t = stage_task(L, (FUSED || ((RESIDUAL_ONLY || TASK) && !BACKWARD_EULER)) ? L.N + 1 : L.N);
   const int i = t.stage;
   const int ts = BACKWARD_EULER ? i + 1 : i;   // time stage of the constraint masks
   const int b = t.g * 4 + ((threadIdx.x >> 3) & 3);
@@ -161,7 +170,79 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_linearize(const
   const bool act = lane < NV;
   const double* X = rec_ptr(L.X, X_NUM, L.G, i, t.g);
 
-  const double q = X[X_Q * SLOT], v = X[X_V * SLOT], lmd = X[X_LMD * SLOT], gmm = X[X_GMM * SLOT];
+  double q = X[X_Q * SLOT], v = X[X_V * SLOT], lmd = X[X_LMD * SLOT], gmm = X[X_GMM * SLOT];
+  // the state of the fused update that the linearisation below continues with
+  double fa = 0.0, fu = 0.0, fbeta = 0.0, fslack[NC], fdual[NC], fqn = 0.0, fvn = 0.0, flmdn = 0.0, fgmmn = 0.0;
+  if (FUSED) {
+    const int N = L.N;
+    const double* D = rec_ptr(L.D, D_NUM, L.G, i, t.g);
+    double* Xw = rec_ptr(L.X2, X_NUM, L.G, i, t.g);
+    // every load first (stores through Xw would fence the loads behind them)
+    const double dlmd = D[D_LMD * SLOT], dgmm = D[D_GMM * SLOT], dq = D[D_Q * SLOT], dv = D[D_V * SLOT];
+    double da = 0.0, du = 0.0, dbeta = 0.0, dqn = 0.0, dvn = 0.0, dlmdn = 0.0, dgmmn = 0.0;
+    if (i != N) {
+      fa = X[X_A * SLOT]; fu = X[X_U * SLOT]; fbeta = X[X_BETA * SLOT];
+      da = D[D_A * SLOT]; du = D[D_U * SLOT]; dbeta = D[D_BETA * SLOT];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        fslack[c] = X[(X_SLACK + c) * SLOT];
+        fdual[c] = X[(X_DUAL + c) * SLOT];
+      }
+      const double* Xn = X + static_cast<size_t>(L.G) * (X_NUM * SLOT);
+      const double* Dn = D + static_cast<size_t>(L.G) * (D_NUM * SLOT);
+      fqn = Xn[X_Q * SLOT]; fvn = Xn[X_V * SLOT]; flmdn = Xn[X_LMD * SLOT]; fgmmn = Xn[X_GMM * SLOT];
+      dqn = Dn[D_Q * SLOT]; dvn = Dn[D_V * SLOT]; dlmdn = Dn[D_LMD * SLOT]; dgmmn = Dn[D_GMM * SLOT];
+    }
+    // step sizes: min over the N per-stage minima (k_update)
+    double ap = 1.0, ad = 1.0;
+    for (int s = lane; s < N; s += OCT) {
+      ap = fmin(ap, L.smin[static_cast<size_t>(s) * L.Bp + b]);
+      ad = fmin(ad, L.smin[(static_cast<size_t>(N) + s) * L.Bp + b]);
+    }
+    ap = oct_min(ap);
+    ad = oct_min(ad);
+    const double amax = ap;
+    if (primal_override) ap = primal_override[b];
+    if (i == 0 && lane == 0) {
+      L.steps[b] = ap;
+      L.steps[L.Bp + b] = ad;
+      L.steps[2 * L.Bp + b] = amax;
+      if (!(ap == ap) || !(ad == ad)) L.status[b] |= 2;
+    }
+    // the padding lane keeps its (zero) record: k_update never touches it
+    const double q_old = q, v_old = v, u_old = fu;
+    if (act) {
+      lmd = fma(ap, dlmd, lmd); gmm = fma(ap, dgmm, gmm); q = fma(ap, dq, q); v = fma(ap, dv, v);
+    }
+    Xw[X_LMD * SLOT] = lmd; Xw[X_GMM * SLOT] = gmm; Xw[X_Q * SLOT] = q; Xw[X_V * SLOT] = v;
+    if (i != N) {
+      if (act) {
+        fa = fma(ap, da, fa); fu = fma(ap, du, fu); fbeta = fma(ap, dbeta, fbeta);
+        fqn = fma(ap, dqn, fqn); fvn = fma(ap, dvn, fvn); flmdn = fma(ap, dlmdn, flmdn); fgmmn = fma(ap, dgmmn, fgmmn);
+        const LaneLimits lim = load_limits(P, lane);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          if (!comp_active(c, i)) continue;
+          const double sl = fslack[c], dl = fdual[c];
+          const double r = con_residual(c, lim, q_old, v_old, u_old, sl);
+          const double dty = sl * dl - P.barrier;
+          const double dx = c < 2 ? dq : (c < 4 ? dv : du);
+          const double dslack = ((c & 1) ? -dx : dx) - r;
+          const double ddual = -fma(dl, dslack, dty) / sl;
+          fslack[c] = fma(ap, dslack, sl);
+          fdual[c] = fma(ad, ddual, dl);
+        }
+      }
+      Xw[X_A * SLOT] = fa; Xw[X_U * SLOT] = fu; Xw[X_BETA * SLOT] = fbeta;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        Xw[(X_SLACK + c) * SLOT] = fslack[c];
+        Xw[(X_DUAL + c) * SLOT] = fdual[c];
+      }
+    } else if (!TASK) {
+      return;   // terminal stage: the update is all there is to do
+    }
+  }
 
   if ((RESIDUAL_ONLY || TASK) && !BACKWARD_EULER && i == L.N) {
     // TerminalOCP::linearizeOCP / computeKKTResidual + squaredNormKKTResidual (ocp/terminal_ocp.hxx:50-66,120-144)
@@ -197,13 +278,15 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_linearize(const
     return;
   }
 
-  const double a = X[X_A * SLOT], u = X[X_U * SLOT], beta = X[X_BETA * SLOT];
+  const double a = FUSED ? fa : X[X_A * SLOT], u = FUSED ? fu : X[X_U * SLOT], beta = FUSED ? fbeta : X[X_BETA * SLOT];
   const bool last = BACKWARD_EULER && (i == L.N - 1);                // TerminalUnParNMPC
   const double* Xn = X + static_cast<size_t>(L.G) * (X_NUM * SLOT);  // next stage, same group
   // forward Euler: (q, v, lmd, gmm) of the next stage; backward Euler: (q, v) of the previous stage
   // (x0 for index 0) and (lmd, gmm) of the next stage (none for the last one)
   double qn, vn, lmdn = 0.0, gmmn = 0.0;
-  if (!BACKWARD_EULER) {
+  if (FUSED) {
+    qn = fqn; vn = fvn; lmdn = flmdn; gmmn = fgmmn;
+  } else if (!BACKWARD_EULER) {
     qn = Xn[X_Q * SLOT]; vn = Xn[X_V * SLOT]; lmdn = Xn[X_LMD * SLOT]; gmmn = Xn[X_GMM * SLOT];
   } else {
     if (i == 0) {
@@ -219,8 +302,8 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_linearize(const
   double slack[NC], dual[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
-    slack[c] = X[(X_SLACK + c) * SLOT];
-    dual[c] = X[(X_DUAL + c) * SLOT];
+    slack[c] = FUSED ? fslack[c] : X[(X_SLACK + c) * SLOT];
+    dual[c] = FUSED ? fdual[c] : X[(X_DUAL + c) * SLOT];
   }
   const LaneLimits lim = load_limits(P, lane);
 
@@ -739,7 +822,6 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_RIC_MINB) k_riccati(const D
     for (int r = 0; r < NV; ++r) {
       W[(W_PQQ + r) * SLOT] = Pqq[r];
       W[(W_PQV + r) * SLOT] = Pqv[r];
-      W[(W_PVQ + r) * SLOT] = Pvq[r];
       W[(W_PVV + r) * SLOT] = Pvv[r];
     }
     W[W_SQ * SLOT] = sq;
@@ -806,6 +888,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_RIC_MINB) k_riccati(const D
 // PARNMPC = true (UnParNMPCSolver): N stages, none terminal, the costate direction is already in D
 // (k_parnmpc_forward_parallel); only the condensed direction and the step sizes are computed.
 // TASK = true: the terminal P_N = Qqq_N is dense (record N of KQ)
+constexpr int EXP_TILE = 9;   // odd stride (doubles) of the Pqv transpose tile of k_expand
 template <bool PARNMPC, bool TASK>
 __global__ void __launch_bounds__(CTA_THREADS, IDOCP_EXP_MINB) k_expand(const DevProblem* __restrict__ Pp, Layout L, int stage_offset) {
   const DevProblem& P = *Pp;
@@ -862,10 +945,21 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_EXP_MINB) k_expand(const De
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     if (!PARNMPC) {
-      w_pqq[k] = W[(W_PQQ + k) * SLOT]; w_pvq[k] = W[(W_PVQ + k) * SLOT];
+      w_pqq[k] = W[(W_PQQ + k) * SLOT];
       w_pqv[k] = W[(W_PQV + k) * SLOT]; w_pvv[k] = W[(W_PVV + k) * SLOT];
     }
     w_dq[k] = W[(W_DQ + k) * SLOT]; w_dv[k] = W[(W_DV + k) * SLOT]; w_m[k] = W[(W_M + k) * SLOT];
+  }
+  if (!PARNMPC) {
+    // column c of Pvq = row c of Pqv: transposed through the octet's tile (stride 9: conflict-free both ways)
+    __shared__ double pvq_tile[OCTETS_PER_CTA * OCT * EXP_TILE];
+    double* tile = pvq_tile + (threadIdx.x >> 3) * (OCT * EXP_TILE);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) tile[k * EXP_TILE + lane] = w_pqv[k];     // tile[row k][column lane]
+    __syncwarp();
+    const int ln = act ? lane : 0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) w_pvq[k] = tile[ln * EXP_TILE + k];       // Pqv[lane][k]
   }
   const double w_sq = PARNMPC ? 0.0 : W[W_SQ * SLOT], w_sv = PARNMPC ? 0.0 : W[W_SV * SLOT];
   const double w_id = W[W_ID * SLOT], w_quu = W[W_QUU * SLOT], w_lu = W[W_LU * SLOT];

@@ -211,6 +211,10 @@ class _BatchSolver:
         self.lib.check(self.lib.L.idocp_b200_get_step_sizes(self._h, dptr(p), dptr(d)))
         return p, d
 
+    def setPipelining(self, enabled):
+        """UnOCPSolver: fuse the update with the linearisation of the new iterate (default on; idocp_b200_set_pipelining)."""
+        self.lib.check(self.lib.L.idocp_b200_set_pipelining(self._h, int(bool(enabled))))
+
     def getUnKKT(self, stage):
         Q = np.zeros((self.batch, 21, 21))
         res = np.zeros((self.batch, 35))

@@ -154,6 +154,12 @@ int idocp_b200_stream(idocp_b200_solver* h, void** out);
 /* per-kernel-class device time: while profiling is enabled every launch is bracketed by CUDA
  * events on the launching stream (no host sync inside the timed region); get_profile resolves them:
  * names[i], total ms[i], calls[i]; returns the number of entries (<= cap) */
+/* UnOCPSolver only, default enabled = 1: updateSolution applies its step and linearises the NEW iterate in one launch
+ * (the linearisation does not depend on the measured state), and the next updateSolution re-uses it unless setSolution /
+ * initConstraints / set_task_reference intervened.  Results are bit-identical either way; with enabled = 0 the call is the
+ * reference's literal sequence linearise, Riccati, expand, update (unocp_solver.cpp:73-134) and get_unkkt shows the
+ * linearisation the last direction came from. */
+int idocp_b200_set_pipelining(idocp_b200_solver* h, int enabled);
 int idocp_b200_set_profiling(idocp_b200_solver* h, int enabled);
 int idocp_b200_get_profile(idocp_b200_solver* h, int cap, const char** names, double* ms, long long* calls);
 

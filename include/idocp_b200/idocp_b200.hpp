@@ -377,6 +377,8 @@ class SolverBase {
     }
   }
   void clearLineSearchFilter() { check(idocp_b200_clear_line_search_filter(h_.get())); }
+  // fuse the update with the linearisation of the new iterate (UnOCPSolver, default on; results are bit-identical)
+  void setPipelining(bool enabled) { check(idocp_b200_set_pipelining(h_.get(), enabled ? 1 : 0)); }
   bool isCurrentSolutionFeasible() {
     std::vector<int> f(batch_);
     check(idocp_b200_is_feasible(h_.get(), f.data()));

@@ -9,7 +9,7 @@ import pytest
 
 import idocp_b200 as I
 from conftest import make_states
-from helpers import check_iteration, check_solution, make_pair, rel_close
+from helpers import DIR_FIELDS, SOL_FIELDS, check_iteration, check_solution, make_pair, rel_close
 
 
 def test_emulator_library_is_not_the_default():
@@ -39,6 +39,7 @@ def test_unocp_condensed_kkt_matches_oracle(emu_lib, oracle):
     prob = I.benchmark_problem(emu_lib)
     q0, v0 = make_states(3, 7)
     solver, oracles = make_pair(I, oracle, emu_lib, prob, q0, v0)
+    solver.setPipelining(False)    # getUnKKT must show the linearisation the direction came from, like the oracle's
     check_iteration(solver, oracles, q0, v0)       # move off the initial guess
     solver.updateSolution(0.0, q0, v0)
     for b, o in enumerate(oracles):
@@ -170,3 +171,46 @@ def test_error_paths(emu_lib):
         s.getSolution("nope")
     with pytest.raises(ValueError):
         s.updateSolution(0.0, np.zeros((3, 7)), np.zeros((3, 7)))
+
+
+def test_pipelined_update_equals_literal_sequence(emu_lib, oracle):
+    """k_linearize<.., FUSED> (update + linearisation of the new iterate kept for the next call) vs the literal
+    linearise / Riccati / expand / update sequence: identical bits, also across setSolution (which invalidates the kept
+    linearisation), computeKKTResidual between the calls, a changed x0, and the filter line search."""
+    prob = I.benchmark_problem(emu_lib)
+    q0, v0 = make_states(5, 11)
+    a = I.UnOCPSolver(prob, 5, lib=emu_lib)
+    b = I.UnOCPSolver(prob, 5, lib=emu_lib)
+    b.setPipelining(False)
+    for s in (a, b):
+        s.setSolution("q", q0)
+        s.setSolution("v", v0)
+
+    def same():
+        for name in SOL_FIELDS:
+            assert np.array_equal(a.getSolution(name), b.getSolution(name), equal_nan=True), name
+        for name in DIR_FIELDS:
+            assert np.array_equal(a.getDirection(name), b.getDirection(name), equal_nan=True), name
+        assert np.array_equal(a.getConstraintData("slack"), b.getConstraintData("slack"), equal_nan=True)
+        assert np.array_equal(a.getConstraintData("dual"), b.getConstraintData("dual"), equal_nan=True)
+        assert np.array_equal(a.getStepSizes(), b.getStepSizes(), equal_nan=True)
+    for it in range(3):
+        for s in (a, b):
+            s.updateSolution(0.0, q0, v0)
+        same()
+    for s in (a, b):                       # KKT residual in between does not disturb the kept linearisation
+        s.computeKKTResidual(0.0, q0, v0)
+    assert np.array_equal(a.KKTError(), b.KKTError())
+    q1, v1 = q0 + 0.01, v0 - 0.02          # MPC: the measured state moves, the linearisation is still valid
+    for s in (a, b):
+        s.updateSolution(0.0, q1, v1)
+    same()
+    for s in (a, b):                       # setSolution re-initialises the constraints: the kept linearisation is stale
+        s.setSolution("q", q1)
+        s.updateSolution(0.0, q1, v1)
+    same()
+    for it in range(2):
+        for s in (a, b):
+            s.updateSolution(0.0, q1, v1, True)
+        same()
+    assert a.launchCount() < b.launchCount()

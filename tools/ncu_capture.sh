@@ -14,4 +14,6 @@ ncu --set full --metrics smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,sms
 python tools/ncu_summary.py "$REP.ncu-rep" "profiles/${LABEL}_ncu_full_${WORKLOAD}.txt" > /dev/null
 python tools/ncu_counters.py "$REP.ncu-rep" "profiles/kernel_counters_${WORKLOAD}.json" "profiles/${LABEL}_ncu_full_${WORKLOAD}.txt"
 mkdir -p gpurun_out/profiles
+# the .ncu-rep is tens of MiB: gpurun merges at most 64 MiB back, so keep it only on request
+[ "${KEEP_REP:-0}" = 1 ] || rm -f "$REP.ncu-rep"
 cp "profiles/${LABEL}_ncu_full_${WORKLOAD}.txt" "profiles/kernel_counters_${WORKLOAD}.json" gpurun_out/profiles/
