@@ -511,6 +511,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="instances per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipelining", action="store_true",
+                    help="iiwa14_unocp: the literal linearise / Riccati / expand / update sequence (A/B of k_linearize<.., FUSED>)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--workload", default="iiwa14_unocp", choices=["iiwa14_unocp", "anymal_trotting", "anymal_running"],
                     help="iiwa14_unocp = BASELINE configs[2] (the headline); anymal_* = configs[3] / configs[4]")
@@ -551,6 +553,8 @@ def main():
     B = args.batch
     q0, v0 = initial_states(rank * B, B, list(prob.q_min), list(prob.q_max))
     solver = I.UnOCPSolver(prob, B, device=local_rank)
+    if args.no_pipelining:
+        solver.setPipelining(False)
     solver.setSolution("q", q0)
     solver.setSolution("v", v0)
     stream = torch.cuda.ExternalStream(solver.stream(), device=local_rank)

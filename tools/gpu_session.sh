@@ -16,6 +16,12 @@ fi
 if has bench; then
   python bench.py --steps 100 --warmup 10 > gpurun_out/${L}_bench.json 2> gpurun_out/${L}_bench.err; echo "bench rc=$?"; cut -c 1-600 gpurun_out/${L}_bench.json
 fi
+if has benchab; then
+  python bench.py --steps 100 --warmup 10 --no-pipelining --no-cpu-baseline > gpurun_out/${L}_bench_nopipe.json 2> gpurun_out/${L}_bench_nopipe.err; cut -c 1-300 gpurun_out/${L}_bench_nopipe.json
+fi
+if has testfast; then
+  timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_baseline_configs.py::test_config2_full_batch_bit_exact_and_iteration_gate -m gpu -x -q > gpurun_out/${L}_pytest_fast.log 2>&1; echo "pytest rc=$?"; tail -n 5 gpurun_out/${L}_pytest_fast.log
+fi
 if has ref; then
   python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/${L}_bench_reference.json 2> gpurun_out/${L}_bench_reference.err; cut -c 1-300 gpurun_out/${L}_bench_reference.json
 fi
@@ -30,7 +36,7 @@ if has launches; then
       python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/${L}_launches_run.log 2>&1; echo "launches rc=$?"
 fi
 if has ncu; then
-  NCU_SKIP=40 NCU_COUNT=8 tools/ncu_capture.sh $L iiwa14_unocp 'k_linearize|k_riccati|k_expand|k_update'
+  NCU_SKIP=40 NCU_COUNT=6 KEEP_REP=1 tools/ncu_capture.sh $L iiwa14_unocp 'k_linearize|k_riccati|k_expand|k_update'
 fi
 if has ncufb; then
   NCU_SKIP=30 NCU_COUNT=6 tools/ncu_capture.sh $L anymal_trotting 'k_fb_robot|k_fb_condense|k_fb_riccati_backward'
