@@ -141,6 +141,7 @@ struct idocp_b200_solver : LaunchProfiler {
   // which the next updateSolution re-uses as long as nothing changed the iterate or the cost reference in between
   bool pipelined = true;
   bool lin_valid = false;
+  int sm_count = 1;            // persistent kernels launch one CTA pair per SM
 
   int stage_offset() const { return kind == IDOCP_B200_SOLVER_UNPARNMPC ? 1 : 0; }
 };
@@ -218,6 +219,7 @@ static int stage_grid(const idocp_b200_solver* h, int nstages) {
 static int group_grid(const idocp_b200_solver* h) { return (h->L.G + WARPS_PER_CTA - 1) / WARPS_PER_CTA; }
 static const int kLinSmem = OCTETS_PER_CTA * OCT * PAIR_TILE * static_cast<int>(sizeof(double));
 static const int kRicSmem = RIC_SMEM_DOUBLES * static_cast<int>(sizeof(double));
+static const int kUlSmem = UL_SMEM_DOUBLES * static_cast<int>(sizeof(double));
 
 static int do_init_constraints(idocp_b200_solver* h) {
   h->lin_valid = false;   // slack / dual change: the kept linearisation is stale
@@ -286,6 +288,13 @@ extern "C" int idocp_b200_create(const idocp_b200_problem* p, int solver_kind, i
   rc |= h->alloc(&h->d_stage, h->stage_doubles);
   if (cudaFuncSetAttribute(k_riccati<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRicSmem) != cudaSuccess) rc |= -1;
   if (cudaFuncSetAttribute(k_riccati<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRicSmem) != cudaSuccess) rc |= -1;
+  if (cudaFuncSetAttribute(k_update_linearize<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUlSmem) != cudaSuccess) rc |= -1;
+  if (cudaFuncSetAttribute(k_update_linearize<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUlSmem) != cudaSuccess) rc |= -1;
+  {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+      h->sm_count = sms;
+  }
   if (par) {
     rc |= parnmpc_alloc(h->PL, h->N, h->Bp, [&](double** pp, size_t n) { return h->alloc(pp, n); });
     if (cudaFuncSetAttribute(k_parnmpc_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, INV_SMEM_BYTES) !=
@@ -444,10 +453,10 @@ static int unocp_update(idocp_b200_solver* h, const double* d_q, const double* d
   if (!(h->pipelined && h->lin_valid)) {
     if (task)
       IDOCP_LAUNCH(h, KC_LINEARIZE, (k_linearize<false, false, true>), stage_grid(h, h->N + 1), CTA_THREADS, kLinSmem,
-                   h->d_prob, h->L, d_q, d_v, nullptr);
+                   h->d_prob, h->L, d_q, d_v);
     else
       IDOCP_LAUNCH(h, KC_LINEARIZE, (k_linearize<false, false, false>), stage_grid(h, h->N), CTA_THREADS, kLinSmem,
-                   h->d_prob, h->L, d_q, d_v, nullptr);
+                   h->d_prob, h->L, d_q, d_v);
   }
   if (task) {
     IDOCP_LAUNCH(h, KC_RICCATI, k_riccati<true>, group_grid(h), CTA_THREADS, kRicSmem, h->d_prob, h->L, d_q, d_v);
@@ -463,13 +472,14 @@ static int unocp_update(idocp_b200_solver* h, const double* d_q, const double* d
     override_alpha = h->LS.alpha;
   }
   if (h->pipelined) {
-    // update + linearisation of the new iterate in one launch; X (old) -> X2 (new), then the two swap roles
+    // step sizes, then update + linearisation of the new iterate in one persistent launch; X (old) -> X2 (new), then the
+    // two swap roles
+    IDOCP_LAUNCH(h, KC_UPDATE, k_step_min, (h->Bp + 127) / 128, 128, 0, h->L, override_alpha);
+    const int ul_grid = std::min(stage_grid(h, h->N + 1), 2 * h->sm_count);
     if (task)
-      IDOCP_LAUNCH(h, KC_UPDATE_LINEARIZE, (k_linearize<false, false, true, true>), stage_grid(h, h->N + 1), CTA_THREADS,
-                   kLinSmem, h->d_prob, h->L, d_q, d_v, override_alpha);
+      IDOCP_LAUNCH(h, KC_UPDATE_LINEARIZE, k_update_linearize<true>, ul_grid, CTA_THREADS, kUlSmem, h->d_prob, h->L);
     else
-      IDOCP_LAUNCH(h, KC_UPDATE_LINEARIZE, (k_linearize<false, false, false, true>), stage_grid(h, h->N + 1), CTA_THREADS,
-                   kLinSmem, h->d_prob, h->L, d_q, d_v, override_alpha);
+      IDOCP_LAUNCH(h, KC_UPDATE_LINEARIZE, k_update_linearize<false>, ul_grid, CTA_THREADS, kUlSmem, h->d_prob, h->L);
     std::swap(h->L.X, h->L.X2);
     h->lin_valid = true;
   } else {
@@ -486,10 +496,10 @@ static int parnmpc_update(idocp_b200_solver* h, double, const double* d_q, const
   // UnBackwardCorrection::coarseUpdate (src/unocp/unbackward_correction.cpp:67-97)
   if (h->prob.task_enabled)
     IDOCP_LAUNCH(h, KC_LINEARIZE, (k_linearize<false, true, true>), stage_grid(h, N), CTA_THREADS, kLinSmem, h->d_prob,
-                 h->L, d_q, d_v, nullptr);
+                 h->L, d_q, d_v);
   else
     IDOCP_LAUNCH(h, KC_LINEARIZE, (k_linearize<false, true, false>), stage_grid(h, N), CTA_THREADS, kLinSmem, h->d_prob,
-                 h->L, d_q, d_v, nullptr);
+                 h->L, d_q, d_v);
   IDOCP_LAUNCH(h, KC_PARNMPC_COARSE, k_parnmpc_invert, N * h->L.G, CTA_THREADS, INV_SMEM_BYTES, h->d_prob, h->L, h->PL);
   // UnBackwardCorrection::backwardCorrection (:100-134)
   if (N > 1) {
@@ -514,10 +524,10 @@ static int parnmpc_update(idocp_b200_solver* h, double, const double* d_q, const
 static int parnmpc_kkt_residual(idocp_b200_solver* h, double, const double* d_q, const double* d_v) {
   if (h->prob.task_enabled)
     IDOCP_LAUNCH(h, KC_KKT, (k_linearize<true, true, true>), stage_grid(h, h->N), CTA_THREADS, kLinSmem, h->d_prob, h->L,
-                 d_q, d_v, nullptr);
+                 d_q, d_v);
   else
     IDOCP_LAUNCH(h, KC_KKT, (k_linearize<true, true, false>), stage_grid(h, h->N), CTA_THREADS, kLinSmem, h->d_prob, h->L,
-                 d_q, d_v, nullptr);
+                 d_q, d_v);
   IDOCP_LAUNCH(h, KC_KKT, k_kkt_sum, (h->Bp + 127) / 128, 128, 0, h->L, h->N);
   CUDA_OK(cudaGetLastError());
   return IDOCP_B200_OK;
@@ -560,10 +570,10 @@ extern "C" int idocp_b200_compute_kkt_residual_device(idocp_b200_solver* h, doub
   if (h->kind == IDOCP_B200_SOLVER_UNPARNMPC) return parnmpc_kkt_residual(h, t, d_q, d_v);
   if (h->prob.task_enabled)
     IDOCP_LAUNCH(h, KC_KKT, (k_linearize<true, false, true>), stage_grid(h, h->N + 1), CTA_THREADS, kLinSmem, h->d_prob,
-                 h->L, d_q, d_v, nullptr);
+                 h->L, d_q, d_v);
   else
     IDOCP_LAUNCH(h, KC_KKT, (k_linearize<true, false, false>), stage_grid(h, h->N + 1), CTA_THREADS, kLinSmem, h->d_prob,
-                 h->L, d_q, d_v, nullptr);
+                 h->L, d_q, d_v);
   IDOCP_LAUNCH(h, KC_KKT, k_kkt_sum, (h->Bp + 127) / 128, 128, 0, h->L, h->N + 1);
   CUDA_OK(cudaGetLastError());
   return IDOCP_B200_OK;

@@ -231,10 +231,10 @@ __device__ __forceinline__ void fb_llt_cta(const double* A, int lda, int n, doub
     for (int e = 0; e < E; ++e) {
       if (ej[e] == k) {
         if (ei[e] == k) {
-          const double x = sqrt(a[e]);
-          if (!(a[e] > 0.0) && *info == 0) *info = code + k + 1;
-          L[k * ldl + k] = x;
-          rd[k] = 1.0 / x;
+          const double r = canon_rsqrt(a[e]);
+          if (!canon_pivot_ok(a[e]) && *info == 0) *info = code + k + 1;
+          rd[k] = r;
+          L[k * ldl + k] = a[e] * r;
         } else {
           L[k * ldl + ei[e]] = a[e];   // still unscaled
         }
@@ -288,10 +288,10 @@ __device__ __forceinline__ void fb_llt_factor_solve_cta(const double* A, int lda
     for (int e = 0; e < EA; ++e) {
       if (aj[e] == k) {
         if (ai[e] == k) {
-          const double x = sqrt(a[e]);
-          if (!(a[e] > 0.0) && *info == 0) *info = code + k + 1;
-          L[k * ldl + k] = x;
-          rd[k] = 1.0 / x;
+          const double r = canon_rsqrt(a[e]);
+          if (!canon_pivot_ok(a[e]) && *info == 0) *info = code + k + 1;
+          rd[k] = r;
+          L[k * ldl + k] = a[e] * r;
         } else {
           L[k * ldl + ai[e]] = a[e];   // still unscaled
         }

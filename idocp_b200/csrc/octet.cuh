@@ -73,6 +73,31 @@ __device__ __forceinline__ void canon_sincos(double x, double* sn, double* cs) {
   *cs = (q == 0) ? c : (q == 1) ? -s : (q == 2) ? -c : s;
 }
 
+// Reciprocal square root of a Cholesky pivot: r ~ 1 / sqrt(x) within about one ulp.  A Cholesky column needs only
+// r (L_ik = A_ik r; L_kk = x r where somebody reads it), and IEEE sqrt followed by an IEEE division is the longest
+// dependent chain of every factorisation here (two library sequences of ~10 dependent FP64 operations each, on the
+// critical path of 7 / 18 / 21 sequential pivots).  Canonical definition, repeated operation by operation by the
+// oracle (oracle/canon_pivot.h): the seed is the single-precision 1 / sqrt(float(x)) formed with two correctly
+// rounded IEEE operations (identical on every IEEE machine), refined by two Newton steps in explicit FP64 fma form
+// (relative error 2e-7 -> 5e-14 -> rounding).  Pivots outside (1e-36, 1e36) are reported as failed factorisations
+// (canon_pivot_ok): beyond that range the single-precision seed would overflow or vanish.
+__device__ __forceinline__ bool canon_pivot_ok(double x) { return x > 1e-36 && x < 1e36; }
+__device__ __forceinline__ double canon_rsqrt(double x) {
+#ifdef IDOCP_B200_EMU
+  const float xf = static_cast<float>(x);
+  const float yf = 1.0f / sqrtf(xf);
+#else
+  const float yf = __fdiv_rn(1.0f, __fsqrt_rn(__double2float_rn(x)));
+#endif
+  double y = static_cast<double>(yf);
+  const double h = 0.5 * x;
+  double e = fma(-(h * y), y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-(h * y), y, 0.5);
+  y = fma(y, e, y);
+  return y;
+}
+
 // natural logarithm of a positive normal double (barrier cost of the line search): the classic
 // k*ln2 + log(1+f) reduction with the degree-14 minimax polynomial in s = f/(2+f), one code path,
 // written with plain IEEE operations so that the oracle repeats it bit for bit (<= 2 ulp).

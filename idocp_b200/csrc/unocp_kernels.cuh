@@ -144,40 +144,32 @@ __global__ void k_set_solution(Layout L, int field, const double* __restrict__ v
 // TASK = true: + TimeVaryingTaskSpace6DCost (task_space_cost.cuh).  With the forward-Euler solver the kernel
 //               then also covers the terminal stage N (TerminalOCP::linearizeOCP, ocp/terminal_ocp.hxx:50-66)
 //               and leaves its dense Hessian / gradient in record N of KQ for k_riccati and k_expand.
-// FUSED = true (UnOCPSolver, forward Euler only): the kernel first applies the step of the iteration that has just been
-//   expanded -- exactly k_update: alpha = min over the stages, s += alpha_p d, slack += alpha_p dslack, dual += alpha_d ddual
-//   (unocp_solver.cpp:114-133) -- reading the old iterate from L.X and writing the new one to L.X2 (ping-pong: the
-//   neighbour stage's warp still needs the OLD record of this stage), and then linearises the NEW iterate for the next
-//   updateSolution call.  The linearisation does not depend on the measured state (q0, v0 only enter the forward
-//   Riccati recursion), so the host keeps it until the iterate or the cost reference changes (capi.cu: lin_valid).
-//   The update's HBM stream hides under the FP64 work of the linearisation; one launch and one read of X less per iteration.
-template <bool RESIDUAL_ONLY, bool BACKWARD_EULER, bool TASK, bool FUSED = false>
-__global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_linearize(const DevProblem* __restrict__ Pp, Layout L,
-                                                                           const double* __restrict__ q0,
-                                                                           const double* __restrict__ v0,
-                                                                           const double* __restrict__ primal_override = nullptr) {
+// FUSED = true (UnOCPSolver, forward Euler only; k_update_linearize below): the task first applies the step of the iteration
+//   that has just been expanded -- s += alpha_p d, slack += alpha_p dslack, dual += alpha_d ddual (unocp_solver.cpp:121-133) --
+//   reading the old iterate / the direction from the records X, D, Xn, Dn (staged in shared memory by the TMA engine) and
+//   writing the new iterate to L.X2 (ping-pong: the neighbour stage's warp still needs the OLD record of this stage), and then
+//   linearises the NEW iterate for the next updateSolution call.  The linearisation does not depend on the measured state
+//   (q0, v0 only enter the forward Riccati recursion), so the host keeps it until the iterate or the cost reference changes
+//   (capi.cu: lin_valid).  The update's HBM stream hides under the FP64 work of the linearisation.
+// X: this thread's pointer into the record of (stage i, group g) -- global memory, or the staged copy when FUSED.
+template <bool RESIDUAL_ONLY, bool BACKWARD_EULER, bool TASK, bool FUSED>
+__device__ __forceinline__ void linearize_task(const DevProblem& P, const Layout& L, const double* __restrict__ q0,
+                                               const double* __restrict__ v0, double* tile, const int i, const int g,
+                                               const double* X, const double* D, const double* Xnf, const double* Dn,
+                                               const double ap, const double ad) {
   static_assert(!FUSED || (!RESIDUAL_ONLY && !BACKWARD_EULER), "the fused update exists for UnOCPSolver::updateSolution only");
-  IDOCP_DYN_SMEM(double, smem);
-  const DevProblem& P = *Pp;
   const int lane = lane_in_octet();
-  const int oct = threadIdx.x >> 3;
-  double* tile = smem + oct * (OCT * PAIR_TILE);
-  const StageTask t = stage_task(L, (FUSED || ((RESIDUAL_ONLY || TASK) && !BACKWARD_EULER)) ? L.N + 1 : L.N);
-  const int i = t.stage;
   const int ts = BACKWARD_EULER ? i + 1 : i;   // time stage of the constraint masks
-  const int b = t.g * 4 + ((threadIdx.x >> 3) & 3);
+  const int b = g * 4 + ((threadIdx.x >> 3) & 3);
   const double dt = P.dt;
   const bool act = lane < NV;
-  const double* X = rec_ptr(L.X, X_NUM, L.G, i, t.g);
 
   double q = X[X_Q * SLOT], v = X[X_V * SLOT], lmd = X[X_LMD * SLOT], gmm = X[X_GMM * SLOT];
   // the state of the fused update that the linearisation below continues with
   double fa = 0.0, fu = 0.0, fbeta = 0.0, fslack[NC], fdual[NC], fqn = 0.0, fvn = 0.0, flmdn = 0.0, fgmmn = 0.0;
   if (FUSED) {
     const int N = L.N;
-    const double* D = rec_ptr(L.D, D_NUM, L.G, i, t.g);
-    double* Xw = rec_ptr(L.X2, X_NUM, L.G, i, t.g);
-    // every load first (stores through Xw would fence the loads behind them)
+    double* Xw = rec_ptr(L.X2, X_NUM, L.G, i, g);
     const double dlmd = D[D_LMD * SLOT], dgmm = D[D_GMM * SLOT], dq = D[D_Q * SLOT], dv = D[D_V * SLOT];
     double da = 0.0, du = 0.0, dbeta = 0.0, dqn = 0.0, dvn = 0.0, dlmdn = 0.0, dgmmn = 0.0;
     if (i != N) {
@@ -188,26 +180,8 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_linearize(const
         fslack[c] = X[(X_SLACK + c) * SLOT];
         fdual[c] = X[(X_DUAL + c) * SLOT];
       }
-      const double* Xn = X + static_cast<size_t>(L.G) * (X_NUM * SLOT);
-      const double* Dn = D + static_cast<size_t>(L.G) * (D_NUM * SLOT);
-      fqn = Xn[X_Q * SLOT]; fvn = Xn[X_V * SLOT]; flmdn = Xn[X_LMD * SLOT]; fgmmn = Xn[X_GMM * SLOT];
+      fqn = Xnf[X_Q * SLOT]; fvn = Xnf[X_V * SLOT]; flmdn = Xnf[X_LMD * SLOT]; fgmmn = Xnf[X_GMM * SLOT];
       dqn = Dn[D_Q * SLOT]; dvn = Dn[D_V * SLOT]; dlmdn = Dn[D_LMD * SLOT]; dgmmn = Dn[D_GMM * SLOT];
-    }
-    // step sizes: min over the N per-stage minima (k_update)
-    double ap = 1.0, ad = 1.0;
-    for (int s = lane; s < N; s += OCT) {
-      ap = fmin(ap, L.smin[static_cast<size_t>(s) * L.Bp + b]);
-      ad = fmin(ad, L.smin[(static_cast<size_t>(N) + s) * L.Bp + b]);
-    }
-    ap = oct_min(ap);
-    ad = oct_min(ad);
-    const double amax = ap;
-    if (primal_override) ap = primal_override[b];
-    if (i == 0 && lane == 0) {
-      L.steps[b] = ap;
-      L.steps[L.Bp + b] = ad;
-      L.steps[2 * L.Bp + b] = amax;
-      if (!(ap == ap) || !(ad == ad)) L.status[b] |= 2;
     }
     // the padding lane keeps its (zero) record: k_update never touches it
     const double q_old = q, v_old = v, u_old = fu;
@@ -269,7 +243,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_linearize(const
       if (lane == 0) L.kkt_stage[static_cast<size_t>(i) * L.Bp + b] = e;
     } else {
       // terminal record: rows of Qqq_N (slot = row, lane = column), lq_N, lv_N
-      double* KQ = rec_ptr(L.KQ, KQ_NUM, L.G, i, t.g);
+      double* KQ = rec_ptr(L.KQ, KQ_NUM, L.G, i, g);
 #pragma unroll
       for (int r = 0; r < NV; ++r) KQ[(KQ_QQ + r) * SLOT] = (r == lane ? P.qf_weight[lane] : 0.0) + (act ? hf[r] : 0.0);
       KQ[KQ_LQ * SLOT] = lq;
@@ -465,8 +439,8 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_linearize(const
     }
     ulq += tq; ulv += tv; ula += ta;
   }
-  double* KQ = rec_ptr(L.KQ, KQ_NUM, L.G, i, t.g);
-  double* W = rec_ptr(L.W, W_NUM, L.G, i, t.g);
+  double* KQ = rec_ptr(L.KQ, KQ_NUM, L.G, i, g);
+  double* W = rec_ptr(L.W, W_NUM, L.G, i, g);
   KQ[KQ_FQ * SLOT] = Fq;
   KQ[KQ_FV * SLOT] = Fv;
   KQ[KQ_LA * SLOT] = ula;
@@ -525,6 +499,100 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_linearize(const
     KQ[(KQ_AQ + r) * SLOT] = aq;
     KQ[(KQ_AV + r) * SLOT] = av;
     KQ[(KQ_AA + r) * SLOT] = aa + (diag ? Qaa_d : 0.0);
+  }
+}
+
+
+template <bool RESIDUAL_ONLY, bool BACKWARD_EULER, bool TASK>
+__global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_linearize(const DevProblem* __restrict__ Pp, Layout L,
+                                                                           const double* __restrict__ q0,
+                                                                           const double* __restrict__ v0) {
+  IDOCP_DYN_SMEM(double, smem);
+  double* tile = smem + (threadIdx.x >> 3) * (OCT * PAIR_TILE);
+  const StageTask t = stage_task(L, ((RESIDUAL_ONLY || TASK) && !BACKWARD_EULER) ? L.N + 1 : L.N);
+  linearize_task<RESIDUAL_ONLY, BACKWARD_EULER, TASK, false>(*Pp, L, q0, v0, tile, t.stage, t.g,
+                                                             rec_ptr(L.X, X_NUM, L.G, t.stage, t.g), nullptr, nullptr, nullptr, 1.0, 1.0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_step_min + k_update_linearize: the tail of a pipelined UnOCPSolver::updateSolution.
+//   k_step_min: alpha_p, alpha_d = min over the N per-stage fraction-to-boundary minima (unocp_solver.cpp:114-115), one
+//     thread per instance; `primal_override` (line search) replaces the primal step when given.
+//   k_update_linearize: PERSISTENT, one CTA pair per SM; a warp walks over its (stage, group) tasks and, while it works on
+//     one, the TMA engine stages the records of the next one (X 19 slots, D 7 slots, the first four slots of the next
+//     stage's X and D, the two step sizes of the group) into the other half of the warp's shared-memory buffer
+//     (cp.async.bulk + mbarrier, tma.cuh).  The non-persistent form of this fusion was slower than k_update + k_linearize
+//     (0.70 vs 0.66 ms): with 2 warps per scheduler (254 registers) the extra loads sat exposed in front of the FP64 work
+//     (long scoreboard 1.6 stall cycles per issue, profiles/r2b_ncu_full_iiwa14_unocp.txt).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_step_min(Layout L, const double* __restrict__ primal_override) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= L.Bp) return;
+  const int N = L.N;
+  double ap = 1.0, ad = 1.0;
+  for (int s = 0; s < N; ++s) {
+    ap = fmin(ap, L.smin[static_cast<size_t>(s) * L.Bp + b]);
+    ad = fmin(ad, L.smin[(static_cast<size_t>(N) + s) * L.Bp + b]);
+  }
+  const double amax = ap;
+  if (primal_override) ap = primal_override[b];
+  L.steps[b] = ap;                 // primal step applied (after the line search, if any)
+  L.steps[L.Bp + b] = ad;          // dual step
+  L.steps[2 * L.Bp + b] = amax;    // fraction-to-boundary primal step
+  if (!(ap == ap) || !(ad == ad)) L.status[b] |= 2;
+}
+
+constexpr int UL_D = X_NUM, UL_XN = UL_D + D_NUM, UL_DN = UL_XN + 4, UL_ST = UL_DN + 4, UL_SLOTS = UL_ST + 1;
+constexpr int UL_OFF_BUF = OCTETS_PER_CTA * OCT * PAIR_TILE;                       // doubles, after the pair tiles
+constexpr int UL_OFF_BARS = UL_OFF_BUF + WARPS_PER_CTA * 2 * UL_SLOTS * SLOT;
+constexpr int UL_SMEM_DOUBLES = UL_OFF_BARS + 2 * WARPS_PER_CTA;
+static_assert(X_LMD == 0 && X_GMM == 1 && X_Q == 2 && X_V == 3 && D_LMD == 0 && D_GMM == 1 && D_Q == 2 && D_V == 3,
+              "the next stage's (lmd, gmm, q, v) and their directions are the first four slots of a record");
+static_assert((UL_OFF_BUF * 8) % 16 == 0, "TMA destinations are 16-byte aligned");
+
+template <bool TASK>
+__global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_update_linearize(const DevProblem* __restrict__ Pp, Layout L) {
+  IDOCP_DYN_SMEM(double, smem);
+  const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
+  double* tile = smem + (threadIdx.x >> 3) * (OCT * PAIR_TILE);
+  double* bufs = smem + UL_OFF_BUF + warp * (2 * UL_SLOTS * SLOT);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + UL_OFF_BARS) + 2 * warp;
+  const int N = L.N;
+  const long ntask = static_cast<long>(N + 1) * L.G;
+  const long nwarps = static_cast<long>(gridDim.x) * WARPS_PER_CTA;
+  long wt = static_cast<long>(blockIdx.x) * WARPS_PER_CTA + warp;
+  if (wl == 0) {
+    tma_bar_init(&bars[0], 1);
+    tma_bar_init(&bars[1], 1);
+  }
+  __syncwarp();
+  auto issue = [&](long task, int buf) {
+    const int st = static_cast<int>(task / L.G), g = static_cast<int>(task % L.G);
+    double* dst = bufs + buf * (UL_SLOTS * SLOT);
+    const double* xr = L.X + (static_cast<size_t>(st) * L.G + g) * (X_NUM * SLOT);
+    const double* dr = L.D + (static_cast<size_t>(st) * L.G + g) * (D_NUM * SLOT);
+    const bool nxt = st != N;
+    tma_bar_expect(&bars[buf], (X_NUM + D_NUM) * SLOT * 8 + 2 * 32 + (nxt ? 8 * SLOT * 8 : 0));
+    tma_load_1d(dst, xr, X_NUM * SLOT * 8, &bars[buf]);
+    tma_load_1d(dst + UL_D * SLOT, dr, D_NUM * SLOT * 8, &bars[buf]);
+    if (nxt) {
+      tma_load_1d(dst + UL_XN * SLOT, xr + static_cast<size_t>(L.G) * (X_NUM * SLOT), 4 * SLOT * 8, &bars[buf]);
+      tma_load_1d(dst + UL_DN * SLOT, dr + static_cast<size_t>(L.G) * (D_NUM * SLOT), 4 * SLOT * 8, &bars[buf]);
+    }
+    tma_load_1d(dst + UL_ST * SLOT, L.steps + static_cast<size_t>(g) * 4, 32, &bars[buf]);
+    tma_load_1d(dst + UL_ST * SLOT + 4, L.steps + L.Bp + static_cast<size_t>(g) * 4, 32, &bars[buf]);
+  };
+  if (wl == 0 && wt < ntask) issue(wt, 0);
+  for (int k = 0; wt < ntask; wt += nwarps, ++k) {
+    const int buf = k & 1;
+    __syncwarp();   // every lane is through with the previous task: its reads of the other buffer and of the pair tile
+    if (wl == 0 && wt + nwarps < ntask) issue(wt + nwarps, buf ^ 1);
+    tma_bar_wait(&bars[buf], (k >> 1) & 1);
+    const double* rec = bufs + buf * (UL_SLOTS * SLOT);
+    const int o4 = (threadIdx.x >> 3) & 3;
+    linearize_task<false, false, TASK, true>(*Pp, L, nullptr, nullptr, tile, static_cast<int>(wt / L.G), static_cast<int>(wt % L.G),
+                                             rec + wl, rec + UL_D * SLOT + wl, rec + UL_XN * SLOT + wl, rec + UL_DN * SLOT + wl,
+                                             rec[UL_ST * SLOT + o4], rec[UL_ST * SLOT + 4 + o4]);
   }
 }
 
@@ -704,10 +772,8 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_RIC_MINB) k_riccati(const D
       double x = tA[k * RIC_TILE + k];
 #pragma unroll
       for (int j = 0; j < k; ++j) x = fma(-Lm[j][k], Lm[j][k], x);
-      if (!(x > 0.0)) chol_fail = 1;
-      x = sqrt(x);
-      Lm[k][k] = x;
-      rdiag[k] = 1.0 / x;
+      if (!canon_pivot_ok(x)) chol_fail = 1;
+      rdiag[k] = canon_rsqrt(x);   // the diagonal L_kk = x rdiag[k] itself is never read
 #pragma unroll
       for (int r = k + 1; r < NV; ++r) {
         double y = tA[k * RIC_TILE + r];

@@ -125,60 +125,61 @@ constexpr int INV_OFF_RES = INV_OFF_TR + NQ3 * INV_LDX; // residual (35)
 constexpr int INV_SMEM_PER_WARP = INV_OFF_RES + 36;
 constexpr int INV_SMEM_BYTES = WARPS_PER_CTA * INV_SMEM_PER_WARP * static_cast<int>(sizeof(double));
 
-// left-looking Cholesky of the lower triangle of the n x n matrix at A (column stride ld), in place;
-// lane = row; the lane keeps its own row of L in registers, the pivot row comes from shared memory
-// as a broadcast.  Eigen::LLT<Lower> semantics; divisions by the pivot are
-// multiplications by its reciprocal rd[k] (canonical arithmetic, oracle llt_lower).  Fully unrolled:
-// every element is the same ascending-j fma chain as in the oracle.  Returns non-zero on a bad pivot.
+// Right-looking Cholesky of the lower triangle of the n x n matrix at A (column stride ld), in place; lane = row.
+// The lane keeps its row of the trailing matrix in registers.  Step k: the pivot comes from lane k by shuffle, every
+// lane scales its entry of column k (L_ik = a_ik r_k, r_k = canon_rsqrt(pivot)), publishes it, and applies the n - 1 - k
+// INDEPENDENT updates a_ic -= L_ik L_ck of its row (L_ck: shared-memory broadcast).  Every element receives its updates
+// in ascending k, i.e. exactly the fma chain of the left-looking oracle (llt_lower), but the dependent chain of the
+// factorisation is one fma per column instead of k (the left-looking form of round 1 was bound by those chains).
+// Eigen::LLT<Lower> semantics.  Returns non-zero on a bad pivot.
 template <int n>
 __device__ __forceinline__ int warp_llt(double* __restrict__ A, int ld, double* __restrict__ rd, int wl) {
   int fail = 0;
-  double Lrow[n];
+  double a[n];
   const int row = wl < n ? wl : n - 1;   // idle lanes shadow the last row (never stored)
 #pragma unroll
-  for (int k = 0; k < n; ++k) {
-    // idle lanes do not touch A: their read of element (n - 1, k) would sit unordered against lane n - 1's store below
-    double x = wl < n ? A[k * ld + row] : 1.0;
+  for (int c = 0; c < n; ++c) a[c] = A[c * ld + row];   // entries c > row are never used
+  __syncwarp();
 #pragma unroll
-    for (int j = 0; j < k; ++j) x = fma(-Lrow[j], A[j * ld + k], x);
-    const double piv = __shfl_sync(FULL, x, k);
-    if (!(piv > 0.0)) fail = 1;
-    const double s = sqrt(piv);
-    const double r = 1.0 / s;
-    Lrow[k] = (wl == k) ? s : x * r;
-    if (wl >= k && wl < n) A[k * ld + wl] = Lrow[k];
+  for (int k = 0; k < n; ++k) {
+    const double piv = __shfl_sync(FULL, a[k], k);
+    if (!canon_pivot_ok(piv)) fail = 1;
+    const double r = canon_rsqrt(piv);
+    const double lk = a[k] * r;          // lane k: L_kk = pivot * r
+    if (wl >= k && wl < n) A[k * ld + wl] = lk;
     if (wl == k) rd[k] = r;
     __syncwarp();
+#pragma unroll
+    for (int c = k + 1; c < n; ++c) a[c] = fma(-lk, A[k * ld + c], a[c]);
   }
   return fail;
 }
 
-// column `c` of (L L^T)^-1: forward + backward substitution of the unit vector e_c (oracle llt_solve)
-// The compiler barrier after every row keeps the (address-independent) shared-memory loads of L from being
-// hoisted above the whole unrolled substitution, which would cost hundreds of registers (spills).
-#ifdef IDOCP_B200_EMU
-#define IDOCP_SCHED_FENCE() __syncwarp()
-#else
-#define IDOCP_SCHED_FENCE() __syncwarp()
-#endif
+// column `c` of (L L^T)^-1: forward + backward substitution of the unit vector e_c, column-oriented: as soon as y_j is
+// final it is subtracted from every later row (forward) / every earlier row (backward), so the rows advance together
+// and the dependent chain is two operations per row.  Forward: row i receives its terms in ascending j; backward: in
+// descending j -- the operation order of the oracle's llt_solve_desc.
+// The warp barrier after every row keeps the (address-independent) shared-memory loads of L from being hoisted above
+// the whole unrolled substitution, which would cost hundreds of registers (spills).
 template <int n>
-__device__ __forceinline__ void warp_llt_solve_unit(const double* __restrict__ Lm, int ld, const double* __restrict__ rd,
-                                                    int c, double (&y)[n]) {
+__device__ __forceinline__ void warp_llt_solve_unit(const double* Lm, int ld, const double* rd, int c, double (&y)[n]) {
+  // Lm / rd deliberately NOT __restrict__: a restrict-qualified read-only pointer lets the compiler hoist the loads across
+  // the warp barriers anyway (1 KB of spills per thread in round 1)
 #pragma unroll
-  for (int i = 0; i < n; ++i) {
-    double acc = (i == c) ? 1.0 : 0.0;
+  for (int i = 0; i < n; ++i) y[i] = (i == c) ? 1.0 : 0.0;
 #pragma unroll
-    for (int j = 0; j < i; ++j) acc = fma(-Lm[j * ld + i], y[j], acc);
-    y[i] = acc * rd[i];
-    IDOCP_SCHED_FENCE();
+  for (int j = 0; j < n; ++j) {
+    y[j] *= rd[j];
+#pragma unroll
+    for (int i = j + 1; i < n; ++i) y[i] = fma(-Lm[j * ld + i], y[j], y[i]);
+    __syncwarp();
   }
 #pragma unroll
-  for (int i = n - 1; i >= 0; --i) {
-    double acc = y[i];
+  for (int j = n - 1; j >= 0; --j) {
+    y[j] *= rd[j];
 #pragma unroll
-    for (int j = i + 1; j < n; ++j) acc = fma(-Lm[i * ld + j], y[j], acc);
-    y[i] = acc * rd[i];
-    IDOCP_SCHED_FENCE();
+    for (int i = 0; i < j; ++i) y[i] = fma(-Lm[i * ld + j], y[j], y[i]);
+    __syncwarp();
   }
 }
 

@@ -25,6 +25,7 @@
 #include <string.h>
 
 #include "model_anymal.h"
+#include "canon_pivot.h"
 
 #define FB_NV 18
 #define FB_NQ 19
@@ -819,10 +820,9 @@ static inline int fb_llt(const double* A, int lda, int n, double* L, int ldl, do
   for (int k = 0; k < n; ++k) {
     double x = A[k * lda + k];
     for (int j = 0; j < k; ++j) x = fma(-L[j * ldl + k], L[j * ldl + k], x);
-    if (!(x > 0.0) && !info) info = k + 1;
-    x = sqrt(x);
-    L[k * ldl + k] = x;
-    rd[k] = 1.0 / x;
+    if (!canon_pivot_ok(x) && !info) info = k + 1;
+    rd[k] = canon_rsqrt(x);
+    L[k * ldl + k] = x * rd[k];
     for (int i = k + 1; i < n; ++i) {
       double y = A[i * lda + k];
       for (int j = 0; j < k; ++j) y = fma(-L[j * ldl + i], L[j * ldl + k], y);

@@ -11,6 +11,7 @@
  */
 #include "idocp_oracle.h"
 #include "model_iiwa14.h"
+#include "canon_pivot.h"
 
 #include <math.h>
 #include <stdlib.h>
@@ -1109,19 +1110,19 @@ static void split_unocp_condensed_direction(stage_t* st, double dt, split_direct
 /* unocp/split_unriccati_factorizer.hxx, src/unocp/unriccati_recursion.cpp)                    */
 /* ------------------------------------------------------------------------------------------ */
 /* Eigen::LLT<MatrixXd, Lower>: unblocked left-looking Cholesky reading the lower triangle only
- * (SURVEY A.7); returns 0 on success, k+1 when pivot k is not positive.  Canonical arithmetic:
- * the divisions by the diagonal are multiplications by its reciprocal rd[k] = 1 / L_kk (one
- * rounding more than Eigen's division, far inside the unpinned Eigen boundary). */
+ * (SURVEY A.7); returns 0 on success, k+1 when pivot k is not positive (or outside the range of
+ * canon_pivot_ok).  Canonical arithmetic: rd[k] = canon_rsqrt(pivot) ~ 1 / L_kk (canon_pivot.h) and the
+ * divisions by the diagonal are multiplications by it (rounding-level deviation from Eigen's
+ * sqrt + division, far inside the unpinned Eigen boundary). */
 static int llt_lower(const double* A, int n, double* L, double* rd) {
   int info = 0;
   for (int i = 0; i < n * n; ++i) L[i] = 0.0;
   for (int k = 0; k < n; ++k) {
     double x = A[k * n + k];
     for (int j = 0; j < k; ++j) x = fma(-L[j * n + k], L[j * n + k], x);
-    if (!(x > 0.0) && !info) info = k + 1;
-    x = sqrt(x);
-    L[k * n + k] = x;
-    rd[k] = 1.0 / x;
+    if (!canon_pivot_ok(x) && !info) info = k + 1;
+    rd[k] = canon_rsqrt(x);
+    L[k * n + k] = x * rd[k];
     for (int i = k + 1; i < n; ++i) {
       double y = A[k * n + i];
       for (int j = 0; j < k; ++j) y = fma(-L[j * n + i], L[j * n + k], y);
@@ -1140,6 +1141,22 @@ static void llt_solve(const double* L, const double* rd, int n, const double* b,
   for (int i = n - 1; i >= 0; --i) {
     double y = x[i];
     for (int j = i + 1; j < n; ++j) y = fma(-L[i * n + j], x[j], y);
+    x[i] = y * rd[i];
+  }
+}
+
+/* the same with the terms of the backward substitution subtracted from the last column backwards (the order in
+ * which a column-oriented sweep delivers them: row i is complete but for one term when x[i+1] becomes final, so the
+ * rows do not form one long dependent chain).  Used by the 21 + 14 unit right-hand sides of invert_unkkt. */
+static void llt_solve_desc(const double* L, const double* rd, int n, const double* b, double* x) {
+  for (int i = 0; i < n; ++i) {
+    double y = b[i];
+    for (int j = 0; j < i; ++j) y = fma(-L[j * n + i], x[j], y);
+    x[i] = y * rd[i];
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double y = x[i];
+    for (int j = n - 1; j > i; --j) y = fma(-L[i * n + j], x[j], y);
     x[i] = y * rd[i];
   }
 }
@@ -1901,7 +1918,7 @@ static int invert_unkkt(double dt, const double* Q, double* Kinv) {
   int info = llt_lower(Q, NQ3, L, rd);
   for (int c = 0; c < NQ3; ++c) {
     for (int k = 0; k < NQ3; ++k) e[k] = (k == c) ? 1.0 : 0.0;
-    llt_solve(L, rd, NQ3, e, x);
+    llt_solve_desc(L, rd, NQ3, e, x);
     for (int r = 0; r < NQ3; ++r) Qinv[c * NQ3 + r] = x[r];
   }
   /* FQinv (14 x 21): rows Fq: -Qinv[q rows] + dt Qinv[v rows]; rows Fv: dt Qinv[a rows] - Qinv[v rows] */
@@ -1923,7 +1940,7 @@ static int invert_unkkt(double dt, const double* Q, double* Kinv) {
   if (!info && info2) info = 100 + info2;
   for (int c = 0; c < NX; ++c) {
     for (int k = 0; k < NX; ++k) e[k] = (k == c) ? 1.0 : 0.0;
-    llt_solve(LS, rdS, NX, e, x);
+    llt_solve_desc(LS, rdS, NX, e, x);
     for (int r = 0; r < NX; ++r) Sinv[c * NX + r] = x[r];
   }
   /* top-left = -Sinv */

@@ -179,5 +179,8 @@ inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *
 template <typename F>
 inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
 #define cudaFuncAttributeMaxDynamicSharedMemorySize 8
+// one emulated SM: persistent kernels launch 2 CTAs and loop over their tasks (the multi-task path is what the tests exercise)
+#define cudaDevAttrMultiProcessorCount 16
+inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 1; return 0; }
 
 inline void sincos_emu(double x, double* s, double* c) { *s = std::sin(x); *c = std::cos(x); }

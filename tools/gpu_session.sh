@@ -31,6 +31,9 @@ fi
 if has running; then
   python bench.py --workload anymal_running --steps 10 --warmup 3 > gpurun_out/${L}_bench_anymal_running.json 2> gpurun_out/${L}_bench_anymal_running.err; cut -c 1-400 gpurun_out/${L}_bench_anymal_running.json
 fi
+if has parnmpc; then
+  python tools/bench_solver.py --solver unparnmpc --batch 16384 --steps 20 > gpurun_out/${L}_bench_solver_unparnmpc.json 2> gpurun_out/${L}_bench_solver_unparnmpc.err; cut -c 1-700 gpurun_out/${L}_bench_solver_unparnmpc.json
+fi
 if has launches; then
   ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 200 --csv --log-file gpurun_out/${L}_launches.csv \
       python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/${L}_launches_run.log 2>&1; echo "launches rc=$?"
