@@ -45,9 +45,12 @@ KERNEL_ALGO_DOUBLES_PER_STAGE = {
     "expand": 119 + 147 + 21 + 21 + 84 + 28,
     # s 49 + slack/dual 84 + d 49 in; s 49 + slack/dual 84 out
     "update": 2 * (49 + 84) + 49,
-    # the fused kernel (update of iteration k + linearisation for iteration k + 1): linearize + the direction in
-    # (d_i 49, d_{i+1} 28) + the new iterate out (s 49 + slack/dual 84)
+    # the persistent fused kernel (update of iteration k + linearisation for iteration k + 1; its step sizes come from
+    # k_step_min, class "step_min"): linearize + the direction in (d_i 49, d_{i+1} 28) + the new iterate out (s 49 + slack/dual 84)
     "update_linearize": (49 + 28 + 84 + 231 + 35 + 147) + (49 + 28) + (49 + 84),
+    # UnParNMPC coarse update (k_parnmpc_invert): Q 231 + res 35 + aux_next 105 + s 35 in; the four blocks of the inverse the
+    # sweeps multiply with (14x14 + 21x14 + 14x14 + 21x14 = 980) + s_new 35 out
+    "parnmpc_coarse": 231 + 35 + 105 + 35 + 980 + 35,
 }
 
 
@@ -55,9 +58,26 @@ KERNEL_ALGO_DOUBLES_PER_STAGE = {
 # (per kernel: DRAM bytes read + written, executed FP64 thread instructions, pipe / issue utilisation of one launch at the
 # bench batch); tools/fp64_peak (DFMA microbenchmark on the B200) writes profiles/fp64_peak.json.
 KERNEL_OF_CLASS = {"linearize": "k_linearize<0,0,0>", "riccati": "k_riccati<0>", "expand": "k_expand<0,0>", "update": "k_update",
-                   "update_linearize": "k_linearize<0,0,0,1>",
+                   "update_linearize": "k_update_linearize<0>",
                    "fb_robot": "k_fb_robot<0>", "fb_condense": "k_fb_condense", "fb_riccati_backward": "k_fb_riccati_backward",
-                   "parnmpc_invert": "k_parnmpc_invert"}
+                   "parnmpc_coarse": "k_parnmpc_invert"}
+# The iiwa14 workloads of bench.py (all through the same code path, run_iiwa):
+#   iiwa14_unocp           BASELINE configs[2] -- the headline: UnOCPSolver, unocp_benchmark problem, N = 20, 16384 states / GPU
+#   iiwa14_unparnmpc_task  BASELINE configs[1]: task_space_ocp problem (T = 6, N = 120, TimeVaryingTaskSpace6DCost, circular
+#                          reference) through UnParNMPCSolver with initBackwardCorrection, as unparnmpc_benchmark.cpp:46-56 drives
+#                          it; 2048 states / GPU = the example's q0 (task_space_ocp.cpp:86-88) + 0.3 U(-1,1), v0 = 0.2 U(-1,1)
+#   iiwa14_unocp_config    BASELINE configs[0]: config_space_ocp problem (T = 3, N = 60) through UnOCPSolver, 8192 states / GPU
+#                          = the example's q0 + 0.3 U(-1,1), v0 = 0.2 U(-1,1)
+IIWA_WORKLOADS = {
+    "iiwa14_unocp": {"solver": "unocp", "problem": "benchmark", "batch": 16384, "seed": 20240001,
+                     "what": "iiwa14 config-space UnOCPSolver (examples/iiwa14/unocp_benchmark.cpp problem), N=20, T=1"},
+    "iiwa14_unparnmpc_task": {"solver": "unparnmpc", "problem": "task", "batch": 2048, "seed": 20240002,
+                              "what": "iiwa14 task_space_ocp problem (examples/iiwa14/task_space_ocp.cpp:55-93, 6D circular "
+                                      "reference) through UnParNMPCSolver + initBackwardCorrection, N=120, T=6"},
+    "iiwa14_unocp_config": {"solver": "unocp", "problem": "config", "batch": 8192, "seed": 20240000,
+                            "what": "iiwa14 config_space_ocp problem (examples/iiwa14/config_space_ocp.cpp:26-61) through "
+                                    "UnOCPSolver, N=60, T=3"},
+}
 # 64 DFMA / clk / SM (ncu: sm__sass_thread_inst_executed_op_dfma_pred_on.avg.peak_sustained) x 148 SMs x 1.965 GHz x 2
 FP64_PEAK_NOMINAL_TFLOPS = 64 * 148 * 1.965e9 * 2 / 1e12
 
@@ -163,6 +183,31 @@ def initial_states(first_instance, count, q_min, q_max):
     return np.ascontiguousarray(c + 0.8 * h * uq), np.ascontiguousarray(0.5 * uv)
 
 
+def workload_states(name, first_instance, count, q_min, q_max):
+    """Initial states of instances first_instance .. first_instance + count - 1 of an iiwa14 workload (counter-based: a
+    shard of the batch is the same numbers on any rank / world size)."""
+    w = IIWA_WORKLOADS[name]
+    if w["problem"] == "benchmark":
+        return initial_states(first_instance, count, q_min, q_max)
+    base = np.array([0, np.pi / 2, 0, np.pi / 2, 0, np.pi / 2, 0]) if w["problem"] == "task" else \
+        np.array([np.pi / 2, 0, np.pi / 2, 0, np.pi / 2, 0, np.pi / 2])
+    inst = np.arange(first_instance, first_instance + count, dtype=np.uint64)[:, None]
+    j = np.arange(NV, dtype=np.uint64)[None, :]
+    uq = 2.0 * splitmix_uniform(w["seed"], inst * np.uint64(14) + j) - 1.0
+    uv = 2.0 * splitmix_uniform(w["seed"], inst * np.uint64(14) + np.uint64(7) + j) - 1.0
+    return np.ascontiguousarray(base + 0.3 * uq), np.ascontiguousarray(0.2 * uv)
+
+
+def workload_problem(name, mod, lib=None):
+    """The problem of an iiwa14 workload from idocp_b200 (mod = idocp_b200, lib = its library) or from the oracle
+    (mod = oracle_py, lib = None): both expose benchmark_problem / task_space_problem / config_space_problem."""
+    kind = IIWA_WORKLOADS[name]["problem"]
+    args = (lib,) if lib is not None else ()
+    if kind == "benchmark":
+        return mod.benchmark_problem(*args, N=HORIZON_N, T=1.0)
+    return mod.task_space_problem(*args) if kind == "task" else mod.config_space_problem(*args)
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -210,16 +255,21 @@ CPU_WARM_SECONDS = 3.0     # both CPU legs warm up for this long first: OpenMP t
                            # frequency ramp cost ~30 % on a cold 20-sweep run (260 k/s vs 382 k/s on one box)
 
 
-def _oracle_batch(q_min, q_max, cores):
+def _oracle_batch(workload, cores):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py as O
-    prob = O.benchmark_problem(N=HORIZON_N, T=1.0)
-    nb = max(cores * 16, 256)
-    q0, v0 = initial_states(0, nb, q_min, q_max)
-    batch = O.Batch(prob, nb)
+    w = IIWA_WORKLOADS[workload]
+    prob = workload_problem(workload, O)
+    nb = max(cores * 16, 256) if prob.N <= 20 else max(cores * 4, 64)
+    q0, v0 = workload_states(workload, 0, nb, list(prob.q_min), list(prob.q_max))
+    batch = O.Batch(prob, nb, kind=w["solver"])
     for b, s in enumerate(batch.solvers):
         s.set_solution("q", q0[b])
         s.set_solution("v", v0[b])
+        if w["problem"] == "task":
+            s.set_task_ref(O.task_ref_table(O.task_space_ref, 0.0, prob.T, prob.N, kind=w["solver"]))
+        if w["solver"] == "unparnmpc":
+            s.init_backward_correction(0.0)
     t_end = time.perf_counter() + CPU_WARM_SECONDS
     sweeps = 0
     while time.perf_counter() < t_end or sweeps < 3:
@@ -230,12 +280,12 @@ def _oracle_batch(q_min, q_max, cores):
     return batch, nb, q0, v0, time.perf_counter() - t0
 
 
-def oracle_throughput(seconds_target, q_min, q_max, threads=None):
-    """cpu_baseline leg: the CPU oracle (restatement of idocp's UnOCPSolver) on the host cores, OpenMP over instances, every
-    instance single-threaded (BASELINE.md mode B), ~seconds_target of sweeps after the warm-up.
+def oracle_throughput(seconds_target, workload="iiwa14_unocp", threads=None):
+    """cpu_baseline leg: the CPU oracle (restatement of idocp's UnOCPSolver / UnParNMPCSolver) on the host cores, OpenMP over
+    instances, every instance single-threaded (BASELINE.md mode B), ~seconds_target of sweeps after the warm-up.
     Returns (units/s, cores, sample, ms per sweep)."""
     cores = threads or os.cpu_count() or 1
-    batch, nb, q0, v0, one = _oracle_batch(q_min, q_max, cores)
+    batch, nb, q0, v0, one = _oracle_batch(workload, cores)
     sweeps = int(max(3, min(4000, seconds_target / max(one, 1e-6))))
     t0 = time.perf_counter()
     for _ in range(sweeps):
@@ -246,18 +296,21 @@ def oracle_throughput(seconds_target, q_min, q_max, threads=None):
     return nb * sweeps / total, cores, sample, total / sweeps * 1e3
 
 
+def iiwa_metric(workload):
+    return {"iiwa14_unocp": "batched SQP iterations/sec (iiwa14 N=20, FP64)",
+            "iiwa14_unparnmpc_task": "batched ParNMPC iterations/sec (iiwa14 task-space N=120, UnParNMPCSolver, FP64)",
+            "iiwa14_unocp_config": "batched SQP iterations/sec (iiwa14 config-space N=60, FP64)"}[workload]
+
+
 def run_reference(args, rank, world):
     """--impl reference: idocp's own CPU algorithm.  The upstream library cannot be built in this image (Eigen / Boost /
     pinocchio / urdfdom absent), so this times the oracle restatement -- with the SAME protocol as the cpu_baseline leg of the
     GPU arm (same instance sample, same warm-up): one step = R sweeps over the sample, R sized for ~0.5 s per step."""
     if rank != 0:
         return
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle_py as O
-    p = O.default_problem()
-    q_min, q_max = list(p.q_min), list(p.q_max)
     cores = os.cpu_count() or 1
-    batch, nb, q0, v0, one = _oracle_batch(q_min, q_max, cores)
+    w = IIWA_WORKLOADS[args.workload]
+    batch, nb, q0, v0, one = _oracle_batch(args.workload, cores)
     per_step = int(max(1, min(1000, round(0.5 / max(one, 1e-6)))))
 
     def step():
@@ -273,12 +326,12 @@ def run_reference(args, rank, world):
     sample = "%d instances x %d sweeps per step x %d steps after %.0f s + %d steps of warm-up, OpenMP over instances, %d threads" % (
         nb, per_step, args.steps, CPU_WARM_SECONDS, args.warmup, cores)
     line = {
-        "impl": "reference", "metric": "batched SQP iterations/sec (iiwa14 N=20, FP64)", "value": value,
+        "impl": "reference", "metric": iiwa_metric(args.workload), "value": value,
         "unit": "instance-iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "iiwa14 UnOCPSolver unocp_benchmark problem, N=20, T=1, random initial states "
-                               "(splitmix64 seed %d); bounded sample: %d instances x %d sweeps per step" % (SEED, nb, per_step)},
+        "config": {"workload": "%s, random initial states (splitmix64 seed %d); bounded sample: %d instances x %d sweeps per step"
+                               % (w["what"], w["seed"], nb, per_step)},
         "cpu_baseline": {"value": value, "unit": "instance-iterations/s", "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "instance-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -382,7 +435,9 @@ def run_anymal(args, rank, local_rank, world):
     lib = I.default_library()
     pr = anymal_problem(args.workload, lib)
     ls = ANYMAL_LINE_SEARCH[args.workload]
-    B = args.batch if args.batch != BATCH_PER_GPU else ANYMAL_BATCH[args.workload]
+    B = args.batch if args.batch else ANYMAL_BATCH[args.workload]
+    if args.scaling == "strong":
+        B //= world
     q0, v0 = P.anymal_initial_states(rank * B, B, q_nominal=pr.q_nominal, seed=ANYMAL_SEED[args.workload])
     solver = P.make_solver(pr, B, q0, v0, device=local_rank, lib=lib)
     n_stages = len(solver.chain())
@@ -478,7 +533,7 @@ def run_anymal(args, rank, local_rank, world):
     line = {
         "metric": anymal_metric(args.workload), "value": value, "unit": "instance-iterations/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%s: OCPSolver on examples/anymal/%s.cpp (T=%g, N=%d, %d stages incl. impulse / aux / lift), %d "
                                "perturbed initial states per GPU (splitmix64 seed %d), line_search=%s"
                                % (args.workload, args.workload, pr.T, pr.N, n_stages, B, ANYMAL_SEED[args.workload], str(ls).lower()),
@@ -503,37 +558,8 @@ def run_anymal(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="instances per GPU")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-pipelining", action="store_true",
-                    help="iiwa14_unocp: the literal linearise / Riccati / expand / update sequence (A/B of k_linearize<.., FUSED>)")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--workload", default="iiwa14_unocp", choices=["iiwa14_unocp", "anymal_trotting", "anymal_running"],
-                    help="iiwa14_unocp = BASELINE configs[2] (the headline); anymal_* = configs[3] / configs[4]")
-    args = ap.parse_args()
-    claim_stdout()
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.warmup < 3:
-        args.warmup = 3
-
-    if args.workload != "iiwa14_unocp":
-        if args.impl == "reference":
-            run_reference_anymal(args, rank)
-        else:
-            run_anymal(args, rank, local_rank, world)
-        return
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
-
+def run_iiwa(args, rank, local_rank, world):
+    """The iiwa14 workloads (IIWA_WORKLOADS): device-resident arm, end-to-end arm, convergence pattern, roofline, cpu_baseline."""
     import torch
     import torch.distributed as dist
     import idocp_b200 as I
@@ -548,15 +574,27 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    w = IIWA_WORKLOADS[args.workload]
+    unocp = w["solver"] == "unocp"
     lib = I.default_library()
-    prob = I.benchmark_problem(lib, N=HORIZON_N, T=1.0)
-    B = args.batch
-    q0, v0 = initial_states(rank * B, B, list(prob.q_min), list(prob.q_max))
-    solver = I.UnOCPSolver(prob, B, device=local_rank)
-    if args.no_pipelining:
+    prob = workload_problem(args.workload, I, lib)
+    N = int(prob.N)
+    # weak scaling: every rank owns a full per-GPU batch; strong scaling: the workload's batch is split over the ranks
+    B_total = args.batch if args.batch else w["batch"]
+    strong = args.scaling == "strong"
+    if strong and B_total % world:
+        raise SystemExit("--scaling strong needs a batch divisible by the number of GPUs")
+    B = B_total // world if strong else B_total
+    q0, v0 = workload_states(args.workload, rank * B, B, list(prob.q_min), list(prob.q_max))
+    solver = (I.UnOCPSolver if unocp else I.UnParNMPCSolver)(prob, B, device=local_rank)
+    if args.no_pipelining and unocp:
         solver.setPipelining(False)
     solver.setSolution("q", q0)
     solver.setSolution("v", v0)
+    if w["problem"] == "task":
+        solver.setTaskReference(I.task_space_circle_ref, 0.0)
+    if not unocp:
+        solver.initBackwardCorrection(0.0)
     stream = torch.cuda.ExternalStream(solver.stream(), device=local_rank)
     q_dev = torch.from_numpy(q0).cuda(local_rank)
     v_dev = torch.from_numpy(v0).cuda(local_rank)
@@ -644,19 +682,22 @@ def main():
     e2e_value = units / (e2e_ms * 1e-3)
     hbm_peak, peak_src = measured_peaks()
     _, fp64_sus, fp64_src = fp64_peak()
-    counters, counters_src = load_kernel_counters("iiwa14_unocp")
+    counters, counters_src = load_kernel_counters(args.workload)
     # dominant kernel by measured device time
-    stages = B * HORIZON_N
+    stages = B * N
     kern = {}
     for name, (ms, calls) in profile.items():
         if calls and name in KERNEL_ALGO_DOUBLES_PER_STAGE:
             kern[name] = kernel_roofline(name, ms / calls, KERNEL_ALGO_DOUBLES_PER_STAGE[name] * 8.0 * stages, counters,
-                                         B == BATCH_PER_GPU, hbm_peak, fp64_sus)
+                                         B == w["batch"], hbm_peak, fp64_sus)
             kern[name]["share"] = ms
+        elif calls:
+            kern[name] = {"ms_per_launch": ms / calls, "launches_per_step": calls / args.steps, "share": ms}
     tot = sum(k["share"] for k in kern.values()) or 1.0
     for k in kern.values():
         k["share"] = k["share"] / tot
-    dom = max(kern, key=lambda n: kern[n]["ms_per_launch"]) if kern else None
+    ranked = [n for n in kern if "algo_gbs" in kern[n]]
+    dom = max(ranked, key=lambda n: kern[n]["ms_per_launch"]) if ranked else None
     roofline = None
     if dom:
         roofline = roofline_object(dom, kern, KERNEL_ALGO_DOUBLES_PER_STAGE[dom] * 8.0 * stages, hbm_peak, peak_src, fp64_sus, fp64_src,
@@ -665,22 +706,25 @@ def main():
                                    "instructions counted by ncu for one launch at this batch (DFMA = 2 flop) / time / measured DFMA "
                                    "peak; `bound` = the larger.  FP64 has no tensor-core path at 7x7 (DESIGN.md section 4)")
         fl = sum(counters[n]["fp64_flop_executed"] for n in kern if n in counters and "fp64_flop_executed" in counters[n])
-        roofline["step_hbm_frac_algorithmic"] = BYTES_PER_UNIT * value / world / 1e9 / hbm_peak
-        roofline["step_fp64_tflops_algorithmic"] = FLOP_PER_UNIT * value / world / 1e12
-        if fl and B == BATCH_PER_GPU:
+        if args.workload == "iiwa14_unocp":
+            roofline["step_hbm_frac_algorithmic"] = BYTES_PER_UNIT * value / world / 1e9 / hbm_peak
+            roofline["step_fp64_tflops_algorithmic"] = FLOP_PER_UNIT * value / world / 1e12
+        if fl and B == w["batch"]:
             roofline["step_fp64_tflops_executed"] = fl / (ms_total / args.steps * 1e-3) / 1e12
             roofline["step_frac_fp64_executed"] = roofline["step_fp64_tflops_executed"] / fp64_sus
             roofline["step_dram_bytes_ncu"] = sum(counters[n].get("dram_bytes", 0.0) for n in kern if n in counters)
 
     line = {
-        "metric": "batched SQP iterations/sec (iiwa14 N=20, FP64)", "value": value, "unit": "instance-iterations/s",
+        "metric": iiwa_metric(args.workload), "value": value, "unit": "instance-iterations/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
         "us_per_iteration": ms_total / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "iiwa14 config-space UnOCPSolver (examples/iiwa14/unocp_benchmark.cpp problem), N=20, "
-                               "T=1, %d random initial states per GPU (splitmix64 seed %d), line_search=false" % (B, SEED),
-                   "batch_per_gpu": B, "horizon": HORIZON_N, "parallelism": "batch-sharded x%d, no collective" % world,
-                   "l2_policy": "working set %.1f GB per GPU >> 126 MB L2 (inputs larger than L2)" % (B * 450e3 / 1e9)},
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s, %d random initial states per GPU (splitmix64 seed %d), line_search=false"
+                               % (w["what"], B, w["seed"]),
+                   "batch_per_gpu": B, "batch_total": B * world, "horizon": N,
+                   "parallelism": "batch-sharded x%d, no collective" % world,
+                   "l2_policy": "working set %.1f GB per GPU >> 126 MB L2 (inputs larger than L2)"
+                                % (B * N * (22.5e3 if unocp else 81e3 / 4) / 1e9)},
         "e2e": {"value": e2e_value, "unit": "instance-iterations/s", "h2d_bytes_per_step": 2 * B * NV * 8,
                 "d2h_bytes_per_step": B * NV * 8, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
@@ -689,17 +733,53 @@ def main():
                                 "what": "updateSolution + computeKKTResidual + KKTError (errors read back) per iteration"},
         "roofline": roofline,
         "clocks": sampler.summary() if rank == 0 else None,
-        "health": {"kkt_max": float(np.nanmax(kkt)), "kkt_nan": int(np.isnan(kkt).sum()),
+        "health": {"kkt_max": float(np.nanmax(kkt)), "kkt_median": float(np.nanmedian(kkt)), "kkt_nan": int(np.isnan(kkt).sum()),
                    "status_nonzero": int((status != 0).sum())},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cval, cores, sample, _ = oracle_throughput(args.cpu_seconds, list(prob.q_min), list(prob.q_max))
+        cval, cores, sample, _ = oracle_throughput(args.cpu_seconds, args.workload)
         line["cpu_baseline"] = {"value": cval, "unit": "instance-iterations/s", "cores": cores, "kind": "port",
                                 "sample": sample}
     if rank == 0:
         emit_line(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=0, help="instances per GPU (total with --scaling strong); 0 = the workload's own")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every GPU owns a full batch (default, the driver's 1-8 GPU run); strong: BASELINE configs[2] "
+                         "taken literally, 16384 instances in total split over the GPUs")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipelining", action="store_true",
+                    help="UnOCPSolver: the literal linearise / Riccati / expand / update sequence (A/B of k_update_linearize)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--workload", default="iiwa14_unocp", choices=list(IIWA_WORKLOADS) + ["anymal_trotting", "anymal_running"],
+                    help="iiwa14_unocp = BASELINE configs[2] (the headline); iiwa14_unocp_config / iiwa14_unparnmpc_task = "
+                         "configs[0] / configs[1]; anymal_* = configs[3] / configs[4]")
+    args = ap.parse_args()
+    claim_stdout()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.warmup < 3:
+        args.warmup = 3
+
+    if args.workload not in IIWA_WORKLOADS:
+        if args.impl == "reference":
+            run_reference_anymal(args, rank)
+        else:
+            run_anymal(args, rank, local_rank, world)
+    elif args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_iiwa(args, rank, local_rank, world)
 
 
 if __name__ == "__main__":

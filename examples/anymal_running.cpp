@@ -17,7 +17,9 @@ int main(int argc, char* argv[]) {
   const int iterations = argc > 2 ? std::atoi(argv[2]) : 350;
   const bool line_search = argc > 3 ? std::atoi(argv[3]) != 0 : false;
   std::vector<int> contact_frames = {14, 24, 34, 44};  // LF, LH, RF, RH
-  idocp::QuadrupedRobot robot("../anymal_b_simple_description/urdf/anymal.urdf", contact_frames);
+  // the reference passes "../anymal_b_simple_description/urdf/anymal.urdf"; a path given here is verified against the compiled-in model
+  const char* urdf_env = std::getenv("IDOCP_B200_ANYMAL_URDF");
+  idocp::QuadrupedRobot robot(urdf_env ? urdf_env : "", contact_frames);
 
   const double stride = 0.4;
   const double additive_stride_hip = 0.2;

@@ -15,7 +15,9 @@ namespace idocp = idocp_b200;
 int main(int argc, char* argv[]) {
   const int batch = argc > 1 ? std::atoi(argv[1]) : 1;
   std::vector<int> contact_frames = {14, 24, 34, 44};  // LF, LH, RF, RH
-  const std::string path_to_urdf = "../anymal_b_simple_description/urdf/anymal.urdf";
+  // the reference passes "../anymal_b_simple_description/urdf/anymal.urdf"; a path given here is verified against the compiled-in model
+  const char* urdf_env = std::getenv("IDOCP_B200_ANYMAL_URDF");
+  const std::string path_to_urdf = urdf_env ? urdf_env : "";
   idocp::QuadrupedRobot robot(path_to_urdf, contact_frames);
 
   const double step_length = 0.15;

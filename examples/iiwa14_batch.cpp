@@ -1,6 +1,6 @@
 // iiwa14_batch.cpp -- drives the batched engine through the C++ host layer (the reference's class API):
 //
-//   iiwa14_batch <problem> <solver> [batch] [iterations] [timing-iterations]
+//   iiwa14_batch <problem> <solver> [batch] [iterations] [timing-iterations] [devices, e.g. 0,1]
 //     problem : benchmark | config | task | task6d   (cost / limits of the reference's three iiwa14 set-ups;
 //               task6d = the task set-up with the constant-reference TaskSpace6DCost)
 //     solver  : unocp | unparnmpc
@@ -13,7 +13,9 @@
 #include <iomanip>
 #include <iostream>
 #include <memory>
+#include <sstream>
 #include <string>
+#include <vector>
 
 #include "idocp_b200/idocp_b200.hpp"
 
@@ -137,16 +139,24 @@ int main(int argc, char* argv[]) {
   const int batch = argc > 3 ? std::atoi(argv[3]) : 1;
   const int iterations = argc > 4 ? std::atoi(argv[4]) : 30;
   const int timing = argc > 5 ? std::atoi(argv[5]) : 0;
-  ob::Robot robot("iiwa14.urdf");
+  std::vector<int> devices;   // e.g. "0,1,2,3": the batch sharded over several GPUs of this node (default: device 0)
+  if (argc > 6) {
+    std::stringstream list(argv[6]);
+    for (std::string item; std::getline(list, item, ',');) devices.push_back(std::atoi(item.c_str()));
+  }
+  if (devices.empty()) devices.push_back(0);
+  // a URDF path (the reference: "../iiwa_description/urdf/iiwa14.urdf") is verified against the compiled-in model
+  const char* urdf_env = std::getenv("IDOCP_B200_IIWA14_URDF");
+  ob::Robot robot(urdf_env ? urdf_env : "");
   Setup s = make_setup(problem, robot);
   ob::JointConstraintsFactory factory(robot);
   auto constraints = factory.create();
   const int nthreads = 1;   // accepted for source compatibility; the batch runs on the GPU
   if (kind == "unocp") {
-    ob::UnOCPSolver solver(robot, s.cost, constraints, s.T, s.N, nthreads, batch);
+    ob::UnOCPSolver solver(robot, s.cost, constraints, s.T, s.N, nthreads, batch, devices);
     run(solver, s, iterations, timing);
   } else if (kind == "unparnmpc") {
-    ob::UnParNMPCSolver solver(robot, s.cost, constraints, s.T, s.N, nthreads, batch);
+    ob::UnParNMPCSolver solver(robot, s.cost, constraints, s.T, s.N, nthreads, batch, devices);
     solver.setSolution("q", s.q0);
     solver.setSolution("v", ob::VectorXd::Zero(7));
     solver.initBackwardCorrection(0.0);

@@ -112,6 +112,12 @@ EXPORTS = [
     "idocp_b200_fb_get_profile", "idocp_b200_fb_record_bytes", "idocp_b200_fb_problem_default",
     "idocp_b200_fb_total_weight", "idocp_b200_fb_contact_frame_positions", "idocp_b200_fb_clear_line_search_filter",
     "idocp_b200_fb_set_strict_discretization",
+    "idocp_b200_create_sharded", "idocp_b200_sharded_destroy", "idocp_b200_sharded_num_shards", "idocp_b200_sharded_shard",
+    "idocp_b200_sharded_set_solution", "idocp_b200_sharded_init_constraints", "idocp_b200_sharded_init_backward_correction",
+    "idocp_b200_sharded_set_task_reference", "idocp_b200_sharded_update_solution", "idocp_b200_sharded_compute_kkt_residual",
+    "idocp_b200_sharded_kkt_error", "idocp_b200_sharded_get_solution", "idocp_b200_sharded_get_stage_solution",
+    "idocp_b200_sharded_get_step_sizes", "idocp_b200_sharded_get_status", "idocp_b200_sharded_clear_line_search_filter",
+    "idocp_b200_sharded_sync",
 ]
 
 
@@ -191,6 +197,23 @@ class Library:
         L.idocp_b200_fb_problem_default.argtypes = [C.POINTER(FbProblem)]
         L.idocp_b200_fb_total_weight.restype = C.c_double
         L.idocp_b200_fb_contact_frame_positions.argtypes = [_dp, _dp]
+        L.idocp_b200_create_sharded.argtypes = [C.POINTER(Problem), C.c_int, C.c_int, _ip, C.c_int, C.POINTER(C.c_void_p)]
+        L.idocp_b200_sharded_destroy.argtypes = [C.c_void_p]
+        L.idocp_b200_sharded_num_shards.argtypes = [C.c_void_p, _ip, _ip]
+        L.idocp_b200_sharded_shard.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.idocp_b200_sharded_set_solution.argtypes = [C.c_void_p, C.c_char_p, _dp, C.c_int]
+        L.idocp_b200_sharded_init_constraints.argtypes = [C.c_void_p]
+        L.idocp_b200_sharded_init_backward_correction.argtypes = [C.c_void_p, C.c_double]
+        L.idocp_b200_sharded_set_task_reference.argtypes = [C.c_void_p, _dp]
+        L.idocp_b200_sharded_update_solution.argtypes = [C.c_void_p, C.c_double, _dp, _dp, C.c_int]
+        L.idocp_b200_sharded_compute_kkt_residual.argtypes = [C.c_void_p, C.c_double, _dp, _dp]
+        L.idocp_b200_sharded_kkt_error.argtypes = [C.c_void_p, _dp]
+        L.idocp_b200_sharded_get_solution.argtypes = [C.c_void_p, C.c_char_p, _dp]
+        L.idocp_b200_sharded_get_stage_solution.argtypes = [C.c_void_p, C.c_char_p, C.c_int, _dp]
+        L.idocp_b200_sharded_get_step_sizes.argtypes = [C.c_void_p, _dp, _dp]
+        L.idocp_b200_sharded_get_status.argtypes = [C.c_void_p, _ip]
+        L.idocp_b200_sharded_clear_line_search_filter.argtypes = [C.c_void_p]
+        L.idocp_b200_sharded_sync.argtypes = [C.c_void_p]
         self.L = L
 
     def check(self, rc):

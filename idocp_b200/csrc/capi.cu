@@ -56,11 +56,11 @@ static int fail(int code, const std::string& msg) {
 
 enum KernelClass { KC_LINEARIZE = 0, KC_RICCATI, KC_EXPAND, KC_UPDATE, KC_KKT, KC_MISC, KC_PARNMPC_COARSE,
                    KC_PARNMPC_CORR, KC_LINESEARCH, KC_FB_LINEARIZE, KC_FB_CONDENSE, KC_FB_RICCATI, KC_FB_FORWARD, KC_FB_EXPAND, KC_FB_UPDATE,
-                   KC_FB_KKT, KC_UPDATE_LINEARIZE, KC_NUM };
+                   KC_FB_KKT, KC_UPDATE_LINEARIZE, KC_STEP_MIN, KC_NUM };
 static const char* kKernelClassNames[KC_NUM] = {"linearize", "riccati", "expand", "update", "kkt", "misc",
                                                 "parnmpc_coarse", "parnmpc_correction", "line_search", "fb_robot", "fb_condense",
                                                 "fb_riccati_backward", "fb_riccati_forward", "fb_expand", "fb_update", "fb_kkt",
-                                                "update_linearize"};
+                                                "update_linearize", "step_min"};
 
 // launch bookkeeping shared by every solver handle: stream, launch counter, per-kernel-class event timing
 struct LaunchProfiler {
@@ -82,6 +82,16 @@ struct LaunchProfiler {
     cudaEvent_t e = nullptr;
     cudaEventCreate(&e);
     return e;
+  }
+  // The caller's q / v may be pinned host memory that it rewrites as soon as the call returns (the normal MPC loop): the
+  // host waits for the H2D copies just enqueued (an event behind them), not for the kernels enqueued after them.
+  cudaEvent_t copies_done = nullptr;
+  int mark_uploads() {            // right behind the copies
+    if (!copies_done && cudaEventCreate(&copies_done) != cudaSuccess) return -1;
+    return cudaEventRecord(copies_done, stream) == cudaSuccess ? 0 : -1;
+  }
+  int wait_for_uploads() {        // after the call's kernels have been enqueued: the wait overlaps their execution
+    return (copies_done && cudaEventSynchronize(copies_done) != cudaSuccess) ? -1 : 0;
   }
   void resolve_profile() {
     if (prof_recs.empty()) return;
@@ -336,6 +346,7 @@ extern "C" int idocp_b200_destroy(idocp_b200_solver* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->resolve_profile();
   for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
+  if (h->copies_done) cudaEventDestroy(h->copies_done);
   for (void* p : h->allocs) cudaFree(p);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -395,6 +406,7 @@ static int upload_x0(idocp_b200_solver* h, const double* q, const double* v) {
   const size_t n = static_cast<size_t>(h->B) * NV * sizeof(double);
   CUDA_OK(cudaMemcpyAsync(h->d_q0, q, n, cudaMemcpyHostToDevice, h->stream));
   CUDA_OK(cudaMemcpyAsync(h->d_v0, v, n, cudaMemcpyHostToDevice, h->stream));
+  if (h->mark_uploads() != 0) return fail(IDOCP_B200_CUDA_ERROR, "upload of q / v failed");
   return IDOCP_B200_OK;
 }
 
@@ -474,7 +486,7 @@ static int unocp_update(idocp_b200_solver* h, const double* d_q, const double* d
   if (h->pipelined) {
     // step sizes, then update + linearisation of the new iterate in one persistent launch; X (old) -> X2 (new), then the
     // two swap roles
-    IDOCP_LAUNCH(h, KC_UPDATE, k_step_min, (h->Bp + 127) / 128, 128, 0, h->L, override_alpha);
+    IDOCP_LAUNCH(h, KC_STEP_MIN, k_step_min, (h->Bp + 127) / 128, 128, 0, h->L, override_alpha);
     const int ul_grid = std::min(stage_grid(h, h->N + 1), 2 * h->sm_count);
     if (task)
       IDOCP_LAUNCH(h, KC_UPDATE_LINEARIZE, k_update_linearize<true>, ul_grid, CTA_THREADS, kUlSmem, h->d_prob, h->L);
@@ -557,9 +569,11 @@ extern "C" int idocp_b200_update_solution(idocp_b200_solver* h, double t, const 
                                           int line_search) {
   if (!h) return fail(IDOCP_B200_INVALID_ARGUMENT, "null handle");
   CUDA_OK(cudaSetDevice(h->device));
-  const int rc = upload_x0(h, q, v);
+  int rc = upload_x0(h, q, v);
   if (rc != IDOCP_B200_OK) return rc;
-  return idocp_b200_update_solution_device(h, t, h->d_q0, h->d_v0, line_search);
+  rc = idocp_b200_update_solution_device(h, t, h->d_q0, h->d_v0, line_search);
+  if (h->wait_for_uploads() != 0) return fail(IDOCP_B200_CUDA_ERROR, "upload of q / v failed");
+  return rc;
 }
 
 extern "C" int idocp_b200_compute_kkt_residual_device(idocp_b200_solver* h, double t, const double* d_q,
@@ -582,9 +596,11 @@ extern "C" int idocp_b200_compute_kkt_residual_device(idocp_b200_solver* h, doub
 extern "C" int idocp_b200_compute_kkt_residual(idocp_b200_solver* h, double t, const double* q, const double* v) {
   if (!h) return fail(IDOCP_B200_INVALID_ARGUMENT, "null handle");
   CUDA_OK(cudaSetDevice(h->device));
-  const int rc = upload_x0(h, q, v);
+  int rc = upload_x0(h, q, v);
   if (rc != IDOCP_B200_OK) return rc;
-  return idocp_b200_compute_kkt_residual_device(h, t, h->d_q0, h->d_v0);
+  rc = idocp_b200_compute_kkt_residual_device(h, t, h->d_q0, h->d_v0);
+  if (h->wait_for_uploads() != 0) return fail(IDOCP_B200_CUDA_ERROR, "upload of q / v failed");
+  return rc;
 }
 
 extern "C" int idocp_b200_kkt_error(idocp_b200_solver* h, double* out) {
@@ -857,5 +873,6 @@ extern "C" int idocp_b200_get_profile(idocp_b200_solver* h, int cap, const char*
   return n;
 }
 
+#include "sharded_capi.inc"
 #include "hybrid_capi.inc"
 #include "fb_capi.inc"

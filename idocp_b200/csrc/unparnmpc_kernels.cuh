@@ -113,74 +113,133 @@ __global__ void __launch_bounds__(CTA_THREADS) k_parnmpc_init_aux(const DevProbl
 // ---------------------------------------------------------------------------------------------
 constexpr int INV_LDQ = NQ3;       // 21 (odd)
 constexpr int INV_LDX = NX2 + 1;   // 15 (odd)
-// per-warp shared memory (doubles)
-constexpr int INV_OFF_A = 0;                          // Q -> L (21 x 21), later BR
-constexpr int INV_OFF_RD = INV_OFF_A + NQ3 * INV_LDQ;  // reciprocal pivots (21)
-constexpr int INV_OFF_FQ = INV_OFF_RD + 24;           // FQinv (14 x 21), column stride 15
-constexpr int INV_OFF_S = INV_OFF_FQ + NQ3 * INV_LDX;  // S (14 x 14); first used as staging of aux_next
+// per-warp shared memory (doubles); every offset is even, so that element e of an array is 16-byte aligned iff e is even
+// (the broadcast operand loads of the factorisations and products are issued two doubles at a time, inv_ld2)
+constexpr int INV_OFF_A = 0;                           // Q -> L (21 x 21, column k of L contiguous), later Qinv -> BR
+constexpr int INV_OFF_LT = INV_OFF_A + 442;            // L^T: row r of L contiguous (backward substitution); LLT(S)^T later
+constexpr int INV_OFF_RD = INV_OFF_LT + 442;           // reciprocal pivots (21)
+constexpr int INV_OFF_FQ = INV_OFF_RD + 24;            // FQinv (14 x 21), column stride 15
+constexpr int INV_OFF_S = INV_OFF_FQ + 316;            // S (14 x 14); first used as staging of aux_next
 constexpr int INV_OFF_LS = INV_OFF_S + NX2 * INV_LDX;  // LLT(S), then TL = -S^-1 in place (14 x 14)
 constexpr int INV_OFF_TL = INV_OFF_LS;
 constexpr int INV_OFF_TR = INV_OFF_TL + NX2 * INV_LDX; // TR (14 x 21)
-constexpr int INV_OFF_RES = INV_OFF_TR + NQ3 * INV_LDX; // residual (35)
+constexpr int INV_OFF_RES = INV_OFF_TR + 316;          // residual (35)
 constexpr int INV_SMEM_PER_WARP = INV_OFF_RES + 36;
 constexpr int INV_SMEM_BYTES = WARPS_PER_CTA * INV_SMEM_PER_WARP * static_cast<int>(sizeof(double));
+static_assert(INV_OFF_LT % 2 == 0 && INV_OFF_FQ % 2 == 0 && INV_OFF_S % 2 == 0 && INV_OFF_LS % 2 == 0 && INV_OFF_TR % 2 == 0 &&
+              INV_SMEM_PER_WARP % 2 == 0, "16-byte alignment of the even elements");
+static_assert(3 * INV_SMEM_BYTES <= 227 * 1024, "three CTAs per SM");
+
+// The products and substitutions below take one operand from shared memory as a warp-wide BROADCAST (every lane reads the
+// same address) and one from registers: one shared-memory wavefront per fma, which is what bounds the kernel (one wavefront
+// per clock and SM against two FP64 warp instructions).  All indices are compile-time constants, so consecutive operands
+// are fetched as one 16-byte load wherever the element index is even: half the wavefronts.
+struct alignas(16) InvD2 {
+  double x, y;
+};
+__device__ __forceinline__ InvD2 inv_ld2(const double* p) { return *reinterpret_cast<const InvD2*>(p); }
+
+// y[i] (-)+= M[BASE + i] * x for i = I .. END-1 (each y[i] is a separate chain; one fma per element)
+template <bool NEG, int I, int END, int BASE, int N>
+__device__ __forceinline__ void inv_axpy(const double* M, double x, double (&y)[N]) {
+  if constexpr (I < END) {
+    if constexpr (((BASE + I) & 1) == 0 && I + 1 < END) {
+      const InvD2 v = inv_ld2(M + BASE + I);
+      y[I] = fma(NEG ? -v.x : v.x, x, y[I]);
+      y[I + 1] = fma(NEG ? -v.y : v.y, x, y[I + 1]);
+      inv_axpy<NEG, I + 2, END, BASE, N>(M, x, y);
+    } else {
+      const double v = M[BASE + I];
+      y[I] = fma(NEG ? -v : v, x, y[I]);
+      inv_axpy<NEG, I + 1, END, BASE, N>(M, x, y);
+    }
+  }
+}
+// t += sum_{k = K .. END-1} M[BASE + k] * x[k], ascending k (one chain)
+template <int K, int END, int BASE, int N>
+__device__ __forceinline__ double inv_dot(const double* M, const double (&x)[N], double t) {
+  if constexpr (K < END) {
+    if constexpr (((BASE + K) & 1) == 0 && K + 1 < END) {
+      const InvD2 v = inv_ld2(M + BASE + K);
+      t = fma(v.x, x[K], t);
+      t = fma(v.y, x[K + 1], t);
+      return inv_dot<K + 2, END, BASE, N>(M, x, t);
+    } else {
+      t = fma(M[BASE + K], x[K], t);
+      return inv_dot<K + 1, END, BASE, N>(M, x, t);
+    }
+  } else {
+    return t;
+  }
+}
 
 // Right-looking Cholesky of the lower triangle of the n x n matrix at A (column stride ld), in place; lane = row.
 // The lane keeps its row of the trailing matrix in registers.  Step k: the pivot comes from lane k by shuffle, every
-// lane scales its entry of column k (L_ik = a_ik r_k, r_k = canon_rsqrt(pivot)), publishes it, and applies the n - 1 - k
-// INDEPENDENT updates a_ic -= L_ik L_ck of its row (L_ck: shared-memory broadcast).  Every element receives its updates
-// in ascending k, i.e. exactly the fma chain of the left-looking oracle (llt_lower), but the dependent chain of the
-// factorisation is one fma per column instead of k (the left-looking form of round 1 was bound by those chains).
-// Eigen::LLT<Lower> semantics.  Returns non-zero on a bad pivot.
-template <int n>
-__device__ __forceinline__ int warp_llt(double* __restrict__ A, int ld, double* __restrict__ rd, int wl) {
+// lane scales its entry of column k (L_ik = a_ik r_k, r_k = canon_rsqrt(pivot)), publishes it (column-major in A, row-major
+// in LT for the backward substitution), and applies the n - 1 - k INDEPENDENT updates a_ic -= L_ik L_ck of its row (L_ck:
+// shared-memory broadcast).  Every element receives its updates in ascending k, i.e. exactly the fma chain of the
+// left-looking oracle (llt_lower), but the dependent chain of the factorisation is one fma per column instead of k (the
+// left-looking form of round 1 was bound by those chains).  Eigen::LLT<Lower> semantics.  Returns non-zero
+// on a bad pivot.
+template <int n, int ld, int K>
+__device__ __forceinline__ void warp_llt_step(double* A, double* LT, double* rd, int wl, double (&a)[n], int& fail) {
+  if constexpr (K < n) {
+    const double piv = __shfl_sync(FULL, a[K], K);
+    if (!canon_pivot_ok(piv)) fail = 1;
+    const double r = canon_rsqrt(piv);
+    const double lk = a[K] * r;          // lane K: L_KK = pivot * r
+    if (wl >= K && wl < n) {
+      A[K * ld + wl] = lk;
+      LT[wl * ld + K] = lk;
+    }
+    if (wl == K) rd[K] = r;
+    __syncwarp();
+    inv_axpy<true, K + 1, n, K * ld, n>(A, lk, a);
+    warp_llt_step<n, ld, K + 1>(A, LT, rd, wl, a, fail);
+  }
+}
+template <int n, int ld>
+__device__ __forceinline__ int warp_llt(double* A, double* LT, double* rd, int wl) {
   int fail = 0;
   double a[n];
   const int row = wl < n ? wl : n - 1;   // idle lanes shadow the last row (never stored)
 #pragma unroll
   for (int c = 0; c < n; ++c) a[c] = A[c * ld + row];   // entries c > row are never used
   __syncwarp();
-#pragma unroll
-  for (int k = 0; k < n; ++k) {
-    const double piv = __shfl_sync(FULL, a[k], k);
-    if (!canon_pivot_ok(piv)) fail = 1;
-    const double r = canon_rsqrt(piv);
-    const double lk = a[k] * r;          // lane k: L_kk = pivot * r
-    if (wl >= k && wl < n) A[k * ld + wl] = lk;
-    if (wl == k) rd[k] = r;
-    __syncwarp();
-#pragma unroll
-    for (int c = k + 1; c < n; ++c) a[c] = fma(-lk, A[k * ld + c], a[c]);
-  }
+  warp_llt_step<n, ld, 0>(A, LT, rd, wl, a, fail);
   return fail;
 }
 
 // column `c` of (L L^T)^-1: forward + backward substitution of the unit vector e_c, column-oriented: as soon as y_j is
-// final it is subtracted from every later row (forward) / every earlier row (backward), so the rows advance together
-// and the dependent chain is two operations per row.  Forward: row i receives its terms in ascending j; backward: in
-// descending j -- the operation order of the oracle's llt_solve_desc.
-// The warp barrier after every row keeps the (address-independent) shared-memory loads of L from being hoisted above
-// the whole unrolled substitution, which would cost hundreds of registers (spills).
-template <int n>
-__device__ __forceinline__ void warp_llt_solve_unit(const double* Lm, int ld, const double* rd, int c, double (&y)[n]) {
-  // Lm / rd deliberately NOT __restrict__: a restrict-qualified read-only pointer lets the compiler hoist the loads across
-  // the warp barriers anyway (1 KB of spills per thread in round 1)
+// final it is subtracted from every later row (forward, column j of L) / every earlier row (backward, row j of L = column j
+// of LT), so the rows advance together and the dependent chain is two operations per row.  Forward: row i receives its
+// terms in ascending j; backward: in descending j -- the operation order of the oracle's llt_solve_desc.
+// The warp barrier after every step keeps the (address-independent) shared-memory loads of L from being hoisted above the
+// whole unrolled substitution (the pointers are deliberately not __restrict__: 1 KB of spills per thread in round 1).
+template <int n, int ld, int J>
+__device__ __forceinline__ void warp_llt_forward(const double* Lm, const double* rd, double (&y)[n]) {
+  if constexpr (J < n) {
+    y[J] *= rd[J];
+    inv_axpy<true, J + 1, n, J * ld, n>(Lm, y[J], y);
+    __syncwarp();
+    warp_llt_forward<n, ld, J + 1>(Lm, rd, y);
+  }
+}
+template <int n, int ld, int J>
+__device__ __forceinline__ void warp_llt_backward(const double* LT, const double* rd, double (&y)[n]) {
+  if constexpr (J >= 0) {
+    y[J] *= rd[J];
+    inv_axpy<true, 0, J, J * ld, n>(LT, y[J], y);
+    __syncwarp();
+    warp_llt_backward<n, ld, J - 1>(LT, rd, y);
+  }
+}
+template <int n, int ld>
+__device__ __forceinline__ void warp_llt_solve_unit(const double* Lm, const double* LT, const double* rd, int c, double (&y)[n]) {
 #pragma unroll
   for (int i = 0; i < n; ++i) y[i] = (i == c) ? 1.0 : 0.0;
-#pragma unroll
-  for (int j = 0; j < n; ++j) {
-    y[j] *= rd[j];
-#pragma unroll
-    for (int i = j + 1; i < n; ++i) y[i] = fma(-Lm[j * ld + i], y[j], y[i]);
-    __syncwarp();
-  }
-#pragma unroll
-  for (int j = n - 1; j >= 0; --j) {
-    y[j] *= rd[j];
-#pragma unroll
-    for (int i = 0; i < j; ++i) y[i] = fma(-Lm[i * ld + j], y[j], y[i]);
-    __syncwarp();
-  }
+  warp_llt_forward<n, ld, 0>(Lm, rd, y);
+  warp_llt_backward<n, ld, n - 1>(LT, rd, y);
 }
 
 // moves `nslots` slots of this warp's instance between a (stage, group) record and a per-lane
@@ -202,8 +261,25 @@ __device__ __forceinline__ void warp_load_slots(const double* __restrict__ rec, 
   }
 }
 
+// y[r] += sum_k M[k * INV_LDX + r] x[k] for a 14 x 14 column-major M (broadcast operand), k ascending per element
+template <int K>
+__device__ __forceinline__ void inv_tl_fq(const double* M, const double (&x)[NX2], double (&y)[NX2]) {
+  if constexpr (K < NX2) {
+    inv_axpy<false, 0, NX2, K * INV_LDX, NX2>(M, x[K], y);
+    inv_tl_fq<K + 1>(M, x, y);
+  }
+}
+// col[r] -= sum_k TR[r * INV_LDX + k] st[k] for the 21 rows of this lane's column of BR
+template <int R>
+__device__ __forceinline__ void inv_br_rows(const double* TR, const double (&st)[NX2], double* col) {
+  if constexpr (R < NQ3) {
+    col[R] -= inv_dot<0, NX2, R * INV_LDX, NX2>(TR, st, 0.0);
+    inv_br_rows<R + 1>(TR, st, col);
+  }
+}
+
 #ifndef IDOCP_INV_MINB
-#define IDOCP_INV_MINB 2   // tools/sweep_inv.sh: 254 regs 6.2 ms, 168 regs 7.9 ms, 128 regs 9.0 ms (spills)
+#define IDOCP_INV_MINB 3   // 164 registers without spills since the column-oriented substitutions: three CTAs per SM
 #endif
 
 __global__ void __launch_bounds__(CTA_THREADS, IDOCP_INV_MINB) k_parnmpc_invert(const DevProblem* __restrict__ Pp,
@@ -218,6 +294,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_INV_MINB) k_parnmpc_invert(
   const double dt = P.dt;
   double* sm = smem + inst * INV_SMEM_PER_WARP;
   double* A = sm + INV_OFF_A;
+  double* LT = sm + INV_OFF_LT;
   double* rd = sm + INV_OFF_RD;
   double* FQ = sm + INV_OFF_FQ;
   double* S = sm + INV_OFF_S;
@@ -254,11 +331,11 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_INV_MINB) k_parnmpc_invert(
   __syncwarp();
 
   // ---- llt_Q_.compute(Q); Qinv = llt_Q_.solve(I): lane c computes column c, then parks it over L (dead) ----
-  int fail = warp_llt<NQ3>(A, INV_LDQ, rd, wl);
+  int fail = warp_llt<NQ3, INV_LDQ>(A, LT, rd, wl);
   const int cq = wl < NQ3 ? wl : 0;
   {
     double y[NQ3];
-    warp_llt_solve_unit<NQ3>(A, INV_LDQ, rd, cq, y);
+    warp_llt_solve_unit<NQ3, INV_LDQ>(A, LT, rd, cq, y);
     __syncwarp();   // every lane is done reading L
     if (wl < NQ3) {
 #pragma unroll
@@ -287,11 +364,11 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_INV_MINB) k_parnmpc_invert(
   }
   __syncwarp();
   // ---- llt_S_.compute(S); TL = -llt_S_.solve(I), written over the factor once every lane has solved ----
-  fail |= warp_llt<NX2>(LS, INV_LDX, rd, wl);
+  fail |= warp_llt<NX2, INV_LDX>(LS, LT, rd, wl);
   {
     double z[NX2];
     const int cs = wl < NX2 ? wl : 0;
-    warp_llt_solve_unit<NX2>(LS, INV_LDX, rd, cs, z);
+    warp_llt_solve_unit<NX2, INV_LDX>(LS, LT, rd, cs, z);
     __syncwarp();
     if (wl < NX2) {
 #pragma unroll
@@ -307,12 +384,10 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_INV_MINB) k_parnmpc_invert(
 #pragma unroll
       for (int k = 0; k < NX2; ++k) fq[k] = FQ[cq * INV_LDX + k];
 #pragma unroll
-      for (int r = 0; r < NX2; ++r) {
-        double t = 0.0;
+      for (int r = 0; r < NX2; ++r) tr[r] = 0.0;
+      inv_tl_fq<0>(TL, fq, tr);          // tr[r] = sum_k TL(r, k) fq[k], ascending k
 #pragma unroll
-        for (int k = 0; k < NX2; ++k) t = fma(TL[k * INV_LDX + r], fq[k], t);
-        tr[r] = -t;
-      }
+      for (int r = 0; r < NX2; ++r) tr[r] = -tr[r];
     }
     if (wl < NQ3) {
 #pragma unroll
@@ -322,21 +397,9 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_INV_MINB) k_parnmpc_invert(
     // ---- BR = Qinv - TR^T (S TR) (21 x 21), in place over the parked Qinv ----
     double st[NX2];
 #pragma unroll
-    for (int r = 0; r < NX2; ++r) {
-      double t = 0.0;
-#pragma unroll
-      for (int k = 0; k < NX2; ++k) t = fma(S[k * INV_LDX + r], tr[k], t);
-      st[r] = t;
-    }
-    if (wl < NQ3) {
-#pragma unroll
-      for (int r = 0; r < NQ3; ++r) {
-        double t = 0.0;
-#pragma unroll
-        for (int k = 0; k < NX2; ++k) t = fma(TR[r * INV_LDX + k], st[k], t);
-        A[wl * INV_LDQ + r] -= t;
-      }
-    }
+    for (int r = 0; r < NX2; ++r) st[r] = 0.0;
+    inv_tl_fq<0>(S, tr, st);             // st[r] = sum_k S(r, k) tr[k]
+    if (wl < NQ3) inv_br_rows<0>(TR, st, A + wl * INV_LDQ);
   }
   __syncwarp();
 

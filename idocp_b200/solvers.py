@@ -262,3 +262,95 @@ class UnParNMPCSolver(_BatchSolver):
 
     def initBackwardCorrection(self, t):
         self.lib.check(self.lib.L.idocp_b200_init_backward_correction(self._h, float(t)))
+
+
+class ShardedSolver:
+    """One UnOCPSolver / UnParNMPCSolver over several GPUs of one node (idocp_b200_create_sharded): the batch is split into
+    contiguous shards, one device + stream per shard, no collective.  Same method names as the single-device classes for
+    the reference API; arrays are (batch, ...) over the WHOLE batch."""
+
+    def __init__(self, problem, batch, devices, kind=SOLVER_UNOCP, lib=None):
+        self.lib = lib or capi.default_library()
+        self.batch, self.N, self.kind, self.problem = int(batch), int(problem.N), kind, problem
+        self._h = C.c_void_p()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        self.lib.check(self.lib.L.idocp_b200_create_sharded(C.byref(problem), kind, self.batch, devs, len(devices),
+                                                            C.byref(self._h)))
+        n = C.c_int(0)
+        first = (C.c_int * (len(devices) + 1))()
+        self.lib.check(self.lib.L.idocp_b200_sharded_num_shards(self._h, C.byref(n), first))
+        self.first = list(first)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.L.idocp_b200_sharded_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _x(self, a):
+        a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+        if a.shape != (self.batch, DIMV):
+            raise ValueError("expected an array of shape (%d, %d)" % (self.batch, DIMV))
+        return a
+
+    def setSolution(self, name, value):
+        value = np.ascontiguousarray(np.asarray(value, dtype=np.float64))
+        if value.shape not in ((DIMV,), (self.batch, DIMV)):
+            raise ValueError("setSolution: bad shape %s" % (value.shape,))
+        self.lib.check(self.lib.L.idocp_b200_sharded_set_solution(self._h, name.encode(), dptr(value), int(value.ndim == 1)))
+
+    def initConstraints(self):
+        self.lib.check(self.lib.L.idocp_b200_sharded_init_constraints(self._h))
+
+    def initBackwardCorrection(self, t):
+        self.lib.check(self.lib.L.idocp_b200_sharded_init_backward_correction(self._h, float(t)))
+
+    def setTaskReference(self, table):
+        table = np.ascontiguousarray(table, dtype=np.float64)
+        self.lib.check(self.lib.L.idocp_b200_sharded_set_task_reference(self._h, dptr(table)))
+
+    def updateSolution(self, t, q, v, line_search=False):
+        q, v = self._x(q), self._x(v)
+        self.lib.check(self.lib.L.idocp_b200_sharded_update_solution(self._h, float(t), dptr(q), dptr(v), int(line_search)))
+
+    def computeKKTResidual(self, t, q, v):
+        q, v = self._x(q), self._x(v)
+        self.lib.check(self.lib.L.idocp_b200_sharded_compute_kkt_residual(self._h, float(t), dptr(q), dptr(v)))
+
+    def KKTError(self):
+        out = np.zeros(self.batch)
+        self.lib.check(self.lib.L.idocp_b200_sharded_kkt_error(self._h, dptr(out)))
+        return out
+
+    def getSolution(self, name):
+        nst = self.N + 1 if (name in ("q", "v", "lmd", "gmm") and self.kind == SOLVER_UNOCP) else self.N
+        out = np.zeros((self.batch, nst, DIMV))
+        self.lib.check(self.lib.L.idocp_b200_sharded_get_solution(self._h, name.encode(), dptr(out)))
+        return out
+
+    def getStageSolution(self, name, stage, out=None):
+        if out is None:
+            out = np.zeros((self.batch, DIMV))
+        self.lib.check(self.lib.L.idocp_b200_sharded_get_stage_solution(self._h, name.encode(), int(stage), dptr(out)))
+        return out
+
+    def getStepSizes(self):
+        p, d = np.zeros(self.batch), np.zeros(self.batch)
+        self.lib.check(self.lib.L.idocp_b200_sharded_get_step_sizes(self._h, dptr(p), dptr(d)))
+        return p, d
+
+    def getStatus(self):
+        out = np.zeros(self.batch, dtype=np.int32)
+        self.lib.check(self.lib.L.idocp_b200_sharded_get_status(self._h, out.ctypes.data_as(C.POINTER(C.c_int))))
+        return out
+
+    def clearLineSearchFilter(self):
+        self.lib.check(self.lib.L.idocp_b200_sharded_clear_line_search_filter(self._h))
+
+    def sync(self):
+        self.lib.check(self.lib.L.idocp_b200_sharded_sync(self._h))

@@ -100,7 +100,10 @@ int idocp_b200_init_constraints(idocp_b200_solver* h);
 int idocp_b200_init_backward_correction(idocp_b200_solver* h, double t);
 
 /* UnOCPSolver::updateSolution(t, q, v, line_search) (unocp_solver.cpp:73-134), one SQP
- * iteration of every instance.  q, v: HOST arrays [batch][dimv] (initial state per instance). */
+ * iteration of every instance.  q, v: HOST arrays [batch][dimv] (initial state per instance), pageable or pinned: the
+ * call returns once q and v have been copied (an event behind the H2D copies), so the caller may rewrite them at once;
+ * the kernels of the iteration are still running then (asynchronous until idocp_b200_sync or a getter).  The same
+ * holds for compute_kkt_residual and the idocp_b200_fb_* twins. */
 int idocp_b200_update_solution(idocp_b200_solver* h, double t, const double* q, const double* v,
                                int line_search);
 /* same, q and v already resident in device memory ([batch][dimv] doubles on the handle's device) */
@@ -162,6 +165,37 @@ int idocp_b200_stream(idocp_b200_solver* h, void** out);
 int idocp_b200_set_pipelining(idocp_b200_solver* h, int enabled);
 int idocp_b200_set_profiling(idocp_b200_solver* h, int enabled);
 int idocp_b200_get_profile(idocp_b200_solver* h, int cap, const char** names, double* ms, long long* calls);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * One solver object over several GPUs of one node (the batch of independent OCP instances is
+ * split into contiguous shards, one device + stream per shard, NO collective on the hot path).  The reference's
+ * counterpart is the `nthreads` argument of its solver constructors (OpenMP over stages, unocp_solver.cpp:11-49):
+ * here the parallel resource is the list of devices.  Every call forwards to the shards with the caller's
+ * [batch][...] arrays offset to each shard's first instance; the per-shard calls only enqueue work, so all GPUs
+ * run concurrently; getters and sync wait for every shard.  Results are those of one idocp_b200_solver over the
+ * whole batch, instance by instance (tests/test_sharded_solver.py).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct idocp_b200_sharded idocp_b200_sharded; /* opaque */
+int idocp_b200_create_sharded(const idocp_b200_problem* p, int solver_kind, int batch, const int* devices,
+                              int n_devices, idocp_b200_sharded** out);
+int idocp_b200_sharded_destroy(idocp_b200_sharded* s);
+/* number of shards and (first != NULL) the first instance of every shard, first[n] = batch */
+int idocp_b200_sharded_num_shards(const idocp_b200_sharded* s, int* n, int* first);
+/* the single-device solver behind shard `index` (borrowed; for the device-pointer entry points and the profile) */
+int idocp_b200_sharded_shard(idocp_b200_sharded* s, int index, idocp_b200_solver** out);
+int idocp_b200_sharded_set_solution(idocp_b200_sharded* s, const char* name, const double* value, int broadcast);
+int idocp_b200_sharded_init_constraints(idocp_b200_sharded* s);
+int idocp_b200_sharded_init_backward_correction(idocp_b200_sharded* s, double t);
+int idocp_b200_sharded_set_task_reference(idocp_b200_sharded* s, const double* table);
+int idocp_b200_sharded_update_solution(idocp_b200_sharded* s, double t, const double* q, const double* v, int line_search);
+int idocp_b200_sharded_compute_kkt_residual(idocp_b200_sharded* s, double t, const double* q, const double* v);
+int idocp_b200_sharded_kkt_error(idocp_b200_sharded* s, double* out /* [batch] */);
+int idocp_b200_sharded_get_solution(idocp_b200_sharded* s, const char* name, double* out /* [batch][stages][dimv] */);
+int idocp_b200_sharded_get_stage_solution(idocp_b200_sharded* s, const char* name, int stage, double* out /* [batch][dimv] */);
+int idocp_b200_sharded_get_step_sizes(idocp_b200_sharded* s, double* primal, double* dual);
+int idocp_b200_sharded_get_status(idocp_b200_sharded* s, int* out);
+int idocp_b200_sharded_clear_line_search_filter(idocp_b200_sharded* s);
+int idocp_b200_sharded_sync(idocp_b200_sharded* s);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Host-side contact schedule of the hybrid OCP (implementation

@@ -63,6 +63,54 @@ namespace detail {
 inline void check(int rc) {
   if (rc < 0) die(std::string("idocp_b200: ") + idocp_b200_last_error());
 }
+// The robot models are compiled into the kernels (tools/gen_robot_model.py), so a URDF path cannot change them.  A path that
+// is given is therefore CHECKED: the file must exist and its kinematic / inertial content -- the text with comments,
+// <visual>, <collision>, <material>, <gazebo>, <transmission> blocks and all white space removed -- must hash (FNV-1a 64)
+// to the URDF the tables were generated from; anything else stops the program like the reference's failed
+// pinocchio::urdf::buildModel (src/robot/robot.cpp:26,62).  An empty path selects the compiled-in model explicitly.
+inline unsigned long long urdf_content_hash(const std::string& text) {
+  std::string s = text;
+  const char* blocks[][2] = {{"<!--", "-->"}, {"<visual", "</visual>"}, {"<collision", "</collision>"},
+                             {"<gazebo", "</gazebo>"}, {"<transmission", "</transmission>"}, {"<material", "</material>"}};
+  for (const auto& b : blocks) {
+    std::string out;
+    size_t i = 0;
+    for (;;) {
+      const size_t j = s.find(b[0], i);
+      if (j == std::string::npos) { out.append(s, i, std::string::npos); break; }
+      out.append(s, i, j - i);
+      const size_t k = s.find(b[1], j);
+      if (k == std::string::npos) break;
+      i = k + std::string(b[1]).size();
+    }
+    s.swap(out);
+  }
+  unsigned long long h = 0xcbf29ce484222325ULL;
+  for (unsigned char c : s) {
+    if (c <= 32) continue;
+    h ^= c;
+    h *= 0x100000001b3ULL;
+  }
+  return h;
+}
+inline void verify_urdf(const std::string& path, std::initializer_list<unsigned long long> accepted, const char* robot) {
+  if (path.empty()) return;
+  std::ifstream f(path, std::ios::binary);
+  if (!f) die("idocp_b200: cannot open the URDF file '" + path + "'");
+  std::stringstream ss;
+  ss << f.rdbuf();
+  const unsigned long long h = urdf_content_hash(ss.str());
+  for (unsigned long long a : accepted)
+    if (a == h) return;
+  std::ostringstream msg;
+  msg << "idocp_b200: '" << path << "' is not the " << robot << " URDF the compiled-in model was generated from (content hash 0x"
+      << std::hex << h << "); the kernels are specialised for that kinematic tree (tools/gen_robot_model.py)";
+  die(msg.str());
+}
+// idocp's examples/iiwa14/iiwa_description/urdf/iiwa14.urdf (= test/urdf/iiwa14/iiwa14.urdf up to mesh paths)
+constexpr unsigned long long kUrdfHashIiwa14 = 0x74d27ade0ac05ccdULL;
+// examples/anymal/anymal_b_simple_description/urdf/anymal.urdf and test/urdf/anymal/anymal.urdf
+constexpr unsigned long long kUrdfHashAnymalExamples = 0x4ad2ccdac3b34101ULL, kUrdfHashAnymalTests = 0xed1cb1b607c99c55ULL;
 inline void copy7(const VectorXd& v, double* dst, const char* what) {
   if (v.size() != IDOCP_B200_DIMV) die(std::string("invalid size: ") + what + ".size() must be 7!");
   for (int i = 0; i < IDOCP_B200_DIMV; ++i) dst[i] = v[i];
@@ -70,10 +118,11 @@ inline void copy7(const VectorXd& v, double* dst, const char* what) {
 }  // namespace detail
 
 // Robot: the fixed-base iiwa14.  The URDF itself is turned into constant tables off-line
-// (tools/gen_robot_model.py); the path is accepted for source compatibility.
+// (tools/gen_robot_model.py); a path, when given, is verified against them (detail::verify_urdf).
 class Robot {
  public:
   explicit Robot(const std::string& path_to_urdf = "") : urdf_(path_to_urdf) {
+    detail::verify_urdf(path_to_urdf, {detail::kUrdfHashIiwa14}, "iiwa14");
     detail::check(idocp_b200_problem_default(IDOCP_B200_ROBOT_IIWA14, &p_));
   }
   int dimq() const { return IDOCP_B200_DIMV; }
@@ -258,49 +307,62 @@ inline idocp_b200_problem make_problem(const Robot& robot, const std::shared_ptr
 
 class SolverBase {
  public:
+  // `devices`: the GPUs of this node the batch is sharded over (contiguous shards, one device + stream each, no collective:
+  // idocp_b200_create_sharded).  This is the GPU counterpart of the reference's `nthreads` (unocp_solver.cpp:11-49).
   SolverBase(int kind, const Robot& robot, const std::shared_ptr<CostFunction>& cost,
-             const std::shared_ptr<Constraints>& constraints, double T, int N, int nthreads, int batch, int device)
+             const std::shared_ptr<Constraints>& constraints, double T, int N, int nthreads, int batch,
+             const std::vector<int>& devices)
       : N_(N), batch_(batch), kind_(kind), T_(T), task_(cost ? cost->task() : nullptr) {
     try {
       if (T <= 0) throw std::out_of_range("invalid value: T must be positive!");
       if (N <= 0) throw std::out_of_range("invalid value: N must be positive!");
       if (nthreads <= 0) throw std::out_of_range("invalid value: nthreads must be positive!");
       if (batch <= 0) throw std::out_of_range("invalid value: batch must be positive!");
+      if (devices.empty()) throw std::out_of_range("invalid value: devices must not be empty!");
     } catch (const std::exception& e) {
       die(e.what());
     }
     const idocp_b200_problem p = make_problem(robot, cost, constraints, T, N);
-    idocp_b200_solver* h = nullptr;
-    check(idocp_b200_create(&p, kind, batch, device, &h));
-    h_ = std::shared_ptr<idocp_b200_solver>(h, [](idocp_b200_solver* x) { idocp_b200_destroy(x); });
+    idocp_b200_sharded* hs = nullptr;
+    check(idocp_b200_create_sharded(&p, kind, batch, devices.data(), static_cast<int>(devices.size()), &hs));
+    hs_ = std::shared_ptr<idocp_b200_sharded>(hs, [](idocp_b200_sharded* x) { idocp_b200_sharded_destroy(x); });
+    int n = 0;
+    first_.resize(devices.size() + 1);
+    check(idocp_b200_sharded_num_shards(hs, &n, first_.data()));
+    for (int k = 0; k < n; ++k) {
+      idocp_b200_solver* h = nullptr;
+      check(idocp_b200_sharded_shard(hs, k, &h));
+      shards_.push_back(h);
+    }
   }
+  int numShards() const { return static_cast<int>(shards_.size()); }
   int batch() const { return batch_; }
-  void initConstraints() { check(idocp_b200_init_constraints(h_.get())); }
+  void initConstraints() { check(idocp_b200_sharded_init_constraints(hs_.get())); }
   // reference signature (one x0, broadcast to the whole batch)
   void updateSolution(double t, const VectorXd& q, const VectorXd& v, bool line_search = false) {
     rep(q, v);
     sampleTaskReference(t);
-    check(idocp_b200_update_solution(h_.get(), t, qb_.data(), vb_.data(), line_search ? 1 : 0));
+    check(idocp_b200_sharded_update_solution(hs_.get(), t, qb_.data(), vb_.data(), line_search ? 1 : 0));
   }
   // batched: q, v row-major [batch][dimv]
   void updateSolution(double t, const double* q, const double* v, bool line_search = false) {
     sampleTaskReference(t);
-    check(idocp_b200_update_solution(h_.get(), t, q, v, line_search ? 1 : 0));
+    check(idocp_b200_sharded_update_solution(hs_.get(), t, q, v, line_search ? 1 : 0));
   }
   void computeKKTResidual(double t, const VectorXd& q, const VectorXd& v) {
     rep(q, v);
     sampleTaskReference(t);
-    check(idocp_b200_compute_kkt_residual(h_.get(), t, qb_.data(), vb_.data()));
+    check(idocp_b200_sharded_compute_kkt_residual(hs_.get(), t, qb_.data(), vb_.data()));
   }
   void computeKKTResidual(double t, const double* q, const double* v) {
     sampleTaskReference(t);
-    check(idocp_b200_compute_kkt_residual(h_.get(), t, q, v));
+    check(idocp_b200_sharded_compute_kkt_residual(hs_.get(), t, q, v));
   }
   // KKT error of instance 0 (the reference return value); KKTErrors() gives all of them
   double KKTError() { return KKTErrors()[0]; }
   std::vector<double> KKTErrors() {
     std::vector<double> k(batch_);
-    check(idocp_b200_kkt_error(h_.get(), k.data()));
+    check(idocp_b200_sharded_kkt_error(hs_.get(), k.data()));
     return k;
   }
   void setSolution(const std::string& name, const VectorXd& value) {
@@ -312,17 +374,17 @@ class SolverBase {
     }
     double x[IDOCP_B200_DIMV];
     copy7(value, x, name.c_str());
-    check(idocp_b200_set_solution(h_.get(), name.c_str(), x, 1));
+    check(idocp_b200_sharded_set_solution(hs_.get(), name.c_str(), x, 1));
   }
   void setSolution(const std::string& name, const double* value_per_instance) {
-    check(idocp_b200_set_solution(h_.get(), name.c_str(), value_per_instance, 0));
+    check(idocp_b200_sharded_set_solution(hs_.get(), name.c_str(), value_per_instance, 0));
   }
   // getSolution(name) of instance `instance`: one VectorXd per stage
   std::vector<VectorXd> getSolution(const std::string& name, int instance = 0) const {
     const bool full = (name == "q" || name == "v" || name == "lmd" || name == "gmm") && kind_ == IDOCP_B200_SOLVER_UNOCP;
     const int ns = full ? N_ + 1 : N_;
     std::vector<double> buf(static_cast<size_t>(batch_) * ns * IDOCP_B200_DIMV);
-    check(idocp_b200_get_solution(h_.get(), name.c_str(), buf.data()));
+    check(idocp_b200_sharded_get_solution(hs_.get(), name.c_str(), buf.data()));
     std::vector<VectorXd> out;
     for (int i = 0; i < ns; ++i) {
       VectorXd x(IDOCP_B200_DIMV);
@@ -332,7 +394,7 @@ class SolverBase {
     return out;
   }
   void getSolutionBatch(const std::string& name, double* out) const {
-    check(idocp_b200_get_solution(h_.get(), name.c_str(), out));
+    check(idocp_b200_sharded_get_solution(hs_.get(), name.c_str(), out));
   }
   // unocp_solver.cpp:312-352 / unparnmpc_solver.cpp: one stage per line, coefficients followed by a blank, default
   // stream formatting.  `instance` selects the member of the batch (the reference has one).
@@ -376,18 +438,19 @@ class SolverBase {
       std::cout << "idocp_b200: printSolution(\"end-effector\") is not provided (frame kinematics live on the device)" << std::endl;
     }
   }
-  void clearLineSearchFilter() { check(idocp_b200_clear_line_search_filter(h_.get())); }
+  void clearLineSearchFilter() { check(idocp_b200_sharded_clear_line_search_filter(hs_.get())); }
   // fuse the update with the linearisation of the new iterate (UnOCPSolver, default on; results are bit-identical)
-  void setPipelining(bool enabled) { check(idocp_b200_set_pipelining(h_.get(), enabled ? 1 : 0)); }
+  void setPipelining(bool enabled) { for (idocp_b200_solver* h : shards_) check(idocp_b200_set_pipelining(h, enabled ? 1 : 0)); }
   bool isCurrentSolutionFeasible() {
     std::vector<int> f(batch_);
-    check(idocp_b200_is_feasible(h_.get(), f.data()));
+    for (size_t k = 0; k < shards_.size(); ++k) check(idocp_b200_is_feasible(shards_[k], f.data() + first_[k]));
     for (int b = 0; b < batch_; ++b)
       if (!f[b]) { std::cout << "INFEASIBLE instance " << b << std::endl; return false; }
     return true;
   }
-  void sync() { check(idocp_b200_sync(h_.get())); }
-  idocp_b200_solver* handle() { return h_.get(); }
+  void sync() { check(idocp_b200_sharded_sync(hs_.get())); }
+  // the single-device solver of shard `shard` (the whole batch when the solver was built on one device)
+  idocp_b200_solver* handle(int shard = 0) { return shards_[shard]; }
 
  protected:
   // the user's compute_q_6d_ref at the time of every stage index (unocp_solver.cpp:80-93: t + i dt, terminal
@@ -406,7 +469,7 @@ class SolverBase {
       for (int k = 0; k < 9; ++k) table[static_cast<size_t>(i) * 12 + k] = ref.rotation.d[k];
       for (int k = 0; k < 3; ++k) table[static_cast<size_t>(i) * 12 + 9 + k] = ref.translation.d[k];
     }
-    check(idocp_b200_set_task_reference(h_.get(), table.data()));
+    check(idocp_b200_sharded_set_task_reference(hs_.get(), table.data()));
     task_sampled_ = true;
     task_t_ = t;
   }
@@ -422,7 +485,9 @@ class SolverBase {
         vb_[static_cast<size_t>(b) * IDOCP_B200_DIMV + j] = y[j];
       }
   }
-  std::shared_ptr<idocp_b200_solver> h_;
+  std::shared_ptr<idocp_b200_sharded> hs_;
+  std::vector<idocp_b200_solver*> shards_;   // borrowed from hs_
+  std::vector<int> first_;                   // first instance of every shard, first_[n] = batch
   int N_, batch_, kind_;
   double T_;
   std::shared_ptr<TimeVaryingTaskSpace6DCost> task_;
@@ -437,7 +502,12 @@ class UnOCPSolver : public detail::SolverBase {
   UnOCPSolver(const Robot& robot, const std::shared_ptr<CostFunction>& cost,
               const std::shared_ptr<Constraints>& constraints, const double T, const int N, const int nthreads = 1,
               const int batch = 1, const int device = 0)
-      : SolverBase(IDOCP_B200_SOLVER_UNOCP, robot, cost, constraints, T, N, nthreads, batch, device) {}
+      : SolverBase(IDOCP_B200_SOLVER_UNOCP, robot, cost, constraints, T, N, nthreads, batch, std::vector<int>{device}) {}
+  // the batch sharded over several GPUs of this node
+  UnOCPSolver(const Robot& robot, const std::shared_ptr<CostFunction>& cost,
+              const std::shared_ptr<Constraints>& constraints, const double T, const int N, const int nthreads,
+              const int batch, const std::vector<int>& devices)
+      : SolverBase(IDOCP_B200_SOLVER_UNOCP, robot, cost, constraints, T, N, nthreads, batch, devices) {}
 };
 
 class UnParNMPCSolver : public detail::SolverBase {
@@ -445,10 +515,14 @@ class UnParNMPCSolver : public detail::SolverBase {
   UnParNMPCSolver(const Robot& robot, const std::shared_ptr<CostFunction>& cost,
                   const std::shared_ptr<Constraints>& constraints, const double T, const int N,
                   const int nthreads = 1, const int batch = 1, const int device = 0)
-      : SolverBase(IDOCP_B200_SOLVER_UNPARNMPC, robot, cost, constraints, T, N, nthreads, batch, device) {}
+      : SolverBase(IDOCP_B200_SOLVER_UNPARNMPC, robot, cost, constraints, T, N, nthreads, batch, std::vector<int>{device}) {}
+  UnParNMPCSolver(const Robot& robot, const std::shared_ptr<CostFunction>& cost,
+                  const std::shared_ptr<Constraints>& constraints, const double T, const int N, const int nthreads,
+                  const int batch, const std::vector<int>& devices)
+      : SolverBase(IDOCP_B200_SOLVER_UNPARNMPC, robot, cost, constraints, T, N, nthreads, batch, devices) {}
   void initBackwardCorrection(const double t) {
     sampleTaskReference(t);
-    detail::check(idocp_b200_init_backward_correction(h_.get(), t));
+    detail::check(idocp_b200_sharded_init_backward_correction(hs_.get(), t));
   }
 };
 

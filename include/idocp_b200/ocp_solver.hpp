@@ -30,6 +30,7 @@ class QuadrupedRobot {
       : urdf_(path_to_urdf), frames_(contact_frames) {
     if (contact_frames != std::vector<int>{14, 24, 34, 44})
       detail::die("invalid argument: the contact frames of ANYmal must be {14, 24, 34, 44}");
+    detail::verify_urdf(path_to_urdf, {detail::kUrdfHashAnymalExamples, detail::kUrdfHashAnymalTests}, "ANYmal");
     detail::check(idocp_b200_fb_problem_default(&p_));
   }
   int dimq() const { return IDOCP_B200_FB_NQ; }

@@ -31,6 +31,16 @@ fi
 if has running; then
   python bench.py --workload anymal_running --steps 10 --warmup 3 > gpurun_out/${L}_bench_anymal_running.json 2> gpurun_out/${L}_bench_anymal_running.err; cut -c 1-400 gpurun_out/${L}_bench_anymal_running.json
 fi
+if has configs01; then
+  python bench.py --workload iiwa14_unparnmpc_task --steps 20 --warmup 5 > gpurun_out/${L}_bench_iiwa14_unparnmpc_task.json 2> gpurun_out/${L}_bench_iiwa14_unparnmpc_task.err; echo "unparnmpc_task rc=$?"; cut -c 1-500 gpurun_out/${L}_bench_iiwa14_unparnmpc_task.json
+  python bench.py --workload iiwa14_unocp_config --steps 50 --warmup 5 > gpurun_out/${L}_bench_iiwa14_unocp_config.json 2> gpurun_out/${L}_bench_iiwa14_unocp_config.err; echo "unocp_config rc=$?"; cut -c 1-500 gpurun_out/${L}_bench_iiwa14_unocp_config.json
+fi
+if has testnew; then
+  timeout 900 python -m pytest tests/test_sharded_solver.py tests/test_cpp_host.py tests/test_gpu_parity.py -m gpu -x -q > gpurun_out/${L}_pytest_new.log 2>&1; echo "pytest rc=$?"; tail -n 5 gpurun_out/${L}_pytest_new.log
+fi
+if has ncuparnmpc; then
+  NCU_SKIP=5 NCU_COUNT=2 tools/ncu_capture.sh $L iiwa14_unparnmpc_task 'k_parnmpc_invert'
+fi
 if has parnmpc; then
   python tools/bench_solver.py --solver unparnmpc --batch 16384 --steps 20 > gpurun_out/${L}_bench_solver_unparnmpc.json 2> gpurun_out/${L}_bench_solver_unparnmpc.err; cut -c 1-700 gpurun_out/${L}_bench_solver_unparnmpc.json
 fi
