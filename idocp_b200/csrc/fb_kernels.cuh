@@ -111,7 +111,7 @@ enum { FBM_SET = 0, FBM_ADD = 1, FBM_SUB = 2 };
 // where the previous one stopped (*rot is advanced by the tile count), so that e.g. four 81-tile products keep all
 // 128 threads busy (3 rounds) instead of using threads 0..80 four times.
 template <int MODE, class Init, class Store>
-__device__ __forceinline__ void fb_mm_f(int m, int n, int k, const double* __restrict__ A, int ars, int acs, const double* __restrict__ B,
+__device__ __forceinline__ void fb_mm_simt_f(int m, int n, int k, const double* __restrict__ A, int ars, int acs, const double* __restrict__ B,
                                         int brs, int bcs, Init init, Store store, int* rot = nullptr) {
   const int tm = (m + 1) >> 1, tn = (n + 1) >> 1, total = tm * tn;
   int first = threadIdx.x;
@@ -155,15 +155,80 @@ __device__ __forceinline__ void fb_mm_f(int m, int n, int k, const double* __res
     if (hi) { store(i1, j0, c10); if (hj) store(i1, j1, c11); }
   }
 }
+// ---------------------------------------------------------------------------------------------------------------------
+// The same products on the FP64 tensor cores.  mma.sync.aligned.m8n8k4.f64 computes, for every element of an 8 x 8 tile,
+// d = fma(a_3, b_3, fma(a_2, b_2, fma(a_1, b_1, fma(a_0, b_0, c)))) -- measured on the B200: bit-identical to the ascending
+// fma chain on 262 144 random elements with widely spread exponents, 120 529 of which tell ascending / descending / fused
+// summation apart (tools/dmma_probe.cu, profiles/dmma_probe.json).  Chaining the accumulator over k in steps of 4 therefore
+// IS the canonical chain of the oracle, and zero-padding the ragged edges adds fma(0, 0, c) = c.  What it buys: the SIMT
+// form reads one shared-memory operand per fma and warp (the LSU was ~65 % busy, FP64 pipe 14-16 %); one DMMA does 256 fma
+// from two operand loads, i.e. 5 x fewer shared-memory wavefronts and 8 x fewer FP64 instructions for the same chain.
+// A warp owns an 8 x 16 strip of C (two tiles sharing the A fragment: two independent accumulator chains).
+// Fragment layout (PTX ISA, m8n8k4 .f64): a = A[g][t], b = B[t][g], c / d = C[g][2 t + {0, 1}] with g = lane / 4, t = lane % 4.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fb_dmma(double& d0, double& d1, double a, double b) {
+#ifndef IDOCP_B200_EMU
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+#else
+  emu_dmma_m8n8k4(d0, d1, a, b);   // the ascending chain the hardware was measured to execute (tests/emu/cuda_emu.h)
+#endif
+}
+template <int MODE, class Init, class Store>
+__device__ __forceinline__ void fb_mm_f(int m, int n, int k, const double* __restrict__ A, int ars, int acs, const double* __restrict__ B,
+                                        int brs, int bcs, Init init, Store store, int* rot = nullptr) {
+#ifdef IDOCP_FB_MM_SIMT
+  fb_mm_simt_f<MODE>(m, n, k, A, ars, acs, B, brs, bcs, init, store, rot);
+#else
+  const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int tm = (m + 7) >> 3, tn = (n + 15) >> 4, total = tm * tn;
+  int first = warp;
+  if (rot) {
+    first = warp - *rot;
+    if (first < 0) first += nw;
+    *rot = (*rot + total) % nw;
+  }
+  for (int s = first; s < total; s += nw) {          // warp-uniform: every lane executes every mma.sync
+    const int i0 = (s / tn) << 3, j0 = (s - (s / tn) * tn) << 4;
+    const int row = i0 + g, ca = j0 + 2 * t, cb = ca + 8, ba = j0 + g, bb = ba + 8;
+    const bool rok = row < m, baok = ba < n, bbok = bb < n;
+    // FBM_SET: a chain that starts with the plain product a_0 b_0 = fma(a_0, b_0, -0.0), sign of zero included
+    double c00 = (k > 0) ? -0.0 : 0.0, c01 = c00, c10 = c00, c11 = c00;
+    if (MODE != FBM_SET) {
+      c00 = (rok && ca < n) ? init(row, ca) : 0.0;
+      c01 = (rok && ca + 1 < n) ? init(row, ca + 1) : 0.0;
+      c10 = (rok && cb < n) ? init(row, cb) : 0.0;
+      c11 = (rok && cb + 1 < n) ? init(row, cb + 1) : 0.0;
+    }
+    const double* ap = A + (rok ? row : 0) * ars + t * acs;
+    const double* bpa = B + (baok ? ba : 0) * bcs + t * brs;
+    const double* bpb = B + (bbok ? bb : 0) * bcs + t * brs;
+    for (int l = 0; l < k; l += 4) {
+      const bool kin = l + t < k;
+      double a = (rok && kin) ? ap[l * acs] : 0.0;
+      const double b0 = (baok && kin) ? bpa[l * brs] : 0.0, b1 = (bbok && kin) ? bpb[l * brs] : 0.0;
+      if (MODE == FBM_SUB) a = -a;
+      fb_dmma(c00, c01, a, b0);
+      fb_dmma(c10, c11, a, b1);
+    }
+    if (rok) {
+      if (ca < n) store(row, ca, c00);
+      if (ca + 1 < n) store(row, ca + 1, c01);
+      if (cb < n) store(row, cb, c10);
+      if (cb + 1 < n) store(row, cb + 1, c11);
+    }
+  }
+#endif
+}
 template <int MODE>
 __device__ __forceinline__ void fb_mm(int m, int n, int k, const double* __restrict__ A, int ars, int acs, const double* __restrict__ B,
                                       int brs, int bcs, double* C, int ldc, int* rot = nullptr) {
   fb_mm_f<MODE>(m, n, k, A, ars, acs, B, brs, bcs, [=](int i, int j) { return C[i * ldc + j]; },
                 [=](int i, int j, double v) { C[i * ldc + j] = v; }, rot);
 }
+// matrix-vector products stay on the SIMT path (one column would waste 7 / 8 of a tensor-core tile)
 template <int MODE>
 __device__ __forceinline__ void fb_mv(int m, int k, const double* A, int ars, int acs, const double* x, double* y) {
-  fb_mm<MODE>(m, 1, k, A, ars, acs, x, 1, 1, y, 1);
+  fb_mm_simt_f<MODE>(m, 1, k, A, ars, acs, x, 1, 1, [=](int i, int j) { return y[i + j]; }, [=](int i, int j, double v) { y[i + j] = v; });
 }
 __device__ inline double fb_sqnorm(const double* x, int n) {
   double acc = 0.0;

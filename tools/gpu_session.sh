@@ -31,6 +31,9 @@ fi
 if has running; then
   python bench.py --workload anymal_running --steps 10 --warmup 3 > gpurun_out/${L}_bench_anymal_running.json 2> gpurun_out/${L}_bench_anymal_running.err; cut -c 1-400 gpurun_out/${L}_bench_anymal_running.json
 fi
+if has dmma; then
+  tools/dmma_probe > gpurun_out/${L}_dmma_probe.json 2> gpurun_out/${L}_dmma_probe.err; cat gpurun_out/${L}_dmma_probe.json
+fi
 if has configs01; then
   python bench.py --workload iiwa14_unparnmpc_task --steps 20 --warmup 5 > gpurun_out/${L}_bench_iiwa14_unparnmpc_task.json 2> gpurun_out/${L}_bench_iiwa14_unparnmpc_task.err; echo "unparnmpc_task rc=$?"; cut -c 1-500 gpurun_out/${L}_bench_iiwa14_unparnmpc_task.json
   python bench.py --workload iiwa14_unocp_config --steps 50 --warmup 5 > gpurun_out/${L}_bench_iiwa14_unocp_config.json 2> gpurun_out/${L}_bench_iiwa14_unocp_config.err; echo "unocp_config rc=$?"; cut -c 1-500 gpurun_out/${L}_bench_iiwa14_unocp_config.json
