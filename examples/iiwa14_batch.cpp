@@ -106,8 +106,22 @@ Setup make_setup(const std::string& problem, ob::Robot& robot) {
     s.cost->push_back(task);
     s.T = 6; s.N = 120;
     s.q0 = bent_arm(false);
+  } else if (problem == "task3d") {        // reach a fixed end-effector POSITION: TaskSpace3DCost
+    robot.setJointEffortLimit(ob::VectorXd::Constant(n, 50));
+    robot.setJointVelocityLimit(ob::VectorXd::Constant(n, M_PI_2));
+    joint_cost->set_v_weight(ob::VectorXd::Constant(n, 0.01));
+    joint_cost->set_vf_weight(ob::VectorXd::Constant(n, 0.01));
+    joint_cost->set_a_weight(ob::VectorXd::Constant(n, 0.01));
+    s.cost->push_back(joint_cost);
+    auto task = std::make_shared<ob::TaskSpace3DCost>(robot, 22);
+    task->set_q_3d_ref(ob::Vector3d(0.546, 0.1, 0.76));
+    task->set_q_3d_weight(ob::Vector3d::Constant(1000));
+    task->set_qf_3d_weight(ob::Vector3d::Constant(1000));
+    s.cost->push_back(task);
+    s.T = 1.5; s.N = 30;
+    s.q0 = bent_arm(false);
   } else {
-    std::cerr << "unknown problem '" << problem << "' (benchmark | config | task | task6d)\n";
+    std::cerr << "unknown problem '" << problem << "' (benchmark | config | task | task6d | task3d)\n";
     std::exit(EXIT_FAILURE);
   }
   return s;

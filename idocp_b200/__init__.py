@@ -5,7 +5,7 @@ Everything numerical runs in the CUDA library ``libidocp_b200.so`` (sm_100a) beh
 """
 from .capi import Idocp_b200Error, Library, Problem, default_library  # noqa: F401
 from .solvers import (ShardedSolver, UnOCPSolver, UnParNMPCSolver, benchmark_problem, config_space_problem,  # noqa: F401
-                      task_space_circle_ref, task_space_problem)
+                      task_space_3d_problem, task_space_circle_ref, task_space_problem)
 
 __version__ = "0.1"
 from .hybrid import ContactSequence, OCPDiscretizer  # noqa: F401,E402

@@ -199,10 +199,16 @@ static void fill_dev_problem(const idocp_b200_problem& p, DevProblem& d) {
   d.gravity = IIWA14_GRAVITY;
   // TimeVaryingTaskSpace6DCost::set_q_6d_weight(position_weight, rotation_weight) stores head<3> = rotation,
   // tail<3> = position (time_varying_task_space_6d_cost.cpp:43-58) and applies them to diff_6d = [linear; angular]
-  d.task_enabled = p.task_enabled ? 1 : 0;
+  // task_enabled == 2: TaskSpace3DCost / TimeVaryingTaskSpace3DCost, the three weights apply to diff_3d as given
+  d.task_enabled = p.task_enabled == 2 ? 2 : (p.task_enabled ? 1 : 0);
   for (int k = 0; k < 3; ++k) {
-    d.task_w6[k] = p.task_q_weight[3 + k];  d.task_w6[3 + k] = p.task_q_weight[k];
-    d.task_wf6[k] = p.task_qf_weight[3 + k]; d.task_wf6[3 + k] = p.task_qf_weight[k];
+    if (d.task_enabled == 2) {
+      d.task_w6[k] = p.task_q_weight[k];   d.task_w6[3 + k] = 0.0;
+      d.task_wf6[k] = p.task_qf_weight[k]; d.task_wf6[3 + k] = 0.0;
+    } else {
+      d.task_w6[k] = p.task_q_weight[3 + k];  d.task_w6[3 + k] = p.task_q_weight[k];
+      d.task_wf6[k] = p.task_qf_weight[3 + k]; d.task_wf6[3 + k] = p.task_qf_weight[k];
+    }
   }
   for (int k = 0; k < 9; ++k) d.ee[k] = IIWA14_EE_PLACEMENT_R[k];
   for (int k = 0; k < 3; ++k) d.ee[9 + k] = IIWA14_EE_PLACEMENT_P[k];

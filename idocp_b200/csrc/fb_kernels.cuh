@@ -17,6 +17,7 @@
 // [slot][instance]: a CTA reads and writes contiguous, aligned runs.
 #pragma once
 #include "fb_math.cuh"
+#include "warp_llt.cuh"
 
 namespace idocp_b200 {
 
@@ -1330,6 +1331,33 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
   }
 }
 
+// X = A^-1 for a small symmetric positive definite A (n x n, lower triangle of A[i*lda + j] read) by ONE warp (all 32 lanes
+// call it): warp_llt.cuh -- right-looking Cholesky with lane = row, then lane c substitutes the unit vector e_c (forward,
+// then backward in descending order = fb_llt / fb_llt_solve of the oracle, bit for bit).  L, LT: n x FB_WLD scratch each
+// (16-byte aligned), rd: n pivots' reciprocal square roots.  The CTA-wide owner-per-element sweep this replaces spent ~14 k
+// warp instructions per 18 x 18 inverse on index bookkeeping and 36 block barriers (LLT(M) was 38 % of k_fb_condense,
+// profiles/r2i_fb_phase_clocks.json); one warp needs ~2 k.  The other warps of the CTA wait at the caller's barrier while
+// the other resident CTAs use the SM.
+template <int n, int ld>
+__device__ __forceinline__ void fb_inverse_warp(const double* A, int lda, double* L, double* LT, double* rd, double* X, int ldx,
+                                                int* info, int code) {
+  const int wl = threadIdx.x & 31;
+  const int row = wl < n ? wl : n - 1;
+  double a[n];
+#pragma unroll
+  for (int c = 0; c < n; ++c) a[c] = A[row * lda + (c <= row ? c : row)];   // entries c > row are never used
+  __syncwarp();
+  const int fail = warp_llt_rows<n, ld>(a, L, LT, rd, wl);
+  if (fail && wl == 0 && *info == 0) *info = code + fail;
+  __syncwarp();
+  double y[n];
+  warp_llt_solve_unit<n, ld>(L, LT, rd, wl < n ? wl : 0, y);
+  if (wl < n) {
+#pragma unroll
+    for (int r = 0; r < n; ++r) X[r * ldx + wl] = y[r];
+  }
+}
+
 // =====================================================================================================
 // K1b: dense condensing of one stage, one CTA (128 threads) per (instance, stage)
 //   computeMJtJinv (robot.hxx:576-615), condenseContactDynamics (contact_dynamics.hxx:105-158) /
@@ -1359,6 +1387,9 @@ struct FbDenseWork {
   int info;
 };
 
+static_assert(offsetof(FbDenseWork, s) % 16 == 0 && (FB_NV * FB_NV + FB_NV) % 2 == 0 && (2 * FB_NV * FB_NV + FB_NV) % 2 == 0 &&
+              (2 * FB_NV * FB_NV + FB_NV + FB_MAXF * FB_NV + FB_MAXF * FB_MAXF) % 2 == 0 && FB_MAXF * FB_NV + FB_MAXF * FB_MAXF >= FB_NV * FB_NV,
+              "warp_llt.cuh reads its broadcast operands two doubles at a time: L, JMi (L^T scratch) and Ls sit at even offsets");
 __global__ void __launch_bounds__(128, 5) k_fb_condense(FbArrays A, const FbLin* lin) {
   IDOCP_DYN_SMEM(FbDenseWork, wp);
   FbDenseWork& w = *wp;
@@ -1398,9 +1429,9 @@ __global__ void __launch_bounds__(128, 5) k_fb_condense(FbArrays A, const FbLin*
   // ---- MJtJinv = [[M, J^T], [J, 0]]^-1 by dense Cholesky ----
   {
     const int n = NV, ld = NVF;
-    FB_FOR(x, n * n) { const int r = x / n; w.s.f.Minv[x] = (x - r * n == r) ? 1.0 : 0.0; }
+    // Minv = M^-1: warp 0 (L in s.f.L, L^T in the JMi / Sm scratch that is not live yet)
+    if (tid < 32) fb_inverse_warp<FB_NV, FB_NV>(w.Mm, n, w.s.f.L, w.s.f.JMi, w.s.f.rd, w.s.f.Minv, n, &w.info, 0);
     __syncthreads();
-    fb_llt_factor_solve_cta<2, 3>(w.Mm, n, n, w.s.f.L, n, w.s.f.rd, w.s.f.Minv, n, n, &w.info, 0);
     FB_PHASE(0, 1);
     FB_PHASE(0, 2);
     fb_mm<FBM_SET>(dimf, n, n, w.dCda, n, 1, w.s.f.Minv, n, 1, w.s.f.JMi, n);
@@ -1409,9 +1440,16 @@ __global__ void __launch_bounds__(128, 5) k_fb_condense(FbArrays A, const FbLin*
     __syncthreads();
     FB_PHASE(0, 3);
     if (dimf > 0) {
-      FB_FOR(x, dimf * dimf) { const int r = x / dimf; w.s.f.Si[x] = (x - r * dimf == r) ? 1.0 : 0.0; }
+      // Si = S^-1: warp 0 again (dimf = 3 contacts' worth of rows each; L^T in the scratch of M's factor, dead by now)
+      if (tid < 32) {
+        switch (dimf) {
+          case 3: fb_inverse_warp<3, FB_MAXF>(w.s.f.Sm, dimf, w.s.f.Ls, w.s.f.L, w.s.f.rds, w.s.f.Si, dimf, &w.info, 100); break;
+          case 6: fb_inverse_warp<6, FB_MAXF>(w.s.f.Sm, dimf, w.s.f.Ls, w.s.f.L, w.s.f.rds, w.s.f.Si, dimf, &w.info, 100); break;
+          case 9: fb_inverse_warp<9, FB_MAXF>(w.s.f.Sm, dimf, w.s.f.Ls, w.s.f.L, w.s.f.rds, w.s.f.Si, dimf, &w.info, 100); break;
+          default: fb_inverse_warp<12, FB_MAXF>(w.s.f.Sm, dimf, w.s.f.Ls, w.s.f.L, w.s.f.rds, w.s.f.Si, dimf, &w.info, 100); break;
+        }
+      }
       __syncthreads();
-      fb_llt_factor_solve_cta<1, 2>(w.s.f.Sm, dimf, dimf, w.s.f.Ls, dimf, w.s.f.rds, w.s.f.Si, dimf, dimf, &w.info, 100);
     }
     FB_PHASE(0, 4);
     FB_FOR(x, dimf * dimf) { const int r = x / dimf, c = x - r * dimf; w.MJtJinv[(n + r) * ld + n + c] = -w.s.f.Si[x]; }
@@ -1563,6 +1601,7 @@ struct FbRicWork {
   int info;
 };
 
+static_assert(offsetof(FbRicWork, L) % 16 == 0, "warp_llt.cuh reads the factor two doubles at a time");
 __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
   IDOCP_DYN_SMEM(FbRicWork, wp);
   FbRicWork& w = *wp;
@@ -1665,7 +1704,17 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
     FB_PHASE(1, 4);
     const double* Qxu = w.Qxu;   // 36 x 12, leading dimension NU
     if (!impulse) {
-      fb_llt_cta<1>(w.Quu, NU, NU, w.L, NU, w.rd, &w.info, 200);
+      // LLT(G), G = Quu (12 x 12): warp 0, lane = row (warp_llt.cuh; the factor only, the solves below read L and rd)
+      if (tid < 32) {
+        const int row = tid < NU ? tid : NU - 1;
+        double a[FB_NU];
+#pragma unroll
+        for (int c = 0; c < FB_NU; ++c) a[c] = w.Quu[row * NU + (c <= row ? c : row)];
+        __syncwarp();
+        const int fail = warp_llt_rows<FB_NU, FB_NU>(a, w.L, nullptr, w.rd, tid);
+        if (fail && tid == 0 && w.info == 0) w.info = 200 + fail;
+      }
+      __syncthreads();
       FB_PHASE(1, 5);
       if (dimi == 0) {
         // K = -G^-1 Qxu^T, k = -G^-1 lu: one right-hand side per thread

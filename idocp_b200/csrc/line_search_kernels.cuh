@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_ls_eval(const DevProblem* __res
       V3 p;
       chain_fk(lane, act ? qt : 0.0, P.model + lane * MODEL_STRIDE, R, p);
       TaskEval te;
-      task_evaluate<false>(R, p, P.ee, L.task_ref + static_cast<size_t>(N) * 12, te);
+      task_evaluate<false>(R, p, P.ee, L.task_ref + static_cast<size_t>(N) * 12, te, P.task_enabled);
       tc += 0.5 * task_weighted_sqnorm(te, P.task_wf6);
     }
     if (lane == 0 && part) LS.cost[static_cast<size_t>(N) * L.Bp + b] = tc;
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_ls_eval(const DevProblem* __res
   chain_fk(lane, act ? qt : 0.0, P.model + lane * MODEL_STRIDE, R, p);
   TaskEval te;
   if (TASK) {
-    task_evaluate<false>(R, p, P.ee, L.task_ref + static_cast<size_t>(last ? N : i) * 12, te);
+    task_evaluate<false>(R, p, P.ee, L.task_ref + static_cast<size_t>(last ? N : i) * 12, te, P.task_enabled);
     cost += 0.5 * dt * task_weighted_sqnorm(te, P.task_w6);
   }
   if (last) {   // TerminalUnParNMPC::stageCost: + computeTerminalCost

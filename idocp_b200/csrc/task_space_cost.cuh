@@ -82,9 +82,12 @@ struct TaskEval {
 
 // R, p: world placement of this lane's joint (chain_fk); ee: [R row-major (9), p (3)] placement of the frame in
 // the last joint's frame; ref: the stage's SE3 reference.
+// kind = DevProblem::task_enabled: 1 = the 6D cost above; 2 = TaskSpace3DCost / TimeVaryingTaskSpace3DCost
+// (src/cost/task_space_3d_cost.cpp:56-140): diff_3d = framePosition - q_3d_ref, J_3d = frameRotation * J_frame(LOCAL).topRows<3>();
+// they ride in the first three entries of diff / JJ (the angular half is zero, and so are its weights).
 template <bool WITH_JACOBIAN>
 __device__ __forceinline__ void task_evaluate(const double (&R)[9], V3 p, const double* __restrict__ ee,
-                                              const double* __restrict__ ref, TaskEval& te) {
+                                              const double* __restrict__ ref, TaskEval& te, int kind) {
   // oMf = oMi[last joint] * frame placement
   double R6[9];
 #pragma unroll
@@ -99,6 +102,20 @@ __device__ __forceinline__ void task_evaluate(const double (&R)[9], V3 p, const 
   const V3 pf = V3{fma(R6[2], ee[11], fma(R6[1], ee[10], fma(R6[0], ee[9], p6.x))),
                    fma(R6[5], ee[11], fma(R6[4], ee[10], fma(R6[3], ee[9], p6.y))),
                    fma(R6[8], ee[11], fma(R6[7], ee[10], fma(R6[6], ee[9], p6.z)))};
+  if (kind == 2) {
+    te.diff[0] = pf.x - ref[9]; te.diff[1] = pf.y - ref[10]; te.diff[2] = pf.z - ref[11];
+    te.diff[3] = 0.0; te.diff[4] = 0.0; te.diff[5] = 0.0;
+    if (WITH_JACOBIAN) {
+      const V3 Sw = V3{R[2], R[5], R[8]};
+      const V3 Jl = mulT3(Rf, cross(p, Sw) + cross(Sw, pf));     // linear rows of getFrameJacobian(frame, LOCAL)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        te.JJ[r] = dot3r(Rf + 3 * r, Jl);                        // frameRotation * J_6d.topRows<3>()
+        te.JJ[3 + r] = 0.0;
+      }
+    }
+    return;
+  }
   // diff_SE3 = SE3_ref^-1 * oMf
   double Rd[9];
 #pragma unroll

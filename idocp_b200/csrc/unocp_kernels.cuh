@@ -229,7 +229,7 @@ __device__ __forceinline__ void linearize_task(const DevProblem& P, const Layout
       V3 p;
       chain_fk(lane, act ? q : 0.0, P.model + lane * MODEL_STRIDE, R, p);
       TaskEval te;
-      task_evaluate<true>(R, p, P.ee, L.task_ref + static_cast<size_t>(i) * 12, te);
+      task_evaluate<true>(R, p, P.ee, L.task_ref + static_cast<size_t>(i) * 12, te, P.task_enabled);
       task_share_columns(lane, te, tile);
       double gf;
       task_gradient_hessian(te, P.task_wf6, tile, gf, hf);
@@ -291,7 +291,7 @@ __device__ __forceinline__ void linearize_task(const DevProblem& P, const Layout
     chain_fk(lane, q, P.model + lane * MODEL_STRIDE, R, p);
     if (TASK) {
       TaskEval te;
-      task_evaluate<true>(R, p, P.ee, L.task_ref + static_cast<size_t>(i) * 12, te);
+      task_evaluate<true>(R, p, P.ee, L.task_ref + static_cast<size_t>(i) * 12, te, P.task_enabled);
       task_share_columns(lane, te, tile);
       task_gradient_hessian(te, P.task_w6, tile, task_g, task_h);
       if (last) task_gradient_hessian(te, P.task_wf6, tile, task_gf, task_hf);

@@ -72,6 +72,20 @@ def task_space_problem(lib=None, N=120, T=6.0):
     return p
 
 
+def task_space_3d_problem(lib=None, N=30, T=1.5):
+    """TaskSpace3DCost / TimeVaryingTaskSpace3DCost (src/cost/task_space_3d_cost.cpp) on the task_space_ocp robot set-up:
+    position error of the end-effector frame, weights 1000 (task_enabled = 2; task_q_weight[0..2] = q_3d_weight)."""
+    p = task_space_problem(lib, N, T)
+    p.task_enabled = 2
+    for k in range(3, 6):
+        p.task_q_weight[k] = 0.0
+        p.task_qf_weight[k] = 0.0
+    for i in range(7):          # a 3D position cost has rank 3 in q: a small posture weight keeps the stage Hessian definite
+        p.q_weight[i] = 0.1     # (UnParNMPC factorises the full 21 x 21 stage Hessian)
+        p.qf_weight[i] = 0.1
+    return p
+
+
 def task_space_circle_ref(t):
     """TimeVaryingTaskSpace6DRef::compute_q_6d_ref of examples/iiwa14/task_space_ocp.cpp:21-46
     -> [R_ref row-major (9), p_ref (3)]."""

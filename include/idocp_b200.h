@@ -69,8 +69,10 @@ typedef struct {
   double v_max[IDOCP_B200_DIMV], u_max[IDOCP_B200_DIMV];
   double barrier;           /* 1e-4  */
   double fraction_rate;     /* 0.995 */
-  int task_enabled;         /* TimeVaryingTaskSpace6DCost on the end-effector frame (frame id 22 of
-                               examples/iiwa14/task_space_ocp.cpp:67) */
+  int task_enabled;         /* task-space cost on the end-effector frame (frame id 22 of examples/iiwa14/task_space_ocp.cpp:67):
+                               0 none; 1 TimeVaryingTaskSpace6DCost / TaskSpace6DCost (log6 pose error);
+                               2 TimeVaryingTaskSpace3DCost / TaskSpace3DCost (src/cost/task_space_3d_cost.cpp: position error;
+                               task_q_weight[0..2] = q_3d_weight, the reference table's rotation entries are ignored) */
   double task_q_weight[6], task_qf_weight[6]; /* [position xyz, rotation xyz] = the arguments of
                                set_q_6d_weight / set_qf_6d_weight (time_varying_task_space_6d_cost.cpp:43-58) */
   double task_center[3], task_radius, task_t0, task_tf; /* reserved (the reference is a host-sampled table) */

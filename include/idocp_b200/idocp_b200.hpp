@@ -209,9 +209,68 @@ class TimeVaryingTaskSpace6DCost {
   const double* q_6d_weight() const { return q_; }
   const double* qf_6d_weight() const { return qf_; }
   const std::shared_ptr<TimeVaryingTaskSpace6DRefBase>& ref() const { return ref_; }
+  // idocp_b200_problem::task_enabled of this component: 1 = 6D (log6 error), 2 = 3D position error (the 3D classes below)
+  int kind() const { return kind_; }
+  void set_kind(int kind) { kind_ = kind; }
  private:
   std::shared_ptr<TimeVaryingTaskSpace6DRefBase> ref_;
   double q_[6], qf_[6];
+  int kind_ = 1;
+};
+
+// cost/time_varying_task_space_3d_cost.hpp:18-38: user-derived position reference (host virtual, sampled per stage)
+class TimeVaryingTaskSpace3DRefBase {
+ public:
+  TimeVaryingTaskSpace3DRefBase() {}
+  virtual ~TimeVaryingTaskSpace3DRefBase() {}
+  virtual void compute_q_3d_ref(const double t, Vector3d& q_3d_ref) const = 0;
+};
+
+// cost/time_varying_task_space_3d_cost.hpp:40-150, src/cost/time_varying_task_space_3d_cost.cpp: 1/2 dt sum w (p_frame - p_ref(t))^2
+// with J_3d = frameRotation * J_frame(LOCAL).topRows<3>().  Device path: the task-space cost kernels in their 3D mode
+// (task_space_cost.cuh, kind 2); the reference table carries p_ref(t) of every stage (rotation entries unused).
+class TimeVaryingTaskSpace3DCost {
+ public:
+  TimeVaryingTaskSpace3DCost(const Robot& robot, const int frame_id, const std::shared_ptr<TimeVaryingTaskSpace3DRefBase>& ref)
+      : adapter_(std::make_shared<Adapter>()), cost_(std::make_shared<TimeVaryingTaskSpace6DCost>(robot, frame_id, adapter_)) {
+    adapter_->ref = ref;
+    cost_->set_kind(2);
+  }
+  void set_ref(const std::shared_ptr<TimeVaryingTaskSpace3DRefBase>& ref) { adapter_->ref = ref; }
+  void set_q_3d_weight(const Vector3d& w) { cost_->set_q_6d_weight(w, Vector3d()); }
+  void set_qf_3d_weight(const Vector3d& w) { cost_->set_qf_6d_weight(w, Vector3d()); }
+  void set_qi_3d_weight(const Vector3d&) {}   // no impulse stages on the fixed-base path
+  const std::shared_ptr<TimeVaryingTaskSpace6DCost>& component() const { return cost_; }
+ private:
+  struct Adapter final : TimeVaryingTaskSpace6DRefBase {
+    std::shared_ptr<TimeVaryingTaskSpace3DRefBase> ref;
+    void compute_q_6d_ref(const double t, SE3& se3_ref) const override {
+      Vector3d p;
+      if (ref) ref->compute_q_3d_ref(t, p);
+      se3_ref = SE3(Matrix3d(), p);
+    }
+  };
+  std::shared_ptr<Adapter> adapter_;
+  std::shared_ptr<TimeVaryingTaskSpace6DCost> cost_;
+};
+
+// cost/task_space_3d_cost.hpp:18-60, src/cost/task_space_3d_cost.cpp:56-140: the same with a constant reference position
+class TaskSpace3DCost {
+ public:
+  TaskSpace3DCost(const Robot& robot, const int frame_id)
+      : ref_(std::make_shared<ConstantRef>()), cost_(std::make_shared<TimeVaryingTaskSpace3DCost>(robot, frame_id, ref_)) {}
+  void set_q_3d_ref(const Vector3d& q_3d_ref) { ref_->p = q_3d_ref; }
+  void set_q_3d_weight(const Vector3d& w) { cost_->set_q_3d_weight(w); }
+  void set_qf_3d_weight(const Vector3d& w) { cost_->set_qf_3d_weight(w); }
+  void set_qi_3d_weight(const Vector3d& w) { cost_->set_qi_3d_weight(w); }
+  const std::shared_ptr<TimeVaryingTaskSpace6DCost>& component() const { return cost_->component(); }
+ private:
+  struct ConstantRef final : TimeVaryingTaskSpace3DRefBase {
+    Vector3d p;
+    void compute_q_3d_ref(const double, Vector3d& q_3d_ref) const override { q_3d_ref = p; }
+  };
+  std::shared_ptr<ConstantRef> ref_;
+  std::shared_ptr<TimeVaryingTaskSpace3DCost> cost_;
 };
 
 // cost/task_space_6d_cost.hpp:22-60, src/cost/task_space_6d_cost.cpp:41-176: the same stage arithmetic as the
@@ -240,8 +299,8 @@ class TaskSpace6DCost {
   std::shared_ptr<TimeVaryingTaskSpace6DCost> cost_;
 };
 
-// closed registry of cost components: one ConfigurationSpaceCost and, optionally, one task-space 6D cost
-// (TimeVaryingTaskSpace6DCost or TaskSpace6DCost; push_back order of the reference examples: configuration cost first)
+// closed registry of cost components: one ConfigurationSpaceCost and, optionally, one task-space cost
+// (TimeVaryingTaskSpace6DCost, TaskSpace6DCost, TimeVaryingTaskSpace3DCost or TaskSpace3DCost; push_back order of the reference examples: configuration cost first)
 class CostFunction {
  public:
   void push_back(const std::shared_ptr<ConfigurationSpaceCost>& c) {
@@ -254,6 +313,8 @@ class CostFunction {
     task_ = c;
   }
   void push_back(const std::shared_ptr<TaskSpace6DCost>& c) { push_back(c->component()); }
+  void push_back(const std::shared_ptr<TimeVaryingTaskSpace3DCost>& c) { push_back(c->component()); }
+  void push_back(const std::shared_ptr<TaskSpace3DCost>& c) { push_back(c->component()); }
   const std::shared_ptr<ConfigurationSpaceCost>& config() const { return config_; }
   const std::shared_ptr<TimeVaryingTaskSpace6DCost>& task() const { return task_; }
  private:
@@ -296,7 +357,7 @@ inline idocp_b200_problem make_problem(const Robot& robot, const std::shared_ptr
   p.T = T;
   p.N = N;
   if (cost->task()) {
-    p.task_enabled = 1;
+    p.task_enabled = cost->task()->kind();
     for (int k = 0; k < 6; ++k) {
       p.task_q_weight[k] = cost->task()->q_6d_weight()[k];
       p.task_qf_weight[k] = cost->task()->qf_6d_weight()[k];

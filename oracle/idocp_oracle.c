@@ -544,11 +544,13 @@ static void jlog3_canon(double theta, v3_t w, double* A) {
 typedef struct {
   double diff[6];        /* log6(SE3_ref^-1 * oMf) = [linear; angular] */
   double JJ[6 * NV];     /* Jlog6 * frame Jacobian (LOCAL), JJ[c * 6 + k] = row k of column c */
+  int kind;              /* 1: 6D cost; 2: TaskSpace3DCost (diff_3d / J_3d in the first three entries, the rest zero) */
 } task_eval_t;
 
 /* diff_6d and JJ_6d of computeStageCostDerivatives (:105-119).  ref12 = [R_ref row-major (9), p_ref (3)]
  * as produced by the user's TimeVaryingTaskSpace6DRefBase::compute_q_6d_ref(t) (sampled on the host). */
-static void task_evaluate(const double* q, const double* ref12, task_eval_t* te, int with_jacobian) {
+static void task_evaluate(const double* q, const double* ref12, task_eval_t* te, int with_jacobian, int kind) {
+  te->kind = kind;
   double R[LANES][9];
   v3_t p[LANES];
   chain_fk(q, R, p);
@@ -564,6 +566,22 @@ static void task_evaluate(const double* q, const double* ref12, task_eval_t* te,
   const v3_t pf = V3(fma(R6[2], ep.z, fma(R6[1], ep.y, fma(R6[0], ep.x, p6.x))),
                      fma(R6[5], ep.z, fma(R6[4], ep.y, fma(R6[3], ep.x, p6.y))),
                      fma(R6[8], ep.z, fma(R6[7], ep.y, fma(R6[6], ep.x, p6.z))));
+  if (kind == 2) {
+    /* TaskSpace3DCost / TimeVaryingTaskSpace3DCost (src/cost/task_space_3d_cost.cpp:56-140): diff_3d = framePosition -
+     * q_3d_ref; J_3d = frameRotation * getFrameJacobian(LOCAL).topRows<3>() */
+    te->diff[0] = pf.x - ref12[9]; te->diff[1] = pf.y - ref12[10]; te->diff[2] = pf.z - ref12[11];
+    te->diff[3] = te->diff[4] = te->diff[5] = 0.0;
+    if (!with_jacobian) return;
+    for (int c = 0; c < NV; ++c) {
+      const v3_t Sw = V3(R[c][2], R[c][5], R[c][8]);
+      const v3_t Jl = mulT3(Rf, vadd(vcross(p[c], Sw), vcross(Sw, pf)));
+      for (int r = 0; r < 3; ++r) {
+        te->JJ[c * 6 + r] = dot3r(Rf + 3 * r, Jl);
+        te->JJ[c * 6 + 3 + r] = 0.0;
+      }
+    }
+    return;
+  }
   /* diff_SE3 = SE3_ref^-1 * oMf */
   double Rd[9];
   for (int r = 0; r < 3; ++r)
@@ -634,7 +652,11 @@ static void task_evaluate(const double* q, const double* ref12, task_eval_t* te,
 /* set_q_6d_weight(position_weight, rotation_weight) stores head<3> = rotation_weight, tail<3> =
  * position_weight (time_varying_task_space_6d_cost.cpp:45-50) while diff_6d = [linear; angular]: the
  * rotation weight multiplies the linear part.  Restated as is.  wpr = [position(3), rotation(3)]. */
-static inline double task_w6(const double* wpr, int k) { return k < 3 ? wpr[3 + k] : wpr[k - 3]; }
+static inline double task_w6k(int kind, const double* wpr, int k) {
+  if (kind == 2) return k < 3 ? wpr[k] : 0.0;   /* TaskSpace3DCost: q_3d_weight applies to diff_3d as given */
+  return k < 3 ? wpr[3 + k] : wpr[k - 3];
+}
+#define task_w6(wpr, k) task_w6k(te->kind, wpr, k)
 
 /* lq += scale * JJ^T diag(w6) diff (:116-118, :132-133) */
 static void task_add_gradient(const task_eval_t* te, const double* wpr, double scale, int use_scale, double* lq) {
@@ -661,9 +683,15 @@ static double task_weighted_sqnorm(const task_eval_t* te, const double* wpr) {
 }
 
 /* parity / test getter: diff_6d (6) and JJ_6d (6 x 7, column-major) for a configuration and a reference */
+void oracle_task_evaluate_kind(const double* q, const double* ref12, int kind, double* diff6, double* JJ) {
+  task_eval_t te;
+  task_evaluate(q, ref12, &te, 1, kind);
+  memcpy(diff6, te.diff, sizeof(te.diff));
+  memcpy(JJ, te.JJ, sizeof(te.JJ));
+}
 void oracle_task_evaluate(const double* q, const double* ref12, double* diff6, double* JJ) {
   task_eval_t te;
-  task_evaluate(q, ref12, &te, 1);
+  task_evaluate(q, ref12, &te, 1, 1);
   memcpy(diff6, te.diff, sizeof(te.diff));
   memcpy(JJ, te.JJ, sizeof(te.JJ));
 }
@@ -921,7 +949,7 @@ static void stage_cost_derivatives(const oracle_problem_t* p, double dt, const s
     st->lu[j] += dt * p->u_weight[j] * (s->u[j] - p->u_ref[j]);
   }
   if (p->task_enabled) {
-    task_evaluate(s->q, ref, &st->te, 1);
+    task_evaluate(s->q, ref, &st->te, 1, p->task_enabled);
     task_add_gradient(&st->te, p->task_q_weight, dt, 1, st->lq);
   }
 }
@@ -938,12 +966,12 @@ static void stage_cost_hessian(const oracle_problem_t* p, double dt, stage_t* st
 /* CostFunction::computeStageCost / computeTerminalCost: sum of the components' values */
 static double task_stage_cost(const oracle_problem_t* p, double dt, const double* q, const double* ref) {
   task_eval_t te;
-  task_evaluate(q, ref, &te, 0);
+  task_evaluate(q, ref, &te, 0, p->task_enabled);
   return 0.5 * dt * task_weighted_sqnorm(&te, p->task_q_weight);
 }
 static double task_terminal_cost(const oracle_problem_t* p, const double* q, const double* ref) {
   task_eval_t te;
-  task_evaluate(q, ref, &te, 0);
+  task_evaluate(q, ref, &te, 0, p->task_enabled);
   return 0.5 * task_weighted_sqnorm(&te, p->task_qf_weight);
 }
 static double stage_cost(const oracle_problem_t* p, double dt, const split_solution_t* s) {
@@ -1442,7 +1470,7 @@ static void terminal_linearize(oracle_unocp_t* o, int with_hessian) {
   }
   task_eval_t te;
   if (p->task_enabled) {   /* TimeVaryingTaskSpace6DCost::computeTerminalCostDerivatives at t + T */
-    task_evaluate(s->q, o->task_ref + (size_t)o->N * 12, &te, 1);
+    task_evaluate(s->q, o->task_ref + (size_t)o->N * 12, &te, 1, p->task_enabled);
     task_add_gradient(&te, p->task_qf_weight, 1.0, 0, o->t_lq);
   }
   for (int j = 0; j < NV; ++j) {
@@ -1794,7 +1822,7 @@ void oracle_unparnmpc_init_backward_correction(oracle_unparnmpc_t* o, double t) 
   for (int j = 0; j < NV; ++j) Qqq[j * NV + j] += o->p.qf_weight[j];
   if (o->p.task_enabled) {
     task_eval_t te;
-    task_evaluate(o->s[o->N - 1].q, o->task_ref + (size_t)(o->N - 1) * 12, &te, 1);
+    task_evaluate(o->s[o->N - 1].q, o->task_ref + (size_t)(o->N - 1) * 12, &te, 1, o->p.task_enabled);
     task_add_hessian(&te, o->p.task_qf_weight, 1.0, 0, Qqq);
   }
   for (int i = 0; i < o->N; ++i) {

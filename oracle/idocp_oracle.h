@@ -38,7 +38,8 @@ typedef struct {
   double fraction_rate;       /* 0.995 */
   /* TimeVaryingTaskSpace6DCost (src/cost/time_varying_task_space_6d_cost.cpp) on the end
    * effector frame, reference = circle of examples/iiwa14/task_space_ocp.cpp:21-46.
-   * Disabled when task_enabled == 0. */
+   * Disabled when task_enabled == 0; task_enabled == 2 selects TaskSpace3DCost / TimeVaryingTaskSpace3DCost
+   * (src/cost/task_space_3d_cost.cpp): position error only, task_q_weight[0..2] = q_3d_weight. */
   int task_enabled;
   double task_q_weight[6], task_qf_weight[6];  /* [position xyz, rotation xyz] = the arguments of set_q_6d_weight /
                                                   set_qf_6d_weight (time_varying_task_space_6d_cost.cpp:43-58) */
@@ -118,6 +119,8 @@ void oracle_unparnmpc_batch_kkt(oracle_unparnmpc_t** os, int batch, double t, co
 void oracle_unocp_set_task_ref(oracle_unocp_t* o, const double* table);
 void oracle_unparnmpc_set_task_ref(oracle_unparnmpc_t* o, const double* table);
 void oracle_task_evaluate(const double* q, const double* ref12, double* diff6, double* JJ);
+/* kind = problem.task_enabled: 1 the 6D cost, 2 TaskSpace3DCost (diff_3d / J_3d in the first three entries / rows) */
+void oracle_task_evaluate_kind(const double* q, const double* ref12, int kind, double* diff6, double* JJ);
 void oracle_frame_kinematics(const double* q, double* oMf12, double* J);
 double oracle_canon_acos(double x);
 

@@ -331,6 +331,27 @@ class Batch:
         return out
 
 
+def task_space_3d_problem(N=30, T=1.5):
+    """TaskSpace3DCost / TimeVaryingTaskSpace3DCost (src/cost/task_space_3d_cost.cpp) on the task_space_ocp robot set-up:
+    position error of the end-effector frame, weights 1000 (task_enabled = 2)."""
+    p = task_space_problem(N, T)
+    p.task_enabled = 2
+    for k in range(3, 6):
+        p.task_q_weight[k] = 0.0
+        p.task_qf_weight[k] = 0.0
+    for i in range(7):          # a 3D position cost has rank 3 in q: a small posture weight keeps the stage Hessian definite
+        p.q_weight[i] = 0.1     # (UnParNMPC factorises the full 21 x 21 stage Hessian)
+        p.qf_weight[i] = 0.1
+    return p
+
+
+def task_evaluate_kind(q, ref12, kind):
+    q, ref12 = _vec(q), _vec(ref12)
+    diff, JJ = np.zeros(6), np.zeros((7, 6))
+    lib().oracle_task_evaluate_kind(_p(q), _p(ref12), int(kind), _p(diff), _p(JJ))
+    return diff, JJ.T.copy()
+
+
 def task_evaluate(q, ref12):
     """diff_6d = log6(SE3_ref^-1 oMf) [lin; ang] and JJ = Jlog6 * J_frame(LOCAL) as numpy (6, 7)."""
     q, ref12 = _vec(q), _vec(ref12)

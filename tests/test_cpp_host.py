@@ -248,3 +248,36 @@ def test_sharded_example_reproduces_golden_convergence():
     with open(os.path.join(GOLDEN, "unocp_golden.json")) as f:
         ref = json.load(f)["unocp_benchmark_reference_instance"]["kkt"]
     assert kkt == ref
+
+
+@pytest.mark.gpu
+def test_task_space_3d_cost_example_equals_the_oracle():
+    """TaskSpace3DCost (src/cost/task_space_3d_cost.cpp) through the C++ host classes (examples/iiwa14_batch.cpp `task3d`):
+    the KKT history equals the oracle's UnOCPSolver in its 3D mode digit for digit."""
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as O
+    O.build()
+    _build()
+    iters = 12
+    out = subprocess.run([EXE, "task3d", "unocp", "2", str(iters), "0"], capture_output=True, text=True, check=True).stdout
+    kkt = [float(x) for x in re.findall(r"KKT error(?: after iteration \d+)? = (\S+)", out)]
+    problem = O.task_space_problem(30, 1.5)
+    problem.task_enabled = 2
+    for k in range(3, 6):
+        problem.task_q_weight[k] = problem.task_qf_weight[k] = 0.0
+    q0, v0 = np.array([0, np.pi / 2, 0, np.pi / 2, 0, np.pi / 2, 0]), np.zeros(7)
+    row = np.array([1.0, 0, 0, 0, 1.0, 0, 0, 0, 1.0, 0.546, 0.1, 0.76])
+    s = O.UnOCPSolver(problem)
+    s.set_solution("q", q0)
+    s.set_solution("v", v0)
+    s.set_task_ref(O.task_ref_table(lambda t: row, 0.0, problem.T, problem.N, "unocp"))
+    s.compute_kkt_residual(0.0, q0, v0)
+    ref = [s.kkt_error()]
+    for _ in range(iters):
+        s.update_solution(0.0, q0, v0, False)
+        s.compute_kkt_residual(0.0, q0, v0)
+        ref.append(s.kkt_error())
+    assert kkt == ref
+    assert ref[-1] < 1e-2 * ref[0]

@@ -27,17 +27,24 @@ RICCATI = ["load FbKKT", "A^T P (6x6 part)", "A^T P, B^T P", "F^T P F (6x6 part)
            "gain K, k (+ Schur)", "P = Q - K^T G K", "symmetrise, sq, sv", "constrained tail", "store FbRic"]
 
 
+VARIANT_SIMT = os.path.join(ROOT, "build", "libidocp_b200_phase_simt.so")   # dense products on the SIMT path (A/B of the DMMA form)
+
+
 def build():
     import __graft_entry__ as g
     os.makedirs(os.path.dirname(VARIANT), exist_ok=True)
-    cmd = ["/usr/local/cuda/bin/nvcc"] + g.NVCC_FLAGS + ["-DFB_PHASE_CLOCKS", "-o", VARIANT, os.path.join(g.CSRC, "capi.cu")]
-    subprocess.run(cmd, cwd=g.CSRC, check=True, capture_output=True)
+    for out, extra in ((VARIANT, []), (VARIANT_SIMT, ["-DIDOCP_FB_MM_SIMT"])):
+        cmd = ["/usr/local/cuda/bin/nvcc"] + g.NVCC_FLAGS + ["-DFB_PHASE_CLOCKS"] + extra + ["-o", out, os.path.join(g.CSRC, "capi.cu")]
+        subprocess.run(cmd, cwd=g.CSRC, check=True, capture_output=True)
 
 
 def main():
+    global VARIANT
     if len(sys.argv) > 1 and sys.argv[1] == "build":
         build()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "simt":
+        VARIANT = VARIANT_SIMT
     import anymal_problems as ap
     import fb_py
     import idocp_b200 as I
