@@ -52,6 +52,9 @@ KERNEL_ALGO_DOUBLES_PER_STAGE = {
     # sweeps multiply with (14x14 + 21x14 + 14x14 + 21x14 = 980) + s_new 35 out
     "parnmpc_coarse": 231 + 35 + 105 + 35 + 980 + 35,
 }
+# UnParNMPC: k_expand<PARNMPC> reads no Riccati data (the costate direction comes from the correction sweeps):
+# expansion 147 + (dq,dv,da) 21 + (q,v,u) 21 + slack/dual 84 in; (du,dbeta) 14 out
+KERNEL_ALGO_DOUBLES_PER_STAGE_PARNMPC = dict(KERNEL_ALGO_DOUBLES_PER_STAGE, expand=147 + 21 + 21 + 84 + 14)
 
 
 # ncu evidence is PARSED, not typed in: tools/ncu_capture.sh (run under gpurun) writes profiles/kernel_counters_<workload>.json
@@ -685,10 +688,11 @@ def run_iiwa(args, rank, local_rank, world):
     counters, counters_src = load_kernel_counters(args.workload)
     # dominant kernel by measured device time
     stages = B * N
+    algo = KERNEL_ALGO_DOUBLES_PER_STAGE if unocp else KERNEL_ALGO_DOUBLES_PER_STAGE_PARNMPC
     kern = {}
     for name, (ms, calls) in profile.items():
-        if calls and name in KERNEL_ALGO_DOUBLES_PER_STAGE:
-            kern[name] = kernel_roofline(name, ms / calls, KERNEL_ALGO_DOUBLES_PER_STAGE[name] * 8.0 * stages, counters,
+        if calls and name in algo:
+            kern[name] = kernel_roofline(name, ms / calls, algo[name] * 8.0 * stages, counters,
                                          B == w["batch"], hbm_peak, fp64_sus)
             kern[name]["share"] = ms
         elif calls:
@@ -700,7 +704,7 @@ def run_iiwa(args, rank, local_rank, world):
     dom = max(ranked, key=lambda n: kern[n]["ms_per_launch"]) if ranked else None
     roofline = None
     if dom:
-        roofline = roofline_object(dom, kern, KERNEL_ALGO_DOUBLES_PER_STAGE[dom] * 8.0 * stages, hbm_peak, peak_src, fp64_sus, fp64_src,
+        roofline = roofline_object(dom, kern, algo[dom] * 8.0 * stages, hbm_peak, peak_src, fp64_sus, fp64_src,
                                    counters_src,
                                    "per kernel: frac_hbm = algorithmic bytes / time / measured copy bandwidth, frac_fp64 = FP64 thread "
                                    "instructions counted by ncu for one launch at this batch (DFMA = 2 flop) / time / measured DFMA "
@@ -734,7 +738,8 @@ def run_iiwa(args, rank, local_rank, world):
         "roofline": roofline,
         "clocks": sampler.summary() if rank == 0 else None,
         "health": {"kkt_max": float(np.nanmax(kkt)), "kkt_median": float(np.nanmedian(kkt)), "kkt_nan": int(np.isnan(kkt).sum()),
-                   "status_nonzero": int((status != 0).sum())},
+                   "status_nonzero": int((status != 0).sum()), "converged_kkt_below_1e-6": int((kkt < 1e-6).sum()),
+                   "iterations_run": int(args.warmup + 2 * args.steps + 3 + conv_steps)},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cval, cores, sample, _ = oracle_throughput(args.cpu_seconds, args.workload)

@@ -119,5 +119,18 @@ int main(int argc, char* argv[]) {
   idocp::ocpbenchmarker::CPUTime(ocp_solver, t, q, v, 20, line_search);
   const auto qs = ocp_solver.getSolution("q");
   std::cout << "base x at the end of the horizon: " << qs.back()[0] << std::endl;
+  if (argc > 2 && std::string(argv[2]) == "mpc") {
+    // a few control ticks of the batch of MPC loops (idocp_b200::BatchedMPC): the measured state stays at the standing
+    // posture here; the first phase is dropped once its switching time (0.5) has passed
+    idocp::BatchedMPC mpc(ocp_solver, 2);
+    std::vector<double> qb(static_cast<size_t>(batch) * robot.dimq()), vb(static_cast<size_t>(batch) * robot.dimv(), 0.0),
+        u0(static_cast<size_t>(batch) * robot.dimu());
+    for (int b = 0; b < batch; ++b)
+      for (int j = 0; j < robot.dimq(); ++j) qb[static_cast<size_t>(b) * robot.dimq() + j] = q[j];
+    for (const double tick : {0.0, 0.2, 0.45, 0.52, 0.6}) {
+      mpc.tick(tick, qb.data(), vb.data(), u0.data());
+      std::cout << "MPC tick t = " << tick << ": u0[0] = " << u0[0] << ", popped phases = " << mpc.numPoppedPhases() << std::endl;
+    }
+  }
   return 0;
 }

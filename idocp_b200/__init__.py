@@ -11,3 +11,4 @@ __version__ = "0.1"
 from .hybrid import ContactSequence, OCPDiscretizer  # noqa: F401,E402
 from .ocp_solver import OCPSolver  # noqa: F401,E402
 from .capi import FbProblem  # noqa: F401,E402
+from .mpc import BatchedMPC  # noqa: F401,E402

@@ -17,7 +17,6 @@
 // [slot][instance]: a CTA reads and writes contiguous, aligned runs.
 #pragma once
 #include "fb_math.cuh"
-#include "warp_llt.cuh"
 
 namespace idocp_b200 {
 
@@ -1331,30 +1330,67 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
   }
 }
 
-// X = A^-1 for a small symmetric positive definite A (n x n, lower triangle of A[i*lda + j] read) by ONE warp (all 32 lanes
-// call it): warp_llt.cuh -- right-looking Cholesky with lane = row, then lane c substitutes the unit vector e_c (forward,
-// then backward in descending order = fb_llt / fb_llt_solve of the oracle, bit for bit).  L, LT: n x FB_WLD scratch each
-// (16-byte aligned), rd: n pivots' reciprocal square roots.  The CTA-wide owner-per-element sweep this replaces spent ~14 k
-// warp instructions per 18 x 18 inverse on index bookkeeping and 36 block barriers (LLT(M) was 38 % of k_fb_condense,
-// profiles/r2i_fb_phase_clocks.json); one warp needs ~2 k.  The other warps of the CTA wait at the caller's barrier while
-// the other resident CTAs use the SM.
-template <int n, int ld>
-__device__ __forceinline__ void fb_inverse_warp(const double* A, int lda, double* L, double* LT, double* rd, double* X, int ldx,
-                                                int* info, int code) {
+// Cholesky factor and inverse of a small symmetric positive definite A (n x n, lower triangle of A[i*lda + j] read) by ONE
+// warp (all 32 lanes call it), in ROLLED loops over shared memory:
+//   factor: right-looking, lane = row; the trailing matrix lives in the scratch W (row-major, odd leading dimension ldw:
+//           conflict-free), column k of the factor is published as L[k*ldl + i] (the oracle's layout) and every element
+//           receives its updates a_ic -= L_ik L_ck in ascending k = fb_llt of the oracle bit for bit;
+//   inverse: lane c substitutes the unit vector e_c in place in X (X[r*ldx + c]), forward then backward in descending
+//           order = fb_llt_solve.
+// History: the CTA-wide owner-per-element sweep spent ~14 k warp instructions per 18 x 18 inverse on index bookkeeping and
+// 36 block barriers (LLT(M) = 28 k cycles, 38 % of k_fb_condense); a fully unrolled register version (warp_llt.cuh, as in
+// the ParNMPC inversion) was SLOWER here, 47 k cycles: one warp per CTA runs ~2.5 k straight-line instructions exactly once
+// per stage, so every fetch misses the instruction cache (profiles/r2j_fb_phase_clocks.json).  Rolled loops keep the code
+// at a few dozen instructions.  The other warps of the CTA wait at the caller's barrier while the other resident CTAs use
+// the SM.
+__device__ __forceinline__ void fb_llt_warp(const double* A, int lda, int n, double* L, int ldl, double* rd, double* W, int ldw,
+                                            int* info, int code) {
   const int wl = threadIdx.x & 31;
-  const int row = wl < n ? wl : n - 1;
-  double a[n];
-#pragma unroll
-  for (int c = 0; c < n; ++c) a[c] = A[row * lda + (c <= row ? c : row)];   // entries c > row are never used
+  if (wl < n)
+    for (int c = 0; c <= wl; ++c) W[wl * ldw + c] = A[wl * lda + c];
   __syncwarp();
-  const int fail = warp_llt_rows<n, ld>(a, L, LT, rd, wl);
+  int fail = 0;
+  for (int k = 0; k < n; ++k) {
+    const double piv = W[k * ldw + k];
+    if (!canon_pivot_ok(piv) && fail == 0) fail = k + 1;
+    const double r = canon_rsqrt(piv);
+    double lk = 0.0;
+    if (wl >= k && wl < n) {
+      lk = W[wl * ldw + k] * r;
+      L[k * ldl + wl] = lk;
+    }
+    if (wl == k) rd[k] = r;
+    __syncwarp();
+    if (wl > k && wl < n) {
+      double* row = W + wl * ldw;
+      const double* col = L + k * ldl;
+#pragma unroll 4
+      for (int c = k + 1; c <= wl; ++c) row[c] = fma(-lk, col[c], row[c]);
+    }
+    __syncwarp();
+  }
   if (fail && wl == 0 && *info == 0) *info = code + fail;
-  __syncwarp();
-  double y[n];
-  warp_llt_solve_unit<n, ld>(L, LT, rd, wl < n ? wl : 0, y);
+}
+__device__ __forceinline__ void fb_inverse_warp(const double* A, int lda, int n, double* L, int ldl, double* rd, double* W, int ldw,
+                                                double* X, int ldx, int* info, int code) {
+  fb_llt_warp(A, lda, n, L, ldl, rd, W, ldw, info, code);
+  const int wl = threadIdx.x & 31;
   if (wl < n) {
-#pragma unroll
-    for (int r = 0; r < n; ++r) X[r * ldx + wl] = y[r];
+    double* x = X + wl;
+    for (int r = 0; r < n; ++r) x[r * ldx] = (r == wl) ? 1.0 : 0.0;
+    for (int j = 0; j < n; ++j) {
+      const double yj = x[j * ldx] * rd[j];
+      x[j * ldx] = yj;
+      const double* col = L + j * ldl;
+#pragma unroll 4
+      for (int i = j + 1; i < n; ++i) x[i * ldx] = fma(-col[i], yj, x[i * ldx]);
+    }
+    for (int j = n - 1; j >= 0; --j) {
+      const double yj = x[j * ldx] * rd[j];
+      x[j * ldx] = yj;
+#pragma unroll 4
+      for (int i = 0; i < j; ++i) x[i * ldx] = fma(-L[i * ldl + j], yj, x[i * ldx]);
+    }
   }
 }
 
@@ -1387,9 +1423,7 @@ struct FbDenseWork {
   int info;
 };
 
-static_assert(offsetof(FbDenseWork, s) % 16 == 0 && (FB_NV * FB_NV + FB_NV) % 2 == 0 && (2 * FB_NV * FB_NV + FB_NV) % 2 == 0 &&
-              (2 * FB_NV * FB_NV + FB_NV + FB_MAXF * FB_NV + FB_MAXF * FB_MAXF) % 2 == 0 && FB_MAXF * FB_NV + FB_MAXF * FB_MAXF >= FB_NV * FB_NV,
-              "warp_llt.cuh reads its broadcast operands two doubles at a time: L, JMi (L^T scratch) and Ls sit at even offsets");
+static_assert(FB_MAXF * FB_NV + FB_MAXF * FB_MAXF >= FB_NV * (FB_NV + 1), "the JMi / Sm scratch holds the 18 x 19 trailing matrix of LLT(M)");
 __global__ void __launch_bounds__(128, 5) k_fb_condense(FbArrays A, const FbLin* lin) {
   IDOCP_DYN_SMEM(FbDenseWork, wp);
   FbDenseWork& w = *wp;
@@ -1429,8 +1463,8 @@ __global__ void __launch_bounds__(128, 5) k_fb_condense(FbArrays A, const FbLin*
   // ---- MJtJinv = [[M, J^T], [J, 0]]^-1 by dense Cholesky ----
   {
     const int n = NV, ld = NVF;
-    // Minv = M^-1: warp 0 (L in s.f.L, L^T in the JMi / Sm scratch that is not live yet)
-    if (tid < 32) fb_inverse_warp<FB_NV, FB_NV>(w.Mm, n, w.s.f.L, w.s.f.JMi, w.s.f.rd, w.s.f.Minv, n, &w.info, 0);
+    // Minv = M^-1: warp 0 (factor in s.f.L, trailing matrix in the JMi / Sm scratch that is not live yet)
+    if (tid < 32) fb_inverse_warp(w.Mm, n, n, w.s.f.L, n, w.s.f.rd, w.s.f.JMi, n + 1, w.s.f.Minv, n, &w.info, 0);
     __syncthreads();
     FB_PHASE(0, 1);
     FB_PHASE(0, 2);
@@ -1440,15 +1474,8 @@ __global__ void __launch_bounds__(128, 5) k_fb_condense(FbArrays A, const FbLin*
     __syncthreads();
     FB_PHASE(0, 3);
     if (dimf > 0) {
-      // Si = S^-1: warp 0 again (dimf = 3 contacts' worth of rows each; L^T in the scratch of M's factor, dead by now)
-      if (tid < 32) {
-        switch (dimf) {
-          case 3: fb_inverse_warp<3, FB_MAXF>(w.s.f.Sm, dimf, w.s.f.Ls, w.s.f.L, w.s.f.rds, w.s.f.Si, dimf, &w.info, 100); break;
-          case 6: fb_inverse_warp<6, FB_MAXF>(w.s.f.Sm, dimf, w.s.f.Ls, w.s.f.L, w.s.f.rds, w.s.f.Si, dimf, &w.info, 100); break;
-          case 9: fb_inverse_warp<9, FB_MAXF>(w.s.f.Sm, dimf, w.s.f.Ls, w.s.f.L, w.s.f.rds, w.s.f.Si, dimf, &w.info, 100); break;
-          default: fb_inverse_warp<12, FB_MAXF>(w.s.f.Sm, dimf, w.s.f.Ls, w.s.f.L, w.s.f.rds, w.s.f.Si, dimf, &w.info, 100); break;
-        }
-      }
+      // Si = S^-1: warp 0 again (trailing matrix in the scratch of M's factor, dead by now)
+      if (tid < 32) fb_inverse_warp(w.s.f.Sm, dimf, dimf, w.s.f.Ls, dimf, w.s.f.rds, w.s.f.L, dimf + 1, w.s.f.Si, dimf, &w.info, 100);
       __syncthreads();
     }
     FB_PHASE(0, 4);
@@ -1601,7 +1628,7 @@ struct FbRicWork {
   int info;
 };
 
-static_assert(offsetof(FbRicWork, L) % 16 == 0, "warp_llt.cuh reads the factor two doubles at a time");
+static_assert(2 * FB_NU * FB_NU >= FB_NU * (FB_NU + 1), "Ginv / DGinv hold the 12 x 13 trailing matrix of LLT(G)");
 __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
   IDOCP_DYN_SMEM(FbRicWork, wp);
   FbRicWork& w = *wp;
@@ -1704,16 +1731,8 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
     FB_PHASE(1, 4);
     const double* Qxu = w.Qxu;   // 36 x 12, leading dimension NU
     if (!impulse) {
-      // LLT(G), G = Quu (12 x 12): warp 0, lane = row (warp_llt.cuh; the factor only, the solves below read L and rd)
-      if (tid < 32) {
-        const int row = tid < NU ? tid : NU - 1;
-        double a[FB_NU];
-#pragma unroll
-        for (int c = 0; c < FB_NU; ++c) a[c] = w.Quu[row * NU + (c <= row ? c : row)];
-        __syncwarp();
-        const int fail = warp_llt_rows<FB_NU, FB_NU>(a, w.L, nullptr, w.rd, tid);
-        if (fail && tid == 0 && w.info == 0) w.info = 200 + fail;
-      }
+      // LLT(G), G = Quu (12 x 12): warp 0 (trailing matrix in the Ginv / DGinv scratch, written only after the factor)
+      if (tid < 32) fb_llt_warp(w.Quu, NU, NU, w.L, NU, w.rd, w.Ginv, NU + 1, &w.info, 200);
       __syncthreads();
       FB_PHASE(1, 5);
       if (dimi == 0) {

@@ -401,6 +401,26 @@ class OCPSolver {
   }
   void sync() { detail::check(idocp_b200_fb_sync(h_.get())); }
   idocp_b200_fb_solver* handle() { return h_.get(); }
+  // time of the first scheduled discrete event (impulse or lift); false when the schedule has none
+  bool firstEventTime(double& time) const {
+    int phases = 0, impulses = 0, lifts = 0;
+    detail::check(idocp_b200_contact_sequence_counts(cs_.get(), &phases, &impulses, &lifts));
+    bool any = false;
+    if (impulses > 0) {
+      int act[4]; double pts[12], ti = 0.0;
+      detail::check(idocp_b200_contact_sequence_get_impulse(cs_.get(), 0, act, pts, &ti));
+      time = ti; any = true;
+    }
+    if (lifts > 0) {
+      double tl = 0.0;
+      detail::check(idocp_b200_contact_sequence_get_lift_time(cs_.get(), 0, &tl));
+      if (!any || tl < time) time = tl;
+      any = true;
+    }
+    return any;
+  }
+  // first control input of every instance: out [batch][12]
+  void getFirstControlInput(double* out) { detail::check(idocp_b200_fb_get(h_.get(), 0, "u", out)); }
 
  private:
   static void pack(const ContactStatus& s, std::vector<int>& a, std::vector<double>& pts) {
@@ -454,6 +474,32 @@ class OCPSolver {
   std::vector<int> kind_, index_, dimf_;
   std::vector<double> t_, q_, v_;
   std::vector<std::array<int, 4>> active_;
+};
+
+// One control tick of a BATCH of MPC loops around OCPSolver (Python twin: idocp_b200/mpc.py).  idocp has no
+// MPC class: its consumers call, every control period, popFrontContactStatus() once the first switching time has passed
+// (ocp_solver.cpp:174-194), updateSolution(t, q, v) a fixed number of times -- the iterate of the previous tick stays in
+// place as the warm start -- and read getSolution(0).u.  tick() is that sequence for all instances at once.
+class BatchedMPC {
+ public:
+  explicit BatchedMPC(OCPSolver& solver, const int iterations = 1, const bool line_search = false)
+      : solver_(solver), iterations_(iterations), line_search_(line_search) {}
+  // q [batch][19], v [batch][18] measured states; u0 [batch][12] receives the first control inputs
+  void tick(const double t, const double* q, const double* v, double* u0) {
+    double te = 0.0;
+    while (solver_.firstEventTime(te) && te <= t) {   // an event before t makes the discretisation ill-defined
+      solver_.popFrontContactStatus();
+      ++popped_;
+    }
+    for (int it = 0; it < iterations_; ++it) solver_.updateSolution(t, q, v, line_search_);
+    solver_.getFirstControlInput(u0);
+  }
+  int numPoppedPhases() const { return popped_; }
+ private:
+  OCPSolver& solver_;
+  int iterations_;
+  bool line_search_;
+  int popped_ = 0;
 };
 
 }  // namespace idocp_b200

@@ -197,3 +197,39 @@ def run_event_entering_horizon_keeps_constraints(lib, fb, batch=1):
             assert np.array_equal(np.asarray(solver.get(e - 1, "slack")), fb.batch_get(oracles, e - 1, "slack"))
         assert compare_batch(oracles, solver, fb, SOL + DIR) == [], t
     assert seen_new
+
+
+def run_mpc_ticks(lib, fb, batch, ticks=(0.0, 0.2, 0.45, 0.52, 0.6, 0.8), iterations=2):
+    """idocp_b200.BatchedMPC: >= 5 control ticks of a batch of MPC loops -- two Newton iterations per tick
+    from the previous tick's solution, the plant moves to the second stage of the solution, the first phase is popped
+    when its switching time has passed -- against the oracle driven with the same explicit calls, every instance bit for
+    bit (first control input, feedback gain, the whole iterate)."""
+    import idocp_b200 as I
+    pr = ap.TrottingProblem()
+    q, v = anymal_states(pr, batch, 20240004)
+    solver = ap.make_product_solver(pr, lib, fb, batch=batch, q0=q, v0=v)
+    oracles = [pr.make_oracle(fb, q0=q[b], v0=v[b]) for b in range(batch)]
+    mpc = I.BatchedMPC(solver, iterations=iterations)
+    pops = 0
+    for t in ticks:
+        u0, (Kq, Kv) = mpc.tick(t, q, v, with_gain=True)
+        cs = oracles[0].cs
+        while cs.counts()[1] + cs.counts()[2] > 0:
+            first = min(([cs.impulse(0)[2]] if cs.counts()[1] else []) + ([cs.lift_time(0)] if cs.counts()[2] else []))
+            if first > t:
+                break
+            for o in oracles:
+                o.cs.pop_front()
+            pops += 1
+        for _ in range(iterations):
+            for o in oracles:
+                pr.set_references(o, t)
+            rcs = [o.update_solution(t, q[b], v[b]) for b, o in enumerate(oracles)]
+            assert all(rc == 0 for rc in rcs), t
+        assert chain_signature(solver.chain()) == chain_signature(oracles[0].chain()), t
+        assert np.array_equal(u0, fb.batch_get(oracles, 0, "u")), t
+        K = fb.batch_get(oracles, 0, "K").reshape(batch, 12, 36)
+        assert np.array_equal(Kq, K[:, :, :18]) and np.array_equal(Kv, K[:, :, 18:]), t
+        assert compare_batch(oracles, solver, fb, SOL) == [], t
+        q, v = fb.batch_get(oracles, 1, "q"), fb.batch_get(oracles, 1, "v")
+    assert mpc.popped == pops and pops >= 1

@@ -281,3 +281,14 @@ def test_task_space_3d_cost_example_equals_the_oracle():
         ref.append(s.kkt_error())
     assert kkt == ref
     assert ref[-1] < 1e-2 * ref[0]
+
+
+@pytest.mark.gpu
+def test_cpp_batched_mpc_ticks():
+    """idocp_b200::BatchedMPC (include/idocp_b200/ocp_solver.hpp) through examples/anymal_trotting.cpp: five control ticks, the
+    first phase popped when its switching time has passed, finite control inputs."""
+    _build_anymal()
+    out = subprocess.run([ANYMAL_EXE, "2", "mpc"], capture_output=True, text=True, check=True).stdout
+    ticks = re.findall(r"MPC tick t = (\S+): u0\[0\] = (\S+), popped phases = (\d+)", out)
+    assert [int(p) for _, _, p in ticks] == [0, 0, 0, 1, 1]
+    assert all(abs(float(u)) < 1e4 for _, u, _ in ticks)

@@ -168,3 +168,8 @@ def test_event_before_t_is_an_error_emu(fb, emu_lib):
 def test_event_entering_horizon_keeps_constraints_emu(fb, emu_lib):
     import fb_scenarios
     fb_scenarios.run_event_entering_horizon_keeps_constraints(emu_lib, fb)
+
+
+def test_batched_mpc_ticks_emu(fb, emu_lib):
+    import fb_scenarios
+    fb_scenarios.run_mpc_ticks(emu_lib, fb, batch=2, ticks=(0.0, 0.3, 0.52), iterations=1)

@@ -62,3 +62,8 @@ def test_event_before_t_is_an_error(fb, gpu_lib):
 def test_event_entering_horizon_keeps_constraints(fb, gpu_lib):
     import fb_scenarios
     fb_scenarios.run_event_entering_horizon_keeps_constraints(gpu_lib, fb, batch=8)
+
+
+def test_batched_mpc_ticks(fb, gpu_lib):
+    import fb_scenarios
+    fb_scenarios.run_mpc_ticks(gpu_lib, fb, batch=16)
