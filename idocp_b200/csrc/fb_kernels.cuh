@@ -17,6 +17,7 @@
 // [slot][instance]: a CTA reads and writes contiguous, aligned runs.
 #pragma once
 #include "fb_math.cuh"
+#include "warp_llt.cuh"
 
 namespace idocp_b200 {
 
@@ -1330,70 +1331,6 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
   }
 }
 
-// Cholesky factor and inverse of a small symmetric positive definite A (n x n, lower triangle of A[i*lda + j] read) by ONE
-// warp (all 32 lanes call it), in ROLLED loops over shared memory:
-//   factor: right-looking, lane = row; the trailing matrix lives in the scratch W (row-major, odd leading dimension ldw:
-//           conflict-free), column k of the factor is published as L[k*ldl + i] (the oracle's layout) and every element
-//           receives its updates a_ic -= L_ik L_ck in ascending k = fb_llt of the oracle bit for bit;
-//   inverse: lane c substitutes the unit vector e_c in place in X (X[r*ldx + c]), forward then backward in descending
-//           order = fb_llt_solve.
-// History: the CTA-wide owner-per-element sweep spent ~14 k warp instructions per 18 x 18 inverse on index bookkeeping and
-// 36 block barriers (LLT(M) = 28 k cycles, 38 % of k_fb_condense); a fully unrolled register version (warp_llt.cuh, as in
-// the ParNMPC inversion) was SLOWER here, 47 k cycles: one warp per CTA runs ~2.5 k straight-line instructions exactly once
-// per stage, so every fetch misses the instruction cache (profiles/r2j_fb_phase_clocks.json).  Rolled loops keep the code
-// at a few dozen instructions.  The other warps of the CTA wait at the caller's barrier while the other resident CTAs use
-// the SM.
-__device__ __forceinline__ void fb_llt_warp(const double* A, int lda, int n, double* L, int ldl, double* rd, double* W, int ldw,
-                                            int* info, int code) {
-  const int wl = threadIdx.x & 31;
-  if (wl < n)
-    for (int c = 0; c <= wl; ++c) W[wl * ldw + c] = A[wl * lda + c];
-  __syncwarp();
-  int fail = 0;
-  for (int k = 0; k < n; ++k) {
-    const double piv = W[k * ldw + k];
-    if (!canon_pivot_ok(piv) && fail == 0) fail = k + 1;
-    const double r = canon_rsqrt(piv);
-    double lk = 0.0;
-    if (wl >= k && wl < n) {
-      lk = W[wl * ldw + k] * r;
-      L[k * ldl + wl] = lk;
-    }
-    if (wl == k) rd[k] = r;
-    __syncwarp();
-    if (wl > k && wl < n) {
-      double* row = W + wl * ldw;
-      const double* col = L + k * ldl;
-#pragma unroll 4
-      for (int c = k + 1; c <= wl; ++c) row[c] = fma(-lk, col[c], row[c]);
-    }
-    __syncwarp();
-  }
-  if (fail && wl == 0 && *info == 0) *info = code + fail;
-}
-__device__ __forceinline__ void fb_inverse_warp(const double* A, int lda, int n, double* L, int ldl, double* rd, double* W, int ldw,
-                                                double* X, int ldx, int* info, int code) {
-  fb_llt_warp(A, lda, n, L, ldl, rd, W, ldw, info, code);
-  const int wl = threadIdx.x & 31;
-  if (wl < n) {
-    double* x = X + wl;
-    for (int r = 0; r < n; ++r) x[r * ldx] = (r == wl) ? 1.0 : 0.0;
-    for (int j = 0; j < n; ++j) {
-      const double yj = x[j * ldx] * rd[j];
-      x[j * ldx] = yj;
-      const double* col = L + j * ldl;
-#pragma unroll 4
-      for (int i = j + 1; i < n; ++i) x[i * ldx] = fma(-col[i], yj, x[i * ldx]);
-    }
-    for (int j = n - 1; j >= 0; --j) {
-      const double yj = x[j * ldx] * rd[j];
-      x[j * ldx] = yj;
-#pragma unroll 4
-      for (int i = 0; i < j; ++i) x[i * ldx] = fma(-L[i * ldl + j], yj, x[i * ldx]);
-    }
-  }
-}
-
 // =====================================================================================================
 // K1b: dense condensing of one stage, one CTA (128 threads) per (instance, stage)
 //   computeMJtJinv (robot.hxx:576-615), condenseContactDynamics (contact_dynamics.hxx:105-158) /
@@ -1463,9 +1400,13 @@ __global__ void __launch_bounds__(128, 5) k_fb_condense(FbArrays A, const FbLin*
   // ---- MJtJinv = [[M, J^T], [J, 0]]^-1 by dense Cholesky ----
   {
     const int n = NV, ld = NVF;
-    // Minv = M^-1: warp 0 (factor in s.f.L, trailing matrix in the JMi / Sm scratch that is not live yet)
-    if (tid < 32) fb_inverse_warp(w.Mm, n, n, w.s.f.L, n, w.s.f.rd, w.s.f.JMi, n + 1, w.s.f.Minv, n, &w.info, 0);
+    // Minv = M^-1 by the whole CTA (owner-per-element sweep, fb_llt_factor_solve_cta).  Two one-warp forms were measured
+    // and are slower for this 18 x 18 inverse: fully unrolled in registers (warp_llt.cuh) 47 k cycles, rolled loops over
+    // shared memory (fb_inverse_warp) 44 k, against 28 k here (profiles/r2j / r2k_fb_phase_clocks.json): one warp per CTA
+    // leaves the SM with five active warps
+    FB_FOR(x, n * n) { const int r = x / n; w.s.f.Minv[x] = (x - r * n == r) ? 1.0 : 0.0; }
     __syncthreads();
+    fb_llt_factor_solve_cta<2, 3>(w.Mm, n, n, w.s.f.L, n, w.s.f.rd, w.s.f.Minv, n, n, &w.info, 0);
     FB_PHASE(0, 1);
     FB_PHASE(0, 2);
     fb_mm<FBM_SET>(dimf, n, n, w.dCda, n, 1, w.s.f.Minv, n, 1, w.s.f.JMi, n);
@@ -1474,9 +1415,9 @@ __global__ void __launch_bounds__(128, 5) k_fb_condense(FbArrays A, const FbLin*
     __syncthreads();
     FB_PHASE(0, 3);
     if (dimf > 0) {
-      // Si = S^-1: warp 0 again (trailing matrix in the scratch of M's factor, dead by now)
-      if (tid < 32) fb_inverse_warp(w.s.f.Sm, dimf, dimf, w.s.f.Ls, dimf, w.s.f.rds, w.s.f.L, dimf + 1, w.s.f.Si, dimf, &w.info, 100);
+      FB_FOR(x, dimf * dimf) { const int r = x / dimf; w.s.f.Si[x] = (x - r * dimf == r) ? 1.0 : 0.0; }
       __syncthreads();
+      fb_llt_factor_solve_cta<1, 2>(w.s.f.Sm, dimf, dimf, w.s.f.Ls, dimf, w.s.f.rds, w.s.f.Si, dimf, dimf, &w.info, 100);
     }
     FB_PHASE(0, 4);
     FB_FOR(x, dimf * dimf) { const int r = x / dimf, c = x - r * dimf; w.MJtJinv[(n + r) * ld + n + c] = -w.s.f.Si[x]; }
@@ -1628,7 +1569,7 @@ struct FbRicWork {
   int info;
 };
 
-static_assert(2 * FB_NU * FB_NU >= FB_NU * (FB_NU + 1), "Ginv / DGinv hold the 12 x 13 trailing matrix of LLT(G)");
+static_assert(offsetof(FbRicWork, L) % 16 == 0, "warp_llt.cuh reads the factor two doubles at a time");
 __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
   IDOCP_DYN_SMEM(FbRicWork, wp);
   FbRicWork& w = *wp;
@@ -1731,8 +1672,17 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
     FB_PHASE(1, 4);
     const double* Qxu = w.Qxu;   // 36 x 12, leading dimension NU
     if (!impulse) {
-      // LLT(G), G = Quu (12 x 12): warp 0 (trailing matrix in the Ginv / DGinv scratch, written only after the factor)
-      if (tid < 32) fb_llt_warp(w.Quu, NU, NU, w.L, NU, w.rd, w.Ginv, NU + 1, &w.info, 200);
+      // LLT(G), G = Quu (12 x 12), factor only: warp 0, lane = row, rows in registers (warp_llt.cuh).  Measured on the whole
+      // kernel: 6.70 ms CTA-wide (fb_llt_cta), 6.05 ms this form, 7.28 ms the rolled one-warp loop (fb_llt_warp)
+      if (tid < 32) {
+        const int row = tid < NU ? tid : NU - 1;
+        double a[FB_NU];
+#pragma unroll
+        for (int c = 0; c < FB_NU; ++c) a[c] = w.Quu[row * NU + (c <= row ? c : row)];
+        __syncwarp();
+        const int fail = warp_llt_rows<FB_NU, FB_NU>(a, w.L, nullptr, w.rd, tid);
+        if (fail && tid == 0 && w.info == 0) w.info = 200 + fail;
+      }
       __syncthreads();
       FB_PHASE(1, 5);
       if (dimi == 0) {
