@@ -1,0 +1,2 @@
+// forwarding header: idocp/unocp/unocp_solver.hpp -> idocp_b200 (see ../../idocp_b200_compat.hpp)
+#include "../../idocp_b200_compat.hpp"

@@ -1,0 +1,2 @@
+// forwarding header: idocp/utils/ocp_benchmarker.hpp -> idocp_b200 (see ../../idocp_b200_compat.hpp)
+#include "../../idocp_b200_compat.hpp"

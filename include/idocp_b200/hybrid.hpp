@@ -65,6 +65,12 @@ class ContactStatus {
     require(contact_points.size() == points_.size(), "contact_points.size()");
     points_ = contact_points;
   }
+  // the reference's signature takes std::vector<Eigen::Vector3d>: any 3-vector type with operator[]
+  template <typename Vector3>
+  void setContactPoints(const std::vector<Vector3>& contact_points) {
+    require(contact_points.size() == points_.size(), "contact_points.size()");
+    for (size_t i = 0; i < points_.size(); ++i) points_[i] = Point3{contact_points[i][0], contact_points[i][1], contact_points[i][2]};
+  }
   const Point3& contactPoint(const int contact_index) const { return points_.at(contact_index); }
   const std::vector<Point3>& contactPoints() const { return points_; }
 

@@ -47,10 +47,34 @@ class VectorXd {
   int size() const { return static_cast<int>(d_.size()); }
   double& operator[](int i) { return d_[i]; }
   double operator[](int i) const { return d_[i]; }
+  double& operator()(int i) { return d_[i]; }
+  double operator()(int i) const { return d_[i]; }
   double& coeffRef(int i) { return d_[i]; }
   double coeff(int i) const { return d_[i]; }
   const double* data() const { return d_.data(); }
   double* data() { return d_.data(); }
+  // Eigen's comma initialiser:  v << 1, 2, 3;
+  struct CommaInitializer {
+    double* p;
+    double* end;
+    CommaInitializer& operator,(double x) {
+      if (p == end) { std::cerr << "invalid size: too many coefficients in the comma initialiser\n"; std::exit(EXIT_FAILURE); }
+      *p++ = x;
+      return *this;
+    }
+    // a nested vector (Eigen block syntax:  q << 0, 0, 1, quat, joints;)
+    CommaInitializer& operator,(const VectorXd& v) {
+      for (int i = 0; i < v.size(); ++i) (*this), v[i];
+      return *this;
+    }
+  };
+  CommaInitializer operator<<(double x) {
+    CommaInitializer c{d_.data(), d_.data() + d_.size()};
+    c, x;
+    return c;
+  }
+  void setConstant(double v) { for (auto& e : d_) e = v; }
+  void setZero() { setConstant(0.0); }
  private:
   std::vector<double> d_;
 };
@@ -117,29 +141,93 @@ inline void copy7(const VectorXd& v, double* dst, const char* what) {
 }
 }  // namespace detail
 
-// Robot: the fixed-base iiwa14.  The URDF itself is turned into constant tables off-line
-// (tools/gen_robot_model.py); a path, when given, is verified against them (detail::verify_urdf).
+// minimal stand-ins for Eigen::Vector3d / Eigen::Matrix3d / pinocchio::SE3 in the task-space reference plug-in
+struct Vector3d {
+  double d[3] = {0, 0, 0};
+  Vector3d() {}
+  Vector3d(double x, double y, double z) { d[0] = x; d[1] = y; d[2] = z; }
+  static Vector3d Constant(double v) { return Vector3d(v, v, v); }
+  static Vector3d Zero() { return Vector3d(); }
+  struct CommaInitializer {
+    double* p;
+    CommaInitializer& operator,(double x) { *p++ = x; return *this; }
+  };
+  CommaInitializer operator<<(double x) { d[0] = x; return CommaInitializer{d + 1}; }
+  double& operator[](int i) { return d[i]; }
+  double& operator()(int i) { return d[i]; }
+  double operator()(int i) const { return d[i]; }
+  double coeff(int i) const { return d[i]; }
+  double& coeffRef(int i) { return d[i]; }
+  double operator[](int i) const { return d[i]; }
+};
+struct Matrix3d {
+  double d[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};   // row-major
+  double& operator()(int r, int c) { return d[3 * r + c]; }
+  double operator()(int r, int c) const { return d[3 * r + c]; }
+  struct CommaInitializer {                    // Eigen fills row by row: R << r00, r01, r02, r10, ...;
+    double* p;
+    CommaInitializer& operator,(double x) { *p++ = x; return *this; }
+  };
+  CommaInitializer operator<<(double x) { d[0] = x; return CommaInitializer{d + 1}; }
+};
+struct SE3 {
+  Matrix3d rotation;
+  Vector3d translation;
+  SE3() {}
+  SE3(const Matrix3d& R, const Vector3d& p) : rotation(R), translation(p) {}
+};
+
+// Robot(path_to_urdf): the fixed-base iiwa14; Robot(path_to_urdf, contact_frames): ANYmal-B with the four foot frames
+// {14, 24, 34, 44} (LF, LH, RF, RH) -- the two constructors of idocp::Robot (include/idocp/robot/robot.hpp:33-47).  The URDFs
+// themselves are turned into constant tables off-line (tools/gen_robot_model.py); a path, when given, is verified against
+// them (detail::verify_urdf).
 class Robot {
  public:
   explicit Robot(const std::string& path_to_urdf = "") : urdf_(path_to_urdf) {
     detail::verify_urdf(path_to_urdf, {detail::kUrdfHashIiwa14}, "iiwa14");
     detail::check(idocp_b200_problem_default(IDOCP_B200_ROBOT_IIWA14, &p_));
   }
-  int dimq() const { return IDOCP_B200_DIMV; }
-  int dimv() const { return IDOCP_B200_DIMV; }
-  int dimu() const { return IDOCP_B200_DIMV; }
-  bool hasFloatingBase() const { return false; }
-  int maxPointContacts() const { return 0; }
-  // robot.hxx:721: the fixed-base iiwa14 has no point contacts
+  Robot(const std::string& path_to_urdf, const std::vector<int>& contact_frames)
+      : urdf_(path_to_urdf), frames_(contact_frames), floating_(true) {
+    if (contact_frames != std::vector<int>{14, 24, 34, 44})
+      detail::die("invalid argument: the contact frames of ANYmal must be {14, 24, 34, 44}");
+    detail::verify_urdf(path_to_urdf, {detail::kUrdfHashAnymalExamples, detail::kUrdfHashAnymalTests}, "ANYmal");
+    detail::check(idocp_b200_fb_problem_default(&fb_));
+  }
+  int dimq() const { return floating_ ? IDOCP_B200_FB_NQ : IDOCP_B200_DIMV; }
+  int dimv() const { return floating_ ? IDOCP_B200_FB_NV : IDOCP_B200_DIMV; }
+  int dimu() const { return floating_ ? IDOCP_B200_FB_NU : IDOCP_B200_DIMV; }
+  int max_dimf() const { return floating_ ? IDOCP_B200_FB_MAXF : 0; }
+  int dim_passive() const { return floating_ ? 6 : 0; }
+  bool hasFloatingBase() const { return floating_; }
+  int maxPointContacts() const { return floating_ ? 4 : 0; }
+  // robot.hxx:721
   ContactStatus createContactStatus() const { return ContactStatus(maxPointContacts()); }
+  double totalWeight() const {
+    if (!floating_) detail::die("idocp_b200: totalWeight() is provided for the floating-base robot");
+    return idocp_b200_fb_total_weight();
+  }
+  void updateFrameKinematics(const VectorXd& q) {
+    if (!floating_ || q.size() != dimq()) detail::die("invalid size: q.size() must be 19 (floating-base robot)");
+    detail::check(idocp_b200_fb_contact_frame_positions(q.data(), points_));
+  }
+  void getContactPoints(std::vector<Vector3d>& contact_points) const {
+    contact_points.resize(4);
+    for (int i = 0; i < 4; ++i) contact_points[i] = Vector3d(points_[3 * i], points_[3 * i + 1], points_[3 * i + 2]);
+  }
   void setJointEffortLimit(const VectorXd& v) { detail::copy7(v, p_.u_max, "joint_effort_limit"); }
   void setJointVelocityLimit(const VectorXd& v) { detail::copy7(v, p_.v_max, "joint_velocity_limit"); }
   void setLowerJointPositionLimit(const VectorXd& v) { detail::copy7(v, p_.q_min, "lower_joint_position_limit"); }
   void setUpperJointPositionLimit(const VectorXd& v) { detail::copy7(v, p_.q_max, "upper_joint_position_limit"); }
-  const idocp_b200_problem& limits() const { return p_; }
+  const idocp_b200_problem& limits() const { return p_; }          // fixed base
+  const idocp_b200_fb_problem& fbLimits() const { return fb_; }    // floating base
  private:
   std::string urdf_;
-  idocp_b200_problem p_;
+  std::vector<int> frames_;
+  bool floating_ = false;
+  idocp_b200_problem p_ = idocp_b200_problem();
+  idocp_b200_fb_problem fb_ = idocp_b200_fb_problem();
+  double points_[12] = {0};
 };
 
 class ConfigurationSpaceCost {
@@ -157,27 +245,6 @@ class ConfigurationSpaceCost {
   const idocp_b200_problem& params() const { return p_; }
  private:
   idocp_b200_problem p_;
-};
-
-// minimal stand-ins for Eigen::Vector3d / Eigen::Matrix3d / pinocchio::SE3 in the task-space reference plug-in
-struct Vector3d {
-  double d[3] = {0, 0, 0};
-  Vector3d() {}
-  Vector3d(double x, double y, double z) { d[0] = x; d[1] = y; d[2] = z; }
-  static Vector3d Constant(double v) { return Vector3d(v, v, v); }
-  double& coeffRef(int i) { return d[i]; }
-  double operator[](int i) const { return d[i]; }
-};
-struct Matrix3d {
-  double d[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};   // row-major
-  double& operator()(int r, int c) { return d[3 * r + c]; }
-  double operator()(int r, int c) const { return d[3 * r + c]; }
-};
-struct SE3 {
-  Matrix3d rotation;
-  Vector3d translation;
-  SE3() {}
-  SE3(const Matrix3d& R, const Vector3d& p) : rotation(R), translation(p) {}
 };
 
 // cost/time_varying_task_space_6d_cost.hpp:22-41: user-derived reference; a HOST virtual, sampled by the solver
@@ -301,8 +368,16 @@ class TaskSpace6DCost {
 
 // closed registry of cost components: one ConfigurationSpaceCost and, optionally, one task-space cost
 // (TimeVaryingTaskSpace6DCost, TaskSpace6DCost, TimeVaryingTaskSpace3DCost or TaskSpace3DCost; push_back order of the reference examples: configuration cost first)
+class ConfigurationSpaceCostBase;   // the configuration-space costs of the floating-base robot (ocp_solver.hpp)
+class ContactForceCost;
 class CostFunction {
  public:
+  // floating-base components (ocp_solver.hpp): one configuration-space cost with a time-dependent reference
+  // (TrottingConfigurationSpaceCost, TimeVaryingConfigurationSpaceCost, FloatingBaseConfigurationSpaceCost) and ContactForceCost
+  void push_back(const std::shared_ptr<ConfigurationSpaceCostBase>& c) { fb_config_ = c; }
+  void push_back(const std::shared_ptr<ContactForceCost>& c) { force_ = c; }
+  const std::shared_ptr<ConfigurationSpaceCostBase>& fbConfig() const { return fb_config_; }
+  const std::shared_ptr<ContactForceCost>& force() const { return force_; }
   void push_back(const std::shared_ptr<ConfigurationSpaceCost>& c) {
     if (config_) detail::die("idocp_b200: only one ConfigurationSpaceCost component is supported");
     if (task_) detail::die("idocp_b200: push the ConfigurationSpaceCost before the task-space cost");
@@ -320,10 +395,21 @@ class CostFunction {
  private:
   std::shared_ptr<ConfigurationSpaceCost> config_;
   std::shared_ptr<TimeVaryingTaskSpace6DCost> task_;
+  std::shared_ptr<ConfigurationSpaceCostBase> fb_config_;
+  std::shared_ptr<ContactForceCost> force_;
 };
 
 class Constraints {
  public:
+  // constraints.hpp push_back: the components are tag classes {id, mu} (ocp_solver.hpp: JointPositionLowerLimit ...
+  // LinearizedImpulseFrictionCone); the fixed-base solvers always use the six joint limits of JointConstraintsFactory
+  template <typename Component>
+  void push_back(const std::shared_ptr<Component>& c) {
+    enable_[c->id] = 1;
+    if (c->mu > 0) mu_ = c->mu;
+  }
+  const int* enable() const { return enable_; }
+  double mu() const { return mu_; }
   void setBarrier(double b) { if (!(b > 0)) detail::die("invalid argment: barrier must be positive"); barrier_ = b; }
   void setFractionToBoundaryRate(double r) {
     if (!(r > 0) || r > 1) detail::die("invalid argment: fraction_to_boundary_rate must be in (0, 1]");
@@ -333,6 +419,8 @@ class Constraints {
   double fractionToBoundaryRate() const { return rate_; }
  private:
   double barrier_ = 1.0e-04, rate_ = 0.995;
+  int enable_[IDOCP_B200_FB_NUM_CONSTRAINTS] = {0};
+  double mu_ = 0.7;
 };
 
 // src/utils/joint_constraints_factory.cpp:22-37: position, velocity, torque lower+upper limits

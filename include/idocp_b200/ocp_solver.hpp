@@ -23,39 +23,11 @@
 
 namespace idocp_b200 {
 
-// Robot(path_to_urdf, contact_frames): ANYmal-B with the four foot frames {14, 24, 34, 44} (LF, LH, RF, RH)
-class QuadrupedRobot {
+// Robot(path_to_urdf, contact_frames) of idocp_b200.hpp is the floating-base robot; this name keeps the default arguments
+class QuadrupedRobot : public Robot {
  public:
   explicit QuadrupedRobot(const std::string& path_to_urdf = "", const std::vector<int>& contact_frames = {14, 24, 34, 44})
-      : urdf_(path_to_urdf), frames_(contact_frames) {
-    if (contact_frames != std::vector<int>{14, 24, 34, 44})
-      detail::die("invalid argument: the contact frames of ANYmal must be {14, 24, 34, 44}");
-    detail::verify_urdf(path_to_urdf, {detail::kUrdfHashAnymalExamples, detail::kUrdfHashAnymalTests}, "ANYmal");
-    detail::check(idocp_b200_fb_problem_default(&p_));
-  }
-  int dimq() const { return IDOCP_B200_FB_NQ; }
-  int dimv() const { return IDOCP_B200_FB_NV; }
-  int dimu() const { return IDOCP_B200_FB_NU; }
-  int max_dimf() const { return IDOCP_B200_FB_MAXF; }
-  int dim_passive() const { return 6; }
-  bool hasFloatingBase() const { return true; }
-  int maxPointContacts() const { return 4; }
-  ContactStatus createContactStatus() const { return ContactStatus(maxPointContacts()); }
-  double totalWeight() const { return idocp_b200_fb_total_weight(); }
-  void updateFrameKinematics(const VectorXd& q) {
-    if (q.size() != dimq()) detail::die("invalid size: q.size() must be 19");
-    detail::check(idocp_b200_fb_contact_frame_positions(q.data(), points_));
-  }
-  void getContactPoints(std::vector<Vector3d>& contact_points) const {
-    contact_points.resize(4);
-    for (int i = 0; i < 4; ++i) contact_points[i] = Vector3d(points_[3 * i], points_[3 * i + 1], points_[3 * i + 2]);
-  }
-  const idocp_b200_fb_problem& limits() const { return p_; }
- private:
-  std::string urdf_;
-  std::vector<int> frames_;
-  idocp_b200_fb_problem p_;
-  double points_[12] = {0};
+      : Robot(path_to_urdf, contact_frames) {}
 };
 
 inline std::vector<Point3> toPoints(const std::vector<Vector3d>& v) {
@@ -97,7 +69,7 @@ typedef ConfigurationSpaceCostBase ConfigurationReferenceBase;
 // cost/configuration_space_cost.hpp for the floating base: constant q_ref, v_ref
 class FloatingBaseConfigurationSpaceCost : public ConfigurationSpaceCostBase {
  public:
-  explicit FloatingBaseConfigurationSpaceCost(const QuadrupedRobot&) : q_ref_(19), v_ref_(18) { q_ref_[6] = 1.0; }
+  explicit FloatingBaseConfigurationSpaceCost(const Robot&) : q_ref_(19), v_ref_(18) { q_ref_[6] = 1.0; }
   void set_q_ref(const VectorXd& q) { if (q.size() != 19) detail::die("invalid size: q_ref.size() must be 19!"); q_ref_ = q; }
   void set_v_ref(const VectorXd& v) { if (v.size() != 18) detail::die("invalid size: v_ref.size() must be 18!"); v_ref_ = v; }
   void update_q_ref(const double, VectorXd& q_ref) const override { q_ref = q_ref_; }
@@ -111,8 +83,8 @@ class FloatingBaseConfigurationSpaceCost : public ConfigurationSpaceCostBase {
 // translation, which is what the reference's examples use; a general twist is rejected.)
 class TimeVaryingConfigurationSpaceCost : public ConfigurationSpaceCostBase {
  public:
-  explicit TimeVaryingConfigurationSpaceCost(const QuadrupedRobot&) {}
-  void set_ref(const QuadrupedRobot&, const double t_begin, const double t_end, const VectorXd& q_begin, const VectorXd& v) {
+  explicit TimeVaryingConfigurationSpaceCost(const Robot&) {}
+  void set_ref(const Robot&, const double t_begin, const double t_end, const VectorXd& q_begin, const VectorXd& v) {
     if (t_begin >= t_end) detail::die("invalid argment: t_begin < t_end must be hold!");
     if (q_begin.size() != 19) detail::die("invalid size: q_begin.size() must be 19!");
     if (v.size() != 18) detail::die("invalid size: v.size() must be 18!");
@@ -150,7 +122,7 @@ struct TrottingSwingAngles {
 // trotting_configuration_space_cost.hpp:52-164
 class TrottingConfigurationSpaceCost : public ConfigurationSpaceCostBase {
  public:
-  explicit TrottingConfigurationSpaceCost(const QuadrupedRobot&) {}
+  explicit TrottingConfigurationSpaceCost(const Robot&) {}
   void set_ref(const double t_start, const double t_period, const VectorXd& q_standing, const double step_length,
                const TrottingSwingAngles& swing_angles) {
     if (q_standing.size() != 19) detail::die("invalid size: q_standing.size() must be 19!");
@@ -192,8 +164,8 @@ class TrottingConfigurationSpaceCost : public ConfigurationSpaceCostBase {
 // contact_force_cost.hpp
 class ContactForceCost {
  public:
-  explicit ContactForceCost(const QuadrupedRobot&) { std::memset(&w_, 0, sizeof(w_)); }
-  void set_f_ref(const QuadrupedRobot& robot) {
+  explicit ContactForceCost(const Robot&) { std::memset(&w_, 0, sizeof(w_)); }
+  void set_f_ref(const Robot& robot) {
     for (int i = 0; i < 4; ++i) { w_.f_ref[3 * i] = 0; w_.f_ref[3 * i + 1] = 0; w_.f_ref[3 * i + 2] = robot.totalWeight() / 4; }
   }
   void set_f_ref(const std::vector<Vector3d>& f) { set3(f, w_.f_ref, "f_ref"); }
@@ -210,19 +182,9 @@ class ContactForceCost {
   idocp_b200_fb_problem w_;
 };
 
-class HybridCostFunction {
- public:
-  void push_back(const std::shared_ptr<ConfigurationSpaceCostBase>& c) { config_ = c; }
-  void push_back(const std::shared_ptr<TrottingConfigurationSpaceCost>& c) { config_ = c; }
-  void push_back(const std::shared_ptr<TimeVaryingConfigurationSpaceCost>& c) { config_ = c; }
-  void push_back(const std::shared_ptr<FloatingBaseConfigurationSpaceCost>& c) { config_ = c; }
-  void push_back(const std::shared_ptr<ContactForceCost>& c) { force_ = c; }
-  const std::shared_ptr<ConfigurationSpaceCostBase>& config() const { return config_; }
-  const std::shared_ptr<ContactForceCost>& force() const { return force_; }
- private:
-  std::shared_ptr<ConfigurationSpaceCostBase> config_;
-  std::shared_ptr<ContactForceCost> force_;
-};
+// idocp::CostFunction / idocp::Constraints are the classes of idocp_b200.hpp; the Hybrid* names of round 1 remain as aliases
+using HybridCostFunction = CostFunction;
+using HybridConstraints = Constraints;
 
 // constraints: closed registry, one tag class per reference component
 struct HybridConstraintComponent {
@@ -231,7 +193,7 @@ struct HybridConstraintComponent {
 };
 #define IDOCP_B200_JOINT_LIMIT(Name, Id)                                   \
   struct Name : HybridConstraintComponent {                                 \
-    explicit Name(const QuadrupedRobot&) : HybridConstraintComponent{Id, 0.0} {} \
+    explicit Name(const Robot&) : HybridConstraintComponent{Id, 0.0} {} \
   }
 IDOCP_B200_JOINT_LIMIT(JointPositionLowerLimit, IDOCP_B200_FB_POSITION_LOWER);
 IDOCP_B200_JOINT_LIMIT(JointPositionUpperLimit, IDOCP_B200_FB_POSITION_UPPER);
@@ -241,49 +203,33 @@ IDOCP_B200_JOINT_LIMIT(JointTorquesLowerLimit, IDOCP_B200_FB_TORQUES_LOWER);
 IDOCP_B200_JOINT_LIMIT(JointTorquesUpperLimit, IDOCP_B200_FB_TORQUES_UPPER);
 #undef IDOCP_B200_JOINT_LIMIT
 struct LinearizedFrictionCone : HybridConstraintComponent {
-  LinearizedFrictionCone(const QuadrupedRobot&, const double mu) : HybridConstraintComponent{IDOCP_B200_FB_FRICTION_CONE, mu} {
+  LinearizedFrictionCone(const Robot&, const double mu) : HybridConstraintComponent{IDOCP_B200_FB_FRICTION_CONE, mu} {
     if (mu <= 0) detail::die("invalid value: mu must be positive!");
   }
 };
 struct LinearizedImpulseFrictionCone : HybridConstraintComponent {
-  LinearizedImpulseFrictionCone(const QuadrupedRobot&, const double mu)
+  LinearizedImpulseFrictionCone(const Robot&, const double mu)
       : HybridConstraintComponent{IDOCP_B200_FB_IMPULSE_FRICTION_CONE, mu} {
     if (mu <= 0) detail::die("invalid value: mu must be positive!");
   }
 };
-class HybridConstraints {
- public:
-  template <typename Component>
-  void push_back(const std::shared_ptr<Component>& c) {
-    enable_[c->id] = 1;
-    if (c->mu > 0) mu_ = c->mu;
-  }
-  void setBarrier(double b) { if (!(b > 0)) detail::die("invalid argment: barrier must be positive"); barrier_ = b; }
-  void setFractionToBoundaryRate(double r) { if (!(r > 0) || r > 1) detail::die("invalid argment: rate"); rate_ = r; }
-  const int* enable() const { return enable_; }
-  double mu() const { return mu_; }
-  double barrier() const { return barrier_; }
-  double fractionToBoundaryRate() const { return rate_; }
- private:
-  int enable_[IDOCP_B200_FB_NUM_CONSTRAINTS] = {0};
-  double mu_ = 0.7, barrier_ = 1.0e-04, rate_ = 0.995;
-};
-
 // OCPSolver(robot, cost, constraints, T, N, max_num_impulse, nthreads) for `batch` instances
 class OCPSolver {
  public:
-  OCPSolver(const QuadrupedRobot& robot, const std::shared_ptr<HybridCostFunction>& cost,
-            const std::shared_ptr<HybridConstraints>& constraints, const double T, const int N, const int max_num_impulse = 0,
+  OCPSolver(const Robot& robot, const std::shared_ptr<CostFunction>& cost,
+            const std::shared_ptr<Constraints>& constraints, const double T, const int N, const int max_num_impulse = 0,
             const int nthreads = 1, const int batch = 1, const int device = 0)
       : cost_(cost), batch_(batch) {
     if (T <= 0) detail::die("invalid value: T must be positive!");
     if (N <= 0) detail::die("invalid value: N must be positive!");
     if (max_num_impulse < 0) detail::die("invalid value: max_num_impulse must be non-negative!");
     if (nthreads <= 0) detail::die("invalid value: nthreads must be positive!");
-    idocp_b200_fb_problem p = robot.limits();
+    if (!robot.hasFloatingBase()) detail::die("idocp_b200: OCPSolver is built for the floating-base robot, Robot(path_to_urdf, contact_frames)");
+    if (!cost || !constraints) detail::die("idocp_b200: cost and constraints must not be null");
+    idocp_b200_fb_problem p = robot.fbLimits();
     p.T = T; p.N = N; p.max_num_impulse = max_num_impulse;
-    if (cost->config()) {
-      const idocp_b200_fb_problem& w = cost->config()->weights();
+    if (cost->fbConfig()) {
+      const idocp_b200_fb_problem& w = cost->fbConfig()->weights();
       std::memcpy(p.q_weight, w.q_weight, sizeof(double) * 18 * 8);   // q_weight .. dvi_weight are contiguous
     }
     if (cost->force()) {
@@ -446,12 +392,12 @@ class OCPSolver {
   void sampleReference(const double t) {
     t_last_ = t;
     const int n = discretize();
-    if (!cost_->config()) return;
+    if (!cost_->fbConfig()) return;
     VectorXd q_ref(19);
     for (int e = 0; e < n; ++e) {
-      cost_->config()->update_q_ref(t_[e], q_ref);
+      cost_->fbConfig()->update_q_ref(t_[e], q_ref);
       const int kind = kind_[e] == 4 ? 0 : kind_[e];
-      const VectorXd v_ref = cost_->config()->v_ref(t_[e]);
+      const VectorXd v_ref = cost_->fbConfig()->v_ref(t_[e]);
       detail::check(idocp_b200_fb_set_cost_reference(h_.get(), kind, index_[e], q_ref.data(), v_ref.data()));
     }
   }
@@ -465,7 +411,7 @@ class OCPSolver {
       for (int j = 0; j < 18; ++j) v_[static_cast<size_t>(b) * 18 + j] = v[j];
     }
   }
-  std::shared_ptr<HybridCostFunction> cost_;
+  std::shared_ptr<CostFunction> cost_;
   std::shared_ptr<idocp_b200_contact_sequence> cs_;
   std::shared_ptr<idocp_b200_fb_solver> h_;
   idocp_b200_fb_problem prob_;
