@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_LIBRARY = os.path.join(_HERE, "libidocp_b200.so")
+# IDOCP_B200_LIBRARY: another nvcc build of the same sources (A/B variants from tools/build_variant.py); never a fallback
+DEFAULT_LIBRARY = os.environ.get("IDOCP_B200_LIBRARY") or os.path.join(_HERE, "libidocp_b200.so")
 
 DIMV = 7
 NUM_CONSTRAINTS = 6
@@ -82,6 +83,8 @@ class FbProblem(C.Structure):
         ("q_min", C.c_double * 12), ("q_max", C.c_double * 12), ("v_max", C.c_double * 12), ("u_max", C.c_double * 12),
         ("mu", C.c_double), ("barrier", C.c_double), ("fraction_rate", C.c_double),
         ("enable", C.c_int * FB_NUM_CONSTRAINTS),
+        ("cone_nonlinear", C.c_int * 2), ("enable_acceleration_limit", C.c_int * 2),
+        ("a_min", C.c_double * 12), ("a_max", C.c_double * 12),
     ]
 
 

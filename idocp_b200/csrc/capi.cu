@@ -233,6 +233,7 @@ static int stage_grid(const idocp_b200_solver* h, int nstages) {
 }
 // grid of a per-instance kernel: one warp per group
 static int group_grid(const idocp_b200_solver* h) { return (h->L.G + WARPS_PER_CTA - 1) / WARPS_PER_CTA; }
+static int ric_grid(const idocp_b200_solver* h) { return (h->L.G + RIC_WARPS - 1) / RIC_WARPS; }
 static const int kLinSmem = OCTETS_PER_CTA * OCT * PAIR_TILE * static_cast<int>(sizeof(double));
 static const int kRicSmem = RIC_SMEM_DOUBLES * static_cast<int>(sizeof(double));
 static const int kUlSmem = UL_SMEM_DOUBLES * static_cast<int>(sizeof(double));
@@ -477,10 +478,10 @@ static int unocp_update(idocp_b200_solver* h, const double* d_q, const double* d
                    h->d_prob, h->L, d_q, d_v);
   }
   if (task) {
-    IDOCP_LAUNCH(h, KC_RICCATI, k_riccati<true>, group_grid(h), CTA_THREADS, kRicSmem, h->d_prob, h->L, d_q, d_v);
+    IDOCP_LAUNCH(h, KC_RICCATI, k_riccati<true>, ric_grid(h), RIC_THREADS, kRicSmem, h->d_prob, h->L, d_q, d_v);
     IDOCP_LAUNCH(h, KC_EXPAND, (k_expand<false, true>), stage_grid(h, h->N + 1), CTA_THREADS, 0, h->d_prob, h->L, 0);
   } else {
-    IDOCP_LAUNCH(h, KC_RICCATI, k_riccati<false>, group_grid(h), CTA_THREADS, kRicSmem, h->d_prob, h->L, d_q, d_v);
+    IDOCP_LAUNCH(h, KC_RICCATI, k_riccati<false>, ric_grid(h), RIC_THREADS, kRicSmem, h->d_prob, h->L, d_q, d_v);
     IDOCP_LAUNCH(h, KC_EXPAND, (k_expand<false, false>), stage_grid(h, h->N + 1), CTA_THREADS, 0, h->d_prob, h->L, 0);
   }
   const double* override_alpha = nullptr;
@@ -493,7 +494,7 @@ static int unocp_update(idocp_b200_solver* h, const double* d_q, const double* d
     // step sizes, then update + linearisation of the new iterate in one persistent launch; X (old) -> X2 (new), then the
     // two swap roles
     IDOCP_LAUNCH(h, KC_STEP_MIN, k_step_min, (h->Bp + 127) / 128, 128, 0, h->L, override_alpha);
-    const int ul_grid = std::min(stage_grid(h, h->N + 1), 2 * h->sm_count);
+    const int ul_grid = std::min(stage_grid(h, h->N + 1), IDOCP_UL_CTAS_PER_SM * h->sm_count);
     if (task)
       IDOCP_LAUNCH(h, KC_UPDATE_LINEARIZE, k_update_linearize<true>, ul_grid, CTA_THREADS, kUlSmem, h->d_prob, h->L);
     else

@@ -22,10 +22,17 @@
 namespace idocp_b200 {
 
 enum { FB_GRID = 0, FB_IMPULSE = 1, FB_AUX = 2, FB_LIFT = 3, FB_TERMINAL = 4 };
-enum { FBC_POS_LO = 0, FBC_POS_UP, FBC_VEL_LO, FBC_VEL_UP, FBC_TRQ_LO, FBC_TRQ_UP, FBC_FRICTION, FBC_IMPULSE_FRICTION, FBC_NCOMP };
-#define FB_NCON 112   /* 6 x 12 joint limits, 20 friction-cone rows, 20 impulse friction-cone rows */
-__host__ __device__ inline int fbc_offset(int c) { return c < FBC_FRICTION ? 12 * c : (c == FBC_FRICTION ? 72 : 92); }
-__host__ __device__ inline int fbc_dim(int c) { return c < FBC_FRICTION ? 12 : 20; }
+enum { FBC_POS_LO = 0, FBC_POS_UP, FBC_VEL_LO, FBC_VEL_UP, FBC_TRQ_LO, FBC_TRQ_UP, FBC_FRICTION, FBC_IMPULSE_FRICTION, FBC_ACC_LO,
+       FBC_ACC_UP, FBC_NCOMP };
+#define FB_NCON 136   /* 6 x 12 joint limits, 20 friction-cone rows, 20 impulse friction-cone rows, 2 x 12 acceleration limits */
+__host__ __device__ inline int fbc_offset(int c) {
+  return c < FBC_FRICTION ? 12 * c : (c == FBC_FRICTION ? 72 : (c == FBC_IMPULSE_FRICTION ? 92 : 112 + 12 * (c - FBC_ACC_LO)));
+}
+__host__ __device__ inline int fbc_dim(int c) { return (c == FBC_FRICTION || c == FBC_IMPULSE_FRICTION) ? 20 : 12; }   // storage
+__host__ __device__ inline int fbc_comp(int idx) {   // component of row idx
+  return idx < 72 ? idx / 12 : (idx < 92 ? FBC_FRICTION : (idx < 112 ? FBC_IMPULSE_FRICTION : (idx < 124 ? FBC_ACC_LO : FBC_ACC_UP)));
+}
+__host__ __device__ inline bool fbc_is_cone(int c) { return c == FBC_FRICTION || c == FBC_IMPULSE_FRICTION; }
 
 struct FbDevProblem {
   double T;
@@ -36,7 +43,12 @@ struct FbDevProblem {
   double q_min[FB_NU], q_max[FB_NU], v_max[FB_NU], u_max[FB_NU];
   double mu, barrier, fraction_rate;
   int enable[FBC_NCOMP];
+  int cone_nonlinear[2];   // FrictionCone / ImpulseFrictionCone (2 rows per contact) instead of the linearised cones (5 rows)
+  double a_min[FB_NU], a_max[FB_NU];   // JointAcceleration{Lower,Upper}Limit
 };
+// rows per contact of cone component c, live rows of a component (the rest of its storage stays zero)
+__host__ __device__ inline int fbc_cone_rows(const FbDevProblem& pr, int c) { return pr.cone_nonlinear[c - FBC_FRICTION] ? 2 : 5; }
+__host__ __device__ inline int fbc_rows(const FbDevProblem& pr, int c) { return fbc_is_cone(c) ? FB_NC * fbc_cone_rows(pr, c) : 12; }
 
 // one element of the hybrid chain (shared by the whole batch)
 struct FbElem {
@@ -443,8 +455,16 @@ __device__ __noinline__ void fb_llt_solve(const double* L, int ldl, const double
   }
 }
 
-// ---- friction cone (constraints/linearized_friction_cone.hpp:72-85, .cpp:25-29) ----
-__device__ inline void fb_friction_residual(double mu, const double* f, double* r) {
+// ---- friction cone (constraints/linearized_friction_cone.hpp:72-85, .cpp:25-29); nonlinear: normalForceResidual and
+// frictionConeResidual of FrictionCone / ImpulseFrictionCone (friction_cone.hpp:72-82), Jacobian rows d(-fz)/df and
+// data.r[i] = (2 fx, 2 fy, -2 mu^2 fz) (friction_cone.cpp:109-111) ----
+__device__ inline void fb_friction_residual(double mu, bool nonlinear, const double* f, double* r) {
+  if (nonlinear) {
+    r[0] = -f[2];
+    r[1] = fma(-((mu * mu) * f[2]), f[2], fma(f[1], f[1], f[0] * f[0]));
+    r[2] = r[3] = r[4] = 0.0;
+    return;
+  }
   const double s = mu * f[2] / 1.41421356237309514547e+00;
   r[0] = -f[2];
   r[1] = f[0] - s;
@@ -452,7 +472,11 @@ __device__ inline void fb_friction_residual(double mu, const double* f, double* 
   r[3] = f[1] - s;
   r[4] = -f[1] - s;
 }
-__device__ inline double fb_friction_jac(double mu, int e, int x) {
+__device__ inline double fb_friction_jac(double mu, bool nonlinear, const double* f, int e, int x) {
+  if (nonlinear) {
+    if (e == 0) return x == 2 ? -1.0 : 0.0;
+    return x == 2 ? -(((2.0 * mu) * mu) * f[2]) : 2.0 * f[x];
+  }
   const double m = -(mu / 1.41421356237309514547e+00);
   if (x == 2) return e == 0 ? -1.0 : m;
   if (x == 0) return e == 1 ? 1.0 : (e == 2 ? -1.0 : 0.0);
@@ -903,21 +927,24 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
   // computePrimalAndDualResidual
   if (!terminal) {
     FBW_FOR(idx, FB_NCON) {
-      const int c = idx < 72 ? idx / 12 : (idx < 92 ? FBC_FRICTION : FBC_IMPULSE_FRICTION);
+      const int c = fbc_comp(idx);
       const int j = idx - fbc_offset(c);
       double res = 0.0, dua = 0.0;
-      if (el.cactive[c]) {
+      if (el.cactive[c] && j < fbc_rows(pr, c)) {
         const double sl = w.slack[idx];
-        if (c >= FBC_FRICTION) {
-          const int i = j / 5;
+        if (fbc_is_cone(c)) {
+          const int rpc = fbc_cone_rows(pr, c);
+          const int i = j / rpc;
           if (el.active[i]) {
             double r5[5];
-            fb_friction_residual(pr.mu, w.f + 3 * i, r5);
-            res = r5[j % 5] + sl;
+            fb_friction_residual(pr.mu, rpc == 2, w.f + 3 * i, r5);
+            res = r5[j % rpc] + sl;
             dua = sl * w.dual[idx] - pr.barrier;
           }
         } else {
           switch (c) {
+            case FBC_ACC_LO: res = pr.a_min[j] - w.a[6 + j] + sl; break;
+            case FBC_ACC_UP: res = w.a[6 + j] - pr.a_max[j] + sl; break;
             case FBC_POS_LO: res = pr.q_min[j] - w.q[7 + j] + sl; break;
             case FBC_POS_UP: res = w.q[7 + j] - pr.q_max[j] + sl; break;
             case FBC_VEL_LO: res = (-pr.v_max[j]) - w.v[6 + j] + sl; break;
@@ -977,6 +1004,11 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
       if (c <= FBC_POS_UP) lq += sg * (dt * w.dual[12 * c + j]);
       else lv += sg * (dt * w.dual[12 * c + j]);
     }
+    for (int c = FBC_ACC_LO; c <= FBC_ACC_UP; ++c) {   // JointAcceleration{Lower,Upper}Limit: la.tail(12) -/+= dt dual
+      if (!el.cactive[c]) continue;
+      const double sg = (c & 1) ? 1.0 : -1.0;
+      la += sg * (dt * w.dual[fbc_offset(c) + j]);
+    }
   }
   if (lane < FB_NU) {
     for (int c = 4; c < 6; ++c) {
@@ -986,10 +1018,15 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
     }
   }
   const int cfr = impulse ? FBC_IMPULSE_FRICTION : FBC_FRICTION;
+  const int rpc = fbc_cone_rows(pr, cfr);
+  const bool nlc = rpc == 2;
   if (ci >= 0 && el.cactive[cfr]) {
-    const double* du5 = w.dual + fbc_offset(cfr) + 5 * ci;
-    double acc = fb_friction_jac(pr.mu, 0, cx) * du5[0];
-    for (int ee = 1; ee < 5; ++ee) acc = fma(fb_friction_jac(pr.mu, ee, cx), du5[ee], acc);
+    const double* du5 = w.dual + fbc_offset(cfr) + rpc * ci;
+    const double* fi = w.f + 3 * ci;
+    double acc = fb_friction_jac(pr.mu, nlc, fi, 0, cx) * du5[0];
+#pragma unroll
+    for (int ee = 1; ee < 5; ++ee)   // fixed trip count + predicate: the row arrays stay in registers
+      if (ee < rpc) acc = fma(fb_friction_jac(pr.mu, nlc, fi, ee, cx), du5[ee], acc);
     lf += dt * acc;
   }
   // linearizeForwardEuler / linearizeImpulseForwardEuler (state_equation.hxx:11-40)
@@ -1176,7 +1213,18 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
       const int j = lane;
       if (j >= 6) qqd += sc * wq[j];
       qvd += sc * wv[j];
-      L.Qaa[j] = 0.0 + sc * wa[j];
+      double qad = 0.0 + sc * wa[j];
+      if (j >= 6) {
+        for (int c = FBC_ACC_LO; c <= FBC_ACC_UP; ++c) {
+          if (!el.cactive[c]) continue;
+          const int idx = fbc_offset(c) + j - 6;
+          const double rs = 1.0 / w.slack[idx];
+          qad += (dt * w.dual[idx]) * rs;
+          const double sg = (c & 1) ? 1.0 : -1.0;
+          la += sg * ((dt * fma(w.dual[idx], w.residual[idx], -w.duality[idx])) * rs);
+        }
+      }
+      L.Qaa[j] = qad;
     }
     double qff_d = 0.0;   // diagonal entry of Qff owned by this lane (stacked row `lane`); no read-modify-write on HBM
     if (ci >= 0) {
@@ -1210,19 +1258,28 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
     if (lane < FB_NV) { L.Qqq_d[lane] = qqd; L.Qvv_d[lane] = qvd; }
     if (ci >= 0 && el.cactive[cfr]) {
       int k = lane / 3;
-      const int o = fbc_offset(cfr) + 5 * ci;
+      const int o = fbc_offset(cfr) + rpc * ci;
+      const double* fi = w.f + 3 * ci;
       double r5[5], w5[5];
+#pragma unroll
       for (int ee = 0; ee < 5; ++ee) {
-        const double rs = 1.0 / w.slack[o + ee];
-        r5[ee] = fma(w.dual[o + ee], w.residual[o + ee], -w.duality[o + ee]) * rs;
-        w5[ee] = w.dual[o + ee] * rs;
+        r5[ee] = 0.0; w5[ee] = 0.0;
+        if (ee < rpc) {
+          const double rs = 1.0 / w.slack[o + ee];
+          r5[ee] = fma(w.dual[o + ee], w.residual[o + ee], -w.duality[o + ee]) * rs;
+          w5[ee] = w.dual[o + ee] * rs;
+        }
       }
-      double acc = fb_friction_jac(pr.mu, 0, cx) * r5[0];
-      for (int ee = 1; ee < 5; ++ee) acc = fma(fb_friction_jac(pr.mu, ee, cx), r5[ee], acc);
+      double acc = fb_friction_jac(pr.mu, nlc, fi, 0, cx) * r5[0];
+#pragma unroll
+      for (int ee = 1; ee < 5; ++ee)
+        if (ee < rpc) acc = fma(fb_friction_jac(pr.mu, nlc, fi, ee, cx), r5[ee], acc);
       lf += dt * acc;
       for (int y = 0; y < 3; ++y) {
-        double h = fb_friction_jac(pr.mu, 0, cx) * (w5[0] * fb_friction_jac(pr.mu, 0, y));
-        for (int ee = 1; ee < 5; ++ee) h = fma(fb_friction_jac(pr.mu, ee, cx), w5[ee] * fb_friction_jac(pr.mu, ee, y), h);
+        double h = fb_friction_jac(pr.mu, nlc, fi, 0, cx) * (w5[0] * fb_friction_jac(pr.mu, nlc, fi, 0, y));
+#pragma unroll
+        for (int ee = 1; ee < 5; ++ee)
+          if (ee < rpc) h = fma(fb_friction_jac(pr.mu, nlc, fi, ee, cx), w5[ee] * fb_friction_jac(pr.mu, nlc, fi, ee, y), h);
         L.Qff[(3 * k + cx) * FB_MAXF + 3 * k + y] = (y == cx ? qff_d : 0.0) + dt * h;
       }
     } else if (ci >= 0) {
@@ -1306,7 +1363,7 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
       double e2 = 0.0;
       for (int c = 0; c < FBC_NCOMP; ++c) {
         if (!el.cactive[c]) continue;
-        e2 += fb_sqnorm(w.residual + fbc_offset(c), fbc_dim(c)) + fb_sqnorm(w.duality + fbc_offset(c), fbc_dim(c));
+        e2 += fb_sqnorm(w.residual + fbc_offset(c), fbc_dim(c)) + fb_sqnorm(w.duality + fbc_offset(c), fbc_dim(c));   // dead rows: 0
       }
       w.part[6] = e2;
     }
@@ -1980,24 +2037,28 @@ __global__ void __launch_bounds__(64) k_fb_expand(FbArrays A) {
   __syncthreads();
   // computeSlackAndDualDirection
   for (int idx = tid; idx < FB_NCON; idx += blockDim.x) {
-    const int c = idx < 72 ? idx / 12 : (idx < 92 ? FBC_FRICTION : FBC_IMPULSE_FRICTION);
+    const int c = fbc_comp(idx);
     const int j = idx - fbc_offset(c);
     double ds = 0.0, dd = 0.0;
-    if (el.cactive[c]) {
-      if (c >= FBC_FRICTION) {
-        const int i = j / 5;
+    if (el.cactive[c] && j < fbc_rows(pr, c)) {
+      if (fbc_is_cone(c)) {
+        const int rpc = fbc_cone_rows(pr, c);
+        const int i = j / rpc;
         ds = 1.0; dd = 1.0;
         if (el.active[i]) {
           int k = 0;
           for (int jj = 0; jj < i; ++jj) k += el.active[jj];
           const double* df = daf + NV + 3 * k;
-          const int ee = j % 5;
-          const double Jdf = fma(fb_friction_jac(pr.mu, ee, 2), df[2], fma(fb_friction_jac(pr.mu, ee, 1), df[1], fb_friction_jac(pr.mu, ee, 0) * df[0]));
+          const double* fi = S.f + 3 * i;
+          const int ee = j % rpc;
+          const bool nlc = rpc == 2;
+          const double Jdf = fma(fb_friction_jac(pr.mu, nlc, fi, ee, 2), df[2],
+                                 fma(fb_friction_jac(pr.mu, nlc, fi, ee, 1), df[1], fb_friction_jac(pr.mu, nlc, fi, ee, 0) * df[0]));
           ds = -Jdf - Dr.residual[idx];
           dd = -fma(S.dual[idx], ds, Dr.duality[idx]) / S.slack[idx];
         }
       } else {
-        const double d = c <= FBC_POS_UP ? dx[6 + j] : (c <= FBC_VEL_UP ? dx[NV + 6 + j] : du[j]);
+        const double d = c <= FBC_POS_UP ? dx[6 + j] : (c <= FBC_VEL_UP ? dx[NV + 6 + j] : (c >= FBC_ACC_LO ? daf[6 + j] : du[j]));
         ds = ((c & 1) ? -d : d) - Dr.residual[idx];
         dd = -fma(S.dual[idx], ds, Dr.duality[idx]) / S.slack[idx];
       }
@@ -2011,8 +2072,8 @@ __global__ void __launch_bounds__(64) k_fb_expand(FbArrays A) {
   if (tid < 2 * FBC_NCOMP) {
     const int c = tid >> 1, o = fbc_offset(c);
     double r = 1.0;
-    if (el.cactive[c]) r = (tid & 1) ? fb_fraction_to_boundary(pr.fraction_rate, fbc_dim(c), S.dual + o, ddual + o)
-                                     : fb_fraction_to_boundary(pr.fraction_rate, fbc_dim(c), S.slack + o, dslack + o);
+    if (el.cactive[c]) r = (tid & 1) ? fb_fraction_to_boundary(pr.fraction_rate, fbc_rows(pr, c), S.dual + o, ddual + o)
+                                     : fb_fraction_to_boundary(pr.fraction_rate, fbc_rows(pr, c), S.slack + o, dslack + o);
     steps[tid] = r;
   }
   __syncthreads();
@@ -2140,7 +2201,7 @@ __global__ void __launch_bounds__(64) k_fb_update(FbArrays A) {
     }
   }
   for (int idx = tid; idx < FB_NCON; idx += blockDim.x) {
-    const int c = idx < 72 ? idx / 12 : (idx < 92 ? FBC_FRICTION : FBC_IMPULSE_FRICTION);
+    const int c = fbc_comp(idx);
     if (el.cactive[c]) {
       S.slack[idx] = fma(ap, Dr.dslack[idx], S.slack[idx]);
       S.dual[idx] = fma(ad, Dr.ddual[idx], S.dual[idx]);
@@ -2178,13 +2239,16 @@ __global__ void k_fb_init_constraints(FbArrays A, const FbInitRow* rows, int n_r
     const int o = fbc_offset(c);
     for (int j = 0; j < fbc_dim(c); ++j) {
       double sl = 0.0, du = 0.0;
-      if (row.cactive[c]) {
-        if (c >= FBC_FRICTION) {
+      if (row.cactive[c] && j < fbc_rows(pr, c)) {
+        if (fbc_is_cone(c)) {
+          const int rpc = fbc_cone_rows(pr, c);
           double r5[5];
-          fb_friction_residual(pr.mu, S.f + 3 * (j / 5), r5);
-          sl = -r5[j % 5];
+          fb_friction_residual(pr.mu, rpc == 2, S.f + 3 * (j / rpc), r5);
+          sl = -r5[j % rpc];
         } else {
           switch (c) {
+            case FBC_ACC_LO: sl = S.a[6 + j] - pr.a_min[j]; break;
+            case FBC_ACC_UP: sl = pr.a_max[j] - S.a[6 + j]; break;
             case FBC_POS_LO: sl = S.q[7 + j] - pr.q_min[j]; break;
             case FBC_POS_UP: sl = pr.q_max[j] - S.q[7 + j]; break;
             case FBC_VEL_LO: sl = S.v[6 + j] - (-pr.v_max[j]); break;
@@ -2277,22 +2341,25 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_ls_eval(FbArrays A, 
   // logs of the trial slacks by all lanes, summed in ascending order below
   if (!terminal) {
     FBW_FOR(idx, FB_NCON) {
-      const int c = idx < 72 ? idx / 12 : (idx < 92 ? FBC_FRICTION : FBC_IMPULSE_FRICTION);
+      const int c = fbc_comp(idx);
+      const int j = idx - fbc_offset(c);
       double lg = 0.0, ar = 0.0;
-      if (el.cactive[c]) {
+      if (el.cactive[c] && j < fbc_rows(pr, c)) {
         lg = canon_log(INITIAL ? w.slack[idx] : fma(alpha, w.dual[idx], w.slack[idx]));
-        const int j = idx - fbc_offset(c);
-        if (c >= FBC_FRICTION) {
-          const int i = j / 5;
+        if (fbc_is_cone(c)) {
+          const int rpc = fbc_cone_rows(pr, c);
+          const int i = j / rpc;
           if (el.active[i]) {
             double r5[5];
-            fb_friction_residual(pr.mu, w.f + 3 * i, r5);
-            ar = fabs(r5[j % 5] + w.slack[idx]);
+            fb_friction_residual(pr.mu, rpc == 2, w.f + 3 * i, r5);
+            ar = fabs(r5[j % rpc] + w.slack[idx]);
           }
         } else {
           const double sl = w.slack[idx];
           double res;
           switch (c) {
+            case FBC_ACC_LO: res = pr.a_min[j] - w.a[6 + j] + sl; break;
+            case FBC_ACC_UP: res = w.a[6 + j] - pr.a_max[j] + sl; break;
             case FBC_POS_LO: res = pr.q_min[j] - w.q[7 + j] + sl; break;
             case FBC_POS_UP: res = w.q[7 + j] - pr.q_max[j] + sl; break;
             case FBC_VEL_LO: res = (-pr.v_max[j]) - w.v[6 + j] + sl; break;
@@ -2328,7 +2395,7 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_ls_eval(FbArrays A, 
       for (int c = 0; c < FBC_NCOMP; ++c) {
         if (!el.cactive[c]) continue;
         double sl = 0.0;
-        for (int j = 0; j < fbc_dim(c); ++j) sl += w.duality[fbc_offset(c) + j];
+        for (int j = 0; j < fbc_rows(pr, c); ++j) sl += w.duality[fbc_offset(c) + j];
         bc += -pr.barrier * sl;
       }
       cost += (impulse ? 1.0 : dt) * bc;
@@ -2343,7 +2410,7 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_ls_eval(FbArrays A, 
     for (int c = 0; c < FBC_NCOMP; ++c) {
       if (!el.cactive[c]) continue;
       double s1 = 0.0;
-      for (int j = 0; j < fbc_dim(c); ++j) s1 += w.residual[fbc_offset(c) + j];
+      for (int j = 0; j < fbc_rows(pr, c); ++j) s1 += w.residual[fbc_offset(c) + j];
       cl1 += s1;
     }
     w.part[0] = cl1;

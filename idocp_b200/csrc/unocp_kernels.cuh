@@ -26,6 +26,9 @@ namespace idocp_b200 {
 #ifndef IDOCP_LIN_MINB
 #define IDOCP_LIN_MINB 2   // min resident CTAs/SM of k_linearize (register cap = 65536 / (128 * MINB))
 #endif
+#ifndef IDOCP_UL_CTAS_PER_SM
+#define IDOCP_UL_CTAS_PER_SM 2   // persistent k_update_linearize: resident CTAs per SM (97 KB of shared memory each)
+#endif
 #ifndef IDOCP_RIC_MINB
 #define IDOCP_RIC_MINB 2
 #endif
@@ -615,16 +618,24 @@ constexpr int RIC_RING = 3;
 constexpr int RIC_RING_SLOTS = 2 * NV + 1 + 2;                                        // Kq, Kv, k | Fq, Fv
 constexpr int RIC_WARP_SLOTS = (RIC_RING * RIC_RING_SLOTS > RIC_BUFA_SLOTS + RIC_BUFX_SLOTS)
                                    ? RIC_RING * RIC_RING_SLOTS : RIC_BUFA_SLOTS + RIC_BUFX_SLOTS;
-constexpr int RIC_OFF_STREAM = OCTETS_PER_CTA * RIC_SMEM_PER_OCT;                     // doubles
-constexpr int RIC_OFF_BARS = RIC_OFF_STREAM + WARPS_PER_CTA * RIC_WARP_SLOTS * SLOT;
+// The sweep is a serial chain per warp, so its duration is (rounds of resident warps) x (one chain): 16384 instances = 4096
+// warps need 4 rounds at 8 warps / SM (3.46 waves) but 3 at 10.  Measured (profiles/r2n_variants.txt): 10 warps / SM caps the
+// kernel at 168 registers (three warps on one scheduler partition) with 600-800 B of spills: 0.423 -> 0.564 ms.  Kept at 4.
+#ifndef IDOCP_RIC_WARPS
+#define IDOCP_RIC_WARPS 4
+#endif
+constexpr int RIC_WARPS = IDOCP_RIC_WARPS;
+constexpr int RIC_THREADS = 32 * RIC_WARPS;
+constexpr int RIC_OFF_STREAM = 4 * RIC_WARPS * RIC_SMEM_PER_OCT;                      // doubles
+constexpr int RIC_OFF_BARS = RIC_OFF_STREAM + RIC_WARPS * RIC_WARP_SLOTS * SLOT;
 constexpr int RIC_NBARS = 2 + RIC_RING;
-constexpr int RIC_SMEM_DOUBLES = RIC_OFF_BARS + RIC_NBARS * WARPS_PER_CTA;
+constexpr int RIC_SMEM_DOUBLES = RIC_OFF_BARS + RIC_NBARS * RIC_WARPS;
 static_assert(KQ_AA == 0 && KQ_QQ == 3 * NV && KQ_FQ == 6 * NV && KQ_NUM == 6 * NV + 5, "record layout");
 static_assert(W_KQ == 0 && W_KV == NV && W_K == 2 * NV && KQ_FV == KQ_FQ + 1, "record layout");
 
 // TASK = true: the terminal Hessian / gradient are dense and come from record N of KQ (k_linearize<.., true>)
 template <bool TASK>
-__global__ void __launch_bounds__(CTA_THREADS, IDOCP_RIC_MINB) k_riccati(const DevProblem* __restrict__ Pp, Layout L,
+__global__ void __launch_bounds__(RIC_THREADS, IDOCP_RIC_MINB) k_riccati(const DevProblem* __restrict__ Pp, Layout L,
                                                          const double* __restrict__ q0,
                                                          const double* __restrict__ v0) {
   IDOCP_DYN_SMEM(double, smem);
@@ -633,7 +644,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_RIC_MINB) k_riccati(const D
   const int oct = threadIdx.x >> 3;
   double* tA = smem + oct * RIC_SMEM_PER_OCT;         // [8][RIC_TILE]
   double* tB = tA + OCT * RIC_TILE;                   // [8][RIC_TILE]
-  int g = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+  int g = blockIdx.x * RIC_WARPS + (threadIdx.x >> 5);
   if (g >= L.G) g = L.G - 1;     // tail warps redo the last group (identical, idempotent stores)
   const int b = g * 4 + (oct & 3);
   const bool valid = b < L.B;    // padded instances (B <= b < Bp) are computed but never reported

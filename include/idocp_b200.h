@@ -277,7 +277,10 @@ int idocp_b200_discretize_ocp(const idocp_b200_contact_sequence* cs, double T, i
  *       the time of every stage (idocp_b200_fb_set_cost_reference), like the 6D reference of the iiwa14 path;
  *   ContactForceCost (src/cost/contact_force_cost.cpp:121-228): f_weight / f_ref, fi_weight / fi_ref (impulses).
  * Constraints = JointConstraintsFactory's six joint limits on the 12 actuated joints + LinearizedFrictionCone +
- * LinearizedImpulseFrictionCone (src/constraints/ *.cpp), enable[] in the order below.
+ * LinearizedImpulseFrictionCone (src/constraints/ *.cpp), enable[] in the order below; cone_nonlinear[0 / 1] selects
+ * FrictionCone / ImpulseFrictionCone (friction_cone.cpp, impulse_friction_cone.cpp: two rows per contact, normal force and
+ * fx^2 + fy^2 - mu^2 fz^2 <= 0) for the enabled cone; enable_acceleration_limit[0 / 1] adds JointAccelerationLowerLimit /
+ * JointAccelerationUpperLimit (joint_acceleration_*_limit.cpp) with the bounds a_min / a_max on the 12 joint accelerations.
  * ------------------------------------------------------------------------------------------------------------ */
 #define IDOCP_B200_FB_NQ 19
 #define IDOCP_B200_FB_NV 18
@@ -296,6 +299,9 @@ typedef struct {
   double q_min[12], q_max[12], v_max[12], u_max[12];           /* Robot::*JointPositionLimit etc. (robot.hxx:699-709) */
   double mu, barrier, fraction_rate;                           /* friction coefficient; PDIPM barrier, fraction-to-boundary */
   int enable[IDOCP_B200_FB_NUM_CONSTRAINTS];
+  int cone_nonlinear[2];                                       /* [0] FrictionCone, [1] ImpulseFrictionCone */
+  int enable_acceleration_limit[2];                            /* [0] lower, [1] upper */
+  double a_min[12], a_max[12];
 } idocp_b200_fb_problem;
 typedef struct idocp_b200_fb_solver idocp_b200_fb_solver; /* opaque */
 

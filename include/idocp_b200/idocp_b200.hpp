@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <map>
 #include <memory>
 #include <sstream>
 #include <stdexcept>
@@ -215,6 +216,13 @@ class Robot {
     contact_points.resize(4);
     for (int i = 0; i < 4; ++i) contact_points[i] = Vector3d(points_[3 * i], points_[3 * i + 1], points_[3 * i + 2]);
   }
+  // robot.hxx:731-735: the contact points of the status become the current positions of the contact frames
+  template <typename ContactStatusType>
+  void setContactPoints(ContactStatusType& contact_status) const {
+    std::vector<Vector3d> pts;
+    getContactPoints(pts);
+    contact_status.setContactPoints(pts);
+  }
   void setJointEffortLimit(const VectorXd& v) { detail::copy7(v, p_.u_max, "joint_effort_limit"); }
   void setJointVelocityLimit(const VectorXd& v) { detail::copy7(v, p_.v_max, "joint_velocity_limit"); }
   void setLowerJointPositionLimit(const VectorXd& v) { detail::copy7(v, p_.q_min, "lower_joint_position_limit"); }
@@ -232,19 +240,36 @@ class Robot {
 
 class ConfigurationSpaceCost {
  public:
-  explicit ConfigurationSpaceCost(const Robot&) { detail::check(idocp_b200_problem_default(0, &p_)); }
-  void set_q_ref(const VectorXd& v) { detail::copy7(v, p_.q_ref, "q_ref"); }
-  void set_v_ref(const VectorXd& v) { detail::copy7(v, p_.v_ref, "v_ref"); }
-  void set_u_ref(const VectorXd& v) { detail::copy7(v, p_.u_ref, "u_ref"); }
-  void set_q_weight(const VectorXd& v) { detail::copy7(v, p_.q_weight, "q_weight"); }
-  void set_v_weight(const VectorXd& v) { detail::copy7(v, p_.v_weight, "v_weight"); }
-  void set_a_weight(const VectorXd& v) { detail::copy7(v, p_.a_weight, "a_weight"); }
-  void set_u_weight(const VectorXd& v) { detail::copy7(v, p_.u_weight, "u_weight"); }
-  void set_qf_weight(const VectorXd& v) { detail::copy7(v, p_.qf_weight, "qf_weight"); }
-  void set_vf_weight(const VectorXd& v) { detail::copy7(v, p_.vf_weight, "vf_weight"); }
+  // one class for both robots, as in the reference (cost/configuration_space_cost.hpp): with the floating-base Robot the
+  // vectors have dimq = 19 / dimv = 18 entries and OCPSolver turns them into its constant-reference configuration cost
+  // (examples/anymal/ocp_benchmark.cpp)
+  explicit ConfigurationSpaceCost(const Robot& robot) : floating_(robot.hasFloatingBase()) { detail::check(idocp_b200_problem_default(0, &p_)); }
+  void set_q_ref(const VectorXd& v) { if (!keep("q_ref", v, 19)) detail::copy7(v, p_.q_ref, "q_ref"); }
+  void set_v_ref(const VectorXd& v) { if (!keep("v_ref", v, 18)) detail::copy7(v, p_.v_ref, "v_ref"); }
+  void set_u_ref(const VectorXd& v) { if (!keep("u_ref", v, 12)) detail::copy7(v, p_.u_ref, "u_ref"); }
+  void set_q_weight(const VectorXd& v) { if (!keep("q_weight", v, 18)) detail::copy7(v, p_.q_weight, "q_weight"); }
+  void set_v_weight(const VectorXd& v) { if (!keep("v_weight", v, 18)) detail::copy7(v, p_.v_weight, "v_weight"); }
+  void set_a_weight(const VectorXd& v) { if (!keep("a_weight", v, 18)) detail::copy7(v, p_.a_weight, "a_weight"); }
+  void set_u_weight(const VectorXd& v) { if (!keep("u_weight", v, 12)) detail::copy7(v, p_.u_weight, "u_weight"); }
+  void set_qf_weight(const VectorXd& v) { if (!keep("qf_weight", v, 18)) detail::copy7(v, p_.qf_weight, "qf_weight"); }
+  void set_vf_weight(const VectorXd& v) { if (!keep("vf_weight", v, 18)) detail::copy7(v, p_.vf_weight, "vf_weight"); }
+  // impulse-stage weights (configuration_space_cost.hpp:61-65): no impulse stages on the fixed-base path
+  void set_qi_weight(const VectorXd& v) { keep("qi_weight", v, 18); }
+  void set_vi_weight(const VectorXd& v) { keep("vi_weight", v, 18); }
+  void set_dvi_weight(const VectorXd& v) { keep("dvi_weight", v, 18); }
   const idocp_b200_problem& params() const { return p_; }
+  bool floating() const { return floating_; }
+  const std::map<std::string, VectorXd>& floatingParams() const { return fb_; }
  private:
+  bool keep(const char* name, const VectorXd& v, int n) {
+    if (!floating_) return false;
+    if (v.size() != n) detail::die(std::string("invalid size: ") + name + ".size() must be " + std::to_string(n) + "!");
+    fb_[name] = v;
+    return true;
+  }
   idocp_b200_problem p_;
+  bool floating_ = false;
+  std::map<std::string, VectorXd> fb_;
 };
 
 // cost/time_varying_task_space_6d_cost.hpp:22-41: user-derived reference; a HOST virtual, sampled by the solver
@@ -379,6 +404,7 @@ class CostFunction {
   const std::shared_ptr<ConfigurationSpaceCostBase>& fbConfig() const { return fb_config_; }
   const std::shared_ptr<ContactForceCost>& force() const { return force_; }
   void push_back(const std::shared_ptr<ConfigurationSpaceCost>& c) {
+    if (c->floating()) { fb_plain_ = c; return; }   // OCPSolver converts it (ocp_solver.hpp)
     if (config_) detail::die("idocp_b200: only one ConfigurationSpaceCost component is supported");
     if (task_) detail::die("idocp_b200: push the ConfigurationSpaceCost before the task-space cost");
     config_ = c;
@@ -391,8 +417,10 @@ class CostFunction {
   void push_back(const std::shared_ptr<TimeVaryingTaskSpace3DCost>& c) { push_back(c->component()); }
   void push_back(const std::shared_ptr<TaskSpace3DCost>& c) { push_back(c->component()); }
   const std::shared_ptr<ConfigurationSpaceCost>& config() const { return config_; }
+  const std::shared_ptr<ConfigurationSpaceCost>& fbPlain() const { return fb_plain_; }
   const std::shared_ptr<TimeVaryingTaskSpace6DCost>& task() const { return task_; }
  private:
+  std::shared_ptr<ConfigurationSpaceCost> fb_plain_;
   std::shared_ptr<ConfigurationSpaceCost> config_;
   std::shared_ptr<TimeVaryingTaskSpace6DCost> task_;
   std::shared_ptr<ConfigurationSpaceCostBase> fb_config_;
@@ -401,13 +429,26 @@ class CostFunction {
 
 class Constraints {
  public:
-  // constraints.hpp push_back: the components are tag classes {id, mu} (ocp_solver.hpp: JointPositionLowerLimit ...
-  // LinearizedImpulseFrictionCone); the fixed-base solvers always use the six joint limits of JointConstraintsFactory
+  // constraints.hpp push_back: the components are tag classes {id, mu, nonlinear, bound} (ocp_solver.hpp:
+  // JointPositionLowerLimit ... LinearizedImpulseFrictionCone, FrictionCone, ImpulseFrictionCone, JointAcceleration*Limit);
+  // the fixed-base solvers always use the six joint limits of JointConstraintsFactory
   template <typename Component>
   void push_back(const std::shared_ptr<Component>& c) {
+    if (c->id >= IDOCP_B200_FB_NUM_CONSTRAINTS) {   // JointAcceleration{Lower,Upper}Limit(robot, amin / amax)
+      const int k = c->id - IDOCP_B200_FB_NUM_CONSTRAINTS;
+      if (static_cast<int>(c->bound.size()) != 12) detail::die("invalid size: the acceleration limit takes one bound per actuated joint (12)");
+      enable_acc_[k] = 1;
+      for (int j = 0; j < 12; ++j) (k == 0 ? a_min_ : a_max_)[j] = c->bound[j];
+      return;
+    }
     enable_[c->id] = 1;
     if (c->mu > 0) mu_ = c->mu;
+    if (c->id >= IDOCP_B200_FB_FRICTION_CONE) cone_nonlinear_[c->id - IDOCP_B200_FB_FRICTION_CONE] = c->nonlinear;
   }
+  const int* coneNonlinear() const { return cone_nonlinear_; }
+  const int* enableAccelerationLimit() const { return enable_acc_; }
+  const double* aMin() const { return a_min_; }
+  const double* aMax() const { return a_max_; }
   const int* enable() const { return enable_; }
   double mu() const { return mu_; }
   void setBarrier(double b) { if (!(b > 0)) detail::die("invalid argment: barrier must be positive"); barrier_ = b; }
@@ -420,6 +461,8 @@ class Constraints {
  private:
   double barrier_ = 1.0e-04, rate_ = 0.995;
   int enable_[IDOCP_B200_FB_NUM_CONSTRAINTS] = {0};
+  int cone_nonlinear_[2] = {0, 0}, enable_acc_[2] = {0, 0};
+  double a_min_[12] = {0}, a_max_[12] = {0};
   double mu_ = 0.7;
 };
 

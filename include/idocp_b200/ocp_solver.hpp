@@ -6,7 +6,8 @@
 //   idocp::Robot(path_to_urdf, contact_frames)   include/idocp/robot/robot.hpp   -> QuadrupedRobot
 //   idocp::TrottingConfigurationSpaceCost        include/idocp/cost/trotting_configuration_space_cost.hpp
 //   idocp::ContactForceCost                      include/idocp/cost/contact_force_cost.hpp
-//   idocp::Joint{Position,Velocity,Torques}{Lower,Upper}Limit, LinearizedFrictionCone, LinearizedImpulseFrictionCone
+//   idocp::Joint{Position,Velocity,Torques,Acceleration}{Lower,Upper}Limit, LinearizedFrictionCone, LinearizedImpulseFrictionCone,
+//   FrictionCone, ImpulseFrictionCone
 //                                                include/idocp/constraints/ *.hpp
 //   idocp::OCPSolver                             include/idocp/ocp/ocp_solver.hpp:28-230
 // The reference's cost / constraint plug-ins are host virtuals; here they are a closed registry of POD-parameterised
@@ -74,6 +75,27 @@ class FloatingBaseConfigurationSpaceCost : public ConfigurationSpaceCostBase {
   void set_v_ref(const VectorXd& v) { if (v.size() != 18) detail::die("invalid size: v_ref.size() must be 18!"); v_ref_ = v; }
   void update_q_ref(const double, VectorXd& q_ref) const override { q_ref = q_ref_; }
   VectorXd v_ref(const double) const override { return v_ref_; }
+  // from a ConfigurationSpaceCost built with the floating-base Robot (name -> vector, idocp_b200.hpp)
+  void adopt(const std::map<std::string, VectorXd>& params) {
+    for (const auto& kv : params) {
+      const std::string& n = kv.first;
+      const VectorXd& v = kv.second;
+      if (n == "q_ref") set_q_ref(v);
+      else if (n == "v_ref") set_v_ref(v);
+      else if (n == "q_weight") set_q_weight(v);
+      else if (n == "v_weight") set_v_weight(v);
+      else if (n == "a_weight") set_a_weight(v);
+      else if (n == "qf_weight") set_qf_weight(v);
+      else if (n == "vf_weight") set_vf_weight(v);
+      else if (n == "qi_weight") set_qi_weight(v);
+      else if (n == "vi_weight") set_vi_weight(v);
+      else if (n == "dvi_weight") set_dvi_weight(v);
+      else if (n == "u_weight" || n == "u_ref") {
+        for (int i = 0; i < v.size(); ++i)
+          if (n == "u_weight" && v[i] != 0.0) detail::die("unsupported: a torque cost (u_weight) on the floating-base path");
+      }
+    }
+  }
  private:
   VectorXd q_ref_, v_ref_;
 };
@@ -190,10 +212,12 @@ using HybridConstraints = Constraints;
 struct HybridConstraintComponent {
   int id;
   double mu;
+  int nonlinear = 0;            // FrictionCone / ImpulseFrictionCone: the cone itself instead of its pyramid
+  std::vector<double> bound;    // JointAcceleration{Lower,Upper}Limit: amin / amax
 };
 #define IDOCP_B200_JOINT_LIMIT(Name, Id)                                   \
   struct Name : HybridConstraintComponent {                                 \
-    explicit Name(const Robot&) : HybridConstraintComponent{Id, 0.0} {} \
+    explicit Name(const Robot&) : HybridConstraintComponent{Id, 0.0, 0, {}} {} \
   }
 IDOCP_B200_JOINT_LIMIT(JointPositionLowerLimit, IDOCP_B200_FB_POSITION_LOWER);
 IDOCP_B200_JOINT_LIMIT(JointPositionUpperLimit, IDOCP_B200_FB_POSITION_UPPER);
@@ -203,14 +227,40 @@ IDOCP_B200_JOINT_LIMIT(JointTorquesLowerLimit, IDOCP_B200_FB_TORQUES_LOWER);
 IDOCP_B200_JOINT_LIMIT(JointTorquesUpperLimit, IDOCP_B200_FB_TORQUES_UPPER);
 #undef IDOCP_B200_JOINT_LIMIT
 struct LinearizedFrictionCone : HybridConstraintComponent {
-  LinearizedFrictionCone(const Robot&, const double mu) : HybridConstraintComponent{IDOCP_B200_FB_FRICTION_CONE, mu} {
+  LinearizedFrictionCone(const Robot&, const double mu) : HybridConstraintComponent{IDOCP_B200_FB_FRICTION_CONE, mu, 0, {}} {
     if (mu <= 0) detail::die("invalid value: mu must be positive!");
   }
 };
 struct LinearizedImpulseFrictionCone : HybridConstraintComponent {
   LinearizedImpulseFrictionCone(const Robot&, const double mu)
-      : HybridConstraintComponent{IDOCP_B200_FB_IMPULSE_FRICTION_CONE, mu} {
+      : HybridConstraintComponent{IDOCP_B200_FB_IMPULSE_FRICTION_CONE, mu, 0, {}} {
     if (mu <= 0) detail::die("invalid value: mu must be positive!");
+  }
+};
+// FrictionCone / ImpulseFrictionCone (src/constraints/friction_cone.cpp, impulse_friction_cone.cpp): two rows per contact,
+// -fz <= 0 and fx^2 + fy^2 - mu^2 fz^2 <= 0; they take the place of the linearised cone of the same level
+struct FrictionCone : HybridConstraintComponent {
+  FrictionCone(const Robot&, const double mu) : HybridConstraintComponent{IDOCP_B200_FB_FRICTION_CONE, mu, 1, {}} {
+    if (mu <= 0) detail::die("invalid value: mu must be positive!");
+  }
+};
+struct ImpulseFrictionCone : HybridConstraintComponent {
+  ImpulseFrictionCone(const Robot&, const double mu) : HybridConstraintComponent{IDOCP_B200_FB_IMPULSE_FRICTION_CONE, mu, 1, {}} {
+    if (mu <= 0) detail::die("invalid value: mu must be positive!");
+  }
+};
+// JointAccelerationLowerLimit(robot, amin) / JointAccelerationUpperLimit(robot, amax) (joint_acceleration_*_limit.cpp:
+// amin <= a.tail(dimc) <= amax on the actuated joints; any vector type with size() and operator[])
+struct JointAccelerationLowerLimit : HybridConstraintComponent {
+  template <typename Vector>
+  JointAccelerationLowerLimit(const Robot&, const Vector& amin) : HybridConstraintComponent{IDOCP_B200_FB_NUM_CONSTRAINTS, 0.0, 0, {}} {
+    for (int j = 0; j < static_cast<int>(amin.size()); ++j) bound.push_back(amin[j]);
+  }
+};
+struct JointAccelerationUpperLimit : HybridConstraintComponent {
+  template <typename Vector>
+  JointAccelerationUpperLimit(const Robot&, const Vector& amax) : HybridConstraintComponent{IDOCP_B200_FB_NUM_CONSTRAINTS + 1, 0.0, 0, {}} {
+    for (int j = 0; j < static_cast<int>(amax.size()); ++j) bound.push_back(amax[j]);
   }
 };
 // OCPSolver(robot, cost, constraints, T, N, max_num_impulse, nthreads) for `batch` instances
@@ -228,6 +278,11 @@ class OCPSolver {
     if (!cost || !constraints) detail::die("idocp_b200: cost and constraints must not be null");
     idocp_b200_fb_problem p = robot.fbLimits();
     p.T = T; p.N = N; p.max_num_impulse = max_num_impulse;
+    if (!cost->fbConfig() && cost->fbPlain()) {   // ConfigurationSpaceCost(robot) of the floating-base robot
+      auto fc = std::make_shared<FloatingBaseConfigurationSpaceCost>(robot);
+      fc->adopt(cost->fbPlain()->floatingParams());
+      cost->push_back(std::shared_ptr<ConfigurationSpaceCostBase>(fc));
+    }
     if (cost->fbConfig()) {
       const idocp_b200_fb_problem& w = cost->fbConfig()->weights();
       std::memcpy(p.q_weight, w.q_weight, sizeof(double) * 18 * 8);   // q_weight .. dvi_weight are contiguous
@@ -238,6 +293,11 @@ class OCPSolver {
     }
     for (int c = 0; c < IDOCP_B200_FB_NUM_CONSTRAINTS; ++c) p.enable[c] = constraints->enable()[c];
     p.mu = constraints->mu(); p.barrier = constraints->barrier(); p.fraction_rate = constraints->fractionToBoundaryRate();
+    for (int k = 0; k < 2; ++k) {
+      p.cone_nonlinear[k] = constraints->coneNonlinear()[k];
+      p.enable_acceleration_limit[k] = constraints->enableAccelerationLimit()[k];
+    }
+    for (int j = 0; j < 12; ++j) { p.a_min[j] = constraints->aMin()[j]; p.a_max[j] = constraints->aMax()[j]; }
     idocp_b200_contact_sequence* cs = nullptr;
     detail::check(idocp_b200_contact_sequence_create(4, 2 * max_num_impulse + 2, &cs));
     cs_.reset(cs, [](idocp_b200_contact_sequence* x) { idocp_b200_contact_sequence_destroy(x); });

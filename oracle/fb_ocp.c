@@ -37,7 +37,7 @@
 #define NPASS 6
 
 enum { K_GRID = 0, K_IMPULSE = 1, K_AUX = 2, K_LIFT = 3, K_TERMINAL = 4 };
-enum { C_POS_LO = 0, C_POS_UP, C_VEL_LO, C_VEL_UP, C_TRQ_LO, C_TRQ_UP, C_FRICTION, C_IMPULSE_FRICTION, NCOMP };
+enum { C_POS_LO = 0, C_POS_UP, C_VEL_LO, C_VEL_UP, C_TRQ_LO, C_TRQ_UP, C_FRICTION, C_IMPULSE_FRICTION, C_ACC_LO, C_ACC_UP, NCOMP };
 
 typedef struct {
   double T;
@@ -46,11 +46,22 @@ typedef struct {
   double f_weight[MAXF], f_ref[MAXF], fi_weight[MAXF], fi_ref[MAXF];
   double q_min[NU], q_max[NU], v_max[NU], u_max[NU];
   double mu, barrier, fraction_rate;
-  int enable[NCOMP];
+  int enable[8];
+  /* appended (idocp_b200_fb_problem keeps its first members): FrictionCone / ImpulseFrictionCone (the nonlinear cones,
+   * src/constraints/friction_cone.cpp, impulse_friction_cone.cpp) instead of the linearised ones; JointAcceleration{Lower,
+   * Upper}Limit (joint_acceleration_*_limit.cpp) with their amin / amax constructor arguments */
+  int cone_nonlinear[2];
+  int enable_acc[2];
+  double a_min[NU], a_max[NU];
 } oracle_fb_problem_t;
+static inline int comp_enabled(const oracle_fb_problem_t* p, int c) { return c < C_ACC_LO ? p->enable[c] : p->enable_acc[c - C_ACC_LO]; }
+static inline int is_cone(int c) { return c == C_FRICTION || c == C_IMPULSE_FRICTION; }
+/* rows per contact: 5 (linearised) or 2 (normal force, cone) */
+static inline int cone_rows(const oracle_fb_problem_t* p, int c) { return p->cone_nonlinear[c - C_FRICTION] ? 2 : 5; }
 
 typedef struct { double slack[20], dual[20], residual[20], duality[20], dslack[20], ddual[20]; } cdata_t;
-static inline int comp_dim(int c) { return c >= C_FRICTION ? 20 : NU; }
+static inline int comp_dim(int c) { return (c == C_FRICTION || c == C_IMPULSE_FRICTION) ? 20 : NU; }   /* storage */
+#define comp_rows(p, c) (is_cone(c) ? FB_NC * cone_rows(p, c) : NU)                                      /* live rows */
 
 typedef struct {
   /* --- SplitSolution / ImpulseSplitSolution (a = dv at an impulse) --- */
@@ -154,6 +165,8 @@ static double l1norm_n(const double* x, int n) {
 static void set_constraint_stage(const oracle_fb_problem_t* p, stage_t* st, int time_stage) {
   st->cstage = time_stage;
   const int pos = time_stage >= 2, vel = time_stage >= 1, acc = time_stage >= 0, imp = time_stage <= -1;
+  st->cactive[C_ACC_LO] = acc && p->enable_acc[0];
+  st->cactive[C_ACC_UP] = acc && p->enable_acc[1];
   st->cactive[C_POS_LO] = pos && p->enable[C_POS_LO];
   st->cactive[C_POS_UP] = pos && p->enable[C_POS_UP];
   st->cactive[C_VEL_LO] = vel && p->enable[C_VEL_LO];
@@ -163,8 +176,15 @@ static void set_constraint_stage(const oracle_fb_problem_t* p, stage_t* st, int 
   st->cactive[C_FRICTION] = acc && p->enable[C_FRICTION];
   st->cactive[C_IMPULSE_FRICTION] = imp && p->enable[C_IMPULSE_FRICTION];
 }
-/* frictionConeResidual (linearized_friction_cone.hpp:72-85) */
-static inline void friction_residual(double mu, const double* f, double* r) {
+/* frictionConeResidual (linearized_friction_cone.hpp:72-85); nonlinear: normalForceResidual, frictionConeResidual
+ * (friction_cone.hpp:72-82) */
+static inline void friction_residual(double mu, int nonlinear, const double* f, double* r) {
+  if (nonlinear) {
+    r[0] = -f[2];
+    r[1] = fma(-((mu * mu) * f[2]), f[2], fma(f[1], f[1], f[0] * f[0]));
+    r[2] = r[3] = r[4] = 0.0;
+    return;
+  }
   const double s = mu * f[2] / 1.41421356237309514547e+00;
   r[0] = -f[2];
   r[1] = f[0] - s;
@@ -172,8 +192,14 @@ static inline void friction_residual(double mu, const double* f, double* r) {
   r[3] = f[1] - s;
   r[4] = -f[1] - s;
 }
-/* Jac_ of the cone (linearized_friction_cone.cpp:25-29), row e */
-static inline void friction_jac_row(double mu, int e, double* row) {
+/* Jac_ of the cone (linearized_friction_cone.cpp:25-29), row e; nonlinear: row 0 = d(-fz)/df, row 1 = data.r[i] =
+ * (2 fx, 2 fy, -2 mu^2 fz) (friction_cone.cpp:109-111) */
+static inline void friction_jac_row(double mu, int nonlinear, const double* f, int e, double* row) {
+  if (nonlinear) {
+    if (e == 0) { row[0] = 0.0; row[1] = 0.0; row[2] = -1.0; }
+    else { row[0] = 2.0 * f[0]; row[1] = 2.0 * f[1]; row[2] = -(((2.0 * mu) * mu) * f[2]); }
+    return;
+  }
   const double m = -(mu / 1.41421356237309514547e+00);
   const double J[5][3] = {{0, 0, -1}, {1, 0, m}, {-1, 0, m}, {0, 1, m}, {0, -1, m}};
   row[0] = J[e][0]; row[1] = J[e][1]; row[2] = J[e][2];
@@ -186,22 +212,26 @@ static inline double limit_margin(const oracle_fb_problem_t* p, int c, const sta
     case C_VEL_LO: return s->v[6 + j] - (-p->v_max[j]);
     case C_VEL_UP: return p->v_max[j] - s->v[6 + j];
     case C_TRQ_LO: return s->u[j] - (-p->u_max[j]);
+    case C_ACC_LO: return s->a[6 + j] - p->a_min[j];
+    case C_ACC_UP: return p->a_max[j] - s->a[6 + j];
     default:       return p->u_max[j] - s->u[j];
   }
 }
-static inline double limit_residual_at(const oracle_fb_problem_t* p, int c, const double* q, const double* v, const double* u, int j,
-                                       double slack) {
+static inline double limit_residual_at(const oracle_fb_problem_t* p, int c, const double* q, const double* v, const double* a,
+                                       const double* u, int j, double slack) {
   switch (c) {
     case C_POS_LO: return p->q_min[j] - q[7 + j] + slack;
     case C_POS_UP: return q[7 + j] - p->q_max[j] + slack;
     case C_VEL_LO: return (-p->v_max[j]) - v[6 + j] + slack;
     case C_VEL_UP: return v[6 + j] - p->v_max[j] + slack;
     case C_TRQ_LO: return (-p->u_max[j]) - u[j] + slack;
+    case C_ACC_LO: return p->a_min[j] - a[6 + j] + slack;
+    case C_ACC_UP: return a[6 + j] - p->a_max[j] + slack;
     default:       return u[j] - p->u_max[j] + slack;
   }
 }
 static inline double limit_residual(const oracle_fb_problem_t* p, int c, const stage_t* s, int j, double slack) {
-  return limit_residual_at(p, c, s->q, s->v, s->u, j, slack);
+  return limit_residual_at(p, c, s->q, s->v, s->a, s->u, j, slack);
 }
 static inline double limit_sign(int c) { return (c & 1) ? 1.0 : -1.0; } /* lower: -, upper: + */
 
@@ -212,13 +242,14 @@ static void set_slack_and_dual(const oracle_fb_problem_t* p, stage_t* st) {
     cdata_t* d = &st->c[c];
     memset(d, 0, sizeof(*d));
     if (!st->cactive[c]) continue;
-    const int n = comp_dim(c);
+    const int n = comp_rows(p, c);
     for (int j = 0; j < n; ++j) {
       double sl;
-      if (c >= C_FRICTION) {
+      if (is_cone(c)) {
+        const int rpc = cone_rows(p, c);
         double r[5];
-        friction_residual(p->mu, st->f[j / 5], r);
-        sl = -r[j % 5];
+        friction_residual(p->mu, rpc == 2, st->f[j / rpc], r);
+        sl = -r[j % rpc];
       } else {
         sl = limit_margin(p, c, st, j);
       }
@@ -233,12 +264,13 @@ static void primal_dual_residual(const oracle_fb_problem_t* p, stage_t* st) {
   for (int c = 0; c < NCOMP; ++c) {
     if (!st->cactive[c]) continue;
     cdata_t* d = &st->c[c];
-    if (c >= C_FRICTION) {
+    if (is_cone(c)) {
+      const int rpc = cone_rows(p, c);
       for (int i = 0; i < FB_NC; ++i) {
         double r[5];
-        if (st->active[i]) friction_residual(p->mu, st->f[i], r);
-        for (int e = 0; e < 5; ++e) {
-          const int j = 5 * i + e;
+        if (st->active[i]) friction_residual(p->mu, rpc == 2, st->f[i], r);
+        for (int e = 0; e < rpc; ++e) {
+          const int j = rpc * i + e;
           if (st->active[i]) {
             d->residual[j] = r[e] + d->slack[j];
             d->duality[j] = d->slack[j] * d->dual[j] - p->barrier;
@@ -256,23 +288,26 @@ static void primal_dual_residual(const oracle_fb_problem_t* p, stage_t* st) {
     }
   }
 }
-static inline double* limit_grad(stage_t* st, int c) { return c <= C_POS_UP ? st->lq + 6 : (c <= C_VEL_UP ? st->lv + 6 : st->lu); }
+static inline double* limit_grad(stage_t* st, int c) {
+  return c <= C_POS_UP ? st->lq + 6 : (c <= C_VEL_UP ? st->lv + 6 : (c >= C_ACC_LO ? st->la + 6 : st->lu));
+}
 
 /* Constraints::augmentDualResidual; dt = 1 at an impulse (no dt argument there) */
 static void augment_dual_residual(const oracle_fb_problem_t* p, stage_t* st, double dt) {
   for (int c = 0; c < NCOMP; ++c) {
     if (!st->cactive[c]) continue;
     const cdata_t* d = &st->c[c];
-    if (c >= C_FRICTION) {
+    if (is_cone(c)) {
+      const int rpc = cone_rows(p, c);
       int k = 0;
       for (int i = 0; i < FB_NC; ++i) {
         if (!st->active[i]) continue;
         for (int x = 0; x < 3; ++x) {
           double acc = 0.0;
-          for (int e = 0; e < 5; ++e) {
+          for (int e = 0; e < rpc; ++e) {
             double row[3];
-            friction_jac_row(p->mu, e, row);
-            acc = (e == 0) ? row[x] * d->dual[5 * i + e] : fma(row[x], d->dual[5 * i + e], acc);
+            friction_jac_row(p->mu, rpc == 2, st->f[i], e, row);
+            acc = (e == 0) ? row[x] * d->dual[rpc * i + e] : fma(row[x], d->dual[rpc * i + e], acc);
           }
           st->lf[3 * k + x] += dt * acc;
         }
@@ -291,25 +326,26 @@ static void condense_slack_and_dual(const oracle_fb_problem_t* p, stage_t* st, d
   for (int c = 0; c < NCOMP; ++c) {
     if (!st->cactive[c]) continue;
     cdata_t* d = &st->c[c];
-    if (c >= C_FRICTION) {
+    if (is_cone(c)) {
+      const int rpc = cone_rows(p, c);
       int k = 0;
       for (int i = 0; i < FB_NC; ++i) {
         if (!st->active[i]) continue;
         double r5[5], w5[5], Jr[5][3];
-        for (int e = 0; e < 5; ++e) {
-          const int j = 5 * i + e;
+        for (int e = 0; e < rpc; ++e) {
+          const int j = rpc * i + e;
           const double rs = 1.0 / d->slack[j];
           r5[e] = fma(d->dual[j], d->residual[j], -d->duality[j]) * rs;
           w5[e] = d->dual[j] * rs;
-          friction_jac_row(p->mu, e, Jr[e]);
+          friction_jac_row(p->mu, rpc == 2, st->f[i], e, Jr[e]);
         }
         for (int x = 0; x < 3; ++x) {
           double acc = Jr[0][x] * r5[0];
-          for (int e = 1; e < 5; ++e) acc = fma(Jr[e][x], r5[e], acc);
+          for (int e = 1; e < rpc; ++e) acc = fma(Jr[e][x], r5[e], acc);
           st->lf[3 * k + x] += dt * acc;
           for (int y = 0; y < 3; ++y) {
             double h = Jr[0][x] * (w5[0] * Jr[0][y]);
-            for (int e = 1; e < 5; ++e) h = fma(Jr[e][x], w5[e] * Jr[e][y], h);
+            for (int e = 1; e < rpc; ++e) h = fma(Jr[e][x], w5[e] * Jr[e][y], h);
             st->Qff[(3 * k + x) * MAXF + 3 * k + y] += dt * h;
           }
         }
@@ -323,6 +359,7 @@ static void condense_slack_and_dual(const oracle_fb_problem_t* p, stage_t* st, d
         const double h = (dt * d->dual[j]) * rs;
         if (c <= C_POS_UP) st->Qxx[(6 + j) * NX + 6 + j] += h;
         else if (c <= C_VEL_UP) st->Qxx[(NV + 6 + j) * NX + NV + 6 + j] += h;
+        else if (c >= C_ACC_LO) st->Qaa[6 + j] += h;
         else st->Quu[(6 + j) * NV + 6 + j] += h;
         l[j] += sg * ((dt * fma(d->dual[j], d->residual[j], -d->duality[j])) * rs);
       }
@@ -334,16 +371,17 @@ static void slack_dual_direction(const oracle_fb_problem_t* p, stage_t* st) {
   for (int c = 0; c < NCOMP; ++c) {
     if (!st->cactive[c]) continue;
     cdata_t* d = &st->c[c];
-    if (c >= C_FRICTION) {
-      for (int j = 0; j < 20; ++j) { d->dslack[j] = 1.0; d->ddual[j] = 1.0; }
+    if (is_cone(c)) {
+      const int rpc = cone_rows(p, c);
+      for (int j = 0; j < FB_NC * rpc; ++j) { d->dslack[j] = 1.0; d->ddual[j] = 1.0; }
       int k = 0;
       for (int i = 0; i < FB_NC; ++i) {
         if (!st->active[i]) continue;
         const double* df = st->daf + NV + 3 * k;
-        for (int e = 0; e < 5; ++e) {
-          const int j = 5 * i + e;
+        for (int e = 0; e < rpc; ++e) {
+          const int j = rpc * i + e;
           double row[3];
-          friction_jac_row(p->mu, e, row);
+          friction_jac_row(p->mu, rpc == 2, st->f[i], e, row);
           const double Jdf = fma(row[2], df[2], fma(row[1], df[1], row[0] * df[0]));
           d->dslack[j] = -Jdf - d->residual[j];
           d->ddual[j] = -fma(d->dual[j], d->dslack[j], d->duality[j]) / d->slack[j];
@@ -351,7 +389,7 @@ static void slack_dual_direction(const oracle_fb_problem_t* p, stage_t* st) {
         ++k;
       }
     } else {
-      const double* dx = c <= C_POS_UP ? st->dq + 6 : (c <= C_VEL_UP ? st->dv + 6 : st->du);
+      const double* dx = c <= C_POS_UP ? st->dq + 6 : (c <= C_VEL_UP ? st->dv + 6 : (c >= C_ACC_LO ? st->daf + 6 : st->du));
       for (int j = 0; j < NU; ++j) {
         d->dslack[j] = ((c & 1) ? -dx[j] : dx[j]) - d->residual[j];
         d->ddual[j] = -fma(d->dual[j], d->dslack[j], d->duality[j]) / d->slack[j];
@@ -373,8 +411,8 @@ static void max_step_sizes(const oracle_fb_problem_t* p, stage_t* st) {
   double mp = 1.0, md = 1.0;
   for (int c = 0; c < NCOMP; ++c) {
     if (!st->cactive[c]) continue;
-    const double a = fraction_to_boundary(p->fraction_rate, comp_dim(c), st->c[c].slack, st->c[c].dslack);
-    const double b = fraction_to_boundary(p->fraction_rate, comp_dim(c), st->c[c].dual, st->c[c].ddual);
+    const double a = fraction_to_boundary(p->fraction_rate, comp_rows(p, c), st->c[c].slack, st->c[c].dslack);
+    const double b = fraction_to_boundary(p->fraction_rate, comp_rows(p, c), st->c[c].dual, st->c[c].ddual);
     if (a < mp) mp = a;
     if (b < md) md = b;
   }
@@ -1322,7 +1360,7 @@ static double trial_stage_cost(const oracle_fb_problem_t* p, const stage_t* st, 
   for (int c = 0; c < NCOMP; ++c) {
     if (!st->cactive[c]) continue;
     double sl = 0.0;
-    for (int j = 0; j < comp_dim(c); ++j)
+    for (int j = 0; j < comp_rows(p, c); ++j)
       sl += oracle_canon_log(alpha > 0.0 ? fma(alpha, st->c[c].dslack[j], st->c[c].slack[j]) : st->c[c].slack[j]);
     bc += -p->barrier * sl;
   }
@@ -1340,14 +1378,15 @@ static double trial_violation(const oracle_fb_problem_t* p, stage_t* st, const e
   for (int c = 0; c < NCOMP; ++c) {
     if (!st->cactive[c]) continue;
     double s1 = 0.0;
-    if (c >= C_FRICTION) {
+    if (is_cone(c)) {
+      const int rpc = cone_rows(p, c);
       for (int i = 0; i < FB_NC; ++i) {
         double r[5];
-        if (st->active[i]) friction_residual(p->mu, st->tf[i], r);
-        for (int x = 0; x < 5; ++x) s1 += st->active[i] ? fabs(r[x] + st->c[c].slack[5 * i + x]) : 0.0;
+        if (st->active[i]) friction_residual(p->mu, rpc == 2, st->tf[i], r);
+        for (int x = 0; x < rpc; ++x) s1 += st->active[i] ? fabs(r[x] + st->c[c].slack[rpc * i + x]) : 0.0;
       }
     } else {
-      for (int j = 0; j < NU; ++j) s1 += fabs(limit_residual_at(p, c, st->tq, st->tv, st->tu, j, st->c[c].slack[j]));
+      for (int j = 0; j < NU; ++j) s1 += fabs(limit_residual_at(p, c, st->tq, st->tv, st->ta, st->tu, j, st->c[c].slack[j]));
     }
     cl1 += s1;
   }
@@ -1598,6 +1637,7 @@ int oracle_fb_ocp_get(const oracle_fb_ocp_t* o, int e, const char* name, double*
   GET("Fqq_prev_inv", Fqq_prev_inv) GET("Fqq_inv", Fqq_inv) GET("laf", laf) GET("Qafqv", Qafqv) GET("Qafu", Qafu)
 #undef GET
   if (!strcmp(name, "kkt")) { out[0] = st->kkt_sq; return 1; }
+  if (!strcmp(name, "active")) { for (int i = 0; i < FB_NC; ++i) out[i] = st->active[i]; return FB_NC; }
   if (!strcmp(name, "ls_cost")) { out[0] = st->ls_cost; return 1; }
   if (!strcmp(name, "ls_viol")) { out[0] = st->ls_viol; return 1; }
   if (!strncmp(name, "slack", 5) || !strncmp(name, "dual", 4)) {

@@ -125,6 +125,19 @@ class TrottingProblem:
             ocp.set_reference(kind, el["index"], self.q_ref(el["t"]), self.v_ref)
 
 
+def with_nonlinear_cones_and_acceleration_limits(pr, cones=True, a_limit=9.0):
+    """SURVEY 8(f3) components on an ANYmal problem: FrictionCone + ImpulseFrictionCone (src/constraints/friction_cone.cpp,
+    impulse_friction_cone.cpp) instead of the linearised cones, JointAcceleration{Lower,Upper}Limit
+    (joint_acceleration_*_limit.cpp) with amin = -a_limit, amax = +a_limit (the unconstrained trot peaks at 18 rad/s^2)."""
+    p = pr.problem
+    p.cone_nonlinear[0] = p.cone_nonlinear[1] = 1 if cones else 0
+    if a_limit is not None:
+        p.enable_acc[0] = p.enable_acc[1] = 1
+        p.set("a_min", np.full(12, -a_limit))
+        p.set("a_max", np.full(12, a_limit))
+    return pr
+
+
 class JumpingProblem(TrottingProblem):
     """A flight phase: all feet leave at t_lift (a lift stage, dimf = 0 afterwards) and touch down at t_land
     (an impulse with four contacts), in the style of examples/anymal/anymal_jumping.cpp."""
@@ -153,6 +166,44 @@ class JumpingProblem(TrottingProblem):
         elif t > self.t_lift:
             q[0] += self.jump_length * (t - self.t_lift) / (self.t_land - self.t_lift)
         return q
+
+
+class StandingBenchmarkProblem(TrottingProblem):
+    """examples/anymal/ocp_benchmark.cpp:26-125: four-foot stance, ConfigurationSpaceCost (constant reference) +
+    ContactForceCost (f_ref = (0, 0, 70)), six joint limits from the URDF and the nonlinear FrictionCone(mu = 0.7);
+    T = 0.5, N = 20, max_num_impulse = 4, 10 iterations."""
+
+    def __init__(self):
+        super().__init__(steps=2)
+        self.T, self.N, self.max_num_impulse = 0.5, 20, 4
+        p = self.problem
+        p.T, p.N, p.max_num_impulse = 0.5, 20, 4
+        for nm in ("q_weight", "qf_weight"):
+            p.set(nm, np.full(18, 10.0))
+        for nm in ("v_weight", "vf_weight"):
+            p.set(nm, np.full(18, 1.0))
+        p.set("a_weight", np.full(18, 0.01))
+        for nm in ("qi_weight", "vi_weight", "dvi_weight", "fi_weight", "fi_ref"):    # never set by the example: zero
+            p.set(nm, np.zeros(len(getattr(p, nm))))
+        p.set("f_weight", np.full(12, 0.001))
+        p.set("f_ref", np.tile([0, 0, 70.0], 4))
+        # the joint limits of the URDF (the trotting example overrides nothing either; the product's Robot holds the same
+        # numbers: idocp_b200_fb_problem_default)
+        self.urdf_limits = True
+        p.mu = 0.7
+        for c in range(8):
+            p.enable[c] = 1 if c < 7 else 0        # no impulse cone in the example
+        p.cone_nonlinear[0] = 1
+        self.v_ref = np.zeros(18)
+
+    def contact_sequence(self, fb):
+        cs = hybrid_py.ContactSequence(4, 2 * self.max_num_impulse + 2)
+        pts = standing_contact_points(fb) if self.standing_points is None else np.array(self.standing_points, dtype=float)
+        cs.set_uniform([1, 1, 1, 1], pts)
+        return cs
+
+    def q_ref(self, t):
+        return Q_STANDING.copy()
 
 
 def make_product_solver(pr, lib, fb, batch, q0=None, v0=None, t=0.0):

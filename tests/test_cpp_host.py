@@ -165,6 +165,40 @@ def test_anymal_trotting_example_reproduces_golden_convergence():
     assert "CPU time per update" in out
 
 
+OCPBENCH_EXE = os.path.join(ROOT, "build", "anymal_ocp_benchmark")
+
+
+def _build_ocp_benchmark():
+    import __graft_entry__ as g
+    g.build_cuda()
+    os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)
+    lib = os.path.join(ROOT, "idocp_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "anymal_ocp_benchmark.cpp"), "-L" + lib, "-lidocp_b200",
+                           "-Wl,-rpath," + lib, "-o", OCPBENCH_EXE])
+
+
+def test_anymal_ocp_benchmark_example_compiles():
+    _build_ocp_benchmark()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("a_limit, golden", [(None, "anymal_ocp_benchmark_golden.json"), ("2.0", "anymal_ocp_benchmark_acc_golden.json")])
+def test_anymal_ocp_benchmark_example_reproduces_golden_convergence(a_limit, golden):
+    """examples/anymal_ocp_benchmark.cpp = the problem of the reference's examples/anymal/ocp_benchmark.cpp (standing ANYmal,
+    ConfigurationSpaceCost(robot) of the floating base, the NONLINEAR FrictionCone) through the C++ host classes; with a
+    third argument also JointAcceleration{Lower,Upper}Limit.  The 10-iteration KKT history equals the oracle's digit for digit."""
+    _build_ocp_benchmark()
+    args = [OCPBENCH_EXE, "2", "10"] + ([a_limit] if a_limit else [])
+    out = subprocess.run(args, capture_output=True, text=True, check=True).stdout
+    kkt = [float(x) for x in re.findall(r"KKT error(?: after iteration \d+)? = (\S+)", out)]
+    with open(os.path.join(GOLDEN, golden)) as f:
+        ref = json.load(f)["kkt"]
+    assert len(kkt) == 11
+    assert kkt == ref
+    assert kkt[-1] < 1e-10
+
+
 RUNNING_EXE = os.path.join(ROOT, "build", "anymal_running")
 
 
@@ -294,7 +328,7 @@ def test_cpp_batched_mpc_ticks():
     assert all(abs(float(u)) < 1e4 for _, u, _ in ticks)
 
 
-REF_EXAMPLES = ["anymal/anymal_trotting.cpp", "anymal/anymal_running.cpp", "iiwa14/unocp_benchmark.cpp", "iiwa14/config_space_ocp.cpp",
+REF_EXAMPLES = ["anymal/anymal_trotting.cpp", "anymal/anymal_running.cpp", "anymal/ocp_benchmark.cpp", "iiwa14/unocp_benchmark.cpp", "iiwa14/config_space_ocp.cpp",
                 "iiwa14/task_space_ocp.cpp", "iiwa14/unparnmpc_benchmark.cpp"]
 
 

@@ -86,6 +86,49 @@ def test_trotting_iterations_bit_exact(fb, emu_lib):
         assert compare(ocp, solver, fb, SOL) == [], it
 
 
+def nonlinear_cone_scenario(fb, lib, batch_states=None):
+    """FrictionCone + ImpulseFrictionCone + JointAcceleration{Lower,Upper}Limit through the kernels vs the
+    oracle: every field, slack / dual of all 136 rows, KKT errors, step sizes; the first two iterations with the filter line search."""
+    pr = ap.with_nonlinear_cones_and_acceleration_limits(ap.TrottingProblem())
+    B = 1 if batch_states is None else len(batch_states[0])
+    q0 = np.tile(pr.q0, (B, 1)) if batch_states is None else batch_states[0]
+    v0 = np.tile(pr.v0, (B, 1)) if batch_states is None else batch_states[1]
+    oracles = [pr.make_oracle(fb, q0=q0[b], v0=v0[b]) for b in range(B)]
+    solver = ap.make_product_solver(pr, lib, fb, batch=B, q0=q0, v0=v0)
+    ne = len(solver.chain())
+
+    def check_slack_dual(tag):
+        for e in range(ne):
+            for nm in ("slack", "dual"):
+                got = np.asarray(solver.get(e, nm))
+                assert got.shape[1] == 136
+                for b, o in enumerate(oracles):
+                    assert np.array_equal(o.get(e, nm), got[b]), (tag, e, nm, b)
+    check_slack_dual("init")
+    for it in range(4):
+        ls = it < 2      # (with the search later the 0.05 floor exceeds the fraction-to-boundary step here and LLT(G) fails)
+        solver.computeKKTResidual(0.0, q0, v0)
+        kkt = solver.KKTError()
+        for b, o in enumerate(oracles):
+            o.compute_kkt_residual(0.0, q0[b], v0[b])
+            assert kkt[b] == o.kkt_error(), (it, b, kkt[b], o.kkt_error())
+        solver.updateSolution(0.0, q0, v0, ls)
+        steps = solver.stepSizes()
+        for b, o in enumerate(oracles):
+            assert o.update_solution(0.0, q0[b], v0[b], ls) == 0
+            assert np.array_equal(steps[b], o.step_sizes()), (it, b, steps[b], o.step_sizes())
+            for names in (KKT + EXP, RIC, DIR, SOL):
+                assert compare(o, solver, fb, names, b=b) == [], (it, b)
+        check_slack_dual(it)
+    # the acceleration limit and the cone rows are live: slack of the first grid stage
+    sl = np.asarray(solver.get(0, "slack"))
+    assert np.all(sl[:, 72:80] > 0) and np.all(sl[:, 80:92] == 0) and np.all(sl[:, 112:136] > 0)
+
+
+def test_nonlinear_cones_and_acceleration_limits_bit_exact(fb, emu_lib):
+    nonlinear_cone_scenario(fb, emu_lib)
+
+
 def test_filter_line_search_bit_exact(fb, emu_lib):
     # LineSearch::computeStepSize for OCPSolver (line_search.hpp:62-93) on a problem where the search backtracks
     pr = ap.JumpingProblem(0.1, 0.6, 0.75, 1.3, 26)

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import anymal_problems as ap
-from test_emu_fb_parity import DIR, EXP, KKT, RIC, SOL, compare
+from test_emu_fb_parity import DIR, EXP, KKT, RIC, SOL, compare, nonlinear_cone_scenario
 
 pytestmark = pytest.mark.gpu
 
@@ -47,6 +47,12 @@ def test_batch_iterations_bit_exact(fb, gpu_lib):
             assert np.array_equal(steps[b], o.step_sizes())
             for names in (KKT + EXP, RIC, DIR, SOL):
                 assert compare(o, solver, fb, names, b=b) == [], (it, b)
+
+
+def test_nonlinear_cones_and_acceleration_limits_bit_exact(fb, gpu_lib):
+    # FrictionCone, ImpulseFrictionCone, JointAcceleration{Lower,Upper}Limit on a batch of perturbed states
+    pr = ap.TrottingProblem()
+    nonlinear_cone_scenario(fb, gpu_lib, perturbed_states(fb, pr, 5, 11))
 
 
 def test_convergence_history_identical(fb, gpu_lib):

@@ -233,3 +233,127 @@ def test_running_gait_one_stride(fb):
     o2 = full.make_oracle(fb)
     k2 = [c["kind"] for c in o2.chain()]
     assert (full.T, full.N) == (7.0, 240) and k2.count(fb.K_IMPULSE) == 26 and k2.count(fb.K_LIFT) == 14   # the example's schedule
+
+
+# ---- FrictionCone / ImpulseFrictionCone, JointAcceleration{Lower,Upper}Limit ----
+SOL_FIELDS = ["q", "v", "a", "u", "f", "lmd", "gmm", "beta", "mu", "nu_passive", "xi"]
+
+
+def cone_g(mu, f):
+    return np.array([-f[2], f[0] ** 2 + f[1] ** 2 - mu ** 2 * f[2] ** 2])
+
+
+def test_nonlinear_cone_and_acceleration_limit_gradients(fb):
+    """augmentDualResidual of FrictionCone / ImpulseFrictionCone (friction_cone.cpp:100-118) and of the acceleration limits
+    (joint_acceleration_lower_limit.cpp:52-56): lf and la of the same iterate with and without the components differ by
+    dt J^T dual, J by central differences of the constraint functions."""
+    pr = ap.with_nonlinear_cones_and_acceleration_limits(ap.TrottingProblem())
+    ocp = pr.make_oracle(fb)
+    run(ocp, pr, 6)
+    pr0 = ap.TrottingProblem()
+    pr0.problem.enable[6] = pr0.problem.enable[7] = 0
+    bare = pr0.make_oracle(fb)
+    ch = ocp.chain()
+    for e in range(len(ch)):
+        for nm in SOL_FIELDS:
+            bare.set(e, nm, ocp.get(e, nm))
+    bare.compute_kkt_residual(0.0, pr.q0, pr.v0)
+    mu, checked = pr.problem.mu, 0
+    for e, c in enumerate(ch[:-1]):
+        imp = c["kind"] == fb.K_IMPULSE
+        dt = 1.0 if imp else c["dt"]
+        dual = ocp.get(e, "dual")
+        f = ocp.get(e, "f").reshape(4, 3)
+        cone = dual[92:112] if imp else dual[72:92]
+        expect, k = np.zeros(12), 0
+        for i in range(4):
+            if not ocp.get(e, "active")[i]:
+                continue
+            J = np.zeros((2, 3))
+            for x in range(3):
+                h = 1e-4 * max(1.0, abs(f[i, x]))
+                fp, fm = f[i].copy(), f[i].copy()
+                fp[x] += h
+                fm[x] -= h
+                J[:, x] = (cone_g(mu, fp) - cone_g(mu, fm)) / (2 * h)
+            expect[3 * k:3 * k + 3] = dt * (J.T @ cone[2 * i:2 * i + 2])
+            k += 1
+        got = ocp.get(e, "lf") - bare.get(e, "lf")
+        assert np.allclose(got[:3 * k], expect[:3 * k], rtol=1e-6, atol=1e-9 * max(1.0, np.abs(ocp.get(e, "lf")).max())), (e, got, expect)
+        assert np.all(cone[8:] == 0.0)        # two rows per contact: the rest of the component's storage is dead
+        checked += k
+        if not imp:
+            dla = ocp.get(e, "la") - bare.get(e, "la")
+            assert np.allclose(dla[6:], dt * (dual[124:136] - dual[112:124]), rtol=1e-9, atol=1e-12)
+            assert np.all(dla[:6] == 0.0)
+        else:
+            assert np.all(dual[112:136] == 0.0)   # acceleration-level constraints do not exist at an impulse
+    assert checked > 60
+
+
+def test_nonlinear_cone_direction_is_the_newton_step_of_the_residual(fb):
+    """computeSlackAndDualDirection (friction_cone.cpp:152-181, joint_acceleration_lower_limit.cpp:72-77): after the step
+    alpha the linear rows satisfy residual+ = (1 - alpha) residual and the cone row
+    residual+ = (1 - alpha) residual + alpha^2 g_quadratic(df)."""
+    pr = ap.with_nonlinear_cones_and_acceleration_limits(ap.TrottingProblem())
+    ocp = pr.make_oracle(fb)
+    run(ocp, pr, 3)
+    ch = ocp.chain()
+    mu, amin, amax = pr.problem.mu, -9.0, 9.0
+
+    def residuals(e, c):
+        sl = ocp.get(e, "slack")
+        f = ocp.get(e, "f").reshape(4, 3)
+        a = ocp.get(e, "a")
+        imp = c["kind"] == fb.K_IMPULSE
+        cone = sl[92:112] if imp else sl[72:92]
+        r = [cone_g(mu, f[i]) + cone[2 * i:2 * i + 2] if ocp.get(e, "active")[i] else np.zeros(2) for i in range(4)]
+        racc = np.zeros(24) if imp else np.concatenate([amin - a[6:] + sl[112:124], a[6:] - amax + sl[124:136]])
+        return np.array(r), racc, f
+    before = [residuals(e, c) for e, c in enumerate(ch[:-1])]
+    assert ocp.update_solution(0.0, pr.q0, pr.v0) == 0
+    alpha = ocp.step_sizes()[0]
+    assert 0 < alpha <= 1
+    for e, c in enumerate(ch[:-1]):
+        r0, a0, f0 = before[e]
+        r1, a1, f1 = residuals(e, c)
+        df = (f1 - f0) / alpha
+        quad = df[:, 0] ** 2 + df[:, 1] ** 2 - mu ** 2 * df[:, 2] ** 2
+        act = ocp.get(e, "active").astype(bool)
+        scale = max(1.0, np.abs(r0).max())
+        assert np.allclose(r1[act, 0], (1 - alpha) * r0[act, 0], atol=1e-9 * scale), e
+        assert np.allclose(r1[act, 1], (1 - alpha) * r0[act, 1] + alpha ** 2 * quad[act], atol=1e-8 * scale), e
+        assert np.allclose(a1, (1 - alpha) * a0, atol=1e-10 * max(1.0, np.abs(a0).max())), e
+
+
+def test_nonlinear_cones_converge_to_a_feasible_trot(fb):
+    # the reference drops the curvature of the cone from the Hessian (friction_cone.cpp:133-136 adds only r r^T), so the
+    # iteration converges linearly, not quadratically
+    pr = ap.with_nonlinear_cones_and_acceleration_limits(ap.TrottingProblem(), a_limit=None)
+    ocp = pr.make_oracle(fb)
+    hist = run(ocp, pr, 60)
+    assert np.all(np.isfinite(hist)) and hist[-1] < 1e-8 * hist[0]
+    mu = pr.problem.mu
+    for e, c in enumerate(ocp.chain()[:-1]):
+        f = ocp.get(e, "f").reshape(4, 3)
+        sl, du = ocp.get(e, "slack"), ocp.get(e, "dual")
+        o = 92 if c["kind"] == fb.K_IMPULSE else 72
+        for i in range(4):
+            if ocp.get(e, "active")[i]:
+                assert f[i, 2] > 0 and f[i, 0] ** 2 + f[i, 1] ** 2 < mu ** 2 * f[i, 2] ** 2
+                assert np.all(sl[o + 2 * i:o + 2 * i + 2] > 0) and np.all(du[o + 2 * i:o + 2 * i + 2] > 0)
+                # complementarity: slack * dual = barrier at the solution
+                assert np.allclose(sl[o + 2 * i:o + 2 * i + 2] * du[o + 2 * i:o + 2 * i + 2], pr.problem.barrier, rtol=1e-5)
+
+
+def test_acceleration_limits_bind_and_converge(fb):
+    pr = ap.with_nonlinear_cones_and_acceleration_limits(ap.TrottingProblem(), cones=False, a_limit=12.0)
+    ocp = pr.make_oracle(fb)
+    hist = run(ocp, pr, 40)
+    assert np.all(np.isfinite(hist)) and hist[-1] < 1e-9
+    amax = 0.0
+    for e, c in enumerate(ocp.chain()[:-1]):
+        if c["kind"] != fb.K_IMPULSE:
+            amax = max(amax, np.abs(ocp.get(e, "a")[6:]).max())
+            assert np.all(ocp.get(e, "slack")[112:136] > 0)
+    assert 11.5 < amax < 12.0      # the limit binds (18 rad/s^2 without it)

@@ -70,6 +70,31 @@ def main():
     with open(os.path.join(ROOT, "tests", "golden", "anymal_running_golden.json"), "w") as f:
         json.dump(rec, f, indent=1)
     print("anymal_running: KKT %.3e -> %.3e, %d stages" % (rec["kkt"][0], rec["kkt"][-1], len(rec["chain"])))
+    # examples/anymal/ocp_benchmark.cpp: standing, nonlinear FrictionCone, 10 iterations; and the same problem with
+    # JointAcceleration{Lower,Upper}Limit (|a| <= 2 rad/s^2) pushed as well
+    for tag, a_limit in (("", None), ("_acc", 2.0)):
+        sp = ap.StandingBenchmarkProblem()
+        if a_limit is not None:
+            ap.with_nonlinear_cones_and_acceleration_limits(sp, cones=True, a_limit=a_limit)
+            sp.problem.cone_nonlinear[1] = 0
+        pts = np.zeros((4, 3))
+        lib.check(lib.L.idocp_b200_fb_contact_frame_positions(capi.dptr(np.ascontiguousarray(ap.Q_STANDING)), capi.dptr(pts)))
+        sp.standing_points = pts
+        ocp = sp.make_oracle(fb_py)
+        rec = {"kkt": [], "primal": [], "dual": []}
+        ocp.compute_kkt_residual(0.0, sp.q0, sp.v0)
+        rec["kkt"].append(ocp.kkt_error())
+        for it in range(10):
+            assert ocp.update_solution(0.0, sp.q0, sp.v0) == 0
+            st = ocp.step_sizes()
+            rec["primal"].append(float(st[0]))
+            rec["dual"].append(float(st[1]))
+            ocp.compute_kkt_residual(0.0, sp.q0, sp.v0)
+            rec["kkt"].append(ocp.kkt_error())
+        rec["final_f_stage0"] = ocp.get(0, "f").tolist()
+        with open(os.path.join(ROOT, "tests", "golden", "anymal_ocp_benchmark%s_golden.json" % tag), "w") as f:
+            json.dump(rec, f, indent=1)
+        print("anymal_ocp_benchmark%s: KKT %.3e -> %.3e" % (tag, rec["kkt"][0], rec["kkt"][-1]), rec["primal"])
 
 
 if __name__ == "__main__":

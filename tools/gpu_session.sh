@@ -51,6 +51,33 @@ fi
 if has parnmpc; then
   python tools/bench_solver.py --solver unparnmpc --batch 16384 --steps 20 > gpurun_out/${L}_bench_solver_unparnmpc.json 2> gpurun_out/${L}_bench_solver_unparnmpc.err; cut -c 1-700 gpurun_out/${L}_bench_solver_unparnmpc.json
 fi
+if has variants; then   # A/B builds from tools/build_variant.py: VARIANT_WORKLOAD (default iiwa14_unocp), VARIANT_STEPS
+  for so in build/variants/*.so; do
+    tag=$(basename $so .so); tag=${tag#libidocp_b200_}
+    IDOCP_B200_LIBRARY=$PWD/$so python bench.py --workload ${VARIANT_WORKLOAD:-iiwa14_unocp} --steps ${VARIANT_STEPS:-100} --warmup 10 --no-cpu-baseline ${VARIANT_ARGS:-} \
+        > gpurun_out/${L}_variant_${tag}.json 2> gpurun_out/${L}_variant_${tag}.err
+    python - "$tag" gpurun_out/${L}_variant_${tag}.json <<'PY'
+import json, sys
+try:
+    d = json.loads(open(sys.argv[2]).read().strip().splitlines()[-1])
+    print("variant", sys.argv[1], "ms_per_step", round(d["ms_per_step"], 4), {k: round(v["ms_per_launch"], 4) for k, v in d["roofline"]["kernels"].items()}, "kkt_max", d["health"]["kkt_max"])
+except Exception as e:
+    print("variant", sys.argv[1], "FAILED", e)
+PY
+  done
+fi
+if has scale; then   # multi-GPU call (gpurun --gpus 8): strong scaling of configs[2] / [3], configs[4] at its definition (8 x 1024)
+  tr() { n=$1; shift; python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + n)) bench.py --gpus $n "$@"; }
+  for n in ${SCALE_NS:-2 4 8}; do
+    tr $n --scaling strong --steps 100 --warmup 10 > gpurun_out/${L}_scale_strong_iiwa14_unocp_n$n.json 2> gpurun_out/${L}_scale_strong_iiwa14_unocp_n$n.err
+    cut -c 1-330 gpurun_out/${L}_scale_strong_iiwa14_unocp_n$n.json
+  done
+  n=${SCALE_NMAX:-8}
+  tr $n --workload anymal_trotting --scaling strong --steps 20 --warmup 5 > gpurun_out/${L}_scale_strong_anymal_trotting_n$n.json 2> gpurun_out/${L}_scale_strong_anymal_trotting_n$n.err
+  cut -c 1-330 gpurun_out/${L}_scale_strong_anymal_trotting_n$n.json
+  tr $n --workload anymal_running --steps 10 --warmup 3 > gpurun_out/${L}_scale_anymal_running_n$n.json 2> gpurun_out/${L}_scale_anymal_running_n$n.err
+  cut -c 1-330 gpurun_out/${L}_scale_anymal_running_n$n.json
+fi
 if has launches; then
   ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 200 --csv --log-file gpurun_out/${L}_launches.csv \
       python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/${L}_launches_run.log 2>&1; echo "launches rc=$?"
