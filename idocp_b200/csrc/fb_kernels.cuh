@@ -33,6 +33,8 @@ __host__ __device__ inline int fbc_comp(int idx) {   // component of row idx
   return idx < 72 ? idx / 12 : (idx < 92 ? FBC_FRICTION : (idx < 112 ? FBC_IMPULSE_FRICTION : (idx < 124 ? FBC_ACC_LO : FBC_ACC_UP)));
 }
 __host__ __device__ inline bool fbc_is_cone(int c) { return c == FBC_FRICTION || c == FBC_IMPULSE_FRICTION; }
+// rows a stage has to walk over: the acceleration-limit rows sit at the end and are skipped while those components are off
+#define FBC_LIVE_ROWS(cactive) (((cactive)[FBC_ACC_LO] | (cactive)[FBC_ACC_UP]) ? FB_NCON : 112)
 
 struct FbDevProblem {
   double T;
@@ -47,8 +49,10 @@ struct FbDevProblem {
   double a_min[FB_NU], a_max[FB_NU];   // JointAcceleration{Lower,Upper}Limit
 };
 // rows per contact of cone component c, live rows of a component (the rest of its storage stays zero)
-__host__ __device__ inline int fbc_cone_rows(const FbDevProblem& pr, int c) { return pr.cone_nonlinear[c - FBC_FRICTION] ? 2 : 5; }
-__host__ __device__ inline int fbc_rows(const FbDevProblem& pr, int c) { return fbc_is_cone(c) ? FB_NC * fbc_cone_rows(pr, c) : 12; }
+// (nl = fbc_cone_bits(pr), read ONCE per kernel: the problem record lives in global memory and these kernels are latency bound)
+__host__ __device__ inline int fbc_cone_bits(const FbDevProblem& pr) { return (pr.cone_nonlinear[0] ? 1 : 0) | (pr.cone_nonlinear[1] ? 2 : 0); }
+__host__ __device__ inline int fbc_cone_rows(int nl, int c) { return ((nl >> (c - FBC_FRICTION)) & 1) ? 2 : 5; }
+__host__ __device__ inline int fbc_rows(int nl, int c) { return fbc_is_cone(c) ? FB_NC * fbc_cone_rows(nl, c) : 12; }
 
 // one element of the hybrid chain (shared by the whole batch)
 struct FbElem {
@@ -483,6 +487,45 @@ __device__ inline double fb_friction_jac(double mu, bool nonlinear, const double
   return e == 3 ? 1.0 : (e == 4 ? -1.0 : 0.0);
 }
 
+// compile-time cone type for the hot kernel (the type is uniform over the launch: one branch, then constant-folded rows)
+template <bool NL>
+__device__ __forceinline__ double fb_friction_jac_t(double mu, const double* f, int e, int x) {
+  return fb_friction_jac(mu, NL, f, e, x);
+}
+// augmentDualResidual of a cone: dt * sum_e J[e][cx] dual[e]
+template <bool NL>
+__device__ __forceinline__ double fb_cone_augment(double mu, const double* fi, const double* du5, int cx) {
+  constexpr int RPC = NL ? 2 : 5;
+  double acc = fb_friction_jac_t<NL>(mu, fi, 0, cx) * du5[0];
+#pragma unroll
+  for (int ee = 1; ee < RPC; ++ee) acc = fma(fb_friction_jac_t<NL>(mu, fi, ee, cx), du5[ee], acc);
+  return acc;
+}
+// condenseSlackAndDual of a cone: gradient term of column cx and the row cx of the 3 x 3 Hessian block J^T diag(dual / slack) J
+template <bool NL>
+__device__ __forceinline__ double fb_cone_condense(double mu, const double* fi, const double* slack, const double* dual,
+                                                   const double* residual, const double* duality, int cx, double* h3) {
+  constexpr int RPC = NL ? 2 : 5;
+  double r5[RPC], w5[RPC];
+#pragma unroll
+  for (int ee = 0; ee < RPC; ++ee) {
+    const double rs = 1.0 / slack[ee];
+    r5[ee] = fma(dual[ee], residual[ee], -duality[ee]) * rs;
+    w5[ee] = dual[ee] * rs;
+  }
+  double acc = fb_friction_jac_t<NL>(mu, fi, 0, cx) * r5[0];
+#pragma unroll
+  for (int ee = 1; ee < RPC; ++ee) acc = fma(fb_friction_jac_t<NL>(mu, fi, ee, cx), r5[ee], acc);
+#pragma unroll
+  for (int y = 0; y < 3; ++y) {
+    double h = fb_friction_jac_t<NL>(mu, fi, 0, cx) * (w5[0] * fb_friction_jac_t<NL>(mu, fi, 0, y));
+#pragma unroll
+    for (int ee = 1; ee < RPC; ++ee) h = fma(fb_friction_jac_t<NL>(mu, fi, ee, cx), w5[ee] * fb_friction_jac_t<NL>(mu, fi, ee, y), h);
+    h3[y] = h;
+  }
+  return acc;
+}
+
 // =====================================================================================================
 // K1a: rigid-body + stage-local linearisation, ONE WARP per (instance, stage)
 //   forward kinematics, RNEA and its derivatives with contact wrenches, Baumgarte / impulse-velocity rows, cost
@@ -824,6 +867,7 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
   const int b = stage / A.n_elems, e = stage - b * A.n_elems;
   const FbElem& el = A.elems[e];
   const FbDevProblem& pr = *A.prob;
+  const int nl = fbc_cone_bits(pr);
   const int kind = el.kind;
   const bool impulse = kind == FB_IMPULSE, terminal = kind == FB_TERMINAL;
   const double dt = (impulse || terminal) ? 1.0 : el.dt;
@@ -926,19 +970,20 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
   }
   // computePrimalAndDualResidual
   if (!terminal) {
-    FBW_FOR(idx, FB_NCON) {
+    const int ncon = FBC_LIVE_ROWS(el.cactive);
+    FBW_FOR(idx, ncon) {
       const int c = fbc_comp(idx);
       const int j = idx - fbc_offset(c);
       double res = 0.0, dua = 0.0;
-      if (el.cactive[c] && j < fbc_rows(pr, c)) {
+      if (el.cactive[c] && j < fbc_rows(nl, c)) {
         const double sl = w.slack[idx];
         if (fbc_is_cone(c)) {
-          const int rpc = fbc_cone_rows(pr, c);
-          const int i = j / rpc;
+          const int rpc = fbc_cone_rows(nl, c);
+          const int i = rpc == 2 ? (j >> 1) : (j / 5);   // no division by a run-time value
           if (el.active[i]) {
             double r5[5];
             fb_friction_residual(pr.mu, rpc == 2, w.f + 3 * i, r5);
-            res = r5[j % rpc] + sl;
+            res = r5[(rpc == 2 ? (j & 1) : (j % 5))] + sl;
             dua = sl * w.dual[idx] - pr.barrier;
           }
         } else {
@@ -1018,15 +1063,12 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
     }
   }
   const int cfr = impulse ? FBC_IMPULSE_FRICTION : FBC_FRICTION;
-  const int rpc = fbc_cone_rows(pr, cfr);
+  const int rpc = fbc_cone_rows(nl, cfr);
   const bool nlc = rpc == 2;
   if (ci >= 0 && el.cactive[cfr]) {
     const double* du5 = w.dual + fbc_offset(cfr) + rpc * ci;
     const double* fi = w.f + 3 * ci;
-    double acc = fb_friction_jac(pr.mu, nlc, fi, 0, cx) * du5[0];
-#pragma unroll
-    for (int ee = 1; ee < 5; ++ee)   // fixed trip count + predicate: the row arrays stay in registers
-      if (ee < rpc) acc = fma(fb_friction_jac(pr.mu, nlc, fi, ee, cx), du5[ee], acc);
+    const double acc = nlc ? fb_cone_augment<true>(pr.mu, fi, du5, cx) : fb_cone_augment<false>(pr.mu, fi, du5, cx);
     lf += dt * acc;
   }
   // linearizeForwardEuler / linearizeImpulseForwardEuler (state_equation.hxx:11-40)
@@ -1260,26 +1302,12 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
       int k = lane / 3;
       const int o = fbc_offset(cfr) + rpc * ci;
       const double* fi = w.f + 3 * ci;
-      double r5[5], w5[5];
-#pragma unroll
-      for (int ee = 0; ee < 5; ++ee) {
-        r5[ee] = 0.0; w5[ee] = 0.0;
-        if (ee < rpc) {
-          const double rs = 1.0 / w.slack[o + ee];
-          r5[ee] = fma(w.dual[o + ee], w.residual[o + ee], -w.duality[o + ee]) * rs;
-          w5[ee] = w.dual[o + ee] * rs;
-        }
-      }
-      double acc = fb_friction_jac(pr.mu, nlc, fi, 0, cx) * r5[0];
-#pragma unroll
-      for (int ee = 1; ee < 5; ++ee)
-        if (ee < rpc) acc = fma(fb_friction_jac(pr.mu, nlc, fi, ee, cx), r5[ee], acc);
+      double h3[3];
+      const double acc = nlc ? fb_cone_condense<true>(pr.mu, fi, w.slack + o, w.dual + o, w.residual + o, w.duality + o, cx, h3)
+                             : fb_cone_condense<false>(pr.mu, fi, w.slack + o, w.dual + o, w.residual + o, w.duality + o, cx, h3);
       lf += dt * acc;
       for (int y = 0; y < 3; ++y) {
-        double h = fb_friction_jac(pr.mu, nlc, fi, 0, cx) * (w5[0] * fb_friction_jac(pr.mu, nlc, fi, 0, y));
-#pragma unroll
-        for (int ee = 1; ee < 5; ++ee)
-          if (ee < rpc) h = fma(fb_friction_jac(pr.mu, nlc, fi, ee, cx), w5[ee] * fb_friction_jac(pr.mu, nlc, fi, ee, y), h);
+        const double h = h3[y];
         L.Qff[(3 * k + cx) * FB_MAXF + 3 * k + y] = (y == cx ? qff_d : 0.0) + dt * h;
       }
     } else if (ci >= 0) {
@@ -1987,6 +2015,7 @@ __global__ void __launch_bounds__(64) k_fb_expand(FbArrays A) {
   const int NV = FB_NV, NX = FB_NX, NU = FB_NU, NVF = FB_NVF;
   const FbElem& el = A.elems[e];
   const FbDevProblem& pr = *A.prob;
+  const int nl = fbc_cone_bits(pr);
   const bool impulse = el.kind == FB_IMPULSE, terminal = el.kind == FB_TERMINAL;
   const size_t rec = (size_t)el.slot * A.B + b;
   FbDir& Dr = A.dir[rec];
@@ -2036,21 +2065,22 @@ __global__ void __launch_bounds__(64) k_fb_expand(FbArrays A) {
   }
   __syncthreads();
   // computeSlackAndDualDirection
-  for (int idx = tid; idx < FB_NCON; idx += blockDim.x) {
+  const int ncon = FBC_LIVE_ROWS(el.cactive);
+  for (int idx = tid; idx < ncon; idx += blockDim.x) {
     const int c = fbc_comp(idx);
     const int j = idx - fbc_offset(c);
     double ds = 0.0, dd = 0.0;
-    if (el.cactive[c] && j < fbc_rows(pr, c)) {
+    if (el.cactive[c] && j < fbc_rows(nl, c)) {
       if (fbc_is_cone(c)) {
-        const int rpc = fbc_cone_rows(pr, c);
-        const int i = j / rpc;
+        const int rpc = fbc_cone_rows(nl, c);
+        const int i = rpc == 2 ? (j >> 1) : (j / 5);   // no division by a run-time value
         ds = 1.0; dd = 1.0;
         if (el.active[i]) {
           int k = 0;
           for (int jj = 0; jj < i; ++jj) k += el.active[jj];
           const double* df = daf + NV + 3 * k;
           const double* fi = S.f + 3 * i;
-          const int ee = j % rpc;
+          const int ee = (rpc == 2 ? (j & 1) : (j % 5));
           const bool nlc = rpc == 2;
           const double Jdf = fma(fb_friction_jac(pr.mu, nlc, fi, ee, 2), df[2],
                                  fma(fb_friction_jac(pr.mu, nlc, fi, ee, 1), df[1], fb_friction_jac(pr.mu, nlc, fi, ee, 0) * df[0]));
@@ -2072,8 +2102,8 @@ __global__ void __launch_bounds__(64) k_fb_expand(FbArrays A) {
   if (tid < 2 * FBC_NCOMP) {
     const int c = tid >> 1, o = fbc_offset(c);
     double r = 1.0;
-    if (el.cactive[c]) r = (tid & 1) ? fb_fraction_to_boundary(pr.fraction_rate, fbc_rows(pr, c), S.dual + o, ddual + o)
-                                     : fb_fraction_to_boundary(pr.fraction_rate, fbc_rows(pr, c), S.slack + o, dslack + o);
+    if (el.cactive[c]) r = (tid & 1) ? fb_fraction_to_boundary(pr.fraction_rate, fbc_rows(nl, c), S.dual + o, ddual + o)
+                                     : fb_fraction_to_boundary(pr.fraction_rate, fbc_rows(nl, c), S.slack + o, dslack + o);
     steps[tid] = r;
   }
   __syncthreads();
@@ -2200,7 +2230,8 @@ __global__ void __launch_bounds__(64) k_fb_update(FbArrays A) {
       S.mu[x] = fma(ap, dbetamu[NV + 3 * k + x % 3], S.mu[x]);
     }
   }
-  for (int idx = tid; idx < FB_NCON; idx += blockDim.x) {
+  const int ncon = FBC_LIVE_ROWS(el.cactive);
+  for (int idx = tid; idx < ncon; idx += blockDim.x) {
     const int c = fbc_comp(idx);
     if (el.cactive[c]) {
       S.slack[idx] = fma(ap, Dr.dslack[idx], S.slack[idx]);
@@ -2234,17 +2265,18 @@ __global__ void k_fb_init_constraints(FbArrays A, const FbInitRow* rows, int n_r
   const int b = g / n_rows;
   const FbInitRow& row = rows[g - b * n_rows];
   const FbDevProblem& pr = *A.prob;
+  const int nl = fbc_cone_bits(pr);
   FbSol& S = A.sol[(size_t)row.slot * A.B + b];
   for (int c = 0; c < FBC_NCOMP; ++c) {
     const int o = fbc_offset(c);
     for (int j = 0; j < fbc_dim(c); ++j) {
       double sl = 0.0, du = 0.0;
-      if (row.cactive[c] && j < fbc_rows(pr, c)) {
+      if (row.cactive[c] && j < fbc_rows(nl, c)) {
         if (fbc_is_cone(c)) {
-          const int rpc = fbc_cone_rows(pr, c);
+          const int rpc = fbc_cone_rows(nl, c);
           double r5[5];
-          fb_friction_residual(pr.mu, rpc == 2, S.f + 3 * (j / rpc), r5);
-          sl = -r5[j % rpc];
+          fb_friction_residual(pr.mu, rpc == 2, S.f + 3 * (rpc == 2 ? (j >> 1) : (j / 5)), r5);
+          sl = -r5[(rpc == 2 ? (j & 1) : (j % 5))];
         } else {
           switch (c) {
             case FBC_ACC_LO: sl = S.a[6 + j] - pr.a_min[j]; break;
@@ -2287,6 +2319,7 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_ls_eval(FbArrays A, 
   const double alpha = INITIAL ? 0.0 : A.ls_alpha[b];
   const FbElem& el = A.elems[e];
   const FbDevProblem& pr = *A.prob;
+  const int nl = fbc_cone_bits(pr);
   const int kind = el.kind;
   const bool impulse = kind == FB_IMPULSE, terminal = kind == FB_TERMINAL;
   const double dt = el.dt;
@@ -2296,7 +2329,8 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_ls_eval(FbArrays A, 
   FbLin& L = lin[rec];
   const int dimf = terminal ? 0 : el.dimf, nvf = FB_NV + dimf;
   // ---- trial point (computeSolution, line_search.hpp:130-158); alpha = 0: the current point itself ----
-  FBW_FOR(i, FB_NCON) { w.slack[i] = S.slack[i]; w.dual[i] = Dr.dslack[i]; }   // w.dual holds dslack here
+  const int ncon = FBC_LIVE_ROWS(el.cactive);
+  FBW_FOR(i, ncon) { w.slack[i] = S.slack[i]; w.dual[i] = Dr.dslack[i]; }   // w.dual holds dslack here
   if (lane < FB_NV) {
     const int j = lane;
     w.v[j] = INITIAL ? S.v[j] : fma(alpha, Dr.dv[j], S.v[j]);
@@ -2340,19 +2374,19 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_ls_eval(FbArrays A, 
   const double* wa = impulse ? pr.dvi_weight : pr.a_weight;
   // logs of the trial slacks by all lanes, summed in ascending order below
   if (!terminal) {
-    FBW_FOR(idx, FB_NCON) {
+    FBW_FOR(idx, ncon) {
       const int c = fbc_comp(idx);
       const int j = idx - fbc_offset(c);
       double lg = 0.0, ar = 0.0;
-      if (el.cactive[c] && j < fbc_rows(pr, c)) {
+      if (el.cactive[c] && j < fbc_rows(nl, c)) {
         lg = canon_log(INITIAL ? w.slack[idx] : fma(alpha, w.dual[idx], w.slack[idx]));
         if (fbc_is_cone(c)) {
-          const int rpc = fbc_cone_rows(pr, c);
-          const int i = j / rpc;
+          const int rpc = fbc_cone_rows(nl, c);
+          const int i = rpc == 2 ? (j >> 1) : (j / 5);   // no division by a run-time value
           if (el.active[i]) {
             double r5[5];
             fb_friction_residual(pr.mu, rpc == 2, w.f + 3 * i, r5);
-            ar = fabs(r5[j % rpc] + w.slack[idx]);
+            ar = fabs(r5[(rpc == 2 ? (j & 1) : (j % 5))] + w.slack[idx]);
           }
         } else {
           const double sl = w.slack[idx];
@@ -2395,7 +2429,7 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_ls_eval(FbArrays A, 
       for (int c = 0; c < FBC_NCOMP; ++c) {
         if (!el.cactive[c]) continue;
         double sl = 0.0;
-        for (int j = 0; j < fbc_rows(pr, c); ++j) sl += w.duality[fbc_offset(c) + j];
+        for (int j = 0; j < fbc_rows(nl, c); ++j) sl += w.duality[fbc_offset(c) + j];
         bc += -pr.barrier * sl;
       }
       cost += (impulse ? 1.0 : dt) * bc;
@@ -2410,7 +2444,7 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_ls_eval(FbArrays A, 
     for (int c = 0; c < FBC_NCOMP; ++c) {
       if (!el.cactive[c]) continue;
       double s1 = 0.0;
-      for (int j = 0; j < fbc_rows(pr, c); ++j) s1 += w.residual[fbc_offset(c) + j];
+      for (int j = 0; j < fbc_rows(nl, c); ++j) s1 += w.residual[fbc_offset(c) + j];
       cl1 += s1;
     }
     w.part[0] = cl1;
