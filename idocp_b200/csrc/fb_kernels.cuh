@@ -338,6 +338,91 @@ __device__ __forceinline__ void fb_llt_cta(const double* A, int lda, int n, doub
     if (ej[e] >= 0 && ei[e] > ej[e]) L[ej[e] * ldl + ei[e]] *= rd[ej[e]];
   __syncthreads();
 }
+// ---- M^-1 of the joint-space inertia with the tree structure of the robot ----
+// M couples a leg joint only with the joints of its own leg and with the base, so eliminating the legs FIRST keeps the factor
+// sparse (pinocchio's cholesky::decompose does the same from the leaves to the root).  Elimination order (oracle/fb_robot.h
+// FB_MPERM): position 4 s + i = joint s of leg i, positions 12..17 = base.  The four pivots 4 s .. 4 s + 3 belong to different
+// legs and are independent: they share ONE barrier step, so the factorisation + forward substitution take 3 + 6 steps and the
+// backward substitution 6 + 3 instead of 18 + 18.  Every element still receives its non-zero updates in ascending (backward:
+// descending) pivot order; the skipped updates have an exactly zero factor, so the bits equal the oracle's dense Cholesky of
+// the permuted matrix.  Minv (n x n, original order) holds the identity on entry... it is rebuilt here; L, rd: scratch.
+__device__ __forceinline__ int fbm_perm(int p) { return p < 12 ? 6 + 3 * (p & 3) + (p >> 2) : p - 12; }
+__device__ __forceinline__ bool fbm_nz(int r, int k) { return k >= 12 || r >= 12 || ((r & 3) == (k & 3)); }   // L[r][k], r >= k
+__device__ __forceinline__ void fb_minv_tree_cta(const double* M, double* L, double* rd, double* X, int* fail, int* info, int code) {
+  constexpr int n = FB_NV, EY = 3;
+  const int t = threadIdx.x;
+  // the 117 structurally non-zero entries of the lower triangle, one per thread: base x legs, base x base, leg blocks
+  int ai = -1, aj = -1;
+  if (t < 72) { ai = 12 + t / 12; aj = t % 12; }
+  else if (t < 93) { int u = t - 72, i = 0; while ((i + 1) * (i + 2) / 2 <= u) ++i; ai = 12 + i; aj = 12 + u - i * (i + 1) / 2; }
+  else if (t < 117) { const int u = t - 93, leg = u / 6, v = u % 6; const int sr = v < 1 ? 0 : (v < 3 ? 1 : 2), sc = v - sr * (sr + 1) / 2; ai = 4 * sr + leg; aj = 4 * sc + leg; }
+  double a = ai >= 0 ? M[fbm_perm(ai) * n + fbm_perm(aj)] : 0.0;
+  int yi[EY], yc[EY];
+  double y[EY];
+#pragma unroll
+  for (int e = 0; e < EY; ++e) {
+    const int x = t + e * 128;
+    yi[e] = -1; yc[e] = 0; y[e] = 0.0;
+    if (x < n * n) { yi[e] = x / n; yc[e] = x - yi[e] * n; y[e] = yi[e] == yc[e] ? 1.0 : 0.0; }
+  }
+  if (t < n) fail[t] = 0;
+  __syncthreads();
+  for (int g = 0; g < 9; ++g) {
+    const int k0 = g < 3 ? 4 * g : 9 + g, nk = g < 3 ? 4 : 1;
+    if (aj >= k0 && aj < k0 + nk) {
+      if (ai == aj) {
+        const double r = canon_rsqrt(a);
+        if (!canon_pivot_ok(a)) fail[aj] = 1;
+        rd[aj] = r;
+        L[aj * n + aj] = a * r;
+      } else {
+        L[aj * n + ai] = a;   // still unscaled
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < EY; ++e)
+      if (yi[e] >= k0 && yi[e] < k0 + nk) X[yi[e] * n + yc[e]] = y[e];   // still unscaled
+    __syncthreads();
+    for (int k = k0; k < k0 + nk; ++k) {
+      const double r = rd[k];
+      if (aj >= k0 + nk && fbm_nz(ai, k) && fbm_nz(aj, k)) {
+        const double lik = L[k * n + ai] * r, ljk = L[k * n + aj] * r;
+        a = fma(-lik, ljk, a);
+      }
+#pragma unroll
+      for (int e = 0; e < EY; ++e) {
+        if (yi[e] == k) y[e] *= r;
+        else if (yi[e] >= k0 + nk && fbm_nz(yi[e], k)) y[e] = fma(-(L[k * n + yi[e]] * r), X[k * n + yc[e]] * r, y[e]);
+      }
+    }
+  }
+  __syncthreads();
+  if (ai > aj) L[aj * n + ai] *= rd[aj];
+  if (t == 0) {
+    for (int k = 0; k < n; ++k)
+      if (fail[k] && *info == 0) *info = code + k + 1;
+  }
+  __syncthreads();
+  for (int g = 8; g >= 0; --g) {
+    const int k0 = g < 3 ? 4 * g : 9 + g, nk = g < 3 ? 4 : 1;
+#pragma unroll
+    for (int e = 0; e < EY; ++e)
+      if (yi[e] >= k0 && yi[e] < k0 + nk) { y[e] *= rd[yi[e]]; X[yi[e] * n + yc[e]] = y[e]; }
+    __syncthreads();
+    for (int j = k0 + nk - 1; j >= k0; --j) {
+#pragma unroll
+      for (int e = 0; e < EY; ++e)
+        if (yi[e] >= 0 && yi[e] < k0 && fbm_nz(j, yi[e])) y[e] = fma(-L[yi[e] * n + j], X[j * n + yc[e]], y[e]);
+    }
+  }
+  __syncthreads();
+  // back to the original order: every entry sits in a register of its owner
+#pragma unroll
+  for (int e = 0; e < EY; ++e)
+    if (yi[e] >= 0) X[fbm_perm(yi[e]) * n + fbm_perm(yc[e])] = y[e];
+  __syncthreads();
+}
+
 // fb_llt_cta and X := (L L^T)^-1 X for an n x m block of right-hand sides (X[i*ldx + c], n m <= 128 EY, every entry owned
 // by one thread in a register) in ONE sweep: column k of the factor and step k of the forward substitution need the same
 // barrier (the forward step uses L_ik = A_ik r_k and the scaled y_k = y_k r_k, both formed from values published before
@@ -1439,7 +1524,7 @@ struct FbDenseWork {
   double laf[FB_NVF];
   union {
     struct { double L[FB_NV * FB_NV], rd[FB_NV], Minv[FB_NV * FB_NV], JMi[FB_MAXF * FB_NV], Sm[FB_MAXF * FB_MAXF], Ls[FB_MAXF * FB_MAXF],
-                 rds[FB_MAXF], Si[FB_MAXF * FB_MAXF]; } f;          // factorisation scratch (dead once MJtJinv is formed)
+                 rds[FB_MAXF], Si[FB_MAXF * FB_MAXF]; int fail[FB_NV + 2]; } f;   // factorisation scratch (dead once MJtJinv is formed)
     struct { double Qafqv[FB_NVF * FB_NX], Qafu[FB_NVF * FB_NV]; } c;   // condensing products
   } s;
   int info;
@@ -1489,9 +1574,8 @@ __global__ void __launch_bounds__(128, 5) k_fb_condense(FbArrays A, const FbLin*
     // and are slower for this 18 x 18 inverse: fully unrolled in registers (warp_llt.cuh) 47 k cycles, rolled loops over
     // shared memory (fb_inverse_warp) 44 k, against 28 k here (profiles/r2j / r2k_fb_phase_clocks.json): one warp per CTA
     // leaves the SM with five active warps
-    FB_FOR(x, n * n) { const int r = x / n; w.s.f.Minv[x] = (x - r * n == r) ? 1.0 : 0.0; }
-    __syncthreads();
-    fb_llt_factor_solve_cta<2, 3>(w.Mm, n, n, w.s.f.L, n, w.s.f.rd, w.s.f.Minv, n, n, &w.info, 0);
+    // (the dense owner-per-element sweep fb_llt_factor_solve_cta<2, 3> took 36 barrier steps: 28 k of the 74 k cycles per stage)
+    fb_minv_tree_cta(w.Mm, w.s.f.L, w.s.f.rd, w.s.f.Minv, w.s.f.fail, &w.info, 0);
     FB_PHASE(0, 1);
     FB_PHASE(0, 2);
     fb_mm<FBM_SET>(dimf, n, n, w.dCda, n, 1, w.s.f.Minv, n, 1, w.s.f.JMi, n);

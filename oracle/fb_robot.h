@@ -846,18 +846,26 @@ static inline void fb_llt_solve(const double* L, int ldl, const double* rd, int 
 }
 
 /* Robot::computeMJtJinv (robot.hxx:576-615): MJtJinv = [[M, J^T], [J, 0]]^-1, (18+dimf)^2 row-major with
- * leading dimension ld.  The reference goes through pinocchio's sparse U D U^T of M; here a dense
- * Cholesky of M gives the same blocks in the reference's order:
+ * leading dimension ld.  The reference goes through pinocchio's sparse U D U^T of M, which eliminates the joints from the
+ * leaves to the root so that the tree sparsity of M survives (a leg joint couples only with its own leg and the base).  Here:
+ * a Cholesky of M in the same kind of order -- FB_MPERM: joint s of leg i at position 4 s + i, the base last -- written as the
+ * plain dense factorisation of the permuted matrix (the structurally zero terms contribute exact zeros, which is what lets the
+ * kernel skip them and share one step between the four legs); info counts pivots in that order.  Blocks in the reference's order:
  *   Minv = M^-1;  S = J Minv J^T;  BR = -S^-1;  BL = J Minv;  TR = BL^T (-BR);  TL = Minv - TR BL;  BL = TR^T */
+static const int FB_MPERM[FB_NV] = {6, 9, 12, 15, 7, 10, 13, 16, 8, 11, 14, 17, 0, 1, 2, 3, 4, 5};
 static inline int fb_MJtJinv(const double* M, const double* J, int dimf, double* out, int ld) {
   const int n = FB_NV;
   double L[FB_NV * FB_NV], rd[FB_NV], Minv[FB_NV * FB_NV], JMi[FB_MAXF * FB_NV], S[FB_MAXF * FB_MAXF], Ls[FB_MAXF * FB_MAXF],
-      rds[FB_MAXF], Si[FB_MAXF * FB_MAXF];
-  int info = fb_llt(M, n, n, L, n, rd);
+      rds[FB_MAXF], Si[FB_MAXF * FB_MAXF], Mp[FB_NV * FB_NV], Xp[FB_NV * FB_NV];
+  for (int r = 0; r < n; ++r)
+    for (int c = 0; c < n; ++c) Mp[r * n + c] = M[FB_MPERM[r] * n + FB_MPERM[c]];
+  int info = fb_llt(Mp, n, n, L, n, rd);
   for (int c = 0; c < n; ++c) {
-    for (int r = 0; r < n; ++r) Minv[r * n + c] = (r == c) ? 1.0 : 0.0;
-    fb_llt_solve(L, n, rd, n, Minv + c, n);
+    for (int r = 0; r < n; ++r) Xp[r * n + c] = (r == c) ? 1.0 : 0.0;
+    fb_llt_solve(L, n, rd, n, Xp + c, n);
   }
+  for (int r = 0; r < n; ++r)
+    for (int c = 0; c < n; ++c) Minv[FB_MPERM[r] * n + FB_MPERM[c]] = Xp[r * n + c];
   for (int r = 0; r < dimf; ++r)
     for (int c = 0; c < n; ++c) {
       double acc = J[r * n] * Minv[c];
