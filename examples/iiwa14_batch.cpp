@@ -17,7 +17,7 @@
 #include <string>
 #include <vector>
 
-#include "idocp_b200/idocp_b200.hpp"
+#include "idocp_b200/ocp_solver.hpp"   // idocp_b200.hpp + the constraint component tag classes (JointAcceleration*Limit)
 
 namespace ob = idocp_b200;
 
@@ -165,6 +165,13 @@ int main(int argc, char* argv[]) {
   Setup s = make_setup(problem, robot);
   ob::JointConstraintsFactory factory(robot);
   auto constraints = factory.create();
+  // optional: JointAccelerationLowerLimit / JointAccelerationUpperLimit (src/constraints/joint_acceleration_*_limit.cpp) with
+  // amin = -limit, amax = +limit on every joint, pushed on top of the factory's six components
+  if (const char* acc = std::getenv("IDOCP_B200_ACC_LIMIT")) {
+    const double limit = std::atof(acc);
+    constraints->push_back(std::make_shared<ob::JointAccelerationLowerLimit>(robot, ob::VectorXd::Constant(7, -limit)));
+    constraints->push_back(std::make_shared<ob::JointAccelerationUpperLimit>(robot, ob::VectorXd::Constant(7, limit)));
+  }
   const int nthreads = 1;   // accepted for source compatibility; the batch runs on the GPU
   if (kind == "unocp") {
     ob::UnOCPSolver solver(robot, s.cost, constraints, s.T, s.N, nthreads, batch, devices);

@@ -39,6 +39,7 @@ class Problem(C.Structure):
         ("task_center", C.c_double * 3), ("task_radius", C.c_double),
         ("task_t0", C.c_double), ("task_tf", C.c_double),
         ("task_rot_ref", C.c_double * 9),
+        ("enable_acceleration_limit", C.c_int * 2), ("a_min", C.c_double * DIMV), ("a_max", C.c_double * DIMV),
     ]
 
 

@@ -196,6 +196,8 @@ static void fill_dev_problem(const idocp_b200_problem& p, DevProblem& d) {
   }
   d.barrier = p.barrier;
   d.fraction_rate = p.fraction_rate;
+  for (int k = 0; k < 2; ++k) d.acc_enable[k] = p.enable_acceleration_limit[k] ? 1 : 0;
+  for (int i = 0; i < NV; ++i) { d.a_min[i] = p.a_min[i]; d.a_max[i] = p.a_max[i]; }
   d.gravity = IIWA14_GRAVITY;
   // TimeVaryingTaskSpace6DCost::set_q_6d_weight(position_weight, rotation_weight) stores head<3> = rotation,
   // tail<3> = position (time_varying_task_space_6d_cost.cpp:43-58) and applies them to diff_6d = [linear; angular]
@@ -286,6 +288,12 @@ extern "C" int idocp_b200_create(const idocp_b200_problem* p, int solver_kind, i
   if (!par) rc |= h->alloc(&L.X2, (N + 1) * G * X_NUM * SLOT);
   rc |= h->alloc(&L.KQ, (N + 1) * G * KQ_NUM * SLOT);   // record N: dense terminal Hessian of the task-space cost
   rc |= h->alloc(&L.task_ref, (N + 1) * 12);
+  if (p->enable_acceleration_limit[0] || p->enable_acceleration_limit[1]) {
+    // JointAcceleration{Lower,Upper}Limit: their slack / dual rows live in their own array and run through the literal kernel
+    // sequence with the ACC instantiations; the six-component kernels and the X record are untouched
+    rc |= h->alloc(&L.XA, N * G * XA_NUM * SLOT);
+    h->pipelined = false;
+  }
   rc |= h->alloc(&L.W, N * G * W_NUM * SLOT);
   rc |= h->alloc(&L.D, (N + 1) * G * D_NUM * SLOT);
   rc |= h->alloc(&L.smin, 2 * N * Bp);
@@ -467,22 +475,37 @@ static int run_line_search(idocp_b200_solver* h, const double* d_q, const double
   return IDOCP_B200_OK;
 }
 
+// k_linearize / k_expand instantiation by the run-time problem flags (task-space cost, acceleration limits)
+template <bool RES, bool BE>
+static void launch_linearize(idocp_b200_solver* h, int cls, int nstages, const double* d_q, const double* d_v) {
+  const bool task = h->prob.task_enabled != 0, acc = h->L.XA != nullptr;
+  const int grid = stage_grid(h, nstages);
+  if (task && acc) IDOCP_LAUNCH(h, cls, (k_linearize<RES, BE, true, true>), grid, CTA_THREADS, kLinSmem, h->d_prob, h->L, d_q, d_v);
+  else if (task) IDOCP_LAUNCH(h, cls, (k_linearize<RES, BE, true, false>), grid, CTA_THREADS, kLinSmem, h->d_prob, h->L, d_q, d_v);
+  else if (acc) IDOCP_LAUNCH(h, cls, (k_linearize<RES, BE, false, true>), grid, CTA_THREADS, kLinSmem, h->d_prob, h->L, d_q, d_v);
+  else IDOCP_LAUNCH(h, cls, (k_linearize<RES, BE, false, false>), grid, CTA_THREADS, kLinSmem, h->d_prob, h->L, d_q, d_v);
+}
+template <bool PARNMPC>
+static void launch_expand(idocp_b200_solver* h, int nstages, int stage_offset) {
+  const bool task = !PARNMPC && h->prob.task_enabled != 0, acc = h->L.XA != nullptr;
+  const int grid = stage_grid(h, nstages);
+  if (task && acc) IDOCP_LAUNCH(h, KC_EXPAND, (k_expand<PARNMPC, !PARNMPC, true>), grid, CTA_THREADS, 0, h->d_prob, h->L, stage_offset);
+  else if (task) IDOCP_LAUNCH(h, KC_EXPAND, (k_expand<PARNMPC, !PARNMPC, false>), grid, CTA_THREADS, 0, h->d_prob, h->L, stage_offset);
+  else if (acc) IDOCP_LAUNCH(h, KC_EXPAND, (k_expand<PARNMPC, false, true>), grid, CTA_THREADS, 0, h->d_prob, h->L, stage_offset);
+  else IDOCP_LAUNCH(h, KC_EXPAND, (k_expand<PARNMPC, false, false>), grid, CTA_THREADS, 0, h->d_prob, h->L, stage_offset);
+}
+
 static int unocp_update(idocp_b200_solver* h, const double* d_q, const double* d_v, int line_search) {
   const bool task = h->prob.task_enabled != 0;
   if (!(h->pipelined && h->lin_valid)) {
-    if (task)
-      IDOCP_LAUNCH(h, KC_LINEARIZE, (k_linearize<false, false, true>), stage_grid(h, h->N + 1), CTA_THREADS, kLinSmem,
-                   h->d_prob, h->L, d_q, d_v);
-    else
-      IDOCP_LAUNCH(h, KC_LINEARIZE, (k_linearize<false, false, false>), stage_grid(h, h->N), CTA_THREADS, kLinSmem,
-                   h->d_prob, h->L, d_q, d_v);
+    launch_linearize<false, false>(h, KC_LINEARIZE, task ? h->N + 1 : h->N, d_q, d_v);
   }
   if (task) {
     IDOCP_LAUNCH(h, KC_RICCATI, k_riccati<true>, ric_grid(h), RIC_THREADS, kRicSmem, h->d_prob, h->L, d_q, d_v);
-    IDOCP_LAUNCH(h, KC_EXPAND, (k_expand<false, true>), stage_grid(h, h->N + 1), CTA_THREADS, 0, h->d_prob, h->L, 0);
+    launch_expand<false>(h, h->N + 1, 0);
   } else {
     IDOCP_LAUNCH(h, KC_RICCATI, k_riccati<false>, ric_grid(h), RIC_THREADS, kRicSmem, h->d_prob, h->L, d_q, d_v);
-    IDOCP_LAUNCH(h, KC_EXPAND, (k_expand<false, false>), stage_grid(h, h->N + 1), CTA_THREADS, 0, h->d_prob, h->L, 0);
+    launch_expand<false>(h, h->N + 1, 0);
   }
   const double* override_alpha = nullptr;
   if (line_search) {
@@ -513,12 +536,7 @@ static int unocp_update(idocp_b200_solver* h, const double* d_q, const double* d
 static int parnmpc_update(idocp_b200_solver* h, double, const double* d_q, const double* d_v, int line_search) {
   const int N = h->N;
   // UnBackwardCorrection::coarseUpdate (src/unocp/unbackward_correction.cpp:67-97)
-  if (h->prob.task_enabled)
-    IDOCP_LAUNCH(h, KC_LINEARIZE, (k_linearize<false, true, true>), stage_grid(h, N), CTA_THREADS, kLinSmem, h->d_prob,
-                 h->L, d_q, d_v);
-  else
-    IDOCP_LAUNCH(h, KC_LINEARIZE, (k_linearize<false, true, false>), stage_grid(h, N), CTA_THREADS, kLinSmem, h->d_prob,
-                 h->L, d_q, d_v);
+  launch_linearize<false, true>(h, KC_LINEARIZE, N, d_q, d_v);
   IDOCP_LAUNCH(h, KC_PARNMPC_COARSE, k_parnmpc_invert, N * h->L.G, CTA_THREADS, INV_SMEM_BYTES, h->d_prob, h->L, h->PL);
   // UnBackwardCorrection::backwardCorrection (:100-134)
   if (N > 1) {
@@ -527,7 +545,7 @@ static int parnmpc_update(idocp_b200_solver* h, double, const double* d_q, const
     IDOCP_LAUNCH(h, KC_PARNMPC_CORR, k_parnmpc_forward_serial, group_grid(h), CTA_THREADS, 0, h->L, h->PL);
   }
   IDOCP_LAUNCH(h, KC_PARNMPC_CORR, k_parnmpc_forward_parallel, stage_grid(h, N), CTA_THREADS, 0, h->L, h->PL);
-  IDOCP_LAUNCH(h, KC_EXPAND, (k_expand<true, false>), stage_grid(h, N), CTA_THREADS, 0, h->d_prob, h->L, 1);
+  launch_expand<true>(h, N, 1);
   const double* override_alpha = nullptr;
   if (line_search) {
     const int rc = run_line_search(h, d_q, d_v);
@@ -541,12 +559,7 @@ static int parnmpc_update(idocp_b200_solver* h, double, const double* d_q, const
 
 // UnParNMPCSolver::computeKKTResidual (src/unocp/unparnmpc_solver.cpp:171-192)
 static int parnmpc_kkt_residual(idocp_b200_solver* h, double, const double* d_q, const double* d_v) {
-  if (h->prob.task_enabled)
-    IDOCP_LAUNCH(h, KC_KKT, (k_linearize<true, true, true>), stage_grid(h, h->N), CTA_THREADS, kLinSmem, h->d_prob, h->L,
-                 d_q, d_v);
-  else
-    IDOCP_LAUNCH(h, KC_KKT, (k_linearize<true, true, false>), stage_grid(h, h->N), CTA_THREADS, kLinSmem, h->d_prob, h->L,
-                 d_q, d_v);
+  launch_linearize<true, true>(h, KC_KKT, h->N, d_q, d_v);
   IDOCP_LAUNCH(h, KC_KKT, k_kkt_sum, (h->Bp + 127) / 128, 128, 0, h->L, h->N);
   CUDA_OK(cudaGetLastError());
   return IDOCP_B200_OK;
@@ -589,12 +602,7 @@ extern "C" int idocp_b200_compute_kkt_residual_device(idocp_b200_solver* h, doub
   (void)t;
   CUDA_OK(cudaSetDevice(h->device));
   if (h->kind == IDOCP_B200_SOLVER_UNPARNMPC) return parnmpc_kkt_residual(h, t, d_q, d_v);
-  if (h->prob.task_enabled)
-    IDOCP_LAUNCH(h, KC_KKT, (k_linearize<true, false, true>), stage_grid(h, h->N + 1), CTA_THREADS, kLinSmem, h->d_prob,
-                 h->L, d_q, d_v);
-  else
-    IDOCP_LAUNCH(h, KC_KKT, (k_linearize<true, false, false>), stage_grid(h, h->N + 1), CTA_THREADS, kLinSmem, h->d_prob,
-                 h->L, d_q, d_v);
+  launch_linearize<true, false>(h, KC_KKT, h->N + 1, d_q, d_v);
   IDOCP_LAUNCH(h, KC_KKT, k_kkt_sum, (h->Bp + 127) / 128, 128, 0, h->L, h->N + 1);
   CUDA_OK(cudaGetLastError());
   return IDOCP_B200_OK;
@@ -706,12 +714,38 @@ __global__ void k_gather_constraints(const double* __restrict__ X, int first_slo
   out[idx] = X[elem_index(X_NUM, G, i, b, first_slot + c, j)];
 }
 
+// out[b][N][2][7]: slots first_slot, first_slot + 1 of the acceleration-limit record
+__global__ void k_gather_acc_rows(const double* __restrict__ XA, int first_slot, int N, int B, int G, double* __restrict__ out) {
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long total = static_cast<long>(B) * N * 2 * NV;
+  if (idx >= total) return;
+  const int j = static_cast<int>(idx % NV);
+  long t = idx / NV;
+  const int c = static_cast<int>(t % 2);
+  t /= 2;
+  const int i = static_cast<int>(t % N);
+  const int b = static_cast<int>(t / N);
+  out[idx] = XA[elem_index(XA_NUM, G, i, b, first_slot + c, j)];
+}
+
 extern "C" int idocp_b200_get_constraint_data(idocp_b200_solver* h, const char* name, double* out) {
   if (!h || !out || !name) return fail(IDOCP_B200_INVALID_ARGUMENT, "get_constraint_data: null pointer");
   int first = -1;
   if (!std::strcmp(name, "slack")) first = X_SLACK;
   else if (!std::strcmp(name, "dual")) first = X_DUAL;
-  else return fail(IDOCP_B200_INVALID_ARGUMENT, "get_constraint_data: name must be slack or dual");
+  else if (!std::strcmp(name, "acc_slack") || !std::strcmp(name, "acc_dual")) {
+    // the two acceleration-limit components: out[batch][N][2][dimv]
+    if (!h->L.XA) return fail(IDOCP_B200_INVALID_ARGUMENT, "get_constraint_data: the acceleration limits are not enabled");
+    CUDA_OK(cudaSetDevice(h->device));
+    const long tot = static_cast<long>(h->B) * h->N * 2 * NV;
+    IDOCP_LAUNCH(h, KC_MISC, k_gather_acc_rows, static_cast<int>((tot + 255) / 256), 256, 0, h->L.XA, name[4] == 's' ? 0 : 2, h->N,
+                 h->B, h->L.G, h->d_stage);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(out, h->d_stage, tot * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return IDOCP_B200_OK;
+  }
+  else return fail(IDOCP_B200_INVALID_ARGUMENT, "get_constraint_data: name must be slack, dual, acc_slack or acc_dual");
   CUDA_OK(cudaSetDevice(h->device));
   const long total = static_cast<long>(h->B) * h->N * NC * NV;
   IDOCP_LAUNCH(h, KC_MISC, k_gather_constraints, static_cast<int>((total + 255) / 256), 256, 0, h->L.X, first, h->N,
@@ -788,6 +822,11 @@ __global__ void k_is_feasible(const DevProblem* __restrict__ Pp, Layout L, int s
       const double u = L.X[elem_index(X_NUM, L.G, i, b, X_U, j)];
       for (int c = 0; c < NC; ++c)
         if (comp_active(c, i + stage_offset) && con_margin(c, lim, q, v, u) < 0) ok = 0;
+      if (L.XA) {   // JointAccelerationLowerLimit / UpperLimit::isFeasible (joint_acceleration_lower_limit.cpp:29-38)
+        const double a = L.X[elem_index(X_NUM, L.G, i, b, X_A, j)];
+        if (P.acc_enable[0] && a < P.a_min[j]) ok = 0;
+        if (P.acc_enable[1] && a > P.a_max[j]) ok = 0;
+      }
     }
   out[b] = ok;
 }
@@ -834,7 +873,7 @@ extern "C" int idocp_b200_set_task_reference(idocp_b200_solver* h, const double*
 // get_unkkt then shows the linearisation the last direction was computed from instead of the one kept for the next call.
 extern "C" int idocp_b200_set_pipelining(idocp_b200_solver* h, int enabled) {
   if (!h) return fail(IDOCP_B200_INVALID_ARGUMENT, "null handle");
-  h->pipelined = enabled != 0;
+  h->pipelined = enabled != 0 && h->L.XA == nullptr;   // the acceleration limits run through the literal sequence only
   h->lin_valid = false;
   return IDOCP_B200_OK;
 }

@@ -32,6 +32,9 @@ struct DevProblem {
   int task_enabled;
   double ee[12];
   double task_w6[6], task_wf6[6];
+  // JointAccelerationLowerLimit / JointAccelerationUpperLimit (src/constraints/joint_acceleration_*_limit.cpp): amin <= a <= amax
+  int acc_enable[2];
+  double a_min[8], a_max[8];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -75,7 +78,10 @@ struct Layout {
   double* kkt_err;    // [Bp]
   int* status;        // [Bp]
   double* task_ref;   // [N+1][12] host-sampled SE3 reference per stage index (R row-major, p); see capi.cu
+  double* XA;         // [N][G][XA_NUM slots]: slack (lower, upper), dual (lower, upper) of the two acceleration-limit components;
+                      // nullptr unless one of them is enabled (the X record and the hot kernels stay as they are otherwise)
 };
+constexpr int XA_NUM = 4;
 
 // element index of (stage, instance b, slot, joint j) in an array with `ns` slots per record
 __host__ __device__ __forceinline__ size_t elem_index(int ns, int G, int stage, int b, int slot, int j) {

@@ -186,6 +186,19 @@ __global__ void __launch_bounds__(CTA_THREADS) k_ls_eval(const DevProblem* __res
     const double rt = con_residual(c, lim, qt, vt, ut, sl);
     c1 += oct_sum_ordered(z * fabs(rt));
   }
+  if (L.XA) {   // acceleration limits (the oracle's component order: after the six joint limits)
+    const AccRows acc = acc_load(P, L, i, t.g, act ? lane : 0);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (!acc.on[k]) continue;
+      const double sl = act ? acc.sl[k] : 1.0;
+      const double r0 = acc_residual(acc, k, a, sl);
+      const double dslack = (k ? -da : da) - r0;
+      const double st = alpha > 0.0 ? fma(alpha, dslack, sl) : sl;
+      bar += -P.barrier * oct_sum_ordered(z * canon_log(st));
+      c1 += oct_sum_ordered(z * fabs(acc_residual(acc, k, at, sl)));
+    }
+  }
   cost += dt * bar;
   // ---- SplitUnOCP::constraintViolation (split_unocp.hxx:199-217) ----
   const double Fq = BACKWARD_EULER ? fma(dt, vt, qnt - qt) : fma(dt, vt, qt - qnt);

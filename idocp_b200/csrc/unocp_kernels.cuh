@@ -83,6 +83,37 @@ __device__ __forceinline__ LaneLimits load_limits(const DevProblem& P, int lane)
   return LaneLimits{P.q_min[lane], P.q_max[lane], P.v_max[lane], P.u_max[lane]};
 }
 
+// The two acceleration-limit components (JointAccelerationLowerLimit / UpperLimit, joint_acceleration_*_limit.cpp): rows of
+// this lane's joint, k = 0 lower (residual amin - a + slack), k = 1 upper (a - amax + slack).  They are processed AFTER the
+// six joint-limit components everywhere (the oracle's component order), from their own array XA.
+struct AccRows {
+  double sl[2], du[2], lim[2];
+  bool on[2];
+};
+__device__ __forceinline__ AccRows acc_load(const DevProblem& P, const Layout& L, int stage, int g, int lane) {
+  const double* XA = rec_ptr(L.XA, XA_NUM, L.G, stage, g);
+  AccRows r;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    r.on[k] = P.acc_enable[k] != 0;
+    r.sl[k] = r.on[k] ? XA[k * SLOT] : 1.0;
+    r.du[k] = r.on[k] ? XA[(2 + k) * SLOT] : 0.0;
+  }
+  r.lim[0] = P.a_min[lane];
+  r.lim[1] = P.a_max[lane];
+  return r;
+}
+__device__ __forceinline__ double acc_residual(const AccRows& r, int k, double a, double slack) {
+  return k == 0 ? r.lim[0] - a + slack : a - r.lim[1] + slack;
+}
+// slack / dual direction of row k for the acceleration direction da (joint_acceleration_lower_limit.cpp:72-77, pdipm.hxx:76-81)
+__device__ __forceinline__ void acc_direction(const AccRows& r, int k, double a, double da, double barrier, double& dslack, double& ddual) {
+  const double res = acc_residual(r, k, a, r.sl[k]);
+  const double dty = r.sl[k] * r.du[k] - barrier;
+  dslack = (k ? -da : da) - res;
+  ddual = -fma(r.du[k], dslack, dty) / r.sl[k];
+}
+
 // warp-task decomposition of the per-stage kernels: task = (stage, group)
 struct StageTask {
   int stage, g;
@@ -117,6 +148,22 @@ __global__ void __launch_bounds__(CTA_THREADS) k_init_constraints(const DevProbl
     }
     X[(X_SLACK + c) * SLOT] = sl;
     X[(X_DUAL + c) * SLOT] = du;
+  }
+  if (L.XA) {   // acceleration limits (time stage >= 0: every stage with controls)
+    double* XA = rec_ptr(L.XA, XA_NUM, L.G, t.stage, t.g);
+    const double a = X[X_A * SLOT];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      double sl = 0.0, du = 0.0;
+      if (P.acc_enable[k] && lane < NV) {
+        sl = k == 0 ? a - P.a_min[lane] : P.a_max[lane] - a;
+        int guard = 0;
+        while (sl < P.barrier && guard < (1 << 20)) { sl += P.barrier; ++guard; }
+        du = P.barrier / sl;
+      }
+      XA[k * SLOT] = sl;
+      XA[(2 + k) * SLOT] = du;
+    }
   }
 }
 
@@ -155,12 +202,13 @@ __global__ void k_set_solution(Layout L, int field, const double* __restrict__ v
 //   (q0, v0 only enter the forward Riccati recursion), so the host keeps it until the iterate or the cost reference changes
 //   (capi.cu: lin_valid).  The update's HBM stream hides under the FP64 work of the linearisation.
 // X: this thread's pointer into the record of (stage i, group g) -- global memory, or the staged copy when FUSED.
-template <bool RESIDUAL_ONLY, bool BACKWARD_EULER, bool TASK, bool FUSED>
+template <bool RESIDUAL_ONLY, bool BACKWARD_EULER, bool TASK, bool FUSED, bool ACC = false>
 __device__ __forceinline__ void linearize_task(const DevProblem& P, const Layout& L, const double* __restrict__ q0,
                                                const double* __restrict__ v0, double* tile, const int i, const int g,
                                                const double* X, const double* D, const double* Xnf, const double* Dn,
                                                const double ap, const double ad) {
   static_assert(!FUSED || (!RESIDUAL_ONLY && !BACKWARD_EULER), "the fused update exists for UnOCPSolver::updateSolution only");
+  static_assert(!FUSED || !ACC, "the acceleration limits run through the literal kernel sequence");
   const int lane = lane_in_octet();
   const int ts = BACKWARD_EULER ? i + 1 : i;   // time stage of the constraint masks
   const int b = g * 4 + ((threadIdx.x >> 3) & 3);
@@ -283,6 +331,8 @@ __device__ __forceinline__ void linearize_task(const DevProblem& P, const Layout
     dual[c] = FUSED ? fdual[c] : X[(X_DUAL + c) * SLOT];
   }
   const LaneLimits lim = load_limits(P, lane);
+  AccRows acc;
+  if (ACC) acc = acc_load(P, L, i, g, act ? lane : 0);
 
   // ---- inverse dynamics and its derivatives (UnconstrainedDynamics::linearizeInverseDynamics) ----
   JointDyn J;
@@ -324,6 +374,14 @@ __device__ __forceinline__ void linearize_task(const DevProblem& P, const Layout
     const double g = dt * dual[c];
     const double sg = (c & 1) ? g : -g;
     if (c < 2) lq += sg; else if (c < 4) lv += sg; else lu += sg;
+  }
+  if (ACC) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (!acc.on[k]) continue;
+      const double g2 = dt * acc.du[k];
+      la += k ? g2 : -g2;
+    }
   }
   double Fq, Fv;
   if (!BACKWARD_EULER) {
@@ -378,6 +436,15 @@ __device__ __forceinline__ void linearize_task(const DevProblem& P, const Layout
       const double dl = slack[c] * dual[c] - P.barrier;
       c2 += oct_sum_ordered(z * (r * r)) + oct_sum_ordered(z * (dl * dl));
     }
+    if (ACC) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (!acc.on[k]) continue;
+        const double r = acc_residual(acc, k, a, acc.sl[k]);
+        const double dl = acc.sl[k] * acc.du[k] - P.barrier;
+        c2 += oct_sum_ordered(z * (r * r)) + oct_sum_ordered(z * (dl * dl));
+      }
+    }
     e += dt * dt * c2;
     if (lane == 0) L.kkt_stage[static_cast<size_t>(i) * L.Bp + b] = e;
     return;
@@ -386,7 +453,7 @@ __device__ __forceinline__ void linearize_task(const DevProblem& P, const Layout
   // ---- Hessian diagonals + constraint condensing (steps 5-6) ----
   double Qqq_d = dt * P.q_weight[lane];
   double Qvv_d = dt * P.v_weight[lane];
-  const double Qaa_d = dt * P.a_weight[lane];
+  double Qaa_d = dt * P.a_weight[lane];
   double Quu_d = dt * P.u_weight[lane];
   // off-diagonal entries of the un-condensed Qqq (task-space Gauss-Newton term only), row r of this lane's column
   double Qqq_off[NV];
@@ -424,6 +491,18 @@ __device__ __forceinline__ void linearize_task(const DevProblem& P, const Layout
       if (c < 2) { Qqq_d += h; lq += sg; }
       else if (c < 4) { Qvv_d += h; lv += sg; }
       else { Quu_d += h; lu += sg; }
+    }
+    if (ACC) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (!acc.on[k]) continue;
+        const double r = acc_residual(acc, k, a, acc.sl[k]);
+        const double dl = acc.sl[k] * acc.du[k] - P.barrier;
+        const double rs = 1.0 / acc.sl[k];
+        Qaa_d += (dt * acc.du[k]) * rs;
+        const double g2 = (dt * fma(acc.du[k], r, -dl)) * rs;
+        la += k ? g2 : -g2;
+      }
     }
   } else {
     Quu_d = 0.0;
@@ -506,14 +585,15 @@ __device__ __forceinline__ void linearize_task(const DevProblem& P, const Layout
 }
 
 
-template <bool RESIDUAL_ONLY, bool BACKWARD_EULER, bool TASK>
+// ACC = true: + the two acceleration-limit components (their own array L.XA; the six-component instantiations are untouched)
+template <bool RESIDUAL_ONLY, bool BACKWARD_EULER, bool TASK, bool ACC = false>
 __global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_linearize(const DevProblem* __restrict__ Pp, Layout L,
                                                                            const double* __restrict__ q0,
                                                                            const double* __restrict__ v0) {
   IDOCP_DYN_SMEM(double, smem);
   double* tile = smem + (threadIdx.x >> 3) * (OCT * PAIR_TILE);
   const StageTask t = stage_task(L, ((RESIDUAL_ONLY || TASK) && !BACKWARD_EULER) ? L.N + 1 : L.N);
-  linearize_task<RESIDUAL_ONLY, BACKWARD_EULER, TASK, false>(*Pp, L, q0, v0, tile, t.stage, t.g,
+  linearize_task<RESIDUAL_ONLY, BACKWARD_EULER, TASK, false, ACC>(*Pp, L, q0, v0, tile, t.stage, t.g,
                                                              rec_ptr(L.X, X_NUM, L.G, t.stage, t.g), nullptr, nullptr, nullptr, 1.0, 1.0);
 }
 
@@ -966,7 +1046,7 @@ __global__ void __launch_bounds__(RIC_THREADS, IDOCP_RIC_MINB) k_riccati(const D
 // (k_parnmpc_forward_parallel); only the condensed direction and the step sizes are computed.
 // TASK = true: the terminal P_N = Qqq_N is dense (record N of KQ)
 constexpr int EXP_TILE = 9;   // odd stride (doubles) of the Pqv transpose tile of k_expand
-template <bool PARNMPC, bool TASK>
+template <bool PARNMPC, bool TASK, bool ACC = false>
 __global__ void __launch_bounds__(CTA_THREADS, IDOCP_EXP_MINB) k_expand(const DevProblem* __restrict__ Pp, Layout L, int stage_offset) {
   const DevProblem& P = *Pp;
   const int lane = lane_in_octet();
@@ -1015,6 +1095,9 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_EXP_MINB) k_expand(const De
       dul[c] = on ? X[(X_DUAL + c) * SLOT] : 0.0;
     }
   }
+  AccRows acc;
+  double xa = 0.0;
+  if (ACC) { acc = acc_load(P, L, i, t.g, act ? lane : 0); xa = X[X_A * SLOT]; }
   // Every W slot of the record goes out before the first use: the kernel is a pure HBM stream, and 12 warps per SM
   // with ~60 loads in flight each (166 registers) reach 6.4 TB/s where 20 warps at 95 registers, loading as the FMA
   // chains consume, reached 5.4 TB/s (0.287 -> 0.249 ms; register CAPS of 80 / 72 for more warps: 0.36 / 0.35 ms).
@@ -1100,6 +1183,16 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_EXP_MINB) k_expand(const De
       min_p = fraction_row(P.fraction_rate, sl, dslack, min_p);
       min_d = fraction_row(P.fraction_rate, dl, ddual, min_d);
     }
+    if (ACC) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (!acc.on[k]) continue;
+        double dslack, ddual;
+        acc_direction(acc, k, xa, da, P.barrier, dslack, ddual);
+        min_p = fraction_row(P.fraction_rate, acc.sl[k], dslack, min_p);
+        min_d = fraction_row(P.fraction_rate, acc.du[k], ddual, min_d);
+      }
+    }
   }
   min_p = oct_min(min_p);
   min_d = oct_min(min_d);
@@ -1181,6 +1274,18 @@ __global__ void __launch_bounds__(CTA_THREADS) k_update(const DevProblem* __rest
     const double ddual = -fma(dl, dslack, dty) / sl;
     X[(X_SLACK + c) * SLOT] = fma(ap, dslack, sl);
     X[(X_DUAL + c) * SLOT] = fma(ad, ddual, dl);
+  }
+  if (L.XA) {
+    const AccRows acc = acc_load(P, L, i, t.g, lane);
+    double* XA = rec_ptr(L.XA, XA_NUM, L.G, i, t.g);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (!acc.on[k]) continue;
+      double dslack, ddual;
+      acc_direction(acc, k, a, da, P.barrier, dslack, ddual);
+      XA[k * SLOT] = fma(ap, dslack, acc.sl[k]);
+      XA[(2 + k) * SLOT] = fma(ad, ddual, acc.du[k]);
+    }
   }
 }
 

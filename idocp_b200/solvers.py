@@ -216,7 +216,8 @@ class _BatchSolver:
         return out
 
     def getConstraintData(self, name):
-        out = np.zeros((self.batch, self.N, NUM_CONSTRAINTS, DIMV))
+        # "slack" / "dual": the six joint-limit components; "acc_slack" / "acc_dual": the two acceleration limits
+        out = np.zeros((self.batch, self.N, 2 if name.startswith("acc_") else NUM_CONSTRAINTS, DIMV))
         self.lib.check(self.lib.L.idocp_b200_get_constraint_data(self._h, name.encode(), dptr(out)))
         return out
 

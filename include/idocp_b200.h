@@ -77,6 +77,11 @@ typedef struct {
                                set_q_6d_weight / set_qf_6d_weight (time_varying_task_space_6d_cost.cpp:43-58) */
   double task_center[3], task_radius, task_t0, task_tf; /* reserved (the reference is a host-sampled table) */
   double task_rot_ref[9];
+  /* JointAccelerationLowerLimit / JointAccelerationUpperLimit (src/constraints/joint_acceleration_*_limit.cpp) with their
+   * constructor arguments amin / amax: [0] lower, [1] upper.  While one is enabled the solver runs the literal kernel
+   * sequence (no pipelining) with the kernel instantiations that carry the two extra components. */
+  int enable_acceleration_limit[2];
+  double a_min[IDOCP_B200_DIMV], a_max[IDOCP_B200_DIMV];
 } idocp_b200_problem;
 
 typedef struct idocp_b200_solver idocp_b200_solver; /* opaque */

@@ -436,9 +436,11 @@ class Constraints {
   void push_back(const std::shared_ptr<Component>& c) {
     if (c->id >= IDOCP_B200_FB_NUM_CONSTRAINTS) {   // JointAcceleration{Lower,Upper}Limit(robot, amin / amax)
       const int k = c->id - IDOCP_B200_FB_NUM_CONSTRAINTS;
-      if (static_cast<int>(c->bound.size()) != 12) detail::die("invalid size: the acceleration limit takes one bound per actuated joint (12)");
+      const int nb = static_cast<int>(c->bound.size());   // 7 (fixed-base iiwa14) or 12 (actuated joints of ANYmal)
+      if (nb != 7 && nb != 12) detail::die("invalid size: the acceleration limit takes one bound per actuated joint (7 or 12)");
       enable_acc_[k] = 1;
-      for (int j = 0; j < 12; ++j) (k == 0 ? a_min_ : a_max_)[j] = c->bound[j];
+      acc_dim_ = nb;
+      for (int j = 0; j < nb; ++j) (k == 0 ? a_min_ : a_max_)[j] = c->bound[j];
       return;
     }
     enable_[c->id] = 1;
@@ -447,6 +449,7 @@ class Constraints {
   }
   const int* coneNonlinear() const { return cone_nonlinear_; }
   const int* enableAccelerationLimit() const { return enable_acc_; }
+  int accelerationLimitDim() const { return acc_dim_; }
   const double* aMin() const { return a_min_; }
   const double* aMax() const { return a_max_; }
   const int* enable() const { return enable_; }
@@ -461,7 +464,7 @@ class Constraints {
  private:
   double barrier_ = 1.0e-04, rate_ = 0.995;
   int enable_[IDOCP_B200_FB_NUM_CONSTRAINTS] = {0};
-  int cone_nonlinear_[2] = {0, 0}, enable_acc_[2] = {0, 0};
+  int cone_nonlinear_[2] = {0, 0}, enable_acc_[2] = {0, 0}, acc_dim_ = 0;
   double a_min_[12] = {0}, a_max_[12] = {0};
   double mu_ = 0.7;
 };
@@ -485,6 +488,12 @@ inline idocp_b200_problem make_problem(const Robot& robot, const std::shared_ptr
   }
   p.barrier = constraints->barrier();
   p.fraction_rate = constraints->fractionToBoundaryRate();
+  if (constraints->enableAccelerationLimit()[0] || constraints->enableAccelerationLimit()[1]) {
+    // JointAccelerationLowerLimit(robot, amin) / JointAccelerationUpperLimit(robot, amax) pushed on top of the factory's six
+    if (constraints->accelerationLimitDim() != IDOCP_B200_DIMV) detail::die("invalid size: amin / amax must have dimv = 7 entries");
+    for (int k = 0; k < 2; ++k) p.enable_acceleration_limit[k] = constraints->enableAccelerationLimit()[k];
+    for (int j = 0; j < IDOCP_B200_DIMV; ++j) { p.a_min[j] = constraints->aMin()[j]; p.a_max[j] = constraints->aMax()[j]; }
+  }
   p.T = T;
   p.N = N;
   if (cost->task()) {

@@ -293,6 +293,8 @@ class OCPSolver {
     }
     for (int c = 0; c < IDOCP_B200_FB_NUM_CONSTRAINTS; ++c) p.enable[c] = constraints->enable()[c];
     p.mu = constraints->mu(); p.barrier = constraints->barrier(); p.fraction_rate = constraints->fractionToBoundaryRate();
+    if ((constraints->enableAccelerationLimit()[0] || constraints->enableAccelerationLimit()[1]) && constraints->accelerationLimitDim() != 12)
+      detail::die("invalid size: amin / amax must have one entry per actuated joint (12)");
     for (int k = 0; k < 2; ++k) {
       p.cone_nonlinear[k] = constraints->coneNonlinear()[k];
       p.enable_acceleration_limit[k] = constraints->enableAccelerationLimit()[k];

@@ -21,7 +21,7 @@
 #endif
 
 #define NV ORACLE_NV
-#define NC ORACLE_NC
+#define NC 8               /* six components of JointConstraintsFactory + the two acceleration limits */
 #define NN (NV * NV)
 
 /* ------------------------------------------------------------------------------------------ */
@@ -751,7 +751,7 @@ typedef struct { double slack[NV], dual[NV], residual[NV], duality[NV], dslack[N
 /* component order = JointConstraintsFactory push_back order regrouped by kinematics level
  * (src/utils/joint_constraints_factory.cpp:30-35, constraints/constraints.hxx:23-34):
  * 0 pos-lower 1 pos-upper | 2 vel-lower 3 vel-upper | 4 torque-lower 5 torque-upper */
-enum { C_POS_LO = 0, C_POS_UP, C_VEL_LO, C_VEL_UP, C_TRQ_LO, C_TRQ_UP };
+enum { C_POS_LO = 0, C_POS_UP, C_VEL_LO, C_VEL_UP, C_TRQ_LO, C_TRQ_UP, C_ACC_LO, C_ACC_UP };
 
 typedef struct {
   /* SplitKKTResidual / SplitKKTMatrix pieces the unconstrained path touches */
@@ -796,11 +796,13 @@ struct oracle_unocp {
 /* constraints/ : pdipm + the six joint-limit components                                       */
 /* ------------------------------------------------------------------------------------------ */
 /* constraints_data.hpp:18-43: which kinematics levels are live at a time stage */
-static void set_active(int time_stage, int* active) {
+static void set_active(const oracle_problem_t* p, int time_stage, int* active) {
   const int pos = time_stage >= 2, vel = time_stage >= 1, acc = time_stage >= 0;
   active[C_POS_LO] = active[C_POS_UP] = pos;
   active[C_VEL_LO] = active[C_VEL_UP] = vel;
   active[C_TRQ_LO] = active[C_TRQ_UP] = acc;
+  active[C_ACC_LO] = acc && p->enable_acc[0];   /* KinematicsLevel::AccelerationLevel (joint_acceleration_lower_limit.cpp:24-26) */
+  active[C_ACC_UP] = acc && p->enable_acc[1];
 }
 
 /* g such that slack = g at initialisation and residual = -g + slack  (e.g.
@@ -812,6 +814,8 @@ static inline double con_margin(const oracle_problem_t* p, int comp, const split
     case C_VEL_LO: return s->v[j] - (-p->v_max[j]);
     case C_VEL_UP: return p->v_max[j] - s->v[j];
     case C_TRQ_LO: return s->u[j] - (-p->u_max[j]);
+    case C_ACC_LO: return s->a[j] - p->a_min[j];
+    case C_ACC_UP: return p->a_max[j] - s->a[j];
     default:       return p->u_max[j] - s->u[j];
   }
 }
@@ -846,6 +850,8 @@ static void compute_primal_dual_residual(const oracle_problem_t* p, stage_t* st,
         case C_VEL_LO: r = (-p->v_max[j]) - s->v[j] + d->slack[j]; break;
         case C_VEL_UP: r = s->v[j] - p->v_max[j] + d->slack[j]; break;
         case C_TRQ_LO: r = (-p->u_max[j]) - s->u[j] + d->slack[j]; break;
+        case C_ACC_LO: r = p->a_min[j] - s->a[j] + d->slack[j]; break;
+        case C_ACC_UP: r = s->a[j] - p->a_max[j] + d->slack[j]; break;
         default:       r = s->u[j] - p->u_max[j] + d->slack[j]; break;
       }
       d->residual[j] = r;
@@ -855,7 +861,7 @@ static void compute_primal_dual_residual(const oracle_problem_t* p, stage_t* st,
 }
 
 static inline double* con_grad(stage_t* st, int comp) {
-  return comp <= C_POS_UP ? st->lq : (comp <= C_VEL_UP ? st->lv : st->lu);
+  return comp <= C_POS_UP ? st->lq : (comp <= C_VEL_UP ? st->lv : (comp >= C_ACC_LO ? st->la : st->lu));
 }
 static inline double con_sign(int comp) { return (comp & 1) ? 1.0 : -1.0; } /* lower: -, upper: + */
 
@@ -883,6 +889,7 @@ static void condense_slack_and_dual(const oracle_problem_t* p, stage_t* st, cons
       const double h = (dt * d->dual[j]) * rs;
       if (c <= C_POS_UP) st->Qqq[j * NV + j] += h;
       else if (c <= C_VEL_UP) st->Qvv[j] += h;
+      else if (c >= C_ACC_LO) st->Qaa[j] += h;
       else st->Quu[j] += h;
       l[j] += sg * ((dt * fma(d->dual[j], d->residual[j], -d->duality[j])) * rs);
     }
@@ -895,7 +902,7 @@ static void compute_slack_dual_direction(stage_t* st, const split_direction_t* d
   for (int c = 0; c < NC; ++c) {
     if (!st->active[c]) continue;
     cdata_t* cd = &st->c[c];
-    const double* dx = c <= C_POS_UP ? d->dq : (c <= C_VEL_UP ? d->dv : d->du);
+    const double* dx = c <= C_POS_UP ? d->dq : (c <= C_VEL_UP ? d->dv : (c >= C_ACC_LO ? d->da : d->du));
     for (int j = 0; j < NV; ++j) {
       cd->dslack[j] = ((c & 1) ? -dx[j] : dx[j]) - cd->residual[j];
       cd->ddual[j] = -fma(cd->dual[j], cd->dslack[j], cd->duality[j]) / cd->slack[j];
@@ -1439,7 +1446,7 @@ void oracle_unocp_set_stage_threads(oracle_unocp_t* o, int nthreads) { o->stage_
 /* UnOCPSolver::initConstraints (:59-70) */
 void oracle_unocp_init_constraints(oracle_unocp_t* o) {
   for (int i = 0; i < o->N; ++i) {
-    set_active(i, o->st[i].active);
+    set_active(&o->p, i, o->st[i].active);
     set_slack_and_dual(&o->p, &o->st[i], &o->s[i]);
   }
 }
@@ -1654,8 +1661,11 @@ int oracle_unocp_get_direction(const oracle_unocp_t* o, const char* name, double
 }
 
 int oracle_unocp_get_constraint_data(const oracle_unocp_t* o, const char* name, double* out) {
+  const int acc = !strncmp(name, "acc_", 4);
+  const int c0 = acc ? C_ACC_LO : 0, nc = acc ? 2 : ORACLE_NC;
+  if (acc) name += 4;
   for (int i = 0; i < o->N; ++i)
-    for (int c = 0; c < NC; ++c) {
+    for (int c = c0; c < c0 + nc; ++c) {
       const cdata_t* d = &o->st[i].c[c];
       const double* src;
       if (!strcmp(name, "slack")) src = d->slack;
@@ -1665,7 +1675,7 @@ int oracle_unocp_get_constraint_data(const oracle_unocp_t* o, const char* name, 
       else if (!strcmp(name, "dslack")) src = d->dslack;
       else if (!strcmp(name, "ddual")) src = d->ddual;
       else return -1;
-      double* dst = out + (i * NC + c) * NV;
+      double* dst = out + (i * nc + c - c0) * NV;
       if (o->st[i].active[c]) memcpy(dst, src, sizeof(double) * NV);
       else memset(dst, 0, sizeof(double) * NV);
     }
@@ -1794,7 +1804,7 @@ void oracle_unparnmpc_destroy(oracle_unparnmpc_t* o) {
 /* UnParNMPCSolver::initConstraints (:54-66): stage index i uses time step i+1 */
 void oracle_unparnmpc_init_constraints(oracle_unparnmpc_t* o) {
   for (int i = 0; i < o->N; ++i) {
-    set_active(i + 1, o->st[i].active);
+    set_active(&o->p, i + 1, o->st[i].active);
     set_slack_and_dual(&o->p, &o->st[i], &o->s[i]);
   }
 }

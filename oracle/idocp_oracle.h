@@ -45,6 +45,10 @@ typedef struct {
                                                   set_qf_6d_weight (time_varying_task_space_6d_cost.cpp:43-58) */
   double task_center[3], task_radius, task_t0, task_tf; /* unused by the engine: the reference is a host-sampled table */
   double task_rot_ref[9];
+  /* JointAccelerationLowerLimit / JointAccelerationUpperLimit (src/constraints/joint_acceleration_*_limit.cpp) with their
+   * constructor arguments amin / amax; [0] lower, [1] upper */
+  int enable_acc[2];
+  double a_min[ORACLE_NV], a_max[ORACLE_NV];
 } oracle_problem_t;
 
 void oracle_problem_default(oracle_problem_t* p);
@@ -70,7 +74,8 @@ int  oracle_unocp_is_feasible(oracle_unocp_t* o);
 int  oracle_unocp_get_solution(const oracle_unocp_t* o, const char* name, double* out);
 /* field in {"dlmd","dgmm","dq","dv","da","du","dbeta"} */
 int  oracle_unocp_get_direction(const oracle_unocp_t* o, const char* name, double* out);
-/* field in {"slack","dual","residual","duality","dslack","ddual"}: out[N*NC*NV], inactive rows = 0 */
+/* field in {"slack","dual","residual","duality","dslack","ddual"}: out[N*NC*NV], inactive rows = 0;
+ * "acc_" + field: the two acceleration-limit components, out[N*2*NV] */
 int  oracle_unocp_get_constraint_data(const oracle_unocp_t* o, const char* name, double* out);
 /* last step sizes: out[0]=primal (after line search), out[1]=dual, out[2]=max primal (before) */
 void oracle_unocp_get_step_sizes(const oracle_unocp_t* o, double* out);

@@ -29,6 +29,7 @@ class Problem(C.Structure):
         ("task_center", C.c_double * 3), ("task_radius", C.c_double),
         ("task_t0", C.c_double), ("task_tf", C.c_double),
         ("task_rot_ref", C.c_double * 9),
+        ("enable_acc", C.c_int * 2), ("a_min", C.c_double * NV), ("a_max", C.c_double * NV),
     ]
 
 
@@ -240,7 +241,7 @@ class UnOCPSolver(_SolverBase):
         self.L.oracle_unocp_set_stage_threads(self.h, int(n))
 
     def get_constraint_data(self, name):
-        out = np.zeros((self.N, NC, NV))
+        out = np.zeros((self.N, 2 if name.startswith("acc_") else NC, NV))
         if self.L.oracle_unocp_get_constraint_data(self.h, name.encode(), _p(out)) < 0:
             raise ValueError(name)
         return out

@@ -26,6 +26,13 @@ def copy_problem(src, dst):
         a, b = getattr(src, name), getattr(dst, name)
         for i in range(7):
             b[i] = a[i]
+    # JointAcceleration{Lower,Upper}Limit: enable flags and bounds (the two structures name the flags differently)
+    for k in range(2):
+        dst.enable_acc[k] = src.enable_acceleration_limit[k]
+    for name in ("a_min", "a_max"):
+        a, b = getattr(src, name), getattr(dst, name)
+        for i in range(7):
+            b[i] = a[i]
     return dst
 
 

@@ -87,6 +87,44 @@ def test_task_space_6d_cost_example_equals_the_oracle():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["unocp", "unparnmpc"])
+def test_acceleration_limit_example_equals_the_oracle(kind):
+    """JointAccelerationLowerLimit / JointAccelerationUpperLimit (src/constraints/joint_acceleration_*_limit.cpp) pushed onto the
+    factory's constraints through the C++ host classes (examples/iiwa14_batch.cpp, IDOCP_B200_ACC_LIMIT): the KKT history equals,
+    digit for digit, the oracle's solver with the two components enabled."""
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as O
+    O.build()
+    _build()
+    iters, limit = 12, 25.0
+    env = dict(os.environ, IDOCP_B200_ACC_LIMIT=str(limit))
+    out = subprocess.run([EXE, "benchmark", kind, "3", str(iters), "0"], capture_output=True, text=True, check=True, env=env).stdout
+    kkt = [float(x) for x in re.findall(r"KKT error(?: after iteration \d+)? = (\S+)", out)]
+    p = O.benchmark_problem()
+    p.enable_acc[0] = p.enable_acc[1] = 1
+    for j in range(7):
+        p.a_min[j], p.a_max[j] = -limit, limit
+    q0, v0 = np.full(7, 2.0), np.zeros(7)              # unocp_benchmark.cpp:44-45
+    s = (O.UnOCPSolver if kind == "unocp" else O.UnParNMPCSolver)(p)
+    s.set_solution("q", q0)
+    s.set_solution("v", v0)
+    if kind != "unocp":
+        s.init_backward_correction(0.0)
+    s.compute_kkt_residual(0.0, q0, v0)
+    ref = [s.kkt_error()]
+    for _ in range(iters):
+        s.update_solution(0.0, q0, v0, False)
+        s.compute_kkt_residual(0.0, q0, v0)
+        ref.append(s.kkt_error())
+    assert len(kkt) == iters + 1
+    assert kkt == ref
+    plain = subprocess.run([EXE, "benchmark", kind, "3", str(iters), "0"], capture_output=True, text=True, check=True).stdout
+    assert [float(x) for x in re.findall(r"KKT error(?: after iteration \d+)? = (\S+)", plain)] != kkt     # the limits are live
+
+
+@pytest.mark.gpu
 def test_save_and_print_solution_formats(tmp_path):
     """UnOCPSolver::saveSolution / printSolution (unocp_solver.cpp:264-352): N + 1 lines of q and v, N lines of a and u,
     7 space-separated coefficients with the stream's default precision; the saved trajectory is the golden final iterate."""

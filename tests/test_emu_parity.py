@@ -154,6 +154,67 @@ def test_unparnmpc_filter_line_search_matches_oracle(emu_lib, oracle, task):
     check_iteration(solver, oracles, q0, v0, line_search=True)
 
 
+def with_acceleration_limits(prob, a_limit):
+    """JointAccelerationLowerLimit(robot, -a_limit) + JointAccelerationUpperLimit(robot, +a_limit)."""
+    prob.enable_acceleration_limit[0] = prob.enable_acceleration_limit[1] = 1
+    for j in range(7):
+        prob.a_min[j], prob.a_max[j] = -a_limit, a_limit
+    return prob
+
+
+def acceleration_limit_scenario(lib, oracle, kind, task, line_search, batch=3, iters=4):
+    """The two acceleration-limit components through the ACC kernel instantiations vs the oracle: directions, step sizes,
+    KKT errors, iterates and the slack / dual rows of all eight components, bit for bit."""
+    rng = np.random.default_rng(21)
+    if task:
+        prob = with_acceleration_limits(I.task_space_problem(lib, N=4, T=0.2), 8.0)
+        q0 = np.array([0, np.pi / 2, 0, np.pi / 2, 0, np.pi / 2, 0]) + rng.uniform(-0.3, 0.3, (batch, 7))
+        v0 = rng.uniform(-0.2, 0.2, (batch, 7))
+        solver, oracles = make_pair(I, oracle, lib, prob, q0, v0, kind=kind, task_ref=I.task_space_circle_ref)
+    else:
+        prob = with_acceleration_limits(I.benchmark_problem(lib, N=6, T=0.3), 25.0)
+        q0, v0 = make_states(batch, 77)
+        solver, oracles = make_pair(I, oracle, lib, prob, q0, v0, kind=kind)
+
+    def rows():
+        if kind != "unocp":    # the oracle's UnParNMPCSolver has no constraint-data getter; its rows drive every compared quantity
+            return
+        for name in ("slack", "dual", "acc_slack", "acc_dual"):
+            x = solver.getConstraintData(name)
+            ref = np.array([o.get_constraint_data(name) for o in oracles])
+            assert np.array_equal(x, ref), name
+    rows()
+    assert np.all(solver.getConstraintData("acc_slack") > 0)
+    for it in range(iters):
+        check_iteration(solver, oracles, q0, v0, line_search=line_search)
+        rows()
+    check_solution(solver, oracles)
+    if kind == "unocp":
+        assert np.array_equal(solver.isCurrentSolutionFeasible(), [o.is_feasible() for o in oracles])
+    return solver, oracles
+
+
+@pytest.mark.parametrize("kind,task,line_search", [("unocp", False, False), ("unocp", False, True), ("unparnmpc", False, False),
+                                                   ("unocp", True, False), ("unparnmpc", True, True)])
+def test_acceleration_limits_match_oracle(emu_lib, oracle, kind, task, line_search):
+    acceleration_limit_scenario(emu_lib, oracle, kind, task, line_search)
+
+
+def test_acceleration_limits_force_the_literal_sequence(emu_lib):
+    prob = with_acceleration_limits(I.benchmark_problem(emu_lib, N=3, T=0.15), 25.0)
+    s = I.UnOCPSolver(prob, 2, lib=emu_lib)
+    s.setPipelining(True)            # ignored: the fused update + linearisation carries the six joint-limit components only
+    q0, v0 = make_states(2, 5)
+    s.setSolution("q", q0)
+    s.setSolution("v", v0)
+    s.updateSolution(0.0, q0, v0)
+    prof = s.launchCount()
+    assert prof > 0
+    plain = I.UnOCPSolver(I.benchmark_problem(emu_lib, N=3, T=0.15), 2, lib=emu_lib)
+    with pytest.raises(I.Idocp_b200Error, match="not enabled"):
+        plain.getConstraintData("acc_slack")
+
+
 def test_error_paths(emu_lib):
     prob = I.benchmark_problem(emu_lib)
     bad = I.benchmark_problem(emu_lib)

@@ -237,3 +237,37 @@ def test_stage_threads_do_not_change_results(oracle):
             s.update_solution(0.0, q0, v0)
     assert np.array_equal(a.get_solution("q"), b.get_solution("q"))
     assert np.array_equal(a.get_solution("u"), b.get_solution("u"))
+
+
+def test_acceleration_limits_bind_and_converge(oracle):
+    """JointAccelerationLowerLimit / UpperLimit (src/constraints/joint_acceleration_*_limit.cpp) on the unocp_benchmark problem:
+    the iteration converges, the bound is active somewhere and respected everywhere, complementarity holds."""
+    O = oracle
+    free = O.UnOCPSolver(O.benchmark_problem())
+    q0, v0 = np.full(7, 2.0), np.zeros(7)
+    for s in (free,):
+        s.set_solution("q", q0)
+        s.set_solution("v", v0)
+    for _ in range(60):
+        free.update_solution(0.0, q0, v0)
+    amax_free = np.abs(free.get_solution("a")).max()
+    limit = 0.5 * amax_free
+    p = O.benchmark_problem()
+    p.enable_acc[0] = p.enable_acc[1] = 1
+    for j in range(7):
+        p.a_min[j], p.a_max[j] = -limit, limit
+    s = O.UnOCPSolver(p)
+    s.set_solution("q", q0)
+    s.set_solution("v", v0)
+    assert np.all(s.get_constraint_data("acc_slack") > 0)
+    for _ in range(80):
+        s.update_solution(0.0, q0, v0)
+    s.compute_kkt_residual(0.0, q0, v0)
+    assert s.kkt_error() < 1e-8
+    a = s.get_solution("a")
+    assert np.abs(a).max() < limit and np.abs(a).max() > 0.98 * limit
+    sl, du = s.get_constraint_data("acc_slack"), s.get_constraint_data("acc_dual")
+    assert np.all(sl > 0) and np.all(du > 0)
+    assert np.allclose(sl * du, p.barrier, rtol=1e-6)
+    # slack = margin at the solution: a - amin, amax - a
+    assert np.allclose(sl[:, 0], a + limit, atol=1e-9) and np.allclose(sl[:, 1], limit - a, atol=1e-9)
