@@ -151,6 +151,10 @@ struct idocp_b200_solver : LaunchProfiler {
   // which the next updateSolution re-uses as long as nothing changed the iterate or the cost reference in between
   bool pipelined = true;
   bool lin_valid = false;
+  // KKT by-product of the fused update + linearisation (k_update_linearize<.., KKT>): switched on by the first computeKKTResidual
+  // of a pipelined solver; kkt_valid = L.kkt_stage holds the stage sums of the current iterate
+  bool kkt_tracking = false;
+  bool kkt_valid = false;
   int sm_count = 1;            // persistent kernels launch one CTA pair per SM
 
   int stage_offset() const { return kind == IDOCP_B200_SOLVER_UNPARNMPC ? 1 : 0; }
@@ -241,7 +245,7 @@ static const int kRicSmem = RIC_SMEM_DOUBLES * static_cast<int>(sizeof(double));
 static const int kUlSmem = UL_SMEM_DOUBLES * static_cast<int>(sizeof(double));
 
 static int do_init_constraints(idocp_b200_solver* h) {
-  h->lin_valid = false;   // slack / dual change: the kept linearisation is stale
+  h->lin_valid = false; h->kkt_valid = false;   // slack / dual change: the kept linearisation is stale
   IDOCP_LAUNCH(h, KC_MISC, k_init_constraints, stage_grid(h, h->N), CTA_THREADS, 0, h->d_prob, h->L,
                h->stage_offset());
   CUDA_OK(cudaGetLastError());
@@ -313,8 +317,10 @@ extern "C" int idocp_b200_create(const idocp_b200_problem* p, int solver_kind, i
   rc |= h->alloc(&h->d_stage, h->stage_doubles);
   if (cudaFuncSetAttribute(k_riccati<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRicSmem) != cudaSuccess) rc |= -1;
   if (cudaFuncSetAttribute(k_riccati<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRicSmem) != cudaSuccess) rc |= -1;
-  if (cudaFuncSetAttribute(k_update_linearize<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUlSmem) != cudaSuccess) rc |= -1;
-  if (cudaFuncSetAttribute(k_update_linearize<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUlSmem) != cudaSuccess) rc |= -1;
+  if (cudaFuncSetAttribute(k_update_linearize<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUlSmem) != cudaSuccess) rc |= -1;
+  if (cudaFuncSetAttribute(k_update_linearize<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUlSmem) != cudaSuccess) rc |= -1;
+  if (cudaFuncSetAttribute(k_update_linearize<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUlSmem) != cudaSuccess) rc |= -1;
+  if (cudaFuncSetAttribute(k_update_linearize<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUlSmem) != cudaSuccess) rc |= -1;
   {
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
@@ -518,12 +524,17 @@ static int unocp_update(idocp_b200_solver* h, const double* d_q, const double* d
     // two swap roles
     IDOCP_LAUNCH(h, KC_STEP_MIN, k_step_min, (h->Bp + 127) / 128, 128, 0, h->L, override_alpha);
     const int ul_grid = std::min(stage_grid(h, h->N + 1), IDOCP_UL_CTAS_PER_SM * h->sm_count);
-    if (task)
-      IDOCP_LAUNCH(h, KC_UPDATE_LINEARIZE, k_update_linearize<true>, ul_grid, CTA_THREADS, kUlSmem, h->d_prob, h->L);
+    if (task && h->kkt_tracking)
+      IDOCP_LAUNCH(h, KC_UPDATE_LINEARIZE, (k_update_linearize<true, true>), ul_grid, CTA_THREADS, kUlSmem, h->d_prob, h->L);
+    else if (task)
+      IDOCP_LAUNCH(h, KC_UPDATE_LINEARIZE, (k_update_linearize<true, false>), ul_grid, CTA_THREADS, kUlSmem, h->d_prob, h->L);
+    else if (h->kkt_tracking)
+      IDOCP_LAUNCH(h, KC_UPDATE_LINEARIZE, (k_update_linearize<false, true>), ul_grid, CTA_THREADS, kUlSmem, h->d_prob, h->L);
     else
-      IDOCP_LAUNCH(h, KC_UPDATE_LINEARIZE, k_update_linearize<false>, ul_grid, CTA_THREADS, kUlSmem, h->d_prob, h->L);
+      IDOCP_LAUNCH(h, KC_UPDATE_LINEARIZE, (k_update_linearize<false, false>), ul_grid, CTA_THREADS, kUlSmem, h->d_prob, h->L);
     std::swap(h->L.X, h->L.X2);
     h->lin_valid = true;
+    h->kkt_valid = h->kkt_tracking;
   } else {
     IDOCP_LAUNCH(h, KC_UPDATE, k_update, stage_grid(h, h->N + 1), CTA_THREADS, 0, h->d_prob, h->L, 0, override_alpha,
                  h->N + 1);
@@ -602,6 +613,13 @@ extern "C" int idocp_b200_compute_kkt_residual_device(idocp_b200_solver* h, doub
   (void)t;
   CUDA_OK(cudaSetDevice(h->device));
   if (h->kind == IDOCP_B200_SOLVER_UNPARNMPC) return parnmpc_kkt_residual(h, t, d_q, d_v);
+  if (h->pipelined && h->lin_valid && h->kkt_valid) {
+    // the fused update + linearisation of the last updateSolution left the stage sums of this very iterate behind
+    IDOCP_LAUNCH(h, KC_KKT, k_kkt_sum, (h->Bp + 127) / 128, 128, 0, h->L, h->N + 1);
+    CUDA_OK(cudaGetLastError());
+    return IDOCP_B200_OK;
+  }
+  if (h->pipelined) h->kkt_tracking = true;   // the caller watches the KKT error: from the next updateSolution on it comes for free
   launch_linearize<true, false>(h, KC_KKT, h->N + 1, d_q, d_v);
   IDOCP_LAUNCH(h, KC_KKT, k_kkt_sum, (h->Bp + 127) / 128, 128, 0, h->L, h->N + 1);
   CUDA_OK(cudaGetLastError());
@@ -865,7 +883,7 @@ extern "C" int idocp_b200_set_task_reference(idocp_b200_solver* h, const double*
   CUDA_OK(cudaMemcpyAsync(h->L.task_ref, table, static_cast<size_t>(h->N + 1) * 12 * sizeof(double),
                           cudaMemcpyHostToDevice, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));  // `table` may be pageable host memory reused by the caller
-  h->lin_valid = false;                       // the kept linearisation used the old reference
+  h->lin_valid = false; h->kkt_valid = false;                       // the kept linearisation used the old reference
   return IDOCP_B200_OK;
 }
 
@@ -874,7 +892,7 @@ extern "C" int idocp_b200_set_task_reference(idocp_b200_solver* h, const double*
 extern "C" int idocp_b200_set_pipelining(idocp_b200_solver* h, int enabled) {
   if (!h) return fail(IDOCP_B200_INVALID_ARGUMENT, "null handle");
   h->pipelined = enabled != 0 && h->L.XA == nullptr;   // the acceleration limits run through the literal sequence only
-  h->lin_valid = false;
+  h->lin_valid = false; h->kkt_valid = false;
   return IDOCP_B200_OK;
 }
 

@@ -202,13 +202,17 @@ __global__ void k_set_solution(Layout L, int field, const double* __restrict__ v
 //   (q0, v0 only enter the forward Riccati recursion), so the host keeps it until the iterate or the cost reference changes
 //   (capi.cu: lin_valid).  The update's HBM stream hides under the FP64 work of the linearisation.
 // X: this thread's pointer into the record of (stage i, group g) -- global memory, or the staged copy when FUSED.
-template <bool RESIDUAL_ONLY, bool BACKWARD_EULER, bool TASK, bool FUSED, bool ACC = false>
+// KKT (with FUSED): also leave the squared KKT norm of the NEW iterate's stage in L.kkt_stage -- the very numbers
+// k_linearize<RESIDUAL_ONLY> would compute from it (same operations on the same values), so that a computeKKTResidual that
+// follows the pipelined updateSolution (ocpbenchmarker::Convergence, an MPC loop that watches the KKT error) only has to sum them
+template <bool RESIDUAL_ONLY, bool BACKWARD_EULER, bool TASK, bool FUSED, bool ACC = false, bool KKT = false>
 __device__ __forceinline__ void linearize_task(const DevProblem& P, const Layout& L, const double* __restrict__ q0,
                                                const double* __restrict__ v0, double* tile, const int i, const int g,
                                                const double* X, const double* D, const double* Xnf, const double* Dn,
                                                const double ap, const double ad) {
   static_assert(!FUSED || (!RESIDUAL_ONLY && !BACKWARD_EULER), "the fused update exists for UnOCPSolver::updateSolution only");
   static_assert(!FUSED || !ACC, "the acceleration limits run through the literal kernel sequence");
+  static_assert(!KKT || FUSED, "the KKT by-product exists for the fused update + linearisation only");
   const int lane = lane_in_octet();
   const int ts = BACKWARD_EULER ? i + 1 : i;   // time stage of the constraint masks
   const int b = g * 4 + ((threadIdx.x >> 3) & 3);
@@ -264,12 +268,12 @@ __device__ __forceinline__ void linearize_task(const DevProblem& P, const Layout
         Xw[(X_SLACK + c) * SLOT] = fslack[c];
         Xw[(X_DUAL + c) * SLOT] = fdual[c];
       }
-    } else if (!TASK) {
+    } else if (!TASK && !KKT) {
       return;   // terminal stage: the update is all there is to do
     }
   }
 
-  if ((RESIDUAL_ONLY || TASK) && !BACKWARD_EULER && i == L.N) {
+  if ((RESIDUAL_ONLY || TASK || KKT) && !BACKWARD_EULER && i == L.N) {
     // TerminalOCP::linearizeOCP / computeKKTResidual + squaredNormKKTResidual (ocp/terminal_ocp.hxx:50-66,120-144)
     double lq = 0.0, lv = 0.0;
     lq += P.qf_weight[lane] * (q - P.q_ref[lane]);
@@ -289,9 +293,12 @@ __device__ __forceinline__ void linearize_task(const DevProblem& P, const Layout
     lq -= lmd;
     lv -= gmm;
     if (!act) { lq = 0.0; lv = 0.0; }
-    if (RESIDUAL_ONLY) {
+    if (RESIDUAL_ONLY || KKT) {
       const double e = oct_sum_ordered(lq * lq) + oct_sum_ordered(lv * lv);
       if (lane == 0) L.kkt_stage[static_cast<size_t>(i) * L.Bp + b] = e;
+    }
+    if (RESIDUAL_ONLY || !TASK) {
+      // (nothing else to do: residual only, or the fused update of a problem without a task-space cost)
     } else {
       // terminal record: rows of Qqq_N (slot = row, lane = column), lq_N, lv_N
       double* KQ = rec_ptr(L.KQ, KQ_NUM, L.G, i, g);
@@ -419,7 +426,7 @@ __device__ __forceinline__ void linearize_task(const DevProblem& P, const Layout
     lu = fma(-dt, beta, lu);
   }
 
-  if (RESIDUAL_ONLY) {
+  if (RESIDUAL_ONLY || KKT) {
     // SplitUnOCP::squaredNormKKTResidual (split_unocp.hxx:164-174), canonical order
     double e = 0.0;
     const double z = act ? 1.0 : 0.0;
@@ -447,7 +454,7 @@ __device__ __forceinline__ void linearize_task(const DevProblem& P, const Layout
     }
     e += dt * dt * c2;
     if (lane == 0) L.kkt_stage[static_cast<size_t>(i) * L.Bp + b] = e;
-    return;
+    if (RESIDUAL_ONLY) return;
   }
 
   // ---- Hessian diagonals + constraint condensing (steps 5-6) ----
@@ -633,7 +640,7 @@ static_assert(X_LMD == 0 && X_GMM == 1 && X_Q == 2 && X_V == 3 && D_LMD == 0 && 
               "the next stage's (lmd, gmm, q, v) and their directions are the first four slots of a record");
 static_assert((UL_OFF_BUF * 8) % 16 == 0, "TMA destinations are 16-byte aligned");
 
-template <bool TASK>
+template <bool TASK, bool KKT = false>
 __global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_update_linearize(const DevProblem* __restrict__ Pp, Layout L) {
   IDOCP_DYN_SMEM(double, smem);
   const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
@@ -673,7 +680,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_update_lineariz
     tma_bar_wait(&bars[buf], (k >> 1) & 1);
     const double* rec = bufs + buf * (UL_SLOTS * SLOT);
     const int o4 = (threadIdx.x >> 3) & 3;
-    linearize_task<false, false, TASK, true>(*Pp, L, nullptr, nullptr, tile, static_cast<int>(wt / L.G), static_cast<int>(wt % L.G),
+    linearize_task<false, false, TASK, true, false, KKT>(*Pp, L, nullptr, nullptr, tile, static_cast<int>(wt / L.G), static_cast<int>(wt % L.G),
                                              rec + wl, rec + UL_D * SLOT + wl, rec + UL_XN * SLOT + wl, rec + UL_DN * SLOT + wl,
                                              rec[UL_ST * SLOT + o4], rec[UL_ST * SLOT + 4 + o4]);
   }

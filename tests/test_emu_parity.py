@@ -275,3 +275,50 @@ def test_pipelined_update_equals_literal_sequence(emu_lib, oracle):
             s.updateSolution(0.0, q1, v1, True)
         same()
     assert a.launchCount() > 0 and b.launchCount() > 0
+
+
+def kkt_by_product_scenario(lib, task):
+    """computeKKTResidual after a pipelined updateSolution: from the second call on the fused update + linearisation leaves the
+    squared stage norms of the new iterate behind (k_update_linearize<.., KKT>) and computeKKTResidual only sums them; the
+    errors equal the literal sequence's bit for bit -- across setSolution, a moved x0 and the line search."""
+    if task:
+        prob = I.task_space_problem(lib, N=4, T=0.2)
+        rng = np.random.default_rng(5)
+        q0 = np.array([0, np.pi / 2, 0, np.pi / 2, 0, np.pi / 2, 0]) + rng.uniform(-0.3, 0.3, (5, 7))
+        v0 = rng.uniform(-0.2, 0.2, (5, 7))
+    else:
+        prob = I.benchmark_problem(lib)
+        q0, v0 = make_states(5, 19)
+    a = I.UnOCPSolver(prob, 5, lib=lib)
+    b = I.UnOCPSolver(prob, 5, lib=lib)
+    b.setPipelining(False)
+    for s in (a, b):
+        s.setSolution("q", q0)
+        s.setSolution("v", v0)
+        if task:
+            s.setTaskReference(I.task_space_circle_ref, 0.0)
+    launches = []
+    for it in range(5):
+        for s in (a, b):
+            s.updateSolution(0.0, q0, v0, it == 3)
+        n0 = a.launchCount()
+        for s in (a, b):
+            s.computeKKTResidual(0.0, q0, v0)
+        launches.append(a.launchCount() - n0)
+        assert np.array_equal(a.KKTError(), b.KKTError(), equal_nan=True), it
+        for name in SOL_FIELDS:
+            assert np.array_equal(a.getSolution(name), b.getSolution(name), equal_nan=True), (it, name)
+    assert launches[0] == 2 and launches[1:] == [1, 1, 1, 1], launches      # k_linearize<residual> + k_kkt_sum, then k_kkt_sum alone
+    for s in (a, b):                       # setSolution invalidates the kept linearisation and its by-product
+        s.setSolution("q", q0 + 0.01)
+        s.computeKKTResidual(0.0, q0, v0)
+    assert np.array_equal(a.KKTError(), b.KKTError(), equal_nan=True)
+    for s in (a, b):
+        s.updateSolution(0.0, q0 + 0.02, v0)
+        s.computeKKTResidual(0.0, q0 + 0.02, v0)
+    assert np.array_equal(a.KKTError(), b.KKTError(), equal_nan=True)
+
+
+@pytest.mark.parametrize("task", [False, True])
+def test_kkt_error_as_by_product_of_the_pipelined_update(emu_lib, task):
+    kkt_by_product_scenario(emu_lib, task)

@@ -78,6 +78,16 @@ if has scale; then   # multi-GPU call (gpurun --gpus 8): strong scaling of confi
   tr $n --workload anymal_running --steps 10 --warmup 3 > gpurun_out/${L}_scale_anymal_running_n$n.json 2> gpurun_out/${L}_scale_anymal_running_n$n.err
   cut -c 1-330 gpurun_out/${L}_scale_anymal_running_n$n.json
 fi
+if has sanitize; then   # compute-sanitizer over small runs of every solver path (tools/sanitize_run.py), all four tools
+  out=gpurun_out/${L}_compute_sanitizer.txt
+  echo "# compute-sanitizer over tools/sanitize_run.py all (label $L)" > $out
+  for tool in memcheck racecheck synccheck initcheck; do
+    echo "== $tool" >> $out
+    timeout 1500 compute-sanitizer --tool $tool python tools/sanitize_run.py all > gpurun_out/${L}_sanitize_$tool.log 2>&1
+    grep -E "ERROR SUMMARY|RACECHECK SUMMARY" gpurun_out/${L}_sanitize_$tool.log >> $out || echo "(no summary line: see ${L}_sanitize_$tool.log)" >> $out
+  done
+  cat $out
+fi
 if has launches; then
   ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 200 --csv --log-file gpurun_out/${L}_launches.csv \
       python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/${L}_launches_run.log 2>&1; echo "launches rc=$?"

@@ -14,8 +14,13 @@ from idocp_b200 import solvers as S  # noqa: E402
 
 
 def anymal(lib):
-    for name, cls, ls in (("trotting", P.AnymalTrotting, False), ("running", P.AnymalRunning, True)):
+    for name, cls, ls in (("trotting", P.AnymalTrotting, False), ("running", P.AnymalRunning, True), ("trotting-f3", P.AnymalTrotting, True)):
         pr = cls(lib=lib)
+        if name.endswith("f3"):   # FrictionCone / ImpulseFrictionCone + JointAcceleration{Lower,Upper}Limit
+            pr.problem.cone_nonlinear[0] = pr.problem.cone_nonlinear[1] = 1
+            pr.problem.enable_acceleration_limit[0] = pr.problem.enable_acceleration_limit[1] = 1
+            for j in range(12):
+                pr.problem.a_min[j], pr.problem.a_max[j] = -9.0, 9.0
         B = 3
         q0, v0 = P.anymal_initial_states(0, B, q_nominal=pr.q_nominal)
         solver = P.make_solver(pr, B, q0, v0, lib=lib)
@@ -28,8 +33,12 @@ def anymal(lib):
 def iiwa(lib):
     rng = np.random.default_rng(1)
     for kind in ("unocp", "unparnmpc"):
-        for task in (False, True):
+        for task, acc in ((False, False), (True, False), (False, True), (True, True)):
             p = S.task_space_problem(lib, N=20, T=1.0) if task else S.benchmark_problem(lib)
+            if acc:   # JointAcceleration{Lower,Upper}Limit: the ACC kernel instantiations and the XA array
+                p.enable_acceleration_limit[0] = p.enable_acceleration_limit[1] = 1
+                for j in range(7):
+                    p.a_min[j], p.a_max[j] = -25.0, 25.0
             B = 5
             solver = (I.UnOCPSolver if kind == "unocp" else I.UnParNMPCSolver)(p, B, lib=lib)
             q = np.tile(np.array([0, np.pi / 2, 0, np.pi / 2, 0, np.pi / 2, 0]), (B, 1)) + rng.uniform(-0.1, 0.1, (B, 7))
@@ -44,7 +53,7 @@ def iiwa(lib):
             for ls in (False, True):
                 solver.updateSolution(0.0, q, v, ls)
             solver.computeKKTResidual(0.0, q, v)
-            print("iiwa", kind, "task" if task else "config", solver.KKTError())
+            print("iiwa", kind, "task" if task else "config", "acc" if acc else "", solver.KKTError())
 
 
 if __name__ == "__main__":
