@@ -61,6 +61,9 @@ int main(int argc, char* argv[]) {
   constraints->push_back(std::make_shared<idocp::JointTorquesUpperLimit>(robot));
   constraints->push_back(std::make_shared<idocp::LinearizedFrictionCone>(robot, mu));
   constraints->push_back(std::make_shared<idocp::LinearizedImpulseFrictionCone>(robot, mu));
+  // optional (IDOCP_B200_CONTACT_DISTANCE=1 | 2): ContactDistance, literally as in the reference or with consistent derivatives
+  if (const char* cd = std::getenv("IDOCP_B200_CONTACT_DISTANCE"))
+    constraints->push_back(std::make_shared<idocp::ContactDistance>(robot, std::atoi(cd) == 2));
 
   // 2 steps
   const double T = 1.55;  // t_start + max_num_impulse_phase * t_period + 0.05

@@ -86,6 +86,7 @@ class FbProblem(C.Structure):
         ("enable", C.c_int * FB_NUM_CONSTRAINTS),
         ("cone_nonlinear", C.c_int * 2), ("enable_acceleration_limit", C.c_int * 2),
         ("a_min", C.c_double * 12), ("a_max", C.c_double * 12),
+        ("enable_contact_distance", C.c_int),
     ]
 
 

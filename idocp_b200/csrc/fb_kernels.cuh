@@ -23,18 +23,22 @@ namespace idocp_b200 {
 
 enum { FB_GRID = 0, FB_IMPULSE = 1, FB_AUX = 2, FB_LIFT = 3, FB_TERMINAL = 4 };
 enum { FBC_POS_LO = 0, FBC_POS_UP, FBC_VEL_LO, FBC_VEL_UP, FBC_TRQ_LO, FBC_TRQ_UP, FBC_FRICTION, FBC_IMPULSE_FRICTION, FBC_ACC_LO,
-       FBC_ACC_UP, FBC_NCOMP };
-#define FB_NCON 136   /* 6 x 12 joint limits, 20 friction-cone rows, 20 impulse friction-cone rows, 2 x 12 acceleration limits */
+       FBC_ACC_UP, FBC_DISTANCE, FBC_NCOMP };
+#define FB_NCON 140   /* 6 x 12 joint limits, 20 + 20 friction-cone rows (stage / impulse), 2 x 12 acceleration limits, 4 contact distances */
 __host__ __device__ inline int fbc_offset(int c) {
-  return c < FBC_FRICTION ? 12 * c : (c == FBC_FRICTION ? 72 : (c == FBC_IMPULSE_FRICTION ? 92 : 112 + 12 * (c - FBC_ACC_LO)));
+  return c < FBC_FRICTION ? 12 * c
+                          : (c == FBC_FRICTION ? 72 : (c == FBC_IMPULSE_FRICTION ? 92 : (c == FBC_DISTANCE ? 136 : 112 + 12 * (c - FBC_ACC_LO))));
 }
-__host__ __device__ inline int fbc_dim(int c) { return (c == FBC_FRICTION || c == FBC_IMPULSE_FRICTION) ? 20 : 12; }   // storage
+__host__ __device__ inline int fbc_dim(int c) {   // storage
+  return (c == FBC_FRICTION || c == FBC_IMPULSE_FRICTION) ? 20 : (c == FBC_DISTANCE ? 4 : 12);
+}
 __host__ __device__ inline int fbc_comp(int idx) {   // component of row idx
-  return idx < 72 ? idx / 12 : (idx < 92 ? FBC_FRICTION : (idx < 112 ? FBC_IMPULSE_FRICTION : (idx < 124 ? FBC_ACC_LO : FBC_ACC_UP)));
+  return idx < 72 ? idx / 12
+                  : (idx < 92 ? FBC_FRICTION : (idx < 112 ? FBC_IMPULSE_FRICTION : (idx < 124 ? FBC_ACC_LO : (idx < 136 ? FBC_ACC_UP : FBC_DISTANCE))));
 }
 __host__ __device__ inline bool fbc_is_cone(int c) { return c == FBC_FRICTION || c == FBC_IMPULSE_FRICTION; }
 // rows a stage has to walk over: the acceleration-limit rows sit at the end and are skipped while those components are off
-#define FBC_LIVE_ROWS(cactive) (((cactive)[FBC_ACC_LO] | (cactive)[FBC_ACC_UP]) ? FB_NCON : 112)
+#define FBC_LIVE_ROWS(cactive) ((cactive)[FBC_DISTANCE] ? FB_NCON : (((cactive)[FBC_ACC_LO] | (cactive)[FBC_ACC_UP]) ? 136 : 112))
 
 struct FbDevProblem {
   double T;
@@ -47,12 +51,13 @@ struct FbDevProblem {
   int enable[FBC_NCOMP];
   int cone_nonlinear[2];   // FrictionCone / ImpulseFrictionCone (2 rows per contact) instead of the linearised cones (5 rows)
   double a_min[FB_NU], a_max[FB_NU];   // JointAcceleration{Lower,Upper}Limit
+  int distance_mode;       // ContactDistance: 1 = row 2 of the LOCAL frame Jacobian (the reference, literally), 2 = d z / d q
 };
 // rows per contact of cone component c, live rows of a component (the rest of its storage stays zero)
 // (nl = fbc_cone_bits(pr), read ONCE per kernel: the problem record lives in global memory and these kernels are latency bound)
 __host__ __device__ inline int fbc_cone_bits(const FbDevProblem& pr) { return (pr.cone_nonlinear[0] ? 1 : 0) | (pr.cone_nonlinear[1] ? 2 : 0); }
 __host__ __device__ inline int fbc_cone_rows(int nl, int c) { return ((nl >> (c - FBC_FRICTION)) & 1) ? 2 : 5; }
-__host__ __device__ inline int fbc_rows(int nl, int c) { return fbc_is_cone(c) ? FB_NC * fbc_cone_rows(nl, c) : 12; }
+__host__ __device__ inline int fbc_rows(int nl, int c) { return fbc_is_cone(c) ? FB_NC * fbc_cone_rows(nl, c) : (c == FBC_DISTANCE ? FB_NC : 12); }
 
 // one element of the hybrid chain (shared by the whole batch)
 struct FbElem {
@@ -72,6 +77,7 @@ struct FbSol {   // SplitSolution / ImpulseSplitSolution (a = dv at an impulse) 
 struct FbDir {   // SplitDirection + the direction part of ConstraintsData
   double dlmd[FB_NV], dgmm[FB_NV], dq[FB_NV], dv[FB_NV], du[FB_NU], daf[FB_NVF], dbetamu[FB_NVF], dnu_passive[FB_NPASS], dxi[FB_MAXF];
   double residual[FB_NCON], duality[FB_NCON], dslack[FB_NCON], ddual[FB_NCON];
+  double cdJ[FB_NC * FB_NV];   // ContactDistance: data.J[i].row(2) of the contacts that are not active (k_fb_robot -> k_fb_expand)
   double max_primal, max_dual, kkt_sq, info;
   double ls_cost, ls_viol;   // LineSearch: stage cost / constraint violation of the trial point
 };
@@ -627,6 +633,7 @@ struct FbLin {
   double Qqq6[36], Qqq_d[FB_NV], Qvv_d[FB_NV], Quu_d[FB_NU], Qaa[FB_NV], Qff[FB_MAXF * FB_MAXF];
   double Fqq6[36], Fqv6[36], Fqq_prev_inv[36];
   double Phix[FB_MAXF * FB_NX], Phia[FB_MAXF * FB_NV];
+  double cdJ[FB_NC * FB_NV], cdw[FB_NC];   // ContactDistance: J2 rows and dt dual / slack (written and read only while it is active)
 };
 
 // Optional per-phase cycle counters of the three heavy kernels (tools/fb_phase_clocks.py builds a variant library with
@@ -1060,7 +1067,7 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
       const int c = fbc_comp(idx);
       const int j = idx - fbc_offset(c);
       double res = 0.0, dua = 0.0;
-      if (el.cactive[c] && j < fbc_rows(nl, c)) {
+      if (el.cactive[c] && j < fbc_rows(nl, c) && c != FBC_DISTANCE) {   // ContactDistance: after the kinematics, below
         const double sl = w.slack[idx];
         if (fbc_is_cone(c)) {
           const int rpc = fbc_cone_rows(nl, c);
@@ -1323,6 +1330,40 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
       if (lane < FB_NU) lu = fma(-dt, w.beta[6 + lane], lu);
     }
   }
+  // ---- ContactDistance (contact_distance.cpp:73-110,134-150) on the contacts that are NOT active: residual = -z + slack with z
+  // the height of the contact frame, lq -= dt dual J2, J2 = row 2 of the frame Jacobian (distance_mode 1: LOCAL frame, the
+  // reference literally; 2: world-aligned = d z / d q).  After the dynamics terms, like the oracle (it needs these kinematics).
+  // (nothing of this block stays in registers: the condensing below re-reads J2 and the residuals, so that the kernel keeps its
+  // register allocation while the component is off)
+  const bool cd_on = !impulse && el.cactive[FBC_DISTANCE];
+  if (cd_on) {
+    const int o = fbc_offset(FBC_DISTANCE);
+    for (int i = 0; i < FB_NC; ++i) {
+      double cdres = 0.0, cddua = 0.0;
+      if (!el.active[i]) {   // (uniform over the warp)
+        const int bi = 1 + ANYMAL_CONTACT_PARENT_JOINT[i];
+        const double* Rf = w.R[bi];
+        __syncwarp();
+        if (lane == 0) fbw_contact_point(w, i, w.frP);
+        __syncwarp();
+        if (lane < FB_NV) {
+          double J[6] = {0, 0, 0, 0, 0, 0};
+          if (fb_in_support(i, lane)) fb_pullback(Rf, w.frP, w.S[lane], J);
+          const double j2 = pr.distance_mode == 2 ? fma(Rf[8], J[2], fma(Rf[7], J[1], Rf[6] * J[0])) : J[2];
+          L.cdJ[i * FB_NV + lane] = j2;
+          Dr.cdJ[i * FB_NV + lane] = j2;
+          lq -= (dt * w.dual[o + i]) * j2;
+        }
+        cdres = -w.frP[2] + w.slack[o + i];
+        cddua = w.slack[o + i] * w.dual[o + i] - pr.barrier;
+      }
+      if (lane == 0) {
+        w.residual[o + i] = cdres; w.duality[o + i] = cddua;
+        Dr.residual[o + i] = cdres; Dr.duality[o + i] = cddua;
+      }
+    }
+    __syncwarp();
+  }
 
   FBW_PHASE(2, 8);
   if (!RESIDUAL_ONLY) {
@@ -1397,6 +1438,19 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
       }
     } else if (ci >= 0) {
       L.Qff[lane * FB_MAXF + lane] = qff_d;
+    }
+    if (cd_on) {   // ContactDistance::condenseSlackAndDual: lq -= g J2 here, Qqq += w J2^T J2 in k_fb_condense (dense 18 x 18)
+      const int o = fbc_offset(FBC_DISTANCE);
+      for (int i = 0; i < FB_NC; ++i) {
+        double wgt = 0.0;
+        if (!el.active[i]) {
+          const double rs = 1.0 / w.slack[o + i];
+          wgt = (dt * w.dual[o + i]) * rs;
+          const double g2 = (dt * fma(w.dual[o + i], w.residual[o + i], -w.duality[o + i])) * rs;
+          if (lane < FB_NV) lq -= g2 * L.cdJ[i * FB_NV + lane];   // written by this very lane above
+        }
+        if (lane == 0) L.cdw[i] = wgt;
+      }
     }
   }
 
@@ -1628,11 +1682,22 @@ __global__ void __launch_bounds__(128, 5) k_fb_condense(FbArrays A, const FbLin*
   {
     const double *Qqq6 = w.Qqq6, *Qqq_d = w.Qqq_d, *Qvv_d = w.Qvv_d;
     double* Qxx = Kt.Qxx;
+    // ContactDistance::condenseSlackAndDual (contact_distance.cpp:91-93): Qqq += (dt dual / slack) J2^T J2 per contact that is
+    // not active -- the one dense term of the stage Hessian; J2 and the weights come from k_fb_robot (FbLin::cdJ, cdw)
+    int cd_mask = 0;
+    if (!impulse && el.cactive[FBC_DISTANCE])
+      for (int i = 0; i < FB_NC; ++i) cd_mask |= el.active[i] ? 0 : (1 << i);
+    const double *cdJ = L.cdJ, *cdw = L.cdw;
     fb_mm_f<FBM_SUB>(NX, NX, nvf, w.MJ_dIDC, 1, NX, Qafqv, NX, 1,
                      [=](int r, int c) {
-                       if (r < 6 && c < 6) return Qqq6[6 * r + c];
-                       if (r == c) return r < NV ? Qqq_d[r] : Qvv_d[r - NV];
-                       return 0.0;
+                       double v = 0.0;
+                       if (r < 6 && c < 6) v = Qqq6[6 * r + c];
+                       else if (r == c) v = r < NV ? Qqq_d[r] : Qvv_d[r - NV];
+                       if (cd_mask && r < NV && c < NV) {
+                         for (int i = 0; i < FB_NC; ++i)
+                           if ((cd_mask >> i) & 1) v += (cdw[i] * cdJ[i * NV + r]) * cdJ[i * NV + c];
+                       }
+                       return v;
                      },
                      [=](int r, int c, double v) { if (!(r >= NV && c < NV)) Qxx[r * NX + c] = v; }, &rot);
   }
@@ -2155,7 +2220,16 @@ __global__ void __launch_bounds__(64) k_fb_expand(FbArrays A) {
     const int j = idx - fbc_offset(c);
     double ds = 0.0, dd = 0.0;
     if (el.cactive[c] && j < fbc_rows(nl, c)) {
-      if (fbc_is_cone(c)) {
+      if (c == FBC_DISTANCE) {   // contact_distance.cpp:112-131: J2 dq - residual for the contacts that are not active
+        ds = 1.0; dd = 1.0;
+        if (!el.active[j]) {
+          const double* J2 = Dr.cdJ + j * NV;
+          double acc = J2[0] * dx[0];
+          for (int l = 1; l < NV; ++l) acc = fma(J2[l], dx[l], acc);
+          ds = acc - Dr.residual[idx];
+          dd = -fma(S.dual[idx], ds, Dr.duality[idx]) / S.slack[idx];
+        }
+      } else if (fbc_is_cone(c)) {
         const int rpc = fbc_cone_rows(nl, c);
         const int i = rpc == 2 ? (j >> 1) : (j / 5);   // no division by a run-time value
         ds = 1.0; dd = 1.0;
@@ -2355,6 +2429,7 @@ __global__ void k_fb_init_constraints(FbArrays A, const FbInitRow* rows, int n_r
     const int o = fbc_offset(c);
     for (int j = 0; j < fbc_dim(c); ++j) {
       double sl = 0.0, du = 0.0;
+      if (c == FBC_DISTANCE && row.cactive[c]) continue;   // needs the forward kinematics: k_fb_init_distance
       if (row.cactive[c] && j < fbc_rows(nl, c)) {
         if (fbc_is_cone(c)) {
           const int rpc = fbc_cone_rows(nl, c);
@@ -2382,6 +2457,33 @@ __global__ void k_fb_init_constraints(FbArrays A, const FbInitRow* rows, int n_r
       S.slack[o + j] = sl;
       S.dual[o + j] = du;
     }
+  }
+}
+
+// ContactDistance::setSlackAndDual (contact_distance.cpp:62-70): slack = height of the contact frame of EVERY contact; needs the
+// forward kinematics, hence a warp per (instance, slot-table row) with the work area of k_fb_robot
+__global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_init_distance(FbArrays A, const FbInitRow* rows, int n_rows) {
+  IDOCP_DYN_SMEM(FbRobotWork, wbase);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x * FB_ROBOT_WARPS + warp;
+  if (g >= A.B * n_rows) return;
+  const int b = g / n_rows;
+  const FbInitRow& row = rows[g - b * n_rows];
+  if (!row.cactive[FBC_DISTANCE]) return;
+  const FbDevProblem& pr = *A.prob;
+  FbRobotWork& w = wbase[warp];
+  FbSol& S = A.sol[(size_t)row.slot * A.B + b];
+  if (lane < FB_NQ) w.q[lane] = S.q[lane];
+  __syncwarp();
+  fbw_forward_kinematics(w, lane, w.q, nullptr, nullptr);
+  if (lane < FB_NC) {
+    double P[3];
+    fbw_contact_point(w, lane, P);
+    double sl = P[2];
+    int guard = 0;
+    while (sl < pr.barrier && guard < (1 << 20)) { sl += pr.barrier; ++guard; }
+    S.slack[fbc_offset(FBC_DISTANCE) + lane] = sl;
+    S.dual[fbc_offset(FBC_DISTANCE) + lane] = pr.barrier / sl;
   }
 }
 
@@ -2464,7 +2566,9 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_ls_eval(FbArrays A, 
       double lg = 0.0, ar = 0.0;
       if (el.cactive[c] && j < fbc_rows(nl, c)) {
         lg = canon_log(INITIAL ? w.slack[idx] : fma(alpha, w.dual[idx], w.slack[idx]));
-        if (fbc_is_cone(c)) {
+        if (c == FBC_DISTANCE) {
+          // violation of the contact distances: after the kinematics of the trial point, below
+        } else if (fbc_is_cone(c)) {
           const int rpc = fbc_cone_rows(nl, c);
           const int i = rpc == 2 ? (j >> 1) : (j / 5);   // no division by a run-time value
           if (el.active[i]) {
@@ -2546,6 +2650,16 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_ls_eval(FbArrays A, 
   const double baumgarte = pr.T / pr.N;
   if (!impulse) {
     fbw_forward_kinematics(w, lane, w.q, w.v, w.a);
+    if (el.cactive[FBC_DISTANCE] && lane == 1) {   // ContactDistance at the trial configuration, un-stepped slack (the last component)
+      double s1 = 0.0;
+      for (int i = 0; i < FB_NC; ++i) {
+        if (el.active[i]) continue;
+        double P[3];
+        fbw_contact_point(w, i, P);
+        s1 += fabs(-P[2] + w.slack[fbc_offset(FBC_DISTANCE) + i]);
+      }
+      w.part[0] += s1;
+    }
     fbw_rnea_derivatives(w, lane, ANYMAL_GRAVITY, true, L, false);
     if (lane < FB_NU) L.IDC[6 + lane] -= w.u[lane];
   } else {

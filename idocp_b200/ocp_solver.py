@@ -17,7 +17,7 @@ _FIELD_DIMS = dict(ls_cost=1, ls_viol=1, q=19, f=12, mu=12, nu_passive=6, xi=12,
                    lu_passive=6, P=12, Qxx=36 * 36, Qxu=36 * 18, Quu=18 * 18, Fvq=324, Fvv=324, Fvu=216, Fqq6=36, Fqv6=36,
                    Fqq_prev_inv=36, MJtJinv=900, MJ_dIDC=30 * 36, MJ_IDC=30, Qafqv=30 * 36, Qafu=30 * 18, laf=30, K=12 * 36, k=12,
                    Pqq=324, Pqv=324, Pvv=324, Phix=12 * 36, Phiu=144, cM=12 * 36, cm=12, kkt=1, info=1, max_primal=1, max_dual=1,
-                   slack=136, dual=136, residual=136, duality=136, dslack=136, ddual=136)
+                   slack=140, dual=140, residual=140, duality=140, dslack=140, ddual=140)
 
 
 class OCPSolver:

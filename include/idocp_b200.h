@@ -285,7 +285,8 @@ int idocp_b200_discretize_ocp(const idocp_b200_contact_sequence* cs, double T, i
  * LinearizedImpulseFrictionCone (src/constraints/ *.cpp), enable[] in the order below; cone_nonlinear[0 / 1] selects
  * FrictionCone / ImpulseFrictionCone (friction_cone.cpp, impulse_friction_cone.cpp: two rows per contact, normal force and
  * fx^2 + fy^2 - mu^2 fz^2 <= 0) for the enabled cone; enable_acceleration_limit[0 / 1] adds JointAccelerationLowerLimit /
- * JointAccelerationUpperLimit (joint_acceleration_*_limit.cpp) with the bounds a_min / a_max on the 12 joint accelerations.
+ * JointAccelerationUpperLimit (joint_acceleration_*_limit.cpp) with the bounds a_min / a_max on the 12 joint accelerations;
+ * enable_contact_distance adds ContactDistance (contact_distance.cpp): the contact frames of the legs in the air stay above z = 0.
  * ------------------------------------------------------------------------------------------------------------ */
 #define IDOCP_B200_FB_NQ 19
 #define IDOCP_B200_FB_NV 18
@@ -307,6 +308,10 @@ typedef struct {
   int cone_nonlinear[2];                                       /* [0] FrictionCone, [1] ImpulseFrictionCone */
   int enable_acceleration_limit[2];                            /* [0] lower, [1] upper */
   double a_min[12], a_max[12];
+  int enable_contact_distance;                                 /* ContactDistance (contact_distance.cpp): 0 off; 1 the reference literally
+                                                                  (gradient rows = row 2 of the LOCAL frame Jacobian, robot.hxx:182-188: not
+                                                                  the derivative of the height, the iteration diverges on a trot); 2 the
+                                                                  consistent variant, rows = d z / d q */
 } idocp_b200_fb_problem;
 typedef struct idocp_b200_fb_solver idocp_b200_fb_solver; /* opaque */
 

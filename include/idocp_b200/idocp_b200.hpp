@@ -434,6 +434,7 @@ class Constraints {
   // the fixed-base solvers always use the six joint limits of JointConstraintsFactory
   template <typename Component>
   void push_back(const std::shared_ptr<Component>& c) {
+    if (c->id == IDOCP_B200_FB_NUM_CONSTRAINTS + 2) { contact_distance_ = c->nonlinear; return; }   // ContactDistance(robot[, consistent])
     if (c->id >= IDOCP_B200_FB_NUM_CONSTRAINTS) {   // JointAcceleration{Lower,Upper}Limit(robot, amin / amax)
       const int k = c->id - IDOCP_B200_FB_NUM_CONSTRAINTS;
       const int nb = static_cast<int>(c->bound.size());   // 7 (fixed-base iiwa14) or 12 (actuated joints of ANYmal)
@@ -450,6 +451,7 @@ class Constraints {
   const int* coneNonlinear() const { return cone_nonlinear_; }
   const int* enableAccelerationLimit() const { return enable_acc_; }
   int accelerationLimitDim() const { return acc_dim_; }
+  int contactDistance() const { return contact_distance_; }
   const double* aMin() const { return a_min_; }
   const double* aMax() const { return a_max_; }
   const int* enable() const { return enable_; }
@@ -464,7 +466,7 @@ class Constraints {
  private:
   double barrier_ = 1.0e-04, rate_ = 0.995;
   int enable_[IDOCP_B200_FB_NUM_CONSTRAINTS] = {0};
-  int cone_nonlinear_[2] = {0, 0}, enable_acc_[2] = {0, 0}, acc_dim_ = 0;
+  int cone_nonlinear_[2] = {0, 0}, enable_acc_[2] = {0, 0}, acc_dim_ = 0, contact_distance_ = 0;
   double a_min_[12] = {0}, a_max_[12] = {0};
   double mu_ = 0.7;
 };

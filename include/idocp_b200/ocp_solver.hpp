@@ -7,7 +7,7 @@
 //   idocp::TrottingConfigurationSpaceCost        include/idocp/cost/trotting_configuration_space_cost.hpp
 //   idocp::ContactForceCost                      include/idocp/cost/contact_force_cost.hpp
 //   idocp::Joint{Position,Velocity,Torques,Acceleration}{Lower,Upper}Limit, LinearizedFrictionCone, LinearizedImpulseFrictionCone,
-//   FrictionCone, ImpulseFrictionCone
+//   FrictionCone, ImpulseFrictionCone, ContactDistance
 //                                                include/idocp/constraints/ *.hpp
 //   idocp::OCPSolver                             include/idocp/ocp/ocp_solver.hpp:28-230
 // The reference's cost / constraint plug-ins are host virtuals; here they are a closed registry of POD-parameterised
@@ -263,6 +263,14 @@ struct JointAccelerationUpperLimit : HybridConstraintComponent {
     for (int j = 0; j < static_cast<int>(amax.size()); ++j) bound.push_back(amax[j]);
   }
 };
+// ContactDistance(robot) (src/constraints/contact_distance.cpp): the contact frames of the legs in the air stay above z = 0.
+// The reference builds the gradient / Hessian rows from row 2 of getFrameJacobian, which is the LOCAL-frame Jacobian
+// (robot.hxx:182-188) and not the derivative of the height unless the foot frame is level; `consistent = true` uses d z / d q
+// instead (the literal form does not converge on a trot, tests/test_oracle_fb_ocp.py).
+struct ContactDistance : HybridConstraintComponent {
+  explicit ContactDistance(const Robot&, const bool consistent = false)
+      : HybridConstraintComponent{IDOCP_B200_FB_NUM_CONSTRAINTS + 2, 0.0, consistent ? 2 : 1, {}} {}
+};
 // OCPSolver(robot, cost, constraints, T, N, max_num_impulse, nthreads) for `batch` instances
 class OCPSolver {
  public:
@@ -300,6 +308,7 @@ class OCPSolver {
       p.enable_acceleration_limit[k] = constraints->enableAccelerationLimit()[k];
     }
     for (int j = 0; j < 12; ++j) { p.a_min[j] = constraints->aMin()[j]; p.a_max[j] = constraints->aMax()[j]; }
+    p.enable_contact_distance = constraints->contactDistance();
     idocp_b200_contact_sequence* cs = nullptr;
     detail::check(idocp_b200_contact_sequence_create(4, 2 * max_num_impulse + 2, &cs));
     cs_.reset(cs, [](idocp_b200_contact_sequence* x) { idocp_b200_contact_sequence_destroy(x); });

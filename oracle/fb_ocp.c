@@ -37,7 +37,7 @@
 #define NPASS 6
 
 enum { K_GRID = 0, K_IMPULSE = 1, K_AUX = 2, K_LIFT = 3, K_TERMINAL = 4 };
-enum { C_POS_LO = 0, C_POS_UP, C_VEL_LO, C_VEL_UP, C_TRQ_LO, C_TRQ_UP, C_FRICTION, C_IMPULSE_FRICTION, C_ACC_LO, C_ACC_UP, NCOMP };
+enum { C_POS_LO = 0, C_POS_UP, C_VEL_LO, C_VEL_UP, C_TRQ_LO, C_TRQ_UP, C_FRICTION, C_IMPULSE_FRICTION, C_ACC_LO, C_ACC_UP, C_DISTANCE, NCOMP };
 
 typedef struct {
   double T;
@@ -53,15 +53,23 @@ typedef struct {
   int cone_nonlinear[2];
   int enable_acc[2];
   double a_min[NU], a_max[NU];
+  /* ContactDistance (src/constraints/contact_distance.cpp): the height of the contact frame of every contact that is NOT
+   * active stays positive; position level.  1 = the reference literally: the gradient / Hessian rows are row 2 of
+   * getFrameJacobian, which is the LOCAL-frame Jacobian (robot.hxx:182-188), i.e. NOT the derivative of the world height
+   * unless the foot frame is level -- the Newton iteration diverges on the trot (tests/test_oracle_fb_ocp.py);
+   * 2 = the consistent variant, row 2 of R_frame J_linear = d z / d q */
+  int enable_distance;
 } oracle_fb_problem_t;
-static inline int comp_enabled(const oracle_fb_problem_t* p, int c) { return c < C_ACC_LO ? p->enable[c] : p->enable_acc[c - C_ACC_LO]; }
+static inline int comp_enabled(const oracle_fb_problem_t* p, int c) {
+  return c < C_ACC_LO ? p->enable[c] : (c == C_DISTANCE ? p->enable_distance : p->enable_acc[c - C_ACC_LO]);
+}
 static inline int is_cone(int c) { return c == C_FRICTION || c == C_IMPULSE_FRICTION; }
 /* rows per contact: 5 (linearised) or 2 (normal force, cone) */
 static inline int cone_rows(const oracle_fb_problem_t* p, int c) { return p->cone_nonlinear[c - C_FRICTION] ? 2 : 5; }
 
 typedef struct { double slack[20], dual[20], residual[20], duality[20], dslack[20], ddual[20]; } cdata_t;
-static inline int comp_dim(int c) { return (c == C_FRICTION || c == C_IMPULSE_FRICTION) ? 20 : NU; }   /* storage */
-#define comp_rows(p, c) (is_cone(c) ? FB_NC * cone_rows(p, c) : NU)                                      /* live rows */
+static inline int comp_dim(int c) { return (c == C_FRICTION || c == C_IMPULSE_FRICTION) ? 20 : (c == C_DISTANCE ? FB_NC : NU); }   /* storage */
+#define comp_rows(p, c) (is_cone(c) ? FB_NC * cone_rows(p, c) : ((c) == C_DISTANCE ? FB_NC : NU))                                /* live rows */
 
 typedef struct {
   /* --- SplitSolution / ImpulseSplitSolution (a = dv at an impulse) --- */
@@ -74,6 +82,7 @@ typedef struct {
   /* --- ConstraintsData --- */
   int cstage, cactive[NCOMP];
   cdata_t c[NCOMP];
+  double cdJ[FB_NC][NV], cdz[FB_NC];   /* ContactDistance: data.J[i].row(2) (LOCAL frame Jacobian) and the frame height */
   /* --- SplitKKTResidual --- */
   double lq[NV], lv[NV], la[NV], lf[MAXF], lu_passive[NPASS], lu[NU], Fq[NV], Fv[NV], Fq_prev[6], P[MAXF];
   /* --- SplitKKTMatrix (only the blocks the path touches) --- */
@@ -165,6 +174,7 @@ static double l1norm_n(const double* x, int n) {
 static void set_constraint_stage(const oracle_fb_problem_t* p, stage_t* st, int time_stage) {
   st->cstage = time_stage;
   const int pos = time_stage >= 2, vel = time_stage >= 1, acc = time_stage >= 0, imp = time_stage <= -1;
+  st->cactive[C_DISTANCE] = pos && p->enable_distance;   /* KinematicsLevel::PositionLevel (contact_distance.cpp:31-33) */
   st->cactive[C_ACC_LO] = acc && p->enable_acc[0];
   st->cactive[C_ACC_UP] = acc && p->enable_acc[1];
   st->cactive[C_POS_LO] = pos && p->enable[C_POS_LO];
@@ -243,9 +253,15 @@ static void set_slack_and_dual(const oracle_fb_problem_t* p, stage_t* st) {
     memset(d, 0, sizeof(*d));
     if (!st->cactive[c]) continue;
     const int n = comp_rows(p, c);
+    fb_kin_t kin;
+    if (c == C_DISTANCE) fb_forward_kinematics(st->q, NULL, NULL, &kin);   /* robot.updateFrameKinematics(s.q) */
     for (int j = 0; j < n; ++j) {
       double sl;
-      if (is_cone(c)) {
+      if (c == C_DISTANCE) {   /* every contact, active or not (contact_distance.cpp:62-70) */
+        double P[3];
+        fb_contact_point(&kin, j, P);
+        sl = P[2];
+      } else if (is_cone(c)) {
         const int rpc = cone_rows(p, c);
         double r[5];
         friction_residual(p->mu, rpc == 2, st->f[j / rpc], r);
@@ -262,7 +278,7 @@ static void set_slack_and_dual(const oracle_fb_problem_t* p, stage_t* st) {
 /* computePrimalAndDualResidual of every live component */
 static void primal_dual_residual(const oracle_fb_problem_t* p, stage_t* st) {
   for (int c = 0; c < NCOMP; ++c) {
-    if (!st->cactive[c]) continue;
+    if (!st->cactive[c] || c == C_DISTANCE) continue;   /* ContactDistance needs the kinematics: contact_distance_stage() */
     cdata_t* d = &st->c[c];
     if (is_cone(c)) {
       const int rpc = cone_rows(p, c);
@@ -295,7 +311,7 @@ static inline double* limit_grad(stage_t* st, int c) {
 /* Constraints::augmentDualResidual; dt = 1 at an impulse (no dt argument there) */
 static void augment_dual_residual(const oracle_fb_problem_t* p, stage_t* st, double dt) {
   for (int c = 0; c < NCOMP; ++c) {
-    if (!st->cactive[c]) continue;
+    if (!st->cactive[c] || c == C_DISTANCE) continue;
     const cdata_t* d = &st->c[c];
     if (is_cone(c)) {
       const int rpc = cone_rows(p, c);
@@ -324,7 +340,7 @@ static void augment_dual_residual(const oracle_fb_problem_t* p, stage_t* st, dou
 static void condense_slack_and_dual(const oracle_fb_problem_t* p, stage_t* st, double dt) {
   primal_dual_residual(p, st);
   for (int c = 0; c < NCOMP; ++c) {
-    if (!st->cactive[c]) continue;
+    if (!st->cactive[c] || c == C_DISTANCE) continue;
     cdata_t* d = &st->c[c];
     if (is_cone(c)) {
       const int rpc = cone_rows(p, c);
@@ -371,7 +387,16 @@ static void slack_dual_direction(const oracle_fb_problem_t* p, stage_t* st) {
   for (int c = 0; c < NCOMP; ++c) {
     if (!st->cactive[c]) continue;
     cdata_t* d = &st->c[c];
-    if (is_cone(c)) {
+    if (c == C_DISTANCE) {   /* contact_distance.cpp:112-131: the rows of active contacts drift like the inactive cone rows */
+      for (int i = 0; i < FB_NC; ++i) {
+        d->dslack[i] = 1.0; d->ddual[i] = 1.0;
+        if (st->active[i]) continue;
+        double acc = st->cdJ[i][0] * st->dq[0];
+        for (int l = 1; l < NV; ++l) acc = fma(st->cdJ[i][l], st->dq[l], acc);
+        d->dslack[i] = acc - d->residual[i];
+        d->ddual[i] = -fma(d->dual[i], d->dslack[i], d->duality[i]) / d->slack[i];
+      }
+    } else if (is_cone(c)) {
       const int rpc = cone_rows(p, c);
       for (int j = 0; j < FB_NC * rpc; ++j) { d->dslack[j] = 1.0; d->ddual[j] = 1.0; }
       int k = 0;
@@ -553,6 +578,46 @@ static void masked_forces(const stage_t* st, double f[FB_NC][3]) {
     for (int x = 0; x < 3; ++x) f[i][x] = st->active[i] ? st->f[i][x] : 0.0;
 }
 
+/* ContactDistance on a stage whose kinematics `kin` are up to date (contact_distance.cpp:73-110,134-150): for every contact
+ * that is NOT active, residual = -z + slack with z the height of the contact frame, duality, and the dual residual
+ * lq -= dt dual J2 with J2 = row 2 of getFrameJacobian (the LOCAL-frame Jacobian -- the reference differentiates the world
+ * height with the local z row; kept).  Evaluated after the dynamics terms because it needs the same kinematics. */
+static void contact_distance_stage(const oracle_fb_problem_t* p, stage_t* st, const fb_kin_t* kin, double dt) {
+  cdata_t* d = &st->c[C_DISTANCE];
+  for (int i = 0; i < FB_NC; ++i) {
+    d->residual[i] = 0.0;
+    d->duality[i] = 0.0;
+    if (st->active[i]) continue;
+    fb_frame_t fr;
+    fb_frame_kinematics(kin, i, 0, &fr);
+    st->cdz[i] = fr.P[2];
+    for (int c = 0; c < NV; ++c) st->cdJ[i][c] = fr.J[2][c];
+    if (p->enable_distance == 2) {   /* consistent variant: row 2 of the WORLD-aligned Jacobian R_f J_lin = d z / d q */
+      const double* Rf = kin->R[1 + ANYMAL_CONTACT_PARENT_JOINT[i]];
+      for (int c = 0; c < NV; ++c) st->cdJ[i][c] = fma(Rf[8], fr.J[2][c], fma(Rf[7], fr.J[1][c], Rf[6] * fr.J[0][c]));
+    }
+    d->residual[i] = -fr.P[2] + d->slack[i];
+    d->duality[i] = d->slack[i] * d->dual[i] - p->barrier;
+    for (int c = 0; c < NV; ++c) st->lq[c] -= (dt * d->dual[i]) * st->cdJ[i][c];
+  }
+}
+/* ContactDistance::condenseSlackAndDual (contact_distance.cpp:87-110): Qqq += (dt dual / slack) J2^T J2,
+ * lq -= (dt (dual residual - duality) / slack) J2 */
+static void condense_contact_distance(stage_t* st, double dt) {
+  const cdata_t* d = &st->c[C_DISTANCE];
+  for (int i = 0; i < FB_NC; ++i) {
+    if (st->active[i]) continue;
+    const double rs = 1.0 / d->slack[i];
+    const double w = (dt * d->dual[i]) * rs;
+    const double g = (dt * fma(d->dual[i], d->residual[i], -d->duality[i])) * rs;
+    for (int r = 0; r < NV; ++r) {
+      st->lq[r] -= g * st->cdJ[i][r];
+      const double wr = w * st->cdJ[i][r];
+      for (int c = 0; c < NV; ++c) st->Qxx[r * NX + c] += wr * st->cdJ[i][c];
+    }
+  }
+}
+
 /* linearizeContactDynamics (:48-83) resp. linearizeImpulseDynamics (impulse_dynamics_forward_euler.hxx:25-45);
  * residual_only: computeContactDynamicsResidual-style evaluation is a subset (derivatives skipped by the caller). */
 static void linearize_contact_dynamics(const oracle_fb_problem_t* p, stage_t* st, int impulse, double dt) {
@@ -638,6 +703,7 @@ static void linearize_contact_dynamics(const oracle_fb_problem_t* p, stage_t* st
     mv(MM_SET, NV, dimf, st->dCda, 1, NV, mu_stack, t18);
     for (int j = 0; j < NV; ++j) st->la[j] = fma(dt, t18[j], st->la[j]);
   }
+  if (!impulse && st->cactive[C_DISTANCE]) contact_distance_stage(p, st, &kin, dt);
 }
 
 /* condenseContactDynamics (:105-158) / condenseImpulseDynamics (impulse_dynamics_forward_euler.hxx:64-105) */
@@ -768,6 +834,7 @@ static void linearize_stage(const oracle_fb_problem_t* p, stage_t* st, const ele
   }
   cost_derivatives(p, st, e->kind, dt, 2);   /* Hessian part only, see below */
   condense_slack_and_dual(p, st, dt);
+  if (!impulse && st->cactive[C_DISTANCE]) condense_contact_distance(st, dt);
   if (e->sw_impulse >= 0) linearize_switching_constraint(st, e->dt, e->dt_next);
   condense_contact_dynamics(st, impulse, dt);
   if (e->sw_impulse >= 0) condense_switching_constraint(st);
@@ -1376,7 +1443,7 @@ static double trial_violation(const oracle_fb_problem_t* p, stage_t* st, const e
   /* constraints: residual with the trial solution and the current slack */
   double cl1 = 0.0;
   for (int c = 0; c < NCOMP; ++c) {
-    if (!st->cactive[c]) continue;
+    if (!st->cactive[c] || c == C_DISTANCE) continue;   /* ContactDistance: below, once the trial kinematics exist */
     double s1 = 0.0;
     if (is_cone(c)) {
       const int rpc = cone_rows(p, c);
@@ -1424,6 +1491,16 @@ static double trial_violation(const oracle_fb_problem_t* p, stage_t* st, const e
     ++k;
   }
   for (int j = 0; j < NV + st->dimf; ++j) idl1 += fabs(IDC[j]);
+  if (!impulse && st->cactive[C_DISTANCE]) {   /* computePrimalAndDualResidual at the trial configuration (contact_distance.cpp:134-150) */
+    double s1 = 0.0;
+    for (int i = 0; i < FB_NC; ++i) {
+      if (st->active[i]) continue;
+      double P[3];
+      fb_contact_point(&kin, i, P);
+      s1 += fabs(-P[2] + st->c[C_DISTANCE].slack[i]);
+    }
+    cl1 += s1;
+  }
   if (impulse) return (cl1 + fx) + idl1;
   double viol = (fx + dt * idl1) + dt * cl1;
   if (e->ls_impulse >= 0) {
@@ -1637,6 +1714,8 @@ int oracle_fb_ocp_get(const oracle_fb_ocp_t* o, int e, const char* name, double*
   GET("Fqq_prev_inv", Fqq_prev_inv) GET("Fqq_inv", Fqq_inv) GET("laf", laf) GET("Qafqv", Qafqv) GET("Qafu", Qafu)
 #undef GET
   if (!strcmp(name, "kkt")) { out[0] = st->kkt_sq; return 1; }
+  if (!strcmp(name, "cdJ")) { memcpy(out, st->cdJ, sizeof(st->cdJ)); return FB_NC * NV; }
+  if (!strcmp(name, "cdz")) { memcpy(out, st->cdz, sizeof(st->cdz)); return FB_NC; }
   if (!strcmp(name, "active")) { for (int i = 0; i < FB_NC; ++i) out[i] = st->active[i]; return FB_NC; }
   if (!strcmp(name, "ls_cost")) { out[0] = st->ls_cost; return 1; }
   if (!strcmp(name, "ls_viol")) { out[0] = st->ls_viol; return 1; }

@@ -121,6 +121,7 @@ class FbProblem(C.Structure):
         ("mu", C.c_double), ("barrier", C.c_double), ("fraction_rate", C.c_double),
         ("enable", C.c_int * NCOMP),
         ("cone_nonlinear", C.c_int * 2), ("enable_acc", C.c_int * 2), ("a_min", C.c_double * NU), ("a_max", C.c_double * NU),
+        ("enable_distance", C.c_int),
     ]
 
     def set(self, name, values):
@@ -135,7 +136,7 @@ _SIZES = dict(ls_cost=1, ls_viol=1, q=19, f=12, mu=12, nu_passive=6, xi=12, u=12
               lu_passive=6, P=12, IDC=30, Qxx=36 * 36, Qxu=36 * 18, Quu=18 * 18, Qff=144, Fvq=324, Fvv=324, Fvu=216, Fqq6=36, Fqv6=36,
               MJtJinv=900, MJ_dIDC=30 * 36, MJ_IDC=30, dIDCdqv=30 * 36, dCda=12 * 18, Mm=324, K=12 * 36, k=12, Pqq=324, Pqv=324,
               Pvv=324, Phix=12 * 36, Phia=12 * 18, Phiu=144, cM=12 * 36, cm=12, Fqq_prev_inv=36, Fqq_inv=36, laf=30,
-              Qafqv=30 * 36, Qafu=30 * 18, kkt=1, active=4, slack=6 * 12 + 40 + 24, dual=6 * 12 + 40 + 24)
+              Qafqv=30 * 36, Qafu=30 * 18, kkt=1, active=4, cdJ=72, cdz=4, slack=6 * 12 + 40 + 24 + 4, dual=6 * 12 + 40 + 24 + 4)
 
 
 class FbOCP:

@@ -237,6 +237,40 @@ def test_anymal_ocp_benchmark_example_reproduces_golden_convergence(a_limit, gol
     assert kkt[-1] < 1e-10
 
 
+@pytest.mark.gpu
+def test_contact_distance_example_equals_the_oracle():
+    """ContactDistance(robot, consistent = true) pushed through the C++ host classes (examples/anymal_trotting.cpp,
+    IDOCP_B200_CONTACT_DISTANCE=2): the 25-iteration KKT history equals the oracle's digit for digit and converges."""
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import anymal_problems as ap
+    import fb_py
+    import oracle_py
+    oracle_py.build()
+    fb_py.lib()
+    _build_anymal()
+    env = dict(os.environ, IDOCP_B200_CONTACT_DISTANCE="2")
+    out = subprocess.run([ANYMAL_EXE, "2"], capture_output=True, text=True, check=True, env=env).stdout
+    kkt = [float(x) for x in re.findall(r"KKT error(?: after iteration \d+)? = (\S+)", out)]
+    with open(os.path.join(GOLDEN, "anymal_trotting_golden.json")) as f:
+        pts = np.array(json.load(f)["contact_points"])
+    pr = ap.TrottingProblem()
+    pr.problem.enable_distance = 2
+    pr.standing_points = pts
+    ocp = pr.make_oracle(fb_py)
+    ocp.compute_kkt_residual(0.0, pr.q0, pr.v0)
+    ref = [ocp.kkt_error()]
+    for _ in range(25):
+        assert ocp.update_solution(0.0, pr.q0, pr.v0) == 0
+        ocp.compute_kkt_residual(0.0, pr.q0, pr.v0)
+        ref.append(ocp.kkt_error())
+    assert len(kkt) == 26
+    assert kkt == ref
+    assert kkt[-1] < 1e-8
+
+
 RUNNING_EXE = os.path.join(ROOT, "build", "anymal_running")
 
 

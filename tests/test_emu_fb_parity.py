@@ -88,7 +88,7 @@ def test_trotting_iterations_bit_exact(fb, emu_lib):
 
 def nonlinear_cone_scenario(fb, lib, batch_states=None):
     """FrictionCone + ImpulseFrictionCone + JointAcceleration{Lower,Upper}Limit through the kernels vs the
-    oracle: every field, slack / dual of all 136 rows, KKT errors, step sizes; the first two iterations with the filter line search."""
+    oracle: every field, slack / dual of all 140 rows, KKT errors, step sizes; the first two iterations with the filter line search."""
     pr = ap.with_nonlinear_cones_and_acceleration_limits(ap.TrottingProblem())
     B = 1 if batch_states is None else len(batch_states[0])
     q0 = np.tile(pr.q0, (B, 1)) if batch_states is None else batch_states[0]
@@ -101,7 +101,7 @@ def nonlinear_cone_scenario(fb, lib, batch_states=None):
         for e in range(ne):
             for nm in ("slack", "dual"):
                 got = np.asarray(solver.get(e, nm))
-                assert got.shape[1] == 136
+                assert got.shape[1] == 140
                 for b, o in enumerate(oracles):
                     assert np.array_equal(o.get(e, nm), got[b]), (tag, e, nm, b)
     check_slack_dual("init")
@@ -127,6 +127,52 @@ def nonlinear_cone_scenario(fb, lib, batch_states=None):
 
 def test_nonlinear_cones_and_acceleration_limits_bit_exact(fb, emu_lib):
     nonlinear_cone_scenario(fb, emu_lib)
+
+
+def contact_distance_scenario(fb, lib, mode, batch_states=None, iters=4):
+    """ContactDistance (src/constraints/contact_distance.cpp) through the kernels vs the oracle: mode 1 = the
+    reference literally (row 2 of the LOCAL frame Jacobian), mode 2 = the consistent variant; every field, all 140 constraint rows,
+    KKT errors, step sizes; mode 2 starts with two iterations of the filter line search."""
+    pr = ap.TrottingProblem()
+    pr.problem.enable_distance = mode
+    B = 1 if batch_states is None else len(batch_states[0])
+    q0 = np.tile(pr.q0, (B, 1)) if batch_states is None else batch_states[0]
+    v0 = np.tile(pr.v0, (B, 1)) if batch_states is None else batch_states[1]
+    oracles = [pr.make_oracle(fb, q0=q0[b], v0=v0[b]) for b in range(B)]
+    solver = ap.make_product_solver(pr, lib, fb, batch=B, q0=q0, v0=v0)
+    ne = len(solver.chain())
+
+    def check_slack_dual(tag):
+        for e in range(ne):
+            for nm in ("slack", "dual"):
+                got = np.asarray(solver.get(e, nm))
+                assert got.shape[1] == 140
+                for b, o in enumerate(oracles):
+                    assert np.array_equal(o.get(e, nm), got[b]), (tag, e, nm, b)
+    check_slack_dual("init")
+    sl = np.asarray(solver.get(5, "slack"))
+    assert np.all(sl[:, 136:140] > 0)            # grid stage 5: position level, the four contact distances are live
+    assert np.all(np.asarray(solver.get(0, "slack"))[:, 136:140] == 0)     # stage 0: not yet (time stage < 2)
+    for it in range(iters):
+        ls = mode == 2 and it < 2     # (mode 1 diverges: with the search its 0.05 floor soon breaks LLT(G))
+        solver.computeKKTResidual(0.0, q0, v0)
+        kkt = solver.KKTError()
+        for b, o in enumerate(oracles):
+            o.compute_kkt_residual(0.0, q0[b], v0[b])
+            assert kkt[b] == o.kkt_error(), (it, b, kkt[b], o.kkt_error())
+        solver.updateSolution(0.0, q0, v0, ls)
+        steps = solver.stepSizes()
+        for b, o in enumerate(oracles):
+            assert o.update_solution(0.0, q0[b], v0[b], ls) == 0
+            assert np.array_equal(steps[b], o.step_sizes()), (it, b, steps[b], o.step_sizes())
+            for names in (KKT + EXP, RIC, DIR, SOL):
+                assert compare(o, solver, fb, names, b=b) == [], (it, b)
+        check_slack_dual(it)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_contact_distance_bit_exact(fb, emu_lib, mode):
+    contact_distance_scenario(fb, emu_lib, mode)
 
 
 def test_filter_line_search_bit_exact(fb, emu_lib):

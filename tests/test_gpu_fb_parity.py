@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import anymal_problems as ap
-from test_emu_fb_parity import DIR, EXP, KKT, RIC, SOL, compare, nonlinear_cone_scenario
+from test_emu_fb_parity import DIR, EXP, KKT, RIC, SOL, compare, contact_distance_scenario, nonlinear_cone_scenario
 
 pytestmark = pytest.mark.gpu
 
@@ -53,6 +53,13 @@ def test_nonlinear_cones_and_acceleration_limits_bit_exact(fb, gpu_lib):
     # FrictionCone, ImpulseFrictionCone, JointAcceleration{Lower,Upper}Limit on a batch of perturbed states
     pr = ap.TrottingProblem()
     nonlinear_cone_scenario(fb, gpu_lib, perturbed_states(fb, pr, 5, 11))
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_contact_distance_bit_exact(fb, gpu_lib, mode):
+    # ContactDistance, literal (1) and consistent (2), on a batch of perturbed states
+    pr = ap.TrottingProblem()
+    contact_distance_scenario(fb, gpu_lib, mode, perturbed_states(fb, pr, 5, 13))
 
 
 def test_convergence_history_identical(fb, gpu_lib):

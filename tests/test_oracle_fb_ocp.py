@@ -357,3 +357,53 @@ def test_acceleration_limits_bind_and_converge(fb):
             amax = max(amax, np.abs(ocp.get(e, "a")[6:]).max())
             assert np.all(ocp.get(e, "slack")[112:136] > 0)
     assert 11.5 < amax < 12.0      # the limit binds (18 rad/s^2 without it)
+
+
+def test_contact_distance_jacobian_and_convergence(fb):
+    """ContactDistance (src/constraints/contact_distance.cpp).  Mode 2 (consistent): the rows J2 are the derivative of the height
+    of the swing feet (central differences on the manifold), the trot converges and the swing feet stay above the ground.
+    Mode 1 (the reference literally: row 2 of the LOCAL frame Jacobian, robot.hxx:182-188): same residuals, but J2 is NOT that
+    derivative -- the shank-fixed foot frame is not level -- and the Newton iteration does not converge on the trot."""
+    def foot_z(q, i):
+        z = np.zeros(18)
+        return fb.contact(q, z, z, i, 0.05, np.zeros(3))["P"][2]
+    results = {}
+    for mode in (1, 2):
+        pr = ap.TrottingProblem()
+        pr.problem.enable_distance = mode
+        rng = np.random.default_rng(3)
+        q0 = fb.integrate(pr.q0, rng.uniform(-0.05, 0.05, 18))
+        ocp = pr.make_oracle(fb, q0=q0, v0=pr.v0)
+        ocp.update_solution(0.0, q0, pr.v0)
+        ocp.compute_kkt_residual(0.0, q0, pr.v0)
+        e = next(e for e, c in enumerate(ocp.chain()) if c["kind"] == fb.K_GRID and c["index"] >= 12 and not all(ocp.get(e, "active")))
+        q = ocp.get(e, "q")
+        J = ocp.get(e, "cdJ").reshape(4, 18)
+        act = ocp.get(e, "active")
+        worst = 0.0
+        for i in range(4):
+            if act[i]:
+                continue
+            assert abs(ocp.get(e, "cdz")[i] - foot_z(q, i)) < 1e-14
+            fd = np.zeros(18)
+            for c in range(18):
+                d = np.zeros(18)
+                d[c] = 1e-6
+                fd[c] = (foot_z(fb.integrate(q, d), i) - foot_z(fb.integrate(q, -d), i)) / 2e-6
+            worst = max(worst, np.abs(J[i] - fd).max())
+            # residual = -z + slack for the legs in the air, zero rows for the legs on the ground
+            sl = ocp.get(e, "slack")[136:140]
+            assert sl[i] > 0
+        results[mode] = worst
+        hist = run(ocp, pr, 30, q=q0)
+        if mode == 2:
+            assert hist[-1] < 1e-8
+            for e2, c in enumerate(ocp.chain()[:-1]):
+                if c["kind"] == fb.K_GRID and c["index"] >= 2:
+                    a2 = ocp.get(e2, "active")
+                    for i in range(4):
+                        if not a2[i]:
+                            assert foot_z(ocp.get(e2, "q"), i) > 0
+        else:
+            assert not hist[-1] < 1e-3      # the reference's rows: no convergence
+    assert results[2] < 1e-7 and results[1] > 1e-2
