@@ -77,7 +77,6 @@ struct FbSol {   // SplitSolution / ImpulseSplitSolution (a = dv at an impulse) 
 struct FbDir {   // SplitDirection + the direction part of ConstraintsData
   double dlmd[FB_NV], dgmm[FB_NV], dq[FB_NV], dv[FB_NV], du[FB_NU], daf[FB_NVF], dbetamu[FB_NVF], dnu_passive[FB_NPASS], dxi[FB_MAXF];
   double residual[FB_NCON], duality[FB_NCON], dslack[FB_NCON], ddual[FB_NCON];
-  double cdJ[FB_NC * FB_NV];   // ContactDistance: data.J[i].row(2) of the contacts that are not active (k_fb_robot -> k_fb_expand)
   double max_primal, max_dual, kkt_sq, info;
   double ls_cost, ls_viol;   // LineSearch: stage cost / constraint violation of the trial point
 };
@@ -1350,8 +1349,7 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
           double J[6] = {0, 0, 0, 0, 0, 0};
           if (fb_in_support(i, lane)) fb_pullback(Rf, w.frP, w.S[lane], J);
           const double j2 = pr.distance_mode == 2 ? fma(Rf[8], J[2], fma(Rf[7], J[1], Rf[6] * J[0])) : J[2];
-          L.cdJ[i * FB_NV + lane] = j2;
-          Dr.cdJ[i * FB_NV + lane] = j2;
+          L.cdJ[i * FB_NV + lane] = j2;   // read again by the condensing below, by k_fb_condense and by k_fb_expand
           lq -= (dt * w.dual[o + i]) * j2;
         }
         cdres = -w.frP[2] + w.slack[o + i];
@@ -1682,22 +1680,11 @@ __global__ void __launch_bounds__(128, 5) k_fb_condense(FbArrays A, const FbLin*
   {
     const double *Qqq6 = w.Qqq6, *Qqq_d = w.Qqq_d, *Qvv_d = w.Qvv_d;
     double* Qxx = Kt.Qxx;
-    // ContactDistance::condenseSlackAndDual (contact_distance.cpp:91-93): Qqq += (dt dual / slack) J2^T J2 per contact that is
-    // not active -- the one dense term of the stage Hessian; J2 and the weights come from k_fb_robot (FbLin::cdJ, cdw)
-    int cd_mask = 0;
-    if (!impulse && el.cactive[FBC_DISTANCE])
-      for (int i = 0; i < FB_NC; ++i) cd_mask |= el.active[i] ? 0 : (1 << i);
-    const double *cdJ = L.cdJ, *cdw = L.cdw;
     fb_mm_f<FBM_SUB>(NX, NX, nvf, w.MJ_dIDC, 1, NX, Qafqv, NX, 1,
                      [=](int r, int c) {
-                       double v = 0.0;
-                       if (r < 6 && c < 6) v = Qqq6[6 * r + c];
-                       else if (r == c) v = r < NV ? Qqq_d[r] : Qvv_d[r - NV];
-                       if (cd_mask && r < NV && c < NV) {
-                         for (int i = 0; i < FB_NC; ++i)
-                           if ((cd_mask >> i) & 1) v += (cdw[i] * cdJ[i * NV + r]) * cdJ[i * NV + c];
-                       }
-                       return v;
+                       if (r < 6 && c < 6) return Qqq6[6 * r + c];
+                       if (r == c) return r < NV ? Qqq_d[r] : Qvv_d[r - NV];
+                       return 0.0;
                      },
                      [=](int r, int c, double v) { if (!(r >= NV && c < NV)) Qxx[r * NX + c] = v; }, &rot);
   }
@@ -1765,6 +1752,19 @@ __global__ void __launch_bounds__(128, 5) k_fb_condense(FbArrays A, const FbLin*
   fb_copy(Ex.Qafu, Qafu, NVF * NV);
   fb_copy(Ex.laf, w.laf, NVF);
   if (tid == 0) Dr.info = (double)w.info;
+  // ---- ContactDistance::condenseSlackAndDual (contact_distance.cpp:91-93): Qqq += (dt dual / slack) J2^T J2 per contact that
+  // is not active -- the one dense term of the stage Hessian, added AFTER the condensed products (the oracle's order) so that
+  // the product kernels above stay as they are; J2 and the weights come from k_fb_robot (FbLin::cdJ, cdw)
+  if (!impulse && el.cactive[FBC_DISTANCE]) {
+    __syncthreads();   // the qq block of Kt.Qxx was written by other threads of this CTA
+    FB_FOR(x, NV * NV) {
+      const int r = x / NV, c = x - r * NV;
+      double v = Kt.Qxx[r * NX + c];
+      for (int i = 0; i < FB_NC; ++i)
+        if (!el.active[i]) v += (L.cdw[i] * L.cdJ[i * NV + r]) * L.cdJ[i * NV + c];
+      Kt.Qxx[r * NX + c] = v;
+    }
+  }
   FB_PHASE(0, 9);
 }
 
@@ -2214,22 +2214,14 @@ __global__ void __launch_bounds__(64) k_fb_expand(FbArrays A) {
   }
   __syncthreads();
   // computeSlackAndDualDirection
-  const int ncon = FBC_LIVE_ROWS(el.cactive);
+  const int ncon_live = FBC_LIVE_ROWS(el.cactive);
+  const int ncon = ncon_live < 136 ? ncon_live : 136;   // the four ContactDistance rows: their own loop below
   for (int idx = tid; idx < ncon; idx += blockDim.x) {
     const int c = fbc_comp(idx);
     const int j = idx - fbc_offset(c);
     double ds = 0.0, dd = 0.0;
     if (el.cactive[c] && j < fbc_rows(nl, c)) {
-      if (c == FBC_DISTANCE) {   // contact_distance.cpp:112-131: J2 dq - residual for the contacts that are not active
-        ds = 1.0; dd = 1.0;
-        if (!el.active[j]) {
-          const double* J2 = Dr.cdJ + j * NV;
-          double acc = J2[0] * dx[0];
-          for (int l = 1; l < NV; ++l) acc = fma(J2[l], dx[l], acc);
-          ds = acc - Dr.residual[idx];
-          dd = -fma(S.dual[idx], ds, Dr.duality[idx]) / S.slack[idx];
-        }
-      } else if (fbc_is_cone(c)) {
+      if (fbc_is_cone(c)) {
         const int rpc = fbc_cone_rows(nl, c);
         const int i = rpc == 2 ? (j >> 1) : (j / 5);   // no division by a run-time value
         ds = 1.0; dd = 1.0;
@@ -2250,6 +2242,24 @@ __global__ void __launch_bounds__(64) k_fb_expand(FbArrays A) {
         ds = ((c & 1) ? -d : d) - Dr.residual[idx];
         dd = -fma(S.dual[idx], ds, Dr.duality[idx]) / S.slack[idx];
       }
+    }
+    dslack[idx] = ds;
+    ddual[idx] = dd;
+    Dr.dslack[idx] = ds;
+    Dr.ddual[idx] = dd;
+  }
+  if (el.cactive[FBC_DISTANCE] && tid < FB_NC) {
+    // ContactDistance::computeSlackAndDualDirection (contact_distance.cpp:112-131): J2 dq - residual for the contacts that are not
+    // active, (1, 1) for the others.  Kept out of the loop above, whose code (and register count) it would change for everybody.
+    const int idx = fbc_offset(FBC_DISTANCE) + tid;
+    double ds = 1.0, dd = 1.0;
+    if (!el.active[tid]) {
+      const double* J2 = A.lin[(size_t)el.slot * A.B + b].cdJ + tid * NV;
+      double acc = J2[0] * dx[0];
+#pragma unroll 1
+      for (int l = 1; l < NV; ++l) acc = fma(J2[l], dx[l], acc);
+      ds = acc - Dr.residual[idx];
+      dd = -fma(S.dual[idx], ds, Dr.duality[idx]) / S.slack[idx];
     }
     dslack[idx] = ds;
     ddual[idx] = dd;

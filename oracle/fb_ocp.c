@@ -601,9 +601,11 @@ static void contact_distance_stage(const oracle_fb_problem_t* p, stage_t* st, co
     for (int c = 0; c < NV; ++c) st->lq[c] -= (dt * d->dual[i]) * st->cdJ[i][c];
   }
 }
-/* ContactDistance::condenseSlackAndDual (contact_distance.cpp:87-110): Qqq += (dt dual / slack) J2^T J2,
- * lq -= (dt (dual residual - duality) / slack) J2 */
-static void condense_contact_distance(stage_t* st, double dt) {
+/* ContactDistance::condenseSlackAndDual (contact_distance.cpp:87-110): lq -= (dt (dual residual - duality) / slack) J2 before
+ * the contact dynamics are condensed (part 0), Qqq += (dt dual / slack) J2^T J2 (part 1).  Part 1 -- the one dense term of the
+ * stage Hessian -- is added AFTER the condensed products: a summation order chosen so that the product kernels of the GPU path
+ * are the same with and without this component. */
+static void condense_contact_distance(stage_t* st, double dt, int part) {
   const cdata_t* d = &st->c[C_DISTANCE];
   for (int i = 0; i < FB_NC; ++i) {
     if (st->active[i]) continue;
@@ -611,7 +613,7 @@ static void condense_contact_distance(stage_t* st, double dt) {
     const double w = (dt * d->dual[i]) * rs;
     const double g = (dt * fma(d->dual[i], d->residual[i], -d->duality[i])) * rs;
     for (int r = 0; r < NV; ++r) {
-      st->lq[r] -= g * st->cdJ[i][r];
+      if (part == 0) { st->lq[r] -= g * st->cdJ[i][r]; continue; }
       const double wr = w * st->cdJ[i][r];
       for (int c = 0; c < NV; ++c) st->Qxx[r * NX + c] += wr * st->cdJ[i][c];
     }
@@ -834,10 +836,11 @@ static void linearize_stage(const oracle_fb_problem_t* p, stage_t* st, const ele
   }
   cost_derivatives(p, st, e->kind, dt, 2);   /* Hessian part only, see below */
   condense_slack_and_dual(p, st, dt);
-  if (!impulse && st->cactive[C_DISTANCE]) condense_contact_distance(st, dt);
+  if (!impulse && st->cactive[C_DISTANCE]) condense_contact_distance(st, dt, 0);
   if (e->sw_impulse >= 0) linearize_switching_constraint(st, e->dt, e->dt_next);
   condense_contact_dynamics(st, impulse, dt);
   if (e->sw_impulse >= 0) condense_switching_constraint(st);
+  if (!impulse && st->cactive[C_DISTANCE]) condense_contact_distance(st, dt, 1);
 }
 
 /* TerminalOCP::linearizeOCP / computeKKTResidual (terminal_ocp.hxx:50-66,120-133) */
