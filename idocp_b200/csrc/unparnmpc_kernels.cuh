@@ -167,6 +167,50 @@ __device__ __forceinline__ void inv_br_rows(const double* TR, const double (&st)
   }
 }
 
+// ---- the three dense products of the inversion on the FP64 tensor cores ----
+// mma.sync.aligned.m8n8k4.f64 is bit-identical to the ascending fma chain (tools/dmma_probe.cu), so
+// C = A B by ONE warp in 8 x 16 strips (two tiles sharing the A fragment), accumulators chained over k from -0.0 (the first
+// fma is then the plain product), ragged edges zero-padded, equals the per-element chain of the oracle.  Operands in shared
+// memory with arbitrary strides; every element goes to `store(i, j, value)`.  Fragments: a = A[g][t], b = B[t][g],
+// c = C[g][2 t + {0, 1}], g = lane / 4, t = lane % 4.  (-DIDOCP_INV_SIMT keeps the SIMT form of the three products for A/B.)
+__device__ __forceinline__ void inv_dmma(double& d0, double& d1, double a, double b) {
+#ifndef IDOCP_B200_EMU
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+#else
+  emu_dmma_m8n8k4(d0, d1, a, b);
+#endif
+}
+template <int M, int N, int K, class Store>
+__device__ __forceinline__ void inv_mm_dmma(int lane, const double* __restrict__ A, int ars, int acs, const double* __restrict__ B, int brs,
+                                            int bcs, Store store) {
+  const int g = lane >> 2, t = lane & 3;
+  constexpr int TM = (M + 7) / 8, TN = (N + 15) / 16;
+#pragma unroll
+  for (int s = 0; s < TM * TN; ++s) {
+    const int i0 = (s / TN) * 8, j0 = (s % TN) * 16;
+    const int row = i0 + g, ca = j0 + 2 * t, cb = ca + 8, ba = j0 + g, bb = ba + 8;
+    const bool rok = row < M, baok = ba < N, bbok = bb < N;
+    double c00 = -0.0, c01 = -0.0, c10 = -0.0, c11 = -0.0;
+    const double* ap = A + (rok ? row : 0) * ars + t * acs;
+    const double* bpa = B + (baok ? ba : 0) * bcs + t * brs;
+    const double* bpb = B + (bbok ? bb : 0) * bcs + t * brs;
+#pragma unroll
+    for (int l = 0; l < K; l += 4) {
+      const bool kin = l + t < K;
+      const double a = (rok && kin) ? ap[l * acs] : 0.0;
+      const double b0 = (baok && kin) ? bpa[l * brs] : 0.0, b1 = (bbok && kin) ? bpb[l * brs] : 0.0;
+      inv_dmma(c00, c01, a, b0);
+      if (j0 + 8 < N) inv_dmma(c10, c11, a, b1);
+    }
+    if (rok) {
+      if (ca < N) store(row, ca, c00);
+      if (ca + 1 < N) store(row, ca + 1, c01);
+      if (cb < N) store(row, cb, c10);
+      if (cb + 1 < N) store(row, cb + 1, c11);
+    }
+  }
+}
+
 #ifndef IDOCP_INV_MINB
 #define IDOCP_INV_MINB 3   // 164 registers without spills since the column-oriented substitutions: three CTAs per SM
 #endif
@@ -265,6 +309,18 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_INV_MINB) k_parnmpc_invert(
     }
   }
   __syncwarp();
+#ifndef IDOCP_INV_SIMT
+  // ---- TR = -(TL FQinv) (14 x 21), ST = S TR (14 x 21, parked over the dead L^T), BR = Qinv - TR^T ST (21 x 21, in place over
+  //      the parked Qinv): three warp-level DMMA products, every element the oracle's ascending chain ----
+  {
+    double* ST = LT;
+    inv_mm_dmma<NX2, NQ3, NX2>(wl, TL, 1, INV_LDX, FQ, 1, INV_LDX, [=](int r, int c, double v) { TR[c * INV_LDX + r] = -v; });
+    __syncwarp();
+    inv_mm_dmma<NX2, NQ3, NX2>(wl, S, 1, INV_LDX, TR, 1, INV_LDX, [=](int r, int c, double v) { ST[c * INV_LDX + r] = v; });
+    __syncwarp();
+    inv_mm_dmma<NQ3, NQ3, NX2>(wl, TR, INV_LDX, 1, ST, 1, INV_LDX, [=](int r, int c, double v) { A[c * INV_LDQ + r] -= v; });
+  }
+#else
   // ---- TR = -(TL FQinv) (14 x 21), lane c = column c (own column of FQinv re-read from shared memory) ----
   {
     double tr[NX2];
@@ -290,6 +346,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_INV_MINB) k_parnmpc_invert(
     inv_tl_fq<0>(S, tr, st);             // st[r] = sum_k S(r, k) tr[k]
     if (wl < NQ3) inv_br_rows<0>(TR, st, A + wl * INV_LDQ);
   }
+#endif
   __syncwarp();
 
   // ---- d = KKT^-1 residual; s_new = s - d (lmd, gmm, a, q, v): lane = row, two passes (35 rows) ----
