@@ -60,10 +60,12 @@ KERNEL_ALGO_DOUBLES_PER_STAGE_PARNMPC = dict(KERNEL_ALGO_DOUBLES_PER_STAGE, expa
 # ncu evidence is PARSED, not typed in: tools/ncu_capture.sh (run under gpurun) writes profiles/kernel_counters_<workload>.json
 # (per kernel: DRAM bytes read + written, executed FP64 thread instructions, pipe / issue utilisation of one launch at the
 # bench batch); tools/fp64_peak (DFMA microbenchmark on the B200) writes profiles/fp64_peak.json.
-KERNEL_OF_CLASS = {"linearize": "k_linearize<0,0,0>", "riccati": "k_riccati<0>", "expand": "k_expand<0,0>", "update": "k_update",
-                   "update_linearize": "k_update_linearize<0>",
-                   "fb_robot": "k_fb_robot<0>", "fb_condense": "k_fb_condense", "fb_riccati_backward": "k_fb_riccati_backward",
-                   "parnmpc_coarse": "k_parnmpc_invert"}
+# (instantiation names as ncu prints them; the older spellings are kept for captures made before the ACC / KKT template flags)
+KERNEL_OF_CLASS = {"linearize": ("k_linearize<0,0,0,0>", "k_linearize<0,0,0>"), "riccati": ("k_riccati<0>",),
+                   "expand": ("k_expand<0,0,0>", "k_expand<0,0>"), "update": ("k_update",),
+                   "update_linearize": ("k_update_linearize<0,0>", "k_update_linearize<0>"),
+                   "fb_robot": ("k_fb_robot<0>",), "fb_condense": ("k_fb_condense",), "fb_riccati_backward": ("k_fb_riccati_backward",),
+                   "parnmpc_coarse": ("k_parnmpc_invert",)}
 # The iiwa14 workloads of bench.py (all through the same code path, run_iiwa):
 #   iiwa14_unocp           BASELINE configs[2] -- the headline: UnOCPSolver, unocp_benchmark problem, N = 20, 16384 states / GPU
 #   iiwa14_unparnmpc_task  BASELINE configs[1]: task_space_ocp problem (T = 6, N = 120, TimeVaryingTaskSpace6DCost, circular
@@ -93,9 +95,11 @@ def load_kernel_counters(workload):
     with open(path) as f:
         rec = json.load(f)
     out = {}
-    for cls, kname in KERNEL_OF_CLASS.items():
-        if kname in rec["kernels"]:
-            out[cls] = rec["kernels"][kname]
+    for cls, names in KERNEL_OF_CLASS.items():
+        for kname in names:
+            if kname in rec["kernels"]:
+                out[cls] = rec["kernels"][kname]
+                break
     return out, "profiles/kernel_counters_%s.json (%s)" % (workload, rec.get("source"))
 
 

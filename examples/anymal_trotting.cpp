@@ -6,6 +6,7 @@
 #include <iomanip>
 #include <iostream>
 #include <memory>
+#include <sstream>
 #include <string>
 
 #include "idocp_b200/ocp_solver.hpp"
@@ -71,7 +72,15 @@ int main(int argc, char* argv[]) {
   const int max_num_impulse_phase = 2;
   const int nthreads = 4;
   const double t = 0;
-  idocp::OCPSolver ocp_solver(robot, cost, constraints, T, N, max_num_impulse_phase + 1, nthreads, batch);
+  // IDOCP_B200_DEVICES="0,1,...": the batch sharded over several GPUs by the one solver object (default: device 0)
+  std::vector<int> devices;
+  if (const char* dl = std::getenv("IDOCP_B200_DEVICES")) {
+    std::stringstream list(dl);
+    for (std::string item; std::getline(list, item, ',');) devices.push_back(std::atoi(item.c_str()));
+  }
+  idocp::OCPSolver ocp_solver = devices.empty()
+      ? idocp::OCPSolver(robot, cost, constraints, T, N, max_num_impulse_phase + 1, nthreads, batch)
+      : idocp::OCPSolver(robot, cost, constraints, T, N, max_num_impulse_phase + 1, nthreads, batch, devices);
 
   robot.updateFrameKinematics(q_standing);
   std::vector<idocp::Vector3d> contact_points(robot.maxPointContacts());

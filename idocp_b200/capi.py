@@ -117,6 +117,12 @@ EXPORTS = [
     "idocp_b200_fb_get_profile", "idocp_b200_fb_record_bytes", "idocp_b200_fb_problem_default",
     "idocp_b200_fb_total_weight", "idocp_b200_fb_contact_frame_positions", "idocp_b200_fb_clear_line_search_filter",
     "idocp_b200_fb_set_strict_discretization",
+    "idocp_b200_fb_create_sharded", "idocp_b200_fb_sharded_destroy", "idocp_b200_fb_sharded_num_shards",
+    "idocp_b200_fb_sharded_set_solution", "idocp_b200_fb_sharded_set_cost_reference", "idocp_b200_fb_sharded_discretize",
+    "idocp_b200_fb_sharded_init_constraints", "idocp_b200_fb_sharded_set_strict_discretization",
+    "idocp_b200_fb_sharded_update_solution", "idocp_b200_fb_sharded_compute_kkt_residual", "idocp_b200_fb_sharded_kkt_error",
+    "idocp_b200_fb_sharded_clear_line_search_filter", "idocp_b200_fb_sharded_get_step_sizes", "idocp_b200_fb_sharded_get",
+    "idocp_b200_fb_sharded_sync", "idocp_b200_fb_sharded_launch_count",
     "idocp_b200_create_sharded", "idocp_b200_sharded_destroy", "idocp_b200_sharded_num_shards", "idocp_b200_sharded_shard",
     "idocp_b200_sharded_set_solution", "idocp_b200_sharded_init_constraints", "idocp_b200_sharded_init_backward_correction",
     "idocp_b200_sharded_set_task_reference", "idocp_b200_sharded_update_solution", "idocp_b200_sharded_compute_kkt_residual",
@@ -199,6 +205,14 @@ class Library:
         L.idocp_b200_fb_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.idocp_b200_fb_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.idocp_b200_fb_get_profile.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), _dp, C.POINTER(C.c_longlong)]
+        # the sharded twins take the same arguments behind the handle
+        for name in ("set_solution", "set_cost_reference", "discretize", "init_constraints", "update_solution", "compute_kkt_residual",
+                     "kkt_error", "get_step_sizes", "get", "sync", "clear_line_search_filter", "set_strict_discretization",
+                     "launch_count"):
+            getattr(L, "idocp_b200_fb_sharded_" + name).argtypes = getattr(L, "idocp_b200_fb_" + name).argtypes
+        L.idocp_b200_fb_create_sharded.argtypes = [C.POINTER(FbProblem), C.c_void_p, C.c_int, _ip, C.c_int, C.POINTER(C.c_void_p)]
+        L.idocp_b200_fb_sharded_destroy.argtypes = [C.c_void_p]
+        L.idocp_b200_fb_sharded_num_shards.argtypes = [C.c_void_p, _ip, _ip]
         L.idocp_b200_fb_problem_default.argtypes = [C.POINTER(FbProblem)]
         L.idocp_b200_fb_total_weight.restype = C.c_double
         L.idocp_b200_fb_contact_frame_positions.argtypes = [_dp, _dp]

@@ -940,3 +940,4 @@ extern "C" int idocp_b200_get_profile(idocp_b200_solver* h, int cap, const char*
 #include "sharded_capi.inc"
 #include "hybrid_capi.inc"
 #include "fb_capi.inc"
+#include "fb_sharded_capi.inc"

@@ -26,20 +26,32 @@ class OCPSolver:
     `problem` is a capi.FbProblem (cost weights, limits, friction); `q_ref(t)` returns the (q_ref, v_ref) pair of the
     configuration-space cost at time t (the reference's update_q_ref, a host-side function of time)."""
 
-    def __init__(self, problem, batch, q_ref=None, device=0, lib=None, max_num_events=None):
+    def __init__(self, problem, batch, q_ref=None, device=0, lib=None, max_num_events=None, devices=None):
+        """devices = [d0, d1, ...]: the batch sharded over several GPUs of this node by ONE solver object
+        (idocp_b200_fb_create_sharded: contiguous split, shared contact schedule, no collective)."""
         self.lib = lib or capi.default_library()
         self.problem = problem
         self.B = int(batch)
         self.q_ref = q_ref
         self.contact_sequence = ContactSequence(4, max_num_events or (2 * problem.max_num_impulse + 2), lib=self.lib)
         self._h = C.c_void_p()
-        self.lib.check(self.lib.L.idocp_b200_fb_create(C.byref(problem), self.contact_sequence._h, self.B, int(device),
-                                                       C.byref(self._h)))
+        self._sharded = devices is not None
+        if self._sharded:
+            dev = (C.c_int * len(devices))(*[int(d) for d in devices])
+            self.lib.check(self.lib.L.idocp_b200_fb_create_sharded(C.byref(problem), self.contact_sequence._h, self.B, dev, len(devices),
+                                                                   C.byref(self._h)))
+        else:
+            self.lib.check(self.lib.L.idocp_b200_fb_create(C.byref(problem), self.contact_sequence._h, self.B, int(device),
+                                                           C.byref(self._h)))
         self._chain = []
+
+    def _f(self, name):
+        """The C-ABI entry point `name` of this solver: idocp_b200_fb_<name> or its sharded twin (same arguments)."""
+        return getattr(self.lib.L, ("idocp_b200_fb_sharded_" if self._sharded else "idocp_b200_fb_") + name)
 
     def __del__(self):
         if getattr(self, "_h", None):
-            self.lib.L.idocp_b200_fb_destroy(self._h)
+            (self.lib.L.idocp_b200_fb_sharded_destroy if self._sharded else self.lib.L.idocp_b200_fb_destroy)(self._h)
             self._h = None
 
     # ---- contact schedule (ocp_solver.cpp:173-194) ----
@@ -64,7 +76,7 @@ class OCPSolver:
         per = 1 if v.ndim == 2 else 0
         if per and v.shape[0] != self.B:
             raise ValueError("per-instance value must have %d rows" % self.B)
-        self.lib.check(self.lib.L.idocp_b200_fb_set_solution(self._h, name.encode(), capi.dptr(v), per))
+        self.lib.check(self._f("set_solution")(self._h, name.encode(), capi.dptr(v), per))
 
     def discretize(self, t):
         cap = capi.MAX_GRID + 1 + 3 * capi.MAX_EVENTS
@@ -72,7 +84,7 @@ class OCPSolver:
         tt, dt = np.zeros(cap), np.zeros(cap)
         dimf, dimi = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
         ip = C.POINTER(C.c_int)
-        n = self.lib.check(self.lib.L.idocp_b200_fb_discretize(self._h, float(t), cap, kind.ctypes.data_as(ip),
+        n = self.lib.check(self._f("discretize")(self._h, float(t), cap, kind.ctypes.data_as(ip),
                                                                index.ctypes.data_as(ip), capi.dptr(tt), capi.dptr(dt),
                                                                dimf.ctypes.data_as(ip), dimi.ctypes.data_as(ip), None))
         self._chain = [dict(kind=int(kind[e]), index=int(index[e]), t=float(tt[e]), dt=float(dt[e]), dimf=int(dimf[e]),
@@ -88,13 +100,13 @@ class OCPSolver:
             q_ref = np.ascontiguousarray(q_ref, dtype=np.float64)
             v_ref = np.ascontiguousarray(v_ref, dtype=np.float64)
             kind = KIND_GRID if el["kind"] == KIND_TERMINAL else el["kind"]
-            self.lib.check(self.lib.L.idocp_b200_fb_set_cost_reference(self._h, kind, el["index"], capi.dptr(q_ref),
+            self.lib.check(self._f("set_cost_reference")(self._h, kind, el["index"], capi.dptr(q_ref),
                                                                        capi.dptr(v_ref)))
         return chain
 
     def initConstraints(self, t):
         self._sample_reference(t)
-        self.lib.check(self.lib.L.idocp_b200_fb_init_constraints(self._h, float(t)))
+        self.lib.check(self._f("init_constraints")(self._h, float(t)))
         self.discretize(t)
 
     def _state(self, q, v):
@@ -105,13 +117,15 @@ class OCPSolver:
     def updateSolution(self, t, q, v, line_search=False):
         self._sample_reference(t)
         q, v = self._state(q, v)
-        self.lib.check(self.lib.L.idocp_b200_fb_update_solution(self._h, float(t), capi.dptr(q), capi.dptr(v), int(line_search)))
+        self.lib.check(self._f("update_solution")(self._h, float(t), capi.dptr(q), capi.dptr(v), int(line_search)))
 
     def updateSolutionResident(self, t, line_search=False):
         """updateSolution with the initial states and the cost reference already resident on the device."""
-        self.lib.check(self.lib.L.idocp_b200_fb_update_solution(self._h, float(t), None, None, int(line_search)))
+        self.lib.check(self._f("update_solution")(self._h, float(t), None, None, int(line_search)))
 
     def stream(self):
+        if self._sharded:
+            raise capi.Idocp_b200Error("stream(): a sharded solver has one stream per device")
         p = C.c_void_p()
         self.lib.check(self.lib.L.idocp_b200_fb_stream(self._h, C.byref(p)))
         return p.value or 0
@@ -119,31 +133,31 @@ class OCPSolver:
     def computeKKTResidual(self, t, q, v):
         self._sample_reference(t)
         q, v = self._state(q, v)
-        self.lib.check(self.lib.L.idocp_b200_fb_compute_kkt_residual(self._h, float(t), capi.dptr(q), capi.dptr(v)))
+        self.lib.check(self._f("compute_kkt_residual")(self._h, float(t), capi.dptr(q), capi.dptr(v)))
 
     def setStrictDiscretization(self, strict):
         """strict (default): a schedule that cannot be discretised at t raises; False: run on like a Release build of
         the reference, whose assert(isWellDefined()) is compiled out (ocp_discretizer.hxx:62-72)."""
-        self.lib.check(self.lib.L.idocp_b200_fb_set_strict_discretization(self._h, int(bool(strict))))
+        self.lib.check(self._f("set_strict_discretization")(self._h, int(bool(strict))))
 
     def clearLineSearchFilter(self):
-        self.lib.check(self.lib.L.idocp_b200_fb_clear_line_search_filter(self._h))
+        self.lib.check(self._f("clear_line_search_filter")(self._h))
 
     def KKTError(self):
         out = np.zeros(self.B)
-        self.lib.check(self.lib.L.idocp_b200_fb_kkt_error(self._h, capi.dptr(out)))
+        self.lib.check(self._f("kkt_error")(self._h, capi.dptr(out)))
         return out
 
     def stepSizes(self):
         out = np.zeros((self.B, 2))
-        self.lib.check(self.lib.L.idocp_b200_fb_get_step_sizes(self._h, capi.dptr(out)))
+        self.lib.check(self._f("get_step_sizes")(self._h, capi.dptr(out)))
         return out
 
     def get(self, stage, name):
         """Field `name` of chain stage `stage` for every instance: (B, dim)."""
         dim = _FIELD_DIMS.get(name, NV)
         out = np.zeros((self.B, dim))
-        got = self.lib.check(self.lib.L.idocp_b200_fb_get(self._h, int(stage), name.encode(), capi.dptr(out)))
+        got = self.lib.check(self._f("get")(self._h, int(stage), name.encode(), capi.dptr(out)))
         assert got == dim, (name, got, dim)
         return out
 
@@ -167,14 +181,16 @@ class OCPSolver:
         return self._chain
 
     def sync(self):
-        self.lib.check(self.lib.L.idocp_b200_fb_sync(self._h))
+        self.lib.check(self._f("sync")(self._h))
 
     def launchCount(self):
         n = C.c_longlong()
-        self.lib.check(self.lib.L.idocp_b200_fb_launch_count(self._h, C.byref(n)))
+        self.lib.check(self._f("launch_count")(self._h, C.byref(n)))
         return n.value
 
     def setProfiling(self, enabled):
+        if self._sharded:
+            raise capi.Idocp_b200Error("profiling is per single-device solver")
         self.lib.check(self.lib.L.idocp_b200_fb_set_profiling(self._h, int(enabled)))
 
     def getProfile(self):

@@ -354,6 +354,30 @@ double idocp_b200_fb_total_weight(void);                               /* Robot:
 /* Robot::updateFrameKinematics(q) + getContactPoints (robot.hxx:233-238,737-743): out[4][3] */
 int idocp_b200_fb_contact_frame_positions(const double* q, double* out);
 
+/* The hybrid OCPSolver over several GPUs of one node (twin of idocp_b200_create_sharded): one single-device solver per entry
+ * of `devices`, the batch split contiguously, the contact sequence shared; every entry point has the signature of its
+ * idocp_b200_fb_* counterpart with the caller's arrays covering the WHOLE batch.  Bit-identical to one solver over the whole
+ * batch (tests/test_sharded_solver.py). */
+typedef struct idocp_b200_fb_sharded idocp_b200_fb_sharded; /* opaque */
+int idocp_b200_fb_create_sharded(const idocp_b200_fb_problem* problem, const idocp_b200_contact_sequence* contact_sequence, int batch,
+                                 const int* devices, int n_devices, idocp_b200_fb_sharded** out);
+int idocp_b200_fb_sharded_destroy(idocp_b200_fb_sharded* s);
+int idocp_b200_fb_sharded_num_shards(const idocp_b200_fb_sharded* s, int* n, int* first);
+int idocp_b200_fb_sharded_set_solution(idocp_b200_fb_sharded* s, const char* name, const double* value, int per_instance);
+int idocp_b200_fb_sharded_set_cost_reference(idocp_b200_fb_sharded* s, int kind, int index, const double* q_ref, const double* v_ref);
+int idocp_b200_fb_sharded_discretize(idocp_b200_fb_sharded* s, double t, int cap, int* kind, int* index, double* stage_t, double* dt,
+                                     int* dimf, int* dimi, int* active);
+int idocp_b200_fb_sharded_init_constraints(idocp_b200_fb_sharded* s, double t);
+int idocp_b200_fb_sharded_set_strict_discretization(idocp_b200_fb_sharded* s, int strict);
+int idocp_b200_fb_sharded_update_solution(idocp_b200_fb_sharded* s, double t, const double* q, const double* v, int line_search);
+int idocp_b200_fb_sharded_compute_kkt_residual(idocp_b200_fb_sharded* s, double t, const double* q, const double* v);
+int idocp_b200_fb_sharded_kkt_error(idocp_b200_fb_sharded* s, double* out /* [batch] */);
+int idocp_b200_fb_sharded_clear_line_search_filter(idocp_b200_fb_sharded* s);
+int idocp_b200_fb_sharded_get_step_sizes(idocp_b200_fb_sharded* s, double* out /* [batch][2] */);
+int idocp_b200_fb_sharded_get(idocp_b200_fb_sharded* s, int stage, const char* name, double* out);
+int idocp_b200_fb_sharded_sync(idocp_b200_fb_sharded* s);
+int idocp_b200_fb_sharded_launch_count(idocp_b200_fb_sharded* s, long long* out);
+
 const char* idocp_b200_last_error(void);
 const char* idocp_b200_version(void);
 

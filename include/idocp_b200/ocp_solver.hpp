@@ -277,6 +277,12 @@ class OCPSolver {
   OCPSolver(const Robot& robot, const std::shared_ptr<CostFunction>& cost,
             const std::shared_ptr<Constraints>& constraints, const double T, const int N, const int max_num_impulse = 0,
             const int nthreads = 1, const int batch = 1, const int device = 0)
+      : OCPSolver(robot, cost, constraints, T, N, max_num_impulse, nthreads, batch, std::vector<int>{device}, false) {}
+  // the batch sharded over several GPUs of this node by ONE solver object (idocp_b200_fb_create_sharded): the GPU counterpart
+  // of the reference's nthreads
+  OCPSolver(const Robot& robot, const std::shared_ptr<CostFunction>& cost,
+            const std::shared_ptr<Constraints>& constraints, const double T, const int N, const int max_num_impulse,
+            const int nthreads, const int batch, const std::vector<int>& devices, const bool sharded = true)
       : cost_(cost), batch_(batch) {
     if (T <= 0) detail::die("invalid value: T must be positive!");
     if (N <= 0) detail::die("invalid value: N must be positive!");
@@ -312,9 +318,16 @@ class OCPSolver {
     idocp_b200_contact_sequence* cs = nullptr;
     detail::check(idocp_b200_contact_sequence_create(4, 2 * max_num_impulse + 2, &cs));
     cs_.reset(cs, [](idocp_b200_contact_sequence* x) { idocp_b200_contact_sequence_destroy(x); });
-    idocp_b200_fb_solver* h = nullptr;
-    detail::check(idocp_b200_fb_create(&p, cs, batch, device, &h));
-    h_.reset(h, [](idocp_b200_fb_solver* x) { idocp_b200_fb_destroy(x); });
+    if (devices.empty()) detail::die("idocp_b200: OCPSolver needs at least one device");
+    if (sharded) {
+      idocp_b200_fb_sharded* sh = nullptr;
+      detail::check(idocp_b200_fb_create_sharded(&p, cs, batch, devices.data(), static_cast<int>(devices.size()), &sh));
+      sh_.reset(sh, [](idocp_b200_fb_sharded* x) { idocp_b200_fb_sharded_destroy(x); });
+    } else {
+      idocp_b200_fb_solver* h = nullptr;
+      detail::check(idocp_b200_fb_create(&p, cs, batch, devices[0], &h));
+      h_.reset(h, [](idocp_b200_fb_solver* x) { idocp_b200_fb_destroy(x); });
+    }
     prob_ = p;
   }
   int batch() const { return batch_; }
@@ -338,17 +351,17 @@ class OCPSolver {
   }
   // setSolution(name, value): broadcast to every instance and stage ("f": one 3-vector for every contact)
   void setSolution(const std::string& name, const VectorXd& value) {
-    detail::check(idocp_b200_fb_set_solution(h_.get(), name.c_str(), value.data(), 0));
+    detail::check(fb_set_solution(name.c_str(), value.data(), 0));
   }
   void setSolution(const std::string& name, const Vector3d& value) {
-    detail::check(idocp_b200_fb_set_solution(h_.get(), name.c_str(), value.d, 0));
+    detail::check(fb_set_solution(name.c_str(), value.d, 0));
   }
   void setSolution(const std::string& name, const double* value_per_instance) {
-    detail::check(idocp_b200_fb_set_solution(h_.get(), name.c_str(), value_per_instance, 1));
+    detail::check(fb_set_solution(name.c_str(), value_per_instance, 1));
   }
   void initConstraints(const double t) {
     sampleReference(t);
-    detail::check(idocp_b200_fb_init_constraints(h_.get(), t));
+    detail::check(fb_init_constraints(t));
   }
   void updateSolution(const double t, const VectorXd& q, const VectorXd& v, const bool line_search = false) {
     replicate(q, v);
@@ -356,7 +369,7 @@ class OCPSolver {
   }
   void updateSolution(const double t, const double* q, const double* v, const bool line_search = false) {
     sampleReference(t);
-    detail::check(idocp_b200_fb_update_solution(h_.get(), t, q, v, line_search ? 1 : 0));
+    detail::check(fb_update_solution(t, q, v, line_search ? 1 : 0));
   }
   void computeKKTResidual(const double t, const VectorXd& q, const VectorXd& v) {
     replicate(q, v);
@@ -364,15 +377,15 @@ class OCPSolver {
   }
   void computeKKTResidual(const double t, const double* q, const double* v) {
     sampleReference(t);
-    detail::check(idocp_b200_fb_compute_kkt_residual(h_.get(), t, q, v));
+    detail::check(fb_compute_kkt_residual(t, q, v));
   }
-  void clearLineSearchFilter() { detail::check(idocp_b200_fb_clear_line_search_filter(h_.get())); }
+  void clearLineSearchFilter() { detail::check(fb_clear_line_search_filter()); }
   // assert(isWellDefined()) of OCPDiscretizer::discretizeOCP as a run-time error (default) or ignored like a Release build
-  void setStrictDiscretization(bool strict) { detail::check(idocp_b200_fb_set_strict_discretization(h_.get(), strict ? 1 : 0)); }
+  void setStrictDiscretization(bool strict) { detail::check(fb_set_strict_discretization(strict ? 1 : 0)); }
   double KKTError() { return KKTErrors()[0]; }
   std::vector<double> KKTErrors() {
     std::vector<double> out(batch_);
-    detail::check(idocp_b200_fb_kkt_error(h_.get(), out.data()));
+    detail::check(fb_kkt_error(out.data()));
     return out;
   }
   // getSolution(name): the grid stages 0..N (q, v) or 0..N-1 (a, f, u) of one instance (ocp_solver.cpp:244-280)
@@ -383,7 +396,7 @@ class OCPSolver {
     for (int e = 0; e < n; ++e) {
       const bool grid = kind_[e] == 0, terminal = kind_[e] == 4;
       if (!(grid || (terminal && (name == "q" || name == "v")))) continue;
-      const int dim = idocp_b200_fb_get(h_.get(), e, name.c_str(), buf.data());
+      const int dim = fb_get(e, name.c_str(), buf.data());
       detail::check(dim);
       VectorXd x(name == "f" ? dimf_[e] : dim);
       if (name == "f") {   // f_stack(): the active contacts only
@@ -404,7 +417,7 @@ class OCPSolver {
     for (int e = 0; e < n; ++e) {
       if (kind_[e] != 0 || index_[e] != time_stage) continue;
       std::vector<double> buf(static_cast<size_t>(batch_) * 12 * 36);
-      detail::check(idocp_b200_fb_get(h_.get(), e, "K", buf.data()));
+      detail::check(fb_get(e, "K", buf.data()));
       Kq.assign(12 * 18, 0.0);
       Kv.assign(12 * 18, 0.0);
       for (int r = 0; r < 12; ++r)
@@ -416,7 +429,7 @@ class OCPSolver {
     }
     detail::die("invalid argument: time_stage outside the horizon");
   }
-  void sync() { detail::check(idocp_b200_fb_sync(h_.get())); }
+  void sync() { detail::check(fb_sync()); }
   idocp_b200_fb_solver* handle() { return h_.get(); }
   // time of the first scheduled discrete event (impulse or lift); false when the schedule has none
   bool firstEventTime(double& time) const {
@@ -437,7 +450,7 @@ class OCPSolver {
     return any;
   }
   // first control input of every instance: out [batch][12]
-  void getFirstControlInput(double* out) { detail::check(idocp_b200_fb_get(h_.get(), 0, "u", out)); }
+  void getFirstControlInput(double* out) { detail::check(fb_get(0, "u", out)); }
 
  private:
   static void pack(const ContactStatus& s, std::vector<int>& a, std::vector<double>& pts) {
@@ -451,7 +464,7 @@ class OCPSolver {
     const int cap = IDOCP_B200_MAX_GRID + 1 + 3 * IDOCP_B200_MAX_EVENTS;
     kind_.assign(cap, 0); index_.assign(cap, 0); t_.assign(cap, 0.0); dimf_.assign(cap, 0);
     std::vector<int> act(static_cast<size_t>(cap) * 4, 0);
-    const int n = idocp_b200_fb_discretize(h_.get(), t_last_, cap, kind_.data(), index_.data(), t_.data(), nullptr, dimf_.data(), nullptr,
+    const int n = fb_discretize(t_last_, cap, kind_.data(), index_.data(), t_.data(), nullptr, dimf_.data(), nullptr,
                                            act.data());
     detail::check(n);
     active_.assign(n, {0, 0, 0, 0});
@@ -469,7 +482,7 @@ class OCPSolver {
       cost_->fbConfig()->update_q_ref(t_[e], q_ref);
       const int kind = kind_[e] == 4 ? 0 : kind_[e];
       const VectorXd v_ref = cost_->fbConfig()->v_ref(t_[e]);
-      detail::check(idocp_b200_fb_set_cost_reference(h_.get(), kind, index_[e], q_ref.data(), v_ref.data()));
+      detail::check(fb_set_cost_reference(kind, index_[e], q_ref.data(), v_ref.data()));
     }
   }
   void replicate(const VectorXd& q, const VectorXd& v) {
@@ -485,6 +498,18 @@ class OCPSolver {
   std::shared_ptr<CostFunction> cost_;
   std::shared_ptr<idocp_b200_contact_sequence> cs_;
   std::shared_ptr<idocp_b200_fb_solver> h_;
+  std::shared_ptr<idocp_b200_fb_sharded> sh_;   // set instead of h_ by the device-list constructor
+  // the C-ABI entry points of this solver: single-device or sharded (same arguments behind the handle)
+#define IDOCP_B200_FB_FWD(name)                                                                       \
+  template <typename... Args>                                                                         \
+  int fb_##name(Args... args) {                                                                       \
+    return sh_ ? idocp_b200_fb_sharded_##name(sh_.get(), args...) : idocp_b200_fb_##name(h_.get(), args...); \
+  }
+  IDOCP_B200_FB_FWD(set_solution) IDOCP_B200_FB_FWD(init_constraints) IDOCP_B200_FB_FWD(update_solution)
+  IDOCP_B200_FB_FWD(compute_kkt_residual) IDOCP_B200_FB_FWD(clear_line_search_filter) IDOCP_B200_FB_FWD(set_strict_discretization)
+  IDOCP_B200_FB_FWD(kkt_error) IDOCP_B200_FB_FWD(get) IDOCP_B200_FB_FWD(sync) IDOCP_B200_FB_FWD(discretize)
+  IDOCP_B200_FB_FWD(set_cost_reference)
+#undef IDOCP_B200_FB_FWD
   idocp_b200_fb_problem prob_;
   int batch_ = 1;
   double t_last_ = 0.0;

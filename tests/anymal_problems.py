@@ -206,7 +206,7 @@ class StandingBenchmarkProblem(TrottingProblem):
         return Q_STANDING.copy()
 
 
-def make_product_solver(pr, lib, fb, batch, q0=None, v0=None, t=0.0):
+def make_product_solver(pr, lib, fb, batch, q0=None, v0=None, t=0.0, devices=None):
     """The product's OCPSolver (idocp_b200/ocp_solver.py over the C-ABI) set up as the example's main() does; q0 / v0
     may be (batch, dim) arrays of per-instance initial states (also used as the initial guess, like the example)."""
     import ctypes as C
@@ -214,7 +214,7 @@ def make_product_solver(pr, lib, fb, batch, q0=None, v0=None, t=0.0):
     p = I.FbProblem()
     assert C.sizeof(p) == C.sizeof(pr.problem)
     C.memmove(C.byref(p), C.byref(pr.problem), C.sizeof(p))
-    solver = I.OCPSolver(p, batch, q_ref=lambda tt: (pr.q_ref(tt), pr.v_ref), lib=lib, max_num_events=60)
+    solver = I.OCPSolver(p, batch, q_ref=lambda tt: (pr.q_ref(tt), pr.v_ref), lib=lib, max_num_events=60, devices=devices)
     ocs = pr.contact_sequence(fb)
     n_phases = ocs.counts()[0]
     a, pts = ocs.phase(0)

@@ -271,6 +271,22 @@ def test_contact_distance_example_equals_the_oracle():
     assert kkt[-1] < 1e-8
 
 
+@pytest.mark.gpu
+def test_anymal_trotting_example_sharded_reproduces_golden_convergence():
+    """OCPSolver(robot, cost, constraints, T, N, max_num_impulse, nthreads, batch, devices): the hybrid solver sharded over a
+    device list by the C++ class itself (idocp_b200_fb_create_sharded; here two shards on device 0, one per GPU when the box has
+    several) prints the golden KKT history."""
+    import torch
+    _build_anymal()
+    n = torch.cuda.device_count()
+    devices = ",".join(str(d) for d in range(n)) if n > 1 else "0,0"
+    out = subprocess.run([ANYMAL_EXE, "5"], capture_output=True, text=True, check=True, env=dict(os.environ, IDOCP_B200_DEVICES=devices)).stdout
+    kkt = [float(x) for x in re.findall(r"KKT error(?: after iteration \d+)? = (\S+)", out)]
+    with open(os.path.join(GOLDEN, "anymal_trotting_golden.json")) as f:
+        ref = json.load(f)["kkt"]
+    assert kkt == ref
+
+
 RUNNING_EXE = os.path.join(ROOT, "build", "anymal_running")
 
 

@@ -70,3 +70,49 @@ def test_sharded_equals_single_gpu(gpu_lib, kind):
     n = torch.cuda.device_count()
     if n > 1:
         run_sharded_equals_single(gpu_lib, list(range(n)), kind, batch=8 * n + 3, iters=4)
+
+
+# ---- the hybrid OCPSolver of the floating-base robot over several devices (idocp_b200_fb_create_sharded) ----
+def run_fb_sharded_equals_single(lib, devices, batch=5, iters=3):
+    import sys
+    import os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+    import anymal_problems as ap
+    import fb_py
+    fb_py.lib()
+    pr = ap.with_nonlinear_cones_and_acceleration_limits(ap.TrottingProblem())
+    rng = np.random.default_rng(8)
+    q0 = np.stack([fb_py.integrate(pr.q0, np.concatenate([rng.uniform(-0.01, 0.01, 3), rng.uniform(-0.02, 0.02, 15)])) for _ in range(batch)])
+    v0 = rng.uniform(-0.1, 0.1, (batch, 18))
+    one = ap.make_product_solver(pr, lib, fb_py, batch=batch, q0=q0, v0=v0)
+    many = ap.make_product_solver(pr, lib, fb_py, batch=batch, q0=q0, v0=v0, devices=devices)
+    assert [c["kind"] for c in one.chain()] == [c["kind"] for c in many.chain()]
+    for it in range(iters):
+        ls = it == iters - 1
+        for s in (one, many):
+            s.computeKKTResidual(0.0, q0, v0)
+        assert np.array_equal(one.KKTError(), many.KKTError(), equal_nan=True), it
+        for s in (one, many):
+            s.updateSolution(0.0, q0, v0, ls)
+        assert np.array_equal(one.stepSizes(), many.stepSizes(), equal_nan=True), it
+    many.sync()
+    for e in (0, 7, len(one.chain()) - 1):
+        for name in ("q", "v", "lmd", "gmm") + (("a", "u", "f", "slack", "dual", "K") if e < len(one.chain()) - 1 else ()):
+            assert np.array_equal(one.get(e, name), many.get(e, name), equal_nan=True), (e, name)
+    Kq1, Kv1 = one.getStateFeedbackGain(3)
+    Kq2, Kv2 = many.getStateFeedbackGain(3)
+    assert np.array_equal(Kq1, Kq2) and np.array_equal(Kv1, Kv2)
+    assert many.launchCount() > one.launchCount()
+
+
+def test_fb_sharded_equals_single_emulator(emu_lib):
+    run_fb_sharded_equals_single(emu_lib, [0, 0, 0])
+
+
+@pytest.mark.gpu
+def test_fb_sharded_equals_single_gpu(gpu_lib):
+    import torch
+    run_fb_sharded_equals_single(gpu_lib, [0, 0], batch=9, iters=4)
+    n = torch.cuda.device_count()
+    if n > 1:
+        run_fb_sharded_equals_single(gpu_lib, list(range(n)), batch=2 * n + 1, iters=3)
