@@ -15,6 +15,7 @@
 #include <memory>
 #include <sstream>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "idocp_b200/ocp_solver.hpp"   // idocp_b200.hpp + the constraint component tag classes (JointAcceleration*Limit)
@@ -136,9 +137,11 @@ void run(Solver& solver, const Setup& s, int iterations, int timing_iterations) 
   std::cout << std::setprecision(17);
   ob::ocpbenchmarker::Convergence(solver, t, s.q0, v0, iterations, false);
   if (timing_iterations > 0) ob::ocpbenchmarker::CPUTime(solver, t, s.q0, v0, timing_iterations, false);
-  if (const char* dir = std::getenv("IDOCP_B200_SAVE_DIR")) {   // trajectory export in the reference's text format
-    for (const char* name : {"q", "v", "a", "u"}) solver.saveSolution(std::string(dir) + "/" + name + ".dat", name);
-    solver.printSolution("u");
+  if constexpr (std::is_base_of<ob::detail::SolverBase, Solver>::value) {
+    if (const char* dir = std::getenv("IDOCP_B200_SAVE_DIR")) {   // trajectory export in the reference's text format
+      for (const char* name : {"q", "v", "a", "u"}) solver.saveSolution(std::string(dir) + "/" + name + ".dat", name);
+      solver.printSolution("u");
+    }
   }
 }
 
@@ -182,8 +185,19 @@ int main(int argc, char* argv[]) {
     solver.setSolution("v", ob::VectorXd::Zero(7));
     solver.initBackwardCorrection(0.0);
     run(solver, s, iterations, timing);
+  } else if (kind == "ocp") {
+    // the general class names on the fixed-base robot (examples/iiwa14/ocp_benchmark.cpp, parnmpc_benchmark.cpp): they forward
+    // to the specialised solvers
+    ob::OCPSolver solver(robot, s.cost, constraints, s.T, s.N, 0, nthreads, batch);
+    run(solver, s, iterations, timing);
+  } else if (kind == "parnmpc") {
+    ob::ParNMPCSolver solver(robot, s.cost, constraints, s.T, s.N, 0, nthreads, batch);
+    solver.setSolution("q", s.q0);
+    solver.setSolution("v", ob::VectorXd::Zero(7));
+    solver.initBackwardCorrection(0.0);
+    run(solver, s, iterations, timing);
   } else {
-    std::cerr << "unknown solver '" << kind << "' (unocp | unparnmpc)\n";
+    std::cerr << "unknown solver '" << kind << "' (unocp | unparnmpc | ocp | parnmpc)\n";
     return EXIT_FAILURE;
   }
   return 0;

@@ -288,7 +288,16 @@ class OCPSolver {
     if (N <= 0) detail::die("invalid value: N must be positive!");
     if (max_num_impulse < 0) detail::die("invalid value: max_num_impulse must be non-negative!");
     if (nthreads <= 0) detail::die("invalid value: nthreads must be positive!");
-    if (!robot.hasFloatingBase()) detail::die("idocp_b200: OCPSolver is built for the floating-base robot, Robot(path_to_urdf, contact_frames)");
+    if (!robot.hasFloatingBase()) {
+      // OCPSolver on a fixed-base robot without contacts (examples/iiwa14/ocp_benchmark.cpp): the same Newton iteration as
+      // UnOCPSolver -- the general class eliminates (a, f) through ContactDynamics with dimf = 0, the specialised one u through
+      // UnconstrainedDynamics; exact eliminations of one KKT system, so the iterates agree up to rounding (stated, not
+      // checkable here: the reference cannot be built).  Forwarded to the specialised GPU solver.
+      if (max_num_impulse != 0) detail::die("idocp_b200: a fixed-base robot has no contacts: max_num_impulse must be 0");
+      un_ = sharded ? std::make_shared<UnOCPSolver>(robot, cost, constraints, T, N, nthreads, batch, devices)
+                    : std::make_shared<UnOCPSolver>(robot, cost, constraints, T, N, nthreads, batch, devices[0]);
+      return;
+    }
     if (!cost || !constraints) detail::die("idocp_b200: cost and constraints must not be null");
     idocp_b200_fb_problem p = robot.fbLimits();
     p.T = T; p.N = N; p.max_num_impulse = max_num_impulse;
@@ -333,6 +342,7 @@ class OCPSolver {
   int batch() const { return batch_; }
   // contact schedule (ocp_solver.cpp:173-194)
   void setContactStatusUniformly(const ContactStatus& s) {
+    if (un_) { if (s.maxPointContacts() != 0) detail::die("idocp_b200: a fixed-base robot has no contacts"); return; }
     std::vector<int> a; std::vector<double> pts;
     pack(s, a, pts);
     detail::check(idocp_b200_contact_sequence_set_uniform(cs_.get(), a.data(), pts.data()));
@@ -351,6 +361,7 @@ class OCPSolver {
   }
   // setSolution(name, value): broadcast to every instance and stage ("f": one 3-vector for every contact)
   void setSolution(const std::string& name, const VectorXd& value) {
+    if (un_) { un_->setSolution(name, value); return; }
     detail::check(fb_set_solution(name.c_str(), value.data(), 0));
   }
   void setSolution(const std::string& name, const Vector3d& value) {
@@ -360,36 +371,46 @@ class OCPSolver {
     detail::check(fb_set_solution(name.c_str(), value_per_instance, 1));
   }
   void initConstraints(const double t) {
+    if (un_) { un_->initConstraints(); return; }
     sampleReference(t);
     detail::check(fb_init_constraints(t));
   }
   void updateSolution(const double t, const VectorXd& q, const VectorXd& v, const bool line_search = false) {
+    if (un_) { un_->updateSolution(t, q, v, line_search); return; }
     replicate(q, v);
     updateSolution(t, q_.data(), v_.data(), line_search);
   }
   void updateSolution(const double t, const double* q, const double* v, const bool line_search = false) {
+    if (un_) { un_->updateSolution(t, q, v, line_search); return; }
     sampleReference(t);
     detail::check(fb_update_solution(t, q, v, line_search ? 1 : 0));
   }
   void computeKKTResidual(const double t, const VectorXd& q, const VectorXd& v) {
+    if (un_) { un_->computeKKTResidual(t, q, v); return; }
     replicate(q, v);
     computeKKTResidual(t, q_.data(), v_.data());
   }
   void computeKKTResidual(const double t, const double* q, const double* v) {
+    if (un_) { un_->computeKKTResidual(t, q, v); return; }
     sampleReference(t);
     detail::check(fb_compute_kkt_residual(t, q, v));
   }
-  void clearLineSearchFilter() { detail::check(fb_clear_line_search_filter()); }
+  void clearLineSearchFilter() {
+    if (un_) { un_->clearLineSearchFilter(); return; }
+    detail::check(fb_clear_line_search_filter());
+  }
   // assert(isWellDefined()) of OCPDiscretizer::discretizeOCP as a run-time error (default) or ignored like a Release build
   void setStrictDiscretization(bool strict) { detail::check(fb_set_strict_discretization(strict ? 1 : 0)); }
   double KKTError() { return KKTErrors()[0]; }
   std::vector<double> KKTErrors() {
+    if (un_) return un_->KKTErrors();
     std::vector<double> out(batch_);
     detail::check(fb_kkt_error(out.data()));
     return out;
   }
   // getSolution(name): the grid stages 0..N (q, v) or 0..N-1 (a, f, u) of one instance (ocp_solver.cpp:244-280)
   std::vector<VectorXd> getSolution(const std::string& name, const int instance = 0) {
+    if (un_) return un_->getSolution(name, instance);
     const int n = discretize();
     std::vector<VectorXd> out;
     std::vector<double> buf(static_cast<size_t>(batch_) * 36 * 36);
@@ -429,7 +450,10 @@ class OCPSolver {
     }
     detail::die("invalid argument: time_stage outside the horizon");
   }
-  void sync() { detail::check(fb_sync()); }
+  void sync() {
+    if (un_) { un_->sync(); return; }
+    detail::check(fb_sync());
+  }
   idocp_b200_fb_solver* handle() { return h_.get(); }
   // time of the first scheduled discrete event (impulse or lift); false when the schedule has none
   bool firstEventTime(double& time) const {
@@ -499,6 +523,7 @@ class OCPSolver {
   std::shared_ptr<idocp_b200_contact_sequence> cs_;
   std::shared_ptr<idocp_b200_fb_solver> h_;
   std::shared_ptr<idocp_b200_fb_sharded> sh_;   // set instead of h_ by the device-list constructor
+  std::shared_ptr<UnOCPSolver> un_;             // fixed-base robot without contacts: the specialised solver does the work
   // the C-ABI entry points of this solver: single-device or sharded (same arguments behind the handle)
 #define IDOCP_B200_FB_FWD(name)                                                                       \
   template <typename... Args>                                                                         \
@@ -516,6 +541,44 @@ class OCPSolver {
   std::vector<int> kind_, index_, dimf_;
   std::vector<double> t_, q_, v_;
   std::vector<std::array<int, 4>> active_;
+};
+
+// ParNMPCSolver(robot, cost, constraints, T, N, max_num_impulse, nthreads) (include/idocp/ocp/parnmpc_solver.hpp:41-193).
+// Fixed-base robot without contacts (examples/iiwa14/parnmpc_benchmark.cpp): forwarded to UnParNMPCSolver, the specialisation the
+// reference ships for exactly this case (same backward-correction iteration with u eliminated first; iterates agree up to
+// rounding -- stated, not checkable here).  Floating-base robot with contacts: SURVEY 8(f1), NOT implemented -- the constructor
+// says so and stops, it never falls back to anything else.
+class ParNMPCSolver {
+ public:
+  ParNMPCSolver(const Robot& robot, const std::shared_ptr<CostFunction>& cost, const std::shared_ptr<Constraints>& constraints,
+                const double T, const int N, const int max_num_impulse = 0, const int nthreads = 1, const int batch = 1,
+                const int device = 0) {
+    if (robot.hasFloatingBase())
+      detail::die("idocp_b200: ParNMPCSolver for the floating-base robot with contacts is not implemented (SURVEY.md 8(f1)); "
+                  "use OCPSolver");
+    if (max_num_impulse != 0) detail::die("idocp_b200: a fixed-base robot has no contacts: max_num_impulse must be 0");
+    un_ = std::make_shared<UnParNMPCSolver>(robot, cost, constraints, T, N, nthreads, batch, device);
+  }
+  void initConstraints(const double = 0.0) { un_->initConstraints(); }
+  void initBackwardCorrection(const double t) { un_->initBackwardCorrection(t); }
+  void updateSolution(const double t, const VectorXd& q, const VectorXd& v, const bool line_search = false) {
+    un_->updateSolution(t, q, v, line_search);
+  }
+  void computeKKTResidual(const double t, const VectorXd& q, const VectorXd& v) { un_->computeKKTResidual(t, q, v); }
+  double KKTError() { return un_->KKTError(); }
+  std::vector<double> KKTErrors() { return un_->KKTErrors(); }
+  void setSolution(const std::string& name, const VectorXd& value) { un_->setSolution(name, value); }
+  void setSolution(const std::string&, const Vector3d&) { detail::die("idocp_b200: a fixed-base robot has no contact forces"); }
+  std::vector<VectorXd> getSolution(const std::string& name, const int instance = 0) { return un_->getSolution(name, instance); }
+  void clearLineSearchFilter() { un_->clearLineSearchFilter(); }
+  bool isCurrentSolutionFeasible() { return un_->isCurrentSolutionFeasible(); }
+  void setContactStatusUniformly(const ContactStatus& s) { if (s.maxPointContacts() != 0) detail::die("idocp_b200: a fixed-base robot has no contacts"); }
+  void pushBackContactStatus(const ContactStatus&, const double) { detail::die("idocp_b200: a fixed-base robot has no contacts"); }
+  void popBackContactStatus() { detail::die("idocp_b200: a fixed-base robot has no contacts"); }
+  void popFrontContactStatus() { detail::die("idocp_b200: a fixed-base robot has no contacts"); }
+  void sync() { un_->sync(); }
+ private:
+  std::shared_ptr<UnParNMPCSolver> un_;
 };
 
 // One control tick of a BATCH of MPC loops around OCPSolver (Python twin: idocp_b200/mpc.py).  idocp has no

@@ -38,6 +38,10 @@ def test_example_compiles_and_fails_loudly_without_gpu():
     ("benchmark", "unparnmpc", 20, "solvers_golden.json", "unparnmpc_benchmark_reference_instance"),
     ("task", "unocp", 30, "solvers_golden.json", "task_space_ocp_unocp"),
     ("task", "unparnmpc", 30, "solvers_golden.json", "task_space_ocp_unparnmpc"),
+    # OCPSolver / ParNMPCSolver on the fixed-base robot (examples/iiwa14/ocp_benchmark.cpp, parnmpc_benchmark.cpp): the general
+    # class names forward to the specialised solvers
+    ("benchmark", "ocp", 50, "unocp_golden.json", "unocp_benchmark_reference_instance"),
+    ("benchmark", "parnmpc", 20, "solvers_golden.json", "unparnmpc_benchmark_reference_instance"),
 ])
 def test_example_reproduces_golden_convergence(problem, kind, iters, golden_file, key):
     """examples/iiwa14_batch.cpp drives the C++ host classes (Robot, ConfigurationSpaceCost,
@@ -416,7 +420,9 @@ def test_cpp_batched_mpc_ticks():
     assert all(abs(float(u)) < 1e4 for _, u, _ in ticks)
 
 
-REF_EXAMPLES = ["anymal/anymal_trotting.cpp", "anymal/anymal_running.cpp", "anymal/ocp_benchmark.cpp", "iiwa14/unocp_benchmark.cpp", "iiwa14/config_space_ocp.cpp",
+REF_EXAMPLES = ["anymal/anymal_trotting.cpp", "anymal/anymal_running.cpp", "anymal/anymal_jumping.cpp", "anymal/ocp_benchmark.cpp",
+                "anymal/parnmpc_benchmark.cpp", "anymal/anymal_trotting_parnmpc.cpp",     # compile; ParNMPCSolver(floating base) stops at run time: 8(f1)
+                "iiwa14/ocp_benchmark.cpp", "iiwa14/parnmpc_benchmark.cpp", "iiwa14/unocp_benchmark.cpp", "iiwa14/config_space_ocp.cpp",
                 "iiwa14/task_space_ocp.cpp", "iiwa14/unparnmpc_benchmark.cpp"]
 
 
