@@ -129,11 +129,11 @@ def test_nonlinear_cones_and_acceleration_limits_bit_exact(fb, emu_lib):
     nonlinear_cone_scenario(fb, emu_lib)
 
 
-def contact_distance_scenario(fb, lib, mode, batch_states=None, iters=4):
+def contact_distance_scenario(fb, lib, mode, batch_states=None, iters=4, problem=None):
     """ContactDistance (src/constraints/contact_distance.cpp) through the kernels vs the oracle: mode 1 = the
     reference literally (row 2 of the LOCAL frame Jacobian), mode 2 = the consistent variant; every field, all 140 constraint rows,
     KKT errors, step sizes; mode 2 starts with two iterations of the filter line search."""
-    pr = ap.TrottingProblem()
+    pr = problem or ap.TrottingProblem()
     pr.problem.enable_distance = mode
     B = 1 if batch_states is None else len(batch_states[0])
     q0 = np.tile(pr.q0, (B, 1)) if batch_states is None else batch_states[0]
@@ -173,6 +173,11 @@ def contact_distance_scenario(fb, lib, mode, batch_states=None, iters=4):
 @pytest.mark.parametrize("mode", [1, 2])
 def test_contact_distance_bit_exact(fb, emu_lib, mode):
     contact_distance_scenario(fb, emu_lib, mode)
+
+
+def test_all_f3_components_together_bit_exact(fb, emu_lib):
+    # nonlinear cones + acceleration limits + contact distances on one problem: all eleven components, 140 rows
+    contact_distance_scenario(fb, emu_lib, 2, problem=ap.with_nonlinear_cones_and_acceleration_limits(ap.TrottingProblem()), iters=3)
 
 
 def test_filter_line_search_bit_exact(fb, emu_lib):

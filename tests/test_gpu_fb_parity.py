@@ -62,6 +62,11 @@ def test_contact_distance_bit_exact(fb, gpu_lib, mode):
     contact_distance_scenario(fb, gpu_lib, mode, perturbed_states(fb, pr, 5, 13))
 
 
+def test_all_f3_components_together_bit_exact(fb, gpu_lib):
+    pr = ap.with_nonlinear_cones_and_acceleration_limits(ap.TrottingProblem())
+    contact_distance_scenario(fb, gpu_lib, 2, perturbed_states(fb, pr, 4, 17), iters=3, problem=pr)
+
+
 def test_convergence_history_identical(fb, gpu_lib):
     # examples/anymal/anymal_trotting.cpp: 25 iterations; iteration-by-iteration KKT errors equal the oracle's bits
     pr = ap.TrottingProblem()
