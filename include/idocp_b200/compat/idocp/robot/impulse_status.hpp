@@ -1,0 +1,2 @@
+// forwarding header: idocp/robot/impulse_status.hpp -> idocp_b200 (see ../../idocp_b200_compat.hpp)
+#include "../../idocp_b200_compat.hpp"

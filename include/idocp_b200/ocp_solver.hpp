@@ -543,6 +543,28 @@ class OCPSolver {
   std::vector<std::array<int, 4>> active_;
 };
 
+// hybrid/collision_checker.hxx:22-53: which contact frames are at or below the ground (z <= 0) at configuration q.  Host
+// arithmetic on the four frame positions (Robot::updateFrameKinematics), not on the solver path.
+class CollisionChecker {
+ public:
+  explicit CollisionChecker(const Robot& robot) : contact_points_(robot.maxPointContacts()) {}
+  CollisionChecker() {}
+  std::vector<bool> check(Robot& robot, const VectorXd& q) {
+    robot.updateFrameKinematics(q);
+    robot.getContactPoints(contact_points_);
+    std::vector<bool> is_impulse;
+    for (const auto& p : contact_points_) is_impulse.push_back(p[2] <= 0);
+    return is_impulse;
+  }
+  const std::vector<Vector3d>& contactFramePositions() const { return contact_points_; }
+  void printContactFramePositions() const {
+    for (size_t i = 0; i < contact_points_.size(); ++i)
+      std::cout << "contact index " << i << ": " << contact_points_[i][0] << " " << contact_points_[i][1] << " " << contact_points_[i][2] << std::endl;
+  }
+ private:
+  std::vector<Vector3d> contact_points_;
+};
+
 // ParNMPCSolver(robot, cost, constraints, T, N, max_num_impulse, nthreads) (include/idocp/ocp/parnmpc_solver.hpp:41-193).
 // Fixed-base robot without contacts (examples/iiwa14/parnmpc_benchmark.cpp): forwarded to UnParNMPCSolver, the specialisation the
 // reference ships for exactly this case (same backward-correction iteration with u eliminated first; iterates agree up to

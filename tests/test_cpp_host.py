@@ -443,3 +443,35 @@ def test_reference_examples_compile_unchanged(example):
                            "-I" + os.path.join(ROOT, "include"), os.path.join("/root/reference/examples", example),
                            "-L" + lib, "-lidocp_b200", "-Wl,-rpath," + lib, "-o", exe])
     assert os.path.exists(exe)
+
+
+def test_collision_checker_host_class(tmp_path):
+    """hybrid/collision_checker.hxx:22-53 on the host classes (no GPU involved: frame positions by host arithmetic): standing
+    robot lifted by 5 cm -> no contact; lowered by 5 cm -> all four feet at or below the ground."""
+    import __graft_entry__ as g
+    g.build_cuda()
+    src = tmp_path / "cc.cpp"
+    src.write_text("""
+#include "idocp/robot/robot.hpp"
+#include "idocp/hybrid/collision_checker.hpp"
+#include <iostream>
+int main() {
+  idocp::Robot robot("", {14, 24, 34, 44});
+  idocp::CollisionChecker checker(robot);
+  Eigen::VectorXd q(19);
+  q << 0, 0, 0.4792, 0, 0, 0, 1, -0.1, 0.7, -1.0, -0.1, -0.7, 1.0, 0.1, 0.7, -1.0, 0.1, -0.7, 1.0;
+  q.coeffRef(2) = 0.4792 + 0.05;
+  for (bool c : checker.check(robot, q)) std::cout << c;
+  q.coeffRef(2) = 0.4792 - 0.05;
+  std::cout << " ";
+  for (bool c : checker.check(robot, q)) std::cout << c;
+  std::cout << " " << checker.contactFramePositions().size() << std::endl;
+  return 0;
+}
+""")
+    lib = os.path.join(ROOT, "idocp_b200")
+    exe = str(tmp_path / "cc")
+    subprocess.check_call(["g++", "-std=c++17", "-I" + os.path.join(ROOT, "include", "idocp_b200", "compat"), "-I" + os.path.join(ROOT, "include"),
+                           str(src), "-L" + lib, "-lidocp_b200", "-Wl,-rpath," + lib, "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
+    assert out == ["0000", "1111", "4"]
