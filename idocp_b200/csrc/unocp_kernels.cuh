@@ -1009,6 +1009,9 @@ __global__ void __launch_bounds__(RIC_THREADS, IDOCP_RIC_MINB) k_riccati(const D
   if (wl == 0) {
     for (int i = 0; i < RIC_RING && i < N; ++i) issue_forward(i);
   }
+#ifdef IDOCP_RIC_SKIP_FWD   // timing experiment only: the backward sweep alone (results are wrong)
+  if (N > 0) return;
+#endif
   for (int i = 0; i < N; ++i) {
     const int e = i % RIC_RING;
     tma_bar_wait(&bars[2 + e], (i / RIC_RING) & 1);
