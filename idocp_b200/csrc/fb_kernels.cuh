@@ -1560,30 +1560,37 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
 //   Results go straight to the HBM records of the Riccati sweep (FbKKT) and of the expansion (FbExp).
 // =====================================================================================================
 struct FbDenseWork {
-  double IDC[FB_NVF], dIDCdqv[FB_NVF * FB_NX];
+  // IDC and dIDCdqv as FbLin holds them (one load).  dIDCdqv is dead once MJ_dIDC = MJtJinv dIDCdqv exists; Qafqv, formed from
+  // MJ_dIDC right after, takes its place
+  double IDC[FB_NVF];
+  union { double dIDCdqv[FB_NVF * FB_NX]; double Qafqv[FB_NVF * FB_NX]; };
   // FbLin from dCda to Fqq_prev_inv, same order
   double dCda[FB_MAXF * FB_NV];
   double lq[FB_NV], lv[FB_NV], la[FB_NV], lf[FB_MAXF], lu_passive[FB_NPASS], lu[FB_NU], Fq[FB_NV], Fv[FB_NV], P[FB_MAXF];
   double Qqq6[36], Qqq_d[FB_NV], Qvv_d[FB_NV], Quu_d[FB_NU], Qaa[FB_NV], Qff[FB_MAXF * FB_MAXF];
   double Fqq6[36], Fqv6[36], Fqq_prev_inv[36];
-  // MJtJinv, MJ_dIDC, MJ_IDC: same order as FbExp.  The joint-space inertia matrix is dead once its Cholesky factor exists
-  // (long before MJ_dIDC is formed) and shares its storage.  Phix / Phia of the switching stages stay in HBM.
+  // MJtJinv, MJ_dIDC, MJ_IDC: same order as FbExp.  The joint-space inertia matrix, its inverse and J M^-1 are dead once
+  // MJtJinv is formed (before MJ_dIDC is) and share its storage.  Phix / Phia of the switching stages stay in HBM.
   double MJtJinv[FB_NVF * FB_NVF];
   union {
     struct { double MJ_dIDC[FB_NVF * FB_NX], MJ_IDC[FB_NVF]; };
-    double Mm[FB_NV * FB_NV];
+    struct { double Mm[FB_NV * FB_NV], Minv[FB_NV * FB_NV], JMi[FB_MAXF * FB_NV], Sm[FB_MAXF * FB_MAXF]; };
   };
   double laf[FB_NVF];
   union {
-    struct { double L[FB_NV * FB_NV], rd[FB_NV], Minv[FB_NV * FB_NV], JMi[FB_MAXF * FB_NV], Sm[FB_MAXF * FB_MAXF], Ls[FB_MAXF * FB_MAXF],
-                 rds[FB_MAXF], Si[FB_MAXF * FB_MAXF]; int fail[FB_NV + 2]; } f;   // factorisation scratch (dead once MJtJinv is formed)
-    struct { double Qafqv[FB_NVF * FB_NX], Qafu[FB_NVF * FB_NV]; } c;   // condensing products
+    struct { double L[FB_NV * FB_NV], rd[FB_NV], Ls[FB_MAXF * FB_MAXF], rds[FB_MAXF], Si[FB_MAXF * FB_MAXF]; int fail[FB_NV + 2]; } f;   // factorisation scratch
+    double Qafu[FB_NVF * FB_NV];                                                                                                        // condensing product
   } s;
   int info;
 };
+// 36 KB: six CTAs share the 228 KB of an SM (43.8 KB, five CTAs, with Qafqv and M^-1 / J M^-1 in storage of their own)
+static_assert(6 * (sizeof(FbDenseWork) + 1024) <= 228 * 1024, "six CTAs of k_fb_condense per SM");
 
+#ifndef IDOCP_FB_DENSE_MINB
+#define IDOCP_FB_DENSE_MINB 6
+#endif
 static_assert(FB_MAXF * FB_NV + FB_MAXF * FB_MAXF >= FB_NV * (FB_NV + 1), "the JMi / Sm scratch holds the 18 x 19 trailing matrix of LLT(M)");
-__global__ void __launch_bounds__(128, 5) k_fb_condense(FbArrays A, const FbLin* lin) {
+__global__ void __launch_bounds__(128, IDOCP_FB_DENSE_MINB) k_fb_condense(FbArrays A, const FbLin* lin) {
   IDOCP_DYN_SMEM(FbDenseWork, wp);
   FbDenseWork& w = *wp;
   const int tid = threadIdx.x;
@@ -1627,27 +1634,27 @@ __global__ void __launch_bounds__(128, 5) k_fb_condense(FbArrays A, const FbLin*
     // shared memory (fb_inverse_warp) 44 k, against 28 k here (profiles/r2j / r2k_fb_phase_clocks.json): one warp per CTA
     // leaves the SM with five active warps
     // (the dense owner-per-element sweep fb_llt_factor_solve_cta<2, 3> took 36 barrier steps: 28 k of the 74 k cycles per stage)
-    fb_minv_tree_cta(w.Mm, w.s.f.L, w.s.f.rd, w.s.f.Minv, w.s.f.fail, &w.info, 0);
+    fb_minv_tree_cta(w.Mm, w.s.f.L, w.s.f.rd, w.Minv, w.s.f.fail, &w.info, 0);
     FB_PHASE(0, 1);
     FB_PHASE(0, 2);
-    fb_mm<FBM_SET>(dimf, n, n, w.dCda, n, 1, w.s.f.Minv, n, 1, w.s.f.JMi, n);
+    fb_mm<FBM_SET>(dimf, n, n, w.dCda, n, 1, w.Minv, n, 1, w.JMi, n);
     __syncthreads();
-    fb_mm<FBM_SET>(dimf, dimf, n, w.s.f.JMi, n, 1, w.dCda, 1, n, w.s.f.Sm, dimf);
+    fb_mm<FBM_SET>(dimf, dimf, n, w.JMi, n, 1, w.dCda, 1, n, w.Sm, dimf);
     __syncthreads();
     FB_PHASE(0, 3);
     if (dimf > 0) {
       FB_FOR(x, dimf * dimf) { const int r = x / dimf; w.s.f.Si[x] = (x - r * dimf == r) ? 1.0 : 0.0; }
       __syncthreads();
-      fb_llt_factor_solve_cta<1, 2>(w.s.f.Sm, dimf, dimf, w.s.f.Ls, dimf, w.s.f.rds, w.s.f.Si, dimf, dimf, &w.info, 100);
+      fb_llt_factor_solve_cta<1, 2>(w.Sm, dimf, dimf, w.s.f.Ls, dimf, w.s.f.rds, w.s.f.Si, dimf, dimf, &w.info, 100);
     }
     FB_PHASE(0, 4);
     FB_FOR(x, dimf * dimf) { const int r = x / dimf, c = x - r * dimf; w.MJtJinv[(n + r) * ld + n + c] = -w.s.f.Si[x]; }
-    fb_mm<FBM_SET>(n, dimf, dimf, w.s.f.JMi, 1, n, w.s.f.Si, dimf, 1, w.MJtJinv + n, ld);     // TR = (J Minv)^T S^-1
+    fb_mm<FBM_SET>(n, dimf, dimf, w.JMi, 1, n, w.s.f.Si, dimf, 1, w.MJtJinv + n, ld);     // TR = (J Minv)^T S^-1
     __syncthreads();
     {                                                                                           // TL = Minv - TR (J Minv)
-      const double* Minv = w.s.f.Minv;
+      const double* Minv = w.Minv;
       double* TL = w.MJtJinv;
-      fb_mm_f<FBM_SUB>(n, n, dimf, w.MJtJinv + n, ld, 1, w.s.f.JMi, n, 1, [=](int r, int c) { return Minv[r * n + c]; },
+      fb_mm_f<FBM_SUB>(n, n, dimf, w.MJtJinv + n, ld, 1, w.JMi, n, 1, [=](int r, int c) { return Minv[r * n + c]; },
                        [=](int r, int c, double v) { TL[r * ld + c] = v; });
     }
     FB_FOR(x, dimf * n) { const int r = x / n, c = x - r * n; w.MJtJinv[(n + r) * ld + c] = w.MJtJinv[c * ld + n + r]; }   // BL = TR^T
@@ -1659,8 +1666,8 @@ __global__ void __launch_bounds__(128, 5) k_fb_condense(FbArrays A, const FbLin*
   fb_mv<FBM_SET>(nvf, nvf, w.MJtJinv, NVF, 1, w.IDC, w.MJ_IDC);
   __syncthreads();
   FB_PHASE(0, 6);
-  double* Qafqv = w.s.c.Qafqv;
-  double* Qafu = w.s.c.Qafu;
+  double* Qafqv = w.Qafqv;
+  double* Qafu = w.s.Qafu;
   FB_FOR(x, NV * NX) { const int r = x / NX; Qafqv[x] = -w.Qaa[r] * w.MJ_dIDC[x]; }
   fb_mm<FBM_SET>(dimf, NX, dimf, w.Qff, MAXF, 1, w.MJ_dIDC + NV * NX, NX, 1, Qafqv + NV * NX, NX);
   if (!impulse) {
@@ -1779,11 +1786,11 @@ struct FbRicWork {
   double Qxx[FB_NX * FB_NX], Qxu[FB_NX * FB_NU], Quu[FB_NU * FB_NU];
   double Fqq6[36], Fqv6[36], Fvq[FB_NV * FB_NV], Fvv[FB_NV * FB_NV], Fvu[FB_NV * FB_NU];
   double lq[FB_NV], lv[FB_NV], lu[FB_NU], Fq[FB_NV], Fv[FB_NV];
-  double Phix[FB_MAXF * FB_NX], Phiu[FB_MAXF * FB_NU], P[FB_MAXF];
+  // Phix / Phiu / P (and the cM / cm of FbRic) exist on the stage before an impulse only (one or two stages of a horizon):
+  // they are operated on where they lie in HBM / L2, which keeps the CTA under 56 KB, i.e. four CTAs on an SM instead of three
   // the factorisation (same order as FbRic): on entry to a stage Pqq / Pqv / Pvv still hold the NEXT stage's P, which is dead once
   // the A^T P / B^T P products are formed, so the stage's own P is built in the same place
-  double K[FB_NU * FB_NX], k[FB_NU], Pqq[FB_NV * FB_NV], Pqv[FB_NV * FB_NV], Pvv[FB_NV * FB_NV], sq[FB_NV], sv[FB_NV], cM[FB_MAXF * FB_NX],
-      cm[FB_MAXF];
+  double K[FB_NU * FB_NX], k[FB_NU], Pqq[FB_NV * FB_NV], Pqv[FB_NV * FB_NV], Pvv[FB_NV * FB_NV], sq[FB_NV], sv[FB_NV];
   double nsq[FB_NV], nsv[FB_NV];
   // scratch whose lifetimes do not overlap shares storage
   union {
@@ -1804,7 +1811,11 @@ struct FbRicWork {
 };
 
 static_assert(offsetof(FbRicWork, L) % 16 == 0, "warp_llt.cuh reads the factor two doubles at a time");
-__global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
+static_assert(4 * (sizeof(FbRicWork) + 1024) <= 228 * 1024, "four CTAs of the backward recursion share the 228 KB of an SM");
+#ifndef IDOCP_FB_RIC_MINB
+#define IDOCP_FB_RIC_MINB 4
+#endif
+__global__ void __launch_bounds__(128, IDOCP_FB_RIC_MINB) k_fb_riccati_backward(FbArrays A) {
   IDOCP_DYN_SMEM(FbRicWork, wp);
   FbRicWork& w = *wp;
   const int tid = threadIdx.x, b = blockIdx.x, n = A.n_elems;
@@ -1843,7 +1854,11 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
     fb_load<2 * FB_NV * FB_NV + FB_NV * FB_NU>(w.Fvq, Kt.Fvq);
     fb_load<2 * FB_NV + FB_NU>(w.lq, Kt.lq);
     fb_load<2 * FB_NV>(w.Fq, Kt.Fq);
-    if (dimi > 0) fb_load<FB_MAXF * FB_NX + FB_MAXF * FB_NU + FB_MAXF>(w.Phix, Kt.Phix);
+    const double* const Phix = Kt.Phix;
+    const double* const Phiu = Kt.Phiu;
+    const double* const Pc = Kt.P;
+    double* const cM = Rc.cM;
+    double* const cm = Rc.cm;
     // the record of the stage before this one is needed ~40 k cycles from now: bring it into the L2 meanwhile
     if (e > 0) fb_prefetch_l2(&A.kkt[(size_t)A.elems[e - 1].slot * A.B + b], (int)sizeof(FbKKT));
     if (tid == 0) w.info = 0;
@@ -1940,11 +1955,11 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
           fb_llt_solve_n<FB_NU>(w.L, NU, w.rd, w.Ginv + tid, NU);
         } else if (tid >= 32 && tid < 32 + dimi) {
           const int r = tid - 32;
-          for (int c = 0; c < NU; ++c) w.DGinv[r * NU + c] = w.Phiu[r * NU + c];
+          for (int c = 0; c < NU; ++c) w.DGinv[r * NU + c] = Phiu[r * NU + c];
           fb_llt_solve_n<FB_NU>(w.L, NU, w.rd, w.DGinv + r * NU, 1);
         }
         __syncthreads();
-        fb_mm<FBM_SET>(dimi, dimi, NU, w.DGinv, NU, 1, w.Phiu, 1, NU, w.Sm, MAXF);
+        fb_mm<FBM_SET>(dimi, dimi, NU, w.DGinv, NU, 1, Phiu, 1, NU, w.Sm, MAXF);
         __syncthreads();
         fb_llt_cta<1>(w.Sm, MAXF, dimi, w.Ls, MAXF, w.rds, &w.info, 300);
         if (tid < NU) {
@@ -1960,19 +1975,19 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
         FB_FOR(x, NU * NX) w.K[x] = -w.K[x];
         if (tid < NU) w.k[tid] = -w.k[tid];
         __syncthreads();
-        fb_mm<FBM_SUB>(NU, NX, dimi, w.SinvDGinv, 1, NU, w.Phix, NX, 1, w.K, NX);
-        fb_mv<FBM_SUB>(NU, dimi, w.SinvDGinv, 1, NU, w.P, w.k);
+        fb_mm<FBM_SUB>(NU, NX, dimi, w.SinvDGinv, 1, NU, Phix, NX, 1, w.K, NX);
+        fb_mv<FBM_SUB>(NU, dimi, w.SinvDGinv, 1, NU, Pc, w.k);
         if (tid >= 64 && tid < 64 + NX) {
           const int c = tid - 64;
-          for (int r = 0; r < dimi; ++r) w.cM[r * NX + c] = w.Phix[r * NX + c];
-          fb_llt_solve(w.Ls, MAXF, w.rds, dimi, w.cM + c, NX);
+          for (int r = 0; r < dimi; ++r) cM[r * NX + c] = Phix[r * NX + c];
+          fb_llt_solve(w.Ls, MAXF, w.rds, dimi, cM + c, NX);
         } else if (tid == 127) {
-          for (int r = 0; r < dimi; ++r) w.cm[r] = w.P[r];
-          fb_llt_solve(w.Ls, MAXF, w.rds, dimi, w.cm, 1);
+          for (int r = 0; r < dimi; ++r) cm[r] = Pc[r];
+          fb_llt_solve(w.Ls, MAXF, w.rds, dimi, cm, 1);
         }
         __syncthreads();
-        fb_mm<FBM_SUB>(dimi, NX, NU, w.SinvDGinv, NU, 1, Qxu, 1, NU, w.cM, NX);
-        fb_mv<FBM_SUB>(dimi, NU, w.SinvDGinv, NU, 1, w.lu, w.cm);
+        fb_mm<FBM_SUB>(dimi, NX, NU, w.SinvDGinv, NU, 1, Qxu, 1, NU, cM, NX);
+        fb_mv<FBM_SUB>(dimi, NU, w.SinvDGinv, NU, 1, w.lu, cm);
         __syncthreads();
       }
     }
@@ -2044,7 +2059,7 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
     __syncthreads();
     FB_PHASE(1, 8);
     if (dimi > 0) {
-      fb_mm<FBM_SET>(NU, NX, dimi, w.Phiu, 1, NU, w.cM, NX, 1, w.DtM, NX);
+      fb_mm<FBM_SET>(NU, NX, dimi, Phiu, 1, NU, cM, NX, 1, w.DtM, NX);
       __syncthreads();
       fb_mm<FBM_SET>(NX, NX, NU, w.K, 1, NX, w.DtM, NX, 1, w.KtDtM, NX);
       __syncthreads();
@@ -2054,13 +2069,13 @@ __global__ void __launch_bounds__(128, 3) k_fb_riccati_backward(FbArrays A) {
         w.Pqv[x] = (w.Pqv[x] - w.KtDtM[r * NX + NV + c]) - w.KtDtM[(NV + c) * NX + r];
         w.Pvv[x] = (w.Pvv[x] - w.KtDtM[(NV + r) * NX + NV + c]) - w.KtDtM[(NV + c) * NX + NV + r];
       }
-      fb_mv<FBM_SUB>(NV, dimi, w.Phix, 1, NX, w.cm, w.sq);
-      fb_mv<FBM_SUB>(NV, dimi, w.Phix + NV, 1, NX, w.cm, w.sv);
+      fb_mv<FBM_SUB>(NV, dimi, Phix, 1, NX, cm, w.sq);
+      fb_mv<FBM_SUB>(NV, dimi, Phix + NV, 1, NX, cm, w.sv);
       __syncthreads();
     }
     FB_PHASE(1, 9);
     // store the factorisation; it stays in place as the "next" one
-    fb_copy(Rc.K, w.K, sizeof(FbRic) / sizeof(double));
+    fb_copy(Rc.K, w.K, (int)(offsetof(FbRic, cM) / sizeof(double)));
     if (tid < NV) { w.nsq[tid] = w.sq[tid]; w.nsv[tid] = w.sv[tid]; }
     FB_PHASE(1, 10);
     if (tid == 0 && w.info) {
