@@ -2118,6 +2118,13 @@ __global__ void __launch_bounds__(64) k_fb_riccati_forward(FbArrays A) {
     const FbKKT& Kt = A.kkt[(size_t)el.slot * A.B + b];
     const FbRic& Rc = A.ric[(size_t)el.slot * A.B + b];
     const double dt = el.dt;
+#ifndef IDOCP_FB_NO_PREFETCH
+    if (e + 1 < n && A.elems[e + 1].kind != FB_TERMINAL) {   // the serial chain pays the DRAM latency of every stage otherwise
+      const size_t nrec = (size_t)A.elems[e + 1].slot * A.B + b;
+      fb_prefetch_l2(A.ric[nrec].K, (NU * NX + NU) * (int)sizeof(double));
+      fb_prefetch_l2(A.kkt[nrec].Fqq6, (int)(offsetof(FbKKT, Phix) - offsetof(FbKKT, Fqq6)));
+    }
+#endif
     if (!impulse) {
       if (tid < NU) {
         double acc = Rc.K[tid * NX] * dq[0];
@@ -2185,6 +2192,12 @@ __global__ void __launch_bounds__(64) k_fb_expand(FbArrays A) {
   FbDir& Dr = A.dir[rec];
   const FbRic& Rc = A.ric[rec];
   const FbSol& S = A.sol[rec];
+#ifndef IDOCP_FB_NO_PREFETCH
+  // every thread walks its own row of P and of the expansion record below (one ascending fma chain per output): put all of the
+  // CTA's DRAM requests in flight first, so that the walks find their lines in the L2
+  fb_prefetch_l2(Rc.Pqq, (3 * NV * NV + 2 * NV) * (int)sizeof(double));
+  if (!terminal) fb_prefetch_l2(A.exp[rec].MJtJinv, (int)offsetof(FbExp, Qafqv));
+#endif
   if (tid < NV) { dx[tid] = Dr.dq[tid]; dx[NV + tid] = Dr.dv[tid]; }
   if (tid >= 32 && tid < 32 + NU) du[tid - 32] = Dr.du[tid - 32];
   __syncthreads();
@@ -2333,6 +2346,14 @@ __global__ void __launch_bounds__(64) k_fb_update(FbArrays A) {
   const FbKKT& Kt = A.kkt[rec];
   const double ap = A.steps[2 * b], ad = A.steps[2 * b + 1];
   const double dt = el.dt;
+#ifndef IDOCP_FB_NO_PREFETCH
+  if (!terminal) {   // the row walks below (see k_fb_expand)
+    const FbExp& Ep = A.exp[rec];
+    fb_prefetch_l2(Ep.MJtJinv, FB_NVF * FB_NVF * (int)sizeof(double));
+    fb_prefetch_l2(Ep.Qafqv, (int)(sizeof(FbExp) - offsetof(FbExp, Qafqv)));
+    if (!impulse) fb_prefetch_l2(Kt.Qxu, (FB_NX * FB_NV + FB_NPASS * FB_NV) * (int)sizeof(double));
+  }
+#endif
   if (tid < NV) { dx[tid] = Dr.dq[tid]; dx[NV + tid] = Dr.dv[tid]; dlmd[tid] = Dr.dlmd[tid]; dqs[tid] = Dr.dq[tid]; }
   if (tid >= 32 && tid < 32 + NU) du[tid - 32] = Dr.du[tid - 32];
   if (tid < FB_NQ) qs[tid] = S.q[tid];
