@@ -4,7 +4,7 @@ Everything numerical runs in the CUDA library ``libidocp_b200.so`` (sm_100a) beh
 ``include/idocp_b200.h``; this package only marshals arguments.  No CPU fallback exists.
 """
 from .capi import Idocp_b200Error, Library, Problem, default_library  # noqa: F401
-from .solvers import (ShardedSolver, UnOCPSolver, UnParNMPCSolver, benchmark_problem, config_space_problem,  # noqa: F401
+from .solvers import (DerivativeChecker, ShardedSolver, UnOCPSolver, UnParNMPCSolver, benchmark_problem, config_space_problem,  # noqa: F401
                       task_space_3d_problem, task_space_circle_ref, task_space_problem)
 
 __version__ = "0.1"

@@ -16,6 +16,7 @@ DEFAULT_LIBRARY = os.environ.get("IDOCP_B200_LIBRARY") or os.path.join(_HERE, "l
 
 DIMV = 7
 NUM_CONSTRAINTS = 6
+DC_DOUBLES = 323   # IDOCP_B200_DC_DOUBLES (include/idocp_b200.h)
 ROBOT_IIWA14 = 0
 SOLVER_UNOCP = 0
 SOLVER_UNPARNMPC = 1
@@ -100,7 +101,7 @@ EXPORTS = [
     "idocp_b200_update_solution_device", "idocp_b200_compute_kkt_residual",
     "idocp_b200_compute_kkt_residual_device", "idocp_b200_kkt_error", "idocp_b200_get_solution", "idocp_b200_get_stage_solution",
     "idocp_b200_get_direction", "idocp_b200_get_constraint_data", "idocp_b200_get_step_sizes",
-    "idocp_b200_get_unkkt", "idocp_b200_get_status", "idocp_b200_is_feasible",
+    "idocp_b200_get_unkkt", "idocp_b200_check_cost_derivatives", "idocp_b200_get_status", "idocp_b200_is_feasible",
     "idocp_b200_clear_line_search_filter", "idocp_b200_sync", "idocp_b200_launch_count", "idocp_b200_stream",
     "idocp_b200_set_task_reference", "idocp_b200_set_profiling", "idocp_b200_get_profile", "idocp_b200_set_pipelining",
     "idocp_b200_contact_sequence_create", "idocp_b200_contact_sequence_destroy",
@@ -162,6 +163,7 @@ class Library:
         L.idocp_b200_get_constraint_data.argtypes = [C.c_void_p, C.c_char_p, _dp]
         L.idocp_b200_get_step_sizes.argtypes = [C.c_void_p, _dp, _dp]
         L.idocp_b200_get_unkkt.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+        L.idocp_b200_check_cost_derivatives.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_double, _dp]
         L.idocp_b200_get_status.argtypes = [C.c_void_p, _ip]
         L.idocp_b200_is_feasible.argtypes = [C.c_void_p, _ip]
         L.idocp_b200_clear_line_search_filter.argtypes = [C.c_void_p]

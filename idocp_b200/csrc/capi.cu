@@ -937,6 +937,7 @@ extern "C" int idocp_b200_get_profile(idocp_b200_solver* h, int cap, const char*
   return n;
 }
 
+#include "derivative_checker.inc"
 #include "sharded_capi.inc"
 #include "hybrid_capi.inc"
 #include "fb_capi.inc"

@@ -946,7 +946,9 @@ __device__ __noinline__ void fbw_dminus(const double* R, const double* p, const 
     }
 }
 
+#ifndef FB_ROBOT_WARPS
 #define FB_ROBOT_WARPS 5
+#endif
 
 template <bool RESIDUAL_ONLY>
 __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, FbLin* lin) {

@@ -12,7 +12,7 @@ import numpy as np
 from . import capi
 from .capi import DIMV, NUM_CONSTRAINTS, SOLVER_UNOCP, SOLVER_UNPARNMPC, Idocp_b200Error, Problem, dptr
 
-__all__ = ["UnOCPSolver", "UnParNMPCSolver", "benchmark_problem", "config_space_problem", "task_space_problem",
+__all__ = ["UnOCPSolver", "UnParNMPCSolver", "DerivativeChecker", "benchmark_problem", "config_space_problem", "task_space_problem",
            "task_space_circle_ref", "Problem"]
 
 
@@ -269,6 +269,79 @@ class _BatchSolver:
 class UnOCPSolver(_BatchSolver):
     """Batched idocp::UnOCPSolver (Riccati recursion)."""
     kind = SOLVER_UNOCP
+
+
+def _is_approx(a, b, prec):
+    """Eigen's a.isApprox(b, prec): |a - b|^2 <= prec^2 min(|a|^2, |b|^2) (Frobenius norms)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.sum((a - b) ** 2)) <= prec * prec * min(float(np.sum(a * a)), float(np.sum(b * b)))
+
+
+class DerivativeChecker:
+    """idocp::DerivativeChecker (include/idocp/utils/derivative_checker.hpp:14-66, src/utils/derivative_checker.cpp:47-312)
+    for the cost of a fixed-base Problem, evaluated ON THE DEVICE (idocp_b200_check_cost_derivatives): at `samples` random split
+    solutions the analytic gradient of the lineariser's device functions is compared with forward differences of the cost
+    value of the line search's device functions (first order), and the analytic Hessian with forward differences of the
+    gradient (second order), block by block with Eigen's isApprox like the reference.  The reference takes one cost
+    component and draws ONE sample; here the problem carries the cost (configuration-space + optional task-space term) and
+    every sample has to pass.  `last_failure` names the block that failed, as the reference's message does."""
+
+    def __init__(self, problem, finite_diff=1.0e-08, test_tol=1.0e-04, samples=8, seed=0, lib=None, task_ref=None, t=0.0):
+        self.finite_diff, self.test_tol = float(finite_diff), float(test_tol)
+        self.samples = int(samples)
+        self._solver = UnOCPSolver(problem, self.samples, lib=lib)
+        if task_ref is not None:
+            self._solver.setTaskReference(task_ref, t)
+        self._rng = np.random.default_rng(seed)
+        self.last_failure = None
+
+    def setFiniteDifference(self, finite_diff=1.0e-08):
+        self.finite_diff = float(finite_diff)
+
+    def setTestTolerance(self, test_tol=1.0e-04):
+        self.test_tol = float(test_tol)
+
+    def evaluate(self, terminal=False, stage=0):
+        """The raw numbers of one device pass over fresh random samples (SplitSolution::Random: uniform in [-1, 1])."""
+        s = self._solver
+        x = [np.ascontiguousarray(self._rng.uniform(-1.0, 1.0, (self.samples, DIMV))) for _ in range(4)]
+        out = np.zeros((self.samples, capi.DC_DOUBLES))
+        s.lib.check(s.lib.L.idocp_b200_check_cost_derivatives(s._h, int(bool(terminal)), int(stage), self.samples, dptr(x[0]), dptr(x[1]),
+                                                             dptr(x[2]), dptr(x[3]), self.finite_diff, dptr(out)))
+        n = DIMV
+        r = dict(cost=out[:, 0], q=x[0], v=x[1], a=x[2], u=x[3])
+        for k, name in enumerate(("lq", "lv", "la", "lu")):
+            r[name] = out[:, 1 + k * n:1 + (k + 1) * n]
+            r[name + "_ref"] = out[:, 29 + k * n:29 + (k + 1) * n]
+        r["Qqq"] = out[:, 57:106].reshape(-1, n, n)
+        for k, name in enumerate(("Qvv", "Qaa", "Quu")):
+            r[name] = np.stack([np.diag(d) for d in out[:, 106 + k * n:106 + (k + 1) * n]])
+        for k, name in enumerate(("Qqq", "Qvv", "Qaa", "Quu")):
+            r[name + "_ref"] = out[:, 127 + 49 * k:127 + 49 * (k + 1)].reshape(-1, n, n)
+        return r
+
+    def _check(self, names, terminal):
+        r = self.evaluate(terminal)
+        for b in range(self.samples):
+            for name in names:
+                if not _is_approx(r[name][b], r[name + "_ref"][b], self.test_tol):
+                    self.last_failure = "%s is not correct! sample %d, %s - %s_ref = %s" % (name, b, name, name,
+                                                                                             (r[name][b] - r[name + "_ref"][b]).ravel())
+                    return False
+        self.last_failure = None
+        return True
+
+    def checkFirstOrderStageCostDerivatives(self):
+        return self._check(("lq", "lv", "la", "lu"), False)
+
+    def checkSecondOrderStageCostDerivatives(self):
+        return self._check(("Qqq", "Qvv", "Qaa", "Quu"), False)
+
+    def checkFirstOrderTerminalCostDerivatives(self):
+        return self._check(("lq", "lv"), True)
+
+    def checkSecondOrderTerminalCostDerivatives(self):
+        return self._check(("Qqq", "Qvv"), True)
 
 
 class UnParNMPCSolver(_BatchSolver):

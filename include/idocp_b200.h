@@ -156,6 +156,21 @@ int idocp_b200_clear_line_search_filter(idocp_b200_solver* h);
  * Call it before updateSolution / computeKKTResidual / initBackwardCorrection whenever t changes. */
 int idocp_b200_set_task_reference(idocp_b200_solver* h, const double* table);
 
+/* Device-side analogue of idocp::DerivativeChecker (include/idocp/utils/derivative_checker.hpp:14-66,
+ * src/utils/derivative_checker.cpp:47-312) for the cost of this handle's problem: for n samples of a split solution
+ * (q, v, a, u rows [n][7], host pointers) the kernel evaluates the cost with the device functions of the line search and its
+ * gradient / Hessian with those of the lineariser, and forms the forward differences the reference compares them with
+ * (step finite_diff).  kind 0: stage cost (includes dt = T / N), 1: terminal cost; the task-space reference is row `stage`
+ * of the table of idocp_b200_set_task_reference.  out[n][IDOCP_B200_DC_DOUBLES]:
+ *   [0] cost | [1..28] lq, lv, la, lu | [29..56] their forward differences | [57..105] Qqq (row-major 7 x 7) |
+ *   [106..126] diagonals of Qvv, Qaa, Quu | [127..175], [176..224], [225..273], [274..322] forward differences of the
+ *   gradient: Qqq, Qvv, Qaa, Quu (row-major, column i = coordinate i moved).
+ * The comparison itself (Eigen's isApprox with the test tolerance) is the host classes' (DerivativeChecker in
+ * include/idocp_b200/idocp_b200.hpp and idocp_b200/solvers.py). */
+#define IDOCP_B200_DC_DOUBLES 323
+int idocp_b200_check_cost_derivatives(idocp_b200_solver* h, int kind, int stage, int n, const double* q, const double* v,
+                                      const double* a, const double* u, double finite_diff, double* out);
+
 int idocp_b200_sync(idocp_b200_solver* h);
 /* number of kernels this handle has launched since creation (bench.py "gpu_launches") */
 int idocp_b200_launch_count(idocp_b200_solver* h, long long* out);

@@ -22,11 +22,13 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
 #include <map>
 #include <memory>
+#include <random>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -655,6 +657,14 @@ class SolverBase {
   // the single-device solver of shard `shard` (the whole batch when the solver was built on one device)
   idocp_b200_solver* handle(int shard = 0) { return shards_[shard]; }
 
+  // DerivativeChecker's device pass (idocp_b200_check_cost_derivatives, first shard): n <= batch samples of (q, v, a, u),
+  // task-space reference at time t; out[n][IDOCP_B200_DC_DOUBLES]
+  void checkCostDerivatives(double t, bool terminal, int n, const double* q, const double* v, const double* a, const double* u,
+                            double finite_diff, double* out) {
+    sampleTaskReference(t);
+    check(idocp_b200_check_cost_derivatives(shards_[0], terminal ? 1 : 0, 0, n, q, v, a, u, finite_diff, out));
+  }
+
  protected:
   // the user's compute_q_6d_ref at the time of every stage index (unocp_solver.cpp:80-93: t + i dt, terminal
   // t + T; unbackward_correction.cpp:73-95: t + (i+1) dt, last stage t + T), re-sampled only when t changes
@@ -727,6 +737,87 @@ class UnParNMPCSolver : public detail::SolverBase {
     sampleTaskReference(t);
     detail::check(idocp_b200_sharded_init_backward_correction(hs_.get(), t));
   }
+};
+
+// include/idocp/utils/derivative_checker.hpp:14-66 (src/utils/derivative_checker.cpp:47-312), evaluated on the device: at
+// `samples` random split solutions (SplitSolution::Random: uniform in [-1, 1]) and a random time the analytic gradient of the
+// cost component -- the lineariser's device functions -- is compared with forward differences of the cost value -- the line
+// search's device functions -- and the analytic Hessian with forward differences of the gradient, block by block with Eigen's
+// isApprox(test_tol); the first block that fails is reported like the reference's message.  The reference draws one sample;
+// here every sample has to pass.  Fixed-base robot only: the stage / impulse costs of the floating-base robot are checked
+// against finite differences on the oracle (tests/test_oracle_fb_ocp.py), which the kernels equal bit for bit.
+class DerivativeChecker {
+ public:
+  explicit DerivativeChecker(const Robot& robot, const double finite_diff = 1.0e-08, const double test_tol = 1.0e-04,
+                             const int samples = 8, const int device = 0)
+      : robot_(robot), finite_diff_(finite_diff), test_tol_(test_tol), samples_(samples), device_(device) {
+    if (robot.hasFloatingBase()) detail::die("idocp_b200: DerivativeChecker covers the fixed-base robot (SURVEY.md 8(f3))");
+    if (samples <= 0) detail::die("invalid value: samples must be positive!");
+  }
+  void setFiniteDifference(const double finite_diff = 1.0e-08) { finite_diff_ = finite_diff; }
+  void setTestTolerance(const double test_tol = 1.0e-04) { test_tol_ = test_tol; }
+  template <class Cost> bool checkFirstOrderStageCostDerivatives(const std::shared_ptr<Cost>& cost) { return run(cost, false, false); }
+  template <class Cost> bool checkSecondOrderStageCostDerivatives(const std::shared_ptr<Cost>& cost) { return run(cost, false, true); }
+  template <class Cost> bool checkFirstOrderTerminalCostDerivatives(const std::shared_ptr<Cost>& cost) { return run(cost, true, false); }
+  template <class Cost> bool checkSecondOrderTerminalCostDerivatives(const std::shared_ptr<Cost>& cost) { return run(cost, true, true); }
+
+ private:
+  static void add(CostFunction& cf, const Robot&, const std::shared_ptr<ConfigurationSpaceCost>& c) { cf.push_back(c); }
+  template <class Task>
+  static void add(CostFunction& cf, const Robot& robot, const std::shared_ptr<Task>& c) {
+    auto zero = std::make_shared<ConfigurationSpaceCost>(robot);   // the solver's problem always carries the quadratic term
+    const VectorXd z = VectorXd::Zero(IDOCP_B200_DIMV);
+    zero->set_q_weight(z); zero->set_v_weight(z); zero->set_a_weight(z); zero->set_u_weight(z); zero->set_qf_weight(z); zero->set_vf_weight(z);
+    cf.push_back(zero);
+    cf.push_back(c);
+  }
+  // Eigen: a.isApprox(b, prec)  <=>  |a - b|^2 <= prec^2 min(|a|^2, |b|^2)
+  static bool approx(const double* a, const double* b, int n, double prec) {
+    double d2 = 0, a2 = 0, b2 = 0;
+    for (int i = 0; i < n; ++i) { d2 += (a[i] - b[i]) * (a[i] - b[i]); a2 += a[i] * a[i]; b2 += b[i] * b[i]; }
+    return d2 <= prec * prec * std::min(a2, b2);
+  }
+  template <class Cost>
+  bool run(const std::shared_ptr<Cost>& cost, bool terminal, bool second) {
+    auto cf = std::make_shared<CostFunction>();
+    add(*cf, robot_, cost);
+    UnOCPSolver solver(robot_, cf, std::make_shared<Constraints>(), 1.0, 2, 1, samples_, device_);   // dt = 0.5
+    const int n = IDOCP_B200_DIMV;
+    std::vector<double> x[4], out(static_cast<size_t>(samples_) * IDOCP_B200_DC_DOUBLES);
+    for (auto& block : x) {
+      block.resize(static_cast<size_t>(samples_) * n);
+      for (auto& e : block) e = uniform();
+    }
+    solver.checkCostDerivatives(std::abs(uniform()), terminal, samples_, x[0].data(), x[1].data(), x[2].data(), x[3].data(), finite_diff_,
+                                out.data());
+    static const char* const first[4] = {"lq", "lv", "la", "lu"};
+    static const char* const hess[4] = {"Qqq", "Qvv", "Qaa", "Quu"};
+    const int blocks = terminal ? 2 : 4;
+    for (int b = 0; b < samples_; ++b) {
+      const double* o = out.data() + static_cast<size_t>(b) * IDOCP_B200_DC_DOUBLES;
+      for (int k = 0; k < blocks; ++k) {
+        bool ok;
+        if (!second) {
+          ok = approx(o + 1 + k * n, o + 29 + k * n, n, test_tol_);
+        } else {
+          double H[49] = {0};
+          if (k == 0) std::copy(o + 57, o + 106, H);
+          else for (int i = 0; i < n; ++i) H[i * n + i] = o[106 + (k - 1) * n + i];
+          ok = approx(H, o + 127 + 49 * k, 49, test_tol_);
+        }
+        if (!ok) {
+          std::cout << (second ? hess[k] : first[k]) << " is not correct! (sample " << b << ")" << std::endl;
+          return false;
+        }
+      }
+    }
+    return true;
+  }
+  double uniform() { return std::uniform_real_distribution<double>(-1.0, 1.0)(rng_); }
+  Robot robot_;
+  double finite_diff_, test_tol_;
+  int samples_, device_;
+  std::mt19937 rng_{20240017u};
 };
 
 // include/idocp/utils/ocp_benchmarker.hxx:13-51
