@@ -120,8 +120,11 @@ constexpr int INV_OFF_A = 0;                           // Q -> L (21 x 21, colum
 constexpr int INV_OFF_LT = INV_OFF_A + 442;            // L^T: row r of L contiguous (backward substitution); LLT(S)^T later
 constexpr int INV_OFF_RD = INV_OFF_LT + 442;           // reciprocal pivots (21)
 constexpr int INV_OFF_FQ = INV_OFF_RD + 24;            // FQinv (14 x 21), column stride 15
-constexpr int INV_OFF_S = INV_OFF_FQ + 316;            // S (14 x 14); first used as staging of aux_next
-constexpr int INV_OFF_LS = INV_OFF_S + NX2 * INV_LDX;  // LLT(S), then TL = -S^-1 in place (14 x 14)
+// S (14 x 14; first used as staging of aux_next) lives in the upper part of the L^T region: L^T of Q is dead when S is formed,
+// LLT(S)^T takes LT[0, 210) only, and S * TR is parked over FQinv (dead once TR exists) -- 15.97 -> 14.29 KB per warp, which is
+// what lets a fourth CTA onto the SM
+constexpr int INV_OFF_S = INV_OFF_LT + 220;
+constexpr int INV_OFF_LS = INV_OFF_FQ + 316;           // LLT(S), then TL = -S^-1 in place (14 x 14)
 constexpr int INV_OFF_TL = INV_OFF_LS;
 constexpr int INV_OFF_TR = INV_OFF_TL + NX2 * INV_LDX; // TR (14 x 21)
 constexpr int INV_OFF_RES = INV_OFF_TR + 316;          // residual (35)
@@ -129,7 +132,8 @@ constexpr int INV_SMEM_PER_WARP = INV_OFF_RES + 36;
 constexpr int INV_SMEM_BYTES = WARPS_PER_CTA * INV_SMEM_PER_WARP * static_cast<int>(sizeof(double));
 static_assert(INV_OFF_LT % 2 == 0 && INV_OFF_FQ % 2 == 0 && INV_OFF_S % 2 == 0 && INV_OFF_LS % 2 == 0 && INV_OFF_TR % 2 == 0 &&
               INV_SMEM_PER_WARP % 2 == 0, "16-byte alignment of the even elements");
-static_assert(3 * INV_SMEM_BYTES <= 227 * 1024, "three CTAs per SM");
+static_assert(INV_OFF_S + NX2 * INV_LDX <= INV_OFF_RD && NX2 * INV_LDX <= 220, "S and LLT(S)^T share the L^T region");
+static_assert(4 * (INV_SMEM_BYTES + 1024) <= 228 * 1024, "four CTAs per SM");
 
 // moves `nslots` slots of this warp's instance between a (stage, group) record and a per-lane
 // functor, 4 slots per warp instruction (lane = 8 * sub + j): all global accesses of the loop are
@@ -212,7 +216,7 @@ __device__ __forceinline__ void inv_mm_dmma(int lane, const double* __restrict__
 }
 
 #ifndef IDOCP_INV_MINB
-#define IDOCP_INV_MINB 3   // 164 registers without spills since the column-oriented substitutions: three CTAs per SM
+#define IDOCP_INV_MINB 4   // 128 registers without spills (164 at three CTAs per SM), 14.3 KB of shared memory per warp
 #endif
 
 __global__ void __launch_bounds__(CTA_THREADS, IDOCP_INV_MINB) k_parnmpc_invert(const DevProblem* __restrict__ Pp,
@@ -310,10 +314,10 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_INV_MINB) k_parnmpc_invert(
   }
   __syncwarp();
 #ifndef IDOCP_INV_SIMT
-  // ---- TR = -(TL FQinv) (14 x 21), ST = S TR (14 x 21, parked over the dead L^T), BR = Qinv - TR^T ST (21 x 21, in place over
+  // ---- TR = -(TL FQinv) (14 x 21), ST = S TR (14 x 21, parked over the dead FQinv), BR = Qinv - TR^T ST (21 x 21, in place over
   //      the parked Qinv): three warp-level DMMA products, every element the oracle's ascending chain ----
   {
-    double* ST = LT;
+    double* ST = FQ;   // FQinv is dead once TR exists
     inv_mm_dmma<NX2, NQ3, NX2>(wl, TL, 1, INV_LDX, FQ, 1, INV_LDX, [=](int r, int c, double v) { TR[c * INV_LDX + r] = -v; });
     __syncwarp();
     inv_mm_dmma<NX2, NQ3, NX2>(wl, S, 1, INV_LDX, TR, 1, INV_LDX, [=](int r, int c, double v) { ST[c * INV_LDX + r] = v; });
