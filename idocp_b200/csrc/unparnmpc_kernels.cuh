@@ -424,6 +424,21 @@ __device__ __forceinline__ void oct_matvec14(const double* __restrict__ M, doubl
   }
 }
 
+// ask the L2 for slots [first_slot, first_slot + nslots) of the (stage, group) record `rec` points into (this thread's
+// rec_ptr): the serial sweeps below would otherwise pay one DRAM round trip per stage.  No effect on results.
+__device__ __forceinline__ void warp_prefetch_slots(const double* rec, int first_slot, int nslots) {
+#if !defined(IDOCP_B200_EMU) && !defined(IDOCP_PARNMPC_NO_PREFETCH)
+  const int lane = threadIdx.x & 31;
+  const char* c = reinterpret_cast<const char*>(rec - lane + first_slot * SLOT);
+  for (int o = lane * 128; o < nslots * SLOT * static_cast<int>(sizeof(double)); o += 32 * 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(c + o));
+#endif
+}
+#ifndef IDOCP_PARNMPC_PREFETCH_DISTANCE
+#define IDOCP_PARNMPC_PREFETCH_DISTANCE 2
+#endif
+constexpr int PARNMPC_PREFETCH_DISTANCE = IDOCP_PARNMPC_PREFETCH_DISTANCE;   // stages ahead of the one being corrected
+
 // ---------------------------------------------------------------------------------------------
 // k_parnmpc_backward_serial: i = N-2 .. 0:  x_res = s_new[i+1].(lmd,gmm) - s[i+1].(lmd,gmm);
 // s_new[i].(lmd,gmm) -= inv_i[0:14, 21:35] x_res.  One octet per instance.
@@ -443,6 +458,11 @@ __global__ void __launch_bounds__(CTA_THREADS) k_parnmpc_backward_serial(Layout 
     const double xh = nl - X[X_LMD * SLOT];
     const double xt = ng - X[X_GMM * SLOT];
     X -= xs; SN -= ss; KI -= ks; XR -= rs;
+    if (i >= PARNMPC_PREFETCH_DISTANCE) {
+      warp_prefetch_slots(KI - PARNMPC_PREFETCH_DISTANCE * ks, KI_BS, KI_BP - KI_BS);
+      warp_prefetch_slots(SN - PARNMPC_PREFETCH_DISTANCE * ss, SN_LMD, 2);
+      warp_prefetch_slots(X - (PARNMPC_PREFETCH_DISTANCE - 1) * xs, X_LMD, 2);
+    }
     XR[XR_H * SLOT] = xh;
     XR[XR_T * SLOT] = xt;
     double y[2];
@@ -487,6 +507,11 @@ __global__ void __launch_bounds__(CTA_THREADS) k_parnmpc_forward_serial(Layout L
     const double xh = nq - X[X_Q * SLOT];
     const double xt = nv - X[X_V * SLOT];
     X += xs; SN += ss; KI += ks; XR += rs;
+    if (i + PARNMPC_PREFETCH_DISTANCE < N) {
+      warp_prefetch_slots(KI + PARNMPC_PREFETCH_DISTANCE * ks, KI_FS, KI_FP - KI_FS);
+      warp_prefetch_slots(SN + PARNMPC_PREFETCH_DISTANCE * ss, SN_Q, 2);
+      warp_prefetch_slots(X + (PARNMPC_PREFETCH_DISTANCE - 1) * xs, X_Q, 2);
+    }
     XR[XR_H * SLOT] = xh;
     XR[XR_T * SLOT] = xt;
     double y[2];
