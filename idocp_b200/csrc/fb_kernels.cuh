@@ -667,7 +667,9 @@ __device__ unsigned long long g_fb_phase[3][32];
 struct FbRobotWork {
   // inputs (same order as FbSol)
   double lmd[FB_NV], gmm[FB_NV], q[FB_NQ], v[FB_NV], a[FB_NV], u[FB_NU], beta[FB_NV], nu_passive[FB_NPASS], f[FB_MAXF], mu[FB_MAXF],
-      xi[FB_MAXF], slack[FB_NCON], dual[FB_NCON];
+      xi[FB_MAXF];
+  // slack / dual of the constraint rows are read where they lie (FbSol, read-only here) and residual / duality live in FbDir only:
+  // 4.5 KB less per warp, i.e. 12 instead of 10 warps per SM
   double nlmd[FB_NV], ngmm[FB_NV], nq[FB_NQ], nv[FB_NV], qprev[FB_NQ];
   double fm[FB_MAXF], mu_stack[FB_MAXF];
   // kinematics (world frame)
@@ -683,8 +685,11 @@ struct FbRobotWork {
   double frP[3], frV[6], frA[6];
   // SE(3) blocks: three relative placements (cost reference, next stage, previous stage)
   double relR[3][9], relp[3][3], relJ[3][36], rellog[3][6], Fqq_prev6[36], Fqq_inv[36], tmp6[36], fq6[6];
-  double residual[FB_NCON], duality[FB_NCON];
   double t18[FB_NV], part[8];
+};
+// the line search evaluates trial slacks and per-row terms of the barrier cost / violation: it keeps the four row arrays
+struct FbLsWork : FbRobotWork {
+  double slack[FB_NCON], dual[FB_NCON], residual[FB_NCON], duality[FB_NCON];
 };
 
 template <int MODE>
@@ -947,11 +952,15 @@ __device__ __noinline__ void fbw_dminus(const double* R, const double* p, const 
 }
 
 #ifndef FB_ROBOT_WARPS
-#define FB_ROBOT_WARPS 5
+#define FB_ROBOT_WARPS 6   // x 2 CTAs per SM: 12 warps (18.6 KB of shared memory and 168 registers each)
 #endif
+#ifndef FB_ROBOT_MINB
+#define FB_ROBOT_MINB 2
+#endif
+#define FB_LS_WARPS 5      // k_fb_ls_eval (FbLsWork, 23 KB per warp)
 
 template <bool RESIDUAL_ONLY>
-__global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, FbLin* lin) {
+__global__ void __launch_bounds__(32 * FB_ROBOT_WARPS, FB_ROBOT_MINB) k_fb_robot(FbArrays A, FbLin* lin) {
   IDOCP_DYN_SMEM(FbRobotWork, wbase);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int stage = blockIdx.x * FB_ROBOT_WARPS + warp;
@@ -975,7 +984,7 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
   // every load of the lane is issued before its first store (a copy loop through generic pointers keeps load -> store order:
   // one DRAM round trip per element)
   {
-    constexpr int NS = (int)(sizeof(FbSol) / sizeof(double)), RS = (NS + 31) / 32;
+    constexpr int NS = (int)(offsetof(FbSol, slack) / sizeof(double)), RS = (NS + 31) / 32;   // lmd ... xi
     const double* src = S.lmd;
     const FbSol& Nx = A.sol[(size_t)(terminal ? el.slot : el.next_slot) * A.B + b];
     const double* qp = el.prev_slot >= 0 ? A.sol[(size_t)el.prev_slot * A.B + b].q : A.q0 + (size_t)b * FB_NQ;
@@ -1069,7 +1078,7 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
       const int j = idx - fbc_offset(c);
       double res = 0.0, dua = 0.0;
       if (el.cactive[c] && j < fbc_rows(nl, c) && c != FBC_DISTANCE) {   // ContactDistance: after the kinematics, below
-        const double sl = w.slack[idx];
+        const double sl = S.slack[idx];
         if (fbc_is_cone(c)) {
           const int rpc = fbc_cone_rows(nl, c);
           const int i = rpc == 2 ? (j >> 1) : (j / 5);   // no division by a run-time value
@@ -1077,7 +1086,7 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
             double r5[5];
             fb_friction_residual(pr.mu, rpc == 2, w.f + 3 * i, r5);
             res = r5[(rpc == 2 ? (j & 1) : (j % 5))] + sl;
-            dua = sl * w.dual[idx] - pr.barrier;
+            dua = sl * S.dual[idx] - pr.barrier;
           }
         } else {
           switch (c) {
@@ -1090,11 +1099,9 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
             case FBC_TRQ_LO: res = (-pr.u_max[j]) - w.u[j] + sl; break;
             default:         res = w.u[j] - pr.u_max[j] + sl; break;
           }
-          dua = sl * w.dual[idx] - pr.barrier;
+          dua = sl * S.dual[idx] - pr.barrier;
         }
       }
-      w.residual[idx] = res;
-      w.duality[idx] = dua;
       Dr.residual[idx] = res;
       Dr.duality[idx] = dua;
     }
@@ -1139,27 +1146,27 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
     for (int c = 0; c < 4; ++c) {
       if (!el.cactive[c]) continue;
       const double sg = (c & 1) ? 1.0 : -1.0;
-      if (c <= FBC_POS_UP) lq += sg * (dt * w.dual[12 * c + j]);
-      else lv += sg * (dt * w.dual[12 * c + j]);
+      if (c <= FBC_POS_UP) lq += sg * (dt * S.dual[12 * c + j]);
+      else lv += sg * (dt * S.dual[12 * c + j]);
     }
     for (int c = FBC_ACC_LO; c <= FBC_ACC_UP; ++c) {   // JointAcceleration{Lower,Upper}Limit: la.tail(12) -/+= dt dual
       if (!el.cactive[c]) continue;
       const double sg = (c & 1) ? 1.0 : -1.0;
-      la += sg * (dt * w.dual[fbc_offset(c) + j]);
+      la += sg * (dt * S.dual[fbc_offset(c) + j]);
     }
   }
   if (lane < FB_NU) {
     for (int c = 4; c < 6; ++c) {
       if (!el.cactive[c]) continue;
       const double sg = (c & 1) ? 1.0 : -1.0;
-      lu += sg * (dt * w.dual[12 * c + lane]);
+      lu += sg * (dt * S.dual[12 * c + lane]);
     }
   }
   const int cfr = impulse ? FBC_IMPULSE_FRICTION : FBC_FRICTION;
   const int rpc = fbc_cone_rows(nl, cfr);
   const bool nlc = rpc == 2;
   if (ci >= 0 && el.cactive[cfr]) {
-    const double* du5 = w.dual + fbc_offset(cfr) + rpc * ci;
+    const double* du5 = S.dual + fbc_offset(cfr) + rpc * ci;
     const double* fi = w.f + 3 * ci;
     const double acc = nlc ? fb_cone_augment<true>(pr.mu, fi, du5, cx) : fb_cone_augment<false>(pr.mu, fi, du5, cx);
     lf += dt * acc;
@@ -1352,13 +1359,12 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
           if (fb_in_support(i, lane)) fb_pullback(Rf, w.frP, w.S[lane], J);
           const double j2 = pr.distance_mode == 2 ? fma(Rf[8], J[2], fma(Rf[7], J[1], Rf[6] * J[0])) : J[2];
           L.cdJ[i * FB_NV + lane] = j2;   // read again by the condensing below, by k_fb_condense and by k_fb_expand
-          lq -= (dt * w.dual[o + i]) * j2;
+          lq -= (dt * S.dual[o + i]) * j2;
         }
-        cdres = -w.frP[2] + w.slack[o + i];
-        cddua = w.slack[o + i] * w.dual[o + i] - pr.barrier;
+        cdres = -w.frP[2] + S.slack[o + i];
+        cddua = S.slack[o + i] * S.dual[o + i] - pr.barrier;
       }
       if (lane == 0) {
-        w.residual[o + i] = cdres; w.duality[o + i] = cddua;
         Dr.residual[o + i] = cdres; Dr.duality[o + i] = cddua;
       }
     }
@@ -1386,10 +1392,10 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
         for (int c = FBC_ACC_LO; c <= FBC_ACC_UP; ++c) {
           if (!el.cactive[c]) continue;
           const int idx = fbc_offset(c) + j - 6;
-          const double rs = 1.0 / w.slack[idx];
-          qad += (dt * w.dual[idx]) * rs;
+          const double rs = 1.0 / S.slack[idx];
+          qad += (dt * S.dual[idx]) * rs;
           const double sg = (c & 1) ? 1.0 : -1.0;
-          la += sg * ((dt * fma(w.dual[idx], w.residual[idx], -w.duality[idx])) * rs);
+          la += sg * ((dt * fma(S.dual[idx], Dr.residual[idx], -Dr.duality[idx])) * rs);
         }
       }
       L.Qaa[j] = qad;
@@ -1404,10 +1410,10 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
       for (int c = 0; c < 4; ++c) {
         if (!el.cactive[c]) continue;
         const int idx = 12 * c + j;
-        const double rs = 1.0 / w.slack[idx];
-        const double h = (dt * w.dual[idx]) * rs;
+        const double rs = 1.0 / S.slack[idx];
+        const double h = (dt * S.dual[idx]) * rs;
         const double sg = (c & 1) ? 1.0 : -1.0;
-        const double g = sg * ((dt * fma(w.dual[idx], w.residual[idx], -w.duality[idx])) * rs);
+        const double g = sg * ((dt * fma(S.dual[idx], Dr.residual[idx], -Dr.duality[idx])) * rs);
         if (c <= FBC_POS_UP) { qqd += h; lq += g; }
         else { qvd += h; lv += g; }
       }
@@ -1416,10 +1422,10 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
       for (int c = 4; c < 6; ++c) {
         if (!el.cactive[c]) continue;
         const int idx = 12 * c + lane;
-        const double rs = 1.0 / w.slack[idx];
-        qud += (dt * w.dual[idx]) * rs;
+        const double rs = 1.0 / S.slack[idx];
+        qud += (dt * S.dual[idx]) * rs;
         const double sg = (c & 1) ? 1.0 : -1.0;
-        lu += sg * ((dt * fma(w.dual[idx], w.residual[idx], -w.duality[idx])) * rs);
+        lu += sg * ((dt * fma(S.dual[idx], Dr.residual[idx], -Dr.duality[idx])) * rs);
       }
       L.Quu_d[lane] = qud;
     }
@@ -1429,8 +1435,8 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
       const int o = fbc_offset(cfr) + rpc * ci;
       const double* fi = w.f + 3 * ci;
       double h3[3];
-      const double acc = nlc ? fb_cone_condense<true>(pr.mu, fi, w.slack + o, w.dual + o, w.residual + o, w.duality + o, cx, h3)
-                             : fb_cone_condense<false>(pr.mu, fi, w.slack + o, w.dual + o, w.residual + o, w.duality + o, cx, h3);
+      const double acc = nlc ? fb_cone_condense<true>(pr.mu, fi, S.slack + o, S.dual + o, Dr.residual + o, Dr.duality + o, cx, h3)
+                             : fb_cone_condense<false>(pr.mu, fi, S.slack + o, S.dual + o, Dr.residual + o, Dr.duality + o, cx, h3);
       lf += dt * acc;
       for (int y = 0; y < 3; ++y) {
         const double h = h3[y];
@@ -1444,9 +1450,9 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
       for (int i = 0; i < FB_NC; ++i) {
         double wgt = 0.0;
         if (!el.active[i]) {
-          const double rs = 1.0 / w.slack[o + i];
-          wgt = (dt * w.dual[o + i]) * rs;
-          const double g2 = (dt * fma(w.dual[o + i], w.residual[o + i], -w.duality[o + i])) * rs;
+          const double rs = 1.0 / S.slack[o + i];
+          wgt = (dt * S.dual[o + i]) * rs;
+          const double g2 = (dt * fma(S.dual[o + i], Dr.residual[o + i], -Dr.duality[o + i])) * rs;
           if (lane < FB_NV) lq -= g2 * L.cdJ[i * FB_NV + lane];   // written by this very lane above
         }
         if (lane == 0) L.cdw[i] = wgt;
@@ -1526,13 +1532,30 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_robot(FbArrays A, Fb
     if (lane == 3) { w.part[3] = fb_sqnorm(L.lu_passive, FB_NPASS); w.part[7] = fb_sqnorm(L.lu, FB_NU); }
     if (lane == 4) w.part[4] = fb_sqnorm(L.Fq, FB_NV) + fb_sqnorm(L.Fv, FB_NV);
     if (lane == 5) w.part[5] = fb_sqnorm(L.IDC, nvf);
-    if (lane == 6) {
+    {
+      // rows of FbDir (L2): the lanes fetch 32 rows at a time and hand them round, every lane running the serial chain
+      // sum_c (|residual_c|^2 + |duality_c|^2) of the reference in its order (dead rows: 0)
       double e2 = 0.0;
       for (int c = 0; c < FBC_NCOMP; ++c) {
         if (!el.cactive[c]) continue;
-        e2 += fb_sqnorm(w.residual + fbc_offset(c), fbc_dim(c)) + fb_sqnorm(w.duality + fbc_offset(c), fbc_dim(c));   // dead rows: 0
+        const int o = fbc_offset(c), n = fbc_dim(c);
+        double part2[2];
+        for (int h = 0; h < 2; ++h) {
+          const double* rows = (h ? Dr.duality : Dr.residual) + o;
+          double acc = 0.0;
+          for (int base = 0; base < n; base += 32) {
+            const double mine = base + lane < n ? rows[base + lane] : 0.0;
+            const int m = n - base < 32 ? n - base : 32;
+            for (int t = 0; t < m; ++t) {
+              const double x = __shfl_sync(0xffffffffu, mine, t);
+              acc = fma(x, x, acc);
+            }
+          }
+          part2[h] = acc;
+        }
+        e2 += part2[0] + part2[1];
       }
-      w.part[6] = e2;
+      if (lane == 6) w.part[6] = e2;
     }
     __syncwarp();
     if (lane == 0) {
@@ -2542,12 +2565,12 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_init_distance(FbArra
 // s + alpha d)  ->  k_fb_ls_filter (thread per instance); finished instances drop out.
 // =====================================================================================================
 template <bool INITIAL>
-__global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_ls_eval(FbArrays A, FbLin* lin) {
-  IDOCP_DYN_SMEM(FbRobotWork, wbase);
+__global__ void __launch_bounds__(32 * FB_LS_WARPS) k_fb_ls_eval(FbArrays A, FbLin* lin) {
+  IDOCP_DYN_SMEM(FbLsWork, wbase);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int stage = blockIdx.x * FB_ROBOT_WARPS + warp;
+  const int stage = blockIdx.x * FB_LS_WARPS + warp;
   if (stage >= A.B * A.n_elems) return;
-  FbRobotWork& w = wbase[warp];
+  FbLsWork& w = wbase[warp];
   const int b = stage / A.n_elems, e = stage - b * A.n_elems;
   if (INITIAL) { if (A.ls_n[b] != 0) return; } else { if (A.ls_state[b] != 0) return; }
   const double alpha = INITIAL ? 0.0 : A.ls_alpha[b];
