@@ -633,15 +633,24 @@ __global__ void k_step_min(Layout L, const double* __restrict__ primal_override)
 }
 
 constexpr int UL_D = X_NUM, UL_XN = UL_D + D_NUM, UL_DN = UL_XN + 4, UL_ST = UL_DN + 4, UL_SLOTS = UL_ST + 1;
-constexpr int UL_OFF_BUF = OCTETS_PER_CTA * OCT * PAIR_TILE;                       // doubles, after the pair tiles
-constexpr int UL_OFF_BARS = UL_OFF_BUF + WARPS_PER_CTA * 2 * UL_SLOTS * SLOT;
-constexpr int UL_SMEM_DOUBLES = UL_OFF_BARS + 2 * WARPS_PER_CTA;
+#ifndef IDOCP_UL_WARPS
+#define IDOCP_UL_WARPS 4   // warps per CTA of the persistent kernel (24.3 KB of shared memory each)
+#endif
+constexpr int UL_WARPS = IDOCP_UL_WARPS, UL_THREADS = 32 * UL_WARPS;
+constexpr int UL_OFF_BUF = UL_WARPS * 4 * OCT * PAIR_TILE;                         // doubles, after the pair tiles
+constexpr int UL_OFF_BARS = UL_OFF_BUF + UL_WARPS * 2 * UL_SLOTS * SLOT;
+constexpr int UL_SMEM_DOUBLES = UL_OFF_BARS + 2 * UL_WARPS;
 static_assert(X_LMD == 0 && X_GMM == 1 && X_Q == 2 && X_V == 3 && D_LMD == 0 && D_GMM == 1 && D_Q == 2 && D_V == 3,
               "the next stage's (lmd, gmm, q, v) and their directions are the first four slots of a record");
 static_assert((UL_OFF_BUF * 8) % 16 == 0, "TMA destinations are 16-byte aligned");
 
 template <bool TASK, bool KKT = false>
-__global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_update_linearize(const DevProblem* __restrict__ Pp, Layout L) {
+#ifdef IDOCP_UL_MAXREG   // register cap given directly (ptxas derives the cap of minBlocks for CTAs of 128 threads)
+#define IDOCP_UL_BOUNDS __maxnreg__(IDOCP_UL_MAXREG)
+#else
+#define IDOCP_UL_BOUNDS __launch_bounds__(UL_THREADS, IDOCP_UL_CTAS_PER_SM)
+#endif
+__global__ void IDOCP_UL_BOUNDS k_update_linearize(const DevProblem* __restrict__ Pp, Layout L) {
   IDOCP_DYN_SMEM(double, smem);
   const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
   double* tile = smem + (threadIdx.x >> 3) * (OCT * PAIR_TILE);
@@ -649,8 +658,8 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_LIN_MINB) k_update_lineariz
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + UL_OFF_BARS) + 2 * warp;
   const int N = L.N;
   const long ntask = static_cast<long>(N + 1) * L.G;
-  const long nwarps = static_cast<long>(gridDim.x) * WARPS_PER_CTA;
-  long wt = static_cast<long>(blockIdx.x) * WARPS_PER_CTA + warp;
+  const long nwarps = static_cast<long>(gridDim.x) * UL_WARPS;
+  long wt = static_cast<long>(blockIdx.x) * UL_WARPS + warp;
   if (wl == 0) {
     tma_bar_init(&bars[0], 1);
     tma_bar_init(&bars[1], 1);
