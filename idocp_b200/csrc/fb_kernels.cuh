@@ -2204,7 +2204,10 @@ __device__ inline double fb_fraction_to_boundary(double rate, int nn, const doub
   return mn;
 }
 
-__global__ void __launch_bounds__(64) k_fb_expand(FbArrays A) {
+#ifndef IDOCP_FB_EXP_MINB
+#define IDOCP_FB_EXP_MINB 0    // unspecified: 38 registers; a cap at 24 CTAs per SM (40 registers) measured 2 % slower (r2zzc)
+#endif
+__global__ void __launch_bounds__(64, IDOCP_FB_EXP_MINB) k_fb_expand(FbArrays A) {
   __shared__ double dx[FB_NX], du[FB_NU], daf[FB_NVF], dslack[FB_NCON], ddual[FB_NCON], steps[2 * FBC_NCOMP];
   const int tid = threadIdx.x;
   const int b = blockIdx.x / A.n_elems, e = blockIdx.x - b * A.n_elems;
@@ -2358,7 +2361,10 @@ __global__ void k_fb_steps(FbArrays A) {
 // (ocp_linearizer.cpp:140-221, contact_dynamics.hxx:171-190, state_equation.hxx:96-108, split_solution.hxx:215-239)
 // grid = B * n_elems, 64 threads.  Reads dgmm of the NEXT stage, which no CTA of this kernel writes.
 // =====================================================================================================
-__global__ void __launch_bounds__(64) k_fb_update(FbArrays A) {
+#ifndef IDOCP_FB_UPD_MINB
+#define IDOCP_FB_UPD_MINB 16   // 64 registers: 16 CTAs (32 warps) per SM; measured 1.07 -> 0.96 ms (r2zzc)
+#endif
+__global__ void __launch_bounds__(64, IDOCP_FB_UPD_MINB) k_fb_update(FbArrays A) {
   __shared__ double dx[FB_NX], du[FB_NU], laf[FB_NVF], dbetamu[FB_NVF], dgn[FB_NV], dlmd[FB_NV], qn[FB_NQ], dqs[FB_NV], qs[FB_NQ];
   const int tid = threadIdx.x;
   const int b = blockIdx.x / A.n_elems, e = blockIdx.x - b * A.n_elems;
