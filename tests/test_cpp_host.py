@@ -475,3 +475,49 @@ int main() {
                            str(src), "-L" + lib, "-lidocp_b200", "-Wl,-rpath," + lib, "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
     assert out == ["0000", "1111", "4"]
+
+
+def test_discretizer_under_the_reference_include_paths(tmp_path):
+    """hybrid/ocp_discretizer.hpp + discrete_event.hpp + contact_sequence.hpp through the forwarding headers (host classes, no GPU):
+    one touch-down inside the horizon splits its grid interval into stage -> impulse -> auxiliary stage
+    (ocp_discretizer.hxx:36-110; the set-up of test/hybrid/ocp_discretizer_test.cpp)."""
+    import __graft_entry__ as g
+    g.build_cuda()
+    src = tmp_path / "disc.cpp"
+    src.write_text("""
+#include "idocp/robot/robot.hpp"
+#include "idocp/robot/contact_status.hpp"
+#include "idocp/hybrid/discrete_event.hpp"
+#include "idocp/hybrid/contact_sequence.hpp"
+#include "idocp/hybrid/ocp_discretizer.hpp"
+#include <iostream>
+int main() {
+  idocp::Robot robot("", {14, 24, 34, 44});
+  const double T = 1.0, t = 0.1;
+  const int N = 20, max_num_events = 5;
+  idocp::ContactSequence contact_sequence(robot, max_num_events);
+  auto pre = robot.createContactStatus(), post = robot.createContactStatus();
+  pre.activateContacts({0, 3});
+  post.activateContacts({0, 1, 2, 3});
+  contact_sequence.setContactStatusUniformly(pre);
+  idocp::DiscreteEvent event(pre, post);
+  std::cout << event.existImpulse() << event.existLift() << " ";
+  const double event_time = t + 0.33;   // inside grid interval 6 of dt = 0.05
+  contact_sequence.push_back(event, event_time);
+  idocp::OCPDiscretizer discretizer(T, N, max_num_events);
+  const bool ok = discretizer.discretizeOCP(contact_sequence, t);
+  std::cout << ok << " " << discretizer.N() << " " << discretizer.N_impulse() << " " << discretizer.N_lift() << " "
+            << discretizer.timeStageBeforeImpulse(0) << " " << discretizer.contactPhase(6) << discretizer.contactPhase(7) << " "
+            << discretizer.isTimeStageBeforeImpulse(6) << discretizer.isTimeStageAfterImpulse(7) << std::endl;
+  std::cout.precision(12);
+  std::cout << discretizer.t_impulse(0) - t << " " << discretizer.dt(6) + discretizer.dt_aux(0) << std::endl;
+  return 0;
+}
+""")
+    lib = os.path.join(ROOT, "idocp_b200")
+    exe = str(tmp_path / "disc")
+    subprocess.check_call(["g++", "-std=c++17", "-I" + os.path.join(ROOT, "include", "idocp_b200", "compat"), "-I" + os.path.join(ROOT, "include"),
+                           str(src), "-L" + lib, "-lidocp_b200", "-Wl,-rpath," + lib, "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
+    assert out[:8] == ["10", "1", "20", "1", "0", "6", "01", "11"], out
+    assert abs(float(out[8]) - 0.33) < 1e-12 and abs(float(out[9]) - 0.05) < 1e-12, out
