@@ -2571,7 +2571,10 @@ __global__ void __launch_bounds__(32 * FB_ROBOT_WARPS) k_fb_init_distance(FbArra
 // s + alpha d)  ->  k_fb_ls_filter (thread per instance); finished instances drop out.
 // =====================================================================================================
 template <bool INITIAL>
-__global__ void __launch_bounds__(32 * FB_LS_WARPS) k_fb_ls_eval(FbArrays A, FbLin* lin) {
+#ifndef IDOCP_FB_LS_MINB
+#define IDOCP_FB_LS_MINB 0
+#endif
+__global__ void __launch_bounds__(32 * FB_LS_WARPS, IDOCP_FB_LS_MINB) k_fb_ls_eval(FbArrays A, FbLin* lin) {
   IDOCP_DYN_SMEM(FbLsWork, wbase);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int stage = blockIdx.x * FB_LS_WARPS + warp;
