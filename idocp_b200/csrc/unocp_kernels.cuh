@@ -1229,7 +1229,10 @@ __global__ void __launch_bounds__(CTA_THREADS, IDOCP_EXP_MINB) k_expand(const De
 // ---------------------------------------------------------------------------------------------
 // `nstages` = N + 1 with the terminal stage at index N (UnOCPSolver) or N without one (UnParNMPCSolver,
 // src/unocp/unparnmpc_solver.cpp:88-101).
-__global__ void __launch_bounds__(CTA_THREADS) k_update(const DevProblem* __restrict__ Pp, Layout L, int stage_offset,
+#ifndef IDOCP_UPD_MINB
+#define IDOCP_UPD_MINB 0
+#endif
+__global__ void __launch_bounds__(CTA_THREADS, IDOCP_UPD_MINB) k_update(const DevProblem* __restrict__ Pp, Layout L, int stage_offset,
                                                         const double* __restrict__ primal_override, int nstages) {
   const DevProblem& P = *Pp;
   const int lane = lane_in_octet();
