@@ -36,3 +36,21 @@ def test_register_budgets_of_the_heavy_kernels():
         for n, r in hits.items():
             alloc = -(-r // 8) * 8                     # registers are allocated in units of 8 per thread
             assert alloc * threads * ctas <= 65536, (n, r, threads, ctas)
+
+
+NO_SPILLS = ["k_parnmpc_invert", "k_fb_riccati_backward", "k_fb_condense", "k_update_linearizeILb0ELb0", "k_fb_expand", "k_expandILb0ELb0ELb0"]
+
+
+def test_kernels_documented_as_spill_free_have_no_spills():
+    """ptxas -v of the product build (build_ptxas.log, written by __graft_entry__.build_cuda): the kernels DESIGN.md calls
+    spill-free report 0 bytes of spill stores / loads."""
+    import os
+    g.build_cuda(force=not os.path.exists(os.path.join(g.ROOT, "build_ptxas.log")))
+    log = open(os.path.join(g.ROOT, "build_ptxas.log")).read()
+    blocks = re.findall(r"Function properties for (\S+)\n\s*(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", log)
+    assert blocks
+    for frag in NO_SPILLS:
+        hits = [(n, int(st), int(ld)) for n, _, st, ld in blocks if frag in n]
+        assert hits, frag
+        for n, st, ld in hits:
+            assert st == 0 and ld == 0, (n, st, ld)
